@@ -1,0 +1,166 @@
+"""Thin Python handle over the C ABI (include/amps_gpu.h) used by tests and bench.py.
+
+Method names follow the reference entry points they stand for:
+  MoveParticles()        <- PIC::Mover::MoveParticles            (src/pic/pic_mover.cpp:580)
+  UpdateJMassMatrix()    <- ECSIM::UpdateJMassMatrix             (src/pic/pic_field_solver_ecsim.cpp:3244)
+  ParticleBuffer upload/download <- PIC::ParticleBuffer          (src/pic/pic_pbuffer.cpp)
+Everything here is plumbing: numpy arrays in, ctypes calls, numpy arrays out.  The compute is in
+libamps_gpu.so; if it is missing or there is no GPU these calls raise.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import Config, MoveStats
+
+
+class AmpsGpuError(RuntimeError):
+    pass
+
+
+def make_config(block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), charge=(-1.0, 1.0), mass=(1.0, 1836.0), species_weight=None, dt=1.0,
+                periodic=True, capacity=1 << 20, device=0, boundary_mode=_capi.BOUNDARY_DELETE, B_conv=1.0, length_conv=1.0,
+                light_speed=1.0):
+    """Normalised-unit ECSIM configuration (_PIC_FIELD_SOLVER_INPUT_UNIT_NORM_, c = 1)."""
+    cfg = Config()
+    ns = len(charge)
+    for d in range(3):
+        cfg.block_cells[d] = block_cells[d]
+        cfg.ghost_cells[d] = ghost_cells[d]
+    cfg.n_species = ns
+    cfg.b_mode = _capi.B_CENTER_BASED
+    cfg.periodic = 1 if periodic else 0
+    cfg.boundary_mode = boundary_mode
+    cfg.time_step_mode = _capi.DT_SINGLE_GLOBAL
+    cfg.device = device
+    cfg.capacity = int(capacity)
+    for s in range(ns):
+        cfg.charge[s] = charge[s]
+        cfg.mass[s] = mass[s]
+        cfg.species_weight[s] = 1.0 if species_weight is None else species_weight[s]
+        cfg.time_step[s] = dt
+    cfg.ecsim_dt_total = dt
+    cfg.ecsim_B_conv = B_conv
+    cfg.ecsim_length_conv = length_conv
+    cfg.ecsim_light_speed = light_speed
+    return cfg
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One device context == one AMPS rank's particle store, mesh copy and J/M arrays."""
+
+    def __init__(self, cfg, mesh):
+        self.lib = _capi.load_library()
+        self.cfg = cfg
+        self.mesh = mesh
+        self._h = C.c_void_p()
+        rc = self.lib.amps_gpu_init(C.byref(cfg), C.byref(self._h))
+        if rc != _capi.OK:
+            msg = self.lib.amps_gpu_last_error(self._h).decode() if self._h else ""
+            raise AmpsGpuError(f"amps_gpu_init failed rc={rc} {msg} (no CPU fallback)")
+        self._ck(self.lib.amps_gpu_mesh_upload(self._h, C.byref(mesh.c)))
+
+    def _ck(self, rc):
+        if rc != _capi.OK:
+            raise AmpsGpuError(f"rc={rc}: {self.lib.amps_gpu_last_error(self._h).decode()}")
+
+    def close(self):
+        if self._h:
+            self.lib.amps_gpu_finalize(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- fields ------------------------------------------------------------------------
+    def fields_upload(self, E_half=None, B_prev=None, B_cur=None):
+        arrs = []
+        for a, n in ((E_half, self.mesh.n_corners), (B_prev, self.mesh.n_centers), (B_cur, self.mesh.n_centers)):
+            if a is not None:
+                a = np.ascontiguousarray(a, dtype=np.float64)
+                assert a.shape == (n, 3), (a.shape, n)
+            arrs.append(a)
+        self._ck(self.lib.amps_gpu_fields_upload(self._h, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2])))
+
+    # ---- PIC::ParticleBuffer ---------------------------------------------------------------
+    def particles_upload(self, x, v, w, species, cells, ptrs=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        n = x.shape[1]
+        assert x.shape == (3, n) and v.shape == (3, n)
+        w = None if w is None else np.ascontiguousarray(w, dtype=np.float64)
+        species = np.ascontiguousarray(species, dtype=np.uint8)
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        ptrs = None if ptrs is None else np.ascontiguousarray(ptrs, dtype=np.int32)
+        self._ck(self.lib.amps_gpu_particles_upload_soa(self._h, _ptr(x), _ptr(v), _ptr(w), _ptr(species), _ptr(cells), _ptr(ptrs), n))
+
+    def particle_count(self):
+        n = C.c_int64()
+        self._ck(self.lib.amps_gpu_particle_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    def particles_download(self):
+        n = self.particle_count()
+        x = np.empty((3, n)), np.empty((3, n))
+        w = np.empty(n)
+        sp = np.empty(n, dtype=np.uint8)
+        cells = np.empty(n, dtype=np.int32)
+        ptrs = np.empty(n, dtype=np.int32)
+        nn = C.c_int64()
+        self._ck(self.lib.amps_gpu_particles_download_soa(self._h, _ptr(x[0]), _ptr(x[1]), _ptr(w), _ptr(sp), _ptr(cells), _ptr(ptrs), n,
+                                                          C.byref(nn)))
+        return {"x": x[0], "v": x[1], "w": w, "species": sp, "cells": cells, "ptrs": ptrs}
+
+    def cell_table(self):
+        t = np.empty(self.mesh.n_cells + 1, dtype=np.int64)
+        self._ck(self.lib.amps_gpu_cell_table_download(self._h, _ptr(t), t.size))
+        return t
+
+    def sort(self):
+        self._ck(self.lib.amps_gpu_sort(self._h))
+
+    # ---- PIC::Mover::MoveParticles -----------------------------------------------------------
+    def MoveParticles(self, mover=_capi.MOVER_LAPENTA2017, stats=True):
+        if stats:
+            st = MoveStats()
+            self._ck(self.lib.amps_gpu_move(self._h, mover, C.byref(st)))
+            return st.as_dict()
+        self._ck(self.lib.amps_gpu_move(self._h, mover, None))
+        return None
+
+    # ---- ECSIM::UpdateJMassMatrix ---------------------------------------------------------
+    def UpdateJMassMatrix(self, diagnostics=True):
+        if diagnostics:
+            e = C.c_double()
+            cfl = (C.c_double * _capi.MAX_SPECIES)()
+            self._ck(self.lib.amps_gpu_deposit_JM(self._h, C.cast(C.byref(e), C.c_void_p), C.cast(cfl, C.c_void_p)))
+            return float(e.value), [float(cfl[s]) for s in range(self.cfg.n_species)]
+        self._ck(self.lib.amps_gpu_deposit_JM(self._h, None, None))
+        return None
+
+    def JM_download(self, want_J=True, want_M=True, out_J=None, out_M=None):
+        nc = self.mesh.n_corners
+        J = (out_J if out_J is not None else np.empty((nc, 3))) if want_J else None
+        M = (out_M if out_M is not None else np.empty((nc, 243))) if want_M else None
+        self._ck(self.lib.amps_gpu_JM_download(self._h, _ptr(J), _ptr(M)))
+        return J, M
+
+    def step(self, mover=_capi.MOVER_LAPENTA2017):
+        self._ck(self.lib.amps_gpu_step(self._h, mover))
+
+    def synchronize(self):
+        self._ck(self.lib.amps_gpu_synchronize(self._h))
+
+    def launch_count(self):
+        return int(self.lib.amps_gpu_launch_count(self._h))
+
+    def stream(self):
+        return self.lib.amps_gpu_stream(self._h)

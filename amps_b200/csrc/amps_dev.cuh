@@ -1,0 +1,98 @@
+// amps_dev.cuh -- device-side data model shared by the kernels of libamps_gpu.so (sm_100a).
+//
+// HBM layout (all library-owned):
+//   particles   SoA, sorted by key = leaf*cellsPerBlock + cell :  x[3][cap] v[3][cap] w[cap] (f64)
+//               spec[cap] (u8)  key[cap] (i32, -1 = deleted)  ptr[cap] (i32, ParticleBuffer slot);
+//               two copies (ping-pong for the counting sort)
+//   cell table  cellStart[nCells+1] (i32) : particle range of each cell
+//   mesh        flattened cTreeNodeAMR arrays + per-leaf LeafGeo + unique node tables
+//   fields      unique-node arrays E_half[nCorners][3], B_prev/B_cur[nCenters][3] and per-leaf
+//               staged tiles (SetBlock_E / SetBlock_B result) padded to 16 B for TMA bulk copies
+//   J, M        J[nCorners][3], M[nCorners][243]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/amps_gpu.h"
+
+namespace amps {
+
+struct LeafGeo {
+  double xmin[3], xmax[3];
+  int imin[3];
+  int isize;
+  int level;
+  int flags;  // AMPS_NODE_*
+  int real;   // paired real leaf of a periodic ghost leaf, else -1
+  int face;   // bit f: no neighbour across face f
+  int node;
+  int pad;
+};
+
+struct DevMesh {
+  int N[3], g[3], TN[3];
+  int nRoot[3];
+  int L;  // max_refinement_level
+  int nNodes, nLeaves, nCorners, nCenters;
+  int cellsPerBlock, nCornerLocal, nCenterLocal;
+  int eTileStride, bTileStride;  // doubles per leaf tile (padded to even => 16 B multiples)
+  int periodic;
+  double xGlobalMin[3], xGlobalMax[3], dxMaxRef[3], dxRoot[3], eps;
+  const int *child;     // [nNodes][8]
+  const int *imin;      // [nNodes][3]
+  const int *isize;     // [nNodes]
+  const int *nodeLeaf;  // [nNodes]
+  const int *nodeFlags; // [nNodes]
+  const int *nodeLevel; // [nNodes]
+  const double *nxmin;  // [nNodes][3]
+  const double *nxmax;  // [nNodes][3]
+  const int *rootNode;  // [nRoot0*nRoot1*nRoot2]
+  const LeafGeo *leaf;  // [nLeaves]
+  const int *cornerUid; // [nLeaves][nCornerLocal]
+  const int *centerUid; // [nLeaves][nCenterLocal]
+};
+
+struct DevSpecies {
+  int n;
+  int timeStepMode;
+  int bMode;
+  int boundaryMode;
+  double charge[AMPS_GPU_MAX_SPECIES], mass[AMPS_GPU_MAX_SPECIES], weight[AMPS_GPU_MAX_SPECIES], dt[AMPS_GPU_MAX_SPECIES];
+  double dtTotal, B_conv, length_conv, LightSpeed;
+};
+
+struct ParticleSoA {
+  double *x[3];
+  double *v[3];
+  double *w;
+  uint8_t *spec;
+  int *key;
+  int *ptr;
+};
+
+// counters written by the mover (device copy of amps_gpu_move_stats + error word)
+struct DevMoveStats {
+  unsigned long long n_moved, n_cross_cell, n_cross_block, n_left_domain, n_not_in_use, n_periodic_wrap, n_error;
+  unsigned long long pad;
+};
+
+// ---- meshAMRgeneric.h:74-75 ----
+__device__ __forceinline__ int cornerLocalNumber(const DevMesh &m, int i, int j, int k) {
+  return i + m.g[0] + (1 + m.TN[0]) * (j + m.g[1] + (k + m.g[2]) * (1 + m.TN[1]));
+}
+__device__ __forceinline__ int centerLocalNumber(const DevMesh &m, int i, int j, int k) {
+  return i + m.g[0] + m.TN[0] * (j + m.g[1] + (k + m.g[2]) * m.TN[1]);
+}
+
+// launch helpers (defined per TU that needs them)
+void launch_stage_tiles(const DevMesh &m, const double *E_half, const double *B_prev, const double *B_cur, double *eTile, double *bPrevTile,
+                        double *bCurTile, cudaStream_t s);
+void launch_move_lapenta(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *eTile, const double *bTile,
+                         int *cellCount, DevMoveStats *stats, int slices, cudaStream_t s);
+void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *nSrc, int *cellCount, int *cellStart, int *cellFill, int *nDst,
+                 long long capacity, bool countValid, void *scanTmp, cudaStream_t s, long long *launches);
+void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
+                    double *energy, unsigned long long *cflBits, cudaStream_t s, long long *launches);
+size_t sort_scan_tmp_bytes(long long nCells);
+
+}  // namespace amps

@@ -1,0 +1,518 @@
+// amps_gpu.cu -- host side of the C ABI declared in include/amps_gpu.h: context, device memory,
+// uploads/downloads and kernel sequencing.  No CPU fallback anywhere: without a CUDA device
+// amps_gpu_init() fails with AMPS_GPU_ERR_NO_DEVICE.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "amps_dev.cuh"
+
+using namespace amps;
+
+struct amps_gpu_ctx {
+  amps_gpu_config cfg;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+
+  DevMesh dm;
+  DevSpecies sp;
+  bool meshReady = false, fieldsReady = false;
+  std::vector<void *> meshAllocs;
+
+  // fields
+  double *d_Ehalf = nullptr, *d_Bprev = nullptr, *d_Bcur = nullptr;
+  double *d_eTile = nullptr, *d_bPrevTile = nullptr, *d_bCurTile = nullptr;
+
+  // particles
+  ParticleSoA buf[2];
+  int cur = 0;
+  int *d_n = nullptr;  // [2]
+  long long nUpper = 0;
+  bool sorted = false, countValid = false;
+  int *d_cellCount = nullptr, *d_cellStart = nullptr, *d_cellFill = nullptr;
+  void *d_scanTmp = nullptr;
+  long long nCells = 0;
+
+  // deposit
+  double *d_J = nullptr, *d_M = nullptr, *d_energy = nullptr;
+  unsigned long long *d_cfl = nullptr;
+  DevMoveStats *d_stats = nullptr;
+};
+
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) {                                                                           \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"; \
+      return AMPS_GPU_ERR_CUDA;                                                                        \
+    }                                                                                                  \
+  } while (0)
+
+#define FAIL(code, msg) \
+  do {                  \
+    ctx->err = (msg);   \
+    return (code);      \
+  } while (0)
+
+template <class T>
+static int dev_alloc(amps_gpu_ctx *ctx, T **p, size_t n) {
+  CK(cudaMalloc((void **)p, n * sizeof(T) + 16));
+  return AMPS_GPU_OK;
+}
+
+static int alloc_particles(amps_gpu_ctx *ctx, ParticleSoA &b, long long cap) {
+  int rc;
+  for (int d = 0; d < 3; d++) {
+    if ((rc = dev_alloc(ctx, &b.x[d], cap))) return rc;
+    if ((rc = dev_alloc(ctx, &b.v[d], cap))) return rc;
+  }
+  if ((rc = dev_alloc(ctx, &b.w, cap))) return rc;
+  if ((rc = dev_alloc(ctx, &b.spec, cap))) return rc;
+  if ((rc = dev_alloc(ctx, &b.key, cap))) return rc;
+  if ((rc = dev_alloc(ctx, &b.ptr, cap))) return rc;
+  return AMPS_GPU_OK;
+}
+static void free_particles(ParticleSoA &b) {
+  for (int d = 0; d < 3; d++) cudaFree(b.x[d]), cudaFree(b.v[d]);
+  cudaFree(b.w), cudaFree(b.spec), cudaFree(b.key), cudaFree(b.ptr);
+}
+
+template <class T>
+static int upload_array(amps_gpu_ctx *ctx, const T **dst, const T *src, size_t n) {
+  T *d = nullptr;
+  CK(cudaMalloc((void **)&d, (n ? n : 1) * sizeof(T)));
+  ctx->meshAllocs.push_back(d);
+  if (n) CK(cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  *dst = d;
+  return AMPS_GPU_OK;
+}
+
+extern "C" {
+
+int amps_gpu_init(const amps_gpu_config *cfg, amps_gpu_ctx **out) {
+  if (!cfg || !out) return AMPS_GPU_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    fprintf(stderr, "amps_gpu_init: no CUDA device visible; this library has no CPU fallback\n");
+    return AMPS_GPU_ERR_NO_DEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return AMPS_GPU_ERR_ARG;
+  if (cfg->n_species < 1 || cfg->n_species > AMPS_GPU_MAX_SPECIES) return AMPS_GPU_ERR_ARG;
+  if (cfg->capacity < 1 || cfg->capacity > 2147483000LL) return AMPS_GPU_ERR_ARG;
+  for (int d = 0; d < 3; d++)
+    if (cfg->block_cells[d] < 1 || cfg->ghost_cells[d] < 1) return AMPS_GPU_ERR_ARG;
+  if (cfg->b_mode != AMPS_B_CENTER_BASED) {
+    fprintf(stderr, "amps_gpu_init: only _PIC_FIELD_SOLVER_B_CENTER_BASED_ is implemented\n");
+    return AMPS_GPU_ERR_ARG;
+  }
+  amps_gpu_ctx *ctx = new amps_gpu_ctx();
+  ctx->cfg = *cfg;
+  memset(&ctx->dm, 0, sizeof(ctx->dm));
+  memset(&ctx->sp, 0, sizeof(ctx->sp));
+  memset(ctx->buf, 0, sizeof(ctx->buf));
+  *out = ctx;  // returned even on failure so that the caller can read last_error
+  CK(cudaSetDevice(cfg->device));
+  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+
+  DevSpecies &sp = ctx->sp;
+  sp.n = cfg->n_species;
+  sp.timeStepMode = cfg->time_step_mode;
+  sp.bMode = cfg->b_mode;
+  sp.boundaryMode = cfg->boundary_mode;
+  for (int s = 0; s < AMPS_GPU_MAX_SPECIES; s++) {
+    sp.charge[s] = cfg->charge[s], sp.mass[s] = cfg->mass[s], sp.weight[s] = cfg->species_weight[s], sp.dt[s] = cfg->time_step[s];
+  }
+  sp.dtTotal = cfg->ecsim_dt_total, sp.B_conv = cfg->ecsim_B_conv, sp.length_conv = cfg->ecsim_length_conv, sp.LightSpeed = cfg->ecsim_light_speed;
+
+  int rc;
+  for (int b = 0; b < 2; b++)
+    if ((rc = alloc_particles(ctx, ctx->buf[b], cfg->capacity))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_n, 2))) return rc;
+  CK(cudaMemset(ctx->d_n, 0, 2 * sizeof(int)));
+  if ((rc = dev_alloc(ctx, &ctx->d_energy, 1))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_cfl, AMPS_GPU_MAX_SPECIES))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_stats, 1))) return rc;
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_finalize(amps_gpu_ctx *ctx) {
+  if (!ctx) return AMPS_GPU_OK;
+  cudaSetDevice(ctx->cfg.device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (void *p : ctx->meshAllocs) cudaFree(p);
+  cudaFree(ctx->d_Ehalf), cudaFree(ctx->d_Bprev), cudaFree(ctx->d_Bcur);
+  cudaFree(ctx->d_eTile), cudaFree(ctx->d_bPrevTile), cudaFree(ctx->d_bCurTile);
+  for (int b = 0; b < 2; b++) free_particles(ctx->buf[b]);
+  cudaFree(ctx->d_n), cudaFree(ctx->d_cellCount), cudaFree(ctx->d_cellStart), cudaFree(ctx->d_cellFill), cudaFree(ctx->d_scanTmp);
+  cudaFree(ctx->d_J), cudaFree(ctx->d_M), cudaFree(ctx->d_energy), cudaFree(ctx->d_cfl), cudaFree(ctx->d_stats);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return AMPS_GPU_OK;
+}
+
+const char *amps_gpu_last_error(const amps_gpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t amps_gpu_launch_count(const amps_gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void *amps_gpu_stream(amps_gpu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int amps_gpu_synchronize(amps_gpu_ctx *ctx) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
+  if (!ctx || !mesh) return AMPS_GPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  if (ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "mesh re-upload: finalize and re-create the context (mesh epochs are a round-2 item)");
+  if (mesh->n_nodes < 1 || mesh->n_leaves < 1 || mesh->n_corners < 1 || mesh->n_centers < 1) FAIL(AMPS_GPU_ERR_ARG, "empty mesh");
+  DevMesh &m = ctx->dm;
+  for (int d = 0; d < 3; d++) {
+    m.N[d] = ctx->cfg.block_cells[d], m.g[d] = ctx->cfg.ghost_cells[d], m.TN[d] = m.N[d] + 2 * m.g[d];
+    m.nRoot[d] = mesh->n_root[d];
+    m.xGlobalMin[d] = mesh->x_global_min[d], m.xGlobalMax[d] = mesh->x_global_max[d];
+    m.dxMaxRef[d] = mesh->dx_max_refinement[d], m.dxRoot[d] = mesh->dx_root_block[d];
+  }
+  m.L = mesh->max_refinement_level;
+  m.eps = mesh->eps;
+  m.nNodes = mesh->n_nodes, m.nLeaves = mesh->n_leaves, m.nCorners = mesh->n_corners, m.nCenters = mesh->n_centers;
+  m.cellsPerBlock = m.N[0] * m.N[1] * m.N[2];
+  m.nCornerLocal = (m.TN[0] + 1) * (m.TN[1] + 1) * (m.TN[2] + 1);
+  m.nCenterLocal = m.TN[0] * m.TN[1] * m.TN[2];
+  m.eTileStride = (3 * m.nCornerLocal + 1) & ~1;
+  m.bTileStride = (3 * m.nCenterLocal + 1) & ~1;
+  m.periodic = ctx->cfg.periodic;
+  const long long nCells = (long long)m.nLeaves * m.cellsPerBlock;
+  if (nCells > 2147483000LL) FAIL(AMPS_GPU_ERR_ARG, "too many cells for 32-bit keys");
+  ctx->nCells = nCells;
+
+  // per-leaf geometry
+  std::vector<LeafGeo> lg(m.nLeaves);
+  for (int l = 0; l < m.nLeaves; l++) {
+    const int n = mesh->leaf_node[l];
+    if (n < 0 || n >= m.nNodes) FAIL(AMPS_GPU_ERR_ARG, "leaf_node out of range");
+    LeafGeo &g = lg[l];
+    for (int d = 0; d < 3; d++) {
+      g.xmin[d] = mesh->node_xmin[3 * n + d], g.xmax[d] = mesh->node_xmax[3 * n + d];
+      g.imin[d] = mesh->node_imin[3 * n + d];
+    }
+    g.isize = mesh->node_isize[n];
+    g.level = mesh->node_level[n];
+    g.flags = mesh->node_flags[n];
+    g.real = mesh->leaf_real[l];
+    g.face = mesh->leaf_face_boundary[l];
+    g.node = n;
+    g.pad = 0;
+  }
+  int rc;
+  const int nRootTot = m.nRoot[0] * m.nRoot[1] * m.nRoot[2];
+  if ((rc = upload_array(ctx, &m.child, mesh->node_child, (size_t)8 * m.nNodes))) return rc;
+  if ((rc = upload_array(ctx, &m.imin, mesh->node_imin, (size_t)3 * m.nNodes))) return rc;
+  if ((rc = upload_array(ctx, &m.isize, mesh->node_isize, (size_t)m.nNodes))) return rc;
+  if ((rc = upload_array(ctx, &m.nodeLeaf, mesh->node_leaf, (size_t)m.nNodes))) return rc;
+  if ((rc = upload_array(ctx, &m.nodeFlags, mesh->node_flags, (size_t)m.nNodes))) return rc;
+  if ((rc = upload_array(ctx, &m.nodeLevel, mesh->node_level, (size_t)m.nNodes))) return rc;
+  if ((rc = upload_array(ctx, &m.nxmin, mesh->node_xmin, (size_t)3 * m.nNodes))) return rc;
+  if ((rc = upload_array(ctx, &m.nxmax, mesh->node_xmax, (size_t)3 * m.nNodes))) return rc;
+  if ((rc = upload_array(ctx, &m.rootNode, mesh->root_node, (size_t)nRootTot))) return rc;
+  if ((rc = upload_array(ctx, &m.leaf, lg.data(), (size_t)m.nLeaves))) return rc;
+  if ((rc = upload_array(ctx, &m.cornerUid, mesh->leaf_corner_uid, (size_t)m.nLeaves * m.nCornerLocal))) return rc;
+  if ((rc = upload_array(ctx, &m.centerUid, mesh->leaf_center_uid, (size_t)m.nLeaves * m.nCenterLocal))) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));  // lg is a local
+
+  if ((rc = dev_alloc(ctx, &ctx->d_Ehalf, (size_t)3 * m.nCorners))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_Bprev, (size_t)3 * m.nCenters))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_Bcur, (size_t)3 * m.nCenters))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_eTile, (size_t)m.nLeaves * m.eTileStride))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_bPrevTile, (size_t)m.nLeaves * m.bTileStride))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_bCurTile, (size_t)m.nLeaves * m.bTileStride))) return rc;
+  CK(cudaMemsetAsync(ctx->d_eTile, 0, sizeof(double) * (size_t)m.nLeaves * m.eTileStride, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_bPrevTile, 0, sizeof(double) * (size_t)m.nLeaves * m.bTileStride, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_bCurTile, 0, sizeof(double) * (size_t)m.nLeaves * m.bTileStride, ctx->stream));
+  if ((rc = dev_alloc(ctx, &ctx->d_cellCount, (size_t)nCells + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_cellStart, (size_t)nCells + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_cellFill, (size_t)nCells + 1))) return rc;
+  CK(cudaMemsetAsync(ctx->d_cellStart, 0, sizeof(int) * ((size_t)nCells + 1), ctx->stream));
+  CK(cudaMalloc(&ctx->d_scanTmp, sort_scan_tmp_bytes(nCells)));
+  if ((rc = dev_alloc(ctx, &ctx->d_J, (size_t)3 * m.nCorners))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_M, (size_t)243 * m.nCorners))) return rc;
+  ctx->meshReady = true;
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_fields_upload(amps_gpu_ctx *ctx, const double *E_half, const double *B_prev, const double *B_cur) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "fields_upload before mesh_upload");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const DevMesh &m = ctx->dm;
+  if (E_half) CK(cudaMemcpyAsync(ctx->d_Ehalf, E_half, sizeof(double) * 3 * (size_t)m.nCorners, cudaMemcpyHostToDevice, ctx->stream));
+  if (B_prev) CK(cudaMemcpyAsync(ctx->d_Bprev, B_prev, sizeof(double) * 3 * (size_t)m.nCenters, cudaMemcpyHostToDevice, ctx->stream));
+  if (B_cur) CK(cudaMemcpyAsync(ctx->d_Bcur, B_cur, sizeof(double) * 3 * (size_t)m.nCenters, cudaMemcpyHostToDevice, ctx->stream));
+  launch_stage_tiles(m, E_half ? ctx->d_Ehalf : nullptr, B_prev ? ctx->d_Bprev : nullptr, B_cur ? ctx->d_Bcur : nullptr, ctx->d_eTile,
+                     ctx->d_bPrevTile, ctx->d_bCurTile, ctx->stream);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  ctx->fieldsReady = true;
+  return AMPS_GPU_OK;
+}
+
+static int do_sort(amps_gpu_ctx *ctx) {
+  ParticleSoA &src = ctx->buf[ctx->cur], &dst = ctx->buf[1 - ctx->cur];
+  launch_sort(ctx->dm, src, dst, ctx->d_n + ctx->cur, ctx->d_cellCount, ctx->d_cellStart, ctx->d_cellFill, ctx->d_n + (1 - ctx->cur), ctx->nUpper,
+              ctx->countValid, ctx->d_scanTmp, ctx->stream, &ctx->launches);
+  CK(cudaGetLastError());
+  ctx->cur = 1 - ctx->cur;
+  ctx->sorted = true;
+  ctx->countValid = false;
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_sort(amps_gpu_ctx *ctx) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "sort before mesh_upload");
+  CK(cudaSetDevice(ctx->cfg.device));
+  return do_sort(ctx);
+}
+
+int amps_gpu_particles_upload_soa(amps_gpu_ctx *ctx, const double *x, const double *v, const double *w, const uint8_t *species,
+                                  const int32_t *cells, const int32_t *ptrs, int64_t n) {
+  if (!ctx || !x || !v || !species || !cells || n < 0) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "particles_upload before mesh_upload");
+  if (n > ctx->cfg.capacity) FAIL(AMPS_GPU_ERR_CAPACITY, "particle capacity exceeded");
+  CK(cudaSetDevice(ctx->cfg.device));
+  for (int64_t i = 0; i < n; i++)
+    if (cells[i] < 0 || cells[i] >= ctx->nCells) FAIL(AMPS_GPU_ERR_ARG, "particle cell out of range");
+  ParticleSoA &b = ctx->buf[ctx->cur];
+  cudaStream_t s = ctx->stream;
+  for (int d = 0; d < 3; d++) {
+    CK(cudaMemcpyAsync(b.x[d], x + (size_t)d * n, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b.v[d], v + (size_t)d * n, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+  }
+  std::vector<double> ones;
+  std::vector<int32_t> iota;
+  if (!w) {
+    ones.assign((size_t)n, 1.0);
+    w = ones.data();
+  }
+  if (!ptrs) {
+    iota.resize((size_t)n);
+    for (int64_t i = 0; i < n; i++) iota[i] = (int32_t)i;
+    ptrs = iota.data();
+  }
+  CK(cudaMemcpyAsync(b.w, w, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(b.spec, species, n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(b.key, cells, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(b.ptr, ptrs, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+  const int n32 = (int)n;
+  CK(cudaMemcpyAsync(ctx->d_n + ctx->cur, &n32, sizeof(int), cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));  // host temporaries
+  ctx->nUpper = n;
+  ctx->countValid = false;
+  return do_sort(ctx);
+}
+
+int amps_gpu_particles_upload_aos(amps_gpu_ctx *ctx, const void *records, const int64_t *ptrs, const int32_t *cells, int64_t n,
+                                  const amps_gpu_aos_layout *lay) {
+  if (!ctx || !records || !cells || !lay || n < 0) return AMPS_GPU_ERR_ARG;
+  // AoS -> SoA on the host (one pass over the records), then the SoA path
+  std::vector<double> x((size_t)3 * n), v((size_t)3 * n), w((size_t)n);
+  std::vector<uint8_t> sp((size_t)n);
+  std::vector<int32_t> pt((size_t)n);
+  const unsigned char *base = (const unsigned char *)records;
+  for (int64_t i = 0; i < n; i++) {
+    const int64_t slot = ptrs ? ptrs[i] : i;
+    const unsigned char *r = base + slot * lay->stride;
+    double t[3];
+    memcpy(t, r + lay->off_x, 24);
+    x[i] = t[0], x[n + i] = t[1], x[2 * n + i] = t[2];
+    memcpy(t, r + lay->off_v, 24);
+    v[i] = t[0], v[n + i] = t[1], v[2 * n + i] = t[2];
+    if (lay->off_w >= 0) memcpy(&w[i], r + lay->off_w, 8);
+    else w[i] = 1.0;
+    sp[i] = r[lay->off_species] & 0x3f;
+    pt[i] = (int32_t)slot;
+  }
+  return amps_gpu_particles_upload_soa(ctx, x.data(), v.data(), w.data(), sp.data(), cells, pt.data(), n);
+}
+
+int amps_gpu_particle_count(amps_gpu_ctx *ctx, int64_t *n) {
+  if (!ctx || !n) return AMPS_GPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  int n32 = 0;
+  CK(cudaMemcpyAsync(&n32, ctx->d_n + ctx->cur, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *n = n32;
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_particles_download_soa(amps_gpu_ctx *ctx, double *x, double *v, double *w, uint8_t *species, int32_t *cells, int32_t *ptrs,
+                                    int64_t n_max, int64_t *n_out) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  int64_t n = 0;
+  int rc = amps_gpu_particle_count(ctx, &n);
+  if (rc) return rc;
+  if (n_out) *n_out = n;
+  if (n > n_max) FAIL(AMPS_GPU_ERR_CAPACITY, "download buffer too small");
+  const ParticleSoA &b = ctx->buf[ctx->cur];
+  cudaStream_t s = ctx->stream;
+  // component-major with stride n_max so that the caller can size buffers before knowing n
+  for (int d = 0; d < 3; d++) {
+    if (x) CK(cudaMemcpyAsync(x + (size_t)d * n_max, b.x[d], sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    if (v) CK(cudaMemcpyAsync(v + (size_t)d * n_max, b.v[d], sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  }
+  if (w) CK(cudaMemcpyAsync(w, b.w, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  if (species) CK(cudaMemcpyAsync(species, b.spec, n, cudaMemcpyDeviceToHost, s));
+  if (cells) CK(cudaMemcpyAsync(cells, b.key, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+  if (ptrs) CK(cudaMemcpyAsync(ptrs, b.ptr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_particles_download_aos(amps_gpu_ctx *ctx, void *records, int64_t *first_cell_particle, int64_t n_max, const amps_gpu_aos_layout *lay,
+                                    int64_t *n_out) {
+  if (!ctx || !records || !lay) return AMPS_GPU_ERR_ARG;
+  int64_t n = 0;
+  int rc = amps_gpu_particle_count(ctx, &n);
+  if (rc) return rc;
+  if (n_out) *n_out = n;
+  std::vector<double> x((size_t)3 * n + 1), v((size_t)3 * n + 1), w((size_t)n + 1);
+  std::vector<uint8_t> sp((size_t)n + 1);
+  std::vector<int32_t> key((size_t)n + 1), pt((size_t)n + 1);
+  int64_t nn;
+  rc = amps_gpu_particles_download_soa(ctx, x.data(), v.data(), w.data(), sp.data(), key.data(), pt.data(), n, &nn);
+  if (rc) return rc;
+  unsigned char *base = (unsigned char *)records;
+  if (first_cell_particle)
+    for (int64_t c = 0; c < ctx->nCells; c++) first_cell_particle[c] = -1;
+  for (int64_t i = 0; i < n; i++) {
+    const int64_t slot = pt[i];
+    if (slot < 0 || slot >= n_max) FAIL(AMPS_GPU_ERR_ARG, "particle slot outside the caller's buffer");
+    unsigned char *r = base + slot * lay->stride;
+    double t[3] = {x[i], x[n + i], x[2 * n + i]};
+    memcpy(r + lay->off_x, t, 24);
+    double u[3] = {v[i], v[n + i], v[2 * n + i]};
+    memcpy(r + lay->off_v, u, 24);
+    if (lay->off_w >= 0) memcpy(r + lay->off_w, &w[i], 8);
+    r[lay->off_species] = (unsigned char)((r[lay->off_species] & 0xc0) | (sp[i] & 0x3f));
+    if (first_cell_particle && key[i] >= 0) {
+      // push on the cell list like the movers do (pic_mover_boris.cpp:1333-1343)
+      int64_t *first = first_cell_particle + key[i];
+      const int64_t old = *first, none = -1;
+      memcpy(r + lay->off_next, &old, 8);
+      memcpy(r + lay->off_prev, &none, 8);
+      if (old != -1) memcpy(base + old * lay->stride + lay->off_prev, &slot, 8);
+      *first = slot;
+    }
+  }
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_cell_table_download(amps_gpu_ctx *ctx, int64_t *cell_start, int64_t n_cells_plus_1) {
+  if (!ctx || !cell_start) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady || n_cells_plus_1 != ctx->nCells + 1) FAIL(AMPS_GPU_ERR_ARG, "cell table size mismatch");
+  if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "cell table is stale: call amps_gpu_sort first");
+  CK(cudaSetDevice(ctx->cfg.device));
+  std::vector<int> tmp((size_t)n_cells_plus_1);
+  CK(cudaMemcpyAsync(tmp.data(), ctx->d_cellStart, sizeof(int) * n_cells_plus_1, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int64_t i = 0; i < n_cells_plus_1; i++) cell_start[i] = tmp[i];
+  return AMPS_GPU_OK;
+}
+
+static int do_move(amps_gpu_ctx *ctx, int mover_id) {
+  if (!ctx->meshReady || !ctx->fieldsReady) FAIL(AMPS_GPU_ERR_STATE, "move before mesh/fields upload");
+  if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "move needs the (block,cell)-sorted layout: call amps_gpu_sort");
+  if (mover_id != AMPS_MOVER_LAPENTA2017) FAIL(AMPS_GPU_ERR_ARG, "mover not implemented yet");
+  const DevMesh &m = ctx->dm;
+  CK(cudaMemsetAsync(ctx->d_cellCount, 0, sizeof(int) * (size_t)ctx->nCells, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevMoveStats), ctx->stream));
+  long long perLeaf = ctx->nUpper / (m.nLeaves > 0 ? m.nLeaves : 1);
+  int slices = (int)((perLeaf + 4095) / 4096);
+  if (slices < 1) slices = 1;
+  if (slices > 64) slices = 64;
+  launch_move_lapenta(m, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_eTile, ctx->d_bPrevTile, ctx->d_cellCount, ctx->d_stats, slices,
+                      ctx->stream);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  ctx->sorted = false;
+  ctx->countValid = true;
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_move(amps_gpu_ctx *ctx, int mover_id, amps_gpu_move_stats *stats) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc = do_move(ctx, mover_id);
+  if (rc) return rc;
+  if (stats) {
+    DevMoveStats h;
+    CK(cudaMemcpyAsync(&h, ctx->d_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    stats->n_moved = (int64_t)h.n_moved;
+    stats->n_cross_cell = (int64_t)h.n_cross_cell;
+    stats->n_cross_block = (int64_t)h.n_cross_block;
+    stats->n_left_domain = (int64_t)h.n_left_domain;
+    stats->n_not_in_use = (int64_t)h.n_not_in_use;
+    stats->n_periodic_wrap = (int64_t)h.n_periodic_wrap;
+    stats->n_error = (int64_t)h.n_error;
+    if (h.n_error) FAIL(AMPS_GPU_ERR_PARTICLE, "mover: particle outside its block / cell not found (the reference would exit())");
+  }
+  return AMPS_GPU_OK;
+}
+
+static int do_deposit(amps_gpu_ctx *ctx) {
+  if (!ctx->meshReady || !ctx->fieldsReady) FAIL(AMPS_GPU_ERR_STATE, "deposit before mesh/fields upload");
+  if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "deposit needs the (block,cell)-sorted layout: call amps_gpu_sort");
+  launch_deposit(ctx->dm, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl,
+                 ctx->stream, &ctx->launches);
+  CK(cudaGetLastError());
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_deposit_JM(amps_gpu_ctx *ctx, double *particle_energy, double *cfl) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc = do_deposit(ctx);
+  if (rc) return rc;
+  if (particle_energy || cfl) {
+    double e;
+    unsigned long long c[AMPS_GPU_MAX_SPECIES];
+    CK(cudaMemcpyAsync(&e, ctx->d_energy, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(c, ctx->d_cfl, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (particle_energy) *particle_energy = e;
+    if (cfl)
+      for (int s = 0; s < ctx->cfg.n_species; s++) memcpy(&cfl[s], &c[s], 8);
+  }
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_JM_download(amps_gpu_ctx *ctx, double *J, double *M) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "JM_download before mesh_upload");
+  CK(cudaSetDevice(ctx->cfg.device));
+  if (J) CK(cudaMemcpyAsync(J, ctx->d_J, sizeof(double) * 3 * (size_t)ctx->dm.nCorners, cudaMemcpyDeviceToHost, ctx->stream));
+  if (M) CK(cudaMemcpyAsync(M, ctx->d_M, sizeof(double) * 243 * (size_t)ctx->dm.nCorners, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_JM_device(amps_gpu_ctx *ctx, double **J_dev, double **M_dev) {
+  if (!ctx || !ctx->meshReady) return AMPS_GPU_ERR_STATE;
+  if (J_dev) *J_dev = ctx->d_J;
+  if (M_dev) *M_dev = ctx->d_M;
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_step(amps_gpu_ctx *ctx, int mover_id) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc;
+  if ((rc = do_move(ctx, mover_id))) return rc;
+  if ((rc = do_sort(ctx))) return rc;
+  return do_deposit(ctx);
+}
+
+}  // extern "C"

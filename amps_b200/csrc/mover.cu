@@ -1,0 +1,428 @@
+// mover.cu -- particle push kernels (sm_100a).  COMPILED WITH --fmad=false:
+// the position update and the cell search must round exactly like the reference's CPU build
+// (no FMA contraction; IEEE fp64 division), else a particle within 1 ulp of a face lands in a
+// different cell than on the CPU (hard part 1).
+//
+// Kernels
+//   stage_tiles_kernel     a2  SetBlock_E/SetBlock_B   src/pic/pic_mover.cpp:86-166
+//   move_lapenta_kernel    a5  PIC::Mover::Lapenta2017 src/pic/pic_mover_boris.cpp:876-1393
+//                          a3  CornerBased::InitStencil             pic_interpolation_routines.cpp:1074-1194
+//                          a4  CellCentered::Linear::InitStencil    pic_interpolation_routines.cpp:224-330,820-907
+//                          a14 findTreeNode / FindCellIndex         meshAMRgeneric.h:2793-2882, 2256-2323
+//                          a16 periodic wrap                        pic_bc_periodic.cpp:86-178
+//
+// Mapping: one CTA per (leaf block, slice of its particle range); the block's E (corner) and
+// B (centre) tiles incl. ghost layer are brought into shared memory by two 1-D TMA bulk copies
+// (cp.async.bulk -> UBLKCP) completing on an mbarrier; one thread per particle, SoA loads are
+// unit-stride.  The new (block,cell) key is histogrammed here so the counting sort needs no
+// extra pass over the particles.
+#include "amps_dev.cuh"
+
+namespace amps {
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copy (TMA engine)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// a2: gather unique-node fields into per-leaf tiles (incl. ghost layers); missing node -> 0
+// ------------------------------------------------------------------------------------------------
+__global__ void stage_tiles_kernel(DevMesh m, const double *__restrict__ E_half, const double *__restrict__ B_prev, const double *__restrict__ B_cur,
+                                   double *__restrict__ eTile, double *__restrict__ bPrevTile, double *__restrict__ bCurTile) {
+  const int leaf = blockIdx.x;
+  if (E_half) {
+    const int *uid = m.cornerUid + (size_t)leaf * m.nCornerLocal;
+    double *dst = eTile + (size_t)leaf * m.eTileStride;
+    for (int i = threadIdx.x; i < m.nCornerLocal; i += blockDim.x) {
+      int u = uid[i];
+      double a = 0.0, b = 0.0, c = 0.0;
+      if (u >= 0) a = E_half[3 * (size_t)u], b = E_half[3 * (size_t)u + 1], c = E_half[3 * (size_t)u + 2];
+      dst[3 * i] = a, dst[3 * i + 1] = b, dst[3 * i + 2] = c;
+    }
+  }
+  const int *cuid = m.centerUid + (size_t)leaf * m.nCenterLocal;
+  for (int pass = 0; pass < 2; pass++) {
+    const double *src = pass ? B_cur : B_prev;
+    double *dst = (pass ? bCurTile : bPrevTile);
+    if (!src) continue;
+    dst += (size_t)leaf * m.bTileStride;
+    for (int i = threadIdx.x; i < m.nCenterLocal; i += blockDim.x) {
+      int u = cuid[i];
+      double a = 0.0, b = 0.0, c = 0.0;
+      if (u >= 0) a = src[3 * (size_t)u], b = src[3 * (size_t)u + 1], c = src[3 * (size_t)u + 2];
+      dst[3 * i] = a, dst[3 * i + 1] = b, dst[3 * i + 2] = c;
+    }
+  }
+}
+
+void launch_stage_tiles(const DevMesh &m, const double *E_half, const double *B_prev, const double *B_cur, double *eTile, double *bPrevTile,
+                        double *bCurTile, cudaStream_t s) {
+  stage_tiles_kernel<<<m.nLeaves, 256, 0, s>>>(m, E_half, B_prev, B_cur, eTile, bPrevTile, bCurTile);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a14: tree search.  findTreeNode(int*) walks up from the start node and down again
+// (meshAMRgeneric.h:2793-2848); the result is the unique leaf containing the lattice point, so the
+// device descends from the root grid directly.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_node_ix(const DevMesh &m, int ix0, int ix1, int ix2) {
+  if (ix0 < 0 || ix1 < 0 || ix2 < 0) return -1;
+  const int r0 = ix0 >> m.L, r1 = ix1 >> m.L, r2 = ix2 >> m.L;
+  if (r0 >= m.nRoot[0] || r1 >= m.nRoot[1] || r2 >= m.nRoot[2]) return -1;
+  int n = m.rootNode[r0 + m.nRoot[0] * (r1 + m.nRoot[1] * r2)];
+  while (true) {
+    const int h = m.isize[n] / 2;
+    const int i = (ix0 - m.imin[3 * n] < h) ? 0 : 1;
+    const int j = (ix1 - m.imin[3 * n + 1] < h) ? 0 : 1;
+    const int k = (ix2 - m.imin[3 * n + 2] < h) ? 0 : 1;
+    const int t = m.child[8 * n + i + 2 * (j + 2 * k)];
+    if (t < 0) return n;
+    n = t;
+  }
+}
+
+// findTreeNode(double*), meshAMRgeneric.h:2851-2882.  Returns node id or -1.
+__device__ __forceinline__ int find_tree_node(const DevMesh &m, const double x[3], const LeafGeo &start) {
+  int ix[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) ix[d] = (int)floor((x[d] - m.xGlobalMin[d]) / m.dxMaxRef[d]);
+  int node;
+  const bool in = ix[0] >= start.imin[0] && ix[0] < start.imin[0] + start.isize && ix[1] >= start.imin[1] && ix[1] < start.imin[1] + start.isize &&
+                  ix[2] >= start.imin[2] && ix[2] < start.imin[2] + start.isize;
+  node = in ? start.node : find_node_ix(m, ix[0], ix[1], ix[2]);
+  if (node >= 0) {
+    bool flag = false;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      const double lo = in ? start.xmin[d] : m.nxmin[3 * node + d];
+      const double hi = in ? start.xmax[d] : m.nxmax[3 * node + d];
+      if (x[d] < lo) ix[d]--, flag = true;
+      if (x[d] >= hi) ix[d]++, flag = true;
+    }
+    if (flag) node = find_node_ix(m, ix[0], ix[1], ix[2]);
+  }
+  return node;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a5: Lapenta2017
+// ------------------------------------------------------------------------------------------------
+template <bool kSmemTiles>
+__global__ void __launch_bounds__(256) move_lapenta_kernel(DevMesh m, DevSpecies sp, ParticleSoA p, const int *__restrict__ cellStart,
+                                                          const double *__restrict__ eTileG, const double *__restrict__ bTileG,
+                                                          int *__restrict__ cellCount, DevMoveStats *__restrict__ stats, int slices) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint64_t mbar;
+  __shared__ LeafGeo sLeaf;
+
+  const int leaf = blockIdx.x / slices, slice = blockIdx.x - leaf * slices;
+  const int C = m.cellsPerBlock;
+  const int begin = cellStart[(size_t)leaf * C], end = cellStart[(size_t)(leaf + 1) * C];
+  const long long len = (long long)end - begin;
+  const int b = begin + (int)(len * slice / slices), e = begin + (int)(len * (slice + 1) / slices);
+  if (b >= e) return;
+
+  const double *sE, *sB;
+  if (kSmemTiles) {
+    double *tE = reinterpret_cast<double *>(smem_raw);
+    double *tB = tE + m.eTileStride;
+    if (threadIdx.x == 0) {
+      sLeaf = m.leaf[leaf];
+      mbar_init(&mbar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t bytesE = (uint32_t)m.eTileStride * 8u, bytesB = (uint32_t)m.bTileStride * 8u;
+      mbar_expect_tx(&mbar, bytesE + bytesB);
+      bulk_g2s(tE, eTileG + (size_t)leaf * m.eTileStride, bytesE, &mbar);
+      bulk_g2s(tB, bTileG + (size_t)leaf * m.bTileStride, bytesB, &mbar);
+    }
+    mbar_wait(&mbar, 0);
+    sE = tE, sB = tB;
+  } else {
+    if (threadIdx.x == 0) sLeaf = m.leaf[leaf];
+    __syncthreads();
+    sE = eTileG + (size_t)leaf * m.eTileStride;
+    sB = bTileG + (size_t)leaf * m.bTileStride;
+  }
+
+  const LeafGeo &lg = sLeaf;
+  // per-block constants of the stencils
+  double dxc[3], span[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    dxc[d] = (lg.xmax[d] - lg.xmin[d]) / m.N[d];  // CornerBased::InitStencil :1086-1088
+    span[d] = lg.xmax[d] - lg.xmin[d];
+  }
+  const int CS0 = 1 + m.TN[0], CS1 = (1 + m.TN[0]) * (1 + m.TN[1]);  // corner strides
+  const int BS0 = m.TN[0], BS1 = m.TN[0] * m.TN[1];                  // centre strides
+
+  unsigned int nMoved = 0, nXCell = 0, nXBlock = 0, nLeft = 0, nNotUsed = 0, nWrap = 0, nErr = 0;
+
+  for (int ip = b + threadIdx.x; ip < e; ip += blockDim.x) {
+    double xInit[3], vInit[3], xFinal[3], vFinal[3];
+    xInit[0] = p.x[0][ip], xInit[1] = p.x[1][ip], xInit[2] = p.x[2][ip];
+    vInit[0] = p.v[0][ip], vInit[1] = p.v[1][ip], vInit[2] = p.v[2][ip];
+    const int spec = p.spec[ip];
+    const int oldKey = p.key[ip];
+    const double dtTotal = (sp.timeStepMode == AMPS_DT_SPECIES_GLOBAL) ? sp.dt[spec] : sp.dt[0];
+    nMoved++;
+    bool err = false;
+
+    // ---- a3: corner stencil for E (mutates xInit: snap to xmax-1e-10dx) ----
+    int iX[3];
+    double xLoc[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      if ((xInit[d] < lg.xmin[d]) || (xInit[d] > lg.xmax[d])) err = true;  // reference: exit("the point is out of block")
+      if (fabs(xInit[d] - lg.xmax[d]) < 1e-10 * dxc[d]) xInit[d] = lg.xmax[d] - 1e-10 * dxc[d];
+      xLoc[d] = (xInit[d] - lg.xmin[d]) / dxc[d];
+      iX[d] = (int)(xLoc[d]);
+      xLoc[d] -= iX[d];
+    }
+    if (err) {
+      nErr++;
+      p.key[ip] = -1;
+      continue;
+    }
+    double E[3] = {0.0, 0.0, 0.0}, B[3] = {0.0, 0.0, 0.0};
+    {
+      // stencil order: iStencil, jStencil, kStencil with k fastest (:1112)
+      const double ax0 = 1.0 - xLoc[0], ax1 = xLoc[0], ay0 = 1.0 - xLoc[1], ay1 = xLoc[1], az0 = 1.0 - xLoc[2], az1 = xLoc[2];
+      double w[8];
+      w[0] = ax0 * ay0 * az0;  // (0,0,0)
+      w[1] = ax0 * ay0 * az1;  // (0,0,1)
+      w[2] = ax0 * ay1 * az0;  // (0,1,0)
+      w[3] = ax0 * ay1 * az1;  // (0,1,1)
+      w[4] = ax1 * ay0 * az0;  // (1,0,0)
+      w[5] = ax1 * ay0 * az1;  // (1,0,1)
+      w[6] = ax1 * ay1 * az0;  // (1,1,0)
+      w[7] = ax1 * ay1 * az1;  // (1,1,1)
+      double norm = 0.0;
+#pragma unroll
+      for (int s = 0; s < 8; s++) norm += w[s];
+      if (norm > 0.0) {
+#pragma unroll
+        for (int s = 0; s < 8; s++) w[s] /= norm;
+      }
+      const int nd0 = cornerLocalNumber(m, iX[0], iX[1], iX[2]);
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        const int nd = nd0 + ((s >> 2) & 1) + ((s >> 1) & 1) * CS0 + (s & 1) * CS1;
+        const double *t = sE + 3 * nd;
+        E[0] += w[s] * t[0];
+        E[1] += w[s] * t[1];
+        E[2] += w[s] * t[2];
+      }
+    }
+    // ---- a4: cell-centred linear stencil for B (uniform / same-level branch) ----
+    {
+      const double iLoc = (xInit[0] - lg.xmin[0]) / span[0] * m.N[0];
+      const double jLoc = (xInit[1] - lg.xmin[1]) / span[1] * m.N[1];
+      const double kLoc = (xInit[2] - lg.xmin[2]) / span[2] * m.N[2];
+      const int i0 = (iLoc < 0.5) ? -1 : (int)(iLoc - 0.50);
+      const int j0 = (jLoc < 0.5) ? -1 : (int)(jLoc - 0.50);
+      const int k0 = (kLoc < 0.5) ? -1 : (int)(kLoc - 0.50);
+      const double w0 = iLoc - (i0 + 0.5), w1 = jLoc - (j0 + 0.5), w2 = kLoc - (k0 + 0.5);
+      double w[8];
+      // loop order i,j,k with k fastest; weight by code i+2j+4k (:850-881)
+      w[0] = (1.0 - w0) * (1.0 - w1) * (1.0 - w2);  // i0 j0 k0
+      w[1] = (1.0 - w0) * (1.0 - w1) * w2;          // i0 j0 k1
+      w[2] = (1.0 - w0) * w1 * (1.0 - w2);          // i0 j1 k0
+      w[3] = (1.0 - w0) * w1 * w2;                  // i0 j1 k1
+      w[4] = w0 * (1.0 - w1) * (1.0 - w2);          // i1 j0 k0
+      w[5] = w0 * (1.0 - w1) * w2;                  // i1 j0 k1
+      w[6] = w0 * w1 * (1.0 - w2);                  // i1 j1 k0
+      w[7] = w0 * w1 * w2;                          // i1 j1 k1
+      // AddCell drops centres outside the global box in non-periodic mode (pic.h:7235-7245)
+      unsigned valid = 0xffu;
+      if (!m.periodic && lg.face) {
+        if ((lg.face & 1) && i0 < 0) valid &= 0xf0u;
+        if ((lg.face & 2) && i0 + 1 >= m.N[0]) valid &= 0x0fu;
+        if ((lg.face & 4) && j0 < 0) valid &= 0xccu;
+        if ((lg.face & 8) && j0 + 1 >= m.N[1]) valid &= 0x33u;
+        if ((lg.face & 16) && k0 < 0) valid &= 0xaau;
+        if ((lg.face & 32) && k0 + 1 >= m.N[2]) valid &= 0x55u;
+      }
+      double norm = 0.0;
+#pragma unroll
+      for (int s = 0; s < 8; s++)
+        if (valid & (1u << s)) norm += w[s];
+      // Normalize(): the reference tests the global StencilTable->Length (:903) => always runs in ECSIM
+      if (norm > 0.0) {
+#pragma unroll
+        for (int s = 0; s < 8; s++) w[s] /= norm;
+      }
+      const int nd0 = centerLocalNumber(m, i0, j0, k0);
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        if (valid & (1u << s)) {
+          const int nd = nd0 + ((s >> 2) & 1) + ((s >> 1) & 1) * BS0 + (s & 1) * BS1;
+          const double *t = sB + 3 * nd;
+          B[0] += w[s] * t[0];
+          B[1] += w[s] * t[1];
+          B[2] += w[s] * t[2];
+        }
+      }
+    }
+
+    // ---- velocity / position update (:1036-1081) ----
+    {
+      const double chargeQ = sp.charge[spec], mass = sp.mass[spec];
+      const double QdT_over_m = chargeQ * dtTotal / mass;
+      const double QdT_over_2m = 0.5 * QdT_over_m;
+      const double QdT_over_2m_squared = QdT_over_2m * QdT_over_2m;
+      double BB[3][3], P[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        P[i] = -QdT_over_2m * B[i];
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+          BB[i][j] = QdT_over_2m_squared * B[i] * B[j];
+          BB[j][i] = BB[i][j];
+        }
+      }
+      const double c0 = 1.0 / (1.0 + QdT_over_2m_squared * (B[0] * B[0] + B[1] * B[1] + B[2] * B[2]));
+      double alpha[3][3];
+      alpha[0][0] = c0 * (1.0 + BB[0][0]);
+      alpha[0][1] = c0 * (-P[2] + BB[0][1]);
+      alpha[0][2] = c0 * (P[1] + BB[0][2]);
+      alpha[1][0] = c0 * (P[2] + BB[1][0]);
+      alpha[1][1] = c0 * (1.0 + BB[1][1]);
+      alpha[1][2] = c0 * (-P[0] + BB[1][2]);
+      alpha[2][0] = c0 * (-P[1] + BB[2][0]);
+      alpha[2][1] = c0 * (P[0] + BB[2][1]);
+      alpha[2][2] = c0 * (1.0 + BB[2][2]);
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        double vp = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) vp += alpha[d][j] * (vInit[j] + QdT_over_2m * E[j]);
+        vFinal[d] = 2.0 * vp - vInit[d];
+      }
+#pragma unroll
+      for (int d = 0; d < 3; d++) xFinal[d] = xInit[d] + dtTotal * vFinal[d];
+    }
+
+    // ---- a14/a15: new block (:1121-1272) ----
+    int node = find_tree_node(m, xFinal, lg);
+    int newKey = -1;
+    if (node < 0) {
+      // left the domain.  DELETE mode (:1165-1167); other modes are handled by the generic mover path
+      nLeft++;
+    } else if (!(m.nodeFlags[node] & AMPS_NODE_USED)) {
+      nNotUsed++;
+    } else {
+      int newLeaf = m.nodeLeaf[node];
+      if (newLeaf < 0) {
+        nLeft++;  // block not allocated on this rank (:1290-1302)
+      } else {
+        // FindCellIndex (:2256-2323)
+        const bool same = (newLeaf == leaf);
+        const int lev = same ? lg.level : m.nodeLevel[node];
+        int ijk[3];
+        bool out = false;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          const double lo = same ? lg.xmin[d] : m.nxmin[3 * node + d];
+          const double hi = same ? lg.xmax[d] : m.nxmax[3 * node + d];
+          if ((xFinal[d] < lo) || (hi < xFinal[d])) out = true;
+          const double dx = m.dxRoot[d] / (1 << lev) / double(m.N[d]);
+          int c = (int)((xFinal[d] - lo) / dx);
+          if (c == m.N[d]) c = m.N[d] - 1;
+          ijk[d] = c;
+        }
+        if (out) {
+          nErr++;  // reference: exit("cannot find the cell")
+        } else {
+          // a16: periodic ghost block -> real block (pic_bc_periodic.cpp:100-134); the cell index is inherited
+          const int realLeaf = same ? -1 : m.leaf[newLeaf].real;
+          if (realLeaf >= 0) {
+            const LeafGeo &gg = m.leaf[newLeaf];
+            const LeafGeo &rg = m.leaf[realLeaf];
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+              const double sh = rg.xmin[d] - gg.xmin[d];
+              xFinal[d] += sh;
+              if (xFinal[d] < rg.xmin[d]) xFinal[d] = rg.xmin[d];
+              if (xFinal[d] >= rg.xmax[d]) xFinal[d] = rg.xmax[d] - 1.0E-10 * (rg.xmax[d] - rg.xmin[d]);
+            }
+            newLeaf = realLeaf;
+            nWrap++;
+          }
+          newKey = newLeaf * C + ijk[0] + m.N[0] * (ijk[1] + m.N[1] * ijk[2]);
+          if (newLeaf != leaf) nXBlock++;
+          else if (newKey != oldKey) nXCell++;
+        }
+      }
+    }
+
+    if (newKey >= 0) {
+      p.x[0][ip] = xFinal[0], p.x[1][ip] = xFinal[1], p.x[2][ip] = xFinal[2];
+      p.v[0][ip] = vFinal[0], p.v[1][ip] = vFinal[1], p.v[2][ip] = vFinal[2];
+      atomicAdd(&cellCount[newKey], 1);
+    }
+    if (newKey != oldKey) p.key[ip] = newKey;
+  }
+
+  // warp-reduce the counters, one atomic per warp and counter
+  unsigned int c[7] = {nMoved, nXCell, nXBlock, nLeft, nNotUsed, nWrap, nErr};
+#pragma unroll
+  for (int q = 0; q < 7; q++) {
+    unsigned int v = c[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    c[q] = v;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    unsigned long long *s = reinterpret_cast<unsigned long long *>(stats);
+#pragma unroll
+    for (int q = 0; q < 7; q++)
+      if (c[q]) atomicAdd(&s[q], (unsigned long long)c[q]);
+  }
+}
+
+void launch_move_lapenta(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *eTile, const double *bTile,
+                         int *cellCount, DevMoveStats *stats, int slices, cudaStream_t s) {
+  const size_t smem = (size_t)(m.eTileStride + m.bTileStride) * sizeof(double);
+  const int grid = m.nLeaves * slices;
+  if (smem <= 200 * 1024) {
+    static bool attrSet = false;
+    if (!attrSet) {
+      cudaFuncSetAttribute(move_lapenta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attrSet = true;
+    }
+    move_lapenta_kernel<true><<<grid, 256, smem, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices);
+  } else {
+    move_lapenta_kernel<false><<<grid, 256, 0, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices);
+  }
+}
+
+}  // namespace amps

@@ -1,0 +1,147 @@
+// sort.cu -- on-device counting sort of the particle SoA by (block,cell) key (sm_100a).
+//
+// Replaces the reference's per-cell doubly linked lists: the temp->first list swap at the end of
+// MoveParticles (src/pic/pic_mover.cpp:1056-1088) and CreateParticleTable
+// (src/pic/pic_pbuffer.cpp:1160-1310, K3 in SURVEY 2.5: count per cell, host prefix sum, fill).
+//   1. histogram of keys        (normally produced by the mover itself)
+//   2. exclusive scan -> cellStart[nCells+1]   (3-phase, all on device)
+//   3. scatter of every SoA component into the ping-pong copy; deleted particles (key<0) drop out
+// All of it is integer/byte work bound by HBM; no host synchronisation.
+#include "amps_dev.cuh"
+
+namespace amps {
+
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void histogram_kernel(const int *__restrict__ key, const int *__restrict__ nSrc, int *__restrict__ cellCount) {
+  const int n = *nSrc;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int k = key[i];
+    if (k >= 0) atomicAdd(&cellCount[k], 1);
+  }
+}
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *sWarp, int &total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) sWarp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = (lane < (blockDim.x >> 5)) ? sWarp[lane] : 0;
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    sWarp[lane] = wi - w;  // exclusive warp offsets
+    if (lane == 31) sWarp[32] = wi;
+  }
+  __syncthreads();
+  total = sWarp[32];
+  const int r = incl - v + sWarp[warp];
+  __syncthreads();
+  return r;
+}
+
+// phase 1: per-tile sums
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums_kernel(const int *__restrict__ in, long long n, int *__restrict__ tileSum) {
+  __shared__ int sWarp[33];
+  const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+  int s = 0;
+#pragma unroll
+  for (int q = 0; q < SCAN_ITEMS; q++)
+    if (base + q < n) s += in[base + q];
+  int total;
+  block_exclusive_scan(s, sWarp, total);
+  if (threadIdx.x == 0) tileSum[blockIdx.x] = total;
+}
+// phase 2: one CTA scans the tile sums in place (exclusive) and writes the grand total
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_offsets_kernel(int *__restrict__ tileSum, int nTiles, int *__restrict__ totalOut) {
+  __shared__ int sWarp[33];
+  int carry = 0;
+  for (int base = 0; base < nTiles; base += SCAN_THREADS) {
+    const int i = base + threadIdx.x;
+    const int v = (i < nTiles) ? tileSum[i] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, sWarp, total);
+    if (i < nTiles) tileSum[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) *totalOut = carry;
+}
+// phase 3: final exclusive scan; also writes out[n] = total
+__global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const int *__restrict__ in, long long n, const int *__restrict__ tileOff,
+                                                                 const int *__restrict__ totalIn, int *__restrict__ out) {
+  __shared__ int sWarp[33];
+  const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  int s = 0;
+#pragma unroll
+  for (int q = 0; q < SCAN_ITEMS; q++) {
+    v[q] = (base + q < n) ? in[base + q] : 0;
+    s += v[q];
+  }
+  int total;
+  int ex = block_exclusive_scan(s, sWarp, total) + tileOff[blockIdx.x];
+#pragma unroll
+  for (int q = 0; q < SCAN_ITEMS; q++) {
+    if (base + q < n) out[base + q] = ex;
+    ex += v[q];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *totalIn;
+}
+
+__global__ void __launch_bounds__(256) scatter_kernel(ParticleSoA src, ParticleSoA dst, const int *__restrict__ nSrc, const int *__restrict__ cellStart,
+                                                     int *__restrict__ cellFill) {
+  const int n = *nSrc;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int k = src.key[i];
+    if (k < 0) continue;
+    const double x0 = src.x[0][i], x1 = src.x[1][i], x2 = src.x[2][i];
+    const double v0 = src.v[0][i], v1 = src.v[1][i], v2 = src.v[2][i];
+    const double w = src.w[i];
+    const uint8_t sp = src.spec[i];
+    const int pt = src.ptr[i];
+    const int pos = cellStart[k] + atomicAdd(&cellFill[k], 1);
+    dst.x[0][pos] = x0, dst.x[1][pos] = x1, dst.x[2][pos] = x2;
+    dst.v[0][pos] = v0, dst.v[1][pos] = v1, dst.v[2][pos] = v2;
+    dst.w[pos] = w;
+    dst.spec[pos] = sp;
+    dst.key[pos] = k;
+    dst.ptr[pos] = pt;
+  }
+}
+
+size_t sort_scan_tmp_bytes(long long nCells) {
+  const long long nTiles = (nCells + SCAN_TILE - 1) / SCAN_TILE;
+  return (size_t)(nTiles + 2) * sizeof(int);
+}
+
+void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *nSrc, int *cellCount, int *cellStart, int *cellFill, int *nDst,
+                 long long nUpper, bool countValid, void *scanTmp, cudaStream_t s, long long *launches) {
+  const long long nCells = (long long)m.nLeaves * m.cellsPerBlock;
+  const int nTiles = (int)((nCells + SCAN_TILE - 1) / SCAN_TILE);
+  int *tileSum = reinterpret_cast<int *>(scanTmp);
+  const int pgrid = (int)((nUpper + 255) / 256 > 148 * 16 ? 148 * 16 : (nUpper + 255) / 256 < 1 ? 1 : (nUpper + 255) / 256);
+  if (!countValid) {
+    cudaMemsetAsync(cellCount, 0, sizeof(int) * nCells, s);
+    histogram_kernel<<<pgrid, 256, 0, s>>>(src.key, nSrc, cellCount);
+    (*launches)++;
+  }
+  scan_tile_sums_kernel<<<nTiles, SCAN_THREADS, 0, s>>>(cellCount, nCells, tileSum);
+  scan_tile_offsets_kernel<<<1, SCAN_THREADS, 0, s>>>(tileSum, nTiles, nDst);
+  scan_write_kernel<<<nTiles, SCAN_THREADS, 0, s>>>(cellCount, nCells, tileSum, nDst, cellStart);
+  cudaMemsetAsync(cellFill, 0, sizeof(int) * nCells, s);
+  scatter_kernel<<<pgrid, 256, 0, s>>>(src, dst, nSrc, cellStart, cellFill);
+  (*launches) += 4;
+}
+
+}  // namespace amps

@@ -1,0 +1,299 @@
+"""Host-side flattening of the AMR block tree for the device.
+
+In AMPS the tree lives in ``cMeshAMRgeneric`` (src/meshAMR/meshAMRgeneric.h); the
+drop-in shim walks ``rootTree`` once per mesh epoch and fills ``amps_gpu_mesh``.
+This module builds the same flattened description for synthetic boxes
+(uniform periodic / open boxes and sphere-refined AMR boxes) so that tests and
+``bench.py`` can run without AMPS.
+
+Geometry conventions follow the reference:
+  * periodic mode wraps the user domain in a one-block shell of "ghost" blocks that
+    are paired with the real block one period away (src/pic/pic_bc_periodic.cpp:502-571);
+  * the lattice used by ``findTreeNode`` has ``1<<max_refinement_level`` points per root
+    block (meshAMRgeneric.h:2365, 2392);
+  * block-local node numbers are ``_getCornerNodeLocalNumber/_getCenterNodeLocalNumber``
+    (meshAMRgeneric.h:74-75).
+The forest (``n_root`` root blocks) generalises the reference's single octree so that
+boxes whose block count is not 2^m-2 (the reference's periodic constraint,
+pic_bc_periodic.cpp:705-747) can be described; ``n_root=(1,1,1)`` is the reference tree.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+
+class FlatMesh:
+    """numpy arrays + the ctypes ``amps_gpu_mesh`` view over them."""
+
+    def __init__(self):
+        self.arrays = {}
+        self.c = _capi.Mesh()
+
+    def _set(self, name, arr, ctype):
+        arr = np.ascontiguousarray(arr)
+        self.arrays[name] = arr
+        setattr(self.c, name, arr.ctypes.data_as(C.POINTER(ctype)))
+
+    # convenience accessors -------------------------------------------------
+    @property
+    def n_leaves(self):
+        return int(self.c.n_leaves)
+
+    @property
+    def n_corners(self):
+        return int(self.c.n_corners)
+
+    @property
+    def n_centers(self):
+        return int(self.c.n_centers)
+
+    @property
+    def cells_per_block(self):
+        return int(np.prod(self.block_cells))
+
+    @property
+    def n_cells(self):
+        return self.n_leaves * self.cells_per_block
+
+    def leaf_xmin(self):
+        return self.arrays["node_xmin"].reshape(-1, 3)[self.arrays["leaf_node"]]
+
+    def leaf_xmax(self):
+        return self.arrays["node_xmax"].reshape(-1, 3)[self.arrays["leaf_node"]]
+
+    def real_leaves(self):
+        """leaves that hold particles (used, not periodic ghosts)."""
+        fl = self.arrays["node_flags"][self.arrays["leaf_node"]]
+        return np.nonzero(((fl & _capi.NODE_USED) != 0) & ((fl & _capi.NODE_PERIODIC_GHOST) == 0))[0]
+
+
+def _local_numbers(N, g, corner):
+    """block-local (i,j,k) grids incl. ghost layers in local-number order."""
+    ext = [N[d] + 2 * g[d] + (1 if corner else 0) for d in range(3)]
+    k, j, i = np.meshgrid(np.arange(ext[2]) - g[2], np.arange(ext[1]) - g[1], np.arange(ext[0]) - g[0], indexing="ij")
+    return i.ravel(), j.ravel(), k.ravel()  # x fastest == local number order
+
+
+def build_mesh(xmin, xmax, n_blocks, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), periodic=True,
+               max_refinement_level=12, refine=None, max_level=0, this_thread=0, owner=None):
+    """Flatten a box mesh.
+
+    xmin/xmax     user ("original") domain
+    n_blocks      level-0 blocks per dimension inside the user domain
+    refine        callable(level, xmin[3], xmax[3]) -> bool : split this block? (AMR)
+    max_level     deepest level ``refine`` may produce
+    owner         callable(leaf_xmin, leaf_xmax) -> rank (domain decomposition); default all on rank 0
+    """
+    N = np.asarray(block_cells, dtype=np.int64)
+    g = np.asarray(ghost_cells, dtype=np.int64)
+    nb = np.asarray(n_blocks, dtype=np.int64)
+    xmin = np.asarray(xmin, dtype=np.float64)
+    xmax = np.asarray(xmax, dtype=np.float64)
+    L = int(max_refinement_level)
+    S = 1 << L
+    shell = 1 if periodic else 0
+    n_root = nb + 2 * shell
+    dx_root = (xmax - xmin) / nb
+    gmin = xmin - shell * dx_root
+    gmax = gmin + n_root * dx_root
+    if periodic:
+        gmax = xmax + shell * dx_root
+
+    m = FlatMesh()
+    m.block_cells = tuple(int(v) for v in N)
+    m.ghost_cells = tuple(int(v) for v in g)
+    m.periodic = bool(periodic)
+    m.user_xmin, m.user_xmax = xmin.copy(), xmax.copy()
+    m.n_blocks_user = tuple(int(v) for v in nb)
+
+    # ---- tree ------------------------------------------------------------
+    parent, child, level, imin, isize, nxmin, nxmax, flags = [], [], [], [], [], [], [], []
+
+    def edge(d, r):  # shared expression so that neighbours agree bitwise
+        return gmin[d] + r * dx_root[d]
+
+    def new_node(par, lev, im, sz, lo, hi, fl):
+        parent.append(par); child.append([-1] * 8); level.append(lev); imin.append(list(im)); isize.append(sz)
+        nxmin.append(list(lo)); nxmax.append(list(hi)); flags.append(fl)
+        return len(parent) - 1
+
+    def split(n):
+        lo, hi = np.array(nxmin[n]), np.array(nxmax[n])
+        mid = 0.5 * (lo + hi)  # bisection as cMeshAMRgeneric::splitTreeNode
+        half = isize[n] // 2
+        for kk in range(2):
+            for jj in range(2):
+                for ii in range(2):
+                    o = (ii, jj, kk)
+                    clo = [lo[d] if o[d] == 0 else mid[d] for d in range(3)]
+                    chi = [mid[d] if o[d] == 0 else hi[d] for d in range(3)]
+                    cim = [imin[n][d] + o[d] * half for d in range(3)]
+                    c = new_node(n, level[n] + 1, cim, half, clo, chi, flags[n])
+                    child[n][ii + 2 * (jj + 2 * kk)] = c
+                    if refine is not None and level[c] < max_level and refine(level[c], np.array(clo), np.array(chi)):
+                        split(c)
+
+    root_node = np.zeros(int(np.prod(n_root)), dtype=np.int32)
+    for rk in range(n_root[2]):
+        for rj in range(n_root[1]):
+            for ri in range(n_root[0]):
+                r = (ri, rj, rk)
+                lo = [edge(d, r[d]) for d in range(3)]
+                hi = [edge(d, r[d] + 1) for d in range(3)]
+                ghost = periodic and any(r[d] == 0 or r[d] == n_root[d] - 1 for d in range(3))
+                fl = _capi.NODE_USED | (_capi.NODE_PERIODIC_GHOST if ghost else 0)
+                n = new_node(-1, 0, [r[d] * S for d in range(3)], S, lo, hi, fl)
+                root_node[ri + n_root[0] * (rj + n_root[1] * rk)] = n
+                if (not ghost) and refine is not None and max_level > 0 and refine(0, np.array(lo), np.array(hi)):
+                    split(n)
+
+    n_nodes = len(parent)
+    child = np.array(child, dtype=np.int32)
+    level = np.array(level, dtype=np.int32)
+    imin = np.array(imin, dtype=np.int32)
+    isize = np.array(isize, dtype=np.int32)
+    nxmin = np.array(nxmin, dtype=np.float64)
+    nxmax = np.array(nxmax, dtype=np.float64)
+    flags = np.array(flags, dtype=np.int32)
+    is_leaf = (child < 0).all(axis=1)
+    leaf_node = np.nonzero(is_leaf)[0].astype(np.int32)
+    n_leaves = len(leaf_node)
+    node_leaf = -np.ones(n_nodes, dtype=np.int32)
+    node_leaf[leaf_node] = np.arange(n_leaves, dtype=np.int32)
+
+    # ---- leaf lookup by lattice point (host mirror of findTreeNode) ---------
+    def find_leaf_ix(ix):
+        r = [ix[d] // S for d in range(3)]
+        if any(ix[d] < 0 or r[d] >= n_root[d] for d in range(3)):
+            return -1
+        n = root_node[r[0] + n_root[0] * (r[1] + n_root[1] * r[2])]
+        while child[n, 0] >= 0:
+            h = isize[n] // 2
+            o = [0 if ix[d] - imin[n, d] < h else 1 for d in range(3)]
+            n = child[n, o[0] + 2 * (o[1] + 2 * o[2])]
+        return int(node_leaf[n])
+
+    m.find_leaf_ix = find_leaf_ix
+
+    # ---- face boundary flags (GetNeibFace(f,0,0)==NULL) and periodic pairing ---------
+    leaf_face_boundary = np.zeros(n_leaves, dtype=np.int32)
+    leaf_real = -np.ones(n_leaves, dtype=np.int32)
+    li = imin[leaf_node].astype(np.int64)
+    ls = isize[leaf_node].astype(np.int64)
+    tot = n_root * S
+    for d in range(3):
+        leaf_face_boundary |= np.where(li[:, d] == 0, 1 << (2 * d), 0).astype(np.int32)
+        leaf_face_boundary |= np.where(li[:, d] + ls == tot[d], 1 << (2 * d + 1), 0).astype(np.int32)
+    if periodic:
+        period = nb * S
+        for l in range(n_leaves):
+            if flags[leaf_node[l]] & _capi.NODE_PERIODIC_GHOST:
+                c = li[l] + ls[l] // 2  # block centre on the lattice
+                c = (c - S) % period + S  # findCorrespondingRealBlock, pic_bc_periodic.cpp:502-519
+                leaf_real[l] = find_leaf_ix([int(v) for v in c])
+
+    # ---- unique corner / centre nodes -------------------------------------------------
+    # integer node keys: corner = imin*N + i*isize  (units: 1/N of a lattice step),
+    #                    centre = 2*imin*N + (2i+1)*isize
+    def keys_for(corner):
+        i, j, k = _local_numbers(N, g, corner)
+        loc = np.stack([i, j, k], axis=1).astype(np.int64)  # [nloc,3]
+        if corner:
+            key = li[:, None, :] * N[None, None, :] + loc[None, :, :] * ls[:, None, None]
+            span = nb * S * N
+            org = shell * S * N
+        else:
+            key = 2 * li[:, None, :] * N[None, None, :] + (2 * loc[None, :, :] + 1) * ls[:, None, None]
+            span = 2 * nb * S * N
+            org = 2 * shell * S * N
+        inside_block = np.ones(loc.shape[0], dtype=bool)
+        for d in range(3):
+            hi = N[d] + (1 if corner else 0)
+            inside_block &= (loc[:, d] >= 0) & (loc[:, d] < hi)
+        if periodic:
+            key = (key - org) % span  # identify periodic images
+            valid = np.ones(key.shape[:2], dtype=bool)
+        else:
+            valid = np.ones(key.shape[:2], dtype=bool)
+            for d in range(3):
+                valid &= (key[:, :, d] >= 0) & (key[:, :, d] <= span[d])
+        enc = (key[:, :, 2] * (span[1] + 1) + key[:, :, 1]) * (span[0] + 1) + key[:, :, 0]
+        return enc, valid, inside_block, key
+
+    def uid_table(corner):
+        enc, valid, inside_block, key = keys_for(corner)
+        own = enc[:, inside_block]  # nodes that blocks really own
+        uniq = np.unique(own.ravel())
+        pos = np.searchsorted(uniq, enc)
+        pos_c = np.minimum(pos, len(uniq) - 1)
+        found = (uniq[pos_c] == enc) & valid
+        uid = np.where(found, pos_c, -1).astype(np.int32)
+        # node coordinates (x fastest ordering of uniq follows the encoding)
+        first = np.full(len(uniq), -1, dtype=np.int64)
+        flat_enc = enc.ravel()
+        flat_ok = found.ravel()
+        idx = np.nonzero(flat_ok)[0]
+        first[pos_c.ravel()[idx][::-1]] = idx[::-1]
+        kk = key.reshape(-1, 3)[first]
+        if corner:
+            xx = (xmin if periodic else gmin)[None, :] + kk / (S * N)[None, :] * dx_root[None, :]
+        else:
+            xx = (xmin if periodic else gmin)[None, :] + kk / (2 * S * N)[None, :] * dx_root[None, :]
+        return uid, len(uniq), xx
+
+    corner_uid, n_corners, corner_x = uid_table(True)
+    center_uid, n_centers, center_x = uid_table(False)
+    m.corner_x, m.center_x = corner_x, center_x
+
+    # ---- ownership --------------------------------------------------------------
+    node_thread = np.zeros(n_nodes, dtype=np.int32)
+    if owner is not None:
+        for l in range(n_leaves):
+            node_thread[leaf_node[l]] = owner(nxmin[leaf_node[l]], nxmax[leaf_node[l]])
+    else:
+        node_thread[:] = this_thread
+
+    c = m.c
+    for d in range(3):
+        c.n_root[d] = int(n_root[d])
+        c.x_global_min[d] = gmin[d]
+        c.x_global_max[d] = gmax[d]
+        c.dx_max_refinement[d] = (gmax[d] - gmin[d]) / (int(n_root[d]) * S)  # == (xmax-xmin)/(1<<L) for one root
+        c.dx_root_block[d] = (gmax[d] - gmin[d]) / int(n_root[d])
+    c.max_refinement_level = L
+    eps = min(0.0001 * c.dx_root_block[d] / float(N[d]) / S for d in range(3))  # meshAMRgeneric.h:2340-2351
+    c.eps = eps
+    c.n_nodes = n_nodes
+    c.n_leaves = n_leaves
+    c.n_corners = n_corners
+    c.n_centers = n_centers
+    m._set("node_parent", np.array(parent, dtype=np.int32), C.c_int32)
+    m._set("node_child", child, C.c_int32)
+    m._set("node_level", level, C.c_int32)
+    m._set("node_imin", imin, C.c_int32)
+    m._set("node_isize", isize, C.c_int32)
+    m._set("node_xmin", nxmin, C.c_double)
+    m._set("node_xmax", nxmax, C.c_double)
+    m._set("node_leaf", node_leaf, C.c_int32)
+    m._set("node_flags", flags, C.c_int32)
+    m._set("node_thread", node_thread, C.c_int32)
+    m._set("root_node", root_node, C.c_int32)
+    m._set("leaf_node", leaf_node, C.c_int32)
+    m._set("leaf_real", leaf_real, C.c_int32)
+    m._set("leaf_face_boundary", leaf_face_boundary, C.c_int32)
+    m._set("leaf_corner_uid", corner_uid, C.c_int32)
+    m._set("leaf_center_uid", center_uid, C.c_int32)
+    return m
+
+
+def uniform_periodic_box(n_cells, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), dx=1.0, origin=(0.0, 0.0, 0.0),
+                         max_refinement_level=12):
+    """BASELINE config 2/3 geometry: [origin, origin+n_cells*dx) periodic, single AMR level."""
+    n_cells = np.asarray(n_cells, dtype=np.int64)
+    N = np.asarray(block_cells, dtype=np.int64)
+    assert (n_cells % N == 0).all(), "n_cells must be a multiple of block_cells"
+    xmin = np.asarray(origin, dtype=np.float64)
+    xmax = xmin + n_cells * dx
+    return build_mesh(xmin, xmax, n_cells // N, block_cells, ghost_cells, True, max_refinement_level)

@@ -1,0 +1,243 @@
+/*
+ * amps_gpu.h -- C ABI of the B200 (sm_100a) charged-particle hot path of AMPS.
+ *
+ * Drop-in boundary for ONE path of SWMFsoftware/AMPS: the particle movers
+ * (PIC::Mover::*) and the ECSIM current / mass-matrix deposition
+ * (PIC::FieldSolver::Electromagnetic::ECSIM::UpdateJMassMatrix).  AMPS has no
+ * plugin ABI of its own; the hooks these entry points sit behind are
+ *
+ *   PIC::Mover::UserDefinedMoverManager            src/pic/pic.h:5919-5920, pic_mover.cpp:589-592
+ *   ECSIM::UpdateJMassMatrix (_CUDA_MODE_ branch)  src/pic/pic_field_solver_ecsim.cpp:3254-3257
+ *   PIC::ParticleBuffer (AoS byte records)         src/pic/picParticleDataMacro.h:18-90
+ *
+ * (all reference paths are relative to the AMPS source tree).  See
+ * INTEGRATION.md for the C++ shim a maintainer adds on the AMPS side.
+ *
+ * Conventions: plain C structs, host pointers unless the name says `_dev`,
+ * every call returns an int status (AMPS_GPU_OK == 0); the library never calls
+ * exit()/abort() (the reference does: exit(__LINE__,__FILE__,msg) -> MPI_Abort).
+ * Device memory is owned by the context; host memory by the caller.  One caller
+ * thread per context (the reference calls these paths from the rank's main
+ * thread, src/pic/pic_time_step.cpp:403-551).
+ */
+#ifndef AMPS_GPU_H
+#define AMPS_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMPS_GPU_MAX_SPECIES 8
+
+/* ---- status codes ------------------------------------------------------- */
+enum {
+  AMPS_GPU_OK = 0,
+  AMPS_GPU_ERR_CUDA = 1,          /* a CUDA runtime call failed; see amps_gpu_last_error() */
+  AMPS_GPU_ERR_ARG = 2,           /* invalid argument / inconsistent description            */
+  AMPS_GPU_ERR_CAPACITY = 3,      /* particle capacity exceeded                              */
+  AMPS_GPU_ERR_STATE = 4,         /* call sequence error (e.g. move before mesh upload)      */
+  AMPS_GPU_ERR_PARTICLE = 5,      /* device-side particle error: the reference would have
+                                     called exit("cannot find the cell ...") pic_mover_boris.cpp:1286 */
+  AMPS_GPU_ERR_NO_DEVICE = 6      /* no CUDA device: there is NO CPU fallback               */
+};
+
+/* ---- movers (PIC::Mover::*, bound by _PIC_PARTICLE_MOVER__MOVE_PARTICLE_TIME_STEP_) --- */
+enum {
+  AMPS_MOVER_LAPENTA2017 = 0,         /* pic_mover_boris.cpp:876-1393 (ECSIM push)             */
+  AMPS_MOVER_BORIS = 1,               /* pic_mover_boris.cpp:126-553                           */
+  AMPS_MOVER_RELATIVISTIC_BORIS = 2,  /* pic_mover_relativistic_boris.cpp:16-588               */
+  AMPS_MOVER_GC_FIRST_ORDER = 3,      /* pic_mover_guiding_center.cpp:629-849                  */
+  AMPS_MOVER_GC_SECOND_ORDER = 4,     /* pic_mover_guiding_center.cpp:293-627                  */
+  AMPS_MOVER_RELATIVISTIC_GCA = 5     /* pic_mover_relativistic_guiding_center.cpp:96-409      */
+};
+
+/* return codes of a per-particle mover, src/pic/pic.h:5955-5960 */
+enum {
+  AMPS_PARTICLE_LEFT_THE_DOMAIN = 2,
+  AMPS_PARTICLE_MOTION_FINISHED = 3,
+  AMPS_PARTICLE_IN_NOT_IN_USE_NODE = 4
+};
+
+/* _PIC_PARTICLE_DOMAIN_BOUNDARY_INTERSECTION_PROCESSING_MODE_ */
+enum {
+  AMPS_BOUNDARY_DELETE = 0,
+  AMPS_BOUNDARY_SPECULAR_REFLECTION = 1,
+  AMPS_BOUNDARY_USER_FUNCTION = 2   /* exit record appended; host replays the callback */
+};
+
+/* _PIC_FIELD_SOLVER_B_MODE_ */
+enum { AMPS_B_CENTER_BASED = 0, AMPS_B_CORNER_BASED = 1 };
+
+/* _SIMULATION_TIME_STEP_MODE_ (pic_mover_boris.cpp:895-904) */
+enum { AMPS_DT_SINGLE_GLOBAL = 0, AMPS_DT_SPECIES_GLOBAL = 1 };
+
+/* node-flag bits of amps_gpu_mesh::node_flags */
+enum {
+  AMPS_NODE_USED = 1,           /* cTreeNodeAMR::IsUsedInCalculationFlag                     */
+  AMPS_NODE_PERIODIC_GHOST = 2  /* cTreeNodeAMR::IsGhostNodeFlag (pic_bc_periodic.cpp:763-766) */
+};
+
+/* ---- configuration: every field is a compile-time macro or a namespace global
+ *      in the reference (ampsConfig.pl rewrites them); here they are run-time. ---- */
+typedef struct amps_gpu_config {
+  int32_t block_cells[3];        /* _BLOCK_CELLS_X/Y/Z_                                        */
+  int32_t ghost_cells[3];        /* _GHOST_CELLS_X/Y/Z_                                        */
+  int32_t n_species;             /* PIC::nTotalSpecies                                         */
+  int32_t b_mode;                /* AMPS_B_CENTER_BASED | AMPS_B_CORNER_BASED                  */
+  int32_t periodic;              /* _PIC_BC__PERIODIC_MODE_                                    */
+  int32_t boundary_mode;         /* AMPS_BOUNDARY_*                                            */
+  int32_t time_step_mode;        /* AMPS_DT_*                                                  */
+  int32_t device;                /* CUDA device ordinal                                        */
+  int64_t capacity;              /* PIC::ParticleBuffer::MaxNPart (device SoA capacity)        */
+  double charge[AMPS_GPU_MAX_SPECIES];   /* ElectricChargeTable after picunits::si2no_q when NORM units */
+  double mass[AMPS_GPU_MAX_SPECIES];     /* MolMass after picunits::si2no_m when NORM units            */
+  double species_weight[AMPS_GPU_MAX_SPECIES]; /* block->GetLocalParticleWeight(spec)                 */
+  double time_step[AMPS_GPU_MAX_SPECIES];      /* PIC::ParticleWeightTimeStep::GlobalTimeStep[]       */
+  /* ECSIM namespace globals, pic_field_solver_ecsim.cpp:186-212 */
+  double ecsim_dt_total;         /* ECSIM::dtTotal                                             */
+  double ecsim_B_conv;           /* ECSIM::B_conv                                              */
+  double ecsim_length_conv;      /* ECSIM::length_conv                                         */
+  double ecsim_light_speed;      /* ECSIM::LightSpeed                                          */
+} amps_gpu_config;
+
+/* ---- flattened AMR mesh (host builds it from cMeshAMRgeneric; K7 in SURVEY 2.5) ----
+ * The tree is a forest: n_root[0..2] root blocks tile [x_global_min,x_global_max];
+ * n_root = {1,1,1} is exactly the reference's single octree
+ * (src/meshAMR/meshAMRgeneric.h:2328-2393).  Node fields mirror cTreeNodeAMR
+ * (meshAMRgeneric.h:825-838).                                                      */
+typedef struct amps_gpu_mesh {
+  int32_t n_root[3];
+  int32_t max_refinement_level;     /* _MAX_REFINMENT_LEVEL_ (lattice depth, not deepest leaf) */
+  double  x_global_min[3], x_global_max[3];
+  double  dx_max_refinement[3];     /* meshAMRgeneric.h:2365                                   */
+  double  dx_root_block[3];         /* dxRootBlock (per root block)                            */
+  double  eps;                      /* cMeshAMRgeneric::EPS, meshAMRgeneric.h:2340             */
+  int32_t n_nodes;
+  const int32_t *node_parent;       /* [n_nodes]      upNode or -1                             */
+  const int32_t *node_child;        /* [n_nodes][8]   downNode[i+2*(j+2*k)] or -1              */
+  const int32_t *node_level;        /* [n_nodes]      RefinmentLevel                           */
+  const int32_t *node_imin;         /* [n_nodes][3]   xMinGlobalIndex                          */
+  const int32_t *node_isize;        /* [n_nodes]      NodeGeometricSizeIndex                   */
+  const double  *node_xmin;         /* [n_nodes][3]                                            */
+  const double  *node_xmax;         /* [n_nodes][3]                                            */
+  const int32_t *node_leaf;         /* [n_nodes]      leaf id or -1                            */
+  const int32_t *node_flags;        /* [n_nodes]      AMPS_NODE_*                              */
+  const int32_t *node_thread;       /* [n_nodes]      cTreeNodeAMR::Thread (owner rank)        */
+  const int32_t *root_node;         /* [n_root0*n_root1*n_root2] node id of root (i+n0*(j+n1*k)) */
+  int32_t n_leaves;
+  const int32_t *leaf_node;         /* [n_leaves]     tree node of the leaf                    */
+  const int32_t *leaf_real;         /* [n_leaves]     periodic: paired real leaf of a ghost leaf, else -1
+                                                      (BlockPairTable, pic_bc_periodic.cpp:555-571) */
+  const int32_t *leaf_face_boundary;/* [n_leaves]     bit f set: GetNeibFace(f)==NULL          */
+  /* unique corner / centre nodes; block-local number = _getCornerNodeLocalNumber /
+     _getCenterNodeLocalNumber incl. ghost layers (meshAMRgeneric.h:74-75); -1 = no node */
+  int32_t n_corners, n_centers;
+  const int32_t *leaf_corner_uid;   /* [n_leaves][(Nx+2g+1)(Ny+2g+1)(Nz+2g+1)]                 */
+  const int32_t *leaf_center_uid;   /* [n_leaves][(Nx+2g)(Ny+2g)(Nz+2g)]                       */
+} amps_gpu_mesh;
+
+/* AoS record description of PIC::ParticleBuffer (picParticleDataMacro.h:18-330) */
+typedef struct amps_gpu_aos_layout {
+  int64_t stride;           /* ParticleDataLength                                             */
+  int32_t off_species;      /* _PIC_PARTICLE_DATA__SPECIES_ID_OFFSET_ (low 6 bits = id)       */
+  int32_t off_v;            /* _PIC_PARTICLE_DATA__VELOCITY_OFFSET_                           */
+  int32_t off_x;            /* _PIC_PARTICLE_DATA__POSITION_OFFSET_                           */
+  int32_t off_w;            /* _PIC_PARTICLE_DATA__WEIGHT_CORRECTION_OFFSET_ or -1            */
+  int32_t off_mu;           /* _PIC_PARTICLE_DATA__MAGNETIC_MOMENT_OFFSET_ or -1              */
+  int32_t off_next;         /* _PIC_PARTICLE_DATA__NEXT_OFFSET_ (download rebuilds the lists) */
+  int32_t off_prev;
+} amps_gpu_aos_layout;
+
+/* counters of one MoveParticles() call */
+typedef struct amps_gpu_move_stats {
+  int64_t n_moved;          /* particles processed                                            */
+  int64_t n_cross_cell;     /* ended in another cell of the same block                        */
+  int64_t n_cross_block;    /* ended in another block (incl. periodic wrap)                   */
+  int64_t n_left_domain;    /* _PARTICLE_LEFT_THE_DOMAIN_                                     */
+  int64_t n_not_in_use;     /* _PARTICLE_IN_NOT_IN_USE_NODE_                                  */
+  int64_t n_periodic_wrap;  /* landed in a periodic ghost block and was shifted               */
+  int64_t n_error;          /* reference would have exit()ed                                  */
+} amps_gpu_move_stats;
+
+typedef struct amps_gpu_ctx amps_gpu_ctx;
+
+/* ---- life cycle ---------------------------------------------------------- */
+/* <- PIC::Init_AfterParser / PIC::ParticleBuffer::Init (pic_pbuffer.cpp:41-222) */
+int amps_gpu_init(const amps_gpu_config *cfg, amps_gpu_ctx **out);
+int amps_gpu_finalize(amps_gpu_ctx *ctx);
+const char *amps_gpu_last_error(const amps_gpu_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py "gpu_launches") */
+int64_t amps_gpu_launch_count(const amps_gpu_ctx *ctx);
+/* cudaStream_t the context launches on (as void*) */
+void *amps_gpu_stream(amps_gpu_ctx *ctx);
+
+/* ---- mesh: <- DomainBlockDecomposition::UpdateBlockTable (pic_mesh.cpp:1644),
+ *      PIC::Mesh::GPU::CopyMeshHost2Device (pic.h:4794-4860)                  ---- */
+int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh);
+
+/* ---- fields: replaces the per-thread SetBlock_E / SetBlock_B gathers
+ *      (pic_mover.cpp:86-166).  Inputs are per UNIQUE node, 3 doubles each:
+ *      E_half = corner OffsetE_HalfTimeStep, B_prev/B_cur = centre (or corner when
+ *      b_mode is corner based) PrevBOffset/CurrentBOffset
+ *      (pic_field_solver_ecsim.cpp:484-538).  Any pointer may be NULL = keep.   ---- */
+int amps_gpu_fields_upload(amps_gpu_ctx *ctx, const double *E_half, const double *B_prev,
+                           const double *B_cur);
+
+/* ---- particle store: PIC::ParticleBuffer as a device SoA sorted by (block,cell) ---- */
+/* AoS records + the cell each one is attached to (global cell = leaf*Nx*Ny*Nz +
+ * i+Nx*(j+Ny*k), i.e. the FirstCellParticleTable slot it hangs on).              */
+int amps_gpu_particles_upload_aos(amps_gpu_ctx *ctx, const void *records, const int64_t *ptrs,
+                                  const int32_t *cells, int64_t n, const amps_gpu_aos_layout *lay);
+/* SoA upload: x[3][n], v[3][n] component-major; w may be NULL (w=1); ptrs = ParticleBuffer
+ * slot of each particle (NULL = 0..n-1), carried through sorts so a download can be
+ * matched to the caller's records.                                                 */
+int amps_gpu_particles_upload_soa(amps_gpu_ctx *ctx, const double *x, const double *v,
+                                  const double *w, const uint8_t *species, const int32_t *cells,
+                                  const int32_t *ptrs, int64_t n);
+int amps_gpu_particle_count(amps_gpu_ctx *ctx, int64_t *n);
+/* current device order; any output pointer may be NULL */
+int amps_gpu_particles_download_soa(amps_gpu_ctx *ctx, double *x, double *v, double *w,
+                                    uint8_t *species, int32_t *cells, int32_t *ptrs, int64_t n_max,
+                                    int64_t *n);
+/* writes records back (ptr i -> slot i of `records`) and threads next/prev lists +
+ * first_cell_particle[n_cells] like FirstCellParticleTable                        */
+int amps_gpu_particles_download_aos(amps_gpu_ctx *ctx, void *records, int64_t *first_cell_particle,
+                                    int64_t n_max, const amps_gpu_aos_layout *lay, int64_t *n);
+/* per-cell particle ranges after a sort: cell_start[n_cells+1] (CreateParticleTable,
+ * pic_pbuffer.cpp:1160-1310)                                                      */
+int amps_gpu_cell_table_download(amps_gpu_ctx *ctx, int64_t *cell_start, int64_t n_cells_plus_1);
+
+/* counting sort by (block,cell); drops deleted particles. Replaces the temp->first list
+ * swap of MoveParticles (pic_mover.cpp:1056-1088) and CreateParticleTable.       */
+int amps_gpu_sort(amps_gpu_ctx *ctx);
+
+/* ---- push: <- PIC::Mover::MoveParticles() (pic_mover.cpp:580-1088) through
+ *      PIC::Mover::UserDefinedMoverManager.  In-place: particle slot i keeps slot i
+ *      until amps_gpu_sort().  Periodic ghost->real wrap (pic_bc_periodic.cpp:86-178)
+ *      is folded into the mover epilogue.  stats may be NULL (no host sync then). ---- */
+int amps_gpu_move(amps_gpu_ctx *ctx, int mover_id, amps_gpu_move_stats *stats);
+
+/* ---- deposit: <- ECSIM::UpdateJMassMatrix() (pic_field_solver_ecsim.cpp:3244-3995).
+ *      Zeroes J[3],M[243] per unique corner, accumulates ProcessCell over all cells of
+ *      real (non periodic-ghost) blocks, which with the unique-corner table also is the
+ *      periodic/ghost corner reduction (ProcessJMassMatrix :1383).  energy (1) and
+ *      cfl (n_species) may be NULL.                                               ---- */
+int amps_gpu_deposit_JM(amps_gpu_ctx *ctx, double *particle_energy, double *cfl);
+/* J[n_corners][3], M[n_corners][243] (neighbour-major, 9 per neighbour as in
+ * IndexMatrix, pic_field_solver_ecsim.cpp:1377-1380); either may be NULL          */
+int amps_gpu_JM_download(amps_gpu_ctx *ctx, double *J, double *M);
+/* device pointers for an on-device consumer (field solve) */
+int amps_gpu_JM_device(amps_gpu_ctx *ctx, double **J_dev, double **M_dev);
+
+/* one fused ECSIM particle phase: move + sort + deposit, no host sync inside */
+int amps_gpu_step(amps_gpu_ctx *ctx, int mover_id);
+
+/* block until all queued work of the context is complete */
+int amps_gpu_synchronize(amps_gpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMPS_GPU_H */

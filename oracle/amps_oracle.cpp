@@ -1,0 +1,1442 @@
+/*
+ * amps_oracle.cpp -- CPU ORACLE (test infrastructure, NOT product code).
+ * See amps_oracle.h for scope and the parity-pinning statement.
+ *
+ * Every routine restates the reference algorithm literally (same operation
+ * order, same data structures) and cites the reference file:line.  Build the
+ * parity variant with  -O2 -ffp-contract=off  (no FMA contraction, SSE2 fp64),
+ * the timing variant with -O3 -march=native -fopenmp.
+ *
+ * Reference paths are relative to the AMPS source tree.
+ */
+#include "amps_oracle.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+typedef unsigned char byte;
+
+// ---------------------------------------------------------------------------------------------
+// node-associated data layout, src/pic/pic_field_solver_ecsim.cpp:484-538 (doubles from
+// ElectricField.RelativeOffset):  E[0:3] E_half[3:6] J[6:9] M[9:252]; centre: B_cur[0:3] B_prev[3:6]
+// (CurrentBOffset / PrevBOffset swap every step, :5697-5700; fixed here)
+// ---------------------------------------------------------------------------------------------
+const int ExOffsetIndex = 0;
+const int OffsetE_HalfTimeStep_d = 3;  // in doubles
+const int JxOffsetIndex = 6;
+const int MassMatrixOffsetIndex = 9;
+const int CornerDataLength = 252;
+const int CurrentBOffset_d = 0;
+const int PrevBOffset_d = 3;
+const int CenterDataLength = 6;
+
+// src/pic/pic_field_solver_ecsim.cpp:1377-1380
+const int IndexMatrix[8][8] = {{0, 2, 8, 6, 18, 20, 26, 24},  {1, 0, 6, 7, 19, 18, 24, 25},
+                               {4, 3, 0, 1, 22, 21, 18, 19},  {3, 5, 2, 0, 21, 23, 20, 18},
+                               {9, 11, 17, 15, 0, 2, 8, 6},   {10, 9, 15, 16, 1, 0, 6, 7},
+                               {13, 12, 9, 10, 4, 3, 0, 1},   {12, 14, 11, 9, 3, 5, 2, 0}};
+
+// particle-mover return codes, src/pic/pic.h:5955-5960
+const int _PARTICLE_LEFT_THE_DOMAIN_ = 2;
+const int _PARTICLE_MOTION_FINISHED_ = 3;
+const int _PARTICLE_IN_NOT_IN_USE_NODE_ = 4;
+const int _ORACLE_ERROR_ = -1;
+
+struct cCornerNode {
+  double *data;  // associated data buffer (CornerDataLength doubles)
+  std::atomic_flag lock_associated_data = ATOMIC_FLAG_INIT;
+};
+struct cCenterNode {
+  double *data;  // CenterDataLength doubles
+};
+
+struct cTempList {
+  long int first, last;
+};
+
+struct cBlock {
+  long int *FirstCellParticleTable;         // src/pic/pic.h:4547
+  long int *tempParticleMovingListTable;    // src/pic/pic.h:4582-4586
+  cTempList *tempThreadTable;               // [thread][cell] (hybrid mode)
+  cCornerNode **cornerNodes;                // [(Nx+2g+1)(Ny+2g+1)(Nz+2g+1)]
+  cCenterNode **centerNodes;                // [(Nx+2g)(Ny+2g)(Nz+2g)]
+};
+
+// cTreeNodeAMR, src/meshAMR/meshAMRgeneric.h:825-838
+struct cTreeNode {
+  double xmin[3], xmax[3];
+  int xMinGlobalIndex[3];
+  int NodeGeometricSizeIndex;
+  cTreeNode *downNode[8];
+  cTreeNode *upNode;
+  int RefinmentLevel;
+  int Thread;
+  bool IsUsedInCalculationFlag;
+  bool IsGhostNodeFlag;
+  cBlock *block;
+  int leaf;
+  int faceBoundary;
+  int id;
+};
+
+// cStencilGeneric, src/pic/pic.h:7202-7293
+const int nMaxStencilLength = 64;
+struct cStencil {
+  int Length;
+  double Weight[nMaxStencilLength];
+  int LocalCellID[nMaxStencilLength];
+  void flush() { Length = 0; }
+  void Normalize() {
+    double norm = 0.0;
+    int i;
+    for (i = 0; i < Length; i++) norm += Weight[i];
+    if (norm > 0.0)
+      for (i = 0; i < Length; i++) Weight[i] /= norm;
+  }
+};
+
+// cCellData, src/pic/pic.h (ECSIM::cCellData): per-corner J[3], M[243]
+struct cCornerData {
+  double *CornerMassMatrix_ptr, *CornerJ_ptr;
+  double CornerMassMatrix[243];
+  double CornerJ[3];
+  cCornerNode *CornerNode;
+};
+struct cCellData {
+  cCornerData CornerData[8];
+  double ParticleEnergy;
+  double cflCell[AMPS_GPU_MAX_SPECIES];
+  void clean() {
+    for (int ic = 0; ic < 8; ic++) {
+      for (int i = 0; i < 243; i++) CornerData[ic].CornerMassMatrix[i] = 0.0;
+      for (int i = 0; i < 3; i++) CornerData[ic].CornerJ[i] = 0.0;
+    }
+    ParticleEnergy = 0.0;
+    for (int s = 0; s < AMPS_GPU_MAX_SPECIES; s++) cflCell[s] = 0.0;
+  }
+};
+
+}  // namespace
+
+struct oracle_ctx {
+  amps_gpu_config cfg;
+  std::string err;
+  // compile-time macros of the reference
+  int _BLOCK_CELLS_X_, _BLOCK_CELLS_Y_, _BLOCK_CELLS_Z_;
+  int _GHOST_CELLS_X_, _GHOST_CELLS_Y_, _GHOST_CELLS_Z_;
+  int _TOTAL_BLOCK_CELLS_X_, _TOTAL_BLOCK_CELLS_Y_, _TOTAL_BLOCK_CELLS_Z_;
+  // cMeshAMRgeneric
+  double xGlobalMin[3], xGlobalMax[3], dx_max_refinment[3], dxRootBlock[3], EPS;
+  int nRoot[3], maxRefinementLevel;
+  std::vector<cTreeNode> nodes;
+  std::vector<cTreeNode *> rootTable;
+  std::vector<cTreeNode *> BlockTable;  // DomainBlockDecomposition::BlockTable (leaf order)
+  std::vector<cBlock> blocks;
+  std::vector<int> leaf_real;
+  int n_corners, n_centers;
+  std::vector<cCornerNode> cornerPool;
+  std::vector<cCenterNode> centerPool;
+  std::vector<double> cornerData, centerData;
+  std::vector<long int> listStorage;
+  std::vector<cTempList> threadListStorage;
+  int nThreadListTables;
+  // PIC::ParticleBuffer (src/pic/pic_pbuffer.cpp)
+  long int MaxNPart, ParticleDataLength, FirstPBufferParticle, NAllPart;
+  byte *ParticleDataBuffer;
+  // per-thread E/B staging, src/pic/pic_mover.cpp:660-711
+  std::vector<std::vector<double>> E_Corner, B_Center;
+
+  int nCornerLocal() const { return (_TOTAL_BLOCK_CELLS_X_ + 1) * (_TOTAL_BLOCK_CELLS_Y_ + 1) * (_TOTAL_BLOCK_CELLS_Z_ + 1); }
+  int nCenterLocal() const { return _TOTAL_BLOCK_CELLS_X_ * _TOTAL_BLOCK_CELLS_Y_ * _TOTAL_BLOCK_CELLS_Z_; }
+  int nCellsBlock() const { return _BLOCK_CELLS_X_ * _BLOCK_CELLS_Y_ * _BLOCK_CELLS_Z_; }
+  // src/meshAMR/meshAMRgeneric.h:74-75
+  int _getCornerNodeLocalNumber(int i, int j, int k) const {
+    return (i + _GHOST_CELLS_X_ + (1 + _TOTAL_BLOCK_CELLS_X_) * (j + _GHOST_CELLS_Y_ + (k + _GHOST_CELLS_Z_) * (1 + _TOTAL_BLOCK_CELLS_Y_)));
+  }
+  int _getCenterNodeLocalNumber(int i, int j, int k) const {
+    return (i + _GHOST_CELLS_X_ + _TOTAL_BLOCK_CELLS_X_ * (j + _GHOST_CELLS_Y_ + (k + _GHOST_CELLS_Z_) * _TOTAL_BLOCK_CELLS_Y_));
+  }
+
+  // ---- PIC::ParticleBuffer accessors, packed layout picParticleDataMacro.h:55-81 ----
+  enum { OFF_NEXT = 0, OFF_PREV = 8, OFF_SPEC = 16, OFF_V = 17, OFF_X = 41, OFF_W = 65, BASIC_LEN = 73 };
+  byte *GetParticleDataPointer(long int ptr) const { return ParticleDataBuffer + ptr * ParticleDataLength; }
+  static long int GetNext(const byte *p) { long int t; memcpy(&t, p + OFF_NEXT, 8); return t; }
+  static long int GetPrev(const byte *p) { long int t; memcpy(&t, p + OFF_PREV, 8); return t; }
+  static void SetNext(long int v, byte *p) { memcpy(p + OFF_NEXT, &v, 8); }
+  static void SetPrev(long int v, byte *p) { memcpy(p + OFF_PREV, &v, 8); }
+  long int GetNext(long int ptr) const { return GetNext(GetParticleDataPointer(ptr)); }
+  void SetNext(long int v, long int ptr) { SetNext(v, GetParticleDataPointer(ptr)); }
+  void SetPrev(long int v, long int ptr) { SetPrev(v, GetParticleDataPointer(ptr)); }
+  // species byte: bits 0-5 id, bit 7 "allocated", src/pic/pic.h:2808-2900
+  static unsigned int GetI(const byte *p) { return (*(p + OFF_SPEC)) & 0x3f; }
+  static void SetI(int spec, byte *p) { *(p + OFF_SPEC) = (byte)((spec & 0x3f) | ((*(p + OFF_SPEC)) & 0xc0)); }
+  static bool IsParticleAllocated(const byte *p) { return ((*(p + OFF_SPEC)) & 0x80) != 0; }
+  static void SetParticleDeleted(byte *p) { *(p + OFF_SPEC) &= 0x7f; }
+  static void SetParticleAllocated(byte *p) { *(p + OFF_SPEC) |= 0x80; }
+  static void GetV(double *v, const byte *p) { memcpy(v, p + OFF_V, 24); }
+  static void SetV(const double *v, byte *p) { memcpy(p + OFF_V, v, 24); }
+  static void GetX(double *x, const byte *p) { memcpy(x, p + OFF_X, 24); }
+  static void SetX(const double *x, byte *p) { memcpy(p + OFF_X, x, 24); }
+  static double GetIndividualStatWeightCorrection(const byte *p) { double w; memcpy(&w, p + OFF_W, 8); return w; }
+  static void SetIndividualStatWeightCorrection(double w, byte *p) { memcpy(p + OFF_W, &w, 8); }
+
+  // src/pic/pic_pbuffer.cpp:371-437 (MPI mode branch)
+  long int GetNewParticle() {
+    if (FirstPBufferParticle == -1) return -1;
+    long int newptr = FirstPBufferParticle;
+    byte *p = GetParticleDataPointer(newptr);
+    FirstPBufferParticle = GetNext(p);
+    NAllPart++;
+    SetParticleAllocated(p);
+    SetPrev(-1, p);
+    SetNext(-1, p);
+    return newptr;
+  }
+  // src/pic/pic_pbuffer.cpp:594-666 (the particle is already detached from its cell list by the caller)
+  void DeleteParticle_withoutTrajectoryTermination(long int ptr) {
+    byte *p = GetParticleDataPointer(ptr);
+    SetParticleDeleted(p);
+#pragma omp critical(oracle_pbuffer)
+    {
+      SetNext(FirstPBufferParticle, p);
+      FirstPBufferParticle = ptr;
+      NAllPart--;
+    }
+  }
+  void DeleteParticle(long int ptr) { DeleteParticle_withoutTrajectoryTermination(ptr); }
+
+  // ---- cMeshAMRgeneric::findTreeNode(int*), src/meshAMR/meshAMRgeneric.h:2793-2848.
+  // Forest extension: when the walk leaves a root block it continues in the root grid.
+  cTreeNode *findTreeNode(int *ix, cTreeNode *startNode) const {
+    int i = 0, j = 0, k = 0, idim;
+    bool inblock;
+    if (startNode == NULL) startNode = rootLookup(ix);
+    if (startNode == NULL) return NULL;
+    while (true) {
+      inblock = true;
+      for (idim = 0; idim < 3; idim++) {
+        if ((ix[idim] < startNode->xMinGlobalIndex[idim]) || (ix[idim] >= startNode->xMinGlobalIndex[idim] + startNode->NodeGeometricSizeIndex)) {
+          inblock = false;
+          break;
+        }
+      }
+      if (inblock == true) {
+        i = (ix[0] - startNode->xMinGlobalIndex[0] < startNode->NodeGeometricSizeIndex / 2) ? 0 : 1;
+        j = (ix[1] - startNode->xMinGlobalIndex[1] < startNode->NodeGeometricSizeIndex / 2) ? 0 : 1;
+        k = (ix[2] - startNode->xMinGlobalIndex[2] < startNode->NodeGeometricSizeIndex / 2) ? 0 : 1;
+        cTreeNode *t = startNode->downNode[i + 2 * (j + 2 * k)];
+        if (t != NULL) {
+          startNode = t;
+          continue;
+        } else
+          return startNode;
+      } else {
+        if (startNode->upNode != 0) {
+          startNode = startNode->upNode;
+          continue;
+        } else {
+          // single octree: return NULL (meshAMRgeneric.h:2840-2842); forest: look in the root grid
+          startNode = rootLookup(ix);
+          if (startNode == NULL) return NULL;
+          continue;
+        }
+      }
+    }
+  }
+  cTreeNode *rootLookup(const int *ix) const {
+    int S = 1 << maxRefinementLevel, r[3];
+    for (int d = 0; d < 3; d++) {
+      if (ix[d] < 0) return NULL;
+      r[d] = ix[d] / S;
+      if (r[d] >= nRoot[d]) return NULL;
+    }
+    return rootTable[r[0] + nRoot[0] * (r[1] + nRoot[1] * r[2])];
+  }
+  // cMeshAMRgeneric::findTreeNode(double*), src/meshAMR/meshAMRgeneric.h:2851-2882
+  cTreeNode *findTreeNode(const double *x, cTreeNode *startNode) const {
+    int idim, ix[3];
+    cTreeNode *res;
+    bool flag;
+    for (idim = 0; idim < 3; idim++) {
+      ix[idim] = (int)floor((x[idim] - xGlobalMin[idim]) / dx_max_refinment[idim]);
+    }
+    res = findTreeNode(ix, startNode);
+    flag = false;
+    if (res != NULL)
+      for (idim = 0; idim < 3; idim++) {
+        if (x[idim] < res->xmin[idim]) ix[idim]--, flag = true;
+        if (x[idim] >= res->xmax[idim]) ix[idim]++, flag = true;
+      }
+    if (flag == true) {
+      res = findTreeNode(ix, res);
+    }
+    return res;
+  }
+  // cMeshAMRgeneric::FindCellIndex, src/meshAMR/meshAMRgeneric.h:2256-2323 (ExitFlag=false)
+  long int FindCellIndex(const double *x, int &i, int &j, int &k, const cTreeNode *startNode) const {
+    double dx;
+    if ((x[0] < startNode->xmin[0]) || (startNode->xmax[0] < x[0])) return -1;
+    dx = dxRootBlock[0] / (1 << startNode->RefinmentLevel) / double(_BLOCK_CELLS_X_);
+    i = (int)((x[0] - startNode->xmin[0]) / dx);
+    if (i == _BLOCK_CELLS_X_) i = _BLOCK_CELLS_X_ - 1;
+    if ((x[1] < startNode->xmin[1]) || (startNode->xmax[1] < x[1])) return -1;
+    dx = dxRootBlock[1] / (1 << startNode->RefinmentLevel) / double(_BLOCK_CELLS_Y_);
+    j = (int)((x[1] - startNode->xmin[1]) / dx);
+    if (j == _BLOCK_CELLS_Y_) j = _BLOCK_CELLS_Y_ - 1;
+    if ((x[2] < startNode->xmin[2]) || (startNode->xmax[2] < x[2])) return -1;
+    dx = dxRootBlock[2] / (1 << startNode->RefinmentLevel) / double(_BLOCK_CELLS_Z_);
+    k = (int)((x[2] - startNode->xmin[2]) / dx);
+    if (k == _BLOCK_CELLS_Z_) k = _BLOCK_CELLS_Z_ - 1;
+    return _getCenterNodeLocalNumber(i, j, k);
+  }
+
+  // cStencilGeneric::AddCell for centre nodes, src/pic/pic.h:7228-7252: in non-periodic mode a
+  // node whose centre lies outside the global box is not added.  The centre coordinate is
+  // rebuilt from the block geometry (cDataCenterNode::GetX()).
+  bool CenterOutsideDomain(const cTreeNode *node, int i, int j, int k) const {
+    if (cfg.periodic) return false;
+    const int N[3] = {_BLOCK_CELLS_X_, _BLOCK_CELLS_Y_, _BLOCK_CELLS_Z_};
+    const int ijk[3] = {i, j, k};
+    for (int d = 0; d < 3; ++d) {
+      const double x = node->xmin[d] + (ijk[d] + 0.5) * ((node->xmax[d] - node->xmin[d]) / N[d]);
+      if (x < xGlobalMin[d] || x > xGlobalMax[d]) return true;
+    }
+    return false;
+  }
+
+  // PIC::InterpolationRoutines::CornerBased::InitStencil, src/pic/pic_interpolation_routines.cpp:1074-1194
+  // returns false where the reference exit()s ("the point is out of block")
+  bool CornerBased_InitStencil(double *x, cTreeNode *node, cStencil &Stencil, double *InterpolationCoefficientTable) const {
+    int iStencil, jStencil, kStencil, iX[3], nd, idim;
+    double w, xLoc[3], dx[3], *xMinNode, *xMaxNode;
+    cCornerNode *CornerNode;
+    cBlock *block;
+
+    xMinNode = node->xmin;
+    xMaxNode = node->xmax;
+    dx[0] = (xMaxNode[0] - xMinNode[0]) / _BLOCK_CELLS_X_;
+    dx[1] = (xMaxNode[1] - xMinNode[1]) / _BLOCK_CELLS_Y_;
+    dx[2] = (xMaxNode[2] - xMinNode[2]) / _BLOCK_CELLS_Z_;
+
+    for (idim = 0; idim < 3; idim++) {
+      if ((x[idim] < xMinNode[idim]) || (x[idim] > xMaxNode[idim])) return false;
+      if (fabs(x[idim] - xMaxNode[idim]) < 1e-10 * dx[idim]) x[idim] = xMaxNode[idim] - 1e-10 * dx[idim];
+      xLoc[idim] = (x[idim] - xMinNode[idim]) / dx[idim];
+      iX[idim] = (int)(xLoc[idim]);
+      xLoc[idim] -= iX[idim];
+    }
+
+    Stencil.flush();
+    if ((block = node->block) == NULL) return true;
+
+    for (iStencil = 0; iStencil < 2; iStencil++)
+      for (jStencil = 0; jStencil < 2; jStencil++)
+        for (kStencil = 0; kStencil < 2; kStencil++) {
+          nd = _getCornerNodeLocalNumber(iStencil + iX[0], jStencil + iX[1], kStencil + iX[2]);
+          CornerNode = block->cornerNodes[nd];
+          // cell-corner order of the table: (0,0,0)(1,0,0)(1,1,0)(0,1,0)(0,0,1)(1,0,1)(1,1,1)(0,1,1)
+          static const int slot[8] = {0, 1, 3, 2, 4, 5, 7, 6};
+          int code = iStencil + 2 * jStencil + 4 * kStencil;
+          if (CornerNode != NULL) {
+            switch (code) {
+              case 0: w = (1.0 - xLoc[0]) * (1.0 - xLoc[1]) * (1.0 - xLoc[2]); break;
+              case 1: w = xLoc[0] * (1.0 - xLoc[1]) * (1.0 - xLoc[2]); break;
+              case 2: w = (1.0 - xLoc[0]) * xLoc[1] * (1.0 - xLoc[2]); break;
+              case 3: w = xLoc[0] * xLoc[1] * (1.0 - xLoc[2]); break;
+              case 4: w = (1.0 - xLoc[0]) * (1.0 - xLoc[1]) * xLoc[2]; break;
+              case 5: w = xLoc[0] * (1.0 - xLoc[1]) * xLoc[2]; break;
+              case 6: w = (1.0 - xLoc[0]) * xLoc[1] * xLoc[2]; break;
+              default: w = xLoc[0] * xLoc[1] * xLoc[2]; break;
+            }
+            InterpolationCoefficientTable[slot[code]] = w;
+            // AddCell (pic.h:7228): in-block corners are inside the global box
+            Stencil.Weight[Stencil.Length] = w;
+            Stencil.LocalCellID[Stencil.Length] = nd;
+            Stencil.Length++;
+          } else {
+            InterpolationCoefficientTable[slot[code]] = 0.0;
+          }
+        }
+    Stencil.Normalize();
+    return true;
+  }
+
+  // CellCentered::Linear::GetTriliniarInterpolationStencil, src/pic/pic_interpolation_routines.cpp:820-907
+  // always_normalize: the reference tests the GLOBAL StencilTable->Length (:903), which in ECSIM
+  // runs is never filled (the movers pass their own stencil object) => Normalize() always runs.
+  void GetTriliniarInterpolationStencil(double iLoc, double jLoc, double kLoc, const double *x, cTreeNode *node, cStencil &Stencil, bool always_normalize) const {
+    cCenterNode *cell;
+    cBlock *block = node->block;
+    Stencil.flush();
+    double w[3], InterpolationWeight;
+    int i, j, k, i0, j0, k0, nd;
+
+    i0 = (iLoc < 0.5) ? -1 : (int)(iLoc - 0.50);
+    j0 = (jLoc < 0.5) ? -1 : (int)(jLoc - 0.50);
+    k0 = (kLoc < 0.5) ? -1 : (int)(kLoc - 0.50);
+
+    w[0] = iLoc - (i0 + 0.5);
+    w[1] = jLoc - (j0 + 0.5);
+    w[2] = kLoc - (k0 + 0.5);
+
+    for (i = 0; i < 2; i++)
+      for (j = 0; j < 2; j++)
+        for (k = 0; k < 2; k++) {
+          nd = _getCenterNodeLocalNumber(i0 + i, j0 + j, k0 + k);
+          switch (i + 2 * j + 4 * k) {
+            case 0: InterpolationWeight = (1.0 - w[0]) * (1.0 - w[1]) * (1.0 - w[2]); break;
+            case 1: InterpolationWeight = w[0] * (1.0 - w[1]) * (1.0 - w[2]); break;
+            case 2: InterpolationWeight = (1.0 - w[0]) * w[1] * (1.0 - w[2]); break;
+            case 3: InterpolationWeight = w[0] * w[1] * (1.0 - w[2]); break;
+            case 4: InterpolationWeight = (1.0 - w[0]) * (1.0 - w[1]) * w[2]; break;
+            case 5: InterpolationWeight = w[0] * (1.0 - w[1]) * w[2]; break;
+            case 6: InterpolationWeight = (1.0 - w[0]) * w[1] * w[2]; break;
+            default: InterpolationWeight = w[0] * w[1] * w[2]; break;
+          }
+          cell = (block == NULL) ? NULL : block->centerNodes[nd];
+          if (cell != NULL) {
+            if (CenterOutsideDomain(node, i0 + i, j0 + j, k0 + k)) continue;  // AddCell, pic.h:7235-7245
+            Stencil.Weight[Stencil.Length] = InterpolationWeight;
+            Stencil.LocalCellID[Stencil.Length] = nd;
+            Stencil.Length++;
+          }
+        }
+
+    if (Stencil.Length == 0) {
+      // Constant::InitStencil fallback, pic_interpolation_routines.cpp:168-220
+      int ci, cj, ck;
+      long int cnd = FindCellIndex(x, ci, cj, ck, node);
+      if (cnd >= 0) {
+        Stencil.Weight[0] = 1.0;
+        Stencil.LocalCellID[0] = (int)cnd;
+        Stencil.Length = 1;
+      }
+      return;
+    } else if (always_normalize || Stencil.Length != 8) {
+      Stencil.Normalize();
+    }
+  }
+  // CellCentered::Linear::InitStencil, src/pic/pic_interpolation_routines.cpp:224-330
+  // (uniform mesh / all neighbours at the same level branch)
+  void CellCentered_Linear_InitStencil(const double *XyzIn_D, cTreeNode *node, cStencil &Stencil, bool always_normalize) const {
+    double iLoc, jLoc, kLoc;
+    double *xmin = node->xmin, *xmax = node->xmax;
+    iLoc = (XyzIn_D[0] - xmin[0]) / (xmax[0] - xmin[0]) * _BLOCK_CELLS_X_;
+    jLoc = (XyzIn_D[1] - xmin[1]) / (xmax[1] - xmin[1]) * _BLOCK_CELLS_Y_;
+    kLoc = (XyzIn_D[2] - xmin[2]) / (xmax[2] - xmin[2]) * _BLOCK_CELLS_Z_;
+    GetTriliniarInterpolationStencil(iLoc, jLoc, kLoc, XyzIn_D, node, Stencil, always_normalize);
+  }
+
+  // PIC::Mover::SetBlock_E / SetBlock_B, src/pic/pic_mover.cpp:86-166
+  void SetBlock_E(double *E_Corner, cTreeNode *node) const {
+    if (!node->block) return;
+    for (int k = -_GHOST_CELLS_Z_; k <= _BLOCK_CELLS_Z_ + _GHOST_CELLS_Z_; k++)
+      for (int j = -_GHOST_CELLS_Y_; j <= _BLOCK_CELLS_Y_ + _GHOST_CELLS_Y_; j++)
+        for (int i = -_GHOST_CELLS_X_; i <= _BLOCK_CELLS_X_ + _GHOST_CELLS_X_; i++) {
+          int LocalCornerId = _getCornerNodeLocalNumber(i, j, k);
+          if (!node->block->cornerNodes[LocalCornerId]) continue;
+          double *ptr = node->block->cornerNodes[LocalCornerId]->data + OffsetE_HalfTimeStep_d;
+          memcpy(&E_Corner[LocalCornerId * 3], ptr, 3 * sizeof(double));
+        }
+  }
+  void SetBlock_B(double *B_C, cTreeNode *node) const {
+    if (!node->block) return;
+    for (int k = -_GHOST_CELLS_Z_; k < _BLOCK_CELLS_Z_ + _GHOST_CELLS_Z_; k++)
+      for (int j = -_GHOST_CELLS_Y_; j < _BLOCK_CELLS_Y_ + _GHOST_CELLS_Y_; j++)
+        for (int i = -_GHOST_CELLS_X_; i < _BLOCK_CELLS_X_ + _GHOST_CELLS_X_; i++) {
+          int LocalCenterId = _getCenterNodeLocalNumber(i, j, k);
+          if (!node->block->centerNodes[LocalCenterId]) continue;
+          double *ptr = node->block->centerNodes[LocalCenterId]->data + PrevBOffset_d;
+          memcpy(&B_C[LocalCenterId * 3], ptr, 3 * sizeof(double));
+        }
+  }
+
+  // attach to the temp moving list, src/pic/pic_mover_boris.cpp:1333-1365
+  void AttachToTempList(long int ptr, byte *ParticleData, cBlock *block, int i, int j, int k, int nThreads, int thread) {
+    int cell = i + _BLOCK_CELLS_X_ * (j + _BLOCK_CELLS_Y_ * k);
+    if (nThreads <= 1) {  // _COMPILATION_MODE__MPI_
+      long int tempFirstCellParticle, *tempFirstCellParticlePtr;
+      tempFirstCellParticlePtr = block->tempParticleMovingListTable + cell;
+      tempFirstCellParticle = (*tempFirstCellParticlePtr);
+      SetNext(tempFirstCellParticle, ParticleData);
+      SetPrev(-1, ParticleData);
+      if (tempFirstCellParticle != -1) SetPrev(ptr, tempFirstCellParticle);
+      *tempFirstCellParticlePtr = ptr;
+    } else {  // _COMPILATION_MODE__HYBRID_, per-thread lists
+      cTempList *t = block->tempThreadTable + (size_t)thread * nCellsBlock() + cell;
+      SetNext(t->first, ParticleData);
+      SetPrev(-1, ParticleData);
+      if (t->last == -1) t->last = ptr;
+      if (t->first != -1) SetPrev(ptr, t->first);
+      t->first = ptr;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // PIC::Mover::Lapenta2017, src/pic/pic_mover_boris.cpp:876-1393 (scalar, non-AVX branch,
+  // _PIC_FIELD_SOLVER_MODE__ELECTROMAGNETIC__ECSIM_, B centre based, no internal sphere)
+  // ------------------------------------------------------------------------------------------
+  int Lapenta2017(byte *ParticleData, long int ptr, cTreeNode *startNode, const double *E_Corner, const double *B_C, int nThreads, int thread,
+                  cTreeNode **newNodeOut) {
+    cTreeNode *newNode = NULL;
+    int idim, i, j, k, spec;
+    double dtTotal;
+    double vInit[3], xInit[3], vFinal[3], xFinal[3];
+
+    GetV(vInit, ParticleData);
+    GetX(xInit, ParticleData);
+    spec = GetI(ParticleData);
+
+    switch (cfg.time_step_mode) {
+      case AMPS_DT_SPECIES_GLOBAL: dtTotal = cfg.time_step[spec]; break;
+      default: dtTotal = cfg.time_step[0];
+    }
+
+    cStencil ElectricFieldStencil, MagneticFieldStencil;
+    double E[4] = {0.0, 0.0, 0.0, 0.0}, B[4] = {0.0, 0.0, 0.0, 0.0};
+    int *LocalCellID, Length;
+    double *Weight;
+    double Wtab[8];
+
+    if (!CornerBased_InitStencil(xInit, startNode, ElectricFieldStencil, Wtab)) return _ORACLE_ERROR_;
+    Length = ElectricFieldStencil.Length;
+    LocalCellID = ElectricFieldStencil.LocalCellID;
+    Weight = ElectricFieldStencil.Weight;
+
+    for (int iStencil = 0; iStencil < Length; iStencil++) {
+      const double *tempE1 = E_Corner + 3 * LocalCellID[iStencil];
+      const double *tempB1 = (cfg.b_mode == AMPS_B_CORNER_BASED) ? B_C + 3 * LocalCellID[iStencil] : NULL;
+      for (idim = 0; idim < 3; idim++) {
+        E[idim] += Weight[iStencil] * tempE1[idim];
+        if (cfg.b_mode == AMPS_B_CORNER_BASED) B[idim] += Weight[iStencil] * tempB1[idim];
+      }
+    }
+
+    if (cfg.b_mode == AMPS_B_CENTER_BASED) {
+      CellCentered_Linear_InitStencil(xInit, startNode, MagneticFieldStencil, true);
+      Length = MagneticFieldStencil.Length;
+      LocalCellID = MagneticFieldStencil.LocalCellID;
+      Weight = MagneticFieldStencil.Weight;
+      for (int iStencil = 0; iStencil < Length; iStencil++) {
+        const double *tempB1 = B_C + 3 * LocalCellID[iStencil];
+        for (idim = 0; idim < 3; idim++) B[idim] += Weight[iStencil] * tempB1[idim];
+      }
+    }
+
+    double QdT_over_m, QdT_over_2m, alpha[3][3];
+    double c0, QdT_over_2m_squared, mass, chargeQ;
+
+    chargeQ = cfg.charge[spec];  // picunits::si2no_q applied by the host once per species
+    mass = cfg.mass[spec];
+
+    QdT_over_m = chargeQ * dtTotal / mass;
+    QdT_over_2m = 0.5 * QdT_over_m;
+    QdT_over_2m_squared = QdT_over_2m * QdT_over_2m;
+
+    double BB[3][3], P[3];
+    for (i = 0; i < 3; i++) {
+      P[i] = -QdT_over_2m * B[i];
+      for (j = 0; j <= i; j++) {
+        BB[i][j] = QdT_over_2m_squared * B[i] * B[j];
+        BB[j][i] = BB[i][j];
+      }
+    }
+    c0 = 1.0 / (1.0 + QdT_over_2m_squared * (B[0] * B[0] + B[1] * B[1] + B[2] * B[2]));
+
+    alpha[0][0] = c0 * (1.0 + BB[0][0]);
+    alpha[0][1] = c0 * (-P[2] + BB[0][1]);
+    alpha[0][2] = c0 * (P[1] + BB[0][2]);
+    alpha[1][0] = c0 * (P[2] + BB[1][0]);
+    alpha[1][1] = c0 * (1.0 + BB[1][1]);
+    alpha[1][2] = c0 * (-P[0] + BB[1][2]);
+    alpha[2][0] = c0 * (-P[1] + BB[2][0]);
+    alpha[2][1] = c0 * (P[0] + BB[2][1]);
+    alpha[2][2] = c0 * (1.0 + BB[2][2]);
+
+    for (idim = 0; idim < 3; idim++) {
+      double vp = 0.0;
+      for (j = 0; j < 3; j++) vp += alpha[idim][j] * (vInit[j] + QdT_over_2m * E[j]);
+      vFinal[idim] = 2.0 * vp - vInit[idim];
+    }
+    for (idim = 0; idim < 3; idim++) xFinal[idim] = xInit[idim] + dtTotal * vFinal[idim];
+
+    newNode = findTreeNode(xFinal, startNode);
+
+    if (newNode == NULL) {
+      // the particle left the computational domain, pic_mover_boris.cpp:1159-1265
+      int code = 0;  // _PARTICLE_DELETED_ON_THE_FACE_
+      if (cfg.boundary_mode != AMPS_BOUNDARY_DELETE) {
+        int nface, nIntersectionFace = -1;
+        double tVelocityIncrement, cx, cv, r0[3], dt, vMiddle[3] = {0.5 * (vInit[0] + vFinal[0]), 0.5 * (vInit[1] + vFinal[1]), 0.5 * (vInit[2] + vFinal[2])}, c, dtIntersection = -1.0;
+        for (nface = 0; nface < 6; nface++) {
+          for (idim = 0, cx = 0.0, cv = 0.0; idim < 3; idim++) {
+            r0[idim] = xInit[idim] - FaceTable[nface].x0[idim];
+            cx += r0[idim] * FaceTable[nface].norm[idim];
+            cv += vMiddle[idim] * FaceTable[nface].norm[idim];
+          }
+          if (cv > 0.0) {
+            dt = -cx / cv;
+            if ((dtIntersection < 0.0) || ((dt < dtIntersection) && (dt > 0.0))) {
+              double cE0 = 0.0, cE1 = 0.0;
+              for (idim = 0; idim < 3; idim++) {
+                c = r0[idim] + dt * vMiddle[idim];
+                cE0 += c * FaceTable[nface].e0[idim], cE1 += c * FaceTable[nface].e1[idim];
+              }
+              if ((cE0 < -EPS) || (cE0 > FaceTable[nface].lE0 + EPS) || (cE1 < -EPS) || (cE1 > FaceTable[nface].lE1 + EPS)) continue;
+              nIntersectionFace = nface, dtIntersection = dt;
+            }
+          }
+        }
+        if (nIntersectionFace == -1) return _ORACLE_ERROR_;
+        for (idim = 0, tVelocityIncrement = ((dtIntersection / dtTotal < 1) ? dtIntersection / dtTotal : 1); idim < 3; idim++) {
+          xInit[idim] += dtIntersection * vMiddle[idim] - FaceTable[nIntersectionFace].norm[idim] * EPS;
+          vInit[idim] += tVelocityIncrement * (vFinal[idim] - vInit[idim]);
+        }
+        newNode = findTreeNode(xInit, startNode);
+        if (newNode == NULL) {
+          double xmin[3], xmax[3];
+          memcpy(xmin, xGlobalMin, 3 * sizeof(double));
+          memcpy(xmax, xGlobalMax, 3 * sizeof(double));
+          for (int ii = 0; ii < 3; ii++) {
+            if (xmin[ii] >= xInit[ii]) xInit[ii] = xmin[ii] + EPS;
+            if (xmax[ii] <= xInit[ii]) xInit[ii] = xmax[ii] - EPS;
+          }
+          newNode = findTreeNode(xInit, startNode);
+          if (newNode == NULL) return _ORACLE_ERROR_;
+        }
+        switch (cfg.boundary_mode) {
+          case AMPS_BOUNDARY_SPECULAR_REFLECTION: {
+            double cc = 0.0;
+            for (int d = 0; d < 3; d++) cc += FaceTable[nIntersectionFace].norm[d] * vInit[d];
+            for (int d = 0; d < 3; d++) vInit[d] -= 2.0 * cc * FaceTable[nIntersectionFace].norm[d];
+            code = 1;  // _PARTICLE_REJECTED_ON_THE_FACE_
+          } break;
+          default:
+            code = 0;  // user function (CutoffRigidity::ProcessOutsideDomainParticles always deletes)
+        }
+        memcpy(vFinal, vInit, 3 * sizeof(double));
+        memcpy(xFinal, xInit, 3 * sizeof(double));
+      }
+      switch (code) {
+        case 0:
+          DeleteParticle(ptr);
+          return _PARTICLE_LEFT_THE_DOMAIN_;
+        default:
+          // the reference exit()s here ("not implemented", pic_mover_boris.cpp:1262-1263)
+          return _ORACLE_ERROR_;
+      }
+    } else {
+      if (newNode->IsUsedInCalculationFlag == false) {
+        DeleteParticle(ptr);
+        return _PARTICLE_IN_NOT_IN_USE_NODE_;
+      }
+    }
+
+    cBlock *block;
+    if (FindCellIndex(xFinal, i, j, k, newNode) == -1) return _ORACLE_ERROR_;
+    if ((block = newNode->block) == NULL) {
+      DeleteParticle(ptr);
+      return _PARTICLE_LEFT_THE_DOMAIN_;
+    }
+
+    AttachToTempList(ptr, ParticleData, block, i, j, k, nThreads, thread);
+    SetV(vFinal, ParticleData);
+    SetX(xFinal, ParticleData);
+    *newNodeOut = newNode;
+    return _PARTICLE_MOTION_FINISHED_;
+  }
+
+  // PIC::Mover::cExternalBoundaryFace + Init, src/pic/pic_mover.cpp:24-28,48-75
+  struct cExternalBoundaryFace {
+    double norm[3];
+    int nX0[3];
+    double e0[3], e1[3], x0[3];
+    double lE0, lE1;
+  } FaceTable[6];
+  void InitFaceTable() {
+    static const cExternalBoundaryFace init[6] = {
+        {{-1.0, 0.0, 0.0}, {0, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}, 0.0, 0.0}, {{1.0, 0.0, 0.0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}, 0.0, 0.0},
+        {{0.0, -1.0, 0.0}, {0, 0, 0}, {1, 0, 0}, {0, 0, 1}, {0, 0, 0}, 0.0, 0.0}, {{0.0, 1.0, 0.0}, {0, 1, 0}, {1, 0, 0}, {0, 0, 1}, {0, 0, 0}, 0.0, 0.0},
+        {{0.0, 0.0, -1.0}, {0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 0}, 0.0, 0.0}, {{0.0, 0.0, 1.0}, {0, 0, 1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 0}, 0.0, 0.0}};
+    for (int nface = 0; nface < 6; nface++) {
+      FaceTable[nface] = init[nface];
+      double cE0 = 0.0, cE1 = 0.0;
+      for (int idim = 0; idim < 3; idim++) {
+        FaceTable[nface].x0[idim] = (FaceTable[nface].nX0[idim] == 0) ? xGlobalMin[idim] : xGlobalMax[idim];
+        cE0 += pow(((FaceTable[nface].e0[idim] + FaceTable[nface].nX0[idim] < 0.5) ? xGlobalMin[idim] : xGlobalMax[idim]) - FaceTable[nface].x0[idim], 2);
+        cE1 += pow(((FaceTable[nface].e1[idim] + FaceTable[nface].nX0[idim] < 0.5) ? xGlobalMin[idim] : xGlobalMax[idim]) - FaceTable[nface].x0[idim], 2);
+      }
+      FaceTable[nface].lE0 = sqrt(cE0);
+      FaceTable[nface].lE1 = sqrt(cE1);
+    }
+  }
+
+  // PIC::BC::ExternalBoundary::Periodic::ExchangeParticlesLocal, src/pic/pic_bc_periodic.cpp:86-178
+  long int ExchangeParticlesLocal(cTreeNode *RealBlock, cTreeNode *GhostBlock) {
+    int i, j, k, idim;
+    long int ptr, NextPtr, nMoved = 0;
+    double dx[3];
+    for (i = 0; i < 3; i++) dx[i] = RealBlock->xmin[i] - GhostBlock->xmin[i];
+    for (int icell = 0; icell < nCellsBlock(); icell++) {
+      int t, ii = icell;
+      double x[3];
+      t = _BLOCK_CELLS_X_ * _BLOCK_CELLS_Y_;
+      k = ii / t;
+      ii = ii % t;
+      j = ii / _BLOCK_CELLS_X_;
+      i = ii % _BLOCK_CELLS_X_;
+      int c = i + _BLOCK_CELLS_X_ * (j + _BLOCK_CELLS_Y_ * k);
+      if ((ptr = GhostBlock->block->FirstCellParticleTable[c]) != -1) {
+        NextPtr = GetNext(ptr);
+        byte *p = GetParticleDataPointer(ptr);
+        GetX(x, p);
+        for (idim = 0; idim < 3; idim++) {
+          x[idim] += dx[idim];
+          if (x[idim] < RealBlock->xmin[idim]) x[idim] = RealBlock->xmin[idim];
+          if (x[idim] >= RealBlock->xmax[idim]) x[idim] = RealBlock->xmax[idim] - 1.0E-10 * (RealBlock->xmax[idim] - RealBlock->xmin[idim]);
+        }
+        SetX(x, p);
+        nMoved++;
+        if (NextPtr != -1) {
+          do {
+            ptr = NextPtr;
+            p = GetParticleDataPointer(ptr);
+            GetX(x, p);
+            for (idim = 0; idim < 3; idim++) {
+              x[idim] += dx[idim];
+              if (x[idim] < RealBlock->xmin[idim]) x[idim] = RealBlock->xmin[idim];
+              if (x[idim] >= RealBlock->xmax[idim]) x[idim] = RealBlock->xmax[idim] - 1.0E-10 * (RealBlock->xmax[idim] - RealBlock->xmin[idim]);
+            }
+            SetX(x, p);
+            nMoved++;
+            NextPtr = GetNext(ptr);
+          } while (NextPtr != -1);
+        }
+        SetNext(RealBlock->block->FirstCellParticleTable[c], ptr);
+        if (RealBlock->block->FirstCellParticleTable[c] != -1) {
+          SetPrev(ptr, RealBlock->block->FirstCellParticleTable[c]);
+        }
+        RealBlock->block->FirstCellParticleTable[c] = GhostBlock->block->FirstCellParticleTable[c];
+        GhostBlock->block->FirstCellParticleTable[c] = -1;
+      }
+    }
+    return nMoved;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // ECSIM::ProcessCell, src/pic/pic_field_solver_ecsim.cpp:1881-2438 (scalar branch, B centre or
+  // corner based, no guiding-centre species, no per-species corner sampling)
+  // ------------------------------------------------------------------------------------------
+  bool ProcessCell(int iCellIn, int jCellIn, int kCellIn, cTreeNode *node, cCellData *CellData, double *MassTable, double *ChargeTable) {
+    std::vector<double *> &B_Center = tlsBCenter();
+    bool res = false;
+    const double dtTotal = cfg.ecsim_dt_total, B_conv = cfg.ecsim_B_conv, length_conv = cfg.ecsim_length_conv, LightSpeed = cfg.ecsim_light_speed;
+    const int nSpecies = cfg.n_species;
+
+    B_Center.assign((cfg.b_mode == AMPS_B_CENTER_BASED) ? nCenterLocal() : nCornerLocal(), NULL);
+    if (cfg.b_mode == AMPS_B_CENTER_BASED) {
+      for (int k = kCellIn - 1; k <= kCellIn + 1; k++)
+        for (int j = jCellIn - 1; j <= jCellIn + 1; j++)
+          for (int i = iCellIn - 1; i <= iCellIn + 1; i++) {
+            int LocalCenterId = _getCenterNodeLocalNumber(i, j, k);
+            if (!node->block->centerNodes[LocalCenterId]) continue;
+            B_Center[LocalCenterId] = node->block->centerNodes[LocalCenterId]->data + CurrentBOffset_d;
+          }
+    }
+
+    int nCell[3] = {_BLOCK_CELLS_X_, _BLOCK_CELLS_Y_, _BLOCK_CELLS_Z_};
+    cBlock *block = node->block;
+    long int *FirstCellParticleTable = block->FirstCellParticleTable;
+    double CellVolume = 1;
+    double dx[3];
+    double GlobalTimeStep = cfg.time_step[0];
+
+    for (int iDim = 0; iDim < 3; iDim++) dx[iDim] = (node->xmax[iDim] - node->xmin[iDim]) / nCell[iDim] * length_conv;
+    for (int iDim = 0; iDim < 3; iDim++) CellVolume *= dx[iDim];
+
+    long int ptr = FirstCellParticleTable[iCellIn + _BLOCK_CELLS_X_ * (jCellIn + _BLOCK_CELLS_Y_ * kCellIn)];
+    double ParticleEnergyCell = 0, vmean_cell[AMPS_GPU_MAX_SPECIES];
+    for (int iSp = 0; iSp < nSpecies; iSp++) vmean_cell[iSp] = 0.0;
+
+    if (ptr != -1) {
+      res = true;
+      double vInit[3] = {0.0, 0.0, 0.0}, xInit[3] = {0.0, 0.0, 0.0};
+      int spec;
+      double Jg[8][3];
+      for (int ii = 0; ii < 8; ii++)
+        for (int jj = 0; jj < 3; jj++) Jg[ii][jj] = 0.0;
+
+      double MassMatrix_GGD[8][8][9];
+      for (int iCorner = 0; iCorner < 8; iCorner++)
+        for (int jCorner = 0; jCorner < 8; jCorner++)
+          for (int idim = 0; idim < 9; idim++) MassMatrix_GGD[iCorner][jCorner][idim] = 0.0;
+
+      long int ptrNext = ptr;
+      byte *ParticleData, *ParticleDataNext;
+      ParticleDataNext = GetParticleDataPointer(ptr);
+
+      static const int cornerOff[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+      for (int ii = 0; ii < 8; ii++) {
+        cCornerNode *cn = block->cornerNodes[_getCornerNodeLocalNumber(iCellIn + cornerOff[ii][0], jCellIn + cornerOff[ii][1], kCellIn + cornerOff[ii][2])];
+        CellData->CornerData[ii].CornerNode = cn;
+        CellData->CornerData[ii].CornerMassMatrix_ptr = cn->data + MassMatrixOffsetIndex;
+        CellData->CornerData[ii].CornerJ_ptr = cn->data + JxOffsetIndex;
+      }
+
+      int cnt = 0, particleNumber[AMPS_GPU_MAX_SPECIES];
+      for (int iSp = 0; iSp < nSpecies; iSp++) particleNumber[iSp] = 0;
+
+      cStencil MagneticFieldStencil, CornerBasedStencil;
+
+      while (ptrNext != -1) {
+        double LocalParticleWeight;
+        ptr = ptrNext;
+        ParticleData = ParticleDataNext;
+
+        spec = GetI(ParticleData);
+        GetV(vInit, ParticleData);
+        GetX(xInit, ParticleData);
+        LocalParticleWeight = cfg.species_weight[spec];
+        LocalParticleWeight *= GetIndividualStatWeightCorrection(ParticleData);
+
+        ptrNext = GetNext(ParticleData);
+        if (ptrNext != -1) ParticleDataNext = GetParticleDataPointer(ptrNext);
+
+        {
+          double B[3] = {0.0, 0.0, 0.0};
+          double Wdummy[8];
+          if (cfg.b_mode == AMPS_B_CENTER_BASED)
+            CellCentered_Linear_InitStencil(xInit, node, MagneticFieldStencil, true);
+          else
+            CornerBased_InitStencil(xInit, node, MagneticFieldStencil, Wdummy);
+
+          int Length = MagneticFieldStencil.Length;
+          double *Weight_table = MagneticFieldStencil.Weight;
+          int *LocalCellID_table = MagneticFieldStencil.LocalCellID;
+
+          for (int iStencil = 0; iStencil < Length; iStencil++) {
+            double *B_temp, Weight = Weight_table[iStencil];
+            int LocalCellID = LocalCellID_table[iStencil];
+            if (cfg.b_mode == AMPS_B_CENTER_BASED)
+              B_temp = B_Center[LocalCellID];
+            else
+              B_temp = block->cornerNodes[LocalCellID]->data + CornerDataLength;  // corner-B extension slot (unused in centre mode)
+            for (int idim = 0; idim < 3; idim++) B[idim] += Weight * B_temp[idim];
+          }
+
+          for (int idim = 0; idim < 3; idim++) {
+            B[idim] *= B_conv;
+            vInit[idim] *= length_conv;
+          }
+
+          double QdT_over_m, QdT_over_2m, alpha[9], chargeQ;
+          double WeightPG[8];
+          double c0, QdT_over_2m_squared;
+          double mass;
+
+          chargeQ = ChargeTable[spec];
+          mass = MassTable[spec];
+          chargeQ *= LocalParticleWeight;
+          mass *= LocalParticleWeight;
+
+          QdT_over_m = chargeQ * dtTotal / mass;
+          QdT_over_2m = 0.5 * QdT_over_m;
+          QdT_over_2m_squared = QdT_over_2m * QdT_over_2m;
+
+          for (int idim = 0; idim < 3; idim++) B[idim] /= LightSpeed;
+
+          double BB[3][3], P[3];
+          for (int ii = 0; ii < 3; ii++) {
+            P[ii] = -QdT_over_2m * B[ii];
+            for (int jj = 0; jj <= ii; jj++) {
+              BB[ii][jj] = QdT_over_2m_squared * B[ii] * B[jj];
+              BB[jj][ii] = BB[ii][jj];
+            }
+          }
+          c0 = 1.0 / (1.0 + QdT_over_2m_squared * (B[0] * B[0] + B[1] * B[1] + B[2] * B[2]));
+
+          alpha[0] = c0 * (1.0 + BB[0][0]);
+          alpha[1] = c0 * (-P[2] + BB[0][1]);
+          alpha[2] = c0 * (P[1] + BB[0][2]);
+          alpha[3] = c0 * (P[2] + BB[1][0]);
+          alpha[4] = c0 * (1.0 + BB[1][1]);
+          alpha[5] = c0 * (-P[0] + BB[1][2]);
+          alpha[6] = c0 * (-P[1] + BB[2][0]);
+          alpha[7] = c0 * (P[0] + BB[2][1]);
+          alpha[8] = c0 * (1.0 + BB[2][2]);
+
+          CornerBased_InitStencil(xInit, node, CornerBasedStencil, WeightPG);
+
+          double vsqr = vInit[0] * vInit[0] + vInit[1] * vInit[1] + vInit[2] * vInit[2];
+          vmean_cell[spec] += sqrt(vsqr) * GlobalTimeStep;
+          ParticleEnergyCell += 0.5 * mass * vsqr;
+
+          double vRot[3] = {0.0, 0.0, 0.0};
+          for (int iDim = 0; iDim < 3; iDim++)
+            for (int jj = 0; jj < 3; jj++) vRot[iDim] += alpha[3 * iDim + jj] * vInit[jj];
+
+          for (int iCorner = 0; iCorner < 8; iCorner++) {
+            double t = chargeQ * WeightPG[iCorner];
+            double *Jg_iCorner = Jg[iCorner];
+            for (int iDim = 0; iDim < 3; iDim++) Jg_iCorner[iDim] += t * vRot[iDim];
+          }
+
+          double matrixConst = chargeQ * QdT_over_2m / CellVolume;
+          for (int iCorner = 0; iCorner < 8; iCorner++) {
+            double tempWeightConst = matrixConst * WeightPG[iCorner];
+            for (int jCorner = 0; jCorner <= iCorner; jCorner++) {
+              double tempWeightProduct = WeightPG[jCorner] * tempWeightConst;
+              double *tmpPtr = MassMatrix_GGD[iCorner][jCorner];
+              tmpPtr[0] += alpha[0] * tempWeightProduct;
+              tmpPtr[1] += alpha[1] * tempWeightProduct;
+              tmpPtr[2] += alpha[2] * tempWeightProduct;
+              tmpPtr[3] += alpha[3] * tempWeightProduct;
+              tmpPtr[4] += alpha[4] * tempWeightProduct;
+              tmpPtr[5] += alpha[5] * tempWeightProduct;
+              tmpPtr[6] += alpha[6] * tempWeightProduct;
+              tmpPtr[7] += alpha[7] * tempWeightProduct;
+              tmpPtr[8] += alpha[8] * tempWeightProduct;
+            }
+          }
+          particleNumber[spec]++;
+        }
+        cnt++;
+
+        if (ptrNext == -1) {
+          CellData->ParticleEnergy += ParticleEnergyCell;
+          for (int iSp = 0; iSp < nSpecies; iSp++) {
+            CellData->cflCell[iSp] = vmean_cell[iSp] / (particleNumber[iSp] * sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]));
+          }
+          for (int iCorner = 0; iCorner < 8; iCorner++) {
+            double *CornerJ = CellData->CornerData[iCorner].CornerJ;
+            for (int ii = 0; ii < 3; ii++) CornerJ[ii] += (Jg[iCorner][ii]) / CellVolume;
+          }
+          for (int iCorner = 0; iCorner < 8; iCorner++) {
+            for (int jCorner = 0; jCorner <= iCorner; jCorner++) {
+              if (iCorner == jCorner) {
+                double *CornerMassMatrix = CellData->CornerData[iCorner].CornerMassMatrix;
+                for (int ii = 0; ii < 3; ii++)
+                  for (int jj = 0; jj < 3; jj++) CornerMassMatrix[3 * ii + jj] += MassMatrix_GGD[iCorner][iCorner][3 * ii + jj];
+              } else {
+                double *CornerMassMatrix_iCorner = CellData->CornerData[iCorner].CornerMassMatrix;
+                double *CornerMassMatrix_jCorner = CellData->CornerData[jCorner].CornerMassMatrix;
+                for (int ii = 0; ii < 3; ii++)
+                  for (int jj = 0; jj < 3; jj++) {
+                    CornerMassMatrix_iCorner[9 * IndexMatrix[iCorner][jCorner] + 3 * ii + jj] += MassMatrix_GGD[iCorner][jCorner][3 * ii + jj];
+                    CornerMassMatrix_jCorner[9 * IndexMatrix[jCorner][iCorner] + 3 * ii + jj] += MassMatrix_GGD[iCorner][jCorner][3 * ii + jj];
+                  }
+              }
+            }
+          }
+        }
+      }
+    }
+    return res;
+  }
+  static std::vector<double *> &tlsBCenter() {
+    static thread_local std::vector<double *> v;
+    return v;
+  }
+};
+
+// =============================================================================================
+// C API
+// =============================================================================================
+extern "C" {
+
+oracle_ctx *oracle_create(const amps_gpu_config *cfg, const amps_gpu_mesh *m) {
+  oracle_ctx *o = new oracle_ctx();
+  o->cfg = *cfg;
+  o->_BLOCK_CELLS_X_ = cfg->block_cells[0], o->_BLOCK_CELLS_Y_ = cfg->block_cells[1], o->_BLOCK_CELLS_Z_ = cfg->block_cells[2];
+  o->_GHOST_CELLS_X_ = cfg->ghost_cells[0], o->_GHOST_CELLS_Y_ = cfg->ghost_cells[1], o->_GHOST_CELLS_Z_ = cfg->ghost_cells[2];
+  o->_TOTAL_BLOCK_CELLS_X_ = o->_BLOCK_CELLS_X_ + 2 * o->_GHOST_CELLS_X_;
+  o->_TOTAL_BLOCK_CELLS_Y_ = o->_BLOCK_CELLS_Y_ + 2 * o->_GHOST_CELLS_Y_;
+  o->_TOTAL_BLOCK_CELLS_Z_ = o->_BLOCK_CELLS_Z_ + 2 * o->_GHOST_CELLS_Z_;
+  for (int d = 0; d < 3; d++) {
+    o->xGlobalMin[d] = m->x_global_min[d], o->xGlobalMax[d] = m->x_global_max[d];
+    o->dx_max_refinment[d] = m->dx_max_refinement[d], o->dxRootBlock[d] = m->dx_root_block[d];
+    o->nRoot[d] = m->n_root[d];
+  }
+  o->EPS = m->eps;
+  o->maxRefinementLevel = m->max_refinement_level;
+  o->InitFaceTable();
+
+  // unique node pools
+  o->n_corners = m->n_corners, o->n_centers = m->n_centers;
+  const int cornerLen = CornerDataLength + 3;  // +3: optional corner-B slot
+  o->cornerData.assign((size_t)m->n_corners * cornerLen, 0.0);
+  o->centerData.assign((size_t)m->n_centers * CenterDataLength, 0.0);
+  o->cornerPool = std::vector<cCornerNode>(m->n_corners);
+  o->centerPool = std::vector<cCenterNode>(m->n_centers);
+  for (int i = 0; i < m->n_corners; i++) o->cornerPool[i].data = o->cornerData.data() + (size_t)i * cornerLen;
+  for (int i = 0; i < m->n_centers; i++) o->centerPool[i].data = o->centerData.data() + (size_t)i * CenterDataLength;
+
+  // tree
+  o->nodes.resize(m->n_nodes);
+  o->blocks.resize(m->n_leaves);
+  o->BlockTable.assign(m->n_leaves, NULL);
+  for (int n = 0; n < m->n_nodes; n++) {
+    cTreeNode &t = o->nodes[n];
+    t.id = n;
+    for (int d = 0; d < 3; d++) {
+      t.xmin[d] = m->node_xmin[3 * n + d], t.xmax[d] = m->node_xmax[3 * n + d];
+      t.xMinGlobalIndex[d] = m->node_imin[3 * n + d];
+    }
+    t.NodeGeometricSizeIndex = m->node_isize[n];
+    for (int c = 0; c < 8; c++) t.downNode[c] = (m->node_child[8 * n + c] >= 0) ? &o->nodes[m->node_child[8 * n + c]] : NULL;
+    t.upNode = (m->node_parent[n] >= 0) ? &o->nodes[m->node_parent[n]] : NULL;
+    t.RefinmentLevel = m->node_level[n];
+    t.Thread = m->node_thread[n];
+    t.IsUsedInCalculationFlag = (m->node_flags[n] & AMPS_NODE_USED) != 0;
+    t.IsGhostNodeFlag = (m->node_flags[n] & AMPS_NODE_PERIODIC_GHOST) != 0;
+    t.leaf = m->node_leaf[n];
+    t.block = NULL;
+    t.faceBoundary = 0;
+  }
+  int nr = m->n_root[0] * m->n_root[1] * m->n_root[2];
+  o->rootTable.resize(nr);
+  for (int i = 0; i < nr; i++) o->rootTable[i] = &o->nodes[m->root_node[i]];
+
+  const int nC = o->nCellsBlock(), nCor = o->nCornerLocal(), nCen = o->nCenterLocal();
+  o->listStorage.assign((size_t)m->n_leaves * nC * 2, -1);
+  o->leaf_real.assign(m->leaf_real, m->leaf_real + m->n_leaves);
+  for (int l = 0; l < m->n_leaves; l++) {
+    cTreeNode *t = &o->nodes[m->leaf_node[l]];
+    cBlock &b = o->blocks[l];
+    t->block = &b;
+    t->faceBoundary = m->leaf_face_boundary[l];
+    o->BlockTable[l] = t;
+    b.FirstCellParticleTable = o->listStorage.data() + (size_t)l * nC * 2;
+    b.tempParticleMovingListTable = b.FirstCellParticleTable + nC;
+    b.tempThreadTable = NULL;
+    b.cornerNodes = new cCornerNode *[nCor];
+    b.centerNodes = new cCenterNode *[nCen];
+    for (int i = 0; i < nCor; i++) {
+      int uid = m->leaf_corner_uid[(size_t)l * nCor + i];
+      b.cornerNodes[i] = (uid >= 0) ? &o->cornerPool[uid] : NULL;
+    }
+    for (int i = 0; i < nCen; i++) {
+      int uid = m->leaf_center_uid[(size_t)l * nCen + i];
+      b.centerNodes[i] = (uid >= 0) ? &o->centerPool[uid] : NULL;
+    }
+  }
+  o->nThreadListTables = 0;
+
+  // PIC::ParticleBuffer::Init, src/pic/pic_pbuffer.cpp:41-222
+  o->MaxNPart = cfg->capacity;
+  o->ParticleDataLength = oracle_ctx::BASIC_LEN;
+  o->ParticleDataBuffer = (byte *)malloc((size_t)o->ParticleDataLength * o->MaxNPart);
+  memset(o->ParticleDataBuffer, 0, (size_t)o->ParticleDataLength * o->MaxNPart);
+  for (long int ptr = 0; ptr < o->MaxNPart - 1; ptr++) {
+    o->SetNext(ptr + 1, ptr);
+    oracle_ctx::SetParticleDeleted(o->GetParticleDataPointer(ptr));
+  }
+  o->SetNext(-1, o->MaxNPart - 1);
+  o->FirstPBufferParticle = 0;
+  o->NAllPart = 0;
+  return o;
+}
+
+void oracle_destroy(oracle_ctx *o) {
+  if (!o) return;
+  for (auto &b : o->blocks) {
+    delete[] b.cornerNodes;
+    delete[] b.centerNodes;
+  }
+  free(o->ParticleDataBuffer);
+  delete o;
+}
+
+const char *oracle_last_error(const oracle_ctx *o) { return o->err.c_str(); }
+int64_t oracle_particle_data_length(const oracle_ctx *o) { return o->ParticleDataLength; }
+int64_t oracle_particle_count(const oracle_ctx *o) { return o->NAllPart; }
+
+void oracle_set_fields(oracle_ctx *o, const double *E_half, const double *B_prev, const double *B_cur) {
+  if (E_half)
+    for (int i = 0; i < o->n_corners; i++) memcpy(o->cornerPool[i].data + OffsetE_HalfTimeStep_d, E_half + 3 * (size_t)i, 24);
+  if (B_prev)
+    for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + PrevBOffset_d, B_prev + 3 * (size_t)i, 24);
+  if (B_cur)
+    for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + CurrentBOffset_d, B_cur + 3 * (size_t)i, 24);
+}
+
+// PIC::ParticleBuffer::InitiateParticle(..., _PIC_INIT_PARTICLE_MODE__ADD2LIST_), src/pic/pic_pbuffer.cpp:939-1027
+int oracle_add_particles(oracle_ctx *o, const double *x, const double *v, const double *w, const uint8_t *species, const int32_t *cells, int64_t n) {
+  const int nC = o->nCellsBlock();
+  for (int64_t p = 0; p < n; p++) {
+    long int ptr = o->GetNewParticle();
+    if (ptr < 0) {
+      o->err = "particle buffer exhausted";
+      return AMPS_GPU_ERR_CAPACITY;
+    }
+    byte *pd = o->GetParticleDataPointer(ptr);
+    double xx[3] = {x[p], x[n + p], x[2 * n + p]}, vv[3] = {v[p], v[n + p], v[2 * n + p]};
+    oracle_ctx::SetX(xx, pd);
+    oracle_ctx::SetV(vv, pd);
+    oracle_ctx::SetI(species[p], pd);
+    oracle_ctx::SetIndividualStatWeightCorrection(w ? w[p] : 1.0, pd);
+    int leaf = cells[p] / nC, cell = cells[p] % nC;
+    long int *first = o->blocks[leaf].FirstCellParticleTable + cell;
+    o->SetNext(*first, ptr);
+    o->SetPrev(-1, ptr);
+    if (*first != -1) o->SetPrev(ptr, *first);
+    *first = ptr;
+  }
+  return AMPS_GPU_OK;
+}
+
+void oracle_get_particles(const oracle_ctx *o, double *x, double *v, double *w, uint8_t *species, int32_t *cells, uint8_t *alive, int64_t n) {
+  const int nC = o->nCellsBlock();
+  if (cells)
+    for (int64_t i = 0; i < n; i++) cells[i] = -1;
+  for (int64_t ptr = 0; ptr < n; ptr++) {
+    const byte *pd = o->GetParticleDataPointer(ptr);
+    double t[3];
+    if (x) {
+      oracle_ctx::GetX(t, pd);
+      x[ptr] = t[0], x[n + ptr] = t[1], x[2 * n + ptr] = t[2];
+    }
+    if (v) {
+      oracle_ctx::GetV(t, pd);
+      v[ptr] = t[0], v[n + ptr] = t[1], v[2 * n + ptr] = t[2];
+    }
+    if (w) w[ptr] = oracle_ctx::GetIndividualStatWeightCorrection(pd);
+    if (species) species[ptr] = (uint8_t)oracle_ctx::GetI(pd);
+    if (alive) alive[ptr] = oracle_ctx::IsParticleAllocated(pd) ? 1 : 0;
+  }
+  if (cells) {
+    for (size_t l = 0; l < o->blocks.size(); l++)
+      for (int c = 0; c < nC; c++) {
+        long int ptr = o->blocks[l].FirstCellParticleTable[c];
+        while (ptr != -1) {
+          if (ptr < n) cells[ptr] = (int32_t)(l * nC + c);
+          ptr = o->GetNext(ptr);
+        }
+      }
+  }
+}
+
+// PIC::Mover::MoveParticles(), src/pic/pic_mover.cpp:580-1088 followed (periodic mode) by
+// PIC::BC::ExternalBoundary::Periodic::ExchangeParticles(), src/pic/pic_time_step.cpp:454-506
+int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats *stats, int32_t *ret_code, int32_t *final_cell) {
+  if (mover_id != AMPS_MOVER_LAPENTA2017) {
+    o->err = "oracle_move: mover not restated yet";
+    return AMPS_GPU_ERR_ARG;
+  }
+#ifndef _OPENMP
+  n_threads = 1;
+#endif
+  if (n_threads < 1) n_threads = 1;
+  const int nC = o->nCellsBlock();
+  const int nLocalBlocks = (int)o->BlockTable.size();
+
+  // per-thread staging arrays, pic_mover.cpp:660-711
+  o->E_Corner.resize(n_threads);
+  o->B_Center.resize(n_threads);
+  for (int t = 0; t < n_threads; t++) {
+    o->E_Corner[t].assign((size_t)o->nCornerLocal() * 3, 0.0);
+    o->B_Center[t].assign((size_t)((o->cfg.b_mode == AMPS_B_CENTER_BASED) ? o->nCenterLocal() : o->nCornerLocal()) * 3, 0.0);
+  }
+  if (n_threads > 1 && o->nThreadListTables != n_threads) {
+    cTempList init = {-1, -1};
+    o->threadListStorage.assign((size_t)nLocalBlocks * n_threads * nC, init);
+    for (int l = 0; l < nLocalBlocks; l++) o->blocks[l].tempThreadTable = o->threadListStorage.data() + (size_t)l * n_threads * nC;
+    o->nThreadListTables = n_threads;
+  }
+
+  long long n_moved = 0, n_cross_cell = 0, n_cross_block = 0, n_left = 0, n_notused = 0, n_error = 0;
+
+  auto process_block = [&](int nLocalNode, int thread, long long *cnt) {
+    cTreeNode *node = o->BlockTable[nLocalNode];
+    cBlock *block = node->block;
+    if (!block) return;
+    double *E_Corner = o->E_Corner[thread].data(), *B_C = o->B_Center[thread].data();
+    o->SetBlock_E(E_Corner, node);
+    o->SetBlock_B(B_C, node);
+    long int *FirstCellParticleTable = block->FirstCellParticleTable;
+    for (int i = 0; i < nC; i++) {
+      long int ParticleList = FirstCellParticleTable[i];
+      if (n_threads <= 1) {
+        // mpi_only, pic_mover.cpp:955-973
+        while (FirstCellParticleTable[i] != -1) {
+          long int ptr = FirstCellParticleTable[i];
+          FirstCellParticleTable[i] = o->GetNext(ptr);
+          cTreeNode *newNode = NULL;
+          int rc = o->Lapenta2017(o->GetParticleDataPointer(ptr), ptr, node, E_Corner, B_C, n_threads, thread, &newNode);
+          cnt[0]++;
+          if (ret_code) ret_code[ptr] = rc;
+          if (rc == _PARTICLE_MOTION_FINISHED_) {
+            if (newNode != node) cnt[2]++;
+          } else if (rc == _PARTICLE_LEFT_THE_DOMAIN_) cnt[3]++;
+          else if (rc == _PARTICLE_IN_NOT_IN_USE_NODE_) cnt[4]++;
+          else cnt[5]++;
+        }
+      } else {
+        // mpi_openmp__split_blocks, pic_mover.cpp:744-759
+        while (ParticleList != -1) {
+          long int ptr = ParticleList;
+          ParticleList = o->GetNext(ParticleList);
+          cTreeNode *newNode = NULL;
+          int rc = o->Lapenta2017(o->GetParticleDataPointer(ptr), ptr, node, E_Corner, B_C, n_threads, thread, &newNode);
+          cnt[0]++;
+          if (ret_code) ret_code[ptr] = rc;
+          if (rc == _PARTICLE_MOTION_FINISHED_) {
+            if (newNode != node) cnt[2]++;
+          } else if (rc == _PARTICLE_LEFT_THE_DOMAIN_) cnt[3]++;
+          else if (rc == _PARTICLE_IN_NOT_IN_USE_NODE_) cnt[4]++;
+          else cnt[5]++;
+        }
+      }
+    }
+  };
+
+  // remember the starting cell of each particle for the cross-cell statistic
+  std::vector<int32_t> startCell;
+  if (stats) {
+    startCell.assign(o->MaxNPart, -1);
+    for (int l = 0; l < nLocalBlocks; l++)
+      for (int c = 0; c < nC; c++)
+        for (long int ptr = o->blocks[l].FirstCellParticleTable[c]; ptr != -1; ptr = o->GetNext(ptr)) startCell[ptr] = l * nC + c;
+  }
+
+  if (n_threads <= 1) {
+    long long cnt[6] = {0, 0, 0, 0, 0, 0};
+    for (int nLocalNode = 0; nLocalNode < nLocalBlocks; nLocalNode++) process_block(nLocalNode, 0, cnt);
+    n_moved = cnt[0], n_cross_block = cnt[2], n_left = cnt[3], n_notused = cnt[4], n_error = cnt[5];
+  } else {
+#ifdef _OPENMP
+#pragma omp parallel num_threads(n_threads) reduction(+ : n_moved, n_cross_block, n_left, n_notused, n_error)
+    {
+      long long cnt[6] = {0, 0, 0, 0, 0, 0};
+      int thread = omp_get_thread_num();
+#pragma omp for schedule(dynamic, 1)
+      for (int nLocalNode = 0; nLocalNode < nLocalBlocks; nLocalNode++) process_block(nLocalNode, thread, cnt);
+      n_moved += cnt[0], n_cross_block += cnt[2], n_left += cnt[3], n_notused += cnt[4], n_error += cnt[5];
+    }
+#endif
+  }
+
+  // update the particle lists, pic_mover.cpp:1056-1088
+  for (int l = 0; l < nLocalBlocks; l++) {
+    cBlock *block = &o->blocks[l];
+    if (n_threads <= 1) {  // update_mpi
+      memcpy(block->FirstCellParticleTable, block->tempParticleMovingListTable, nC * sizeof(long int));
+      for (int c = 0; c < nC; c++) block->tempParticleMovingListTable[c] = -1;
+    } else {  // update_openmp
+      for (int c = 0; c < nC; c++) block->FirstCellParticleTable[c] = -1;
+      for (int thread_OpenMP = 0; thread_OpenMP < n_threads; thread_OpenMP++)
+        for (int c = 0; c < nC; c++) {
+          cTempList *t = block->tempThreadTable + (size_t)thread_OpenMP * nC + c;
+          long int LastParticle = t->last;
+          if (LastParticle != -1) {
+            long int FirstParticle = t->first;
+            long int *FirstCellParticlePtr = block->FirstCellParticleTable + c;
+            o->SetNext(*FirstCellParticlePtr, LastParticle);
+            if (*FirstCellParticlePtr != -1) o->SetPrev(LastParticle, *FirstCellParticlePtr);
+            *FirstCellParticlePtr = FirstParticle;
+          }
+          t->first = -1;
+          t->last = -1;
+        }
+    }
+  }
+
+  // periodic wrap, pic_bc_periodic.cpp:55-83
+  long long n_wrap = 0;
+  if (o->cfg.periodic) {
+    for (int l = 0; l < nLocalBlocks; l++)
+      if (o->leaf_real[l] >= 0) n_wrap += o->ExchangeParticlesLocal(o->BlockTable[o->leaf_real[l]], o->BlockTable[l]);
+  }
+
+  if (final_cell || stats) {
+    std::vector<int32_t> fc(o->MaxNPart, -1);
+    for (int l = 0; l < nLocalBlocks; l++)
+      for (int c = 0; c < nC; c++)
+        for (long int ptr = o->blocks[l].FirstCellParticleTable[c]; ptr != -1; ptr = o->GetNext(ptr)) fc[ptr] = l * nC + c;
+    if (final_cell) memcpy(final_cell, fc.data(), sizeof(int32_t) * o->MaxNPart);
+    if (stats) {
+      n_cross_cell = 0;
+      long long xb = 0;
+      for (long int p = 0; p < o->MaxNPart; p++)
+        if (startCell[p] >= 0 && fc[p] >= 0 && fc[p] != startCell[p]) {
+          if (fc[p] / nC == startCell[p] / nC) n_cross_cell++;
+          else xb++;
+        }
+      n_cross_block = xb;
+    }
+  }
+  if (stats) {
+    stats->n_moved = n_moved;
+    stats->n_cross_cell = n_cross_cell;
+    stats->n_cross_block = n_cross_block;
+    stats->n_left_domain = n_left;
+    stats->n_not_in_use = n_notused;
+    stats->n_periodic_wrap = n_wrap;
+    stats->n_error = n_error;
+  }
+  return n_error ? AMPS_GPU_ERR_PARTICLE : AMPS_GPU_OK;
+}
+
+// ECSIM::UpdateJMassMatrix(), src/pic/pic_field_solver_ecsim.cpp:3244-3995 (serial / OpenMP loop :3794-3907)
+int oracle_deposit_JM(oracle_ctx *o, int n_threads, double *J, double *M, double *energy, double *cfl) {
+#ifndef _OPENMP
+  n_threads = 1;
+#endif
+  if (n_threads < 1) n_threads = 1;
+  const int nC = o->nCellsBlock();
+  const int nLocalBlocks = (int)o->BlockTable.size();
+  const int nSpecies = o->cfg.n_species;
+  const int NX = o->_BLOCK_CELLS_X_, NY = o->_BLOCK_CELLS_Y_;
+
+  // SetCornerNodeAssociatedDataValue(0.0,...), :3266-3267
+  for (int i = 0; i < o->n_corners; i++) {
+    double *d = o->cornerPool[i].data;
+    for (int k = 0; k < 3; k++) d[JxOffsetIndex + k] = 0.0;
+    for (int k = 0; k < 243; k++) d[MassMatrixOffsetIndex + k] = 0.0;
+  }
+
+  double MassTable[AMPS_GPU_MAX_SPECIES], ChargeTable[AMPS_GPU_MAX_SPECIES];
+  for (int s = 0; s < AMPS_GPU_MAX_SPECIES; s++) MassTable[s] = o->cfg.mass[s], ChargeTable[s] = o->cfg.charge[s];
+
+  std::vector<double> ParticleEnergyTable(n_threads, 0.0);
+  std::vector<double> cflTable((size_t)n_threads * AMPS_GPU_MAX_SPECIES, 0.0);
+  std::vector<cCellData> CellDataTable(n_threads);
+
+  const long nTotalCells = (long)nLocalBlocks * nC;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(n_threads)
+#endif
+  {
+#ifdef _OPENMP
+    int this_thread_id = omp_get_thread_num();
+#else
+    int this_thread_id = 0;
+#endif
+    cCellData *CellData_TH = &CellDataTable[this_thread_id];
+#ifdef _OPENMP
+#pragma omp for schedule(guided)
+#endif
+    for (long CellCounter = 0; CellCounter < nTotalCells; CellCounter++) {
+      int nLocalNode, ii = (int)(CellCounter % nC);
+      int i, j, k;
+      nLocalNode = (int)(CellCounter / nC);
+      k = ii / (NY * NX);
+      ii -= k * NY * NX;
+      j = ii / NX;
+      ii -= j * NX;
+      i = ii;
+
+      cTreeNode *node = o->BlockTable[nLocalNode];
+      if (node->block == NULL) continue;
+      if (o->cfg.periodic) {
+        // boundary ("ghost") blocks are skipped, :3815-3825
+        if (node->faceBoundary != 0) continue;
+      }
+
+      CellData_TH->clean();
+      bool flag = o->ProcessCell(i, j, k, node, CellData_TH, MassTable, ChargeTable);
+
+      if (flag == true) {
+        int CornerUpdateTable[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+        int CornerUpdateTableLength = 8;
+        while (CornerUpdateTableLength > 0) {
+          for (int it = 0; it < CornerUpdateTableLength; it++) {
+            int icor = CornerUpdateTable[it];
+            if (CellData_TH->CornerData[icor].CornerNode->lock_associated_data.test_and_set(std::memory_order_acquire) == false) {
+              // NOTE (reference quirk): the cell energy is added once per corner, :3860
+              ParticleEnergyTable[this_thread_id] += CellData_TH->ParticleEnergy;
+              for (int iSp = 0; iSp < nSpecies; iSp++) {
+                double *c = &cflTable[(size_t)this_thread_id * AMPS_GPU_MAX_SPECIES + iSp];
+                if (CellData_TH->cflCell[iSp] > *c) *c = CellData_TH->cflCell[iSp];
+              }
+              double *target = CellData_TH->CornerData[icor].CornerJ_ptr;
+              double *source = CellData_TH->CornerData[icor].CornerJ;
+              for (int idim = 0; idim < 3; idim++) target[idim] += source[idim];
+              target = CellData_TH->CornerData[icor].CornerMassMatrix_ptr;
+              source = CellData_TH->CornerData[icor].CornerMassMatrix;
+              for (int q = 0; q < 243; q++) target[q] += source[q];
+              CornerUpdateTable[it] = CornerUpdateTable[CornerUpdateTableLength - 1];
+              CornerUpdateTableLength--;
+              CellData_TH->CornerData[icor].CornerNode->lock_associated_data.clear(std::memory_order_release);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  double ParticleEnergy = 0.0;
+  for (int i = 0; i < n_threads; i++) ParticleEnergy += ParticleEnergyTable[i];
+  if (energy) *energy = ParticleEnergy;
+  if (cfl)
+    for (int iSp = 0; iSp < nSpecies; iSp++) {
+      cfl[iSp] = cflTable[iSp];
+      for (int i = 0; i < n_threads; i++)
+        if (cfl[iSp] < cflTable[(size_t)i * AMPS_GPU_MAX_SPECIES + iSp]) cfl[iSp] = cflTable[(size_t)i * AMPS_GPU_MAX_SPECIES + iSp];
+    }
+  // periodic / shared corners are the same node objects here, so ProcessJMassMatrix (:1383) is implicit
+  if (J)
+    for (int i = 0; i < o->n_corners; i++) memcpy(J + 3 * (size_t)i, o->cornerPool[i].data + JxOffsetIndex, 24);
+  if (M)
+    for (int i = 0; i < o->n_corners; i++) memcpy(M + 243 * (size_t)i, o->cornerPool[i].data + MassMatrixOffsetIndex, 243 * 8);
+  return AMPS_GPU_OK;
+}
+
+int oracle_find_tree_node(const oracle_ctx *o, const double *x, int start_leaf) {
+  cTreeNode *start = (start_leaf >= 0) ? o->BlockTable[start_leaf] : NULL;
+  cTreeNode *r = o->findTreeNode(x, start);
+  return r ? r->leaf : -1;
+}
+int oracle_find_cell_index(const oracle_ctx *o, const double *x, int leaf, int *ijk) {
+  int i = 0, j = 0, k = 0;
+  long int r = o->FindCellIndex(x, i, j, k, o->BlockTable[leaf]);
+  ijk[0] = i, ijk[1] = j, ijk[2] = k;
+  return (int)r;
+}
+int oracle_corner_stencil(const oracle_ctx *o, double *x_inout, int leaf, double *W, int *ids, double *wnorm) {
+  cStencil s;
+  if (!o->CornerBased_InitStencil(x_inout, o->BlockTable[leaf], s, W)) return -1;
+  for (int i = 0; i < s.Length; i++) ids[i] = s.LocalCellID[i], wnorm[i] = s.Weight[i];
+  return s.Length;
+}
+int oracle_center_stencil(const oracle_ctx *o, const double *x, int leaf, int *ids, double *w) {
+  cStencil s;
+  o->CellCentered_Linear_InitStencil(x, o->BlockTable[leaf], s, true);
+  for (int i = 0; i < s.Length; i++) ids[i] = s.LocalCellID[i], w[i] = s.Weight[i];
+  return s.Length;
+}
+
+// PIC::ParticleBuffer::CheckParticleList, src/pic/pic_pbuffer.cpp:807-: every allocated particle is on
+// exactly one cell list and prev/next are consistent
+int oracle_check_particle_lists(const oracle_ctx *o) {
+  const int nC = o->nCellsBlock();
+  std::vector<uint8_t> seen(o->MaxNPart, 0);
+  long int nList = 0;
+  for (size_t l = 0; l < o->blocks.size(); l++)
+    for (int c = 0; c < nC; c++) {
+      long int prev = -1;
+      for (long int ptr = o->blocks[l].FirstCellParticleTable[c]; ptr != -1; ptr = o->GetNext(ptr)) {
+        const byte *pd = o->GetParticleDataPointer(ptr);
+        if (!oracle_ctx::IsParticleAllocated(pd)) return 1;
+        if (seen[ptr]) return 2;
+        if (oracle_ctx::GetPrev(pd) != prev) return 3;
+        seen[ptr] = 1;
+        prev = ptr;
+        nList++;
+      }
+    }
+  if (nList != o->NAllPart) return 4;
+  return 0;
+}
+
+}  // extern "C"

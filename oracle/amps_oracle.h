@@ -1,0 +1,80 @@
+/*
+ * amps_oracle.h -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A literal CPU restatement of the AMPS reference algorithms on the hot path
+ * (movers + ECSIM J/mass-matrix deposition) using the reference's own data
+ * structures: AoS byte particle records with next/prev links, per-cell lists
+ * (FirstCellParticleTable / tempParticleMovingListTable), a pointer tree of
+ * cTreeNodeAMR-like nodes, corner/centre node objects with associated-data
+ * buffers.  Each function cites the reference file:line it follows.
+ *
+ * PARITY PINNING: the reference's golden outputs for this path live in an
+ * external, un-vendored data repository, and the reference
+ * cannot be compiled here (needs MPI, the Perl-generated build/ tree and
+ * un-vendored SWMF share/ headers).  For the ECSIM push/deposit the oracle is
+ * therefore pinned only by the structural invariants the reference states
+ * (sum W = 1, symmetric mass matrix scatter, CPU-variant agreement) =>
+ * "parity unpinned" for those; the relativistic Boris mover is pinned against
+ * the in-tree Stormer cutoff CSVs and against srcEarth/gridless compiled from
+ * the reference sources (oracle/_ref).  See DESIGN.md.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library.
+ */
+#ifndef AMPS_ORACLE_H
+#define AMPS_ORACLE_H
+
+#include <stdint.h>
+#include "../include/amps_gpu.h" /* POD descriptions only (config, mesh, stats) */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oracle_ctx oracle_ctx;
+
+/* PIC::ParticleBuffer::Init + mesh construction from the flattened description */
+oracle_ctx *oracle_create(const amps_gpu_config *cfg, const amps_gpu_mesh *mesh);
+void oracle_destroy(oracle_ctx *);
+const char *oracle_last_error(const oracle_ctx *);
+
+/* byte layout of one particle record (packed, picParticleDataMacro.h:55-81) */
+int64_t oracle_particle_data_length(const oracle_ctx *);
+
+/* corner E_half[n_corners][3], centre B_prev/B_cur[n_centers][3] */
+void oracle_set_fields(oracle_ctx *, const double *E_half, const double *B_prev, const double *B_cur);
+
+/* InitiateParticle(...,ADD2LIST) for n particles: particle i gets ptr i */
+int oracle_add_particles(oracle_ctx *, const double *x, const double *v, const double *w,
+                         const uint8_t *species, const int32_t *cells, int64_t n);
+int64_t oracle_particle_count(const oracle_ctx *);
+
+/* PIC::Mover::MoveParticles() with the Lapenta2017 (or other) mover, followed by
+ * PIC::BC::ExternalBoundary::Periodic::ExchangeParticles() when periodic.
+ * n_threads>1 = OpenMP split by blocks (pic_mover.cpp:716-766).
+ * per-particle outputs (indexed by ptr, may be NULL): return code, final cell (-1 deleted) */
+int oracle_move(oracle_ctx *, int mover_id, int n_threads, amps_gpu_move_stats *stats,
+                int32_t *ret_code, int32_t *final_cell);
+
+/* read back by ptr (slot i): x[3][n] v[3][n] component-major like the SoA upload */
+void oracle_get_particles(const oracle_ctx *, double *x, double *v, double *w, uint8_t *species,
+                          int32_t *cells, uint8_t *alive, int64_t n);
+
+/* ECSIM::UpdateJMassMatrix(): J[n_corners][3], M[n_corners][243] */
+int oracle_deposit_JM(oracle_ctx *, int n_threads, double *J, double *M, double *energy, double *cfl);
+
+/* stand-alone pieces for unit parity tests */
+int oracle_find_tree_node(const oracle_ctx *, const double *x, int start_leaf); /* leaf id or -1 */
+int oracle_find_cell_index(const oracle_ctx *, const double *x, int leaf, int *ijk);
+/* CornerBased::InitStencil: W[8] in cell-corner order, local ids[8], normalised weights[8]; returns Length */
+int oracle_corner_stencil(const oracle_ctx *, double *x_inout, int leaf, double *W, int *ids, double *wnorm);
+/* CellCentered::Linear::InitStencil: returns Length */
+int oracle_center_stencil(const oracle_ctx *, const double *x, int leaf, int *ids, double *w);
+
+/* ParticleBuffer list checks (CheckParticleList, pic_pbuffer.cpp:807) : 0 ok */
+int oracle_check_particle_lists(const oracle_ctx *);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

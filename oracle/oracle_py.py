@@ -1,0 +1,139 @@
+"""ctypes wrapper of the CPU oracle (TEST INFRASTRUCTURE -- see oracle/amps_oracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_libs = {}
+
+
+def load(kind="parity"):
+    """kind: 'parity' (-O2 -ffp-contract=off) or 'fast' (-O3 -march=x86-64-v3 -fopenmp)."""
+    if kind in _libs:
+        return _libs[kind]
+    path = os.path.join(HERE, "_build", f"liboracle_{kind}.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-s", "-C", HERE])
+    lib = C.CDLL(path)
+    vp = C.c_void_p
+    lib.oracle_create.restype = vp
+    lib.oracle_create.argtypes = [vp, vp]
+    lib.oracle_destroy.argtypes = [vp]
+    lib.oracle_last_error.restype = C.c_char_p
+    lib.oracle_last_error.argtypes = [vp]
+    lib.oracle_particle_data_length.restype = C.c_int64
+    lib.oracle_particle_data_length.argtypes = [vp]
+    lib.oracle_set_fields.argtypes = [vp, vp, vp, vp]
+    lib.oracle_add_particles.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64]
+    lib.oracle_particle_count.restype = C.c_int64
+    lib.oracle_particle_count.argtypes = [vp]
+    lib.oracle_move.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    lib.oracle_get_particles.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int64]
+    lib.oracle_deposit_JM.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    lib.oracle_find_tree_node.argtypes = [vp, vp, C.c_int]
+    lib.oracle_find_cell_index.argtypes = [vp, vp, C.c_int, vp]
+    lib.oracle_corner_stencil.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+    lib.oracle_center_stencil.argtypes = [vp, vp, C.c_int, vp, vp]
+    lib.oracle_check_particle_lists.argtypes = [vp]
+    _libs[kind] = lib
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    def __init__(self, cfg, mesh, kind="parity"):
+        self.lib = load(kind)
+        self.cfg, self.mesh = cfg, mesh
+        self.h = self.lib.oracle_create(C.byref(cfg), C.byref(mesh.c))
+        self.capacity = int(cfg.capacity)
+        self.n_added = 0
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_fields(self, E_half=None, B_prev=None, B_cur=None):
+        a = [None if t is None else np.ascontiguousarray(t, dtype=np.float64) for t in (E_half, B_prev, B_cur)]
+        self.lib.oracle_set_fields(self.h, _p(a[0]), _p(a[1]), _p(a[2]))
+
+    def add_particles(self, x, v, w, species, cells):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        n = x.shape[1]
+        w = None if w is None else np.ascontiguousarray(w, dtype=np.float64)
+        species = np.ascontiguousarray(species, dtype=np.uint8)
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        rc = self.lib.oracle_add_particles(self.h, _p(x), _p(v), _p(w), _p(species), _p(cells), n)
+        assert rc == 0, self.lib.oracle_last_error(self.h)
+        self.n_added += n
+
+    def move(self, mover=0, n_threads=1, want_stats=True):
+        from amps_b200._capi import MoveStats
+
+        st = MoveStats()
+        ret = np.zeros(self.capacity, dtype=np.int32)
+        fc = np.zeros(self.capacity, dtype=np.int32)
+        rc = self.lib.oracle_move(self.h, mover, n_threads, C.cast(C.byref(st), C.c_void_p) if want_stats else None, _p(ret), _p(fc))
+        return rc, st.as_dict(), ret[: self.n_added], fc[: self.n_added]
+
+    def move_fast(self, mover=0, n_threads=1):
+        """timing path: no per-particle outputs, no statistics pass"""
+        return self.lib.oracle_move(self.h, mover, n_threads, None, None, None)
+
+    def particles(self):
+        n = self.n_added
+        x, v, w = np.empty((3, n)), np.empty((3, n)), np.empty(n)
+        sp = np.empty(n, dtype=np.uint8)
+        cells = np.empty(n, dtype=np.int32)
+        alive = np.empty(n, dtype=np.uint8)
+        self.lib.oracle_get_particles(self.h, _p(x), _p(v), _p(w), _p(sp), _p(cells), _p(alive), n)
+        return {"x": x, "v": v, "w": w, "species": sp, "cells": cells, "alive": alive}
+
+    def deposit(self, n_threads=1, want_arrays=True):
+        nc = self.mesh.n_corners
+        J = np.empty((nc, 3)) if want_arrays else None
+        M = np.empty((nc, 243)) if want_arrays else None
+        e = C.c_double()
+        cfl = (C.c_double * 8)()
+        self.lib.oracle_deposit_JM(self.h, n_threads, _p(J), _p(M), C.cast(C.byref(e), C.c_void_p), C.cast(cfl, C.c_void_p))
+        return J, M, float(e.value), [float(cfl[s]) for s in range(self.cfg.n_species)]
+
+    def find_tree_node(self, x, start_leaf=-1):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        return self.lib.oracle_find_tree_node(self.h, _p(x), start_leaf)
+
+    def find_cell_index(self, x, leaf):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        ijk = np.zeros(3, dtype=np.int32)
+        r = self.lib.oracle_find_cell_index(self.h, _p(x), leaf, _p(ijk))
+        return r, ijk
+
+    def corner_stencil(self, x, leaf):
+        x = np.array(x, dtype=np.float64)
+        W = np.zeros(8)
+        ids = np.zeros(8, dtype=np.int32)
+        wn = np.zeros(8)
+        n = self.lib.oracle_corner_stencil(self.h, _p(x), leaf, _p(W), _p(ids), _p(wn))
+        return n, x, W, ids, wn
+
+    def center_stencil(self, x, leaf):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        ids = np.zeros(64, dtype=np.int32)
+        w = np.zeros(64)
+        n = self.lib.oracle_center_stencil(self.h, _p(x), leaf, _p(ids), _p(w))
+        return n, ids[:n], w[:n]
+
+    def check_lists(self):
+        return self.lib.oracle_check_particle_lists(self.h)

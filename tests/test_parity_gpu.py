@@ -1,0 +1,29 @@
+"""GPU parity tests proper: the CUDA path through the C ABI against the CPU oracle on the same seeded inputs."""
+import pytest
+
+from tests import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "cube16_ppc8": dict(n_cells=(16, 16, 16), ppc=8, seed=3),
+    "slab_32x16x8_blocks_16x8x4": dict(n_cells=(32, 16, 8), ppc=6, seed=5, block_cells=(16, 8, 4)),  # fast-wave geometry
+    "cube24_fast": dict(n_cells=(24, 24, 24), ppc=4, seed=7, vscale=8.0),  # many cell/block crossers and periodic wraps
+    "ghost2": dict(n_cells=(16, 16, 16), ppc=4, seed=9, ghost_cells=(2, 2, 2)),
+    "single_block_dim": dict(n_cells=(8, 16, 8), ppc=8, seed=11),
+    "open_box": dict(n_cells=(16, 16, 16), ppc=6, seed=13, periodic=False, vscale=6.0),  # DELETE boundary
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_one_step_parity(name):
+    res = pu.run_parity_case(**CASES[name])
+    print(name, res)
+    assert res["oracle_lists"] == 0
+    assert res["cell_mismatch"] == 0, res           # bit-exact block/cell assignment
+    assert res["stats_equal"], res                   # bit-exact crossing counts
+    assert res["max_rel_x"] <= pu.REL_TOL and res["max_rel_v"] <= pu.REL_TOL, res
+    assert res["sorted_ok"] and res["table_ok"] and res["perm_ok"], res
+    assert res["max_rel_J"] <= pu.REL_TOL and res["max_rel_M"] <= pu.REL_TOL, res
+    assert res["rel_energy"] <= pu.REL_TOL and res["rel_cfl"] <= pu.REL_TOL, res
+    assert res["gpu_launches"] > 0
