@@ -139,6 +139,7 @@ PROTOTYPES = {
     "amps_gpu_JM_download": (C.c_int, [_vp, _vp, _vp]),
     "amps_gpu_JM_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "amps_gpu_step": (C.c_int, [_vp, C.c_int]),
+    "amps_gpu_profile": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "amps_gpu_synchronize": (C.c_int, [_vp]),
 }
 

@@ -156,6 +156,15 @@ class Context:
     def step(self, mover=_capi.MOVER_LAPENTA2017):
         self._ck(self.lib.amps_gpu_step(self._h, mover))
 
+    PHASES = ("move", "sort", "deposit", "exchange")
+
+    def profile(self, enable=True):
+        """returns {phase: (ms, count)} accumulated since the last call; (re)arms the event recording"""
+        ms = (C.c_double * 4)()
+        cnt = (C.c_int64 * 4)()
+        self._ck(self.lib.amps_gpu_profile(self._h, 1 if enable else 0, C.cast(ms, C.c_void_p), C.cast(cnt, C.c_void_p)))
+        return {p: (float(ms[i]), int(cnt[i])) for i, p in enumerate(self.PHASES)}
+
     def synchronize(self):
         self._ck(self.lib.amps_gpu_synchronize(self._h))
 

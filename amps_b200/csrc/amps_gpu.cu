@@ -39,6 +39,38 @@ struct amps_gpu_ctx {
   double *d_J = nullptr, *d_M = nullptr, *d_energy = nullptr;
   unsigned long long *d_cfl = nullptr;
   DevMoveStats *d_stats = nullptr;
+
+  // phase profiling (CUDA events on ctx->stream around move / sort / deposit)
+  bool profile = false;
+  std::vector<cudaEvent_t> evPool;
+  size_t evUsed = 0;
+  std::vector<std::pair<int, std::pair<size_t, size_t>>> evSpans;  // phase, (begin,end) event index
+  double phaseMs[AMPS_GPU_N_PHASES] = {0, 0, 0, 0};
+  long long phaseCount[AMPS_GPU_N_PHASES] = {0, 0, 0, 0};
+};
+
+static size_t prof_mark(amps_gpu_ctx *ctx) {
+  if (ctx->evUsed == ctx->evPool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ctx->evPool.push_back(e);
+  }
+  cudaEventRecord(ctx->evPool[ctx->evUsed], ctx->stream);
+  return ctx->evUsed++;
+}
+struct ProfScope {
+  amps_gpu_ctx *ctx;
+  int phase;
+  size_t b;
+  ProfScope(amps_gpu_ctx *c, int ph) : ctx(c), phase(ph), b(0) {
+    if (ctx->profile) b = prof_mark(ctx);
+  }
+  ~ProfScope() {
+    if (ctx->profile) {
+      size_t e = prof_mark(ctx);
+      ctx->evSpans.push_back({phase, {b, e}});
+    }
+  }
 };
 
 #define CK(call)                                                                                       \
@@ -143,6 +175,7 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (void *p : ctx->meshAllocs) cudaFree(p);
+  for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
   cudaFree(ctx->d_Ehalf), cudaFree(ctx->d_Bprev), cudaFree(ctx->d_Bcur);
   cudaFree(ctx->d_eTile), cudaFree(ctx->d_bPrevTile), cudaFree(ctx->d_bCurTile);
   for (int b = 0; b < 2; b++) free_particles(ctx->buf[b]);
@@ -259,6 +292,7 @@ int amps_gpu_fields_upload(amps_gpu_ctx *ctx, const double *E_half, const double
 }
 
 static int do_sort(amps_gpu_ctx *ctx) {
+  ProfScope prof(ctx, AMPS_GPU_PHASE_SORT);
   ParticleSoA &src = ctx->buf[ctx->cur], &dst = ctx->buf[1 - ctx->cur];
   launch_sort(ctx->dm, src, dst, ctx->d_n + ctx->cur, ctx->d_cellCount, ctx->d_cellStart, ctx->d_cellFill, ctx->d_n + (1 - ctx->cur), ctx->nUpper,
               ctx->countValid, ctx->d_scanTmp, ctx->stream, &ctx->launches);
@@ -426,6 +460,7 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "move needs the (block,cell)-sorted layout: call amps_gpu_sort");
   if (mover_id != AMPS_MOVER_LAPENTA2017) FAIL(AMPS_GPU_ERR_ARG, "mover not implemented yet");
   const DevMesh &m = ctx->dm;
+  ProfScope prof(ctx, AMPS_GPU_PHASE_MOVE);
   CK(cudaMemsetAsync(ctx->d_cellCount, 0, sizeof(int) * (size_t)ctx->nCells, ctx->stream));
   CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevMoveStats), ctx->stream));
   long long perLeaf = ctx->nUpper / (m.nLeaves > 0 ? m.nLeaves : 1);
@@ -465,6 +500,7 @@ int amps_gpu_move(amps_gpu_ctx *ctx, int mover_id, amps_gpu_move_stats *stats) {
 static int do_deposit(amps_gpu_ctx *ctx) {
   if (!ctx->meshReady || !ctx->fieldsReady) FAIL(AMPS_GPU_ERR_STATE, "deposit before mesh/fields upload");
   if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "deposit needs the (block,cell)-sorted layout: call amps_gpu_sort");
+  ProfScope prof(ctx, AMPS_GPU_PHASE_DEPOSIT);
   launch_deposit(ctx->dm, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl,
                  ctx->stream, &ctx->launches);
   CK(cudaGetLastError());
@@ -503,6 +539,27 @@ int amps_gpu_JM_device(amps_gpu_ctx *ctx, double **J_dev, double **M_dev) {
   if (!ctx || !ctx->meshReady) return AMPS_GPU_ERR_STATE;
   if (J_dev) *J_dev = ctx->d_J;
   if (M_dev) *M_dev = ctx->d_M;
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_profile(amps_gpu_ctx *ctx, int enable, double *phase_ms, int64_t *phase_count) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (auto &sp : ctx->evSpans) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->evPool[sp.second.first], ctx->evPool[sp.second.second]);
+    ctx->phaseMs[sp.first] += ms;
+    ctx->phaseCount[sp.first]++;
+  }
+  ctx->evSpans.clear();
+  ctx->evUsed = 0;
+  for (int i = 0; i < AMPS_GPU_N_PHASES; i++) {
+    if (phase_ms) phase_ms[i] = ctx->phaseMs[i];
+    if (phase_count) phase_count[i] = ctx->phaseCount[i];
+    ctx->phaseMs[i] = 0, ctx->phaseCount[i] = 0;
+  }
+  ctx->profile = enable != 0;
   return AMPS_GPU_OK;
 }
 

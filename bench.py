@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- particle push+deposit updates/s of the ECSIM particle phase on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path over the resident plasma: PIC::Mover::MoveParticles (Lapenta2017)
++ counting sort by (block,cell) [the list hand-off] + ECSIM::UpdateJMassMatrix, i.e. amps_gpu_step().
+N=1 workload = BASELINE configs[1]: ECSIM uniform periodic box, 64^3 cells, 64 ppc per species (e/p),
+single AMR level, synthetic Maxwellian (3.36e7 particles; inputs are >> L2 so no L2 flush is needed).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+`--impl reference` times the CPU restatement of the reference path (oracle port, all host threads) on a
+bounded sample of the same workload; the real AMPS cannot be built here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle push+deposit updates/s"
+UNIT = "updates/s"
+ALG_BYTES_FIXED = 105.0  # 57 B read (x,v,w,species) + 48 B write (x',v') per update
+ALG_BYTES_PER_CELL = 4000.0  # zero+flush of J[3],M[243] per corner/cell (3936 B) + E/B tile (64 B)
+ALG_FLOP_PER_UPDATE = 1050.0
+# share of the per-update algorithmic bytes that each kernel must move at minimum ("kernels")
+KERNEL_ALG_BYTES = {
+    "move": lambda P: 57.0 + 48.0 + 64.0 / P,  # read state, write x',v'; E/B tiles
+    "sort": lambda P: 0.0,  # implementation overhead, not counted by SURVEY 8d
+    "deposit": lambda P: 57.0 + 3936.0 / P,  # re-read state; zero + flush J,M
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [c.strip() for c in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_box(n_cells, ppc, block_cells=(8, 8, 8), seed=100, capacity_slack=1.02):
+    from amps_b200 import api, mesh as meshmod, workload
+
+    m = meshmod.uniform_periodic_box(n_cells, block_cells, (1, 1, 1))
+    charge, mass, wgt = workload.species_tables(ppc, 1.0)
+    parts = workload.maxwellian_box(m, ppc, seed=seed)
+    n = parts[0].shape[1]
+    cfg = api.make_config(block_cells, (1, 1, 1), charge, mass, wgt, 1.0, periodic=True, capacity=int(n * capacity_slack) + 1024)
+    E, B = workload.box_fields(m, E_amp=0.0)
+    return m, cfg, parts, (E, B, B.copy())
+
+
+def cpu_port_rate(n_cells, ppc, steps, threads):
+    """oracle (CPU port of the reference path) on a bounded sample: move + list swap + periodic wrap + deposit"""
+    from oracle.oracle_py import Oracle
+
+    m, cfg, parts, fields = build_box(n_cells, ppc)
+    try:
+        o = Oracle(cfg, m, "fast")
+    except OSError:
+        o = Oracle(cfg, m, "parity")
+    o.set_fields(*fields)
+    o.add_particles(*parts)
+    n = parts[0].shape[1]
+    o.move_fast(0, threads)  # warm-up step (page faults, list order)
+    o.deposit(threads, want_arrays=False)
+    per_step = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        o.move_fast(0, threads)
+        o.deposit(threads, want_arrays=False)
+        per_step.append(time.perf_counter() - t0)
+    o.close()
+    return n, per_step
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = cores
+    cells = (32, 32, 32)
+    n, per_step = cpu_port_rate(cells, args.ppc, max(1, args.steps), threads)
+    dt = float(np.sum(per_step))
+    val = n * len(per_step) / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(per_step), "warmup": 1,
+        "ms_per_step": 1e3 * dt / len(per_step), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"ECSIM uniform periodic box {args.cells}^3 cells, {args.ppc} ppc/species e+p, 8^3-cell blocks, Maxwellian, dt=1",
+                   "sample": f"{cells[0]}^3-cell sub-box of the same plasma ({n} particles) per step"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{cells[0]}^3 cells x {args.ppc} ppc x 2 species = {n} particles, {len(per_step)} steps, OpenMP by blocks/cells"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cells", type=int, default=64, help="box edge in cells (per GPU for N>1)")
+    ap.add_argument("--ppc", type=int, default=64, help="particles per cell per species")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; amps_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from amps_b200 import api
+
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    P = 2 * args.ppc
+
+    t_gen = time.time()
+    m, cfg, parts, fields = build_box((args.cells,) * 3, args.ppc, seed=100 + rank)
+    cfg.device = local
+    n_part = parts[0].shape[1]
+    t_gen = time.time() - t_gen
+    ctx = api.Context(cfg, m)
+    ctx.fields_upload(*fields)
+    ctx.particles_upload(*parts)
+    del parts
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for _ in range(W):
+        ctx.step()
+    barrier()
+    ctx.profile(True)
+    launches0 = ctx.launch_count()
+
+    # ---- timed region: exactly K steps, inputs resident in HBM ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    ev0.record(stream)
+    for _ in range(K):
+        ctx.step()
+    ev1.record(stream)
+    barrier()
+    t1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t0, t1)
+    phases = ctx.profile(False)
+    launches = ctx.launch_count() - launches0
+    n_now = ctx.particle_count()
+
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+        nn = torch.tensor([n_part], dtype=torch.float64, device="cuda")
+        dist.all_reduce(nn, op=dist.ReduceOp.SUM)
+        n_total = float(nn.item())
+    else:
+        n_total = float(n_part)
+    value = n_total * K / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with HOST buffers: fields in (H2D), step, J+M out (D2H) ----
+    Eh = torch.from_numpy(fields[0]).pin_memory().numpy()
+    Bp = torch.from_numpy(fields[1]).pin_memory().numpy()
+    Bc = torch.from_numpy(fields[2]).pin_memory().numpy()
+    Jh = torch.empty((m.n_corners, 3), dtype=torch.float64).pin_memory().numpy()
+    Mh = torch.empty((m.n_corners, 243), dtype=torch.float64).pin_memory().numpy()
+    h2d = Eh.nbytes + Bp.nbytes + Bc.nbytes
+    d2h = Jh.nbytes + Mh.nbytes
+    KE = max(1, args.e2e_steps)
+    ctx.fields_upload(Eh, Bp, Bc)
+    ctx.step()
+    ctx.JM_download(out_J=Jh, out_M=Mh)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    te0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(KE):
+        ctx.fields_upload(Eh, Bp, Bc)
+        ctx.step()
+        ctx.JM_download(out_J=Jh, out_M=Mh)
+    e1.record(stream)
+    barrier()
+    te = time.perf_counter() - te0
+    e2e_ms = max(e0.elapsed_time(e1), te * 1e3)  # the D2H read is synchronous: host wall time covers it
+    if world > 1:
+        tt = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+    e2e_value = n_total * KE / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (CUDA-event time of its launches inside the timed region) ----
+    peak, peak_src = load_peaks()
+    dom = max(("move", "sort", "deposit"), key=lambda p: phases[p][0])
+    dom_ms = phases[dom][0] / max(1, phases[dom][1])
+    dom_alg = "deposit" if dom == "sort" else dom
+    alg_bytes = KERNEL_ALG_BYTES[dom_alg](P) * n_part
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    step_alg = (ALG_BYTES_FIXED + ALG_BYTES_PER_CELL / P)
+    roofline = {"bound": "hbm", "kernel": {"move": "move_lapenta_kernel", "sort": "scatter_kernel", "deposit": "deposit_kernel"}[dom],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "ms_per_launch": dom_ms, "alg_bytes_per_update": KERNEL_ALG_BYTES[dom_alg](P)}
+    step_gbs = step_alg * (n_part * K / (ms * 1e-3)) / 1e9 if world == 1 else step_alg * (value / world) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"ECSIM uniform periodic box {args.cells}^3 cells per GPU, {args.ppc} ppc/species e+p, 8^3-cell blocks, "
+                               f"single AMR level, Maxwellian v_th,e=0.05, dt=1 (BASELINE configs[1])",
+                   "particles_per_gpu": n_part, "particles_after": n_now, "l2": "inputs (2.2 GB particle SoA) larger than L2, no flush",
+                   "step": "move(Lapenta2017)+counting sort+UpdateJMassMatrix", "gen_s": round(t_gen, 1)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": KE,
+                "ms_per_step": e2e_ms / KE},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "phases_ms_per_step": {p: (phases[p][0] / max(1, phases[p][1])) for p in ("move", "sort", "deposit")},
+        "roofline_step": {"alg_bytes_per_update": step_alg, "achieved_gbs_per_gpu": step_gbs, "frac_hbm": step_gbs / peak,
+                          "fp64_tflops_per_gpu": ALG_FLOP_PER_UPDATE * (value / world) / 1e12},
+    }
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        n_cpu, per = cpu_port_rate((32, 32, 32), args.ppc, 2, cores)
+        v = n_cpu * len(per) / float(np.sum(per))
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"32^3 cells x {args.ppc} ppc x 2 species = {n_cpu} particles, {len(per)} steps, oracle -O3 OpenMP"}
+    print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

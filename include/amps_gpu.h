@@ -234,6 +234,13 @@ int amps_gpu_JM_device(amps_gpu_ctx *ctx, double **J_dev, double **M_dev);
 /* one fused ECSIM particle phase: move + sort + deposit, no host sync inside */
 int amps_gpu_step(amps_gpu_ctx *ctx, int mover_id);
 
+/* Phase timing with CUDA events recorded on the context's stream (what the reference prints from
+ * ECSIM::CumulativeTiming::{ParticleMoverTime,UpdateJMassMatrixTime}, pic_field_solver_ecsim.cpp:154-181).
+ * Synchronises, returns the ms and call counts accumulated per phase since the last call, clears
+ * them, and enables/disables recording for the following calls.                          */
+enum { AMPS_GPU_PHASE_MOVE = 0, AMPS_GPU_PHASE_SORT = 1, AMPS_GPU_PHASE_DEPOSIT = 2, AMPS_GPU_PHASE_EXCHANGE = 3, AMPS_GPU_N_PHASES = 4 };
+int amps_gpu_profile(amps_gpu_ctx *ctx, int enable, double *phase_ms, int64_t *phase_count);
+
 /* block until all queued work of the context is complete */
 int amps_gpu_synchronize(amps_gpu_ctx *ctx);
 
