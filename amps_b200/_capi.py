@@ -140,6 +140,7 @@ PROTOTYPES = {
     "amps_gpu_JM_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "amps_gpu_step": (C.c_int, [_vp, C.c_int]),
     "amps_gpu_profile": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "amps_gpu_selftest_division": (C.c_int, [_vp, _vp, _vp, C.c_int64, _i64p]),
     "amps_gpu_synchronize": (C.c_int, [_vp]),
 }
 

@@ -165,6 +165,14 @@ class Context:
         self._ck(self.lib.amps_gpu_profile(self._h, 1 if enable else 0, C.cast(ms, C.c_void_p), C.cast(cnt, C.c_void_p)))
         return {p: (float(ms[i]), int(cnt[i])) for i, p in enumerate(self.PHASES)}
 
+    def selftest_division(self, a, b):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        assert a.size == b.size
+        bad = C.c_int64()
+        self._ck(self.lib.amps_gpu_selftest_division(self._h, _ptr(a), _ptr(b), a.size, C.byref(bad)))
+        return int(bad.value)
+
     def synchronize(self):
         self._ck(self.lib.amps_gpu_synchronize(self._h))
 

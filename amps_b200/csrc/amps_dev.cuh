@@ -94,5 +94,6 @@ void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
                     double *energy, unsigned long long *cflBits, cudaStream_t s, long long *launches);
 size_t sort_scan_tmp_bytes(long long nCells);
+void launch_division_selftest(const double *a, const double *b, int n, unsigned long long *out, cudaStream_t s);
 
 }  // namespace amps

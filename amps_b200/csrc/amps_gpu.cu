@@ -563,6 +563,26 @@ int amps_gpu_profile(amps_gpu_ctx *ctx, int enable, double *phase_ms, int64_t *p
   return AMPS_GPU_OK;
 }
 
+int amps_gpu_selftest_division(amps_gpu_ctx *ctx, const double *a, const double *b, int64_t n, int64_t *n_mismatch) {
+  if (!ctx || !a || !b || !n_mismatch || n < 1) return AMPS_GPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  double *da = nullptr, *db = nullptr;
+  unsigned long long *dout = nullptr, h = 0;
+  CK(cudaMalloc(&da, n * sizeof(double)));
+  CK(cudaMalloc(&db, n * sizeof(double)));
+  CK(cudaMalloc(&dout, sizeof(unsigned long long)));
+  CK(cudaMemcpyAsync(da, a, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(db, b, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(dout, 0, sizeof(unsigned long long), ctx->stream));
+  launch_division_selftest(da, db, (int)n, dout, ctx->stream);
+  ctx->launches++;
+  CK(cudaMemcpyAsync(&h, dout, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(da), cudaFree(db), cudaFree(dout);
+  *n_mismatch = (int64_t)h;
+  return AMPS_GPU_OK;
+}
+
 int amps_gpu_step(amps_gpu_ctx *ctx, int mover_id) {
   if (!ctx) return AMPS_GPU_ERR_ARG;
   CK(cudaSetDevice(ctx->cfg.device));

@@ -50,6 +50,112 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Correctly rounded fp64 quotients with a shared reciprocal.  An IEEE fp64 division costs ~25
+// instructions; the mover needs ~30 of them per particle to round exactly like the CPU reference,
+// and most divide by a per-block constant (dx, xmax-xmin, dx_max_refinement) or by one stencil norm.
+// Given y = RN(1/b), two Newton corrections give a faithful quotient and Markstein's final step
+//     r = fma(-q,b,a);  q' = fma(r,y,q)
+// returns RN(a/b) exactly (Markstein 1990; Muller et al., Handbook of FP Arithmetic, thm 4.7-4.8).
+// Excluded and routed to the plain division: b with an all-ones significand, tiny |a| (the exact
+// residual could underflow).  tests/test_division_gpu.py checks bit equality against '/'.
+// ------------------------------------------------------------------------------------------------
+struct Recip {
+  double y;
+  bool ok;
+};
+__device__ __forceinline__ bool allones_significand(double b) {
+  return (((unsigned long long)__double_as_longlong(b)) & 0x000FFFFFFFFFFFFFull) == 0x000FFFFFFFFFFFFFull;
+}
+// the IEEE division, kept out of line: it is the rarely taken fallback of ~30 call sites and inlining it
+// made the mover's loop body overflow the instruction cache
+__device__ __noinline__ double div_slow(double a, double b) { return a / b; }
+__device__ __forceinline__ Recip make_recip(double b) {
+  Recip r;
+  r.y = div_slow(1.0, b);
+  r.ok = !allones_significand(b) && fabs(b) > 1e-150 && fabs(b) < 1e150;
+  return r;
+}
+// exponent field outside [128,1792): zero, denormal, |a| < 2^-895, |a| >= 2^769, inf, nan
+__device__ __forceinline__ bool exp_unsafe(double a) {
+  const unsigned e = (((unsigned)__double2hiint(a)) >> 20) & 0x7ffu;
+  return (e - 128u) >= 1664u;
+}
+// unguarded Markstein sequence: exact for y = RN(1/b), b without an all-ones significand, a "exp safe"
+__device__ __forceinline__ double div_fast(double a, double b, double y) {
+  double q = a * y;
+  double r = fma(-q, b, a);
+  q = fma(r, y, q);
+  r = fma(-q, b, a);
+  return fma(r, y, q);
+}
+__device__ __forceinline__ double div_rn(double a, double b, const Recip &rc) {
+  if (!rc.ok || exp_unsafe(a)) return div_slow(a, b);
+  return div_fast(a, b, rc.y);
+}
+// three quotients by per-block constants with one combined guard
+__device__ __forceinline__ void div_rn3(const double (&a)[3], const double (&b)[3], const Recip (&rc)[3], bool allOk, double (&q)[3]) {
+  if (allOk && !(exp_unsafe(a[0]) | exp_unsafe(a[1]) | exp_unsafe(a[2]))) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) q[d] = div_fast(a[d], b[d], rc[d].y);
+  } else {
+#pragma unroll
+    for (int d = 0; d < 3; d++) q[d] = div_slow(a[d], b[d]);
+  }
+}
+// w[0..7] /= norm for a trilinear stencil whose weights sum to norm ~ 1 (a3/a4 Normalize()).
+// norm == 1: identity.  norm == 1-2^-53 (all-ones significand): a/norm = a(1+2^-53+...) rounds to the
+// next double above a.  1-4*2^-53 <= norm <= 1+8*2^-52: RN(1/norm) == 2-norm, then Markstein.  Anything
+// else (stencils that lost cells at a domain boundary, zero weights) takes the IEEE division.
+__device__ __forceinline__ void normalize8(double (&w)[8], double norm) {
+  if (norm == 1.0 || !(norm > 0.0)) return;
+  int hmin = __double2hiint(w[0]);
+#pragma unroll
+  for (int s = 1; s < 8; s++) hmin = min(hmin, __double2hiint(w[s]));  // weights are >= 0: hi words order like the values
+  const bool safe = (norm >= 0x1.ffffffffffffcp-1) && (norm <= 0x1.0000000000008p+0) && (hmin >= 0x0C000000);
+  if (safe) {
+    if (norm == 0x1.fffffffffffffp-1) {
+#pragma unroll
+      for (int s = 0; s < 8; s++) w[s] = __longlong_as_double(__double_as_longlong(w[s]) + 1);
+    } else {
+      const double y = 2.0 - norm;
+#pragma unroll
+      for (int s = 0; s < 8; s++) w[s] = div_fast(w[s], norm, y);
+    }
+  } else {
+#pragma unroll 1
+    for (int s = 0; s < 8; s++) w[s] = div_slow(w[s], norm);
+  }
+}
+
+// self test: out[0] += number of (a,b) pairs for which the helpers differ from IEEE '/'
+__global__ void division_selftest_kernel(const double *__restrict__ a, const double *__restrict__ b, int n, unsigned long long *out) {
+  unsigned long long bad = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double bb = b[i];
+    const Recip rc = make_recip(bb);
+    double w[8], ref[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      const double aa = a[(i + s * 7919) % n];
+      w[s] = aa;
+      ref[s] = aa / bb;
+      if (div_rn(aa, bb, rc) != ref[s] && !(ref[s] != ref[s])) bad++;
+    }
+    normalize8(w, bb);
+    if (bb > 0.0 && bb != 1.0) {
+#pragma unroll
+      for (int s = 0; s < 8; s++)
+        if (w[s] != ref[s] && !(ref[s] != ref[s])) bad++;
+    }
+  }
+  if (bad) atomicAdd(out, bad);
+}
+void launch_division_selftest(const double *a, const double *b, int n, unsigned long long *out, cudaStream_t s) {
+  division_selftest_kernel<<<148 * 4, 256, 0, s>>>(a, b, n, out);
+}
+
 // ------------------------------------------------------------------------------------------------
 // a2: gather unique-node fields into per-leaf tiles (incl. ghost layers); missing node -> 0
 // ------------------------------------------------------------------------------------------------
@@ -108,10 +214,16 @@ __device__ __forceinline__ int find_node_ix(const DevMesh &m, int ix0, int ix1, 
 }
 
 // findTreeNode(double*), meshAMRgeneric.h:2851-2882.  Returns node id or -1.
-__device__ __forceinline__ int find_tree_node(const DevMesh &m, const double x[3], const LeafGeo &start) {
+__device__ __forceinline__ int find_tree_node(const DevMesh &m, const double x[3], const LeafGeo &start, const Recip (&rRef)[3], bool allOk) {
   int ix[3];
+  {
+    const double a[3] = {x[0] - m.xGlobalMin[0], x[1] - m.xGlobalMin[1], x[2] - m.xGlobalMin[2]};
+    const double b[3] = {m.dxMaxRef[0], m.dxMaxRef[1], m.dxMaxRef[2]};
+    double q[3];
+    div_rn3(a, b, rRef, allOk, q);
 #pragma unroll
-  for (int d = 0; d < 3; d++) ix[d] = (int)floor((x[d] - m.xGlobalMin[d]) / m.dxMaxRef[d]);
+    for (int d = 0; d < 3; d++) ix[d] = (int)floor(q[d]);
+  }
   int node;
   const bool in = ix[0] >= start.imin[0] && ix[0] < start.imin[0] + start.isize && ix[1] >= start.imin[1] && ix[1] < start.imin[1] + start.isize &&
                   ix[2] >= start.imin[2] && ix[2] < start.imin[2] + start.isize;
@@ -133,8 +245,14 @@ __device__ __forceinline__ int find_tree_node(const DevMesh &m, const double x[3
 // ------------------------------------------------------------------------------------------------
 // a5: Lapenta2017
 // ------------------------------------------------------------------------------------------------
+struct BlockConst {
+  double dxc[3], span[3], dxCell[3];
+  Recip rDxc[3], rSpan[3], rCell[3], rRef[3];
+  double qdt2m[AMPS_GPU_MAX_SPECIES], dt[AMPS_GPU_MAX_SPECIES];
+};
+
 template <bool kSmemTiles>
-__global__ void __launch_bounds__(256) move_lapenta_kernel(DevMesh m, DevSpecies sp, ParticleSoA p, const int *__restrict__ cellStart,
+__global__ void __launch_bounds__(256, 2) move_lapenta_kernel(DevMesh m, DevSpecies sp, ParticleSoA p, const int *__restrict__ cellStart,
                                                           const double *__restrict__ eTileG, const double *__restrict__ bTileG,
                                                           int *__restrict__ cellCount, DevMoveStats *__restrict__ stats, int slices) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -174,12 +292,33 @@ __global__ void __launch_bounds__(256) move_lapenta_kernel(DevMesh m, DevSpecies
   }
 
   const LeafGeo &lg = sLeaf;
-  // per-block constants of the stencils
+  // per-block constants of the stencils and their shared reciprocals (computed once per CTA)
+  __shared__ BlockConst sC;
+  if (threadIdx.x < 3) {
+    const int d = threadIdx.x;
+    sC.dxc[d] = (lg.xmax[d] - lg.xmin[d]) / m.N[d];  // CornerBased::InitStencil :1086-1088
+    sC.span[d] = lg.xmax[d] - lg.xmin[d];
+    sC.dxCell[d] = m.dxRoot[d] / (1 << lg.level) / double(m.N[d]);  // FindCellIndex :2275
+    sC.rDxc[d] = make_recip(sC.dxc[d]);
+    sC.rSpan[d] = make_recip(sC.span[d]);
+    sC.rCell[d] = make_recip(sC.dxCell[d]);
+    sC.rRef[d] = make_recip(m.dxMaxRef[d]);
+  } else if (threadIdx.x >= 32 && threadIdx.x < 32 + AMPS_GPU_MAX_SPECIES) {
+    const int sidx = threadIdx.x - 32;
+    const double dts = (sp.timeStepMode == AMPS_DT_SPECIES_GLOBAL) ? sp.dt[sidx] : sp.dt[0];
+    const double QdT_over_m = (sidx < sp.n) ? sp.charge[sidx] * dts / sp.mass[sidx] : 0.0;  // :1036
+    sC.qdt2m[sidx] = 0.5 * QdT_over_m;
+    sC.dt[sidx] = dts;
+  }
+  __syncthreads();
   double dxc[3], span[3];
+  Recip rDxc[3], rSpan[3], rRef[3], rCell[3];
+  bool blockOk = true;
 #pragma unroll
   for (int d = 0; d < 3; d++) {
-    dxc[d] = (lg.xmax[d] - lg.xmin[d]) / m.N[d];  // CornerBased::InitStencil :1086-1088
-    span[d] = lg.xmax[d] - lg.xmin[d];
+    dxc[d] = sC.dxc[d], span[d] = sC.span[d];
+    rDxc[d] = sC.rDxc[d], rSpan[d] = sC.rSpan[d], rRef[d] = sC.rRef[d], rCell[d] = sC.rCell[d];
+    blockOk = blockOk && rDxc[d].ok && rSpan[d].ok && rRef[d].ok && rCell[d].ok;
   }
   const int CS0 = 1 + m.TN[0], CS1 = (1 + m.TN[0]) * (1 + m.TN[1]);  // corner strides
   const int BS0 = m.TN[0], BS1 = m.TN[0] * m.TN[1];                  // centre strides
@@ -192,18 +331,23 @@ __global__ void __launch_bounds__(256) move_lapenta_kernel(DevMesh m, DevSpecies
     vInit[0] = p.v[0][ip], vInit[1] = p.v[1][ip], vInit[2] = p.v[2][ip];
     const int spec = p.spec[ip];
     const int oldKey = p.key[ip];
-    const double dtTotal = (sp.timeStepMode == AMPS_DT_SPECIES_GLOBAL) ? sp.dt[spec] : sp.dt[0];
+    const double dtTotal = sC.dt[spec];
     nMoved++;
     bool err = false;
 
     // ---- a3: corner stencil for E (mutates xInit: snap to xmax-1e-10dx) ----
     int iX[3];
     double xLoc[3];
+    double off[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) {
       if ((xInit[d] < lg.xmin[d]) || (xInit[d] > lg.xmax[d])) err = true;  // reference: exit("the point is out of block")
       if (fabs(xInit[d] - lg.xmax[d]) < 1e-10 * dxc[d]) xInit[d] = lg.xmax[d] - 1e-10 * dxc[d];
-      xLoc[d] = (xInit[d] - lg.xmin[d]) / dxc[d];
+      off[d] = xInit[d] - lg.xmin[d];
+    }
+    div_rn3(off, dxc, rDxc, blockOk, xLoc);
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
       iX[d] = (int)(xLoc[d]);
       xLoc[d] -= iX[d];
     }
@@ -228,10 +372,7 @@ __global__ void __launch_bounds__(256) move_lapenta_kernel(DevMesh m, DevSpecies
       double norm = 0.0;
 #pragma unroll
       for (int s = 0; s < 8; s++) norm += w[s];
-      if (norm > 0.0) {
-#pragma unroll
-        for (int s = 0; s < 8; s++) w[s] /= norm;
-      }
+      normalize8(w, norm);  // Stencil.Normalize(): w[s] /= norm
       const int nd0 = cornerLocalNumber(m, iX[0], iX[1], iX[2]);
 #pragma unroll
       for (int s = 0; s < 8; s++) {
@@ -244,9 +385,11 @@ __global__ void __launch_bounds__(256) move_lapenta_kernel(DevMesh m, DevSpecies
     }
     // ---- a4: cell-centred linear stencil for B (uniform / same-level branch) ----
     {
-      const double iLoc = (xInit[0] - lg.xmin[0]) / span[0] * m.N[0];
-      const double jLoc = (xInit[1] - lg.xmin[1]) / span[1] * m.N[1];
-      const double kLoc = (xInit[2] - lg.xmin[2]) / span[2] * m.N[2];
+      double qLoc[3];
+      div_rn3(off, span, rSpan, blockOk, qLoc);  // (x-xmin)/(xmax-xmin), :278-280
+      const double iLoc = qLoc[0] * m.N[0];
+      const double jLoc = qLoc[1] * m.N[1];
+      const double kLoc = qLoc[2] * m.N[2];
       const int i0 = (iLoc < 0.5) ? -1 : (int)(iLoc - 0.50);
       const int j0 = (jLoc < 0.5) ? -1 : (int)(jLoc - 0.50);
       const int k0 = (kLoc < 0.5) ? -1 : (int)(kLoc - 0.50);
@@ -276,10 +419,7 @@ __global__ void __launch_bounds__(256) move_lapenta_kernel(DevMesh m, DevSpecies
       for (int s = 0; s < 8; s++)
         if (valid & (1u << s)) norm += w[s];
       // Normalize(): the reference tests the global StencilTable->Length (:903) => always runs in ECSIM
-      if (norm > 0.0) {
-#pragma unroll
-        for (int s = 0; s < 8; s++) w[s] /= norm;
-      }
+      normalize8(w, norm);
       const int nd0 = centerLocalNumber(m, i0, j0, k0);
 #pragma unroll
       for (int s = 0; s < 8; s++) {
@@ -295,9 +435,7 @@ __global__ void __launch_bounds__(256) move_lapenta_kernel(DevMesh m, DevSpecies
 
     // ---- velocity / position update (:1036-1081) ----
     {
-      const double chargeQ = sp.charge[spec], mass = sp.mass[spec];
-      const double QdT_over_m = chargeQ * dtTotal / mass;
-      const double QdT_over_2m = 0.5 * QdT_over_m;
+      const double QdT_over_2m = sC.qdt2m[spec];  // 0.5*(chargeQ*dtTotal/mass)
       const double QdT_over_2m_squared = QdT_over_2m * QdT_over_2m;
       double BB[3][3], P[3];
 #pragma unroll
@@ -332,7 +470,7 @@ __global__ void __launch_bounds__(256) move_lapenta_kernel(DevMesh m, DevSpecies
     }
 
     // ---- a14/a15: new block (:1121-1272) ----
-    int node = find_tree_node(m, xFinal, lg);
+    int node = find_tree_node(m, xFinal, lg, rRef, blockOk);
     int newKey = -1;
     if (node < 0) {
       // left the domain.  DELETE mode (:1165-1167); other modes are handled by the generic mover path
@@ -354,8 +492,13 @@ __global__ void __launch_bounds__(256) move_lapenta_kernel(DevMesh m, DevSpecies
           const double lo = same ? lg.xmin[d] : m.nxmin[3 * node + d];
           const double hi = same ? lg.xmax[d] : m.nxmax[3 * node + d];
           if ((xFinal[d] < lo) || (hi < xFinal[d])) out = true;
-          const double dx = m.dxRoot[d] / (1 << lev) / double(m.N[d]);
-          int c = (int)((xFinal[d] - lo) / dx);
+          int c;
+          if (lev == lg.level) {
+            c = (int)div_rn(xFinal[d] - lo, sC.dxCell[d], rCell[d]);
+          } else {
+            const double dx = m.dxRoot[d] / (1 << lev) / double(m.N[d]);
+            c = (int)div_slow(xFinal[d] - lo, dx);
+          }
           if (c == m.N[d]) c = m.N[d] - 1;
           ijk[d] = c;
         }

@@ -241,6 +241,10 @@ int amps_gpu_step(amps_gpu_ctx *ctx, int mover_id);
 enum { AMPS_GPU_PHASE_MOVE = 0, AMPS_GPU_PHASE_SORT = 1, AMPS_GPU_PHASE_DEPOSIT = 2, AMPS_GPU_PHASE_EXCHANGE = 3, AMPS_GPU_N_PHASES = 4 };
 int amps_gpu_profile(amps_gpu_ctx *ctx, int enable, double *phase_ms, int64_t *phase_count);
 
+/* Device self test of the mover's shared-reciprocal quotients: counts (a[i],b[j]) pairs whose result
+ * differs from the IEEE fp64 division (must be 0; the cell assignment parity depends on it).   */
+int amps_gpu_selftest_division(amps_gpu_ctx *ctx, const double *a, const double *b, int64_t n, int64_t *n_mismatch);
+
 /* block until all queued work of the context is complete */
 int amps_gpu_synchronize(amps_gpu_ctx *ctx);
 

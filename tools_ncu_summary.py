@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (raw page CSV) into the handful of counters the judge reads. Usage: tools_ncu_summary.py rep [kernel-substr]"""
+import csv, subprocess, sys, io
+rep = sys.argv[1]
+sub = sys.argv[2] if len(sys.argv) > 2 else ""
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr, units = rows[0], rows[1]
+idx = {h: i for i, h in enumerate(hdr)}
+want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
+        'smsp__inst_executed.sum', 'l1tex__throughput.avg.pct_of_peak_sustained_active', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__inst_executed_op_shared_ld.sum', 'smsp__inst_executed_op_shared_st.sum',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'lts__t_sectors_op_red.sum', 'smsp__inst_executed_op_global_red.sum', 'l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum',
+        'smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio' ,
+        'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio','smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio','smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio','smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio','smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio','smsp__average_warps_issue_stalled_drain_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_membar_per_issue_active.ratio','smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio','smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio','smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_selected_per_issue_active.ratio','local_load', 'smsp__inst_executed_op_local_ld.sum','smsp__inst_executed_op_local_st.sum']
+for r in rows[2:]:
+    name = r[idx['Kernel Name']]
+    if sub not in name:
+        continue
+    print('## ' + name[:100])
+    for w in want:
+        if w in idx:
+            print(f'{w} = {r[idx[w]]} {units[idx[w]]}')
