@@ -27,6 +27,11 @@ struct LeafGeo {
   int face;   // bit f: no neighbour across face f
   int node;
   int pad;
+  // derived per-leaf constants of the deposit (host computed at mesh upload)
+  double dxc[3];     // (xmax-xmin)/N                       CornerBased::InitStencil :1086-1088
+  double invdxc[3];  // 1/dxc
+  double invV;       // 1/CellVolume, CellVolume = prod(dxc*length_conv)   ProcessCell :1959-1961
+  double diag;       // sqrt(sum (dxc*length_conv)^2)       ProcessCell :2358
 };
 
 struct DevMesh {
@@ -92,7 +97,7 @@ void launch_move_lapenta(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, 
 void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *nSrc, int *cellCount, int *cellStart, int *cellFill, int *nDst,
                  long long capacity, bool countValid, void *scanTmp, cudaStream_t s, long long *launches);
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
-                    double *energy, unsigned long long *cflBits, cudaStream_t s, long long *launches);
+                    double *energy, unsigned long long *cflBits, int nSM, cudaStream_t s, long long *launches);
 size_t sort_scan_tmp_bytes(long long nCells);
 void launch_division_selftest(const double *a, const double *b, int n, unsigned long long *out, cudaStream_t s);
 

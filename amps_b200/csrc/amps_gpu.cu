@@ -1,6 +1,7 @@
 // amps_gpu.cu -- host side of the C ABI declared in include/amps_gpu.h: context, device memory,
 // uploads/downloads and kernel sequencing.  No CPU fallback anywhere: without a CUDA device
 // amps_gpu_init() fails with AMPS_GPU_ERR_NO_DEVICE.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -15,6 +16,7 @@ struct amps_gpu_ctx {
   std::string err;
   cudaStream_t stream = nullptr;
   long long launches = 0;
+  int nSM = 148;
 
   DevMesh dm;
   DevSpecies sp;
@@ -148,6 +150,7 @@ int amps_gpu_init(const amps_gpu_config *cfg, amps_gpu_ctx **out) {
   *out = ctx;  // returned even on failure so that the caller can read last_error
   CK(cudaSetDevice(cfg->device));
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(cudaDeviceGetAttribute(&ctx->nSM, cudaDevAttrMultiProcessorCount, cfg->device));
 
   DevSpecies &sp = ctx->sp;
   sp.n = cfg->n_species;
@@ -238,6 +241,18 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
     g.face = mesh->leaf_face_boundary[l];
     g.node = n;
     g.pad = 0;
+    {
+      double vol = 1, d2 = 0;
+      for (int d = 0; d < 3; d++) {
+        g.dxc[d] = (g.xmax[d] - g.xmin[d]) / m.N[d];
+        g.invdxc[d] = 1.0 / g.dxc[d];
+        const double dxl = g.dxc[d] * ctx->cfg.ecsim_length_conv;
+        vol *= dxl;
+        d2 += dxl * dxl;
+      }
+      g.invV = 1.0 / vol;
+      g.diag = sqrt(d2);
+    }
   }
   int rc;
   const int nRootTot = m.nRoot[0] * m.nRoot[1] * m.nRoot[2];
@@ -502,7 +517,7 @@ static int do_deposit(amps_gpu_ctx *ctx) {
   if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "deposit needs the (block,cell)-sorted layout: call amps_gpu_sort");
   ProfScope prof(ctx, AMPS_GPU_PHASE_DEPOSIT);
   launch_deposit(ctx->dm, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl,
-                 ctx->stream, &ctx->launches);
+                 ctx->nSM, ctx->stream, &ctx->launches);
   CK(cudaGetLastError());
   return AMPS_GPU_OK;
 }

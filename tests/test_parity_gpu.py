@@ -11,6 +11,7 @@ CASES = {
     "cube24_fast": dict(n_cells=(24, 24, 24), ppc=4, seed=7, vscale=8.0),  # many cell/block crossers and periodic wraps
     "ghost2": dict(n_cells=(16, 16, 16), ppc=4, seed=9, ghost_cells=(2, 2, 2)),
     "single_block_dim": dict(n_cells=(8, 16, 8), ppc=8, seed=11),
+    "dense_cells_320": dict(n_cells=(8, 8, 8), ppc=160, seed=17),  # cells larger than one deposit chunk / ring batch
     "open_box": dict(n_cells=(16, 16, 16), ppc=6, seed=13, periodic=False, vscale=6.0),  # DELETE boundary
 }
 
