@@ -36,7 +36,7 @@ namespace amps {
 constexpr int ROW = 26;  // doubles per particle row: XX[0..2] - YZ[4..12] - a[14..25] (k alpha[9], q~ alpha v/V [3])
 constexpr int OFF_YZ = 4, OFF_A = 14;
 constexpr int CHUNK = 32;                  // particles per phase-1 pass (one per lane)
-constexpr int DEP_WARPS = 4, DEP_THREADS = 32 * DEP_WARPS, DEP_CTAS_PER_SM = 3;
+constexpr int DEP_WARPS = 4, DEP_THREADS = 32 * DEP_WARPS, DEP_CTAS_PER_SM = 2;
 constexpr int N_TILES = 6, N_SLICES = 5;   // 30 active lanes
 constexpr int N_T = 27 * 12;               // class sums per cell
 constexpr int SLAB = CHUNK * ROW;          // doubles of row storage per warp (>= N_T: reused for the totals)
@@ -45,6 +45,13 @@ static_assert(SLAB >= N_T, "the totals must fit in the row slab");
 __device__ __forceinline__ void atomicMaxPositiveDouble(unsigned long long *addr, double v) {
   // v >= 0 and not NaN: the bit patterns of non-negative doubles order like unsigned integers
   atomicMax(addr, (unsigned long long)__double_as_longlong(v));
+}
+// 1/x for x >= 1 to ~2 ulp: float seed + two Newton steps (the IEEE division costs ~4x more)
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y = (double)__frcp_rn((float)x);
+  y = y * fma(-x, y, 2.0);
+  y = y * fma(-x, y, 2.0);
+  return y;
 }
 // corner offsets of the cell-corner order (0,0,0)(1,0,0)(1,1,0)(0,1,0)(0,0,1)(1,0,1)(1,1,1)(0,1,1) as arithmetic
 __device__ __forceinline__ int cox(int c) { return ((c + 1) >> 1) & 1; }
@@ -64,6 +71,18 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
                                                                               double *__restrict__ M) {
   __shared__ __align__(16) double sRows[DEP_WARPS][SLAB];
   __shared__ double sBall[DEP_WARPS][27 * 3];  // B_cur on the 3x3x3 centres around the warp's cell
+  // flush tables: output o = (c*8+c')*9+col -> corner c (3 bits) | offset inside M[corner] (8 bits) | T index (9 bits)
+  __shared__ unsigned int sFlush[576];
+  __shared__ unsigned short sJcls[64];  // T index (without column) of pair (c,c')
+  __shared__ double sQdt2m[AMPS_GPU_MAX_SPECIES];
+  if (threadIdx.x < AMPS_GPU_MAX_SPECIES)
+    sQdt2m[threadIdx.x] = (threadIdx.x < sp.n) ? 0.5 * (sp.charge[threadIdx.x] * sp.dtTotal / sp.mass[threadIdx.x]) : 0.0;
+  for (int o = threadIdx.x; o < 576; o += DEP_THREADS) {
+    const int c = o / 72, r = o - 72 * c, d = r / 9, col = r - 9 * d;
+    sFlush[o] = (unsigned)c | ((unsigned)(9 * index_matrix(c, d) + col) << 3) | ((unsigned)(pair_class(c, d) * 12 + col) << 11);
+    if (o < 64) sJcls[o] = (unsigned short)(pair_class(o >> 3, o & 7) * 12);
+  }
+  __syncthreads();
 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warpGlobal = blockIdx.x * DEP_WARPS + wib, nWarps = gridDim.x * DEP_WARPS;
@@ -107,16 +126,30 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
 #pragma unroll
     for (int i = 0; i < 54; i++) acc[i] = 0.0;
 
+    // software prefetch: the particle of the NEXT chunk is loaded while phase 2 of the current one runs
+    double nx0 = 0, nx1 = 0, nx2 = 0, nv0 = 0, nv1 = 0, nv2 = 0, nw = 0;
+    int nspec = 0;
+    if (begin + lane < end) {
+      const int ip = begin + lane;
+      nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
+      nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
+      nw = p.w[ip], nspec = p.spec[ip];
+    }
     for (int base = begin; base < end; base += CHUNK) {
       const int np = min(CHUNK, end - base);
       __syncwarp();  // sB visible; previous chunk consumed
       // ---------------- phase 1: lane <-> particle ----------------
+      const double x0 = nx0, x1 = nx1, x2 = nx2, pw = nw;
+      double v0 = nv0, v1 = nv1, v2 = nv2;
+      const int spec = nspec;
+      if (base + CHUNK + lane < end) {
+        const int ip = base + CHUNK + lane;
+        nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
+        nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
+        nw = p.w[ip], nspec = p.spec[ip];
+      }
       if (lane < np) {
-        const int ip = base + lane;
-        const double x0 = p.x[0][ip], x1 = p.x[1][ip], x2 = p.x[2][ip];
-        double v0 = p.v[0][ip], v1 = p.v[1][ip], v2 = p.v[2][ip];
-        const int spec = p.spec[ip];
-        const double LocalParticleWeight = sp.weight[spec] * p.w[ip];
+        const double LocalParticleWeight = sp.weight[spec] * pw;
         double *row = rows + lane * ROW;
         // local coordinates: CornerBased::InitStencil (pic_interpolation_routines.cpp:1090-1098)
         double xl[3];
@@ -193,11 +226,11 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
         }
         v0 *= sp.length_conv, v1 *= sp.length_conv, v2 *= sp.length_conv;
         const double chargeQ = sp.charge[spec] * LocalParticleWeight;
-        const double mass = sp.mass[spec] * LocalParticleWeight;
-        const double QdT_over_2m = 0.5 * (chargeQ * sp.dtTotal / mass);
+        // beta = q~ dt / 2 m~ : the statistical weight cancels (to 1 ulp), so it is a per-species constant
+        const double QdT_over_2m = sQdt2m[spec];
         const double s2 = QdT_over_2m * QdT_over_2m;
         const double P0 = -QdT_over_2m * B0, P1 = -QdT_over_2m * B1, P2 = -QdT_over_2m * B2;
-        const double c0 = 1.0 / (1.0 + s2 * (B0 * B0 + B1 * B1 + B2 * B2));
+        const double c0 = fast_rcp(1.0 + s2 * (B0 * B0 + B1 * B1 + B2 * B2));
         double al[9];
         al[0] = c0 * (1.0 + s2 * B0 * B0);
         al[1] = c0 * (-P2 + s2 * B0 * B1);
@@ -251,9 +284,12 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
 #pragma unroll
     for (int i = 0; i < 54; i++) {
       double v = acc[i];
-      v += __shfl_down_sync(0xffffffffu, (lane >= 24 && lane < 30) ? v : 0.0, 24);
-      v += __shfl_down_sync(0xffffffffu, (lane >= 12 && lane < 24) ? v : 0.0, 12);
-      v += __shfl_down_sync(0xffffffffu, (lane >= 6 && lane < 12) ? v : 0.0, 6);
+      double t2 = __shfl_down_sync(0xffffffffu, v, 24);
+      if (lane < 6) v += t2;
+      t2 = __shfl_down_sync(0xffffffffu, v, 12);
+      if (lane < 12) v += t2;
+      t2 = __shfl_down_sync(0xffffffffu, v, 6);
+      if (lane < 6) v += t2;
       acc[i] = v;
     }
     __syncwarp();  // phase 2 finished reading the slab
@@ -269,11 +305,11 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     }
     __syncwarp();
     // ---- flush the mass matrix: 64 ordered corner pairs x 9 (both (c,c') and (c',c) get the same block, :2411-2420)
-#pragma unroll 2
+#pragma unroll 6
     for (int o = lane; o < 576; o += 32) {
-      const int c = o / 72, r = o - 72 * c, d = r / 9, col = r - 9 * d;
-      const int ui = __shfl_sync(0xffffffffu, uidLane, c);
-      atomicAdd(M + (size_t)ui * 243 + 9 * index_matrix(c, d) + col, rows[pair_class(c, d) * 12 + col]);
+      const unsigned e = sFlush[o];
+      const int ui = __shfl_sync(0xffffffffu, uidLane, e & 7u);
+      atomicAdd(M + (size_t)ui * 243 + ((e >> 3) & 255u), rows[e >> 11]);
     }
     // ---- current: J[c] = sum_c' T[cls(c,c')][9..11] ----
     {
@@ -282,7 +318,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
       if (lane < 24) {
         double val = 0.0;
 #pragma unroll
-        for (int d = 0; d < 8; d++) val += rows[pair_class(c, d) * 12 + 9 + dcol];
+        for (int d = 0; d < 8; d++) val += rows[sJcls[c * 8 + d] + 9 + dcol];
         atomicAdd(J + (size_t)ui * 3 + dcol, val);
       }
     }
