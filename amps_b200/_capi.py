@@ -86,6 +86,12 @@ class Mesh(C.Structure):
         ("n_centers", C.c_int32),
         ("leaf_corner_uid", _i32p),
         ("leaf_center_uid", _i32p),
+        ("this_rank", C.c_int32),
+        ("n_ranks", C.c_int32),
+        ("n_global_leaves", C.c_int32),
+        ("leaf_owner", _i32p),
+        ("leaf_global_id", _i32p),
+        ("global_leaf_to_local", _i32p),
     ]
 
 
@@ -138,6 +144,11 @@ PROTOTYPES = {
     "amps_gpu_deposit_JM": (C.c_int, [_vp, _vp, _vp]),
     "amps_gpu_JM_download": (C.c_int, [_vp, _vp, _vp]),
     "amps_gpu_JM_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "amps_gpu_comm_unique_id": (C.c_int, [_vp]),
+    "amps_gpu_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "amps_gpu_set_shared_corners": (C.c_int, [_vp, C.c_int, _vp, C.c_int64]),
+    "amps_gpu_migrate": (C.c_int, [_vp, _i64p, _i64p]),
+    "amps_gpu_exchange_JM": (C.c_int, [_vp]),
     "amps_gpu_step": (C.c_int, [_vp, C.c_int]),
     "amps_gpu_profile": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "amps_gpu_selftest_division": (C.c_int, [_vp, _vp, _vp, C.c_int64, _i64p]),

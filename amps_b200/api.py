@@ -156,6 +156,42 @@ class Context:
     def step(self, mover=_capi.MOVER_LAPENTA2017):
         self._ck(self.lib.amps_gpu_step(self._h, mover))
 
+    # ---- multi-GPU (one rank per GPU) -------------------------------------------------------
+    def comm_init(self, dist):
+        """Join the library's NCCL communicator; `dist` = torch.distributed (initialised) used only to broadcast the id
+        and to gather the corner keys that define the J/M exchange lists."""
+        import torch
+
+        from . import mesh as meshmod
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        assert rank == self.mesh.rank and world == self.mesh.n_ranks
+        idbuf = (C.c_ubyte * 128)()
+        if rank == 0:
+            rc = self.lib.amps_gpu_comm_unique_id(C.cast(idbuf, C.c_void_p))
+            if rc != _capi.OK:
+                raise AmpsGpuError("amps_gpu_comm_unique_id failed: libnccl.so.2 not loadable")
+        obj = [bytes(idbuf) if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        idbuf = (C.c_ubyte * 128).from_buffer_copy(obj[0])
+        self._ck(self.lib.amps_gpu_comm_init(self._h, C.cast(idbuf, C.c_void_p), rank, world))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, self.mesh.corner_target_gkeys)
+        lists = meshmod.shared_corner_lists(self.mesh, gathered)
+        for peer, uids in lists.items():
+            uids = np.ascontiguousarray(uids, dtype=np.int32)
+            self._ck(self.lib.amps_gpu_set_shared_corners(self._h, peer, _ptr(uids), uids.size))
+        self.shared_lists = lists
+        return lists
+
+    def migrate(self):
+        ns, nr = C.c_int64(), C.c_int64()
+        self._ck(self.lib.amps_gpu_migrate(self._h, C.byref(ns), C.byref(nr)))
+        return int(ns.value), int(nr.value)
+
+    def exchange_JM(self):
+        self._ck(self.lib.amps_gpu_exchange_JM(self._h))
+
     PHASES = ("move", "sort", "deposit", "exchange")
 
     def profile(self, enable=True):

@@ -99,6 +99,12 @@ void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
                     double *energy, unsigned long long *cflBits, int nSM, cudaStream_t s, long long *launches);
 size_t sort_scan_tmp_bytes(long long nCells);
+void launch_pack_leavers(const DevMesh &m, ParticleSoA p, const int *nSlots, long long nUpper, const int *leafOwner, const int *leafGlobal, int me,
+                         double *sendBuf, long long capPerPeer, int *sendCount, int *cellCount, int *errFlag, cudaStream_t s);
+void launch_unpack_arrivals(const DevMesh &m, const double *recvBuf, int nRecv, ParticleSoA p, int *nSlots, const int *g2l, const int *leafOwner, int me,
+                            long long capacity, int *cellCount, int *errFlag, cudaStream_t s);
+void launch_pack_corners(const int *uids, int n, const double *J, const double *M, double *buf, cudaStream_t s);
+void launch_add_corners(const int *uids, int n, double *J, double *M, const double *buf, cudaStream_t s);
 void launch_division_selftest(const double *a, const double *b, int n, unsigned long long *out, cudaStream_t s);
 
 }  // namespace amps

@@ -1,6 +1,9 @@
 // amps_gpu.cu -- host side of the C ABI declared in include/amps_gpu.h: context, device memory,
 // uploads/downloads and kernel sequencing.  No CPU fallback anywhere: without a CUDA device
 // amps_gpu_init() fails with AMPS_GPU_ERR_NO_DEVICE.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -41,6 +44,18 @@ struct amps_gpu_ctx {
   double *d_J = nullptr, *d_M = nullptr, *d_energy = nullptr;
   unsigned long long *d_cfl = nullptr;
   DevMoveStats *d_stats = nullptr;
+
+  // domain decomposition / NCCL
+  int rank = 0, nRanks = 1;
+  int *d_leafOwner = nullptr, *d_leafGlobal = nullptr, *d_g2l = nullptr;
+  ncclComm_t comm = nullptr;
+  double *d_sendBuf = nullptr, *d_recvBuf = nullptr;
+  long long capPerPeer = 0;
+  int *d_sendCount = nullptr, *d_allCounts = nullptr, *d_errFlag = nullptr;
+  std::vector<int *> d_sharedUid;      // per peer
+  std::vector<long long> nShared;      // per peer
+  double *d_cornerSend = nullptr, *d_cornerRecv = nullptr;
+  long long cornerBufDoubles = 0;
 
   // phase profiling (CUDA events on ctx->stream around move / sort / deposit)
   bool profile = false;
@@ -123,6 +138,55 @@ static int upload_array(amps_gpu_ctx *ctx, const T **dst, const T *src, size_t n
   return AMPS_GPU_OK;
 }
 
+// ---- NCCL resolved at run time: the library has no link-time dependency on libnccl, and inside a process that
+//      already loaded one (torch's bundled copy) the same instance is reused ----
+struct NcclApi {
+  void *h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+static NcclApi &nccl_api() {
+  static NcclApi a;
+  if (a.h || a.ok) return a;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    a.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (a.h) break;
+  }
+  if (!a.h) return a;
+#define LOADSYM(field, sym) a.field = reinterpret_cast<decltype(a.field)>(dlsym(a.h, sym))
+  LOADSYM(GetUniqueId, "ncclGetUniqueId");
+  LOADSYM(CommInitRank, "ncclCommInitRank");
+  LOADSYM(CommDestroy, "ncclCommDestroy");
+  LOADSYM(GroupStart, "ncclGroupStart");
+  LOADSYM(GroupEnd, "ncclGroupEnd");
+  LOADSYM(Send, "ncclSend");
+  LOADSYM(Recv, "ncclRecv");
+  LOADSYM(AllGather, "ncclAllGather");
+  LOADSYM(AllReduce, "ncclAllReduce");
+  LOADSYM(GetErrorString, "ncclGetErrorString");
+#undef LOADSYM
+  a.ok = a.GetUniqueId && a.CommInitRank && a.GroupStart && a.GroupEnd && a.Send && a.Recv && a.AllGather && a.AllReduce;
+  return a;
+}
+#define NCK(call)                                                                                            \
+  do {                                                                                                       \
+    ncclResult_t r_ = (call);                                                                                \
+    if (r_ != ncclSuccess) {                                                                                 \
+      ctx->err = std::string(#call) + ": " + (nccl_api().GetErrorString ? nccl_api().GetErrorString(r_) : "nccl error"); \
+      return AMPS_GPU_ERR_CUDA;                                                                              \
+    }                                                                                                        \
+  } while (0)
+
 extern "C" {
 
 int amps_gpu_init(const amps_gpu_config *cfg, amps_gpu_ctx **out) {
@@ -179,6 +243,10 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (void *p : ctx->meshAllocs) cudaFree(p);
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
+  if (ctx->comm && nccl_api().CommDestroy) nccl_api().CommDestroy(ctx->comm);
+  cudaFree(ctx->d_sendBuf), cudaFree(ctx->d_recvBuf), cudaFree(ctx->d_sendCount), cudaFree(ctx->d_allCounts), cudaFree(ctx->d_errFlag);
+  for (int *p : ctx->d_sharedUid) cudaFree(p);
+  cudaFree(ctx->d_cornerSend), cudaFree(ctx->d_cornerRecv);
   cudaFree(ctx->d_Ehalf), cudaFree(ctx->d_Bprev), cudaFree(ctx->d_Bcur);
   cudaFree(ctx->d_eTile), cudaFree(ctx->d_bPrevTile), cudaFree(ctx->d_bCurTile);
   for (int b = 0; b < 2; b++) free_particles(ctx->buf[b]);
@@ -268,6 +336,26 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
   if ((rc = upload_array(ctx, &m.leaf, lg.data(), (size_t)m.nLeaves))) return rc;
   if ((rc = upload_array(ctx, &m.cornerUid, mesh->leaf_corner_uid, (size_t)m.nLeaves * m.nCornerLocal))) return rc;
   if ((rc = upload_array(ctx, &m.centerUid, mesh->leaf_center_uid, (size_t)m.nLeaves * m.nCenterLocal))) return rc;
+  ctx->rank = (mesh->n_ranks > 1) ? mesh->this_rank : 0;
+  ctx->nRanks = (mesh->n_ranks > 1) ? mesh->n_ranks : 1;
+  if (ctx->nRanks > 1) {
+    if (!mesh->leaf_owner || !mesh->leaf_global_id || !mesh->global_leaf_to_local || mesh->n_global_leaves < 1)
+      FAIL(AMPS_GPU_ERR_ARG, "n_ranks > 1 needs leaf_owner, leaf_global_id and global_leaf_to_local");
+    const int *t1, *t2, *t3;
+    if ((rc = upload_array(ctx, &t1, mesh->leaf_owner, (size_t)m.nLeaves))) return rc;
+    if ((rc = upload_array(ctx, &t2, mesh->leaf_global_id, (size_t)m.nLeaves))) return rc;
+    if ((rc = upload_array(ctx, &t3, mesh->global_leaf_to_local, (size_t)mesh->n_global_leaves))) return rc;
+    ctx->d_leafOwner = const_cast<int *>(t1), ctx->d_leafGlobal = const_cast<int *>(t2), ctx->d_g2l = const_cast<int *>(t3);
+    ctx->capPerPeer = ctx->cfg.capacity / 32 > 65536 ? ctx->cfg.capacity / 32 : 65536;
+    if ((rc = dev_alloc(ctx, &ctx->d_sendBuf, (size_t)ctx->nRanks * ctx->capPerPeer * 8))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_recvBuf, (size_t)ctx->nRanks * ctx->capPerPeer * 8))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_sendCount, (size_t)ctx->nRanks))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_allCounts, (size_t)ctx->nRanks * ctx->nRanks))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_errFlag, 1))) return rc;
+    CK(cudaMemsetAsync(ctx->d_errFlag, 0, sizeof(int), ctx->stream));
+    ctx->d_sharedUid.assign(ctx->nRanks, nullptr);
+    ctx->nShared.assign(ctx->nRanks, 0);
+  }
   CK(cudaStreamSynchronize(ctx->stream));  // lg is a local
 
   if ((rc = dev_alloc(ctx, &ctx->d_Ehalf, (size_t)3 * m.nCorners))) return rc;
@@ -598,13 +686,159 @@ int amps_gpu_selftest_division(amps_gpu_ctx *ctx, const double *a, const double 
   return AMPS_GPU_OK;
 }
 
+int amps_gpu_comm_unique_id(void *id128) {
+  if (!id128) return AMPS_GPU_ERR_ARG;
+  NcclApi &a = nccl_api();
+  if (!a.ok) return AMPS_GPU_ERR_STATE;
+  ncclUniqueId id;
+  if (a.GetUniqueId(&id) != ncclSuccess) return AMPS_GPU_ERR_CUDA;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, 128);
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_comm_init(amps_gpu_ctx *ctx, const void *id128, int rank, int n_ranks) {
+  if (!ctx || !id128) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "comm_init before mesh_upload");
+  if (rank != ctx->rank || n_ranks != ctx->nRanks) FAIL(AMPS_GPU_ERR_ARG, "rank / n_ranks differ from the mesh description");
+  NcclApi &a = nccl_api();
+  if (!a.ok) FAIL(AMPS_GPU_ERR_STATE, "libnccl.so.2 could not be loaded");
+  CK(cudaSetDevice(ctx->cfg.device));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  NCK(a.CommInitRank(&ctx->comm, n_ranks, id, rank));
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_set_shared_corners(amps_gpu_ctx *ctx, int peer, const int32_t *uids, int64_t n) {
+  if (!ctx || peer < 0 || n < 0 || (n > 0 && !uids)) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady || ctx->nRanks <= 1 || peer >= ctx->nRanks || peer == ctx->rank) FAIL(AMPS_GPU_ERR_ARG, "bad peer");
+  CK(cudaSetDevice(ctx->cfg.device));
+  for (int64_t i = 0; i < n; i++)
+    if (uids[i] < 0 || uids[i] >= ctx->dm.nCorners) FAIL(AMPS_GPU_ERR_ARG, "shared corner id out of range");
+  cudaFree(ctx->d_sharedUid[peer]);
+  ctx->d_sharedUid[peer] = nullptr;
+  ctx->nShared[peer] = n;
+  if (n) {
+    CK(cudaMalloc(&ctx->d_sharedUid[peer], n * sizeof(int)));
+    CK(cudaMemcpy(ctx->d_sharedUid[peer], uids, n * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  long long tot = 0;
+  for (long long v : ctx->nShared) tot += v;
+  if (tot * 246 > ctx->cornerBufDoubles) {
+    cudaFree(ctx->d_cornerSend), cudaFree(ctx->d_cornerRecv);
+    ctx->cornerBufDoubles = tot * 246;
+    CK(cudaMalloc(&ctx->d_cornerSend, ctx->cornerBufDoubles * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_cornerRecv, ctx->cornerBufDoubles * sizeof(double)));
+  }
+  return AMPS_GPU_OK;
+}
+
+static int do_migrate(amps_gpu_ctx *ctx, int64_t *n_sent, int64_t *n_received) {
+  if (n_sent) *n_sent = 0;
+  if (n_received) *n_received = 0;
+  if (ctx->nRanks <= 1) return AMPS_GPU_OK;
+  if (!ctx->comm) FAIL(AMPS_GPU_ERR_STATE, "migrate before amps_gpu_comm_init");
+  if (!ctx->countValid) FAIL(AMPS_GPU_ERR_STATE, "migrate must follow amps_gpu_move (it edits the mover's cell histogram)");
+  ProfScope prof(ctx, AMPS_GPU_PHASE_EXCHANGE);
+  NcclApi &a = nccl_api();
+  const int R = ctx->nRanks, me = ctx->rank;
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemsetAsync(ctx->d_sendCount, 0, sizeof(int) * R, s));
+  launch_pack_leavers(ctx->dm, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper, ctx->d_leafOwner, ctx->d_leafGlobal, me, ctx->d_sendBuf,
+                      ctx->capPerPeer, ctx->d_sendCount, ctx->d_cellCount, ctx->d_errFlag, s);
+  ctx->launches++;
+  // counts: every rank learns the whole R x R matrix (the reference's first message, pic_parallel.cpp:267-301)
+  NCK(a.AllGather(ctx->d_sendCount, ctx->d_allCounts, R, ncclInt, ctx->comm, s));
+  std::vector<int> all((size_t)R * R);
+  int err = 0;
+  CK(cudaMemcpyAsync(all.data(), ctx->d_allCounts, sizeof(int) * R * R, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&err, ctx->d_errFlag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (err) FAIL(AMPS_GPU_ERR_CAPACITY, "migration send buffer overflow (more than capacity/32 leavers to one rank)");
+  long long nRecv = 0, nSend = 0;
+  std::vector<long long> roff(R, 0);
+  for (int r = 0; r < R; r++) {
+    roff[r] = nRecv;
+    if (r != me) nRecv += all[(size_t)r * R + me], nSend += all[(size_t)me * R + r];
+  }
+  if (nRecv > (long long)R * ctx->capPerPeer) FAIL(AMPS_GPU_ERR_CAPACITY, "migration receive buffer overflow");
+  NCK(a.GroupStart());
+  for (int r = 0; r < R; r++) {
+    if (r == me) continue;
+    const int ns = all[(size_t)me * R + r], nr = all[(size_t)r * R + me];
+    if (ns > 0) NCK(a.Send(ctx->d_sendBuf + (size_t)r * ctx->capPerPeer * 8, (size_t)ns * 8, ncclDouble, r, ctx->comm, s));
+    if (nr > 0) NCK(a.Recv(ctx->d_recvBuf + (size_t)roff[r] * 8, (size_t)nr * 8, ncclDouble, r, ctx->comm, s));
+  }
+  NCK(a.GroupEnd());
+  if (ctx->nUpper + nRecv > ctx->cfg.capacity) FAIL(AMPS_GPU_ERR_CAPACITY, "particle capacity exceeded by arriving particles");
+  launch_unpack_arrivals(ctx->dm, ctx->d_recvBuf, (int)nRecv, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->d_g2l, ctx->d_leafOwner, me,
+                         ctx->cfg.capacity, ctx->d_cellCount, ctx->d_errFlag, s);
+  if (nRecv) ctx->launches += 2;
+  ctx->nUpper += nRecv;
+  CK(cudaGetLastError());
+  if (n_sent) *n_sent = nSend;
+  if (n_received) *n_received = nRecv;
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_migrate(amps_gpu_ctx *ctx, int64_t *n_sent, int64_t *n_received) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  return do_migrate(ctx, n_sent, n_received);
+}
+
+static int do_exchange_JM(amps_gpu_ctx *ctx) {
+  if (ctx->nRanks <= 1) return AMPS_GPU_OK;
+  if (!ctx->comm) FAIL(AMPS_GPU_ERR_STATE, "exchange_JM before amps_gpu_comm_init");
+  ProfScope prof(ctx, AMPS_GPU_PHASE_EXCHANGE);
+  NcclApi &a = nccl_api();
+  const int R = ctx->nRanks, me = ctx->rank;
+  cudaStream_t s = ctx->stream;
+  // all partial sums are packed before any is added, so every sharer ends with the same total
+  long long off = 0;
+  std::vector<long long> offs(R, 0);
+  for (int r = 0; r < R; r++) {
+    offs[r] = off;
+    if (r == me || ctx->nShared[r] == 0) continue;
+    launch_pack_corners(ctx->d_sharedUid[r], (int)ctx->nShared[r], ctx->d_J, ctx->d_M, ctx->d_cornerSend + off * 246, s);
+    ctx->launches++;
+    off += ctx->nShared[r];
+  }
+  NCK(a.GroupStart());
+  for (int r = 0; r < R; r++) {
+    if (r == me || ctx->nShared[r] == 0) continue;
+    NCK(a.Send(ctx->d_cornerSend + offs[r] * 246, (size_t)ctx->nShared[r] * 246, ncclDouble, r, ctx->comm, s));
+    NCK(a.Recv(ctx->d_cornerRecv + offs[r] * 246, (size_t)ctx->nShared[r] * 246, ncclDouble, r, ctx->comm, s));
+  }
+  NCK(a.GroupEnd());
+  for (int r = 0; r < R; r++) {
+    if (r == me || ctx->nShared[r] == 0) continue;
+    launch_add_corners(ctx->d_sharedUid[r], (int)ctx->nShared[r], ctx->d_J, ctx->d_M, ctx->d_cornerRecv + offs[r] * 246, s);
+    ctx->launches++;
+  }
+  // MPI_Reduce(ParticleEnergy, SUM), MPI_Reduce(cfl, MAX): non-negative doubles order like their bit patterns
+  NCK(a.AllReduce(ctx->d_energy, ctx->d_energy, 1, ncclDouble, ncclSum, ctx->comm, s));
+  NCK(a.AllReduce(ctx->d_cfl, ctx->d_cfl, AMPS_GPU_MAX_SPECIES, ncclUint64, ncclMax, ctx->comm, s));
+  CK(cudaGetLastError());
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_exchange_JM(amps_gpu_ctx *ctx) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  return do_exchange_JM(ctx);
+}
+
 int amps_gpu_step(amps_gpu_ctx *ctx, int mover_id) {
   if (!ctx) return AMPS_GPU_ERR_ARG;
   CK(cudaSetDevice(ctx->cfg.device));
   int rc;
   if ((rc = do_move(ctx, mover_id))) return rc;
+  if ((rc = do_migrate(ctx, nullptr, nullptr))) return rc;
   if ((rc = do_sort(ctx))) return rc;
-  return do_deposit(ctx);
+  if ((rc = do_deposit(ctx))) return rc;
+  return do_exchange_JM(ctx);
 }
 
 }  // extern "C"

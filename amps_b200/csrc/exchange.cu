@@ -1,0 +1,120 @@
+// exchange.cu -- device side of the cross-rank exchanges (sm_100a), one rank per GPU.
+//
+//   a17 PIC::Parallel::ExchangeParticleData   src/pic/pic_parallel.cpp:50-488
+//       The reference walks the per-cell lists of the boundary-layer blocks and sends {cell descriptor,
+//       particle bytes}; here the mover has already written the new (block,cell) key of every particle, so a
+//       leaver is any particle whose block is owned by another rank: it is appended to that rank's send
+//       buffer (8 doubles: x,v,w and the GLOBAL cell id + species), removed from the local histogram and
+//       marked deleted.  Arrivals are appended behind the resident particles with their key translated to the
+//       local block numbering and counted into the histogram; the counting sort that follows files them.
+//   a12 SyncMassMatrix / ProcessJMassMatrix    src/pic/ecsim/halo_sync.cpp:79-124, pic_field_solver_ecsim.cpp:1383
+//       corners that two ranks deposit into exchange their partial J[3], M[243] and add.
+// The transfers themselves are NCCL send/recv over NVLink issued by amps_gpu.cu on the context's stream.
+#include "amps_dev.cuh"
+
+namespace amps {
+
+__global__ void __launch_bounds__(256) pack_leavers_kernel(ParticleSoA p, const int *__restrict__ nSlots, const int *__restrict__ leafOwner,
+                                                          const int *__restrict__ leafGlobal, int C, int me, double *__restrict__ sendBuf,
+                                                          long long capPerPeer, int *__restrict__ sendCount, int *__restrict__ cellCount,
+                                                          int *__restrict__ errFlag) {
+  const int n = *nSlots;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int k = p.key[i];
+    if (k < 0) continue;
+    const int leaf = k / C;
+    const int dest = leafOwner[leaf];
+    if (dest == me) continue;
+    const int slot = atomicAdd(&sendCount[dest], 1);
+    if (slot >= capPerPeer) {
+      atomicExch(errFlag, 1);
+      continue;  // the particle stays (in a foreign block); the host reports AMPS_GPU_ERR_CAPACITY
+    }
+    double *r = sendBuf + ((size_t)dest * capPerPeer + slot) * 8;
+    const long long gkey = (long long)leafGlobal[leaf] * C + (k - leaf * C);
+    r[0] = p.x[0][i], r[1] = p.x[1][i], r[2] = p.x[2][i];
+    r[3] = p.v[0][i], r[4] = p.v[1][i], r[5] = p.v[2][i];
+    r[6] = p.w[i];
+    r[7] = __longlong_as_double((gkey << 8) | (long long)p.spec[i]);
+    atomicSub(&cellCount[k], 1);
+    p.key[i] = -1;
+  }
+}
+
+__global__ void __launch_bounds__(256) unpack_arrivals_kernel(const double *__restrict__ recvBuf, int nRecv, ParticleSoA p, int *__restrict__ nSlots,
+                                                             const int *__restrict__ g2l, const int *__restrict__ leafOwner, int C, int me,
+                                                             long long capacity, int *__restrict__ cellCount, int *__restrict__ errFlag) {
+  const int base = *nSlots;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nRecv; j += gridDim.x * blockDim.x) {
+    const double *r = recvBuf + (size_t)j * 8;
+    const long long meta = __double_as_longlong(r[7]);
+    const long long gkey = meta >> 8;
+    const int gleaf = (int)(gkey / C);
+    const int leaf = g2l[gleaf];
+    const long long i = (long long)base + j;
+    if (leaf < 0 || leafOwner[leaf] != me || i >= capacity) {
+      atomicExch(errFlag, 2);
+      if (i < capacity) p.key[i] = -1;
+      continue;
+    }
+    const int k = leaf * C + (int)(gkey - (long long)gleaf * C);
+    p.x[0][i] = r[0], p.x[1][i] = r[1], p.x[2][i] = r[2];
+    p.v[0][i] = r[3], p.v[1][i] = r[4], p.v[2][i] = r[5];
+    p.w[i] = r[6];
+    p.spec[i] = (uint8_t)(meta & 0xff);
+    p.key[i] = k;
+    p.ptr[i] = -1;  // no ParticleBuffer slot on this rank yet (GetNewParticle on download)
+    atomicAdd(&cellCount[k], 1);
+  }
+}
+__global__ void bump_count_kernel(int *nSlots, int nRecv, long long capacity) {
+  long long v = (long long)*nSlots + nRecv;
+  *nSlots = (int)(v > capacity ? capacity : v);
+}
+
+__global__ void __launch_bounds__(256) pack_corners_kernel(const int *__restrict__ uids, int n, const double *__restrict__ J,
+                                                          const double *__restrict__ M, double *__restrict__ buf) {
+  const long long total = (long long)n * 246;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e / 246), q = (int)(e - (long long)c * 246);
+    const int u = uids[c];
+    buf[e] = (q < 3) ? J[(size_t)u * 3 + q] : M[(size_t)u * 243 + (q - 3)];
+  }
+}
+__global__ void __launch_bounds__(256) add_corners_kernel(const int *__restrict__ uids, int n, double *__restrict__ J, double *__restrict__ M,
+                                                         const double *__restrict__ buf) {
+  const long long total = (long long)n * 246;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e / 246), q = (int)(e - (long long)c * 246);
+    const int u = uids[c];
+    if (q < 3) J[(size_t)u * 3 + q] += buf[e];
+    else M[(size_t)u * 243 + (q - 3)] += buf[e];
+  }
+}
+
+static inline int grid_for(long long n) {
+  long long g = (n + 255) / 256;
+  if (g < 1) g = 1;
+  if (g > 148 * 16) g = 148 * 16;
+  return (int)g;
+}
+
+void launch_pack_leavers(const DevMesh &m, ParticleSoA p, const int *nSlots, long long nUpper, const int *leafOwner, const int *leafGlobal, int me,
+                         double *sendBuf, long long capPerPeer, int *sendCount, int *cellCount, int *errFlag, cudaStream_t s) {
+  pack_leavers_kernel<<<grid_for(nUpper), 256, 0, s>>>(p, nSlots, leafOwner, leafGlobal, m.cellsPerBlock, me, sendBuf, capPerPeer, sendCount, cellCount,
+                                                      errFlag);
+}
+void launch_unpack_arrivals(const DevMesh &m, const double *recvBuf, int nRecv, ParticleSoA p, int *nSlots, const int *g2l, const int *leafOwner, int me,
+                            long long capacity, int *cellCount, int *errFlag, cudaStream_t s) {
+  if (nRecv <= 0) return;
+  unpack_arrivals_kernel<<<grid_for(nRecv), 256, 0, s>>>(recvBuf, nRecv, p, nSlots, g2l, leafOwner, m.cellsPerBlock, me, capacity, cellCount, errFlag);
+  bump_count_kernel<<<1, 1, 0, s>>>(nSlots, nRecv, capacity);
+}
+void launch_pack_corners(const int *uids, int n, const double *J, const double *M, double *buf, cudaStream_t s) {
+  if (n > 0) pack_corners_kernel<<<grid_for((long long)n * 246), 256, 0, s>>>(uids, n, J, M, buf);
+}
+void launch_add_corners(const int *uids, int n, double *J, double *M, const double *buf, cudaStream_t s) {
+  if (n > 0) add_corners_kernel<<<grid_for((long long)n * 246), 256, 0, s>>>(uids, n, J, M, buf);
+}
+
+}  // namespace amps

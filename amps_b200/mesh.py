@@ -64,9 +64,11 @@ class FlatMesh:
         return self.arrays["node_xmax"].reshape(-1, 3)[self.arrays["leaf_node"]]
 
     def real_leaves(self):
-        """leaves that hold particles (used, not periodic ghosts)."""
+        """leaves that hold particles on this rank (used, not periodic ghosts, owned)."""
         fl = self.arrays["node_flags"][self.arrays["leaf_node"]]
-        return np.nonzero(((fl & _capi.NODE_USED) != 0) & ((fl & _capi.NODE_PERIODIC_GHOST) == 0))[0]
+        ok = ((fl & _capi.NODE_USED) != 0) & ((fl & _capi.NODE_PERIODIC_GHOST) == 0)
+        ok &= self.arrays["leaf_owner"] == self.rank
+        return np.nonzero(ok)[0]
 
 
 def _local_numbers(N, g, corner):
@@ -77,14 +79,19 @@ def _local_numbers(N, g, corner):
 
 
 def build_mesh(xmin, xmax, n_blocks, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), periodic=True,
-               max_refinement_level=12, refine=None, max_level=0, this_thread=0, owner=None):
+               max_refinement_level=12, refine=None, max_level=0, rank=0, n_ranks=1, decomp=None):
     """Flatten a box mesh.
 
     xmin/xmax     user ("original") domain
     n_blocks      level-0 blocks per dimension inside the user domain
     refine        callable(level, xmin[3], xmax[3]) -> bool : split this block? (AMR)
     max_level     deepest level ``refine`` may produce
-    owner         callable(leaf_xmin, leaf_xmax) -> rank (domain decomposition); default all on rank 0
+    rank,n_ranks  this process and the number of processes (one per GPU)
+    decomp        (px,py,pz) Cartesian split of the user domain, px*py*pz == n_ranks.  Like the reference's
+                  space-filling-curve chunks (meshAMRgeneric.h:11787) every rank owns a contiguous set of blocks;
+                  the rank keeps the whole tree but allocates only its own blocks, the blocks around them
+                  (DomainBoundaryLayerNodesList, meshAMRgeneric.h:1812) and the real images of adjacent
+                  periodic ghost blocks.
     """
     N = np.asarray(block_cells, dtype=np.int64)
     g = np.asarray(ghost_cells, dtype=np.int64)
@@ -158,13 +165,13 @@ def build_mesh(xmin, xmax, n_blocks, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1
     nxmax = np.array(nxmax, dtype=np.float64)
     flags = np.array(flags, dtype=np.int32)
     is_leaf = (child < 0).all(axis=1)
-    leaf_node = np.nonzero(is_leaf)[0].astype(np.int32)
-    n_leaves = len(leaf_node)
-    node_leaf = -np.ones(n_nodes, dtype=np.int32)
-    node_leaf[leaf_node] = np.arange(n_leaves, dtype=np.int32)
+    gleaf_node = np.nonzero(is_leaf)[0].astype(np.int32)  # global leaf list (same on every rank)
+    n_gleaves = len(gleaf_node)
+    node_gleaf = -np.ones(n_nodes, dtype=np.int32)
+    node_gleaf[gleaf_node] = np.arange(n_gleaves, dtype=np.int32)
 
     # ---- leaf lookup by lattice point (host mirror of findTreeNode) ---------
-    def find_leaf_ix(ix):
+    def find_gleaf_ix(ix):
         r = [ix[d] // S for d in range(3)]
         if any(ix[d] < 0 or r[d] >= n_root[d] for d in range(3)):
             return -1
@@ -173,87 +180,156 @@ def build_mesh(xmin, xmax, n_blocks, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1
             h = isize[n] // 2
             o = [0 if ix[d] - imin[n, d] < h else 1 for d in range(3)]
             n = child[n, o[0] + 2 * (o[1] + 2 * o[2])]
-        return int(node_leaf[n])
+        return int(node_gleaf[n])
+
+    gli = imin[gleaf_node].astype(np.int64)
+    gls = isize[gleaf_node].astype(np.int64)
+    tot = n_root * S
+    gflags = flags[gleaf_node]
+    g_is_ghost = (gflags & _capi.NODE_PERIODIC_GHOST) != 0
+
+    # ---- periodic pairing on the global leaf list (findCorrespondingRealBlock, pic_bc_periodic.cpp:502-519)
+    gleaf_real = -np.ones(n_gleaves, dtype=np.int32)
+    if periodic:
+        period = nb * S
+        for l in np.nonzero(g_is_ghost)[0]:
+            c = gli[l] + gls[l] // 2
+            c = (c - S) % period + S
+            gleaf_real[l] = find_gleaf_ix([int(v) for v in c])
+
+    # ---- ownership: Cartesian split of the user domain ----------------------
+    if decomp is None:
+        decomp = (n_ranks, 1, 1)
+    decomp = np.asarray(decomp, dtype=np.int64)
+    assert int(np.prod(decomp)) == n_ranks
+    ctr = gli + (gls // 2)[:, None] - shell * S  # block centre on the lattice of the user domain
+    ext = nb * S
+    gowner = np.zeros(n_gleaves, dtype=np.int32)
+    real_mask = ~g_is_ghost
+    rc = np.clip((ctr * decomp[None, :]) // ext[None, :], 0, decomp[None, :] - 1)
+    gowner[:] = (rc[:, 0] + decomp[0] * (rc[:, 1] + decomp[1] * rc[:, 2])).astype(np.int32)
+    if periodic:
+        gh = np.nonzero(g_is_ghost)[0]
+        gowner[gh] = gowner[gleaf_real[gh]]
+
+    # ---- local leaves: own + boundary layer + real images of adjacent ghost blocks ----
+    own = np.nonzero(real_mask & (gowner == rank))[0]
+    if n_ranks == 1:
+        local = np.arange(n_gleaves)
+    else:
+        loc = set(int(v) for v in own)
+        extra = []
+        for l in own:
+            lo, sz = gli[l], int(gls[l])
+            # probe one lattice point beyond every face/edge/corner (and the mid points for finer neighbours)
+            probes = (-1, 0, sz // 2, sz - 1, sz)
+            for a in probes:
+                for b in probes:
+                    for c3 in probes:
+                        if 0 <= a < sz and 0 <= b < sz and 0 <= c3 < sz:
+                            continue
+                        g2 = find_gleaf_ix([int(lo[0] + a), int(lo[1] + b), int(lo[2] + c3)])
+                        if g2 >= 0 and g2 not in loc:
+                            loc.add(g2)
+                            extra.append(g2)
+        for g2 in list(extra):
+            r2 = int(gleaf_real[g2])
+            if r2 >= 0 and r2 not in loc:
+                loc.add(r2)
+                extra.append(r2)
+        local = np.concatenate([own, np.array(sorted(extra), dtype=np.int64)]) if extra else own
+    local = np.asarray(local, dtype=np.int64)
+    n_leaves = len(local)
+    n_own = len(own) if n_ranks > 1 else n_leaves
+    leaf_node = gleaf_node[local].astype(np.int32)
+    g2l = -np.ones(n_gleaves, dtype=np.int32)
+    g2l[local] = np.arange(n_leaves, dtype=np.int32)
+    node_leaf = -np.ones(n_nodes, dtype=np.int32)
+    node_leaf[leaf_node] = np.arange(n_leaves, dtype=np.int32)
+    leaf_owner = gowner[local].astype(np.int32)
+    leaf_real = np.where(gleaf_real[local] >= 0, g2l[np.maximum(gleaf_real[local], 0)], -1).astype(np.int32)
+
+    def find_leaf_ix(ix):
+        g2 = find_gleaf_ix(ix)
+        return -1 if g2 < 0 else int(g2l[g2])
 
     m.find_leaf_ix = find_leaf_ix
 
-    # ---- face boundary flags (GetNeibFace(f,0,0)==NULL) and periodic pairing ---------
+    # ---- face boundary flags (GetNeibFace(f,0,0)==NULL) ---------------------
+    li = gli[local]
+    ls = gls[local]
     leaf_face_boundary = np.zeros(n_leaves, dtype=np.int32)
-    leaf_real = -np.ones(n_leaves, dtype=np.int32)
-    li = imin[leaf_node].astype(np.int64)
-    ls = isize[leaf_node].astype(np.int64)
-    tot = n_root * S
     for d in range(3):
         leaf_face_boundary |= np.where(li[:, d] == 0, 1 << (2 * d), 0).astype(np.int32)
         leaf_face_boundary |= np.where(li[:, d] + ls == tot[d], 1 << (2 * d + 1), 0).astype(np.int32)
-    if periodic:
-        period = nb * S
-        for l in range(n_leaves):
-            if flags[leaf_node[l]] & _capi.NODE_PERIODIC_GHOST:
-                c = li[l] + ls[l] // 2  # block centre on the lattice
-                c = (c - S) % period + S  # findCorrespondingRealBlock, pic_bc_periodic.cpp:502-519
-                leaf_real[l] = find_leaf_ix([int(v) for v in c])
 
     # ---- unique corner / centre nodes -------------------------------------------------
     # integer node keys: corner = imin*N + i*isize  (units: 1/N of a lattice step),
     #                    centre = 2*imin*N + (2i+1)*isize
+    # Only leaves that hold particles on this rank (own, or every leaf for a single rank) get node tables.
+    has_nodes = np.zeros(n_leaves, dtype=bool)
+    has_nodes[:n_own] = True
+
     def keys_for(corner):
         i, j, k = _local_numbers(N, g, corner)
-        loc = np.stack([i, j, k], axis=1).astype(np.int64)  # [nloc,3]
+        loc3 = np.stack([i, j, k], axis=1).astype(np.int64)  # [nloc,3]
         if corner:
-            key = li[:, None, :] * N[None, None, :] + loc[None, :, :] * ls[:, None, None]
+            key = li[:, None, :] * N[None, None, :] + loc3[None, :, :] * ls[:, None, None]
             span = nb * S * N
             org = shell * S * N
         else:
-            key = 2 * li[:, None, :] * N[None, None, :] + (2 * loc[None, :, :] + 1) * ls[:, None, None]
+            key = 2 * li[:, None, :] * N[None, None, :] + (2 * loc3[None, :, :] + 1) * ls[:, None, None]
             span = 2 * nb * S * N
             org = 2 * shell * S * N
-        inside_block = np.ones(loc.shape[0], dtype=bool)
+        inside_block = np.ones(loc3.shape[0], dtype=bool)
         for d in range(3):
             hi = N[d] + (1 if corner else 0)
-            inside_block &= (loc[:, d] >= 0) & (loc[:, d] < hi)
+            inside_block &= (loc3[:, d] >= 0) & (loc3[:, d] < hi)
+        valid = np.ones(key.shape[:2], dtype=bool)
         if periodic:
             key = (key - org) % span  # identify periodic images
-            valid = np.ones(key.shape[:2], dtype=bool)
         else:
-            valid = np.ones(key.shape[:2], dtype=bool)
             for d in range(3):
                 valid &= (key[:, :, d] >= 0) & (key[:, :, d] <= span[d])
         enc = (key[:, :, 2] * (span[1] + 1) + key[:, :, 1]) * (span[0] + 1) + key[:, :, 0]
-        return enc, valid, inside_block, key
+        return enc, valid, inside_block, key, span
 
     def uid_table(corner):
-        enc, valid, inside_block, key = keys_for(corner)
-        own = enc[:, inside_block]  # nodes that blocks really own
-        uniq = np.unique(own.ravel())
-        pos = np.searchsorted(uniq, enc)
-        pos_c = np.minimum(pos, len(uniq) - 1)
-        found = (uniq[pos_c] == enc) & valid
+        enc, valid, inside_block, key, span = keys_for(corner)
+        valid = valid & has_nodes[:, None]
+        if n_ranks == 1:
+            # nodes that blocks really own; ghost-layer positions only resolve to such nodes
+            pool = np.unique(enc[:, inside_block].ravel())
+        else:
+            # every node an own block's tile can touch is kept locally (its value arrives with the field upload)
+            pool = np.unique(enc[valid])
+        pos = np.searchsorted(pool, enc)
+        pos_c = np.minimum(pos, len(pool) - 1)
+        found = (pool[pos_c] == enc) & valid
         uid = np.where(found, pos_c, -1).astype(np.int32)
-        # node coordinates (x fastest ordering of uniq follows the encoding)
-        first = np.full(len(uniq), -1, dtype=np.int64)
-        flat_enc = enc.ravel()
+        first = np.full(len(pool), -1, dtype=np.int64)
         flat_ok = found.ravel()
         idx = np.nonzero(flat_ok)[0]
         first[pos_c.ravel()[idx][::-1]] = idx[::-1]
         kk = key.reshape(-1, 3)[first]
-        if corner:
-            xx = (xmin if periodic else gmin)[None, :] + kk / (S * N)[None, :] * dx_root[None, :]
-        else:
-            xx = (xmin if periodic else gmin)[None, :] + kk / (2 * S * N)[None, :] * dx_root[None, :]
-        return uid, len(uniq), xx
+        x0 = xmin if periodic else gmin
+        den = (S * N) if corner else (2 * S * N)
+        xx = x0[None, :] + kk / den[None, :] * dx_root[None, :]
+        # deposit targets: in-block corners of own leaves (global keys, for the cross-rank corner exchange)
+        targets = np.unique(enc[:n_own][:, inside_block].ravel()) if corner else None
+        return uid, len(pool), xx, pool, targets
 
-    corner_uid, n_corners, corner_x = uid_table(True)
-    center_uid, n_centers, center_x = uid_table(False)
+    corner_uid, n_corners, corner_x, corner_gkey, corner_targets = uid_table(True)
+    center_uid, n_centers, center_x, center_gkey, _ = uid_table(False)
     m.corner_x, m.center_x = corner_x, center_x
+    m.corner_gkey, m.center_gkey = corner_gkey, center_gkey
+    m.corner_target_gkeys = corner_targets
+    m.rank, m.n_ranks, m.n_own_leaves = rank, n_ranks, n_own
+    m.leaf_global = local.astype(np.int32)
+    m.n_global_leaves = n_gleaves
 
-    # ---- ownership --------------------------------------------------------------
     node_thread = np.zeros(n_nodes, dtype=np.int32)
-    if owner is not None:
-        for l in range(n_leaves):
-            node_thread[leaf_node[l]] = owner(nxmin[leaf_node[l]], nxmax[leaf_node[l]])
-    else:
-        node_thread[:] = this_thread
+    node_thread[gleaf_node] = gowner
 
     c = m.c
     for d in range(3):
@@ -269,6 +345,9 @@ def build_mesh(xmin, xmax, n_blocks, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1
     c.n_leaves = n_leaves
     c.n_corners = n_corners
     c.n_centers = n_centers
+    c.this_rank = rank
+    c.n_ranks = n_ranks
+    c.n_global_leaves = n_gleaves
     m._set("node_parent", np.array(parent, dtype=np.int32), C.c_int32)
     m._set("node_child", child, C.c_int32)
     m._set("node_level", level, C.c_int32)
@@ -285,15 +364,33 @@ def build_mesh(xmin, xmax, n_blocks, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1
     m._set("leaf_face_boundary", leaf_face_boundary, C.c_int32)
     m._set("leaf_corner_uid", corner_uid, C.c_int32)
     m._set("leaf_center_uid", center_uid, C.c_int32)
+    m._set("leaf_owner", leaf_owner, C.c_int32)
+    m._set("leaf_global_id", m.leaf_global, C.c_int32)
+    m._set("global_leaf_to_local", g2l, C.c_int32)
     return m
 
 
+def shared_corner_lists(m, all_targets):
+    """Per peer rank: local uids of the corners whose J/M this rank AND the peer deposit into, both sides in the
+    order of the global corner key.  all_targets[r] = corner_target_gkeys of rank r (gathered by the caller)."""
+    out = {}
+    mine = m.corner_target_gkeys
+    for r, other in enumerate(all_targets):
+        if r == m.rank:
+            continue
+        common = np.intersect1d(mine, other, assume_unique=True)
+        if len(common):
+            out[r] = np.searchsorted(m.corner_gkey, common).astype(np.int32)
+    return out
+
+
 def uniform_periodic_box(n_cells, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), dx=1.0, origin=(0.0, 0.0, 0.0),
-                         max_refinement_level=12):
+                         max_refinement_level=12, rank=0, n_ranks=1, decomp=None):
     """BASELINE config 2/3 geometry: [origin, origin+n_cells*dx) periodic, single AMR level."""
     n_cells = np.asarray(n_cells, dtype=np.int64)
     N = np.asarray(block_cells, dtype=np.int64)
     assert (n_cells % N == 0).all(), "n_cells must be a multiple of block_cells"
     xmin = np.asarray(origin, dtype=np.float64)
     xmax = xmin + n_cells * dx
-    return build_mesh(xmin, xmax, n_cells // N, block_cells, ghost_cells, True, max_refinement_level)
+    return build_mesh(xmin, xmax, n_cells // N, block_cells, ghost_cells, True, max_refinement_level, rank=rank, n_ranks=n_ranks,
+                      decomp=decomp)

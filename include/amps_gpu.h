@@ -136,6 +136,14 @@ typedef struct amps_gpu_mesh {
   int32_t n_corners, n_centers;
   const int32_t *leaf_corner_uid;   /* [n_leaves][(Nx+2g+1)(Ny+2g+1)(Nz+2g+1)]                 */
   const int32_t *leaf_center_uid;   /* [n_leaves][(Nx+2g)(Ny+2g)(Nz+2g)]                       */
+  /* domain decomposition (one rank per GPU).  n_ranks <= 1: the three tables may be NULL.     */
+  int32_t this_rank, n_ranks;       /* PIC::ThisThread, PIC::nTotalThreads                     */
+  int32_t n_global_leaves;          /* leaves of the whole tree (same numbering on every rank) */
+  const int32_t *leaf_owner;        /* [n_leaves]  cTreeNodeAMR::Thread of each LOCAL leaf: own blocks, the boundary
+                                       layer (DomainBoundaryLayerNodesList, meshAMRgeneric.h:1812) and real images of
+                                       adjacent periodic ghost blocks                           */
+  const int32_t *leaf_global_id;    /* [n_leaves]  global leaf number of each local leaf        */
+  const int32_t *global_leaf_to_local; /* [n_global_leaves] local leaf or -1                    */
 } amps_gpu_mesh;
 
 /* AoS record description of PIC::ParticleBuffer (picParticleDataMacro.h:18-330) */
@@ -231,7 +239,23 @@ int amps_gpu_JM_download(amps_gpu_ctx *ctx, double *J, double *M);
 /* device pointers for an on-device consumer (field solve) */
 int amps_gpu_JM_device(amps_gpu_ctx *ctx, double **J_dev, double **M_dev);
 
-/* one fused ECSIM particle phase: move + sort + deposit, no host sync inside */
+/* ---- multi-GPU: one rank per GPU, NCCL over NVLink (libnccl is resolved with dlopen at the first call) ----
+ * <- MPI_GLOBAL_COMMUNICATOR.  Rank 0 creates the id, the host broadcasts its 128 bytes (MPI_Bcast /
+ *    torch.distributed), every rank joins.                                                     */
+int amps_gpu_comm_unique_id(void *id128);
+int amps_gpu_comm_init(amps_gpu_ctx *ctx, const void *id128, int rank, int n_ranks);
+/* corners that this rank and `peer` both deposit into: local unique-corner ids, both sides ordered by the
+ * same global corner key (amps_b200/mesh.py: shared_corner_lists)                               */
+int amps_gpu_set_shared_corners(amps_gpu_ctx *ctx, int peer, const int32_t *uids, int64_t n);
+/* <- PIC::Parallel::ExchangeParticleData (pic_parallel.cpp:50-488): call between move and sort.
+ *    n_sent / n_received may be NULL.                                                          */
+int amps_gpu_migrate(amps_gpu_ctx *ctx, int64_t *n_sent, int64_t *n_received);
+/* <- SyncMassMatrix / ProcessCornerBlockBoundaryNodes (ecsim/halo_sync.cpp:79-124) + the MPI_Reduce of the
+ *    particle energy (SUM) and cfl (MAX) (pic_field_solver_ecsim.cpp:3972-3977): call after deposit.  */
+int amps_gpu_exchange_JM(amps_gpu_ctx *ctx);
+
+/* one fused ECSIM particle phase: move (+ migrate) + sort + deposit (+ corner exchange), no host sync inside
+ * on a single rank; the migration needs one small device->host read of the counts          */
 int amps_gpu_step(amps_gpu_ctx *ctx, int mover_id);
 
 /* Phase timing with CUDA events recorded on the context's stream (what the reference prints from

@@ -1,0 +1,129 @@
+"""Multi-rank parity driver (launched with torchrun, one rank per GPU).
+
+Every rank builds its view of the same periodic box (Cartesian block decomposition), uploads the particles of its own
+blocks, runs one ECSIM particle phase (move -> NCCL migration -> sort -> deposit -> NCCL corner exchange) through the
+C ABI, and rank 0 compares the union with the single-domain CPU oracle:
+  * every particle ends in the same global (block,cell) with bit-identical x', v', on the rank that owns the block
+  * J, M of every corner (summed across the ranks that share it) within 1e-10 of the array maximum
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    from amps_b200 import api, mesh as meshmod, workload
+    from tests import parity_util as pu
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    decomp = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
+    n_cells = (32, 32, 16)
+    ppc, seed, vscale = 6, 31, 6.0
+
+    # the global problem (identical on every rank)
+    mg = meshmod.uniform_periodic_box(n_cells)
+    charge, mass, wgt = workload.species_tables(ppc, 1.0)
+    x, v, w, sp, gcells = workload.maxwellian_box(mg, ppc, seed=seed)
+    v *= vscale
+    w = np.random.default_rng(seed + 1).uniform(0.5, 1.5, size=w.shape)
+    E, B = workload.box_fields(mg, E_amp=0.01)
+    Bcur = B * 1.01 + 0.001
+    C = mg.cells_per_block
+    n = x.shape[1]
+
+    # this rank's view
+    m = meshmod.uniform_periodic_box(n_cells, rank=rank, n_ranks=world, decomp=decomp)
+    g2l = m.arrays["global_leaf_to_local"]
+    gleaf_of_global_mesh = mg.leaf_global  # single-rank mesh: local == global numbering
+    assert (gleaf_of_global_mesh == np.arange(mg.n_leaves)).all()
+    pl = g2l[gcells // C]
+    mine = (pl >= 0) & (m.arrays["leaf_owner"][np.maximum(pl, 0)] == rank)
+    idx = np.nonzero(mine)[0]
+    lcells = (pl[idx] * C + gcells[idx] % C).astype(np.int32)
+    # fields on this rank's unique nodes: same analytic field evaluated through the global key
+    def pick(garr, gkeys_global, lkeys):
+        pos = np.searchsorted(gkeys_global, lkeys)
+        assert (gkeys_global[pos] == lkeys).all()
+        return garr[pos]
+    El = pick(E, mg.corner_gkey, m.corner_gkey)
+    Bl = pick(B, mg.center_gkey, m.center_gkey)
+    Bcl = pick(Bcur, mg.center_gkey, m.center_gkey)
+
+    cfg = api.make_config((8, 8, 8), (1, 1, 1), charge, mass, wgt, 1.0, periodic=True, capacity=n + 1024, device=local)
+    g = api.Context(cfg, m)
+    g.comm_init(dist)
+    g.fields_upload(El, Bl, Bcl)
+    g.particles_upload(x[:, idx], v[:, idx], w[idx], sp[idx], lcells, ptrs=idx.astype(np.int32))
+    st = g.MoveParticles()
+    ns, nr = g.migrate()
+    g.sort()
+    after = g.particles_download()
+    en, cfl = g.UpdateJMassMatrix()   # local partial sums
+    g.exchange_JM()
+    J, M = g.JM_download()
+    import ctypes
+    e2 = ctypes.c_double()
+    g.synchronize()
+    res = {"rank": rank, "stats": st, "sent": ns, "recv": nr, "n_after": int(after["x"].shape[1])}
+    # global cell of every resident particle
+    lg = m.leaf_global
+    keys = after["cells"].astype(np.int64)
+    gk = lg[keys // C].astype(np.int64) * C + keys % C
+    owner_ok = bool((m.arrays["leaf_owner"][keys // C] == rank).all())
+    payload = {"res": res, "x": after["x"], "v": after["v"], "gk": gk, "owner_ok": owner_ok,
+               "J": J, "M": M, "ckeys": m.corner_gkey, "targets": m.corner_target_gkeys}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, payload)
+    ok = True
+    if rank == 0:
+        cfg1 = api.make_config((8, 8, 8), (1, 1, 1), charge, mass, wgt, 1.0, periodic=True, capacity=n + 16)
+        ora = pu.run_oracle(mg, cfg1, (x, v, w, sp, gcells), (E, B, Bcur))
+        ocell = ora["final_cell"].astype(np.int64)
+        ox, ov = ora["particles"]["x"], ora["particles"]["v"]
+        # particles: match by (global cell, x0 bits) since arrivals lose their ptr
+        allx = np.concatenate([p["x"] for p in gathered], axis=1)
+        allv = np.concatenate([p["v"] for p in gathered], axis=1)
+        allk = np.concatenate([p["gk"] for p in gathered])
+        out = {"n_total": int(allx.shape[1]), "n_expected": int(n)}
+        def order(k, xx):
+            return np.lexsort((xx[2].view(np.int64), xx[1].view(np.int64), xx[0].view(np.int64), k))
+        o1, o2 = order(allk, allx), order(ocell, ox)
+        out["cells_equal"] = bool(allx.shape[1] == n and (allk[o1] == ocell[o2]).all())
+        out["x_bit_equal"] = bool(allx.shape[1] == n and (allx[:, o1] == ox[:, o2]).all())
+        out["v_bit_equal"] = bool(allx.shape[1] == n and (allv[:, o1] == ov[:, o2]).all())
+        out["owner_ok"] = all(p["owner_ok"] for p in gathered)
+        out["sent_total"] = sum(p["res"]["sent"] for p in gathered)
+        out["recv_total"] = sum(p["res"]["recv"] for p in gathered)
+        # corners: every rank's value at its deposit targets must equal the oracle's total
+        relJ = relM = 0.0
+        sJ, sM = np.abs(ora["J"]).max(), np.abs(ora["M"]).max()
+        for p in gathered:
+            lpos = np.searchsorted(p["ckeys"], p["targets"])
+            gpos = np.searchsorted(mg.corner_gkey, p["targets"])
+            relJ = max(relJ, float(np.abs(p["J"][lpos] - ora["J"][gpos]).max() / sJ))
+            relM = max(relM, float(np.abs(p["M"][lpos] - ora["M"][gpos]).max() / sM))
+        out["max_rel_J"], out["max_rel_M"] = relJ, relM
+        st_sum = {k: sum(p["res"]["stats"][k] for p in gathered) for k in ora["stats"]}
+        out["stats_equal"] = st_sum == ora["stats"]
+        out["stats_gpu"], out["stats_oracle"] = st_sum, ora["stats"]
+        ok = (out["cells_equal"] and out["x_bit_equal"] and out["v_bit_equal"] and out["owner_ok"] and relJ <= 1e-10 and relM <= 1e-10
+              and out["stats_equal"] and out["sent_total"] == out["recv_total"] and out["sent_total"] > 0)
+        out["ok"] = ok
+        print("MP_PARITY " + json.dumps(out))
+    g.close()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,73 @@
+"""Host-side logic of the N>1 path on CPU: world_size-2 (and 4) gloo processes build their rank views of one box and
+exchange the corner keys exactly like Context.comm_init does; no GPU involved."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from amps_b200 import mesh as meshmod, workload
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    decomp = {2: (2, 1, 1), 4: (2, 2, 1)}[world]
+    n_cells = (32, 32, 16)
+    m = meshmod.uniform_periodic_box(n_cells, rank=rank, n_ranks=world, decomp=decomp)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, m.corner_target_gkeys)
+    lists = meshmod.shared_corner_lists(m, gathered)
+    # symmetric exchange: what I send to r has the size r expects from me, in the same global-key order
+    sizes = {r: len(u) for r, u in lists.items()}
+    keys = {r: m.corner_gkey[u] for r, u in lists.items()}
+    info = [None] * world
+    dist.all_gather_object(info, (sizes, keys))
+    ok = True
+    for r, (sz, ky) in enumerate(info):
+        if r == rank:
+            continue
+        ok &= sz.get(rank, 0) == sizes.get(r, 0)
+        if rank in ky:
+            ok &= bool((ky[rank] == keys[r]).all())
+    # ownership is a partition of the real blocks; every particle of the global plasma has exactly one owner
+    mg = meshmod.uniform_periodic_box(n_cells)
+    x, v, w, sp, gcells = workload.maxwellian_box(mg, 2, seed=1)
+    C = mg.cells_per_block
+    pl = m.arrays["global_leaf_to_local"][gcells // C]
+    mine = (pl >= 0) & (m.arrays["leaf_owner"][np.maximum(pl, 0)] == rank)
+    counts = [None] * world
+    dist.all_gather_object(counts, int(mine.sum()))
+    ok &= sum(counts) == x.shape[1]
+    # local geometry: boundary-layer blocks are adjacent to own blocks, ghost blocks carry their real image locally
+    real = m.arrays["leaf_real"]
+    fl = m.arrays["node_flags"][m.arrays["leaf_node"]]
+    ghost = (fl & 2) != 0
+    ok &= bool((real[ghost] >= 0).all()) and bool((real[~ghost] == -1).all())
+    ok &= m.n_own_leaves == int(np.prod(np.array(n_cells) // 8)) // world
+    q.put((rank, bool(ok), sizes))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_rank_views_are_consistent(world):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), res
+    # 2 ranks split along x share two faces (x = 16 and the periodic seam): 2 * 32*16... corners
+    if world == 2:
+        assert all(sum(r[2].values()) == 2 * 32 * 16 for r in res), res
