@@ -54,6 +54,11 @@ class Config(C.Structure):
         ("ecsim_B_conv", C.c_double),
         ("ecsim_length_conv", C.c_double),
         ("ecsim_light_speed", C.c_double),
+        ("coupler_interpolation", C.c_int32),
+        ("backward_time_integration", C.c_int32),
+        ("speed_of_light", C.c_double),
+        ("internal_sphere_radius", C.c_double),
+        ("exit_record_capacity", C.c_int64),
     ]
 
 
@@ -108,6 +113,14 @@ class AosLayout(C.Structure):
     ]
 
 
+class ExitRecord(C.Structure):
+    _fields_ = [("ptr", C.c_int32), ("species", C.c_int32), ("face", C.c_int32), ("leaf", C.c_int32), ("x", C.c_double * 3), ("v", C.c_double * 3)]
+
+
+CPLR_CONSTANT, CPLR_LINEAR = 0, 1
+EXIT_SPHERE = 6
+
+
 class MoveStats(C.Structure):
     _fields_ = [
         ("n_moved", C.c_int64),
@@ -133,6 +146,8 @@ PROTOTYPES = {
     "amps_gpu_stream": (_vp, [_vp]),
     "amps_gpu_mesh_upload": (C.c_int, [_vp, C.POINTER(Mesh)]),
     "amps_gpu_fields_upload": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "amps_gpu_background_upload": (C.c_int, [_vp, _vp, _vp]),
+    "amps_gpu_exit_records": (C.c_int, [_vp, _vp, C.c_int64, _i64p]),
     "amps_gpu_particles_upload_aos": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.POINTER(AosLayout)]),
     "amps_gpu_particles_upload_soa": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64]),
     "amps_gpu_particle_count": (C.c_int, [_vp, _i64p]),

@@ -44,6 +44,11 @@ def make_config(block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), charge=(-1.0, 1.0)
     cfg.ecsim_B_conv = B_conv
     cfg.ecsim_length_conv = length_conv
     cfg.ecsim_light_speed = light_speed
+    cfg.coupler_interpolation = _capi.CPLR_LINEAR
+    cfg.backward_time_integration = 0
+    cfg.speed_of_light = 299792458.0
+    cfg.internal_sphere_radius = 0.0
+    cfg.exit_record_capacity = 0
     return cfg
 
 
@@ -89,6 +94,23 @@ class Context:
                 assert a.shape == (n, 3), (a.shape, n)
             arrs.append(a)
         self._ck(self.lib.amps_gpu_fields_upload(self._h, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2])))
+
+    def background_upload(self, E_center=None, B_center=None):
+        """coupler table (E, B on unique centre nodes) of the test-particle movers"""
+        arrs = []
+        for a in (E_center, B_center):
+            if a is not None:
+                a = np.ascontiguousarray(a, dtype=np.float64)
+                assert a.shape == (self.mesh.n_centers, 3)
+            arrs.append(a)
+        self._ck(self.lib.amps_gpu_background_upload(self._h, _ptr(arrs[0]), _ptr(arrs[1])))
+
+    def exit_records(self, max_records=1 << 20):
+        buf = (_capi.ExitRecord * max_records)()
+        n = C.c_int64()
+        self._ck(self.lib.amps_gpu_exit_records(self._h, C.cast(buf, C.c_void_p), max_records, C.byref(n)))
+        k = min(int(n.value), max_records, int(self.cfg.exit_record_capacity))
+        return int(n.value), [(r.ptr, r.species, r.face, r.leaf, tuple(r.x), tuple(r.v)) for r in buf[:k]]
 
     # ---- PIC::ParticleBuffer ---------------------------------------------------------------
     def particles_upload(self, x, v, w, species, cells, ptrs=None):

@@ -105,6 +105,10 @@ void launch_unpack_arrivals(const DevMesh &m, const double *recvBuf, int nRecv, 
                             long long capacity, int *cellCount, int *errFlag, cudaStream_t s);
 void launch_pack_corners(const int *uids, int n, const double *J, const double *M, double *buf, cudaStream_t s);
 void launch_add_corners(const int *uids, int n, double *J, double *M, const double *buf, cudaStream_t s);
+void launch_stage_background(const DevMesh &m, const double *E, const double *B, double *tile, cudaStream_t s);
+void launch_move_relativistic_boris(const DevMesh &m, const DevSpecies &sp, int interp, int backward, double c, double rSphere, long long exitCap,
+                                    ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, int *cellCount, DevMoveStats *stats,
+                                    amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s);
 void launch_division_selftest(const double *a, const double *b, int n, unsigned long long *out, cudaStream_t s);
 
 }  // namespace amps

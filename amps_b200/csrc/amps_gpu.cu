@@ -45,6 +45,12 @@ struct amps_gpu_ctx {
   unsigned long long *d_cfl = nullptr;
   DevMoveStats *d_stats = nullptr;
 
+  // coupler table of the test-particle movers + exit records
+  double *d_bgE = nullptr, *d_bgB = nullptr, *d_bgTile = nullptr;
+  bool backgroundReady = false;
+  amps_gpu_exit_record *d_exitBuf = nullptr;
+  unsigned long long *d_exitCount = nullptr;
+
   // domain decomposition / NCCL
   int rank = 0, nRanks = 1;
   int *d_leafOwner = nullptr, *d_leafGlobal = nullptr, *d_g2l = nullptr;
@@ -234,6 +240,10 @@ int amps_gpu_init(const amps_gpu_config *cfg, amps_gpu_ctx **out) {
   if ((rc = dev_alloc(ctx, &ctx->d_energy, 1))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_cfl, AMPS_GPU_MAX_SPECIES))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_stats, 1))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_exitCount, 1))) return rc;
+  CK(cudaMemset(ctx->d_exitCount, 0, sizeof(unsigned long long)));
+  if (cfg->exit_record_capacity > 0)
+    if ((rc = dev_alloc(ctx, &ctx->d_exitBuf, (size_t)cfg->exit_record_capacity))) return rc;
   return AMPS_GPU_OK;
 }
 
@@ -244,6 +254,7 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   for (void *p : ctx->meshAllocs) cudaFree(p);
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
   if (ctx->comm && nccl_api().CommDestroy) nccl_api().CommDestroy(ctx->comm);
+  cudaFree(ctx->d_bgE), cudaFree(ctx->d_bgB), cudaFree(ctx->d_bgTile), cudaFree(ctx->d_exitBuf), cudaFree(ctx->d_exitCount);
   cudaFree(ctx->d_sendBuf), cudaFree(ctx->d_recvBuf), cudaFree(ctx->d_sendCount), cudaFree(ctx->d_allCounts), cudaFree(ctx->d_errFlag);
   for (int *p : ctx->d_sharedUid) cudaFree(p);
   cudaFree(ctx->d_cornerSend), cudaFree(ctx->d_cornerRecv);
@@ -391,6 +402,42 @@ int amps_gpu_fields_upload(amps_gpu_ctx *ctx, const double *E_half, const double
   ctx->launches++;
   CK(cudaGetLastError());
   ctx->fieldsReady = true;
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_background_upload(amps_gpu_ctx *ctx, const double *E_center, const double *B_center) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "background_upload before mesh_upload");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const DevMesh &m = ctx->dm;
+  int rc;
+  if (!ctx->d_bgTile) {
+    if ((rc = dev_alloc(ctx, &ctx->d_bgE, (size_t)3 * m.nCenters))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_bgB, (size_t)3 * m.nCenters))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_bgTile, (size_t)m.nLeaves * m.nCenterLocal * 6))) return rc;
+    CK(cudaMemsetAsync(ctx->d_bgTile, 0, sizeof(double) * (size_t)m.nLeaves * m.nCenterLocal * 6, ctx->stream));
+  }
+  if (E_center) CK(cudaMemcpyAsync(ctx->d_bgE, E_center, sizeof(double) * 3 * (size_t)m.nCenters, cudaMemcpyHostToDevice, ctx->stream));
+  if (B_center) CK(cudaMemcpyAsync(ctx->d_bgB, B_center, sizeof(double) * 3 * (size_t)m.nCenters, cudaMemcpyHostToDevice, ctx->stream));
+  launch_stage_background(m, E_center ? ctx->d_bgE : nullptr, B_center ? ctx->d_bgB : nullptr, ctx->d_bgTile, ctx->stream);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  ctx->backgroundReady = true;
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_exit_records(amps_gpu_ctx *ctx, amps_gpu_exit_record *buf, int64_t max_records, int64_t *n) {
+  if (!ctx || !n) return AMPS_GPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  unsigned long long cnt = 0;
+  CK(cudaMemcpyAsync(&cnt, ctx->d_exitCount, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *n = (int64_t)cnt;
+  long long have = (long long)cnt < ctx->cfg.exit_record_capacity ? (long long)cnt : ctx->cfg.exit_record_capacity;
+  if (have > max_records) have = max_records;
+  if (buf && have > 0) CK(cudaMemcpyAsync(buf, ctx->d_exitBuf, sizeof(amps_gpu_exit_record) * have, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_exitCount, 0, sizeof(unsigned long long), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return AMPS_GPU_OK;
 }
 
@@ -559,13 +606,25 @@ int amps_gpu_cell_table_download(amps_gpu_ctx *ctx, int64_t *cell_start, int64_t
 }
 
 static int do_move(amps_gpu_ctx *ctx, int mover_id) {
-  if (!ctx->meshReady || !ctx->fieldsReady) FAIL(AMPS_GPU_ERR_STATE, "move before mesh/fields upload");
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "move before mesh upload");
   if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "move needs the (block,cell)-sorted layout: call amps_gpu_sort");
-  if (mover_id != AMPS_MOVER_LAPENTA2017) FAIL(AMPS_GPU_ERR_ARG, "mover not implemented yet");
+  if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS) FAIL(AMPS_GPU_ERR_ARG, "mover not implemented yet");
+  if (mover_id == AMPS_MOVER_LAPENTA2017 && !ctx->fieldsReady) FAIL(AMPS_GPU_ERR_STATE, "Lapenta2017 needs amps_gpu_fields_upload");
+  if (mover_id == AMPS_MOVER_RELATIVISTIC_BORIS && !ctx->backgroundReady) FAIL(AMPS_GPU_ERR_STATE, "Relativistic::Boris needs amps_gpu_background_upload");
   const DevMesh &m = ctx->dm;
   ProfScope prof(ctx, AMPS_GPU_PHASE_MOVE);
   CK(cudaMemsetAsync(ctx->d_cellCount, 0, sizeof(int) * (size_t)ctx->nCells, ctx->stream));
   CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevMoveStats), ctx->stream));
+  if (mover_id == AMPS_MOVER_RELATIVISTIC_BORIS) {
+    launch_move_relativistic_boris(m, ctx->sp, ctx->cfg.coupler_interpolation, ctx->cfg.backward_time_integration, ctx->cfg.speed_of_light,
+                                   ctx->cfg.internal_sphere_radius, ctx->cfg.exit_record_capacity, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper,
+                                   ctx->d_bgTile, ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount, ctx->stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    ctx->sorted = false;
+    ctx->countValid = true;
+    return AMPS_GPU_OK;
+  }
   long long perLeaf = ctx->nUpper / (m.nLeaves > 0 ? m.nLeaves : 1);
   int slices = (int)((perLeaf + 4095) / 4096);
   if (slices < 1) slices = 1;

@@ -1,0 +1,410 @@
+// mover_tp.cu -- test-particle movers on the coupler's centre-node table (sm_100a).  COMPILED WITH --fmad=false
+// so that positions, velocities and the (block,cell) assignment round exactly like the reference CPU build.
+//
+//   a7  PIC::Mover::Relativistic::Boris   src/pic/pic_mover_relativistic_boris.cpp:16-583
+//       gamma-aware Boris rotation sub-cycled with the local gyro period (dt = min(dtLeft, 1/f_g), :115-125),
+//       backward-time mode (:128-132, :169-173), internal sphere (:270-302), domain exit search (:305-455)
+//   a15 domain exit: DELETE, or the face-intersection search whose result is handed to the host callbacks as an
+//       exit record (USER_FUNCTION = Earth::CutoffRigidity::ProcessOutsideDomainParticles); SPECULAR is an error
+//       in this mover exactly as in the reference (:452-453 "not implemented")
+//   fields: PIC::CPLR::InitInterpolationStencil (pic_swmf.cpp:76-90, cell-centred constant | linear) +
+//       GetBackgroundElectricField/MagneticField (pic.h:8338-8425) on per-leaf centre tiles [nCenterLocal][6]
+//
+// Mapping: thread <-> particle.  The trip count of the sub-cycle loop varies per particle and a particle may
+// cross several blocks inside one call, so the field tiles are read from global memory (L2 resident) instead of
+// being staged per block.
+#include "amps_dev.cuh"
+#include "mover_common.cuh"
+
+namespace amps {
+
+__global__ void stage_background_kernel(DevMesh m, const double *__restrict__ E, const double *__restrict__ B, double *__restrict__ tile) {
+  const int leaf = blockIdx.x;
+  const int *cuid = m.centerUid + (size_t)leaf * m.nCenterLocal;
+  double *dst = tile + (size_t)leaf * m.nCenterLocal * 6;
+  for (int i = threadIdx.x; i < m.nCenterLocal; i += blockDim.x) {
+    const int u = cuid[i];
+    for (int d = 0; d < 3; d++) {
+      if (E) dst[6 * i + d] = (u >= 0) ? E[3 * (size_t)u + d] : 0.0;
+      if (B) dst[6 * i + 3 + d] = (u >= 0) ? B[3 * (size_t)u + d] : 0.0;
+    }
+  }
+}
+void launch_stage_background(const DevMesh &m, const double *E, const double *B, double *tile, cudaStream_t s) {
+  stage_background_kernel<<<m.nLeaves, 256, 0, s>>>(m, E, B, tile);
+}
+
+struct FaceGeo {  // PIC::Mover::cExternalBoundaryFace after Init (pic_mover.cpp:24-28, 48-75)
+  double norm[6][3], e0[6][3], e1[6][3], x0[6][3], lE0[6], lE1[6];
+};
+__device__ __forceinline__ void init_faces(const DevMesh &m, FaceGeo &f) {
+  const double nrm[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+  const int nX0[6][3] = {{0, 0, 0}, {1, 0, 0}, {0, 0, 0}, {0, 1, 0}, {0, 0, 0}, {0, 0, 1}};
+  const double e0[6][3] = {{0, 1, 0}, {0, 1, 0}, {1, 0, 0}, {1, 0, 0}, {1, 0, 0}, {1, 0, 0}};
+  const double e1[6][3] = {{0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 1, 0}, {0, 1, 0}};
+  for (int n = 0; n < 6; n++) {
+    double cE0 = 0.0, cE1 = 0.0;
+    for (int d = 0; d < 3; d++) {
+      f.norm[n][d] = nrm[n][d], f.e0[n][d] = e0[n][d], f.e1[n][d] = e1[n][d];
+      f.x0[n][d] = (nX0[n][d] == 0) ? m.xGlobalMin[d] : m.xGlobalMax[d];
+      const double a0 = ((e0[n][d] + nX0[n][d] < 0.5) ? m.xGlobalMin[d] : m.xGlobalMax[d]) - f.x0[n][d];
+      const double a1 = ((e1[n][d] + nX0[n][d] < 0.5) ? m.xGlobalMin[d] : m.xGlobalMax[d]) - f.x0[n][d];
+      cE0 += a0 * a0, cE1 += a1 * a1;  // pow(.,2)
+    }
+    f.lE0[n] = sqrt(cE0), f.lE1[n] = sqrt(cE1);
+  }
+}
+
+// plain-division variant of the tree search (this mover is not bound by the division count)
+__device__ __forceinline__ int find_tree_node_plain(const DevMesh &m, const double x[3], int startNode) {
+  int ix[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) ix[d] = (int)floor((x[d] - m.xGlobalMin[d]) / m.dxMaxRef[d]);
+  int node = find_node_ix(m, ix[0], ix[1], ix[2]);
+  (void)startNode;
+  if (node >= 0) {
+    bool flag = false;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      if (x[d] < m.nxmin[3 * node + d]) ix[d]--, flag = true;
+      if (x[d] >= m.nxmax[3 * node + d]) ix[d]++, flag = true;
+    }
+    if (flag) node = find_node_ix(m, ix[0], ix[1], ix[2]);
+  }
+  return node;
+}
+
+// FindCellIndex (meshAMRgeneric.h:2256-2323); returns false where the reference returns -1
+__device__ __forceinline__ bool find_cell_index(const DevMesh &m, const double x[3], int node, int ijk[3]) {
+  const int lev = m.nodeLevel[node];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const double lo = m.nxmin[3 * node + d], hi = m.nxmax[3 * node + d];
+    if ((x[d] < lo) || (hi < x[d])) return false;
+    const double dx = m.dxRoot[d] / (1 << lev) / double(m.N[d]);
+    int c = (int)((x[d] - lo) / dx);
+    if (c == m.N[d]) c = m.N[d] - 1;
+    ijk[d] = c;
+  }
+  return true;
+}
+
+// E, B at x inside leaf `leaf` through the coupler stencil; false = the reference would exit()
+__device__ __forceinline__ bool background_fields(const DevMesh &m, int interp, const double *__restrict__ tile, const double x[3], int leaf,
+                                                  double E[3], double B[3]) {
+  const LeafGeo &lg = m.leaf[leaf];
+  const double *T = tile + (size_t)leaf * m.nCenterLocal * 6;
+  E[0] = E[1] = E[2] = 0.0, B[0] = B[1] = B[2] = 0.0;
+  if (interp == AMPS_CPLR_CELL_CENTERED_LINEAR) {
+    // GetTriliniarInterpolationStencil (:820-907), Normalize only when Length != 8
+    const double iLoc = (x[0] - lg.xmin[0]) / (lg.xmax[0] - lg.xmin[0]) * m.N[0];
+    const double jLoc = (x[1] - lg.xmin[1]) / (lg.xmax[1] - lg.xmin[1]) * m.N[1];
+    const double kLoc = (x[2] - lg.xmin[2]) / (lg.xmax[2] - lg.xmin[2]) * m.N[2];
+    const int i0 = (iLoc < 0.5) ? -1 : (int)(iLoc - 0.50);
+    const int j0 = (jLoc < 0.5) ? -1 : (int)(jLoc - 0.50);
+    const int k0 = (kLoc < 0.5) ? -1 : (int)(kLoc - 0.50);
+    const double w0 = iLoc - (i0 + 0.5), w1 = jLoc - (j0 + 0.5), w2 = kLoc - (k0 + 0.5);
+    double w[8];
+    w[0] = (1.0 - w0) * (1.0 - w1) * (1.0 - w2);
+    w[1] = (1.0 - w0) * (1.0 - w1) * w2;
+    w[2] = (1.0 - w0) * w1 * (1.0 - w2);
+    w[3] = (1.0 - w0) * w1 * w2;
+    w[4] = w0 * (1.0 - w1) * (1.0 - w2);
+    w[5] = w0 * (1.0 - w1) * w2;
+    w[6] = w0 * w1 * (1.0 - w2);
+    w[7] = w0 * w1 * w2;
+    unsigned valid = 0xffu;
+    if (!m.periodic && lg.face) {
+      if ((lg.face & 1) && i0 < 0) valid &= 0xf0u;
+      if ((lg.face & 2) && i0 + 1 >= m.N[0]) valid &= 0x0fu;
+      if ((lg.face & 4) && j0 < 0) valid &= 0xccu;
+      if ((lg.face & 8) && j0 + 1 >= m.N[1]) valid &= 0x33u;
+      if ((lg.face & 16) && k0 < 0) valid &= 0xaau;
+      if ((lg.face & 32) && k0 + 1 >= m.N[2]) valid &= 0x55u;
+    }
+    if (valid != 0xffu) {
+      double norm = 0.0;
+#pragma unroll
+      for (int s = 0; s < 8; s++)
+        if (valid & (1u << s)) norm += w[s];
+      if (norm > 0.0) {
+#pragma unroll
+        for (int s = 0; s < 8; s++) w[s] /= norm;
+      }
+    }
+    const int nd0 = centerLocalNumber(m, i0, j0, k0);
+    const int BS0 = m.TN[0], BS1 = m.TN[0] * m.TN[1];
+    // E over the whole stencil first, then B (two loops in the reference)
+#pragma unroll
+    for (int s = 0; s < 8; s++)
+      if (valid & (1u << s)) {
+        const double *t = T + 6 * (nd0 + ((s >> 2) & 1) + ((s >> 1) & 1) * BS0 + (s & 1) * BS1);
+        E[0] += w[s] * t[0], E[1] += w[s] * t[1], E[2] += w[s] * t[2];
+      }
+#pragma unroll
+    for (int s = 0; s < 8; s++)
+      if (valid & (1u << s)) {
+        const double *t = T + 6 * (nd0 + ((s >> 2) & 1) + ((s >> 1) & 1) * BS0 + (s & 1) * BS1) + 3;
+        B[0] += w[s] * t[0], B[1] += w[s] * t[1], B[2] += w[s] * t[2];
+      }
+    return true;
+  }
+  // Constant::InitStencil (:168-220): the cell that contains x, weight 1
+  int ijk[3];
+  if (!find_cell_index(m, x, lg.node, ijk)) return false;
+  const double *t = T + 6 * centerLocalNumber(m, ijk[0], ijk[1], ijk[2]);
+#pragma unroll
+  for (int d = 0; d < 3; d++) E[d] += 1.0 * t[d], B[d] += 1.0 * t[3 + d];
+  return true;
+}
+
+struct TpParams {
+  int interp, backward, boundaryMode;
+  double c, rSphere;
+  long long exitCap;
+};
+
+__device__ __forceinline__ void add_exit_record(amps_gpu_exit_record *buf, unsigned long long *count, long long cap, int ptr, int spec, int face,
+                                                int leaf, const double x[3], const double v[3]) {
+  const unsigned long long i = atomicAdd(count, 1ull);
+  if ((long long)i < cap) {
+    amps_gpu_exit_record r;
+    r.ptr = ptr, r.species = spec, r.face = face, r.leaf = leaf;
+    for (int d = 0; d < 3; d++) r.x[d] = x[d], r.v[d] = v[d];
+    buf[i] = r;
+  }
+}
+
+__global__ void __launch_bounds__(128) move_relativistic_boris_kernel(DevMesh m, DevSpecies sp, TpParams tp, ParticleSoA p, const int *__restrict__ nSlots,
+                                                                     const double *__restrict__ bgTile, int *__restrict__ cellCount,
+                                                                     DevMoveStats *__restrict__ stats, amps_gpu_exit_record *__restrict__ exitBuf,
+                                                                     unsigned long long *__restrict__ exitCount) {
+  __shared__ FaceGeo sFace;
+  if (threadIdx.x == 0) init_faces(m, sFace);
+  __syncthreads();
+  const int n = *nSlots;
+  const int C = m.cellsPerBlock;
+  unsigned int nMoved = 0, nXCell = 0, nXBlock = 0, nLeft = 0, nNotUsed = 0, nWrap = 0, nErr = 0;
+  const double SpeedOfLight = tp.c;
+  const bool backward = tp.backward != 0;
+
+  for (int ip = blockIdx.x * blockDim.x + threadIdx.x; ip < n; ip += gridDim.x * blockDim.x) {
+    const int oldKey = p.key[ip];
+    if (oldKey < 0) continue;
+    nMoved++;
+    double xInit[3] = {p.x[0][ip], p.x[1][ip], p.x[2][ip]};
+    double vInit[3] = {p.v[0][ip], p.v[1][ip], p.v[2][ip]};
+    double xFinal[3], vFinal[3];
+    const int spec = p.spec[ip];
+    const int startLeaf = oldKey / C;
+    const double ElectricCharge = sp.charge[spec], mass = sp.mass[spec];
+    double dtTotalIn = (sp.timeStepMode == AMPS_DT_SPECIES_GLOBAL) ? sp.dt[spec] : sp.dt[0];
+    int leaf = startLeaf, node = m.leaf[startLeaf].node;
+    int outcome = 0;  // 0 running/finished, 1 left domain, 2 not in use, 3 error
+    if (dtTotalIn == 0.0) {
+      for (int d = 0; d < 3; d++) xFinal[d] = xInit[d], vFinal[d] = vInit[d];
+    } else
+      while (dtTotalIn > 0.0) {
+        double gamma = 1.0 / sqrt(1.0 - (vInit[0] * vInit[0] + vInit[1] * vInit[1] + vInit[2] * vInit[2]) / (SpeedOfLight * SpeedOfLight));
+        double E[3], B[3];
+        if (!background_fields(m, tp.interp, bgTile, xInit, leaf, E, B)) {
+          outcome = 3;
+          break;
+        }
+        double dt;
+        const double absB = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]);
+        if (absB > 1.0E-25) {
+          const double PiTimes2 = 6.28318530717958647692528676655900576839433879875021;
+          const double g2 = 1.0 / sqrt(1.0 - (vInit[0] * vInit[0] + vInit[1] * vInit[1] + vInit[2] * vInit[2]) / (SpeedOfLight * SpeedOfLight));
+          const double GyroFreq = fabs(ElectricCharge) * absB / (PiTimes2 * mass * g2);
+          const double dtMax = 1.0 / GyroFreq;
+          dt = (dtMax < dtTotalIn) ? dtMax : dtTotalIn;
+        } else
+          dt = dtTotalIn;
+        dtTotalIn -= dt;
+        if (backward)
+          for (int d = 0; d < 3; d++) vInit[d] = -vInit[d], B[d] = -B[d];
+        const double QdT_over_twoM = ElectricCharge * dt / (2.0 * mass);
+        double uMinus[3];
+        for (int d = 0; d < 3; d++) uMinus[d] = gamma * vInit[d] + QdT_over_twoM * E[d];
+        double t[3], s[3], uPrime[3], uPlus[3], l = 0.0;
+        gamma = sqrt(1.0 + (uMinus[0] * uMinus[0] + uMinus[1] * uMinus[1] + uMinus[2] * uMinus[2]) / (SpeedOfLight * SpeedOfLight));
+        for (int d = 0; d < 3; d++) {
+          t[d] = QdT_over_twoM / gamma * B[d];
+          l += t[d] * t[d];
+        }
+        uPrime[0] = uMinus[1] * t[2] - uMinus[2] * t[1];
+        uPrime[1] = uMinus[2] * t[0] - uMinus[0] * t[2];
+        uPrime[2] = uMinus[0] * t[1] - uMinus[1] * t[0];
+        for (int d = 0; d < 3; d++) uPrime[d] += uMinus[d];
+        for (int d = 0; d < 3; d++) s[d] = 2.0 * t[d] / (1.0 + l);
+        uPlus[0] = uPrime[1] * s[2] - uPrime[2] * s[1];
+        uPlus[1] = uPrime[2] * s[0] - uPrime[0] * s[2];
+        uPlus[2] = uPrime[0] * s[1] - uPrime[1] * s[0];
+        for (int d = 0; d < 3; d++) uPlus[d] += uMinus[d];
+        double uFinal[3];
+        for (int d = 0; d < 3; d++) uFinal[d] = uPlus[d] + QdT_over_twoM * E[d];
+        gamma = sqrt(1.0 + (uFinal[0] * uFinal[0] + uFinal[1] * uFinal[1] + uFinal[2] * uFinal[2]) / (SpeedOfLight * SpeedOfLight));
+        for (int d = 0; d < 3; d++) {
+          vFinal[d] = uFinal[d] / gamma;
+          xFinal[d] = xInit[d] + vFinal[d] * dt;
+        }
+        if (backward)
+          for (int d = 0; d < 3; d++) vFinal[d] = -vFinal[d], vInit[d] = -vInit[d];
+
+        // internal sphere (:270-302): project on the sphere, hand to the callback, delete
+        int newNode;
+        if (tp.rSphere > 0.0) {
+          const double rFinal2 = xFinal[0] * xFinal[0] + xFinal[1] * xFinal[1] + xFinal[2] * xFinal[2];
+          if (rFinal2 < tp.rSphere * tp.rSphere) {
+            const double r = sqrt(rFinal2);
+            for (int d = 0; d < 3; d++) xFinal[d] *= tp.rSphere / r;
+            newNode = find_tree_node_plain(m, xFinal, node);
+            add_exit_record(exitBuf, exitCount, tp.exitCap, p.ptr[ip], spec, AMPS_EXIT_SPHERE, newNode >= 0 ? m.nodeLeaf[newNode] : -1, xFinal, vFinal);
+            outcome = 1;
+            break;
+          }
+        }
+        newNode = find_tree_node_plain(m, xFinal, node);
+        if (newNode < 0) {
+          if (tp.boundaryMode == AMPS_BOUNDARY_DELETE) {
+            outcome = 1;
+            break;
+          }
+          // face-intersection search (:320-446; reference defects restated as intended, see the oracle)
+          int nIntersectionFace = -1;
+          double vEffective[3], r0[3], dtIntersection = -1.0;
+          for (int d = 0; d < 3; d++) vEffective[d] = backward ? xInit[d] - xFinal[d] : xFinal[d] - xInit[d];
+          for (int nface = 0; nface < 6; nface++) {
+            double cx = 0.0, cv = 0.0, rr[3];
+            for (int d = 0; d < 3; d++) {
+              rr[d] = (backward ? xFinal[d] : xInit[d]) - sFace.x0[nface][d];
+              cx += rr[d] * sFace.norm[nface][d];
+              cv += vEffective[d] * sFace.norm[nface][d];
+            }
+            const double dtEffective = backward ? ((cv < 0.0) ? -cx / cv : -1.0) : ((cv > 0.0) ? -cx / cv : -1.0);
+            if (dtEffective > 0.0) {
+              if ((dtIntersection < 0.0) || ((dtEffective < dtIntersection) && (dtEffective > 0.0))) {
+                double cE0 = 0.0, cE1 = 0.0;
+                for (int d = 0; d < 3; d++) {
+                  const double c = rr[d] + dtEffective * vEffective[d];
+                  cE0 += c * sFace.e0[nface][d], cE1 += c * sFace.e1[nface][d];
+                }
+                if ((cE0 < -m.eps) || (cE0 > sFace.lE0[nface] + m.eps) || (cE1 < -m.eps) || (cE1 > sFace.lE1[nface] + m.eps)) continue;
+                nIntersectionFace = nface, dtIntersection = dtEffective;
+                for (int d = 0; d < 3; d++) r0[d] = rr[d];
+              }
+            }
+          }
+          (void)r0;
+          if (nIntersectionFace == -1) {
+            outcome = 3;
+            break;
+          }
+          if (backward) {
+            for (int d = 0; d < 3; d++) {
+              xInit[d] = xFinal[d] + dtIntersection * (xInit[d] - xFinal[d]) - sFace.norm[nIntersectionFace][d] * m.eps;
+              vInit[d] = vFinal[d] + dtIntersection * (vInit[d] - vFinal[d]);
+            }
+          } else {
+            for (int d = 0; d < 3; d++) {
+              xInit[d] += dtIntersection * (xFinal[d] - xInit[d]) - sFace.norm[nIntersectionFace][d] * m.eps;
+              vInit[d] += dtIntersection * (vFinal[d] - vInit[d]);
+            }
+          }
+          newNode = find_tree_node_plain(m, xInit, node);
+          if (newNode < 0) {
+            for (int d = 0; d < 3; d++) {
+              if (m.xGlobalMin[d] >= xInit[d]) xInit[d] = m.xGlobalMin[d] + m.eps;
+              if (m.xGlobalMax[d] <= xInit[d]) xInit[d] = m.xGlobalMax[d] - m.eps;
+            }
+            newNode = find_tree_node_plain(m, xInit, node);
+            if (newNode < 0) {
+              outcome = 3;
+              break;
+            }
+          }
+          if (tp.boundaryMode == AMPS_BOUNDARY_USER_FUNCTION) {
+            add_exit_record(exitBuf, exitCount, tp.exitCap, p.ptr[ip], spec, nIntersectionFace, m.nodeLeaf[newNode], xInit, vInit);
+            outcome = 1;  // the callback deletes (srcEarth/CutoffRigidity.cpp:129-230)
+          } else {
+            outcome = 3;  // SPECULAR: _PARTICLE_REJECTED_ON_THE_FACE_ -> exit("not implemented") in the reference
+          }
+          break;
+        }
+        if (!(m.nodeFlags[newNode] & AMPS_NODE_USED)) {
+          outcome = 2;
+          break;
+        }
+        const int newLeaf = m.nodeLeaf[newNode];
+        if (newLeaf < 0) {  // fields of a block that is not allocated on this rank
+          outcome = 3;
+          break;
+        }
+        node = newNode, leaf = newLeaf;
+        for (int d = 0; d < 3; d++) xInit[d] = xFinal[d], vInit[d] = vFinal[d];
+      }
+
+    int newKey = -1;
+    if (outcome == 0) {
+      int ijk[3];
+      if (!find_cell_index(m, xFinal, node, ijk)) {
+        outcome = 3;
+      } else {
+        int newLeaf = leaf;
+        const int realLeaf = m.leaf[newLeaf].real;
+        if (realLeaf >= 0) {  // periodic ghost -> real (pic_bc_periodic.cpp:100-134)
+          const LeafGeo &gg = m.leaf[newLeaf];
+          const LeafGeo &rg = m.leaf[realLeaf];
+          for (int d = 0; d < 3; d++) {
+            xFinal[d] += rg.xmin[d] - gg.xmin[d];
+            if (xFinal[d] < rg.xmin[d]) xFinal[d] = rg.xmin[d];
+            if (xFinal[d] >= rg.xmax[d]) xFinal[d] = rg.xmax[d] - 1.0E-10 * (rg.xmax[d] - rg.xmin[d]);
+          }
+          newLeaf = realLeaf;
+          nWrap++;
+        }
+        newKey = newLeaf * C + ijk[0] + m.N[0] * (ijk[1] + m.N[1] * ijk[2]);
+        if (newLeaf != startLeaf) nXBlock++;
+        else if (newKey != oldKey) nXCell++;
+      }
+    }
+    if (outcome == 1) nLeft++;
+    else if (outcome == 2) nNotUsed++;
+    else if (outcome == 3) nErr++;
+    if (newKey >= 0) {
+      p.x[0][ip] = xFinal[0], p.x[1][ip] = xFinal[1], p.x[2][ip] = xFinal[2];
+      p.v[0][ip] = vFinal[0], p.v[1][ip] = vFinal[1], p.v[2][ip] = vFinal[2];
+      atomicAdd(&cellCount[newKey], 1);
+    }
+    if (newKey != oldKey) p.key[ip] = newKey;
+  }
+
+  unsigned int c[7] = {nMoved, nXCell, nXBlock, nLeft, nNotUsed, nWrap, nErr};
+#pragma unroll
+  for (int q = 0; q < 7; q++) {
+    unsigned int v = c[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    c[q] = v;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    unsigned long long *s = reinterpret_cast<unsigned long long *>(stats);
+#pragma unroll
+    for (int q = 0; q < 7; q++)
+      if (c[q]) atomicAdd(&s[q], (unsigned long long)c[q]);
+  }
+}
+
+void launch_move_relativistic_boris(const DevMesh &m, const DevSpecies &sp, int interp, int backward, double c, double rSphere, long long exitCap,
+                                    ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, int *cellCount, DevMoveStats *stats,
+                                    amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s) {
+  TpParams tp;
+  tp.interp = interp, tp.backward = backward, tp.boundaryMode = sp.boundaryMode, tp.c = c, tp.rSphere = rSphere, tp.exitCap = exitCap;
+  long long g = (nUpper + 127) / 128;
+  if (g < 1) g = 1;
+  if (g > 148 * 32) g = 148 * 32;
+  move_relativistic_boris_kernel<<<(int)g, 128, 0, s>>>(m, sp, tp, p, nSlots, bgTile, cellCount, stats, exitBuf, exitCount);
+}
+
+}  // namespace amps

@@ -91,14 +91,18 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_box(n_cells, ppc, block_cells=(8, 8, 8), seed=100, capacity_slack=1.02):
+DECOMP = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def build_box(n_cells, ppc, block_cells=(8, 8, 8), seed=100, capacity_slack=1.02, rank=0, world=1):
     from amps_b200 import api, mesh as meshmod, workload
 
-    m = meshmod.uniform_periodic_box(n_cells, block_cells, (1, 1, 1))
+    m = meshmod.uniform_periodic_box(n_cells, block_cells, (1, 1, 1), rank=rank, n_ranks=world, decomp=DECOMP[world])
     charge, mass, wgt = workload.species_tables(ppc, 1.0)
     parts = workload.maxwellian_box(m, ppc, seed=seed)
     n = parts[0].shape[1]
-    cfg = api.make_config(block_cells, (1, 1, 1), charge, mass, wgt, 1.0, periodic=True, capacity=int(n * capacity_slack) + 1024)
+    cfg = api.make_config(block_cells, (1, 1, 1), charge, mass, wgt, 1.0, periodic=True,
+                          capacity=int(n * (capacity_slack if world == 1 else 1.10)) + 1024)
     E, B = workload.box_fields(m, E_amp=0.0)
     return m, cfg, parts, (E, B, B.copy())
 
@@ -190,11 +194,16 @@ def main():
     P = 2 * args.ppc
 
     t_gen = time.time()
-    m, cfg, parts, fields = build_box((args.cells,) * 3, args.ppc, seed=100 + rank)
+    # weak scaling: every GPU owns an args.cells^3 sub-box of one periodic box (Cartesian block decomposition)
+    dec = DECOMP[world]
+    n_cells = tuple(args.cells * dec[d] for d in range(3))
+    m, cfg, parts, fields = build_box(n_cells, args.ppc, seed=100 + rank, rank=rank, world=world)
     cfg.device = local
     n_part = parts[0].shape[1]
     t_gen = time.time() - t_gen
     ctx = api.Context(cfg, m)
+    if world > 1:
+        ctx.comm_init(dist)
     ctx.fields_upload(*fields)
     ctx.particles_upload(*parts)
     del parts
@@ -283,7 +292,7 @@ def main():
     # ---- roofline of the dominant kernel (CUDA-event time of its launches inside the timed region) ----
     peak, peak_src = load_peaks()
     dom = max(("move", "sort", "deposit"), key=lambda p: phases[p][0])
-    dom_ms = phases[dom][0] / max(1, phases[dom][1])
+    dom_ms = phases[dom][0] / max(1, K)
     dom_alg = "deposit" if dom == "sort" else dom
     alg_bytes = KERNEL_ALG_BYTES[dom_alg](P) * n_part
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
@@ -295,8 +304,9 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"ECSIM uniform periodic box {args.cells}^3 cells per GPU, {args.ppc} ppc/species e+p, 8^3-cell blocks, "
-                               f"single AMR level, Maxwellian v_th,e=0.05, dt=1 (BASELINE configs[1])",
+        "config": {"workload": f"ECSIM uniform periodic box {n_cells[0]}x{n_cells[1]}x{n_cells[2]} cells ({args.cells}^3 per GPU, block decomposition "
+                               f"{dec[0]}x{dec[1]}x{dec[2]}), {args.ppc} ppc/species e+p, 8^3-cell blocks, single AMR level, Maxwellian "
+                               f"v_th,e=0.05, dt=1 (BASELINE configs[1]" + ("" if world == 1 else "; NCCL particle migration + corner J/M exchange each step") + ")",
                    "particles_per_gpu": n_part, "particles_after": n_now, "l2": "inputs (2.2 GB particle SoA) larger than L2, no flush",
                    "step": "move(Lapenta2017)+counting sort+UpdateJMassMatrix", "gen_s": round(t_gen, 1)},
         "clocks": clocks,
@@ -304,7 +314,7 @@ def main():
                 "ms_per_step": e2e_ms / KE},
         "gpu_launches": int(launches),
         "roofline": roofline,
-        "phases_ms_per_step": {p: (phases[p][0] / max(1, phases[p][1])) for p in ("move", "sort", "deposit")},
+        "phases_ms_per_step": {p: (phases[p][0] / max(1, K)) for p in ("move", "sort", "deposit", "exchange")},
         "roofline_step": {"alg_bytes_per_update": step_alg, "achieved_gbs_per_gpu": step_gbs, "frac_hbm": step_gbs / peak,
                           "fp64_tflops_per_gpu": ALG_FLOP_PER_UPDATE * (value / world) / 1e12},
     }

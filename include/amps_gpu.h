@@ -100,7 +100,30 @@ typedef struct amps_gpu_config {
   double ecsim_B_conv;           /* ECSIM::B_conv                                              */
   double ecsim_length_conv;      /* ECSIM::length_conv                                         */
   double ecsim_light_speed;      /* ECSIM::LightSpeed                                          */
+  /* test-particle movers (Boris / Relativistic::Boris / guiding centre): fields come from the coupler's
+     centre-node table through PIC::CPLR::InitInterpolationStencil (pic_swmf.cpp:76-90)          */
+  int32_t coupler_interpolation;     /* AMPS_CPLR_CELL_CENTERED_CONSTANT | _LINEAR  (_PIC_COUPLER__INTERPOLATION_MODE_) */
+  int32_t backward_time_integration; /* BackwardTimeIntegrationMode (pic_mover_relativistic_boris.cpp:128-132)           */
+  double speed_of_light;             /* SpeedOfLight (constants.h), SI                                                     */
+  double internal_sphere_radius;     /* max(_RADIUS_(_TARGET_),Planet->Radius), 0 = no internal sphere (:272)            */
+  int64_t exit_record_capacity;      /* records kept for the host callbacks (0 = only count)                              */
 } amps_gpu_config;
+
+/* _PIC_COUPLER__INTERPOLATION_MODE_ */
+enum { AMPS_CPLR_CELL_CENTERED_CONSTANT = 0, AMPS_CPLR_CELL_CENTERED_LINEAR = 1 };
+
+/* one particle that left through a domain face or hit the internal sphere: what
+ * fProcessOutsideDomainParticles (pic.h:6043) / ParticleSphereInteraction (pic_mover_relativistic_boris.cpp:290)
+ * receive; the host replays the callbacks (e.g. Earth::CutoffRigidity::ProcessOutsideDomainParticles,
+ * srcEarth/CutoffRigidity.cpp:129-230)                                                        */
+typedef struct amps_gpu_exit_record {
+  int32_t ptr;       /* ParticleBuffer slot                                         */
+  int32_t species;
+  int32_t face;      /* nIntersectionFace 0..5, AMPS_EXIT_SPHERE for the internal sphere */
+  int32_t leaf;      /* local leaf the callback gets as newNode                     */
+  double x[3], v[3]; /* xInit, vInit at the intersection                            */
+} amps_gpu_exit_record;
+enum { AMPS_EXIT_SPHERE = 6 };
 
 /* ---- flattened AMR mesh (host builds it from cMeshAMRgeneric; K7 in SURVEY 2.5) ----
  * The tree is a forest: n_root[0..2] root blocks tile [x_global_min,x_global_max];
@@ -192,6 +215,12 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh);
  *      (pic_field_solver_ecsim.cpp:484-538).  Any pointer may be NULL = keep.   ---- */
 int amps_gpu_fields_upload(amps_gpu_ctx *ctx, const double *E_half, const double *B_prev,
                            const double *B_cur);
+
+/* background E, B of the coupler on the unique centre nodes, [n_centers][3] each (DATAFILE::Offset::ElectricField /
+ * MagneticField of cDataCenterNode, pic.h:8338-8425); either may be NULL = keep / zero            */
+int amps_gpu_background_upload(amps_gpu_ctx *ctx, const double *E_center, const double *B_center);
+/* exit records accumulated by the movers since the last call (clears them) */
+int amps_gpu_exit_records(amps_gpu_ctx *ctx, amps_gpu_exit_record *buf, int64_t max_records, int64_t *n);
 
 /* ---- particle store: PIC::ParticleBuffer as a device SoA sorted by (block,cell) ---- */
 /* AoS records + the cell each one is attached to (global cell = leaf*Nx*Ny*Nz +

@@ -38,7 +38,10 @@ const int MassMatrixOffsetIndex = 9;
 const int CornerDataLength = 252;
 const int CurrentBOffset_d = 0;
 const int PrevBOffset_d = 3;
-const int CenterDataLength = 6;
+const int BackgroundE_d = 6;   // coupler table: DATAFILE::Offset::ElectricField
+const int BackgroundB_d = 9;   // coupler table: DATAFILE::Offset::MagneticField
+const int CenterDataLength = 12;
+const double SpeedOfLight_SI = 299792458.0;  // src/general/constants.h:40
 
 // src/pic/pic_field_solver_ecsim.cpp:1377-1380
 const int IndexMatrix[8][8] = {{0, 2, 8, 6, 18, 20, 26, 24},  {1, 0, 6, 7, 19, 18, 24, 25},
@@ -656,6 +659,251 @@ struct oracle_ctx {
     return _PARTICLE_MOTION_FINISHED_;
   }
 
+
+  // exit records handed to fProcessOutsideDomainParticles / ParticleSphereInteraction
+  std::vector<amps_gpu_exit_record> exitRecords;
+  void AddExitRecord(long int ptr, int spec, int face, cTreeNode *node, const double *x, const double *v) {
+#pragma omp critical(oracle_exit)
+    {
+      amps_gpu_exit_record r;
+      r.ptr = (int)ptr, r.species = spec, r.face = face, r.leaf = node ? node->leaf : -1;
+      for (int d = 0; d < 3; d++) r.x[d] = x[d], r.v[d] = v[d];
+      exitRecords.push_back(r);
+    }
+  }
+
+  // PIC::CPLR::InitInterpolationStencil (pic_swmf.cpp:76-90) + GetBackgroundElectricField/MagneticField
+  // (pic.h:8338-8425) on the coupler's centre-node table.  Here the stencil IS the global StencilTable, so the
+  // "Length != 8 -> Normalize" test of GetTriliniarInterpolationStencil (:903) applies as written.
+  bool GetBackgroundFields(const double *x, cTreeNode *node, double *E, double *B) const {
+    cStencil Stencil;
+    if (cfg.coupler_interpolation == AMPS_CPLR_CELL_CENTERED_LINEAR) {
+      CellCentered_Linear_InitStencil(x, node, Stencil, false);
+    } else {
+      int i, j, k;
+      long int nd = FindCellIndex(x, i, j, k, node);
+      if (nd < 0 || node->block == NULL || node->block->centerNodes[nd] == NULL) return false;
+      Stencil.Weight[0] = 1.0, Stencil.LocalCellID[0] = (int)nd, Stencil.Length = 1;
+    }
+    for (int idim = 0; idim < 3; idim++) E[idim] = 0.0, B[idim] = 0.0;
+    for (int iStencil = 0; iStencil < Stencil.Length; iStencil++) {
+      const double *t = node->block->centerNodes[Stencil.LocalCellID[iStencil]]->data + BackgroundE_d;
+      for (int idim = 0; idim < 3; idim++) E[idim] += Stencil.Weight[iStencil] * t[idim];
+    }
+    for (int iStencil = 0; iStencil < Stencil.Length; iStencil++) {
+      const double *t = node->block->centerNodes[Stencil.LocalCellID[iStencil]]->data + BackgroundB_d;
+      for (int idim = 0; idim < 3; idim++) B[idim] += Stencil.Weight[iStencil] * t[idim];
+    }
+    return true;
+  }
+
+  // domain-exit search shared by the test-particle movers, pic_mover_relativistic_boris.cpp:320-446.
+  // NOTE (reference defects, restated as intended): nIntersectionFace is read uninitialised when no face is found
+  // (:381 tests it against -1) -> initialised to -1 here; the position shift at :387/:393 indexes the face table with
+  // the loop variable `nface` (== 6 after the loop, out of bounds) -> the intersection face is used.
+  // returns the reference's `code`: 0 = _PARTICLE_DELETED_ON_THE_FACE_, -1 = would exit()
+  int ProcessDomainExit(long int ptr, int spec, double *xInit, double *vInit, double *xFinal, double *vFinal, cTreeNode *startNode, cTreeNode **newNodeOut) {
+    int idim, nface, nIntersectionFace = -1;
+    double cx, cv, r0[3], dtEffective, vEffective[3], c, dtIntersection = -1.0;
+    const bool backward = cfg.backward_time_integration != 0;
+    if (backward) for (idim = 0; idim < 3; idim++) vEffective[idim] = xInit[idim] - xFinal[idim];
+    else for (idim = 0; idim < 3; idim++) vEffective[idim] = xFinal[idim] - xInit[idim];
+    for (nface = 0; nface < 6; nface++) {
+      if (backward) {
+        for (idim = 0, cx = 0.0, cv = 0.0; idim < 3; idim++) {
+          r0[idim] = xFinal[idim] - FaceTable[nface].x0[idim];
+          cx += r0[idim] * FaceTable[nface].norm[idim];
+          cv += vEffective[idim] * FaceTable[nface].norm[idim];
+        }
+        dtEffective = (cv < 0.0) ? -cx / cv : -1.0;
+      } else {
+        for (idim = 0, cx = 0.0, cv = 0.0; idim < 3; idim++) {
+          r0[idim] = xInit[idim] - FaceTable[nface].x0[idim];
+          cx += r0[idim] * FaceTable[nface].norm[idim];
+          cv += vEffective[idim] * FaceTable[nface].norm[idim];
+        }
+        dtEffective = (cv > 0.0) ? -cx / cv : -1.0;
+      }
+      if (dtEffective > 0.0) {
+        if ((dtIntersection < 0.0) || ((dtEffective < dtIntersection) && (dtEffective > 0.0))) {
+          double cE0 = 0.0, cE1 = 0.0;
+          for (idim = 0; idim < 3; idim++) {
+            c = r0[idim] + dtEffective * vEffective[idim];
+            cE0 += c * FaceTable[nface].e0[idim], cE1 += c * FaceTable[nface].e1[idim];
+          }
+          if ((cE0 < -EPS) || (cE0 > FaceTable[nface].lE0 + EPS) || (cE1 < -EPS) || (cE1 > FaceTable[nface].lE1 + EPS)) continue;
+          nIntersectionFace = nface, dtIntersection = dtEffective;
+        }
+      }
+    }
+    if (nIntersectionFace == -1) return -1;
+    if (backward) {
+      for (idim = 0; idim < 3; idim++) {
+        xInit[idim] = xFinal[idim] + dtIntersection * (xInit[idim] - xFinal[idim]) - FaceTable[nIntersectionFace].norm[idim] * EPS;
+        vInit[idim] = vFinal[idim] + dtIntersection * (vInit[idim] - vFinal[idim]);
+      }
+    } else {
+      for (idim = 0; idim < 3; idim++) {
+        xInit[idim] += dtIntersection * (xFinal[idim] - xInit[idim]) - FaceTable[nIntersectionFace].norm[idim] * EPS;
+        vInit[idim] += dtIntersection * (vFinal[idim] - vInit[idim]);
+      }
+    }
+    cTreeNode *newNode = findTreeNode(xInit, startNode);
+    if (newNode == NULL) {
+      for (int ii = 0; ii < 3; ii++) {
+        if (xGlobalMin[ii] >= xInit[ii]) xInit[ii] = xGlobalMin[ii] + EPS;
+        if (xGlobalMax[ii] <= xInit[ii]) xInit[ii] = xGlobalMax[ii] - EPS;
+      }
+      newNode = findTreeNode(xInit, startNode);
+      if (newNode == NULL) return -1;
+    }
+    int code;
+    switch (cfg.boundary_mode) {
+      case AMPS_BOUNDARY_USER_FUNCTION:
+        // ProcessOutsideDomainParticles(ptr,xInit,vInit,nIntersectionFace,newNode): recorded for the host; the
+        // cutoff-rigidity callback always deletes (srcEarth/CutoffRigidity.cpp:129-230)
+        AddExitRecord(ptr, spec, nIntersectionFace, newNode, xInit, vInit);
+        code = 0;
+        break;
+      case AMPS_BOUNDARY_SPECULAR_REFLECTION: {
+        double cc = 0.0;
+        for (int d = 0; d < 3; d++) cc += FaceTable[nIntersectionFace].norm[d] * vInit[d];
+        for (int d = 0; d < 3; d++) vInit[d] -= 2.0 * cc * FaceTable[nIntersectionFace].norm[d];
+        code = 1;  // _PARTICLE_REJECTED_ON_THE_FACE_ -> the reference exit()s ("not implemented", :452-453)
+      } break;
+      default:
+        return -1;
+    }
+    memcpy(vFinal, vInit, 3 * sizeof(double));
+    memcpy(xFinal, xInit, 3 * sizeof(double));
+    *newNodeOut = newNode;
+    return code;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // PIC::Mover::Relativistic::Boris, src/pic/pic_mover_relativistic_boris.cpp:16-583 (scalar branch)
+  // ------------------------------------------------------------------------------------------
+  int Relativistic_Boris(byte *ParticleData, long int ptr, double dtTotalIn, cTreeNode *startNode, int nThreads, int thread, cTreeNode **newNodeOut) {
+    cTreeNode *newNode = NULL;
+    double gamma;
+    double mass, QdT_over_twoM, ElectricCharge;
+    int idim, i, j, k, spec;
+    double uMinus[3], E[3], B[3];
+    double vInit[3], xInit[3], xFinal[3], vFinal[4];
+    const double SpeedOfLight = cfg.speed_of_light;
+    const bool backward = cfg.backward_time_integration != 0;
+
+    GetV(vInit, ParticleData);
+    GetX(xInit, ParticleData);
+    spec = GetI(ParticleData);
+    ElectricCharge = cfg.charge[spec];
+    mass = cfg.mass[spec];
+
+    if (dtTotalIn == 0.0) {
+      memcpy(xFinal, xInit, 3 * sizeof(double));
+      memcpy(vFinal, vInit, 3 * sizeof(double));
+      newNode = startNode;
+    } else
+      while (dtTotalIn > 0.0) {
+        gamma = 1.0 / sqrt(1.0 - (vInit[0] * vInit[0] + vInit[1] * vInit[1] + vInit[2] * vInit[2]) / (SpeedOfLight * SpeedOfLight));
+        if (!GetBackgroundFields(xInit, startNode, E, B)) return _ORACLE_ERROR_;
+
+        double dt, GyroFreq, dtMax;
+        if (sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) > 1.0E-25) {
+          // ::Relativistic::GetGyroFrequency, specfunc.h:1290
+          const double PiTimes2 = 6.28318530717958647692;
+          GyroFreq = fabs(ElectricCharge) * sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) /
+                     (PiTimes2 * mass * (1.0 / sqrt(1.0 - (vInit[0] * vInit[0] + vInit[1] * vInit[1] + vInit[2] * vInit[2]) / (SpeedOfLight * SpeedOfLight))));
+          dtMax = 1.0 / GyroFreq;
+          dt = (dtMax < dtTotalIn) ? dtMax : dtTotalIn;
+        } else
+          dt = dtTotalIn;
+        dtTotalIn -= dt;
+
+        if (backward)
+          for (idim = 0; idim < 3; idim++) vInit[idim] = -vInit[idim], B[idim] = -B[idim];
+
+        QdT_over_twoM = ElectricCharge * dt / (2.0 * mass);
+        for (idim = 0; idim < 3; idim++) uMinus[idim] = gamma * vInit[idim] + QdT_over_twoM * E[idim];
+
+        double t[3], s[3], uPrime[3], uPlus[3], l = 0.0;
+        gamma = sqrt(1.0 + (uMinus[0] * uMinus[0] + uMinus[1] * uMinus[1] + uMinus[2] * uMinus[2]) / (SpeedOfLight * SpeedOfLight));
+        for (idim = 0; idim < 3; idim++) {
+          t[idim] = QdT_over_twoM / gamma * B[idim];
+          l += t[idim] * t[idim];  // pow(t,2)
+        }
+        // Vector3D::CrossProduct(uPrime,uMinus,t)
+        uPrime[0] = uMinus[1] * t[2] - uMinus[2] * t[1];
+        uPrime[1] = uMinus[2] * t[0] - uMinus[0] * t[2];
+        uPrime[2] = uMinus[0] * t[1] - uMinus[1] * t[0];
+        for (idim = 0; idim < 3; idim++) uPrime[idim] += uMinus[idim];
+        for (idim = 0; idim < 3; idim++) s[idim] = 2.0 * t[idim] / (1.0 + l);
+        uPlus[0] = uPrime[1] * s[2] - uPrime[2] * s[1];
+        uPlus[1] = uPrime[2] * s[0] - uPrime[0] * s[2];
+        uPlus[2] = uPrime[0] * s[1] - uPrime[1] * s[0];
+        for (idim = 0; idim < 3; idim++) uPlus[idim] += uMinus[idim];
+
+        double uFinal[3];
+        for (idim = 0; idim < 3; idim++) uFinal[idim] = uPlus[idim] + QdT_over_twoM * E[idim];
+        gamma = sqrt(1.0 + (uFinal[0] * uFinal[0] + uFinal[1] * uFinal[1] + uFinal[2] * uFinal[2]) / (SpeedOfLight * SpeedOfLight));
+        for (idim = 0; idim < 3; idim++) {
+          vFinal[idim] = uFinal[idim] / gamma;
+          xFinal[idim] = xInit[idim] + vFinal[idim] * dt;
+        }
+        if (backward)
+          for (idim = 0; idim < 3; idim++) vFinal[idim] = -vFinal[idim], vInit[idim] = -vInit[idim];
+
+        // internal sphere (:270-302)
+        if (cfg.internal_sphere_radius > 0.0) {
+          const double rSphere = cfg.internal_sphere_radius;
+          double rFinal2;
+          if ((rFinal2 = xFinal[0] * xFinal[0] + xFinal[1] * xFinal[1] + xFinal[2] * xFinal[2]) < rSphere * rSphere) {
+            double r = sqrt(rFinal2);
+            for (idim = 0; idim < 3; idim++) xFinal[idim] *= rSphere / r;
+            newNode = findTreeNode(xFinal, startNode);
+            // ParticleSphereInteraction(spec,ptr,xFinal,vFinal,dt,newNode,...): recorded; the cutoff-rigidity model deletes
+            AddExitRecord(ptr, spec, AMPS_EXIT_SPHERE, newNode, xFinal, vFinal);
+            DeleteParticle(ptr);
+            return _PARTICLE_LEFT_THE_DOMAIN_;
+          } else
+            newNode = findTreeNode(xFinal, startNode);
+        } else
+          newNode = findTreeNode(xFinal, startNode);
+
+        if (newNode == NULL) {
+          int code = 0;
+          if (cfg.boundary_mode != AMPS_BOUNDARY_DELETE) {
+            code = ProcessDomainExit(ptr, spec, xInit, vInit, xFinal, vFinal, startNode, &newNode);
+          }
+          switch (code) {
+            case 0:
+              DeleteParticle(ptr);
+              return _PARTICLE_LEFT_THE_DOMAIN_;
+            default:
+              return _ORACLE_ERROR_;
+          }
+        } else {
+          if (newNode->IsUsedInCalculationFlag == false) {
+            DeleteParticle(ptr);
+            return _PARTICLE_IN_NOT_IN_USE_NODE_;
+          }
+        }
+        if (newNode->block == NULL) return _ORACLE_ERROR_;  // fields of a block that is not allocated here
+        startNode = newNode;
+        memcpy(xInit, xFinal, 3 * sizeof(double));
+        memcpy(vInit, vFinal, 3 * sizeof(double));
+      }
+
+    cBlock *block;
+    if (FindCellIndex(xFinal, i, j, k, newNode) == -1) return _ORACLE_ERROR_;
+    if ((block = newNode->block) == NULL) return _ORACLE_ERROR_;
+    AttachToTempList(ptr, ParticleData, block, i, j, k, nThreads, thread);
+    SetV(vFinal, ParticleData);
+    SetX(xFinal, ParticleData);
+    *newNodeOut = newNode;
+    return _PARTICLE_MOTION_FINISHED_;
+  }
+
   // PIC::Mover::cExternalBoundaryFace + Init, src/pic/pic_mover.cpp:24-28,48-75
   struct cExternalBoundaryFace {
     double norm[3];
@@ -1070,6 +1318,20 @@ void oracle_set_fields(oracle_ctx *o, const double *E_half, const double *B_prev
     for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + CurrentBOffset_d, B_cur + 3 * (size_t)i, 24);
 }
 
+void oracle_set_background(oracle_ctx *o, const double *E_center, const double *B_center) {
+  if (E_center)
+    for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + BackgroundE_d, E_center + 3 * (size_t)i, 24);
+  if (B_center)
+    for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + BackgroundB_d, B_center + 3 * (size_t)i, 24);
+}
+int64_t oracle_exit_records(oracle_ctx *o, amps_gpu_exit_record *buf, int64_t max_records) {
+  int64_t n = (int64_t)o->exitRecords.size();
+  if (buf)
+    for (int64_t i = 0; i < n && i < max_records; i++) buf[i] = o->exitRecords[i];
+  o->exitRecords.clear();
+  return n;
+}
+
 // PIC::ParticleBuffer::InitiateParticle(..., _PIC_INIT_PARTICLE_MODE__ADD2LIST_), src/pic/pic_pbuffer.cpp:939-1027
 int oracle_add_particles(oracle_ctx *o, const double *x, const double *v, const double *w, const uint8_t *species, const int32_t *cells, int64_t n) {
   const int nC = o->nCellsBlock();
@@ -1129,7 +1391,7 @@ void oracle_get_particles(const oracle_ctx *o, double *x, double *v, double *w, 
 // PIC::Mover::MoveParticles(), src/pic/pic_mover.cpp:580-1088 followed (periodic mode) by
 // PIC::BC::ExternalBoundary::Periodic::ExchangeParticles(), src/pic/pic_time_step.cpp:454-506
 int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats *stats, int32_t *ret_code, int32_t *final_cell) {
-  if (mover_id != AMPS_MOVER_LAPENTA2017) {
+  if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS) {
     o->err = "oracle_move: mover not restated yet";
     return AMPS_GPU_ERR_ARG;
   }
@@ -1161,8 +1423,17 @@ int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats 
     cBlock *block = node->block;
     if (!block) return;
     double *E_Corner = o->E_Corner[thread].data(), *B_C = o->B_Center[thread].data();
-    o->SetBlock_E(E_Corner, node);
-    o->SetBlock_B(B_C, node);
+    if (mover_id == AMPS_MOVER_LAPENTA2017) {
+      o->SetBlock_E(E_Corner, node);
+      o->SetBlock_B(B_C, node);
+    }
+    auto mover = [&](long int ptr, cTreeNode **newNode) -> int {
+      byte *pd = o->GetParticleDataPointer(ptr);
+      if (mover_id == AMPS_MOVER_LAPENTA2017) return o->Lapenta2017(pd, ptr, node, E_Corner, B_C, n_threads, thread, newNode);
+      const int spec = oracle_ctx::GetI(pd);
+      const double dtLocal = (o->cfg.time_step_mode == AMPS_DT_SPECIES_GLOBAL) ? o->cfg.time_step[spec] : o->cfg.time_step[0];
+      return o->Relativistic_Boris(pd, ptr, dtLocal, node, n_threads, thread, newNode);
+    };
     long int *FirstCellParticleTable = block->FirstCellParticleTable;
     for (int i = 0; i < nC; i++) {
       long int ParticleList = FirstCellParticleTable[i];
@@ -1172,7 +1443,7 @@ int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats 
           long int ptr = FirstCellParticleTable[i];
           FirstCellParticleTable[i] = o->GetNext(ptr);
           cTreeNode *newNode = NULL;
-          int rc = o->Lapenta2017(o->GetParticleDataPointer(ptr), ptr, node, E_Corner, B_C, n_threads, thread, &newNode);
+          int rc = mover(ptr, &newNode);
           cnt[0]++;
           if (ret_code) ret_code[ptr] = rc;
           if (rc == _PARTICLE_MOTION_FINISHED_) {
@@ -1187,7 +1458,7 @@ int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats 
           long int ptr = ParticleList;
           ParticleList = o->GetNext(ParticleList);
           cTreeNode *newNode = NULL;
-          int rc = o->Lapenta2017(o->GetParticleDataPointer(ptr), ptr, node, E_Corner, B_C, n_threads, thread, &newNode);
+          int rc = mover(ptr, &newNode);
           cnt[0]++;
           if (ret_code) ret_code[ptr] = rc;
           if (rc == _PARTICLE_MOTION_FINISHED_) {

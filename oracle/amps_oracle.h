@@ -44,6 +44,11 @@ int64_t oracle_particle_data_length(const oracle_ctx *);
 /* corner E_half[n_corners][3], centre B_prev/B_cur[n_centers][3] */
 void oracle_set_fields(oracle_ctx *, const double *E_half, const double *B_prev, const double *B_cur);
 
+/* coupler table for the test-particle movers: E, B on the unique centre nodes [n_centers][3] */
+void oracle_set_background(oracle_ctx *, const double *E_center, const double *B_center);
+/* exit records (domain faces / internal sphere) accumulated since the last call; returns their number */
+int64_t oracle_exit_records(oracle_ctx *, amps_gpu_exit_record *buf, int64_t max_records);
+
 /* InitiateParticle(...,ADD2LIST) for n particles: particle i gets ptr i */
 int oracle_add_particles(oracle_ctx *, const double *x, const double *v, const double *w,
                          const uint8_t *species, const int32_t *cells, int64_t n);

@@ -29,6 +29,9 @@ def load(kind="parity"):
     lib.oracle_particle_data_length.restype = C.c_int64
     lib.oracle_particle_data_length.argtypes = [vp]
     lib.oracle_set_fields.argtypes = [vp, vp, vp, vp]
+    lib.oracle_set_background.argtypes = [vp, vp, vp]
+    lib.oracle_exit_records.restype = C.c_int64
+    lib.oracle_exit_records.argtypes = [vp, vp, C.c_int64]
     lib.oracle_add_particles.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64]
     lib.oracle_particle_count.restype = C.c_int64
     lib.oracle_particle_count.argtypes = [vp]
@@ -67,6 +70,17 @@ class Oracle:
     def set_fields(self, E_half=None, B_prev=None, B_cur=None):
         a = [None if t is None else np.ascontiguousarray(t, dtype=np.float64) for t in (E_half, B_prev, B_cur)]
         self.lib.oracle_set_fields(self.h, _p(a[0]), _p(a[1]), _p(a[2]))
+
+    def set_background(self, E_center=None, B_center=None):
+        a = [None if t is None else np.ascontiguousarray(t, dtype=np.float64) for t in (E_center, B_center)]
+        self.lib.oracle_set_background(self.h, _p(a[0]), _p(a[1]))
+
+    def exit_records(self, max_records=1 << 20):
+        from amps_b200._capi import ExitRecord
+
+        buf = (ExitRecord * max_records)()
+        n = int(self.lib.oracle_exit_records(self.h, C.cast(buf, C.c_void_p), max_records))
+        return n, [(r.ptr, r.species, r.face, r.leaf, tuple(r.x), tuple(r.v)) for r in buf[:min(n, max_records)]]
 
     def add_particles(self, x, v, w, species, cells):
         x = np.ascontiguousarray(x, dtype=np.float64)
