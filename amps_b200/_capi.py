@@ -59,6 +59,7 @@ class Config(C.Structure):
         ("speed_of_light", C.c_double),
         ("internal_sphere_radius", C.c_double),
         ("exit_record_capacity", C.c_int64),
+        ("gravity_gm", C.c_double),
     ]
 
 

@@ -49,6 +49,7 @@ def make_config(block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), charge=(-1.0, 1.0)
     cfg.speed_of_light = 299792458.0
     cfg.internal_sphere_radius = 0.0
     cfg.exit_record_capacity = 0
+    cfg.gravity_gm = 0.0
     return cfg
 
 

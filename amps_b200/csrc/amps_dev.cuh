@@ -93,7 +93,8 @@ __device__ __forceinline__ int centerLocalNumber(const DevMesh &m, int i, int j,
 void launch_stage_tiles(const DevMesh &m, const double *E_half, const double *B_prev, const double *B_cur, double *eTile, double *bPrevTile,
                         double *bCurTile, cudaStream_t s);
 void launch_move_lapenta(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *eTile, const double *bTile,
-                         int *cellCount, DevMoveStats *stats, int slices, cudaStream_t s);
+                         int *cellCount, DevMoveStats *stats, int slices, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount,
+                         long long exitCap, cudaStream_t s);
 void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *nSrc, int *cellCount, int *cellStart, int *cellFill, int *nDst,
                  long long capacity, bool countValid, void *scanTmp, cudaStream_t s, long long *launches);
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
@@ -109,6 +110,9 @@ void launch_stage_background(const DevMesh &m, const double *E, const double *B,
 void launch_move_relativistic_boris(const DevMesh &m, const DevSpecies &sp, int interp, int backward, double c, double rSphere, long long exitCap,
                                     ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, int *cellCount, DevMoveStats *stats,
                                     amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s);
+void launch_move_boris(const DevMesh &m, const DevSpecies &sp, int interp, int backward, double c, double rSphere, long long exitCap, double gravityGM,
+                       ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, int *cellCount, DevMoveStats *stats,
+                       amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s);
 void launch_division_selftest(const double *a, const double *b, int n, unsigned long long *out, cudaStream_t s);
 
 }  // namespace amps

@@ -608,13 +608,24 @@ int amps_gpu_cell_table_download(amps_gpu_ctx *ctx, int64_t *cell_start, int64_t
 static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "move before mesh upload");
   if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "move needs the (block,cell)-sorted layout: call amps_gpu_sort");
-  if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS) FAIL(AMPS_GPU_ERR_ARG, "mover not implemented yet");
+  if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS && mover_id != AMPS_MOVER_BORIS)
+    FAIL(AMPS_GPU_ERR_ARG, "mover not implemented yet");
   if (mover_id == AMPS_MOVER_LAPENTA2017 && !ctx->fieldsReady) FAIL(AMPS_GPU_ERR_STATE, "Lapenta2017 needs amps_gpu_fields_upload");
-  if (mover_id == AMPS_MOVER_RELATIVISTIC_BORIS && !ctx->backgroundReady) FAIL(AMPS_GPU_ERR_STATE, "Relativistic::Boris needs amps_gpu_background_upload");
+  if (mover_id != AMPS_MOVER_LAPENTA2017 && !ctx->backgroundReady) FAIL(AMPS_GPU_ERR_STATE, "the test-particle movers need amps_gpu_background_upload");
   const DevMesh &m = ctx->dm;
   ProfScope prof(ctx, AMPS_GPU_PHASE_MOVE);
   CK(cudaMemsetAsync(ctx->d_cellCount, 0, sizeof(int) * (size_t)ctx->nCells, ctx->stream));
   CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevMoveStats), ctx->stream));
+  if (mover_id == AMPS_MOVER_BORIS) {
+    launch_move_boris(m, ctx->sp, ctx->cfg.coupler_interpolation, ctx->cfg.backward_time_integration, ctx->cfg.speed_of_light,
+                      ctx->cfg.internal_sphere_radius, ctx->cfg.exit_record_capacity, ctx->cfg.gravity_gm, ctx->buf[ctx->cur], ctx->d_n + ctx->cur,
+                      ctx->nUpper, ctx->d_bgTile, ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount, ctx->stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    ctx->sorted = false;
+    ctx->countValid = true;
+    return AMPS_GPU_OK;
+  }
   if (mover_id == AMPS_MOVER_RELATIVISTIC_BORIS) {
     launch_move_relativistic_boris(m, ctx->sp, ctx->cfg.coupler_interpolation, ctx->cfg.backward_time_integration, ctx->cfg.speed_of_light,
                                    ctx->cfg.internal_sphere_radius, ctx->cfg.exit_record_capacity, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper,
@@ -630,7 +641,7 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   if (slices < 1) slices = 1;
   if (slices > 64) slices = 64;
   launch_move_lapenta(m, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_eTile, ctx->d_bPrevTile, ctx->d_cellCount, ctx->d_stats, slices,
-                      ctx->stream);
+                      ctx->d_exitBuf, ctx->d_exitCount, ctx->cfg.exit_record_capacity, ctx->stream);
   ctx->launches++;
   CK(cudaGetLastError());
   ctx->sorted = false;

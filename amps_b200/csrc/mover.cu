@@ -127,10 +127,13 @@ struct BlockConst {
 template <bool kSmemTiles>
 __global__ void __launch_bounds__(256, 2) move_lapenta_kernel(DevMesh m, DevSpecies sp, ParticleSoA p, const int *__restrict__ cellStart,
                                                           const double *__restrict__ eTileG, const double *__restrict__ bTileG,
-                                                          int *__restrict__ cellCount, DevMoveStats *__restrict__ stats, int slices) {
+                                                          int *__restrict__ cellCount, DevMoveStats *__restrict__ stats, int slices,
+                                                          amps_gpu_exit_record *__restrict__ exitBuf, unsigned long long *__restrict__ exitCount,
+                                                          long long exitCap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint64_t mbar;
   __shared__ LeafGeo sLeaf;
+  __shared__ FaceGeo sFace;
 
   const int leaf = blockIdx.x / slices, slice = blockIdx.x - leaf * slices;
   const int C = m.cellsPerBlock;
@@ -176,6 +179,8 @@ __global__ void __launch_bounds__(256, 2) move_lapenta_kernel(DevMesh m, DevSpec
     sC.rSpan[d] = make_recip(sC.span[d]);
     sC.rCell[d] = make_recip(sC.dxCell[d]);
     sC.rRef[d] = make_recip(m.dxMaxRef[d]);
+  } else if (threadIdx.x == 64) {
+    if (sp.boundaryMode != AMPS_BOUNDARY_DELETE) init_faces(m, sFace);
   } else if (threadIdx.x >= 32 && threadIdx.x < 32 + AMPS_GPU_MAX_SPECIES) {
     const int sidx = threadIdx.x - 32;
     const double dts = (sp.timeStepMode == AMPS_DT_SPECIES_GLOBAL) ? sp.dt[sidx] : sp.dt[0];
@@ -346,8 +351,22 @@ __global__ void __launch_bounds__(256, 2) move_lapenta_kernel(DevMesh m, DevSpec
     int node = find_tree_node(m, xFinal, lg, rRef, blockOk);
     int newKey = -1;
     if (node < 0) {
-      // left the domain.  DELETE mode (:1165-1167); other modes are handled by the generic mover path
-      nLeft++;
+      // left the domain (:1159-1265): DELETE, or the face search + exit record for the host callback
+      if (sp.boundaryMode == AMPS_BOUNDARY_DELETE) {
+        nLeft++;
+      } else {
+        // copies keep the hot path's x/v in registers (the out-of-line exit search takes its arguments by address)
+        int face, exitNode;
+        double ex[3] = {xInit[0], xInit[1], xInit[2]}, ev[3] = {vInit[0], vInit[1], vInit[2]};
+        double fx[3] = {xFinal[0], xFinal[1], xFinal[2]}, fv[3] = {vFinal[0], vFinal[1], vFinal[2]};
+        const int code = domain_exit_vmiddle(m, sFace, sp.boundaryMode, dtTotal, ex, ev, fx, fv, lg.node, &face, &exitNode);
+        if (code == 0) {
+          add_exit_record(exitBuf, exitCount, exitCap, p.ptr[ip], spec, face, m.nodeLeaf[exitNode], ex, ev);
+          nLeft++;
+        } else {
+          nErr++;  // specular: _PARTICLE_REJECTED_ON_THE_FACE_ -> exit("not implemented") :1262-1263
+        }
+      }
     } else if (!(m.nodeFlags[node] & AMPS_NODE_USED)) {
       nNotUsed++;
     } else {
@@ -408,25 +427,12 @@ __global__ void __launch_bounds__(256, 2) move_lapenta_kernel(DevMesh m, DevSpec
     if (newKey != oldKey) p.key[ip] = newKey;
   }
 
-  // warp-reduce the counters, one atomic per warp and counter
-  unsigned int c[7] = {nMoved, nXCell, nXBlock, nLeft, nNotUsed, nWrap, nErr};
-#pragma unroll
-  for (int q = 0; q < 7; q++) {
-    unsigned int v = c[q];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    c[q] = v;
-  }
-  if ((threadIdx.x & 31) == 0) {
-    unsigned long long *s = reinterpret_cast<unsigned long long *>(stats);
-#pragma unroll
-    for (int q = 0; q < 7; q++)
-      if (c[q]) atomicAdd(&s[q], (unsigned long long)c[q]);
-  }
+  flush_move_counters(stats, nMoved, nXCell, nXBlock, nLeft, nNotUsed, nWrap, nErr);
 }
 
 void launch_move_lapenta(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *eTile, const double *bTile,
-                         int *cellCount, DevMoveStats *stats, int slices, cudaStream_t s) {
+                         int *cellCount, DevMoveStats *stats, int slices, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount,
+                         long long exitCap, cudaStream_t s) {
   const size_t smem = (size_t)(m.eTileStride + m.bTileStride) * sizeof(double);
   const int grid = m.nLeaves * slices;
   if (smem <= 200 * 1024) {
@@ -435,9 +441,9 @@ void launch_move_lapenta(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, 
       cudaFuncSetAttribute(move_lapenta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attrSet = true;
     }
-    move_lapenta_kernel<true><<<grid, 256, smem, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices);
+    move_lapenta_kernel<true><<<grid, 256, smem, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap);
   } else {
-    move_lapenta_kernel<false><<<grid, 256, 0, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices);
+    move_lapenta_kernel<false><<<grid, 256, 0, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap);
   }
 }
 

@@ -133,5 +133,133 @@ __device__ __forceinline__ int find_tree_node(const DevMesh &m, const double x[3
   return node;
 }
 
+struct FaceGeo {  // PIC::Mover::cExternalBoundaryFace after Init (pic_mover.cpp:24-28, 48-75)
+  double norm[6][3], e0[6][3], e1[6][3], x0[6][3], lE0[6], lE1[6];
+};
+__device__ __forceinline__ void init_faces(const DevMesh &m, FaceGeo &f) {
+  const double nrm[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+  const int nX0[6][3] = {{0, 0, 0}, {1, 0, 0}, {0, 0, 0}, {0, 1, 0}, {0, 0, 0}, {0, 0, 1}};
+  const double e0[6][3] = {{0, 1, 0}, {0, 1, 0}, {1, 0, 0}, {1, 0, 0}, {1, 0, 0}, {1, 0, 0}};
+  const double e1[6][3] = {{0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 1, 0}, {0, 1, 0}};
+  for (int n = 0; n < 6; n++) {
+    double cE0 = 0.0, cE1 = 0.0;
+    for (int d = 0; d < 3; d++) {
+      f.norm[n][d] = nrm[n][d], f.e0[n][d] = e0[n][d], f.e1[n][d] = e1[n][d];
+      f.x0[n][d] = (nX0[n][d] == 0) ? m.xGlobalMin[d] : m.xGlobalMax[d];
+      const double a0 = ((e0[n][d] + nX0[n][d] < 0.5) ? m.xGlobalMin[d] : m.xGlobalMax[d]) - f.x0[n][d];
+      const double a1 = ((e1[n][d] + nX0[n][d] < 0.5) ? m.xGlobalMin[d] : m.xGlobalMax[d]) - f.x0[n][d];
+      cE0 += a0 * a0, cE1 += a1 * a1;  // pow(.,2)
+    }
+    f.lE0[n] = sqrt(cE0), f.lE1[n] = sqrt(cE1);
+  }
+}
+
+__device__ __forceinline__ void add_exit_record(amps_gpu_exit_record *buf, unsigned long long *count, long long cap, int ptr, int spec, int face,
+                                                int leaf, const double x[3], const double v[3]) {
+  const unsigned long long i = atomicAdd(count, 1ull);
+  if ((long long)i < cap) {
+    amps_gpu_exit_record r;
+    r.ptr = ptr, r.species = spec, r.face = face, r.leaf = leaf;
+    for (int d = 0; d < 3; d++) r.x[d] = x[d], r.v[d] = v[d];
+    buf[i] = r;
+  }
+}
+
+
+// warp-reduce the per-thread counters of a mover and add them to the device statistics
+__device__ __forceinline__ void flush_move_counters(DevMoveStats *stats, unsigned nMoved, unsigned nXCell, unsigned nXBlock, unsigned nLeft, unsigned nNotUsed,
+                                                    unsigned nWrap, unsigned nErr) {
+  unsigned int c[7] = {nMoved, nXCell, nXBlock, nLeft, nNotUsed, nWrap, nErr};
+#pragma unroll
+  for (int q = 0; q < 7; q++) {
+    unsigned int v = c[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    c[q] = v;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    unsigned long long *s = reinterpret_cast<unsigned long long *>(stats);
+#pragma unroll
+    for (int q = 0; q < 7; q++)
+      if (c[q]) atomicAdd(&s[q], (unsigned long long)c[q]);
+  }
+}
+
+// tree search with plain IEEE divisions (exit handling and the test-particle movers)
+__device__ __forceinline__ int find_tree_node_slow(const DevMesh &m, const double x[3]) {
+  int ix[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) ix[d] = (int)floor(div_slow(x[d] - m.xGlobalMin[d], m.dxMaxRef[d]));
+  int node = find_node_ix(m, ix[0], ix[1], ix[2]);
+  if (node >= 0) {
+    bool flag = false;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      if (x[d] < m.nxmin[3 * node + d]) ix[d]--, flag = true;
+      if (x[d] >= m.nxmax[3 * node + d]) ix[d]++, flag = true;
+    }
+    if (flag) node = find_node_ix(m, ix[0], ix[1], ix[2]);
+  }
+  return node;
+}
+
+// a15: domain exit of the single-step movers (Boris :362-462, Lapenta2017 :1159-1265): mid-velocity ray against the six
+// faces, EPS inset, clamp into the box.  Updates xInit/vInit (and copies them to xFinal/vFinal) like the reference.
+// returns 0 = _PARTICLE_DELETED_ON_THE_FACE_ (user function: the caller records the exit), 1 = _PARTICLE_REJECTED_ON_THE_FACE_
+// (specular: the reference then exit()s "not implemented"), -1 = the reference would exit()
+static __device__ __noinline__ int domain_exit_vmiddle(const DevMesh &m, const FaceGeo &f, int boundaryMode, double dtTotal, double xInit[3], double vInit[3],
+                                                double xFinal[3], double vFinal[3], int startNode, int *faceOut, int *nodeOut) {
+  (void)startNode;
+  int nIntersectionFace = -1;
+  const double vMiddle[3] = {0.5 * (vInit[0] + vFinal[0]), 0.5 * (vInit[1] + vFinal[1]), 0.5 * (vInit[2] + vFinal[2])};
+  double dtIntersection = -1.0;
+  for (int nface = 0; nface < 6; nface++) {
+    double cx = 0.0, cv = 0.0, r0[3];
+    for (int d = 0; d < 3; d++) {
+      r0[d] = xInit[d] - f.x0[nface][d];
+      cx += r0[d] * f.norm[nface][d];
+      cv += vMiddle[d] * f.norm[nface][d];
+    }
+    if (cv > 0.0) {
+      const double dt = -cx / cv;
+      if ((dtIntersection < 0.0) || ((dt < dtIntersection) && (dt > 0.0))) {
+        double cE0 = 0.0, cE1 = 0.0;
+        for (int d = 0; d < 3; d++) {
+          const double c = r0[d] + dt * vMiddle[d];
+          cE0 += c * f.e0[nface][d], cE1 += c * f.e1[nface][d];
+        }
+        if ((cE0 < -m.eps) || (cE0 > f.lE0[nface] + m.eps) || (cE1 < -m.eps) || (cE1 > f.lE1[nface] + m.eps)) continue;
+        nIntersectionFace = nface, dtIntersection = dt;
+      }
+    }
+  }
+  if (nIntersectionFace == -1) return -1;
+  const double tVelocityIncrement = ((dtIntersection / dtTotal < 1) ? dtIntersection / dtTotal : 1);
+  for (int d = 0; d < 3; d++) {
+    xInit[d] += dtIntersection * vMiddle[d] - f.norm[nIntersectionFace][d] * m.eps;
+    vInit[d] += tVelocityIncrement * (vFinal[d] - vInit[d]);
+  }
+  int newNode = find_tree_node_slow(m, xInit);
+  if (newNode < 0) {
+    for (int d = 0; d < 3; d++) {
+      if (m.xGlobalMin[d] >= xInit[d]) xInit[d] = m.xGlobalMin[d] + m.eps;
+      if (m.xGlobalMax[d] <= xInit[d]) xInit[d] = m.xGlobalMax[d] - m.eps;
+    }
+    newNode = find_tree_node_slow(m, xInit);
+    if (newNode < 0) return -1;
+  }
+  int code;
+  if (boundaryMode == AMPS_BOUNDARY_USER_FUNCTION) code = 0;
+  else if (boundaryMode == AMPS_BOUNDARY_SPECULAR_REFLECTION) {
+    double cc = 0.0;
+    for (int d = 0; d < 3; d++) cc += f.norm[nIntersectionFace][d] * vInit[d];
+    for (int d = 0; d < 3; d++) vInit[d] -= 2.0 * cc * f.norm[nIntersectionFace][d];
+    code = 1;
+  } else
+    return -1;
+  for (int d = 0; d < 3; d++) vFinal[d] = vInit[d], xFinal[d] = xInit[d];
+  *faceOut = nIntersectionFace, *nodeOut = newNode;
+  return code;
+}
 
 }  // namespace amps

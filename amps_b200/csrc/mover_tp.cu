@@ -34,27 +34,6 @@ void launch_stage_background(const DevMesh &m, const double *E, const double *B,
   stage_background_kernel<<<m.nLeaves, 256, 0, s>>>(m, E, B, tile);
 }
 
-struct FaceGeo {  // PIC::Mover::cExternalBoundaryFace after Init (pic_mover.cpp:24-28, 48-75)
-  double norm[6][3], e0[6][3], e1[6][3], x0[6][3], lE0[6], lE1[6];
-};
-__device__ __forceinline__ void init_faces(const DevMesh &m, FaceGeo &f) {
-  const double nrm[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
-  const int nX0[6][3] = {{0, 0, 0}, {1, 0, 0}, {0, 0, 0}, {0, 1, 0}, {0, 0, 0}, {0, 0, 1}};
-  const double e0[6][3] = {{0, 1, 0}, {0, 1, 0}, {1, 0, 0}, {1, 0, 0}, {1, 0, 0}, {1, 0, 0}};
-  const double e1[6][3] = {{0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 1, 0}, {0, 1, 0}};
-  for (int n = 0; n < 6; n++) {
-    double cE0 = 0.0, cE1 = 0.0;
-    for (int d = 0; d < 3; d++) {
-      f.norm[n][d] = nrm[n][d], f.e0[n][d] = e0[n][d], f.e1[n][d] = e1[n][d];
-      f.x0[n][d] = (nX0[n][d] == 0) ? m.xGlobalMin[d] : m.xGlobalMax[d];
-      const double a0 = ((e0[n][d] + nX0[n][d] < 0.5) ? m.xGlobalMin[d] : m.xGlobalMax[d]) - f.x0[n][d];
-      const double a1 = ((e1[n][d] + nX0[n][d] < 0.5) ? m.xGlobalMin[d] : m.xGlobalMax[d]) - f.x0[n][d];
-      cE0 += a0 * a0, cE1 += a1 * a1;  // pow(.,2)
-    }
-    f.lE0[n] = sqrt(cE0), f.lE1[n] = sqrt(cE1);
-  }
-}
-
 // plain-division variant of the tree search (this mover is not bound by the division count)
 __device__ __forceinline__ int find_tree_node_plain(const DevMesh &m, const double x[3], int startNode) {
   int ix[3];
@@ -163,17 +142,6 @@ struct TpParams {
   double c, rSphere;
   long long exitCap;
 };
-
-__device__ __forceinline__ void add_exit_record(amps_gpu_exit_record *buf, unsigned long long *count, long long cap, int ptr, int spec, int face,
-                                                int leaf, const double x[3], const double v[3]) {
-  const unsigned long long i = atomicAdd(count, 1ull);
-  if ((long long)i < cap) {
-    amps_gpu_exit_record r;
-    r.ptr = ptr, r.species = spec, r.face = face, r.leaf = leaf;
-    for (int d = 0; d < 3; d++) r.x[d] = x[d], r.v[d] = v[d];
-    buf[i] = r;
-  }
-}
 
 __global__ void __launch_bounds__(128) move_relativistic_boris_kernel(DevMesh m, DevSpecies sp, TpParams tp, ParticleSoA p, const int *__restrict__ nSlots,
                                                                      const double *__restrict__ bgTile, int *__restrict__ cellCount,
@@ -380,20 +348,7 @@ __global__ void __launch_bounds__(128) move_relativistic_boris_kernel(DevMesh m,
     if (newKey != oldKey) p.key[ip] = newKey;
   }
 
-  unsigned int c[7] = {nMoved, nXCell, nXBlock, nLeft, nNotUsed, nWrap, nErr};
-#pragma unroll
-  for (int q = 0; q < 7; q++) {
-    unsigned int v = c[q];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    c[q] = v;
-  }
-  if ((threadIdx.x & 31) == 0) {
-    unsigned long long *s = reinterpret_cast<unsigned long long *>(stats);
-#pragma unroll
-    for (int q = 0; q < 7; q++)
-      if (c[q]) atomicAdd(&s[q], (unsigned long long)c[q]);
-  }
+  flush_move_counters(stats, nMoved, nXCell, nXBlock, nLeft, nNotUsed, nWrap, nErr);
 }
 
 void launch_move_relativistic_boris(const DevMesh &m, const DevSpecies &sp, int interp, int backward, double c, double rSphere, long long exitCap,
@@ -405,6 +360,165 @@ void launch_move_relativistic_boris(const DevMesh &m, const DevSpecies &sp, int 
   if (g < 1) g = 1;
   if (g > 148 * 32) g = 148 * 32;
   move_relativistic_boris_kernel<<<(int)g, 128, 0, s>>>(m, sp, tp, p, nSlots, bgTile, cellCount, stats, exitBuf, exitCount);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a6: PIC::Mover::Boris + BorisSplitAcceleration_default  src/pic/pic_mover_boris.cpp:126-553, :22-123
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) move_boris_kernel(DevMesh m, DevSpecies sp, TpParams tp, double gravityGM, ParticleSoA p, const int *__restrict__ nSlots,
+                                                        const double *__restrict__ bgTile, int *__restrict__ cellCount, DevMoveStats *__restrict__ stats,
+                                                        amps_gpu_exit_record *__restrict__ exitBuf, unsigned long long *__restrict__ exitCount) {
+  __shared__ FaceGeo sFace;
+  if (threadIdx.x == 0) init_faces(m, sFace);
+  __syncthreads();
+  const int n = *nSlots;
+  const int C = m.cellsPerBlock;
+  unsigned int nMoved = 0, nXCell = 0, nXBlock = 0, nLeft = 0, nNotUsed = 0, nWrap = 0, nErr = 0;
+
+  for (int ip = blockIdx.x * blockDim.x + threadIdx.x; ip < n; ip += gridDim.x * blockDim.x) {
+    const int oldKey = p.key[ip];
+    if (oldKey < 0) continue;
+    nMoved++;
+    double xInit[3] = {p.x[0][ip], p.x[1][ip], p.x[2][ip]};
+    double vInit[3] = {p.v[0][ip], p.v[1][ip], p.v[2][ip]};
+    double xFinal[3], vFinal[3];
+    const int spec = p.spec[ip];
+    const int startLeaf = oldKey / C;
+    const int startNode = m.leaf[startLeaf].node;
+    const double dtTotal = (sp.timeStepMode == AMPS_DT_SPECIES_GLOBAL) ? sp.dt[spec] : sp.dt[0];
+    int outcome = 0, node = -1;
+
+    // BorisSplitAcceleration_default: fields in the cell of x (fail-safe: search the block again)
+    double acclInit[3] = {0.0, 0.0, 0.0}, rotInit[3] = {0.0, 0.0, 0.0};
+    {
+      int fieldLeaf = startLeaf, ijk[3];
+      if (!find_cell_index(m, xInit, startNode, ijk)) {
+        const int fn = find_tree_node_plain(m, xInit, startNode);
+        fieldLeaf = (fn >= 0) ? m.nodeLeaf[fn] : -1;
+        if (fieldLeaf < 0 || !find_cell_index(m, xInit, fn, ijk)) outcome = 3;
+      }
+      double E[3], B[3];
+      if (outcome == 0 && !background_fields(m, tp.interp, bgTile, xInit, fieldLeaf, E, B)) outcome = 3;
+      if (outcome == 0) {
+        const double ElectricCharge = sp.charge[spec], mass = sp.mass[spec];
+        if (ElectricCharge != 0.0) {
+          const double Charge2Mass = ElectricCharge / mass;
+          for (int d = 0; d < 3; d++) {
+            acclInit[d] += Charge2Mass * E[d];
+            rotInit[d] -= Charge2Mass * B[d];
+          }
+        }
+        if (gravityGM != 0.0) {
+          const double r2 = xInit[0] * xInit[0] + xInit[1] * xInit[1] + xInit[2] * xInit[2];
+          const double r = sqrt(r2);
+          for (int d = 0; d < 3; d++) acclInit[d] -= gravityGM / r2 * xInit[d] / r;
+        }
+      }
+    }
+    if (outcome == 0) {
+      double dtTempOverTwo, dtTemp;
+      if (tp.backward) dtTemp = -dtTotal, dtTempOverTwo = -dtTotal / 2.0;
+      else dtTemp = dtTotal, dtTempOverTwo = dtTotal / 2.0;
+      double u[3], h[3], U[3];
+      u[0] = vInit[0] + dtTempOverTwo * acclInit[0];
+      u[1] = vInit[1] + dtTempOverTwo * acclInit[1];
+      u[2] = vInit[2] + dtTempOverTwo * acclInit[2];
+      h[0] = -dtTempOverTwo * rotInit[0];
+      h[1] = -dtTempOverTwo * rotInit[1];
+      h[2] = -dtTempOverTwo * rotInit[2];
+      const double h2 = h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
+      const double uh = u[0] * h[0] + u[1] * h[1] + u[2] * h[2];
+      U[0] = ((1 - h2) * u[0] + 2 * (u[1] * h[2] - h[1] * u[2] + uh * h[0])) / (1 + h2);
+      U[1] = ((1 - h2) * u[1] + 2 * (u[2] * h[0] - h[2] * u[0] + uh * h[1])) / (1 + h2);
+      U[2] = ((1 - h2) * u[2] + 2 * (u[0] * h[1] - h[0] * u[1] + uh * h[2])) / (1 + h2);
+      vFinal[0] = U[0] + dtTempOverTwo * acclInit[0];
+      vFinal[1] = U[1] + dtTempOverTwo * acclInit[1];
+      vFinal[2] = U[2] + dtTempOverTwo * acclInit[2];
+      xFinal[0] = xInit[0] + dtTemp * vFinal[0];
+      xFinal[1] = xInit[1] + dtTemp * vFinal[1];
+      xFinal[2] = xInit[2] + dtTemp * vFinal[2];
+
+      bool hitSphere = false;
+      if (tp.rSphere > 0.0) {
+        const double R = tp.rSphere;
+        const double dx0 = xFinal[0] - 0.0, dx1 = xFinal[1] - 0.0, dx2 = xFinal[2] - 0.0;
+        const double r2 = dx0 * dx0 + dx1 * dx1 + dx2 * dx2;
+        if (r2 < R * R) {
+          double r = sqrt(r2);
+          if (r <= 0.0) r = 1.0;
+          xFinal[0] = 0.0 + dx0 * (R / r);
+          xFinal[1] = 0.0 + dx1 * (R / r);
+          xFinal[2] = 0.0 + dx2 * (R / r);
+          const int nn = find_tree_node_plain(m, xFinal, startNode);
+          add_exit_record(exitBuf, exitCount, tp.exitCap, p.ptr[ip], spec, AMPS_EXIT_SPHERE, nn >= 0 ? m.nodeLeaf[nn] : -1, xFinal, vFinal);
+          outcome = 1;
+          hitSphere = true;
+        }
+      }
+      if (!hitSphere) {
+        node = find_tree_node_plain(m, xFinal, startNode);
+        if (node < 0) {
+          if (tp.boundaryMode == AMPS_BOUNDARY_DELETE) outcome = 1;
+          else {
+            int face, exitNode;
+            const int code = domain_exit_vmiddle(m, sFace, tp.boundaryMode, dtTotal, xInit, vInit, xFinal, vFinal, startNode, &face, &exitNode);
+            if (code == 0) {
+              add_exit_record(exitBuf, exitCount, tp.exitCap, p.ptr[ip], spec, face, m.nodeLeaf[exitNode], xInit, vInit);
+              outcome = 1;
+            } else
+              outcome = 3;  // specular: _PARTICLE_REJECTED_ON_THE_FACE_ -> exit("not implemented") :461
+          }
+        } else if (!(m.nodeFlags[node] & AMPS_NODE_USED))
+          outcome = 2;
+      }
+    }
+
+    int newKey = -1;
+    if (outcome == 0) {
+      int ijk[3];
+      int newLeaf = m.nodeLeaf[node];
+      if (!find_cell_index(m, xFinal, node, ijk)) outcome = 3;
+      else if (newLeaf < 0) outcome = 1;  // block not allocated here (:1290-1302 analogue)
+      else {
+        const int realLeaf = m.leaf[newLeaf].real;
+        if (realLeaf >= 0) {
+          const LeafGeo &gg = m.leaf[newLeaf];
+          const LeafGeo &rg = m.leaf[realLeaf];
+          for (int d = 0; d < 3; d++) {
+            xFinal[d] += rg.xmin[d] - gg.xmin[d];
+            if (xFinal[d] < rg.xmin[d]) xFinal[d] = rg.xmin[d];
+            if (xFinal[d] >= rg.xmax[d]) xFinal[d] = rg.xmax[d] - 1.0E-10 * (rg.xmax[d] - rg.xmin[d]);
+          }
+          newLeaf = realLeaf;
+          nWrap++;
+        }
+        newKey = newLeaf * C + ijk[0] + m.N[0] * (ijk[1] + m.N[1] * ijk[2]);
+        if (newLeaf != startLeaf) nXBlock++;
+        else if (newKey != oldKey) nXCell++;
+      }
+    }
+    if (outcome == 1) nLeft++;
+    else if (outcome == 2) nNotUsed++;
+    else if (outcome == 3) nErr++;
+    if (newKey >= 0) {
+      p.x[0][ip] = xFinal[0], p.x[1][ip] = xFinal[1], p.x[2][ip] = xFinal[2];
+      p.v[0][ip] = vFinal[0], p.v[1][ip] = vFinal[1], p.v[2][ip] = vFinal[2];
+      atomicAdd(&cellCount[newKey], 1);
+    }
+    if (newKey != oldKey) p.key[ip] = newKey;
+  }
+  flush_move_counters(stats, nMoved, nXCell, nXBlock, nLeft, nNotUsed, nWrap, nErr);
+}
+
+void launch_move_boris(const DevMesh &m, const DevSpecies &sp, int interp, int backward, double c, double rSphere, long long exitCap, double gravityGM,
+                       ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, int *cellCount, DevMoveStats *stats,
+                       amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s) {
+  TpParams tp;
+  tp.interp = interp, tp.backward = backward, tp.boundaryMode = sp.boundaryMode, tp.c = c, tp.rSphere = rSphere, tp.exitCap = exitCap;
+  long long g = (nUpper + 127) / 128;
+  if (g < 1) g = 1;
+  if (g > 148 * 32) g = 148 * 32;
+  move_boris_kernel<<<(int)g, 128, 0, s>>>(m, sp, tp, gravityGM, p, nSlots, bgTile, cellCount, stats, exitBuf, exitCount);
 }
 
 }  // namespace amps

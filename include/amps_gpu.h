@@ -107,6 +107,7 @@ typedef struct amps_gpu_config {
   double speed_of_light;             /* SpeedOfLight (constants.h), SI                                                     */
   double internal_sphere_radius;     /* max(_RADIUS_(_TARGET_),Planet->Radius), 0 = no internal sphere (:272)            */
   int64_t exit_record_capacity;      /* records kept for the host callbacks (0 = only count)                              */
+  double gravity_gm;                 /* GravityConstant*_MASS_(_TARGET_) of BorisSplitAcceleration_default (:110-118), 0 = off */
 } amps_gpu_config;
 
 /* _PIC_COUPLER__INTERPOLATION_MODE_ */

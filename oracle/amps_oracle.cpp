@@ -625,7 +625,9 @@ struct oracle_ctx {
             code = 1;  // _PARTICLE_REJECTED_ON_THE_FACE_
           } break;
           default:
-            code = 0;  // user function (CutoffRigidity::ProcessOutsideDomainParticles always deletes)
+            // user function: recorded for the host (CutoffRigidity::ProcessOutsideDomainParticles always deletes)
+            AddExitRecord(ptr, spec, nIntersectionFace, newNode, xInit, vInit);
+            code = 0;
         }
         memcpy(vFinal, vInit, 3 * sizeof(double));
         memcpy(xFinal, xInit, 3 * sizeof(double));
@@ -897,6 +899,182 @@ struct oracle_ctx {
     cBlock *block;
     if (FindCellIndex(xFinal, i, j, k, newNode) == -1) return _ORACLE_ERROR_;
     if ((block = newNode->block) == NULL) return _ORACLE_ERROR_;
+    AttachToTempList(ptr, ParticleData, block, i, j, k, nThreads, thread);
+    SetV(vFinal, ParticleData);
+    SetX(xFinal, ParticleData);
+    *newNodeOut = newNode;
+    return _PARTICLE_MOTION_FINISHED_;
+  }
+
+
+  // domain exit of the single-step movers (Boris :362-462, Lapenta2017 :1159-1265): mid-velocity ray against the six
+  // faces.  returns code 0 = _PARTICLE_DELETED_ON_THE_FACE_, 1 = _PARTICLE_REJECTED_ON_THE_FACE_, -1 = exit()
+  int ProcessDomainExit_vMiddle(long int ptr, int spec, double dtTotal, double *xInit, double *vInit, double *xFinal, double *vFinal, cTreeNode *startNode,
+                                cTreeNode **newNodeOut) {
+    int idim, nface, nIntersectionFace = -1;
+    double tVelocityIncrement, cx, cv, r0[3], dt, vMiddle[3] = {0.5 * (vInit[0] + vFinal[0]), 0.5 * (vInit[1] + vFinal[1]), 0.5 * (vInit[2] + vFinal[2])}, c,
+                                                  dtIntersection = -1.0;
+    for (nface = 0; nface < 6; nface++) {
+      for (idim = 0, cx = 0.0, cv = 0.0; idim < 3; idim++) {
+        r0[idim] = xInit[idim] - FaceTable[nface].x0[idim];
+        cx += r0[idim] * FaceTable[nface].norm[idim];
+        cv += vMiddle[idim] * FaceTable[nface].norm[idim];
+      }
+      if (cv > 0.0) {
+        dt = -cx / cv;
+        if ((dtIntersection < 0.0) || ((dt < dtIntersection) && (dt > 0.0))) {
+          double cE0 = 0.0, cE1 = 0.0;
+          for (idim = 0; idim < 3; idim++) {
+            c = r0[idim] + dt * vMiddle[idim];
+            cE0 += c * FaceTable[nface].e0[idim], cE1 += c * FaceTable[nface].e1[idim];
+          }
+          if ((cE0 < -EPS) || (cE0 > FaceTable[nface].lE0 + EPS) || (cE1 < -EPS) || (cE1 > FaceTable[nface].lE1 + EPS)) continue;
+          nIntersectionFace = nface, dtIntersection = dt;
+        }
+      }
+    }
+    if (nIntersectionFace == -1) return -1;
+    for (idim = 0, tVelocityIncrement = ((dtIntersection / dtTotal < 1) ? dtIntersection / dtTotal : 1); idim < 3; idim++) {
+      xInit[idim] += dtIntersection * vMiddle[idim] - FaceTable[nIntersectionFace].norm[idim] * EPS;
+      vInit[idim] += tVelocityIncrement * (vFinal[idim] - vInit[idim]);
+    }
+    cTreeNode *newNode = findTreeNode(xInit, startNode);
+    if (newNode == NULL) {
+      for (int ii = 0; ii < 3; ii++) {
+        if (xGlobalMin[ii] >= xInit[ii]) xInit[ii] = xGlobalMin[ii] + EPS;
+        if (xGlobalMax[ii] <= xInit[ii]) xInit[ii] = xGlobalMax[ii] - EPS;
+      }
+      newNode = findTreeNode(xInit, startNode);
+      if (newNode == NULL) return -1;
+    }
+    int code;
+    switch (cfg.boundary_mode) {
+      case AMPS_BOUNDARY_USER_FUNCTION:
+        AddExitRecord(ptr, spec, nIntersectionFace, newNode, xInit, vInit);
+        code = 0;
+        break;
+      case AMPS_BOUNDARY_SPECULAR_REFLECTION: {
+        double cc = 0.0;
+        for (int d = 0; d < 3; d++) cc += FaceTable[nIntersectionFace].norm[d] * vInit[d];
+        for (int d = 0; d < 3; d++) vInit[d] -= 2.0 * cc * FaceTable[nIntersectionFace].norm[d];
+        code = 1;
+      } break;
+      default:
+        return -1;
+    }
+    memcpy(vFinal, vInit, 3 * sizeof(double));
+    memcpy(xFinal, xInit, 3 * sizeof(double));
+    *newNodeOut = newNode;
+    return code;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // PIC::Mover::Boris + BorisSplitAcceleration_default, src/pic/pic_mover_boris.cpp:126-553, :22-123
+  // (scalar branch, planar symmetry, Lorentz force from the coupler table [+ central gravity])
+  // ------------------------------------------------------------------------------------------
+  int Boris(byte *ParticleData, long int ptr, double dtTotal, cTreeNode *startNode, int nThreads, int thread, cTreeNode **newNodeOut) {
+    cTreeNode *newNode = NULL;
+    int idim, i, j, k, spec;
+    double vInit[3], xInit[3] = {0.0, 0.0, 0.0}, vFinal[3], xFinal[3];
+    double u[3] = {0.0, 0.0, 0.0}, U[3] = {0.0, 0.0, 0.0};
+    double acclInit[3], rotInit[3];
+    GetV(vInit, ParticleData);
+    GetX(xInit, ParticleData);
+    spec = GetI(ParticleData);
+
+    {  // BorisSplitAcceleration_default
+      double accl_LOCAL[3] = {0.0, 0.0, 0.0}, rotation_LOCAL[3] = {0.0, 0.0, 0.0};
+      double E[3] = {0.0, 0.0, 0.0}, B[3] = {0.0, 0.0, 0.0};
+      cTreeNode *fieldNode = startNode;
+      if (fieldNode->block == NULL) return _ORACLE_ERROR_;
+      long int nd = FindCellIndex(xInit, i, j, k, fieldNode);
+      if (nd == -1) {
+        fieldNode = findTreeNode(xInit, fieldNode);
+        if (fieldNode == NULL || fieldNode->block == NULL) return _ORACLE_ERROR_;
+        nd = FindCellIndex(xInit, i, j, k, fieldNode);
+        if (nd == -1) return _ORACLE_ERROR_;
+      }
+      if (!GetBackgroundFields(xInit, fieldNode, E, B)) return _ORACLE_ERROR_;
+      double ElectricCharge = cfg.charge[spec], mass = cfg.mass[spec], Charge2Mass;
+      if (ElectricCharge != 0.0) {
+        Charge2Mass = ElectricCharge / mass;
+        for (idim = 0; idim < 3; idim++) {
+          accl_LOCAL[idim] += Charge2Mass * E[idim];
+          rotation_LOCAL[idim] -= Charge2Mass * B[idim];
+        }
+      }
+      if (cfg.gravity_gm != 0.0) {  // GravityConstant*_MASS_(_TARGET_)
+        double r2 = xInit[0] * xInit[0] + xInit[1] * xInit[1] + xInit[2] * xInit[2];
+        double r = sqrt(r2);
+        for (idim = 0; idim < 3; idim++) accl_LOCAL[idim] -= cfg.gravity_gm / r2 * xInit[idim] / r;
+      }
+      memcpy(acclInit, accl_LOCAL, 3 * sizeof(double));
+      memcpy(rotInit, rotation_LOCAL, 3 * sizeof(double));
+    }
+
+    double dtTempOverTwo, dtTemp;
+    if (cfg.backward_time_integration) dtTemp = -dtTotal, dtTempOverTwo = -dtTotal / 2.0;
+    else dtTemp = dtTotal, dtTempOverTwo = dtTotal / 2.0;
+
+    u[0] = vInit[0] + dtTempOverTwo * acclInit[0];
+    u[1] = vInit[1] + dtTempOverTwo * acclInit[1];
+    u[2] = vInit[2] + dtTempOverTwo * acclInit[2];
+    double h[3];
+    h[0] = -dtTempOverTwo * rotInit[0];
+    h[1] = -dtTempOverTwo * rotInit[1];
+    h[2] = -dtTempOverTwo * rotInit[2];
+    double h2 = h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
+    double uh = u[0] * h[0] + u[1] * h[1] + u[2] * h[2];
+    U[0] = ((1 - h2) * u[0] + 2 * (u[1] * h[2] - h[1] * u[2] + uh * h[0])) / (1 + h2);
+    U[1] = ((1 - h2) * u[1] + 2 * (u[2] * h[0] - h[2] * u[0] + uh * h[1])) / (1 + h2);
+    U[2] = ((1 - h2) * u[2] + 2 * (u[0] * h[1] - h[0] * u[1] + uh * h[2])) / (1 + h2);
+    vFinal[0] = U[0] + dtTempOverTwo * acclInit[0];
+    vFinal[1] = U[1] + dtTempOverTwo * acclInit[1];
+    vFinal[2] = U[2] + dtTempOverTwo * acclInit[2];
+    xFinal[0] = xInit[0] + dtTemp * vFinal[0];
+    xFinal[1] = xInit[1] + dtTemp * vFinal[1];
+    xFinal[2] = xInit[2] + dtTemp * vFinal[2];
+
+    // internal sphere centred at the origin (:296-358)
+    if (cfg.internal_sphere_radius > 0.0) {
+      const double R = cfg.internal_sphere_radius;
+      const double dx0 = xFinal[0] - 0.0, dx1 = xFinal[1] - 0.0, dx2 = xFinal[2] - 0.0;
+      const double r2 = dx0 * dx0 + dx1 * dx1 + dx2 * dx2;
+      if (r2 < R * R) {
+        double r = sqrt(r2);
+        if (r <= 0.0) r = 1.0;
+        xFinal[0] = 0.0 + dx0 * (R / r);
+        xFinal[1] = 0.0 + dx1 * (R / r);
+        xFinal[2] = 0.0 + dx2 * (R / r);
+        newNode = findTreeNode(xFinal, startNode);
+        AddExitRecord(ptr, spec, AMPS_EXIT_SPHERE, newNode, xFinal, vFinal);
+        DeleteParticle(ptr);
+        return _PARTICLE_LEFT_THE_DOMAIN_;
+      } else
+        newNode = findTreeNode(xFinal, startNode);
+    } else
+      newNode = findTreeNode(xFinal, startNode);
+
+    if (newNode == NULL) {
+      int code = 0;
+      if (cfg.boundary_mode != AMPS_BOUNDARY_DELETE) code = ProcessDomainExit_vMiddle(ptr, spec, dtTotal, xInit, vInit, xFinal, vFinal, startNode, &newNode);
+      switch (code) {
+        case 0:
+          DeleteParticle(ptr);
+          return _PARTICLE_LEFT_THE_DOMAIN_;
+        default:
+          return _ORACLE_ERROR_;  // exit("not implemented") :461
+      }
+    } else if (newNode->IsUsedInCalculationFlag == false) {
+      DeleteParticle(ptr);
+      return _PARTICLE_IN_NOT_IN_USE_NODE_;
+    }
+    cBlock *block;
+    if (FindCellIndex(xFinal, i, j, k, newNode) == -1) return _ORACLE_ERROR_;
+    if ((block = newNode->block) == NULL) {
+      DeleteParticle(ptr);
+      return _PARTICLE_LEFT_THE_DOMAIN_;
+    }
     AttachToTempList(ptr, ParticleData, block, i, j, k, nThreads, thread);
     SetV(vFinal, ParticleData);
     SetX(xFinal, ParticleData);
@@ -1391,7 +1569,7 @@ void oracle_get_particles(const oracle_ctx *o, double *x, double *v, double *w, 
 // PIC::Mover::MoveParticles(), src/pic/pic_mover.cpp:580-1088 followed (periodic mode) by
 // PIC::BC::ExternalBoundary::Periodic::ExchangeParticles(), src/pic/pic_time_step.cpp:454-506
 int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats *stats, int32_t *ret_code, int32_t *final_cell) {
-  if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS) {
+  if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS && mover_id != AMPS_MOVER_BORIS) {
     o->err = "oracle_move: mover not restated yet";
     return AMPS_GPU_ERR_ARG;
   }
@@ -1432,6 +1610,7 @@ int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats 
       if (mover_id == AMPS_MOVER_LAPENTA2017) return o->Lapenta2017(pd, ptr, node, E_Corner, B_C, n_threads, thread, newNode);
       const int spec = oracle_ctx::GetI(pd);
       const double dtLocal = (o->cfg.time_step_mode == AMPS_DT_SPECIES_GLOBAL) ? o->cfg.time_step[spec] : o->cfg.time_step[0];
+      if (mover_id == AMPS_MOVER_BORIS) return o->Boris(pd, ptr, dtLocal, node, n_threads, thread, newNode);
       return o->Relativistic_Boris(pd, ptr, dtLocal, node, n_threads, thread, newNode);
     };
     long int *FirstCellParticleTable = block->FirstCellParticleTable;

@@ -34,7 +34,7 @@ def rel_scaled(a, b):
 
 
 def make_case(n_cells=(16, 16, 16), ppc=8, seed=3, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), E_amp=0.01, dt=1.0, vscale=1.0,
-              periodic=True, extra_capacity=0):
+              periodic=True, extra_capacity=0, boundary_mode=0):
     if periodic:
         m = meshmod.uniform_periodic_box(n_cells, block_cells, ghost_cells)
     else:
@@ -45,7 +45,9 @@ def make_case(n_cells=(16, 16, 16), ppc=8, seed=3, block_cells=(8, 8, 8), ghost_
     v *= vscale
     rng = np.random.default_rng(seed + 1)
     w = rng.uniform(0.5, 1.5, size=w.shape)  # exercise the individual weight correction
-    cfg = api.make_config(block_cells, ghost_cells, charge, mass, wgt, dt, periodic=periodic, capacity=x.shape[1] + extra_capacity + 16)
+    cfg = api.make_config(block_cells, ghost_cells, charge, mass, wgt, dt, periodic=periodic, capacity=x.shape[1] + extra_capacity + 16,
+                          boundary_mode=boundary_mode)
+    cfg.exit_record_capacity = x.shape[1]
     E, B = workload.box_fields(m, E_amp=E_amp)
     Bcur = B * 1.01 + 0.001  # B_cur != B_prev so that a mix-up of the two shows
     return m, cfg, (x, v, w, sp, cells), (E, B, Bcur)
@@ -59,10 +61,12 @@ def run_oracle(m, cfg, parts, fields, n_threads=1, kind="parity"):
     o.add_particles(x, v, w, sp, cells)
     rc, st, ret, fc = o.move(0, n_threads)
     pp = o.particles()
+    nrec, recs = o.exit_records()
     lists_ok = o.check_lists()
     J, M, en, cfl = o.deposit(n_threads)
     o.close()
-    return {"rc": rc, "stats": st, "ret": ret, "final_cell": fc, "particles": pp, "J": J, "M": M, "energy": en, "cfl": cfl, "lists": lists_ok}
+    return {"rc": rc, "stats": st, "ret": ret, "final_cell": fc, "particles": pp, "J": J, "M": M, "energy": en, "cfl": cfl, "lists": lists_ok,
+            "records": sorted(recs), "n_records": nrec}
 
 
 def run_gpu(m, cfg, parts, fields):
@@ -74,6 +78,7 @@ def run_gpu(m, cfg, parts, fields):
     n0 = g.particle_count()
     st = g.MoveParticles()
     moved = g.particles_download()  # slot i still holds the particle it held before the move
+    nrec, recs = g.exit_records()
     g.sort()
     table = g.cell_table()
     srt = g.particles_download()
@@ -81,7 +86,8 @@ def run_gpu(m, cfg, parts, fields):
     J, M = g.JM_download()
     launches = g.launch_count()
     g.close()
-    return {"n0": n0, "stats": st, "moved": moved, "sorted": srt, "table": table, "J": J, "M": M, "energy": en, "cfl": cfl, "launches": launches}
+    return {"n0": n0, "stats": st, "moved": moved, "sorted": srt, "table": table, "J": J, "M": M, "energy": en, "cfl": cfl, "launches": launches,
+            "records": sorted(recs), "n_records": nrec}
 
 
 def compare(m, parts, ora, gpu):
@@ -121,6 +127,8 @@ def compare(m, parts, ora, gpu):
     res["rel_energy"] = abs(gpu["energy"] - ora["energy"]) / max(abs(ora["energy"]), 1e-300)
     res["rel_cfl"] = max(abs(a - b) / max(abs(b), 1e-300) for a, b in zip(gpu["cfl"], ora["cfl"]))
     res["oracle_lists"] = ora["lists"]
+    res["n_records"] = ora["n_records"]
+    res["records_equal"] = (gpu["n_records"] == ora["n_records"]) and (gpu["records"] == ora["records"])
     res["gpu_launches"] = gpu["launches"]
     return res
 

@@ -25,7 +25,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_struct_layouts_match_the_header():
     # sizes the C compiler gives the structs (kept in sync by hand; a mismatch would corrupt every call)
-    assert ctypes.sizeof(_capi.Config) == 3 * 4 + 3 * 4 + 6 * 4 + 8 + 4 * 8 * 8 + 4 * 8 + 2 * 4 + 2 * 8 + 8
+    assert ctypes.sizeof(_capi.Config) == 3 * 4 + 3 * 4 + 6 * 4 + 8 + 4 * 8 * 8 + 4 * 8 + 2 * 4 + 2 * 8 + 8 + 8
     assert ctypes.sizeof(_capi.ExitRecord) == 4 * 4 + 6 * 8
     assert ctypes.sizeof(_capi.MoveStats) == 7 * 8
     assert ctypes.sizeof(_capi.AosLayout) == 8 + 7 * 4 + 4

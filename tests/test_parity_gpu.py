@@ -12,6 +12,7 @@ CASES = {
     "ghost2": dict(n_cells=(16, 16, 16), ppc=4, seed=9, ghost_cells=(2, 2, 2)),
     "single_block_dim": dict(n_cells=(8, 16, 8), ppc=8, seed=11),
     "dense_cells_320": dict(n_cells=(8, 8, 8), ppc=160, seed=17),  # cells larger than one deposit chunk / ring batch
+    "open_box_user_function": dict(n_cells=(16, 16, 16), ppc=6, seed=15, periodic=False, vscale=6.0, boundary_mode=2),  # exit records
     "open_box": dict(n_cells=(16, 16, 16), ppc=6, seed=13, periodic=False, vscale=6.0),  # DELETE boundary
 }
 
@@ -28,3 +29,4 @@ def test_one_step_parity(name):
     assert res["max_rel_J"] <= pu.REL_TOL and res["max_rel_M"] <= pu.REL_TOL, res
     assert res["rel_energy"] <= pu.REL_TOL and res["rel_cfl"] <= pu.REL_TOL, res
     assert res["gpu_launches"] > 0
+    assert res.get("records_equal", True), res
