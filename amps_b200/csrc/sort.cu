@@ -15,6 +15,17 @@ constexpr int SCAN_THREADS = 512;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
+// one atomic per distinct key in the warp (the input is nearly sorted: typically 1-3 keys per warp)
+__device__ __forceinline__ int warp_aggregated_slot(int *__restrict__ counter, int key) {
+  const unsigned mask = __match_any_sync(__activemask(), key);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(mask) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(&counter[key], __popc(mask));
+  base = __shfl_sync(mask, base, leader);
+  return base + __popc(mask & ((1u << lane) - 1u));
+}
+
 __global__ void histogram_kernel(const int *__restrict__ key, const int *__restrict__ nSrc, int *__restrict__ cellCount) {
   const int n = *nSrc;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -110,7 +121,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(ParticleSoA src, ParticleS
     const double w = src.w[i];
     const uint8_t sp = src.spec[i];
     const int pt = src.ptr[i];
-    const int pos = cellStart[k] + atomicAdd(&cellFill[k], 1);
+    const int pos = cellStart[k] + warp_aggregated_slot(cellFill, k);
     dst.x[0][pos] = x0, dst.x[1][pos] = x1, dst.x[2][pos] = x2;
     dst.v[0][pos] = v0, dst.v[1][pos] = v1, dst.v[2][pos] = v2;
     dst.w[pos] = w;
