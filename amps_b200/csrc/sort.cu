@@ -110,24 +110,36 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const int *__r
   if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *totalIn;
 }
 
+struct ParticleRegs {
+  double x0, x1, x2, v0, v1, v2, w;
+  int k, pt;
+  uint8_t sp;
+};
+__device__ __forceinline__ void load_particle(const ParticleSoA &src, int i, ParticleRegs &r) {
+  r.x0 = src.x[0][i], r.x1 = src.x[1][i], r.x2 = src.x[2][i];
+  r.v0 = src.v[0][i], r.v1 = src.v[1][i], r.v2 = src.v[2][i];
+  r.w = src.w[i], r.sp = src.spec[i], r.pt = src.ptr[i];
+}
+__device__ __forceinline__ void store_particle(const ParticleSoA &dst, int pos, const ParticleRegs &r) {
+  dst.x[0][pos] = r.x0, dst.x[1][pos] = r.x1, dst.x[2][pos] = r.x2;
+  dst.v[0][pos] = r.v0, dst.v[1][pos] = r.v1, dst.v[2][pos] = r.v2;
+  dst.w[pos] = r.w, dst.spec[pos] = r.sp, dst.key[pos] = r.k, dst.ptr[pos] = r.pt;
+}
+
+// two particles per thread and iteration: twice the loads in flight per warp (the kernel is latency bound)
 __global__ void __launch_bounds__(256) scatter_kernel(ParticleSoA src, ParticleSoA dst, const int *__restrict__ nSrc, const int *__restrict__ cellStart,
                                                      int *__restrict__ cellFill) {
   const int n = *nSrc;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int k = src.key[i];
-    if (k < 0) continue;
-    const double x0 = src.x[0][i], x1 = src.x[1][i], x2 = src.x[2][i];
-    const double v0 = src.v[0][i], v1 = src.v[1][i], v2 = src.v[2][i];
-    const double w = src.w[i];
-    const uint8_t sp = src.spec[i];
-    const int pt = src.ptr[i];
-    const int pos = cellStart[k] + warp_aggregated_slot(cellFill, k);
-    dst.x[0][pos] = x0, dst.x[1][pos] = x1, dst.x[2][pos] = x2;
-    dst.v[0][pos] = v0, dst.v[1][pos] = v1, dst.v[2][pos] = v2;
-    dst.w[pos] = w;
-    dst.spec[pos] = sp;
-    dst.key[pos] = k;
-    dst.ptr[pos] = pt;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
+    const int j = i + stride;
+    ParticleRegs a, b;
+    a.k = src.key[i];
+    b.k = (j < n) ? src.key[j] : -1;
+    if (a.k >= 0) load_particle(src, i, a);
+    if (b.k >= 0) load_particle(src, j, b);
+    if (a.k >= 0) store_particle(dst, cellStart[a.k] + warp_aggregated_slot(cellFill, a.k), a);
+    if (b.k >= 0) store_particle(dst, cellStart[b.k] + warp_aggregated_slot(cellFill, b.k), b);
   }
 }
 
