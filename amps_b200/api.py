@@ -50,6 +50,7 @@ def make_config(block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), charge=(-1.0, 1.0)
     cfg.internal_sphere_radius = 0.0
     cfg.exit_record_capacity = 0
     cfg.gravity_gm = 0.0
+    cfg.carry_magnetic_moment = 0
     return cfg
 
 
@@ -105,6 +106,28 @@ class Context:
                 assert a.shape == (self.mesh.n_centers, 3)
             arrs.append(a)
         self._ck(self.lib.amps_gpu_background_upload(self._h, _ptr(arrs[0]), _ptr(arrs[1])))
+
+    def background_upload_gca(self, var15_center):
+        """15 drift variables of Relativistic::GuidingCenter on the unique centre nodes (pic.h:8643-8680)"""
+        a = np.ascontiguousarray(var15_center, dtype=np.float64)
+        assert a.shape == (self.mesh.n_centers, 15)
+        self._ck(self.lib.amps_gpu_background_upload_gca(self._h, _ptr(a)))
+
+    def InitiateMagneticMoment(self):
+        """PIC::Mover::Relativistic::GuidingCenter::InitiateMagneticMoment for every resident particle"""
+        self._ck(self.lib.amps_gpu_magnetic_moment_init(self._h))
+
+    def magnetic_moment_upload(self, mu_by_ptr):
+        a = np.ascontiguousarray(mu_by_ptr, dtype=np.float64)
+        self._ck(self.lib.amps_gpu_magnetic_moment_upload(self._h, _ptr(a), a.shape[0]))
+
+    def magnetic_moment_download(self):
+        """mu in the current device order (pair with particles_download()['ptrs'])"""
+        n = self.particle_count()
+        mu = np.empty(max(n, 1))
+        k = C.c_int64()
+        self._ck(self.lib.amps_gpu_magnetic_moment_download(self._h, _ptr(mu), mu.shape[0], C.byref(k)))
+        return mu[: int(k.value)]
 
     def exit_records(self, max_records=1 << 20):
         buf = (_capi.ExitRecord * max_records)()

@@ -73,6 +73,7 @@ struct ParticleSoA {
   uint8_t *spec;
   int *key;
   int *ptr;
+  double *mu;  // magnetic moment (guiding-centre movers), nullptr unless cfg.carry_magnetic_moment
 };
 
 // counters written by the mover (device copy of amps_gpu_move_stats + error word)
@@ -100,6 +101,8 @@ void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
                     double *energy, unsigned long long *cflBits, int nSM, cudaStream_t s, long long *launches);
 size_t sort_scan_tmp_bytes(long long nCells);
+// migration record: 8 doubles (x,v,w,meta) + mu when the particles carry it
+inline int migration_record_len(const ParticleSoA &p) { return p.mu ? 9 : 8; }
 void launch_pack_leavers(const DevMesh &m, ParticleSoA p, const int *nSlots, long long nUpper, const int *leafOwner, const int *leafGlobal, int me,
                          double *sendBuf, long long capPerPeer, int *sendCount, int *cellCount, int *errFlag, cudaStream_t s);
 void launch_unpack_arrivals(const DevMesh &m, const double *recvBuf, int nRecv, ParticleSoA p, int *nSlots, const int *g2l, const int *leafOwner, int me,
@@ -113,6 +116,13 @@ void launch_move_relativistic_boris(const DevMesh &m, const DevSpecies &sp, int 
 void launch_move_boris(const DevMesh &m, const DevSpecies &sp, int interp, int backward, double c, double rSphere, long long exitCap, double gravityGM,
                        ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, int *cellCount, DevMoveStats *stats,
                        amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s);
+void launch_stage_background_gca(const DevMesh &m, const double *var15, double *tile, cudaStream_t s);
+void launch_magnetic_moment_init(const DevMesh &m, const DevSpecies &sp, int interp, double c, ParticleSoA p, const int *nSlots, long long nUpper,
+                                 const double *bgTile, DevMoveStats *stats, cudaStream_t s);
+void launch_magnetic_moment_set(ParticleSoA p, const int *nSlots, long long nUpper, const double *muByPtr, long long nMu, cudaStream_t s);
+void launch_move_relativistic_gca(const DevMesh &m, const DevSpecies &sp, int interp, double c, double rSphere, long long exitCap, ParticleSoA p,
+                                  const int *nSlots, long long nUpper, const double *bgTile, const double *gcaTile, int *cellCount, DevMoveStats *stats,
+                                  amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s);
 void launch_division_selftest(const double *a, const double *b, int n, unsigned long long *out, cudaStream_t s);
 
 }  // namespace amps

@@ -47,6 +47,8 @@ struct amps_gpu_ctx {
 
   // coupler table of the test-particle movers + exit records
   double *d_bgE = nullptr, *d_bgB = nullptr, *d_bgTile = nullptr;
+  double *d_gcaVar = nullptr, *d_gcaTile = nullptr;  // relativistic GCA: 15 drift variables per centre node
+  bool gcaReady = false;
   bool backgroundReady = false;
   amps_gpu_exit_record *d_exitBuf = nullptr;
   unsigned long long *d_exitCount = nullptr;
@@ -127,11 +129,16 @@ static int alloc_particles(amps_gpu_ctx *ctx, ParticleSoA &b, long long cap) {
   if ((rc = dev_alloc(ctx, &b.spec, cap))) return rc;
   if ((rc = dev_alloc(ctx, &b.key, cap))) return rc;
   if ((rc = dev_alloc(ctx, &b.ptr, cap))) return rc;
+  b.mu = nullptr;
+  if (ctx->cfg.carry_magnetic_moment) {
+    if ((rc = dev_alloc(ctx, &b.mu, cap))) return rc;
+    CK(cudaMemsetAsync(b.mu, 0, sizeof(double) * cap, ctx->stream));
+  }
   return AMPS_GPU_OK;
 }
 static void free_particles(ParticleSoA &b) {
   for (int d = 0; d < 3; d++) cudaFree(b.x[d]), cudaFree(b.v[d]);
-  cudaFree(b.w), cudaFree(b.spec), cudaFree(b.key), cudaFree(b.ptr);
+  cudaFree(b.w), cudaFree(b.spec), cudaFree(b.key), cudaFree(b.ptr), cudaFree(b.mu);
 }
 
 template <class T>
@@ -254,6 +261,7 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   for (void *p : ctx->meshAllocs) cudaFree(p);
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
   if (ctx->comm && nccl_api().CommDestroy) nccl_api().CommDestroy(ctx->comm);
+  cudaFree(ctx->d_gcaVar), cudaFree(ctx->d_gcaTile);
   cudaFree(ctx->d_bgE), cudaFree(ctx->d_bgB), cudaFree(ctx->d_bgTile), cudaFree(ctx->d_exitBuf), cudaFree(ctx->d_exitCount);
   cudaFree(ctx->d_sendBuf), cudaFree(ctx->d_recvBuf), cudaFree(ctx->d_sendCount), cudaFree(ctx->d_allCounts), cudaFree(ctx->d_errFlag);
   for (int *p : ctx->d_sharedUid) cudaFree(p);
@@ -358,8 +366,8 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
     if ((rc = upload_array(ctx, &t3, mesh->global_leaf_to_local, (size_t)mesh->n_global_leaves))) return rc;
     ctx->d_leafOwner = const_cast<int *>(t1), ctx->d_leafGlobal = const_cast<int *>(t2), ctx->d_g2l = const_cast<int *>(t3);
     ctx->capPerPeer = ctx->cfg.capacity / 32 > 65536 ? ctx->cfg.capacity / 32 : 65536;
-    if ((rc = dev_alloc(ctx, &ctx->d_sendBuf, (size_t)ctx->nRanks * ctx->capPerPeer * 8))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_recvBuf, (size_t)ctx->nRanks * ctx->capPerPeer * 8))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_sendBuf, (size_t)ctx->nRanks * ctx->capPerPeer * 9))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_recvBuf, (size_t)ctx->nRanks * ctx->capPerPeer * 9))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_sendCount, (size_t)ctx->nRanks))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_allCounts, (size_t)ctx->nRanks * ctx->nRanks))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_errFlag, 1))) return rc;
@@ -423,6 +431,70 @@ int amps_gpu_background_upload(amps_gpu_ctx *ctx, const double *E_center, const 
   ctx->launches++;
   CK(cudaGetLastError());
   ctx->backgroundReady = true;
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_background_upload_gca(amps_gpu_ctx *ctx, const double *var15_center) {
+  if (!ctx || !var15_center) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "background_upload_gca before mesh_upload");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const DevMesh &m = ctx->dm;
+  int rc;
+  if (!ctx->d_gcaTile) {
+    if ((rc = dev_alloc(ctx, &ctx->d_gcaVar, (size_t)15 * m.nCenters))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_gcaTile, (size_t)m.nLeaves * m.nCenterLocal * 15))) return rc;
+  }
+  CK(cudaMemcpyAsync(ctx->d_gcaVar, var15_center, sizeof(double) * 15 * (size_t)m.nCenters, cudaMemcpyHostToDevice, ctx->stream));
+  launch_stage_background_gca(m, ctx->d_gcaVar, ctx->d_gcaTile, ctx->stream);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  ctx->gcaReady = true;
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_magnetic_moment_init(amps_gpu_ctx *ctx) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "magnetic_moment_init needs cfg.carry_magnetic_moment");
+  if (!ctx->meshReady || !ctx->backgroundReady) FAIL(AMPS_GPU_ERR_STATE, "magnetic_moment_init needs the mesh and amps_gpu_background_upload");
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevMoveStats), ctx->stream));
+  launch_magnetic_moment_init(ctx->dm, ctx->sp, ctx->cfg.coupler_interpolation, ctx->cfg.speed_of_light, ctx->buf[ctx->cur], ctx->d_n + ctx->cur,
+                              ctx->nUpper, ctx->d_bgTile, ctx->d_stats, ctx->stream);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  DevMoveStats h;
+  CK(cudaMemcpyAsync(&h, ctx->d_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (h.n_error) FAIL(AMPS_GPU_ERR_PARTICLE, "magnetic_moment_init: a particle lies outside the cell table of its block");
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_magnetic_moment_upload(amps_gpu_ctx *ctx, const double *mu_by_ptr, int64_t n) {
+  if (!ctx || !mu_by_ptr || n < 0) return AMPS_GPU_ERR_ARG;
+  if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "magnetic_moment_upload needs cfg.carry_magnetic_moment");
+  CK(cudaSetDevice(ctx->cfg.device));
+  double *d = nullptr;
+  CK(cudaMallocAsync((void **)&d, sizeof(double) * (size_t)(n ? n : 1), ctx->stream));
+  CK(cudaMemcpyAsync(d, mu_by_ptr, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  launch_magnetic_moment_set(ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper, d, n, ctx->stream);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaFreeAsync(d, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_magnetic_moment_download(amps_gpu_ctx *ctx, double *mu, int64_t n_max, int64_t *n) {
+  if (!ctx || !n) return AMPS_GPU_ERR_ARG;
+  if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "magnetic_moment_download needs cfg.carry_magnetic_moment");
+  CK(cudaSetDevice(ctx->cfg.device));
+  int cnt = 0;
+  CK(cudaMemcpyAsync(&cnt, ctx->d_n + ctx->cur, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *n = cnt;
+  if (cnt > n_max) FAIL(AMPS_GPU_ERR_CAPACITY, "magnetic_moment_download: n_max too small");
+  if (mu && cnt > 0) CK(cudaMemcpyAsync(mu, ctx->buf[ctx->cur].mu, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return AMPS_GPU_OK;
 }
 
@@ -608,8 +680,15 @@ int amps_gpu_cell_table_download(amps_gpu_ctx *ctx, int64_t *cell_start, int64_t
 static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "move before mesh upload");
   if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "move needs the (block,cell)-sorted layout: call amps_gpu_sort");
-  if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS && mover_id != AMPS_MOVER_BORIS)
+  if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS && mover_id != AMPS_MOVER_BORIS &&
+      mover_id != AMPS_MOVER_RELATIVISTIC_GCA)
     FAIL(AMPS_GPU_ERR_ARG, "mover not implemented yet");
+  if (mover_id == AMPS_MOVER_RELATIVISTIC_GCA) {
+    if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "the guiding-centre movers need cfg.carry_magnetic_moment");
+    if (!ctx->gcaReady) FAIL(AMPS_GPU_ERR_STATE, "Relativistic::GuidingCenter needs amps_gpu_background_upload_gca");
+    if (ctx->cfg.boundary_mode != AMPS_BOUNDARY_DELETE)
+      FAIL(AMPS_GPU_ERR_STATE, "Relativistic::GuidingCenter implements the DELETE boundary only (reference :262-279)");
+  }
   if (mover_id == AMPS_MOVER_LAPENTA2017 && !ctx->fieldsReady) FAIL(AMPS_GPU_ERR_STATE, "Lapenta2017 needs amps_gpu_fields_upload");
   if (mover_id != AMPS_MOVER_LAPENTA2017 && !ctx->backgroundReady) FAIL(AMPS_GPU_ERR_STATE, "the test-particle movers need amps_gpu_background_upload");
   const DevMesh &m = ctx->dm;
@@ -620,6 +699,16 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
     launch_move_boris(m, ctx->sp, ctx->cfg.coupler_interpolation, ctx->cfg.backward_time_integration, ctx->cfg.speed_of_light,
                       ctx->cfg.internal_sphere_radius, ctx->cfg.exit_record_capacity, ctx->cfg.gravity_gm, ctx->buf[ctx->cur], ctx->d_n + ctx->cur,
                       ctx->nUpper, ctx->d_bgTile, ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount, ctx->stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    ctx->sorted = false;
+    ctx->countValid = true;
+    return AMPS_GPU_OK;
+  }
+  if (mover_id == AMPS_MOVER_RELATIVISTIC_GCA) {
+    launch_move_relativistic_gca(m, ctx->sp, ctx->cfg.coupler_interpolation, ctx->cfg.speed_of_light, ctx->cfg.internal_sphere_radius,
+                                 ctx->cfg.exit_record_capacity, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper, ctx->d_bgTile, ctx->d_gcaTile,
+                                 ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
     ctx->sorted = false;
@@ -813,6 +902,7 @@ static int do_migrate(amps_gpu_ctx *ctx, int64_t *n_sent, int64_t *n_received) {
   ProfScope prof(ctx, AMPS_GPU_PHASE_EXCHANGE);
   NcclApi &a = nccl_api();
   const int R = ctx->nRanks, me = ctx->rank;
+  const size_t recLen = (size_t)migration_record_len(ctx->buf[ctx->cur]);
   cudaStream_t s = ctx->stream;
   CK(cudaMemsetAsync(ctx->d_sendCount, 0, sizeof(int) * R, s));
   launch_pack_leavers(ctx->dm, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper, ctx->d_leafOwner, ctx->d_leafGlobal, me, ctx->d_sendBuf,
@@ -837,8 +927,8 @@ static int do_migrate(amps_gpu_ctx *ctx, int64_t *n_sent, int64_t *n_received) {
   for (int r = 0; r < R; r++) {
     if (r == me) continue;
     const int ns = all[(size_t)me * R + r], nr = all[(size_t)r * R + me];
-    if (ns > 0) NCK(a.Send(ctx->d_sendBuf + (size_t)r * ctx->capPerPeer * 8, (size_t)ns * 8, ncclDouble, r, ctx->comm, s));
-    if (nr > 0) NCK(a.Recv(ctx->d_recvBuf + (size_t)roff[r] * 8, (size_t)nr * 8, ncclDouble, r, ctx->comm, s));
+    if (ns > 0) NCK(a.Send(ctx->d_sendBuf + (size_t)r * ctx->capPerPeer * recLen, (size_t)ns * recLen, ncclDouble, r, ctx->comm, s));
+    if (nr > 0) NCK(a.Recv(ctx->d_recvBuf + (size_t)roff[r] * recLen, (size_t)nr * recLen, ncclDouble, r, ctx->comm, s));
   }
   NCK(a.GroupEnd());
   if (ctx->nUpper + nRecv > ctx->cfg.capacity) FAIL(AMPS_GPU_ERR_CAPACITY, "particle capacity exceeded by arriving particles");

@@ -4,7 +4,7 @@
 //       The reference walks the per-cell lists of the boundary-layer blocks and sends {cell descriptor,
 //       particle bytes}; here the mover has already written the new (block,cell) key of every particle, so a
 //       leaver is any particle whose block is owned by another rank: it is appended to that rank's send
-//       buffer (8 doubles: x,v,w and the GLOBAL cell id + species), removed from the local histogram and
+//       buffer (8 doubles: x,v,w and the GLOBAL cell id + species; 9 with the magnetic moment), removed from the local histogram and
 //       marked deleted.  Arrivals are appended behind the resident particles with their key translated to the
 //       local block numbering and counted into the histogram; the counting sort that follows files them.
 //   a12 SyncMassMatrix / ProcessJMassMatrix    src/pic/ecsim/halo_sync.cpp:79-124, pic_field_solver_ecsim.cpp:1383
@@ -30,12 +30,14 @@ __global__ void __launch_bounds__(256) pack_leavers_kernel(ParticleSoA p, const 
       atomicExch(errFlag, 1);
       continue;  // the particle stays (in a foreign block); the host reports AMPS_GPU_ERR_CAPACITY
     }
-    double *r = sendBuf + ((size_t)dest * capPerPeer + slot) * 8;
+    const int L = p.mu ? 9 : 8;
+    double *r = sendBuf + ((size_t)dest * capPerPeer + slot) * L;
     const long long gkey = (long long)leafGlobal[leaf] * C + (k - leaf * C);
     r[0] = p.x[0][i], r[1] = p.x[1][i], r[2] = p.x[2][i];
     r[3] = p.v[0][i], r[4] = p.v[1][i], r[5] = p.v[2][i];
     r[6] = p.w[i];
     r[7] = __longlong_as_double((gkey << 8) | (long long)p.spec[i]);
+    if (p.mu) r[8] = p.mu[i];
     atomicSub(&cellCount[k], 1);
     p.key[i] = -1;
   }
@@ -46,7 +48,7 @@ __global__ void __launch_bounds__(256) unpack_arrivals_kernel(const double *__re
                                                              long long capacity, int *__restrict__ cellCount, int *__restrict__ errFlag) {
   const int base = *nSlots;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nRecv; j += gridDim.x * blockDim.x) {
-    const double *r = recvBuf + (size_t)j * 8;
+    const double *r = recvBuf + (size_t)j * (p.mu ? 9 : 8);
     const long long meta = __double_as_longlong(r[7]);
     const long long gkey = meta >> 8;
     const int gleaf = (int)(gkey / C);
@@ -61,6 +63,7 @@ __global__ void __launch_bounds__(256) unpack_arrivals_kernel(const double *__re
     p.x[0][i] = r[0], p.x[1][i] = r[1], p.x[2][i] = r[2];
     p.v[0][i] = r[3], p.v[1][i] = r[4], p.v[2][i] = r[5];
     p.w[i] = r[6];
+    if (p.mu) p.mu[i] = r[8];
     p.spec[i] = (uint8_t)(meta & 0xff);
     p.key[i] = k;
     p.ptr[i] = -1;  // no ParticleBuffer slot on this rank yet (GetNewParticle on download)

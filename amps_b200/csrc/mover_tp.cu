@@ -521,4 +521,353 @@ void launch_move_boris(const DevMesh &m, const DevSpecies &sp, int interp, int b
   move_boris_kernel<<<(int)g, 128, 0, s>>>(m, sp, tp, gravityGM, p, nSlots, bgTile, cellCount, stats, exitBuf, exitCount);
 }
 
+// ------------------------------------------------------------------------------------------------
+// a9: PIC::Mover::Relativistic::GuidingCenter  src/pic/pic_mover_relativistic_guiding_center.cpp
+//     InitiateMagneticMoment :19-93, Mover_FirstOrder :96-409 (DELETE boundary; the other branches of the
+//     reference exit() or use an undefined face), fields + 15 drift variables through the coupler stencil
+//     (GetVarForRelativisticGCA, pic.h:8643-8680) on per-leaf tiles [nCenterLocal][15]
+// ------------------------------------------------------------------------------------------------
+__global__ void stage_background_gca_kernel(DevMesh m, const double *__restrict__ var, double *__restrict__ tile) {
+  const int leaf = blockIdx.x;
+  const int *cuid = m.centerUid + (size_t)leaf * m.nCenterLocal;
+  double *dst = tile + (size_t)leaf * m.nCenterLocal * 15;
+  for (int e = threadIdx.x; e < m.nCenterLocal * 15; e += blockDim.x) {
+    const int i = e / 15, q = e - 15 * i;
+    const int u = cuid[i];
+    dst[e] = (u >= 0) ? var[15 * (size_t)u + q] : 0.0;
+  }
+}
+void launch_stage_background_gca(const DevMesh &m, const double *var15, double *tile, cudaStream_t s) {
+  stage_background_gca_kernel<<<m.nLeaves, 256, 0, s>>>(m, var15, tile);
+}
+
+// the coupler stencil at x inside `leaf` (same arithmetic as background_fields), kept for several gathers
+struct BgStencil {
+  double w[8];
+  int nd[8];
+  int n;
+};
+__device__ __forceinline__ bool background_stencil(const DevMesh &m, int interp, const double x[3], int leaf, BgStencil &st) {
+  const LeafGeo &lg = m.leaf[leaf];
+  if (interp == AMPS_CPLR_CELL_CENTERED_LINEAR) {
+    const double iLoc = (x[0] - lg.xmin[0]) / (lg.xmax[0] - lg.xmin[0]) * m.N[0];
+    const double jLoc = (x[1] - lg.xmin[1]) / (lg.xmax[1] - lg.xmin[1]) * m.N[1];
+    const double kLoc = (x[2] - lg.xmin[2]) / (lg.xmax[2] - lg.xmin[2]) * m.N[2];
+    const int i0 = (iLoc < 0.5) ? -1 : (int)(iLoc - 0.50);
+    const int j0 = (jLoc < 0.5) ? -1 : (int)(jLoc - 0.50);
+    const int k0 = (kLoc < 0.5) ? -1 : (int)(kLoc - 0.50);
+    const double w0 = iLoc - (i0 + 0.5), w1 = jLoc - (j0 + 0.5), w2 = kLoc - (k0 + 0.5);
+    double w[8];
+    w[0] = (1.0 - w0) * (1.0 - w1) * (1.0 - w2);
+    w[1] = (1.0 - w0) * (1.0 - w1) * w2;
+    w[2] = (1.0 - w0) * w1 * (1.0 - w2);
+    w[3] = (1.0 - w0) * w1 * w2;
+    w[4] = w0 * (1.0 - w1) * (1.0 - w2);
+    w[5] = w0 * (1.0 - w1) * w2;
+    w[6] = w0 * w1 * (1.0 - w2);
+    w[7] = w0 * w1 * w2;
+    unsigned valid = 0xffu;
+    if (!m.periodic && lg.face) {
+      if ((lg.face & 1) && i0 < 0) valid &= 0xf0u;
+      if ((lg.face & 2) && i0 + 1 >= m.N[0]) valid &= 0x0fu;
+      if ((lg.face & 4) && j0 < 0) valid &= 0xccu;
+      if ((lg.face & 8) && j0 + 1 >= m.N[1]) valid &= 0x33u;
+      if ((lg.face & 16) && k0 < 0) valid &= 0xaau;
+      if ((lg.face & 32) && k0 + 1 >= m.N[2]) valid &= 0x55u;
+    }
+    double norm = 0.0;
+    if (valid != 0xffu) {
+      for (int s = 0; s < 8; s++)
+        if (valid & (1u << s)) norm += w[s];
+    }
+    const int nd0 = centerLocalNumber(m, i0, j0, k0);
+    const int BS0 = m.TN[0], BS1 = m.TN[0] * m.TN[1];
+    st.n = 0;
+    for (int s = 0; s < 8; s++)
+      if (valid & (1u << s)) {
+        st.w[st.n] = (valid != 0xffu && norm > 0.0) ? w[s] / norm : w[s];
+        st.nd[st.n] = nd0 + ((s >> 2) & 1) + ((s >> 1) & 1) * BS0 + (s & 1) * BS1;
+        st.n++;
+      }
+    return true;
+  }
+  int ijk[3];
+  if (!find_cell_index(m, x, lg.node, ijk)) return false;
+  st.n = 1, st.w[0] = 1.0, st.nd[0] = centerLocalNumber(m, ijk[0], ijk[1], ijk[2]);
+  return true;
+}
+template <int K>
+__device__ __forceinline__ void background_gather(const BgStencil &st, const double *__restrict__ T, int stride, int off, double out[K]) {
+  for (int q = 0; q < K; q++) out[q] = 0.0;
+  for (int s = 0; s < st.n; s++) {
+    const double *t = T + (size_t)stride * st.nd[s] + off;
+    for (int q = 0; q < K; q++) out[q] += st.w[s] * t[q];
+  }
+}
+
+__global__ void __launch_bounds__(128) magnetic_moment_init_kernel(DevMesh m, DevSpecies sp, int interp, double SpeedOfLight, ParticleSoA p,
+                                                                  const int *__restrict__ nSlots, const double *__restrict__ bgTile,
+                                                                  DevMoveStats *__restrict__ stats) {
+  const int n = *nSlots;
+  const int C = m.cellsPerBlock;
+  unsigned int nErr = 0;
+  for (int ip = blockIdx.x * blockDim.x + threadIdx.x; ip < n; ip += gridDim.x * blockDim.x) {
+    const int key = p.key[ip];
+    if (key < 0) continue;
+    const double x[3] = {p.x[0][ip], p.x[1][ip], p.x[2][ip]};
+    const double v[3] = {p.v[0][ip], p.v[1][ip], p.v[2][ip]};
+    const int leaf = key / C;
+    BgStencil st;
+    if (!background_stencil(m, interp, x, leaf, st)) {
+      nErr++;
+      continue;
+    }
+    const double *T = bgTile + (size_t)leaf * m.nCenterLocal * 6;
+    double B[3], E[3];
+    background_gather<3>(st, T, 6, 3, B);
+    background_gather<3>(st, T, 6, 0, E);
+    const double AbsB = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) + 1E-15;
+    double vE[3];
+    vE[0] = E[1] * B[2] - E[2] * B[1];
+    vE[1] = E[2] * B[0] - E[0] * B[2];
+    vE[2] = E[0] * B[1] - E[1] * B[0];
+    if (AbsB > 0.0)
+      for (int d = 0; d < 3; d++) vE[d] /= AbsB * AbsB;
+    const double vE_norm = sqrt(vE[0] * vE[0] + vE[1] * vE[1] + vE[2] * vE[2]);
+    const double v_norm = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    const double c2 = SpeedOfLight * SpeedOfLight;
+    const double kappa = 1 / sqrt(1 - vE_norm * vE_norm / (c2));
+    const double gamma = 1 / sqrt(1 - v_norm * v_norm / (c2));
+    double mu = 0.0;
+    double B_star[3], v_star[3];
+    const double gamma_star = gamma / kappa;
+    double vE_cross_E[3];
+    const double B_dot_vE = B[0] * vE[0] + B[1] * vE[1] + B[2] * vE[2];
+    vE_cross_E[0] = vE[1] * E[2] - vE[2] * E[1];
+    vE_cross_E[1] = vE[2] * E[0] - vE[0] * E[2];
+    vE_cross_E[2] = vE[0] * E[1] - vE[1] * E[0];
+    for (int d = 0; d < 3; d++) {
+      B_star[d] = kappa * (B[d] - vE_cross_E[d] / c2);
+      if (vE_norm > 0) B_star[d] -= (kappa - 1) * B_dot_vE * vE[d] / (vE_norm * vE_norm);
+      v_star[d] = v[d] - vE[d];
+    }
+    const double Bstar_norm = sqrt(B_star[0] * B_star[0] + B_star[1] * B_star[1] + B_star[2] * B_star[2]);
+    if (Bstar_norm > 0.0) {
+      const double vstar_norm = sqrt(v_star[0] * v_star[0] + v_star[1] * v_star[1] + v_star[2] * v_star[2]);
+      const double vstar_par = (v_star[0] * B_star[0] + v_star[1] * B_star[1] + v_star[2] * B_star[2]) / Bstar_norm;
+      const double m0 = sp.mass[p.spec[ip]];
+      mu = 0.5 * (gamma_star * gamma_star) * m0 * (vstar_norm * vstar_norm - vstar_par * vstar_par) / Bstar_norm;
+    }
+    p.mu[ip] = mu;
+  }
+  flush_move_counters(stats, 0, 0, 0, 0, 0, 0, nErr);
+}
+void launch_magnetic_moment_init(const DevMesh &m, const DevSpecies &sp, int interp, double c, ParticleSoA p, const int *nSlots, long long nUpper,
+                                 const double *bgTile, DevMoveStats *stats, cudaStream_t s) {
+  long long g = (nUpper + 127) / 128;
+  if (g < 1) g = 1;
+  if (g > 148 * 32) g = 148 * 32;
+  magnetic_moment_init_kernel<<<(int)g, 128, 0, s>>>(m, sp, interp, c, p, nSlots, bgTile, stats);
+}
+
+__global__ void magnetic_moment_set_kernel(ParticleSoA p, const int *__restrict__ nSlots, const double *__restrict__ muByPtr, long long nMu) {
+  const int n = *nSlots;
+  for (int ip = blockIdx.x * blockDim.x + threadIdx.x; ip < n; ip += gridDim.x * blockDim.x) {
+    const int pt = p.ptr[ip];
+    if (pt >= 0 && pt < nMu) p.mu[ip] = muByPtr[pt];
+  }
+}
+void launch_magnetic_moment_set(ParticleSoA p, const int *nSlots, long long nUpper, const double *muByPtr, long long nMu, cudaStream_t s) {
+  long long g = (nUpper + 255) / 256;
+  if (g < 1) g = 1;
+  if (g > 148 * 16) g = 148 * 16;
+  magnetic_moment_set_kernel<<<(int)g, 256, 0, s>>>(p, nSlots, muByPtr, nMu);
+}
+
+__global__ void __launch_bounds__(128) move_relativistic_gca_kernel(DevMesh m, DevSpecies sp, TpParams tp, ParticleSoA p, const int *__restrict__ nSlots,
+                                                                   const double *__restrict__ bgTile, const double *__restrict__ gcaTile,
+                                                                   int *__restrict__ cellCount, DevMoveStats *__restrict__ stats,
+                                                                   amps_gpu_exit_record *__restrict__ exitBuf, unsigned long long *__restrict__ exitCount) {
+  const int n = *nSlots;
+  const int C = m.cellsPerBlock;
+  unsigned int nMoved = 0, nXCell = 0, nXBlock = 0, nLeft = 0, nNotUsed = 0, nWrap = 0, nErr = 0;
+  const double c2 = tp.c * tp.c;
+
+  for (int ip = blockIdx.x * blockDim.x + threadIdx.x; ip < n; ip += gridDim.x * blockDim.x) {
+    const int oldKey = p.key[ip];
+    if (oldKey < 0) continue;
+    nMoved++;
+    const double xInit[3] = {p.x[0][ip], p.x[1][ip], p.x[2][ip]};
+    const double vInit[3] = {p.v[0][ip], p.v[1][ip], p.v[2][ip]};
+    double xFinal[3], vFinal[3] = {0.0, 0.0, 0.0};
+    const int spec = p.spec[ip];
+    const int startLeaf = oldKey / C;
+    const int startNode = m.leaf[startLeaf].node;
+    const double ElectricCharge = sp.charge[spec], mass = sp.mass[spec];
+    const double dtTotal = (sp.timeStepMode == AMPS_DT_SPECIES_GLOBAL) ? sp.dt[spec] : sp.dt[0];
+    int outcome = 0, node = -1;
+    const double Mr = p.mu[ip];
+    double uPar = 0.0;
+    double bHat[3] = {0.0, 0.0, 0.0};
+
+    {
+      const double vNorm = sqrt(vInit[0] * vInit[0] + vInit[1] * vInit[1] + vInit[2] * vInit[2]);
+      const double lfac = 1 / sqrt(1.0 - vNorm * vNorm / c2);
+      BgStencil st;
+      if (!background_stencil(m, tp.interp, xInit, startLeaf, st)) outcome = 3;
+      else {
+        double B[3], E[3], var15[15];
+        background_gather<3>(st, bgTile + (size_t)startLeaf * m.nCenterLocal * 6, 6, 3, B);
+        background_gather<3>(st, bgTile + (size_t)startLeaf * m.nCenterLocal * 6, 6, 0, E);
+        background_gather<15>(st, gcaTile + (size_t)startLeaf * m.nCenterLocal * 15, 15, 0, var15);
+        const double *b_dot_grad_b = var15, *vE_dot_grad_b = var15 + 3, *b_dot_grad_vE = var15 + 6, *vE_dot_grad_vE = var15 + 9, *grad_kappaB = var15 + 12;
+        const double bNorm = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]);
+        double ePar = 0.0;
+        if (bNorm > 0.0) {
+          for (int d = 0; d < 3; d++) {
+            bHat[d] = B[d] / bNorm;
+            ePar += E[d] * bHat[d];
+          }
+        }
+        const double vPar = vInit[0] * bHat[0] + vInit[1] * bHat[1] + vInit[2] * bHat[2];
+        uPar = lfac * vPar;
+        double vE[3], vENorm = 0.0;
+        vE[0] = E[1] * bHat[2] - E[2] * bHat[1];
+        vE[1] = E[2] * bHat[0] - E[0] * bHat[2];
+        vE[2] = E[0] * bHat[1] - E[1] * bHat[0];
+        if (bNorm > 0.0) {
+          for (int d = 0; d < 3; d++) {
+            vE[d] = vE[d] / bNorm;
+            vENorm += vE[d] * vE[d];
+          }
+        }
+        vENorm = sqrt(vENorm);
+        const double kappa = 1 / sqrt(1 - vENorm * vENorm / c2);
+        const double gamma = sqrt(1.0 + (uPar * uPar + 2.0 * Mr * bNorm / mass) / c2) * kappa;
+        double utmp1[3] = {0.0, 0.0, 0.0}, utmp2[3], utmp3[3];
+        double temp = bNorm / (kappa * kappa);
+        if (bNorm > 0.0)
+          for (int d = 0; d < 3; d++) utmp1[d] = bHat[d] / temp;
+        for (int d = 0; d < 3; d++) {
+          utmp2[d] = Mr / (gamma * ElectricCharge) * grad_kappaB[d] +
+                     mass / ElectricCharge * (uPar * uPar / gamma * b_dot_grad_b[d] + uPar * vE_dot_grad_b[d] + uPar * b_dot_grad_vE[d] + gamma * vE_dot_grad_vE[d]);
+        }
+        for (int d = 0; d < 3; d++) utmp2[d] = utmp2[d] + uPar * ePar / (gamma)*vE[d];
+        double u[3];
+        utmp3[0] = utmp1[1] * utmp2[2] - utmp1[2] * utmp2[1];
+        utmp3[1] = utmp1[2] * utmp2[0] - utmp1[0] * utmp2[2];
+        utmp3[2] = utmp1[0] * utmp2[1] - utmp1[1] * utmp2[0];
+        for (int d = 0; d < 3; d++) {
+          u[d] = vE[d] + utmp3[d];
+          u[d] += uPar / gamma * bHat[d];
+        }
+        double dupardt = ElectricCharge / mass * ePar;
+        temp = Mr / (mass * gamma);
+        for (int d = 0; d < 3; d++) {
+          dupardt += -temp * bHat[d] * grad_kappaB[d] + vE[d] * (uPar * b_dot_grad_b[d] + gamma * vE_dot_grad_b[d]);
+          xFinal[d] = xInit[d] + dtTotal * u[d];
+        }
+        uPar += dupardt * dtTotal;
+      }
+    }
+
+    if (outcome == 0 && tp.rSphere > 0.0) {
+      const double rFinal = sqrt(xFinal[0] * xFinal[0] + xFinal[1] * xFinal[1] + xFinal[2] * xFinal[2]);
+      if (rFinal < tp.rSphere) {
+        add_exit_record(exitBuf, exitCount, tp.exitCap, p.ptr[ip], spec, AMPS_EXIT_SPHERE, startLeaf, xInit, vInit);
+        outcome = 1;
+      }
+    }
+    int newLeaf = -1;
+    if (outcome == 0) {
+      node = find_tree_node_plain(m, xFinal, startNode);
+      if (node < 0) outcome = 1;  // DELETE
+      else if ((newLeaf = m.nodeLeaf[node]) < 0) outcome = 3;  // "the block is empty" :348
+    }
+    if (outcome == 0) {
+      BgStencil st;
+      if (!background_stencil(m, tp.interp, xFinal, newLeaf, st)) outcome = 3;
+      else {
+        double B[3], E[3];
+        background_gather<3>(st, bgTile + (size_t)newLeaf * m.nCenterLocal * 6, 6, 3, B);
+        background_gather<3>(st, bgTile + (size_t)newLeaf * m.nCenterLocal * 6, 6, 0, E);
+        const double bNorm = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]);
+        if (bNorm > 0.0)  // otherwise bHat of the first stage stays, as in the reference
+          for (int d = 0; d < 3; d++) bHat[d] = B[d] / bNorm;
+        double vE[3], vENorm = 0.0;
+        vE[0] = E[1] * bHat[2] - E[2] * bHat[1];
+        vE[1] = E[2] * bHat[0] - E[0] * bHat[2];
+        vE[2] = E[0] * bHat[1] - E[1] * bHat[0];
+        if (bNorm > 0.0) {
+          for (int d = 0; d < 3; d++) {
+            vE[d] = vE[d] / bNorm;
+            vENorm += vE[d] * vE[d];
+          }
+        }
+        vENorm = sqrt(vENorm);
+        const double kappa = 1 / sqrt(1 - vENorm * vENorm / c2);
+        const double gamma = sqrt(1.0 + (uPar * uPar + 2.0 * Mr * bNorm / mass) / c2) * kappa;
+        const double vPar = uPar / gamma;
+        double res = (1 - 1 / (gamma * gamma)) * c2 - vPar * vPar;
+        if (bNorm == 0 && res < 0) res = 0.0;
+        if (bNorm > 0 && res < 0) outcome = 1;  // DeleteParticle, _PARTICLE_LEFT_THE_DOMAIN_ :308-311
+        else {
+          const double vPerp = sqrt(res);
+          const double diff = (1.0 - bHat[0]) * (1.0 - bHat[0]) + (0.0 - bHat[1]) * (0.0 - bHat[1]) + (0.0 - bHat[2]) * (0.0 - bHat[2]);
+          const double e0 = (diff > 0.0) ? 1.0 : 0.0, e1 = (diff > 0.0) ? 0.0 : 1.0, e2 = 0.0;
+          double ePerp[3];
+          ePerp[0] = e1 * bHat[2] - e2 * bHat[1];
+          ePerp[1] = e2 * bHat[0] - e0 * bHat[2];
+          ePerp[2] = e0 * bHat[1] - e1 * bHat[0];
+          for (int d = 0; d < 3; d++) vFinal[d] += vPerp * ePerp[d] + vPar * bHat[d];
+        }
+      }
+    }
+
+    int newKey = -1;
+    if (outcome == 0) {
+      int ijk[3];
+      if (!find_cell_index(m, xFinal, node, ijk)) outcome = 3;
+      else {
+        const int realLeaf = m.leaf[newLeaf].real;
+        if (realLeaf >= 0) {
+          const LeafGeo &gg = m.leaf[newLeaf];
+          const LeafGeo &rg = m.leaf[realLeaf];
+          for (int d = 0; d < 3; d++) {
+            xFinal[d] += rg.xmin[d] - gg.xmin[d];
+            if (xFinal[d] < rg.xmin[d]) xFinal[d] = rg.xmin[d];
+            if (xFinal[d] >= rg.xmax[d]) xFinal[d] = rg.xmax[d] - 1.0E-10 * (rg.xmax[d] - rg.xmin[d]);
+          }
+          newLeaf = realLeaf;
+          nWrap++;
+        }
+        newKey = newLeaf * C + ijk[0] + m.N[0] * (ijk[1] + m.N[1] * ijk[2]);
+        if (newLeaf != startLeaf) nXBlock++;
+        else if (newKey != oldKey) nXCell++;
+      }
+    }
+    if (outcome == 1) nLeft++;
+    else if (outcome == 2) nNotUsed++;
+    else if (outcome == 3) nErr++;
+    if (newKey >= 0) {
+      p.x[0][ip] = xFinal[0], p.x[1][ip] = xFinal[1], p.x[2][ip] = xFinal[2];
+      p.v[0][ip] = vFinal[0], p.v[1][ip] = vFinal[1], p.v[2][ip] = vFinal[2];
+      atomicAdd(&cellCount[newKey], 1);
+    }
+    if (newKey != oldKey) p.key[ip] = newKey;
+  }
+  flush_move_counters(stats, nMoved, nXCell, nXBlock, nLeft, nNotUsed, nWrap, nErr);
+}
+
+void launch_move_relativistic_gca(const DevMesh &m, const DevSpecies &sp, int interp, double c, double rSphere, long long exitCap, ParticleSoA p,
+                                  const int *nSlots, long long nUpper, const double *bgTile, const double *gcaTile, int *cellCount, DevMoveStats *stats,
+                                  amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s) {
+  TpParams tp;
+  tp.interp = interp, tp.backward = 0, tp.boundaryMode = sp.boundaryMode, tp.c = c, tp.rSphere = rSphere, tp.exitCap = exitCap;
+  long long g = (nUpper + 127) / 128;
+  if (g < 1) g = 1;
+  if (g > 148 * 32) g = 148 * 32;
+  move_relativistic_gca_kernel<<<(int)g, 128, 0, s>>>(m, sp, tp, p, nSlots, bgTile, gcaTile, cellCount, stats, exitBuf, exitCount);
+}
+
 }  // namespace amps

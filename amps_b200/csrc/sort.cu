@@ -138,8 +138,16 @@ __global__ void __launch_bounds__(256) scatter_kernel(ParticleSoA src, ParticleS
     b.k = (j < n) ? src.key[j] : -1;
     if (a.k >= 0) load_particle(src, i, a);
     if (b.k >= 0) load_particle(src, j, b);
-    if (a.k >= 0) store_particle(dst, cellStart[a.k] + warp_aggregated_slot(cellFill, a.k), a);
-    if (b.k >= 0) store_particle(dst, cellStart[b.k] + warp_aggregated_slot(cellFill, b.k), b);
+    if (a.k >= 0) {
+      const int pos = cellStart[a.k] + warp_aggregated_slot(cellFill, a.k);
+      store_particle(dst, pos, a);
+      if (src.mu) dst.mu[pos] = src.mu[i];
+    }
+    if (b.k >= 0) {
+      const int pos = cellStart[b.k] + warp_aggregated_slot(cellFill, b.k);
+      store_particle(dst, pos, b);
+      if (src.mu) dst.mu[pos] = src.mu[j];
+    }
   }
 }
 

@@ -108,6 +108,8 @@ typedef struct amps_gpu_config {
   double internal_sphere_radius;     /* max(_RADIUS_(_TARGET_),Planet->Radius), 0 = no internal sphere (:272)            */
   int64_t exit_record_capacity;      /* records kept for the host callbacks (0 = only count)                              */
   double gravity_gm;                 /* GravityConstant*_MASS_(_TARGET_) of BorisSplitAcceleration_default (:110-118), 0 = off */
+  int32_t carry_magnetic_moment;     /* _USE_MAGNETIC_MOMENT_: particles carry mu (picParticleDataMacro.h:178-187); needed by the GCA movers */
+  int32_t reserved0;
 } amps_gpu_config;
 
 /* _PIC_COUPLER__INTERPOLATION_MODE_ */
@@ -220,6 +222,18 @@ int amps_gpu_fields_upload(amps_gpu_ctx *ctx, const double *E_half, const double
 /* background E, B of the coupler on the unique centre nodes, [n_centers][3] each (DATAFILE::Offset::ElectricField /
  * MagneticField of cDataCenterNode, pic.h:8338-8425); either may be NULL = keep / zero            */
 int amps_gpu_background_upload(amps_gpu_ctx *ctx, const double *E_center, const double *B_center);
+/* the 15 tabulated drift variables of the relativistic guiding-centre mover on the unique centre nodes, [n_centers][15]:
+ * b.grad(b), vE.grad(b), b.grad(vE), vE.grad(vE), grad(kappa*B), 3 components each in that order
+ * (PIC::CPLR::GetVarForRelativisticGCA, pic.h:8643-8680; produced by DATAFILE, pic_datafile.cpp:1164-1340)   */
+int amps_gpu_background_upload_gca(amps_gpu_ctx *ctx, const double *var15_center);
+/* PIC::Mover::Relativistic::GuidingCenter::InitiateMagneticMoment (pic_mover_relativistic_guiding_center.cpp:19-93)
+ * for every resident particle (the reference calls it from InitiateParticle, pic_pbuffer.cpp:988); needs
+ * carry_magnetic_moment and the background table                                                           */
+int amps_gpu_magnetic_moment_init(amps_gpu_ctx *ctx);
+/* mu_by_ptr[ptr] -> device (SetMagneticMoment on the records the particles came from); n = length of mu_by_ptr */
+int amps_gpu_magnetic_moment_upload(amps_gpu_ctx *ctx, const double *mu_by_ptr, int64_t n);
+/* current device order (pair with the ptrs of amps_gpu_particles_download_soa) */
+int amps_gpu_magnetic_moment_download(amps_gpu_ctx *ctx, double *mu, int64_t n_max, int64_t *n);
 /* exit records accumulated by the movers since the last call (clears them) */
 int amps_gpu_exit_records(amps_gpu_ctx *ctx, amps_gpu_exit_record *buf, int64_t max_records, int64_t *n);
 

@@ -40,7 +40,8 @@ const int CurrentBOffset_d = 0;
 const int PrevBOffset_d = 3;
 const int BackgroundE_d = 6;   // coupler table: DATAFILE::Offset::ElectricField
 const int BackgroundB_d = 9;   // coupler table: DATAFILE::Offset::MagneticField
-const int CenterDataLength = 12;
+const int BackgroundGCA_d = 12; // 15 tabulated derivative variables of the relativistic GCA (pic_datafile.cpp:1164-1340)
+const int CenterDataLength = 27;
 const double SpeedOfLight_SI = 299792458.0;  // src/general/constants.h:40
 
 // src/pic/pic_field_solver_ecsim.cpp:1377-1380
@@ -171,7 +172,10 @@ struct oracle_ctx {
   }
 
   // ---- PIC::ParticleBuffer accessors, packed layout picParticleDataMacro.h:55-81 ----
-  enum { OFF_NEXT = 0, OFF_PREV = 8, OFF_SPEC = 16, OFF_V = 17, OFF_X = 41, OFF_W = 65, BASIC_LEN = 73 };
+  // + _PIC_PARTICLE_DATA__MAGNETIC_MOMENT_OFFSET_ (picParticleDataMacro.h:178-187) right after the basic data
+  enum { OFF_NEXT = 0, OFF_PREV = 8, OFF_SPEC = 16, OFF_V = 17, OFF_X = 41, OFF_W = 65, OFF_MU = 73, BASIC_LEN = 81 };
+  static double GetMagneticMoment(const byte *p) { double m; memcpy(&m, p + OFF_MU, 8); return m; }
+  static void SetMagneticMoment(double m, byte *p) { memcpy(p + OFF_MU, &m, 8); }
   byte *GetParticleDataPointer(long int ptr) const { return ParticleDataBuffer + ptr * ParticleDataLength; }
   static long int GetNext(const byte *p) { long int t; memcpy(&t, p + OFF_NEXT, 8); return t; }
   static long int GetPrev(const byte *p) { long int t; memcpy(&t, p + OFF_PREV, 8); return t; }
@@ -1082,6 +1086,212 @@ struct oracle_ctx {
     return _PARTICLE_MOTION_FINISHED_;
   }
 
+
+  // fields + the 15 GCA variables through the coupler stencil (pic.h:8338-8425, 8643-8680)
+  bool GetBackgroundFieldsGCA(const double *x, cTreeNode *node, double *E, double *B, double *v15) const {
+    cStencil Stencil;
+    if (cfg.coupler_interpolation == AMPS_CPLR_CELL_CENTERED_LINEAR) {
+      CellCentered_Linear_InitStencil(x, node, Stencil, false);
+    } else {
+      int i, j, k;
+      long int nd = FindCellIndex(x, i, j, k, node);
+      if (nd < 0 || node->block == NULL || node->block->centerNodes[nd] == NULL) return false;
+      Stencil.Weight[0] = 1.0, Stencil.LocalCellID[0] = (int)nd, Stencil.Length = 1;
+    }
+    for (int idim = 0; idim < 3; idim++) E[idim] = 0.0, B[idim] = 0.0;
+    // call order of the movers: B, E, then var15
+    for (int iStencil = 0; iStencil < Stencil.Length; iStencil++) {
+      const double *t = node->block->centerNodes[Stencil.LocalCellID[iStencil]]->data + BackgroundB_d;
+      for (int idim = 0; idim < 3; idim++) B[idim] += Stencil.Weight[iStencil] * t[idim];
+    }
+    for (int iStencil = 0; iStencil < Stencil.Length; iStencil++) {
+      const double *t = node->block->centerNodes[Stencil.LocalCellID[iStencil]]->data + BackgroundE_d;
+      for (int idim = 0; idim < 3; idim++) E[idim] += Stencil.Weight[iStencil] * t[idim];
+    }
+    if (v15) {
+      for (int iVar = 0; iVar < 15; iVar++) v15[iVar] = 0.0;
+      for (int iStencil = 0; iStencil < Stencil.Length; iStencil++) {
+        const double *t = node->block->centerNodes[Stencil.LocalCellID[iStencil]]->data + BackgroundGCA_d;
+        for (int iVar = 0; iVar < 15; iVar++) v15[iVar] += Stencil.Weight[iStencil] * t[iVar];
+      }
+    }
+    return true;
+  }
+
+  // PIC::Mover::Relativistic::GuidingCenter::InitiateMagneticMoment, pic_mover_relativistic_guiding_center.cpp:19-93
+  // NOTE (reference defect, restated as intended): :45 reads |vE| before vE is computed (uninitialised stack); here
+  // vE = E x B / B^2 is formed first and vE_norm is its length.
+  bool RelGCA_InitiateMagneticMoment(int spec, const double *x, const double *v, byte *ParticleData, cTreeNode *node) {
+    double B[3] = {0.0, 0.0, 0.0}, AbsB = 0.0, E[3] = {0.0, 0.0, 0.0};
+    if (!GetBackgroundFieldsGCA(x, node, E, B, NULL)) return false;
+    AbsB = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) + 1E-15;
+    double vE[3];
+    vE[0] = E[1] * B[2] - E[2] * B[1];
+    vE[1] = E[2] * B[0] - E[0] * B[2];
+    vE[2] = E[0] * B[1] - E[1] * B[0];
+    if (AbsB > 0.0)
+      for (int idim = 0; idim < 3; idim++) vE[idim] /= AbsB * AbsB;
+    double vE_norm = sqrt(vE[0] * vE[0] + vE[1] * vE[1] + vE[2] * vE[2]);
+    double v_norm = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    double kappa, gamma, gamma_star, c2 = cfg.speed_of_light * cfg.speed_of_light;
+    kappa = 1 / sqrt(1 - vE_norm * vE_norm / (c2));
+    gamma = 1 / sqrt(1 - v_norm * v_norm / (c2));
+    double m0, mu = 0.0;
+    double B_star[3], v_star[3];
+    gamma_star = gamma / kappa;
+    double vE_cross_E[3], B_dot_vE = B[0] * vE[0] + B[1] * vE[1] + B[2] * vE[2];
+    vE_cross_E[0] = vE[1] * E[2] - vE[2] * E[1];
+    vE_cross_E[1] = vE[2] * E[0] - vE[0] * E[2];
+    vE_cross_E[2] = vE[0] * E[1] - vE[1] * E[0];
+    for (int idim = 0; idim < 3; idim++) {
+      B_star[idim] = kappa * (B[idim] - vE_cross_E[idim] / c2);
+      if (vE_norm > 0) B_star[idim] -= (kappa - 1) * B_dot_vE * vE[idim] / (vE_norm * vE_norm);
+      v_star[idim] = v[idim] - vE[idim];
+    }
+    double Bstar_norm = sqrt(B_star[0] * B_star[0] + B_star[1] * B_star[1] + B_star[2] * B_star[2]);
+    if (Bstar_norm > 0.0) {
+      double vstar_par;
+      double vstar_norm = sqrt(v_star[0] * v_star[0] + v_star[1] * v_star[1] + v_star[2] * v_star[2]);
+      vstar_par = (v_star[0] * B_star[0] + v_star[1] * B_star[1] + v_star[2] * B_star[2]) / Bstar_norm;
+      m0 = cfg.mass[spec];
+      mu = 0.5 * (gamma_star * gamma_star) * m0 * (vstar_norm * vstar_norm - vstar_par * vstar_par) / Bstar_norm;
+    }
+    SetMagneticMoment(mu, ParticleData);
+    return true;
+  }
+
+  // PIC::Mover::Relativistic::GuidingCenter::Mover_FirstOrder, pic_mover_relativistic_guiding_center.cpp:96-409
+  // (DELETE boundary; the reference's USER_FUNCTION branch exit()s and its SPECULAR branch uses an undefined face)
+  int RelGCA_Mover_FirstOrder(byte *ParticleData, long int ptr, double dtTotal, cTreeNode *startNode, int nThreads, int thread, cTreeNode **newNodeOut) {
+    cTreeNode *newNode = NULL;
+    double mass, ElectricCharge;
+    int i, j, k, spec;
+    double vInit[3], xInit[3], xFinal[3], vFinal[3] = {0.0, 0.0, 0.0};
+    double var15[15];
+    double *b_dot_grad_b = var15, *vE_dot_grad_b = var15 + 3, *b_dot_grad_vE = var15 + 6, *vE_dot_grad_vE = var15 + 9, *grad_kappaB = var15 + 12;
+    double B[3], E[3];
+    GetV(vInit, ParticleData);
+    GetX(xInit, ParticleData);
+    spec = GetI(ParticleData);
+    ElectricCharge = cfg.charge[spec];
+    mass = cfg.mass[spec];
+    double vNorm = sqrt(vInit[0] * vInit[0] + vInit[1] * vInit[1] + vInit[2] * vInit[2]);
+    double c2 = cfg.speed_of_light * cfg.speed_of_light;
+    double lfac = 1 / sqrt(1.0 - vNorm * vNorm / c2);
+    if (!GetBackgroundFieldsGCA(xInit, startNode, E, B, var15)) return _ORACLE_ERROR_;
+    double bNorm = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]);
+    double bHat[3] = {0.0, 0.0, 0.0};
+    double ePar = 0.0;
+    if (bNorm > 0.0) {
+      for (int idim = 0; idim < 3; idim++) {
+        bHat[idim] = B[idim] / bNorm;
+        ePar += E[idim] * bHat[idim];
+      }
+    }
+    double vPar = vInit[0] * bHat[0] + vInit[1] * bHat[1] + vInit[2] * bHat[2];
+    double vPerp = sqrt(vNorm * vNorm - vPar * vPar);
+    (void)vPerp;
+    double uPar = lfac * vPar;
+    double Mr = GetMagneticMoment(ParticleData);
+    double vE[3], vENorm = 0.0;
+    vE[0] = E[1] * bHat[2] - E[2] * bHat[1];
+    vE[1] = E[2] * bHat[0] - E[0] * bHat[2];
+    vE[2] = E[0] * bHat[1] - E[1] * bHat[0];
+    if (bNorm > 0.0) {
+      for (int idim = 0; idim < 3; idim++) {
+        vE[idim] = vE[idim] / bNorm;
+        vENorm += vE[idim] * vE[idim];
+      }
+    }
+    vENorm = sqrt(vENorm);
+    double kappa, gamma;
+    kappa = 1 / sqrt(1 - vENorm * vENorm / c2);
+    gamma = sqrt(1.0 + (uPar * uPar + 2.0 * Mr * bNorm / mass) / c2) * kappa;
+    double utmp1[3] = {0.0, 0.0, 0.0}, utmp2[3], utmp3[3];
+    double temp = bNorm / (kappa * kappa);
+    if (bNorm > 0.0)
+      for (int idim = 0; idim < 3; idim++) utmp1[idim] = bHat[idim] / temp;
+    for (int idim = 0; idim < 3; idim++) {
+      utmp2[idim] = Mr / (gamma * ElectricCharge) * grad_kappaB[idim] +
+                    mass / ElectricCharge * (uPar * uPar / gamma * b_dot_grad_b[idim] + uPar * vE_dot_grad_b[idim] + uPar * b_dot_grad_vE[idim] + gamma * vE_dot_grad_vE[idim]);
+    }
+    for (int idim = 0; idim < 3; idim++) utmp2[idim] = utmp2[idim] + uPar * ePar / (gamma)*vE[idim];
+    double u[3];
+    utmp3[0] = utmp1[1] * utmp2[2] - utmp1[2] * utmp2[1];
+    utmp3[1] = utmp1[2] * utmp2[0] - utmp1[0] * utmp2[2];
+    utmp3[2] = utmp1[0] * utmp2[1] - utmp1[1] * utmp2[0];
+    for (int idim = 0; idim < 3; idim++) {
+      u[idim] = vE[idim] + utmp3[idim];
+      u[idim] += uPar / gamma * bHat[idim];
+    }
+    double dupardt;
+    dupardt = ElectricCharge / mass * ePar;
+    temp = Mr / (mass * gamma);
+    for (int idim = 0; idim < 3; idim++) {
+      dupardt += -temp * bHat[idim] * grad_kappaB[idim] + vE[idim] * (uPar * b_dot_grad_b[idim] + gamma * vE_dot_grad_b[idim]);
+      xFinal[idim] = xInit[idim] + dtTotal * u[idim];
+    }
+    uPar += dupardt * dtTotal;
+
+    if (cfg.internal_sphere_radius > 0.0) {
+      double rFinal = sqrt(xFinal[0] * xFinal[0] + xFinal[1] * xFinal[1] + xFinal[2] * xFinal[2]);
+      if (rFinal < cfg.internal_sphere_radius) {
+        AddExitRecord(ptr, spec, AMPS_EXIT_SPHERE, startNode, xInit, vInit);
+        DeleteParticle(ptr);
+        return _PARTICLE_LEFT_THE_DOMAIN_;
+      }
+    }
+    newNode = findTreeNode(xFinal, startNode);
+    if (newNode == NULL) {
+      if (cfg.boundary_mode != AMPS_BOUNDARY_DELETE) return _ORACLE_ERROR_;
+      DeleteParticle(ptr);
+      return _PARTICLE_LEFT_THE_DOMAIN_;
+    } else {
+      if (newNode->block == NULL) return _ORACLE_ERROR_;
+      if (!GetBackgroundFieldsGCA(xFinal, newNode, E, B, NULL)) return _ORACLE_ERROR_;
+      bNorm = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]);
+      if (bNorm > 0.0)
+        for (int idim = 0; idim < 3; idim++) bHat[idim] = B[idim] / bNorm;
+      vE[0] = E[1] * bHat[2] - E[2] * bHat[1];
+      vE[1] = E[2] * bHat[0] - E[0] * bHat[2];
+      vE[2] = E[0] * bHat[1] - E[1] * bHat[0];
+      vENorm = 0.0;
+      if (bNorm > 0.0) {
+        for (int idim = 0; idim < 3; idim++) {
+          vE[idim] = vE[idim] / bNorm;
+          vENorm += vE[idim] * vE[idim];
+        }
+      }
+      vENorm = sqrt(vENorm);
+      kappa = 1 / sqrt(1 - vENorm * vENorm / c2);
+      gamma = sqrt(1.0 + (uPar * uPar + 2.0 * Mr * bNorm / mass) / c2) * kappa;
+      vPar = uPar / gamma;
+      double res = (1 - 1 / (gamma * gamma)) * c2 - vPar * vPar;
+      if (bNorm == 0 && res < 0) res = 0.0;
+      if (bNorm > 0 && res < 0) {
+        DeleteParticle(ptr);
+        return _PARTICLE_LEFT_THE_DOMAIN_;
+      }
+      vPerp = sqrt(res);
+      double e0[3] = {1.0, 0.0, 0.0}, e1[3] = {0.0, 1.0, 0.0};
+      double ePerp[3] = {1.0, 0.0, 0.0};
+      double diff = (e0[0] - bHat[0]) * (e0[0] - bHat[0]) + (e0[1] - bHat[1]) * (e0[1] - bHat[1]) + (e0[2] - bHat[2]) * (e0[2] - bHat[2]);
+      const double *ee = (diff > 0.0) ? e0 : e1;
+      ePerp[0] = ee[1] * bHat[2] - ee[2] * bHat[1];
+      ePerp[1] = ee[2] * bHat[0] - ee[0] * bHat[2];
+      ePerp[2] = ee[0] * bHat[1] - ee[1] * bHat[0];
+      for (int idim = 0; idim < 3; idim++) vFinal[idim] += vPerp * ePerp[idim] + vPar * bHat[idim];
+    }
+    cBlock *block;
+    if (FindCellIndex(xFinal, i, j, k, newNode) == -1) return _ORACLE_ERROR_;
+    if ((block = newNode->block) == NULL) return _ORACLE_ERROR_;
+    AttachToTempList(ptr, ParticleData, block, i, j, k, nThreads, thread);
+    SetV(vFinal, ParticleData);
+    SetX(xFinal, ParticleData);
+    *newNodeOut = newNode;
+    return _PARTICLE_MOTION_FINISHED_;
+  }
+
   // PIC::Mover::cExternalBoundaryFace + Init, src/pic/pic_mover.cpp:24-28,48-75
   struct cExternalBoundaryFace {
     double norm[3];
@@ -1502,6 +1712,23 @@ void oracle_set_background(oracle_ctx *o, const double *E_center, const double *
   if (B_center)
     for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + BackgroundB_d, B_center + 3 * (size_t)i, 24);
 }
+void oracle_set_background_gca(oracle_ctx *o, const double *var15) {
+  for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + BackgroundGCA_d, var15 + 15 * (size_t)i, 15 * 8);
+}
+// InitiateMagneticMoment for every particle on the cell lists; mu (by ptr) is returned in mu_out when not NULL
+int oracle_magnetic_moment_init(oracle_ctx *o, double *mu_out, int64_t n) {
+  const int nC = o->nCellsBlock();
+  for (size_t l = 0; l < o->blocks.size(); l++)
+    for (int c = 0; c < nC; c++)
+      for (long int ptr = o->blocks[l].FirstCellParticleTable[c]; ptr != -1; ptr = o->GetNext(ptr)) {
+        byte *pd = o->GetParticleDataPointer(ptr);
+        double x[3], v[3];
+        oracle_ctx::GetX(x, pd), oracle_ctx::GetV(v, pd);
+        if (!o->RelGCA_InitiateMagneticMoment(oracle_ctx::GetI(pd), x, v, pd, o->BlockTable[l])) return AMPS_GPU_ERR_PARTICLE;
+        if (mu_out && ptr < n) mu_out[ptr] = oracle_ctx::GetMagneticMoment(pd);
+      }
+  return AMPS_GPU_OK;
+}
 int64_t oracle_exit_records(oracle_ctx *o, amps_gpu_exit_record *buf, int64_t max_records) {
   int64_t n = (int64_t)o->exitRecords.size();
   if (buf)
@@ -1569,7 +1796,8 @@ void oracle_get_particles(const oracle_ctx *o, double *x, double *v, double *w, 
 // PIC::Mover::MoveParticles(), src/pic/pic_mover.cpp:580-1088 followed (periodic mode) by
 // PIC::BC::ExternalBoundary::Periodic::ExchangeParticles(), src/pic/pic_time_step.cpp:454-506
 int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats *stats, int32_t *ret_code, int32_t *final_cell) {
-  if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS && mover_id != AMPS_MOVER_BORIS) {
+  if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS && mover_id != AMPS_MOVER_BORIS &&
+      mover_id != AMPS_MOVER_RELATIVISTIC_GCA) {
     o->err = "oracle_move: mover not restated yet";
     return AMPS_GPU_ERR_ARG;
   }
@@ -1611,6 +1839,7 @@ int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats 
       const int spec = oracle_ctx::GetI(pd);
       const double dtLocal = (o->cfg.time_step_mode == AMPS_DT_SPECIES_GLOBAL) ? o->cfg.time_step[spec] : o->cfg.time_step[0];
       if (mover_id == AMPS_MOVER_BORIS) return o->Boris(pd, ptr, dtLocal, node, n_threads, thread, newNode);
+      if (mover_id == AMPS_MOVER_RELATIVISTIC_GCA) return o->RelGCA_Mover_FirstOrder(pd, ptr, dtLocal, node, n_threads, thread, newNode);
       return o->Relativistic_Boris(pd, ptr, dtLocal, node, n_threads, thread, newNode);
     };
     long int *FirstCellParticleTable = block->FirstCellParticleTable;

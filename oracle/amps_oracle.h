@@ -46,6 +46,10 @@ void oracle_set_fields(oracle_ctx *, const double *E_half, const double *B_prev,
 
 /* coupler table for the test-particle movers: E, B on the unique centre nodes [n_centers][3] */
 void oracle_set_background(oracle_ctx *, const double *E_center, const double *B_center);
+/* the 15 tabulated variables of the relativistic GCA on the unique centre nodes [n_centers][15] */
+void oracle_set_background_gca(oracle_ctx *, const double *var15);
+/* Relativistic::GuidingCenter::InitiateMagneticMoment for every listed particle; mu_out[ptr] if not NULL */
+int oracle_magnetic_moment_init(oracle_ctx *, double *mu_out, int64_t n);
 /* exit records (domain faces / internal sphere) accumulated since the last call; returns their number */
 int64_t oracle_exit_records(oracle_ctx *, amps_gpu_exit_record *buf, int64_t max_records);
 

@@ -32,6 +32,8 @@ def load(kind="parity"):
     lib.oracle_set_background.argtypes = [vp, vp, vp]
     lib.oracle_exit_records.restype = C.c_int64
     lib.oracle_exit_records.argtypes = [vp, vp, C.c_int64]
+    lib.oracle_set_background_gca.argtypes = [vp, vp]
+    lib.oracle_magnetic_moment_init.argtypes = [vp, vp, C.c_int64]
     lib.oracle_add_particles.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64]
     lib.oracle_particle_count.restype = C.c_int64
     lib.oracle_particle_count.argtypes = [vp]
@@ -74,6 +76,16 @@ class Oracle:
     def set_background(self, E_center=None, B_center=None):
         a = [None if t is None else np.ascontiguousarray(t, dtype=np.float64) for t in (E_center, B_center)]
         self.lib.oracle_set_background(self.h, _p(a[0]), _p(a[1]))
+
+    def set_background_gca(self, var15):
+        a = np.ascontiguousarray(var15, dtype=np.float64)
+        self.lib.oracle_set_background_gca(self.h, _p(a))
+
+    def magnetic_moment_init(self):
+        mu = np.zeros(self.n_added)
+        rc = self.lib.oracle_magnetic_moment_init(self.h, _p(mu), self.n_added)
+        assert rc == 0
+        return mu
 
     def exit_records(self, max_records=1 << 20):
         from amps_b200._capi import ExitRecord

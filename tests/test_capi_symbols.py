@@ -23,12 +23,24 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert set(syms) == set(_capi.PROTOTYPES), set(syms) ^ set(_capi.PROTOTYPES)
 
 
-def test_struct_layouts_match_the_header():
-    # sizes the C compiler gives the structs (kept in sync by hand; a mismatch would corrupt every call)
-    assert ctypes.sizeof(_capi.Config) == 3 * 4 + 3 * 4 + 6 * 4 + 8 + 4 * 8 * 8 + 4 * 8 + 2 * 4 + 2 * 8 + 8 + 8
-    assert ctypes.sizeof(_capi.ExitRecord) == 4 * 4 + 6 * 8
-    assert ctypes.sizeof(_capi.MoveStats) == 7 * 8
-    assert ctypes.sizeof(_capi.AosLayout) == 8 + 7 * 4 + 4
+def test_struct_layouts_match_the_header(tmp_path):
+    # sizes and a few offsets as the C compiler sees them; a mismatch would corrupt every call
+    import subprocess
+
+    src = tmp_path / "sz.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "amps_gpu.h"\n'
+        "int main(void){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(amps_gpu_config), sizeof(amps_gpu_mesh),"
+        " sizeof(amps_gpu_exit_record), sizeof(amps_gpu_move_stats), sizeof(amps_gpu_aos_layout),"
+        " offsetof(amps_gpu_config, capacity), offsetof(amps_gpu_config, speed_of_light), offsetof(amps_gpu_config, carry_magnetic_moment));"
+        "return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(t) for t in subprocess.check_output([str(exe)]).split()]
+    want = [ctypes.sizeof(_capi.Config), ctypes.sizeof(_capi.Mesh), ctypes.sizeof(_capi.ExitRecord), ctypes.sizeof(_capi.MoveStats),
+            ctypes.sizeof(_capi.AosLayout), _capi.Config.capacity.offset, _capi.Config.speed_of_light.offset,
+            _capi.Config.carry_magnetic_moment.offset]
+    assert got == want, (got, want)
 
 
 def test_init_fails_loudly_without_a_device():

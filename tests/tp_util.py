@@ -107,3 +107,94 @@ def load_ref_gridless():
     lib.ref_boris_uniform.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int]
     lib.ref_boris_dipole.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
     return lib
+
+
+# ---- relativistic guiding-centre fixtures (config 5, srcMoverTest) -----------------------------------------
+def _bg_analytic(x, uniform_B=None, E_uniform=None, convection=True):
+    if uniform_B is None:
+        r = np.sqrt((x ** 2).sum(1))
+        B = dipole(np.where(r[:, None] < 0.5 * RE, x + 0.5 * RE, x))
+        vbg = np.array([-4.0e5 if convection else 0.0, 0.0, 0.0])
+        E = -np.cross(np.broadcast_to(vbg, B.shape), B)
+    else:
+        B = np.broadcast_to(np.asarray(uniform_B, dtype=np.float64), x.shape).copy()
+        E = np.broadcast_to(np.asarray((0.0, 0.0, 0.0) if E_uniform is None else E_uniform, dtype=np.float64), x.shape).copy()
+    return E, B
+
+
+def gca_var15(x, h, **kw):
+    """b.grad(b), vE.grad(b), b.grad(vE), vE.grad(vE), grad(kappa*B) by central differences of the analytic field
+    (the reference tabulates the same five vectors from its data file, pic_datafile.cpp:1164-1340)"""
+    def derived(xx):
+        E, B = _bg_analytic(xx, **kw)
+        Bn = np.sqrt((B ** 2).sum(1))
+        b = B / Bn[:, None]
+        vE = np.cross(E, B) / (Bn ** 2)[:, None]
+        kappa = 1.0 / np.sqrt(1.0 - (vE ** 2).sum(1) / CLIGHT ** 2)
+        return b, vE, kappa * Bn
+
+    b, vE, _ = derived(x)
+    grad_b = np.empty((x.shape[0], 3, 3))  # [n][j][i] = d_j b_i
+    grad_vE = np.empty((x.shape[0], 3, 3))
+    grad_kB = np.empty((x.shape[0], 3))
+    for j in range(3):
+        e = np.zeros(3)
+        e[j] = h
+        bp, vp, kp = derived(x + e)
+        bm, vm, km = derived(x - e)
+        grad_b[:, j, :] = (bp - bm) / (2 * h)
+        grad_vE[:, j, :] = (vp - vm) / (2 * h)
+        grad_kB[:, j] = (kp - km) / (2 * h)
+    out = np.empty((x.shape[0], 15))
+    out[:, 0:3] = np.einsum("nj,nji->ni", b, grad_b)
+    out[:, 3:6] = np.einsum("nj,nji->ni", vE, grad_b)
+    out[:, 6:9] = np.einsum("nj,nji->ni", b, grad_vE)
+    out[:, 9:12] = np.einsum("nj,nji->ni", vE, grad_vE)
+    out[:, 12:15] = grad_kB
+    return out
+
+
+def make_gca_case(n_particles=4096, seed=2, dt=0.02, interp=_capi.CPLR_LINEAR, sphere=True, uniform_B=None, E_uniform=None,
+                  rigidity_gv=(0.001, 0.05), convection=True, **kw):
+    m, cfg, parts, _ = make_tp_case(n_particles=n_particles, seed=seed, dt=dt, interp=interp, boundary=_capi.BOUNDARY_DELETE, sphere=sphere,
+                                    uniform_B=uniform_B, rigidity_gv=rigidity_gv, **kw)
+    E, B = _bg_analytic(m.center_x, uniform_B=uniform_B, E_uniform=E_uniform, convection=convection)
+    var15 = gca_var15(m.center_x, 1.0e3, uniform_B=uniform_B, E_uniform=E_uniform, convection=convection)
+    cfg.carry_magnetic_moment = 1
+    return m, cfg, parts, (E, B), var15
+
+
+def run_oracle_gca(m, cfg, parts, bg, var15, n_threads=1):
+    o = Oracle(cfg, m)
+    o.set_background(*bg)
+    o.set_background_gca(var15)
+    o.add_particles(*parts)
+    mu = o.magnetic_moment_init()
+    rc, st, ret, fc = o.move(_capi.MOVER_RELATIVISTIC_GCA, n_threads)
+    pp = o.particles()
+    nrec, recs = o.exit_records()
+    lists = o.check_lists()
+    o.close()
+    return {"rc": rc, "stats": st, "ret": ret, "final_cell": fc, "particles": pp, "records": sorted(recs), "n_records": nrec, "lists": lists, "mu": mu}
+
+
+def run_gpu_gca(m, cfg, parts, bg, var15):
+    g = api.Context(cfg, m)
+    g.background_upload(*bg)
+    g.background_upload_gca(var15)
+    g.particles_upload(*parts)
+    g.InitiateMagneticMoment()
+    mu0 = g.magnetic_moment_download()
+    ptr0 = g.particles_download()["ptrs"]
+    st = g.MoveParticles(_capi.MOVER_RELATIVISTIC_GCA)
+    moved = g.particles_download()
+    nrec, recs = g.exit_records()
+    g.sort()
+    n_after = g.particle_count()
+    srt = g.particles_download()
+    mu1 = g.magnetic_moment_download()
+    g.close()
+    mu_by_ptr = np.empty(len(ptr0))
+    mu_by_ptr[ptr0] = mu0
+    return {"stats": st, "moved": moved, "records": sorted(recs), "n_records": nrec, "n_after": n_after, "mu": mu_by_ptr, "sorted": srt,
+            "mu_sorted": mu1}
