@@ -61,7 +61,7 @@ class Config(C.Structure):
         ("exit_record_capacity", C.c_int64),
         ("gravity_gm", C.c_double),
         ("carry_magnetic_moment", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("ideal_mhd", C.c_int32),
     ]
 
 
@@ -152,7 +152,8 @@ PROTOTYPES = {
     "amps_gpu_background_upload": (C.c_int, [_vp, _vp, _vp]),
     "amps_gpu_exit_records": (C.c_int, [_vp, _vp, C.c_int64, _i64p]),
     "amps_gpu_background_upload_gca": (C.c_int, [_vp, _vp]),
-    "amps_gpu_magnetic_moment_init": (C.c_int, [_vp]),
+    "amps_gpu_magnetic_moment_init": (C.c_int, [_vp, C.c_int]),
+    "amps_gpu_background_upload_gradB": (C.c_int, [_vp, _vp]),
     "amps_gpu_magnetic_moment_upload": (C.c_int, [_vp, _vp, C.c_int64]),
     "amps_gpu_magnetic_moment_download": (C.c_int, [_vp, _vp, C.c_int64, _i64p]),
     "amps_gpu_particles_upload_aos": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.POINTER(AosLayout)]),

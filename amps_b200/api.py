@@ -51,6 +51,7 @@ def make_config(block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), charge=(-1.0, 1.0)
     cfg.exit_record_capacity = 0
     cfg.gravity_gm = 0.0
     cfg.carry_magnetic_moment = 0
+    cfg.ideal_mhd = 1
     return cfg
 
 
@@ -113,9 +114,15 @@ class Context:
         assert a.shape == (self.mesh.n_centers, 15)
         self._ck(self.lib.amps_gpu_background_upload_gca(self._h, _ptr(a)))
 
-    def InitiateMagneticMoment(self):
-        """PIC::Mover::Relativistic::GuidingCenter::InitiateMagneticMoment for every resident particle"""
-        self._ck(self.lib.amps_gpu_magnetic_moment_init(self._h))
+    def background_upload_gradB(self, gradB_center):
+        """grad B on the unique centre nodes, [n_centers][9] (pic.h:8434-8470)"""
+        a = np.ascontiguousarray(gradB_center, dtype=np.float64)
+        assert a.shape == (self.mesh.n_centers, 9)
+        self._ck(self.lib.amps_gpu_background_upload_gradB(self._h, _ptr(a)))
+
+    def InitiateMagneticMoment(self, mover=_capi.MOVER_RELATIVISTIC_GCA):
+        """(Relativistic::)GuidingCenter::InitiateMagneticMoment for every resident particle"""
+        self._ck(self.lib.amps_gpu_magnetic_moment_init(self._h, mover))
 
     def magnetic_moment_upload(self, mu_by_ptr):
         a = np.ascontiguousarray(mu_by_ptr, dtype=np.float64)

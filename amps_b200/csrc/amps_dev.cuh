@@ -2,7 +2,7 @@
 //
 // HBM layout (all library-owned):
 //   particles   SoA, sorted by key = leaf*cellsPerBlock + cell :  x[3][cap] v[3][cap] w[cap] (f64)
-//               spec[cap] (u8)  key[cap] (i32, -1 = deleted)  ptr[cap] (i32, ParticleBuffer slot);
+//               spec[cap] (u8: bits 0-5 species, bit 6 InitFlag as in the reference record)  key[cap] (i32, -1 = deleted)  ptr[cap] (i32, ParticleBuffer slot);
 //               two copies (ping-pong for the counting sort)
 //   cell table  cellStart[nCells+1] (i32) : particle range of each cell
 //   mesh        flattened cTreeNodeAMR arrays + per-leaf LeafGeo + unique node tables
@@ -116,7 +116,12 @@ void launch_move_relativistic_boris(const DevMesh &m, const DevSpecies &sp, int 
 void launch_move_boris(const DevMesh &m, const DevSpecies &sp, int interp, int backward, double c, double rSphere, long long exitCap, double gravityGM,
                        ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, int *cellCount, DevMoveStats *stats,
                        amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s);
-void launch_stage_background_gca(const DevMesh &m, const double *var15, double *tile, cudaStream_t s);
+void launch_stage_center_table(const DevMesh &m, int nVar, const double *var, double *tile, cudaStream_t s);
+void launch_gc_magnetic_moment_init(const DevMesh &m, const DevSpecies &sp, int interp, ParticleSoA p, const int *nSlots, long long nUpper,
+                                    const double *bgTile, DevMoveStats *stats, cudaStream_t s);
+void launch_move_guiding_center(const DevMesh &m, const DevSpecies &sp, int order, int interp, int idealMhd, double rSphere, long long exitCap,
+                                ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *gradBTile, int *cellCount,
+                                DevMoveStats *stats, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s);
 void launch_magnetic_moment_init(const DevMesh &m, const DevSpecies &sp, int interp, double c, ParticleSoA p, const int *nSlots, long long nUpper,
                                  const double *bgTile, DevMoveStats *stats, cudaStream_t s);
 void launch_magnetic_moment_set(ParticleSoA p, const int *nSlots, long long nUpper, const double *muByPtr, long long nMu, cudaStream_t s);

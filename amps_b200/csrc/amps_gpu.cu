@@ -49,6 +49,8 @@ struct amps_gpu_ctx {
   double *d_bgE = nullptr, *d_bgB = nullptr, *d_bgTile = nullptr;
   double *d_gcaVar = nullptr, *d_gcaTile = nullptr;  // relativistic GCA: 15 drift variables per centre node
   bool gcaReady = false;
+  double *d_gradBVar = nullptr, *d_gradBTile = nullptr;  // guiding centre: grad B, 9 values per centre node
+  bool gradBReady = false;
   bool backgroundReady = false;
   amps_gpu_exit_record *d_exitBuf = nullptr;
   unsigned long long *d_exitCount = nullptr;
@@ -261,7 +263,7 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   for (void *p : ctx->meshAllocs) cudaFree(p);
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
   if (ctx->comm && nccl_api().CommDestroy) nccl_api().CommDestroy(ctx->comm);
-  cudaFree(ctx->d_gcaVar), cudaFree(ctx->d_gcaTile);
+  cudaFree(ctx->d_gcaVar), cudaFree(ctx->d_gcaTile), cudaFree(ctx->d_gradBVar), cudaFree(ctx->d_gradBTile);
   cudaFree(ctx->d_bgE), cudaFree(ctx->d_bgB), cudaFree(ctx->d_bgTile), cudaFree(ctx->d_exitBuf), cudaFree(ctx->d_exitCount);
   cudaFree(ctx->d_sendBuf), cudaFree(ctx->d_recvBuf), cudaFree(ctx->d_sendCount), cudaFree(ctx->d_allCounts), cudaFree(ctx->d_errFlag);
   for (int *p : ctx->d_sharedUid) cudaFree(p);
@@ -445,21 +447,45 @@ int amps_gpu_background_upload_gca(amps_gpu_ctx *ctx, const double *var15_center
     if ((rc = dev_alloc(ctx, &ctx->d_gcaTile, (size_t)m.nLeaves * m.nCenterLocal * 15))) return rc;
   }
   CK(cudaMemcpyAsync(ctx->d_gcaVar, var15_center, sizeof(double) * 15 * (size_t)m.nCenters, cudaMemcpyHostToDevice, ctx->stream));
-  launch_stage_background_gca(m, ctx->d_gcaVar, ctx->d_gcaTile, ctx->stream);
+  launch_stage_center_table(m, 15, ctx->d_gcaVar, ctx->d_gcaTile, ctx->stream);
   ctx->launches++;
   CK(cudaGetLastError());
   ctx->gcaReady = true;
   return AMPS_GPU_OK;
 }
 
-int amps_gpu_magnetic_moment_init(amps_gpu_ctx *ctx) {
+int amps_gpu_background_upload_gradB(amps_gpu_ctx *ctx, const double *gradB_center) {
+  if (!ctx || !gradB_center) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "background_upload_gradB before mesh_upload");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const DevMesh &m = ctx->dm;
+  int rc;
+  if (!ctx->d_gradBTile) {
+    if ((rc = dev_alloc(ctx, &ctx->d_gradBVar, (size_t)9 * m.nCenters))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_gradBTile, (size_t)m.nLeaves * m.nCenterLocal * 9))) return rc;
+  }
+  CK(cudaMemcpyAsync(ctx->d_gradBVar, gradB_center, sizeof(double) * 9 * (size_t)m.nCenters, cudaMemcpyHostToDevice, ctx->stream));
+  launch_stage_center_table(m, 9, ctx->d_gradBVar, ctx->d_gradBTile, ctx->stream);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  ctx->gradBReady = true;
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_magnetic_moment_init(amps_gpu_ctx *ctx, int mover_id) {
   if (!ctx) return AMPS_GPU_ERR_ARG;
+  if (mover_id != AMPS_MOVER_RELATIVISTIC_GCA && mover_id != AMPS_MOVER_GC_FIRST_ORDER && mover_id != AMPS_MOVER_GC_SECOND_ORDER)
+    FAIL(AMPS_GPU_ERR_ARG, "magnetic_moment_init: not a guiding-centre mover");
   if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "magnetic_moment_init needs cfg.carry_magnetic_moment");
   if (!ctx->meshReady || !ctx->backgroundReady) FAIL(AMPS_GPU_ERR_STATE, "magnetic_moment_init needs the mesh and amps_gpu_background_upload");
   CK(cudaSetDevice(ctx->cfg.device));
   CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevMoveStats), ctx->stream));
-  launch_magnetic_moment_init(ctx->dm, ctx->sp, ctx->cfg.coupler_interpolation, ctx->cfg.speed_of_light, ctx->buf[ctx->cur], ctx->d_n + ctx->cur,
-                              ctx->nUpper, ctx->d_bgTile, ctx->d_stats, ctx->stream);
+  if (mover_id == AMPS_MOVER_RELATIVISTIC_GCA)
+    launch_magnetic_moment_init(ctx->dm, ctx->sp, ctx->cfg.coupler_interpolation, ctx->cfg.speed_of_light, ctx->buf[ctx->cur], ctx->d_n + ctx->cur,
+                                ctx->nUpper, ctx->d_bgTile, ctx->d_stats, ctx->stream);
+  else
+    launch_gc_magnetic_moment_init(ctx->dm, ctx->sp, ctx->cfg.coupler_interpolation, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper,
+                                   ctx->d_bgTile, ctx->d_stats, ctx->stream);
   ctx->launches++;
   CK(cudaGetLastError());
   DevMoveStats h;
@@ -587,7 +613,7 @@ int amps_gpu_particles_upload_aos(amps_gpu_ctx *ctx, const void *records, const 
     v[i] = t[0], v[n + i] = t[1], v[2 * n + i] = t[2];
     if (lay->off_w >= 0) memcpy(&w[i], r + lay->off_w, 8);
     else w[i] = 1.0;
-    sp[i] = r[lay->off_species] & 0x3f;
+    sp[i] = r[lay->off_species] & 0x7f;  // species + InitFlag (bit 6)
     pt[i] = (int32_t)slot;
   }
   return amps_gpu_particles_upload_soa(ctx, x.data(), v.data(), w.data(), sp.data(), cells, pt.data(), n);
@@ -651,7 +677,7 @@ int amps_gpu_particles_download_aos(amps_gpu_ctx *ctx, void *records, int64_t *f
     double u[3] = {v[i], v[n + i], v[2 * n + i]};
     memcpy(r + lay->off_v, u, 24);
     if (lay->off_w >= 0) memcpy(r + lay->off_w, &w[i], 8);
-    r[lay->off_species] = (unsigned char)((r[lay->off_species] & 0xc0) | (sp[i] & 0x3f));
+    r[lay->off_species] = (unsigned char)((r[lay->off_species] & 0x80) | (sp[i] & 0x7f));
     if (first_cell_particle && key[i] >= 0) {
       // push on the cell list like the movers do (pic_mover_boris.cpp:1333-1343)
       int64_t *first = first_cell_particle + key[i];
@@ -681,8 +707,12 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "move before mesh upload");
   if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "move needs the (block,cell)-sorted layout: call amps_gpu_sort");
   if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS && mover_id != AMPS_MOVER_BORIS &&
-      mover_id != AMPS_MOVER_RELATIVISTIC_GCA)
-    FAIL(AMPS_GPU_ERR_ARG, "mover not implemented yet");
+      mover_id != AMPS_MOVER_RELATIVISTIC_GCA && mover_id != AMPS_MOVER_GC_FIRST_ORDER && mover_id != AMPS_MOVER_GC_SECOND_ORDER)
+    FAIL(AMPS_GPU_ERR_ARG, "unknown mover id");
+  if (mover_id == AMPS_MOVER_GC_FIRST_ORDER || mover_id == AMPS_MOVER_GC_SECOND_ORDER) {
+    if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "the guiding-centre movers need cfg.carry_magnetic_moment");
+    if (!ctx->gradBReady) FAIL(AMPS_GPU_ERR_STATE, "GuidingCenter needs amps_gpu_background_upload_gradB");
+  }
   if (mover_id == AMPS_MOVER_RELATIVISTIC_GCA) {
     if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "the guiding-centre movers need cfg.carry_magnetic_moment");
     if (!ctx->gcaReady) FAIL(AMPS_GPU_ERR_STATE, "Relativistic::GuidingCenter needs amps_gpu_background_upload_gca");
@@ -699,6 +729,16 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
     launch_move_boris(m, ctx->sp, ctx->cfg.coupler_interpolation, ctx->cfg.backward_time_integration, ctx->cfg.speed_of_light,
                       ctx->cfg.internal_sphere_radius, ctx->cfg.exit_record_capacity, ctx->cfg.gravity_gm, ctx->buf[ctx->cur], ctx->d_n + ctx->cur,
                       ctx->nUpper, ctx->d_bgTile, ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount, ctx->stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    ctx->sorted = false;
+    ctx->countValid = true;
+    return AMPS_GPU_OK;
+  }
+  if (mover_id == AMPS_MOVER_GC_FIRST_ORDER || mover_id == AMPS_MOVER_GC_SECOND_ORDER) {
+    launch_move_guiding_center(m, ctx->sp, mover_id == AMPS_MOVER_GC_SECOND_ORDER ? 2 : 1, ctx->cfg.coupler_interpolation, ctx->cfg.ideal_mhd,
+                               ctx->cfg.internal_sphere_radius, ctx->cfg.exit_record_capacity, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper,
+                               ctx->d_bgTile, ctx->d_gradBTile, ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
     ctx->sorted = false;

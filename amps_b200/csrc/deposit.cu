@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
       const int ip = begin + lane;
       nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
       nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
-      nw = p.w[ip], nspec = p.spec[ip];
+      nw = p.w[ip], nspec = p.spec[ip] & 0x3f;
     }
     for (int base = begin; base < end; base += CHUNK) {
       const int np = min(CHUNK, end - base);
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
         const int ip = base + CHUNK + lane;
         nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
         nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
-        nw = p.w[ip], nspec = p.spec[ip];
+        nw = p.w[ip], nspec = p.spec[ip] & 0x3f;
       }
       if (lane < np) {
         const double LocalParticleWeight = sp.weight[spec] * pw;
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(256) diag_kernel(DevMesh m, DevSpecies sp, Par
     for (int s = 0; s < AMPS_GPU_MAX_SPECIES; s++) vm[s] = 0.0, cnt[s] = 0;
     for (int ip = begin + lane; ip < end; ip += 32) {
       const double v0 = p.v[0][ip] * sp.length_conv, v1 = p.v[1][ip] * sp.length_conv, v2 = p.v[2][ip] * sp.length_conv;
-      const int spec = p.spec[ip];
+      const int spec = p.spec[ip] & 0x3f;
       const double mass = sp.mass[spec] * (sp.weight[spec] * p.w[ip]);
       const double vsqr = v0 * v0 + v1 * v1 + v2 * v2;
       e += 0.5 * mass * vsqr;

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256, 2) move_lapenta_kernel(DevMesh m, DevSpec
     double xInit[3], vInit[3], xFinal[3], vFinal[3];
     xInit[0] = p.x[0][ip], xInit[1] = p.x[1][ip], xInit[2] = p.x[2][ip];
     vInit[0] = p.v[0][ip], vInit[1] = p.v[1][ip], vInit[2] = p.v[2][ip];
-    const int spec = p.spec[ip];
+    const int spec = p.spec[ip] & 0x3f;
     const int oldKey = p.key[ip];
     const double dtTotal = sC.dt[spec];
     nMoved++;

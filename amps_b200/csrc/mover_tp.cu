@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(128) move_relativistic_boris_kernel(DevMesh m,
     double xInit[3] = {p.x[0][ip], p.x[1][ip], p.x[2][ip]};
     double vInit[3] = {p.v[0][ip], p.v[1][ip], p.v[2][ip]};
     double xFinal[3], vFinal[3];
-    const int spec = p.spec[ip];
+    const int spec = p.spec[ip] & 0x3f;
     const int startLeaf = oldKey / C;
     const double ElectricCharge = sp.charge[spec], mass = sp.mass[spec];
     double dtTotalIn = (sp.timeStepMode == AMPS_DT_SPECIES_GLOBAL) ? sp.dt[spec] : sp.dt[0];
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(128) move_boris_kernel(DevMesh m, DevSpecies s
     double xInit[3] = {p.x[0][ip], p.x[1][ip], p.x[2][ip]};
     double vInit[3] = {p.v[0][ip], p.v[1][ip], p.v[2][ip]};
     double xFinal[3], vFinal[3];
-    const int spec = p.spec[ip];
+    const int spec = p.spec[ip] & 0x3f;
     const int startLeaf = oldKey / C;
     const int startNode = m.leaf[startLeaf].node;
     const double dtTotal = (sp.timeStepMode == AMPS_DT_SPECIES_GLOBAL) ? sp.dt[spec] : sp.dt[0];
@@ -527,18 +527,18 @@ void launch_move_boris(const DevMesh &m, const DevSpecies &sp, int interp, int b
 //     reference exit() or use an undefined face), fields + 15 drift variables through the coupler stencil
 //     (GetVarForRelativisticGCA, pic.h:8643-8680) on per-leaf tiles [nCenterLocal][15]
 // ------------------------------------------------------------------------------------------------
-__global__ void stage_background_gca_kernel(DevMesh m, const double *__restrict__ var, double *__restrict__ tile) {
+__global__ void stage_center_table_kernel(DevMesh m, int nVar, const double *__restrict__ var, double *__restrict__ tile) {
   const int leaf = blockIdx.x;
   const int *cuid = m.centerUid + (size_t)leaf * m.nCenterLocal;
-  double *dst = tile + (size_t)leaf * m.nCenterLocal * 15;
-  for (int e = threadIdx.x; e < m.nCenterLocal * 15; e += blockDim.x) {
-    const int i = e / 15, q = e - 15 * i;
+  double *dst = tile + (size_t)leaf * m.nCenterLocal * nVar;
+  for (int e = threadIdx.x; e < m.nCenterLocal * nVar; e += blockDim.x) {
+    const int i = e / nVar, q = e - nVar * i;
     const int u = cuid[i];
-    dst[e] = (u >= 0) ? var[15 * (size_t)u + q] : 0.0;
+    dst[e] = (u >= 0) ? var[nVar * (size_t)u + q] : 0.0;
   }
 }
-void launch_stage_background_gca(const DevMesh &m, const double *var15, double *tile, cudaStream_t s) {
-  stage_background_gca_kernel<<<m.nLeaves, 256, 0, s>>>(m, var15, tile);
+void launch_stage_center_table(const DevMesh &m, int nVar, const double *var, double *tile, cudaStream_t s) {
+  stage_center_table_kernel<<<m.nLeaves, 256, 0, s>>>(m, nVar, var, tile);
 }
 
 // the coupler stencil at x inside `leaf` (same arithmetic as background_fields), kept for several gathers
@@ -566,14 +566,21 @@ __device__ __forceinline__ bool background_stencil(const DevMesh &m, int interp,
     w[5] = w0 * (1.0 - w1) * w2;
     w[6] = w0 * w1 * (1.0 - w2);
     w[7] = w0 * w1 * w2;
+    // x may lie outside the leaf (GuidingCenter::Mover_FirstOrder :713): indices past the ghost layer are
+    // out-of-bounds reads in the reference -> error
+    if (!(iLoc >= -1.0e9 && iLoc <= 1.0e9 && jLoc >= -1.0e9 && jLoc <= 1.0e9 && kLoc >= -1.0e9 && kLoc <= 1.0e9)) return false;
+    if (i0 < -m.g[0] || i0 + 1 > m.N[0] + m.g[0] - 1 || j0 < -m.g[1] || j0 + 1 > m.N[1] + m.g[1] - 1 || k0 < -m.g[2] ||
+        k0 + 1 > m.N[2] + m.g[2] - 1)
+      return false;
     unsigned valid = 0xffu;
-    if (!m.periodic && lg.face) {
-      if ((lg.face & 1) && i0 < 0) valid &= 0xf0u;
-      if ((lg.face & 2) && i0 + 1 >= m.N[0]) valid &= 0x0fu;
-      if ((lg.face & 4) && j0 < 0) valid &= 0xccu;
-      if ((lg.face & 8) && j0 + 1 >= m.N[1]) valid &= 0x33u;
-      if ((lg.face & 16) && k0 < 0) valid &= 0xaau;
-      if ((lg.face & 32) && k0 + 1 >= m.N[2]) valid &= 0x55u;
+    if (!m.periodic && lg.face) {  // AddCell drops centres outside the domain (pic.h:7235-7245)
+      const int o0[3] = {i0, j0, k0};
+      const unsigned lowMask[3] = {0x0fu, 0x33u, 0x55u};  // stencil slots whose index along d is o0[d]
+      for (int d = 0; d < 3; d++)
+        for (int b = 0; b < 2; b++) {
+          const int a = o0[d] + b;
+          if (((lg.face >> (2 * d)) & 1 && a < 0) || ((lg.face >> (2 * d + 1)) & 1 && a >= m.N[d])) valid &= b ? lowMask[d] : ~lowMask[d] & 0xffu;
+        }
     }
     double norm = 0.0;
     if (valid != 0xffu) {
@@ -655,7 +662,7 @@ __global__ void __launch_bounds__(128) magnetic_moment_init_kernel(DevMesh m, De
     if (Bstar_norm > 0.0) {
       const double vstar_norm = sqrt(v_star[0] * v_star[0] + v_star[1] * v_star[1] + v_star[2] * v_star[2]);
       const double vstar_par = (v_star[0] * B_star[0] + v_star[1] * B_star[1] + v_star[2] * B_star[2]) / Bstar_norm;
-      const double m0 = sp.mass[p.spec[ip]];
+      const double m0 = sp.mass[p.spec[ip] & 0x3f];
       mu = 0.5 * (gamma_star * gamma_star) * m0 * (vstar_norm * vstar_norm - vstar_par * vstar_par) / Bstar_norm;
     }
     p.mu[ip] = mu;
@@ -700,7 +707,7 @@ __global__ void __launch_bounds__(128) move_relativistic_gca_kernel(DevMesh m, D
     const double xInit[3] = {p.x[0][ip], p.x[1][ip], p.x[2][ip]};
     const double vInit[3] = {p.v[0][ip], p.v[1][ip], p.v[2][ip]};
     double xFinal[3], vFinal[3] = {0.0, 0.0, 0.0};
-    const int spec = p.spec[ip];
+    const int spec = p.spec[ip] & 0x3f;
     const int startLeaf = oldKey / C;
     const int startNode = m.leaf[startLeaf].node;
     const double ElectricCharge = sp.charge[spec], mass = sp.mass[spec];
@@ -868,6 +875,277 @@ void launch_move_relativistic_gca(const DevMesh &m, const DevSpecies &sp, int in
   if (g < 1) g = 1;
   if (g > 148 * 32) g = 148 * 32;
   move_relativistic_gca_kernel<<<(int)g, 128, 0, s>>>(m, sp, tp, p, nSlots, bgTile, gcaTile, cellCount, stats, exitBuf, exitCount);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a8: PIC::Mover::GuidingCenter  src/pic/pic_mover_guiding_center.cpp  (coupler mode, relativity off)
+//     InitiateMagneticMoment :85-144, GuidingCenterMotion_default :146-289, Mover_SecondOrder :292-619,
+//     Mover_FirstOrder :622-849.  The reference writes |B| as pow(B.B,0.5); sqrt is used here (glibc's pow differs
+//     from the correctly rounded root in ~0.1% of the arguments, so x and v agree with the CPU oracle to a few ulp
+//     instead of bit for bit -- the parity tests state the tolerance).
+// ------------------------------------------------------------------------------------------------
+struct GcTables {
+  const double *bg;     // [leaf][nCenterLocal][6]  E, B
+  const double *gradB;  // [leaf][nCenterLocal][9]
+};
+
+__device__ __forceinline__ bool gc_initiate_magnetic_moment(const DevMesh &m, const DevSpecies &sp, int interp, const GcTables &T, int spec,
+                                                            const double x[3], double v[3], int leaf, double &muOut) {
+  BgStencil st;
+  if (!background_stencil(m, interp, x, leaf, st)) return false;
+  double B[3];
+  background_gather<3>(st, T.bg + (size_t)leaf * m.nCenterLocal * 6, 6, 3, B);
+  const double AbsB = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) + 1E-15;
+  double v_par = 0.0, mu = 0.0;
+  const double b[3] = {B[0] / AbsB, B[1] / AbsB, B[2] / AbsB};
+  if (AbsB > 0.0) {
+    v_par = v[0] * b[0] + v[1] * b[1] + v[2] * b[2];
+    const double v2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const double gamma2 = 1.0;
+    const double m0 = sp.mass[spec];
+    mu = 0.5 * gamma2 * m0 * (v2 - v_par * v_par) / AbsB;
+  }
+  v[0] = v_par * b[0];
+  v[1] = v_par * b[1];
+  v[2] = v_par * b[2];
+  muOut = mu;
+  return true;
+}
+
+__device__ __forceinline__ bool gc_motion(const DevMesh &m, const DevSpecies &sp, int interp, int idealMhd, const GcTables &T, double Vguide_perp[3],
+                                          double &ForceParal, double &AbsBOut, double bOut[3], const double *PParal, int spec, double mu,
+                                          const double x[3], const double v[3], int leaf) {
+  BgStencil st;
+  if (!background_stencil(m, interp, x, leaf, st)) return false;
+  double E[3], B[3], gradB[9];
+  const double *tb = T.bg + (size_t)leaf * m.nCenterLocal * 6;
+  background_gather<3>(st, tb, 6, 0, E);
+  background_gather<3>(st, tb, 6, 3, B);
+  background_gather<9>(st, T.gradB + (size_t)leaf * m.nCenterLocal * 9, 9, 0, gradB);
+  const double AbsB = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) + 1E-15;
+  double b[3], gradAbsB[3];
+  b[0] = B[0] / AbsB;
+  b[1] = B[1] / AbsB;
+  b[2] = B[2] / AbsB;
+  gradAbsB[0] = b[0] * gradB[0] + b[1] * gradB[3] + b[2] * gradB[6];
+  gradAbsB[1] = b[0] * gradB[1] + b[1] * gradB[4] + b[2] * gradB[7];
+  gradAbsB[2] = b[0] * gradB[2] + b[1] * gradB[5] + b[2] * gradB[8];
+  const double q = sp.charge[spec], m0 = sp.mass[spec], gamma = 1.0;
+  const double p_par = (PParal == nullptr) ? gamma * m0 * (v[0] * b[0] + v[1] * b[1] + v[2] * b[2]) : *PParal;
+  double msc, vec[3];
+  double V[3] = {0.0, 0.0, 0.0};
+  V[0] += (E[1] * b[2] - E[2] * b[1]) / AbsB;
+  V[1] += (E[2] * b[0] - E[0] * b[2]) / AbsB;
+  V[2] += (E[0] * b[1] - E[1] * b[0]) / AbsB;
+  msc = mu / (q * gamma) / AbsB;
+  V[0] += msc * (b[1] * gradAbsB[2] - b[2] * gradAbsB[1]);
+  V[1] += msc * (b[2] * gradAbsB[0] - b[0] * gradAbsB[2]);
+  V[2] += msc * (b[0] * gradAbsB[1] - b[1] * gradAbsB[0]);
+  msc = p_par * p_par / (q * gamma * m0) / AbsB / AbsB;
+  vec[0] = b[0] * gradB[0] + b[1] * gradB[1] + b[2] * gradB[2];
+  vec[1] = b[0] * gradB[3] + b[1] * gradB[4] + b[2] * gradB[5];
+  vec[2] = b[0] * gradB[6] + b[1] * gradB[7] + b[2] * gradB[8];
+  V[0] += msc * (b[1] * vec[2] - b[2] * vec[1]);
+  V[1] += msc * (b[2] * vec[0] - b[0] * vec[2]);
+  V[2] += msc * (b[0] * vec[1] - b[1] * vec[0]);
+  if (idealMhd) ForceParal = -mu / gamma * (gradAbsB[0] * b[0] + gradAbsB[1] * b[1] + gradAbsB[2] * b[2]);
+  else ForceParal = q * (E[0] * b[0] + E[1] * b[1] + E[2] * b[2]) - mu / gamma * (gradAbsB[0] * b[0] + gradAbsB[1] * b[1] + gradAbsB[2] * b[2]);
+  for (int d = 0; d < 3; d++) Vguide_perp[d] = V[d], bOut[d] = b[d];
+  AbsBOut = AbsB;
+  return true;
+}
+
+// GuidingCenter::InitiateMagneticMoment for every resident particle (InitiateParticle, pic_pbuffer.cpp:988): mu and v || B
+__global__ void __launch_bounds__(128) gc_magnetic_moment_init_kernel(DevMesh m, DevSpecies sp, int interp, GcTables T, ParticleSoA p,
+                                                                     const int *__restrict__ nSlots, DevMoveStats *__restrict__ stats) {
+  const int n = *nSlots;
+  unsigned int nErr = 0;
+  for (int ip = blockIdx.x * blockDim.x + threadIdx.x; ip < n; ip += gridDim.x * blockDim.x) {
+    const int key = p.key[ip];
+    if (key < 0) continue;
+    const double x[3] = {p.x[0][ip], p.x[1][ip], p.x[2][ip]};
+    double v[3] = {p.v[0][ip], p.v[1][ip], p.v[2][ip]};
+    double mu;
+    if (!gc_initiate_magnetic_moment(m, sp, interp, T, p.spec[ip] & 0x3f, x, v, key / m.cellsPerBlock, mu)) {
+      nErr++;
+      continue;
+    }
+    p.mu[ip] = mu;
+    p.v[0][ip] = v[0], p.v[1][ip] = v[1], p.v[2][ip] = v[2];
+  }
+  flush_move_counters(stats, 0, 0, 0, 0, 0, 0, nErr);
+}
+void launch_gc_magnetic_moment_init(const DevMesh &m, const DevSpecies &sp, int interp, ParticleSoA p, const int *nSlots, long long nUpper,
+                                    const double *bgTile, DevMoveStats *stats, cudaStream_t s) {
+  long long g = (nUpper + 127) / 128;
+  if (g < 1) g = 1;
+  if (g > 148 * 32) g = 148 * 32;
+  GcTables T;
+  T.bg = bgTile, T.gradB = nullptr;
+  gc_magnetic_moment_init_kernel<<<(int)g, 128, 0, s>>>(m, sp, interp, T, p, nSlots, stats);
+}
+
+template <bool kSecondOrder>
+__global__ void __launch_bounds__(128) move_guiding_center_kernel(DevMesh m, DevSpecies sp, TpParams tp, int idealMhd, GcTables T, ParticleSoA p,
+                                                                 const int *__restrict__ nSlots, int *__restrict__ cellCount,
+                                                                 DevMoveStats *__restrict__ stats, amps_gpu_exit_record *__restrict__ exitBuf,
+                                                                 unsigned long long *__restrict__ exitCount) {
+  const int n = *nSlots;
+  const int C = m.cellsPerBlock;
+  unsigned int nMoved = 0, nXCell = 0, nXBlock = 0, nLeft = 0, nNotUsed = 0, nWrap = 0, nErr = 0;
+
+  for (int ip = blockIdx.x * blockDim.x + threadIdx.x; ip < n; ip += gridDim.x * blockDim.x) {
+    const int oldKey = p.key[ip];
+    if (oldKey < 0) continue;
+    nMoved++;
+    double x[3] = {p.x[0][ip], p.x[1][ip], p.x[2][ip]};
+    double v[3] = {p.v[0][ip], p.v[1][ip], p.v[2][ip]};
+    const unsigned char specByte = p.spec[ip];
+    const int spec = specByte & 0x3f;
+    const int startLeaf = oldKey / C;
+    const int startNode = m.leaf[startLeaf].node;
+    const double m0 = sp.mass[spec];
+    const double dtTotal = (sp.timeStepMode == AMPS_DT_SPECIES_GLOBAL) ? sp.dt[spec] : sp.dt[0];
+    int outcome = 0, node = -1;
+    double xFinal[3], vFinal[3];
+    double mu = p.mu[ip];
+
+    if (!kSecondOrder) {
+      if (!(specByte & 0x40)) {  // TestInitFlag == false (:640-644)
+        p.spec[ip] = specByte | 0x40;
+        if (!gc_initiate_magnetic_moment(m, sp, tp.interp, T, spec, x, v, startLeaf, mu)) outcome = 3;
+        else p.mu[ip] = mu;
+      }
+      double Vg[3], Fpar = 0.0, AbsBInit, bInit[3], pp = 0.0;
+      if (outcome == 0 && !gc_motion(m, sp, tp.interp, idealMhd, T, Vg, Fpar, AbsBInit, bInit, nullptr, spec, mu, x, v, startLeaf)) outcome = 3;
+      if (outcome == 0) {
+        double misc = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        if (v[0] * bInit[0] + v[1] * bInit[1] + v[2] * bInit[2] < 0.0) misc *= -1.0;
+        for (int d = 0; d < 3; d++) v[d] = misc * bInit[d];
+        pp = m0 * (v[0] * bInit[0] + v[1] * bInit[1] + v[2] * bInit[2]);
+        for (int d = 0; d < 3; d++) x[d] += dtTotal * (Vg[d] + v[d]);
+        pp += dtTotal * Fpar;
+        node = find_tree_node_plain(m, x, -1);  // FindBlock
+        if (node < 0) outcome = 1;
+      }
+      if (outcome == 0) {
+        BgStencil st;
+        if (!background_stencil(m, tp.interp, x, startLeaf, st)) outcome = 3;  // the START block, as written (:713)
+        else {
+          double bFinal[3];
+          background_gather<3>(st, T.bg + (size_t)startLeaf * m.nCenterLocal * 6, 6, 3, bFinal);
+          const double l0 = sqrt(bFinal[0] * bFinal[0] + bFinal[1] * bFinal[1] + bFinal[2] * bFinal[2]);
+          if (l0 > 0.0) {
+            const double l = 1.0 / l0;
+            for (int d = 0; d < 3; d++) bFinal[d] *= l;
+          }
+          const double misc = pp / m0;
+          for (int d = 0; d < 3; d++) v[d] = misc * bFinal[d];
+          if (tp.rSphere > 0.0 && x[0] * x[0] + x[1] * x[1] + x[2] * x[2] < tp.rSphere * tp.rSphere) outcome = 1;  // no callback (:748-758)
+          else {
+            node = find_tree_node_plain(m, x, startNode);
+            if (node < 0) outcome = 3;
+          }
+        }
+      }
+      for (int d = 0; d < 3; d++) xFinal[d] = x[d], vFinal[d] = v[d];
+    } else {
+      double VgInit[3], FparInit = 0.0, AbsBInit, bInit[3];
+      if (!gc_motion(m, sp, tp.interp, idealMhd, T, VgInit, FparInit, AbsBInit, bInit, nullptr, spec, mu, x, v, startLeaf)) outcome = 3;
+      double pInit = 0.0, pMiddle = 0.0, xMiddle[3];
+      if (outcome == 0) {
+        double misc = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        if (v[0] * bInit[0] + v[1] * bInit[1] + v[2] * bInit[2] < 0) misc *= -1.0;
+        v[0] = misc * bInit[0];
+        v[1] = misc * bInit[1];
+        v[2] = misc * bInit[2];
+        pInit = m0 * (v[0] * bInit[0] + v[1] * bInit[1] + v[2] * bInit[2]);
+        const double dtTemp = dtTotal / 2.0;
+        for (int d = 0; d < 3; d++) xMiddle[d] = x[d] + dtTemp * (VgInit[d] + v[d]);
+        pMiddle = pInit + dtTemp * FparInit;
+        node = find_tree_node_plain(m, xMiddle, -1);  // FindBlock
+        if (node < 0) outcome = 1;
+        else if (m.nodeLeaf[node] < 0) outcome = 3;
+      }
+      if (outcome == 0) {
+        double VgMid[3], FparMid = 0.0, AbsBMid, bMid[3];
+        const double vMiddle0[3] = {0.0, 0.0, 0.0};
+        if (!gc_motion(m, sp, tp.interp, idealMhd, T, VgMid, FparMid, AbsBMid, bMid, &pMiddle, spec, mu, xMiddle, vMiddle0, m.nodeLeaf[node])) outcome = 3;
+        else {
+          double misc = pMiddle / m0;
+          double vMiddle[3];
+          for (int d = 0; d < 3; d++) vMiddle[d] = misc * bMid[d];
+          for (int d = 0; d < 3; d++) xFinal[d] = x[d] + dtTotal * (VgMid[d] + vMiddle[d]);
+          const double pFinal = pInit + dtTotal * FparMid;
+          misc = pFinal / m0;
+          for (int d = 0; d < 3; d++) vFinal[d] = misc * bMid[d];
+          bool hit = false;
+          if (tp.rSphere > 0.0) {
+            const double rFinal2 = xFinal[0] * xFinal[0] + xFinal[1] * xFinal[1] + xFinal[2] * xFinal[2];
+            if (rFinal2 < tp.rSphere * tp.rSphere) {
+              const double r = sqrt(rFinal2);
+              for (int d = 0; d < 3; d++) xFinal[d] *= tp.rSphere / r;
+              const int nn = find_tree_node_plain(m, xFinal, startNode);
+              add_exit_record(exitBuf, exitCount, tp.exitCap, p.ptr[ip], spec, AMPS_EXIT_SPHERE, nn >= 0 ? m.nodeLeaf[nn] : -1, xFinal, vFinal);
+              outcome = 1, hit = true;
+            }
+          }
+          if (!hit) {
+            node = find_tree_node_plain(m, xFinal, startNode);
+            if (node < 0) outcome = 1;
+          }
+        }
+      }
+    }
+
+    int newKey = -1;
+    if (outcome == 0) {
+      int ijk[3];
+      int newLeaf = m.nodeLeaf[node];
+      if (!find_cell_index(m, xFinal, node, ijk) || newLeaf < 0) outcome = 3;
+      else {
+        const int realLeaf = m.leaf[newLeaf].real;
+        if (realLeaf >= 0) {
+          const LeafGeo &gg = m.leaf[newLeaf];
+          const LeafGeo &rg = m.leaf[realLeaf];
+          for (int d = 0; d < 3; d++) {
+            xFinal[d] += rg.xmin[d] - gg.xmin[d];
+            if (xFinal[d] < rg.xmin[d]) xFinal[d] = rg.xmin[d];
+            if (xFinal[d] >= rg.xmax[d]) xFinal[d] = rg.xmax[d] - 1.0E-10 * (rg.xmax[d] - rg.xmin[d]);
+          }
+          newLeaf = realLeaf;
+          nWrap++;
+        }
+        newKey = newLeaf * C + ijk[0] + m.N[0] * (ijk[1] + m.N[1] * ijk[2]);
+        if (newLeaf != startLeaf) nXBlock++;
+        else if (newKey != oldKey) nXCell++;
+      }
+    }
+    if (outcome == 1) nLeft++;
+    else if (outcome == 2) nNotUsed++;
+    else if (outcome == 3) nErr++;
+    if (newKey >= 0) {
+      p.x[0][ip] = xFinal[0], p.x[1][ip] = xFinal[1], p.x[2][ip] = xFinal[2];
+      p.v[0][ip] = vFinal[0], p.v[1][ip] = vFinal[1], p.v[2][ip] = vFinal[2];
+      atomicAdd(&cellCount[newKey], 1);
+    }
+    if (newKey != oldKey) p.key[ip] = newKey;
+  }
+  flush_move_counters(stats, nMoved, nXCell, nXBlock, nLeft, nNotUsed, nWrap, nErr);
+}
+
+void launch_move_guiding_center(const DevMesh &m, const DevSpecies &sp, int order, int interp, int idealMhd, double rSphere, long long exitCap,
+                                ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *gradBTile, int *cellCount,
+                                DevMoveStats *stats, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s) {
+  TpParams tp;
+  tp.interp = interp, tp.backward = 0, tp.boundaryMode = sp.boundaryMode, tp.c = 0.0, tp.rSphere = rSphere, tp.exitCap = exitCap;
+  GcTables T;
+  T.bg = bgTile, T.gradB = gradBTile;
+  long long g = (nUpper + 127) / 128;
+  if (g < 1) g = 1;
+  if (g > 148 * 32) g = 148 * 32;
+  if (order == 2) move_guiding_center_kernel<true><<<(int)g, 128, 0, s>>>(m, sp, tp, idealMhd, T, p, nSlots, cellCount, stats, exitBuf, exitCount);
+  else move_guiding_center_kernel<false><<<(int)g, 128, 0, s>>>(m, sp, tp, idealMhd, T, p, nSlots, cellCount, stats, exitBuf, exitCount);
 }
 
 }  // namespace amps

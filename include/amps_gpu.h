@@ -109,7 +109,7 @@ typedef struct amps_gpu_config {
   int64_t exit_record_capacity;      /* records kept for the host callbacks (0 = only count)                              */
   double gravity_gm;                 /* GravityConstant*_MASS_(_TARGET_) of BorisSplitAcceleration_default (:110-118), 0 = off */
   int32_t carry_magnetic_moment;     /* _USE_MAGNETIC_MOMENT_: particles carry mu (picParticleDataMacro.h:178-187); needed by the GCA movers */
-  int32_t reserved0;
+  int32_t ideal_mhd;                 /* _PIC__IDEAL_MHD_MODE_ (picGlobal.dfn:339, default ON): E.b = 0 in the guiding-centre parallel force */
 } amps_gpu_config;
 
 /* _PIC_COUPLER__INTERPOLATION_MODE_ */
@@ -226,10 +226,15 @@ int amps_gpu_background_upload(amps_gpu_ctx *ctx, const double *E_center, const 
  * b.grad(b), vE.grad(b), b.grad(vE), vE.grad(vE), grad(kappa*B), 3 components each in that order
  * (PIC::CPLR::GetVarForRelativisticGCA, pic.h:8643-8680; produced by DATAFILE, pic_datafile.cpp:1164-1340)   */
 int amps_gpu_background_upload_gca(amps_gpu_ctx *ctx, const double *var15_center);
-/* PIC::Mover::Relativistic::GuidingCenter::InitiateMagneticMoment (pic_mover_relativistic_guiding_center.cpp:19-93)
- * for every resident particle (the reference calls it from InitiateParticle, pic_pbuffer.cpp:988); needs
- * carry_magnetic_moment and the background table                                                           */
-int amps_gpu_magnetic_moment_init(amps_gpu_ctx *ctx);
+/* grad B of the coupler on the unique centre nodes, [n_centers][9] = {d/dx,d/dy,d/dz} of Bx, then By, then Bz
+ * (PIC::CPLR::GetBackgroundMagneticFieldGradient, pic.h:8434-8470); read by the guiding-centre movers          */
+int amps_gpu_background_upload_gradB(amps_gpu_ctx *ctx, const double *gradB_center);
+/* InitiateMagneticMoment for every resident particle, as InitiateParticle does (pic_pbuffer.cpp:986-997):
+ * mover_id = AMPS_MOVER_RELATIVISTIC_GCA -> Relativistic::GuidingCenter (pic_mover_relativistic_guiding_center.cpp:19-93);
+ * AMPS_MOVER_GC_FIRST_ORDER/_SECOND_ORDER -> GuidingCenter (pic_mover_guiding_center.cpp:85-144; this one also aligns
+ * v with B).  Needs carry_magnetic_moment and the background table.  GuidingCenter::Mover_FirstOrder does the
+ * same by itself for particles whose InitFlag (bit 6 of the species byte) is clear.                          */
+int amps_gpu_magnetic_moment_init(amps_gpu_ctx *ctx, int mover_id);
 /* mu_by_ptr[ptr] -> device (SetMagneticMoment on the records the particles came from); n = length of mu_by_ptr */
 int amps_gpu_magnetic_moment_upload(amps_gpu_ctx *ctx, const double *mu_by_ptr, int64_t n);
 /* current device order (pair with the ptrs of amps_gpu_particles_download_soa) */

@@ -41,7 +41,8 @@ const int PrevBOffset_d = 3;
 const int BackgroundE_d = 6;   // coupler table: DATAFILE::Offset::ElectricField
 const int BackgroundB_d = 9;   // coupler table: DATAFILE::Offset::MagneticField
 const int BackgroundGCA_d = 12; // 15 tabulated derivative variables of the relativistic GCA (pic_datafile.cpp:1164-1340)
-const int CenterDataLength = 27;
+const int BackgroundGradB_d = 27; // DATAFILE::Offset::MagneticFieldGradient, 9 values {d/dx,d/dy,d/dz} of Bx, By, Bz (pic.h:8434-8470)
+const int CenterDataLength = 36;
 const double SpeedOfLight_SI = 299792458.0;  // src/general/constants.h:40
 
 // src/pic/pic_field_solver_ecsim.cpp:1377-1380
@@ -187,6 +188,9 @@ struct oracle_ctx {
   // species byte: bits 0-5 id, bit 7 "allocated", src/pic/pic.h:2808-2900
   static unsigned int GetI(const byte *p) { return (*(p + OFF_SPEC)) & 0x3f; }
   static void SetI(int spec, byte *p) { *(p + OFF_SPEC) = (byte)((spec & 0x3f) | ((*(p + OFF_SPEC)) & 0xc0)); }
+  // InitFlag: bit 6 of the species byte (pic.h:3668-3690)
+  static bool TestInitFlag(const byte *p) { return ((*(p + OFF_SPEC)) & 0x40) != 0; }
+  static void SetInitFlag(bool t, byte *p) { if (t) *(p + OFF_SPEC) |= 0x40; else *(p + OFF_SPEC) &= 0xbf; }
   static bool IsParticleAllocated(const byte *p) { return ((*(p + OFF_SPEC)) & 0x80) != 0; }
   static void SetParticleDeleted(byte *p) { *(p + OFF_SPEC) &= 0x7f; }
   static void SetParticleAllocated(byte *p) { *(p + OFF_SPEC) |= 0x80; }
@@ -1292,6 +1296,256 @@ struct oracle_ctx {
     return _PARTICLE_MOTION_FINISHED_;
   }
 
+
+  // ------------------------------------------------------------------------------------------
+  // a8: PIC::Mover::GuidingCenter, src/pic/pic_mover_guiding_center.cpp  (coupler mode, relativity off)
+  // ------------------------------------------------------------------------------------------
+  // PIC::CPLR::InitInterpolationStencil(x,node) for a point that may lie OUTSIDE `node` (Mover_FirstOrder :713 builds the
+  // stencil of the new position in the start block).  Indices beyond the block's ghost layer are out-of-bounds reads in
+  // the reference -> reported as an error here (returns false), like every place where the reference exit()s.
+  bool GC_InitStencil(const double *x, cTreeNode *node, cStencil &Stencil) const {
+    if (node == NULL || node->block == NULL) return false;
+    if (cfg.coupler_interpolation == AMPS_CPLR_CELL_CENTERED_LINEAR) {
+      const int N[3] = {_BLOCK_CELLS_X_, _BLOCK_CELLS_Y_, _BLOCK_CELLS_Z_}, G[3] = {_GHOST_CELLS_X_, _GHOST_CELLS_Y_, _GHOST_CELLS_Z_};
+      for (int d = 0; d < 3; d++) {
+        double loc = (x[d] - node->xmin[d]) / (node->xmax[d] - node->xmin[d]) * N[d];
+        if (!(loc >= -1.0e9 && loc <= 1.0e9)) return false;
+        int i0 = (loc < 0.5) ? -1 : (int)(loc - 0.50);
+        if (i0 < -G[d] || i0 + 1 > N[d] + G[d] - 1) return false;
+      }
+      CellCentered_Linear_InitStencil(x, node, Stencil, false);
+      return Stencil.Length > 0;
+    }
+    int i, j, k;
+    long int nd = FindCellIndex(x, i, j, k, node);
+    if (nd < 0 || node->block->centerNodes[nd] == NULL) return false;
+    Stencil.Weight[0] = 1.0, Stencil.LocalCellID[0] = (int)nd, Stencil.Length = 1;
+    return true;
+  }
+  void GC_Gather(const cStencil &Stencil, cTreeNode *node, int offset, int nVars, double *out) const {
+    for (int i = 0; i < nVars; i++) out[i] = 0.0;
+    for (int iStencil = 0; iStencil < Stencil.Length; iStencil++) {
+      const double *t = node->block->centerNodes[Stencil.LocalCellID[iStencil]]->data + offset;
+      for (int i = 0; i < nVars; i++) out[i] += Stencil.Weight[iStencil] * t[i];
+    }
+  }
+
+  // InitiateMagneticMoment, :85-144: mu from the perpendicular speed, then v is ALIGNED with B
+  bool GC_InitiateMagneticMoment(int spec, const double *x, double *v, byte *ParticleData, cTreeNode *node) {
+    double B[3] = {0.0, 0.0, 0.0}, AbsB = 0.0;
+    cStencil Stencil;
+    if (!GC_InitStencil(x, node, Stencil)) return false;
+    GC_Gather(Stencil, node, BackgroundB_d, 3, B);
+    AbsB = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) + 1E-15;
+    double v_par = 0.0, v2, gamma2, m0, mu = 0.0;
+    double b[3] = {B[0] / AbsB, B[1] / AbsB, B[2] / AbsB};
+    if (AbsB > 0.0) {
+      v_par = v[0] * b[0] + v[1] * b[1] + v[2] * b[2];
+      v2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+      gamma2 = 1.0;
+      m0 = cfg.mass[spec];
+      mu = 0.5 * gamma2 * m0 * (v2 - v_par * v_par) / AbsB;
+    }
+    v[0] = v_par * b[0];
+    v[1] = v_par * b[1];
+    v[2] = v_par * b[2];
+    SetMagneticMoment(mu, ParticleData);
+    return true;
+  }
+
+  // GuidingCenterMotion_default, :146-289
+  bool GC_GuidingCenterMotion(double *Vguide_perp, double &ForceParal, double &BAbsoluteValue, double *BDirection, const double *PParal, int spec,
+                              double mu, const double *x, const double *v, cTreeNode *startNode) const {
+    double Vguide_perp_LOC[3] = {0.0, 0.0, 0.0}, ForceParal_LOC = 0.0;
+    double E[3], gradB[9], gradAbsB[3], AbsB = 0.0;
+    double b[3], B[3];
+    cStencil Stencil;
+    if (!GC_InitStencil(x, startNode, Stencil)) return false;
+    GC_Gather(Stencil, startNode, BackgroundE_d, 3, E);
+    GC_Gather(Stencil, startNode, BackgroundB_d, 3, B);
+    GC_Gather(Stencil, startNode, BackgroundGradB_d, 9, gradB);
+    AbsB = pow(B[0] * B[0] + B[1] * B[1] + B[2] * B[2], 0.5) + 1E-15;
+    b[0] = B[0] / AbsB;
+    b[1] = B[1] / AbsB;
+    b[2] = B[2] / AbsB;
+    gradAbsB[0] = b[0] * gradB[0] + b[1] * gradB[3] + b[2] * gradB[6];
+    gradAbsB[1] = b[0] * gradB[1] + b[1] * gradB[4] + b[2] * gradB[7];
+    gradAbsB[2] = b[0] * gradB[2] + b[1] * gradB[5] + b[2] * gradB[8];
+    double q = cfg.charge[spec];
+    double m0 = cfg.mass[spec];
+    double gamma = 1.0;
+    double p_par;
+    p_par = (PParal == NULL) ? gamma * m0 * (v[0] * b[0] + v[1] * b[1] + v[2] * b[2]) : *PParal;
+    double msc, vec[3] = {0.0, 0.0, 0.0};
+    Vguide_perp_LOC[0] += (E[1] * b[2] - E[2] * b[1]) / AbsB;
+    Vguide_perp_LOC[1] += (E[2] * b[0] - E[0] * b[2]) / AbsB;
+    Vguide_perp_LOC[2] += (E[0] * b[1] - E[1] * b[0]) / AbsB;
+    msc = mu / (q * gamma) / AbsB;
+    Vguide_perp_LOC[0] += msc * (b[1] * gradAbsB[2] - b[2] * gradAbsB[1]);
+    Vguide_perp_LOC[1] += msc * (b[2] * gradAbsB[0] - b[0] * gradAbsB[2]);
+    Vguide_perp_LOC[2] += msc * (b[0] * gradAbsB[1] - b[1] * gradAbsB[0]);
+    msc = p_par * p_par / (q * gamma * m0) / AbsB / AbsB;
+    vec[0] = b[0] * gradB[0] + b[1] * gradB[1] + b[2] * gradB[2];
+    vec[1] = b[0] * gradB[3] + b[1] * gradB[4] + b[2] * gradB[5];
+    vec[2] = b[0] * gradB[6] + b[1] * gradB[7] + b[2] * gradB[8];
+    Vguide_perp_LOC[0] += msc * (b[1] * vec[2] - b[2] * vec[1]);
+    Vguide_perp_LOC[1] += msc * (b[2] * vec[0] - b[0] * vec[2]);
+    Vguide_perp_LOC[2] += msc * (b[0] * vec[1] - b[1] * vec[0]);
+    if (cfg.ideal_mhd) {  // _PIC__IDEAL_MHD_MODE_ (picGlobal.dfn:339, default ON): E.b = 0
+      ForceParal_LOC = -mu / gamma * (gradAbsB[0] * b[0] + gradAbsB[1] * b[1] + gradAbsB[2] * b[2]);
+    } else {
+      ForceParal_LOC = q * (E[0] * b[0] + E[1] * b[1] + E[2] * b[2]) - mu / gamma * (gradAbsB[0] * b[0] + gradAbsB[1] * b[1] + gradAbsB[2] * b[2]);
+    }
+    memcpy(Vguide_perp, Vguide_perp_LOC, 3 * sizeof(double));
+    memcpy(BDirection, b, 3 * sizeof(double));
+    ForceParal = ForceParal_LOC;
+    BAbsoluteValue = AbsB;
+    return true;
+  }
+
+  // Mover_FirstOrder, :622-849
+  int GC_Mover_FirstOrder(byte *ParticleData, long int ptr, double dtTotal, cTreeNode *startNode, int nThreads, int thread, cTreeNode **newNodeOut) {
+    cTreeNode *newNode = NULL;
+    double AbsBInit = 0.0, bInit[3] = {0.0, 0.0, 0.0};
+    double v[3], p = 0.0, x[3];
+    int idim, i, j, k, spec;
+    double misc, mu;
+    GetV(v, ParticleData);
+    GetX(x, ParticleData);
+    spec = GetI(ParticleData);
+    double m0 = cfg.mass[spec];
+    if (TestInitFlag(ParticleData) == false) {
+      SetInitFlag(true, ParticleData);
+      if (!GC_InitiateMagneticMoment(spec, x, v, ParticleData, startNode)) return _ORACLE_ERROR_;
+    }
+    mu = GetMagneticMoment(ParticleData);
+    double Vguide_perpInit[3] = {0.0, 0.0, 0.0}, ForceParalInit = 0.0;
+    if (!GC_GuidingCenterMotion(Vguide_perpInit, ForceParalInit, AbsBInit, bInit, NULL, spec, mu, x, v, startNode)) return _ORACLE_ERROR_;
+    misc = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (v[0] * bInit[0] + v[1] * bInit[1] + v[2] * bInit[2] < 0.0) misc *= -1.0;
+    for (idim = 0; idim < 3; idim++) v[idim] = misc * bInit[idim];
+    p = m0 * (v[0] * bInit[0] + v[1] * bInit[1] + v[2] * bInit[2]);
+    for (idim = 0; idim < 3; idim++) x[idim] += dtTotal * (Vguide_perpInit[idim] + v[idim]);
+    p += dtTotal * ForceParalInit;
+    newNode = findTreeNode(x, NULL);  // PIC::Mesh::Search::FindBlock
+    if (newNode == NULL) {
+      DeleteParticle(ptr);
+      return _PARTICLE_LEFT_THE_DOMAIN_;
+    }
+    double bFinal[3];
+    {
+      cStencil Stencil;
+      if (!GC_InitStencil(x, startNode, Stencil)) return _ORACLE_ERROR_;  // the START node, as written (:713)
+      GC_Gather(Stencil, startNode, BackgroundB_d, 3, bFinal);
+    }
+    {
+      // Vector3D::Normalize, src/general/specfunc.h:969-981
+      double l, l0 = sqrt(bFinal[0] * bFinal[0] + bFinal[1] * bFinal[1] + bFinal[2] * bFinal[2]);
+      if (l0 > 0.0) {
+        l = 1.0 / l0;
+        for (int idim2 = 0; idim2 < 3; idim2++) bFinal[idim2] *= l;
+      }
+    }
+    misc = p / m0;
+    for (idim = 0; idim < 3; idim++) v[idim] = misc * bFinal[idim];
+    if (cfg.internal_sphere_radius > 0.0) {
+      double rFinal2;
+      if ((rFinal2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2]) < cfg.internal_sphere_radius * cfg.internal_sphere_radius) {
+        DeleteParticle(ptr);  // the sphere callback is commented out in this mover (:748-758)
+        return _PARTICLE_LEFT_THE_DOMAIN_;
+      } else
+        newNode = findTreeNode(x, startNode);
+    } else
+      newNode = findTreeNode(x, startNode);
+    if (newNode == NULL) return _ORACLE_ERROR_;
+    if (FindCellIndex(x, i, j, k, newNode) == -1) return _ORACLE_ERROR_;
+    cBlock *block;
+    if ((block = newNode->block) == NULL) return _ORACLE_ERROR_;
+    AttachToTempList(ptr, ParticleData, block, i, j, k, nThreads, thread);
+    SetV(v, ParticleData);
+    SetX(x, ParticleData);
+    *newNodeOut = newNode;
+    return _PARTICLE_MOTION_FINISHED_;
+  }
+
+  // Mover_SecondOrder, :292-619 (predictor-corrector)
+  int GC_Mover_SecondOrder(byte *ParticleData, long int ptr, double dtTotal, cTreeNode *startNode, int nThreads, int thread, cTreeNode **newNodeOut) {
+    cTreeNode *newNode = NULL;
+    double dtTemp;
+    double AbsBInit = 0.0, bInit[3] = {0.0, 0.0, 0.0};
+    double vInit[3] = {0.0, 0.0, 0.0}, pInit = 0.0, xInit[3] = {0.0, 0.0, 0.0};
+    double AbsBMiddle = 0.0, bMiddle[3] = {0.0, 0.0, 0.0};
+    double vMiddle[3] = {0.0, 0.0, 0.0}, pMiddle = 0.0, xMiddle[3] = {0.0, 0.0, 0.0};
+    double vFinal[3] = {0.0, 0.0, 0.0}, pFinal = 0.0, xFinal[3] = {0.0, 0.0, 0.0};
+    int i, j, k, spec;
+    double misc;
+    GetV(vInit, ParticleData);
+    GetX(xInit, ParticleData);
+    spec = GetI(ParticleData);
+    double m0 = cfg.mass[spec];
+    double mu = GetMagneticMoment(ParticleData);
+    double Vguide_perpInit[3] = {0.0, 0.0, 0.0}, ForceParalInit = 0.0;
+    if (!GC_GuidingCenterMotion(Vguide_perpInit, ForceParalInit, AbsBInit, bInit, NULL, spec, mu, xInit, vInit, startNode)) return _ORACLE_ERROR_;
+    misc = pow(vInit[0] * vInit[0] + vInit[1] * vInit[1] + vInit[2] * vInit[2], 0.5);
+    if (vInit[0] * bInit[0] + vInit[1] * bInit[1] + vInit[2] * bInit[2] < 0) misc *= -1.0;
+    vInit[0] = misc * bInit[0];
+    vInit[1] = misc * bInit[1];
+    vInit[2] = misc * bInit[2];
+    pInit = m0 * (vInit[0] * bInit[0] + vInit[1] * bInit[1] + vInit[2] * bInit[2]);
+    dtTemp = dtTotal / 2.0;
+    xMiddle[0] = xInit[0] + dtTemp * (Vguide_perpInit[0] + vInit[0]);
+    xMiddle[1] = xInit[1] + dtTemp * (Vguide_perpInit[1] + vInit[1]);
+    xMiddle[2] = xInit[2] + dtTemp * (Vguide_perpInit[2] + vInit[2]);
+    pMiddle = pInit + dtTemp * ForceParalInit;
+    newNode = findTreeNode(xMiddle, NULL);  // FindBlock
+    if (newNode == NULL) {
+      DeleteParticle(ptr);
+      return _PARTICLE_LEFT_THE_DOMAIN_;
+    }
+    double Vguide_perpMiddle[3] = {0.0, 0.0, 0.0}, ForceParalMiddle = 0.0;
+    if (!GC_GuidingCenterMotion(Vguide_perpMiddle, ForceParalMiddle, AbsBMiddle, bMiddle, &pMiddle, spec, mu, xMiddle, vMiddle, newNode)) return _ORACLE_ERROR_;
+    misc = pMiddle / m0;
+    vMiddle[0] = misc * bMiddle[0];
+    vMiddle[1] = misc * bMiddle[1];
+    vMiddle[2] = misc * bMiddle[2];
+    xFinal[0] = xInit[0] + dtTotal * (Vguide_perpMiddle[0] + vMiddle[0]);
+    xFinal[1] = xInit[1] + dtTotal * (Vguide_perpMiddle[1] + vMiddle[1]);
+    xFinal[2] = xInit[2] + dtTotal * (Vguide_perpMiddle[2] + vMiddle[2]);
+    pFinal = pInit + dtTotal * ForceParalMiddle;
+    misc = pFinal / m0;
+    vFinal[0] = misc * bMiddle[0];
+    vFinal[1] = misc * bMiddle[1];
+    vFinal[2] = misc * bMiddle[2];
+    if (cfg.internal_sphere_radius > 0.0) {
+      double rFinal2;
+      const double R = cfg.internal_sphere_radius;
+      if ((rFinal2 = xFinal[0] * xFinal[0] + xFinal[1] * xFinal[1] + xFinal[2] * xFinal[2]) < R * R) {
+        double r = sqrt(rFinal2);
+        for (int idim = 0; idim < 3; idim++) xFinal[idim] *= R / r;
+        newNode = findTreeNode(xFinal, startNode);
+        // ParticleSphereInteraction -> _PARTICLE_DELETED_ON_THE_FACE_: handed to the host as an exit record
+        AddExitRecord(ptr, spec, AMPS_EXIT_SPHERE, newNode, xFinal, vFinal);
+        DeleteParticle(ptr);
+        return _PARTICLE_LEFT_THE_DOMAIN_;
+      } else {
+        newNode = findTreeNode(xFinal, startNode);
+      }
+    } else
+      newNode = findTreeNode(xFinal, startNode);
+    if (newNode == NULL) {
+      DeleteParticle(ptr);
+      return _PARTICLE_LEFT_THE_DOMAIN_;
+    }
+    if (FindCellIndex(xFinal, i, j, k, newNode) == -1) return _ORACLE_ERROR_;
+    cBlock *block;
+    if ((block = newNode->block) == NULL) return _ORACLE_ERROR_;
+    AttachToTempList(ptr, ParticleData, block, i, j, k, nThreads, thread);
+    SetV(vFinal, ParticleData);
+    SetX(xFinal, ParticleData);
+    *newNodeOut = newNode;
+    return _PARTICLE_MOTION_FINISHED_;
+  }
+
   // PIC::Mover::cExternalBoundaryFace + Init, src/pic/pic_mover.cpp:24-28,48-75
   struct cExternalBoundaryFace {
     double norm[3];
@@ -1715,8 +1969,18 @@ void oracle_set_background(oracle_ctx *o, const double *E_center, const double *
 void oracle_set_background_gca(oracle_ctx *o, const double *var15) {
   for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + BackgroundGCA_d, var15 + 15 * (size_t)i, 15 * 8);
 }
+void oracle_set_background_gradB(oracle_ctx *o, const double *gradB) {
+  for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + BackgroundGradB_d, gradB + 9 * (size_t)i, 9 * 8);
+}
+void oracle_get_magnetic_moment(const oracle_ctx *o, double *mu, uint8_t *init_flag, int64_t n) {
+  for (int64_t ptr = 0; ptr < n; ptr++) {
+    const byte *pd = o->GetParticleDataPointer(ptr);
+    if (mu) mu[ptr] = oracle_ctx::GetMagneticMoment(pd);
+    if (init_flag) init_flag[ptr] = oracle_ctx::TestInitFlag(pd) ? 1 : 0;
+  }
+}
 // InitiateMagneticMoment for every particle on the cell lists; mu (by ptr) is returned in mu_out when not NULL
-int oracle_magnetic_moment_init(oracle_ctx *o, double *mu_out, int64_t n) {
+int oracle_magnetic_moment_init(oracle_ctx *o, int mover_id, double *mu_out, int64_t n) {
   const int nC = o->nCellsBlock();
   for (size_t l = 0; l < o->blocks.size(); l++)
     for (int c = 0; c < nC; c++)
@@ -1724,7 +1988,12 @@ int oracle_magnetic_moment_init(oracle_ctx *o, double *mu_out, int64_t n) {
         byte *pd = o->GetParticleDataPointer(ptr);
         double x[3], v[3];
         oracle_ctx::GetX(x, pd), oracle_ctx::GetV(v, pd);
-        if (!o->RelGCA_InitiateMagneticMoment(oracle_ctx::GetI(pd), x, v, pd, o->BlockTable[l])) return AMPS_GPU_ERR_PARTICLE;
+        if (mover_id == AMPS_MOVER_RELATIVISTIC_GCA) {
+          if (!o->RelGCA_InitiateMagneticMoment(oracle_ctx::GetI(pd), x, v, pd, o->BlockTable[l])) return AMPS_GPU_ERR_PARTICLE;
+        } else {  // GuidingCenter::InitiateMagneticMoment also aligns v with B (the reference passes GetV(ptr))
+          if (!o->GC_InitiateMagneticMoment(oracle_ctx::GetI(pd), x, v, pd, o->BlockTable[l])) return AMPS_GPU_ERR_PARTICLE;
+          oracle_ctx::SetV(v, pd);
+        }
         if (mu_out && ptr < n) mu_out[ptr] = oracle_ctx::GetMagneticMoment(pd);
       }
   return AMPS_GPU_OK;
@@ -1797,7 +2066,7 @@ void oracle_get_particles(const oracle_ctx *o, double *x, double *v, double *w, 
 // PIC::BC::ExternalBoundary::Periodic::ExchangeParticles(), src/pic/pic_time_step.cpp:454-506
 int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats *stats, int32_t *ret_code, int32_t *final_cell) {
   if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS && mover_id != AMPS_MOVER_BORIS &&
-      mover_id != AMPS_MOVER_RELATIVISTIC_GCA) {
+      mover_id != AMPS_MOVER_RELATIVISTIC_GCA && mover_id != AMPS_MOVER_GC_FIRST_ORDER && mover_id != AMPS_MOVER_GC_SECOND_ORDER) {
     o->err = "oracle_move: mover not restated yet";
     return AMPS_GPU_ERR_ARG;
   }
@@ -1840,6 +2109,8 @@ int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats 
       const double dtLocal = (o->cfg.time_step_mode == AMPS_DT_SPECIES_GLOBAL) ? o->cfg.time_step[spec] : o->cfg.time_step[0];
       if (mover_id == AMPS_MOVER_BORIS) return o->Boris(pd, ptr, dtLocal, node, n_threads, thread, newNode);
       if (mover_id == AMPS_MOVER_RELATIVISTIC_GCA) return o->RelGCA_Mover_FirstOrder(pd, ptr, dtLocal, node, n_threads, thread, newNode);
+      if (mover_id == AMPS_MOVER_GC_FIRST_ORDER) return o->GC_Mover_FirstOrder(pd, ptr, dtLocal, node, n_threads, thread, newNode);
+      if (mover_id == AMPS_MOVER_GC_SECOND_ORDER) return o->GC_Mover_SecondOrder(pd, ptr, dtLocal, node, n_threads, thread, newNode);
       return o->Relativistic_Boris(pd, ptr, dtLocal, node, n_threads, thread, newNode);
     };
     long int *FirstCellParticleTable = block->FirstCellParticleTable;

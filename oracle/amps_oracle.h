@@ -48,8 +48,13 @@ void oracle_set_fields(oracle_ctx *, const double *E_half, const double *B_prev,
 void oracle_set_background(oracle_ctx *, const double *E_center, const double *B_center);
 /* the 15 tabulated variables of the relativistic GCA on the unique centre nodes [n_centers][15] */
 void oracle_set_background_gca(oracle_ctx *, const double *var15);
-/* Relativistic::GuidingCenter::InitiateMagneticMoment for every listed particle; mu_out[ptr] if not NULL */
-int oracle_magnetic_moment_init(oracle_ctx *, double *mu_out, int64_t n);
+/* grad B on the unique centre nodes [n_centers][9] = {d/dx,d/dy,d/dz} of Bx, By, Bz */
+void oracle_set_background_gradB(oracle_ctx *, const double *gradB);
+/* (Relativistic::)GuidingCenter::InitiateMagneticMoment for every listed particle (mover_id picks the variant);
+ * mu_out[ptr] if not NULL */
+int oracle_magnetic_moment_init(oracle_ctx *, int mover_id, double *mu_out, int64_t n);
+/* by ptr: magnetic moment and InitFlag (bit 6 of the species byte) */
+void oracle_get_magnetic_moment(const oracle_ctx *, double *mu, uint8_t *init_flag, int64_t n);
 /* exit records (domain faces / internal sphere) accumulated since the last call; returns their number */
 int64_t oracle_exit_records(oracle_ctx *, amps_gpu_exit_record *buf, int64_t max_records);
 

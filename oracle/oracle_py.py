@@ -33,7 +33,9 @@ def load(kind="parity"):
     lib.oracle_exit_records.restype = C.c_int64
     lib.oracle_exit_records.argtypes = [vp, vp, C.c_int64]
     lib.oracle_set_background_gca.argtypes = [vp, vp]
-    lib.oracle_magnetic_moment_init.argtypes = [vp, vp, C.c_int64]
+    lib.oracle_magnetic_moment_init.argtypes = [vp, C.c_int, vp, C.c_int64]
+    lib.oracle_set_background_gradB.argtypes = [vp, vp]
+    lib.oracle_get_magnetic_moment.argtypes = [vp, vp, vp, C.c_int64]
     lib.oracle_add_particles.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64]
     lib.oracle_particle_count.restype = C.c_int64
     lib.oracle_particle_count.argtypes = [vp]
@@ -81,11 +83,21 @@ class Oracle:
         a = np.ascontiguousarray(var15, dtype=np.float64)
         self.lib.oracle_set_background_gca(self.h, _p(a))
 
-    def magnetic_moment_init(self):
+    def set_background_gradB(self, gradB):
+        a = np.ascontiguousarray(gradB, dtype=np.float64)
+        self.lib.oracle_set_background_gradB(self.h, _p(a))
+
+    def magnetic_moment_init(self, mover=5):
         mu = np.zeros(self.n_added)
-        rc = self.lib.oracle_magnetic_moment_init(self.h, _p(mu), self.n_added)
+        rc = self.lib.oracle_magnetic_moment_init(self.h, mover, _p(mu), self.n_added)
         assert rc == 0
         return mu
+
+    def magnetic_moment(self):
+        mu = np.zeros(self.n_added)
+        flag = np.zeros(self.n_added, dtype=np.uint8)
+        self.lib.oracle_get_magnetic_moment(self.h, _p(mu), _p(flag), self.n_added)
+        return mu, flag
 
     def exit_records(self, max_records=1 << 20):
         from amps_b200._capi import ExitRecord

@@ -198,3 +198,73 @@ def run_gpu_gca(m, cfg, parts, bg, var15):
     mu_by_ptr[ptr0] = mu0
     return {"stats": st, "moved": moved, "records": sorted(recs), "n_records": nrec, "n_after": n_after, "mu": mu_by_ptr, "sorted": srt,
             "mu_sorted": mu1}
+
+
+# ---- non-relativistic guiding centre (pic_mover_guiding_center.cpp) ----------------------------------------
+def gc_gradB(x, h, **kw):
+    """gradB[3*i+j] = d B_i / d x_j by central differences of the analytic field (layout of pic.h:8439-8442)"""
+    out = np.empty((x.shape[0], 9))
+    for j in range(3):
+        e = np.zeros(3)
+        e[j] = h
+        _, Bp = _bg_analytic(x + e, **kw)
+        _, Bm = _bg_analytic(x - e, **kw)
+        d = (Bp - Bm) / (2 * h)
+        for i in range(3):
+            out[:, 3 * i + j] = d[:, i]
+    return out
+
+
+def make_gc_case(n_particles=4096, seed=3, dt=0.01, interp=_capi.CPLR_LINEAR, sphere=True, uniform_B=None, E_uniform=None,
+                 rigidity_gv=(0.001, 0.02), convection=True, ideal_mhd=1, **kw):
+    m, cfg, parts, _ = make_tp_case(n_particles=n_particles, seed=seed, dt=dt, interp=interp, boundary=_capi.BOUNDARY_DELETE, sphere=sphere,
+                                    uniform_B=uniform_B, rigidity_gv=rigidity_gv, **kw)
+    E, B = _bg_analytic(m.center_x, uniform_B=uniform_B, E_uniform=E_uniform, convection=convection)
+    gradB = gc_gradB(m.center_x, 1.0e3, uniform_B=uniform_B, E_uniform=E_uniform, convection=convection)
+    cfg.carry_magnetic_moment = 1
+    cfg.ideal_mhd = ideal_mhd
+    return m, cfg, parts, (E, B), gradB
+
+
+def run_oracle_gc(m, cfg, parts, bg, gradB, mover, pre_init, n_threads=1):
+    o = Oracle(cfg, m)
+    o.set_background(*bg)
+    o.set_background_gradB(gradB)
+    o.add_particles(*parts)
+    mu0 = o.magnetic_moment_init(mover) if pre_init else None
+    v0 = o.particles()["v"] if pre_init else None
+    rc, st, ret, fc = o.move(mover, n_threads)
+    pp = o.particles()
+    mu1, flag = o.magnetic_moment()
+    nrec, recs = o.exit_records()
+    lists = o.check_lists()
+    o.close()
+    return {"rc": rc, "stats": st, "ret": ret, "final_cell": fc, "particles": pp, "records": sorted(recs), "n_records": nrec, "lists": lists,
+            "mu0": mu0, "v0": v0, "mu": mu1, "flag": flag}
+
+
+def run_gpu_gc(m, cfg, parts, bg, gradB, mover, pre_init):
+    g = api.Context(cfg, m)
+    g.background_upload(*bg)
+    g.background_upload_gradB(gradB)
+    g.particles_upload(*parts)
+    n = parts[0].shape[1]
+    mu0 = v0 = None
+    if pre_init:
+        g.InitiateMagneticMoment(mover)
+        d = g.particles_download()
+        mu0, v0 = np.empty(n), np.empty((3, n))
+        mu0[d["ptrs"]] = g.magnetic_moment_download()
+        v0[:, d["ptrs"]] = d["v"]
+    st = g.MoveParticles(mover)
+    moved = g.particles_download()
+    mu_dev = g.magnetic_moment_download()
+    nrec, recs = g.exit_records()
+    g.sort()
+    n_after = g.particle_count()
+    g.close()
+    mu1 = np.empty(n)
+    mu1[moved["ptrs"]] = mu_dev
+    flag = np.empty(n, dtype=np.uint8)
+    flag[moved["ptrs"]] = (moved["species"] >> 6) & 1
+    return {"stats": st, "moved": moved, "records": sorted(recs), "n_records": nrec, "n_after": n_after, "mu0": mu0, "v0": v0, "mu": mu1, "flag": flag}
