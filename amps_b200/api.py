@@ -181,10 +181,13 @@ class Context:
         self._ck(self.lib.amps_gpu_sort(self._h))
 
     # ---- PIC::Mover::MoveParticles -----------------------------------------------------------
-    def MoveParticles(self, mover=_capi.MOVER_LAPENTA2017, stats=True):
+    def MoveParticles(self, mover=_capi.MOVER_LAPENTA2017, stats=True, raise_on_particle_error=True):
         if stats:
             st = MoveStats()
-            self._ck(self.lib.amps_gpu_move(self._h, mover, C.byref(st)))
+            rc = self.lib.amps_gpu_move(self._h, mover, C.byref(st))
+            if rc == _capi.ERR_PARTICLE and not raise_on_particle_error:
+                return st.as_dict()  # n_error particles hit a place where the reference exit()s; they were dropped
+            self._ck(rc)
             return st.as_dict()
         self._ck(self.lib.amps_gpu_move(self._h, mover, None))
         return None

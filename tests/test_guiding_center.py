@@ -83,7 +83,9 @@ def test_gpu_parity_gc(name, mover):
     pre = mover == GC2
     ora = tp.run_oracle_gc(m, cfg, parts, bg, gradB, mover, pre)
     gpu = tp.run_gpu_gc(m, cfg, parts, bg, gradB, mover, pre)
-    assert ora["rc"] == 0
+    # first order + piecewise-constant coupler: a particle that leaves its block makes the reference exit() (the final
+    # field is looked up in the START block, :713); both sides count those in n_error and drop them
+    assert ora["rc"] in (0, _capi.ERR_PARTICLE)
     n = parts[0].shape[1]
     tol = 1e-12
     if pre:

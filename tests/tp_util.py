@@ -256,7 +256,7 @@ def run_gpu_gc(m, cfg, parts, bg, gradB, mover, pre_init):
         mu0, v0 = np.empty(n), np.empty((3, n))
         mu0[d["ptrs"]] = g.magnetic_moment_download()
         v0[:, d["ptrs"]] = d["v"]
-    st = g.MoveParticles(mover)
+    st = g.MoveParticles(mover, raise_on_particle_error=False)
     moved = g.particles_download()
     mu_dev = g.magnetic_moment_download()
     nrec, recs = g.exit_records()
