@@ -91,7 +91,8 @@ class Context:
     # ---- fields ------------------------------------------------------------------------
     def fields_upload(self, E_half=None, B_prev=None, B_cur=None):
         arrs = []
-        for a, n in ((E_half, self.mesh.n_corners), (B_prev, self.mesh.n_centers), (B_cur, self.mesh.n_centers)):
+        nb = self.mesh.n_corners if self.cfg.b_mode == _capi.B_CORNER_BASED else self.mesh.n_centers
+        for a, n in ((E_half, self.mesh.n_corners), (B_prev, nb), (B_cur, nb)):
             if a is not None:
                 a = np.ascontiguousarray(a, dtype=np.float64)
                 assert a.shape == (n, 3), (a.shape, n)

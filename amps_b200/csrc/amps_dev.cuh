@@ -91,7 +91,7 @@ __device__ __forceinline__ int centerLocalNumber(const DevMesh &m, int i, int j,
 }
 
 // launch helpers (defined per TU that needs them)
-void launch_stage_tiles(const DevMesh &m, const double *E_half, const double *B_prev, const double *B_cur, double *eTile, double *bPrevTile,
+void launch_stage_tiles(const DevMesh &m, bool cornerB, const double *E_half, const double *B_prev, const double *B_cur, double *eTile, double *bPrevTile,
                         double *bCurTile, cudaStream_t s);
 void launch_move_lapenta(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *eTile, const double *bTile,
                          int *cellCount, DevMoveStats *stats, int slices, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount,

@@ -217,10 +217,7 @@ int amps_gpu_init(const amps_gpu_config *cfg, amps_gpu_ctx **out) {
   if (cfg->capacity < 1 || cfg->capacity > 2147483000LL) return AMPS_GPU_ERR_ARG;
   for (int d = 0; d < 3; d++)
     if (cfg->block_cells[d] < 1 || cfg->ghost_cells[d] < 1) return AMPS_GPU_ERR_ARG;
-  if (cfg->b_mode != AMPS_B_CENTER_BASED) {
-    fprintf(stderr, "amps_gpu_init: only _PIC_FIELD_SOLVER_B_CENTER_BASED_ is implemented\n");
-    return AMPS_GPU_ERR_ARG;
-  }
+  if (cfg->b_mode != AMPS_B_CENTER_BASED && cfg->b_mode != AMPS_B_CORNER_BASED) return AMPS_GPU_ERR_ARG;
   amps_gpu_ctx *ctx = new amps_gpu_ctx();
   ctx->cfg = *cfg;
   memset(&ctx->dm, 0, sizeof(ctx->dm));
@@ -307,7 +304,7 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
   m.nCornerLocal = (m.TN[0] + 1) * (m.TN[1] + 1) * (m.TN[2] + 1);
   m.nCenterLocal = m.TN[0] * m.TN[1] * m.TN[2];
   m.eTileStride = (3 * m.nCornerLocal + 1) & ~1;
-  m.bTileStride = (3 * m.nCenterLocal + 1) & ~1;
+  m.bTileStride = (ctx->cfg.b_mode == AMPS_B_CORNER_BASED) ? m.eTileStride : ((3 * m.nCenterLocal + 1) & ~1);
   m.periodic = ctx->cfg.periodic;
   const long long nCells = (long long)m.nLeaves * m.cellsPerBlock;
   if (nCells > 2147483000LL) FAIL(AMPS_GPU_ERR_ARG, "too many cells for 32-bit keys");
@@ -380,8 +377,9 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
   CK(cudaStreamSynchronize(ctx->stream));  // lg is a local
 
   if ((rc = dev_alloc(ctx, &ctx->d_Ehalf, (size_t)3 * m.nCorners))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->d_Bprev, (size_t)3 * m.nCenters))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->d_Bcur, (size_t)3 * m.nCenters))) return rc;
+  const size_t nBNodes = (ctx->cfg.b_mode == AMPS_B_CORNER_BASED) ? m.nCorners : m.nCenters;
+  if ((rc = dev_alloc(ctx, &ctx->d_Bprev, (size_t)3 * nBNodes))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_Bcur, (size_t)3 * nBNodes))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_eTile, (size_t)m.nLeaves * m.eTileStride))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_bPrevTile, (size_t)m.nLeaves * m.bTileStride))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_bCurTile, (size_t)m.nLeaves * m.bTileStride))) return rc;
@@ -405,9 +403,10 @@ int amps_gpu_fields_upload(amps_gpu_ctx *ctx, const double *E_half, const double
   CK(cudaSetDevice(ctx->cfg.device));
   const DevMesh &m = ctx->dm;
   if (E_half) CK(cudaMemcpyAsync(ctx->d_Ehalf, E_half, sizeof(double) * 3 * (size_t)m.nCorners, cudaMemcpyHostToDevice, ctx->stream));
-  if (B_prev) CK(cudaMemcpyAsync(ctx->d_Bprev, B_prev, sizeof(double) * 3 * (size_t)m.nCenters, cudaMemcpyHostToDevice, ctx->stream));
-  if (B_cur) CK(cudaMemcpyAsync(ctx->d_Bcur, B_cur, sizeof(double) * 3 * (size_t)m.nCenters, cudaMemcpyHostToDevice, ctx->stream));
-  launch_stage_tiles(m, E_half ? ctx->d_Ehalf : nullptr, B_prev ? ctx->d_Bprev : nullptr, B_cur ? ctx->d_Bcur : nullptr, ctx->d_eTile,
+  const size_t nBNodes = (ctx->cfg.b_mode == AMPS_B_CORNER_BASED) ? m.nCorners : m.nCenters;
+  if (B_prev) CK(cudaMemcpyAsync(ctx->d_Bprev, B_prev, sizeof(double) * 3 * nBNodes, cudaMemcpyHostToDevice, ctx->stream));
+  if (B_cur) CK(cudaMemcpyAsync(ctx->d_Bcur, B_cur, sizeof(double) * 3 * nBNodes, cudaMemcpyHostToDevice, ctx->stream));
+  launch_stage_tiles(m, ctx->cfg.b_mode == AMPS_B_CORNER_BASED, E_half ? ctx->d_Ehalf : nullptr, B_prev ? ctx->d_Bprev : nullptr, B_cur ? ctx->d_Bcur : nullptr, ctx->d_eTile,
                      ctx->d_bPrevTile, ctx->d_bCurTile, ctx->stream);
   ctx->launches++;
   CK(cudaGetLastError());

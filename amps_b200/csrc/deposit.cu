@@ -65,6 +65,7 @@ __device__ __forceinline__ int index_matrix(int c, int d) {
   return nb_slot(cox(d) - cox(c)) + 3 * nb_slot(coy(d) - coy(c)) + 9 * nb_slot(coz(d) - coz(c));
 }
 
+template <bool kCornerB>
 __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(DevMesh m, DevSpecies sp, ParticleSoA p,
                                                                               const int *__restrict__ cellStart,
                                                                               const double *__restrict__ bCurTile, double *__restrict__ J,
@@ -114,10 +115,18 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     {
       // stage the 27 centre values of B_cur the cell's stencils can touch
       const double *bT = bCurTile + (size_t)leaf * m.bTileStride;
-      for (int e = lane; e < 81; e += 32) {
-        const int n = e / 3, d = e - 3 * n;
-        const int di = n % 3 - 1, dj = (n / 3) % 3 - 1, dk = n / 9 - 1;
-        sB[e] = __ldg(bT + 3 * centerLocalNumber(m, ic + di, jc + dj, kc + dk) + d);
+      if (kCornerB) {
+        // _PIC_FIELD_SOLVER_B_CORNER_BASED_: B_cur on the 8 corners of the cell, slot = 4*di + 2*dj + dk (:1932-1946)
+        if (lane < 24) {
+          const int n = lane / 3, d = lane - 3 * n;
+          sB[lane] = __ldg(bT + 3 * cornerLocalNumber(m, ic + ((n >> 2) & 1), jc + ((n >> 1) & 1), kc + (n & 1)) + d);
+        }
+      } else {
+        for (int e = lane; e < 81; e += 32) {
+          const int n = e / 3, d = e - 3 * n;
+          const int di = n % 3 - 1, dj = (n / 3) % 3 - 1, dk = n / 9 - 1;
+          sB[e] = __ldg(bT + 3 * centerLocalNumber(m, ic + di, jc + dj, kc + dk) + d);
+        }
       }
     }
     const double invV = lg.invV;
@@ -180,7 +189,21 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
         // B at the particle: cell-centred trilinear stencil on B_cur (:2100-2129); relative to this cell the
         // stencil cells are -1/0 (particle in the lower half) or 0/+1 (upper half) per dimension
         double B0 = 0.0, B1 = 0.0, B2 = 0.0;
-        {
+        if (kCornerB) {
+          // CornerBased::InitStencil on B_cur (:2102-2129): the trilinear corner weights (they sum to 1 within 2 ulp,
+          // Normalize() changes B by <= 3e-16 relative)
+          const double X0 = 1.0 - xl[0], X1 = xl[0], Y0 = 1.0 - xl[1], Y1 = xl[1], Z0 = 1.0 - xl[2], Z1 = xl[2];
+          const double b00 = X0 * Y0, b01 = X0 * Y1, b10 = X1 * Y0, b11 = X1 * Y1;
+          const double ws[8] = {b00 * Z0, b00 * Z1, b01 * Z0, b01 * Z1, b10 * Z0, b10 * Z1, b11 * Z0, b11 * Z1};
+#pragma unroll
+          for (int s = 0; s < 8; s++) {
+            B0 = fma(ws[s], sB[3 * s], B0);
+            B1 = fma(ws[s], sB[3 * s + 1], B1);
+            B2 = fma(ws[s], sB[3 * s + 2], B2);
+          }
+          const double sc = sp.B_conv * invc;
+          B0 *= sc, B1 *= sc, B2 *= sc;
+        } else {
           int o[3];
           double w[3];
 #pragma unroll
@@ -386,7 +409,8 @@ void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const
   cudaMemsetAsync(M, 0, sizeof(double) * 243 * (size_t)m.nCorners, s);
   cudaMemsetAsync(energy, 0, sizeof(double), s);
   cudaMemsetAsync(cflBits, 0, sizeof(unsigned long long) * AMPS_GPU_MAX_SPECIES, s);
-  deposit_kernel<<<nSM * DEP_CTAS_PER_SM, DEP_THREADS, 0, s>>>(m, sp, p, cellStart, bCurTile, J, M);
+  if (sp.bMode == AMPS_B_CORNER_BASED) deposit_kernel<true><<<nSM * DEP_CTAS_PER_SM, DEP_THREADS, 0, s>>>(m, sp, p, cellStart, bCurTile, J, M);
+  else deposit_kernel<false><<<nSM * DEP_CTAS_PER_SM, DEP_THREADS, 0, s>>>(m, sp, p, cellStart, bCurTile, J, M);
   diag_kernel<<<nSM * 4, 256, 0, s>>>(m, sp, p, cellStart, energy, cflBits);
   (*launches) += 2;
 }

@@ -82,7 +82,7 @@ void launch_division_selftest(const double *a, const double *b, int n, unsigned 
 // ------------------------------------------------------------------------------------------------
 // a2: gather unique-node fields into per-leaf tiles (incl. ghost layers); missing node -> 0
 // ------------------------------------------------------------------------------------------------
-__global__ void stage_tiles_kernel(DevMesh m, const double *__restrict__ E_half, const double *__restrict__ B_prev, const double *__restrict__ B_cur,
+__global__ void stage_tiles_kernel(DevMesh m, bool cornerB, const double *__restrict__ E_half, const double *__restrict__ B_prev, const double *__restrict__ B_cur,
                                    double *__restrict__ eTile, double *__restrict__ bPrevTile, double *__restrict__ bCurTile) {
   const int leaf = blockIdx.x;
   if (E_half) {
@@ -95,13 +95,16 @@ __global__ void stage_tiles_kernel(DevMesh m, const double *__restrict__ E_half,
       dst[3 * i] = a, dst[3 * i + 1] = b, dst[3 * i + 2] = c;
     }
   }
-  const int *cuid = m.centerUid + (size_t)leaf * m.nCenterLocal;
+  // B lives on the centre nodes, or on the corner nodes with _PIC_FIELD_SOLVER_B_CORNER_BASED_ (OffsetB_corner,
+  // pic_field_solver_ecsim.cpp:534-538)
+  const int *cuid = cornerB ? m.cornerUid + (size_t)leaf * m.nCornerLocal : m.centerUid + (size_t)leaf * m.nCenterLocal;
+  const int nLocal = cornerB ? m.nCornerLocal : m.nCenterLocal;
   for (int pass = 0; pass < 2; pass++) {
     const double *src = pass ? B_cur : B_prev;
     double *dst = (pass ? bCurTile : bPrevTile);
     if (!src) continue;
     dst += (size_t)leaf * m.bTileStride;
-    for (int i = threadIdx.x; i < m.nCenterLocal; i += blockDim.x) {
+    for (int i = threadIdx.x; i < nLocal; i += blockDim.x) {
       int u = cuid[i];
       double a = 0.0, b = 0.0, c = 0.0;
       if (u >= 0) a = src[3 * (size_t)u], b = src[3 * (size_t)u + 1], c = src[3 * (size_t)u + 2];
@@ -110,9 +113,9 @@ __global__ void stage_tiles_kernel(DevMesh m, const double *__restrict__ E_half,
   }
 }
 
-void launch_stage_tiles(const DevMesh &m, const double *E_half, const double *B_prev, const double *B_cur, double *eTile, double *bPrevTile,
-                        double *bCurTile, cudaStream_t s) {
-  stage_tiles_kernel<<<m.nLeaves, 256, 0, s>>>(m, E_half, B_prev, B_cur, eTile, bPrevTile, bCurTile);
+void launch_stage_tiles(const DevMesh &m, bool cornerB, const double *E_half, const double *B_prev, const double *B_cur, double *eTile,
+                        double *bPrevTile, double *bCurTile, cudaStream_t s) {
+  stage_tiles_kernel<<<m.nLeaves, 256, 0, s>>>(m, cornerB, E_half, B_prev, B_cur, eTile, bPrevTile, bCurTile);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -124,7 +127,7 @@ struct BlockConst {
   double qdt2m[AMPS_GPU_MAX_SPECIES], dt[AMPS_GPU_MAX_SPECIES];
 };
 
-template <bool kSmemTiles>
+template <bool kSmemTiles, bool kCornerB>
 __global__ void __launch_bounds__(256, 2) move_lapenta_kernel(DevMesh m, DevSpecies sp, ParticleSoA p, const int *__restrict__ cellStart,
                                                           const double *__restrict__ eTileG, const double *__restrict__ bTileG,
                                                           int *__restrict__ cellCount, DevMoveStats *__restrict__ stats, int slices,
@@ -259,10 +262,16 @@ __global__ void __launch_bounds__(256, 2) move_lapenta_kernel(DevMesh m, DevSpec
         E[0] += w[s] * t[0];
         E[1] += w[s] * t[1];
         E[2] += w[s] * t[2];
+        if (kCornerB) {  // _PIC_FIELD_SOLVER_B_CORNER_BASED_: same stencil on the corner B (:952-965)
+          const double *tb = sB + 3 * nd;
+          B[0] += w[s] * tb[0];
+          B[1] += w[s] * tb[1];
+          B[2] += w[s] * tb[2];
+        }
       }
     }
     // ---- a4: cell-centred linear stencil for B (uniform / same-level branch) ----
-    {
+    if (!kCornerB) {
       double qLoc[3];
       div_rn3(off, span, rSpan, blockOk, qLoc);  // (x-xmin)/(xmax-xmin), :278-280
       const double iLoc = qLoc[0] * m.N[0];
@@ -435,15 +444,22 @@ void launch_move_lapenta(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, 
                          long long exitCap, cudaStream_t s) {
   const size_t smem = (size_t)(m.eTileStride + m.bTileStride) * sizeof(double);
   const int grid = m.nLeaves * slices;
+  const bool cornerB = sp.bMode == AMPS_B_CORNER_BASED;
   if (smem <= 200 * 1024) {
     static bool attrSet = false;
     if (!attrSet) {
-      cudaFuncSetAttribute(move_lapenta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(move_lapenta_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(move_lapenta_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attrSet = true;
     }
-    move_lapenta_kernel<true><<<grid, 256, smem, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap);
+    if (cornerB)
+      move_lapenta_kernel<true, true><<<grid, 256, smem, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap);
+    else
+      move_lapenta_kernel<true, false><<<grid, 256, smem, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap);
+  } else if (cornerB) {
+    move_lapenta_kernel<false, true><<<grid, 256, 0, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap);
   } else {
-    move_lapenta_kernel<false><<<grid, 256, 0, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap);
+    move_lapenta_kernel<false, false><<<grid, 256, 0, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap);
   }
 }
 

@@ -63,6 +63,9 @@ class FlatMesh:
     def leaf_xmax(self):
         return self.arrays["node_xmax"].reshape(-1, 3)[self.arrays["leaf_node"]]
 
+    def leaf_level(self):
+        return self.arrays["node_level"][self.arrays["leaf_node"]]
+
     def real_leaves(self):
         """leaves that hold particles on this rank (used, not periodic ghosts, owned)."""
         fl = self.arrays["node_flags"][self.arrays["leaf_node"]]

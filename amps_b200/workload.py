@@ -22,24 +22,60 @@ def species_tables(ppc, dt=1.0, dx=1.0):
     return charge, mass, (wgt, wgt)
 
 
-def box_fields(mesh, E_amp=0.0):
-    """E_half on unique corners, B on unique centres.  E_amp != 0 adds a smooth test field."""
+def box_fields(mesh, E_amp=0.0, b_on_corners=False):
+    """E_half on unique corners, B on unique centres (or on the corners for _PIC_FIELD_SOLVER_B_CORNER_BASED_).
+    E_amp != 0 adds a smooth test field."""
     L = mesh.user_xmax - mesh.user_xmin
     xc = mesh.corner_x
-    xb = mesh.center_x
+    xb = mesh.corner_x if b_on_corners else mesh.center_x
     E = np.zeros((mesh.n_corners, 3))
     if E_amp != 0.0:
         ph = 2.0 * np.pi * (xc - mesh.user_xmin[None, :]) / L[None, :]
         E[:, 0] = E_amp * np.sin(ph[:, 1]) * np.cos(ph[:, 2])
         E[:, 1] = E_amp * np.sin(ph[:, 2]) * np.cos(ph[:, 0])
         E[:, 2] = E_amp * np.sin(ph[:, 0]) * np.cos(ph[:, 1])
-    B = np.zeros((mesh.n_centers, 3))
+    B = np.zeros((xb.shape[0], 3))
     B[:, 1] = 0.04 + 0.004 * np.sin(2.0 * np.pi * (xb[:, 0] - mesh.user_xmin[0]) / L[0])
     if E_amp != 0.0:  # make all B components and gradients non-trivial for parity tests
         ph = 2.0 * np.pi * (xb - mesh.user_xmin[None, :]) / L[None, :]
         B[:, 0] = 0.01 * np.cos(ph[:, 1])
         B[:, 2] = 0.02 * np.sin(ph[:, 1] + ph[:, 2])
     return E, B
+
+
+def amr_sphere_box(n_blocks, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), radii=(12.0, 6.0), rank=0, n_ranks=1, decomp=None):
+    """BASELINE config 4 geometry (scaled by the caller): open box [0,n)^3 of unit base cells, one more refinement level
+    inside every sphere radii[l] (in base cells) about the centre; outer boundary = DELETE."""
+    n_blocks = np.asarray(n_blocks, dtype=np.int64)
+    N = np.asarray(block_cells, dtype=np.int64)
+    hi = (n_blocks * N).astype(np.float64)
+    ctr = 0.5 * hi
+
+    def refine(level, lo, up):
+        if level >= len(radii):
+            return False
+        near = np.clip(ctr, lo, up)  # closest point of the block to the centre
+        return float(np.linalg.norm(near - ctr)) < radii[level]
+
+    from . import mesh as meshmod
+    return meshmod.build_mesh((0.0, 0.0, 0.0), tuple(hi), tuple(int(v) for v in n_blocks), block_cells, ghost_cells, periodic=False,
+                              refine=refine, max_level=len(radii), rank=rank, n_ranks=n_ranks, decomp=decomp)
+
+
+def maxwellian_amr(mesh, ppc_by_level, seed=100, drift=(0.02, 0.0, 0.0)):
+    """"mixed ppc": ppc_by_level[l] particles per cell and species on the leaves of level l; w_corr keeps the
+    number density uniform (cell volume 8^-l, fewer particles per cell)."""
+    lev = mesh.leaf_level()
+    parts = []
+    for l, ppc in enumerate(ppc_by_level):
+        leaves = np.nonzero(lev == l)[0]
+        if len(leaves) == 0:
+            continue
+        x, v, w, sp, cells = maxwellian_box(mesh, ppc, seed=seed + 7919 * l, drift=drift, leaves=leaves)
+        w *= (ppc_by_level[0] / ppc) / 8.0 ** l
+        parts.append((x, v, w, sp, cells))
+    return (np.concatenate([p[0] for p in parts], axis=1), np.concatenate([p[1] for p in parts], axis=1), np.concatenate([p[2] for p in parts]),
+            np.concatenate([p[3] for p in parts]), np.concatenate([p[4] for p in parts]))
 
 
 def maxwellian_box(mesh, ppc, seed=100, drift=(0.0, 0.0, 0.0), leaves=None, chunk_cells=1 << 15):

@@ -36,6 +36,7 @@ const int OffsetE_HalfTimeStep_d = 3;  // in doubles
 const int JxOffsetIndex = 6;
 const int MassMatrixOffsetIndex = 9;
 const int CornerDataLength = 252;
+const int OffsetB_corner_d = 252;  // _PIC_FIELD_SOLVER_B_CORNER_BASED_: 6 more doubles per corner, B_cur[0:3] B_prev[3:6] (:534-538)
 const int CurrentBOffset_d = 0;
 const int PrevBOffset_d = 3;
 const int BackgroundE_d = 6;   // coupler table: DATAFILE::Offset::ElectricField
@@ -462,6 +463,17 @@ struct oracle_ctx {
   }
   void SetBlock_B(double *B_C, cTreeNode *node) const {
     if (!node->block) return;
+    if (cfg.b_mode == AMPS_B_CORNER_BASED) {  // pic_mover.cpp:106-118: block corners only, no ghost layer
+      for (int k = 0; k <= _BLOCK_CELLS_Z_; k++)
+        for (int j = 0; j <= _BLOCK_CELLS_Y_; j++)
+          for (int i = 0; i <= _BLOCK_CELLS_X_; i++) {
+            int LocalCornerId = _getCornerNodeLocalNumber(i, j, k);
+            if (!node->block->cornerNodes[LocalCornerId]) continue;
+            double *ptr = node->block->cornerNodes[LocalCornerId]->data + OffsetB_corner_d + PrevBOffset_d;
+            memcpy(&B_C[LocalCornerId * 3], ptr, 3 * sizeof(double));
+          }
+      return;
+    }
     for (int k = -_GHOST_CELLS_Z_; k < _BLOCK_CELLS_Z_ + _GHOST_CELLS_Z_; k++)
       for (int j = -_GHOST_CELLS_Y_; j < _BLOCK_CELLS_Y_ + _GHOST_CELLS_Y_; j++)
         for (int i = -_GHOST_CELLS_X_; i < _BLOCK_CELLS_X_ + _GHOST_CELLS_X_; i++) {
@@ -1720,7 +1732,7 @@ struct oracle_ctx {
             if (cfg.b_mode == AMPS_B_CENTER_BASED)
               B_temp = B_Center[LocalCellID];
             else
-              B_temp = block->cornerNodes[LocalCellID]->data + CornerDataLength;  // corner-B extension slot (unused in centre mode)
+              B_temp = block->cornerNodes[LocalCellID]->data + OffsetB_corner_d + CurrentBOffset_d;  // B_corner[LocalCellID] (:1932-1946)
             for (int idim = 0; idim < 3; idim++) B[idim] += Weight * B_temp[idim];
           }
 
@@ -1863,7 +1875,7 @@ oracle_ctx *oracle_create(const amps_gpu_config *cfg, const amps_gpu_mesh *m) {
 
   // unique node pools
   o->n_corners = m->n_corners, o->n_centers = m->n_centers;
-  const int cornerLen = CornerDataLength + 3;  // +3: optional corner-B slot
+  const int cornerLen = CornerDataLength + 6;  // + corner B_cur, B_prev
   o->cornerData.assign((size_t)m->n_corners * cornerLen, 0.0);
   o->centerData.assign((size_t)m->n_centers * CenterDataLength, 0.0);
   o->cornerPool = std::vector<cCornerNode>(m->n_corners);
@@ -1954,6 +1966,13 @@ int64_t oracle_particle_count(const oracle_ctx *o) { return o->NAllPart; }
 void oracle_set_fields(oracle_ctx *o, const double *E_half, const double *B_prev, const double *B_cur) {
   if (E_half)
     for (int i = 0; i < o->n_corners; i++) memcpy(o->cornerPool[i].data + OffsetE_HalfTimeStep_d, E_half + 3 * (size_t)i, 24);
+  if (o->cfg.b_mode == AMPS_B_CORNER_BASED) {  // B_prev, B_cur are [n_corners][3]
+    if (B_prev)
+      for (int i = 0; i < o->n_corners; i++) memcpy(o->cornerPool[i].data + OffsetB_corner_d + PrevBOffset_d, B_prev + 3 * (size_t)i, 24);
+    if (B_cur)
+      for (int i = 0; i < o->n_corners; i++) memcpy(o->cornerPool[i].data + OffsetB_corner_d + CurrentBOffset_d, B_cur + 3 * (size_t)i, 24);
+    return;
+  }
   if (B_prev)
     for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + PrevBOffset_d, B_prev + 3 * (size_t)i, 24);
   if (B_cur)

@@ -34,21 +34,30 @@ def rel_scaled(a, b):
 
 
 def make_case(n_cells=(16, 16, 16), ppc=8, seed=3, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), E_amp=0.01, dt=1.0, vscale=1.0,
-              periodic=True, extra_capacity=0, boundary_mode=0):
-    if periodic:
+              periodic=True, extra_capacity=0, boundary_mode=0, b_mode=0, amr_radii=None, ppc_by_level=None):
+    if amr_radii is not None:  # BASELINE config 4 (scaled): sphere-refined open box, mixed ppc, drifting Maxwellian
+        nb = [n_cells[d] // block_cells[d] for d in range(3)]
+        m = workload.amr_sphere_box(nb, block_cells, ghost_cells, radii=amr_radii)
+        periodic = False
+    elif periodic:
         m = meshmod.uniform_periodic_box(n_cells, block_cells, ghost_cells)
     else:
         nb = [n_cells[d] // block_cells[d] for d in range(3)]
         m = meshmod.build_mesh((0.0, 0.0, 0.0), tuple(float(c) for c in n_cells), nb, block_cells, ghost_cells, periodic=False)
     charge, mass, wgt = workload.species_tables(ppc, dt)
-    x, v, w, sp, cells = workload.maxwellian_box(m, ppc, seed=seed)
+    if amr_radii is not None:
+        x, v, w, sp, cells = workload.maxwellian_amr(m, ppc_by_level or (ppc,) * (len(amr_radii) + 1), seed=seed)
+    else:
+        x, v, w, sp, cells = workload.maxwellian_box(m, ppc, seed=seed)
+        w[:] = 1.0
     v *= vscale
     rng = np.random.default_rng(seed + 1)
-    w = rng.uniform(0.5, 1.5, size=w.shape)  # exercise the individual weight correction
+    w = w * rng.uniform(0.5, 1.5, size=w.shape)  # exercise the individual weight correction
     cfg = api.make_config(block_cells, ghost_cells, charge, mass, wgt, dt, periodic=periodic, capacity=x.shape[1] + extra_capacity + 16,
                           boundary_mode=boundary_mode)
     cfg.exit_record_capacity = x.shape[1]
-    E, B = workload.box_fields(m, E_amp=E_amp)
+    cfg.b_mode = b_mode
+    E, B = workload.box_fields(m, E_amp=E_amp, b_on_corners=(b_mode == _capi.B_CORNER_BASED))
     Bcur = B * 1.01 + 0.001  # B_cur != B_prev so that a mix-up of the two shows
     return m, cfg, (x, v, w, sp, cells), (E, B, Bcur)
 
