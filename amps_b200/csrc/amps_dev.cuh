@@ -26,7 +26,7 @@ struct LeafGeo {
   int real;   // paired real leaf of a periodic ghost leaf, else -1
   int face;   // bit f: no neighbour across face f
   int node;
-  int pad;
+  int neib;   // minNeibRefinmentLevel (low 16 bits, signed) | maxNeibRefinmentLevel << 16   (meshAMRgeneric.h:829)
   // derived per-leaf constants of the deposit (host computed at mesh upload)
   double dxc[3];     // (xmax-xmin)/N                       CornerBased::InitStencil :1086-1088
   double invdxc[3];  // 1/dxc
@@ -111,23 +111,26 @@ void launch_pack_corners(const int *uids, int n, const double *J, const double *
 void launch_add_corners(const int *uids, int n, double *J, double *M, const double *buf, cudaStream_t s);
 void launch_stage_background(const DevMesh &m, const double *E, const double *B, double *tile, cudaStream_t s);
 void launch_move_relativistic_boris(const DevMesh &m, const DevSpecies &sp, int interp, int backward, double c, double rSphere, long long exitCap,
-                                    ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, int *cellCount, DevMoveStats *stats,
-                                    amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s);
+                                    ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *uE, const double *uB,
+                                    int *cellCount, DevMoveStats *stats, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount,
+                                    cudaStream_t s);
 void launch_move_boris(const DevMesh &m, const DevSpecies &sp, int interp, int backward, double c, double rSphere, long long exitCap, double gravityGM,
-                       ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, int *cellCount, DevMoveStats *stats,
-                       amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s);
+                       ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *uE, const double *uB, int *cellCount,
+                       DevMoveStats *stats, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s);
 void launch_stage_center_table(const DevMesh &m, int nVar, const double *var, double *tile, cudaStream_t s);
 void launch_gc_magnetic_moment_init(const DevMesh &m, const DevSpecies &sp, int interp, ParticleSoA p, const int *nSlots, long long nUpper,
-                                    const double *bgTile, DevMoveStats *stats, cudaStream_t s);
+                                    const double *bgTile, const double *uE, const double *uB, DevMoveStats *stats, cudaStream_t s);
 void launch_move_guiding_center(const DevMesh &m, const DevSpecies &sp, int order, int interp, int idealMhd, double rSphere, long long exitCap,
-                                ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *gradBTile, int *cellCount,
-                                DevMoveStats *stats, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s);
+                                ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *gradBTile, const double *uE,
+                                const double *uB, const double *uGradB, int *cellCount, DevMoveStats *stats, amps_gpu_exit_record *exitBuf,
+                                unsigned long long *exitCount, cudaStream_t s);
 void launch_magnetic_moment_init(const DevMesh &m, const DevSpecies &sp, int interp, double c, ParticleSoA p, const int *nSlots, long long nUpper,
-                                 const double *bgTile, DevMoveStats *stats, cudaStream_t s);
+                                 const double *bgTile, const double *uE, const double *uB, DevMoveStats *stats, cudaStream_t s);
 void launch_magnetic_moment_set(ParticleSoA p, const int *nSlots, long long nUpper, const double *muByPtr, long long nMu, cudaStream_t s);
 void launch_move_relativistic_gca(const DevMesh &m, const DevSpecies &sp, int interp, double c, double rSphere, long long exitCap, ParticleSoA p,
-                                  const int *nSlots, long long nUpper, const double *bgTile, const double *gcaTile, int *cellCount, DevMoveStats *stats,
-                                  amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s);
+                                  const int *nSlots, long long nUpper, const double *bgTile, const double *gcaTile, const double *uE, const double *uB,
+                                  const double *uVar, int *cellCount, DevMoveStats *stats, amps_gpu_exit_record *exitBuf,
+                                  unsigned long long *exitCount, cudaStream_t s);
 void launch_division_selftest(const double *a, const double *b, int n, unsigned long long *out, cudaStream_t s);
 
 }  // namespace amps

@@ -326,7 +326,53 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
     g.real = mesh->leaf_real[l];
     g.face = mesh->leaf_face_boundary[l];
     g.node = n;
-    g.pad = 0;
+    {
+      // SetNeibRefinmentLevelLimits (meshAMRgeneric.h:1018-1048): levels of the 24 face, 8 corner and 24 edge neighbours
+      // found by lattice probes (neibNodeFace/Corner/Edge, :505-725)
+      int mn = -1, mx = -1;
+      auto probe = [&](int ix0, int ix1, int ix2) {
+        if (ix0 < 0 || ix1 < 0 || ix2 < 0) return;
+        const int r0 = ix0 >> m.L, r1 = ix1 >> m.L, r2 = ix2 >> m.L;
+        if (r0 >= m.nRoot[0] || r1 >= m.nRoot[1] || r2 >= m.nRoot[2]) return;
+        int q = mesh->root_node[r0 + m.nRoot[0] * (r1 + m.nRoot[1] * r2)];
+        while (true) {
+          const int h = mesh->node_isize[q] / 2;
+          const int i = (ix0 - mesh->node_imin[3 * q] < h) ? 0 : 1, j = (ix1 - mesh->node_imin[3 * q + 1] < h) ? 0 : 1,
+                    k = (ix2 - mesh->node_imin[3 * q + 2] < h) ? 0 : 1;
+          const int t = mesh->node_child[8 * q + i + 2 * (j + 2 * k)];
+          if (t < 0) break;
+          q = t;
+        }
+        const int lv = mesh->node_level[q];
+        if (mn == -1 || mn > lv) mn = lv;
+        if (mx < lv) mx = lv;
+      };
+      const int S = g.isize, h = (S > 1) ? S / 2 : 0;
+      // offsets along one direction: -1 (beyond the low side), S (beyond the high side), 0 and S/2 (the two halves inside)
+      const int out[2] = {-1, S}, in[2] = {0, h};
+      for (int dn = 0; dn < 3; dn++) {  // faces: normal dn, 2 sides x 2 x 2 sub-faces
+        const int t0 = (dn + 1) % 3, t1 = (dn + 2) % 3;
+        for (int sd = 0; sd < 2; sd++)
+          for (int a = 0; a < 2; a++)
+            for (int b = 0; b < 2; b++) {
+              int ix[3];
+              ix[dn] = g.imin[dn] + out[sd], ix[t0] = g.imin[t0] + in[a], ix[t1] = g.imin[t1] + in[b];
+              probe(ix[0], ix[1], ix[2]);
+            }
+      }
+      for (int c = 0; c < 8; c++) probe(g.imin[0] + out[c & 1], g.imin[1] + out[(c >> 1) & 1], g.imin[2] + out[(c >> 2) & 1]);
+      for (int de = 0; de < 3; de++) {  // edges along de: 4 transverse corners x 2 segments
+        const int t0 = (de + 1) % 3, t1 = (de + 2) % 3;
+        for (int a = 0; a < 2; a++)
+          for (int b = 0; b < 2; b++)
+            for (int sg = 0; sg < 2; sg++) {
+              int ix[3];
+              ix[de] = g.imin[de] + in[sg], ix[t0] = g.imin[t0] + out[a], ix[t1] = g.imin[t1] + out[b];
+              probe(ix[0], ix[1], ix[2]);
+            }
+      }
+      g.neib = (mn & 0xffff) | ((mx & 0xffff) << 16);
+    }
     {
       double vol = 1, d2 = 0;
       for (int d = 0; d < 3; d++) {
@@ -425,6 +471,8 @@ int amps_gpu_background_upload(amps_gpu_ctx *ctx, const double *E_center, const 
     if ((rc = dev_alloc(ctx, &ctx->d_bgB, (size_t)3 * m.nCenters))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_bgTile, (size_t)m.nLeaves * m.nCenterLocal * 6))) return rc;
     CK(cudaMemsetAsync(ctx->d_bgTile, 0, sizeof(double) * (size_t)m.nLeaves * m.nCenterLocal * 6, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_bgE, 0, sizeof(double) * 3 * (size_t)m.nCenters, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_bgB, 0, sizeof(double) * 3 * (size_t)m.nCenters, ctx->stream));
   }
   if (E_center) CK(cudaMemcpyAsync(ctx->d_bgE, E_center, sizeof(double) * 3 * (size_t)m.nCenters, cudaMemcpyHostToDevice, ctx->stream));
   if (B_center) CK(cudaMemcpyAsync(ctx->d_bgB, B_center, sizeof(double) * 3 * (size_t)m.nCenters, cudaMemcpyHostToDevice, ctx->stream));
@@ -481,10 +529,10 @@ int amps_gpu_magnetic_moment_init(amps_gpu_ctx *ctx, int mover_id) {
   CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevMoveStats), ctx->stream));
   if (mover_id == AMPS_MOVER_RELATIVISTIC_GCA)
     launch_magnetic_moment_init(ctx->dm, ctx->sp, ctx->cfg.coupler_interpolation, ctx->cfg.speed_of_light, ctx->buf[ctx->cur], ctx->d_n + ctx->cur,
-                                ctx->nUpper, ctx->d_bgTile, ctx->d_stats, ctx->stream);
+                                ctx->nUpper, ctx->d_bgTile, ctx->d_bgE, ctx->d_bgB, ctx->d_stats, ctx->stream);
   else
     launch_gc_magnetic_moment_init(ctx->dm, ctx->sp, ctx->cfg.coupler_interpolation, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper,
-                                   ctx->d_bgTile, ctx->d_stats, ctx->stream);
+                                   ctx->d_bgTile, ctx->d_bgE, ctx->d_bgB, ctx->d_stats, ctx->stream);
   ctx->launches++;
   CK(cudaGetLastError());
   DevMoveStats h;
@@ -727,7 +775,8 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   if (mover_id == AMPS_MOVER_BORIS) {
     launch_move_boris(m, ctx->sp, ctx->cfg.coupler_interpolation, ctx->cfg.backward_time_integration, ctx->cfg.speed_of_light,
                       ctx->cfg.internal_sphere_radius, ctx->cfg.exit_record_capacity, ctx->cfg.gravity_gm, ctx->buf[ctx->cur], ctx->d_n + ctx->cur,
-                      ctx->nUpper, ctx->d_bgTile, ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount, ctx->stream);
+                      ctx->nUpper, ctx->d_bgTile, ctx->d_bgE, ctx->d_bgB, ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount,
+                      ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
     ctx->sorted = false;
@@ -737,7 +786,7 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   if (mover_id == AMPS_MOVER_GC_FIRST_ORDER || mover_id == AMPS_MOVER_GC_SECOND_ORDER) {
     launch_move_guiding_center(m, ctx->sp, mover_id == AMPS_MOVER_GC_SECOND_ORDER ? 2 : 1, ctx->cfg.coupler_interpolation, ctx->cfg.ideal_mhd,
                                ctx->cfg.internal_sphere_radius, ctx->cfg.exit_record_capacity, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper,
-                               ctx->d_bgTile, ctx->d_gradBTile, ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount, ctx->stream);
+                               ctx->d_bgTile, ctx->d_gradBTile, ctx->d_bgE, ctx->d_bgB, ctx->d_gradBVar, ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
     ctx->sorted = false;
@@ -747,7 +796,7 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   if (mover_id == AMPS_MOVER_RELATIVISTIC_GCA) {
     launch_move_relativistic_gca(m, ctx->sp, ctx->cfg.coupler_interpolation, ctx->cfg.speed_of_light, ctx->cfg.internal_sphere_radius,
                                  ctx->cfg.exit_record_capacity, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper, ctx->d_bgTile, ctx->d_gcaTile,
-                                 ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount, ctx->stream);
+                                 ctx->d_bgE, ctx->d_bgB, ctx->d_gcaVar, ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
     ctx->sorted = false;
@@ -757,7 +806,8 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   if (mover_id == AMPS_MOVER_RELATIVISTIC_BORIS) {
     launch_move_relativistic_boris(m, ctx->sp, ctx->cfg.coupler_interpolation, ctx->cfg.backward_time_integration, ctx->cfg.speed_of_light,
                                    ctx->cfg.internal_sphere_radius, ctx->cfg.exit_record_capacity, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper,
-                                   ctx->d_bgTile, ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount, ctx->stream);
+                                   ctx->d_bgTile, ctx->d_bgE, ctx->d_bgB, ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount,
+                                   ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
     ctx->sorted = false;

@@ -68,10 +68,35 @@ __device__ __forceinline__ bool find_cell_index(const DevMesh &m, const double x
   return true;
 }
 
+}  // namespace amps
+#include "cplr_stencil.cuh"
+namespace amps {
+
+// unique-node tables of the coupler (read by the AMR stencil, whose cells belong to several blocks)
+struct CplrUnique {
+  const double *E, *B;  // [nCenters][3]
+};
+template <int K>
+__device__ __forceinline__ void cplr_gather_unique(const BgStencil &st, const double *__restrict__ U, double out[K]) {
+  for (int q = 0; q < K; q++) out[q] = 0.0;
+  for (int s = 0; s < st.n; s++) {
+    const double *t = U + (size_t)K * st.nd[s];
+    for (int q = 0; q < K; q++) out[q] += st.w[s] * t[q];
+  }
+}
+__device__ __noinline__ bool background_fields_amr(const DevMesh &m, const CplrUnique &U, const double x[3], int leaf, double E[3], double B[3]) {
+  BgStencil st;
+  if (!cplr_linear_stencil_amr(m, x, leaf, st) || st.n == 0 || st.overflow) return false;
+  cplr_gather_unique<3>(st, U.E, E);
+  cplr_gather_unique<3>(st, U.B, B);
+  return true;
+}
+
 // E, B at x inside leaf `leaf` through the coupler stencil; false = the reference would exit()
-__device__ __forceinline__ bool background_fields(const DevMesh &m, int interp, const double *__restrict__ tile, const double x[3], int leaf,
-                                                  double E[3], double B[3]) {
+__device__ __forceinline__ bool background_fields(const DevMesh &m, int interp, const double *__restrict__ tile, const CplrUnique &U,
+                                                  const double x[3], int leaf, double E[3], double B[3]) {
   const LeafGeo &lg = m.leaf[leaf];
+  if (interp == AMPS_CPLR_CELL_CENTERED_LINEAR && !leaf_single_level(lg)) return background_fields_amr(m, U, x, leaf, E, B);
   const double *T = tile + (size_t)leaf * m.nCenterLocal * 6;
   E[0] = E[1] = E[2] = 0.0, B[0] = B[1] = B[2] = 0.0;
   if (interp == AMPS_CPLR_CELL_CENTERED_LINEAR) {
@@ -141,6 +166,7 @@ struct TpParams {
   int interp, backward, boundaryMode;
   double c, rSphere;
   long long exitCap;
+  CplrUnique U;
 };
 
 __global__ void __launch_bounds__(128) move_relativistic_boris_kernel(DevMesh m, DevSpecies sp, TpParams tp, ParticleSoA p, const int *__restrict__ nSlots,
@@ -175,7 +201,7 @@ __global__ void __launch_bounds__(128) move_relativistic_boris_kernel(DevMesh m,
       while (dtTotalIn > 0.0) {
         double gamma = 1.0 / sqrt(1.0 - (vInit[0] * vInit[0] + vInit[1] * vInit[1] + vInit[2] * vInit[2]) / (SpeedOfLight * SpeedOfLight));
         double E[3], B[3];
-        if (!background_fields(m, tp.interp, bgTile, xInit, leaf, E, B)) {
+        if (!background_fields(m, tp.interp, bgTile, tp.U, xInit, leaf, E, B)) {
           outcome = 3;
           break;
         }
@@ -352,10 +378,12 @@ __global__ void __launch_bounds__(128) move_relativistic_boris_kernel(DevMesh m,
 }
 
 void launch_move_relativistic_boris(const DevMesh &m, const DevSpecies &sp, int interp, int backward, double c, double rSphere, long long exitCap,
-                                    ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, int *cellCount, DevMoveStats *stats,
-                                    amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s) {
+                                    ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *uE, const double *uB,
+                                    int *cellCount, DevMoveStats *stats, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount,
+                                    cudaStream_t s) {
   TpParams tp;
   tp.interp = interp, tp.backward = backward, tp.boundaryMode = sp.boundaryMode, tp.c = c, tp.rSphere = rSphere, tp.exitCap = exitCap;
+  tp.U.E = uE, tp.U.B = uB;
   long long g = (nUpper + 127) / 128;
   if (g < 1) g = 1;
   if (g > 148 * 32) g = 148 * 32;
@@ -398,7 +426,7 @@ __global__ void __launch_bounds__(128) move_boris_kernel(DevMesh m, DevSpecies s
         if (fieldLeaf < 0 || !find_cell_index(m, xInit, fn, ijk)) outcome = 3;
       }
       double E[3], B[3];
-      if (outcome == 0 && !background_fields(m, tp.interp, bgTile, xInit, fieldLeaf, E, B)) outcome = 3;
+      if (outcome == 0 && !background_fields(m, tp.interp, bgTile, tp.U, xInit, fieldLeaf, E, B)) outcome = 3;
       if (outcome == 0) {
         const double ElectricCharge = sp.charge[spec], mass = sp.mass[spec];
         if (ElectricCharge != 0.0) {
@@ -511,10 +539,11 @@ __global__ void __launch_bounds__(128) move_boris_kernel(DevMesh m, DevSpecies s
 }
 
 void launch_move_boris(const DevMesh &m, const DevSpecies &sp, int interp, int backward, double c, double rSphere, long long exitCap, double gravityGM,
-                       ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, int *cellCount, DevMoveStats *stats,
-                       amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s) {
+                       ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *uE, const double *uB, int *cellCount,
+                       DevMoveStats *stats, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s) {
   TpParams tp;
   tp.interp = interp, tp.backward = backward, tp.boundaryMode = sp.boundaryMode, tp.c = c, tp.rSphere = rSphere, tp.exitCap = exitCap;
+  tp.U.E = uE, tp.U.B = uB;
   long long g = (nUpper + 127) / 128;
   if (g < 1) g = 1;
   if (g > 148 * 32) g = 148 * 32;
@@ -542,13 +571,11 @@ void launch_stage_center_table(const DevMesh &m, int nVar, const double *var, do
 }
 
 // the coupler stencil at x inside `leaf` (same arithmetic as background_fields), kept for several gathers
-struct BgStencil {
-  double w[8];
-  int nd[8];
-  int n;
-};
 __device__ __forceinline__ bool background_stencil(const DevMesh &m, int interp, const double x[3], int leaf, BgStencil &st) {
   const LeafGeo &lg = m.leaf[leaf];
+  if (interp == AMPS_CPLR_CELL_CENTERED_LINEAR && !leaf_single_level(lg))
+    return cplr_linear_stencil_amr(m, x, leaf, st) && st.n > 0 && !st.overflow;
+  st.uid = 0, st.overflow = 0;
   if (interp == AMPS_CPLR_CELL_CENTERED_LINEAR) {
     const double iLoc = (x[0] - lg.xmin[0]) / (lg.xmax[0] - lg.xmin[0]) * m.N[0];
     const double jLoc = (x[1] - lg.xmin[1]) / (lg.xmax[1] - lg.xmin[1]) * m.N[1];
@@ -603,16 +630,19 @@ __device__ __forceinline__ bool background_stencil(const DevMesh &m, int interp,
   st.n = 1, st.w[0] = 1.0, st.nd[0] = centerLocalNumber(m, ijk[0], ijk[1], ijk[2]);
   return true;
 }
+// T = the leaf's tile (stride doubles per centre, value at +off); U = the unique-node table [nCenters][K] used when the
+// stencil holds unique ids (AMR)
 template <int K>
-__device__ __forceinline__ void background_gather(const BgStencil &st, const double *__restrict__ T, int stride, int off, double out[K]) {
+__device__ __forceinline__ void background_gather(const BgStencil &st, const double *__restrict__ T, int stride, int off,
+                                                  const double *__restrict__ U, double out[K]) {
   for (int q = 0; q < K; q++) out[q] = 0.0;
   for (int s = 0; s < st.n; s++) {
-    const double *t = T + (size_t)stride * st.nd[s] + off;
+    const double *t = st.uid ? U + (size_t)K * st.nd[s] : T + (size_t)stride * st.nd[s] + off;
     for (int q = 0; q < K; q++) out[q] += st.w[s] * t[q];
   }
 }
 
-__global__ void __launch_bounds__(128) magnetic_moment_init_kernel(DevMesh m, DevSpecies sp, int interp, double SpeedOfLight, ParticleSoA p,
+__global__ void __launch_bounds__(128) magnetic_moment_init_kernel(DevMesh m, DevSpecies sp, int interp, CplrUnique U, double SpeedOfLight, ParticleSoA p,
                                                                   const int *__restrict__ nSlots, const double *__restrict__ bgTile,
                                                                   DevMoveStats *__restrict__ stats) {
   const int n = *nSlots;
@@ -631,8 +661,8 @@ __global__ void __launch_bounds__(128) magnetic_moment_init_kernel(DevMesh m, De
     }
     const double *T = bgTile + (size_t)leaf * m.nCenterLocal * 6;
     double B[3], E[3];
-    background_gather<3>(st, T, 6, 3, B);
-    background_gather<3>(st, T, 6, 0, E);
+    background_gather<3>(st, T, 6, 3, U.B, B);
+    background_gather<3>(st, T, 6, 0, U.E, E);
     const double AbsB = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) + 1E-15;
     double vE[3];
     vE[0] = E[1] * B[2] - E[2] * B[1];
@@ -670,11 +700,13 @@ __global__ void __launch_bounds__(128) magnetic_moment_init_kernel(DevMesh m, De
   flush_move_counters(stats, 0, 0, 0, 0, 0, 0, nErr);
 }
 void launch_magnetic_moment_init(const DevMesh &m, const DevSpecies &sp, int interp, double c, ParticleSoA p, const int *nSlots, long long nUpper,
-                                 const double *bgTile, DevMoveStats *stats, cudaStream_t s) {
+                                 const double *bgTile, const double *uE, const double *uB, DevMoveStats *stats, cudaStream_t s) {
   long long g = (nUpper + 127) / 128;
   if (g < 1) g = 1;
   if (g > 148 * 32) g = 148 * 32;
-  magnetic_moment_init_kernel<<<(int)g, 128, 0, s>>>(m, sp, interp, c, p, nSlots, bgTile, stats);
+  CplrUnique U;
+  U.E = uE, U.B = uB;
+  magnetic_moment_init_kernel<<<(int)g, 128, 0, s>>>(m, sp, interp, U, c, p, nSlots, bgTile, stats);
 }
 
 __global__ void magnetic_moment_set_kernel(ParticleSoA p, const int *__restrict__ nSlots, const double *__restrict__ muByPtr, long long nMu) {
@@ -693,7 +725,7 @@ void launch_magnetic_moment_set(ParticleSoA p, const int *nSlots, long long nUpp
 
 __global__ void __launch_bounds__(128) move_relativistic_gca_kernel(DevMesh m, DevSpecies sp, TpParams tp, ParticleSoA p, const int *__restrict__ nSlots,
                                                                    const double *__restrict__ bgTile, const double *__restrict__ gcaTile,
-                                                                   int *__restrict__ cellCount, DevMoveStats *__restrict__ stats,
+                                                                   const double *__restrict__ uVar, int *__restrict__ cellCount, DevMoveStats *__restrict__ stats,
                                                                    amps_gpu_exit_record *__restrict__ exitBuf, unsigned long long *__restrict__ exitCount) {
   const int n = *nSlots;
   const int C = m.cellsPerBlock;
@@ -724,9 +756,9 @@ __global__ void __launch_bounds__(128) move_relativistic_gca_kernel(DevMesh m, D
       if (!background_stencil(m, tp.interp, xInit, startLeaf, st)) outcome = 3;
       else {
         double B[3], E[3], var15[15];
-        background_gather<3>(st, bgTile + (size_t)startLeaf * m.nCenterLocal * 6, 6, 3, B);
-        background_gather<3>(st, bgTile + (size_t)startLeaf * m.nCenterLocal * 6, 6, 0, E);
-        background_gather<15>(st, gcaTile + (size_t)startLeaf * m.nCenterLocal * 15, 15, 0, var15);
+        background_gather<3>(st, bgTile + (size_t)startLeaf * m.nCenterLocal * 6, 6, 3, tp.U.B, B);
+        background_gather<3>(st, bgTile + (size_t)startLeaf * m.nCenterLocal * 6, 6, 0, tp.U.E, E);
+        background_gather<15>(st, gcaTile + (size_t)startLeaf * m.nCenterLocal * 15, 15, 0, uVar, var15);
         const double *b_dot_grad_b = var15, *vE_dot_grad_b = var15 + 3, *b_dot_grad_vE = var15 + 6, *vE_dot_grad_vE = var15 + 9, *grad_kappaB = var15 + 12;
         const double bNorm = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]);
         double ePar = 0.0;
@@ -796,8 +828,8 @@ __global__ void __launch_bounds__(128) move_relativistic_gca_kernel(DevMesh m, D
       if (!background_stencil(m, tp.interp, xFinal, newLeaf, st)) outcome = 3;
       else {
         double B[3], E[3];
-        background_gather<3>(st, bgTile + (size_t)newLeaf * m.nCenterLocal * 6, 6, 3, B);
-        background_gather<3>(st, bgTile + (size_t)newLeaf * m.nCenterLocal * 6, 6, 0, E);
+        background_gather<3>(st, bgTile + (size_t)newLeaf * m.nCenterLocal * 6, 6, 3, tp.U.B, B);
+        background_gather<3>(st, bgTile + (size_t)newLeaf * m.nCenterLocal * 6, 6, 0, tp.U.E, E);
         const double bNorm = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]);
         if (bNorm > 0.0)  // otherwise bHat of the first stage stays, as in the reference
           for (int d = 0; d < 3; d++) bHat[d] = B[d] / bNorm;
@@ -867,14 +899,16 @@ __global__ void __launch_bounds__(128) move_relativistic_gca_kernel(DevMesh m, D
 }
 
 void launch_move_relativistic_gca(const DevMesh &m, const DevSpecies &sp, int interp, double c, double rSphere, long long exitCap, ParticleSoA p,
-                                  const int *nSlots, long long nUpper, const double *bgTile, const double *gcaTile, int *cellCount, DevMoveStats *stats,
-                                  amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s) {
+                                  const int *nSlots, long long nUpper, const double *bgTile, const double *gcaTile, const double *uE, const double *uB,
+                                  const double *uVar, int *cellCount, DevMoveStats *stats, amps_gpu_exit_record *exitBuf,
+                                  unsigned long long *exitCount, cudaStream_t s) {
   TpParams tp;
   tp.interp = interp, tp.backward = 0, tp.boundaryMode = sp.boundaryMode, tp.c = c, tp.rSphere = rSphere, tp.exitCap = exitCap;
+  tp.U.E = uE, tp.U.B = uB;
   long long g = (nUpper + 127) / 128;
   if (g < 1) g = 1;
   if (g > 148 * 32) g = 148 * 32;
-  move_relativistic_gca_kernel<<<(int)g, 128, 0, s>>>(m, sp, tp, p, nSlots, bgTile, gcaTile, cellCount, stats, exitBuf, exitCount);
+  move_relativistic_gca_kernel<<<(int)g, 128, 0, s>>>(m, sp, tp, p, nSlots, bgTile, gcaTile, uVar, cellCount, stats, exitBuf, exitCount);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -887,6 +921,7 @@ void launch_move_relativistic_gca(const DevMesh &m, const DevSpecies &sp, int in
 struct GcTables {
   const double *bg;     // [leaf][nCenterLocal][6]  E, B
   const double *gradB;  // [leaf][nCenterLocal][9]
+  const double *uE, *uB, *uGradB;  // unique-node tables (AMR stencils)
 };
 
 __device__ __forceinline__ bool gc_initiate_magnetic_moment(const DevMesh &m, const DevSpecies &sp, int interp, const GcTables &T, int spec,
@@ -894,7 +929,7 @@ __device__ __forceinline__ bool gc_initiate_magnetic_moment(const DevMesh &m, co
   BgStencil st;
   if (!background_stencil(m, interp, x, leaf, st)) return false;
   double B[3];
-  background_gather<3>(st, T.bg + (size_t)leaf * m.nCenterLocal * 6, 6, 3, B);
+  background_gather<3>(st, T.bg + (size_t)leaf * m.nCenterLocal * 6, 6, 3, T.uB, B);
   const double AbsB = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) + 1E-15;
   double v_par = 0.0, mu = 0.0;
   const double b[3] = {B[0] / AbsB, B[1] / AbsB, B[2] / AbsB};
@@ -919,9 +954,9 @@ __device__ __forceinline__ bool gc_motion(const DevMesh &m, const DevSpecies &sp
   if (!background_stencil(m, interp, x, leaf, st)) return false;
   double E[3], B[3], gradB[9];
   const double *tb = T.bg + (size_t)leaf * m.nCenterLocal * 6;
-  background_gather<3>(st, tb, 6, 0, E);
-  background_gather<3>(st, tb, 6, 3, B);
-  background_gather<9>(st, T.gradB + (size_t)leaf * m.nCenterLocal * 9, 9, 0, gradB);
+  background_gather<3>(st, tb, 6, 0, T.uE, E);
+  background_gather<3>(st, tb, 6, 3, T.uB, B);
+  background_gather<9>(st, T.gradB + (size_t)leaf * m.nCenterLocal * 9, 9, 0, T.uGradB, gradB);
   const double AbsB = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) + 1E-15;
   double b[3], gradAbsB[3];
   b[0] = B[0] / AbsB;
@@ -976,12 +1011,12 @@ __global__ void __launch_bounds__(128) gc_magnetic_moment_init_kernel(DevMesh m,
   flush_move_counters(stats, 0, 0, 0, 0, 0, 0, nErr);
 }
 void launch_gc_magnetic_moment_init(const DevMesh &m, const DevSpecies &sp, int interp, ParticleSoA p, const int *nSlots, long long nUpper,
-                                    const double *bgTile, DevMoveStats *stats, cudaStream_t s) {
+                                    const double *bgTile, const double *uE, const double *uB, DevMoveStats *stats, cudaStream_t s) {
   long long g = (nUpper + 127) / 128;
   if (g < 1) g = 1;
   if (g > 148 * 32) g = 148 * 32;
   GcTables T;
-  T.bg = bgTile, T.gradB = nullptr;
+  T.bg = bgTile, T.gradB = nullptr, T.uE = uE, T.uB = uB, T.uGradB = nullptr;
   gc_magnetic_moment_init_kernel<<<(int)g, 128, 0, s>>>(m, sp, interp, T, p, nSlots, stats);
 }
 
@@ -1033,7 +1068,7 @@ __global__ void __launch_bounds__(128) move_guiding_center_kernel(DevMesh m, Dev
         if (!background_stencil(m, tp.interp, x, startLeaf, st)) outcome = 3;  // the START block, as written (:713)
         else {
           double bFinal[3];
-          background_gather<3>(st, T.bg + (size_t)startLeaf * m.nCenterLocal * 6, 6, 3, bFinal);
+          background_gather<3>(st, T.bg + (size_t)startLeaf * m.nCenterLocal * 6, 6, 3, T.uB, bFinal);
           const double l0 = sqrt(bFinal[0] * bFinal[0] + bFinal[1] * bFinal[1] + bFinal[2] * bFinal[2]);
           if (l0 > 0.0) {
             const double l = 1.0 / l0;
@@ -1135,12 +1170,13 @@ __global__ void __launch_bounds__(128) move_guiding_center_kernel(DevMesh m, Dev
 }
 
 void launch_move_guiding_center(const DevMesh &m, const DevSpecies &sp, int order, int interp, int idealMhd, double rSphere, long long exitCap,
-                                ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *gradBTile, int *cellCount,
-                                DevMoveStats *stats, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s) {
+                                ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *gradBTile, const double *uE,
+                                const double *uB, const double *uGradB, int *cellCount, DevMoveStats *stats, amps_gpu_exit_record *exitBuf,
+                                unsigned long long *exitCount, cudaStream_t s) {
   TpParams tp;
   tp.interp = interp, tp.backward = 0, tp.boundaryMode = sp.boundaryMode, tp.c = 0.0, tp.rSphere = rSphere, tp.exitCap = exitCap;
   GcTables T;
-  T.bg = bgTile, T.gradB = gradBTile;
+  T.bg = bgTile, T.gradB = gradBTile, T.uE = uE, T.uB = uB, T.uGradB = uGradB;
   long long g = (nUpper + 127) / 128;
   if (g < 1) g = 1;
   if (g > 148 * 32) g = 148 * 32;

@@ -297,13 +297,17 @@ def build_mesh(xmin, xmax, n_blocks, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1
         enc = (key[:, :, 2] * (span[1] + 1) + key[:, :, 1]) * (span[0] + 1) + key[:, :, 0]
         return enc, valid, inside_block, key, span
 
+    amr = bool((level[gleaf_node] > 0).any())
+
     def uid_table(corner):
         enc, valid, inside_block, key, span = keys_for(corner)
         valid = valid & has_nodes[:, None]
-        if n_ranks == 1:
+        if n_ranks == 1 and not amr:
             # nodes that blocks really own; ghost-layer positions only resolve to such nodes
             pool = np.unique(enc[:, inside_block].ravel())
         else:
+            # AMR: the ghost cells of a block next to a coarser/finer one are nodes of their own (the reference
+            # allocates them per block and the coupler fills them, srcEarth/main_lib.cpp:686-800)
             # every node an own block's tile can touch is kept locally (its value arrives with the field upload)
             pool = np.unique(enc[valid])
         pos = np.searchsorted(pool, enc)

@@ -86,6 +86,7 @@ struct cTreeNode {
   cTreeNode *downNode[8];
   cTreeNode *upNode;
   int RefinmentLevel;
+  int minNeibRefinmentLevel, maxNeibRefinmentLevel;  // meshAMRgeneric.h:829, SetNeibRefinmentLevelLimits :1018-1048
   int Thread;
   bool IsUsedInCalculationFlag;
   bool IsGhostNodeFlag;
@@ -101,7 +102,11 @@ struct cStencil {
   int Length;
   double Weight[nMaxStencilLength];
   int LocalCellID[nMaxStencilLength];
-  void flush() { Length = 0; }
+  cCenterNode *cell[nMaxStencilLength];  // centre stencils of the coupler (cells of several blocks on AMR meshes)
+  bool overflow;                         // the reference exit()s when Length would exceed nMaxStencilLength
+  cStencil() : Length(0), overflow(false) {}
+  void flush() { Length = 0, overflow = false; }
+  void MultiplyScalar(double a) { for (int i = 0; i < Length; i++) Weight[i] *= a; }
   void Normalize() {
     double norm = 0.0;
     int i;
@@ -449,6 +454,382 @@ struct oracle_ctx {
     GetTriliniarInterpolationStencil(iLoc, jLoc, kLoc, XyzIn_D, node, Stencil, always_normalize);
   }
 
+
+  // ------------------------------------------------------------------------------------------
+  // a4, AMR branch: neighbours by lattice probe (meshAMRgeneric.h:505-725), neighbour level limits (:1018-1048)
+  // ------------------------------------------------------------------------------------------
+  cTreeNode *neibNodeCorner(cTreeNode *n, int i) const {
+    int ix[3];
+    for (int d = 0; d < 3; d++) ix[d] = ((i >> d) & 1) ? n->xMinGlobalIndex[d] + n->NodeGeometricSizeIndex : n->xMinGlobalIndex[d] - 1;
+    return findTreeNode(ix, n);
+  }
+  cTreeNode *neibNodeFace(cTreeNode *n, int i) const {
+    int ix[3];
+    for (int d = 0; d < 3; d++) ix[d] = n->xMinGlobalIndex[d];
+    int nface = i / 4;
+    i -= 4 * nface;
+    int jFace = i / 2, iFace = i % 2;
+    const int dn = nface / 2;                                // normal direction
+    const int t0 = (dn == 0) ? 1 : 0, t1 = (dn == 2) ? 1 : 2;  // tangential directions in the reference's order
+    ix[dn] -= 1;
+    if ((iFace == 1) && (n->NodeGeometricSizeIndex > 1)) ix[t0] += n->NodeGeometricSizeIndex / 2;
+    if ((jFace == 1) && (n->NodeGeometricSizeIndex > 1)) ix[t1] += n->NodeGeometricSizeIndex / 2;
+    if (nface & 1) ix[dn] += 1 + n->NodeGeometricSizeIndex;
+    return findTreeNode(ix, n);
+  }
+  cTreeNode *neibNodeEdge(cTreeNode *n, int i) const {
+    static const int Increment[12][3] = {{0, -1, -1}, {0, 1, -1}, {0, 1, 1}, {0, -1, 1}, {-1, 0, -1}, {1, 0, -1},
+                                         {1, 0, 1},   {-1, 0, 1}, {-1, -1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 1, 0}};
+    static const int Direction[12] = {0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2};
+    int ix[3];
+    int iedge = i / 2, isegment = i % 2;
+    for (int idim = 0; idim < 3; idim++) {
+      ix[idim] = n->xMinGlobalIndex[idim];
+      if (Increment[iedge][idim] == -1) ix[idim] -= 1;
+      else if (Increment[iedge][idim] == 1) ix[idim] += n->NodeGeometricSizeIndex;
+    }
+    if (isegment == 1)
+      if (n->NodeGeometricSizeIndex > 1) ix[Direction[iedge]] += n->NodeGeometricSizeIndex / 2;
+    return findTreeNode(ix, n);
+  }
+  cTreeNode *GetNeibFace(cTreeNode *n, int nface, int iFace, int jFace) const { return neibNodeFace(n, iFace + 2 * (jFace + 2 * nface)); }
+  cTreeNode *GetNeibEdge(cTreeNode *n, int nedge, int iEdge) const { return neibNodeEdge(n, iEdge + 2 * nedge); }
+  cTreeNode *GetNeibCorner(cTreeNode *n, int c) const { return neibNodeCorner(n, c); }
+  void SetNeibRefinmentLevelLimits(cTreeNode *n) const {
+    cTreeNode *node;
+    int i;
+    n->minNeibRefinmentLevel = -1, n->maxNeibRefinmentLevel = -1;
+    for (i = 0; i < 6 * 4; i++)
+      if ((node = neibNodeFace(n, i)) != NULL) {
+        if ((n->minNeibRefinmentLevel == -1) || (n->minNeibRefinmentLevel > node->RefinmentLevel)) n->minNeibRefinmentLevel = node->RefinmentLevel;
+        if (n->maxNeibRefinmentLevel < node->RefinmentLevel) n->maxNeibRefinmentLevel = node->RefinmentLevel;
+      }
+    for (i = 0; i < 8; i++)
+      if ((node = neibNodeCorner(n, i)) != NULL) {
+        if ((n->minNeibRefinmentLevel == -1) || (n->minNeibRefinmentLevel > node->RefinmentLevel)) n->minNeibRefinmentLevel = node->RefinmentLevel;
+        if (n->maxNeibRefinmentLevel < node->RefinmentLevel) n->maxNeibRefinmentLevel = node->RefinmentLevel;
+      }
+    for (i = 0; i < 12 * 2; i++)
+      if ((node = neibNodeEdge(n, i)) != NULL) {
+        if ((n->minNeibRefinmentLevel == -1) || (n->minNeibRefinmentLevel > node->RefinmentLevel)) n->minNeibRefinmentLevel = node->RefinmentLevel;
+        if (n->maxNeibRefinmentLevel < node->RefinmentLevel) n->maxNeibRefinmentLevel = node->RefinmentLevel;
+      }
+  }
+
+  // cStencilGeneric::AddCell (pic.h:7228-7252) for the centre (i,j,k) of `node`
+  void CplrAddCell(cStencil &S, double w, cTreeNode *node, int i, int j, int k, cCenterNode *c, int id) const {
+    if (S.Length == nMaxStencilLength) {
+      S.overflow = true;
+      return;
+    }
+    if (CenterOutsideDomain(node, i, j, k)) return;
+    S.Weight[S.Length] = w;
+    S.cell[S.Length] = c;
+    S.LocalCellID[S.Length] = id;
+    S.Length++;
+  }
+  // AddPhysicalStencilCell, pic_interpolation_routines.cpp:124-134
+  void AddPhysicalStencilCell(cStencil &S, double Weight, cTreeNode *node, int i, int j, int k, cCenterNode *cell, int LocalCellID) const {
+    for (int iElement = 0; iElement < S.Length; iElement++)
+      if (S.cell[iElement] == cell) {
+        S.Weight[iElement] += Weight;
+        return;
+      }
+    CplrAddCell(S, Weight, node, i, j, k, cell, LocalCellID);
+  }
+  // cStencilGeneric::Add, pic.h:7274-7292 (the position test of AddCell already passed when t was built)
+  void StencilAdd(cStencil &S, const cStencil &t) const {
+    for (int i = 0; i < t.Length; i++) {
+      cCenterNode *el = t.cell[i];
+      bool flag = false;
+      for (int j = 0; j < S.Length; j++)
+        if (S.cell[j] == el) {
+          flag = true;
+          S.Weight[j] += t.Weight[i];
+          break;
+        }
+      if (flag == false) {
+        if (S.Length == nMaxStencilLength) {
+          S.overflow = true;
+          return;
+        }
+        S.Weight[S.Length] = t.Weight[i], S.cell[S.Length] = el, S.LocalCellID[S.Length] = t.LocalCellID[i];
+        S.Length++;
+      }
+    }
+  }
+  // Constant::InitStencil (:168-220); false where the reference exit()s
+  bool CplrConstantStencil(const double *x, cTreeNode *node, cStencil &S) const {
+    S.flush();
+    if (node == NULL || node->block == NULL) return false;
+    int i, j, k;
+    long int nd = FindCellIndex(x, i, j, k, node);
+    if (nd < 0) return false;
+    cCenterNode *cell = node->block->centerNodes[nd];
+    if (cell == NULL) return false;
+    CplrAddCell(S, 1.0, node, i, j, k, cell, (int)nd);
+    return true;
+  }
+  // GetTriliniarInterpolationStencil (:820-909) with cell pointers; StencilTable = the object the reference tests at :903
+  bool CplrTrilinearStencil(double iLoc, double jLoc, double kLoc, const double *x, cTreeNode *node, cStencil &Stencil, const cStencil *StencilTable) const {
+    cBlock *block = node->block;
+    if (block == NULL) return false;
+    Stencil.flush();
+    double w[3], InterpolationWeight;
+    int i, j, k, i0, j0, k0, nd;
+    i0 = (iLoc < 0.5) ? -1 : (int)(iLoc - 0.50);
+    j0 = (jLoc < 0.5) ? -1 : (int)(jLoc - 0.50);
+    k0 = (kLoc < 0.5) ? -1 : (int)(kLoc - 0.50);
+    // indices past the ghost layer are out-of-bounds reads in the reference
+    if (i0 < -_GHOST_CELLS_X_ || i0 + 1 > _BLOCK_CELLS_X_ + _GHOST_CELLS_X_ - 1 || j0 < -_GHOST_CELLS_Y_ || j0 + 1 > _BLOCK_CELLS_Y_ + _GHOST_CELLS_Y_ - 1 ||
+        k0 < -_GHOST_CELLS_Z_ || k0 + 1 > _BLOCK_CELLS_Z_ + _GHOST_CELLS_Z_ - 1)
+      return false;
+    w[0] = iLoc - (i0 + 0.5);
+    w[1] = jLoc - (j0 + 0.5);
+    w[2] = kLoc - (k0 + 0.5);
+    for (i = 0; i < 2; i++)
+      for (j = 0; j < 2; j++)
+        for (k = 0; k < 2; k++) {
+          nd = _getCenterNodeLocalNumber(i0 + i, j0 + j, k0 + k);
+          switch (i + 2 * j + 4 * k) {
+            case 0: InterpolationWeight = (1.0 - w[0]) * (1.0 - w[1]) * (1.0 - w[2]); break;
+            case 1: InterpolationWeight = w[0] * (1.0 - w[1]) * (1.0 - w[2]); break;
+            case 2: InterpolationWeight = (1.0 - w[0]) * w[1] * (1.0 - w[2]); break;
+            case 3: InterpolationWeight = w[0] * w[1] * (1.0 - w[2]); break;
+            case 4: InterpolationWeight = (1.0 - w[0]) * (1.0 - w[1]) * w[2]; break;
+            case 5: InterpolationWeight = w[0] * (1.0 - w[1]) * w[2]; break;
+            case 6: InterpolationWeight = (1.0 - w[0]) * w[1] * w[2]; break;
+            default: InterpolationWeight = w[0] * w[1] * w[2]; break;
+          }
+          cCenterNode *cell = block->centerNodes[nd];
+          if (cell != NULL) CplrAddCell(Stencil, InterpolationWeight, node, i0 + i, j0 + j, k0 + k, cell, nd);
+        }
+    if (Stencil.Length == 0) return CplrConstantStencil(x, node, Stencil);
+    else if (StencilTable->Length != 8) Stencil.Normalize();
+    return true;
+  }
+  // GetTriliniarInterpolationMutiBlockStencil (:912-1070)
+  bool CplrMultiBlockStencil(const double *x, cTreeNode *node, cStencil &Stencil) const {
+    long int nd;
+    cCenterNode *cell;
+    Stencil.flush();
+    const int nCells[3] = {_BLOCK_CELLS_X_, _BLOCK_CELLS_Y_, _BLOCK_CELLS_Z_};
+    const int nGhost[3] = {_GHOST_CELLS_X_, _GHOST_CELLS_Y_, _GHOST_CELLS_Z_};
+    double dxCell[3];
+    int idim;
+    for (idim = 0; idim < 3; idim++) dxCell[idim] = (node->xmax[idim] - node->xmin[idim]) / nCells[idim];
+    int ijkStencilMin[3];
+    double xStencilLower[3], xLoc[3];
+    for (idim = 0; idim < 3; idim++) {
+      ijkStencilMin[idim] = (x[idim] - node->xmin[idim] < 0.5 * dxCell[idim]) ? -1 : (int)((x[idim] - node->xmin[idim] - 0.5 * dxCell[idim]) / dxCell[idim]);
+      xStencilLower[idim] = node->xmin[idim] + (ijkStencilMin[idim] + 0.5) * dxCell[idim];
+      xLoc[idim] = (x[idim] - xStencilLower[idim]) / dxCell[idim];
+      if (xLoc[idim] < 0.0) xLoc[idim] = 0.0;
+      if (xLoc[idim] > 1.0) xLoc[idim] = 1.0;
+    }
+    bool GeometryAvailable = true;
+    bool PhysicalStencilAvailable = true;
+    for (int di = 0; di < 2; di++)
+      for (int dj = 0; dj < 2; dj++)
+        for (int dk = 0; dk < 2; dk++) {
+          int ijk[3] = {ijkStencilMin[0] + di, ijkStencilMin[1] + dj, ijkStencilMin[2] + dk};
+          double xLogical[3];
+          for (idim = 0; idim < 3; idim++) xLogical[idim] = node->xmin[idim] + (ijk[idim] + 0.5) * dxCell[idim];
+          double StencilElementWeight;
+          switch (di + 2 * dj + 4 * dk) {
+            case 0: StencilElementWeight = (1.0 - xLoc[0]) * (1.0 - xLoc[1]) * (1.0 - xLoc[2]); break;
+            case 1: StencilElementWeight = xLoc[0] * (1.0 - xLoc[1]) * (1.0 - xLoc[2]); break;
+            case 2: StencilElementWeight = (1.0 - xLoc[0]) * xLoc[1] * (1.0 - xLoc[2]); break;
+            case 3: StencilElementWeight = xLoc[0] * xLoc[1] * (1.0 - xLoc[2]); break;
+            case 4: StencilElementWeight = (1.0 - xLoc[0]) * (1.0 - xLoc[1]) * xLoc[2]; break;
+            case 5: StencilElementWeight = xLoc[0] * (1.0 - xLoc[1]) * xLoc[2]; break;
+            case 6: StencilElementWeight = (1.0 - xLoc[0]) * xLoc[1] * xLoc[2]; break;
+            default: StencilElementWeight = xLoc[0] * xLoc[1] * xLoc[2]; break;
+          }
+          cTreeNode *StencilNode = findTreeNode(xLogical, node);
+          if ((StencilNode == NULL) || (StencilNode->IsUsedInCalculationFlag == false)) {
+            GeometryAvailable = false;
+            continue;
+          }
+          if (StencilNode->RefinmentLevel == node->RefinmentLevel) {
+            bool inTile = true;
+            for (idim = 0; idim < 3; idim++)
+              if (ijk[idim] < -nGhost[idim] || ijk[idim] > nCells[idim] + nGhost[idim] - 1) inTile = false;
+            nd = inTile ? _getCenterNodeLocalNumber(ijk[0], ijk[1], ijk[2]) : -1;
+            cell = (node->block == NULL || !inTile) ? NULL : node->block->centerNodes[nd];
+            if (cell != NULL) AddPhysicalStencilCell(Stencil, StencilElementWeight, node, ijk[0], ijk[1], ijk[2], cell, (int)nd);
+            else PhysicalStencilAvailable = false;
+          } else {
+            int iNeib[3];
+            for (idim = 0; idim < 3; idim++) iNeib[idim] = 2 * ((int)((xLogical[idim] - StencilNode->xmin[idim]) / dxCell[idim]));
+            for (int ii = 0; ii < 2; ii++)
+              for (int jj = 0; jj < 2; jj++)
+                for (int kk = 0; kk < 2; kk++) {
+                  const int iFine = iNeib[0] + ii, jFine = iNeib[1] + jj, kFine = iNeib[2] + kk;
+                  const double FineCellWeight = (1.0 / 8.0) * StencilElementWeight;
+                  const int f[3] = {iFine, jFine, kFine};
+                  bool inTile = true;
+                  for (idim = 0; idim < 3; idim++)
+                    if (f[idim] < -nGhost[idim] || f[idim] > nCells[idim] + nGhost[idim] - 1) inTile = false;
+                  nd = inTile ? _getCenterNodeLocalNumber(iFine, jFine, kFine) : -1;
+                  cell = (StencilNode->block == NULL || !inTile) ? NULL : StencilNode->block->centerNodes[nd];
+                  if (cell != NULL) AddPhysicalStencilCell(Stencil, FineCellWeight, StencilNode, iFine, jFine, kFine, cell, (int)nd);
+                  else PhysicalStencilAvailable = false;
+                }
+          }
+        }
+    if (GeometryAvailable == false) {
+      cTreeNode *InterpolationNode = findTreeNode(x, node);
+      if ((InterpolationNode != NULL) && (InterpolationNode->block != NULL)) return CplrConstantStencil(x, InterpolationNode, Stencil);
+      Stencil.flush();
+      return true;
+    }
+    if (PhysicalStencilAvailable == false) {
+      cTreeNode *InterpolationNode = findTreeNode(x, node);
+      if ((InterpolationNode != NULL) && (InterpolationNode->block != NULL)) return CplrConstantStencil(x, InterpolationNode, Stencil);
+      Stencil.flush();
+    }
+    return true;
+  }
+  // CellCentered::Linear::InitStencil (:224-706), _PIC_CELL_CENTERED_LINEAR_INTERPOLATION_ROUTINE__AMPS_, non-uniform mesh type.
+  // Fills Stencil.cell[]; false where the reference exit()s / reads out of bounds.
+  bool CplrLinearStencil(const double *XyzIn_D, cTreeNode *node, cStencil &Stencil) const {
+    Stencil.flush();
+    if (node == NULL || node->block == NULL) return false;
+    double iLoc, jLoc, kLoc;
+    double *xmin = node->xmin, *xmax = node->xmax;
+    iLoc = (XyzIn_D[0] - xmin[0]) / (xmax[0] - xmin[0]) * _BLOCK_CELLS_X_;
+    jLoc = (XyzIn_D[1] - xmin[1]) / (xmax[1] - xmin[1]) * _BLOCK_CELLS_Y_;
+    kLoc = (XyzIn_D[2] - xmin[2]) / (xmax[2] - xmin[2]) * _BLOCK_CELLS_Z_;
+    if (!(iLoc >= -1.0e9 && iLoc <= 1.0e9 && jLoc >= -1.0e9 && jLoc <= 1.0e9 && kLoc >= -1.0e9 && kLoc <= 1.0e9)) return false;
+    if ((node->RefinmentLevel == node->minNeibRefinmentLevel) && (node->RefinmentLevel == node->maxNeibRefinmentLevel)) {
+      return CplrTrilinearStencil(iLoc, jLoc, kLoc, XyzIn_D, node, Stencil, &Stencil);
+    } else if ((1.0 < iLoc) && (iLoc < _BLOCK_CELLS_X_ - 1) && (1.0 < jLoc) && (jLoc < _BLOCK_CELLS_Y_ - 1) && (1.0 < kLoc) && (kLoc < _BLOCK_CELLS_Z_ - 1)) {
+      return CplrTrilinearStencil(iLoc, jLoc, kLoc, XyzIn_D, node, Stencil, &Stencil);
+    } else if (node->RefinmentLevel == node->minNeibRefinmentLevel) {
+      if ((0.5 < iLoc) && (iLoc < _BLOCK_CELLS_X_ - 0.5) && (0.5 < jLoc) && (jLoc < _BLOCK_CELLS_Y_ - 0.5) && (0.5 < kLoc) && (kLoc < _BLOCK_CELLS_Z_ - 0.5)) {
+        return CplrTrilinearStencil(iLoc, jLoc, kLoc, XyzIn_D, node, Stencil, &Stencil);
+      } else {
+        return CplrMultiBlockStencil(XyzIn_D, node, Stencil);
+      }
+    } else {
+      cTreeNode *CoarserBlock = NULL;
+      cTreeNode *NeibNode;
+      int idim, iFace = 0;
+      double dxCell[3];
+      dxCell[0] = (xmax[0] - xmin[0]) / _BLOCK_CELLS_X_;
+      dxCell[1] = (xmax[1] - xmin[1]) / _BLOCK_CELLS_Y_;
+      dxCell[2] = (xmax[2] - xmin[2]) / _BLOCK_CELLS_Z_;
+      int nBlockCells[3] = {_BLOCK_CELLS_X_, _BLOCK_CELLS_Y_, _BLOCK_CELLS_Z_};
+      double dmin = 10.0 * _BLOCK_CELLS_X_ * _BLOCK_CELLS_Y_ * _BLOCK_CELLS_Z_;
+      bool CornerTestFlagTable[8] = {false, false, false, false, false, false, false, false};
+      bool EdgeTestFlagTable[12] = {false, false, false, false, false, false, false, false, false, false, false, false};
+      double xLoc[3] = {iLoc, jLoc, kLoc};
+      // distance of the point to the block boundary across direction d: low side -> xLoc, high side -> N - xLoc
+      auto usable = [&](cTreeNode *nb) -> bool {
+        if (nb == NULL) return false;
+        if (!((nb->RefinmentLevel < node->RefinmentLevel) && (nb->IsUsedInCalculationFlag == true))) return false;
+        int cnt = 0;
+        for (int ii = 0; ii < 3; ii++)
+          if ((nb->xmin[ii] - dxCell[ii] <= XyzIn_D[ii]) && (nb->xmax[ii] + dxCell[ii] >= XyzIn_D[ii])) cnt++;
+        return cnt == 3;
+      };
+      for (idim = 0; idim < 3; idim++) {
+        if (xLoc[idim] <= 1.0) iFace = 2 * idim;
+        else if (xLoc[idim] >= nBlockCells[idim] - 1.0) iFace = 2 * idim + 1;
+        else continue;
+
+        NeibNode = GetNeibFace(node, iFace, 0, 0);
+        if (usable(NeibNode)) {
+          const int d = iFace / 2;
+          if ((iFace & 1) == 0) {
+            if ((xLoc[d] < 1.0) && (xLoc[d] < dmin)) dmin = xLoc[d], CoarserBlock = NeibNode;
+          } else {
+            if ((xLoc[d] > nBlockCells[d] - 1) && (nBlockCells[d] - xLoc[d] < dmin)) dmin = nBlockCells[d] - xLoc[d], CoarserBlock = NeibNode;
+          }
+        }
+
+        static const int faceEdges[6][4] = {{4, 11, 7, 8}, {5, 10, 6, 9}, {0, 9, 3, 8}, {1, 10, 2, 11}, {0, 5, 1, 4}, {3, 6, 2, 7}};
+        // edge -> the two transverse directions and their sides (0 low, 1 high), in the order the reference tests them
+        static const int edgeDir[12][2] = {{1, 2}, {1, 2}, {1, 2}, {1, 2}, {0, 2}, {0, 2}, {0, 2}, {0, 2}, {0, 1}, {0, 1}, {0, 1}, {0, 1}};
+        static const int edgeSide[12][2] = {{0, 0}, {0, 1}, {1, 1}, {1, 0}, {0, 0}, {1, 0}, {1, 1}, {0, 1}, {0, 0}, {1, 0}, {1, 1}, {0, 1}};
+        for (int iEdge = 0; iEdge < 4; iEdge++)
+          if (EdgeTestFlagTable[faceEdges[iFace][iEdge]] == false) {
+            const int e = faceEdges[iFace][iEdge];
+            EdgeTestFlagTable[e] = true;
+            NeibNode = GetNeibEdge(node, e, 0);
+            if (usable(NeibNode)) {
+              bool in = true;
+              double dist[2];
+              for (int q = 0; q < 2; q++) {
+                const int d = edgeDir[e][q];
+                if (edgeSide[e][q] == 0) {
+                  in = in && (xLoc[d] < 1.0);
+                  dist[q] = xLoc[d];
+                } else {
+                  in = in && (xLoc[d] > nBlockCells[d] - 1);
+                  dist[q] = nBlockCells[d] - xLoc[d];
+                }
+              }
+              if (in)
+                for (int q = 0; q < 2; q++)
+                  if (dist[q] < dmin) dmin = dist[q], CoarserBlock = NeibNode;
+            }
+          }
+
+        static const int FaceNodeMap[6][4] = {{0, 2, 4, 6}, {1, 3, 5, 7}, {0, 1, 4, 5}, {2, 3, 6, 7}, {0, 1, 2, 3}, {4, 5, 6, 7}};
+        for (int iCorner = 0; iCorner < 4; iCorner++)
+          if (CornerTestFlagTable[FaceNodeMap[iFace][iCorner]] == false) {
+            const int c = FaceNodeMap[iFace][iCorner];
+            CornerTestFlagTable[c] = true;
+            NeibNode = GetNeibCorner(node, c);
+            if (usable(NeibNode)) {
+              bool in = true;
+              double dist[3];
+              for (int d = 0; d < 3; d++) {
+                if (((c >> d) & 1) == 0) {
+                  in = in && (xLoc[d] < 1.0);
+                  dist[d] = xLoc[d];
+                } else {
+                  in = in && (xLoc[d] > nBlockCells[d] - 1);
+                  dist[d] = nBlockCells[d] - xLoc[d];
+                }
+              }
+              if (in)
+                for (int d = 0; d < 3; d++)
+                  if (dist[d] < dmin) dmin = dist[d], CoarserBlock = NeibNode;
+            }
+          }
+      }
+
+      if (CoarserBlock != NULL) {
+        if (!CplrMultiBlockStencil(XyzIn_D, CoarserBlock, Stencil)) return false;
+        if ((0.5 < dmin) && (dmin <= 1.0)) {
+          cStencil FineStencil;
+          // the fine stencil is normalised iff the *outer* stencil's Length != 8 (the reference tests StencilTable, :903)
+          if (!CplrTrilinearStencil(iLoc, jLoc, kLoc, XyzIn_D, node, FineStencil, &Stencil)) return false;
+          Stencil.MultiplyScalar(1.0 - (dmin - 0.5) / 0.5);
+          FineStencil.MultiplyScalar((dmin - 0.5) / 0.5);
+          StencilAdd(Stencil, FineStencil);
+        }
+        return !Stencil.overflow;
+      }
+      return CplrTrilinearStencil(iLoc, jLoc, kLoc, XyzIn_D, node, Stencil, &Stencil);
+    }
+  }
+  // PIC::CPLR::InitInterpolationStencil, pic_swmf.cpp:76-90
+  bool CplrInitStencil(const double *x, cTreeNode *node, cStencil &Stencil) const {
+    bool ok = (cfg.coupler_interpolation == AMPS_CPLR_CELL_CENTERED_LINEAR) ? CplrLinearStencil(x, node, Stencil) : CplrConstantStencil(x, node, Stencil);
+    return ok && !Stencil.overflow && Stencil.Length > 0;
+  }
+  void CplrGather(const cStencil &Stencil, int offset, int nVars, double *out) const {
+    for (int i = 0; i < nVars; i++) out[i] = 0.0;
+    for (int iStencil = 0; iStencil < Stencil.Length; iStencil++) {
+      const double *t = Stencil.cell[iStencil]->data + offset;
+      for (int i = 0; i < nVars; i++) out[i] += Stencil.Weight[iStencil] * t[i];
+    }
+  }
+
   // PIC::Mover::SetBlock_E / SetBlock_B, src/pic/pic_mover.cpp:86-166
   void SetBlock_E(double *E_Corner, cTreeNode *node) const {
     if (!node->block) return;
@@ -699,23 +1080,9 @@ struct oracle_ctx {
   // "Length != 8 -> Normalize" test of GetTriliniarInterpolationStencil (:903) applies as written.
   bool GetBackgroundFields(const double *x, cTreeNode *node, double *E, double *B) const {
     cStencil Stencil;
-    if (cfg.coupler_interpolation == AMPS_CPLR_CELL_CENTERED_LINEAR) {
-      CellCentered_Linear_InitStencil(x, node, Stencil, false);
-    } else {
-      int i, j, k;
-      long int nd = FindCellIndex(x, i, j, k, node);
-      if (nd < 0 || node->block == NULL || node->block->centerNodes[nd] == NULL) return false;
-      Stencil.Weight[0] = 1.0, Stencil.LocalCellID[0] = (int)nd, Stencil.Length = 1;
-    }
-    for (int idim = 0; idim < 3; idim++) E[idim] = 0.0, B[idim] = 0.0;
-    for (int iStencil = 0; iStencil < Stencil.Length; iStencil++) {
-      const double *t = node->block->centerNodes[Stencil.LocalCellID[iStencil]]->data + BackgroundE_d;
-      for (int idim = 0; idim < 3; idim++) E[idim] += Stencil.Weight[iStencil] * t[idim];
-    }
-    for (int iStencil = 0; iStencil < Stencil.Length; iStencil++) {
-      const double *t = node->block->centerNodes[Stencil.LocalCellID[iStencil]]->data + BackgroundB_d;
-      for (int idim = 0; idim < 3; idim++) B[idim] += Stencil.Weight[iStencil] * t[idim];
-    }
+    if (!CplrInitStencil(x, node, Stencil)) return false;
+    CplrGather(Stencil, BackgroundE_d, 3, E);
+    CplrGather(Stencil, BackgroundB_d, 3, B);
     return true;
   }
 
@@ -1106,31 +1473,10 @@ struct oracle_ctx {
   // fields + the 15 GCA variables through the coupler stencil (pic.h:8338-8425, 8643-8680)
   bool GetBackgroundFieldsGCA(const double *x, cTreeNode *node, double *E, double *B, double *v15) const {
     cStencil Stencil;
-    if (cfg.coupler_interpolation == AMPS_CPLR_CELL_CENTERED_LINEAR) {
-      CellCentered_Linear_InitStencil(x, node, Stencil, false);
-    } else {
-      int i, j, k;
-      long int nd = FindCellIndex(x, i, j, k, node);
-      if (nd < 0 || node->block == NULL || node->block->centerNodes[nd] == NULL) return false;
-      Stencil.Weight[0] = 1.0, Stencil.LocalCellID[0] = (int)nd, Stencil.Length = 1;
-    }
-    for (int idim = 0; idim < 3; idim++) E[idim] = 0.0, B[idim] = 0.0;
-    // call order of the movers: B, E, then var15
-    for (int iStencil = 0; iStencil < Stencil.Length; iStencil++) {
-      const double *t = node->block->centerNodes[Stencil.LocalCellID[iStencil]]->data + BackgroundB_d;
-      for (int idim = 0; idim < 3; idim++) B[idim] += Stencil.Weight[iStencil] * t[idim];
-    }
-    for (int iStencil = 0; iStencil < Stencil.Length; iStencil++) {
-      const double *t = node->block->centerNodes[Stencil.LocalCellID[iStencil]]->data + BackgroundE_d;
-      for (int idim = 0; idim < 3; idim++) E[idim] += Stencil.Weight[iStencil] * t[idim];
-    }
-    if (v15) {
-      for (int iVar = 0; iVar < 15; iVar++) v15[iVar] = 0.0;
-      for (int iStencil = 0; iStencil < Stencil.Length; iStencil++) {
-        const double *t = node->block->centerNodes[Stencil.LocalCellID[iStencil]]->data + BackgroundGCA_d;
-        for (int iVar = 0; iVar < 15; iVar++) v15[iVar] += Stencil.Weight[iStencil] * t[iVar];
-      }
-    }
+    if (!CplrInitStencil(x, node, Stencil)) return false;
+    CplrGather(Stencil, BackgroundB_d, 3, B);
+    CplrGather(Stencil, BackgroundE_d, 3, E);
+    if (v15) CplrGather(Stencil, BackgroundGCA_d, 15, v15);
     return true;
   }
 
@@ -1315,31 +1661,10 @@ struct oracle_ctx {
   // PIC::CPLR::InitInterpolationStencil(x,node) for a point that may lie OUTSIDE `node` (Mover_FirstOrder :713 builds the
   // stencil of the new position in the start block).  Indices beyond the block's ghost layer are out-of-bounds reads in
   // the reference -> reported as an error here (returns false), like every place where the reference exit()s.
-  bool GC_InitStencil(const double *x, cTreeNode *node, cStencil &Stencil) const {
-    if (node == NULL || node->block == NULL) return false;
-    if (cfg.coupler_interpolation == AMPS_CPLR_CELL_CENTERED_LINEAR) {
-      const int N[3] = {_BLOCK_CELLS_X_, _BLOCK_CELLS_Y_, _BLOCK_CELLS_Z_}, G[3] = {_GHOST_CELLS_X_, _GHOST_CELLS_Y_, _GHOST_CELLS_Z_};
-      for (int d = 0; d < 3; d++) {
-        double loc = (x[d] - node->xmin[d]) / (node->xmax[d] - node->xmin[d]) * N[d];
-        if (!(loc >= -1.0e9 && loc <= 1.0e9)) return false;
-        int i0 = (loc < 0.5) ? -1 : (int)(loc - 0.50);
-        if (i0 < -G[d] || i0 + 1 > N[d] + G[d] - 1) return false;
-      }
-      CellCentered_Linear_InitStencil(x, node, Stencil, false);
-      return Stencil.Length > 0;
-    }
-    int i, j, k;
-    long int nd = FindCellIndex(x, i, j, k, node);
-    if (nd < 0 || node->block->centerNodes[nd] == NULL) return false;
-    Stencil.Weight[0] = 1.0, Stencil.LocalCellID[0] = (int)nd, Stencil.Length = 1;
-    return true;
-  }
+  bool GC_InitStencil(const double *x, cTreeNode *node, cStencil &Stencil) const { return CplrInitStencil(x, node, Stencil); }
   void GC_Gather(const cStencil &Stencil, cTreeNode *node, int offset, int nVars, double *out) const {
-    for (int i = 0; i < nVars; i++) out[i] = 0.0;
-    for (int iStencil = 0; iStencil < Stencil.Length; iStencil++) {
-      const double *t = node->block->centerNodes[Stencil.LocalCellID[iStencil]]->data + offset;
-      for (int i = 0; i < nVars; i++) out[i] += Stencil.Weight[iStencil] * t[i];
-    }
+    (void)node;
+    CplrGather(Stencil, offset, nVars, out);
   }
 
   // InitiateMagneticMoment, :85-144: mu from the perpendicular speed, then v is ALIGNED with B
@@ -1933,6 +2258,7 @@ oracle_ctx *oracle_create(const amps_gpu_config *cfg, const amps_gpu_mesh *m) {
     }
   }
   o->nThreadListTables = 0;
+  for (int n = 0; n < m->n_nodes; n++) o->SetNeibRefinmentLevelLimits(&o->nodes[n]);
 
   // PIC::ParticleBuffer::Init, src/pic/pic_pbuffer.cpp:41-222
   o->MaxNPart = cfg->capacity;
@@ -2383,6 +2709,18 @@ int oracle_center_stencil(const oracle_ctx *o, const double *x, int leaf, int *i
   o->CellCentered_Linear_InitStencil(x, o->BlockTable[leaf], s, true);
   for (int i = 0; i < s.Length; i++) ids[i] = s.LocalCellID[i], w[i] = s.Weight[i];
   return s.Length;
+}
+
+// PIC::CPLR::InitInterpolationStencil at x in `leaf` (AMR capable): unique centre-node ids and weights; -1 = the reference exit()s
+int oracle_coupler_stencil(const oracle_ctx *o, const double *x, int leaf, int *uids, double *w) {
+  cStencil s;
+  if (!o->CplrInitStencil(x, o->BlockTable[leaf], s)) return -1;
+  for (int i = 0; i < s.Length; i++) uids[i] = (int)(s.cell[i] - o->centerPool.data()), w[i] = s.Weight[i];
+  return s.Length;
+}
+// (min, max) neighbour refinement levels of a leaf (SetNeibRefinmentLevelLimits)
+void oracle_neib_levels(const oracle_ctx *o, int leaf, int *minmax) {
+  minmax[0] = o->BlockTable[leaf]->minNeibRefinmentLevel, minmax[1] = o->BlockTable[leaf]->maxNeibRefinmentLevel;
 }
 
 // PIC::ParticleBuffer::CheckParticleList, src/pic/pic_pbuffer.cpp:807-: every allocated particle is on

@@ -85,6 +85,10 @@ int oracle_corner_stencil(const oracle_ctx *, double *x_inout, int leaf, double 
 /* CellCentered::Linear::InitStencil: returns Length */
 int oracle_center_stencil(const oracle_ctx *, const double *x, int leaf, int *ids, double *w);
 
+/* PIC::CPLR::InitInterpolationStencil (AMR capable): unique centre ids + weights (<=64); returns Length, -1 = reference exit() */
+int oracle_coupler_stencil(const oracle_ctx *, const double *x, int leaf, int *uids, double *w);
+void oracle_neib_levels(const oracle_ctx *, int leaf, int *minmax);
+
 /* ParticleBuffer list checks (CheckParticleList, pic_pbuffer.cpp:807) : 0 ok */
 int oracle_check_particle_lists(const oracle_ctx *);
 

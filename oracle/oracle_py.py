@@ -47,6 +47,8 @@ def load(kind="parity"):
     lib.oracle_corner_stencil.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     lib.oracle_center_stencil.argtypes = [vp, vp, C.c_int, vp, vp]
     lib.oracle_check_particle_lists.argtypes = [vp]
+    lib.oracle_coupler_stencil.argtypes = [vp, vp, C.c_int, vp, vp]
+    lib.oracle_neib_levels.argtypes = [vp, C.c_int, vp]
     _libs[kind] = lib
     return lib
 
@@ -172,6 +174,18 @@ class Oracle:
         w = np.zeros(64)
         n = self.lib.oracle_center_stencil(self.h, _p(x), leaf, _p(ids), _p(w))
         return n, ids[:n], w[:n]
+
+    def coupler_stencil(self, x, leaf):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        ids = np.zeros(64, dtype=np.int32)
+        w = np.zeros(64)
+        n = self.lib.oracle_coupler_stencil(self.h, _p(x), leaf, _p(ids), _p(w))
+        return n, ids[:max(n, 0)], w[:max(n, 0)]
+
+    def neib_levels(self, leaf):
+        mm = np.zeros(2, dtype=np.int32)
+        self.lib.oracle_neib_levels(self.h, leaf, _p(mm))
+        return int(mm[0]), int(mm[1])
 
     def check_lists(self):
         return self.lib.oracle_check_particle_lists(self.h)

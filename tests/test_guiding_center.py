@@ -72,6 +72,7 @@ GC_CASES = {
     "dipole_constant": dict(interp=_capi.CPLR_CONSTANT),
     "dipole_Epar_sphere": dict(ideal_mhd=0, dt=0.05),
     "uniform_ExB": dict(uniform_B=(1.0e-6, -2.0e-6, 2.0e-5), E_uniform=(2.0e-4, 1.0e-3, 0.0), sphere=False, dt=0.02),
+    "amr_dipole": dict(amr_levels=2, n_blocks=4, dt=0.05),                            # AMR branch of the coupler stencil
 }
 
 

@@ -80,6 +80,12 @@ CASES = {
     "backward_linear_user": dict(backward=True, interp=_capi.CPLR_LINEAR, boundary=_capi.BOUNDARY_USER_FUNCTION, sphere=True),
     "backward_constant_delete": dict(backward=True, interp=_capi.CPLR_CONSTANT, boundary=_capi.BOUNDARY_DELETE, sphere=True),
     "forward_linear_nosphere": dict(backward=False, interp=_capi.CPLR_LINEAR, boundary=_capi.BOUNDARY_USER_FUNCTION, sphere=False, dt=0.5),
+    # config 1 geometry: cells grow with the distance from the planet (3 levels); the coupler stencil takes the AMR
+    # branch of CellCentered::Linear::InitStencil (coarse-lattice stencil, 2x2x2 fine averages, blending)
+    "amr_backward_linear_user": dict(backward=True, interp=_capi.CPLR_LINEAR, boundary=_capi.BOUNDARY_USER_FUNCTION, sphere=True, amr_levels=2,
+                                     n_blocks=4, dt=0.1),
+    "amr_forward_linear_ghost2": dict(backward=False, interp=_capi.CPLR_LINEAR, boundary=_capi.BOUNDARY_DELETE, sphere=True, amr_levels=2,
+                                      n_blocks=4, dt=0.1, ghost_cells=(2, 2, 2)),
 }
 
 

@@ -87,6 +87,7 @@ GCA_CASES = {
     "dipole_constant": dict(interp=_capi.CPLR_CONSTANT),
     "dipole_long_step_exits": dict(dt=2.0, rigidity_gv=(0.01, 0.5)),
     "uniform_ExB": dict(uniform_B=(1.0e-6, -2.0e-6, 2.0e-5), E_uniform=(2.0e-4, 1.0e-3, 0.0), sphere=False, dt=0.05),
+    "amr_dipole": dict(amr_levels=2, n_blocks=4, dt=0.5, rigidity_gv=(0.01, 0.5)),   # AMR branch of the coupler stencil
 }
 
 

@@ -25,9 +25,17 @@ def dipole(x):
 
 
 def make_tp_case(n_particles=4096, half_width_re=8.0, n_blocks=8, block_cells=(4, 4, 4), seed=1, dt=0.05, backward=False,
-                 interp=_capi.CPLR_LINEAR, boundary=_capi.BOUNDARY_USER_FUNCTION, sphere=True, uniform_B=None, rigidity_gv=(0.5, 20.0)):
+                 interp=_capi.CPLR_LINEAR, boundary=_capi.BOUNDARY_USER_FUNCTION, sphere=True, uniform_B=None, rigidity_gv=(0.5, 20.0),
+                 amr_levels=0, ghost_cells=(1, 1, 1)):
     L = half_width_re * RE
-    m = meshmod.build_mesh((-L, -L, -L), (L, L, L), (n_blocks,) * 3, block_cells, (1, 1, 1), periodic=False)
+    refine = None
+    if amr_levels > 0:
+        # cell size grows with the distance from the planet, like dx = 0.25 R_E (r/R_E) of input/earth-cutoff-rigidity.input
+        def refine(level, lo, hi):
+            near = np.clip(np.zeros(3), lo, hi)
+            r = float(np.linalg.norm(near)) / RE
+            return r < half_width_re * (0.45, 0.12, 0.03)[level]  # nested so that neighbours differ by one level at most
+    m = meshmod.build_mesh((-L, -L, -L), (L, L, L), (n_blocks,) * 3, block_cells, ghost_cells, periodic=False, refine=refine, max_level=amr_levels)
     xc = m.center_x
     if uniform_B is None:
         r = np.sqrt((xc ** 2).sum(1))
@@ -51,16 +59,17 @@ def make_tp_case(n_particles=4096, half_width_re=8.0, n_blocks=8, block_cells=(4
     speed = p / (gamma * MP)
     v = (d * speed[:, None]).T.copy()
     sp = np.zeros(n_particles, dtype=np.uint8)
-    # cells from positions (uniform open box)
+    # cells from positions: leaf by the findTreeNode lattice, then the cell inside the leaf
     N = np.array(block_cells)
-    dx_block = 2 * L / n_blocks
-    bidx = np.floor((x.T + L) / dx_block).astype(np.int64)
-    leaf = np.array([m.find_leaf_ix([int(b[0] * 4096 + 1), int(b[1] * 4096 + 1), int(b[2] * 4096 + 1)]) for b in bidx])
-    lo = m.leaf_xmin()[leaf]
-    cidx = np.floor((x.T - lo) / (dx_block / N)).astype(np.int64)
-    cidx = np.minimum(cidx, N - 1)
+    gmin = np.array([m.c.x_global_min[d] for d in range(3)])
+    dxr = np.array([m.c.dx_max_refinement[d] for d in range(3)])
+    lat = np.floor((x.T - gmin) / dxr).astype(np.int64)
+    leaf = np.array([m.find_leaf_ix([int(b[0]), int(b[1]), int(b[2])]) for b in lat])
+    lo, hi = m.leaf_xmin()[leaf], m.leaf_xmax()[leaf]
+    cidx = np.floor((x.T - lo) / ((hi - lo) / N)).astype(np.int64)
+    cidx = np.clip(cidx, 0, N - 1)
     cells = (leaf * int(N.prod()) + cidx[:, 0] + N[0] * (cidx[:, 1] + N[1] * cidx[:, 2])).astype(np.int32)
-    cfg = api.make_config(block_cells, (1, 1, 1), (QP,), (MP,), (1.0,), dt, periodic=False, capacity=n_particles + 16, boundary_mode=boundary)
+    cfg = api.make_config(block_cells, ghost_cells, (QP,), (MP,), (1.0,), dt, periodic=False, capacity=n_particles + 16, boundary_mode=boundary)
     cfg.time_step_mode = _capi.DT_SPECIES_GLOBAL
     cfg.coupler_interpolation = interp
     cfg.backward_time_integration = 1 if backward else 0
