@@ -61,6 +61,8 @@ class Config(C.Structure):
         ("exit_record_capacity", C.c_int64),
         ("gravity_gm", C.c_double),
         ("carry_magnetic_moment", C.c_int32),
+        ("exact_arithmetic", C.c_int32),
+        ("reserved1", C.c_int32),
         ("ideal_mhd", C.c_int32),
     ]
 
@@ -146,6 +148,7 @@ PROTOTYPES = {
     "amps_gpu_finalize": (C.c_int, [_vp]),
     "amps_gpu_last_error": (C.c_char_p, [_vp]),
     "amps_gpu_launch_count": (C.c_int64, [_vp]),
+    "amps_gpu_last_move_redo": (C.c_int, [_vp, _i64p]),
     "amps_gpu_stream": (_vp, [_vp]),
     "amps_gpu_mesh_upload": (C.c_int, [_vp, C.POINTER(Mesh)]),
     "amps_gpu_fields_upload": (C.c_int, [_vp, _vp, _vp, _vp]),

@@ -52,6 +52,7 @@ def make_config(block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), charge=(-1.0, 1.0)
     cfg.gravity_gm = 0.0
     cfg.carry_magnetic_moment = 0
     cfg.ideal_mhd = 1
+    cfg.exact_arithmetic = 0
     return cfg
 
 
@@ -271,6 +272,11 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.amps_gpu_launch_count(self._h))
+
+    def last_move_redo(self):
+        n = C.c_int64()
+        self._ck(self.lib.amps_gpu_last_move_redo(self._h, C.byref(n)))
+        return int(n.value)
 
     def stream(self):
         return self.lib.amps_gpu_stream(self._h)

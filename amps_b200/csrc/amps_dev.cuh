@@ -95,7 +95,11 @@ void launch_stage_tiles(const DevMesh &m, bool cornerB, const double *E_half, co
                         double *bCurTile, cudaStream_t s);
 void launch_move_lapenta(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *eTile, const double *bTile,
                          int *cellCount, DevMoveStats *stats, int slices, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount,
-                         long long exitCap, cudaStream_t s);
+                         long long exitCap, const unsigned char *redoMask, const int *redoLeafList, const int *nRedoLeaves, cudaStream_t s);
+// leafRedo[nLeaves] (flagged particles per block), redoLeafList[nLeaves] + nRedoLeaves (blocks with any), all zeroed by the caller
+void launch_move_lapenta_fast(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *eTile, const double *bTile,
+                              int *cellCount, DevMoveStats *stats, int slices, unsigned char *redoMask, int *leafRedo, int *redoLeafList,
+                              int *nRedoLeaves, cudaStream_t s);
 void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *nSrc, int *cellCount, int *cellStart, int *cellFill, int *nDst,
                  long long capacity, bool countValid, void *scanTmp, cudaStream_t s, long long *launches);
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,

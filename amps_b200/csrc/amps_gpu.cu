@@ -49,6 +49,9 @@ struct amps_gpu_ctx {
   double *d_bgE = nullptr, *d_bgB = nullptr, *d_bgTile = nullptr;
   double *d_gcaVar = nullptr, *d_gcaTile = nullptr;  // relativistic GCA: 15 drift variables per centre node
   bool gcaReady = false;
+  bool meshRefined = false;  // some leaf is below level 0
+  unsigned char *d_redoMask = nullptr;  // particles the fast mover left to the exact kernel
+  int *d_leafRedo = nullptr;  // [nLeaves] counts, then [nLeaves] list of flagged blocks, then 1 counter
   double *d_gradBVar = nullptr, *d_gradBTile = nullptr;  // guiding centre: grad B, 9 values per centre node
   bool gradBReady = false;
   bool backgroundReady = false;
@@ -261,6 +264,7 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
   if (ctx->comm && nccl_api().CommDestroy) nccl_api().CommDestroy(ctx->comm);
   cudaFree(ctx->d_gcaVar), cudaFree(ctx->d_gcaTile), cudaFree(ctx->d_gradBVar), cudaFree(ctx->d_gradBTile);
+  cudaFree(ctx->d_redoMask), cudaFree(ctx->d_leafRedo);
   cudaFree(ctx->d_bgE), cudaFree(ctx->d_bgB), cudaFree(ctx->d_bgTile), cudaFree(ctx->d_exitBuf), cudaFree(ctx->d_exitCount);
   cudaFree(ctx->d_sendBuf), cudaFree(ctx->d_recvBuf), cudaFree(ctx->d_sendCount), cudaFree(ctx->d_allCounts), cudaFree(ctx->d_errFlag);
   for (int *p : ctx->d_sharedUid) cudaFree(p);
@@ -277,6 +281,18 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
 
 const char *amps_gpu_last_error(const amps_gpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int64_t amps_gpu_launch_count(const amps_gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int amps_gpu_last_move_redo(amps_gpu_ctx *ctx, int64_t *n) {
+  if (!ctx || !n) return AMPS_GPU_ERR_ARG;
+  *n = 0;
+  if (!ctx->d_leafRedo || ctx->cfg.exact_arithmetic) return AMPS_GPU_OK;
+  CK(cudaSetDevice(ctx->cfg.device));
+  std::vector<int> h((size_t)ctx->dm.nLeaves);
+  CK(cudaMemcpyAsync(h.data(), ctx->d_leafRedo, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int v : h) *n += v;
+  return AMPS_GPU_OK;
+}
 void *amps_gpu_stream(amps_gpu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int amps_gpu_synchronize(amps_gpu_ctx *ctx) {
@@ -322,6 +338,7 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
     }
     g.isize = mesh->node_isize[n];
     g.level = mesh->node_level[n];
+    if (g.level > 0) ctx->meshRefined = true;
     g.flags = mesh->node_flags[n];
     g.real = mesh->leaf_real[l];
     g.face = mesh->leaf_face_boundary[l];
@@ -767,6 +784,10 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
       FAIL(AMPS_GPU_ERR_STATE, "Relativistic::GuidingCenter implements the DELETE boundary only (reference :262-279)");
   }
   if (mover_id == AMPS_MOVER_LAPENTA2017 && !ctx->fieldsReady) FAIL(AMPS_GPU_ERR_STATE, "Lapenta2017 needs amps_gpu_fields_upload");
+  if (mover_id == AMPS_MOVER_LAPENTA2017 && ctx->meshRefined && ctx->cfg.b_mode == AMPS_B_CENTER_BASED)
+    FAIL(AMPS_GPU_ERR_STATE,
+         "ECSIM on a refined mesh needs _PIC_FIELD_SOLVER_B_CORNER_BASED_: with centre-based B the reference indexes the start block's "
+         "buffer with stencil ids of other blocks (pic_mover_boris.cpp:975-990)");
   if (mover_id != AMPS_MOVER_LAPENTA2017 && !ctx->backgroundReady) FAIL(AMPS_GPU_ERR_STATE, "the test-particle movers need amps_gpu_background_upload");
   const DevMesh &m = ctx->dm;
   ProfScope prof(ctx, AMPS_GPU_PHASE_MOVE);
@@ -818,9 +839,26 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   int slices = (int)((perLeaf + 4095) / 4096);
   if (slices < 1) slices = 1;
   if (slices > 64) slices = 64;
-  launch_move_lapenta(m, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_eTile, ctx->d_bPrevTile, ctx->d_cellCount, ctx->d_stats, slices,
-                      ctx->d_exitBuf, ctx->d_exitCount, ctx->cfg.exit_record_capacity, ctx->stream);
-  ctx->launches++;
+  if (ctx->cfg.exact_arithmetic) {
+    launch_move_lapenta(m, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_eTile, ctx->d_bPrevTile, ctx->d_cellCount, ctx->d_stats, slices,
+                        ctx->d_exitBuf, ctx->d_exitCount, ctx->cfg.exit_record_capacity, nullptr, nullptr, nullptr, ctx->stream);
+    ctx->launches++;
+  } else {
+    // fast pass (FMA, reciprocals) for every particle that stays clear of cell faces; the exact kernel finishes the flagged rest
+    int rc;
+    if (!ctx->d_redoMask) {
+      if ((rc = dev_alloc(ctx, &ctx->d_redoMask, (size_t)ctx->cfg.capacity))) return rc;
+      if ((rc = dev_alloc(ctx, &ctx->d_leafRedo, (size_t)2 * m.nLeaves + 1))) return rc;
+    }
+    CK(cudaMemsetAsync(ctx->d_redoMask, 0, (size_t)ctx->nUpper, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_leafRedo, 0, sizeof(int) * ((size_t)2 * m.nLeaves + 1), ctx->stream));
+    int *redoList = ctx->d_leafRedo + m.nLeaves, *nRedoLeaves = ctx->d_leafRedo + 2 * (size_t)m.nLeaves;
+    launch_move_lapenta_fast(m, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_eTile, ctx->d_bPrevTile, ctx->d_cellCount, ctx->d_stats, slices,
+                             ctx->d_redoMask, ctx->d_leafRedo, redoList, nRedoLeaves, ctx->stream);
+    launch_move_lapenta(m, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_eTile, ctx->d_bPrevTile, ctx->d_cellCount, ctx->d_stats, slices,
+                        ctx->d_exitBuf, ctx->d_exitCount, ctx->cfg.exit_record_capacity, ctx->d_redoMask, redoList, nRedoLeaves, ctx->stream);
+    ctx->launches += 2;
+  }
   CK(cudaGetLastError());
   ctx->sorted = false;
   ctx->countValid = true;
@@ -851,6 +889,8 @@ int amps_gpu_move(amps_gpu_ctx *ctx, int mover_id, amps_gpu_move_stats *stats) {
 static int do_deposit(amps_gpu_ctx *ctx) {
   if (!ctx->meshReady || !ctx->fieldsReady) FAIL(AMPS_GPU_ERR_STATE, "deposit before mesh/fields upload");
   if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "deposit needs the (block,cell)-sorted layout: call amps_gpu_sort");
+  if (ctx->meshRefined && ctx->cfg.b_mode == AMPS_B_CENTER_BASED)
+    FAIL(AMPS_GPU_ERR_STATE, "ECSIM on a refined mesh needs _PIC_FIELD_SOLVER_B_CORNER_BASED_ (see amps_gpu_move)");
   ProfScope prof(ctx, AMPS_GPU_PHASE_DEPOSIT);
   launch_deposit(ctx->dm, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl,
                  ctx->nSM, ctx->stream, &ctx->launches);

@@ -65,11 +65,13 @@ __device__ __forceinline__ int index_matrix(int c, int d) {
   return nb_slot(cox(d) - cox(c)) + 3 * nb_slot(coy(d) - coy(c)) + 9 * nb_slot(coz(d) - coz(c));
 }
 
-template <bool kCornerB>
+// kDiag: the energy / cfl diagnostics (diag_kernel below) are folded into phase 1 when there are at most two species
+template <bool kCornerB, bool kDiag>
 __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(DevMesh m, DevSpecies sp, ParticleSoA p,
                                                                               const int *__restrict__ cellStart,
                                                                               const double *__restrict__ bCurTile, double *__restrict__ J,
-                                                                              double *__restrict__ M) {
+                                                                              double *__restrict__ M, double *__restrict__ energyOut,
+                                                                              unsigned long long *__restrict__ cflBits) {
   __shared__ __align__(16) double sRows[DEP_WARPS][SLAB];
   __shared__ double sBall[DEP_WARPS][27 * 3];  // B_cur on the 3x3x3 centres around the warp's cell
   // flush tables: output o = (c*8+c')*9+col -> corner c (3 bits) | offset inside M[corner] (8 bits) | T index (9 bits)
@@ -96,6 +98,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
   const int tile = active ? lane % N_TILES : 0, slice = active ? lane / N_TILES : 0;
   const int px = tile % 3, h = tile / 3;  // classes px*9 .. px*9+8, columns 6h .. 6h+5
   const double invc = 1.0 / sp.LightSpeed;
+  double eAcc = 0.0, cflMax = 0.0;  // kDiag: per-lane energy; lane s keeps the cfl of species s
 
   for (int cell = warpGlobal; cell < nCells; cell += nWarps) {
     const int begin = cellStart[cell], end = cellStart[cell + 1];
@@ -134,6 +137,8 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     double acc[54];
 #pragma unroll
     for (int i = 0; i < 54; i++) acc[i] = 0.0;
+    double vm0 = 0.0, vm1 = 0.0;  // kDiag: sum |v| dt of species 0 / 1 seen by this lane
+    int cnt01 = 0;                // counts: species 0 in the low half, species 1 in the high half
 
     // software prefetch: the particle of the NEXT chunk is loaded while phase 2 of the current one runs
     double nx0 = 0, nx1 = 0, nx2 = 0, nv0 = 0, nv1 = 0, nv2 = 0, nw = 0;
@@ -248,6 +253,13 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
           B0 *= sc, B1 *= sc, B2 *= sc;
         }
         v0 *= sp.length_conv, v1 *= sp.length_conv, v2 *= sp.length_conv;
+        if (kDiag) {  // ParticleEnergyCell, vmean_cell (:2228-2238)
+          const double vsqr = v0 * v0 + v1 * v1 + v2 * v2;
+          eAcc = fma(0.5 * (sp.mass[spec] * LocalParticleWeight), vsqr, eAcc);
+          const double vabs = sqrt(vsqr) * sp.dt[0];
+          if (spec == 0) vm0 += vabs, cnt01 += 1;
+          else vm1 += vabs, cnt01 += 0x10000;
+        }
         const double chargeQ = sp.charge[spec] * LocalParticleWeight;
         // beta = q~ dt / 2 m~ : the statistical weight cancels (to 1 ulp), so it is a per-species constant
         const double QdT_over_2m = sQdt2m[spec];
@@ -303,6 +315,16 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
       }
     }
 
+    if (kDiag) {  // cfl of the cell per species (:2355-2359): sum|v|dt / (count |dx|)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) vm0 += __shfl_xor_sync(0xffffffffu, vm0, o), vm1 += __shfl_xor_sync(0xffffffffu, vm1, o);
+      const int c = __reduce_add_sync(0xffffffffu, cnt01);
+      const int cs = (lane == 0) ? (c & 0xffff) : (c >> 16);
+      if (lane < 2 && cs > 0) {  // 0/0 = NaN never wins the reference's '>' comparison
+        const double cfl = ((lane == 0) ? vm0 : vm1) / (cs * lg.diag);
+        if (cfl > cflMax) cflMax = cfl;
+      }
+    }
     // ---- fold the 5 slices: lanes 24..29 -> 0..5, 12..17 -> 0..5 and 18..23 -> 6..11, 6..11 -> 0..5 ----
 #pragma unroll
     for (int i = 0; i < 54; i++) {
@@ -345,6 +367,12 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
         atomicAdd(J + (size_t)ui * 3 + dcol, val);
       }
     }
+  }
+  if (kDiag) {  // energy is added once per corner in the reference's flush loops (x8, :3860)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) eAcc += __shfl_xor_sync(0xffffffffu, eAcc, o);
+    if (lane == 0 && eAcc != 0.0) atomicAdd(energyOut, 8.0 * eAcc);
+    if (lane < 2 && lane < sp.n && cflMax > 0.0) atomicMaxPositiveDouble(&cflBits[lane], cflMax);
   }
 }
 
@@ -409,10 +437,18 @@ void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const
   cudaMemsetAsync(M, 0, sizeof(double) * 243 * (size_t)m.nCorners, s);
   cudaMemsetAsync(energy, 0, sizeof(double), s);
   cudaMemsetAsync(cflBits, 0, sizeof(unsigned long long) * AMPS_GPU_MAX_SPECIES, s);
-  if (sp.bMode == AMPS_B_CORNER_BASED) deposit_kernel<true><<<nSM * DEP_CTAS_PER_SM, DEP_THREADS, 0, s>>>(m, sp, p, cellStart, bCurTile, J, M);
-  else deposit_kernel<false><<<nSM * DEP_CTAS_PER_SM, DEP_THREADS, 0, s>>>(m, sp, p, cellStart, bCurTile, J, M);
-  diag_kernel<<<nSM * 4, 256, 0, s>>>(m, sp, p, cellStart, energy, cflBits);
-  (*launches) += 2;
+  const int grid = nSM * DEP_CTAS_PER_SM;
+  const bool corner = sp.bMode == AMPS_B_CORNER_BASED;
+  if (sp.n <= 2) {
+    if (corner) deposit_kernel<true, true><<<grid, DEP_THREADS, 0, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits);
+    else deposit_kernel<false, true><<<grid, DEP_THREADS, 0, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits);
+    (*launches) += 1;
+  } else {
+    if (corner) deposit_kernel<true, false><<<grid, DEP_THREADS, 0, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits);
+    else deposit_kernel<false, false><<<grid, DEP_THREADS, 0, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits);
+    diag_kernel<<<nSM * 4, 256, 0, s>>>(m, sp, p, cellStart, energy, cflBits);
+    (*launches) += 2;
+  }
 }
 
 }  // namespace amps

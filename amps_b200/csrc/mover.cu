@@ -18,39 +18,9 @@
 // extra pass over the particles.
 #include "amps_dev.cuh"
 #include "mover_common.cuh"
+#include "tma.cuh"
 
 namespace amps {
-
-// ------------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + 1-D bulk async copy (TMA engine)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
-               "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-
 
 // self test: out[0] += number of (a,b) pairs for which the helpers differ from IEEE '/'
 __global__ void division_selftest_kernel(const double *__restrict__ a, const double *__restrict__ b, int n, unsigned long long *out) {
@@ -132,28 +102,38 @@ __global__ void __launch_bounds__(256, 2) move_lapenta_kernel(DevMesh m, DevSpec
                                                           const double *__restrict__ eTileG, const double *__restrict__ bTileG,
                                                           int *__restrict__ cellCount, DevMoveStats *__restrict__ stats, int slices,
                                                           amps_gpu_exit_record *__restrict__ exitBuf, unsigned long long *__restrict__ exitCount,
-                                                          long long exitCap) {
+                                                          long long exitCap, const unsigned char *__restrict__ redoMask,
+                                                          const int *__restrict__ redoLeafList, const int *__restrict__ nRedoLeaves) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint64_t mbar;
   __shared__ LeafGeo sLeaf;
   __shared__ FaceGeo sFace;
+  __shared__ BlockConst sC;
 
-  const int leaf = blockIdx.x / slices, slice = blockIdx.x - leaf * slices;
+  unsigned int nMoved = 0, nXCell = 0, nXBlock = 0, nLeft = 0, nNotUsed = 0, nWrap = 0, nErr = 0;
+  // work item = (leaf block, slice).  Normal launch: one item per CTA.  Second pass behind move_lapenta_fast_kernel
+  // (redoLeafList != nullptr): a small grid strides over the blocks that hold flagged particles (usually none).
+  const int nWork = redoLeafList ? *nRedoLeaves * slices : (int)gridDim.x;
+  uint32_t mbarParity = 0;
+  if (kSmemTiles && threadIdx.x == 0) {
+    mbar_init(&mbar, 1);
+    fence_mbar_init();
+  }
+  for (int work = blockIdx.x; work < nWork; work += gridDim.x) {
+  const int slot = work / slices, slice = work - slot * slices;
+  const int leaf = redoLeafList ? redoLeafList[slot] : slot;
   const int C = m.cellsPerBlock;
   const int begin = cellStart[(size_t)leaf * C], end = cellStart[(size_t)(leaf + 1) * C];
   const long long len = (long long)end - begin;
   const int b = begin + (int)(len * slice / slices), e = begin + (int)(len * (slice + 1) / slices);
-  if (b >= e) return;
+  if (b >= e) continue;
+  __syncthreads();  // the previous work item is done with sLeaf / sC / the tiles
 
   const double *sE, *sB;
   if (kSmemTiles) {
     double *tE = reinterpret_cast<double *>(smem_raw);
     double *tB = tE + m.eTileStride;
-    if (threadIdx.x == 0) {
-      sLeaf = m.leaf[leaf];
-      mbar_init(&mbar, 1);
-      fence_mbar_init();
-    }
+    if (threadIdx.x == 0) sLeaf = m.leaf[leaf];
     __syncthreads();
     if (threadIdx.x == 0) {
       const uint32_t bytesE = (uint32_t)m.eTileStride * 8u, bytesB = (uint32_t)m.bTileStride * 8u;
@@ -161,7 +141,8 @@ __global__ void __launch_bounds__(256, 2) move_lapenta_kernel(DevMesh m, DevSpec
       bulk_g2s(tE, eTileG + (size_t)leaf * m.eTileStride, bytesE, &mbar);
       bulk_g2s(tB, bTileG + (size_t)leaf * m.bTileStride, bytesB, &mbar);
     }
-    mbar_wait(&mbar, 0);
+    mbar_wait(&mbar, mbarParity);
+    mbarParity ^= 1u;
     sE = tE, sB = tB;
   } else {
     if (threadIdx.x == 0) sLeaf = m.leaf[leaf];
@@ -171,8 +152,7 @@ __global__ void __launch_bounds__(256, 2) move_lapenta_kernel(DevMesh m, DevSpec
   }
 
   const LeafGeo &lg = sLeaf;
-  // per-block constants of the stencils and their shared reciprocals (computed once per CTA)
-  __shared__ BlockConst sC;
+  // per-block constants of the stencils and their shared reciprocals (computed once per work item)
   if (threadIdx.x < 3) {
     const int d = threadIdx.x;
     sC.dxc[d] = (lg.xmax[d] - lg.xmin[d]) / m.N[d];  // CornerBased::InitStencil :1086-1088
@@ -204,9 +184,8 @@ __global__ void __launch_bounds__(256, 2) move_lapenta_kernel(DevMesh m, DevSpec
   const int CS0 = 1 + m.TN[0], CS1 = (1 + m.TN[0]) * (1 + m.TN[1]);  // corner strides
   const int BS0 = m.TN[0], BS1 = m.TN[0] * m.TN[1];                  // centre strides
 
-  unsigned int nMoved = 0, nXCell = 0, nXBlock = 0, nLeft = 0, nNotUsed = 0, nWrap = 0, nErr = 0;
-
   for (int ip = b + threadIdx.x; ip < e; ip += blockDim.x) {
+    if (redoMask && !redoMask[ip]) continue;
     double xInit[3], vInit[3], xFinal[3], vFinal[3];
     xInit[0] = p.x[0][ip], xInit[1] = p.x[1][ip], xInit[2] = p.x[2][ip];
     vInit[0] = p.v[0][ip], vInit[1] = p.v[1][ip], vInit[2] = p.v[2][ip];
@@ -435,15 +414,17 @@ __global__ void __launch_bounds__(256, 2) move_lapenta_kernel(DevMesh m, DevSpec
     }
     if (newKey != oldKey) p.key[ip] = newKey;
   }
+  }  // work items
 
   flush_move_counters(stats, nMoved, nXCell, nXBlock, nLeft, nNotUsed, nWrap, nErr);
 }
 
 void launch_move_lapenta(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *eTile, const double *bTile,
                          int *cellCount, DevMoveStats *stats, int slices, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount,
-                         long long exitCap, cudaStream_t s) {
+                         long long exitCap, const unsigned char *redoMask, const int *redoLeafList, const int *nRedoLeaves, cudaStream_t s) {
   const size_t smem = (size_t)(m.eTileStride + m.bTileStride) * sizeof(double);
-  const int grid = m.nLeaves * slices;
+  int grid = m.nLeaves * slices;
+  if (redoLeafList && grid > 148 * 2) grid = 148 * 2;  // second pass: persistent CTAs over the (short) list of flagged blocks
   const bool cornerB = sp.bMode == AMPS_B_CORNER_BASED;
   if (smem <= 200 * 1024) {
     static bool attrSet = false;
@@ -453,13 +434,13 @@ void launch_move_lapenta(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, 
       attrSet = true;
     }
     if (cornerB)
-      move_lapenta_kernel<true, true><<<grid, 256, smem, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap);
+      move_lapenta_kernel<true, true><<<grid, 256, smem, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap, redoMask, redoLeafList, nRedoLeaves);
     else
-      move_lapenta_kernel<true, false><<<grid, 256, smem, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap);
+      move_lapenta_kernel<true, false><<<grid, 256, smem, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap, redoMask, redoLeafList, nRedoLeaves);
   } else if (cornerB) {
-    move_lapenta_kernel<false, true><<<grid, 256, 0, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap);
+    move_lapenta_kernel<false, true><<<grid, 256, 0, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap, redoMask, redoLeafList, nRedoLeaves);
   } else {
-    move_lapenta_kernel<false, false><<<grid, 256, 0, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap);
+    move_lapenta_kernel<false, false><<<grid, 256, 0, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap, redoMask, redoLeafList, nRedoLeaves);
   }
 }
 

@@ -127,7 +127,7 @@ __device__ __forceinline__ void store_particle(const ParticleSoA &dst, int pos, 
 }
 
 // two particles per thread and iteration: twice the loads in flight per warp (the kernel is latency bound)
-__global__ void __launch_bounds__(256) scatter_kernel(ParticleSoA src, ParticleSoA dst, const int *__restrict__ nSrc, const int *__restrict__ cellStart,
+__global__ void __launch_bounds__(256, 5) scatter_kernel(ParticleSoA src, ParticleSoA dst, const int *__restrict__ nSrc, const int *__restrict__ cellStart,
                                                      int *__restrict__ cellFill) {
   const int n = *nSrc;
   const int stride = gridDim.x * blockDim.x;

@@ -109,6 +109,10 @@ typedef struct amps_gpu_config {
   int64_t exit_record_capacity;      /* records kept for the host callbacks (0 = only count)                              */
   double gravity_gm;                 /* GravityConstant*_MASS_(_TARGET_) of BorisSplitAcceleration_default (:110-118), 0 = off */
   int32_t carry_magnetic_moment;     /* _USE_MAGNETIC_MOMENT_: particles carry mu (picParticleDataMacro.h:178-187); needed by the GCA movers */
+  int32_t exact_arithmetic;          /* 1: Lapenta2017 rounds every operation like the CPU build (no FMA contraction, IEEE quotients):
+                                        x', v' bit-identical.  0 (default): contracted arithmetic for every particle whose x' stays clear
+                                        of cell faces, the exact kernel for the rest -> keys/counters still bit-exact, x', v' to ~1e-14 */
+  int32_t reserved1;
   int32_t ideal_mhd;                 /* _PIC__IDEAL_MHD_MODE_ (picGlobal.dfn:339, default ON): E.b = 0 in the guiding-centre parallel force */
 } amps_gpu_config;
 
@@ -204,6 +208,9 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx);
 const char *amps_gpu_last_error(const amps_gpu_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py "gpu_launches") */
 int64_t amps_gpu_launch_count(const amps_gpu_ctx *ctx);
+/* diagnostic: particles the last Lapenta2017 move handed from the contracted-arithmetic kernel to the exact one
+ * (0 with exact_arithmetic = 1 or before the first move)                                          */
+int amps_gpu_last_move_redo(amps_gpu_ctx *ctx, int64_t *n);
 /* cudaStream_t the context launches on (as void*) */
 void *amps_gpu_stream(amps_gpu_ctx *ctx);
 

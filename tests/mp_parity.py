@@ -60,6 +60,7 @@ def main():
     Bcl = pick(Bcur, mg.center_gkey, m.center_gkey)
 
     cfg = api.make_config((8, 8, 8), (1, 1, 1), charge, mass, wgt, 1.0, periodic=True, capacity=n + 1024, device=local)
+    cfg.exact_arithmetic = 1  # the sharding must not change a bit: compared bit for bit with the single-domain oracle
     g = api.Context(cfg, m)
     g.comm_init(dist)
     g.fields_upload(El, Bl, Bcl)

@@ -34,7 +34,7 @@ def rel_scaled(a, b):
 
 
 def make_case(n_cells=(16, 16, 16), ppc=8, seed=3, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), E_amp=0.01, dt=1.0, vscale=1.0,
-              periodic=True, extra_capacity=0, boundary_mode=0, b_mode=0, amr_radii=None, ppc_by_level=None):
+              periodic=True, extra_capacity=0, boundary_mode=0, b_mode=0, amr_radii=None, ppc_by_level=None, exact_arithmetic=0):
     if amr_radii is not None:  # BASELINE config 4 (scaled): sphere-refined open box, mixed ppc, drifting Maxwellian
         nb = [n_cells[d] // block_cells[d] for d in range(3)]
         m = workload.amr_sphere_box(nb, block_cells, ghost_cells, radii=amr_radii)
@@ -57,6 +57,7 @@ def make_case(n_cells=(16, 16, 16), ppc=8, seed=3, block_cells=(8, 8, 8), ghost_
                           boundary_mode=boundary_mode)
     cfg.exit_record_capacity = x.shape[1]
     cfg.b_mode = b_mode
+    cfg.exact_arithmetic = exact_arithmetic
     E, B = workload.box_fields(m, E_amp=E_amp, b_on_corners=(b_mode == _capi.B_CORNER_BASED))
     Bcur = B * 1.01 + 0.001  # B_cur != B_prev so that a mix-up of the two shows
     return m, cfg, (x, v, w, sp, cells), (E, B, Bcur)
@@ -94,8 +95,9 @@ def run_gpu(m, cfg, parts, fields):
     en, cfl = g.UpdateJMassMatrix()
     J, M = g.JM_download()
     launches = g.launch_count()
+    n_redo = g.last_move_redo()
     g.close()
-    return {"n0": n0, "stats": st, "moved": moved, "sorted": srt, "table": table, "J": J, "M": M, "energy": en, "cfl": cfl, "launches": launches,
+    return {"n_redo": n_redo, "n0": n0, "stats": st, "moved": moved, "sorted": srt, "table": table, "J": J, "M": M, "energy": en, "cfl": cfl, "launches": launches,
             "records": sorted(recs), "n_records": nrec}
 
 
@@ -139,6 +141,7 @@ def compare(m, parts, ora, gpu):
     res["n_records"] = ora["n_records"]
     res["records_equal"] = (gpu["n_records"] == ora["n_records"]) and (gpu["records"] == ora["records"])
     res["gpu_launches"] = gpu["launches"]
+    res["n_redo"] = gpu["n_redo"]
     return res
 
 

@@ -33,15 +33,22 @@ def test_oracle_matches_golden():
 
 
 @pytest.mark.gpu
-def test_gpu_matches_golden():
+@pytest.mark.parametrize("exact", [1, 0])
+def test_gpu_matches_golden(exact):
     m, cfg, parts, fields = _inputs()
+    cfg.exact_arithmetic = exact
     gpu = pu.run_gpu(m, cfg, parts, fields)
     n = parts[0].shape[1]
     mv = gpu["moved"]
     gx, gv, gc = np.empty((3, n)), np.empty((3, n)), np.empty(n, dtype=np.int64)
     gx[:, mv["ptrs"]], gv[:, mv["ptrs"]], gc[mv["ptrs"]] = mv["x"], mv["v"], mv["cells"]
     assert (gc == G["final_cell"]).all()                      # bit-exact cell assignment
-    assert (gx == G["x_out"]).all() and (gv == G["v_out"]).all()
+    if exact:   # every operation rounded like the CPU build
+        assert (gx == G["x_out"]).all() and (gv == G["v_out"]).all()
+    else:       # contracted arithmetic away from cell faces: a few ulp (contract: 1e-10)
+        alive = G["final_cell"] >= 0
+        assert pu.rel_elementwise(gx[:, alive], G["x_out"][:, alive]) <= 1e-12
+        assert pu.rel_elementwise(gv[:, alive], G["v_out"][:, alive]) <= 1e-10
     assert [gpu["stats"][k] for k in sorted(gpu["stats"])] == list(G["stats"])
     assert pu.rel_scaled(gpu["J"], G["J"]) <= pu.REL_TOL and pu.rel_scaled(gpu["M"], G["M"]) <= pu.REL_TOL
     assert abs(gpu["energy"] - float(G["energy"])) <= pu.REL_TOL * float(G["energy"])
