@@ -39,8 +39,8 @@ constexpr int CHUNK = 32;                  // particles per phase-1 pass (one pe
 constexpr int DEP_WARPS = 4, DEP_THREADS = 32 * DEP_WARPS, DEP_CTAS_PER_SM = 2;
 constexpr int N_TILES = 6, N_SLICES = 5;   // 30 active lanes
 constexpr int N_T = 27 * 12;               // class sums per cell
-constexpr int SLAB = CHUNK * ROW;          // doubles of row storage per warp (>= N_T: reused for the totals)
-static_assert(SLAB >= N_T, "the totals must fit in the row slab");
+constexpr int SLAB = N_SLICES * N_T;       // doubles per warp: the particle rows of a chunk, later the 5 slice partials of T
+static_assert(SLAB >= CHUNK * ROW, "the particle rows must fit in the slab");
 
 __device__ __forceinline__ void atomicMaxPositiveDouble(unsigned long long *addr, double v) {
   // v >= 0 and not NaN: the bit patterns of non-negative doubles order like unsigned integers
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
                                                                               const double *__restrict__ bCurTile, double *__restrict__ J,
                                                                               double *__restrict__ M, double *__restrict__ energyOut,
                                                                               unsigned long long *__restrict__ cflBits) {
-  __shared__ __align__(16) double sRows[DEP_WARPS][SLAB];
+  extern __shared__ __align__(16) double sRows[];  // [DEP_WARPS][SLAB]
   __shared__ double sBall[DEP_WARPS][27 * 3];  // B_cur on the 3x3x3 centres around the warp's cell
   // flush tables: output o = (c*8+c')*9+col -> corner c (3 bits) | offset inside M[corner] (8 bits) | T index (9 bits)
   __shared__ unsigned int sFlush[576];
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
   const int warpGlobal = blockIdx.x * DEP_WARPS + wib, nWarps = gridDim.x * DEP_WARPS;
   const int nCells = m.nLeaves * m.cellsPerBlock;
   const int C = m.cellsPerBlock;
-  double *rows = sRows[wib];
+  double *rows = sRows + (size_t)wib * SLAB;
   double *sB = sBall[wib];
 
   const bool active = lane < N_TILES * N_SLICES;
@@ -325,28 +325,23 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
         if (cfl > cflMax) cflMax = cfl;
       }
     }
-    // ---- fold the 5 slices: lanes 24..29 -> 0..5, 12..17 -> 0..5 and 18..23 -> 6..11, 6..11 -> 0..5 ----
-#pragma unroll
-    for (int i = 0; i < 54; i++) {
-      double v = acc[i];
-      double t2 = __shfl_down_sync(0xffffffffu, v, 24);
-      if (lane < 6) v += t2;
-      t2 = __shfl_down_sync(0xffffffffu, v, 12);
-      if (lane < 12) v += t2;
-      t2 = __shfl_down_sync(0xffffffffu, v, 6);
-      if (lane < 6) v += t2;
-      acc[i] = v;
-    }
+    // ---- fold the 5 slices through shared memory: every lane stores its 54 partial sums at their T index in its
+    //      slice's copy, then lane l sums entries l, l+32, ... over the slices (in place into copy 0) ----
     __syncwarp();  // phase 2 finished reading the slab
-    if (lane < N_TILES) {
-      // totals T[cls*12 + col] into the (now free) row slab
-      double *r = rows + (px * 9) * 12 + 6 * h;
+    if (active) {
+      double *r = rows + slice * N_T + (px * 9) * 12 + 6 * h;
 #pragma unroll
       for (int j = 0; j < 9; j++) {
         reinterpret_cast<double2 *>(r + 12 * j)[0] = make_double2(acc[6 * j + 0], acc[6 * j + 1]);
         reinterpret_cast<double2 *>(r + 12 * j)[1] = make_double2(acc[6 * j + 2], acc[6 * j + 3]);
         reinterpret_cast<double2 *>(r + 12 * j)[2] = make_double2(acc[6 * j + 4], acc[6 * j + 5]);
       }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < (N_T + 31) / 32; q++) {
+      const int i = lane + 32 * q;
+      if (i < N_T) rows[i] = ((rows[i] + rows[N_T + i]) + (rows[2 * N_T + i] + rows[3 * N_T + i])) + rows[4 * N_T + i];
     }
     __syncwarp();
     // ---- flush the mass matrix: 64 ordered corner pairs x 9 (both (c,c') and (c',c) get the same block, :2411-2420)
@@ -438,14 +433,23 @@ void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const
   cudaMemsetAsync(energy, 0, sizeof(double), s);
   cudaMemsetAsync(cflBits, 0, sizeof(unsigned long long) * AMPS_GPU_MAX_SPECIES, s);
   const int grid = nSM * DEP_CTAS_PER_SM;
+  const size_t smem = sizeof(double) * DEP_WARPS * SLAB;
+  static bool attrSet = false;
+  if (!attrSet) {
+    cudaFuncSetAttribute(deposit_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(deposit_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(deposit_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(deposit_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attrSet = true;
+  }
   const bool corner = sp.bMode == AMPS_B_CORNER_BASED;
   if (sp.n <= 2) {
-    if (corner) deposit_kernel<true, true><<<grid, DEP_THREADS, 0, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits);
-    else deposit_kernel<false, true><<<grid, DEP_THREADS, 0, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits);
+    if (corner) deposit_kernel<true, true><<<grid, DEP_THREADS, smem, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits);
+    else deposit_kernel<false, true><<<grid, DEP_THREADS, smem, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits);
     (*launches) += 1;
   } else {
-    if (corner) deposit_kernel<true, false><<<grid, DEP_THREADS, 0, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits);
-    else deposit_kernel<false, false><<<grid, DEP_THREADS, 0, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits);
+    if (corner) deposit_kernel<true, false><<<grid, DEP_THREADS, smem, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits);
+    else deposit_kernel<false, false><<<grid, DEP_THREADS, smem, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits);
     diag_kernel<<<nSM * 4, 256, 0, s>>>(m, sp, p, cellStart, energy, cflBits);
     (*launches) += 2;
   }

@@ -19,7 +19,7 @@ namespace amps {
 
 constexpr double MOVE_GUARD = 1.0e-8;
 #ifndef FAST_CTAS
-#define FAST_CTAS 3
+#define FAST_CTAS 2
 #endif
 
 struct FastBlockConst {
@@ -92,11 +92,31 @@ __global__ void __launch_bounds__(256, FAST_CTAS) move_lapenta_fast_kernel(DevMe
 
   unsigned int nMoved = 0, nXCell = 0, nXBlock = 0, nWrap = 0, nRedo = 0;
 
+  // software pipeline: the loads of the NEXT particle are in flight while the current one is pushed (the kernel is
+  // bound by the latency of these loads otherwise: one thread owns every 256th particle of the slice)
+  double nx0 = 0.0, nx1 = 0.0, nx2 = 0.0, nv0 = 0.0, nv1 = 0.0, nv2 = 0.0;
+  int nspec = 0, nkey = 0;
+  {
+    const int ip = b + threadIdx.x;
+    if (ip < e) {
+      nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
+      nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
+      nspec = p.spec[ip], nkey = p.key[ip];
+    }
+  }
   for (int ip = b + threadIdx.x; ip < e; ip += blockDim.x) {
-    double x0 = p.x[0][ip], x1 = p.x[1][ip], x2 = p.x[2][ip];
-    const double v0 = p.v[0][ip], v1 = p.v[1][ip], v2 = p.v[2][ip];
-    const int spec = p.spec[ip] & 0x3f;
-    const int oldKey = p.key[ip];
+    double x0 = nx0, x1 = nx1, x2 = nx2;
+    const double v0 = nv0, v1 = nv1, v2 = nv2;
+    const int spec = nspec & 0x3f;
+    const int oldKey = nkey;
+    {
+      const int np = ip + blockDim.x;
+      if (np < e) {
+        nx0 = p.x[0][np], nx1 = p.x[1][np], nx2 = p.x[2][np];
+        nv0 = p.v[0][np], nv1 = p.v[1][np], nv2 = p.v[2][np];
+        nspec = p.spec[np], nkey = p.key[np];
+      }
+    }
     bool redo = false;
 
     // ---- a3: corner stencil (the snap to xmax-1e-10dx compares inputs only: same decision as the reference) ----
