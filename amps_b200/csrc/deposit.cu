@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
       const int ip = begin + lane;
       nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
       nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
-      nw = p.w[ip], nspec = p.spec[ip] & 0x3f;
+      nw = p.w[ip], nspec = p.spec[ip];
     }
     for (int base = begin; base < end; base += CHUNK) {
       const int np = min(CHUNK, end - base);
@@ -155,12 +155,12 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
       // ---------------- phase 1: lane <-> particle ----------------
       const double x0 = nx0, x1 = nx1, x2 = nx2, pw = nw;
       double v0 = nv0, v1 = nv1, v2 = nv2;
-      const int spec = nspec;
+      const int spec = nspec & 0x3f;  // masked at use: the load stays in flight during phase 2
       if (base + CHUNK + lane < end) {
         const int ip = base + CHUNK + lane;
         nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
         nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
-        nw = p.w[ip], nspec = p.spec[ip] & 0x3f;
+        nw = p.w[ip], nspec = p.spec[ip];
       }
       if (lane < np) {
         const double LocalParticleWeight = sp.weight[spec] * pw;

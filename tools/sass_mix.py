@@ -8,7 +8,8 @@ ia, isrc, iex, ith, ist = hdr.index("Address"), hdr.index("Source"), hdr.index("
 mix = collections.Counter(); stall = collections.Counter(); tot = 0; totst = 0
 recs = []
 for r in rows[2:]:
-    if len(r) <= ist: continue
+    if r and r[0] == "Kernel Name": break  # several launches in one export: the first one is enough
+    if len(r) <= ist or r[0] == "Address": continue
     op = r[isrc].strip().split()
     if not op: continue
     o = op[1] if op[0].startswith('@') else op[0]
