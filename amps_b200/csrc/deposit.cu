@@ -77,9 +77,12 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
   // flush tables: output o = (c*8+c')*9+col -> corner c (3 bits) | offset inside M[corner] (8 bits) | T index (9 bits)
   __shared__ unsigned int sFlush[576];
   __shared__ unsigned short sJcls[64];  // T index (without column) of pair (c,c')
-  __shared__ double sQdt2m[AMPS_GPU_MAX_SPECIES];
-  if (threadIdx.x < AMPS_GPU_MAX_SPECIES)
-    sQdt2m[threadIdx.x] = (threadIdx.x < sp.n) ? 0.5 * (sp.charge[threadIdx.x] * sp.dtTotal / sp.mass[threadIdx.x]) : 0.0;
+  __shared__ double sQdt2m[AMPS_GPU_MAX_SPECIES], sInvBeta[AMPS_GPU_MAX_SPECIES];
+  if (threadIdx.x < AMPS_GPU_MAX_SPECIES) {
+    const double b = (threadIdx.x < sp.n) ? 0.5 * (sp.charge[threadIdx.x] * sp.dtTotal / sp.mass[threadIdx.x]) : 0.0;
+    sQdt2m[threadIdx.x] = b;
+    sInvBeta[threadIdx.x] = (b != 0.0) ? 1.0 / b : 0.0;  // neutral species deposit nothing
+  }
   for (int o = threadIdx.x; o < 576; o += DEP_THREADS) {
     const int c = o / 72, r = o - 72 * c, d = r / 9, col = r - 9 * d;
     sFlush[o] = (unsigned)c | ((unsigned)(9 * index_matrix(c, d) + col) << 3) | ((unsigned)(pair_class(c, d) * 12 + col) << 11);
@@ -100,8 +103,11 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
   const double invc = 1.0 / sp.LightSpeed;
   double eAcc = 0.0, cflMax = 0.0;  // kDiag: per-lane energy; lane s keeps the cfl of species s
 
+  int nBegin = 0, nEnd = 0;  // cell table entry of the NEXT cell (requested one cell ahead)
+  if (warpGlobal < nCells) nBegin = cellStart[warpGlobal], nEnd = cellStart[warpGlobal + 1];
   for (int cell = warpGlobal; cell < nCells; cell += nWarps) {
-    const int begin = cellStart[cell], end = cellStart[cell + 1];
+    const int begin = nBegin, end = nEnd;
+    if (cell + nWarps < nCells) nBegin = cellStart[cell + nWarps], nEnd = cellStart[cell + nWarps + 1];
     if (begin == end) continue;  // ProcessCell returns false: nothing is flushed
     const int leaf = cell / C;
     const LeafGeo &lg = m.leaf[leaf];
@@ -112,6 +118,16 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     const int jc = (cin - kc * m.N[0] * m.N[1]) / m.N[0];
     const int ic = cin - kc * m.N[0] * m.N[1] - jc * m.N[0];
 
+    // software prefetch: the particle of the NEXT chunk is loaded while phase 2 of the current one runs; the first
+    // chunk's loads are issued before the B staging so that the two latencies overlap
+    double nx0 = 0, nx1 = 0, nx2 = 0, nv0 = 0, nv1 = 0, nv2 = 0, nw = 0;
+    int nspec = 0;
+    if (begin + lane < end) {
+      const int ip = begin + lane;
+      nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
+      nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
+      nw = p.w[ip], nspec = p.spec[ip];
+    }
     __syncwarp();  // previous cell's totals fully flushed
     int uidLane = 0;
     if (lane < 8) uidLane = m.cornerUid[(size_t)leaf * m.nCornerLocal + cornerLocalNumber(m, ic + cox(lane), jc + coy(lane), kc + coz(lane))];
@@ -140,15 +156,6 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     double vm0 = 0.0, vm1 = 0.0;  // kDiag: sum |v| dt of species 0 / 1 seen by this lane
     int cnt01 = 0;                // counts: species 0 in the low half, species 1 in the high half
 
-    // software prefetch: the particle of the NEXT chunk is loaded while phase 2 of the current one runs
-    double nx0 = 0, nx1 = 0, nx2 = 0, nv0 = 0, nv1 = 0, nv2 = 0, nw = 0;
-    int nspec = 0;
-    if (begin + lane < end) {
-      const int ip = begin + lane;
-      nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
-      nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
-      nw = p.w[ip], nspec = p.spec[ip];
-    }
     for (int base = begin; base < end; base += CHUNK) {
       const int np = min(CHUNK, end - base);
       __syncwarp();  // sB visible; previous chunk consumed
@@ -262,29 +269,28 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
         }
         const double chargeQ = sp.charge[spec] * LocalParticleWeight;
         // beta = q~ dt / 2 m~ : the statistical weight cancels (to 1 ulp), so it is a per-species constant
-        const double QdT_over_2m = sQdt2m[spec];
-        const double s2 = QdT_over_2m * QdT_over_2m;
-        const double P0 = -QdT_over_2m * B0, P1 = -QdT_over_2m * B1, P2 = -QdT_over_2m * B2;
+        const double beta = sQdt2m[spec];
+        const double s2 = beta * beta;
         const double c0 = fast_rcp(1.0 + s2 * (B0 * B0 + B1 * B1 + B2 * B2));
-        double al[9];
-        al[0] = c0 * (1.0 + s2 * B0 * B0);
-        al[1] = c0 * (-P2 + s2 * B0 * B1);
-        al[2] = c0 * (P1 + s2 * B0 * B2);
-        al[3] = c0 * (P2 + s2 * B1 * B0);
-        al[4] = c0 * (1.0 + s2 * B1 * B1);
-        al[5] = c0 * (-P0 + s2 * B1 * B2);
-        al[6] = c0 * (-P1 + s2 * B2 * B0);
-        al[7] = c0 * (P0 + s2 * B2 * B1);
-        al[8] = c0 * (1.0 + s2 * B2 * B2);
-        const double kk = chargeQ * QdT_over_2m * invV;  // matrixConst (:2311)
-        const double qV = chargeQ * invV;                 // Jg/CellVolume (:2367)
+        // k alpha with k = matrixConst = q~ beta / V (:2311) and alpha = c0 (I - beta [B]x + beta^2 B B^T) (:1056-1067):
+        // symmetric part S_ij = kc (delta_ij + beta^2 B_i B_j), antisymmetric part from kc beta B
+        const double kc = (chargeQ * beta * invV) * c0;
+        const double cB0 = kc * B0, cB1 = kc * B1, cB2 = kc * B2;
+        const double t0 = s2 * B0, t1 = s2 * B1, t2 = s2 * B2;
+        const double S01 = t0 * cB1, S02 = t0 * cB2, S12 = t1 * cB2;
+        const double A0 = beta * cB0, A1 = beta * cB1, A2 = beta * cB2;  // kc * (-P_i)
+        const double a0 = fma(t0, cB0, kc), a1 = S01 + A2, a2 = S02 - A1;
+        const double a3 = S01 - A2, a4 = fma(t1, cB1, kc), a5 = S12 + A0;
+        const double a6 = S02 + A1, a7 = S12 - A0, a8 = fma(t2, cB2, kc);
+        // Jg/CellVolume = q~/V alpha v = (k alpha v)/beta (:2367)
+        const double ib = sInvBeta[spec];
         double2 *a = reinterpret_cast<double2 *>(row + OFF_A);
-        a[0] = make_double2(kk * al[0], kk * al[1]);
-        a[1] = make_double2(kk * al[2], kk * al[3]);
-        a[2] = make_double2(kk * al[4], kk * al[5]);
-        a[3] = make_double2(kk * al[6], kk * al[7]);
-        a[4] = make_double2(kk * al[8], qV * (al[0] * v0 + al[1] * v1 + al[2] * v2));
-        a[5] = make_double2(qV * (al[3] * v0 + al[4] * v1 + al[5] * v2), qV * (al[6] * v0 + al[7] * v1 + al[8] * v2));
+        a[0] = make_double2(a0, a1);
+        a[1] = make_double2(a2, a3);
+        a[2] = make_double2(a4, a5);
+        a[3] = make_double2(a6, a7);
+        a[4] = make_double2(a8, ib * (a0 * v0 + a1 * v1 + a2 * v2));
+        a[5] = make_double2(ib * (a3 * v0 + a4 * v1 + a5 * v2), ib * (a6 * v0 + a7 * v1 + a8 * v2));
       }
       __syncwarp();
       // ---------------- phase 2: register-tile accumulation ----------------
