@@ -211,6 +211,12 @@ class Context:
         self._ck(self.lib.amps_gpu_JM_download(self._h, _ptr(J), _ptr(M)))
         return J, M
 
+    def diagnostics(self):
+        e = C.c_double()
+        cfl = (C.c_double * _capi.MAX_SPECIES)()
+        self._ck(self.lib.amps_gpu_diagnostics(self._h, C.cast(C.byref(e), C.c_void_p), C.cast(cfl, C.c_void_p)))
+        return float(e.value), [float(cfl[s]) for s in range(self.cfg.n_species)]
+
     def step(self, mover=_capi.MOVER_LAPENTA2017):
         self._ck(self.lib.amps_gpu_step(self._h, mover))
 

@@ -101,9 +101,10 @@ void launch_move_lapenta_fast(const DevMesh &m, const DevSpecies &sp, ParticleSo
                               int *cellCount, DevMoveStats *stats, int slices, unsigned char *redoMask, int *leafRedo, int *redoLeafList,
                               int *nRedoLeaves, cudaStream_t s);
 void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *nSrc, int *cellCount, int *cellStart, int *cellFill, int *nDst,
-                 long long capacity, bool countValid, void *scanTmp, cudaStream_t s, long long *launches);
+                 long long capacity, bool countValid, void *scanTmp, int *perm, cudaStream_t s, long long *launches);
+// perm != nullptr: p is the UNSORTED store, particle i of the sorted order is p[perm[i]]; the kernel also writes the sorted copy to dst
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
-                    double *energy, unsigned long long *cflBits, int nSM, cudaStream_t s, long long *launches);
+                    double *energy, unsigned long long *cflBits, int nSM, const int *perm, ParticleSoA dst, cudaStream_t s, long long *launches);
 size_t sort_scan_tmp_bytes(long long nCells);
 // migration record: 8 doubles (x,v,w,meta) + mu when the particles carry it
 inline int migration_record_len(const ParticleSoA &p) { return p.mu ? 9 : 8; }

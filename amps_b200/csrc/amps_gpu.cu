@@ -51,6 +51,7 @@ struct amps_gpu_ctx {
   bool gcaReady = false;
   bool meshRefined = false;  // some leaf is below level 0
   unsigned char *d_redoMask = nullptr;  // particles the fast mover left to the exact kernel
+  int *d_perm = nullptr;      // sorted position -> slot (fused sort + deposit inside amps_gpu_step)
   int *d_leafRedo = nullptr;  // [nLeaves] counts, then [nLeaves] list of flagged blocks, then 1 counter
   double *d_gradBVar = nullptr, *d_gradBTile = nullptr;  // guiding centre: grad B, 9 values per centre node
   bool gradBReady = false;
@@ -264,7 +265,7 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
   if (ctx->comm && nccl_api().CommDestroy) nccl_api().CommDestroy(ctx->comm);
   cudaFree(ctx->d_gcaVar), cudaFree(ctx->d_gcaTile), cudaFree(ctx->d_gradBVar), cudaFree(ctx->d_gradBTile);
-  cudaFree(ctx->d_redoMask), cudaFree(ctx->d_leafRedo);
+  cudaFree(ctx->d_redoMask), cudaFree(ctx->d_leafRedo), cudaFree(ctx->d_perm);
   cudaFree(ctx->d_bgE), cudaFree(ctx->d_bgB), cudaFree(ctx->d_bgTile), cudaFree(ctx->d_exitBuf), cudaFree(ctx->d_exitCount);
   cudaFree(ctx->d_sendBuf), cudaFree(ctx->d_recvBuf), cudaFree(ctx->d_sendCount), cudaFree(ctx->d_allCounts), cudaFree(ctx->d_errFlag);
   for (int *p : ctx->d_sharedUid) cudaFree(p);
@@ -607,8 +608,35 @@ static int do_sort(amps_gpu_ctx *ctx) {
   ProfScope prof(ctx, AMPS_GPU_PHASE_SORT);
   ParticleSoA &src = ctx->buf[ctx->cur], &dst = ctx->buf[1 - ctx->cur];
   launch_sort(ctx->dm, src, dst, ctx->d_n + ctx->cur, ctx->d_cellCount, ctx->d_cellStart, ctx->d_cellFill, ctx->d_n + (1 - ctx->cur), ctx->nUpper,
-              ctx->countValid, ctx->d_scanTmp, ctx->stream, &ctx->launches);
+              ctx->countValid, ctx->d_scanTmp, nullptr, ctx->stream, &ctx->launches);
   CK(cudaGetLastError());
+  ctx->cur = 1 - ctx->cur;
+  ctx->sorted = true;
+  ctx->countValid = false;
+  return AMPS_GPU_OK;
+}
+
+// amps_gpu_step: the counting sort only builds the permutation (8 B per particle); the deposit gathers through it and
+// writes the sorted copy while it has the particle in registers.  Same end state as do_sort + do_deposit.
+static int do_sort_deposit_fused(amps_gpu_ctx *ctx) {
+  if (!ctx->meshReady || !ctx->fieldsReady) FAIL(AMPS_GPU_ERR_STATE, "deposit before mesh/fields upload");
+  if (ctx->meshRefined && ctx->cfg.b_mode == AMPS_B_CENTER_BASED)
+    FAIL(AMPS_GPU_ERR_STATE, "ECSIM on a refined mesh needs _PIC_FIELD_SOLVER_B_CORNER_BASED_ (see amps_gpu_move)");
+  int rc;
+  if (!ctx->d_perm && (rc = dev_alloc(ctx, &ctx->d_perm, (size_t)ctx->cfg.capacity))) return rc;
+  ParticleSoA &src = ctx->buf[ctx->cur], &dst = ctx->buf[1 - ctx->cur];
+  {
+    ProfScope prof(ctx, AMPS_GPU_PHASE_SORT);
+    launch_sort(ctx->dm, src, dst, ctx->d_n + ctx->cur, ctx->d_cellCount, ctx->d_cellStart, ctx->d_cellFill, ctx->d_n + (1 - ctx->cur), ctx->nUpper,
+                ctx->countValid, ctx->d_scanTmp, ctx->d_perm, ctx->stream, &ctx->launches);
+    CK(cudaGetLastError());
+  }
+  {
+    ProfScope prof(ctx, AMPS_GPU_PHASE_DEPOSIT);
+    launch_deposit(ctx->dm, ctx->sp, src, ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl, ctx->nSM, ctx->d_perm, dst,
+                   ctx->stream, &ctx->launches);
+    CK(cudaGetLastError());
+  }
   ctx->cur = 1 - ctx->cur;
   ctx->sorted = true;
   ctx->countValid = false;
@@ -893,7 +921,7 @@ static int do_deposit(amps_gpu_ctx *ctx) {
     FAIL(AMPS_GPU_ERR_STATE, "ECSIM on a refined mesh needs _PIC_FIELD_SOLVER_B_CORNER_BASED_ (see amps_gpu_move)");
   ProfScope prof(ctx, AMPS_GPU_PHASE_DEPOSIT);
   launch_deposit(ctx->dm, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl,
-                 ctx->nSM, ctx->stream, &ctx->launches);
+                 ctx->nSM, nullptr, ctx->buf[ctx->cur], ctx->stream, &ctx->launches);
   CK(cudaGetLastError());
   return AMPS_GPU_OK;
 }
@@ -913,6 +941,20 @@ int amps_gpu_deposit_JM(amps_gpu_ctx *ctx, double *particle_energy, double *cfl)
     if (cfl)
       for (int s = 0; s < ctx->cfg.n_species; s++) memcpy(&cfl[s], &c[s], 8);
   }
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_diagnostics(amps_gpu_ctx *ctx, double *particle_energy, double *cfl) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  double e;
+  unsigned long long c[AMPS_GPU_MAX_SPECIES];
+  CK(cudaMemcpyAsync(&e, ctx->d_energy, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(c, ctx->d_cfl, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (particle_energy) *particle_energy = e;
+  if (cfl)
+    for (int s = 0; s < ctx->cfg.n_species; s++) memcpy(&cfl[s], &c[s], 8);
   return AMPS_GPU_OK;
 }
 
@@ -1125,8 +1167,7 @@ int amps_gpu_step(amps_gpu_ctx *ctx, int mover_id) {
   int rc;
   if ((rc = do_move(ctx, mover_id))) return rc;
   if ((rc = do_migrate(ctx, nullptr, nullptr))) return rc;
-  if ((rc = do_sort(ctx))) return rc;
-  if ((rc = do_deposit(ctx))) return rc;
+  if ((rc = do_sort_deposit_fused(ctx))) return rc;
   return do_exchange_JM(ctx);
 }
 

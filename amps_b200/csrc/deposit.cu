@@ -66,12 +66,15 @@ __device__ __forceinline__ int index_matrix(int c, int d) {
 }
 
 // kDiag: the energy / cfl diagnostics (diag_kernel below) are folded into phase 1 when there are at most two species
-template <bool kCornerB, bool kDiag>
+// kGather: the counting sort only produced the permutation; sorted particle i is p[perm[i]] and this kernel writes it to dst[i]
+//          (the physical reordering costs no extra pass: its reads are the deposit's own reads)
+template <bool kCornerB, bool kDiag, bool kGather>
 __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(DevMesh m, DevSpecies sp, ParticleSoA p,
                                                                               const int *__restrict__ cellStart,
                                                                               const double *__restrict__ bCurTile, double *__restrict__ J,
                                                                               double *__restrict__ M, double *__restrict__ energyOut,
-                                                                              unsigned long long *__restrict__ cflBits) {
+                                                                              unsigned long long *__restrict__ cflBits,
+                                                                              const int *__restrict__ perm, ParticleSoA dst) {
   extern __shared__ __align__(16) double sRows[];  // [DEP_WARPS][SLAB]
   __shared__ double sBall[DEP_WARPS][27 * 3];  // B_cur on the 3x3x3 centres around the warp's cell
   // flush tables: output o = (c*8+c')*9+col -> corner c (3 bits) | offset inside M[corner] (8 bits) | T index (9 bits)
@@ -112,7 +115,16 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     const int leaf = cell / C;
     const LeafGeo &lg = m.leaf[leaf];
     const int face = lg.face;
-    if (m.periodic && face != 0) continue;  // periodic "ghost" (boundary) blocks are skipped, :3815-3825
+    if (m.periodic && face != 0) {  // periodic "ghost" (boundary) blocks are skipped, :3815-3825
+      if (kGather)  // (no particle should be here after the wrap; keep the store complete anyway)
+        for (int ip = begin + lane; ip < end; ip += 32) {
+          const int sidx = perm[ip];
+          for (int d = 0; d < 3; d++) dst.x[d][ip] = p.x[d][sidx], dst.v[d][ip] = p.v[d][sidx];
+          dst.w[ip] = p.w[sidx], dst.spec[ip] = p.spec[sidx], dst.key[ip] = cell, dst.ptr[ip] = p.ptr[sidx];
+          if (p.mu) dst.mu[ip] = p.mu[sidx];
+        }
+      continue;
+    }
     const int cin = cell - leaf * C;
     const int kc = cin / (m.N[0] * m.N[1]);
     const int jc = (cin - kc * m.N[0] * m.N[1]) / m.N[0];
@@ -122,12 +134,15 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     // chunk's loads are issued before the B staging so that the two latencies overlap
     double nx0 = 0, nx1 = 0, nx2 = 0, nv0 = 0, nv1 = 0, nv2 = 0, nw = 0;
     int nspec = 0;
+    int nsrc = 0, nsrc2 = 0;  // kGather: source slot of the prefetched particle / of the one after it
     if (begin + lane < end) {
-      const int ip = begin + lane;
+      const int ip = kGather ? perm[begin + lane] : begin + lane;
+      nsrc = ip;
       nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
       nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
       nw = p.w[ip], nspec = p.spec[ip];
     }
+    if (kGather && begin + CHUNK + lane < end) nsrc2 = perm[begin + CHUNK + lane];
     __syncwarp();  // previous cell's totals fully flushed
     int uidLane = 0;
     if (lane < 8) uidLane = m.cornerUid[(size_t)leaf * m.nCornerLocal + cornerLocalNumber(m, ic + cox(lane), jc + coy(lane), kc + coz(lane))];
@@ -163,11 +178,21 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
       const double x0 = nx0, x1 = nx1, x2 = nx2, pw = nw;
       double v0 = nv0, v1 = nv1, v2 = nv2;
       const int spec = nspec & 0x3f;  // masked at use: the load stays in flight during phase 2
+      if (kGather && lane < np) {
+        // the sorted copy (the scatter of the counting sort, fused): slot base+lane of dst <- slot nsrc of p
+        const int o = base + lane;
+        dst.x[0][o] = x0, dst.x[1][o] = x1, dst.x[2][o] = x2;
+        dst.v[0][o] = v0, dst.v[1][o] = v1, dst.v[2][o] = v2;
+        dst.w[o] = pw, dst.spec[o] = (uint8_t)nspec, dst.key[o] = cell, dst.ptr[o] = p.ptr[nsrc];
+        if (p.mu) dst.mu[o] = p.mu[nsrc];
+      }
       if (base + CHUNK + lane < end) {
-        const int ip = base + CHUNK + lane;
+        const int ip = kGather ? nsrc2 : base + CHUNK + lane;
+        nsrc = ip;
         nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
         nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
         nw = p.w[ip], nspec = p.spec[ip];
+        if (kGather && base + 2 * CHUNK + lane < end) nsrc2 = perm[base + 2 * CHUNK + lane];
       }
       if (lane < np) {
         const double LocalParticleWeight = sp.weight[spec] * pw;
@@ -432,7 +457,7 @@ __global__ void __launch_bounds__(256) diag_kernel(DevMesh m, DevSpecies sp, Par
 }
 
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
-                    double *energy, unsigned long long *cflBits, int nSM, cudaStream_t s, long long *launches) {
+                    double *energy, unsigned long long *cflBits, int nSM, const int *perm, ParticleSoA dst, cudaStream_t s, long long *launches) {
   // zero J, M (SetCornerNodeAssociatedDataValue, :3266-3267) and the diagnostics
   cudaMemsetAsync(J, 0, sizeof(double) * 3 * (size_t)m.nCorners, s);
   cudaMemsetAsync(M, 0, sizeof(double) * 243 * (size_t)m.nCorners, s);
@@ -440,24 +465,29 @@ void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const
   cudaMemsetAsync(cflBits, 0, sizeof(unsigned long long) * AMPS_GPU_MAX_SPECIES, s);
   const int grid = nSM * DEP_CTAS_PER_SM;
   const size_t smem = sizeof(double) * DEP_WARPS * SLAB;
-  static bool attrSet = false;
-  if (!attrSet) {
-    cudaFuncSetAttribute(deposit_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(deposit_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(deposit_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(deposit_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attrSet = true;
-  }
-  const bool corner = sp.bMode == AMPS_B_CORNER_BASED;
-  if (sp.n <= 2) {
-    if (corner) deposit_kernel<true, true><<<grid, DEP_THREADS, smem, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits);
-    else deposit_kernel<false, true><<<grid, DEP_THREADS, smem, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits);
-    (*launches) += 1;
+  const bool corner = sp.bMode == AMPS_B_CORNER_BASED, diag = sp.n <= 2, gather = perm != nullptr;
+#define AMPS_DEP_LAUNCH(CB, DG, GA)                                                                                          \
+  do {                                                                                                                       \
+    static bool attrSet = false;                                                                                             \
+    if (!attrSet) {                                                                                                          \
+      cudaFuncSetAttribute(deposit_kernel<CB, DG, GA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+      attrSet = true;                                                                                                        \
+    }                                                                                                                        \
+    deposit_kernel<CB, DG, GA><<<grid, DEP_THREADS, smem, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits, perm, dst); \
+  } while (0)
+  if (corner) {
+    if (diag) { if (gather) AMPS_DEP_LAUNCH(true, true, true); else AMPS_DEP_LAUNCH(true, true, false); }
+    else { if (gather) AMPS_DEP_LAUNCH(true, false, true); else AMPS_DEP_LAUNCH(true, false, false); }
   } else {
-    if (corner) deposit_kernel<true, false><<<grid, DEP_THREADS, smem, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits);
-    else deposit_kernel<false, false><<<grid, DEP_THREADS, smem, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits);
-    diag_kernel<<<nSM * 4, 256, 0, s>>>(m, sp, p, cellStart, energy, cflBits);
-    (*launches) += 2;
+    if (diag) { if (gather) AMPS_DEP_LAUNCH(false, true, true); else AMPS_DEP_LAUNCH(false, true, false); }
+    else { if (gather) AMPS_DEP_LAUNCH(false, false, true); else AMPS_DEP_LAUNCH(false, false, false); }
+  }
+#undef AMPS_DEP_LAUNCH
+  (*launches) += 1;
+  if (!diag) {
+    // more than two species: the diagnostics run as their own pass over the SORTED store
+    diag_kernel<<<nSM * 4, 256, 0, s>>>(m, sp, gather ? dst : p, cellStart, energy, cflBits);
+    (*launches) += 1;
   }
 }
 

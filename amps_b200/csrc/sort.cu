@@ -151,13 +151,29 @@ __global__ void __launch_bounds__(256, 5) scatter_kernel(ParticleSoA src, Partic
   }
 }
 
+// permutation only: perm[position in the (block,cell)-sorted order] = current slot.  8 B per particle instead of the 130 B of
+// the full scatter; the deposit that follows gathers through perm and writes the sorted copy as a by-product.
+__global__ void __launch_bounds__(256, 5) perm_kernel(const int *__restrict__ key, const int *__restrict__ nSrc, const int *__restrict__ cellStart,
+                                                     int *__restrict__ cellFill, int *__restrict__ perm) {
+  const int n = *nSrc;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
+    const int j = i + stride;
+    const int ka = key[i];
+    const int kb = (j < n) ? key[j] : -1;
+    if (ka >= 0) perm[cellStart[ka] + warp_aggregated_slot(cellFill, ka)] = i;
+    if (kb >= 0) perm[cellStart[kb] + warp_aggregated_slot(cellFill, kb)] = j;
+  }
+}
+
 size_t sort_scan_tmp_bytes(long long nCells) {
   const long long nTiles = (nCells + SCAN_TILE - 1) / SCAN_TILE;
   return (size_t)(nTiles + 2) * sizeof(int);
 }
 
+// perm != nullptr: only the permutation is produced (dst is not written)
 void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *nSrc, int *cellCount, int *cellStart, int *cellFill, int *nDst,
-                 long long nUpper, bool countValid, void *scanTmp, cudaStream_t s, long long *launches) {
+                 long long nUpper, bool countValid, void *scanTmp, int *perm, cudaStream_t s, long long *launches) {
   const long long nCells = (long long)m.nLeaves * m.cellsPerBlock;
   const int nTiles = (int)((nCells + SCAN_TILE - 1) / SCAN_TILE);
   int *tileSum = reinterpret_cast<int *>(scanTmp);
@@ -171,7 +187,8 @@ void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *
   scan_tile_offsets_kernel<<<1, SCAN_THREADS, 0, s>>>(tileSum, nTiles, nDst);
   scan_write_kernel<<<nTiles, SCAN_THREADS, 0, s>>>(cellCount, nCells, tileSum, nDst, cellStart);
   cudaMemsetAsync(cellFill, 0, sizeof(int) * nCells, s);
-  scatter_kernel<<<pgrid, 256, 0, s>>>(src, dst, nSrc, cellStart, cellFill);
+  if (perm) perm_kernel<<<pgrid, 256, 0, s>>>(src.key, nSrc, cellStart, cellFill, perm);
+  else scatter_kernel<<<pgrid, 256, 0, s>>>(src, dst, nSrc, cellStart, cellFill);
   (*launches) += 4;
 }
 

@@ -291,6 +291,9 @@ int amps_gpu_move(amps_gpu_ctx *ctx, int mover_id, amps_gpu_move_stats *stats);
 int amps_gpu_deposit_JM(amps_gpu_ctx *ctx, double *particle_energy, double *cfl);
 /* J[n_corners][3], M[n_corners][243] (neighbour-major, 9 per neighbour as in
  * IndexMatrix, pic_field_solver_ecsim.cpp:1377-1380); either may be NULL          */
+/* particle energy and per-species cfl of the last deposit (amps_gpu_deposit_JM or amps_gpu_step; after
+ * amps_gpu_exchange_JM they are the all-reduced values)                                            */
+int amps_gpu_diagnostics(amps_gpu_ctx *ctx, double *particle_energy, double *cfl);
 int amps_gpu_JM_download(amps_gpu_ctx *ctx, double *J, double *M);
 /* device pointers for an on-device consumer (field solve) */
 int amps_gpu_JM_device(amps_gpu_ctx *ctx, double **J_dev, double **M_dev);
