@@ -211,6 +211,12 @@ class Context:
         self._ck(self.lib.amps_gpu_JM_download(self._h, _ptr(J), _ptr(M)))
         return J, M
 
+    def step_JM(self, out_J, out_M, mover=_capi.MOVER_LAPENTA2017):
+        """step() + JM_download() with the download pipelined behind the deposit (pin out_J / out_M for real overlap)"""
+        assert out_J.shape == (self.mesh.n_corners, 3) and out_M.shape == (self.mesh.n_corners, 243)
+        self._ck(self.lib.amps_gpu_step_JM(self._h, mover, _ptr(out_J), _ptr(out_M)))
+        return out_J, out_M
+
     def diagnostics(self):
         e = C.c_double()
         cfl = (C.c_double * _capi.MAX_SPECIES)()

@@ -52,6 +52,14 @@ struct amps_gpu_ctx {
   bool meshRefined = false;  // some leaf is below level 0
   unsigned char *d_redoMask = nullptr;  // particles the fast mover left to the exact kernel
   int *d_perm = nullptr;      // sorted position -> slot (fused sort + deposit inside amps_gpu_step)
+  // amps_gpu_step_JM: the deposit runs in cell ranges; the corners whose last contributing cell lies in range k form the
+  // uid runs dlRuns[dlRunStart[k] .. dlRunStart[k+1]) and are copied to the host while range k+1 is deposited
+  struct DlRun { int uid0, n; };
+  std::vector<int> dlCellEnd;      // [nChunks] end cell of each range
+  std::vector<int> dlRunStart;     // [nChunks+1]
+  std::vector<DlRun> dlRuns;
+  cudaStream_t copyStream = nullptr;
+  std::vector<cudaEvent_t> dlEvents;
   int *d_leafRedo = nullptr;  // [nLeaves] counts, then [nLeaves] list of flagged blocks, then 1 counter
   double *d_gradBVar = nullptr, *d_gradBTile = nullptr;  // guiding centre: grad B, 9 values per centre node
   bool gradBReady = false;
@@ -266,6 +274,8 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   if (ctx->comm && nccl_api().CommDestroy) nccl_api().CommDestroy(ctx->comm);
   cudaFree(ctx->d_gcaVar), cudaFree(ctx->d_gcaTile), cudaFree(ctx->d_gradBVar), cudaFree(ctx->d_gradBTile);
   cudaFree(ctx->d_redoMask), cudaFree(ctx->d_leafRedo), cudaFree(ctx->d_perm);
+  for (cudaEvent_t e : ctx->dlEvents) cudaEventDestroy(e);
+  if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   cudaFree(ctx->d_bgE), cudaFree(ctx->d_bgB), cudaFree(ctx->d_bgTile), cudaFree(ctx->d_exitBuf), cudaFree(ctx->d_exitCount);
   cudaFree(ctx->d_sendBuf), cudaFree(ctx->d_recvBuf), cudaFree(ctx->d_sendCount), cudaFree(ctx->d_allCounts), cudaFree(ctx->d_errFlag);
   for (int *p : ctx->d_sharedUid) cudaFree(p);
@@ -402,6 +412,67 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
       }
       g.invV = 1.0 / vol;
       g.diag = sqrt(d2);
+    }
+  }
+  // ---- download schedule of amps_gpu_step_JM: for every corner the last cell range that deposits into it ----
+  {
+    // ranges of leaves: whole z-layers of root blocks on an unrefined mesh (leaves and corner ids are both z-major there, so
+    // the corners finished by a range are one contiguous run), equal shares of the leaf list otherwise
+    std::vector<int> leafEnd;
+    const int perLayer = m.nRoot[0] * m.nRoot[1];
+    if (!ctx->meshRefined && m.nLeaves == perLayer * m.nRoot[2] && m.nRoot[2] >= 4) {
+      const int group = (m.nRoot[2] + 9) / 10;  // at most ~10 ranges
+      for (int z = group; z < m.nRoot[2]; z += group) leafEnd.push_back(z * perLayer);
+      leafEnd.push_back(m.nLeaves);
+    } else {
+      const int nEq = (m.nLeaves >= 64) ? 8 : 1;
+      for (int k = 0; k < nEq; k++) leafEnd.push_back((int)((long long)m.nLeaves * (k + 1) / nEq));
+    }
+    const int nChunks = (int)leafEnd.size();
+    std::vector<int> lastChunk((size_t)m.nCorners, -1);
+    ctx->dlCellEnd.assign(nChunks, 0);
+    for (int k = 0; k < nChunks; k++) {
+      const int l0 = k ? leafEnd[k - 1] : 0, l1 = leafEnd[k];
+      ctx->dlCellEnd[k] = l1 * m.cellsPerBlock;
+      for (int l = l0; l < l1; l++) {
+        if (ctx->cfg.periodic && mesh->leaf_face_boundary[l] != 0) continue;  // periodic ghost blocks deposit nothing
+        const int *cu = mesh->leaf_corner_uid + (size_t)l * m.nCornerLocal;
+        for (int kk = 0; kk <= m.N[2]; kk++)
+          for (int jj = 0; jj <= m.N[1]; jj++)
+            for (int ii = 0; ii <= m.N[0]; ii++) {
+              const int u = cu[ii + m.g[0] + (m.TN[0] + 1) * (jj + m.g[1] + (kk + m.g[2]) * (m.TN[1] + 1))];
+              if (u >= 0) lastChunk[u] = k;  // ranges are visited in order: the last writer wins
+            }
+      }
+    }
+    ctx->dlRunStart.assign(nChunks + 1, 0);
+    ctx->dlRuns.clear();
+    for (int k = 0; k < nChunks; k++) {
+      ctx->dlRunStart[k] = (int)ctx->dlRuns.size();
+      for (int u = 0; u < m.nCorners;) {
+        // corners no cell deposits into (ghost-layer nodes) stay zero: they travel with range 0
+        const int ck = lastChunk[u] < 0 ? 0 : lastChunk[u];
+        if (ck != k) {
+          u++;
+          continue;
+        }
+        int v = u + 1;
+        while (v < m.nCorners && (lastChunk[v] < 0 ? 0 : lastChunk[v]) == k) v++;
+        // runs closer than 2048 corners are merged: a few corners travel twice (their final copy comes later on the
+        // same stream), but a range costs two API calls instead of hundreds
+        const int first = ctx->dlRunStart[k];
+        if ((int)ctx->dlRuns.size() > first && u - (ctx->dlRuns.back().uid0 + ctx->dlRuns.back().n) < 256)
+          ctx->dlRuns.back().n = v - ctx->dlRuns.back().uid0;
+        else
+          ctx->dlRuns.push_back({u, v - u});
+        u = v;
+      }
+    }
+    ctx->dlRunStart[nChunks] = (int)ctx->dlRuns.size();
+    if (ctx->dlRuns.size() > 4096) {  // scattered ownership (e.g. unordered AMR leaves): one range, one run
+      ctx->dlCellEnd.assign(1, m.nLeaves * m.cellsPerBlock);
+      ctx->dlRunStart = {0, 1};
+      ctx->dlRuns = {{0, m.nCorners}};
     }
   }
   int rc;
@@ -634,7 +705,7 @@ static int do_sort_deposit_fused(amps_gpu_ctx *ctx) {
   {
     ProfScope prof(ctx, AMPS_GPU_PHASE_DEPOSIT);
     launch_deposit(ctx->dm, ctx->sp, src, ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl, ctx->nSM, ctx->d_perm, dst,
-                   ctx->stream, &ctx->launches);
+                   0, -1, ctx->stream, &ctx->launches);
     CK(cudaGetLastError());
   }
   ctx->cur = 1 - ctx->cur;
@@ -921,7 +992,7 @@ static int do_deposit(amps_gpu_ctx *ctx) {
     FAIL(AMPS_GPU_ERR_STATE, "ECSIM on a refined mesh needs _PIC_FIELD_SOLVER_B_CORNER_BASED_ (see amps_gpu_move)");
   ProfScope prof(ctx, AMPS_GPU_PHASE_DEPOSIT);
   launch_deposit(ctx->dm, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl,
-                 ctx->nSM, nullptr, ctx->buf[ctx->cur], ctx->stream, &ctx->launches);
+                 ctx->nSM, nullptr, ctx->buf[ctx->cur], 0, -1, ctx->stream, &ctx->launches);
   CK(cudaGetLastError());
   return AMPS_GPU_OK;
 }
@@ -1159,6 +1230,88 @@ int amps_gpu_exchange_JM(amps_gpu_ctx *ctx) {
   if (!ctx) return AMPS_GPU_ERR_ARG;
   CK(cudaSetDevice(ctx->cfg.device));
   return do_exchange_JM(ctx);
+}
+
+int amps_gpu_step(amps_gpu_ctx *ctx, int mover_id);
+// amps_gpu_step + amps_gpu_JM_download with the download pipelined behind the deposit
+int amps_gpu_step_JM(amps_gpu_ctx *ctx, int mover_id, double *J_host, double *M_host) {
+  if (!ctx || !J_host || !M_host) return AMPS_GPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc;
+  if (ctx->nRanks > 1) {  // shared corners change in the exchange: no early download
+    if ((rc = amps_gpu_step(ctx, mover_id))) return rc;
+    return amps_gpu_JM_download(ctx, J_host, M_host);
+  }
+  if ((rc = do_move(ctx, mover_id))) return rc;
+  if (!ctx->meshReady || !ctx->fieldsReady) FAIL(AMPS_GPU_ERR_STATE, "deposit before mesh/fields upload");
+  if (ctx->meshRefined && ctx->cfg.b_mode == AMPS_B_CENTER_BASED)
+    FAIL(AMPS_GPU_ERR_STATE, "ECSIM on a refined mesh needs _PIC_FIELD_SOLVER_B_CORNER_BASED_ (see amps_gpu_move)");
+  if (!ctx->d_perm && (rc = dev_alloc(ctx, &ctx->d_perm, (size_t)ctx->cfg.capacity))) return rc;
+  const int nChunks = (int)ctx->dlCellEnd.size();
+  if (!ctx->copyStream) CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  while ((int)ctx->dlEvents.size() < nChunks) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->dlEvents.push_back(e);
+  }
+  ParticleSoA &src = ctx->buf[ctx->cur], &dst = ctx->buf[1 - ctx->cur];
+  const bool dbg = getenv("AMPS_GPU_DEBUG_TIMELINE") != nullptr;
+  std::vector<cudaEvent_t> tk, tc0, tc1;
+  cudaEvent_t t00 = nullptr;
+  if (dbg) {
+    cudaEventCreate(&t00);
+    cudaEventRecord(t00, ctx->stream);
+  }
+  {
+    ProfScope prof(ctx, AMPS_GPU_PHASE_SORT);
+    launch_sort(ctx->dm, src, dst, ctx->d_n + ctx->cur, ctx->d_cellCount, ctx->d_cellStart, ctx->d_cellFill, ctx->d_n + (1 - ctx->cur), ctx->nUpper,
+                ctx->countValid, ctx->d_scanTmp, ctx->d_perm, ctx->stream, &ctx->launches);
+    CK(cudaGetLastError());
+  }
+  {
+    ProfScope prof(ctx, AMPS_GPU_PHASE_DEPOSIT);
+    int c0 = 0;
+    for (int k = 0; k < nChunks; k++) {
+      if (dbg) {
+        cudaEvent_t a, b, c;
+        cudaEventCreate(&a), cudaEventCreate(&b), cudaEventCreate(&c);
+        tk.push_back(a), tc0.push_back(b), tc1.push_back(c);
+      }
+      launch_deposit(ctx->dm, ctx->sp, src, ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl, ctx->nSM, ctx->d_perm,
+                     dst, c0, ctx->dlCellEnd[k], ctx->stream, &ctx->launches);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(ctx->dlEvents[k], ctx->stream));
+      if (dbg) cudaEventRecord(tk[k], ctx->stream);
+      CK(cudaStreamWaitEvent(ctx->copyStream, ctx->dlEvents[k], 0));
+      if (dbg) cudaEventRecord(tc0[k], ctx->copyStream);
+      for (int r = ctx->dlRunStart[k]; r < ctx->dlRunStart[k + 1]; r++) {
+        const size_t u0 = (size_t)ctx->dlRuns[r].uid0, n = (size_t)ctx->dlRuns[r].n;
+        CK(cudaMemcpyAsync(M_host + 243 * u0, ctx->d_M + 243 * u0, sizeof(double) * 243 * n, cudaMemcpyDeviceToHost, ctx->copyStream));
+      }
+      if (dbg) cudaEventRecord(tc1[k], ctx->copyStream);
+      c0 = ctx->dlCellEnd[k];
+    }
+    // J is 1% of the volume: one copy behind the last range
+    CK(cudaMemcpyAsync(J_host, ctx->d_J, sizeof(double) * 3 * (size_t)ctx->dm.nCorners, cudaMemcpyDeviceToHost, ctx->copyStream));
+  }
+  ctx->cur = 1 - ctx->cur;
+  ctx->sorted = true;
+  ctx->countValid = false;
+  CK(cudaStreamSynchronize(ctx->copyStream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (dbg) {
+    for (int k = 0; k < nChunks; k++) {
+      float a, b, c;
+      cudaEventElapsedTime(&a, t00, tk[k]), cudaEventElapsedTime(&b, t00, tc0[k]), cudaEventElapsedTime(&c, t00, tc1[k]);
+      size_t bytes = 0;
+      for (int r = ctx->dlRunStart[k]; r < ctx->dlRunStart[k + 1]; r++) bytes += (size_t)ctx->dlRuns[r].n * 243 * 8;
+      fprintf(stderr, "range %d: kernel done %.3f ms, copy %.3f -> %.3f ms, %.1f MB in %d runs\n", k, a, b, c, bytes / 1e6,
+              ctx->dlRunStart[k + 1] - ctx->dlRunStart[k]);
+      cudaEventDestroy(tk[k]), cudaEventDestroy(tc0[k]), cudaEventDestroy(tc1[k]);
+    }
+    cudaEventDestroy(t00);
+  }
+  return AMPS_GPU_OK;
 }
 
 int amps_gpu_step(amps_gpu_ctx *ctx, int mover_id) {

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
                                                                               const double *__restrict__ bCurTile, double *__restrict__ J,
                                                                               double *__restrict__ M, double *__restrict__ energyOut,
                                                                               unsigned long long *__restrict__ cflBits,
-                                                                              const int *__restrict__ perm, ParticleSoA dst) {
+                                                                              const int *__restrict__ perm, ParticleSoA dst, int cell0, int cell1) {
   extern __shared__ __align__(16) double sRows[];  // [DEP_WARPS][SLAB]
   __shared__ double sBall[DEP_WARPS][27 * 3];  // B_cur on the 3x3x3 centres around the warp's cell
   // flush tables: output o = (c*8+c')*9+col -> corner c (3 bits) | offset inside M[corner] (8 bits) | T index (9 bits)
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warpGlobal = blockIdx.x * DEP_WARPS + wib, nWarps = gridDim.x * DEP_WARPS;
-  const int nCells = m.nLeaves * m.cellsPerBlock;
+  const int nCells = cell1;  // this launch deposits the cells [cell0, cell1)
   const int C = m.cellsPerBlock;
   double *rows = sRows + (size_t)wib * SLAB;
   double *sB = sBall[wib];
@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
   double eAcc = 0.0, cflMax = 0.0;  // kDiag: per-lane energy; lane s keeps the cfl of species s
 
   int nBegin = 0, nEnd = 0;  // cell table entry of the NEXT cell (requested one cell ahead)
-  if (warpGlobal < nCells) nBegin = cellStart[warpGlobal], nEnd = cellStart[warpGlobal + 1];
-  for (int cell = warpGlobal; cell < nCells; cell += nWarps) {
+  if (cell0 + warpGlobal < nCells) nBegin = cellStart[cell0 + warpGlobal], nEnd = cellStart[cell0 + warpGlobal + 1];
+  for (int cell = cell0 + warpGlobal; cell < nCells; cell += nWarps) {
     const int begin = nBegin, end = nEnd;
     if (cell + nWarps < nCells) nBegin = cellStart[cell + nWarps], nEnd = cellStart[cell + nWarps + 1];
     if (begin == end) continue;  // ProcessCell returns false: nothing is flushed
@@ -457,12 +457,17 @@ __global__ void __launch_bounds__(256) diag_kernel(DevMesh m, DevSpecies sp, Par
 }
 
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
-                    double *energy, unsigned long long *cflBits, int nSM, const int *perm, ParticleSoA dst, cudaStream_t s, long long *launches) {
-  // zero J, M (SetCornerNodeAssociatedDataValue, :3266-3267) and the diagnostics
-  cudaMemsetAsync(J, 0, sizeof(double) * 3 * (size_t)m.nCorners, s);
-  cudaMemsetAsync(M, 0, sizeof(double) * 243 * (size_t)m.nCorners, s);
-  cudaMemsetAsync(energy, 0, sizeof(double), s);
-  cudaMemsetAsync(cflBits, 0, sizeof(unsigned long long) * AMPS_GPU_MAX_SPECIES, s);
+                    double *energy, unsigned long long *cflBits, int nSM, const int *perm, ParticleSoA dst, int cell0, int cell1, cudaStream_t s,
+                    long long *launches) {
+  const int nCellsAll = m.nLeaves * m.cellsPerBlock;
+  if (cell1 < 0 || cell1 > nCellsAll) cell1 = nCellsAll;
+  if (cell0 == 0) {
+    // zero J, M (SetCornerNodeAssociatedDataValue, :3266-3267) and the diagnostics; later cell ranges of the same deposit add to them
+    cudaMemsetAsync(J, 0, sizeof(double) * 3 * (size_t)m.nCorners, s);
+    cudaMemsetAsync(M, 0, sizeof(double) * 243 * (size_t)m.nCorners, s);
+    cudaMemsetAsync(energy, 0, sizeof(double), s);
+    cudaMemsetAsync(cflBits, 0, sizeof(unsigned long long) * AMPS_GPU_MAX_SPECIES, s);
+  }
   const int grid = nSM * DEP_CTAS_PER_SM;
   const size_t smem = sizeof(double) * DEP_WARPS * SLAB;
   const bool corner = sp.bMode == AMPS_B_CORNER_BASED, diag = sp.n <= 2, gather = perm != nullptr;
@@ -473,7 +478,7 @@ void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const
       cudaFuncSetAttribute(deposit_kernel<CB, DG, GA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
       attrSet = true;                                                                                                        \
     }                                                                                                                        \
-    deposit_kernel<CB, DG, GA><<<grid, DEP_THREADS, smem, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits, perm, dst); \
+    deposit_kernel<CB, DG, GA><<<grid, DEP_THREADS, smem, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits, perm, dst, cell0, cell1); \
   } while (0)
   if (corner) {
     if (diag) { if (gather) AMPS_DEP_LAUNCH(true, true, true); else AMPS_DEP_LAUNCH(true, true, false); }
@@ -484,8 +489,8 @@ void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const
   }
 #undef AMPS_DEP_LAUNCH
   (*launches) += 1;
-  if (!diag) {
-    // more than two species: the diagnostics run as their own pass over the SORTED store
+  if (!diag && cell1 == nCellsAll) {
+    // more than two species: the diagnostics run as their own pass over the SORTED store (after the last cell range)
     diag_kernel<<<nSM * 4, 256, 0, s>>>(m, sp, gather ? dst : p, cellStart, energy, cflBits);
     (*launches) += 1;
   }

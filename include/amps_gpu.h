@@ -291,6 +291,10 @@ int amps_gpu_move(amps_gpu_ctx *ctx, int mover_id, amps_gpu_move_stats *stats);
 int amps_gpu_deposit_JM(amps_gpu_ctx *ctx, double *particle_energy, double *cfl);
 /* J[n_corners][3], M[n_corners][243] (neighbour-major, 9 per neighbour as in
  * IndexMatrix, pic_field_solver_ecsim.cpp:1377-1380); either may be NULL          */
+/* amps_gpu_step followed by amps_gpu_JM_download, with the download pipelined: the deposit runs in ranges of blocks and the
+ * corners whose last contributing block lies in a finished range travel to the host (pinned memory for real overlap) while the
+ * next range is deposited.  Same results as the two calls.                                         */
+int amps_gpu_step_JM(amps_gpu_ctx *ctx, int mover_id, double *J_host, double *M_host);
 /* particle energy and per-species cfl of the last deposit (amps_gpu_deposit_JM or amps_gpu_step; after
  * amps_gpu_exchange_JM they are the all-reduced values)                                            */
 int amps_gpu_diagnostics(amps_gpu_ctx *ctx, double *particle_energy, double *cfl);

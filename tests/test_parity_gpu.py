@@ -75,3 +75,35 @@ def test_fused_step_equals_the_separate_phases(name):
     assert pu.rel_scaled(J, ref["J"]) <= 1e-12 and pu.rel_scaled(M, ref["M"]) <= 1e-12
     assert abs(en - ref["energy"]) <= 1e-12 * abs(ref["energy"])
     assert max(abs(p - q) for p, q in zip(cfl, ref["cfl"])) <= 1e-12 * max(ref["cfl"])
+
+
+@pytest.mark.parametrize("name", ["cube24_fast", "open_box", "amr_3_levels_corner_B"])
+def test_pipelined_step_download_equals_step_then_download(name):
+    """amps_gpu_step_JM (deposit in block ranges, J/M of finished corners copied out meanwhile) == step + JM_download"""
+    import numpy as np
+    from amps_b200 import api
+
+    kw = dict(CASES[name])
+    if name == "cube24_fast":
+        kw["n_cells"] = (32, 32, 32)   # 64 blocks: the schedule really has 8 ranges
+    m, cfg, parts, fields = pu.make_case(**kw)
+    x, v, w, sp, cells = parts
+    E, B, Bcur = fields
+    out = []
+    for pipelined in (False, True):
+        g = api.Context(cfg, m)
+        g.fields_upload(E, B, Bcur)
+        g.particles_upload(x, v, w, sp, cells)
+        if pipelined:
+            J, M = np.full((m.n_corners, 3), np.nan), np.full((m.n_corners, 243), np.nan)
+            g.step_JM(J, M)
+        else:
+            g.step()
+            J, M = g.JM_download()
+        out.append((J, M, g.diagnostics(), g.particles_download()))
+        g.close()
+    (J0, M0, d0, p0), (J1, M1, d1, p1) = out
+    assert not np.isnan(J1).any() and not np.isnan(M1).any()          # every corner was copied
+    assert pu.rel_scaled(J1, J0) <= 1e-12 and pu.rel_scaled(M1, M0) <= 1e-12
+    assert abs(d0[0] - d1[0]) <= 1e-12 * abs(d0[0])
+    assert (np.sort(p0["ptrs"]) == np.sort(p1["ptrs"])).all() and (p0["cells"] == p1["cells"]).all()
