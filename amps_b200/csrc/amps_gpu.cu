@@ -779,7 +779,16 @@ int amps_gpu_particles_upload_aos(amps_gpu_ctx *ctx, const void *records, const 
     sp[i] = r[lay->off_species] & 0x7f;  // species + InitFlag (bit 6)
     pt[i] = (int32_t)slot;
   }
-  return amps_gpu_particles_upload_soa(ctx, x.data(), v.data(), w.data(), sp.data(), cells, pt.data(), n);
+  int rc = amps_gpu_particles_upload_soa(ctx, x.data(), v.data(), w.data(), sp.data(), cells, pt.data(), n);
+  if (rc) return rc;
+  if (ctx->cfg.carry_magnetic_moment && lay->off_mu >= 0 && n > 0) {  // _PIC_PARTICLE_DATA__MAGNETIC_MOMENT_OFFSET_
+    int64_t maxSlot = 0;
+    for (int64_t i = 0; i < n; i++) maxSlot = pt[i] > maxSlot ? pt[i] : maxSlot;
+    std::vector<double> mu((size_t)maxSlot + 1, 0.0);
+    for (int64_t i = 0; i < n; i++) memcpy(&mu[pt[i]], base + (int64_t)pt[i] * lay->stride + lay->off_mu, 8);
+    rc = amps_gpu_magnetic_moment_upload(ctx, mu.data(), maxSlot + 1);
+  }
+  return rc;
 }
 
 int amps_gpu_particle_count(amps_gpu_ctx *ctx, int64_t *n) {
@@ -829,6 +838,12 @@ int amps_gpu_particles_download_aos(amps_gpu_ctx *ctx, void *records, int64_t *f
   rc = amps_gpu_particles_download_soa(ctx, x.data(), v.data(), w.data(), sp.data(), key.data(), pt.data(), n, &nn);
   if (rc) return rc;
   unsigned char *base = (unsigned char *)records;
+  std::vector<double> mu;
+  if (ctx->cfg.carry_magnetic_moment && lay->off_mu >= 0) {
+    mu.resize((size_t)n + 1);
+    int64_t nm;
+    if ((rc = amps_gpu_magnetic_moment_download(ctx, mu.data(), n, &nm))) return rc;
+  }
   if (first_cell_particle)
     for (int64_t c = 0; c < ctx->nCells; c++) first_cell_particle[c] = -1;
   for (int64_t i = 0; i < n; i++) {
@@ -840,6 +855,7 @@ int amps_gpu_particles_download_aos(amps_gpu_ctx *ctx, void *records, int64_t *f
     double u[3] = {v[i], v[n + i], v[2 * n + i]};
     memcpy(r + lay->off_v, u, 24);
     if (lay->off_w >= 0) memcpy(r + lay->off_w, &w[i], 8);
+    if (!mu.empty()) memcpy(r + lay->off_mu, &mu[i], 8);
     r[lay->off_species] = (unsigned char)((r[lay->off_species] & 0x80) | (sp[i] & 0x7f));
     if (first_cell_particle && key[i] >= 0) {
       // push on the cell list like the movers do (pic_mover_boris.cpp:1333-1343)
