@@ -315,9 +315,15 @@ def main():
     alg_bytes = KERNEL_ALG_BYTES[dom_alg](P) * n_part
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     step_alg = (ALG_BYTES_FIXED + ALG_BYTES_PER_CELL / P)
-    roofline = {"bound": "hbm", "kernel": {"move": "move_lapenta_kernel", "sort": "scatter_kernel", "deposit": "deposit_kernel"}[dom],
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "ms_per_launch": dom_ms, "alg_bytes_per_update": KERNEL_ALG_BYTES[dom_alg](P)}
+    # DRAM bytes of one launch from the `ncu --set full` capture of this very workload (profiles/r1_final_ncu_summary.txt:
+    # dram__bytes_read.sum + dram__bytes_write.sum); only quoted for the default size
+    ncu_traffic = {"move": 1.811606e9 + 1.602758e9, "deposit": 3.079941e9 + 2.743525e9, "sort": 0.139221e9 + 0.089466e9}
+    traffic = ncu_traffic[dom] if (args.cells == 64 and args.ppc == 64 and world == 1) else None
+    roofline = {"bound": "hbm", "kernel": {"move": "move_lapenta_fast_kernel", "sort": "perm_kernel", "deposit": "deposit_kernel"}[dom],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "ms_per_launch": dom_ms, "alg_bytes_per_update": KERNEL_ALG_BYTES[dom_alg](P),
+                "note": "the kernel is bound by the fp64 pipe (ncu: 36 % of peak, 8 warps/SM at 239 registers), not by HBM; inside "
+                        "amps_gpu_step it also writes the sorted particle copy (65 B/particle), which the algorithmic bytes do not count"}
     step_gbs = step_alg * (n_part * K / (ms * 1e-3)) / 1e9 if world == 1 else step_alg * (value / world) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
@@ -326,7 +332,8 @@ def main():
                                f"{dec[0]}x{dec[1]}x{dec[2]}), {args.ppc} ppc/species e+p, 8^3-cell blocks, single AMR level, Maxwellian "
                                f"v_th,e=0.05, dt=1 (BASELINE configs[1]" + ("" if world == 1 else "; NCCL particle migration + corner J/M exchange each step") + ")",
                    "particles_per_gpu": n_part, "particles_after": n_now, "l2": "inputs (2.2 GB particle SoA) larger than L2, no flush",
-                   "step": "move(Lapenta2017)+counting sort+UpdateJMassMatrix", "gen_s": round(t_gen, 1)},
+                   "step": "amps_gpu_step: move(Lapenta2017; contracted arithmetic + exact pass near cell faces) + permutation sort + "
+                           "UpdateJMassMatrix (gathers through the permutation, writes the sorted copy)", "gen_s": round(t_gen, 1)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": KE,
                 "ms_per_step": e2e_ms / KE},
