@@ -135,12 +135,14 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     double nx0 = 0, nx1 = 0, nx2 = 0, nv0 = 0, nv1 = 0, nv2 = 0, nw = 0;
     int nspec = 0;
     int nsrc = 0, nsrc2 = 0;  // kGather: source slot of the prefetched particle / of the one after it
+    int nptr = 0;             // kGather: its ParticleBuffer slot (travels to the sorted copy)
     if (begin + lane < end) {
       const int ip = kGather ? perm[begin + lane] : begin + lane;
       nsrc = ip;
       nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
       nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
       nw = p.w[ip], nspec = p.spec[ip];
+      if (kGather) nptr = p.ptr[ip];
     }
     if (kGather && begin + CHUNK + lane < end) nsrc2 = perm[begin + CHUNK + lane];
     __syncwarp();  // previous cell's totals fully flushed
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
         const int o = base + lane;
         dst.x[0][o] = x0, dst.x[1][o] = x1, dst.x[2][o] = x2;
         dst.v[0][o] = v0, dst.v[1][o] = v1, dst.v[2][o] = v2;
-        dst.w[o] = pw, dst.spec[o] = (uint8_t)nspec, dst.key[o] = cell, dst.ptr[o] = p.ptr[nsrc];
+        dst.w[o] = pw, dst.spec[o] = (uint8_t)nspec, dst.key[o] = cell, dst.ptr[o] = nptr;
         if (p.mu) dst.mu[o] = p.mu[nsrc];
       }
       if (base + CHUNK + lane < end) {
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
         nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
         nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
         nw = p.w[ip], nspec = p.spec[ip];
+        if (kGather) nptr = p.ptr[ip];
         if (kGather && base + 2 * CHUNK + lane < end) nsrc2 = perm[base + 2 * CHUNK + lane];
       }
       if (lane < np) {
