@@ -121,3 +121,140 @@ def maxwellian_box(mesh, ppc, seed=100, drift=(0.0, 0.0, 0.0), leaves=None, chun
         cells[sl] = np.repeat(leaves[li] * C + ci, 2 * ppc).astype(np.int32)
     w = np.ones(npart)
     return x, v, w, species, cells
+
+
+# ---- test-particle workloads (BASELINE configs[0] and [4]): protons in an Earth-like dipole (+ a weak convection E) tabulated on the
+# centre nodes of an open box, like srcEarth/main_lib.cpp:686-813 tabulates T96 and srcMoverTest/main_lib.cpp:127-225 its dipole
+RE = 6.371e6
+QP, MP, CLIGHT = 1.602176634e-19, 1.67262192369e-27, 299792458.0
+B0 = 3.1e-5
+
+
+def dipole(x):
+    r2 = (x ** 2).sum(1)
+    r5 = r2 ** 2.5
+    k = -B0 * RE ** 3
+    B = np.empty_like(x)
+    B[:, 0] = k * 3.0 * x[:, 2] * x[:, 0] / r5
+    B[:, 1] = k * 3.0 * x[:, 2] * x[:, 1] / r5
+    B[:, 2] = k * (3.0 * x[:, 2] ** 2 - r2) / r5
+    return B
+
+
+def background_analytic(x, uniform_B=None, E_uniform=None, convection=True):
+    if uniform_B is None:
+        r = np.sqrt((x ** 2).sum(1))
+        B = dipole(np.where(r[:, None] < 0.5 * RE, x + 0.5 * RE, x))
+        vbg = np.array([-4.0e5 if convection else 0.0, 0.0, 0.0])
+        E = -np.cross(np.broadcast_to(vbg, B.shape), B)
+    else:
+        B = np.broadcast_to(np.asarray(uniform_B, dtype=np.float64), x.shape).copy()
+        E = np.broadcast_to(np.asarray((0.0, 0.0, 0.0) if E_uniform is None else E_uniform, dtype=np.float64), x.shape).copy()
+    return E, B
+
+
+def gca_var15(x, h, **kw):
+    """b.grad(b), vE.grad(b), b.grad(vE), vE.grad(vE), grad(kappa*B) by central differences of the analytic field
+    (the reference tabulates the same five vectors from its data file, pic_datafile.cpp:1164-1340)"""
+    def derived(xx):
+        E, B = background_analytic(xx, **kw)
+        Bn = np.sqrt((B ** 2).sum(1))
+        b = B / Bn[:, None]
+        vE = np.cross(E, B) / (Bn ** 2)[:, None]
+        kappa = 1.0 / np.sqrt(1.0 - (vE ** 2).sum(1) / CLIGHT ** 2)
+        return b, vE, kappa * Bn
+
+    b, vE, _ = derived(x)
+    grad_b = np.empty((x.shape[0], 3, 3))  # [n][j][i] = d_j b_i
+    grad_vE = np.empty((x.shape[0], 3, 3))
+    grad_kB = np.empty((x.shape[0], 3))
+    for j in range(3):
+        e = np.zeros(3)
+        e[j] = h
+        bp, vp, kp = derived(x + e)
+        bm, vm, km = derived(x - e)
+        grad_b[:, j, :] = (bp - bm) / (2 * h)
+        grad_vE[:, j, :] = (vp - vm) / (2 * h)
+        grad_kB[:, j] = (kp - km) / (2 * h)
+    out = np.empty((x.shape[0], 15))
+    out[:, 0:3] = np.einsum("nj,nji->ni", b, grad_b)
+    out[:, 3:6] = np.einsum("nj,nji->ni", vE, grad_b)
+    out[:, 6:9] = np.einsum("nj,nji->ni", b, grad_vE)
+    out[:, 9:12] = np.einsum("nj,nji->ni", vE, grad_vE)
+    out[:, 12:15] = grad_kB
+    return out
+
+
+def gc_gradB(x, h, **kw):
+    """gradB[3*i+j] = d B_i / d x_j by central differences of the analytic field (layout of pic.h:8439-8442)"""
+    out = np.empty((x.shape[0], 9))
+    for j in range(3):
+        e = np.zeros(3)
+        e[j] = h
+        _, Bp = background_analytic(x + e, **kw)
+        _, Bm = background_analytic(x - e, **kw)
+        d = (Bp - Bm) / (2 * h)
+        for i in range(3):
+            out[:, 3 * i + j] = d[:, i]
+    return out
+
+
+
+
+def dipole_test_particles(n_particles, half_width_re=8.0, n_blocks=8, block_cells=(4, 4, 4), ghost_cells=(1, 1, 1), amr_levels=0, seed=1,
+                          rigidity_gv=(0.5, 20.0)):
+    """Mesh + protons launched in the shell 1.2..6 R_E with isotropic directions and log-uniform rigidity.  Returns
+    (mesh, (x, v, w, species, cells))."""
+    from . import mesh as meshmod
+
+    L = half_width_re * RE
+    refine = None
+    if amr_levels > 0:
+        # cell size grows with the distance from the planet, like dx = 0.25 R_E (r/R_E) of input/earth-cutoff-rigidity.input
+        def refine(level, lo, hi):
+            near = np.clip(np.zeros(3), lo, hi)
+            r = float(np.linalg.norm(near)) / RE
+            return r < half_width_re * (0.45, 0.12, 0.03)[level]  # nested so that neighbours differ by one level at most
+    m = meshmod.build_mesh((-L, -L, -L), (L, L, L), (n_blocks,) * 3, block_cells, ghost_cells, periodic=False, refine=refine, max_level=amr_levels)
+    rng = np.random.default_rng(seed)
+    u = rng.standard_normal((n_particles, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    rad = RE * rng.uniform(1.2, min(6.0, half_width_re - 0.5), n_particles)
+    x = (u * rad[:, None]).T.copy()
+    d = rng.standard_normal((n_particles, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    R = np.exp(rng.uniform(np.log(rigidity_gv[0]), np.log(rigidity_gv[1]), n_particles)) * 1e9  # volts
+    p = R * QP / CLIGHT
+    gamma = np.sqrt(1.0 + (p / (MP * CLIGHT)) ** 2)
+    speed = p / (gamma * MP)
+    v = (d * speed[:, None]).T.copy()
+    sp = np.zeros(n_particles, dtype=np.uint8)
+    cells = locate_cells(m, x)
+    return m, (x, v, np.ones(n_particles), sp, cells)
+
+
+def locate_cells(m, x):
+    """(block, cell) key of every position: leaf by the findTreeNode lattice (vectorised descent), then the cell inside the leaf"""
+    N = np.array(m.block_cells)
+    gmin = np.array([m.c.x_global_min[d] for d in range(3)])
+    dxr = np.array([m.c.dx_max_refinement[d] for d in range(3)])
+    lat = np.floor((x.T - gmin) / dxr).astype(np.int64)
+    S = 1 << int(m.c.max_refinement_level)
+    nroot = np.array([m.c.n_root[d] for d in range(3)])
+    r = lat // S
+    node = m.arrays["root_node"][r[:, 0] + nroot[0] * (r[:, 1] + nroot[1] * r[:, 2])].astype(np.int64)
+    child = m.arrays["node_child"].reshape(-1, 8)
+    imin = m.arrays["node_imin"].reshape(-1, 3)
+    isize = m.arrays["node_isize"]
+    while True:
+        has = child[node, 0] >= 0
+        if not has.any():
+            break
+        h = (isize[node] // 2)[:, None]
+        o = (lat - imin[node] >= h).astype(np.int64)
+        nxt = child[node, o[:, 0] + 2 * (o[:, 1] + 2 * o[:, 2])]
+        node = np.where(has, nxt, node)
+    leaf = m.arrays["node_leaf"][node].astype(np.int64)
+    lo, hi = m.leaf_xmin()[leaf], m.leaf_xmax()[leaf]
+    cidx = np.clip(np.floor((x.T - lo) / ((hi - lo) / N)).astype(np.int64), 0, N - 1)
+    return (leaf * int(N.prod()) + cidx[:, 0] + N[0] * (cidx[:, 1] + N[1] * cidx[:, 2])).astype(np.int32)

@@ -156,6 +156,59 @@ def run_reference(args):
     _emit(line)
 
 
+def bench_test_particle_movers(torch, n_particles=2_000_000):
+    """BASELINE configs[0] / [4] (scaled): pushes/s of the test-particle movers on one GPU, extra information next to the
+    headline line.  Relativistic Boris: protons traced backward in a dipole on a 3-level AMR mesh with 4^3-cell blocks, sub-cycled
+    by the local gyro period (pushes counted as mover calls, sub-cycles not counted).  Relativistic GCA: the MoverTest field
+    (dipole + E = -v x B) on 5^3-cell blocks with 2 ghost layers."""
+    from amps_b200 import _capi, api, workload as wl
+
+    out = {}
+    cases = {
+        "relativistic_boris_dipole_amr": dict(mover=_capi.MOVER_RELATIVISTIC_BORIS, kw=dict(amr_levels=2, n_blocks=4), dt=0.05, backward=1,
+                                              boundary=_capi.BOUNDARY_USER_FUNCTION),
+        "relativistic_gca_dipole": dict(mover=_capi.MOVER_RELATIVISTIC_GCA, kw=dict(n_blocks=8, block_cells=(5, 5, 5), ghost_cells=(2, 2, 2),
+                                                                                    rigidity_gv=(0.001, 0.05)), dt=0.05, backward=0,
+                                        boundary=_capi.BOUNDARY_DELETE),
+    }
+    for name, c in cases.items():
+        m, parts = wl.dipole_test_particles(n_particles, **c["kw"])
+        bc = c["kw"].get("block_cells", (4, 4, 4))
+        gc = c["kw"].get("ghost_cells", (1, 1, 1))
+        cfg = api.make_config(bc, gc, (wl.QP,), (wl.MP,), (1.0,), c["dt"], periodic=False, capacity=n_particles + 16, boundary_mode=c["boundary"])
+        cfg.time_step_mode = _capi.DT_SPECIES_GLOBAL
+        cfg.coupler_interpolation = _capi.CPLR_LINEAR
+        cfg.backward_time_integration = c["backward"]
+        cfg.speed_of_light = wl.CLIGHT
+        cfg.internal_sphere_radius = wl.RE
+        cfg.exit_record_capacity = n_particles
+        gca = c["mover"] == _capi.MOVER_RELATIVISTIC_GCA
+        cfg.carry_magnetic_moment = 1 if gca else 0
+        E, B = wl.background_analytic(m.center_x)
+        ctx = api.Context(cfg, m)
+        ctx.background_upload(E, B)
+        if gca:
+            ctx.background_upload_gca(wl.gca_var15(m.center_x, 1.0e3))
+        best = None
+        for rep in range(3):
+            ctx.particles_upload(*parts)
+            if gca:
+                ctx.InitiateMagneticMoment(_capi.MOVER_RELATIVISTIC_GCA)
+            ctx.profile(True)
+            st = ctx.MoveParticles(c["mover"], raise_on_particle_error=False)
+            ctx.sort()
+            ph = ctx.profile(False)
+            ms = ph["move"][0]
+            best = ms if best is None else min(best, ms)
+        out[name] = {"pushes_per_s": n_particles / (best * 1e-3), "ms_per_move": best, "particles": n_particles,
+                     "alg_bytes_per_push": 113.0 if gca else 105.0,
+                     "achieved_gbs": (113.0 if gca else 105.0) * n_particles / (best * 1e-3) / 1e9,
+                     "left_domain": st["n_left_domain"], "errors": st["n_error"],
+                     "mesh": f"{m.c.n_leaves} blocks of {bc[0]}^3 cells, levels {sorted(set(int(v) for v in m.leaf_level()))}"}
+        ctx.close()
+    return out
+
+
 _REAL_STDOUT = None
 
 
@@ -186,6 +239,7 @@ def main():
     ap.add_argument("--ppc", type=int, default=64, help="particles per cell per species")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-tp", action="store_true", help="skip the test-particle mover side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -343,6 +397,11 @@ def main():
         "roofline_step": {"alg_bytes_per_update": step_alg, "achieved_gbs_per_gpu": step_gbs, "frac_hbm": step_gbs / peak,
                           "fp64_tflops_per_gpu": ALG_FLOP_PER_UPDATE * (value / world) / 1e12},
     }
+    if world == 1 and not args.no_tp:
+        try:
+            line["test_particle_movers"] = bench_test_particle_movers(torch)
+        except Exception as exc:  # extra information only: never lose the headline line
+            line["test_particle_movers"] = {"error": repr(exc)}
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         n_cpu, per = cpu_port_rate((32, 32, 32), args.ppc, 2, cores)

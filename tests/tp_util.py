@@ -8,20 +8,8 @@ import numpy as np
 from amps_b200 import _capi, api, mesh as meshmod
 from oracle.oracle_py import Oracle
 
-RE = 6.371e6
-QP, MP, CLIGHT = 1.602176634e-19, 1.67262192369e-27, 299792458.0
-B0 = 3.1e-5
-
-
-def dipole(x):
-    r2 = (x ** 2).sum(1)
-    r5 = r2 ** 2.5
-    k = -B0 * RE ** 3
-    B = np.empty_like(x)
-    B[:, 0] = k * 3.0 * x[:, 2] * x[:, 0] / r5
-    B[:, 1] = k * 3.0 * x[:, 2] * x[:, 1] / r5
-    B[:, 2] = k * (3.0 * x[:, 2] ** 2 - r2) / r5
-    return B
+from amps_b200.workload import B0, CLIGHT, MP, QP, RE, dipole, gc_gradB, gca_var15  # noqa: F401
+from amps_b200.workload import background_analytic as _bg_analytic
 
 
 def make_tp_case(n_particles=4096, half_width_re=8.0, n_blocks=8, block_cells=(4, 4, 4), seed=1, dt=0.05, backward=False,
@@ -119,50 +107,6 @@ def load_ref_gridless():
 
 
 # ---- relativistic guiding-centre fixtures (config 5, srcMoverTest) -----------------------------------------
-def _bg_analytic(x, uniform_B=None, E_uniform=None, convection=True):
-    if uniform_B is None:
-        r = np.sqrt((x ** 2).sum(1))
-        B = dipole(np.where(r[:, None] < 0.5 * RE, x + 0.5 * RE, x))
-        vbg = np.array([-4.0e5 if convection else 0.0, 0.0, 0.0])
-        E = -np.cross(np.broadcast_to(vbg, B.shape), B)
-    else:
-        B = np.broadcast_to(np.asarray(uniform_B, dtype=np.float64), x.shape).copy()
-        E = np.broadcast_to(np.asarray((0.0, 0.0, 0.0) if E_uniform is None else E_uniform, dtype=np.float64), x.shape).copy()
-    return E, B
-
-
-def gca_var15(x, h, **kw):
-    """b.grad(b), vE.grad(b), b.grad(vE), vE.grad(vE), grad(kappa*B) by central differences of the analytic field
-    (the reference tabulates the same five vectors from its data file, pic_datafile.cpp:1164-1340)"""
-    def derived(xx):
-        E, B = _bg_analytic(xx, **kw)
-        Bn = np.sqrt((B ** 2).sum(1))
-        b = B / Bn[:, None]
-        vE = np.cross(E, B) / (Bn ** 2)[:, None]
-        kappa = 1.0 / np.sqrt(1.0 - (vE ** 2).sum(1) / CLIGHT ** 2)
-        return b, vE, kappa * Bn
-
-    b, vE, _ = derived(x)
-    grad_b = np.empty((x.shape[0], 3, 3))  # [n][j][i] = d_j b_i
-    grad_vE = np.empty((x.shape[0], 3, 3))
-    grad_kB = np.empty((x.shape[0], 3))
-    for j in range(3):
-        e = np.zeros(3)
-        e[j] = h
-        bp, vp, kp = derived(x + e)
-        bm, vm, km = derived(x - e)
-        grad_b[:, j, :] = (bp - bm) / (2 * h)
-        grad_vE[:, j, :] = (vp - vm) / (2 * h)
-        grad_kB[:, j] = (kp - km) / (2 * h)
-    out = np.empty((x.shape[0], 15))
-    out[:, 0:3] = np.einsum("nj,nji->ni", b, grad_b)
-    out[:, 3:6] = np.einsum("nj,nji->ni", vE, grad_b)
-    out[:, 6:9] = np.einsum("nj,nji->ni", b, grad_vE)
-    out[:, 9:12] = np.einsum("nj,nji->ni", vE, grad_vE)
-    out[:, 12:15] = grad_kB
-    return out
-
-
 def make_gca_case(n_particles=4096, seed=2, dt=0.02, interp=_capi.CPLR_LINEAR, sphere=True, uniform_B=None, E_uniform=None,
                   rigidity_gv=(0.001, 0.05), convection=True, **kw):
     m, cfg, parts, _ = make_tp_case(n_particles=n_particles, seed=seed, dt=dt, interp=interp, boundary=_capi.BOUNDARY_DELETE, sphere=sphere,
@@ -210,20 +154,6 @@ def run_gpu_gca(m, cfg, parts, bg, var15):
 
 
 # ---- non-relativistic guiding centre (pic_mover_guiding_center.cpp) ----------------------------------------
-def gc_gradB(x, h, **kw):
-    """gradB[3*i+j] = d B_i / d x_j by central differences of the analytic field (layout of pic.h:8439-8442)"""
-    out = np.empty((x.shape[0], 9))
-    for j in range(3):
-        e = np.zeros(3)
-        e[j] = h
-        _, Bp = _bg_analytic(x + e, **kw)
-        _, Bm = _bg_analytic(x - e, **kw)
-        d = (Bp - Bm) / (2 * h)
-        for i in range(3):
-            out[:, 3 * i + j] = d[:, i]
-    return out
-
-
 def make_gc_case(n_particles=4096, seed=3, dt=0.01, interp=_capi.CPLR_LINEAR, sphere=True, uniform_B=None, E_uniform=None,
                  rigidity_gv=(0.001, 0.02), convection=True, ideal_mhd=1, **kw):
     m, cfg, parts, _ = make_tp_case(n_particles=n_particles, seed=seed, dt=dt, interp=interp, boundary=_capi.BOUNDARY_DELETE, sphere=sphere,
