@@ -570,12 +570,20 @@ void launch_stage_center_table(const DevMesh &m, int nVar, const double *var, do
   stage_center_table_kernel<<<m.nLeaves, 256, 0, s>>>(m, nVar, var, tile);
 }
 
-// the coupler stencil at x inside `leaf` (same arithmetic as background_fields), kept for several gathers
-__device__ __forceinline__ bool background_stencil(const DevMesh &m, int interp, const double x[3], int leaf, BgStencil &st) {
+// the coupler stencil at x inside `leaf` (same arithmetic as background_fields), kept for several gathers.
+// Single-level neighbourhoods (and the piecewise-constant coupler) use the 8-slot register form: slot s = 4i+2j+k of the
+// 2x2x2 centres from nd0, weight 0 for centres outside the domain (adding w*t = 0 in the reference's slot order leaves
+// every partial sum unchanged).  Leaves next to another refinement level use the 64-entry list of unique centre ids.
+struct BgStencil8 {
+  double w[8];
+  int nd0, BS0, BS1;
+};
+// returns 0 = the reference would exit(), 1 = s8 holds the stencil, 2 = `big` holds it (AMR)
+__device__ __forceinline__ int background_stencil(const DevMesh &m, int interp, const double x[3], int leaf, BgStencil8 &s8, BgStencil &big) {
   const LeafGeo &lg = m.leaf[leaf];
   if (interp == AMPS_CPLR_CELL_CENTERED_LINEAR && !leaf_single_level(lg))
-    return cplr_linear_stencil_amr(m, x, leaf, st) && st.n > 0 && !st.overflow;
-  st.uid = 0, st.overflow = 0;
+    return (cplr_linear_stencil_amr(m, x, leaf, big) && big.n > 0 && !big.overflow) ? 2 : 0;
+  s8.BS0 = m.TN[0], s8.BS1 = m.TN[0] * m.TN[1];
   if (interp == AMPS_CPLR_CELL_CENTERED_LINEAR) {
     const double iLoc = (x[0] - lg.xmin[0]) / (lg.xmax[0] - lg.xmin[0]) * m.N[0];
     const double jLoc = (x[1] - lg.xmin[1]) / (lg.xmax[1] - lg.xmin[1]) * m.N[1];
@@ -595,50 +603,69 @@ __device__ __forceinline__ bool background_stencil(const DevMesh &m, int interp,
     w[7] = w0 * w1 * w2;
     // x may lie outside the leaf (GuidingCenter::Mover_FirstOrder :713): indices past the ghost layer are
     // out-of-bounds reads in the reference -> error
-    if (!(iLoc >= -1.0e9 && iLoc <= 1.0e9 && jLoc >= -1.0e9 && jLoc <= 1.0e9 && kLoc >= -1.0e9 && kLoc <= 1.0e9)) return false;
+    if (!(iLoc >= -1.0e9 && iLoc <= 1.0e9 && jLoc >= -1.0e9 && jLoc <= 1.0e9 && kLoc >= -1.0e9 && kLoc <= 1.0e9)) return 0;
     if (i0 < -m.g[0] || i0 + 1 > m.N[0] + m.g[0] - 1 || j0 < -m.g[1] || j0 + 1 > m.N[1] + m.g[1] - 1 || k0 < -m.g[2] ||
         k0 + 1 > m.N[2] + m.g[2] - 1)
-      return false;
+      return 0;
     unsigned valid = 0xffu;
     if (!m.periodic && lg.face) {  // AddCell drops centres outside the domain (pic.h:7235-7245)
       const int o0[3] = {i0, j0, k0};
       const unsigned lowMask[3] = {0x0fu, 0x33u, 0x55u};  // stencil slots whose index along d is o0[d]
+#pragma unroll
       for (int d = 0; d < 3; d++)
+#pragma unroll
         for (int b = 0; b < 2; b++) {
           const int a = o0[d] + b;
           if (((lg.face >> (2 * d)) & 1 && a < 0) || ((lg.face >> (2 * d + 1)) & 1 && a >= m.N[d])) valid &= b ? lowMask[d] : ~lowMask[d] & 0xffu;
         }
     }
+    if (valid == 0u) return 0;
     double norm = 0.0;
     if (valid != 0xffu) {
+#pragma unroll
       for (int s = 0; s < 8; s++)
         if (valid & (1u << s)) norm += w[s];
     }
-    const int nd0 = centerLocalNumber(m, i0, j0, k0);
-    const int BS0 = m.TN[0], BS1 = m.TN[0] * m.TN[1];
-    st.n = 0;
-    for (int s = 0; s < 8; s++)
-      if (valid & (1u << s)) {
-        st.w[st.n] = (valid != 0xffu && norm > 0.0) ? w[s] / norm : w[s];
-        st.nd[st.n] = nd0 + ((s >> 2) & 1) + ((s >> 1) & 1) * BS0 + (s & 1) * BS1;
-        st.n++;
-      }
-    return true;
+    s8.nd0 = centerLocalNumber(m, i0, j0, k0);
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      double ws = w[s];
+      if (valid != 0xffu) ws = (valid & (1u << s)) ? ((norm > 0.0) ? w[s] / norm : w[s]) : 0.0;
+      s8.w[s] = ws;
+    }
+    return 1;
   }
   int ijk[3];
-  if (!find_cell_index(m, x, lg.node, ijk)) return false;
-  st.n = 1, st.w[0] = 1.0, st.nd[0] = centerLocalNumber(m, ijk[0], ijk[1], ijk[2]);
-  return true;
+  if (!find_cell_index(m, x, lg.node, ijk)) return 0;
+  s8.nd0 = centerLocalNumber(m, ijk[0], ijk[1], ijk[2]);
+  s8.w[0] = 1.0;
+#pragma unroll
+  for (int s = 1; s < 8; s++) s8.w[s] = 0.0;
+  s8.BS0 = 0, s8.BS1 = 0;  // every slot reads the cell itself; only slot 0 carries weight
+  return 1;
 }
 // T = the leaf's tile (stride doubles per centre, value at +off); U = the unique-node table [nCenters][K] used when the
 // stencil holds unique ids (AMR)
 template <int K>
-__device__ __forceinline__ void background_gather(const BgStencil &st, const double *__restrict__ T, int stride, int off,
+__device__ __forceinline__ void background_gather(int kind, const BgStencil8 &s8, const BgStencil &st, const double *__restrict__ T, int stride, int off,
                                                   const double *__restrict__ U, double out[K]) {
+#pragma unroll
   for (int q = 0; q < K; q++) out[q] = 0.0;
-  for (int s = 0; s < st.n; s++) {
-    const double *t = st.uid ? U + (size_t)K * st.nd[s] : T + (size_t)stride * st.nd[s] + off;
-    for (int q = 0; q < K; q++) out[q] += st.w[s] * t[q];
+  if (kind == 1) {
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      const double *t = T + (size_t)stride * (s8.nd0 + ((s >> 2) & 1) + ((s >> 1) & 1) * s8.BS0 + (s & 1) * s8.BS1) + off;
+      const double ws = s8.w[s];
+      if (ws != 0.0) {  // slots without weight are skipped like the cells the reference never adds
+#pragma unroll
+        for (int q = 0; q < K; q++) out[q] += ws * t[q];
+      }
+    }
+  } else {
+    for (int s = 0; s < st.n; s++) {
+      const double *t = U + (size_t)K * st.nd[s];
+      for (int q = 0; q < K; q++) out[q] += st.w[s] * t[q];
+    }
   }
 }
 
@@ -655,14 +682,16 @@ __global__ void __launch_bounds__(128) magnetic_moment_init_kernel(DevMesh m, De
     const double v[3] = {p.v[0][ip], p.v[1][ip], p.v[2][ip]};
     const int leaf = key / C;
     BgStencil st;
-    if (!background_stencil(m, interp, x, leaf, st)) {
+    BgStencil8 s8;
+    const int kind = background_stencil(m, interp, x, leaf, s8, st);
+    if (!kind) {
       nErr++;
       continue;
     }
     const double *T = bgTile + (size_t)leaf * m.nCenterLocal * 6;
     double B[3], E[3];
-    background_gather<3>(st, T, 6, 3, U.B, B);
-    background_gather<3>(st, T, 6, 0, U.E, E);
+    background_gather<3>(kind, s8, st, T, 6, 3, U.B, B);
+    background_gather<3>(kind, s8, st, T, 6, 0, U.E, E);
     const double AbsB = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) + 1E-15;
     double vE[3];
     vE[0] = E[1] * B[2] - E[2] * B[1];
@@ -753,12 +782,14 @@ __global__ void __launch_bounds__(128) move_relativistic_gca_kernel(DevMesh m, D
       const double vNorm = sqrt(vInit[0] * vInit[0] + vInit[1] * vInit[1] + vInit[2] * vInit[2]);
       const double lfac = 1 / sqrt(1.0 - vNorm * vNorm / c2);
       BgStencil st;
-      if (!background_stencil(m, tp.interp, xInit, startLeaf, st)) outcome = 3;
+      BgStencil8 s8;
+      const int kind = background_stencil(m, tp.interp, xInit, startLeaf, s8, st);
+      if (!kind) outcome = 3;
       else {
         double B[3], E[3], var15[15];
-        background_gather<3>(st, bgTile + (size_t)startLeaf * m.nCenterLocal * 6, 6, 3, tp.U.B, B);
-        background_gather<3>(st, bgTile + (size_t)startLeaf * m.nCenterLocal * 6, 6, 0, tp.U.E, E);
-        background_gather<15>(st, gcaTile + (size_t)startLeaf * m.nCenterLocal * 15, 15, 0, uVar, var15);
+        background_gather<3>(kind, s8, st, bgTile + (size_t)startLeaf * m.nCenterLocal * 6, 6, 3, tp.U.B, B);
+        background_gather<3>(kind, s8, st, bgTile + (size_t)startLeaf * m.nCenterLocal * 6, 6, 0, tp.U.E, E);
+        background_gather<15>(kind, s8, st, gcaTile + (size_t)startLeaf * m.nCenterLocal * 15, 15, 0, uVar, var15);
         const double *b_dot_grad_b = var15, *vE_dot_grad_b = var15 + 3, *b_dot_grad_vE = var15 + 6, *vE_dot_grad_vE = var15 + 9, *grad_kappaB = var15 + 12;
         const double bNorm = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]);
         double ePar = 0.0;
@@ -825,11 +856,13 @@ __global__ void __launch_bounds__(128) move_relativistic_gca_kernel(DevMesh m, D
     }
     if (outcome == 0) {
       BgStencil st;
-      if (!background_stencil(m, tp.interp, xFinal, newLeaf, st)) outcome = 3;
+      BgStencil8 s8;
+      const int kind = background_stencil(m, tp.interp, xFinal, newLeaf, s8, st);
+      if (!kind) outcome = 3;
       else {
         double B[3], E[3];
-        background_gather<3>(st, bgTile + (size_t)newLeaf * m.nCenterLocal * 6, 6, 3, tp.U.B, B);
-        background_gather<3>(st, bgTile + (size_t)newLeaf * m.nCenterLocal * 6, 6, 0, tp.U.E, E);
+        background_gather<3>(kind, s8, st, bgTile + (size_t)newLeaf * m.nCenterLocal * 6, 6, 3, tp.U.B, B);
+        background_gather<3>(kind, s8, st, bgTile + (size_t)newLeaf * m.nCenterLocal * 6, 6, 0, tp.U.E, E);
         const double bNorm = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]);
         if (bNorm > 0.0)  // otherwise bHat of the first stage stays, as in the reference
           for (int d = 0; d < 3; d++) bHat[d] = B[d] / bNorm;
@@ -927,9 +960,11 @@ struct GcTables {
 __device__ __forceinline__ bool gc_initiate_magnetic_moment(const DevMesh &m, const DevSpecies &sp, int interp, const GcTables &T, int spec,
                                                             const double x[3], double v[3], int leaf, double &muOut) {
   BgStencil st;
-  if (!background_stencil(m, interp, x, leaf, st)) return false;
+  BgStencil8 s8;
+  const int kind = background_stencil(m, interp, x, leaf, s8, st);
+  if (!kind) return false;
   double B[3];
-  background_gather<3>(st, T.bg + (size_t)leaf * m.nCenterLocal * 6, 6, 3, T.uB, B);
+  background_gather<3>(kind, s8, st, T.bg + (size_t)leaf * m.nCenterLocal * 6, 6, 3, T.uB, B);
   const double AbsB = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) + 1E-15;
   double v_par = 0.0, mu = 0.0;
   const double b[3] = {B[0] / AbsB, B[1] / AbsB, B[2] / AbsB};
@@ -951,12 +986,14 @@ __device__ __forceinline__ bool gc_motion(const DevMesh &m, const DevSpecies &sp
                                           double &ForceParal, double &AbsBOut, double bOut[3], const double *PParal, int spec, double mu,
                                           const double x[3], const double v[3], int leaf) {
   BgStencil st;
-  if (!background_stencil(m, interp, x, leaf, st)) return false;
+  BgStencil8 s8;
+  const int kind = background_stencil(m, interp, x, leaf, s8, st);
+  if (!kind) return false;
   double E[3], B[3], gradB[9];
   const double *tb = T.bg + (size_t)leaf * m.nCenterLocal * 6;
-  background_gather<3>(st, tb, 6, 0, T.uE, E);
-  background_gather<3>(st, tb, 6, 3, T.uB, B);
-  background_gather<9>(st, T.gradB + (size_t)leaf * m.nCenterLocal * 9, 9, 0, T.uGradB, gradB);
+  background_gather<3>(kind, s8, st, tb, 6, 0, T.uE, E);
+  background_gather<3>(kind, s8, st, tb, 6, 3, T.uB, B);
+  background_gather<9>(kind, s8, st, T.gradB + (size_t)leaf * m.nCenterLocal * 9, 9, 0, T.uGradB, gradB);
   const double AbsB = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) + 1E-15;
   double b[3], gradAbsB[3];
   b[0] = B[0] / AbsB;
@@ -1065,10 +1102,12 @@ __global__ void __launch_bounds__(128) move_guiding_center_kernel(DevMesh m, Dev
       }
       if (outcome == 0) {
         BgStencil st;
-        if (!background_stencil(m, tp.interp, x, startLeaf, st)) outcome = 3;  // the START block, as written (:713)
+        BgStencil8 s8;
+        const int kind = background_stencil(m, tp.interp, x, startLeaf, s8, st);
+        if (!kind) outcome = 3;  // the START block, as written (:713)
         else {
           double bFinal[3];
-          background_gather<3>(st, T.bg + (size_t)startLeaf * m.nCenterLocal * 6, 6, 3, T.uB, bFinal);
+          background_gather<3>(kind, s8, st, T.bg + (size_t)startLeaf * m.nCenterLocal * 6, 6, 3, T.uB, bFinal);
           const double l0 = sqrt(bFinal[0] * bFinal[0] + bFinal[1] * bFinal[1] + bFinal[2] * bFinal[2]);
           if (l0 > 0.0) {
             const double l = 1.0 / l0;
