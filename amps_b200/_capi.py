@@ -135,6 +135,7 @@ class MoveStats(C.Structure):
         ("n_not_in_use", C.c_int64),
         ("n_periodic_wrap", C.c_int64),
         ("n_error", C.c_int64),
+        ("n_sub_steps", C.c_int64),
     ]
 
     def as_dict(self):

@@ -79,7 +79,7 @@ struct ParticleSoA {
 // counters written by the mover (device copy of amps_gpu_move_stats + error word)
 struct DevMoveStats {
   unsigned long long n_moved, n_cross_cell, n_cross_block, n_left_domain, n_not_in_use, n_periodic_wrap, n_error;
-  unsigned long long pad;
+  unsigned long long n_sub_steps;
 };
 
 // ---- meshAMRgeneric.h:74-75 ----

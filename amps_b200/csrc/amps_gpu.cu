@@ -996,6 +996,7 @@ int amps_gpu_move(amps_gpu_ctx *ctx, int mover_id, amps_gpu_move_stats *stats) {
     stats->n_not_in_use = (int64_t)h.n_not_in_use;
     stats->n_periodic_wrap = (int64_t)h.n_periodic_wrap;
     stats->n_error = (int64_t)h.n_error;
+    stats->n_sub_steps = (int64_t)h.n_sub_steps;
     if (h.n_error) FAIL(AMPS_GPU_ERR_PARTICLE, "mover: particle outside its block / cell not found (the reference would exit())");
   }
   return AMPS_GPU_OK;

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(128) move_relativistic_boris_kernel(DevMesh m,
   __syncthreads();
   const int n = *nSlots;
   const int C = m.cellsPerBlock;
-  unsigned int nMoved = 0, nXCell = 0, nXBlock = 0, nLeft = 0, nNotUsed = 0, nWrap = 0, nErr = 0;
+  unsigned int nMoved = 0, nXCell = 0, nXBlock = 0, nLeft = 0, nNotUsed = 0, nWrap = 0, nErr = 0, nSub = 0;
   const double SpeedOfLight = tp.c;
   const bool backward = tp.backward != 0;
 
@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(128) move_relativistic_boris_kernel(DevMesh m,
       for (int d = 0; d < 3; d++) xFinal[d] = xInit[d], vFinal[d] = vInit[d];
     } else
       while (dtTotalIn > 0.0) {
+        nSub++;
         double gamma = 1.0 / sqrt(1.0 - (vInit[0] * vInit[0] + vInit[1] * vInit[1] + vInit[2] * vInit[2]) / (SpeedOfLight * SpeedOfLight));
         double E[3], B[3];
         if (!background_fields(m, tp.interp, bgTile, tp.U, xInit, leaf, E, B)) {
@@ -374,6 +375,12 @@ __global__ void __launch_bounds__(128) move_relativistic_boris_kernel(DevMesh m,
     if (newKey != oldKey) p.key[ip] = newKey;
   }
 
+  {
+    unsigned v = nSub;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&stats->n_sub_steps, (unsigned long long)v);
+  }
   flush_move_counters(stats, nMoved, nXCell, nXBlock, nLeft, nNotUsed, nWrap, nErr);
 }
 

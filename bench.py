@@ -203,7 +203,8 @@ def bench_test_particle_movers(torch, n_particles=2_000_000):
         out[name] = {"pushes_per_s": n_particles / (best * 1e-3), "ms_per_move": best, "particles": n_particles,
                      "alg_bytes_per_push": 113.0 if gca else 105.0,
                      "achieved_gbs": (113.0 if gca else 105.0) * n_particles / (best * 1e-3) / 1e9,
-                     "left_domain": st["n_left_domain"], "errors": st["n_error"],
+                     "left_domain": st["n_left_domain"], "errors": st["n_error"], "sub_steps": st["n_sub_steps"],
+                     "sub_steps_per_s": (st["n_sub_steps"] / (best * 1e-3)) if st["n_sub_steps"] else None,
                      "mesh": f"{m.c.n_leaves} blocks of {bc[0]}^3 cells, levels {sorted(set(int(v) for v in m.leaf_level()))}"}
         ctx.close()
     return out

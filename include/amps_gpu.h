@@ -197,6 +197,8 @@ typedef struct amps_gpu_move_stats {
   int64_t n_not_in_use;     /* _PARTICLE_IN_NOT_IN_USE_NODE_                                  */
   int64_t n_periodic_wrap;  /* landed in a periodic ghost block and was shifted               */
   int64_t n_error;          /* reference would have exit()ed                                  */
+  int64_t n_sub_steps;      /* Relativistic::Boris: gyro-period sub-steps taken (pic_mover_relativistic_boris.cpp:115-125); 0 for the
+                               movers that do not sub-cycle                                                          */
 } amps_gpu_move_stats;
 
 typedef struct amps_gpu_ctx amps_gpu_ctx;

@@ -163,6 +163,7 @@ struct oracle_ctx {
   int nThreadListTables;
   // PIC::ParticleBuffer (src/pic/pic_pbuffer.cpp)
   long int MaxNPart, ParticleDataLength, FirstPBufferParticle, NAllPart;
+  long long nSubSteps = 0;  // Relativistic::Boris sub-steps of the current move (statistic)
   byte *ParticleDataBuffer;
   // per-thread E/B staging, src/pic/pic_mover.cpp:660-711
   std::vector<std::vector<double>> E_Corner, B_Center;
@@ -1194,6 +1195,8 @@ struct oracle_ctx {
       newNode = startNode;
     } else
       while (dtTotalIn > 0.0) {
+#pragma omp atomic
+        nSubSteps++;
         gamma = 1.0 / sqrt(1.0 - (vInit[0] * vInit[0] + vInit[1] * vInit[1] + vInit[2] * vInit[2]) / (SpeedOfLight * SpeedOfLight));
         if (!GetBackgroundFields(xInit, startNode, E, B)) return _ORACLE_ERROR_;
 
@@ -2437,6 +2440,7 @@ int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats 
   }
 
   long long n_moved = 0, n_cross_cell = 0, n_cross_block = 0, n_left = 0, n_notused = 0, n_error = 0;
+  o->nSubSteps = 0;
 
   auto process_block = [&](int nLocalNode, int thread, long long *cnt) {
     cTreeNode *node = o->BlockTable[nLocalNode];
@@ -2578,6 +2582,7 @@ int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats 
     stats->n_not_in_use = n_notused;
     stats->n_periodic_wrap = n_wrap;
     stats->n_error = n_error;
+    stats->n_sub_steps = o->nSubSteps;
   }
   return n_error ? AMPS_GPU_ERR_PARTICLE : AMPS_GPU_OK;
 }

@@ -112,8 +112,8 @@ def test_cpp_host_matches_oracle(tmp_path, name, kw):
     st_b, n_b, buf_b, first_b, J_b, M_b, e_b, cfl_b = read_blobs(str(tmp_path / "out.bin"))
     ora = pu.run_oracle(m, cfg, parts, fields)
     n = parts[0].shape[1]
-    stats = struct.unpack("<7q", st_b[:56])
-    keys = ["n_moved", "n_cross_cell", "n_cross_block", "n_left_domain", "n_not_in_use", "n_periodic_wrap", "n_error"]
+    stats = struct.unpack("<8q", st_b[:64])
+    keys = ["n_moved", "n_cross_cell", "n_cross_block", "n_left_domain", "n_not_in_use", "n_periodic_wrap", "n_error", "n_sub_steps"]
     assert dict(zip(keys, stats)) == ora["stats"]
     buf = np.frombuffer(buf_b, dtype=np.uint8).reshape(cap, STRIDE)
     first = np.frombuffer(first_b, dtype=np.int64)

@@ -28,7 +28,7 @@ def test_oracle_matches_golden():
     ora = pu.run_oracle(m, cfg, parts, fields)
     assert (ora["final_cell"] == G["final_cell"]).all()
     assert (ora["particles"]["x"] == G["x_out"]).all() and (ora["particles"]["v"] == G["v_out"]).all()
-    assert [ora["stats"][k] for k in sorted(ora["stats"])] == list(G["stats"])
+    assert [ora["stats"][k] for k in sorted(ora["stats"]) if k != "n_sub_steps"] == list(G["stats"])  # fixture predates n_sub_steps
     assert (ora["J"] == G["J"]).all() and (ora["M"] == G["M"]).all()
 
 
@@ -49,6 +49,6 @@ def test_gpu_matches_golden(exact):
         alive = G["final_cell"] >= 0
         assert pu.rel_elementwise(gx[:, alive], G["x_out"][:, alive]) <= 1e-12
         assert pu.rel_elementwise(gv[:, alive], G["v_out"][:, alive]) <= 1e-10
-    assert [gpu["stats"][k] for k in sorted(gpu["stats"])] == list(G["stats"])
+    assert [gpu["stats"][k] for k in sorted(gpu["stats"]) if k != "n_sub_steps"] == list(G["stats"])
     assert pu.rel_scaled(gpu["J"], G["J"]) <= pu.REL_TOL and pu.rel_scaled(gpu["M"], G["M"]) <= pu.REL_TOL
     assert abs(gpu["energy"] - float(G["energy"])) <= pu.REL_TOL * float(G["energy"])
