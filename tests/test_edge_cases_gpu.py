@@ -1,0 +1,115 @@
+"""Edge cases of the ECSIM path through the C ABI: empty store, single particle, particles that land exactly on cell / block /
+periodic faces (the fast mover must hand them to the exact kernel), capacity errors, state errors."""
+import numpy as np
+import pytest
+
+from amps_b200 import _capi, api, mesh as meshmod, workload
+from tests import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(n_cells=(16, 16, 16), capacity=1024, **kw):
+    m = meshmod.uniform_periodic_box(n_cells, (8, 8, 8), (1, 1, 1))
+    charge, mass, wgt = workload.species_tables(8, 1.0)
+    cfg = api.make_config((8, 8, 8), (1, 1, 1), charge, mass, wgt, 1.0, periodic=True, capacity=capacity, **kw)
+    E, B = workload.box_fields(m, E_amp=0.0)
+    return m, cfg, (E, B, B)
+
+
+def test_empty_store_steps_and_deposits_zero():
+    m, cfg, f = _ctx()
+    g = api.Context(cfg, m)
+    g.fields_upload(*f)
+    z = np.zeros((3, 0))
+    g.particles_upload(z, z, np.zeros(0), np.zeros(0, dtype=np.uint8), np.zeros(0, dtype=np.int32))
+    assert g.particle_count() == 0
+    st = g.MoveParticles()
+    assert st["n_moved"] == 0
+    g.sort()
+    en, cfl = g.UpdateJMassMatrix()
+    J, M = g.JM_download()
+    assert en == 0.0 and not J.any() and not M.any()
+    g.step()
+    J, M = np.ones((m.n_corners, 3)), np.ones((m.n_corners, 243))
+    g.step_JM(J, M)
+    assert not J.any() and not M.any() and g.particle_count() == 0
+    g.close()
+
+
+def test_single_particle_matches_oracle():
+    m, cfg, f = _ctx()
+    x = np.array([[3.25], [9.5], [12.75]])
+    v = np.array([[0.3], [-0.2], [0.1]])
+    cells = workload.locate_cells(m, x)
+    parts = (x, v, np.ones(1), np.zeros(1, dtype=np.uint8), cells)
+    cfg.exit_record_capacity = 4
+    ora = pu.run_oracle(m, cfg, parts, f)
+    gpu = pu.run_gpu(m, cfg, parts, f)
+    res = pu.compare(m, parts, ora, gpu)
+    assert res["cell_mismatch"] == 0 and res["stats_equal"] and res["max_rel_x"] <= pu.REL_TOL and res["max_rel_M"] <= pu.REL_TOL, res
+
+
+@pytest.mark.parametrize("exact", [0, 1])
+def test_particles_landing_exactly_on_faces(exact):
+    """E = B = 0: x' = x + v exactly.  Every particle lands on a cell face, many on block faces and on the periodic boundary:
+    the integer part of (x'-xmin)/dx decides the cell, so the contracted-arithmetic kernel may not finish any of them."""
+    m, cfg, _ = _ctx(n_cells=(16, 16, 16), capacity=20000)
+    cfg.exact_arithmetic = exact
+    E = np.zeros((m.n_corners, 3))
+    B = np.zeros((m.n_centers, 3))
+    rng = np.random.default_rng(5)
+    n = 12000
+    xi = rng.integers(0, 16, size=(3, n)).astype(np.float64)
+    x = xi + 0.5
+    s = rng.choice([-1.5, -0.5, 0.5, 1.5], size=(3, n))          # x' = integer: on a face in all three dimensions
+    s[2, : n // 2] = rng.uniform(-0.4, 0.4, n // 2)              # ... or in two of them
+    v = s.copy()
+    cells = workload.locate_cells(m, x)
+    parts = (x, v, np.ones(n), rng.integers(0, 2, n).astype(np.uint8), cells)
+    f = (E, B, B)
+    ora = pu.run_oracle(m, cfg, parts, f)
+    gpu = pu.run_gpu(m, cfg, parts, f)
+    res = pu.compare(m, parts, ora, gpu)
+    assert res["cell_mismatch"] == 0 and res["stats_equal"], res
+    assert res["bit_mismatch_xv"] == 0, res                      # nothing to round: both paths give the same doubles
+    assert res["stats_oracle"]["n_periodic_wrap"] > 0 and res["stats_oracle"]["n_cross_block"] > 0
+    if not exact:
+        assert res["n_redo"] == n                                # all of them went through the exact kernel
+    assert res["max_rel_J"] <= pu.REL_TOL and res["max_rel_M"] <= pu.REL_TOL
+
+
+def test_capacity_and_state_errors_are_reported():
+    m, cfg, f = _ctx(capacity=100)
+    g = api.Context(cfg, m)
+    n = 200
+    x = np.full((3, n), 4.5)
+    with pytest.raises(api.AmpsGpuError):                        # more particles than PIC::ParticleBuffer::MaxNPart
+        g.particles_upload(x, x * 0, np.ones(n), np.zeros(n, dtype=np.uint8), workload.locate_cells(m, x))
+    with pytest.raises(api.AmpsGpuError):                        # cell id outside the mesh
+        g.particles_upload(x[:, :4], x[:, :4] * 0, np.ones(4), np.zeros(4, dtype=np.uint8), np.full(4, m.n_cells, dtype=np.int32))
+    g.particles_upload(x[:, :4], x[:, :4] * 0, np.ones(4), np.zeros(4, dtype=np.uint8), workload.locate_cells(m, x[:, :4]))
+    with pytest.raises(api.AmpsGpuError):                        # Lapenta2017 before the fields were uploaded
+        g.MoveParticles()
+    g.fields_upload(*f)
+    g.MoveParticles()
+    with pytest.raises(api.AmpsGpuError):                        # the deposit needs the sorted layout
+        g.UpdateJMassMatrix()
+    g.sort()
+    g.UpdateJMassMatrix()
+    with pytest.raises(api.AmpsGpuError):                        # unknown mover id
+        g.MoveParticles(99)
+    g.close()
+
+
+def test_wrong_cell_on_upload_is_an_error_like_the_reference_exit():
+    # a particle filed under a cell that does not contain it: the reference exit()s ("the point is out of block")
+    m, cfg, f = _ctx()
+    g = api.Context(cfg, m)
+    g.fields_upload(*f)
+    x = np.array([[3.5], [3.5], [3.5]])
+    far = workload.locate_cells(m, x + 8.0)
+    g.particles_upload(x, x * 0, np.ones(1), np.zeros(1, dtype=np.uint8), far)
+    with pytest.raises(api.AmpsGpuError):
+        g.MoveParticles()
+    g.close()
