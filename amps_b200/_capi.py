@@ -19,6 +19,7 @@ MOVER_RELATIVISTIC_BORIS = 2
 MOVER_GC_FIRST_ORDER = 3
 MOVER_GC_SECOND_ORDER = 4
 MOVER_RELATIVISTIC_GCA = 5
+MOVER_MARKIDIS2010 = 6
 
 PARTICLE_LEFT_THE_DOMAIN = 2
 PARTICLE_MOTION_FINISHED = 3

@@ -120,8 +120,8 @@ void launch_move_relativistic_boris(const DevMesh &m, const DevSpecies &sp, int 
                                     ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *uE, const double *uB,
                                     int *cellCount, DevMoveStats *stats, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount,
                                     cudaStream_t s);
-void launch_move_boris(const DevMesh &m, const DevSpecies &sp, int interp, int backward, double c, double rSphere, long long exitCap, double gravityGM,
-                       ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *uE, const double *uB, int *cellCount,
+void launch_move_boris(const DevMesh &m, const DevSpecies &sp, bool markidis, int interp, int backward, double c, double rSphere, long long exitCap,
+                       double gravityGM, ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *uE, const double *uB, int *cellCount,
                        DevMoveStats *stats, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s);
 void launch_stage_center_table(const DevMesh &m, int nVar, const double *var, double *tile, cudaStream_t s);
 void launch_gc_magnetic_moment_init(const DevMesh &m, const DevSpecies &sp, int interp, ParticleSoA p, const int *nSlots, long long nUpper,

@@ -886,7 +886,8 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "move before mesh upload");
   if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "move needs the (block,cell)-sorted layout: call amps_gpu_sort");
   if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS && mover_id != AMPS_MOVER_BORIS &&
-      mover_id != AMPS_MOVER_RELATIVISTIC_GCA && mover_id != AMPS_MOVER_GC_FIRST_ORDER && mover_id != AMPS_MOVER_GC_SECOND_ORDER)
+      mover_id != AMPS_MOVER_RELATIVISTIC_GCA && mover_id != AMPS_MOVER_GC_FIRST_ORDER && mover_id != AMPS_MOVER_GC_SECOND_ORDER &&
+      mover_id != AMPS_MOVER_MARKIDIS2010)
     FAIL(AMPS_GPU_ERR_ARG, "unknown mover id");
   if (mover_id == AMPS_MOVER_GC_FIRST_ORDER || mover_id == AMPS_MOVER_GC_SECOND_ORDER) {
     if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "the guiding-centre movers need cfg.carry_magnetic_moment");
@@ -908,8 +909,8 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   ProfScope prof(ctx, AMPS_GPU_PHASE_MOVE);
   CK(cudaMemsetAsync(ctx->d_cellCount, 0, sizeof(int) * (size_t)ctx->nCells, ctx->stream));
   CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevMoveStats), ctx->stream));
-  if (mover_id == AMPS_MOVER_BORIS) {
-    launch_move_boris(m, ctx->sp, ctx->cfg.coupler_interpolation, ctx->cfg.backward_time_integration, ctx->cfg.speed_of_light,
+  if (mover_id == AMPS_MOVER_BORIS || mover_id == AMPS_MOVER_MARKIDIS2010) {
+    launch_move_boris(m, ctx->sp, mover_id == AMPS_MOVER_MARKIDIS2010, ctx->cfg.coupler_interpolation, ctx->cfg.backward_time_integration, ctx->cfg.speed_of_light,
                       ctx->cfg.internal_sphere_radius, ctx->cfg.exit_record_capacity, ctx->cfg.gravity_gm, ctx->buf[ctx->cur], ctx->d_n + ctx->cur,
                       ctx->nUpper, ctx->d_bgTile, ctx->d_bgE, ctx->d_bgB, ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount,
                       ctx->stream);

@@ -400,6 +400,8 @@ void launch_move_relativistic_boris(const DevMesh &m, const DevSpecies &sp, int 
 // ------------------------------------------------------------------------------------------------
 // a6: PIC::Mover::Boris + BorisSplitAcceleration_default  src/pic/pic_mover_boris.cpp:126-553, :22-123
 // ------------------------------------------------------------------------------------------------
+// kMarkidis: PIC::Mover::Markidis2010 (pic_mover_boris.cpp:557-835): same skeleton, eqs 22-23 of Markidis et al. 2010 for the velocity
+template <bool kMarkidis>
 __global__ void __launch_bounds__(128) move_boris_kernel(DevMesh m, DevSpecies sp, TpParams tp, double gravityGM, ParticleSoA p, const int *__restrict__ nSlots,
                                                         const double *__restrict__ bgTile, int *__restrict__ cellCount, DevMoveStats *__restrict__ stats,
                                                         amps_gpu_exit_record *__restrict__ exitBuf, unsigned long long *__restrict__ exitCount) {
@@ -423,9 +425,31 @@ __global__ void __launch_bounds__(128) move_boris_kernel(DevMesh m, DevSpecies s
     const double dtTotal = (sp.timeStepMode == AMPS_DT_SPECIES_GLOBAL) ? sp.dt[spec] : sp.dt[0];
     int outcome = 0, node = -1;
 
+    bool pushed = false;
+    if (kMarkidis) {
+      double E[3], B[3];
+      if (!background_fields(m, tp.interp, bgTile, tp.U, xInit, startLeaf, E, B)) outcome = 3;
+      else {
+        const double QdT_over_m = sp.charge[spec] * dtTotal / sp.mass[spec];
+        const double QdT_over_2m = 0.5 * QdT_over_m;
+        double v_prime[3];
+        for (int d = 0; d < 3; d++) v_prime[d] = vInit[d] + QdT_over_m * E[d];
+        const double Denominator = 1.0 / (1.0 + QdT_over_2m * QdT_over_2m * (B[0] * B[0] + B[1] * B[1] + B[2] * B[2]));
+        double n1[3];
+        n1[0] = v_prime[1] * B[2] - v_prime[2] * B[1];
+        n1[1] = v_prime[2] * B[0] - v_prime[0] * B[2];
+        n1[2] = v_prime[0] * B[1] - v_prime[1] * B[0];
+        const double n2 = QdT_over_2m * QdT_over_2m * (v_prime[0] * B[0] + v_prime[1] * B[1] + v_prime[2] * B[2]);
+        for (int d = 0; d < 3; d++) {
+          vFinal[d] = Denominator * (v_prime[d] + QdT_over_2m * n1[d] + n2 * B[d]);
+          xFinal[d] = xInit[d] + dtTotal * vFinal[d];
+        }
+        pushed = true;
+      }
+    }
     // BorisSplitAcceleration_default: fields in the cell of x (fail-safe: search the block again)
     double acclInit[3] = {0.0, 0.0, 0.0}, rotInit[3] = {0.0, 0.0, 0.0};
-    {
+    if (!kMarkidis) {
       int fieldLeaf = startLeaf, ijk[3];
       if (!find_cell_index(m, xInit, startNode, ijk)) {
         const int fn = find_tree_node_plain(m, xInit, startNode);
@@ -450,7 +474,7 @@ __global__ void __launch_bounds__(128) move_boris_kernel(DevMesh m, DevSpecies s
         }
       }
     }
-    if (outcome == 0) {
+    if (!kMarkidis && outcome == 0) {
       double dtTempOverTwo, dtTemp;
       if (tp.backward) dtTemp = -dtTotal, dtTempOverTwo = -dtTotal / 2.0;
       else dtTemp = dtTotal, dtTempOverTwo = dtTotal / 2.0;
@@ -472,7 +496,9 @@ __global__ void __launch_bounds__(128) move_boris_kernel(DevMesh m, DevSpecies s
       xFinal[0] = xInit[0] + dtTemp * vFinal[0];
       xFinal[1] = xInit[1] + dtTemp * vFinal[1];
       xFinal[2] = xInit[2] + dtTemp * vFinal[2];
-
+    }
+    (void)pushed;
+    if (outcome == 0) {
       bool hitSphere = false;
       if (tp.rSphere > 0.0) {
         const double R = tp.rSphere;
@@ -504,7 +530,7 @@ __global__ void __launch_bounds__(128) move_boris_kernel(DevMesh m, DevSpecies s
               outcome = 3;  // specular: _PARTICLE_REJECTED_ON_THE_FACE_ -> exit("not implemented") :461
           }
         } else if (!(m.nodeFlags[node] & AMPS_NODE_USED))
-          outcome = 2;
+          outcome = kMarkidis ? 3 : 2;  // Markidis2010 has no "not in use" return: its block==NULL test exit()s (:803)
       }
     }
 
@@ -513,7 +539,7 @@ __global__ void __launch_bounds__(128) move_boris_kernel(DevMesh m, DevSpecies s
       int ijk[3];
       int newLeaf = m.nodeLeaf[node];
       if (!find_cell_index(m, xFinal, node, ijk)) outcome = 3;
-      else if (newLeaf < 0) outcome = 1;  // block not allocated here (:1290-1302 analogue)
+      else if (newLeaf < 0) outcome = kMarkidis ? 3 : 1;  // block not allocated here (:1290-1302 analogue)
       else {
         const int realLeaf = m.leaf[newLeaf].real;
         if (realLeaf >= 0) {
@@ -545,8 +571,8 @@ __global__ void __launch_bounds__(128) move_boris_kernel(DevMesh m, DevSpecies s
   flush_move_counters(stats, nMoved, nXCell, nXBlock, nLeft, nNotUsed, nWrap, nErr);
 }
 
-void launch_move_boris(const DevMesh &m, const DevSpecies &sp, int interp, int backward, double c, double rSphere, long long exitCap, double gravityGM,
-                       ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *uE, const double *uB, int *cellCount,
+void launch_move_boris(const DevMesh &m, const DevSpecies &sp, bool markidis, int interp, int backward, double c, double rSphere, long long exitCap,
+                       double gravityGM, ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *uE, const double *uB, int *cellCount,
                        DevMoveStats *stats, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s) {
   TpParams tp;
   tp.interp = interp, tp.backward = backward, tp.boundaryMode = sp.boundaryMode, tp.c = c, tp.rSphere = rSphere, tp.exitCap = exitCap;
@@ -554,7 +580,8 @@ void launch_move_boris(const DevMesh &m, const DevSpecies &sp, int interp, int b
   long long g = (nUpper + 127) / 128;
   if (g < 1) g = 1;
   if (g > 148 * 32) g = 148 * 32;
-  move_boris_kernel<<<(int)g, 128, 0, s>>>(m, sp, tp, gravityGM, p, nSlots, bgTile, cellCount, stats, exitBuf, exitCount);
+  if (markidis) move_boris_kernel<true><<<(int)g, 128, 0, s>>>(m, sp, tp, gravityGM, p, nSlots, bgTile, cellCount, stats, exitBuf, exitCount);
+  else move_boris_kernel<false><<<(int)g, 128, 0, s>>>(m, sp, tp, gravityGM, p, nSlots, bgTile, cellCount, stats, exitBuf, exitCount);
 }
 
 // ------------------------------------------------------------------------------------------------

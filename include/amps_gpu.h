@@ -50,7 +50,8 @@ enum {
   AMPS_MOVER_RELATIVISTIC_BORIS = 2,  /* pic_mover_relativistic_boris.cpp:16-588               */
   AMPS_MOVER_GC_FIRST_ORDER = 3,      /* pic_mover_guiding_center.cpp:629-849                  */
   AMPS_MOVER_GC_SECOND_ORDER = 4,     /* pic_mover_guiding_center.cpp:293-627                  */
-  AMPS_MOVER_RELATIVISTIC_GCA = 5     /* pic_mover_relativistic_guiding_center.cpp:96-409      */
+  AMPS_MOVER_RELATIVISTIC_GCA = 5,    /* pic_mover_relativistic_guiding_center.cpp:96-409      */
+  AMPS_MOVER_MARKIDIS2010 = 6         /* pic_mover_boris.cpp:557-835 (energy-conserving scheme, coupler fields) */
 };
 
 /* return codes of a per-particle mover, src/pic/pic.h:5955-5960 */

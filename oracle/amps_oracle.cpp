@@ -1473,6 +1473,62 @@ struct oracle_ctx {
   }
 
 
+  // PIC::Mover::Markidis2010, src/pic/pic_mover_boris.cpp:557-835 (Markidis et al. 2010, eqs 22-23; fields from the coupler).
+  // The exit search is the vMiddle one shared with Boris (nIntersectionFace is read uninitialised at :722 when no face is
+  // found: restated as intended, see ProcessDomainExit_vMiddle).
+  int Markidis2010(byte *ParticleData, long int ptr, double dtTotal, cTreeNode *startNode, int nThreads, int thread, cTreeNode **newNodeOut) {
+    cTreeNode *newNode = NULL;
+    double vInit[3], xInit[3] = {0.0, 0.0, 0.0}, vFinal[3], xFinal[3], B[3], E[3];
+    int idim, i, j, k, spec;
+    GetV(vInit, ParticleData);
+    GetX(xInit, ParticleData);
+    spec = GetI(ParticleData);
+    if (!GetBackgroundFields(xInit, startNode, E, B)) return _ORACLE_ERROR_;
+    double v_prime[3], QdT_over_m, QdT_over_2m;
+    QdT_over_m = cfg.charge[spec] * dtTotal / cfg.mass[spec];
+    QdT_over_2m = 0.5 * QdT_over_m;
+    for (idim = 0; idim < 3; idim++) v_prime[idim] = vInit[idim] + QdT_over_m * E[idim];
+    double Denominator = 1.0 / (1.0 + QdT_over_2m * QdT_over_2m * (B[0] * B[0] + B[1] * B[1] + B[2] * B[2]));
+    double n1[3], n2;
+    n1[0] = v_prime[1] * B[2] - v_prime[2] * B[1];  // Vector3D::CrossProduct, specfunc.h:780-806
+    n1[1] = v_prime[2] * B[0] - v_prime[0] * B[2];
+    n1[2] = v_prime[0] * B[1] - v_prime[1] * B[0];
+    n2 = QdT_over_2m * QdT_over_2m * (v_prime[0] * B[0] + v_prime[1] * B[1] + v_prime[2] * B[2]);
+    for (idim = 0; idim < 3; idim++) {
+      vFinal[idim] = Denominator * (v_prime[idim] + QdT_over_2m * n1[idim] + n2 * B[idim]);
+      xFinal[idim] = xInit[idim] + dtTotal * vFinal[idim];
+    }
+    if (cfg.internal_sphere_radius > 0.0) {
+      const double R = cfg.internal_sphere_radius;
+      double rFinal2;
+      if ((rFinal2 = xFinal[0] * xFinal[0] + xFinal[1] * xFinal[1] + xFinal[2] * xFinal[2]) < R * R) {
+        double r = sqrt(rFinal2);
+        for (idim = 0; idim < 3; idim++) xFinal[idim] *= R / r;
+        newNode = findTreeNode(xFinal, startNode);
+        AddExitRecord(ptr, spec, AMPS_EXIT_SPHERE, newNode, xFinal, vFinal);  // ParticleSphereInteraction -> deleted
+        DeleteParticle(ptr);
+        return _PARTICLE_LEFT_THE_DOMAIN_;
+      } else
+        newNode = findTreeNode(xFinal, startNode);
+    } else
+      newNode = findTreeNode(xFinal, startNode);
+    if (newNode == NULL) {
+      int code = 0;
+      if (cfg.boundary_mode != AMPS_BOUNDARY_DELETE) code = ProcessDomainExit_vMiddle(ptr, spec, dtTotal, xInit, vInit, xFinal, vFinal, startNode, &newNode);
+      if (code != 0) return _ORACLE_ERROR_;  // exit("not implemented") :787
+      DeleteParticle(ptr);
+      return _PARTICLE_LEFT_THE_DOMAIN_;
+    }
+    cBlock *block;
+    if (FindCellIndex(xFinal, i, j, k, newNode) == -1) return _ORACLE_ERROR_;
+    if ((block = newNode->block) == NULL) return _ORACLE_ERROR_;
+    AttachToTempList(ptr, ParticleData, block, i, j, k, nThreads, thread);
+    SetV(vFinal, ParticleData);
+    SetX(xFinal, ParticleData);
+    *newNodeOut = newNode;
+    return _PARTICLE_MOTION_FINISHED_;
+  }
+
   // fields + the 15 GCA variables through the coupler stencil (pic.h:8338-8425, 8643-8680)
   bool GetBackgroundFieldsGCA(const double *x, cTreeNode *node, double *E, double *B, double *v15) const {
     cStencil Stencil;
@@ -2414,7 +2470,8 @@ void oracle_get_particles(const oracle_ctx *o, double *x, double *v, double *w, 
 // PIC::BC::ExternalBoundary::Periodic::ExchangeParticles(), src/pic/pic_time_step.cpp:454-506
 int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats *stats, int32_t *ret_code, int32_t *final_cell) {
   if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS && mover_id != AMPS_MOVER_BORIS &&
-      mover_id != AMPS_MOVER_RELATIVISTIC_GCA && mover_id != AMPS_MOVER_GC_FIRST_ORDER && mover_id != AMPS_MOVER_GC_SECOND_ORDER) {
+      mover_id != AMPS_MOVER_RELATIVISTIC_GCA && mover_id != AMPS_MOVER_GC_FIRST_ORDER && mover_id != AMPS_MOVER_GC_SECOND_ORDER &&
+      mover_id != AMPS_MOVER_MARKIDIS2010) {
     o->err = "oracle_move: mover not restated yet";
     return AMPS_GPU_ERR_ARG;
   }
@@ -2460,6 +2517,7 @@ int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats 
       if (mover_id == AMPS_MOVER_RELATIVISTIC_GCA) return o->RelGCA_Mover_FirstOrder(pd, ptr, dtLocal, node, n_threads, thread, newNode);
       if (mover_id == AMPS_MOVER_GC_FIRST_ORDER) return o->GC_Mover_FirstOrder(pd, ptr, dtLocal, node, n_threads, thread, newNode);
       if (mover_id == AMPS_MOVER_GC_SECOND_ORDER) return o->GC_Mover_SecondOrder(pd, ptr, dtLocal, node, n_threads, thread, newNode);
+      if (mover_id == AMPS_MOVER_MARKIDIS2010) return o->Markidis2010(pd, ptr, dtLocal, node, n_threads, thread, newNode);
       return o->Relativistic_Boris(pd, ptr, dtLocal, node, n_threads, thread, newNode);
     };
     long int *FirstCellParticleTable = block->FirstCellParticleTable;

@@ -113,12 +113,36 @@ def test_oracle_threads_agree_and_exits_are_recorded():
     assert st["n_moved"] == 2048 and st["n_error"] == 0
 
 
+def test_markidis2010_oracle_matches_the_closed_form():
+    """PIC::Mover::Markidis2010 (pic_mover_boris.cpp:557-835) in uniform fields: eqs 22-23 evaluated with numpy"""
+    Bu = np.array([1.0e-6, -2.0e-6, 2.0e-5])
+    m, cfg, parts, bg = tp.make_tp_case(n_particles=1024, dt=0.01, sphere=False, boundary=_capi.BOUNDARY_DELETE, uniform_B=Bu,
+                                        rigidity_gv=(0.001, 0.01))
+    E = np.broadcast_to(np.array([2.0e-4, 1.0e-3, -3.0e-4]), bg[1].shape).copy()
+    ora = tp.run_oracle_tp(m, cfg, parts, (E, bg[1]), mover=_capi.MOVER_MARKIDIS2010)
+    assert ora["rc"] == 0 and ora["lists"] == 0
+    alive = ora["final_cell"] >= 0
+    assert alive.sum() > 900
+    x0, v0 = parts[0][:, alive].T, parts[1][:, alive].T
+    b1 = tp.QP * 0.01 / tp.MP
+    b2 = 0.5 * b1
+    vp = v0 + b1 * E[0]
+    den = 1.0 / (1.0 + b2 * b2 * (Bu @ Bu))
+    vf = den * (vp + b2 * np.cross(vp, Bu) + (b2 * b2 * (vp @ Bu))[:, None] * Bu)
+    assert np.allclose(ora["particles"]["v"][:, alive].T, vf, rtol=1e-12)
+    assert np.allclose(ora["particles"]["x"][:, alive].T, x0 + 0.01 * vf, rtol=1e-12)
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("mover", [_capi.MOVER_RELATIVISTIC_BORIS, _capi.MOVER_BORIS])
+@pytest.mark.parametrize("mover", [_capi.MOVER_RELATIVISTIC_BORIS, _capi.MOVER_BORIS, _capi.MOVER_MARKIDIS2010])
 @pytest.mark.parametrize("name", list(CASES))
 def test_gpu_parity(name, mover):
     kw = dict(CASES[name])
     dt = kw.pop("dt", 0.3)
+    if mover == _capi.MOVER_MARKIDIS2010:
+        dt *= 0.02
+        kw["rigidity_gv"] = (0.001, 0.05)
+        kw["backward"] = False          # the scheme has no backward-time mode
     if mover == _capi.MOVER_BORIS:
         dt *= 0.02   # single step without sub-cycling: keep the rotation angle moderate
         kw["rigidity_gv"] = (0.001, 0.05)  # non-relativistic protons
