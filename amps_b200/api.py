@@ -217,6 +217,12 @@ class Context:
         self._ck(self.lib.amps_gpu_step_JM(self._h, mover, _ptr(out_J), _ptr(out_M)))
         return out_J, out_M
 
+    def ComputeNetCharge(self, charge_conv=1.0):
+        """ECSIM::ComputeNetCharge: rho_new on the unique centre nodes"""
+        rho = np.empty(self.mesh.n_centers)
+        self._ck(self.lib.amps_gpu_net_charge(self._h, charge_conv, _ptr(rho)))
+        return rho
+
     def diagnostics(self):
         e = C.c_double()
         cfl = (C.c_double * _capi.MAX_SPECIES)()

@@ -106,6 +106,8 @@ void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
                     double *energy, unsigned long long *cflBits, int nSM, const int *perm, ParticleSoA dst, int cell0, int cell1, cudaStream_t s,
                     long long *launches);  // cells [cell0, cell1); cell1 < 0 = all; J, M and the diagnostics are zeroed when cell0 == 0
+void launch_net_charge(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, double chargeConv, double *rho, long long nUpper,
+                       cudaStream_t s);
 size_t sort_scan_tmp_bytes(long long nCells);
 // migration record: 8 doubles (x,v,w,meta) + mu when the particles carry it
 inline int migration_record_len(const ParticleSoA &p) { return p.mu ? 9 : 8; }

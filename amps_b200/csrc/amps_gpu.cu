@@ -52,6 +52,7 @@ struct amps_gpu_ctx {
   bool meshRefined = false;  // some leaf is below level 0
   unsigned char *d_redoMask = nullptr;  // particles the fast mover left to the exact kernel
   int *d_perm = nullptr;      // sorted position -> slot (fused sort + deposit inside amps_gpu_step)
+  double *d_rho = nullptr;    // ComputeNetCharge: rho_new on the unique centre nodes
   // amps_gpu_step_JM: the deposit runs in cell ranges; the corners whose last contributing cell lies in range k form the
   // uid runs dlRuns[dlRunStart[k] .. dlRunStart[k+1]) and are copied to the host while range k+1 is deposited
   struct DlRun { int uid0, n; };
@@ -273,7 +274,7 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
   if (ctx->comm && nccl_api().CommDestroy) nccl_api().CommDestroy(ctx->comm);
   cudaFree(ctx->d_gcaVar), cudaFree(ctx->d_gcaTile), cudaFree(ctx->d_gradBVar), cudaFree(ctx->d_gradBTile);
-  cudaFree(ctx->d_redoMask), cudaFree(ctx->d_leafRedo), cudaFree(ctx->d_perm);
+  cudaFree(ctx->d_redoMask), cudaFree(ctx->d_leafRedo), cudaFree(ctx->d_perm), cudaFree(ctx->d_rho);
   for (cudaEvent_t e : ctx->dlEvents) cudaEventDestroy(e);
   if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   cudaFree(ctx->d_bgE), cudaFree(ctx->d_bgB), cudaFree(ctx->d_bgTile), cudaFree(ctx->d_exitBuf), cudaFree(ctx->d_exitCount);
@@ -1030,6 +1031,23 @@ int amps_gpu_deposit_JM(amps_gpu_ctx *ctx, double *particle_energy, double *cfl)
     if (cfl)
       for (int s = 0; s < ctx->cfg.n_species; s++) memcpy(&cfl[s], &c[s], 8);
   }
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_net_charge(amps_gpu_ctx *ctx, double charge_conv, double *rho_center) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "net_charge before mesh_upload");
+  if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "net_charge needs the (block,cell)-sorted layout: call amps_gpu_sort");
+  if (ctx->meshRefined) FAIL(AMPS_GPU_ERR_STATE, "ComputeNetCharge is defined on single-level meshes (the reference indexes a block-local array)");
+  if ((size_t)ctx->dm.nCenterLocal * sizeof(double) > 48 * 1024) FAIL(AMPS_GPU_ERR_ARG, "block too large for the shared-memory centre tile");
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc;
+  if (!ctx->d_rho && (rc = dev_alloc(ctx, &ctx->d_rho, (size_t)ctx->dm.nCenters))) return rc;
+  launch_net_charge(ctx->dm, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, charge_conv, ctx->d_rho, ctx->nUpper, ctx->stream);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  if (rho_center) CK(cudaMemcpyAsync(rho_center, ctx->d_rho, sizeof(double) * (size_t)ctx->dm.nCenters, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return AMPS_GPU_OK;
 }
 

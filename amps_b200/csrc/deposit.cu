@@ -459,6 +459,89 @@ __global__ void __launch_bounds__(256) diag_kernel(DevMesh m, DevSpecies sp, Par
   if (lane < sp.n && cflMax > 0.0) atomicMaxPositiveDouble(&cflBits[lane], cflMax);
 }
 
+// ------------------------------------------------------------------------------------------------
+// f4 (first half): ECSIM::ComputeNetCharge  src/pic/pic_field_solver_ecsim.cpp:4690-4828
+// rho_new on the unique centre nodes: every particle spreads q~ over the 8 centres of its cell-centred trilinear stencil.
+// Like the reference (a local q_Center array per block) one CTA accumulates a block's (N+2)^3 centres in shared memory
+// (fp64 shared atomics) and flushes them once, divided by the cell volume, with global REDs.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) net_charge_kernel(DevMesh m, DevSpecies sp, ParticleSoA p, const int *__restrict__ cellStart, double chargeConv,
+                                                        int slices, double *__restrict__ rho) {
+  extern __shared__ double sQ[];  // [TN0*TN1*TN2] block-local centre numbering
+  const int leaf = blockIdx.x / slices, slice = blockIdx.x - leaf * slices;
+  const int C = m.cellsPerBlock;
+  const LeafGeo &lg = m.leaf[leaf];
+  if (m.periodic && lg.face != 0) return;  // boundary "ghost" block (:4711-4722)
+  const int begin = cellStart[(size_t)leaf * C], end = cellStart[(size_t)(leaf + 1) * C];
+  const long long len = (long long)end - begin;
+  const int b = begin + (int)(len * slice / slices), e = begin + (int)(len * (slice + 1) / slices);
+  if (b >= e) return;
+  for (int i = threadIdx.x; i < m.nCenterLocal; i += blockDim.x) sQ[i] = 0.0;
+  __syncthreads();
+  const int BS0 = m.TN[0], BS1 = m.TN[0] * m.TN[1];
+  for (int ip = b + threadIdx.x; ip < e; ip += blockDim.x) {
+    const double x[3] = {p.x[0][ip], p.x[1][ip], p.x[2][ip]};
+    const int spec = p.spec[ip] & 0x3f;
+    const double chargeQ = (sp.charge[spec] * chargeConv) * (sp.weight[spec] * p.w[ip]);
+    double loc[3], wd[3];
+    int o[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      loc[d] = (x[d] - lg.xmin[d]) / (lg.xmax[d] - lg.xmin[d]) * m.N[d];
+      o[d] = (loc[d] < 0.5) ? -1 : (int)(loc[d] - 0.50);
+      wd[d] = loc[d] - (o[d] + 0.5);
+    }
+    double w[8];
+    w[0] = (1.0 - wd[0]) * (1.0 - wd[1]) * (1.0 - wd[2]);
+    w[1] = (1.0 - wd[0]) * (1.0 - wd[1]) * wd[2];
+    w[2] = (1.0 - wd[0]) * wd[1] * (1.0 - wd[2]);
+    w[3] = (1.0 - wd[0]) * wd[1] * wd[2];
+    w[4] = wd[0] * (1.0 - wd[1]) * (1.0 - wd[2]);
+    w[5] = wd[0] * (1.0 - wd[1]) * wd[2];
+    w[6] = wd[0] * wd[1] * (1.0 - wd[2]);
+    w[7] = wd[0] * wd[1] * wd[2];
+    unsigned valid = 0xffu;
+    if (!m.periodic && lg.face) {  // AddCell drops centres outside the global box; the rest is re-normalised (Length != 8)
+      if ((lg.face & 1) && o[0] < 0) valid &= 0xf0u;
+      if ((lg.face & 2) && o[0] + 1 >= m.N[0]) valid &= 0x0fu;
+      if ((lg.face & 4) && o[1] < 0) valid &= 0xccu;
+      if ((lg.face & 8) && o[1] + 1 >= m.N[1]) valid &= 0x33u;
+      if ((lg.face & 16) && o[2] < 0) valid &= 0xaau;
+      if ((lg.face & 32) && o[2] + 1 >= m.N[2]) valid &= 0x55u;
+    }
+    double inv = 1.0;
+    if (valid != 0xffu) {
+      double norm = 0.0;
+#pragma unroll
+      for (int s = 0; s < 8; s++)
+        if (valid & (1u << s)) norm += w[s];
+      if (norm > 0.0) inv = 1.0 / norm;
+    }
+    const int nd0 = centerLocalNumber(m, o[0], o[1], o[2]);
+#pragma unroll
+    for (int s = 0; s < 8; s++)
+      if (valid & (1u << s)) atomicAdd(&sQ[nd0 + ((s >> 2) & 1) + ((s >> 1) & 1) * BS0 + (s & 1) * BS1], (w[s] * inv) * chargeQ);
+  }
+  __syncthreads();
+  const double invVol = lg.invdxc[0] * lg.invdxc[1] * lg.invdxc[2];  // 1/CellVolume, CellVolume = prod dx (:4737-4739)
+  const int *cuid = m.centerUid + (size_t)leaf * m.nCenterLocal;
+  for (int i = threadIdx.x; i < m.nCenterLocal; i += blockDim.x) {
+    const double q = sQ[i];
+    const int u = cuid[i];
+    if (q != 0.0 && u >= 0) atomicAdd(&rho[u], q * invVol);
+  }
+}
+
+void launch_net_charge(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, double chargeConv, double *rho, long long nUpper,
+                       cudaStream_t s) {
+  cudaMemsetAsync(rho, 0, sizeof(double) * (size_t)m.nCenters, s);
+  long long perLeaf = nUpper / (m.nLeaves > 0 ? m.nLeaves : 1);
+  int slices = (int)((perLeaf + 8191) / 8192);
+  if (slices < 1) slices = 1;
+  if (slices > 32) slices = 32;
+  net_charge_kernel<<<m.nLeaves * slices, 256, sizeof(double) * m.nCenterLocal, s>>>(m, sp, p, cellStart, chargeConv, slices, rho);
+}
+
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
                     double *energy, unsigned long long *cflBits, int nSM, const int *perm, ParticleSoA dst, int cell0, int cell1, cudaStream_t s,
                     long long *launches) {

@@ -298,6 +298,10 @@ int amps_gpu_deposit_JM(amps_gpu_ctx *ctx, double *particle_energy, double *cfl)
  * corners whose last contributing block lies in a finished range travel to the host (pinned memory for real overlap) while the
  * next range is deposited.  Same results as the two calls.                                         */
 int amps_gpu_step_JM(amps_gpu_ctx *ctx, int mover_id, double *J_host, double *M_host);
+/* ECSIM::ComputeNetCharge() (pic_field_solver_ecsim.cpp:4690-4828, the particle pass of divECorrection): rho_new on the unique
+ * centre nodes, [n_centers]; charge_conv multiplies cfg.charge[] (ECSIM::charge_conv).  rho_center may be NULL (result stays
+ * on the device).  Single-rank: the sum over ranks of shared centres is the caller's (ProcessNetCharge).            */
+int amps_gpu_net_charge(amps_gpu_ctx *ctx, double charge_conv, double *rho_center);
 /* particle energy and per-species cfl of the last deposit (amps_gpu_deposit_JM or amps_gpu_step; after
  * amps_gpu_exchange_JM they are the all-reduced values)                                            */
 int amps_gpu_diagnostics(amps_gpu_ctx *ctx, double *particle_energy, double *cfl);

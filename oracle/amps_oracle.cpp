@@ -43,7 +43,8 @@ const int BackgroundE_d = 6;   // coupler table: DATAFILE::Offset::ElectricField
 const int BackgroundB_d = 9;   // coupler table: DATAFILE::Offset::MagneticField
 const int BackgroundGCA_d = 12; // 15 tabulated derivative variables of the relativistic GCA (pic_datafile.cpp:1164-1340)
 const int BackgroundGradB_d = 27; // DATAFILE::Offset::MagneticFieldGradient, 9 values {d/dx,d/dy,d/dz} of Bx, By, Bz (pic.h:8434-8470)
-const int CenterDataLength = 36;
+const int netChargeNew_d = 36;  // centre buffer: rho_new of the div-E correction (netChargeNewIndex, pic_field_solver_ecsim.cpp:484-538)
+const int CenterDataLength = 37;
 const double SpeedOfLight_SI = 299792458.0;  // src/general/constants.h:40
 
 // src/pic/pic_field_solver_ecsim.cpp:1377-1380
@@ -1942,6 +1943,62 @@ struct oracle_ctx {
     return _PARTICLE_MOTION_FINISHED_;
   }
 
+  // ECSIM::ComputeNetCharge, src/pic/pic_field_solver_ecsim.cpp:4690-4828 (without UpdateOldNetCharge): the charge of every particle
+  // goes to the 8 cell centres of its trilinear stencil, block by block through a local q_Center array; the sum of the ghost
+  // copies into the real nodes (ProcessBlockBoundaryNodes / ProcessNetCharge :1417-1425) is implicit in the unique centre nodes.
+  int ComputeNetCharge(double charge_conv) {
+    for (int i = 0; i < n_centers; i++) centerPool[i].data[netChargeNew_d] = 0.0;  // SetCenterNodeAssociatedDataValue
+    double q_I[AMPS_GPU_MAX_SPECIES];
+    for (int iSp = 0; iSp < cfg.n_species; iSp++) q_I[iSp] = cfg.charge[iSp] * charge_conv;
+    std::vector<double> q_Center((size_t)nCenterLocal());
+    for (size_t nLocalNode = 0; nLocalNode < blocks.size(); nLocalNode++) {
+      cTreeNode *node = BlockTable[nLocalNode];
+      if (node->block == NULL) continue;
+      if (cfg.periodic && node->faceBoundary != 0) continue;  // boundary "ghost" block
+      cBlock *block = node->block;
+      int nCell[3] = {_BLOCK_CELLS_X_, _BLOCK_CELLS_Y_, _BLOCK_CELLS_Z_};
+      long int *FirstCellParticleTable = block->FirstCellParticleTable;
+      double CellVolume = 1;
+      double dx[3];
+      for (int iDim = 0; iDim < 3; iDim++) dx[iDim] = (node->xmax[iDim] - node->xmin[iDim]) / nCell[iDim];
+      for (int iDim = 0; iDim < 3; iDim++) CellVolume *= dx[iDim];
+      for (int k = -1; k < _BLOCK_CELLS_Z_ + 1; k++)
+        for (int j = -1; j < _BLOCK_CELLS_Y_ + 1; j++)
+          for (int i = -1; i < _BLOCK_CELLS_X_ + 1; i++) {
+            int LocalCenterId = _getCenterNodeLocalNumber(i, j, k);
+            if (!block->centerNodes[LocalCenterId]) continue;
+            q_Center[LocalCenterId] = 0.0;
+          }
+      for (int k = 0; k < _BLOCK_CELLS_Z_; k++)
+        for (int j = 0; j < _BLOCK_CELLS_Y_; j++)
+          for (int i = 0; i < _BLOCK_CELLS_X_; i++) {
+            long int ptr = FirstCellParticleTable[i + _BLOCK_CELLS_X_ * (j + _BLOCK_CELLS_Y_ * k)];
+            while (ptr != -1) {
+              byte *ParticleData = GetParticleDataPointer(ptr);
+              double xInit[3];
+              int spec = GetI(ParticleData);
+              GetX(xInit, ParticleData);
+              double LocalParticleWeight = cfg.species_weight[spec];
+              LocalParticleWeight *= GetIndividualStatWeightCorrection(ParticleData);
+              double chargeQ = q_I[spec] * LocalParticleWeight;
+              cStencil NetChargeStencil;
+              CellCentered_Linear_InitStencil(xInit, node, NetChargeStencil, false);  // the StencilTable overload: Normalize() only if Length != 8
+              for (int iStencil = 0; iStencil < NetChargeStencil.Length; iStencil++)
+                q_Center[NetChargeStencil.LocalCellID[iStencil]] += NetChargeStencil.Weight[iStencil] * chargeQ;
+              ptr = GetNext(ParticleData);
+            }
+          }
+      for (int k = -1; k < _BLOCK_CELLS_Z_ + 1; k++)
+        for (int j = -1; j < _BLOCK_CELLS_Y_ + 1; j++)
+          for (int i = -1; i < _BLOCK_CELLS_X_ + 1; i++) {
+            int LocalCenterId = _getCenterNodeLocalNumber(i, j, k);
+            if (!block->centerNodes[LocalCenterId]) continue;
+            block->centerNodes[LocalCenterId]->data[netChargeNew_d] += q_Center[LocalCenterId] / CellVolume;
+          }
+    }
+    return AMPS_GPU_OK;
+  }
+
   // PIC::Mover::cExternalBoundaryFace + Init, src/pic/pic_mover.cpp:24-28,48-75
   struct cExternalBoundaryFace {
     double norm[3];
@@ -2369,6 +2426,11 @@ void oracle_set_background(oracle_ctx *o, const double *E_center, const double *
     for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + BackgroundE_d, E_center + 3 * (size_t)i, 24);
   if (B_center)
     for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + BackgroundB_d, B_center + 3 * (size_t)i, 24);
+}
+int oracle_net_charge(oracle_ctx *o, double charge_conv, double *rho) {
+  int rc = o->ComputeNetCharge(charge_conv);
+  for (int i = 0; i < o->n_centers; i++) rho[i] = o->centerPool[i].data[netChargeNew_d];
+  return rc;
 }
 void oracle_set_background_gca(oracle_ctx *o, const double *var15) {
   for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + BackgroundGCA_d, var15 + 15 * (size_t)i, 15 * 8);

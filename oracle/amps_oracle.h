@@ -77,6 +77,9 @@ void oracle_get_particles(const oracle_ctx *, double *x, double *v, double *w, u
 /* ECSIM::UpdateJMassMatrix(): J[n_corners][3], M[n_corners][243] */
 int oracle_deposit_JM(oracle_ctx *, int n_threads, double *J, double *M, double *energy, double *cfl);
 
+/* ECSIM::ComputeNetCharge(): rho_new on the unique centre nodes [n_centers] */
+int oracle_net_charge(oracle_ctx *, double charge_conv, double *rho);
+
 /* stand-alone pieces for unit parity tests */
 int oracle_find_tree_node(const oracle_ctx *, const double *x, int start_leaf); /* leaf id or -1 */
 int oracle_find_cell_index(const oracle_ctx *, const double *x, int leaf, int *ijk);

@@ -47,6 +47,7 @@ def load(kind="parity"):
     lib.oracle_corner_stencil.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     lib.oracle_center_stencil.argtypes = [vp, vp, C.c_int, vp, vp]
     lib.oracle_check_particle_lists.argtypes = [vp]
+    lib.oracle_net_charge.argtypes = [vp, C.c_double, vp]
     lib.oracle_coupler_stencil.argtypes = [vp, vp, C.c_int, vp, vp]
     lib.oracle_neib_levels.argtypes = [vp, C.c_int, vp]
     _libs[kind] = lib
@@ -186,6 +187,11 @@ class Oracle:
         mm = np.zeros(2, dtype=np.int32)
         self.lib.oracle_neib_levels(self.h, leaf, _p(mm))
         return int(mm[0]), int(mm[1])
+
+    def net_charge(self, charge_conv=1.0):
+        rho = np.zeros(self.mesh.n_centers)
+        assert self.lib.oracle_net_charge(self.h, charge_conv, _p(rho)) == 0
+        return rho
 
     def check_lists(self):
         return self.lib.oracle_check_particle_lists(self.h)
