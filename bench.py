@@ -107,7 +107,7 @@ def build_box(n_cells, ppc, block_cells=(8, 8, 8), seed=100, capacity_slack=1.02
     return m, cfg, parts, (E, B, B.copy())
 
 
-def cpu_port_rate(n_cells, ppc, steps, threads):
+def cpu_port_rate(n_cells, ppc, steps, threads, warmup=1):
     """oracle (CPU port of the reference path) on a bounded sample: move + list swap + periodic wrap + deposit"""
     from oracle.oracle_py import Oracle
 
@@ -119,8 +119,9 @@ def cpu_port_rate(n_cells, ppc, steps, threads):
     o.set_fields(*fields)
     o.add_particles(*parts)
     n = parts[0].shape[1]
-    o.move_fast(0, threads)  # warm-up step (page faults, list order)
-    o.deposit(threads, want_arrays=False)
+    for _ in range(max(1, warmup)):  # warm-up steps (page faults, list order)
+        o.move_fast(0, threads)
+        o.deposit(threads, want_arrays=False)
     per_step = []
     for _ in range(steps):
         t0 = time.perf_counter()
@@ -139,11 +140,12 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     threads = cores
     cells = (32, 32, 32)
-    n, per_step = cpu_port_rate(cells, args.ppc, max(1, args.steps), threads)
+    W = max(1, args.warmup)
+    n, per_step = cpu_port_rate(cells, args.ppc, max(1, args.steps), threads, warmup=W)
     dt = float(np.sum(per_step))
     val = n * len(per_step) / dt
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(per_step), "warmup": 1,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(per_step), "warmup": W,
         "ms_per_step": 1e3 * dt / len(per_step), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"ECSIM uniform periodic box {args.cells}^3 cells, {args.ppc} ppc/species e+p, 8^3-cell blocks, Maxwellian, dt=1",
