@@ -2843,6 +2843,16 @@ int oracle_coupler_stencil(const oracle_ctx *o, const double *x, int leaf, int *
   for (int i = 0; i < s.Length; i++) uids[i] = (int)(s.cell[i] - o->centerPool.data()), w[i] = s.Weight[i];
   return s.Length;
 }
+// neighbour of a leaf: kind 0 = GetNeibFace(idx,0,0), 1 = GetNeibEdge(idx,0), 2 = GetNeibCorner(idx); returns the node id or -1,
+// geometry in lo/hi/level
+int oracle_neib(const oracle_ctx *o, int leaf, int kind, int idx, double *lo, double *hi, int *level) {
+  cTreeNode *n = o->BlockTable[leaf];
+  cTreeNode *nb = (kind == 0) ? o->GetNeibFace(n, idx, 0, 0) : (kind == 1) ? o->GetNeibEdge(n, idx, 0) : o->GetNeibCorner(n, idx);
+  if (!nb) return -1;
+  for (int d = 0; d < 3; d++) lo[d] = nb->xmin[d], hi[d] = nb->xmax[d];
+  *level = nb->RefinmentLevel;
+  return nb->id;
+}
 // (min, max) neighbour refinement levels of a leaf (SetNeibRefinmentLevelLimits)
 void oracle_neib_levels(const oracle_ctx *o, int leaf, int *minmax) {
   minmax[0] = o->BlockTable[leaf]->minNeibRefinmentLevel, minmax[1] = o->BlockTable[leaf]->maxNeibRefinmentLevel;

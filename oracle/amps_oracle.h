@@ -14,9 +14,11 @@
  * un-vendored SWMF share/ headers).  For the ECSIM push/deposit the oracle is
  * therefore pinned only by the structural invariants the reference states
  * (sum W = 1, symmetric mass matrix scatter, CPU-variant agreement) =>
- * "parity unpinned" for those; the relativistic Boris mover is pinned against
- * the in-tree Stormer cutoff CSVs and against srcEarth/gridless compiled from
- * the reference sources (oracle/_ref).  See DESIGN.md.
+ * "parity unpinned" for those; the relativistic Boris momentum rotation is pinned
+ * against srcEarth/gridless, and the tree search / cell index / neighbour probes /
+ * neighbour level limits against the reference's own mesh class, both compiled
+ * from the reference sources into oracle/_ref (tests/test_reference_mesh.py,
+ * tests/test_relativistic_boris.py).  See DESIGN.md.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.
@@ -91,6 +93,7 @@ int oracle_center_stencil(const oracle_ctx *, const double *x, int leaf, int *id
 /* PIC::CPLR::InitInterpolationStencil (AMR capable): unique centre ids + weights (<=64); returns Length, -1 = reference exit() */
 int oracle_coupler_stencil(const oracle_ctx *, const double *x, int leaf, int *uids, double *w);
 void oracle_neib_levels(const oracle_ctx *, int leaf, int *minmax);
+int oracle_neib(const oracle_ctx *, int leaf, int kind, int idx, double *lo, double *hi, int *level);
 
 /* ParticleBuffer list checks (CheckParticleList, pic_pbuffer.cpp:807) : 0 ok */
 int oracle_check_particle_lists(const oracle_ctx *);

@@ -50,6 +50,7 @@ def load(kind="parity"):
     lib.oracle_net_charge.argtypes = [vp, C.c_double, vp]
     lib.oracle_coupler_stencil.argtypes = [vp, vp, C.c_int, vp, vp]
     lib.oracle_neib_levels.argtypes = [vp, C.c_int, vp]
+    lib.oracle_neib.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     _libs[kind] = lib
     return lib
 
@@ -182,6 +183,12 @@ class Oracle:
         w = np.zeros(64)
         n = self.lib.oracle_coupler_stencil(self.h, _p(x), leaf, _p(ids), _p(w))
         return n, ids[:max(n, 0)], w[:max(n, 0)]
+
+    def neib(self, leaf, kind, idx):
+        lo, hi = np.zeros(3), np.zeros(3)
+        lev = C.c_int()
+        r = self.lib.oracle_neib(self.h, leaf, kind, idx, _p(lo), _p(hi), C.cast(C.byref(lev), C.c_void_p))
+        return None if r < 0 else (lo, hi, int(lev.value))
 
     def neib_levels(self, leaf):
         mm = np.zeros(2, dtype=np.int32)
