@@ -55,6 +55,10 @@ struct DevMesh {
   const LeafGeo *leaf;  // [nLeaves]
   const int *cornerUid; // [nLeaves][nCornerLocal]
   const int *centerUid; // [nLeaves][nCenterLocal]
+  // deposit order: the nDepReal leaves that deposit (ascending), then the periodic "ghost" leaves that do not
+  const int *depLeaf;        // [nLeaves]
+  const int *depRealBefore;  // [nLeaves+1] number of depositing leaves with a smaller index
+  int nDepReal;
 };
 
 struct DevSpecies {

@@ -490,6 +490,19 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
   if ((rc = upload_array(ctx, &m.leaf, lg.data(), (size_t)m.nLeaves))) return rc;
   if ((rc = upload_array(ctx, &m.cornerUid, mesh->leaf_corner_uid, (size_t)m.nLeaves * m.nCornerLocal))) return rc;
   if ((rc = upload_array(ctx, &m.centerUid, mesh->leaf_center_uid, (size_t)m.nLeaves * m.nCenterLocal))) return rc;
+  {
+    std::vector<int> depLeaf, ghostLeaf, realBefore((size_t)m.nLeaves + 1, 0);
+    for (int l = 0; l < m.nLeaves; l++) {
+      const bool ghost = ctx->cfg.periodic && mesh->leaf_face_boundary[l] != 0;
+      (ghost ? ghostLeaf : depLeaf).push_back(l);
+      realBefore[l + 1] = (int)depLeaf.size();
+    }
+    m.nDepReal = (int)depLeaf.size();
+    depLeaf.insert(depLeaf.end(), ghostLeaf.begin(), ghostLeaf.end());
+    if ((rc = upload_array(ctx, &m.depLeaf, depLeaf.data(), depLeaf.size()))) return rc;
+    if ((rc = upload_array(ctx, &m.depRealBefore, realBefore.data(), realBefore.size()))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));  // the vectors are locals
+  }
   ctx->rank = (mesh->n_ranks > 1) ? mesh->this_rank : 0;
   ctx->nRanks = (mesh->n_ranks > 1) ? mesh->n_ranks : 1;
   if (ctx->nRanks > 1) {

@@ -95,8 +95,11 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warpGlobal = blockIdx.x * DEP_WARPS + wib, nWarps = gridDim.x * DEP_WARPS;
-  const int nCells = cell1;  // this launch deposits the cells [cell0, cell1)
   const int C = m.cellsPerBlock;
+  // this launch deposits the cells [cell0, cell1) (whole leaves).  The warps walk the cells of the depositing leaves only
+  // (m.depLeaf: periodic "ghost" blocks are skipped, :3815-3825), so that a warp's next cell is known one cell ahead and its
+  // first particles are requested while the current cell is still being accumulated.
+  const int idx0 = m.depRealBefore[cell0 / C] * C, idx1 = m.depRealBefore[cell1 / C] * C;
   double *rows = sRows + (size_t)wib * SLAB;
   double *sB = sBall[wib];
 
@@ -106,45 +109,54 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
   const double invc = 1.0 / sp.LightSpeed;
   double eAcc = 0.0, cflMax = 0.0;  // kDiag: per-lane energy; lane s keeps the cfl of species s
 
-  int nBegin = 0, nEnd = 0;  // cell table entry of the NEXT cell (requested one cell ahead)
-  if (cell0 + warpGlobal < nCells) nBegin = cellStart[cell0 + warpGlobal], nEnd = cellStart[cell0 + warpGlobal + 1];
-  for (int cell = cell0 + warpGlobal; cell < nCells; cell += nWarps) {
-    const int begin = nBegin, end = nEnd;
-    if (cell + nWarps < nCells) nBegin = cellStart[cell + nWarps], nEnd = cellStart[cell + nWarps + 1];
-    if (begin == end) continue;  // ProcessCell returns false: nothing is flushed
+  // software prefetch: the particle of the NEXT chunk (of this cell, or the first chunk of the warp's next cell) is loaded
+  // while phase 2 of the current one runs
+  double nx0 = 0, nx1 = 0, nx2 = 0, nv0 = 0, nv1 = 0, nv2 = 0, nw = 0;
+  int nspec = 0;
+  int nsrc = 0, nsrc2 = 0;  // kGather: source slot of the prefetched particle / of the one a chunk later
+  int nptr = 0;             // kGather: its ParticleBuffer slot (travels to the sorted copy)
+  bool pre = false;         // the first chunk of the next cell is already in flight
+
+  int idx = idx0 + warpGlobal;
+  int ncell = 0, nBegin = 0, nEnd = 0;  // the warp's NEXT cell and its cell table entry (requested one cell ahead)
+  if (idx < idx1) {
+    const int rl = idx / C;
+    ncell = m.depLeaf[rl] * C + (idx - rl * C);
+    nBegin = cellStart[ncell], nEnd = cellStart[ncell + 1];
+  }
+  while (idx < idx1) {
+    const int cell = ncell, begin = nBegin, end = nEnd;
+    idx += nWarps;
+    if (idx < idx1) {
+      const int rl = idx / C;
+      ncell = m.depLeaf[rl] * C + (idx - rl * C);
+      nBegin = cellStart[ncell], nEnd = cellStart[ncell + 1];
+    } else {
+      nBegin = nEnd = 0;
+    }
+    if (begin == end) continue;  // ProcessCell returns false: nothing is flushed (never prefetched: pre is false)
     const int leaf = cell / C;
     const LeafGeo &lg = m.leaf[leaf];
     const int face = lg.face;
-    if (m.periodic && face != 0) {  // periodic "ghost" (boundary) blocks are skipped, :3815-3825
-      if (kGather)  // (no particle should be here after the wrap; keep the store complete anyway)
-        for (int ip = begin + lane; ip < end; ip += 32) {
-          const int sidx = perm[ip];
-          for (int d = 0; d < 3; d++) dst.x[d][ip] = p.x[d][sidx], dst.v[d][ip] = p.v[d][sidx];
-          dst.w[ip] = p.w[sidx], dst.spec[ip] = p.spec[sidx], dst.key[ip] = cell, dst.ptr[ip] = p.ptr[sidx];
-          if (p.mu) dst.mu[ip] = p.mu[sidx];
-        }
-      continue;
-    }
     const int cin = cell - leaf * C;
     const int kc = cin / (m.N[0] * m.N[1]);
     const int jc = (cin - kc * m.N[0] * m.N[1]) / m.N[0];
     const int ic = cin - kc * m.N[0] * m.N[1] - jc * m.N[0];
 
-    // software prefetch: the particle of the NEXT chunk is loaded while phase 2 of the current one runs; the first
-    // chunk's loads are issued before the B staging so that the two latencies overlap
-    double nx0 = 0, nx1 = 0, nx2 = 0, nv0 = 0, nv1 = 0, nv2 = 0, nw = 0;
-    int nspec = 0;
-    int nsrc = 0, nsrc2 = 0;  // kGather: source slot of the prefetched particle / of the one after it
-    int nptr = 0;             // kGather: its ParticleBuffer slot (travels to the sorted copy)
-    if (begin + lane < end) {
-      const int ip = kGather ? perm[begin + lane] : begin + lane;
-      nsrc = ip;
-      nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
-      nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
-      nw = p.w[ip], nspec = p.spec[ip];
-      if (kGather) nptr = p.ptr[ip];
+    if (!pre) {
+      // first cell of the warp, or the previous one was empty: the first chunk's loads are issued before the B staging so
+      // that the two latencies overlap
+      if (begin + lane < end) {
+        const int ip = kGather ? perm[begin + lane] : begin + lane;
+        nsrc = ip;
+        nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
+        nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
+        nw = p.w[ip], nspec = p.spec[ip];
+        if (kGather) nptr = p.ptr[ip];
+      }
+      if (kGather && begin + CHUNK + lane < end) nsrc2 = perm[begin + CHUNK + lane];
     }
-    if (kGather && begin + CHUNK + lane < end) nsrc2 = perm[begin + CHUNK + lane];
+    pre = false;
     __syncwarp();  // previous cell's totals fully flushed
     int uidLane = 0;
     if (lane < 8) uidLane = m.cornerUid[(size_t)leaf * m.nCornerLocal + cornerLocalNumber(m, ic + cox(lane), jc + coy(lane), kc + coz(lane))];
@@ -188,14 +200,33 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
         dst.w[o] = pw, dst.spec[o] = (uint8_t)nspec, dst.key[o] = cell, dst.ptr[o] = nptr;
         if (p.mu) dst.mu[o] = p.mu[nsrc];
       }
-      if (base + CHUNK + lane < end) {
-        const int ip = kGather ? nsrc2 : base + CHUNK + lane;
-        nsrc = ip;
-        nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
-        nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
-        nw = p.w[ip], nspec = p.spec[ip];
-        if (kGather) nptr = p.ptr[ip];
-        if (kGather && base + 2 * CHUNK + lane < end) nsrc2 = perm[base + 2 * CHUNK + lane];
+      if (base + CHUNK < end) {  // (warp-uniform) the next chunk of this cell
+        if (base + CHUNK + lane < end) {
+          const int ip = kGather ? nsrc2 : base + CHUNK + lane;
+          nsrc = ip;
+          nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
+          nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
+          nw = p.w[ip], nspec = p.spec[ip];
+          if (kGather) nptr = p.ptr[ip];
+        }
+        if (kGather) {  // the permutation entry a chunk further: of this cell, else of the first chunk of the next cell
+          if (base + 2 * CHUNK < end) {
+            if (base + 2 * CHUNK + lane < end) nsrc2 = perm[base + 2 * CHUNK + lane];
+          } else if (nBegin + lane < nEnd) {
+            nsrc2 = perm[nBegin + lane];
+          }
+        }
+      } else if (nBegin < nEnd) {  // last chunk of this cell: request the first chunk of the warp's next cell
+        pre = true;
+        if (nBegin + lane < nEnd) {
+          const int ip = kGather ? ((end - begin > CHUNK) ? nsrc2 : perm[nBegin + lane]) : nBegin + lane;
+          nsrc = ip;
+          nx0 = p.x[0][ip], nx1 = p.x[1][ip], nx2 = p.x[2][ip];
+          nv0 = p.v[0][ip], nv1 = p.v[1][ip], nv2 = p.v[2][ip];
+          nw = p.w[ip], nspec = p.spec[ip];
+          if (kGather) nptr = p.ptr[ip];
+        }
+        if (kGather && nBegin + CHUNK + lane < nEnd) nsrc2 = perm[nBegin + CHUNK + lane];
       }
       if (lane < np) {
         const double LocalParticleWeight = sp.weight[spec] * pw;
@@ -394,6 +425,20 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
 #pragma unroll
         for (int d = 0; d < 8; d++) val += rows[sJcls[c * 8 + d] + 9 + dcol];
         atomicAdd(J + (size_t)ui * 3 + dcol, val);
+      }
+    }
+  }
+  if (kGather && m.periodic && cell0 == 0) {
+    // periodic "ghost" (boundary) blocks deposit nothing and hold no particle after the wrap; should one be there (uploaded
+    // outside the real domain and not moved yet), it still travels to the sorted copy
+    for (int g = m.nDepReal + warpGlobal; g < m.nLeaves; g += nWarps) {
+      const int leaf = m.depLeaf[g];
+      const int b = cellStart[(size_t)leaf * C], e = cellStart[(size_t)(leaf + 1) * C];
+      for (int ip = b + lane; ip < e; ip += 32) {
+        const int sidx = perm[ip];
+        for (int d = 0; d < 3; d++) dst.x[d][ip] = p.x[d][sidx], dst.v[d][ip] = p.v[d][sidx];
+        dst.w[ip] = p.w[sidx], dst.spec[ip] = p.spec[sidx], dst.key[ip] = p.key[sidx], dst.ptr[ip] = p.ptr[sidx];
+        if (p.mu) dst.mu[ip] = p.mu[sidx];
       }
     }
   }
