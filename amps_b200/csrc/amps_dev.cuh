@@ -108,8 +108,8 @@ void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *
                  long long capacity, bool countValid, void *scanTmp, int *perm, cudaStream_t s, long long *launches);
 // perm != nullptr: p is the UNSORTED store, particle i of the sorted order is p[perm[i]]; the kernel also writes the sorted copy to dst
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
-                    double *energy, unsigned long long *cflBits, int nSM, const int *perm, ParticleSoA dst, int cell0, int cell1, cudaStream_t s,
-                    long long *launches);  // cells [cell0, cell1); cell1 < 0 = all; J, M and the diagnostics are zeroed when cell0 == 0
+                    double *energy, unsigned long long *cflBits, int nSM, const int *perm, ParticleSoA dst, int cell0, int cell1, bool jmZeroed,
+                    cudaStream_t s, long long *launches);  // cells [cell0, cell1); cell1 < 0 = all; J, M and the diagnostics are zeroed when cell0 == 0
 void launch_net_charge(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, double chargeConv, double *rho, long long nUpper,
                        cudaStream_t s);
 size_t sort_scan_tmp_bytes(long long nCells);

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "amps_dev.cuh"
@@ -85,6 +86,10 @@ struct amps_gpu_ctx {
   std::vector<cudaEvent_t> evPool;
   size_t evUsed = 0;
   std::vector<std::pair<int, std::pair<size_t, size_t>>> evSpans;  // phase, (begin,end) event index
+  cudaEvent_t evCounts = nullptr;  // migration: the counts have reached the host
+  bool jmZeroed = false;           // J, M were zeroed ahead of the deposit that follows
+  std::map<int, double> subMs;                                      // debug: sub-phase id (>= 16) -> ms
+  bool subPhases = getenv("AMPS_GPU_DEBUG_SUBPHASES") != nullptr;
   double phaseMs[AMPS_GPU_N_PHASES] = {0, 0, 0, 0};
   long long phaseCount[AMPS_GPU_N_PHASES] = {0, 0, 0, 0};
 };
@@ -110,6 +115,20 @@ struct ProfScope {
       size_t e = prof_mark(ctx);
       ctx->evSpans.push_back({phase, {b, e}});
     }
+  }
+};
+
+// debug (AMPS_GPU_DEBUG_SUBPHASES): spans inside the exchange phase, printed by amps_gpu_profile
+struct Sub {
+  amps_gpu_ctx *c;
+  int id;
+  size_t b = 0;
+  bool on;
+  Sub(amps_gpu_ctx *cc, int i) : c(cc), id(i), on(cc->profile && cc->subPhases) {
+    if (on) b = prof_mark(c);
+  }
+  void end() {
+    if (on) c->evSpans.push_back({id, {b, prof_mark(c)}}), on = false;
   }
 };
 
@@ -277,6 +296,7 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   cudaFree(ctx->d_redoMask), cudaFree(ctx->d_leafRedo), cudaFree(ctx->d_perm), cudaFree(ctx->d_rho);
   for (cudaEvent_t e : ctx->dlEvents) cudaEventDestroy(e);
   if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+  if (ctx->evCounts) cudaEventDestroy(ctx->evCounts);
   cudaFree(ctx->d_bgE), cudaFree(ctx->d_bgB), cudaFree(ctx->d_bgTile), cudaFree(ctx->d_exitBuf), cudaFree(ctx->d_exitCount);
   cudaFree(ctx->d_sendBuf), cudaFree(ctx->d_recvBuf), cudaFree(ctx->d_sendCount), cudaFree(ctx->d_allCounts), cudaFree(ctx->d_errFlag);
   for (int *p : ctx->d_sharedUid) cudaFree(p);
@@ -719,7 +739,7 @@ static int do_sort_deposit_fused(amps_gpu_ctx *ctx) {
   {
     ProfScope prof(ctx, AMPS_GPU_PHASE_DEPOSIT);
     launch_deposit(ctx->dm, ctx->sp, src, ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl, ctx->nSM, ctx->d_perm, dst,
-                   0, -1, ctx->stream, &ctx->launches);
+                   0, -1, ctx->jmZeroed, ctx->stream, &ctx->launches);
     CK(cudaGetLastError());
   }
   ctx->cur = 1 - ctx->cur;
@@ -1024,7 +1044,7 @@ static int do_deposit(amps_gpu_ctx *ctx) {
     FAIL(AMPS_GPU_ERR_STATE, "ECSIM on a refined mesh needs _PIC_FIELD_SOLVER_B_CORNER_BASED_ (see amps_gpu_move)");
   ProfScope prof(ctx, AMPS_GPU_PHASE_DEPOSIT);
   launch_deposit(ctx->dm, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl,
-                 ctx->nSM, nullptr, ctx->buf[ctx->cur], 0, -1, ctx->stream, &ctx->launches);
+                 ctx->nSM, nullptr, ctx->buf[ctx->cur], 0, -1, false, ctx->stream, &ctx->launches);
   CK(cudaGetLastError());
   return AMPS_GPU_OK;
 }
@@ -1102,8 +1122,19 @@ int amps_gpu_profile(amps_gpu_ctx *ctx, int enable, double *phase_ms, int64_t *p
   for (auto &sp : ctx->evSpans) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->evPool[sp.second.first], ctx->evPool[sp.second.second]);
+    if (sp.first >= AMPS_GPU_N_PHASES) {  // sub-phases of the exchange (AMPS_GPU_DEBUG_SUBPHASES)
+      ctx->subMs[sp.first] += ms;
+      continue;
+    }
     ctx->phaseMs[sp.first] += ms;
     ctx->phaseCount[sp.first]++;
+  }
+  if (!ctx->subMs.empty()) {
+    if (ctx->rank == 0) {
+      static const char *names[] = {"mig_pack", "mig_counts", "mig_sendrecv", "mig_unpack", "jm_pack", "jm_sendrecv", "jm_add", "jm_allreduce"};
+      for (auto &kv : ctx->subMs) fprintf(stderr, "[amps_gpu] sub-phase %s: %.3f ms total\n", names[(kv.first - 16) & 7], kv.second);
+    }
+    ctx->subMs.clear();
   }
   ctx->evSpans.clear();
   ctx->evUsed = 0;
@@ -1154,6 +1185,11 @@ int amps_gpu_comm_init(amps_gpu_ctx *ctx, const void *id128, int rank, int n_ran
   NcclApi &a = nccl_api();
   if (!a.ok) FAIL(AMPS_GPU_ERR_STATE, "libnccl.so.2 could not be loaded");
   CK(cudaSetDevice(ctx->cfg.device));
+  // the shared-corner exchange is a handful of 10-50 MB point-to-point messages per step: NCCL's default of 2 channels per
+  // peer moves them at ~45 GB/s, 16 channels at ~170 GB/s over NVLink (measured, B200 x2).  NCCL reads the variables once per
+  // process, at its first communicator: a host that initialises NCCL earlier (torch) sets them itself (bench.py does).
+  setenv("NCCL_MIN_P2P_NCHANNELS", "16", 0);
+  setenv("NCCL_MAX_P2P_NCHANNELS", "32", 0);
   ncclUniqueId id;
   memcpy(&id, id128, 128);
   NCK(a.CommInitRank(&ctx->comm, n_ranks, id, rank));
@@ -1184,7 +1220,7 @@ int amps_gpu_set_shared_corners(amps_gpu_ctx *ctx, int peer, const int32_t *uids
   return AMPS_GPU_OK;
 }
 
-static int do_migrate(amps_gpu_ctx *ctx, int64_t *n_sent, int64_t *n_received) {
+static int do_migrate(amps_gpu_ctx *ctx, int64_t *n_sent, int64_t *n_received, bool zeroJM = false) {
   if (n_sent) *n_sent = 0;
   if (n_received) *n_received = 0;
   if (ctx->nRanks <= 1) return AMPS_GPU_OK;
@@ -1195,17 +1231,31 @@ static int do_migrate(amps_gpu_ctx *ctx, int64_t *n_sent, int64_t *n_received) {
   const int R = ctx->nRanks, me = ctx->rank;
   const size_t recLen = (size_t)migration_record_len(ctx->buf[ctx->cur]);
   cudaStream_t s = ctx->stream;
+  Sub s0(ctx, 16);
   CK(cudaMemsetAsync(ctx->d_sendCount, 0, sizeof(int) * R, s));
   launch_pack_leavers(ctx->dm, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper, ctx->d_leafOwner, ctx->d_leafGlobal, me, ctx->d_sendBuf,
                       ctx->capPerPeer, ctx->d_sendCount, ctx->d_cellCount, ctx->d_errFlag, s);
   ctx->launches++;
+  s0.end();
+  Sub s1(ctx, 17);
   // counts: every rank learns the whole R x R matrix (the reference's first message, pic_parallel.cpp:267-301)
   NCK(a.AllGather(ctx->d_sendCount, ctx->d_allCounts, R, ncclInt, ctx->comm, s));
   std::vector<int> all((size_t)R * R);
   int err = 0;
   CK(cudaMemcpyAsync(all.data(), ctx->d_allCounts, sizeof(int) * R * R, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(&err, ctx->d_errFlag, sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  if (zeroJM) {
+    // inside amps_gpu_step: the device zeroes J and M (SetCornerNodeAssociatedDataValue, :3266-3267) while the host waits for
+    // the counts and enqueues the transfers
+    if (!ctx->evCounts) CK(cudaEventCreateWithFlags(&ctx->evCounts, cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->evCounts, s));
+    CK(cudaMemsetAsync(ctx->d_J, 0, sizeof(double) * 3 * (size_t)ctx->dm.nCorners, s));
+    CK(cudaMemsetAsync(ctx->d_M, 0, sizeof(double) * 243 * (size_t)ctx->dm.nCorners, s));
+    ctx->jmZeroed = true;
+    CK(cudaEventSynchronize(ctx->evCounts));
+  } else {
+    CK(cudaStreamSynchronize(s));
+  }
   if (err) FAIL(AMPS_GPU_ERR_CAPACITY, "migration send buffer overflow (more than capacity/32 leavers to one rank)");
   long long nRecv = 0, nSend = 0;
   std::vector<long long> roff(R, 0);
@@ -1214,6 +1264,8 @@ static int do_migrate(amps_gpu_ctx *ctx, int64_t *n_sent, int64_t *n_received) {
     if (r != me) nRecv += all[(size_t)r * R + me], nSend += all[(size_t)me * R + r];
   }
   if (nRecv > (long long)R * ctx->capPerPeer) FAIL(AMPS_GPU_ERR_CAPACITY, "migration receive buffer overflow");
+  s1.end();
+  Sub s2(ctx, 18);
   NCK(a.GroupStart());
   for (int r = 0; r < R; r++) {
     if (r == me) continue;
@@ -1222,9 +1274,12 @@ static int do_migrate(amps_gpu_ctx *ctx, int64_t *n_sent, int64_t *n_received) {
     if (nr > 0) NCK(a.Recv(ctx->d_recvBuf + (size_t)roff[r] * recLen, (size_t)nr * recLen, ncclDouble, r, ctx->comm, s));
   }
   NCK(a.GroupEnd());
+  s2.end();
   if (ctx->nUpper + nRecv > ctx->cfg.capacity) FAIL(AMPS_GPU_ERR_CAPACITY, "particle capacity exceeded by arriving particles");
+  Sub s3(ctx, 19);
   launch_unpack_arrivals(ctx->dm, ctx->d_recvBuf, (int)nRecv, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->d_g2l, ctx->d_leafOwner, me,
                          ctx->cfg.capacity, ctx->d_cellCount, ctx->d_errFlag, s);
+  s3.end();
   if (nRecv) ctx->launches += 2;
   ctx->nUpper += nRecv;
   CK(cudaGetLastError());
@@ -1247,6 +1302,7 @@ static int do_exchange_JM(amps_gpu_ctx *ctx) {
   const int R = ctx->nRanks, me = ctx->rank;
   cudaStream_t s = ctx->stream;
   // all partial sums are packed before any is added, so every sharer ends with the same total
+  Sub j0(ctx, 20);
   long long off = 0;
   std::vector<long long> offs(R, 0);
   for (int r = 0; r < R; r++) {
@@ -1256,6 +1312,8 @@ static int do_exchange_JM(amps_gpu_ctx *ctx) {
     ctx->launches++;
     off += ctx->nShared[r];
   }
+  j0.end();
+  Sub j1(ctx, 21);
   NCK(a.GroupStart());
   for (int r = 0; r < R; r++) {
     if (r == me || ctx->nShared[r] == 0) continue;
@@ -1263,14 +1321,19 @@ static int do_exchange_JM(amps_gpu_ctx *ctx) {
     NCK(a.Recv(ctx->d_cornerRecv + offs[r] * 246, (size_t)ctx->nShared[r] * 246, ncclDouble, r, ctx->comm, s));
   }
   NCK(a.GroupEnd());
+  j1.end();
+  Sub j2(ctx, 22);
   for (int r = 0; r < R; r++) {
     if (r == me || ctx->nShared[r] == 0) continue;
     launch_add_corners(ctx->d_sharedUid[r], (int)ctx->nShared[r], ctx->d_J, ctx->d_M, ctx->d_cornerRecv + offs[r] * 246, s);
     ctx->launches++;
   }
+  j2.end();
+  Sub j3(ctx, 23);
   // MPI_Reduce(ParticleEnergy, SUM), MPI_Reduce(cfl, MAX): non-negative doubles order like their bit patterns
   NCK(a.AllReduce(ctx->d_energy, ctx->d_energy, 1, ncclDouble, ncclSum, ctx->comm, s));
   NCK(a.AllReduce(ctx->d_cfl, ctx->d_cfl, AMPS_GPU_MAX_SPECIES, ncclUint64, ncclMax, ctx->comm, s));
+  j3.end();
   CK(cudaGetLastError());
   return AMPS_GPU_OK;
 }
@@ -1327,7 +1390,7 @@ int amps_gpu_step_JM(amps_gpu_ctx *ctx, int mover_id, double *J_host, double *M_
         tk.push_back(a), tc0.push_back(b), tc1.push_back(c);
       }
       launch_deposit(ctx->dm, ctx->sp, src, ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl, ctx->nSM, ctx->d_perm,
-                     dst, c0, ctx->dlCellEnd[k], ctx->stream, &ctx->launches);
+                     dst, c0, ctx->dlCellEnd[k], false, ctx->stream, &ctx->launches);
       CK(cudaGetLastError());
       CK(cudaEventRecord(ctx->dlEvents[k], ctx->stream));
       if (dbg) cudaEventRecord(tk[k], ctx->stream);
@@ -1367,9 +1430,12 @@ int amps_gpu_step(amps_gpu_ctx *ctx, int mover_id) {
   if (!ctx) return AMPS_GPU_ERR_ARG;
   CK(cudaSetDevice(ctx->cfg.device));
   int rc;
+  ctx->jmZeroed = false;
   if ((rc = do_move(ctx, mover_id))) return rc;
-  if ((rc = do_migrate(ctx, nullptr, nullptr))) return rc;
-  if ((rc = do_sort_deposit_fused(ctx))) return rc;
+  if ((rc = do_migrate(ctx, nullptr, nullptr, ctx->meshReady && ctx->fieldsReady))) return rc;
+  rc = do_sort_deposit_fused(ctx);
+  ctx->jmZeroed = false;
+  if (rc) return rc;
   return do_exchange_JM(ctx);
 }
 

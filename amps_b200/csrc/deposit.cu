@@ -588,14 +588,16 @@ void launch_net_charge(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, co
 }
 
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
-                    double *energy, unsigned long long *cflBits, int nSM, const int *perm, ParticleSoA dst, int cell0, int cell1, cudaStream_t s,
-                    long long *launches) {
+                    double *energy, unsigned long long *cflBits, int nSM, const int *perm, ParticleSoA dst, int cell0, int cell1, bool jmZeroed,
+                    cudaStream_t s, long long *launches) {
   const int nCellsAll = m.nLeaves * m.cellsPerBlock;
   if (cell1 < 0 || cell1 > nCellsAll) cell1 = nCellsAll;
   if (cell0 == 0) {
     // zero J, M (SetCornerNodeAssociatedDataValue, :3266-3267) and the diagnostics; later cell ranges of the same deposit add to them
-    cudaMemsetAsync(J, 0, sizeof(double) * 3 * (size_t)m.nCorners, s);
-    cudaMemsetAsync(M, 0, sizeof(double) * 243 * (size_t)m.nCorners, s);
+    if (!jmZeroed) {  // (the multi-rank step zeroes them while the host handles the migration counts)
+      cudaMemsetAsync(J, 0, sizeof(double) * 3 * (size_t)m.nCorners, s);
+      cudaMemsetAsync(M, 0, sizeof(double) * 243 * (size_t)m.nCorners, s);
+    }
     cudaMemsetAsync(energy, 0, sizeof(double), s);
     cudaMemsetAsync(cflBits, 0, sizeof(unsigned long long) * AMPS_GPU_MAX_SPECIES, s);
   }

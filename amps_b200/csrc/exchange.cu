@@ -19,9 +19,17 @@ __global__ void __launch_bounds__(256) pack_leavers_kernel(ParticleSoA p, const 
                                                           long long capPerPeer, int *__restrict__ sendCount, int *__restrict__ cellCount,
                                                           int *__restrict__ errFlag) {
   const int n = *nSlots;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int k = p.key[i];
-    if (k < 0) continue;
+  // leavers are rare: the scan reads four keys per 16-byte load (the key array is a 256-byte aligned allocation)
+  const int n4 = (n + 3) >> 2;
+  const int4 *key4 = reinterpret_cast<const int4 *>(p.key);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += gridDim.x * blockDim.x) {
+    const int4 kk = key4[q];
+    const int ks[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+    const int i = 4 * q + j;
+    const int k = ks[j];
+    if (i >= n || k < 0) continue;
     const int leaf = k / C;
     const int dest = leafOwner[leaf];
     if (dest == me) continue;
@@ -40,6 +48,7 @@ __global__ void __launch_bounds__(256) pack_leavers_kernel(ParticleSoA p, const 
     if (p.mu) r[8] = p.mu[i];
     atomicSub(&cellCount[k], 1);
     p.key[i] = -1;
+    }
   }
 }
 
@@ -104,7 +113,7 @@ static inline int grid_for(long long n) {
 
 void launch_pack_leavers(const DevMesh &m, ParticleSoA p, const int *nSlots, long long nUpper, const int *leafOwner, const int *leafGlobal, int me,
                          double *sendBuf, long long capPerPeer, int *sendCount, int *cellCount, int *errFlag, cudaStream_t s) {
-  pack_leavers_kernel<<<grid_for(nUpper), 256, 0, s>>>(p, nSlots, leafOwner, leafGlobal, m.cellsPerBlock, me, sendBuf, capPerPeer, sendCount, cellCount,
+  pack_leavers_kernel<<<grid_for((nUpper + 3) / 4), 256, 0, s>>>(p, nSlots, leafOwner, leafGlobal, m.cellsPerBlock, me, sendBuf, capPerPeer, sendCount, cellCount,
                                                       errFlag);
 }
 void launch_unpack_arrivals(const DevMesh &m, const double *recvBuf, int nRecv, ParticleSoA p, int *nSlots, const int *g2l, const int *leafOwner, int me,

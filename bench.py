@@ -14,6 +14,11 @@ bounded sample of the same workload; the real AMPS cannot be built here (DESIGN.
 import argparse
 import json
 import os
+
+# the shared-corner exchange is a few 10-50 MB point-to-point messages per step; NCCL's default of 2 channels per peer
+# moves them at ~45 GB/s.  NCCL reads these once per process (torch initialises it first here), see amps_gpu_comm_init.
+os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "16")
+os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
 import subprocess
 import sys
 import threading
