@@ -55,9 +55,9 @@ struct DevMesh {
   const LeafGeo *leaf;  // [nLeaves]
   const int *cornerUid; // [nLeaves][nCornerLocal]
   const int *centerUid; // [nLeaves][nCenterLocal]
-  // deposit order: the nDepReal leaves that deposit (ascending), then the periodic "ghost" leaves that do not
-  const int *depLeaf;        // [nLeaves]
-  const int *depRealBefore;  // [nLeaves+1] number of depositing leaves with a smaller index
+  // deposit order: the nDepReal leaves that deposit (on several ranks: those that touch a shared corner first), then the
+  // periodic "ghost" leaves that do not
+  const int *depLeaf;  // [nLeaves]
   int nDepReal;
 };
 
@@ -94,6 +94,16 @@ __device__ __forceinline__ int centerLocalNumber(const DevMesh &m, int i, int j,
   return i + m.g[0] + m.TN[0] * (j + m.g[1] + (k + m.g[2]) * m.TN[1]);
 }
 
+// launch_deposit flags
+enum : unsigned {
+  DEP_ZERO_JM = 1,     // zero J, M first
+  DEP_ZERO_DIAG = 2,   // zero the energy / cfl accumulators first
+  DEP_GHOST_PASS = 4,  // (gather) also copy the particles of the periodic ghost leaves into the sorted store
+  DEP_FINAL = 8,       // last range of a deposit: run the >2-species diagnostics pass
+  DEP_SPARE_SMS = 16,  // leave a few SMs to concurrently running exchange kernels
+  DEP_ALL = DEP_ZERO_JM | DEP_ZERO_DIAG | DEP_GHOST_PASS | DEP_FINAL
+};
+
 // launch helpers (defined per TU that needs them)
 void launch_stage_tiles(const DevMesh &m, bool cornerB, const double *E_half, const double *B_prev, const double *B_cur, double *eTile, double *bPrevTile,
                         double *bCurTile, cudaStream_t s);
@@ -108,7 +118,7 @@ void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *
                  long long capacity, bool countValid, void *scanTmp, int *perm, cudaStream_t s, long long *launches);
 // perm != nullptr: p is the UNSORTED store, particle i of the sorted order is p[perm[i]]; the kernel also writes the sorted copy to dst
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
-                    double *energy, unsigned long long *cflBits, int nSM, const int *perm, ParticleSoA dst, int cell0, int cell1, bool jmZeroed,
+                    double *energy, unsigned long long *cflBits, int nSM, const int *perm, ParticleSoA dst, int dep0, int dep1, unsigned flags,
                     cudaStream_t s, long long *launches);  // cells [cell0, cell1); cell1 < 0 = all; J, M and the diagnostics are zeroed when cell0 == 0
 void launch_net_charge(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, double chargeConv, double *rho, long long nUpper,
                        cudaStream_t s);

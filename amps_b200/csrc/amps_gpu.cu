@@ -86,6 +86,17 @@ struct amps_gpu_ctx {
   std::vector<cudaEvent_t> evPool;
   size_t evUsed = 0;
   std::vector<std::pair<int, std::pair<size_t, size_t>>> evSpans;  // phase, (begin,end) event index
+  // deposit order (DevMesh::depLeaf) and the overlap of the shared-corner exchange with the deposit of the interior leaves
+  std::vector<int> h_leafCornerUid;           // [nLeaves][nCornerLocal] host copy (to find the leaves that touch shared corners)
+  std::vector<char> h_leafGhost;              // [nLeaves] periodic ghost block: deposits nothing
+  std::vector<int> h_realBefore;              // [nLeaves+1] depositing leaves with a smaller index (ascending order only)
+  std::vector<std::vector<int>> h_sharedUid;  // per peer
+  int *d_depLeaf = nullptr;
+  int nDepBoundary = 0;                       // leading entries of depLeaf that touch a shared corner (0: order is ascending)
+  bool depDirty = false;                      // shared corners changed since depLeaf was built
+  cudaStream_t commStream = nullptr;
+  cudaEvent_t evBoundary = nullptr, evRecv = nullptr;
+  bool overlapJM = false;                     // the deposit just enqueued recorded evBoundary: the exchange may start there
   cudaEvent_t evCounts = nullptr;  // migration: the counts have reached the host
   bool jmZeroed = false;           // J, M were zeroed ahead of the deposit that follows
   std::map<int, double> subMs;                                      // debug: sub-phase id (>= 16) -> ms
@@ -297,6 +308,9 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   for (cudaEvent_t e : ctx->dlEvents) cudaEventDestroy(e);
   if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   if (ctx->evCounts) cudaEventDestroy(ctx->evCounts);
+  if (ctx->evBoundary) cudaEventDestroy(ctx->evBoundary);
+  if (ctx->evRecv) cudaEventDestroy(ctx->evRecv);
+  if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
   cudaFree(ctx->d_bgE), cudaFree(ctx->d_bgB), cudaFree(ctx->d_bgTile), cudaFree(ctx->d_exitBuf), cudaFree(ctx->d_exitCount);
   cudaFree(ctx->d_sendBuf), cudaFree(ctx->d_recvBuf), cudaFree(ctx->d_sendCount), cudaFree(ctx->d_allCounts), cudaFree(ctx->d_errFlag);
   for (int *p : ctx->d_sharedUid) cudaFree(p);
@@ -511,17 +525,22 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
   if ((rc = upload_array(ctx, &m.cornerUid, mesh->leaf_corner_uid, (size_t)m.nLeaves * m.nCornerLocal))) return rc;
   if ((rc = upload_array(ctx, &m.centerUid, mesh->leaf_center_uid, (size_t)m.nLeaves * m.nCenterLocal))) return rc;
   {
-    std::vector<int> depLeaf, ghostLeaf, realBefore((size_t)m.nLeaves + 1, 0);
+    ctx->h_leafGhost.assign((size_t)m.nLeaves, 0);
+    ctx->h_realBefore.assign((size_t)m.nLeaves + 1, 0);
+    std::vector<int> depLeaf, ghostLeaf;
     for (int l = 0; l < m.nLeaves; l++) {
       const bool ghost = ctx->cfg.periodic && mesh->leaf_face_boundary[l] != 0;
+      ctx->h_leafGhost[l] = ghost;
       (ghost ? ghostLeaf : depLeaf).push_back(l);
-      realBefore[l + 1] = (int)depLeaf.size();
+      ctx->h_realBefore[l + 1] = (int)depLeaf.size();
     }
     m.nDepReal = (int)depLeaf.size();
     depLeaf.insert(depLeaf.end(), ghostLeaf.begin(), ghostLeaf.end());
     if ((rc = upload_array(ctx, &m.depLeaf, depLeaf.data(), depLeaf.size()))) return rc;
-    if ((rc = upload_array(ctx, &m.depRealBefore, realBefore.data(), realBefore.size()))) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));  // the vectors are locals
+    ctx->d_depLeaf = const_cast<int *>(m.depLeaf);
+    ctx->nDepBoundary = 0, ctx->depDirty = false;
+    if (mesh->n_ranks > 1) ctx->h_leafCornerUid.assign(mesh->leaf_corner_uid, mesh->leaf_corner_uid + (size_t)m.nLeaves * m.nCornerLocal);
+    CK(cudaStreamSynchronize(ctx->stream));  // depLeaf is a local
   }
   ctx->rank = (mesh->n_ranks > 1) ? mesh->this_rank : 0;
   ctx->nRanks = (mesh->n_ranks > 1) ? mesh->n_ranks : 1;
@@ -542,6 +561,7 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
     CK(cudaMemsetAsync(ctx->d_errFlag, 0, sizeof(int), ctx->stream));
     ctx->d_sharedUid.assign(ctx->nRanks, nullptr);
     ctx->nShared.assign(ctx->nRanks, 0);
+    ctx->h_sharedUid.assign(ctx->nRanks, std::vector<int>());
   }
   CK(cudaStreamSynchronize(ctx->stream));  // lg is a local
 
@@ -723,12 +743,50 @@ static int do_sort(amps_gpu_ctx *ctx) {
 
 // amps_gpu_step: the counting sort only builds the permutation (8 B per particle); the deposit gathers through it and
 // writes the sorted copy while it has the particle in registers.  Same end state as do_sort + do_deposit.
+// several ranks: the leaves that touch a corner shared with another rank are deposited first, so that the exchange of those
+// corners (pack, send/recv) runs next to the deposit of the interior leaves
+static int rebuild_deposit_order(amps_gpu_ctx *ctx) {
+  const DevMesh &m = ctx->dm;
+  std::vector<char> shared((size_t)m.nCorners, 0);
+  for (auto &v : ctx->h_sharedUid)
+    for (int u : v) shared[u] = 1;
+  std::vector<int> bnd, inner, ghost;
+  for (int l = 0; l < m.nLeaves; l++) {
+    if (ctx->h_leafGhost[l]) {
+      ghost.push_back(l);
+      continue;
+    }
+    const int *cu = ctx->h_leafCornerUid.data() + (size_t)l * m.nCornerLocal;
+    bool touches = false;
+    for (int kk = 0; kk <= m.N[2] && !touches; kk++)
+      for (int jj = 0; jj <= m.N[1] && !touches; jj++)
+        for (int ii = 0; ii <= m.N[0]; ii++) {
+          const int u = cu[ii + m.g[0] + (m.TN[0] + 1) * (jj + m.g[1] + (kk + m.g[2]) * (m.TN[1] + 1))];
+          if (u >= 0 && shared[u]) {
+            touches = true;
+            break;
+          }
+        }
+    (touches ? bnd : inner).push_back(l);
+  }
+  ctx->nDepBoundary = (int)bnd.size();
+  bnd.insert(bnd.end(), inner.begin(), inner.end());
+  bnd.insert(bnd.end(), ghost.begin(), ghost.end());
+  CK(cudaMemcpy(ctx->d_depLeaf, bnd.data(), sizeof(int) * bnd.size(), cudaMemcpyHostToDevice));
+  ctx->depDirty = false;
+  return AMPS_GPU_OK;
+}
+
 static int do_sort_deposit_fused(amps_gpu_ctx *ctx) {
   if (!ctx->meshReady || !ctx->fieldsReady) FAIL(AMPS_GPU_ERR_STATE, "deposit before mesh/fields upload");
   if (ctx->meshRefined && ctx->cfg.b_mode == AMPS_B_CENTER_BASED)
     FAIL(AMPS_GPU_ERR_STATE, "ECSIM on a refined mesh needs _PIC_FIELD_SOLVER_B_CORNER_BASED_ (see amps_gpu_move)");
   int rc;
   if (!ctx->d_perm && (rc = dev_alloc(ctx, &ctx->d_perm, (size_t)ctx->cfg.capacity))) return rc;
+  if (ctx->depDirty && ctx->nRanks > 1) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    if ((rc = rebuild_deposit_order(ctx))) return rc;
+  }
   ParticleSoA &src = ctx->buf[ctx->cur], &dst = ctx->buf[1 - ctx->cur];
   {
     ProfScope prof(ctx, AMPS_GPU_PHASE_SORT);
@@ -738,8 +796,23 @@ static int do_sort_deposit_fused(amps_gpu_ctx *ctx) {
   }
   {
     ProfScope prof(ctx, AMPS_GPU_PHASE_DEPOSIT);
-    launch_deposit(ctx->dm, ctx->sp, src, ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl, ctx->nSM, ctx->d_perm, dst,
-                   0, -1, ctx->jmZeroed, ctx->stream, &ctx->launches);
+    const unsigned zero = ctx->jmZeroed ? 0u : (unsigned)DEP_ZERO_JM;
+    const int nB = ctx->nDepBoundary;
+    if (ctx->nRanks > 1 && ctx->comm && nB > 0 && nB < ctx->dm.nDepReal) {
+      launch_deposit(ctx->dm, ctx->sp, src, ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl, ctx->nSM, ctx->d_perm,
+                     dst, 0, nB, zero | DEP_ZERO_DIAG | DEP_GHOST_PASS, ctx->stream, &ctx->launches);
+      if (!ctx->evBoundary) {
+        CK(cudaEventCreateWithFlags(&ctx->evBoundary, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->evRecv, cudaEventDisableTiming));
+      }
+      CK(cudaEventRecord(ctx->evBoundary, ctx->stream));  // every shared corner has its local sum
+      ctx->overlapJM = true;
+      launch_deposit(ctx->dm, ctx->sp, src, ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl, ctx->nSM, ctx->d_perm,
+                     dst, nB, -1, DEP_FINAL | DEP_SPARE_SMS, ctx->stream, &ctx->launches);
+    } else {
+      launch_deposit(ctx->dm, ctx->sp, src, ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl, ctx->nSM, ctx->d_perm,
+                     dst, 0, -1, zero | DEP_ZERO_DIAG | DEP_GHOST_PASS | DEP_FINAL, ctx->stream, &ctx->launches);
+    }
     CK(cudaGetLastError());
   }
   ctx->cur = 1 - ctx->cur;
@@ -1044,7 +1117,7 @@ static int do_deposit(amps_gpu_ctx *ctx) {
     FAIL(AMPS_GPU_ERR_STATE, "ECSIM on a refined mesh needs _PIC_FIELD_SOLVER_B_CORNER_BASED_ (see amps_gpu_move)");
   ProfScope prof(ctx, AMPS_GPU_PHASE_DEPOSIT);
   launch_deposit(ctx->dm, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl,
-                 ctx->nSM, nullptr, ctx->buf[ctx->cur], 0, -1, false, ctx->stream, &ctx->launches);
+                 ctx->nSM, nullptr, ctx->buf[ctx->cur], 0, -1, DEP_ALL, ctx->stream, &ctx->launches);
   CK(cudaGetLastError());
   return AMPS_GPU_OK;
 }
@@ -1205,6 +1278,8 @@ int amps_gpu_set_shared_corners(amps_gpu_ctx *ctx, int peer, const int32_t *uids
   cudaFree(ctx->d_sharedUid[peer]);
   ctx->d_sharedUid[peer] = nullptr;
   ctx->nShared[peer] = n;
+  ctx->h_sharedUid[peer].assign(uids, uids + n);
+  ctx->depDirty = true;
   if (n) {
     CK(cudaMalloc(&ctx->d_sharedUid[peer], n * sizeof(int)));
     CK(cudaMemcpy(ctx->d_sharedUid[peer], uids, n * sizeof(int), cudaMemcpyHostToDevice));
@@ -1300,7 +1375,19 @@ static int do_exchange_JM(amps_gpu_ctx *ctx) {
   ProfScope prof(ctx, AMPS_GPU_PHASE_EXCHANGE);
   NcclApi &a = nccl_api();
   const int R = ctx->nRanks, me = ctx->rank;
-  cudaStream_t s = ctx->stream;
+  // inside amps_gpu_step the shared corners are final once the boundary leaves are deposited (evBoundary): pack and
+  // send/recv run on a second stream next to the deposit of the interior leaves, the main stream joins for the add
+  const bool overlap = ctx->overlapJM;
+  ctx->overlapJM = false;
+  if (overlap) {
+    if (!ctx->commStream) {
+      int lo = 0, hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CK(cudaStreamCreateWithPriority(&ctx->commStream, cudaStreamNonBlocking, hi));
+    }
+    CK(cudaStreamWaitEvent(ctx->commStream, ctx->evBoundary, 0));
+  }
+  cudaStream_t s = overlap ? ctx->commStream : ctx->stream;
   // all partial sums are packed before any is added, so every sharer ends with the same total
   Sub j0(ctx, 20);
   long long off = 0;
@@ -1322,6 +1409,11 @@ static int do_exchange_JM(amps_gpu_ctx *ctx) {
   }
   NCK(a.GroupEnd());
   j1.end();
+  if (overlap) {
+    CK(cudaEventRecord(ctx->evRecv, s));
+    s = ctx->stream;
+    CK(cudaStreamWaitEvent(s, ctx->evRecv, 0));
+  }
   Sub j2(ctx, 22);
   for (int r = 0; r < R; r++) {
     if (r == me || ctx->nShared[r] == 0) continue;
@@ -1390,7 +1482,9 @@ int amps_gpu_step_JM(amps_gpu_ctx *ctx, int mover_id, double *J_host, double *M_
         tk.push_back(a), tc0.push_back(b), tc1.push_back(c);
       }
       launch_deposit(ctx->dm, ctx->sp, src, ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl, ctx->nSM, ctx->d_perm,
-                     dst, c0, ctx->dlCellEnd[k], false, ctx->stream, &ctx->launches);
+                     dst, ctx->h_realBefore[c0 / ctx->dm.cellsPerBlock], ctx->h_realBefore[ctx->dlCellEnd[k] / ctx->dm.cellsPerBlock],
+                     (k == 0 ? DEP_ZERO_JM | DEP_ZERO_DIAG | DEP_GHOST_PASS : 0u) | (k == nChunks - 1 ? (unsigned)DEP_FINAL : 0u), ctx->stream,
+                     &ctx->launches);
       CK(cudaGetLastError());
       CK(cudaEventRecord(ctx->dlEvents[k], ctx->stream));
       if (dbg) cudaEventRecord(tk[k], ctx->stream);

@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
                                                                               const double *__restrict__ bCurTile, double *__restrict__ J,
                                                                               double *__restrict__ M, double *__restrict__ energyOut,
                                                                               unsigned long long *__restrict__ cflBits,
-                                                                              const int *__restrict__ perm, ParticleSoA dst, int cell0, int cell1) {
+                                                                              const int *__restrict__ perm, ParticleSoA dst, int dep0, int dep1,
+                                                                              int ghostPass) {
   extern __shared__ __align__(16) double sRows[];  // [DEP_WARPS][SLAB]
   __shared__ double sBall[DEP_WARPS][27 * 3];  // B_cur on the 3x3x3 centres around the warp's cell
   // flush tables: output o = (c*8+c')*9+col -> corner c (3 bits) | offset inside M[corner] (8 bits) | T index (9 bits)
@@ -96,10 +97,10 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warpGlobal = blockIdx.x * DEP_WARPS + wib, nWarps = gridDim.x * DEP_WARPS;
   const int C = m.cellsPerBlock;
-  // this launch deposits the cells [cell0, cell1) (whole leaves).  The warps walk the cells of the depositing leaves only
-  // (m.depLeaf: periodic "ghost" blocks are skipped, :3815-3825), so that a warp's next cell is known one cell ahead and its
-  // first particles are requested while the current cell is still being accumulated.
-  const int idx0 = m.depRealBefore[cell0 / C] * C, idx1 = m.depRealBefore[cell1 / C] * C;
+  // this launch deposits the cells of the leaves m.depLeaf[dep0 .. dep1).  The warps walk the cells of the depositing leaves
+  // only (periodic "ghost" blocks are skipped, :3815-3825), so that a warp's next cell is known one cell ahead and its first
+  // particles are requested while the current cell is still being accumulated.
+  const int idx0 = dep0 * C, idx1 = dep1 * C;
   double *rows = sRows + (size_t)wib * SLAB;
   double *sB = sBall[wib];
 
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
       }
     }
   }
-  if (kGather && m.periodic && cell0 == 0) {
+  if (kGather && m.periodic && ghostPass) {
     // periodic "ghost" (boundary) blocks deposit nothing and hold no particle after the wrap; should one be there (uploaded
     // outside the real domain and not moved yet), it still travels to the sorted copy
     for (int g = m.nDepReal + warpGlobal; g < m.nLeaves; g += nWarps) {
@@ -588,22 +589,22 @@ void launch_net_charge(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, co
 }
 
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
-                    double *energy, unsigned long long *cflBits, int nSM, const int *perm, ParticleSoA dst, int cell0, int cell1, bool jmZeroed,
+                    double *energy, unsigned long long *cflBits, int nSM, const int *perm, ParticleSoA dst, int dep0, int dep1, unsigned flags,
                     cudaStream_t s, long long *launches) {
-  const int nCellsAll = m.nLeaves * m.cellsPerBlock;
-  if (cell1 < 0 || cell1 > nCellsAll) cell1 = nCellsAll;
-  if (cell0 == 0) {
-    // zero J, M (SetCornerNodeAssociatedDataValue, :3266-3267) and the diagnostics; later cell ranges of the same deposit add to them
-    if (!jmZeroed) {  // (the multi-rank step zeroes them while the host handles the migration counts)
-      cudaMemsetAsync(J, 0, sizeof(double) * 3 * (size_t)m.nCorners, s);
-      cudaMemsetAsync(M, 0, sizeof(double) * 243 * (size_t)m.nCorners, s);
-    }
+  if (dep1 < 0 || dep1 > m.nDepReal) dep1 = m.nDepReal;
+  if (flags & DEP_ZERO_JM) {  // SetCornerNodeAssociatedDataValue, :3266-3267; later ranges of the same deposit add to them
+    cudaMemsetAsync(J, 0, sizeof(double) * 3 * (size_t)m.nCorners, s);
+    cudaMemsetAsync(M, 0, sizeof(double) * 243 * (size_t)m.nCorners, s);
+  }
+  if (flags & DEP_ZERO_DIAG) {
     cudaMemsetAsync(energy, 0, sizeof(double), s);
     cudaMemsetAsync(cflBits, 0, sizeof(unsigned long long) * AMPS_GPU_MAX_SPECIES, s);
   }
-  const int grid = nSM * DEP_CTAS_PER_SM;
+  // DEP_SPARE_SMS: a few SMs stay free for the exchange kernels that run next to this launch
+  const int grid = ((flags & DEP_SPARE_SMS) && nSM > 32 ? nSM - 8 : nSM) * DEP_CTAS_PER_SM;
   const size_t smem = sizeof(double) * DEP_WARPS * SLAB;
   const bool corner = sp.bMode == AMPS_B_CORNER_BASED, diag = sp.n <= 2, gather = perm != nullptr;
+  const int ghostPass = (flags & DEP_GHOST_PASS) ? 1 : 0;
 #define AMPS_DEP_LAUNCH(CB, DG, GA)                                                                                          \
   do {                                                                                                                       \
     static bool attrSet = false;                                                                                             \
@@ -611,7 +612,7 @@ void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const
       cudaFuncSetAttribute(deposit_kernel<CB, DG, GA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
       attrSet = true;                                                                                                        \
     }                                                                                                                        \
-    deposit_kernel<CB, DG, GA><<<grid, DEP_THREADS, smem, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits, perm, dst, cell0, cell1); \
+    deposit_kernel<CB, DG, GA><<<grid, DEP_THREADS, smem, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits, perm, dst, dep0, dep1, ghostPass); \
   } while (0)
   if (corner) {
     if (diag) { if (gather) AMPS_DEP_LAUNCH(true, true, true); else AMPS_DEP_LAUNCH(true, true, false); }
@@ -622,8 +623,8 @@ void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const
   }
 #undef AMPS_DEP_LAUNCH
   (*launches) += 1;
-  if (!diag && cell1 == nCellsAll) {
-    // more than two species: the diagnostics run as their own pass over the SORTED store (after the last cell range)
+  if (!diag && (flags & DEP_FINAL)) {
+    // more than two species: the diagnostics run as their own pass over the SORTED store (after the last range)
     diag_kernel<<<nSM * 4, 256, 0, s>>>(m, sp, gather ? dst : p, cellStart, energy, cflBits);
     (*launches) += 1;
   }
