@@ -172,6 +172,9 @@ PROTOTYPES = {
     "amps_gpu_deposit_JM": (C.c_int, [_vp, _vp, _vp]),
     "amps_gpu_diagnostics": (C.c_int, [_vp, _vp, _vp]),
     "amps_gpu_net_charge": (C.c_int, [_vp, C.c_double, _vp]),
+    "amps_gpu_species_moments": (C.c_int, [_vp, _vp]),
+    "amps_gpu_phi_upload": (C.c_int, [_vp, _vp]),
+    "amps_gpu_correct_particle_location": (C.c_int, [_vp, C.c_double, C.c_double, _vp, _vp]),
     "amps_gpu_step_JM": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "amps_gpu_JM_download": (C.c_int, [_vp, _vp, _vp]),
     "amps_gpu_JM_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),

@@ -223,6 +223,24 @@ class Context:
         self._ck(self.lib.amps_gpu_net_charge(self._h, charge_conv, _ptr(rho)))
         return rho
 
+    def ComputeSpeciesMoments(self, download=True):
+        """corner species moments of UpdateJMassMatrix (_PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_): [n_corners, n_species, 10]"""
+        out = np.empty((self.mesh.n_corners, self.cfg.n_species, 10)) if download else None
+        self._ck(self.lib.amps_gpu_species_moments(self._h, _ptr(out) if download else None))
+        return out
+
+    def SetPhi(self, phi_center):
+        phi = np.ascontiguousarray(phi_center, dtype=np.float64)
+        assert phi.shape == (self.mesh.n_centers,)
+        self._ck(self.lib.amps_gpu_phi_upload(self._h, _ptr(phi)))
+
+    def CorrectParticleLocation(self, charge_conv=1.0, mass_conv=1.0):
+        """ECSIM::CorrectParticleLocation -> (n_displaced, n_deleted); call sort() afterwards"""
+        nd, nx = C.c_int64(), C.c_int64()
+        self._ck(self.lib.amps_gpu_correct_particle_location(self._h, charge_conv, mass_conv, C.cast(C.byref(nd), C.c_void_p),
+                                                            C.cast(C.byref(nx), C.c_void_p)))
+        return int(nd.value), int(nx.value)
+
     def diagnostics(self):
         e = C.c_double()
         cfl = (C.c_double * _capi.MAX_SPECIES)()

@@ -120,6 +120,10 @@ void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
                     double *energy, unsigned long long *cflBits, int nSM, const int *perm, ParticleSoA dst, int dep0, int dep1, unsigned flags,
                     cudaStream_t s, long long *launches);  // cells [cell0, cell1); cell1 < 0 = all; J, M and the diagnostics are zeroed when cell0 == 0
+void launch_species_moments(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, double *spec, int nSM, cudaStream_t s);
+void launch_correct_particle_location(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *nSlots, long long nUpper, const double *phi,
+                                      const double *spec, const unsigned *neibMask, double qom0, int *cellCount, unsigned long long *counters,
+                                      cudaStream_t s);
 void launch_net_charge(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, double chargeConv, double *rho, long long nUpper,
                        cudaStream_t s);
 size_t sort_scan_tmp_bytes(long long nCells);

@@ -54,6 +54,11 @@ struct amps_gpu_ctx {
   unsigned char *d_redoMask = nullptr;  // particles the fast mover left to the exact kernel
   int *d_perm = nullptr;      // sorted position -> slot (fused sort + deposit inside amps_gpu_step)
   double *d_rho = nullptr;    // ComputeNetCharge: rho_new on the unique centre nodes
+  double *d_spec = nullptr;   // species moments on the unique corners [nCorners][n_species][10]
+  double *d_phi = nullptr;    // div-E correction potential on the unique centre nodes
+  unsigned *d_neibMask = nullptr;            // [nLeaves] bit (sx+1)+3(sy+1)+9(sz+1): no (in use) neighbour block in that direction
+  unsigned long long *d_cplCount = nullptr;  // CorrectParticleLocation: displaced, deleted, errors
+  bool specReady = false, phiReady = false;
   // amps_gpu_step_JM: the deposit runs in cell ranges; the corners whose last contributing cell lies in range k form the
   // uid runs dlRuns[dlRunStart[k] .. dlRunStart[k+1]) and are copied to the host while range k+1 is deposited
   struct DlRun { int uid0, n; };
@@ -308,6 +313,7 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   for (cudaEvent_t e : ctx->dlEvents) cudaEventDestroy(e);
   if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   if (ctx->evCounts) cudaEventDestroy(ctx->evCounts);
+  cudaFree(ctx->d_spec), cudaFree(ctx->d_phi), cudaFree(ctx->d_cplCount);
   if (ctx->evBoundary) cudaEventDestroy(ctx->evBoundary);
   if (ctx->evRecv) cudaEventDestroy(ctx->evRecv);
   if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
@@ -539,6 +545,33 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
     if ((rc = upload_array(ctx, &m.depLeaf, depLeaf.data(), depLeaf.size()))) return rc;
     ctx->d_depLeaf = const_cast<int *>(m.depLeaf);
     ctx->nDepBoundary = 0, ctx->depDirty = false;
+    // isBoundaryCell (pic_field_solver_ecsim.cpp:6963-6999) asks for the face / edge / corner neighbour blocks: on a single-level
+    // mesh they are the adjacent root blocks (refined meshes: CorrectParticleLocation is rejected like ComputeNetCharge)
+    std::vector<unsigned> neibMask((size_t)m.nLeaves, 0u);
+    if (!ctx->meshRefined)
+      for (int l = 0; l < m.nLeaves; l++) {
+        const int n = mesh->leaf_node[l];
+        int r[3];
+        for (int d = 0; d < 3; d++) r[d] = mesh->node_imin[3 * n + d] >> m.L;
+        for (int q = 0; q < 27; q++) {
+          if (q == 13) continue;
+          const int s[3] = {q % 3 - 1, (q / 3) % 3 - 1, q / 9 - 1};
+          bool bad = false;
+          int rr[3];
+          for (int d = 0; d < 3; d++) {
+            rr[d] = r[d] + s[d];
+            if (rr[d] < 0 || rr[d] >= m.nRoot[d]) bad = true;
+          }
+          if (!bad) {
+            const int nb = mesh->root_node[rr[0] + m.nRoot[0] * (rr[1] + m.nRoot[1] * rr[2])];
+            bad = nb < 0 || !(mesh->node_flags[nb] & AMPS_NODE_USED);
+          }
+          if (bad) neibMask[l] |= 1u << q;
+        }
+      }
+    const unsigned *dmask;
+    if ((rc = upload_array(ctx, &dmask, neibMask.data(), neibMask.size()))) return rc;
+    ctx->d_neibMask = const_cast<unsigned *>(dmask);
     if (mesh->n_ranks > 1) ctx->h_leafCornerUid.assign(mesh->leaf_corner_uid, mesh->leaf_corner_uid + (size_t)m.nLeaves * m.nCornerLocal);
     CK(cudaStreamSynchronize(ctx->stream));  // depLeaf is a local
   }
@@ -1137,6 +1170,61 @@ int amps_gpu_deposit_JM(amps_gpu_ctx *ctx, double *particle_energy, double *cfl)
     if (cfl)
       for (int s = 0; s < ctx->cfg.n_species; s++) memcpy(&cfl[s], &c[s], 8);
   }
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_species_moments(amps_gpu_ctx *ctx, double *spec_corner) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "species_moments before mesh_upload");
+  if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "species_moments needs the (block,cell)-sorted layout: call amps_gpu_sort");
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc;
+  const size_t n = (size_t)ctx->dm.nCorners * 10 * ctx->sp.n;
+  if (!ctx->d_spec && (rc = dev_alloc(ctx, &ctx->d_spec, n))) return rc;
+  launch_species_moments(ctx->dm, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_spec, ctx->nSM, ctx->stream);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  ctx->specReady = true;
+  if (spec_corner) {
+    CK(cudaMemcpyAsync(spec_corner, ctx->d_spec, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_phi_upload(amps_gpu_ctx *ctx, const double *phi_center) {
+  if (!ctx || !phi_center) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "phi_upload before mesh_upload");
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc;
+  if (!ctx->d_phi && (rc = dev_alloc(ctx, &ctx->d_phi, (size_t)ctx->dm.nCenters))) return rc;
+  CK(cudaMemcpyAsync(ctx->d_phi, phi_center, sizeof(double) * (size_t)ctx->dm.nCenters, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->phiReady = true;
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_correct_particle_location(amps_gpu_ctx *ctx, double charge_conv, double mass_conv, int64_t *n_displaced, int64_t *n_deleted) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "correct_particle_location before mesh_upload");
+  if (!ctx->specReady || !ctx->phiReady) FAIL(AMPS_GPU_ERR_STATE, "correct_particle_location needs amps_gpu_species_moments and amps_gpu_phi_upload");
+  if (ctx->meshRefined) FAIL(AMPS_GPU_ERR_STATE, "CorrectParticleLocation is defined on single-level meshes (the reference indexes a block-local array)");
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc;
+  if (!ctx->d_cplCount && (rc = dev_alloc(ctx, &ctx->d_cplCount, 3))) return rc;
+  const double qom0 = (ctx->cfg.charge[0] * charge_conv) / (ctx->cfg.mass[0] * mass_conv);  // :4449-4452
+  launch_correct_particle_location(ctx->dm, ctx->sp, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper, ctx->d_phi, ctx->d_spec, ctx->d_neibMask,
+                                   qom0, ctx->d_cellCount, ctx->d_cplCount, ctx->stream);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  unsigned long long c[3];
+  CK(cudaMemcpyAsync(c, ctx->d_cplCount, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->sorted = false;       // the lists of the reference are rebuilt (exchangeParticleLocal): amps_gpu_sort re-files the store
+  ctx->countValid = true;    // like a mover, the pass leaves the cell histogram of the survivors (amps_gpu_migrate edits it)
+  if (n_displaced) *n_displaced = (int64_t)c[0];
+  if (n_deleted) *n_deleted = (int64_t)c[1];
+  if (c[2]) FAIL(AMPS_GPU_ERR_PARTICLE, "CorrectParticleLocation: cannot find the cell where a particle is located (the reference exits here)");
   return AMPS_GPU_OK;
 }
 

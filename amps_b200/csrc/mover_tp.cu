@@ -1257,4 +1257,248 @@ void launch_move_guiding_center(const DevMesh &m, const DevSpecies &sp, int orde
   else move_guiding_center_kernel<false><<<(int)g, 128, 0, s>>>(m, sp, tp, idealMhd, T, p, nSlots, cellCount, stats, exitBuf, exitCount);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// f4: the species moments on the corners (the _PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_ part of ProcessCell /
+// UpdateJMassMatrix, src/pic/pic_field_solver_ecsim.cpp:2270-2300, :2384-2392, :3874-3879): per species s and corner c
+//   spec[c][s][0..9] += sum_p m~ W_c {1, vx, vy, vz, vx vx, vy vy, vz vz, vx vy, vy vz, vx vz} / CellVolume.
+// One warp per cell of the sorted store; for one species at a time every lane keeps the 8 x 10 sums of its particles in
+// registers, the warp folds them through shared memory and issues 80 REDs per (cell, species).
+// ------------------------------------------------------------------------------------------------
+constexpr int SM_WARPS = 2;
+__global__ void __launch_bounds__(32 * SM_WARPS) species_moments_kernel(DevMesh m, DevSpecies sp, ParticleSoA p, const int *__restrict__ cellStart,
+                                                                        double *__restrict__ spec) {
+  __shared__ double sAcc[SM_WARPS][32][81];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warpGlobal = blockIdx.x * SM_WARPS + wib, nWarps = gridDim.x * SM_WARPS;
+  const int C = m.cellsPerBlock, nS = sp.n;
+  const int nIdx = m.nDepReal * C;
+  for (int idx = warpGlobal; idx < nIdx; idx += nWarps) {
+    const int rl = idx / C;
+    const int leaf = m.depLeaf[rl];
+    const int cell = leaf * C + (idx - rl * C);
+    const int begin = cellStart[cell], end = cellStart[cell + 1];
+    if (begin == end) continue;
+    const LeafGeo &lg = m.leaf[leaf];
+    const int cin = cell - leaf * C;
+    const int kc = cin / (m.N[0] * m.N[1]);
+    const int jc = (cin - kc * m.N[0] * m.N[1]) / m.N[0];
+    const int ic = cin - kc * m.N[0] * m.N[1] - jc * m.N[0];
+    int uidLane = 0;
+    if (lane < 8) {
+      const int cx = ((lane + 1) >> 1) & 1, cy = (lane >> 1) & 1, cz = (lane >> 2) & 1;  // cell-corner order (a3)
+      uidLane = m.cornerUid[(size_t)leaf * m.nCornerLocal + cornerLocalNumber(m, ic + cx, jc + cy, kc + cz)];
+    }
+    // which species are present in the cell
+    unsigned present = 0;
+    for (int ip = begin + lane; ip < end; ip += 32) present |= 1u << (p.spec[ip] & 0x3f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) present |= __shfl_xor_sync(0xffffffffu, present, o);
+    for (int s = 0; s < nS; s++) {
+      if (!(present & (1u << s))) continue;
+      double acc[80];
+#pragma unroll
+      for (int q = 0; q < 80; q++) acc[q] = 0.0;
+      for (int ip = begin + lane; ip < end; ip += 32) {
+        if ((p.spec[ip] & 0x3f) != s) continue;
+        const double mass = sp.mass[s] * (sp.weight[s] * p.w[ip]);
+        const double v0 = p.v[0][ip] * sp.length_conv, v1 = p.v[1][ip] * sp.length_conv, v2 = p.v[2][ip] * sp.length_conv;
+        double xl[3];
+        {
+          const double xx[3] = {p.x[0][ip], p.x[1][ip], p.x[2][ip]};
+#pragma unroll
+          for (int d = 0; d < 3; d++) {  // CornerBased::InitStencil (pic_interpolation_routines.cpp:1090-1098)
+            double xs = xx[d];
+            const double xmx = lg.xmax[d], dxc = lg.dxc[d];
+            if (fabs(xs - xmx) < 1e-10 * dxc) xs = xmx - 1e-10 * dxc;
+            double r = (xs - lg.xmin[d]) / dxc;
+            r -= (int)r;
+            xl[d] = r;
+          }
+        }
+        const double X[2] = {1.0 - xl[0], xl[0]}, Y[2] = {1.0 - xl[1], xl[1]}, Z[2] = {1.0 - xl[2], xl[2]};
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const int cx = ((c + 1) >> 1) & 1, cy = (c >> 1) & 1, cz = (c >> 2) & 1;
+          const double t = mass * (X[cx] * Y[cy] * Z[cz]);
+          const double t0 = t * v0, t1 = t * v1, t2 = t * v2;
+          acc[10 * c + 0] += t;
+          acc[10 * c + 1] += t0;
+          acc[10 * c + 2] += t1;
+          acc[10 * c + 3] += t2;
+          acc[10 * c + 4] += t0 * v0;
+          acc[10 * c + 5] += t1 * v1;
+          acc[10 * c + 6] += t2 * v2;
+          acc[10 * c + 7] += t0 * v1;
+          acc[10 * c + 8] += t1 * v2;
+          acc[10 * c + 9] += t0 * v2;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 80; q++) sAcc[wib][lane][q] = acc[q];
+      __syncwarp();
+      for (int q = lane; q < 80; q += 32) {
+        double sum = 0.0;
+        for (int l = 0; l < 32; l++) sum += sAcc[wib][l][q];
+        const int c = q / 10, k = q - 10 * c;
+        const int ui = __shfl_sync(__activemask(), uidLane, c);
+        atomicAdd(spec + ((size_t)ui * nS + s) * 10 + k, sum * lg.invV);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+void launch_species_moments(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, double *spec, int nSM, cudaStream_t s) {
+  cudaMemsetAsync(spec, 0, sizeof(double) * (size_t)m.nCorners * 10 * sp.n, s);
+  species_moments_kernel<<<nSM * 8, 32 * SM_WARPS, 0, s>>>(m, sp, p, cellStart, spec);
+}
+
+// ------------------------------------------------------------------------------------------------
+// f4: ECSIM::CorrectParticleLocation  src/pic/pic_field_solver_ecsim.cpp:4440-4688
+// Species 0 is displaced along -grad(phi)/(4 pi rho_e) (phi on the cell centres, rho_e = species-0 density on the closest
+// corner, at most 0.1 cell) and re-filed; other species and cells at a block side without an (in use) neighbour keep their
+// position.  A particle still filed in a periodic ghost block is lost from every list in the reference (exchangeParticleLocal
+// :4366-4438 overwrites those lists) and is dropped here.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double cpl_interp2D(double vmm, double vpm, double vpp, double vmp, double dx, double dy) {  // :216-232
+  return vmm * (1 - dx) * (1 - dy) + vpm * dx * (1 - dy) + vpp * dx * dy + vmp * (1 - dx) * dy;
+}
+__global__ void __launch_bounds__(128) correct_particle_location_kernel(DevMesh m, DevSpecies sp, ParticleSoA p, const int *__restrict__ nSlots,
+                                                                        const double *__restrict__ phi, const double *__restrict__ spec,
+                                                                        const unsigned *__restrict__ neibMask, double qom0,
+                                                                        int *__restrict__ cellCount, unsigned long long *__restrict__ counters) {
+  const int n = *nSlots;
+  const int C = m.cellsPerBlock, nS = sp.n;
+  const double Pi = 3.14159265358979323846264338327950288419716939937510582;
+  unsigned nDisp = 0, nDel = 0, nErr = 0;
+  for (int ip = blockIdx.x * blockDim.x + threadIdx.x; ip < n; ip += gridDim.x * blockDim.x) {
+    const int key = p.key[ip];
+    if (key < 0) continue;
+    const int leaf = key / C;
+    const LeafGeo &lg = m.leaf[leaf];
+    if (m.periodic && lg.face != 0) {  // not walked, then overwritten by exchangeParticleLocal
+      p.key[ip] = -1;
+      nDel++;
+      continue;
+    }
+    if ((p.spec[ip] & 0x3f) != 0) {  // xFinal = xInit: same block, same cell
+      atomicAdd(&cellCount[key], 1);
+      continue;
+    }
+    const int cin = key - leaf * C;
+    int index[3];
+    index[2] = cin / (m.N[0] * m.N[1]);
+    index[1] = (cin - index[2] * m.N[0] * m.N[1]) / m.N[0];
+    index[0] = cin - index[2] * m.N[0] * m.N[1] - index[1] * m.N[0];
+    double dx[3], xNode[3], xCell[3];
+    for (int d = 0; d < 3; d++) {
+      dx[d] = (lg.xmax[d] - lg.xmin[d]) / m.N[d] * sp.length_conv;
+      xNode[d] = lg.xmin[d] + dx[d] * index[d];
+      xCell[d] = lg.xmin[d] + dx[d] * (index[d] + 0.5);
+    }
+    {
+      // isBoundaryCell != 0 (:6963-6999): a neighbour across the block sides this cell touches is missing or not in use
+      const unsigned mask = neibMask[leaf];
+      bool atBoundary = false;
+      if (mask) {
+        int lo[3], hi[3];
+        for (int d = 0; d < 3; d++) {
+          lo[d] = fabs(xCell[d] - 0.5 * dx[d] - lg.xmin[d]) < m.eps;
+          hi[d] = fabs(xCell[d] + 0.5 * dx[d] - lg.xmax[d]) < m.eps;
+        }
+        for (int q = 0; q < 27 && !atBoundary; q++) {
+          if (q == 13 || !(mask & (1u << q))) continue;
+          const int s[3] = {q % 3 - 1, (q / 3) % 3 - 1, q / 9 - 1};
+          bool touched = true;
+          for (int d = 0; d < 3; d++)
+            if ((s[d] < 0 && !lo[d]) || (s[d] > 0 && !hi[d])) touched = false;
+          atBoundary = touched;
+        }
+      }
+      if (atBoundary) {
+        atomicAdd(&cellCount[key], 1);
+        continue;
+      }
+    }
+    const double xInit[3] = {p.x[0][ip], p.x[1][ip], p.x[2][ip]};
+    double xRel[3];
+    int iClosestNode[3];
+    for (int d = 0; d < 3; d++) {
+      xRel[d] = (xInit[d] - xNode[d]) / dx[d];
+      iClosestNode[d] = (int)(index[d] + round(xRel[d]));
+    }
+    for (int d = 0; d < 3; d++) xRel[d] = xRel[d] >= 0.5 ? xRel[d] - 0.5 : xRel[d] + 0.5;
+    // Phi[ix-1..ix][iy-1..iy][iz-1..iz] with ix = iClosestNode+1: the centres iClosestNode-1, iClosestNode of the block
+    const int *cuid = m.centerUid + (size_t)leaf * m.nCenterLocal;
+    double P[2][2][2];
+    for (int a = 0; a < 2; a++)
+      for (int b = 0; b < 2; b++)
+        for (int c = 0; c < 2; c++) {
+          const int u = cuid[centerLocalNumber(m, iClosestNode[0] - 1 + a, iClosestNode[1] - 1 + b, iClosestNode[2] - 1 + c)];
+          P[a][b][c] = (u >= 0) ? phi[u] : 0.0;
+        }
+    double GradPhi[3];
+    GradPhi[0] = cpl_interp2D(P[1][0][0] - P[0][0][0], P[1][1][0] - P[0][1][0], P[1][1][1] - P[0][1][1], P[1][0][1] - P[0][0][1], xRel[1], xRel[2]);
+    GradPhi[1] = cpl_interp2D(P[0][1][0] - P[0][0][0], P[1][1][0] - P[1][0][0], P[1][1][1] - P[1][0][1], P[0][1][1] - P[0][0][1], xRel[0], xRel[2]);
+    GradPhi[2] = cpl_interp2D(P[0][0][1] - P[0][0][0], P[1][0][1] - P[1][0][0], P[1][1][1] - P[1][1][0], P[0][1][1] - P[0][1][0], xRel[0], xRel[1]);
+    for (int d = 0; d < 3; d++) GradPhi[d] /= dx[d];
+    const int cu = m.cornerUid[(size_t)leaf * m.nCornerLocal + cornerLocalNumber(m, iClosestNode[0], iClosestNode[1], iClosestNode[2])];
+    const double eChargeDens = spec[(size_t)cu * nS * 10] * qom0;  // SpeciesDataIndex[0] + Rho_
+    const double eps = 0.9;
+    double displacement[3], temp;
+    if (eChargeDens != 0) temp = 1. / (4. * Pi * eChargeDens);
+    else temp = 0;
+    for (int d = 0; d < 3; d++) displacement[d] = -eps * GradPhi[d] * temp;
+    const double epsLimit = 0.1;
+    if (fabs(displacement[0] / dx[0]) > epsLimit || fabs(displacement[1] / dx[1]) > epsLimit || fabs(displacement[2] / dx[2]) > epsLimit) {
+      // (pow(d,2) of the reference: d*d is the correctly rounded square)
+      const double dl = sqrt(displacement[0] * displacement[0] + displacement[1] * displacement[1] + displacement[2] * displacement[2]);
+      for (int d = 0; d < 3; d++) displacement[d] *= epsLimit * dx[0] / dl;
+    }
+    double xFinal[3];
+    for (int d = 0; d < 3; d++) xFinal[d] = xInit[d] + displacement[d];
+    nDisp++;
+    const int newNode = find_tree_node_plain(m, xFinal, lg.node);
+    int newKey = -1;
+    if (newNode < 0 || m.nodeLeaf[newNode] < 0) {
+      nDel++;  // DeleteParticle: outside the domain, or a node without a block
+    } else {
+      int ijk[3];
+      if (!find_cell_index(m, xFinal, newNode, ijk)) {
+        nErr++;  // exit("cannot find the cell") in the reference
+        p.key[ip] = -1;
+        continue;
+      }
+      newKey = m.nodeLeaf[newNode] * C + ijk[0] + m.N[0] * (ijk[1] + m.N[1] * ijk[2]);
+      p.x[0][ip] = xFinal[0], p.x[1][ip] = xFinal[1], p.x[2][ip] = xFinal[2];
+      atomicAdd(&cellCount[newKey], 1);
+    }
+    if (newKey != key) p.key[ip] = newKey;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nDisp += __shfl_xor_sync(0xffffffffu, nDisp, o);
+    nDel += __shfl_xor_sync(0xffffffffu, nDel, o);
+    nErr += __shfl_xor_sync(0xffffffffu, nErr, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (nDisp) atomicAdd(&counters[0], (unsigned long long)nDisp);
+    if (nDel) atomicAdd(&counters[1], (unsigned long long)nDel);
+    if (nErr) atomicAdd(&counters[2], (unsigned long long)nErr);
+  }
+}
+
+void launch_correct_particle_location(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *nSlots, long long nUpper, const double *phi,
+                                      const double *spec, const unsigned *neibMask, double qom0, int *cellCount, unsigned long long *counters,
+                                      cudaStream_t s) {
+  cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned long long), s);
+  cudaMemsetAsync(cellCount, 0, sizeof(int) * (size_t)m.nLeaves * m.cellsPerBlock, s);  // the histogram the sort / migration use
+  long long g = (nUpper + 127) / 128;
+  if (g < 1) g = 1;
+  if (g > 148 * 32) g = 148 * 32;
+  correct_particle_location_kernel<<<(int)g, 128, 0, s>>>(m, sp, p, nSlots, phi, spec, neibMask, qom0, cellCount, counters);
+}
+
 }  // namespace amps

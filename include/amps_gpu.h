@@ -302,6 +302,23 @@ int amps_gpu_step_JM(amps_gpu_ctx *ctx, int mover_id, double *J_host, double *M_
  * centre nodes, [n_centers]; charge_conv multiplies cfg.charge[] (ECSIM::charge_conv).  rho_center may be NULL (result stays
  * on the device).  Single-rank: the sum over ranks of shared centres is the caller's (ProcessNetCharge).            */
 int amps_gpu_net_charge(amps_gpu_ctx *ctx, double charge_conv, double *rho_center);
+
+/* The per-species corner moments UpdateJMassMatrix samples when _PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_ is on
+ * (pic_field_solver_ecsim.cpp:2270-2300 per particle, :2384-2392 per cell, :3874-3879 flush; corner buffer from
+ * SpeciesDataIndex[0] = 9+243 on, :527-531): spec_corner[n_corners][n_species][10] =
+ * {Rho, RhoUx, RhoUy, RhoUz, RhoUxUx, RhoUyUy, RhoUzUz, RhoUxUy, RhoUyUz, RhoUxUz} (mass density moments / cell volume).
+ * Needs the sorted layout.  The result stays on the device for amps_gpu_correct_particle_location; spec_corner may be NULL. */
+int amps_gpu_species_moments(amps_gpu_ctx *ctx, double *spec_corner);
+
+/* phi of the div-E correction on the unique centre nodes (centre buffer, phiIndex; written by the reference's Poisson solve,
+ * divECorrection :4341-4352): phi_center[n_centers].                                                                   */
+int amps_gpu_phi_upload(amps_gpu_ctx *ctx, const double *phi_center);
+
+/* ECSIM::CorrectParticleLocation() (pic_field_solver_ecsim.cpp:4440-4688), the particle shift of divECorrection: species 0 moves
+ * by -0.9 grad(phi) / (4 pi rho_e), at most 0.1 cell, rho_e = species-0 density on the closest corner times q/m (charge_conv,
+ * mass_conv as in :4449-4452); every particle is re-filed (call amps_gpu_sort afterwards).  Particles that leave the domain are
+ * deleted (n_deleted).  Single-level meshes; the reference runs it with periodic boundaries only (:4361-4363).             */
+int amps_gpu_correct_particle_location(amps_gpu_ctx *ctx, double charge_conv, double mass_conv, int64_t *n_displaced, int64_t *n_deleted);
 /* particle energy and per-species cfl of the last deposit (amps_gpu_deposit_JM or amps_gpu_step; after
  * amps_gpu_exchange_JM they are the all-reduced values)                                            */
 int amps_gpu_diagnostics(amps_gpu_ctx *ctx, double *particle_energy, double *cfl);

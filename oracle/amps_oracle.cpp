@@ -159,6 +159,8 @@ struct oracle_ctx {
   std::vector<cCornerNode> cornerPool;
   std::vector<cCenterNode> centerPool;
   std::vector<double> cornerData, centerData;
+  std::vector<double> cornerSpec;  // [n_corners][10*n_species]: corner buffer from SpeciesDataIndex[0] on (:527-531)
+  std::vector<double> phiCenter;   // [n_centers]: centre buffer, phiIndex (div-E correction potential)
   std::vector<long int> listStorage;
   std::vector<cTempList> threadListStorage;
   int nThreadListTables;
@@ -1943,6 +1945,235 @@ struct oracle_ctx {
     return _PARTICLE_MOTION_FINISHED_;
   }
 
+  // The _PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_ part of UpdateJMassMatrix / ProcessCell, src/pic/pic_field_solver_ecsim.cpp:
+  // zero :3269-3271, per particle :2270-2300, per cell :2384-2392, flush :3874-3879.  Restated as its own pass over the same
+  // cells in the same order (the sums per corner see the same terms in the same order as inside ProcessCell).
+  // Rho_=0 RhoUx_..RhoUz_=1..3 RhoUxUx_ RhoUyUy_ RhoUzUz_ = 4..6 RhoUxUy_ RhoUyUz_ RhoUxUz_ = 7..9 (:138-147)
+  int ComputeSpeciesMoments() {
+    const int nS = cfg.n_species;
+    cornerSpec.assign((size_t)n_corners * 10 * nS, 0.0);
+    const double length_conv = cfg.ecsim_length_conv;
+    static const int cornerOff[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+    std::vector<double> SpeciesData_GI((size_t)8 * 10 * nS), SpecData((size_t)8 * 10 * nS);
+    for (size_t nLocalNode = 0; nLocalNode < blocks.size(); nLocalNode++) {
+      cTreeNode *node = BlockTable[nLocalNode];
+      if (node->block == NULL) continue;
+      if (cfg.periodic && node->faceBoundary != 0) continue;  // boundary "ghost" block, :3815-3825
+      cBlock *block = node->block;
+      int nCell[3] = {_BLOCK_CELLS_X_, _BLOCK_CELLS_Y_, _BLOCK_CELLS_Z_};
+      double CellVolume = 1, dx[3];
+      for (int iDim = 0; iDim < 3; iDim++) dx[iDim] = (node->xmax[iDim] - node->xmin[iDim]) / nCell[iDim] * length_conv;
+      for (int iDim = 0; iDim < 3; iDim++) CellVolume *= dx[iDim];
+      for (int k = 0; k < _BLOCK_CELLS_Z_; k++)
+        for (int j = 0; j < _BLOCK_CELLS_Y_; j++)
+          for (int i = 0; i < _BLOCK_CELLS_X_; i++) {
+            long int ptr = block->FirstCellParticleTable[i + _BLOCK_CELLS_X_ * (j + _BLOCK_CELLS_Y_ * k)];
+            if (ptr == -1) continue;
+            for (size_t q = 0; q < SpeciesData_GI.size(); q++) SpeciesData_GI[q] = 0.0, SpecData[q] = 0.0;
+            cStencil CornerBasedStencil;
+            while (ptr != -1) {
+              byte *ParticleData = GetParticleDataPointer(ptr);
+              double vInit[3], xInit[3], WeightPG[8];
+              int spec = GetI(ParticleData);
+              GetV(vInit, ParticleData);
+              GetX(xInit, ParticleData);
+              double LocalParticleWeight = cfg.species_weight[spec];
+              LocalParticleWeight *= GetIndividualStatWeightCorrection(ParticleData);
+              for (int idim = 0; idim < 3; idim++) vInit[idim] *= length_conv;
+              double mass = cfg.mass[spec] * LocalParticleWeight;
+              CornerBased_InitStencil(xInit, node, CornerBasedStencil, WeightPG);
+              for (int ii = 0; ii < 8; ii++) {
+                double *G = SpeciesData_GI.data() + (size_t)ii * 10 * nS + 10 * spec;
+                double t = mass * WeightPG[ii];
+                double t0 = t * vInit[0];
+                double t1 = t * vInit[1];
+                double t2 = t * vInit[2];
+                G[0] += t;
+                G[1] += t0;
+                G[2] += t1;
+                G[3] += t2;
+                G[4] += t0 * vInit[0];
+                G[5] += t1 * vInit[1];
+                G[6] += t2 * vInit[2];
+                G[7] += t0 * vInit[1];
+                G[8] += t1 * vInit[2];
+                G[9] += t0 * vInit[2];
+              }
+              ptr = GetNext(ParticleData);
+            }
+            for (int iCorner = 0; iCorner < 8; iCorner++)
+              for (int ii = 0; ii < 10 * nS; ii++) SpecData[(size_t)iCorner * 10 * nS + ii] += SpeciesData_GI[(size_t)iCorner * 10 * nS + ii] / CellVolume;
+            for (int icor = 0; icor < 8; icor++) {
+              cCornerNode *cn = block->cornerNodes[_getCornerNodeLocalNumber(i + cornerOff[icor][0], j + cornerOff[icor][1], k + cornerOff[icor][2])];
+              double *target = cornerSpec.data() + (size_t)(cn - cornerPool.data()) * 10 * nS;
+              for (int ii = 0; ii < 10 * nS; ii++) target[ii] += SpecData[(size_t)icor * 10 * nS + ii];
+            }
+          }
+    }
+    return AMPS_GPU_OK;
+  }
+
+  // ECSIM::isBoundaryCell != 0, src/pic/pic_field_solver_ecsim.cpp:6963-6999 with isFaceBoundary / isEdgeBoundary / isCornerBoundary
+  // (:6487-6961), for a cell centre x inside `node`: the case tables reduce to "one of the face, edge or corner neighbours across
+  // the block sides this cell touches is missing or not used in the calculation" (edge ids :6550-6790, corner id = ix+2iy+4iz).
+  bool isBoundaryCellNonZero(const double *x, const double *dx, cTreeNode *node) const {
+    int lo[3], hi[3];
+    for (int idim = 0; idim < 3; idim++) {
+      lo[idim] = fabs(x[idim] - 0.5 * dx[idim] - node->xmin[idim]) < EPS;
+      hi[idim] = fabs(x[idim] + 0.5 * dx[idim] - node->xmax[idim]) < EPS;
+    }
+    static const int edgeId[3][2][2] = {
+        // edges along x: (y side, z side) -> 0:(ymin,zmin) 1:(ymax,zmin) 2:(ymax,zmax) 3:(ymin,zmax)
+        {{0, 3}, {1, 2}},
+        // edges along y: (x side, z side) -> 4:(xmin,zmin) 5:(xmax,zmin) 6:(xmax,zmax) 7:(xmin,zmax)
+        {{4, 7}, {5, 6}},
+        // edges along z: (x side, y side) -> 8:(xmin,ymin) 9:(xmax,ymin) 10:(xmax,ymax) 11:(xmin,ymax)
+        {{8, 11}, {9, 10}}};
+    auto bad = [](cTreeNode *nb) { return nb == NULL || nb->IsUsedInCalculationFlag == false; };
+    // side[d]: -1 none, 0 min, 1 max (a one-cell-wide block would touch both; the reference's switch matches neither pattern then)
+    for (int sx = -1; sx <= 1; sx++)
+      for (int sy = -1; sy <= 1; sy++)
+        for (int sz = -1; sz <= 1; sz++) {
+          const int s[3] = {sx, sy, sz};
+          int n = 0;
+          bool touched = true;
+          for (int d = 0; d < 3; d++)
+            if (s[d] >= 0) {
+              n++;
+              if (!(s[d] == 0 ? lo[d] : hi[d])) touched = false;
+            }
+          if (n == 0 || !touched) continue;
+          cTreeNode *nb;
+          if (n == 1) {
+            int d = (sx >= 0) ? 0 : (sy >= 0) ? 1 : 2;
+            nb = GetNeibFace(node, 2 * d + s[d], 0, 0);
+          } else if (n == 2) {
+            if (sx < 0) nb = GetNeibEdge(node, edgeId[0][sy][sz], 0);
+            else if (sy < 0) nb = GetNeibEdge(node, edgeId[1][sx][sz], 0);
+            else nb = GetNeibEdge(node, edgeId[2][sx][sy], 0);
+          } else {
+            nb = GetNeibCorner(node, sx + 2 * sy + 4 * sz);
+          }
+          if (bad(nb)) return true;
+        }
+    return false;
+  }
+
+  // ECSIM::CorrectParticleLocation, src/pic/pic_field_solver_ecsim.cpp:4440-4688 (+ exchangeParticleLocal :4366-4438, MPI mode):
+  // species 0 is displaced along -grad(phi) / (4 pi rho_e) (limited to 0.1 dx), every particle is re-filed under its cell.
+  static double interp2D(double vmm, double vpm, double vpp, double vmp, double dx, double dy) {  // :216-232
+    return vmm * (1 - dx) * (1 - dy) + vpm * dx * (1 - dy) + vpp * dx * dy + vmp * (1 - dx) * dy;
+  }
+  int CorrectParticleLocation(double charge_conv, double mass_conv, long long *nDisplaced, long long *nDeleted) {
+    const double Pi = 3.14159265358979323846264338327950288419716939937510582;  // src/general/constants.h
+    const double length_conv = cfg.ecsim_length_conv;
+    const int nS = cfg.n_species;
+    double qom[AMPS_GPU_MAX_SPECIES];
+    for (int iSp = 0; iSp < nS; iSp++) qom[iSp] = (cfg.charge[iSp] * charge_conv) / (cfg.mass[iSp] * mass_conv);
+    if (cornerSpec.size() != (size_t)n_corners * 10 * nS || phiCenter.size() != (size_t)n_centers) return AMPS_GPU_ERR_STATE;
+    *nDisplaced = 0, *nDeleted = 0;
+    const int NX = _BLOCK_CELLS_X_, NY = _BLOCK_CELLS_Y_, NZ = _BLOCK_CELLS_Z_;
+    std::vector<double> Phi((size_t)(NX + 2) * (NY + 2) * (NZ + 2));
+    auto PHI = [&](int a, int b, int c) -> double & { return Phi[((size_t)a * (NY + 2) + b) * (NZ + 2) + c]; };
+    for (size_t nLocalNode = 0; nLocalNode < blocks.size(); nLocalNode++) {
+      cTreeNode *node = BlockTable[nLocalNode];
+      if (node->block == NULL) continue;
+      if (cfg.periodic && node->faceBoundary != 0) continue;  // 'ghost' block of the periodic boundary, :4459-4470
+      int nCell[3] = {NX, NY, NZ};
+      cBlock *block = node->block;
+      long int *FirstCellParticleTable = block->FirstCellParticleTable;
+      double dx[3];
+      for (int iDim = 0; iDim < 3; iDim++) dx[iDim] = (node->xmax[iDim] - node->xmin[iDim]) / nCell[iDim] * length_conv;
+      for (int k = -1; k < NZ + 1; k++)
+        for (int j = -1; j < NY + 1; j++)
+          for (int i = -1; i < NX + 1; i++) {
+            int LocalCenterId = _getCenterNodeLocalNumber(i, j, k);
+            PHI(i + 1, j + 1, k + 1) = 0.0;  // (left uninitialised by the reference when the node does not exist)
+            if (!block->centerNodes[LocalCenterId]) continue;
+            PHI(i + 1, j + 1, k + 1) = phiCenter[block->centerNodes[LocalCenterId] - centerPool.data()];
+          }
+      for (int k = 0; k < NZ; k++)
+        for (int j = 0; j < NY; j++)
+          for (int i = 0; i < NX; i++) {
+            long int ptr = FirstCellParticleTable[i + NX * (j + NY * k)];
+            if (ptr == -1) continue;
+            double xInit[3] = {0.0, 0.0, 0.0};
+            int spec;
+            double xNode[3], xCell[3];
+            int index[3] = {i, j, k};
+            for (int iDim = 0; iDim < 3; iDim++) {
+              xNode[iDim] = node->xmin[iDim] + dx[iDim] * index[iDim];
+              xCell[iDim] = node->xmin[iDim] + dx[iDim] * (index[iDim] + 0.5);
+            }
+            bool atBoundary = isBoundaryCellNonZero(xCell, dx, node);
+            long int ptrNext = ptr;
+            while (ptrNext != -1) {
+              ptr = ptrNext;
+              byte *ParticleData = GetParticleDataPointer(ptr);
+              spec = GetI(ParticleData);
+              GetX(xInit, ParticleData);
+              ptrNext = GetNext(ParticleData);
+              double xFinal[3];
+              if (spec != 0 || atBoundary) {
+                for (int idim = 0; idim < 3; idim++) xFinal[idim] = xInit[idim];
+              } else {
+                double xRel[3];
+                for (int iDim = 0; iDim < 3; iDim++) xRel[iDim] = (xInit[iDim] - xNode[iDim]) / dx[iDim];
+                int iClosestNode[3];
+                for (int iDim = 0; iDim < 3; iDim++) iClosestNode[iDim] = int(index[iDim] + round(xRel[iDim]));
+                int ix = iClosestNode[0] + 1, iy = iClosestNode[1] + 1, iz = iClosestNode[2] + 1;
+                for (int iDim = 0; iDim < 3; iDim++) xRel[iDim] = xRel[iDim] >= 0.5 ? xRel[iDim] - 0.5 : xRel[iDim] + 0.5;
+                double GradPhi[3];
+                GradPhi[0] = interp2D(PHI(ix, iy - 1, iz - 1) - PHI(ix - 1, iy - 1, iz - 1), PHI(ix, iy, iz - 1) - PHI(ix - 1, iy, iz - 1),
+                                      PHI(ix, iy, iz) - PHI(ix - 1, iy, iz), PHI(ix, iy - 1, iz) - PHI(ix - 1, iy - 1, iz), xRel[1], xRel[2]);
+                GradPhi[1] = interp2D(PHI(ix - 1, iy, iz - 1) - PHI(ix - 1, iy - 1, iz - 1), PHI(ix, iy, iz - 1) - PHI(ix, iy - 1, iz - 1),
+                                      PHI(ix, iy, iz) - PHI(ix, iy - 1, iz), PHI(ix - 1, iy, iz) - PHI(ix - 1, iy - 1, iz), xRel[0], xRel[2]);
+                GradPhi[2] = interp2D(PHI(ix - 1, iy - 1, iz) - PHI(ix - 1, iy - 1, iz - 1), PHI(ix, iy - 1, iz) - PHI(ix, iy - 1, iz - 1),
+                                      PHI(ix, iy, iz) - PHI(ix, iy, iz - 1), PHI(ix - 1, iy, iz) - PHI(ix - 1, iy, iz - 1), xRel[0], xRel[1]);
+                for (int iDim = 0; iDim < 3; iDim++) GradPhi[iDim] /= dx[iDim];
+                double eChargeDens, eps = 0.9;
+                int localCornerId = _getCornerNodeLocalNumber(iClosestNode[0], iClosestNode[1], iClosestNode[2]);
+                eChargeDens = cornerSpec[(size_t)(block->cornerNodes[localCornerId] - cornerPool.data()) * 10 * nS + 0] * qom[0];
+                double displacement[3], temp;
+                if (eChargeDens != 0) temp = 1. / (4. * Pi * eChargeDens);
+                else temp = 0;
+                for (int iDim = 0; iDim < 3; iDim++) displacement[iDim] = -eps * GradPhi[iDim] * temp;
+                double epsLimit = 0.1;
+                if (fabs(displacement[0] / dx[0]) > epsLimit || fabs(displacement[1] / dx[1]) > epsLimit || fabs(displacement[2] / dx[2]) > epsLimit) {
+                  double dl = sqrt(pow(displacement[0], 2) + pow(displacement[1], 2) + pow(displacement[2], 2));
+                  for (int iDim = 0; iDim < 3; iDim++) displacement[iDim] *= epsLimit * dx[0] / dl;
+                }
+                for (int iDim = 0; iDim < 3; iDim++) xFinal[iDim] = xInit[iDim] + displacement[iDim];
+                (*nDisplaced)++;
+              }
+              int ip, jp, kp;
+              cTreeNode *newNode = findTreeNode(xFinal, node);
+              if (newNode == NULL) {
+                DeleteParticle(ptr);
+                (*nDeleted)++;
+              } else if (newNode->block == NULL) {
+                DeleteParticle(ptr);
+                (*nDeleted)++;
+              } else {
+                if (FindCellIndex(xFinal, ip, jp, kp, newNode) == -1) return AMPS_GPU_ERR_PARTICLE;
+                AttachToTempList(ptr, ParticleData, newNode->block, ip, jp, kp, 1, 0);
+                SetX(xFinal, ParticleData);
+              }
+            }
+          }
+    }
+    // exchangeParticleLocal (:4366-4438, _COMPILATION_MODE__MPI_): temp lists become the cell lists of EVERY block
+    const int nC = nCellsBlock();
+    for (size_t l = 0; l < blocks.size(); l++) {
+      cBlock *block = &blocks[l];
+      // (a periodic ghost block's own list was not walked above; the reference overwrites it with the temp list all the same, so
+      //  a particle still filed there - none after a MoveParticles - is no longer on any list)
+      memcpy(block->FirstCellParticleTable, block->tempParticleMovingListTable, nC * sizeof(long int));
+      for (int c = 0; c < nC; c++) block->tempParticleMovingListTable[c] = -1;
+    }
+    return AMPS_GPU_OK;
+  }
+
   // ECSIM::ComputeNetCharge, src/pic/pic_field_solver_ecsim.cpp:4690-4828 (without UpdateOldNetCharge): the charge of every particle
   // goes to the 8 cell centres of its trilinear stencil, block by block through a local q_Center array; the sum of the ghost
   // copies into the real nodes (ProcessBlockBoundaryNodes / ProcessNetCharge :1417-1425) is implicit in the unique centre nodes.
@@ -2426,6 +2657,27 @@ void oracle_set_background(oracle_ctx *o, const double *E_center, const double *
     for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + BackgroundE_d, E_center + 3 * (size_t)i, 24);
   if (B_center)
     for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + BackgroundB_d, B_center + 3 * (size_t)i, 24);
+}
+int oracle_species_moments(oracle_ctx *o, double *spec) {
+  int rc = o->ComputeSpeciesMoments();
+  if (spec) memcpy(spec, o->cornerSpec.data(), sizeof(double) * o->cornerSpec.size());
+  return rc;
+}
+void oracle_set_phi(oracle_ctx *o, const double *phi_center) { o->phiCenter.assign(phi_center, phi_center + o->n_centers); }
+int oracle_correct_particle_location(oracle_ctx *o, double charge_conv, double mass_conv, int32_t *final_cell, int64_t *n_displaced,
+                                     int64_t *n_deleted) {
+  long long nd = 0, nx = 0;
+  int rc = o->CorrectParticleLocation(charge_conv, mass_conv, &nd, &nx);
+  if (n_displaced) *n_displaced = nd;
+  if (n_deleted) *n_deleted = nx;
+  if (final_cell) {
+    const int nC = o->nCellsBlock();
+    for (long int p = 0; p < o->MaxNPart; p++) final_cell[p] = -1;
+    for (size_t l = 0; l < o->blocks.size(); l++)
+      for (int c = 0; c < nC; c++)
+        for (long int ptr = o->blocks[l].FirstCellParticleTable[c]; ptr != -1; ptr = o->GetNext(ptr)) final_cell[ptr] = (int32_t)(l * nC + c);
+  }
+  return rc;
 }
 int oracle_net_charge(oracle_ctx *o, double charge_conv, double *rho) {
   int rc = o->ComputeNetCharge(charge_conv);

@@ -81,6 +81,13 @@ int oracle_deposit_JM(oracle_ctx *, int n_threads, double *J, double *M, double 
 
 /* ECSIM::ComputeNetCharge(): rho_new on the unique centre nodes [n_centers] */
 int oracle_net_charge(oracle_ctx *, double charge_conv, double *rho);
+/* the _PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_ part of UpdateJMassMatrix: [n_corners][10*n_species] (spec may be NULL) */
+int oracle_species_moments(oracle_ctx *, double *spec);
+/* phi of the div-E correction on the unique centre nodes [n_centers] */
+void oracle_set_phi(oracle_ctx *, const double *phi_center);
+/* ECSIM::CorrectParticleLocation(): needs oracle_species_moments + oracle_set_phi; final_cell[MaxNPart] = block*cells+cell or -1 */
+int oracle_correct_particle_location(oracle_ctx *, double charge_conv, double mass_conv, int32_t *final_cell, int64_t *n_displaced,
+                                     int64_t *n_deleted);
 
 /* stand-alone pieces for unit parity tests */
 int oracle_find_tree_node(const oracle_ctx *, const double *x, int start_leaf); /* leaf id or -1 */

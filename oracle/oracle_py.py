@@ -48,6 +48,9 @@ def load(kind="parity"):
     lib.oracle_center_stencil.argtypes = [vp, vp, C.c_int, vp, vp]
     lib.oracle_check_particle_lists.argtypes = [vp]
     lib.oracle_net_charge.argtypes = [vp, C.c_double, vp]
+    lib.oracle_species_moments.argtypes = [vp, vp]
+    lib.oracle_set_phi.argtypes = [vp, vp]
+    lib.oracle_correct_particle_location.argtypes = [vp, C.c_double, C.c_double, vp, vp, vp]
     lib.oracle_coupler_stencil.argtypes = [vp, vp, C.c_int, vp, vp]
     lib.oracle_neib_levels.argtypes = [vp, C.c_int, vp]
     lib.oracle_neib.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
@@ -199,6 +202,25 @@ class Oracle:
         rho = np.zeros(self.mesh.n_centers)
         assert self.lib.oracle_net_charge(self.h, charge_conv, _p(rho)) == 0
         return rho
+
+    def species_moments(self):
+        """corner species moments of UpdateJMassMatrix (_PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_): [n_corners, n_species, 10]"""
+        out = np.zeros((self.mesh.n_corners, self.cfg.n_species, 10))
+        assert self.lib.oracle_species_moments(self.h, _p(out)) == 0
+        return out
+
+    def set_phi(self, phi_center):
+        phi = np.ascontiguousarray(phi_center, dtype=np.float64)
+        assert phi.shape == (self.mesh.n_centers,)
+        self.lib.oracle_set_phi(self.h, _p(phi))
+
+    def correct_particle_location(self, charge_conv=1.0, mass_conv=1.0):
+        """ECSIM::CorrectParticleLocation -> (rc, n_displaced, n_deleted, final_cell[n_added])"""
+        fc = np.zeros(self.capacity, dtype=np.int32)
+        nd, nx = C.c_int64(), C.c_int64()
+        rc = self.lib.oracle_correct_particle_location(self.h, charge_conv, mass_conv, _p(fc), C.cast(C.byref(nd), C.c_void_p),
+                                                       C.cast(C.byref(nx), C.c_void_p))
+        return rc, int(nd.value), int(nx.value), fc[: self.n_added]
 
     def check_lists(self):
         return self.lib.oracle_check_particle_lists(self.h)
