@@ -74,6 +74,12 @@ class Context:
             raise AmpsGpuError(f"amps_gpu_init failed rc={rc} {msg} (no CPU fallback)")
         self._ck(self.lib.amps_gpu_mesh_upload(self._h, C.byref(mesh.c)))
 
+    def mesh_upload(self, mesh):
+        """a new mesh epoch (UpdateBlockTable after nMeshModificationCounter changed): the resident particles and fields are dropped
+        with the old mesh and must be uploaded again"""
+        self._ck(self.lib.amps_gpu_mesh_upload(self._h, C.byref(mesh.c)))
+        self.mesh = mesh
+
     def _ck(self, rc):
         if rc != _capi.OK:
             raise AmpsGpuError(f"rc={rc}: {self.lib.amps_gpu_last_error(self._h).decode()}")

@@ -353,10 +353,50 @@ int amps_gpu_synchronize(amps_gpu_ctx *ctx) {
   return AMPS_GPU_OK;
 }
 
+// frees what amps_gpu_mesh_upload and the per-mesh uploads allocated (see there)
+static int release_mesh(amps_gpu_ctx *ctx) {
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->copyStream) CK(cudaStreamSynchronize(ctx->copyStream));
+  if (ctx->commStream) CK(cudaStreamSynchronize(ctx->commStream));
+  for (void *p : ctx->meshAllocs) cudaFree(p);
+  ctx->meshAllocs.clear();
+  auto drop = [](auto *&p) {
+    cudaFree(p);
+    p = nullptr;
+  };
+  drop(ctx->d_gcaVar), drop(ctx->d_gcaTile), drop(ctx->d_gradBVar), drop(ctx->d_gradBTile);
+  drop(ctx->d_leafRedo), drop(ctx->d_rho), drop(ctx->d_spec), drop(ctx->d_phi);
+  drop(ctx->d_bgE), drop(ctx->d_bgB), drop(ctx->d_bgTile);
+  drop(ctx->d_sendBuf), drop(ctx->d_recvBuf), drop(ctx->d_sendCount), drop(ctx->d_allCounts), drop(ctx->d_errFlag);
+  for (int *&p : ctx->d_sharedUid) drop(p);
+  ctx->d_sharedUid.clear(), ctx->nShared.clear(), ctx->h_sharedUid.clear();
+  drop(ctx->d_cornerSend), drop(ctx->d_cornerRecv);
+  ctx->cornerBufDoubles = 0;
+  drop(ctx->d_Ehalf), drop(ctx->d_Bprev), drop(ctx->d_Bcur), drop(ctx->d_eTile), drop(ctx->d_bPrevTile), drop(ctx->d_bCurTile);
+  drop(ctx->d_cellCount), drop(ctx->d_cellStart), drop(ctx->d_cellFill), drop(ctx->d_scanTmp), drop(ctx->d_J), drop(ctx->d_M);
+  ctx->d_leafOwner = ctx->d_leafGlobal = ctx->d_g2l = nullptr;  // (were in meshAllocs)
+  ctx->d_depLeaf = nullptr, ctx->d_neibMask = nullptr;
+  ctx->h_leafCornerUid.clear(), ctx->h_leafGhost.clear(), ctx->h_realBefore.clear();
+  ctx->dlCellEnd.clear(), ctx->dlRunStart.clear(), ctx->dlRuns.clear();
+  ctx->meshReady = ctx->fieldsReady = ctx->gcaReady = ctx->gradBReady = ctx->backgroundReady = ctx->specReady = ctx->phiReady = false;
+  ctx->meshRefined = false;
+  ctx->nDepBoundary = 0, ctx->depDirty = false, ctx->overlapJM = false, ctx->jmZeroed = false;
+  CK(cudaMemsetAsync(ctx->d_n, 0, 2 * sizeof(int), ctx->stream));
+  ctx->cur = 0, ctx->nUpper = 0, ctx->sorted = false, ctx->countValid = false;
+  memset(&ctx->dm, 0, sizeof(ctx->dm));
+  return AMPS_GPU_OK;
+}
+
 int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
   if (!ctx || !mesh) return AMPS_GPU_ERR_ARG;
   CK(cudaSetDevice(ctx->cfg.device));
-  if (ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "mesh re-upload: finalize and re-create the context (mesh epochs are a round-2 item)");
+  if (ctx->meshReady) {
+    // a new mesh epoch (the reference rebuilds BlockTable when nMeshModificationCounter changes, pic_mesh.cpp:1658): everything
+    // sized by the old mesh goes, and so do the resident particles and fields - their (block,cell) keys and node ids named the
+    // old blocks; the host uploads them again.  Communicator, capacity and species tables stay.
+    int rcRelease;
+    if ((rcRelease = release_mesh(ctx))) return rcRelease;
+  }
   if (mesh->n_nodes < 1 || mesh->n_leaves < 1 || mesh->n_corners < 1 || mesh->n_centers < 1) FAIL(AMPS_GPU_ERR_ARG, "empty mesh");
   DevMesh &m = ctx->dm;
   for (int d = 0; d < 3; d++) {
@@ -1102,10 +1142,8 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   } else {
     // fast pass (FMA, reciprocals) for every particle that stays clear of cell faces; the exact kernel finishes the flagged rest
     int rc;
-    if (!ctx->d_redoMask) {
-      if ((rc = dev_alloc(ctx, &ctx->d_redoMask, (size_t)ctx->cfg.capacity))) return rc;
-      if ((rc = dev_alloc(ctx, &ctx->d_leafRedo, (size_t)2 * m.nLeaves + 1))) return rc;
-    }
+    if (!ctx->d_redoMask && (rc = dev_alloc(ctx, &ctx->d_redoMask, (size_t)ctx->cfg.capacity))) return rc;
+    if (!ctx->d_leafRedo && (rc = dev_alloc(ctx, &ctx->d_leafRedo, (size_t)2 * m.nLeaves + 1))) return rc;  // (per mesh epoch)
     CK(cudaMemsetAsync(ctx->d_redoMask, 0, (size_t)ctx->nUpper, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_leafRedo, 0, sizeof(int) * ((size_t)2 * m.nLeaves + 1), ctx->stream));
     int *redoList = ctx->d_leafRedo + m.nLeaves, *nRedoLeaves = ctx->d_leafRedo + 2 * (size_t)m.nLeaves;

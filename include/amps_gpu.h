@@ -218,7 +218,11 @@ int amps_gpu_last_move_redo(amps_gpu_ctx *ctx, int64_t *n);
 void *amps_gpu_stream(amps_gpu_ctx *ctx);
 
 /* ---- mesh: <- DomainBlockDecomposition::UpdateBlockTable (pic_mesh.cpp:1644),
- *      PIC::Mesh::GPU::CopyMeshHost2Device (pic.h:4794-4860)                  ---- */
+ *      PIC::Mesh::GPU::CopyMeshHost2Device (pic.h:4794-4860)                  ----
+ * Calling it again on a live context starts a new mesh epoch (the reference rebuilds BlockTable whenever
+ * nMeshModificationCounter changed): everything sized by the old mesh is released, and the resident particles, fields,
+ * background tables and shared-corner lists are dropped with it (their keys and node ids named the old blocks) - the host
+ * uploads them again.  The communicator, the capacity and the species tables of amps_gpu_init stay.                       */
 int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh);
 
 /* ---- fields: replaces the per-thread SetBlock_E / SetBlock_B gathers

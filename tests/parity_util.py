@@ -79,10 +79,15 @@ def run_oracle(m, cfg, parts, fields, n_threads=1, kind="parity"):
             "records": sorted(recs), "n_records": nrec}
 
 
-def run_gpu(m, cfg, parts, fields):
+def run_gpu(m, cfg, parts, fields, ctx=None):
+    """ctx: an existing context (of another mesh epoch) to re-use: the mesh is uploaded again and the context stays open"""
     x, v, w, sp, cells = parts
     E, B, Bcur = fields
-    g = api.Context(cfg, m)
+    if ctx is None:
+        g = api.Context(cfg, m)
+    else:
+        g = ctx
+        g.mesh_upload(m)
     g.fields_upload(E, B, Bcur)
     g.particles_upload(x, v, w, sp, cells)
     n0 = g.particle_count()
@@ -96,7 +101,8 @@ def run_gpu(m, cfg, parts, fields):
     J, M = g.JM_download()
     launches = g.launch_count()
     n_redo = g.last_move_redo()
-    g.close()
+    if ctx is None:
+        g.close()
     return {"n_redo": n_redo, "n0": n0, "stats": st, "moved": moved, "sorted": srt, "table": table, "J": J, "M": M, "energy": en, "cfl": cfl, "launches": launches,
             "records": sorted(recs), "n_records": nrec}
 

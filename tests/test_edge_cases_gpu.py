@@ -113,3 +113,25 @@ def test_wrong_cell_on_upload_is_an_error_like_the_reference_exit():
     with pytest.raises(api.AmpsGpuError):
         g.MoveParticles()
     g.close()
+
+
+@pytest.mark.gpu
+def test_mesh_reupload_starts_a_new_epoch():
+    """amps_gpu_mesh_upload on a live context (UpdateBlockTable after a mesh modification): the step on the new mesh matches the
+    oracle of the new mesh; one context goes through three meshes (block size, ghost layers and boundary mode are properties of
+    the context, like the reference's compile-time switches)"""
+    # (same ppc: the species weights are part of the context's configuration)
+    kws = [dict(n_cells=(16, 16, 16), ppc=5, seed=71), dict(n_cells=(32, 16, 24), ppc=5, seed=73), dict(n_cells=(16, 8, 8), ppc=5, seed=75)]
+    cases = [pu.make_case(**kw) for kw in kws]
+    cap = max(c[1].capacity for c in cases)
+    g = None
+    for m, cfg, parts, fields in cases:
+        cfg.capacity = cap
+        cfg.exit_record_capacity = cap
+        if g is None:
+            g = api.Context(cfg, m)
+        ora = pu.run_oracle(m, cfg, parts, fields)
+        gpu = pu.run_gpu(m, cfg, parts, fields, ctx=g)
+        res = pu.compare(m, parts, ora, gpu)
+        assert res["cell_mismatch"] == 0 and res["max_rel_x"] <= pu.REL_TOL and res["max_rel_J"] <= pu.REL_TOL and res["max_rel_M"] <= pu.REL_TOL, res
+    g.close()
