@@ -1,0 +1,117 @@
+"""Known-answer test of the reference for the test-particle path: the vertical Størmer cutoff of a centred dipole,
+Rc = R0 cos^4(lambda) / r^2, srcEarth/test/C1 (tests/golden/reference_C1_stormer.csv is that test's table, unchanged).
+Protons are traced backward in time with PIC::Mover::Relativistic::Boris (a7) through the dipole tabulated on an AMR mesh, like
+the reference's Mode3D MESH variant: a vertical arrival 1.6 x above the cutoff connects to the outer boundary, one 0.6 x below
+does not (the reference accepts 5-35 % around Rc, run_C1.py:322-337)."""
+import csv
+import math
+import os
+
+import numpy as np
+import pytest
+
+from amps_b200 import _capi, api, mesh as meshmod, workload
+from amps_b200.workload import B0, CLIGHT, MP, QP, RE
+from oracle.oracle_py import Oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _table():
+    with open(os.path.join(HERE, "golden", "reference_C1_stormer.csv")) as f:
+        return [(float(r["alt_km"]), float(r["lat_deg"]), float(r["Rc_stormer_GV"])) for r in csv.DictReader(f)]
+
+
+def test_table_is_the_stormer_formula():
+    # run_C1.py:43-46,105-106: R0 = 0.299792458 * 0.25 * B_eq * Re with B_eq = 3.12e-5 T, Re = 6371.2 km
+    R0 = 0.299792458 * 0.25 * 3.12e-5 * (6371.2 * 1000.0)
+    for alt, lat, rc in _table():
+        r_re = (6371.2 + alt) / 6371.2
+        assert abs(R0 * math.cos(math.radians(lat)) ** 4 / r_re ** 2 - rc) <= 1e-9 * rc
+
+
+def _case(rows, factors):
+    """one proton per (table row, factor): launched at the row's point, arriving vertically with rigidity factor * Rc of OUR dipole
+    (B_eq = workload.B0 at workload.RE; the cutoff scales linearly with B_eq Re)"""
+    L = 16.0 * RE
+
+    def refine(level, lo, hi):  # dx = 1, 0.5, 0.25, 0.125 Re towards the planet (2:1 balanced)
+        near = np.clip(np.zeros(3), lo, hi)
+        return float(np.linalg.norm(near)) / RE < (9.0, 5.0, 3.0)[level]
+
+    m = meshmod.build_mesh((-L, -L, -L), (L, L, L), (8, 8, 8), (4, 4, 4), (1, 1, 1), periodic=False, refine=refine, max_level=3)
+    xc = m.center_x
+    r = np.sqrt((xc ** 2).sum(1))
+    B = workload.dipole(np.where(r[:, None] < 0.5 * RE, xc + 0.5 * RE, xc))
+    E = np.zeros_like(B)
+    R0 = 0.299792458 * 0.25 * B0 * RE  # GV
+    xs, vs, expect = [], [], []
+    for alt, lat, _ in rows:
+        rr = RE + alt * 1e3
+        lam = math.radians(lat)
+        pos = rr * np.array([math.cos(lam), 0.0, math.sin(lam)])
+        rc = R0 * math.cos(lam) ** 4 / (rr / RE) ** 2
+        for f in factors:
+            p = f * rc * 1e9 * QP / CLIGHT
+            gamma = math.sqrt(1.0 + (p / (MP * CLIGHT)) ** 2)
+            xs.append(pos)
+            vs.append(-pos / rr * (p / (gamma * MP)))  # arrival velocity: vertically down
+            expect.append(f > 1.0)
+    x, v = np.array(xs).T.copy(), np.array(vs).T.copy()
+    n = x.shape[1]
+    cells = workload.locate_cells(m, x)
+    cfg = api.make_config((4, 4, 4), (1, 1, 1), (QP,), (MP,), (1.0,), 5.0e-4, periodic=False, capacity=n + 16, boundary_mode=_capi.BOUNDARY_USER_FUNCTION)
+    cfg.time_step_mode = _capi.DT_SPECIES_GLOBAL
+    cfg.coupler_interpolation = _capi.CPLR_LINEAR
+    cfg.backward_time_integration = 1
+    cfg.speed_of_light = CLIGHT
+    cfg.internal_sphere_radius = RE
+    cfg.exit_record_capacity = n
+    return m, cfg, (x, v, np.ones(n), np.zeros(n, dtype=np.uint8), cells), (E, B), np.array(expect)
+
+
+def _classify(n, records):
+    """True: left through the outer boundary (allowed); False: hit the planet or still inside (forbidden)"""
+    out = np.zeros(n, dtype=bool)
+    for ptr, spec, face, leaf, xx, vv in records:
+        if face != _capi.EXIT_SPHERE:
+            out[ptr] = True
+    return out
+
+
+N_STEPS = 4000  # 2 s of flight at dt = 5e-4 s (150 km per step at the speed of light): a path of 94 R_E
+
+
+def test_oracle_brackets_the_vertical_cutoff():
+    rows = [r for r in _table() if r[0] == 9000.0 and abs(r[1]) <= 30.0]
+    m, cfg, parts, bg, expect = _case(rows, (0.6, 1.6))
+    o = Oracle(cfg, m)
+    o.set_background(*bg)
+    o.add_particles(*parts)
+    for it in range(N_STEPS):
+        rc, st, ret, fc = o.move(_capi.MOVER_RELATIVISTIC_BORIS, 1)
+        assert rc == 0
+        if (fc < 0).all():
+            break
+    nrec, recs = o.exit_records()
+    o.close()
+    got = _classify(len(expect), recs)
+    assert (got == expect).all(), (got, expect)
+
+
+@pytest.mark.gpu
+def test_gpu_brackets_the_vertical_cutoff():
+    rows = _table()
+    m, cfg, parts, bg, expect = _case(rows, (0.6, 1.6))
+    g = api.Context(cfg, m)
+    g.background_upload(*bg)
+    g.particles_upload(*parts)
+    for it in range(4 * N_STEPS):  # (the 0.26 GV protons of the 60 degree rows move at a quarter of the speed of light)
+        g.MoveParticles(_capi.MOVER_RELATIVISTIC_BORIS, stats=False)
+        g.sort()
+        if it % 100 == 99 and g.particle_count() == 0:
+            break
+    nrec, recs = g.exit_records()
+    g.close()
+    got = _classify(len(expect), recs)
+    assert (got == expect).all(), (got, expect)
