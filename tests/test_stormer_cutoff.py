@@ -2,7 +2,9 @@
 Rc = R0 cos^4(lambda) / r^2, srcEarth/test/C1 (tests/golden/reference_C1_stormer.csv is that test's table, unchanged).
 Protons are traced backward in time with PIC::Mover::Relativistic::Boris (a7) through the dipole tabulated on an AMR mesh, like
 the reference's Mode3D MESH variant: a vertical arrival 1.6 x above the cutoff connects to the outer boundary, one 0.6 x below
-does not (the reference accepts 5-35 % around Rc, run_C1.py:322-337)."""
+does not (the reference accepts 5-35 % around Rc, run_C1.py:322-337).  srcEarth/test/C4/reference_C4_invariants.csv (also unchanged
+in tests/golden/) lists, for factors 0.5 and 2, whether the trajectory must reach the outer box, and bounds the rigidity change
+along it by 1e-6 (E = 0: the magnetic force does no work); both are asserted for every row."""
 import csv
 import math
 import os
@@ -30,6 +32,18 @@ def test_table_is_the_stormer_formula():
         assert abs(R0 * math.cos(math.radians(lat)) ** 4 / r_re ** 2 - rc) <= 1e-9 * rc
 
 
+def _table_c4():
+    with open(os.path.join(HERE, "golden", "reference_C4_invariants.csv")) as f:
+        return [(float(r["alt_km"]), float(r["lat_deg"]), float(r["factor"]), float(r["R_GV"]), float(r["Rc_stormer_GV"]), int(r["expected_allowed"]),
+                 float(r["rel_dR_limit"])) for r in csv.DictReader(f)]
+
+
+def test_c4_table_is_consistent_with_c1():
+    c1 = {(a, l): rc for a, l, rc in _table()}
+    for alt, lat, factor, R, rc, allowed, lim in _table_c4():
+        assert abs(rc - c1[(alt, lat)]) <= 1e-9 * rc and abs(R - factor * rc) <= 1e-9 * R and allowed == (factor > 1.0)
+
+
 def _case(rows, factors):
     """one proton per (table row, factor): launched at the row's point, arriving vertically with rigidity factor * Rc of OUR dipole
     (B_eq = workload.B0 at workload.RE; the cutoff scales linearly with B_eq Re)"""
@@ -45,7 +59,7 @@ def _case(rows, factors):
     B = workload.dipole(np.where(r[:, None] < 0.5 * RE, xc + 0.5 * RE, xc))
     E = np.zeros_like(B)
     R0 = 0.299792458 * 0.25 * B0 * RE  # GV
-    xs, vs, expect = [], [], []
+    xs, vs, expect, rig = [], [], [], []
     for alt, lat, _ in rows:
         rr = RE + alt * 1e3
         lam = math.radians(lat)
@@ -57,6 +71,7 @@ def _case(rows, factors):
             xs.append(pos)
             vs.append(-pos / rr * (p / (gamma * MP)))  # arrival velocity: vertically down
             expect.append(f > 1.0)
+            rig.append(f * rc)
     x, v = np.array(xs).T.copy(), np.array(vs).T.copy()
     n = x.shape[1]
     cells = workload.locate_cells(m, x)
@@ -67,7 +82,7 @@ def _case(rows, factors):
     cfg.speed_of_light = CLIGHT
     cfg.internal_sphere_radius = RE
     cfg.exit_record_capacity = n
-    return m, cfg, (x, v, np.ones(n), np.zeros(n, dtype=np.uint8), cells), (E, B), np.array(expect)
+    return m, cfg, (x, v, np.ones(n), np.zeros(n, dtype=np.uint8), cells), (E, B), np.array(expect), np.array(rig)
 
 
 def _classify(n, records):
@@ -79,12 +94,29 @@ def _classify(n, records):
     return out
 
 
+def _rigidity_gv(v):
+    """rigidity of a proton with velocity v: p c / q in GV"""
+    v = np.asarray(v)
+    b2 = float((v ** 2).sum()) / CLIGHT ** 2
+    return MP * math.sqrt(float((v ** 2).sum())) / math.sqrt(1.0 - b2) * CLIGHT / QP * 1e-9
+
+
+def _check_c4(recs, expect, rig, lim):
+    got = _classify(len(expect), recs)
+    assert (got == expect).all(), (got, expect)
+    seen = 0
+    for ptr, spec, face, leaf, xx, vv in recs:  # every trajectory that ended (outer box or planet): |rel_dR| <= rel_dR_limit
+        assert abs(_rigidity_gv(vv) - rig[ptr]) <= lim * rig[ptr], (ptr, _rigidity_gv(vv), rig[ptr])
+        seen += 1
+    assert seen >= int(expect.sum())
+
+
 N_STEPS = 4000  # 2 s of flight at dt = 5e-4 s (150 km per step at the speed of light): a path of 94 R_E
 
 
 def test_oracle_brackets_the_vertical_cutoff():
     rows = [r for r in _table() if r[0] == 9000.0 and abs(r[1]) <= 30.0]
-    m, cfg, parts, bg, expect = _case(rows, (0.6, 1.6))
+    m, cfg, parts, bg, expect, rig = _case(rows, (0.6, 1.6))
     o = Oracle(cfg, m)
     o.set_background(*bg)
     o.add_particles(*parts)
@@ -102,7 +134,7 @@ def test_oracle_brackets_the_vertical_cutoff():
 @pytest.mark.gpu
 def test_gpu_brackets_the_vertical_cutoff():
     rows = _table()
-    m, cfg, parts, bg, expect = _case(rows, (0.6, 1.6))
+    m, cfg, parts, bg, expect, rig = _case(rows, (0.6, 1.6))
     g = api.Context(cfg, m)
     g.background_upload(*bg)
     g.particles_upload(*parts)
@@ -115,3 +147,50 @@ def test_gpu_brackets_the_vertical_cutoff():
     g.close()
     got = _classify(len(expect), recs)
     assert (got == expect).all(), (got, expect)
+
+
+def _c4_case():
+    tab = _table_c4()
+    rows = sorted({(alt, lat, rc) for alt, lat, f, R, rc, a, lim in tab})
+    m, cfg, parts, bg, expect, rig = _case(rows, (0.5, 2.0))
+    # our dipole is B_eq = 3.1e-5 T at 6371 km instead of 3.12e-5 T at 6371.2 km: the table's R_GV scale by the same 0.6 %
+    want = {(alt, lat, f): bool(a) for alt, lat, f, R, rc, a, lim in tab}
+    k = 0
+    for alt, lat, rc in rows:
+        for f in (0.5, 2.0):
+            assert expect[k] == want[(alt, lat, f)]
+            k += 1
+    return m, cfg, parts, bg, expect, rig, max(r[6] for r in tab)
+
+
+def test_oracle_c4_exits_and_rigidity_conservation():
+    m, cfg, parts, bg, expect, rig, lim = _c4_case()
+    keep = np.array([abs(math.degrees(math.asin(parts[0][2, i] / np.linalg.norm(parts[0][:, i])))) <= 31.0 for i in range(len(expect))])
+    sub = tuple(a[..., keep] if a.ndim > 1 else a[keep] for a in parts)  # the fast rows keep the CPU suite short
+    o = Oracle(cfg, m)
+    o.set_background(*bg)
+    o.add_particles(*sub)
+    for it in range(N_STEPS):
+        rc, st, ret, fc = o.move(_capi.MOVER_RELATIVISTIC_BORIS, 1)
+        assert rc == 0
+        if (fc < 0).all():
+            break
+    nrec, recs = o.exit_records()
+    o.close()
+    _check_c4(recs, expect[keep], rig[keep], lim)
+
+
+@pytest.mark.gpu
+def test_gpu_c4_exits_and_rigidity_conservation():
+    m, cfg, parts, bg, expect, rig, lim = _c4_case()
+    g = api.Context(cfg, m)
+    g.background_upload(*bg)
+    g.particles_upload(*parts)
+    for it in range(6 * N_STEPS):
+        g.MoveParticles(_capi.MOVER_RELATIVISTIC_BORIS, stats=False)
+        g.sort()
+        if it % 100 == 99 and g.particle_count() == 0:
+            break
+    nrec, recs = g.exit_records()
+    g.close()
+    _check_c4(recs, expect, rig, lim)
