@@ -20,6 +20,8 @@ MOVER_GC_FIRST_ORDER = 3
 MOVER_GC_SECOND_ORDER = 4
 MOVER_RELATIVISTIC_GCA = 5
 MOVER_MARKIDIS2010 = 6
+MOVER_GYROKINETIC_FIRST_ORDER = 7
+MOVER_GYROKINETIC_SECOND_ORDER = 8
 
 PARTICLE_LEFT_THE_DOMAIN = 2
 PARTICLE_MOTION_FINISHED = 3
@@ -63,7 +65,7 @@ class Config(C.Structure):
         ("gravity_gm", C.c_double),
         ("carry_magnetic_moment", C.c_int32),
         ("exact_arithmetic", C.c_int32),
-        ("reserved1", C.c_int32),
+        ("carry_v_parallel", C.c_int32),
         ("ideal_mhd", C.c_int32),
     ]
 
@@ -116,6 +118,7 @@ class AosLayout(C.Structure):
         ("off_mu", C.c_int32),
         ("off_next", C.c_int32),
         ("off_prev", C.c_int32),
+        ("off_vpar", C.c_int32),
     ]
 
 
@@ -171,6 +174,8 @@ PROTOTYPES = {
     "amps_gpu_move": (C.c_int, [_vp, C.c_int, C.POINTER(MoveStats)]),
     "amps_gpu_deposit_JM": (C.c_int, [_vp, _vp, _vp]),
     "amps_gpu_diagnostics": (C.c_int, [_vp, _vp, _vp]),
+    "amps_gpu_v_parallel_upload": (C.c_int, [_vp, _vp, C.c_int64]),
+    "amps_gpu_v_parallel_download": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "amps_gpu_net_charge": (C.c_int, [_vp, C.c_double, _vp]),
     "amps_gpu_species_moments": (C.c_int, [_vp, _vp]),
     "amps_gpu_phi_upload": (C.c_int, [_vp, _vp]),

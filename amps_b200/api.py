@@ -51,6 +51,7 @@ def make_config(block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), charge=(-1.0, 1.0)
     cfg.exit_record_capacity = 0
     cfg.gravity_gm = 0.0
     cfg.carry_magnetic_moment = 0
+    cfg.carry_v_parallel = 0
     cfg.ideal_mhd = 1
     cfg.exact_arithmetic = 0
     return cfg
@@ -143,6 +144,18 @@ class Context:
         k = C.c_int64()
         self._ck(self.lib.amps_gpu_magnetic_moment_download(self._h, _ptr(mu), mu.shape[0], C.byref(k)))
         return mu[: int(k.value)]
+
+    def v_parallel_upload(self, vpar_by_ptr):
+        a = np.ascontiguousarray(vpar_by_ptr, dtype=np.float64)
+        self._ck(self.lib.amps_gpu_v_parallel_upload(self._h, _ptr(a), a.shape[0]))
+
+    def v_parallel_download(self):
+        """v_parallel in the current device order (pair with particles_download()['ptrs'])"""
+        n = self.particle_count()
+        a = np.empty(max(n, 1))
+        k = C.c_int64()
+        self._ck(self.lib.amps_gpu_v_parallel_download(self._h, _ptr(a), a.shape[0], C.byref(k)))
+        return a[: int(k.value)]
 
     def exit_records(self, max_records=1 << 20):
         buf = (_capi.ExitRecord * max_records)()

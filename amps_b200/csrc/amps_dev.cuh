@@ -78,6 +78,7 @@ struct ParticleSoA {
   int *key;
   int *ptr;
   double *mu;  // magnetic moment (guiding-centre movers), nullptr unless cfg.carry_magnetic_moment
+  double *vpar;  // v_parallel (gyrokinetic movers), nullptr unless cfg.carry_v_parallel
 };
 
 // counters written by the mover (device copy of amps_gpu_move_stats + error word)
@@ -120,6 +121,9 @@ void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *
 void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, const double *bCurTile, double *J, double *M,
                     double *energy, unsigned long long *cflBits, int nSM, const int *perm, ParticleSoA dst, int dep0, int dep1, unsigned flags,
                     cudaStream_t s, long long *launches);  // cells [cell0, cell1); cell1 < 0 = all; J, M and the diagnostics are zeroed when cell0 == 0
+void launch_move_gyrokinetic(const DevMesh &m, const DevSpecies &sp, int order, int interp, double rSphere, ParticleSoA p, const int *nSlots,
+                             long long nUpper, const double *bgTile, const double *gradBTile, const double *uE, const double *uB,
+                             const double *uGradB, int *cellCount, DevMoveStats *stats, cudaStream_t s);
 void launch_species_moments(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, double *spec, int nSM, cudaStream_t s);
 void launch_correct_particle_location(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *nSlots, long long nUpper, const double *phi,
                                       const double *spec, const unsigned *neibMask, double qom0, int *cellCount, unsigned long long *counters,
@@ -128,7 +132,7 @@ void launch_net_charge(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, co
                        cudaStream_t s);
 size_t sort_scan_tmp_bytes(long long nCells);
 // migration record: 8 doubles (x,v,w,meta) + mu when the particles carry it
-inline int migration_record_len(const ParticleSoA &p) { return p.mu ? 9 : 8; }
+__host__ __device__ inline int migration_record_len(const ParticleSoA &p) { return 8 + (p.mu ? 1 : 0) + (p.vpar ? 1 : 0); }
 void launch_pack_leavers(const DevMesh &m, ParticleSoA p, const int *nSlots, long long nUpper, const int *leafOwner, const int *leafGlobal, int me,
                          double *sendBuf, long long capPerPeer, int *sendCount, int *cellCount, int *errFlag, cudaStream_t s);
 void launch_unpack_arrivals(const DevMesh &m, const double *recvBuf, int nRecv, ParticleSoA p, int *nSlots, const int *g2l, const int *leafOwner, int me,
@@ -152,7 +156,8 @@ void launch_move_guiding_center(const DevMesh &m, const DevSpecies &sp, int orde
                                 unsigned long long *exitCount, cudaStream_t s);
 void launch_magnetic_moment_init(const DevMesh &m, const DevSpecies &sp, int interp, double c, ParticleSoA p, const int *nSlots, long long nUpper,
                                  const double *bgTile, const double *uE, const double *uB, DevMoveStats *stats, cudaStream_t s);
-void launch_magnetic_moment_set(ParticleSoA p, const int *nSlots, long long nUpper, const double *muByPtr, long long nMu, cudaStream_t s);
+void launch_magnetic_moment_set(ParticleSoA p, double *target, const int *nSlots, long long nUpper, const double *muByPtr, long long nMu,
+                                cudaStream_t s);
 void launch_move_relativistic_gca(const DevMesh &m, const DevSpecies &sp, int interp, double c, double rSphere, long long exitCap, ParticleSoA p,
                                   const int *nSlots, long long nUpper, const double *bgTile, const double *gcaTile, const double *uE, const double *uB,
                                   const double *uVar, int *cellCount, DevMoveStats *stats, amps_gpu_exit_record *exitBuf,

@@ -184,11 +184,16 @@ static int alloc_particles(amps_gpu_ctx *ctx, ParticleSoA &b, long long cap) {
     if ((rc = dev_alloc(ctx, &b.mu, cap))) return rc;
     CK(cudaMemsetAsync(b.mu, 0, sizeof(double) * cap, ctx->stream));
   }
+  b.vpar = nullptr;
+  if (ctx->cfg.carry_v_parallel) {
+    if ((rc = dev_alloc(ctx, &b.vpar, cap))) return rc;
+    CK(cudaMemsetAsync(b.vpar, 0, sizeof(double) * cap, ctx->stream));
+  }
   return AMPS_GPU_OK;
 }
 static void free_particles(ParticleSoA &b) {
   for (int d = 0; d < 3; d++) cudaFree(b.x[d]), cudaFree(b.v[d]);
-  cudaFree(b.w), cudaFree(b.spec), cudaFree(b.key), cudaFree(b.ptr), cudaFree(b.mu);
+  cudaFree(b.w), cudaFree(b.spec), cudaFree(b.key), cudaFree(b.ptr), cudaFree(b.mu), cudaFree(b.vpar);
 }
 
 template <class T>
@@ -758,14 +763,13 @@ int amps_gpu_magnetic_moment_init(amps_gpu_ctx *ctx, int mover_id) {
   return AMPS_GPU_OK;
 }
 
-int amps_gpu_magnetic_moment_upload(amps_gpu_ctx *ctx, const double *mu_by_ptr, int64_t n) {
-  if (!ctx || !mu_by_ptr || n < 0) return AMPS_GPU_ERR_ARG;
-  if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "magnetic_moment_upload needs cfg.carry_magnetic_moment");
+static int upload_by_ptr(amps_gpu_ctx *ctx, bool vpar, const double *mu_by_ptr, int64_t n) {
   CK(cudaSetDevice(ctx->cfg.device));
   double *d = nullptr;
   CK(cudaMallocAsync((void **)&d, sizeof(double) * (size_t)(n ? n : 1), ctx->stream));
   CK(cudaMemcpyAsync(d, mu_by_ptr, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  launch_magnetic_moment_set(ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper, d, n, ctx->stream);
+  launch_magnetic_moment_set(ctx->buf[ctx->cur], vpar ? ctx->buf[ctx->cur].vpar : ctx->buf[ctx->cur].mu, ctx->d_n + ctx->cur, ctx->nUpper, d, n,
+                             ctx->stream);
   ctx->launches++;
   CK(cudaGetLastError());
   CK(cudaFreeAsync(d, ctx->stream));
@@ -773,18 +777,38 @@ int amps_gpu_magnetic_moment_upload(amps_gpu_ctx *ctx, const double *mu_by_ptr, 
   return AMPS_GPU_OK;
 }
 
-int amps_gpu_magnetic_moment_download(amps_gpu_ctx *ctx, double *mu, int64_t n_max, int64_t *n) {
-  if (!ctx || !n) return AMPS_GPU_ERR_ARG;
-  if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "magnetic_moment_download needs cfg.carry_magnetic_moment");
+int amps_gpu_magnetic_moment_upload(amps_gpu_ctx *ctx, const double *mu_by_ptr, int64_t n) {
+  if (!ctx || !mu_by_ptr || n < 0) return AMPS_GPU_ERR_ARG;
+  if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "magnetic_moment_upload needs cfg.carry_magnetic_moment");
+  return upload_by_ptr(ctx, false, mu_by_ptr, n);
+}
+int amps_gpu_v_parallel_upload(amps_gpu_ctx *ctx, const double *vpar_by_ptr, int64_t n) {
+  if (!ctx || !vpar_by_ptr || n < 0) return AMPS_GPU_ERR_ARG;
+  if (!ctx->cfg.carry_v_parallel) FAIL(AMPS_GPU_ERR_STATE, "v_parallel_upload needs cfg.carry_v_parallel");
+  return upload_by_ptr(ctx, true, vpar_by_ptr, n);
+}
+
+static int download_current_order(amps_gpu_ctx *ctx, bool vpar, double *mu, int64_t n_max, int64_t *n) {
   CK(cudaSetDevice(ctx->cfg.device));
   int cnt = 0;
   CK(cudaMemcpyAsync(&cnt, ctx->d_n + ctx->cur, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   *n = cnt;
   if (cnt > n_max) FAIL(AMPS_GPU_ERR_CAPACITY, "magnetic_moment_download: n_max too small");
-  if (mu && cnt > 0) CK(cudaMemcpyAsync(mu, ctx->buf[ctx->cur].mu, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mu && cnt > 0)
+    CK(cudaMemcpyAsync(mu, vpar ? ctx->buf[ctx->cur].vpar : ctx->buf[ctx->cur].mu, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return AMPS_GPU_OK;
+}
+int amps_gpu_magnetic_moment_download(amps_gpu_ctx *ctx, double *mu, int64_t n_max, int64_t *n) {
+  if (!ctx || !n) return AMPS_GPU_ERR_ARG;
+  if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "magnetic_moment_download needs cfg.carry_magnetic_moment");
+  return download_current_order(ctx, false, mu, n_max, n);
+}
+int amps_gpu_v_parallel_download(amps_gpu_ctx *ctx, double *vpar, int64_t n_max, int64_t *n) {
+  if (!ctx || !n) return AMPS_GPU_ERR_ARG;
+  if (!ctx->cfg.carry_v_parallel) FAIL(AMPS_GPU_ERR_STATE, "v_parallel_download needs cfg.carry_v_parallel");
+  return download_current_order(ctx, true, vpar, n_max, n);
 }
 
 int amps_gpu_exit_records(amps_gpu_ctx *ctx, amps_gpu_exit_record *buf, int64_t max_records, int64_t *n) {
@@ -968,6 +992,13 @@ int amps_gpu_particles_upload_aos(amps_gpu_ctx *ctx, const void *records, const 
     for (int64_t i = 0; i < n; i++) memcpy(&mu[pt[i]], base + (int64_t)pt[i] * lay->stride + lay->off_mu, 8);
     rc = amps_gpu_magnetic_moment_upload(ctx, mu.data(), maxSlot + 1);
   }
+  if (!rc && ctx->cfg.carry_v_parallel && lay->off_vpar >= 0 && n > 0) {  // _PIC_PARTICLE_DATA__V_PARALLEL_OFFSET_
+    int64_t maxSlot = 0;
+    for (int64_t i = 0; i < n; i++) maxSlot = pt[i] > maxSlot ? pt[i] : maxSlot;
+    std::vector<double> vp((size_t)maxSlot + 1, 0.0);
+    for (int64_t i = 0; i < n; i++) memcpy(&vp[pt[i]], base + (int64_t)pt[i] * lay->stride + lay->off_vpar, 8);
+    rc = amps_gpu_v_parallel_upload(ctx, vp.data(), maxSlot + 1);
+  }
   return rc;
 }
 
@@ -1024,6 +1055,12 @@ int amps_gpu_particles_download_aos(amps_gpu_ctx *ctx, void *records, int64_t *f
     int64_t nm;
     if ((rc = amps_gpu_magnetic_moment_download(ctx, mu.data(), n, &nm))) return rc;
   }
+  std::vector<double> vpar;
+  if (ctx->cfg.carry_v_parallel && lay->off_vpar >= 0) {
+    vpar.resize((size_t)n + 1);
+    int64_t nm;
+    if ((rc = amps_gpu_v_parallel_download(ctx, vpar.data(), n, &nm))) return rc;
+  }
   if (first_cell_particle)
     for (int64_t c = 0; c < ctx->nCells; c++) first_cell_particle[c] = -1;
   for (int64_t i = 0; i < n; i++) {
@@ -1036,6 +1073,7 @@ int amps_gpu_particles_download_aos(amps_gpu_ctx *ctx, void *records, int64_t *f
     memcpy(r + lay->off_v, u, 24);
     if (lay->off_w >= 0) memcpy(r + lay->off_w, &w[i], 8);
     if (!mu.empty()) memcpy(r + lay->off_mu, &mu[i], 8);
+    if (!vpar.empty()) memcpy(r + lay->off_vpar, &vpar[i], 8);
     r[lay->off_species] = (unsigned char)((r[lay->off_species] & 0x80) | (sp[i] & 0x7f));
     if (first_cell_particle && key[i] >= 0) {
       // push on the cell list like the movers do (pic_mover_boris.cpp:1333-1343)
@@ -1067,8 +1105,13 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "move needs the (block,cell)-sorted layout: call amps_gpu_sort");
   if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS && mover_id != AMPS_MOVER_BORIS &&
       mover_id != AMPS_MOVER_RELATIVISTIC_GCA && mover_id != AMPS_MOVER_GC_FIRST_ORDER && mover_id != AMPS_MOVER_GC_SECOND_ORDER &&
-      mover_id != AMPS_MOVER_MARKIDIS2010)
+      mover_id != AMPS_MOVER_MARKIDIS2010 && mover_id != AMPS_MOVER_GYROKINETIC_FIRST_ORDER && mover_id != AMPS_MOVER_GYROKINETIC_SECOND_ORDER)
     FAIL(AMPS_GPU_ERR_ARG, "unknown mover id");
+  if (mover_id == AMPS_MOVER_GYROKINETIC_FIRST_ORDER || mover_id == AMPS_MOVER_GYROKINETIC_SECOND_ORDER) {
+    if (!ctx->cfg.carry_magnetic_moment || !ctx->cfg.carry_v_parallel)
+      FAIL(AMPS_GPU_ERR_STATE, "the gyrokinetic movers need cfg.carry_magnetic_moment and cfg.carry_v_parallel");
+    if (!ctx->gradBReady) FAIL(AMPS_GPU_ERR_STATE, "PIC::GYROKINETIC needs amps_gpu_background_upload_gradB");
+  }
   if (mover_id == AMPS_MOVER_GC_FIRST_ORDER || mover_id == AMPS_MOVER_GC_SECOND_ORDER) {
     if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "the guiding-centre movers need cfg.carry_magnetic_moment");
     if (!ctx->gradBReady) FAIL(AMPS_GPU_ERR_STATE, "GuidingCenter needs amps_gpu_background_upload_gradB");
@@ -1104,6 +1147,16 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
     launch_move_guiding_center(m, ctx->sp, mover_id == AMPS_MOVER_GC_SECOND_ORDER ? 2 : 1, ctx->cfg.coupler_interpolation, ctx->cfg.ideal_mhd,
                                ctx->cfg.internal_sphere_radius, ctx->cfg.exit_record_capacity, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper,
                                ctx->d_bgTile, ctx->d_gradBTile, ctx->d_bgE, ctx->d_bgB, ctx->d_gradBVar, ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount, ctx->stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    ctx->sorted = false;
+    ctx->countValid = true;
+    return AMPS_GPU_OK;
+  }
+  if (mover_id == AMPS_MOVER_GYROKINETIC_FIRST_ORDER || mover_id == AMPS_MOVER_GYROKINETIC_SECOND_ORDER) {
+    launch_move_gyrokinetic(m, ctx->sp, mover_id == AMPS_MOVER_GYROKINETIC_SECOND_ORDER ? 2 : 1, ctx->cfg.coupler_interpolation,
+                            ctx->cfg.internal_sphere_radius, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper, ctx->d_bgTile, ctx->d_gradBTile,
+                            ctx->d_bgE, ctx->d_bgB, ctx->d_gradBVar, ctx->d_cellCount, ctx->d_stats, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
     ctx->sorted = false;

@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
         dst.v[0][o] = v0, dst.v[1][o] = v1, dst.v[2][o] = v2;
         dst.w[o] = pw, dst.spec[o] = (uint8_t)nspec, dst.key[o] = cell, dst.ptr[o] = nptr;
         if (p.mu) dst.mu[o] = p.mu[nsrc];
+        if (p.vpar) dst.vpar[o] = p.vpar[nsrc];
       }
       if (base + CHUNK < end) {  // (warp-uniform) the next chunk of this cell
         if (base + CHUNK + lane < end) {
@@ -440,6 +441,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
         for (int d = 0; d < 3; d++) dst.x[d][ip] = p.x[d][sidx], dst.v[d][ip] = p.v[d][sidx];
         dst.w[ip] = p.w[sidx], dst.spec[ip] = p.spec[sidx], dst.key[ip] = p.key[sidx], dst.ptr[ip] = p.ptr[sidx];
         if (p.mu) dst.mu[ip] = p.mu[sidx];
+        if (p.vpar) dst.vpar[ip] = p.vpar[sidx];
       }
     }
   }

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) pack_leavers_kernel(ParticleSoA p, const 
       atomicExch(errFlag, 1);
       continue;  // the particle stays (in a foreign block); the host reports AMPS_GPU_ERR_CAPACITY
     }
-    const int L = p.mu ? 9 : 8;
+    const int L = migration_record_len(p);
     double *r = sendBuf + ((size_t)dest * capPerPeer + slot) * L;
     const long long gkey = (long long)leafGlobal[leaf] * C + (k - leaf * C);
     r[0] = p.x[0][i], r[1] = p.x[1][i], r[2] = p.x[2][i];
@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) pack_leavers_kernel(ParticleSoA p, const 
     r[6] = p.w[i];
     r[7] = __longlong_as_double((gkey << 8) | (long long)p.spec[i]);
     if (p.mu) r[8] = p.mu[i];
+    if (p.vpar) r[L - 1] = p.vpar[i];
     atomicSub(&cellCount[k], 1);
     p.key[i] = -1;
     }
@@ -57,7 +58,8 @@ __global__ void __launch_bounds__(256) unpack_arrivals_kernel(const double *__re
                                                              long long capacity, int *__restrict__ cellCount, int *__restrict__ errFlag) {
   const int base = *nSlots;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nRecv; j += gridDim.x * blockDim.x) {
-    const double *r = recvBuf + (size_t)j * (p.mu ? 9 : 8);
+    const int L = migration_record_len(p);
+    const double *r = recvBuf + (size_t)j * L;
     const long long meta = __double_as_longlong(r[7]);
     const long long gkey = meta >> 8;
     const int gleaf = (int)(gkey / C);
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(256) unpack_arrivals_kernel(const double *__re
     p.v[0][i] = r[3], p.v[1][i] = r[4], p.v[2][i] = r[5];
     p.w[i] = r[6];
     if (p.mu) p.mu[i] = r[8];
+    if (p.vpar) p.vpar[i] = r[L - 1];
     p.spec[i] = (uint8_t)(meta & 0xff);
     p.key[i] = k;
     p.ptr[i] = -1;  // no ParticleBuffer slot on this rank yet (GetNewParticle on download)

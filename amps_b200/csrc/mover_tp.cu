@@ -772,18 +772,21 @@ void launch_magnetic_moment_init(const DevMesh &m, const DevSpecies &sp, int int
   magnetic_moment_init_kernel<<<(int)g, 128, 0, s>>>(m, sp, interp, U, c, p, nSlots, bgTile, stats);
 }
 
-__global__ void magnetic_moment_set_kernel(ParticleSoA p, const int *__restrict__ nSlots, const double *__restrict__ muByPtr, long long nMu) {
+// target = p.mu or p.vpar
+__global__ void magnetic_moment_set_kernel(ParticleSoA p, double *__restrict__ target, const int *__restrict__ nSlots,
+                                           const double *__restrict__ muByPtr, long long nMu) {
   const int n = *nSlots;
   for (int ip = blockIdx.x * blockDim.x + threadIdx.x; ip < n; ip += gridDim.x * blockDim.x) {
     const int pt = p.ptr[ip];
-    if (pt >= 0 && pt < nMu) p.mu[ip] = muByPtr[pt];
+    if (pt >= 0 && pt < nMu) target[ip] = muByPtr[pt];
   }
 }
-void launch_magnetic_moment_set(ParticleSoA p, const int *nSlots, long long nUpper, const double *muByPtr, long long nMu, cudaStream_t s) {
+void launch_magnetic_moment_set(ParticleSoA p, double *target, const int *nSlots, long long nUpper, const double *muByPtr, long long nMu,
+                                cudaStream_t s) {
   long long g = (nUpper + 255) / 256;
   if (g < 1) g = 1;
   if (g > 148 * 16) g = 148 * 16;
-  magnetic_moment_set_kernel<<<(int)g, 256, 0, s>>>(p, nSlots, muByPtr, nMu);
+  magnetic_moment_set_kernel<<<(int)g, 256, 0, s>>>(p, target, nSlots, muByPtr, nMu);
 }
 
 __global__ void __launch_bounds__(128) move_relativistic_gca_kernel(DevMesh m, DevSpecies sp, TpParams tp, ParticleSoA p, const int *__restrict__ nSlots,
@@ -1257,6 +1260,185 @@ void launch_move_guiding_center(const DevMesh &m, const DevSpecies &sp, int orde
   else move_guiding_center_kernel<false><<<(int)g, 128, 0, s>>>(m, sp, tp, idealMhd, T, p, nSlots, cellCount, stats, exitBuf, exitCount);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// f2: PIC::GYROKINETIC::Mover_FirstOrder / Mover_SecondOrder  src/pic/gyro/gyro_mover.cpp:383-720 (coupler fields)
+// reduced state (x, v_parallel, mu); v = b v_parallel + v_drift is rebuilt at the final position (CommitReducedStateAndVelocity)
+// ------------------------------------------------------------------------------------------------
+// EvalRHS, :245-336; false where the reference reads outside the block's table
+__device__ __forceinline__ bool gyro_eval_rhs(const DevMesh &m, const DevSpecies &sp, int interp, const GcTables &T, const double x[3], int leaf,
+                                              double vpar, double mu, int spec, double &absB, double b[3], double vdrift[3], double &dvpar_dt) {
+  absB = 0.0;
+  b[0] = 0.0, b[1] = 0.0, b[2] = 0.0;
+  vdrift[0] = 0.0, vdrift[1] = 0.0, vdrift[2] = 0.0;
+  dvpar_dt = 0.0;
+  BgStencil st;
+  BgStencil8 s8;
+  const int kind = background_stencil(m, interp, x, leaf, s8, st);
+  if (!kind) return false;
+  double E[3], B[3], gradB[9];
+  const double *tb = T.bg + (size_t)leaf * m.nCenterLocal * 6;
+  background_gather<3>(kind, s8, st, tb, 6, 0, T.uE, E);
+  background_gather<3>(kind, s8, st, tb, 6, 3, T.uB, B);
+  background_gather<9>(kind, s8, st, T.gradB + (size_t)leaf * m.nCenterLocal * 9, 9, 0, T.uGradB, gradB);
+  const double absB2_ = B[0] * B[0] + B[1] * B[1] + B[2] * B[2];
+  if (absB2_ <= 0.0) return true;
+  absB = sqrt(absB2_);
+  const double inv = 1.0 / absB;
+  b[0] = B[0] * inv, b[1] = B[1] * inv, b[2] = B[2] * inv;
+  const double mm = sp.mass[spec], q = sp.charge[spec];
+  const double absB2 = absB * absB;
+  const double invAbsB2 = 1.0 / absB2;
+  double gradAbsB[3];
+  {
+    const double invAbsB = 1.0 / absB;
+    for (int j = 0; j < 3; j++) gradAbsB[j] = (B[0] * gradB[0 * 3 + j] + B[1] * gradB[1 * 3 + j] + B[2] * gradB[2 * 3 + j]) * invAbsB;
+  }
+  const double Epar = E[0] * b[0] + E[1] * b[1] + E[2] * b[2];
+  const double bDotGradAbsB = b[0] * gradAbsB[0] + b[1] * gradAbsB[1] + b[2] * gradAbsB[2];
+  dvpar_dt = (q / mm) * Epar - (mu / mm) * bDotGradAbsB;
+  const double ExB[3] = {E[1] * B[2] - E[2] * B[1], E[2] * B[0] - E[0] * B[2], E[0] * B[1] - E[1] * B[0]};
+  vdrift[0] = ExB[0] * invAbsB2;
+  vdrift[1] = ExB[1] * invAbsB2;
+  vdrift[2] = ExB[2] * invAbsB2;
+  if (q != 0.0 && mu != 0.0) {
+    const double BxG[3] = {B[1] * gradAbsB[2] - B[2] * gradAbsB[1], B[2] * gradAbsB[0] - B[0] * gradAbsB[2], B[0] * gradAbsB[1] - B[1] * gradAbsB[0]};
+    const double c = (mu / q) * invAbsB2;
+    vdrift[0] += c * BxG[0];
+    vdrift[1] += c * BxG[1];
+    vdrift[2] += c * BxG[2];
+  }
+  double BB[3];
+  BB[0] = B[0] * gradB[0 * 3 + 0] + B[1] * gradB[0 * 3 + 1] + B[2] * gradB[0 * 3 + 2];
+  BB[1] = B[0] * gradB[1 * 3 + 0] + B[1] * gradB[1 * 3 + 1] + B[2] * gradB[1 * 3 + 2];
+  BB[2] = B[0] * gradB[2 * 3 + 0] + B[1] * gradB[2 * 3 + 1] + B[2] * gradB[2 * 3 + 2];
+  if (q != 0.0 && vpar != 0.0) {
+    const double BxBB[3] = {B[1] * BB[2] - B[2] * BB[1], B[2] * BB[0] - B[0] * BB[2], B[0] * BB[1] - B[1] * BB[0]};
+    const double invAbsB4 = 1.0 / (absB2 * absB2);
+    const double c = (mm * vpar * vpar / q) * invAbsB4;
+    vdrift[0] += c * BxBB[0];
+    vdrift[1] += c * BxBB[1];
+    vdrift[2] += c * BxBB[2];
+  }
+  if (!isfinite(vdrift[0]) || !isfinite(vdrift[1]) || !isfinite(vdrift[2]) || !isfinite(dvpar_dt)) {
+    vdrift[0] = 0.0, vdrift[1] = 0.0, vdrift[2] = 0.0;
+    dvpar_dt = 0.0;
+  }
+  return true;
+}
+
+template <bool kSecondOrder>
+__global__ void __launch_bounds__(128) move_gyrokinetic_kernel(DevMesh m, DevSpecies sp, TpParams tp, GcTables T, ParticleSoA p,
+                                                              const int *__restrict__ nSlots, int *__restrict__ cellCount,
+                                                              DevMoveStats *__restrict__ stats) {
+  const int n = *nSlots;
+  const int C = m.cellsPerBlock;
+  unsigned int nMoved = 0, nXCell = 0, nXBlock = 0, nLeft = 0, nNotUsed = 0, nWrap = 0, nErr = 0;
+  for (int ip = blockIdx.x * blockDim.x + threadIdx.x; ip < n; ip += gridDim.x * blockDim.x) {
+    const int oldKey = p.key[ip];
+    if (oldKey < 0) continue;
+    nMoved++;
+    const double x0[3] = {p.x[0][ip], p.x[1][ip], p.x[2][ip]};
+    const int spec = p.spec[ip] & 0x3f;
+    const int startLeaf = oldKey / C;
+    const int startNode = m.leaf[startLeaf].node;
+    const double dtTotal = (sp.timeStepMode == AMPS_DT_SPECIES_GLOBAL) ? sp.dt[spec] : sp.dt[0];
+    const double mu = p.mu[ip];
+    const double vpar0 = p.vpar[ip];
+    int outcome = 0, node = -1;
+    double x[3], vparNew = vpar0, vFinal[3] = {0.0, 0.0, 0.0};
+
+    double absB, b[3], vdrift[3], dvpar_dt;
+    if (!gyro_eval_rhs(m, sp, tp.interp, T, x0, startLeaf, vpar0, mu, spec, absB, b, vdrift, dvpar_dt)) outcome = 3;
+    if (outcome == 0) {
+      if (!kSecondOrder) {
+        for (int d = 0; d < 3; d++) x[d] = x0[d] + dtTotal * (vdrift[d] + b[d] * vpar0);
+        vparNew = vpar0 + dtTotal * dvpar_dt;
+      } else {
+        double xHalf[3];
+        for (int d = 0; d < 3; d++) xHalf[d] = x0[d] + 0.5 * dtTotal * (vdrift[d] + b[d] * vpar0);
+        const double vparHalf = vpar0 + 0.5 * dtTotal * dvpar_dt;
+        const int nodeHalf = find_tree_node_plain(m, xHalf, -1);  // FindBlock
+        if (nodeHalf < 0) outcome = 1;
+        else if (m.nodeLeaf[nodeHalf] < 0) outcome = 3;
+        else {
+          double absBH, bH[3], vdriftH[3], dvpar_dtH;
+          if (!gyro_eval_rhs(m, sp, tp.interp, T, xHalf, m.nodeLeaf[nodeHalf], vparHalf, mu, spec, absBH, bH, vdriftH, dvpar_dtH)) outcome = 3;
+          else {
+            for (int d = 0; d < 3; d++) x[d] = x0[d] + dtTotal * (vdriftH[d] + bH[d] * vparHalf);
+            vparNew = vpar0 + dtTotal * dvpar_dtH;
+          }
+        }
+      }
+    }
+    if (outcome == 0) {
+      node = find_tree_node_plain(m, x, -1);  // FindBlock
+      if (node < 0) outcome = 1;
+      else if (m.nodeLeaf[node] < 0) outcome = 3;
+    }
+    if (outcome == 0) {
+      // EvalRHS at the final point for the stored drift; CommitReducedStateAndVelocity evaluates b there once more (same values)
+      double absB1, b1[3], vdrift1[3], dummy;
+      if (!gyro_eval_rhs(m, sp, tp.interp, T, x, m.nodeLeaf[node], vparNew, mu, spec, absB1, b1, vdrift1, dummy)) outcome = 3;
+      else {
+        for (int d = 0; d < 3; d++) vFinal[d] = b1[d] * vparNew + vdrift1[d];
+        if (tp.rSphere > 0.0 && x[0] * x[0] + x[1] * x[1] + x[2] * x[2] < tp.rSphere * tp.rSphere) outcome = 1;
+        else {
+          node = find_tree_node_plain(m, x, startNode);
+          if (node < 0) outcome = 3;
+        }
+      }
+    }
+    int newKey = -1;
+    if (outcome == 0) {
+      int ijk[3];
+      int newLeaf = m.nodeLeaf[node];
+      if (!find_cell_index(m, x, node, ijk) || newLeaf < 0) outcome = 3;
+      else {
+        const int realLeaf = m.leaf[newLeaf].real;
+        if (realLeaf >= 0) {  // periodic ghost -> real (pic_bc_periodic.cpp:100-134)
+          const LeafGeo &gg = m.leaf[newLeaf];
+          const LeafGeo &rg = m.leaf[realLeaf];
+          for (int d = 0; d < 3; d++) {
+            x[d] += rg.xmin[d] - gg.xmin[d];
+            if (x[d] < rg.xmin[d]) x[d] = rg.xmin[d];
+            if (x[d] >= rg.xmax[d]) x[d] = rg.xmax[d] - 1.0E-10 * (rg.xmax[d] - rg.xmin[d]);
+          }
+          newLeaf = realLeaf;
+          nWrap++;
+        }
+        newKey = newLeaf * C + ijk[0] + m.N[0] * (ijk[1] + m.N[1] * ijk[2]);
+        if (newLeaf != startLeaf) nXBlock++;
+        else if (newKey != oldKey) nXCell++;
+      }
+    }
+    if (outcome == 1) nLeft++;
+    else if (outcome == 2) nNotUsed++;
+    else if (outcome == 3) nErr++;
+    if (newKey >= 0) {
+      p.x[0][ip] = x[0], p.x[1][ip] = x[1], p.x[2][ip] = x[2];
+      p.v[0][ip] = vFinal[0], p.v[1][ip] = vFinal[1], p.v[2][ip] = vFinal[2];
+      p.vpar[ip] = vparNew;
+      atomicAdd(&cellCount[newKey], 1);
+    }
+    if (newKey != oldKey) p.key[ip] = newKey;
+  }
+  flush_move_counters(stats, nMoved, nXCell, nXBlock, nLeft, nNotUsed, nWrap, nErr);
+}
+
+void launch_move_gyrokinetic(const DevMesh &m, const DevSpecies &sp, int order, int interp, double rSphere, ParticleSoA p, const int *nSlots,
+                             long long nUpper, const double *bgTile, const double *gradBTile, const double *uE, const double *uB,
+                             const double *uGradB, int *cellCount, DevMoveStats *stats, cudaStream_t s) {
+  TpParams tp;
+  tp.interp = interp, tp.backward = 0, tp.boundaryMode = sp.boundaryMode, tp.c = 0.0, tp.rSphere = rSphere, tp.exitCap = 0;
+  GcTables T;
+  T.bg = bgTile, T.gradB = gradBTile, T.uE = uE, T.uB = uB, T.uGradB = uGradB;
+  long long g = (nUpper + 127) / 128;
+  if (g < 1) g = 1;
+  if (g > 148 * 32) g = 148 * 32;
+  if (order == 2) move_gyrokinetic_kernel<true><<<(int)g, 128, 0, s>>>(m, sp, tp, T, p, nSlots, cellCount, stats);
+  else move_gyrokinetic_kernel<false><<<(int)g, 128, 0, s>>>(m, sp, tp, T, p, nSlots, cellCount, stats);
+}
 
 // ------------------------------------------------------------------------------------------------
 // f4: the species moments on the corners (the _PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_ part of ProcessCell /

@@ -142,11 +142,13 @@ __global__ void __launch_bounds__(256, 5) scatter_kernel(ParticleSoA src, Partic
       const int pos = cellStart[a.k] + warp_aggregated_slot(cellFill, a.k);
       store_particle(dst, pos, a);
       if (src.mu) dst.mu[pos] = src.mu[i];
+      if (src.vpar) dst.vpar[pos] = src.vpar[i];
     }
     if (b.k >= 0) {
       const int pos = cellStart[b.k] + warp_aggregated_slot(cellFill, b.k);
       store_particle(dst, pos, b);
       if (src.mu) dst.mu[pos] = src.mu[j];
+      if (src.vpar) dst.vpar[pos] = src.vpar[j];
     }
   }
 }

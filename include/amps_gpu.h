@@ -51,7 +51,9 @@ enum {
   AMPS_MOVER_GC_FIRST_ORDER = 3,      /* pic_mover_guiding_center.cpp:629-849                  */
   AMPS_MOVER_GC_SECOND_ORDER = 4,     /* pic_mover_guiding_center.cpp:293-627                  */
   AMPS_MOVER_RELATIVISTIC_GCA = 5,    /* pic_mover_relativistic_guiding_center.cpp:96-409      */
-  AMPS_MOVER_MARKIDIS2010 = 6         /* pic_mover_boris.cpp:557-835 (energy-conserving scheme, coupler fields) */
+  AMPS_MOVER_MARKIDIS2010 = 6,        /* pic_mover_boris.cpp:557-835 (energy-conserving scheme, coupler fields) */
+  AMPS_MOVER_GYROKINETIC_FIRST_ORDER = 7,  /* gyro/gyro_mover.cpp:386-544  PIC::GYROKINETIC::Mover_FirstOrder     */
+  AMPS_MOVER_GYROKINETIC_SECOND_ORDER = 8  /* gyro/gyro_mover.cpp:544-720  PIC::GYROKINETIC::Mover_SecondOrder    */
 };
 
 /* return codes of a per-particle mover, src/pic/pic.h:5955-5960 */
@@ -113,7 +115,8 @@ typedef struct amps_gpu_config {
   int32_t exact_arithmetic;          /* 1: Lapenta2017 rounds every operation like the CPU build (no FMA contraction, IEEE quotients):
                                         x', v' bit-identical.  0 (default): contracted arithmetic for every particle whose x' stays clear
                                         of cell faces, the exact kernel for the rest -> keys/counters still bit-exact, x', v' to ~1e-14 */
-  int32_t reserved1;
+  int32_t carry_v_parallel;          /* particles carry v_parallel (_PIC_PARTICLE_DATA__V_PARALLEL_OFFSET_, picParticleDataMacro.h): the reduced state
+                                        of the gyrokinetic movers (needs carry_magnetic_moment as well)                     */
   int32_t ideal_mhd;                 /* _PIC__IDEAL_MHD_MODE_ (picGlobal.dfn:339, default ON): E.b = 0 in the guiding-centre parallel force */
 } amps_gpu_config;
 
@@ -187,6 +190,8 @@ typedef struct amps_gpu_aos_layout {
   int32_t off_mu;           /* _PIC_PARTICLE_DATA__MAGNETIC_MOMENT_OFFSET_ or -1              */
   int32_t off_next;         /* _PIC_PARTICLE_DATA__NEXT_OFFSET_ (download rebuilds the lists) */
   int32_t off_prev;
+  int32_t off_vpar;         /* _PIC_PARTICLE_DATA__V_PARALLEL_OFFSET_ or -1 (gyrokinetic movers; v_normal and the stored drift
+                               velocity are functions of the state and are not carried)          */
 } amps_gpu_aos_layout;
 
 /* counters of one MoveParticles() call */
@@ -253,6 +258,9 @@ int amps_gpu_magnetic_moment_init(amps_gpu_ctx *ctx, int mover_id);
 int amps_gpu_magnetic_moment_upload(amps_gpu_ctx *ctx, const double *mu_by_ptr, int64_t n);
 /* current device order (pair with the ptrs of amps_gpu_particles_download_soa) */
 int amps_gpu_magnetic_moment_download(amps_gpu_ctx *ctx, double *mu, int64_t n_max, int64_t *n);
+/* v_parallel of the gyrokinetic reduced state (PB::SetVParallel / GetVParallel), same conventions as the magnetic moment */
+int amps_gpu_v_parallel_upload(amps_gpu_ctx *ctx, const double *vpar_by_ptr, int64_t n);
+int amps_gpu_v_parallel_download(amps_gpu_ctx *ctx, double *vpar, int64_t n_max, int64_t *n);
 /* exit records accumulated by the movers since the last call (clears them) */
 int amps_gpu_exit_records(amps_gpu_ctx *ctx, amps_gpu_exit_record *buf, int64_t max_records, int64_t *n);
 

@@ -184,7 +184,10 @@ struct oracle_ctx {
 
   // ---- PIC::ParticleBuffer accessors, packed layout picParticleDataMacro.h:55-81 ----
   // + _PIC_PARTICLE_DATA__MAGNETIC_MOMENT_OFFSET_ (picParticleDataMacro.h:178-187) right after the basic data
-  enum { OFF_NEXT = 0, OFF_PREV = 8, OFF_SPEC = 16, OFF_V = 17, OFF_X = 41, OFF_W = 65, OFF_MU = 73, BASIC_LEN = 81 };
+  // + _PIC_PARTICLE_DATA__V_PARALLEL_OFFSET_ of the gyrokinetic reduced state behind it
+  enum { OFF_NEXT = 0, OFF_PREV = 8, OFF_SPEC = 16, OFF_V = 17, OFF_X = 41, OFF_W = 65, OFF_MU = 73, OFF_VPAR = 81, BASIC_LEN = 89 };
+  static double GetVParallel(const byte *p) { double m; memcpy(&m, p + OFF_VPAR, 8); return m; }
+  static void SetVParallel(double m, byte *p) { memcpy(p + OFF_VPAR, &m, 8); }
   static double GetMagneticMoment(const byte *p) { double m; memcpy(&m, p + OFF_MU, 8); return m; }
   static void SetMagneticMoment(double m, byte *p) { memcpy(p + OFF_MU, &m, 8); }
   byte *GetParticleDataPointer(long int ptr) const { return ParticleDataBuffer + ptr * ParticleDataLength; }
@@ -1867,6 +1870,174 @@ struct oracle_ctx {
     return _PARTICLE_MOTION_FINISHED_;
   }
 
+  // ------------------------------------------------------------------------------------------
+  // f2: PIC::GYROKINETIC, src/pic/gyro/gyro_mover.cpp (coupler fields; the reduced state is (x, v_parallel, mu))
+  // ------------------------------------------------------------------------------------------
+  // EvalRHS, :245-336 (GetEBandGradB :196-218 coupler branch, GetAbsBAndUnitB :220-232, GetGradAbsB :234-243)
+  bool Gyro_EvalRHS(const double *x, cTreeNode *node, double vpar, double mu, int spec, double &absB, double *b, double *vdrift, double &dvpar_dt) const {
+    absB = 0.0;
+    b[0] = 0.0, b[1] = 0.0, b[2] = 0.0;
+    vdrift[0] = 0.0, vdrift[1] = 0.0, vdrift[2] = 0.0;
+    dvpar_dt = 0.0;
+    double E[3], B[3], gradB[9];
+    if (node == NULL) return true;
+    cStencil Stencil;
+    if (!GC_InitStencil(x, node, Stencil)) return false;  // (out-of-bounds read in the reference)
+    GC_Gather(Stencil, node, BackgroundE_d, 3, E);
+    GC_Gather(Stencil, node, BackgroundB_d, 3, B);
+    GC_Gather(Stencil, node, BackgroundGradB_d, 9, gradB);
+    const double absB2_ = B[0] * B[0] + B[1] * B[1] + B[2] * B[2];
+    if (absB2_ <= 0.0) return true;
+    absB = sqrt(absB2_);
+    const double inv = 1.0 / absB;
+    b[0] = B[0] * inv, b[1] = B[1] * inv, b[2] = B[2] * inv;
+    const double m = cfg.mass[spec], q = cfg.charge[spec];
+    const double absB2 = absB * absB;
+    const double invAbsB2 = 1.0 / absB2;
+    double gradAbsB[3];
+    {
+      const double invAbsB = 1.0 / absB;
+      for (int j = 0; j < 3; j++) gradAbsB[j] = (B[0] * gradB[0 * 3 + j] + B[1] * gradB[1 * 3 + j] + B[2] * gradB[2 * 3 + j]) * invAbsB;
+    }
+    const double Epar = E[0] * b[0] + E[1] * b[1] + E[2] * b[2];
+    const double bDotGradAbsB = b[0] * gradAbsB[0] + b[1] * gradAbsB[1] + b[2] * gradAbsB[2];
+    dvpar_dt = (q / m) * Epar - (mu / m) * bDotGradAbsB;
+    double ExB[3] = {E[1] * B[2] - E[2] * B[1], E[2] * B[0] - E[0] * B[2], E[0] * B[1] - E[1] * B[0]};
+    vdrift[0] = ExB[0] * invAbsB2;
+    vdrift[1] = ExB[1] * invAbsB2;
+    vdrift[2] = ExB[2] * invAbsB2;
+    if (q != 0.0 && mu != 0.0) {
+      double BxGradAbsB[3] = {B[1] * gradAbsB[2] - B[2] * gradAbsB[1], B[2] * gradAbsB[0] - B[0] * gradAbsB[2], B[0] * gradAbsB[1] - B[1] * gradAbsB[0]};
+      const double c = (mu / q) * invAbsB2;
+      vdrift[0] += c * BxGradAbsB[0];
+      vdrift[1] += c * BxGradAbsB[1];
+      vdrift[2] += c * BxGradAbsB[2];
+    }
+    double BB[3];
+    BB[0] = B[0] * gradB[0 * 3 + 0] + B[1] * gradB[0 * 3 + 1] + B[2] * gradB[0 * 3 + 2];
+    BB[1] = B[0] * gradB[1 * 3 + 0] + B[1] * gradB[1 * 3 + 1] + B[2] * gradB[1 * 3 + 2];
+    BB[2] = B[0] * gradB[2 * 3 + 0] + B[1] * gradB[2 * 3 + 1] + B[2] * gradB[2 * 3 + 2];
+    if (q != 0.0 && vpar != 0.0) {
+      double BxBB[3] = {B[1] * BB[2] - B[2] * BB[1], B[2] * BB[0] - B[0] * BB[2], B[0] * BB[1] - B[1] * BB[0]};
+      const double invAbsB4 = 1.0 / (absB2 * absB2);
+      const double c = (m * vpar * vpar / q) * invAbsB4;
+      vdrift[0] += c * BxBB[0];
+      vdrift[1] += c * BxBB[1];
+      vdrift[2] += c * BxBB[2];
+    }
+    if (!std::isfinite(vdrift[0]) || !std::isfinite(vdrift[1]) || !std::isfinite(vdrift[2]) || !std::isfinite(dvpar_dt)) {
+      vdrift[0] = 0.0, vdrift[1] = 0.0, vdrift[2] = 0.0;
+      dvpar_dt = 0.0;
+    }
+    return true;
+  }
+  // CommitReducedStateAndVelocity, :338-381 (v_normal and the stored drift velocity are functions of the state: not kept here)
+  bool Gyro_Commit(byte *ParticleData, int spec, const double *x, cTreeNode *node, double vpar, double mu, const double *vdrift_to_store) {
+    double absB = 0.0, b[3] = {0.0, 0.0, 0.0};
+    double vdrift_dummy[3] = {0.0, 0.0, 0.0};
+    double dvpar_dt_dummy = 0.0;
+    if (!Gyro_EvalRHS(x, node, vpar, mu, spec, absB, b, vdrift_dummy, dvpar_dt_dummy)) return false;
+    SetVParallel(vpar, ParticleData);
+    double v[3];
+    v[0] = b[0] * vpar + vdrift_to_store[0];
+    v[1] = b[1] * vpar + vdrift_to_store[1];
+    v[2] = b[2] * vpar + vdrift_to_store[2];
+    SetV(v, ParticleData);
+    return true;
+  }
+  // the tail both movers share: internal sphere, findTreeNode, FindCellIndex, temp list (:451-541, :630-719)
+  int Gyro_File(byte *ParticleData, long int ptr, const double *x, cTreeNode *startNode, int nThreads, int thread, cTreeNode **newNodeOut) {
+    cTreeNode *newNode;
+    if (cfg.internal_sphere_radius > 0.0) {
+      double r2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+      if (r2 < cfg.internal_sphere_radius * cfg.internal_sphere_radius) {
+        DeleteParticle(ptr);
+        return _PARTICLE_LEFT_THE_DOMAIN_;
+      } else
+        newNode = findTreeNode(x, startNode);
+    } else
+      newNode = findTreeNode(x, startNode);
+    int i, j, k;
+    cBlock *block;
+    if (newNode == NULL) return _ORACLE_ERROR_;
+    if (FindCellIndex(x, i, j, k, newNode) == -1) return _ORACLE_ERROR_;  // exit("cannot find cell index for moved particle")
+    if ((block = newNode->block) == NULL) return _ORACLE_ERROR_;          // exit("destination block is empty")
+    AttachToTempList(ptr, ParticleData, block, i, j, k, nThreads, thread);
+    *newNodeOut = newNode;
+    return _PARTICLE_MOTION_FINISHED_;
+  }
+  // Mover_FirstOrder, :383-544
+  int Gyro_Mover_FirstOrder(byte *ParticleData, long int ptr, double dtTotal, cTreeNode *startNode, int nThreads, int thread, cTreeNode **newNodeOut) {
+    double x[3];
+    GetX(x, ParticleData);
+    int spec = GetI(ParticleData);
+    const double mu = GetMagneticMoment(ParticleData);
+    double vpar = GetVParallel(ParticleData);
+    double absB = 0.0, b[3] = {0.0, 0.0, 0.0};
+    double vdrift[3] = {0.0, 0.0, 0.0};
+    double dvpar_dt = 0.0;
+    if (!Gyro_EvalRHS(x, startNode, vpar, mu, spec, absB, b, vdrift, dvpar_dt)) return _ORACLE_ERROR_;
+    x[0] += dtTotal * (vdrift[0] + b[0] * vpar);
+    x[1] += dtTotal * (vdrift[1] + b[1] * vpar);
+    x[2] += dtTotal * (vdrift[2] + b[2] * vpar);
+    SetX(x, ParticleData);  // (x is a pointer into the record in the reference)
+    vpar += dtTotal * dvpar_dt;
+    cTreeNode *newNode = findTreeNode(x, NULL);  // PIC::Mesh::Search::FindBlock
+    if (newNode == NULL) {
+      DeleteParticle(ptr);
+      return _PARTICLE_LEFT_THE_DOMAIN_;
+    }
+    double absB1 = 0.0, b1[3] = {0.0, 0.0, 0.0};
+    double vdrift1[3] = {0.0, 0.0, 0.0};
+    double dvpar_dt_dummy = 0.0;
+    if (!Gyro_EvalRHS(x, newNode, vpar, mu, spec, absB1, b1, vdrift1, dvpar_dt_dummy)) return _ORACLE_ERROR_;
+    if (!Gyro_Commit(ParticleData, spec, x, newNode, vpar, mu, vdrift1)) return _ORACLE_ERROR_;
+    return Gyro_File(ParticleData, ptr, x, startNode, nThreads, thread, newNodeOut);
+  }
+  // Mover_SecondOrder, :544-720 (midpoint)
+  int Gyro_Mover_SecondOrder(byte *ParticleData, long int ptr, double dtTotal, cTreeNode *startNode, int nThreads, int thread, cTreeNode **newNodeOut) {
+    double x[3];
+    GetX(x, ParticleData);
+    int spec = GetI(ParticleData);
+    const double mu = GetMagneticMoment(ParticleData);
+    const double vpar0 = GetVParallel(ParticleData);
+    const double x0[3] = {x[0], x[1], x[2]};
+    double absB0 = 0.0, b0[3] = {0.0, 0.0, 0.0};
+    double vdrift0[3] = {0.0, 0.0, 0.0};
+    double dvpar_dt0 = 0.0;
+    if (!Gyro_EvalRHS(x0, startNode, vpar0, mu, spec, absB0, b0, vdrift0, dvpar_dt0)) return _ORACLE_ERROR_;
+    double xHalf[3];
+    xHalf[0] = x0[0] + 0.5 * dtTotal * (vdrift0[0] + b0[0] * vpar0);
+    xHalf[1] = x0[1] + 0.5 * dtTotal * (vdrift0[1] + b0[1] * vpar0);
+    xHalf[2] = x0[2] + 0.5 * dtTotal * (vdrift0[2] + b0[2] * vpar0);
+    const double vparHalf = vpar0 + 0.5 * dtTotal * dvpar_dt0;
+    cTreeNode *nodeHalf = findTreeNode(xHalf, NULL);  // FindBlock
+    if (nodeHalf == NULL) {
+      DeleteParticle(ptr);
+      return _PARTICLE_LEFT_THE_DOMAIN_;
+    }
+    double absBH = 0.0, bH[3] = {0.0, 0.0, 0.0};
+    double vdriftH[3] = {0.0, 0.0, 0.0};
+    double dvpar_dtH = 0.0;
+    if (!Gyro_EvalRHS(xHalf, nodeHalf, vparHalf, mu, spec, absBH, bH, vdriftH, dvpar_dtH)) return _ORACLE_ERROR_;
+    x[0] = x0[0] + dtTotal * (vdriftH[0] + bH[0] * vparHalf);
+    x[1] = x0[1] + dtTotal * (vdriftH[1] + bH[1] * vparHalf);
+    x[2] = x0[2] + dtTotal * (vdriftH[2] + bH[2] * vparHalf);
+    SetX(x, ParticleData);
+    const double vpar1 = vpar0 + dtTotal * dvpar_dtH;
+    cTreeNode *newNode = findTreeNode(x, NULL);  // FindBlock
+    if (newNode == NULL) {
+      DeleteParticle(ptr);
+      return _PARTICLE_LEFT_THE_DOMAIN_;
+    }
+    double absB1 = 0.0, b1[3] = {0.0, 0.0, 0.0};
+    double vdrift1[3] = {0.0, 0.0, 0.0};
+    double dvpar_dt_dummy = 0.0;
+    if (!Gyro_EvalRHS(x, newNode, vpar1, mu, spec, absB1, b1, vdrift1, dvpar_dt_dummy)) return _ORACLE_ERROR_;
+    if (!Gyro_Commit(ParticleData, spec, x, newNode, vpar1, mu, vdrift1)) return _ORACLE_ERROR_;
+    return Gyro_File(ParticleData, ptr, x, startNode, nThreads, thread, newNodeOut);
+  }
+
   // Mover_SecondOrder, :292-619 (predictor-corrector)
   int GC_Mover_SecondOrder(byte *ParticleData, long int ptr, double dtTotal, cTreeNode *startNode, int nThreads, int thread, cTreeNode **newNodeOut) {
     cTreeNode *newNode = NULL;
@@ -2690,6 +2861,17 @@ void oracle_set_background_gca(oracle_ctx *o, const double *var15) {
 void oracle_set_background_gradB(oracle_ctx *o, const double *gradB) {
   for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + BackgroundGradB_d, gradB + 9 * (size_t)i, 9 * 8);
 }
+// the reduced state of the gyrokinetic movers, by ptr (PB::SetMagneticMoment / SetVParallel at injection)
+void oracle_set_reduced_state(oracle_ctx *o, const double *mu, const double *vpar, int64_t n) {
+  for (int64_t ptr = 0; ptr < n; ptr++) {
+    byte *pd = o->GetParticleDataPointer(ptr);
+    if (mu) oracle_ctx::SetMagneticMoment(mu[ptr], pd);
+    if (vpar) oracle_ctx::SetVParallel(vpar[ptr], pd);
+  }
+}
+void oracle_get_v_parallel(const oracle_ctx *o, double *vpar, int64_t n) {
+  for (int64_t ptr = 0; ptr < n; ptr++) vpar[ptr] = oracle_ctx::GetVParallel(o->GetParticleDataPointer(ptr));
+}
 void oracle_get_magnetic_moment(const oracle_ctx *o, double *mu, uint8_t *init_flag, int64_t n) {
   for (int64_t ptr = 0; ptr < n; ptr++) {
     const byte *pd = o->GetParticleDataPointer(ptr);
@@ -2785,7 +2967,7 @@ void oracle_get_particles(const oracle_ctx *o, double *x, double *v, double *w, 
 int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats *stats, int32_t *ret_code, int32_t *final_cell) {
   if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS && mover_id != AMPS_MOVER_BORIS &&
       mover_id != AMPS_MOVER_RELATIVISTIC_GCA && mover_id != AMPS_MOVER_GC_FIRST_ORDER && mover_id != AMPS_MOVER_GC_SECOND_ORDER &&
-      mover_id != AMPS_MOVER_MARKIDIS2010) {
+      mover_id != AMPS_MOVER_MARKIDIS2010 && mover_id != AMPS_MOVER_GYROKINETIC_FIRST_ORDER && mover_id != AMPS_MOVER_GYROKINETIC_SECOND_ORDER) {
     o->err = "oracle_move: mover not restated yet";
     return AMPS_GPU_ERR_ARG;
   }
@@ -2832,6 +3014,8 @@ int oracle_move(oracle_ctx *o, int mover_id, int n_threads, amps_gpu_move_stats 
       if (mover_id == AMPS_MOVER_GC_FIRST_ORDER) return o->GC_Mover_FirstOrder(pd, ptr, dtLocal, node, n_threads, thread, newNode);
       if (mover_id == AMPS_MOVER_GC_SECOND_ORDER) return o->GC_Mover_SecondOrder(pd, ptr, dtLocal, node, n_threads, thread, newNode);
       if (mover_id == AMPS_MOVER_MARKIDIS2010) return o->Markidis2010(pd, ptr, dtLocal, node, n_threads, thread, newNode);
+      if (mover_id == AMPS_MOVER_GYROKINETIC_FIRST_ORDER) return o->Gyro_Mover_FirstOrder(pd, ptr, dtLocal, node, n_threads, thread, newNode);
+      if (mover_id == AMPS_MOVER_GYROKINETIC_SECOND_ORDER) return o->Gyro_Mover_SecondOrder(pd, ptr, dtLocal, node, n_threads, thread, newNode);
       return o->Relativistic_Boris(pd, ptr, dtLocal, node, n_threads, thread, newNode);
     };
     long int *FirstCellParticleTable = block->FirstCellParticleTable;

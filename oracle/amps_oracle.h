@@ -57,6 +57,9 @@ void oracle_set_background_gradB(oracle_ctx *, const double *gradB);
 int oracle_magnetic_moment_init(oracle_ctx *, int mover_id, double *mu_out, int64_t n);
 /* by ptr: magnetic moment and InitFlag (bit 6 of the species byte) */
 void oracle_get_magnetic_moment(const oracle_ctx *, double *mu, uint8_t *init_flag, int64_t n);
+/* gyrokinetic reduced state by ptr: mu and v_parallel (either may be NULL) */
+void oracle_set_reduced_state(oracle_ctx *, const double *mu, const double *vpar, int64_t n);
+void oracle_get_v_parallel(const oracle_ctx *, double *vpar, int64_t n);
 /* exit records (domain faces / internal sphere) accumulated since the last call; returns their number */
 int64_t oracle_exit_records(oracle_ctx *, amps_gpu_exit_record *buf, int64_t max_records);
 

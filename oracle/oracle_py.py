@@ -36,6 +36,8 @@ def load(kind="parity"):
     lib.oracle_magnetic_moment_init.argtypes = [vp, C.c_int, vp, C.c_int64]
     lib.oracle_set_background_gradB.argtypes = [vp, vp]
     lib.oracle_get_magnetic_moment.argtypes = [vp, vp, vp, C.c_int64]
+    lib.oracle_set_reduced_state.argtypes = [vp, vp, vp, C.c_int64]
+    lib.oracle_get_v_parallel.argtypes = [vp, vp, C.c_int64]
     lib.oracle_add_particles.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64]
     lib.oracle_particle_count.restype = C.c_int64
     lib.oracle_particle_count.argtypes = [vp]
@@ -105,6 +107,17 @@ class Oracle:
         flag = np.zeros(self.n_added, dtype=np.uint8)
         self.lib.oracle_get_magnetic_moment(self.h, _p(mu), _p(flag), self.n_added)
         return mu, flag
+
+    def set_reduced_state(self, mu, vpar):
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        vpar = np.ascontiguousarray(vpar, dtype=np.float64)
+        assert mu.shape == (self.n_added,) and vpar.shape == (self.n_added,)
+        self.lib.oracle_set_reduced_state(self.h, _p(mu), _p(vpar), self.n_added)
+
+    def v_parallel(self):
+        a = np.empty(self.n_added)
+        self.lib.oracle_get_v_parallel(self.h, _p(a), self.n_added)
+        return a
 
     def exit_records(self, max_records=1 << 20):
         from amps_b200._capi import ExitRecord

@@ -58,6 +58,7 @@ def write_case(path, m, cfg, parts, fields):
     rec[:, OFF_PREV:OFF_PREV + 8] = prv.view(np.uint8).reshape(n, 8)
     lay = _capi.AosLayout()
     lay.stride, lay.off_species, lay.off_v, lay.off_x, lay.off_w, lay.off_mu, lay.off_next, lay.off_prev = STRIDE, OFF_SPEC, OFF_V, OFF_X, OFF_W, -1, OFF_NEXT, OFF_PREV
+    lay.off_vpar = -1
     with open(path, "wb") as f:
         blob(f, bytes(cfg))
         c = m.c
