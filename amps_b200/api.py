@@ -242,6 +242,18 @@ class Context:
         self._ck(self.lib.amps_gpu_net_charge(self._h, charge_conv, _ptr(rho)))
         return rho
 
+    def SampleCells(self):
+        """PIC::Sampling: add one sample of the resident particles to the collecting buffer on the device"""
+        self._ck(self.lib.amps_gpu_sample_cells(self._h))
+
+    def sample_download(self, clear=False):
+        """-> (buffer [n_cells, n_species, 13], particles sampled per species)"""
+        n_cells = self.mesh.c.n_leaves * int(np.prod(self.mesh.block_cells))
+        out = np.empty((n_cells, self.cfg.n_species, 13))
+        cnt = np.zeros(_capi.MAX_SPECIES, dtype=np.int64)
+        self._ck(self.lib.amps_gpu_sample_download(self._h, _ptr(out), _ptr(cnt), 1 if clear else 0))
+        return out, cnt[: self.cfg.n_species]
+
     def ComputeSpeciesMoments(self, download=True):
         """corner species moments of UpdateJMassMatrix (_PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_): [n_corners, n_species, 10]"""
         out = np.empty((self.mesh.n_corners, self.cfg.n_species, 10)) if download else None

@@ -124,6 +124,8 @@ void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const
 void launch_move_gyrokinetic(const DevMesh &m, const DevSpecies &sp, int order, int interp, double rSphere, ParticleSoA p, const int *nSlots,
                              long long nUpper, const double *bgTile, const double *gradBTile, const double *uE, const double *uB,
                              const double *uGradB, int *cellCount, DevMoveStats *stats, cudaStream_t s);
+void launch_sample_cells(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, double *sample, unsigned long long *nSampled,
+                         int nSM, cudaStream_t s);
 void launch_species_moments(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, double *spec, int nSM, cudaStream_t s);
 void launch_correct_particle_location(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *nSlots, long long nUpper, const double *phi,
                                       const double *spec, const unsigned *neibMask, double qom0, int *cellCount, unsigned long long *counters,

@@ -54,6 +54,8 @@ struct amps_gpu_ctx {
   unsigned char *d_redoMask = nullptr;  // particles the fast mover left to the exact kernel
   int *d_perm = nullptr;      // sorted position -> slot (fused sort + deposit inside amps_gpu_step)
   double *d_rho = nullptr;    // ComputeNetCharge: rho_new on the unique centre nodes
+  double *d_sample = nullptr;                 // PIC::Sampling collecting buffer [nCells][n_species][13]
+  unsigned long long *d_nSampled = nullptr;   // particles sampled per species
   double *d_spec = nullptr;   // species moments on the unique corners [nCorners][n_species][10]
   double *d_phi = nullptr;    // div-E correction potential on the unique centre nodes
   unsigned *d_neibMask = nullptr;            // [nLeaves] bit (sx+1)+3(sy+1)+9(sz+1): no (in use) neighbour block in that direction
@@ -318,7 +320,7 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   for (cudaEvent_t e : ctx->dlEvents) cudaEventDestroy(e);
   if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   if (ctx->evCounts) cudaEventDestroy(ctx->evCounts);
-  cudaFree(ctx->d_spec), cudaFree(ctx->d_phi), cudaFree(ctx->d_cplCount);
+  cudaFree(ctx->d_spec), cudaFree(ctx->d_phi), cudaFree(ctx->d_cplCount), cudaFree(ctx->d_sample), cudaFree(ctx->d_nSampled);
   if (ctx->evBoundary) cudaEventDestroy(ctx->evBoundary);
   if (ctx->evRecv) cudaEventDestroy(ctx->evRecv);
   if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
@@ -370,7 +372,7 @@ static int release_mesh(amps_gpu_ctx *ctx) {
     p = nullptr;
   };
   drop(ctx->d_gcaVar), drop(ctx->d_gcaTile), drop(ctx->d_gradBVar), drop(ctx->d_gradBTile);
-  drop(ctx->d_leafRedo), drop(ctx->d_rho), drop(ctx->d_spec), drop(ctx->d_phi);
+  drop(ctx->d_leafRedo), drop(ctx->d_rho), drop(ctx->d_spec), drop(ctx->d_phi), drop(ctx->d_sample), drop(ctx->d_nSampled);
   drop(ctx->d_bgE), drop(ctx->d_bgB), drop(ctx->d_bgTile);
   drop(ctx->d_sendBuf), drop(ctx->d_recvBuf), drop(ctx->d_sendCount), drop(ctx->d_allCounts), drop(ctx->d_errFlag);
   for (int *&p : ctx->d_sharedUid) drop(p);
@@ -1261,6 +1263,43 @@ int amps_gpu_deposit_JM(amps_gpu_ctx *ctx, double *particle_energy, double *cfl)
     if (cfl)
       for (int s = 0; s < ctx->cfg.n_species; s++) memcpy(&cfl[s], &c[s], 8);
   }
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_sample_cells(amps_gpu_ctx *ctx) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "sample_cells before mesh_upload");
+  if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "sample_cells needs the (block,cell)-sorted layout: call amps_gpu_sort");
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc;
+  const size_t n = (size_t)ctx->nCells * ctx->sp.n * 13;
+  if (!ctx->d_sample) {
+    if ((rc = dev_alloc(ctx, &ctx->d_sample, n))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_nSampled, (size_t)AMPS_GPU_MAX_SPECIES))) return rc;
+    CK(cudaMemsetAsync(ctx->d_sample, 0, sizeof(double) * n, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_nSampled, 0, sizeof(unsigned long long) * AMPS_GPU_MAX_SPECIES, ctx->stream));
+  }
+  launch_sample_cells(ctx->dm, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_sample, ctx->d_nSampled, ctx->nSM, ctx->stream);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_sample_download(amps_gpu_ctx *ctx, double *sample, int64_t *n_sampled, int clear) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  if (!ctx->d_sample) FAIL(AMPS_GPU_ERR_STATE, "sample_download before amps_gpu_sample_cells");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const size_t n = (size_t)ctx->nCells * ctx->sp.n * 13;
+  unsigned long long cnt[AMPS_GPU_MAX_SPECIES];
+  if (sample) CK(cudaMemcpyAsync(sample, ctx->d_sample, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(cnt, ctx->d_nSampled, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+  if (clear) {
+    CK(cudaMemsetAsync(ctx->d_sample, 0, sizeof(double) * n, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_nSampled, 0, sizeof(cnt), ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (n_sampled)
+    for (int s = 0; s < ctx->sp.n; s++) n_sampled[s] = (int64_t)cnt[s];
   return AMPS_GPU_OK;
 }
 

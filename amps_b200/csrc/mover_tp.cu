@@ -1538,6 +1538,57 @@ void launch_species_moments(const DevMesh &m, const DevSpecies &sp, ParticleSoA 
 }
 
 // ------------------------------------------------------------------------------------------------
+// f3: PIC::Sampling::ProcessCell  src/pic/pic.cpp:705-990 on the sorted store: per cell and species 13 sums (weight, number,
+// number density, w v, w v^2, w |v|, w v_i v_(i+1)) ADDED to the collecting buffer sample[cell][species][13].  One warp per cell.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sample_cells_kernel(DevMesh m, DevSpecies sp, ParticleSoA p, const int *__restrict__ cellStart,
+                                                          double *__restrict__ sample, unsigned long long *__restrict__ nSampled) {
+  const int lane = threadIdx.x & 31;
+  const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
+  const int C = m.cellsPerBlock, nS = sp.n, nCells = m.nLeaves * C;
+  for (int cell = warpGlobal; cell < nCells; cell += nWarps) {
+    const int begin = cellStart[cell], end = cellStart[cell + 1];
+    if (begin == end) continue;
+    const LeafGeo &lg = m.leaf[cell / C];
+    const double Measure = ((lg.xmax[0] - lg.xmin[0]) / m.N[0]) * ((lg.xmax[1] - lg.xmin[1]) / m.N[1]) * ((lg.xmax[2] - lg.xmin[2]) / m.N[2]);
+    unsigned present = 0;
+    for (int ip = begin + lane; ip < end; ip += 32) present |= 1u << (p.spec[ip] & 0x3f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) present |= __shfl_xor_sync(0xffffffffu, present, o);
+    for (int s = 0; s < nS; s++) {
+      if (!(present & (1u << s))) continue;
+      double a[13];
+#pragma unroll
+      for (int q = 0; q < 13; q++) a[q] = 0.0;
+      for (int ip = begin + lane; ip < end; ip += 32) {
+        if ((p.spec[ip] & 0x3f) != s) continue;
+        const double w = sp.weight[s] * p.w[ip];
+        const double v0 = p.v[0][ip], v1 = p.v[1][ip], v2 = p.v[2][ip];
+        a[0] += w, a[1] += 1.0, a[2] += w / Measure;
+        a[3] += v0 * w, a[4] += v1 * w, a[5] += v2 * w;
+        a[6] += (v0 * v0) * w, a[7] += (v1 * v1) * w, a[8] += (v2 * v2) * w;
+        a[9] += sqrt(v0 * v0 + v1 * v1 + v2 * v2) * w;
+        a[10] += (v0 * v1) * w, a[11] += (v1 * v2) * w, a[12] += (v2 * v0) * w;
+      }
+#pragma unroll
+      for (int q = 0; q < 13; q++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
+      if (lane == 0) {
+        double *d = sample + ((size_t)cell * nS + s) * 13;  // the cell belongs to this warp: no atomics
+#pragma unroll
+        for (int q = 0; q < 13; q++) d[q] += a[q];
+        atomicAdd(&nSampled[s], (unsigned long long)(a[1] + 0.5));
+      }
+    }
+  }
+}
+void launch_sample_cells(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, double *sample, unsigned long long *nSampled,
+                         int nSM, cudaStream_t s) {
+  sample_cells_kernel<<<nSM * 8, 256, 0, s>>>(m, sp, p, cellStart, sample, nSampled);
+}
+
+// ------------------------------------------------------------------------------------------------
 // f4: ECSIM::CorrectParticleLocation  src/pic/pic_field_solver_ecsim.cpp:4440-4688
 // Species 0 is displaced along -grad(phi)/(4 pi rho_e) (phi on the cell centres, rho_e = species-0 density on the closest
 // corner, at most 0.1 cell) and re-filed; other species and cells at a block side without an (in use) neighbour keep their

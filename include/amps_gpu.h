@@ -315,6 +315,16 @@ int amps_gpu_step_JM(amps_gpu_ctx *ctx, int mover_id, double *J_host, double *M_
  * on the device).  Single-rank: the sum over ranks of shared centres is the caller's (ProcessNetCharge).            */
 int amps_gpu_net_charge(amps_gpu_ctx *ctx, double charge_conv, double *rho_center);
 
+/* PIC::Sampling::SamplingManager() + ProcessCell (pic.cpp:1045-1082, :705-990) on the device store: one more sample is ADDED to the
+ * collecting buffer sample[n_leaves*cells][n_species][13] = {ParticleWeight, ParticleNumber, NumberDensity (w / cell volume),
+ * ParticleVelocity[3] (w v), ParticleVelocity2[3] (w v_i^2), ParticleSpeed (w |v|), ParticleVelocity2Tensor[3] (w v_i v_(i+1)%3)} --
+ * the sampled datums of pic.h:4117-4130 with the velocity tensor on; parallel/tangential temperature, internal degrees of freedom,
+ * dust and user sampling are not sampled.  Every block is sampled, ghost blocks included, like the reference.  Needs the sorted
+ * layout.  amps_gpu_sample_download copies the buffer (may be NULL) and the number of particles sampled per species since the
+ * last clear (localSimulatedSpeciesParticleNumber); clear != 0 starts a new collecting period.                                  */
+int amps_gpu_sample_cells(amps_gpu_ctx *ctx);
+int amps_gpu_sample_download(amps_gpu_ctx *ctx, double *sample, int64_t *n_sampled, int clear);
+
 /* The per-species corner moments UpdateJMassMatrix samples when _PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_ is on
  * (pic_field_solver_ecsim.cpp:2270-2300 per particle, :2384-2392 per cell, :3874-3879 flush; corner buffer from
  * SpeciesDataIndex[0] = 9+243 on, :527-531): spec_corner[n_corners][n_species][10] =

@@ -161,6 +161,8 @@ struct oracle_ctx {
   std::vector<double> cornerData, centerData;
   std::vector<double> cornerSpec;  // [n_corners][10*n_species]: corner buffer from SpeciesDataIndex[0] on (:527-531)
   std::vector<double> phiCenter;   // [n_centers]: centre buffer, phiIndex (div-E correction potential)
+  std::vector<double> cellSample;  // [n_leaves*cells][n_species][13]: the collecting sampling buffer of the cells (pic.h:4117-4130)
+  std::vector<long long> sampledParticles;  // localSimulatedSpeciesParticleNumber
   std::vector<long int> listStorage;
   std::vector<cTempList> threadListStorage;
   int nThreadListTables;
@@ -2116,6 +2118,55 @@ struct oracle_ctx {
     return _PARTICLE_MOTION_FINISHED_;
   }
 
+  // f3: PIC::Sampling::SamplingManager + ProcessCell, src/pic/pic.cpp:1045-1082, :705-990 (velocity tensor on, parallel/tangential
+  // temperature, internal degrees of freedom, dust and user sampling off).  Per cell and species, added to the collecting buffer:
+  //  [0] DatumParticleWeight  [1] DatumParticleNumber  [2] DatumNumberDensity (w / cell->Measure, Measure = cell volume)
+  //  [3..5] DatumParticleVelocity (w v)  [6..8] DatumParticleVelocity2 (w v_i^2)  [9] DatumParticleSpeed (w |v|)
+  //  [10..12] DatumParticleVelocity2Tensor (w v_i v_{(i+1)%3})
+  int SampleCells() {
+    const int nS = cfg.n_species, nC = nCellsBlock();
+    if (cellSample.size() != blocks.size() * (size_t)nC * nS * 13) cellSample.assign(blocks.size() * (size_t)nC * nS * 13, 0.0);
+    if (sampledParticles.size() != (size_t)nS) sampledParticles.assign(nS, 0);
+    for (size_t nLocalNode = 0; nLocalNode < blocks.size(); nLocalNode++) {
+      cTreeNode *node = BlockTable[nLocalNode];
+      cBlock *block = node->block;
+      if (!block) continue;
+      double Measure = 1.0;
+      Measure *= (node->xmax[0] - node->xmin[0]) / _BLOCK_CELLS_X_;
+      Measure *= (node->xmax[1] - node->xmin[1]) / _BLOCK_CELLS_Y_;
+      Measure *= (node->xmax[2] - node->xmin[2]) / _BLOCK_CELLS_Z_;
+      for (int c = 0; c < nC; c++) {
+        long int ptr = block->FirstCellParticleTable[c];
+        double *cell = cellSample.data() + (nLocalNode * nC + c) * (size_t)nS * 13;
+        while (ptr != -1) {
+          byte *ParticleData = GetParticleDataPointer(ptr);
+          double v[3], Speed2 = 0.0, miscv2[3], v2tensor[3];
+          int s = GetI(ParticleData);
+          GetV(v, ParticleData);
+          sampledParticles[s]++;
+          double LocalParticleWeight = cfg.species_weight[s];
+          LocalParticleWeight *= GetIndividualStatWeightCorrection(ParticleData);
+          double *d = cell + (size_t)s * 13;
+          d[0] += LocalParticleWeight * 1.0;
+          d[1] += 1.0 * 1.0;
+          d[2] += (LocalParticleWeight / Measure) * 1.0;
+          for (int idim = 0; idim < 3; idim++) {
+            double v2 = v[idim] * v[idim];
+            Speed2 += v2;
+            miscv2[idim] = v2;
+          }
+          for (int i = 0; i < 3; i++) d[3 + i] += v[i] * LocalParticleWeight;
+          for (int i = 0; i < 3; i++) d[6 + i] += miscv2[i] * LocalParticleWeight;
+          d[9] += sqrt(Speed2) * LocalParticleWeight;
+          for (int idim = 0; idim < 3; idim++) v2tensor[idim] = v[idim] * v[(idim + 1) % 3];
+          for (int i = 0; i < 3; i++) d[10 + i] += v2tensor[i] * LocalParticleWeight;
+          ptr = GetNext(ParticleData);
+        }
+      }
+    }
+    return AMPS_GPU_OK;
+  }
+
   // The _PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_ part of UpdateJMassMatrix / ProcessCell, src/pic/pic_field_solver_ecsim.cpp:
   // zero :3269-3271, per particle :2270-2300, per cell :2384-2392, flush :3874-3879.  Restated as its own pass over the same
   // cells in the same order (the sums per corner see the same terms in the same order as inside ProcessCell).
@@ -2828,6 +2879,13 @@ void oracle_set_background(oracle_ctx *o, const double *E_center, const double *
     for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + BackgroundE_d, E_center + 3 * (size_t)i, 24);
   if (B_center)
     for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + BackgroundB_d, B_center + 3 * (size_t)i, 24);
+}
+int oracle_sample_cells(oracle_ctx *o, double *sample, int64_t *n_sampled) {
+  int rc = o->SampleCells();
+  if (sample) memcpy(sample, o->cellSample.data(), sizeof(double) * o->cellSample.size());
+  if (n_sampled)
+    for (int s = 0; s < o->cfg.n_species; s++) n_sampled[s] = o->sampledParticles[s];
+  return rc;
 }
 int oracle_species_moments(oracle_ctx *o, double *spec) {
   int rc = o->ComputeSpeciesMoments();

@@ -51,6 +51,7 @@ def load(kind="parity"):
     lib.oracle_check_particle_lists.argtypes = [vp]
     lib.oracle_net_charge.argtypes = [vp, C.c_double, vp]
     lib.oracle_species_moments.argtypes = [vp, vp]
+    lib.oracle_sample_cells.argtypes = [vp, vp, vp]
     lib.oracle_set_phi.argtypes = [vp, vp]
     lib.oracle_correct_particle_location.argtypes = [vp, C.c_double, C.c_double, vp, vp, vp]
     lib.oracle_coupler_stencil.argtypes = [vp, vp, C.c_int, vp, vp]
@@ -215,6 +216,14 @@ class Oracle:
         rho = np.zeros(self.mesh.n_centers)
         assert self.lib.oracle_net_charge(self.h, charge_conv, _p(rho)) == 0
         return rho
+
+    def sample_cells(self):
+        """PIC::Sampling: one more sample in the collecting buffer -> (buffer [n_cells, n_species, 13], particles sampled so far per species)"""
+        n_cells = self.mesh.c.n_leaves * int(np.prod(self.mesh.block_cells))
+        out = np.zeros((n_cells, self.cfg.n_species, 13))
+        cnt = np.zeros(self.cfg.n_species, dtype=np.int64)
+        assert self.lib.oracle_sample_cells(self.h, _p(out), _p(cnt)) == 0
+        return out, cnt
 
     def species_moments(self):
         """corner species moments of UpdateJMassMatrix (_PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_): [n_corners, n_species, 10]"""
