@@ -34,6 +34,36 @@ def test_empty_store_steps_and_deposits_zero():
     J, M = np.ones((m.n_corners, 3)), np.ones((m.n_corners, 243))
     g.step_JM(J, M)
     assert not J.any() and not M.any() and g.particle_count() == 0
+    # the other particle passes on an empty store: zeros, no error
+    assert not g.ComputeNetCharge(1.0).any()
+    assert not g.ComputeSpeciesMoments().any()
+    g.SetPhi(np.linspace(0.0, 1.0, m.n_centers))
+    assert g.CorrectParticleLocation(1.0, 1.0) == (0, 0)
+    g.sort()
+    g.SampleCells()
+    s, cnt = g.sample_download(clear=True)
+    assert not s.any() and not cnt.any()
+    g.close()
+
+
+def test_only_ions_are_not_shifted_and_one_species_cells():
+    """CorrectParticleLocation moves species 0 only; cells that hold one species leave the other species' moments and samples zero"""
+    m, cfg, parts, fields = pu.make_case(n_cells=(16, 16, 16), ppc=3, seed=91)
+    x, v, w, sp, cells = parts
+    ions = sp == 1
+    g = api.Context(cfg, m)
+    g.particles_upload(x[:, ions], v[:, ions], w[ions], sp[ions], cells[ions])
+    mom = g.ComputeSpeciesMoments()
+    assert not mom[:, 0, :].any() and mom[:, 1, 0].min() >= 0 and mom[:, 1, 0].sum() > 0
+    g.SetPhi(np.sin(np.arange(m.n_centers) * 0.37))
+    assert g.CorrectParticleLocation(1.0, 1.0) == (0, 0)
+    g.sort()
+    d = g.particles_download()
+    order = np.argsort(d["ptrs"])
+    assert (d["x"][:, order] == x[:, ions]).all() and (d["cells"][order] == cells[ions]).all()
+    g.SampleCells()
+    s, cnt = g.sample_download()
+    assert cnt[0] == 0 and cnt[1] == ions.sum() and not s[:, 0, :].any()
     g.close()
 
 
