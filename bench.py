@@ -112,8 +112,9 @@ def build_box(n_cells, ppc, block_cells=(8, 8, 8), seed=100, capacity_slack=1.02
     return m, cfg, parts, (E, B, B.copy())
 
 
-def cpu_port_rate(n_cells, ppc, steps, threads, warmup=1):
-    """oracle (CPU port of the reference path) on a bounded sample: move + list swap + periodic wrap + deposit"""
+def cpu_port_rate(n_cells, ppc, steps, threads, warmup=1, min_seconds=0.0, max_steps=400):
+    """oracle (CPU port of the reference path) on a bounded sample: move + list swap + periodic wrap + deposit.
+    At least `steps` steps, and further ones until `min_seconds` of timed CPU work are reached (at most max_steps)."""
     from oracle.oracle_py import Oracle
 
     m, cfg, parts, fields = build_box(n_cells, ppc)
@@ -128,7 +129,7 @@ def cpu_port_rate(n_cells, ppc, steps, threads, warmup=1):
         o.move_fast(0, threads)
         o.deposit(threads, want_arrays=False)
     per_step = []
-    for _ in range(steps):
+    while len(per_step) < steps or (sum(per_step) < min_seconds and len(per_step) < max_steps):
         t0 = time.perf_counter()
         o.move_fast(0, threads)
         o.deposit(threads, want_arrays=False)
@@ -412,7 +413,7 @@ def main():
             line["test_particle_movers"] = {"error": repr(exc)}
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        n_cpu, per = cpu_port_rate((32, 32, 32), args.ppc, 2, cores)
+        n_cpu, per = cpu_port_rate((32, 32, 32), args.ppc, 2, cores, min_seconds=12.0)  # a bounded sample: ~12 s of CPU work
         v = n_cpu * len(per) / float(np.sum(per))
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"32^3 cells x {args.ppc} ppc x 2 species = {n_cpu} particles, {len(per)} steps, oracle -O3 OpenMP"}
