@@ -177,6 +177,9 @@ PROTOTYPES = {
     "amps_gpu_v_parallel_upload": (C.c_int, [_vp, _vp, C.c_int64]),
     "amps_gpu_v_parallel_download": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "amps_gpu_net_charge": (C.c_int, [_vp, C.c_double, _vp]),
+    "amps_gpu_JM_packed_slots": (C.POINTER(C.c_int32), []),
+    "amps_gpu_JM_download_packed": (C.c_int, [_vp, _vp]),
+    "amps_gpu_step_JM_packed": (C.c_int, [_vp, C.c_int, _vp]),
     "amps_gpu_sample_cells": (C.c_int, [_vp]),
     "amps_gpu_sample_download": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "amps_gpu_species_moments": (C.c_int, [_vp, _vp]),

@@ -236,6 +236,44 @@ class Context:
         self._ck(self.lib.amps_gpu_step_JM(self._h, mover, _ptr(out_J), _ptr(out_M)))
         return out_J, out_M
 
+    def packed_slots(self):
+        p = self.lib.amps_gpu_JM_packed_slots()
+        return [int(p[i]) for i in range(14)]
+
+    def JM_download_packed(self):
+        out = np.empty((self.mesh.n_corners, 129))
+        self._ck(self.lib.amps_gpu_JM_download_packed(self._h, _ptr(out)))
+        return out
+
+    def step_JM_packed(self, out, mover=_capi.MOVER_LAPENTA2017):
+        """step() + the packed J/M rows (J[3] + 14 of the 27 neighbour blocks), download pipelined behind the deposit"""
+        assert out.shape == (self.mesh.n_corners, 129)
+        self._ck(self.lib.amps_gpu_step_JM_packed(self._h, mover, _ptr(out)))
+        return out
+
+    def expand_packed(self, packed):
+        """host side of the packed format (what the AMPS shim does while scattering into the corner buffers): J [n,3], M [n,243]"""
+        nb = self.mesh.corner_neighbours()  # [n_corners, 27] unique corner at offset slot, -1 outside
+        slots = self.packed_slots()
+        n = packed.shape[0]
+        J = packed[:, :3].copy()
+        M = np.zeros((n, 27, 9))
+        blocks = packed[:, 3:].reshape(n, 14, 9)
+        for b, s in enumerate(slots):
+            M[:, s, :] = blocks[:, b, :]
+        code = {0: 0, -1: 1, 1: 2}
+        inv = {v: k for k, v in code.items()}
+        for s in range(27):
+            if s in slots:
+                continue
+            d = (inv[s % 3], inv[(s // 3) % 3], inv[s // 9])
+            so = code[-d[0]] + 3 * code[-d[1]] + 9 * code[-d[2]]  # the opposite slot is one of the 14
+            b = slots.index(so)
+            partner = nb[:, s]
+            ok = partner >= 0
+            M[ok, s, :] = blocks[partner[ok], b, :]
+        return J, M.reshape(n, 243)
+
     def ComputeNetCharge(self, charge_conv=1.0):
         """ECSIM::ComputeNetCharge: rho_new on the unique centre nodes"""
         rho = np.empty(self.mesh.n_centers)

@@ -126,6 +126,7 @@ void launch_move_gyrokinetic(const DevMesh &m, const DevSpecies &sp, int order, 
                              const double *uGradB, int *cellCount, DevMoveStats *stats, cudaStream_t s);
 void launch_sample_cells(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, double *sample, unsigned long long *nSampled,
                          int nSM, cudaStream_t s);
+void launch_pack_jm_half(int uid0, int n, const double *J, const double *M, double *out, const int *slots14, cudaStream_t s);
 void launch_species_moments(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *cellStart, double *spec, int nSM, cudaStream_t s);
 void launch_correct_particle_location(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const int *nSlots, long long nUpper, const double *phi,
                                       const double *spec, const unsigned *neibMask, double qom0, int *cellCount, unsigned long long *counters,

@@ -54,6 +54,7 @@ struct amps_gpu_ctx {
   unsigned char *d_redoMask = nullptr;  // particles the fast mover left to the exact kernel
   int *d_perm = nullptr;      // sorted position -> slot (fused sort + deposit inside amps_gpu_step)
   double *d_rho = nullptr;    // ComputeNetCharge: rho_new on the unique centre nodes
+  double *d_pack = nullptr;                   // packed J + half mass matrix [nCorners][129] (amps_gpu_step_JM_packed)
   double *d_sample = nullptr;                 // PIC::Sampling collecting buffer [nCells][n_species][13]
   unsigned long long *d_nSampled = nullptr;   // particles sampled per species
   double *d_spec = nullptr;   // species moments on the unique corners [nCorners][n_species][10]
@@ -320,7 +321,7 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   for (cudaEvent_t e : ctx->dlEvents) cudaEventDestroy(e);
   if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   if (ctx->evCounts) cudaEventDestroy(ctx->evCounts);
-  cudaFree(ctx->d_spec), cudaFree(ctx->d_phi), cudaFree(ctx->d_cplCount), cudaFree(ctx->d_sample), cudaFree(ctx->d_nSampled);
+  cudaFree(ctx->d_spec), cudaFree(ctx->d_phi), cudaFree(ctx->d_cplCount), cudaFree(ctx->d_sample), cudaFree(ctx->d_nSampled), cudaFree(ctx->d_pack);
   if (ctx->evBoundary) cudaEventDestroy(ctx->evBoundary);
   if (ctx->evRecv) cudaEventDestroy(ctx->evRecv);
   if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
@@ -372,7 +373,7 @@ static int release_mesh(amps_gpu_ctx *ctx) {
     p = nullptr;
   };
   drop(ctx->d_gcaVar), drop(ctx->d_gcaTile), drop(ctx->d_gradBVar), drop(ctx->d_gradBTile);
-  drop(ctx->d_leafRedo), drop(ctx->d_rho), drop(ctx->d_spec), drop(ctx->d_phi), drop(ctx->d_sample), drop(ctx->d_nSampled);
+  drop(ctx->d_leafRedo), drop(ctx->d_rho), drop(ctx->d_spec), drop(ctx->d_phi), drop(ctx->d_sample), drop(ctx->d_nSampled), drop(ctx->d_pack);
   drop(ctx->d_bgE), drop(ctx->d_bgB), drop(ctx->d_bgTile);
   drop(ctx->d_sendBuf), drop(ctx->d_recvBuf), drop(ctx->d_sendCount), drop(ctx->d_allCounts), drop(ctx->d_errFlag);
   for (int *&p : ctx->d_sharedUid) drop(p);
@@ -1656,14 +1657,55 @@ int amps_gpu_exchange_JM(amps_gpu_ctx *ctx) {
 
 int amps_gpu_step(amps_gpu_ctx *ctx, int mover_id);
 // amps_gpu_step + amps_gpu_JM_download with the download pipelined behind the deposit
-int amps_gpu_step_JM(amps_gpu_ctx *ctx, int mover_id, double *J_host, double *M_host) {
-  if (!ctx || !J_host || !M_host) return AMPS_GPU_ERR_ARG;
+// neighbour slots kept by the packed rows: slot = sx + 3 sy + 9 sz with the per-dimension code 0 -> 0, -1 -> 1, +1 -> 2 (:625-637);
+// self, then of every pair (d, -d) the one whose highest non-zero dimension (z, then y, then x) points to +1
+static const int kPackedSlots[14] = {0, 2, 6, 7, 8, 18, 19, 20, 21, 22, 23, 24, 25, 26};
+const int32_t *amps_gpu_JM_packed_slots(void) {
+  static const int32_t s[14] = {0, 2, 6, 7, 8, 18, 19, 20, 21, 22, 23, 24, 25, 26};
+  return s;
+}
+
+static int pack_JM_all(amps_gpu_ctx *ctx, double *JM_packed_host, cudaStream_t s) {
+  int rc;
+  if (ctx->meshRefined) FAIL(AMPS_GPU_ERR_STATE, "the packed J/M rows pair the neighbour slots of equal cells: single-level meshes only");
+  if (!ctx->d_pack && (rc = dev_alloc(ctx, &ctx->d_pack, (size_t)ctx->dm.nCorners * 129))) return rc;
+  launch_pack_jm_half(0, ctx->dm.nCorners, ctx->d_J, ctx->d_M, ctx->d_pack, kPackedSlots, s);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(JM_packed_host, ctx->d_pack, sizeof(double) * 129 * (size_t)ctx->dm.nCorners, cudaMemcpyDeviceToHost, s));
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_JM_download_packed(amps_gpu_ctx *ctx, double *JM_packed_host) {
+  if (!ctx || !JM_packed_host) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "JM_download_packed before mesh_upload");
   CK(cudaSetDevice(ctx->cfg.device));
   int rc;
+  if ((rc = pack_JM_all(ctx, JM_packed_host, ctx->stream))) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AMPS_GPU_OK;
+}
+
+static int do_step_JM(amps_gpu_ctx *ctx, int mover_id, double *J_host, double *M_host, double *JM_packed_host);
+int amps_gpu_step_JM(amps_gpu_ctx *ctx, int mover_id, double *J_host, double *M_host) {
+  if (!ctx || !J_host || !M_host) return AMPS_GPU_ERR_ARG;
+  return do_step_JM(ctx, mover_id, J_host, M_host, nullptr);
+}
+int amps_gpu_step_JM_packed(amps_gpu_ctx *ctx, int mover_id, double *JM_packed_host) {
+  if (!ctx || !JM_packed_host) return AMPS_GPU_ERR_ARG;
+  return do_step_JM(ctx, mover_id, nullptr, nullptr, JM_packed_host);
+}
+static int do_step_JM(amps_gpu_ctx *ctx, int mover_id, double *J_host, double *M_host, double *JM_packed_host) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc;
+  const bool packed = JM_packed_host != nullptr;
+  if (packed && ctx->meshRefined) FAIL(AMPS_GPU_ERR_STATE, "the packed J/M rows pair the neighbour slots of equal cells: single-level meshes only");
   if (ctx->nRanks > 1) {  // shared corners change in the exchange: no early download
     if ((rc = amps_gpu_step(ctx, mover_id))) return rc;
+    if (packed) return amps_gpu_JM_download_packed(ctx, JM_packed_host);
     return amps_gpu_JM_download(ctx, J_host, M_host);
   }
+  if (packed && !ctx->d_pack && (rc = dev_alloc(ctx, &ctx->d_pack, (size_t)ctx->dm.nCorners * 129))) return rc;
   if ((rc = do_move(ctx, mover_id))) return rc;
   if (!ctx->meshReady || !ctx->fieldsReady) FAIL(AMPS_GPU_ERR_STATE, "deposit before mesh/fields upload");
   if (ctx->meshRefined && ctx->cfg.b_mode == AMPS_B_CENTER_BASED)
@@ -1710,13 +1752,19 @@ int amps_gpu_step_JM(amps_gpu_ctx *ctx, int mover_id, double *J_host, double *M_
       if (dbg) cudaEventRecord(tc0[k], ctx->copyStream);
       for (int r = ctx->dlRunStart[k]; r < ctx->dlRunStart[k + 1]; r++) {
         const size_t u0 = (size_t)ctx->dlRuns[r].uid0, n = (size_t)ctx->dlRuns[r].n;
-        CK(cudaMemcpyAsync(M_host + 243 * u0, ctx->d_M + 243 * u0, sizeof(double) * 243 * n, cudaMemcpyDeviceToHost, ctx->copyStream));
+        if (packed) {
+          launch_pack_jm_half((int)u0, (int)n, ctx->d_J, ctx->d_M, ctx->d_pack, kPackedSlots, ctx->copyStream);
+          ctx->launches++;
+          CK(cudaMemcpyAsync(JM_packed_host + 129 * u0, ctx->d_pack + 129 * u0, sizeof(double) * 129 * n, cudaMemcpyDeviceToHost, ctx->copyStream));
+        } else {
+          CK(cudaMemcpyAsync(M_host + 243 * u0, ctx->d_M + 243 * u0, sizeof(double) * 243 * n, cudaMemcpyDeviceToHost, ctx->copyStream));
+        }
       }
       if (dbg) cudaEventRecord(tc1[k], ctx->copyStream);
       c0 = ctx->dlCellEnd[k];
     }
-    // J is 1% of the volume: one copy behind the last range
-    CK(cudaMemcpyAsync(J_host, ctx->d_J, sizeof(double) * 3 * (size_t)ctx->dm.nCorners, cudaMemcpyDeviceToHost, ctx->copyStream));
+    // J is 1% of the volume: one copy behind the last range (the packed rows carry it)
+    if (!packed) CK(cudaMemcpyAsync(J_host, ctx->d_J, sizeof(double) * 3 * (size_t)ctx->dm.nCorners, cudaMemcpyDeviceToHost, ctx->copyStream));
   }
   ctx->cur = 1 - ctx->cur;
   ctx->sorted = true;

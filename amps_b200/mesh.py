@@ -63,6 +63,24 @@ class FlatMesh:
     def leaf_xmax(self):
         return self.arrays["node_xmax"].reshape(-1, 3)[self.arrays["leaf_node"]]
 
+    def corner_neighbours(self):
+        """[n_corners, 27] unique corner at neighbour slot sx+3sy+9sz (per-dimension code 0 -> 0, -1 -> 1, +1 -> 2, the numbering of
+        the ECSIM mass matrix, pic_field_solver_ecsim.cpp:625-637), -1 where there is none; from the leaves' corner tables"""
+        N, g = np.array(self.block_cells), np.array(self.ghost_cells)
+        T = N + 2 * g + 1
+        cu = self.arrays["leaf_corner_uid"].reshape(-1, T[2], T[1], T[0]).astype(np.int64)
+        nb = np.full((self.n_corners, 27), -1, dtype=np.int64)
+        code = {0: 0, -1: 1, 1: 2}
+        core = cu[:, g[2]:g[2] + N[2] + 1, g[1]:g[1] + N[1] + 1, g[0]:g[0] + N[0] + 1]
+        for dz in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    s = code[dx] + 3 * code[dy] + 9 * code[dz]
+                    sh = cu[:, g[2] + dz:g[2] + dz + N[2] + 1, g[1] + dy:g[1] + dy + N[1] + 1, g[0] + dx:g[0] + dx + N[0] + 1]
+                    ok = (core >= 0) & (sh >= 0)
+                    nb[core[ok], s] = sh[ok]
+        return nb
+
     def leaf_level(self):
         return self.arrays["node_level"][self.arrays["leaf_node"]]
 

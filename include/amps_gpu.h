@@ -315,6 +315,16 @@ int amps_gpu_step_JM(amps_gpu_ctx *ctx, int mover_id, double *J_host, double *M_
  * on the device).  Single-rank: the sum over ranks of shared centres is the caller's (ProcessNetCharge).            */
 int amps_gpu_net_charge(amps_gpu_ctx *ctx, double charge_conv, double *rho_center);
 
+/* J and M in packed rows: JM_packed[n_corners][129] = J[3], then the 9 doubles of the 14 neighbour slots listed by
+ * amps_gpu_JM_packed_slots() (self, and of every pair of opposite neighbours the one whose highest non-zero dimension is +1).
+ * The mass matrix is symmetric by construction - ProcessCell adds the same 3x3 block to corner c under neighbour c' and to corner
+ * c' under neighbour c (pic_field_solver_ecsim.cpp:2411-2420), i.e. M[c][slot(d)] == M[c+d][slot(-d)] - so the host rebuilds the
+ * other 13 slots while it scatters the rows into the corner buffers, and 270 MB instead of 516 MB cross PCIe per step at 64^3
+ * cells.  amps_gpu_step_JM_packed is amps_gpu_step_JM with this row format (same pipelining behind the deposit).               */
+const int32_t *amps_gpu_JM_packed_slots(void);
+int amps_gpu_JM_download_packed(amps_gpu_ctx *ctx, double *JM_packed_host);
+int amps_gpu_step_JM_packed(amps_gpu_ctx *ctx, int mover_id, double *JM_packed_host);
+
 /* PIC::Sampling::SamplingManager() + ProcessCell (pic.cpp:1045-1082, :705-990) on the device store: one more sample is ADDED to the
  * collecting buffer sample[n_leaves*cells][n_species][13] = {ParticleWeight, ParticleNumber, NumberDensity (w / cell volume),
  * ParticleVelocity[3] (w v), ParticleVelocity2[3] (w v_i^2), ParticleSpeed (w |v|), ParticleVelocity2Tensor[3] (w v_i v_(i+1)%3)} --

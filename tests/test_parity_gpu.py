@@ -107,3 +107,36 @@ def test_pipelined_step_download_equals_step_then_download(name):
     assert pu.rel_scaled(J1, J0) <= 1e-12 and pu.rel_scaled(M1, M0) <= 1e-12
     assert abs(d0[0] - d1[0]) <= 1e-12 * abs(d0[0])
     assert (np.sort(p0["ptrs"]) == np.sort(p1["ptrs"])).all() and (p0["cells"] == p1["cells"]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cube24_fast", "open_box", "ghost2"])
+def test_packed_rows_rebuild_the_full_mass_matrix(name):
+    """amps_gpu_step_JM_packed / amps_gpu_JM_download_packed ship J and 14 of the 27 neighbour blocks per corner; the other 13 are
+    the mirror images (ProcessCell adds the same 3x3 block to both corners of a pair, :2411-2420).  Rebuilt on the host, the rows
+    equal the full download: the shipped half exactly, the mirrored half to the summation order of the atomics."""
+    import numpy as np
+    from amps_b200 import api
+
+    kw = dict(CASES[name])
+    if name == "cube24_fast":
+        kw["n_cells"] = (32, 32, 32)
+    m, cfg, parts, fields = pu.make_case(**kw)
+    x, v, w, sp, cells = parts
+    E, B, Bcur = fields
+    g = api.Context(cfg, m)
+    g.fields_upload(E, B, Bcur)
+    g.particles_upload(x, v, w, sp, cells)
+    packed = np.full((m.n_corners, 129), np.nan)
+    g.step_JM_packed(packed)
+    J0, M0 = g.JM_download()
+    again = g.JM_download_packed()
+    J1, M1 = g.expand_packed(packed)
+    slots = g.packed_slots()
+    g.close()
+    assert not np.isnan(packed).any() and (again == packed).all()      # pipelined ranges == one pack of everything
+    assert (J1 == J0).all()
+    M0r, M1r = M0.reshape(-1, 27, 9), M1.reshape(-1, 27, 9)
+    assert (M1r[:, slots, :] == M0r[:, slots, :]).all()
+    assert pu.rel_scaled(M1, M0) <= 1e-12
+    assert np.abs(M0r[:, [s for s in range(27) if s not in slots], :]).max() > 0
