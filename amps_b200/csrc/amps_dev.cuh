@@ -59,6 +59,7 @@ struct DevMesh {
   // periodic "ghost" leaves that do not
   const int *depLeaf;  // [nLeaves]
   int nDepReal;
+
 };
 
 struct DevSpecies {
@@ -141,6 +142,7 @@ void launch_pack_leavers(const DevMesh &m, ParticleSoA p, const int *nSlots, lon
 void launch_unpack_arrivals(const DevMesh &m, const double *recvBuf, int nRecv, ParticleSoA p, int *nSlots, const int *g2l, const int *leafOwner, int me,
                             long long capacity, int *cellCount, int *errFlag, cudaStream_t s);
 void launch_pack_corners(const int *uids, int n, const double *J, const double *M, double *buf, cudaStream_t s);
+void launch_add_corners_atomic(const int *uids, int n, double *J, double *M, const double *buf, cudaStream_t s);
 void launch_add_corners(const int *uids, int n, double *J, double *M, const double *buf, cudaStream_t s);
 void launch_stage_background(const DevMesh &m, const double *E, const double *B, double *tile, cudaStream_t s);
 void launch_move_relativistic_boris(const DevMesh &m, const DevSpecies &sp, int interp, int backward, double c, double rSphere, long long exitCap,

@@ -99,6 +99,9 @@ struct amps_gpu_ctx {
   std::vector<char> h_leafGhost;              // [nLeaves] periodic ghost block: deposits nothing
   std::vector<int> h_realBefore;              // [nLeaves+1] depositing leaves with a smaller index (ascending order only)
   std::vector<std::vector<int>> h_sharedUid;  // per peer
+  int *d_sharedUidAll = nullptr;              // the peers' lists concatenated in rank order (one pack / one add launch)
+  long long nSharedAll = 0;
+  bool sharedAllDirty = true;
   int *d_depLeaf = nullptr;
   int nDepBoundary = 0;                       // leading entries of depLeaf that touch a shared corner (0: order is ascending)
   bool depDirty = false;                      // shared corners changed since depLeaf was built
@@ -328,7 +331,7 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   cudaFree(ctx->d_bgE), cudaFree(ctx->d_bgB), cudaFree(ctx->d_bgTile), cudaFree(ctx->d_exitBuf), cudaFree(ctx->d_exitCount);
   cudaFree(ctx->d_sendBuf), cudaFree(ctx->d_recvBuf), cudaFree(ctx->d_sendCount), cudaFree(ctx->d_allCounts), cudaFree(ctx->d_errFlag);
   for (int *p : ctx->d_sharedUid) cudaFree(p);
-  cudaFree(ctx->d_cornerSend), cudaFree(ctx->d_cornerRecv);
+  cudaFree(ctx->d_cornerSend), cudaFree(ctx->d_cornerRecv), cudaFree(ctx->d_sharedUidAll);
   cudaFree(ctx->d_Ehalf), cudaFree(ctx->d_Bprev), cudaFree(ctx->d_Bcur);
   cudaFree(ctx->d_eTile), cudaFree(ctx->d_bPrevTile), cudaFree(ctx->d_bCurTile);
   for (int b = 0; b < 2; b++) free_particles(ctx->buf[b]);
@@ -378,6 +381,8 @@ static int release_mesh(amps_gpu_ctx *ctx) {
   drop(ctx->d_sendBuf), drop(ctx->d_recvBuf), drop(ctx->d_sendCount), drop(ctx->d_allCounts), drop(ctx->d_errFlag);
   for (int *&p : ctx->d_sharedUid) drop(p);
   ctx->d_sharedUid.clear(), ctx->nShared.clear(), ctx->h_sharedUid.clear();
+  drop(ctx->d_sharedUidAll);
+  ctx->nSharedAll = 0, ctx->sharedAllDirty = true;
   drop(ctx->d_cornerSend), drop(ctx->d_cornerRecv);
   ctx->cornerBufDoubles = 0;
   drop(ctx->d_Ehalf), drop(ctx->d_Bprev), drop(ctx->d_Bcur), drop(ctx->d_eTile), drop(ctx->d_bPrevTile), drop(ctx->d_bCurTile);
@@ -1499,6 +1504,7 @@ int amps_gpu_set_shared_corners(amps_gpu_ctx *ctx, int peer, const int32_t *uids
   ctx->nShared[peer] = n;
   ctx->h_sharedUid[peer].assign(uids, uids + n);
   ctx->depDirty = true;
+  ctx->sharedAllDirty = true;
   if (n) {
     CK(cudaMalloc(&ctx->d_sharedUid[peer], n * sizeof(int)));
     CK(cudaMemcpy(ctx->d_sharedUid[peer], uids, n * sizeof(int), cudaMemcpyHostToDevice));
@@ -1609,14 +1615,29 @@ static int do_exchange_JM(amps_gpu_ctx *ctx) {
   cudaStream_t s = overlap ? ctx->commStream : ctx->stream;
   // all partial sums are packed before any is added, so every sharer ends with the same total
   Sub j0(ctx, 20);
+  if (ctx->sharedAllDirty) {
+    std::vector<int> all;
+    for (int r = 0; r < R; r++)
+      if (r != me) all.insert(all.end(), ctx->h_sharedUid[r].begin(), ctx->h_sharedUid[r].end());
+    cudaFree(ctx->d_sharedUidAll);
+    ctx->d_sharedUidAll = nullptr;
+    ctx->nSharedAll = (long long)all.size();
+    if (!all.empty()) {
+      CK(cudaMalloc(&ctx->d_sharedUidAll, all.size() * sizeof(int)));
+      CK(cudaMemcpy(ctx->d_sharedUidAll, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    ctx->sharedAllDirty = false;
+  }
   long long off = 0;
   std::vector<long long> offs(R, 0);
   for (int r = 0; r < R; r++) {
     offs[r] = off;
     if (r == me || ctx->nShared[r] == 0) continue;
-    launch_pack_corners(ctx->d_sharedUid[r], (int)ctx->nShared[r], ctx->d_J, ctx->d_M, ctx->d_cornerSend + off * 246, s);
-    ctx->launches++;
     off += ctx->nShared[r];
+  }
+  if (ctx->nSharedAll > 0) {
+    launch_pack_corners(ctx->d_sharedUidAll, (int)ctx->nSharedAll, ctx->d_J, ctx->d_M, ctx->d_cornerSend, s);
+    ctx->launches++;
   }
   j0.end();
   Sub j1(ctx, 21);
@@ -1634,9 +1655,8 @@ static int do_exchange_JM(amps_gpu_ctx *ctx) {
     CK(cudaStreamWaitEvent(s, ctx->evRecv, 0));
   }
   Sub j2(ctx, 22);
-  for (int r = 0; r < R; r++) {
-    if (r == me || ctx->nShared[r] == 0) continue;
-    launch_add_corners(ctx->d_sharedUid[r], (int)ctx->nShared[r], ctx->d_J, ctx->d_M, ctx->d_cornerRecv + offs[r] * 246, s);
+  if (ctx->nSharedAll > 0) {
+    launch_add_corners_atomic(ctx->d_sharedUidAll, (int)ctx->nSharedAll, ctx->d_J, ctx->d_M, ctx->d_cornerRecv, s);
     ctx->launches++;
   }
   j2.end();

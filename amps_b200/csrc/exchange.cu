@@ -14,6 +14,31 @@
 
 namespace amps {
 
+// one candidate: append it to its owner's send buffer when the owner is another rank
+__device__ __forceinline__ void pack_one_leaver(const ParticleSoA &p, int i, int k, const int *__restrict__ leafOwner, const int *__restrict__ leafGlobal,
+                                                int C, int me, double *__restrict__ sendBuf, long long capPerPeer, int *__restrict__ sendCount,
+                                                int *__restrict__ cellCount, int *__restrict__ errFlag) {
+  const int leaf = k / C;
+  const int dest = leafOwner[leaf];
+  if (dest == me) return;
+  const int slot = atomicAdd(&sendCount[dest], 1);
+  if (slot >= capPerPeer) {
+    atomicExch(errFlag, 1);
+    return;  // the particle stays (in a foreign block); the host reports AMPS_GPU_ERR_CAPACITY
+  }
+  const int L = migration_record_len(p);
+  double *r = sendBuf + ((size_t)dest * capPerPeer + slot) * L;
+  const long long gkey = (long long)leafGlobal[leaf] * C + (k - leaf * C);
+  r[0] = p.x[0][i], r[1] = p.x[1][i], r[2] = p.x[2][i];
+  r[3] = p.v[0][i], r[4] = p.v[1][i], r[5] = p.v[2][i];
+  r[6] = p.w[i];
+  r[7] = __longlong_as_double((gkey << 8) | (long long)p.spec[i]);
+  if (p.mu) r[8] = p.mu[i];
+  if (p.vpar) r[L - 1] = p.vpar[i];
+  atomicSub(&cellCount[k], 1);
+  p.key[i] = -1;
+}
+
 __global__ void __launch_bounds__(256) pack_leavers_kernel(ParticleSoA p, const int *__restrict__ nSlots, const int *__restrict__ leafOwner,
                                                           const int *__restrict__ leafGlobal, int C, int me, double *__restrict__ sendBuf,
                                                           long long capPerPeer, int *__restrict__ sendCount, int *__restrict__ cellCount,
@@ -30,25 +55,7 @@ __global__ void __launch_bounds__(256) pack_leavers_kernel(ParticleSoA p, const 
     const int i = 4 * q + j;
     const int k = ks[j];
     if (i >= n || k < 0) continue;
-    const int leaf = k / C;
-    const int dest = leafOwner[leaf];
-    if (dest == me) continue;
-    const int slot = atomicAdd(&sendCount[dest], 1);
-    if (slot >= capPerPeer) {
-      atomicExch(errFlag, 1);
-      continue;  // the particle stays (in a foreign block); the host reports AMPS_GPU_ERR_CAPACITY
-    }
-    const int L = migration_record_len(p);
-    double *r = sendBuf + ((size_t)dest * capPerPeer + slot) * L;
-    const long long gkey = (long long)leafGlobal[leaf] * C + (k - leaf * C);
-    r[0] = p.x[0][i], r[1] = p.x[1][i], r[2] = p.x[2][i];
-    r[3] = p.v[0][i], r[4] = p.v[1][i], r[5] = p.v[2][i];
-    r[6] = p.w[i];
-    r[7] = __longlong_as_double((gkey << 8) | (long long)p.spec[i]);
-    if (p.mu) r[8] = p.mu[i];
-    if (p.vpar) r[L - 1] = p.vpar[i];
-    atomicSub(&cellCount[k], 1);
-    p.key[i] = -1;
+    pack_one_leaver(p, i, k, leafOwner, leafGlobal, C, me, sendBuf, capPerPeer, sendCount, cellCount, errFlag);
     }
   }
 }
@@ -127,6 +134,19 @@ __global__ void __launch_bounds__(256) pack_jm_half_kernel(int uid0, int n, cons
   }
 }
 
+// all peers in one launch: the lists of the peers are concatenated in rank order like the buffers; a corner shared with several
+// ranks appears once per peer, hence the atomics
+__global__ void __launch_bounds__(256) add_corners_atomic_kernel(const int *__restrict__ uids, int n, double *__restrict__ J, double *__restrict__ M,
+                                                                const double *__restrict__ buf) {
+  const long long total = (long long)n * 246;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e / 246), q = (int)(e - (long long)c * 246);
+    const int u = uids[c];
+    if (q < 3) atomicAdd(&J[(size_t)u * 3 + q], buf[e]);
+    else atomicAdd(&M[(size_t)u * 243 + (q - 3)], buf[e]);
+  }
+}
+
 static inline int grid_for(long long n) {
   long long g = (n + 255) / 256;
   if (g < 1) g = 1;
@@ -155,6 +175,9 @@ void launch_pack_jm_half(int uid0, int n, const double *J, const double *M, doub
 }
 void launch_pack_corners(const int *uids, int n, const double *J, const double *M, double *buf, cudaStream_t s) {
   if (n > 0) pack_corners_kernel<<<grid_for((long long)n * 246), 256, 0, s>>>(uids, n, J, M, buf);
+}
+void launch_add_corners_atomic(const int *uids, int n, double *J, double *M, const double *buf, cudaStream_t s) {
+  if (n > 0) add_corners_atomic_kernel<<<grid_for((long long)n * 246), 256, 0, s>>>(uids, n, J, M, buf);
 }
 void launch_add_corners(const int *uids, int n, double *J, double *M, const double *buf, cudaStream_t s) {
   if (n > 0) add_corners_kernel<<<grid_for((long long)n * 246), 256, 0, s>>>(uids, n, J, M, buf);
