@@ -15,20 +15,21 @@
 // J[c] = sum_c' T[cls(c,c')][9..11].  That is 324 accumulators per cell and 324 DFMA per particle.
 //
 // The kernel is bound by the fp64 pipe and by shared-memory bandwidth, not by HBM (57 B/particle in,
-// ~4 KB/cell out).  Mapping: ONE WARP PER CELL, no block-level synchronisation at all; ~12 warps per SM
-// are resident and drift apart, so the latency-bound phase of one warp overlaps the DFMA-bound phase of
-// the others.  Per 32-particle chunk of its cell a warp runs
+// ~4 KB/cell out).  Mapping: ONE WARP PER CELL, no block-level synchronisation at all; 8 warps per SM
+// (240 registers) are resident and drift apart, so the latency-bound phase of one warp overlaps the DFMA-bound
+// phase of the others.  Per 32-particle chunk of its cell a warp runs
 //   phase 1  lane <-> particle: B gather (27 centres of the cell staged in shared memory), alpha, weights ->
 //            one 208-byte row per particle in the warp's shared-memory slab (row stride 26 doubles: the
 //            16-byte vector accesses of consecutive rows are bank-conflict free)
 //   phase 2  30 lanes = 6 register tiles (9 classes of one px  x  6 of the 12 columns) x 5 particle slices;
 //            per particle a lane issues 8 LDS.128 + 2 LDS.64 for 9 DMUL + 54 DFMA
 // and per cell
-//   reduce   the 5 slice partials are folded with 3 shuffle rounds (lanes 24..29 -> 0..5, 12..17 -> 0..5, ...)
+//   reduce   the 5 slice partials are folded through the slab (every lane stores its 54 sums, then sums 11 entries over the slices)
 //   flush    one fp64 RED per value into J[nCorners][3], M[nCorners][243] (576 + 24 per cell).
+// The particles of the next chunk - of this cell or, in its last chunk, of the warp's next cell - are requested one chunk ahead.
 //
-// The energy / cfl diagnostics of UpdateJMassMatrix (:2228-2238, :2355-2359, :3860-3864) are a separate
-// streaming kernel (diag_kernel).
+// The energy / cfl diagnostics of UpdateJMassMatrix (:2228-2238, :2355-2359, :3860-3864) are folded into phase 1 for at most
+// two species (kDiag), a separate streaming kernel (diag_kernel) otherwise.
 #include "amps_dev.cuh"
 
 namespace amps {
