@@ -96,6 +96,19 @@ __device__ __forceinline__ int centerLocalNumber(const DevMesh &m, int i, int j,
   return i + m.g[0] + m.TN[0] * (j + m.g[1] + (k + m.g[2]) * m.TN[1]);
 }
 
+// "done once per device" flags of the launch helpers (function attributes are per device; a process may drive several)
+struct OncePerDevice {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 // launch_deposit flags
 enum : unsigned {
   DEP_ZERO_JM = 1,     // zero J, M first

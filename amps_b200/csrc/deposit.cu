@@ -610,11 +610,8 @@ void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const
   const int ghostPass = (flags & DEP_GHOST_PASS) ? 1 : 0;
 #define AMPS_DEP_LAUNCH(CB, DG, GA)                                                                                          \
   do {                                                                                                                       \
-    static bool attrSet = false;                                                                                             \
-    if (!attrSet) {                                                                                                          \
-      cudaFuncSetAttribute(deposit_kernel<CB, DG, GA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
-      attrSet = true;                                                                                                        \
-    }                                                                                                                        \
+    static OncePerDevice once;                                                                                               \
+    if (once.first()) cudaFuncSetAttribute(deposit_kernel<CB, DG, GA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     deposit_kernel<CB, DG, GA><<<grid, DEP_THREADS, smem, s>>>(m, sp, p, cellStart, bCurTile, J, M, energy, cflBits, perm, dst, dep0, dep1, ghostPass); \
   } while (0)
   if (corner) {

@@ -117,9 +117,11 @@ __global__ void __launch_bounds__(256) add_corners_kernel(const int *__restrict_
 // The mass matrix is symmetric by construction: ProcessCell adds the SAME 3x3 block to corner c under neighbour c' and to corner
 // c' under neighbour c (pic_field_solver_ecsim.cpp:2411-2420), so M[c][slot(d)] == M[c+d][slot(-d)].  The packed row of a corner
 // keeps J[3] and the 14 neighbour slots of AMPS_GPU_JM_PACKED_SLOTS (self + one of each +-d pair): 129 of the 246 doubles.
-__constant__ int cPackedSlot[14];
+struct PackedSlots {
+  int s[14];
+};
 __global__ void __launch_bounds__(256) pack_jm_half_kernel(int uid0, int n, const double *__restrict__ J, const double *__restrict__ M,
-                                                          double *__restrict__ out) {
+                                                          double *__restrict__ out, PackedSlots slots) {
   const long long total = (long long)n * 129;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(e / 129), q = (int)(e - (long long)c * 129);
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(256) pack_jm_half_kernel(int uid0, int n, cons
     if (q < 3) v = J[u * 3 + q];
     else {
       const int b = (q - 3) / 9, r = (q - 3) - 9 * b;
-      v = M[u * 243 + 9 * cPackedSlot[b] + r];
+      v = M[u * 243 + 9 * slots.s[b] + r];
     }
     out[u * 129 + q] = v;
   }
@@ -166,12 +168,9 @@ void launch_unpack_arrivals(const DevMesh &m, const double *recvBuf, int nRecv, 
   bump_count_kernel<<<1, 1, 0, s>>>(nSlots, nRecv, capacity);
 }
 void launch_pack_jm_half(int uid0, int n, const double *J, const double *M, double *out, const int *slots14, cudaStream_t s) {
-  static bool set = false;
-  if (!set) {
-    cudaMemcpyToSymbol(cPackedSlot, slots14, 14 * sizeof(int));
-    set = true;
-  }
-  if (n > 0) pack_jm_half_kernel<<<grid_for((long long)n * 129), 256, 0, s>>>(uid0, n, J, M, out);
+  PackedSlots ps;
+  for (int i = 0; i < 14; i++) ps.s[i] = slots14[i];
+  if (n > 0) pack_jm_half_kernel<<<grid_for((long long)n * 129), 256, 0, s>>>(uid0, n, J, M, out, ps);
 }
 void launch_pack_corners(const int *uids, int n, const double *J, const double *M, double *buf, cudaStream_t s) {
   if (n > 0) pack_corners_kernel<<<grid_for((long long)n * 246), 256, 0, s>>>(uids, n, J, M, buf);

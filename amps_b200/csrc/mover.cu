@@ -427,11 +427,10 @@ void launch_move_lapenta(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, 
   if (redoLeafList && grid > 148 * 2) grid = 148 * 2;  // second pass: persistent CTAs over the (short) list of flagged blocks
   const bool cornerB = sp.bMode == AMPS_B_CORNER_BASED;
   if (smem <= 200 * 1024) {
-    static bool attrSet = false;
-    if (!attrSet) {
+    static OncePerDevice once;
+    if (once.first()) {
       cudaFuncSetAttribute(move_lapenta_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaFuncSetAttribute(move_lapenta_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attrSet = true;
     }
     if (cornerB)
       move_lapenta_kernel<true, true><<<grid, 256, smem, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, exitBuf, exitCount, exitCap, redoMask, redoLeafList, nRedoLeaves);

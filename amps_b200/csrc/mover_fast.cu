@@ -266,11 +266,10 @@ void launch_move_lapenta_fast(const DevMesh &m, const DevSpecies &sp, ParticleSo
   const int grid = m.nLeaves * slices;
   const bool cornerB = sp.bMode == AMPS_B_CORNER_BASED;
   if (smem <= 200 * 1024) {
-    static bool attrSet = false;
-    if (!attrSet) {
+    static OncePerDevice once;
+    if (once.first()) {
       cudaFuncSetAttribute(move_lapenta_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaFuncSetAttribute(move_lapenta_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attrSet = true;
     }
     if (cornerB) move_lapenta_fast_kernel<true, true><<<grid, 256, smem, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, redoMask, leafRedo, redoLeafList, nRedoLeaves);
     else move_lapenta_fast_kernel<true, false><<<grid, 256, smem, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, redoMask, leafRedo, redoLeafList, nRedoLeaves);

@@ -165,3 +165,57 @@ def test_mesh_reupload_starts_a_new_epoch():
         res = pu.compare(m, parts, ora, gpu)
         assert res["cell_mismatch"] == 0 and res["max_rel_x"] <= pu.REL_TOL and res["max_rel_J"] <= pu.REL_TOL and res["max_rel_M"] <= pu.REL_TOL, res
     g.close()
+
+
+@pytest.mark.gpu
+def test_aos_round_trip_carries_the_reduced_state():
+    """amps_gpu_particles_upload_aos / _download_aos on 89-byte records (the packed basic record + magnetic moment + v_parallel,
+    picParticleDataMacro.h): x, v, w, the species byte with its InitFlag, mu and v_parallel come back in the caller's slots after a
+    sort, and the rebuilt cell lists hold every particle once"""
+    import ctypes as C
+
+    OFF_NEXT, OFF_PREV, OFF_SPEC, OFF_V, OFF_X, OFF_W, OFF_MU, OFF_VPAR, STRIDE = 0, 8, 16, 17, 41, 65, 73, 81, 89
+    m, cfg, parts, fields = pu.make_case(n_cells=(16, 16, 16), ppc=3, seed=95)
+    x, v, w, sp, cells = parts
+    n = x.shape[1]
+    cfg.carry_magnetic_moment, cfg.carry_v_parallel = 1, 1
+    rng = np.random.default_rng(7)
+    slots = rng.permutation(n + 50)[:n].astype(np.int64)          # the particles sit in scattered ParticleBuffer slots
+    mu, vpar = rng.uniform(0.0, 1.0, n), rng.standard_normal(n)
+    spb = (sp | np.where(rng.uniform(size=n) < 0.5, 0x40, 0)).astype(np.uint8)  # InitFlag on half of them
+    buf = np.zeros((n + 50, STRIDE), dtype=np.uint8)
+    for off, arr in ((OFF_V, v.T), (OFF_X, x.T)):
+        buf[slots[:, None], off + np.arange(24)[None, :]] = np.ascontiguousarray(arr).view(np.uint8).reshape(n, 24)
+    for off, arr in ((OFF_W, w), (OFF_MU, mu), (OFF_VPAR, vpar)):
+        buf[slots[:, None], off + np.arange(8)[None, :]] = np.ascontiguousarray(arr).view(np.uint8).reshape(n, 8)
+    buf[slots, OFF_SPEC] = spb | 0x80                                # allocated bit
+    lay = _capi.AosLayout()
+    lay.stride, lay.off_species, lay.off_v, lay.off_x, lay.off_w, lay.off_mu, lay.off_next, lay.off_prev, lay.off_vpar = (
+        STRIDE, OFF_SPEC, OFF_V, OFF_X, OFF_W, OFF_MU, OFF_NEXT, OFF_PREV, OFF_VPAR)
+    g = api.Context(cfg, m)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    g._ck(g.lib.amps_gpu_particles_upload_aos(g._h, vp(buf), vp(slots), vp(np.ascontiguousarray(cells, dtype=np.int32)), n, C.byref(lay)))
+    g.sort()
+    out = np.zeros_like(buf)
+    out[:, OFF_SPEC] = 0x80
+    n_cells = m.c.n_leaves * int(np.prod(m.block_cells))
+    first = np.zeros(n_cells, dtype=np.int64)
+    nn = C.c_int64()
+    g._ck(g.lib.amps_gpu_particles_download_aos(g._h, vp(out), vp(first), n + 50, C.byref(lay), C.byref(nn)))
+    g.close()
+    assert nn.value == n
+    for off, ln in ((OFF_V, 24), (OFF_X, 24), (OFF_W, 8), (OFF_MU, 8), (OFF_VPAR, 8)):
+        assert (out[slots, off:off + ln] == buf[slots, off:off + ln]).all(), off
+    assert (out[slots, OFF_SPEC] == buf[slots, OFF_SPEC]).all()
+    # walk the lists: every slot exactly once, in its cell
+    nxt = out[:, OFF_NEXT:OFF_NEXT + 8].copy().view(np.int64).ravel()
+    seen = np.zeros(n + 50, dtype=np.int32)
+    cell_of = np.full(n + 50, -1, dtype=np.int64)
+    cell_of[slots] = cells
+    for c in np.nonzero(first >= 0)[0]:
+        p = first[c]
+        while p != -1:
+            seen[p] += 1
+            assert cell_of[p] == c
+            p = nxt[p]
+    assert (seen[slots] == 1).all() and seen.sum() == n
