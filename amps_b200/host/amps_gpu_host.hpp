@@ -6,6 +6,9 @@
 //   PIC::Mover::MoveParticles()    pic_mover.cpp:580-1088 (UserDefinedMoverManager hook, pic.h:5919)   -> MoveParticles()
 //   ECSIM::UpdateJMassMatrix()     pic_field_solver_ecsim.cpp:3244-3995                                  -> UpdateJMassMatrix()
 //   PIC::Mover::SetBlock_E/B       pic_mover.cpp:86-166                                                  -> SetFields()
+//   ECSIM::ComputeNetCharge()      pic_field_solver_ecsim.cpp:4690-4828                                  -> ComputeNetCharge()
+//   ECSIM::CorrectParticleLocation :4440-4688 (with the species corner moments of ProcessCell :2270-2300) -> CorrectParticleLocation()
+//   PIC::Sampling::SamplingManager pic.cpp:1045-1082, ProcessCell :705-990                               -> Sampling(), SampledData()
 //
 // Header only; needs nothing but amps_gpu.h and the C++ standard library.  Errors become std::runtime_error carrying
 // amps_gpu_last_error (AMPS maps them to exit(__LINE__,__FILE__,msg)).  There is no CPU fallback.
@@ -86,6 +89,33 @@ class EcsimHost {
 
   // one call for a whole particle phase when nothing on the host needs the intermediate state
   void MoveAndDeposit(double *J, double *M, int mover = AMPS_MOVER_LAPENTA2017) { check(amps_gpu_step_JM(ctx_, mover, J, M)); }
+
+  // the same with the packed rows JM[n_corners][129] (J + the 14 independent neighbour blocks, amps_gpu_JM_packed_slots):
+  // half the PCIe volume; the caller mirrors the other 13 blocks while scattering into the corner buffers
+  void MoveAndDepositPacked(double *JM129, int mover = AMPS_MOVER_LAPENTA2017) { check(amps_gpu_step_JM_packed(ctx_, mover, JM129)); }
+
+  // ECSIM::ComputeNetCharge(): rho_new on the unique centre nodes
+  void ComputeNetCharge(double charge_conv, double *rho_center) { check(amps_gpu_net_charge(ctx_, charge_conv, rho_center)); }
+
+  // ECSIM::CorrectParticleLocation() with phi of the Poisson solve on the unique centre nodes; returns {shifted, deleted}.
+  // The species corner moments it reads are sampled here (UpdateJMassMatrix does that in the reference); the lists are rebuilt.
+  struct ShiftCount {
+    int64_t shifted, deleted;
+  };
+  ShiftCount CorrectParticleLocation(const double *phi_center, double charge_conv, double mass_conv) {
+    ShiftCount c{0, 0};
+    check(amps_gpu_species_moments(ctx_, nullptr));
+    check(amps_gpu_phi_upload(ctx_, phi_center));
+    check(amps_gpu_correct_particle_location(ctx_, charge_conv, mass_conv, &c.shifted, &c.deleted));
+    check(amps_gpu_migrate(ctx_, nullptr, nullptr));  // PIC::Parallel::ExchangeParticleData()
+    check(amps_gpu_sort(ctx_));                        // exchangeParticleLocal(): the cell lists
+    return c;
+  }
+
+  // PIC::Sampling: one more sample of the resident particles in the collecting buffer on the device
+  void Sampling() { check(amps_gpu_sample_cells(ctx_)); }
+  // the collecting buffer sample[n_cells][n_species][13] and the particles sampled per species; clear starts a new period
+  void SampledData(double *sample, int64_t *n_sampled, bool clear) { check(amps_gpu_sample_download(ctx_, sample, n_sampled, clear ? 1 : 0)); }
 
   // epoch end: records and lists back into the caller's buffer
   int64_t DownloadParticles(ParticleBufferView &pb, long int *FirstCellParticleTable) {

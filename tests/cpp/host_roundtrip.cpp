@@ -80,6 +80,13 @@ int main(int argc, char **argv) {
     std::vector<double> J((size_t)mesh.n_corners * 3), M((size_t)mesh.n_corners * 243), cfl(AMPS_GPU_MAX_SPECIES, 0.0);
     double energy = 0.0;
     host.UpdateJMassMatrix(J.data(), M.data(), &energy, cfl.data());
+    // the other particle passes of the host layer on the moved, re-filed store
+    std::vector<double> rho((size_t)mesh.n_centers);
+    host.ComputeNetCharge(0.7, rho.data());
+    std::vector<double> sample((size_t)host.n_cells() * cfg.n_species * 13);
+    std::vector<int64_t> nSampled(AMPS_GPU_MAX_SPECIES, 0);
+    host.Sampling();
+    host.SampledData(sample.data(), nSampled.data(), true);
     // wipe the lists so that the download provably rebuilds them
     std::fill(first.begin(), first.end(), -7L);
     const int64_t n = host.DownloadParticles(pb, first.data());
@@ -93,6 +100,9 @@ int main(int argc, char **argv) {
     write_blob(o, M.data(), (int64_t)M.size() * 8);
     write_blob(o, &energy, 8);
     write_blob(o, cfl.data(), (int64_t)cfl.size() * 8);
+    write_blob(o, rho.data(), (int64_t)rho.size() * 8);
+    write_blob(o, sample.data(), (int64_t)sample.size() * 8);
+    write_blob(o, nSampled.data(), (int64_t)nSampled.size() * 8);
     fclose(o);
   } catch (const std::exception &e) {
     fprintf(stderr, "host_roundtrip: %s\n", e.what());

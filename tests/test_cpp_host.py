@@ -110,8 +110,21 @@ def test_cpp_host_matches_oracle(tmp_path, name, kw):
     cap = write_case(str(tmp_path / "case.bin"), m, cfg, parts, fields)
     r = subprocess.run([exe, str(tmp_path / "case.bin"), str(tmp_path / "out.bin")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 0 and "HOST_ROUNDTRIP_OK" in r.stdout, r.stderr
-    st_b, n_b, buf_b, first_b, J_b, M_b, e_b, cfl_b = read_blobs(str(tmp_path / "out.bin"))
+    st_b, n_b, buf_b, first_b, J_b, M_b, e_b, cfl_b, rho_b, smp_b, cnt_b = read_blobs(str(tmp_path / "out.bin"))
     ora = pu.run_oracle(m, cfg, parts, fields)
+    # ComputeNetCharge and Sampling of the host layer after the move: against the oracle in the same state
+    from oracle.oracle_py import Oracle
+    o = Oracle(cfg, m)
+    o.set_fields(*fields)
+    o.add_particles(*parts)
+    o.move(0, 1)
+    rho_ref = o.net_charge(0.7)
+    smp_ref, cnt_ref = o.sample_cells()
+    o.close()
+    assert pu.rel_scaled(np.frombuffer(rho_b), rho_ref) <= pu.REL_TOL
+    smp = np.frombuffer(smp_b).reshape(smp_ref.shape)
+    assert (smp[:, :, 1] == smp_ref[:, :, 1]).all() and pu.rel_scaled(smp, smp_ref) <= 1e-12
+    assert (np.frombuffer(cnt_b, dtype=np.int64)[: cfg.n_species] == cnt_ref).all()
     n = parts[0].shape[1]
     stats = struct.unpack("<8q", st_b[:64])
     keys = ["n_moved", "n_cross_cell", "n_cross_block", "n_left_domain", "n_not_in_use", "n_periodic_wrap", "n_error", "n_sub_steps"]
