@@ -34,7 +34,8 @@ def rel_scaled(a, b):
 
 
 def make_case(n_cells=(16, 16, 16), ppc=8, seed=3, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), E_amp=0.01, dt=1.0, vscale=1.0,
-              periodic=True, extra_capacity=0, boundary_mode=0, b_mode=0, amr_radii=None, ppc_by_level=None, exact_arithmetic=0):
+              periodic=True, extra_capacity=0, boundary_mode=0, b_mode=0, amr_radii=None, ppc_by_level=None, exact_arithmetic=0,
+              four_species=False):
     if amr_radii is not None:  # BASELINE config 4 (scaled): sphere-refined open box, mixed ppc, drifting Maxwellian
         nb = [n_cells[d] // block_cells[d] for d in range(3)]
         m = workload.amr_sphere_box(nb, block_cells, ghost_cells, radii=amr_radii)
@@ -51,6 +52,12 @@ def make_case(n_cells=(16, 16, 16), ppc=8, seed=3, block_cells=(8, 8, 8), ghost_
         x, v, w, sp, cells = workload.maxwellian_box(m, ppc, seed=seed)
         w[:] = 1.0
     v *= vscale
+    if four_species:
+        # e-, p+, a heavy ion and a NEUTRAL species (charge 0: pushed ballistically, deposits nothing, counts in energy and cfl):
+        # more than two species take the separate diagnostics kernel of the deposit
+        charge, mass, wgt = tuple(charge) + (1.0, 0.0), tuple(mass) + (16.0 * mass[1], 4.0 * mass[1]), tuple(wgt) + (wgt[0], 0.5 * wgt[0])
+        r4 = np.random.default_rng(seed + 2).uniform(size=sp.shape)
+        sp = np.where((sp == 1) & (r4 < 0.3), 2, np.where((sp == 1) & (r4 > 0.7), 3, sp)).astype(np.uint8)
     rng = np.random.default_rng(seed + 1)
     w = w * rng.uniform(0.5, 1.5, size=w.shape)  # exercise the individual weight correction
     cfg = api.make_config(block_cells, ghost_cells, charge, mass, wgt, dt, periodic=periodic, capacity=x.shape[1] + extra_capacity + 16,

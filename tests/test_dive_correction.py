@@ -66,7 +66,8 @@ def test_correct_particle_location_cpu():
 
 
 CASES = [dict(n_cells=(16, 16, 16), ppc=8, seed=55), dict(n_cells=(32, 16, 8), ppc=5, seed=57, block_cells=(16, 8, 4)),
-         dict(n_cells=(16, 16, 16), ppc=4, seed=59, ghost_cells=(2, 2, 2)), dict(n_cells=(16, 16, 16), ppc=6, seed=61, periodic=False)]
+         dict(n_cells=(16, 16, 16), ppc=4, seed=59, ghost_cells=(2, 2, 2)), dict(n_cells=(16, 16, 16), ppc=6, seed=61, periodic=False),
+         dict(n_cells=(16, 16, 16), ppc=6, seed=63, four_species=True)]
 
 
 @pytest.mark.gpu

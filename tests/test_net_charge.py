@@ -29,7 +29,8 @@ def test_total_charge_is_conserved_cpu():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kw", [dict(n_cells=(16, 16, 16), ppc=8, seed=43), dict(n_cells=(16, 16, 16), ppc=6, seed=45, periodic=False),
-                                dict(n_cells=(32, 16, 8), ppc=5, seed=47, block_cells=(16, 8, 4)), dict(n_cells=(16, 16, 16), ppc=4, seed=49, ghost_cells=(2, 2, 2))])
+                                dict(n_cells=(32, 16, 8), ppc=5, seed=47, block_cells=(16, 8, 4)), dict(n_cells=(16, 16, 16), ppc=4, seed=49, ghost_cells=(2, 2, 2)),
+                                dict(n_cells=(16, 16, 16), ppc=6, seed=51, four_species=True)])
 def test_gpu_net_charge_matches_oracle(kw):
     m, cfg, parts, fields = pu.make_case(**kw)
     ref = _oracle_rho(m, cfg, parts, 0.7)

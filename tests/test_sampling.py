@@ -32,7 +32,7 @@ def test_oracle_samples_are_the_cell_sums():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kw", [dict(n_cells=(16, 16, 16), ppc=8, seed=83), dict(n_cells=(32, 16, 8), ppc=5, seed=85, block_cells=(16, 8, 4)),
-                                dict(n_cells=(16, 16, 16), ppc=6, seed=87, periodic=False)])
+                                dict(n_cells=(16, 16, 16), ppc=6, seed=87, periodic=False), dict(n_cells=(16, 16, 16), ppc=6, seed=89, four_species=True)])
 def test_gpu_sampling_matches_oracle(kw):
     m, cfg, parts, fields = pu.make_case(**kw)
     x, v, w, sp, cells = parts
