@@ -14,6 +14,8 @@ CASES = {
     "dense_cells_320": dict(n_cells=(8, 8, 8), ppc=160, seed=17),  # cells larger than one deposit chunk / ring batch
     "open_box_user_function": dict(n_cells=(16, 16, 16), ppc=6, seed=15, periodic=False, vscale=6.0, boundary_mode=2),  # exit records
     "open_box": dict(n_cells=(16, 16, 16), ppc=6, seed=13, periodic=False, vscale=6.0),  # DELETE boundary
+    # 16^3-cell blocks: the E + B tiles (300 KB) do not fit in shared memory, the movers read them through L2 (kSmemTiles = false)
+    "big_blocks_16": dict(n_cells=(32, 32, 32), ppc=2, seed=27, block_cells=(16, 16, 16), vscale=4.0),
     "four_species_neutral": dict(n_cells=(16, 16, 16), ppc=8, seed=25, four_species=True, vscale=3.0),  # > 2 species: diag_kernel path
     # _PIC_FIELD_SOLVER_B_CORNER_BASED_: B on the corner nodes, same stencil as E (pic_mover_boris.cpp:952-965)
     "corner_B_periodic": dict(n_cells=(16, 16, 16), ppc=8, seed=19, b_mode=1),
