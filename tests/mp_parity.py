@@ -61,14 +61,20 @@ def main():
 
     cfg = api.make_config((8, 8, 8), (1, 1, 1), charge, mass, wgt, 1.0, periodic=True, capacity=n + 1024, device=local)
     cfg.exact_arithmetic = 1  # the sharding must not change a bit: compared bit for bit with the single-domain oracle
+    # the optional per-particle state (magnetic moment, v_parallel) rides along in the migration records: tag every particle
+    cfg.carry_magnetic_moment, cfg.carry_v_parallel = 1, 1
+    mu0, vp0 = 1.0 + 1e-3 * np.arange(n), -2.0 - 1e-3 * np.arange(n)
     g = api.Context(cfg, m)
     g.comm_init(dist)
     g.fields_upload(El, Bl, Bcl)
     g.particles_upload(x[:, idx], v[:, idx], w[idx], sp[idx], lcells, ptrs=idx.astype(np.int32))
+    g.magnetic_moment_upload(mu0)   # by ptr = global particle index
+    g.v_parallel_upload(vp0)
     st = g.MoveParticles()
     ns, nr = g.migrate()
     g.sort()
     after = g.particles_download()
+    mu_after, vp_after = g.magnetic_moment_download(), g.v_parallel_download()
     en, cfl = g.UpdateJMassMatrix()   # local partial sums
     g.exchange_JM()
     J, M = g.JM_download()
@@ -81,7 +87,7 @@ def main():
     keys = after["cells"].astype(np.int64)
     gk = lg[keys // C].astype(np.int64) * C + keys % C
     owner_ok = bool((m.arrays["leaf_owner"][keys // C] == rank).all())
-    payload = {"res": res, "x": after["x"], "v": after["v"], "gk": gk, "owner_ok": owner_ok,
+    payload = {"res": res, "x": after["x"], "v": after["v"], "gk": gk, "owner_ok": owner_ok, "mu": mu_after, "vpar": vp_after,
                "J": J, "M": M, "ckeys": m.corner_gkey, "targets": m.corner_target_gkeys}
     gathered = [None] * world
     dist.all_gather_object(gathered, payload)
@@ -102,6 +108,9 @@ def main():
         out["cells_equal"] = bool(allx.shape[1] == n and (allk[o1] == ocell[o2]).all())
         out["x_bit_equal"] = bool(allx.shape[1] == n and (allx[:, o1] == ox[:, o2]).all())
         out["v_bit_equal"] = bool(allx.shape[1] == n and (allv[:, o1] == ov[:, o2]).all())
+        allmu = np.concatenate([p["mu"] for p in gathered])
+        allvp = np.concatenate([p["vpar"] for p in gathered])
+        out["reduced_state_travels"] = bool(allx.shape[1] == n and (allmu[o1] == mu0[o2]).all() and (allvp[o1] == vp0[o2]).all())
         out["owner_ok"] = all(p["owner_ok"] for p in gathered)
         out["sent_total"] = sum(p["res"]["sent"] for p in gathered)
         out["recv_total"] = sum(p["res"]["recv"] for p in gathered)
@@ -117,7 +126,8 @@ def main():
         st_sum = {k: sum(p["res"]["stats"][k] for p in gathered) for k in ora["stats"]}
         out["stats_equal"] = st_sum == ora["stats"]
         out["stats_gpu"], out["stats_oracle"] = st_sum, ora["stats"]
-        ok = (out["cells_equal"] and out["x_bit_equal"] and out["v_bit_equal"] and out["owner_ok"] and relJ <= 1e-10 and relM <= 1e-10
+        ok = (out["cells_equal"] and out["x_bit_equal"] and out["v_bit_equal"] and out["owner_ok"] and out["reduced_state_travels"]
+              and relJ <= 1e-10 and relM <= 1e-10
               and out["stats_equal"] and out["sent_total"] == out["recv_total"] and out["sent_total"] > 0)
         out["ok"] = ok
         print("MP_PARITY " + json.dumps(out))
