@@ -27,7 +27,9 @@ struct FastBlockConst {
   double qdt2m[AMPS_GPU_MAX_SPECIES], dt[AMPS_GPU_MAX_SPECIES];
 };
 
-template <bool kSmemTiles, bool kCornerB>
+// kCube10: 8^3-cell blocks with one ghost layer (tiles of 11^3 corners / 10^3 centres): the strides of the two stencils are
+// compile-time constants, so the 8 + 8 node addresses are immediate offsets of one base
+template <bool kSmemTiles, bool kCornerB, bool kCube10>
 __global__ void __launch_bounds__(256, FAST_CTAS) move_lapenta_fast_kernel(DevMesh m, DevSpecies sp, ParticleSoA p, const int *__restrict__ cellStart,
                                                                    const double *__restrict__ eTileG, const double *__restrict__ bTileG,
                                                                    int *__restrict__ cellCount, DevMoveStats *__restrict__ stats, int slices,
@@ -86,8 +88,8 @@ __global__ void __launch_bounds__(256, FAST_CTAS) move_lapenta_fast_kernel(DevMe
   __syncthreads();
   if (kSmemTiles) mbar_wait(&mbar, 0);
 
-  const int CS0 = 1 + m.TN[0], CS1 = (1 + m.TN[0]) * (1 + m.TN[1]);  // corner strides
-  const int BS0 = m.TN[0], BS1 = m.TN[0] * m.TN[1];                  // centre strides
+  const int CS0 = kCube10 ? 11 : 1 + m.TN[0], CS1 = kCube10 ? 121 : (1 + m.TN[0]) * (1 + m.TN[1]);  // corner strides
+  const int BS0 = kCube10 ? 10 : m.TN[0], BS1 = kCube10 ? 100 : m.TN[0] * m.TN[1];                  // centre strides
   const bool openFace = (!m.periodic) && lg.face != 0;
 
   unsigned int nMoved = 0, nXCell = 0, nXBlock = 0, nWrap = 0, nRedo = 0;
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(256, FAST_CTAS) move_lapenta_fast_kernel(DevMe
       const double ax0 = 1.0 - xl[0], ax1 = xl[0], ay0 = 1.0 - xl[1], ay1 = xl[1], az0 = 1.0 - xl[2], az1 = xl[2];
       const double a00 = ax0 * ay0, a01 = ax0 * ay1, a10 = ax1 * ay0, a11 = ax1 * ay1;
       const double w[8] = {a00 * az0, a00 * az1, a01 * az0, a01 * az1, a10 * az0, a10 * az1, a11 * az0, a11 * az1};
-      const int nd0 = cornerLocalNumber(m, iX[0], iX[1], iX[2]);
+      const int nd0 = kCube10 ? (iX[0] + 1 + 11 * (iX[1] + 1 + (iX[2] + 1) * 11)) : cornerLocalNumber(m, iX[0], iX[1], iX[2]);
 #pragma unroll
       for (int s = 0; s < 8; s++) {
         const int nd = nd0 + ((s >> 2) & 1) + ((s >> 1) & 1) * CS0 + (s & 1) * CS1;
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(256, FAST_CTAS) move_lapenta_fast_kernel(DevMe
         const double w0 = iLoc - (i0 + 0.5), w1 = jLoc - (j0 + 0.5), w2 = kLoc - (k0 + 0.5);
         const double a00 = (1.0 - w0) * (1.0 - w1), a01 = (1.0 - w0) * w1, a10 = w0 * (1.0 - w1), a11 = w0 * w1;
         const double w[8] = {a00 * (1.0 - w2), a00 * w2, a01 * (1.0 - w2), a01 * w2, a10 * (1.0 - w2), a10 * w2, a11 * (1.0 - w2), a11 * w2};
-        const int nd0 = centerLocalNumber(m, i0, j0, k0);
+        const int nd0 = kCube10 ? (i0 + 1 + 10 * (j0 + 1 + (k0 + 1) * 10)) : centerLocalNumber(m, i0, j0, k0);
 #pragma unroll
         for (int s = 0; s < 8; s++) {
           const int nd = nd0 + ((s >> 2) & 1) + ((s >> 1) & 1) * BS0 + (s & 1) * BS1;
@@ -265,19 +267,29 @@ void launch_move_lapenta_fast(const DevMesh &m, const DevSpecies &sp, ParticleSo
   const size_t smem = (size_t)(m.eTileStride + m.bTileStride) * sizeof(double);
   const int grid = m.nLeaves * slices;
   const bool cornerB = sp.bMode == AMPS_B_CORNER_BASED;
+  const bool cube10 = m.TN[0] == 10 && m.TN[1] == 10 && m.TN[2] == 10 && m.g[0] == 1 && m.g[1] == 1 && m.g[2] == 1;
+#define AMPS_FAST_ARGS m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, redoMask, leafRedo, redoLeafList, nRedoLeaves
   if (smem <= 200 * 1024) {
     static OncePerDevice once;
     if (once.first()) {
-      cudaFuncSetAttribute(move_lapenta_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cudaFuncSetAttribute(move_lapenta_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(move_lapenta_fast_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(move_lapenta_fast_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(move_lapenta_fast_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(move_lapenta_fast_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }
-    if (cornerB) move_lapenta_fast_kernel<true, true><<<grid, 256, smem, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, redoMask, leafRedo, redoLeafList, nRedoLeaves);
-    else move_lapenta_fast_kernel<true, false><<<grid, 256, smem, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, redoMask, leafRedo, redoLeafList, nRedoLeaves);
+    if (cube10) {
+      if (cornerB) move_lapenta_fast_kernel<true, true, true><<<grid, 256, smem, s>>>(AMPS_FAST_ARGS);
+      else move_lapenta_fast_kernel<true, false, true><<<grid, 256, smem, s>>>(AMPS_FAST_ARGS);
+    } else {
+      if (cornerB) move_lapenta_fast_kernel<true, true, false><<<grid, 256, smem, s>>>(AMPS_FAST_ARGS);
+      else move_lapenta_fast_kernel<true, false, false><<<grid, 256, smem, s>>>(AMPS_FAST_ARGS);
+    }
   } else if (cornerB) {
-    move_lapenta_fast_kernel<false, true><<<grid, 256, 0, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, redoMask, leafRedo, redoLeafList, nRedoLeaves);
+    move_lapenta_fast_kernel<false, true, false><<<grid, 256, 0, s>>>(AMPS_FAST_ARGS);
   } else {
-    move_lapenta_fast_kernel<false, false><<<grid, 256, 0, s>>>(m, sp, p, cellStart, eTile, bTile, cellCount, stats, slices, redoMask, leafRedo, redoLeafList, nRedoLeaves);
+    move_lapenta_fast_kernel<false, false, false><<<grid, 256, 0, s>>>(AMPS_FAST_ARGS);
   }
+#undef AMPS_FAST_ARGS
 }
 
 }  // namespace amps
