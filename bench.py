@@ -400,7 +400,7 @@ def main():
     step_alg = (ALG_BYTES_FIXED + ALG_BYTES_PER_CELL / P)
     # DRAM bytes of one launch from the `ncu --set full` capture of this very workload (profiles/r1_final_ncu_summary.txt:
     # dram__bytes_read.sum + dram__bytes_write.sum); only quoted for the default size
-    ncu_traffic = {"move": 1.811565e9 + 1.601744e9, "deposit": 3.109853e9 + 2.754746e9, "sort": 0.139332e9 + 0.093713e9}
+    ncu_traffic = {"move": 1.811547e9 + 1.601237e9, "deposit": 3.109853e9 + 2.754746e9, "sort": 0.139332e9 + 0.093713e9}
     traffic = ncu_traffic[dom] if (args.cells == 64 and args.ppc == 64 and world == 1) else None
     roofline = {"bound": "hbm", "kernel": {"move": "move_lapenta_fast_kernel", "sort": "perm_kernel", "deposit": "deposit_kernel"}[dom],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
