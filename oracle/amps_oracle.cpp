@@ -1210,10 +1210,7 @@ struct oracle_ctx {
 
         double dt, GyroFreq, dtMax;
         if (sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) > 1.0E-25) {
-          // ::Relativistic::GetGyroFrequency, specfunc.h:1290
-          const double PiTimes2 = 6.28318530717958647692;
-          GyroFreq = fabs(ElectricCharge) * sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) /
-                     (PiTimes2 * mass * (1.0 / sqrt(1.0 - (vInit[0] * vInit[0] + vInit[1] * vInit[1] + vInit[2] * vInit[2]) / (SpeedOfLight * SpeedOfLight))));
+          GyroFreq = RelGyroFrequency(vInit, mass, ElectricCharge, B, SpeedOfLight);
           dtMax = 1.0 / GyroFreq;
           dt = (dtMax < dtTotalIn) ? dtMax : dtTotalIn;
         } else
@@ -1842,14 +1839,7 @@ struct oracle_ctx {
       if (!GC_InitStencil(x, startNode, Stencil)) return _ORACLE_ERROR_;  // the START node, as written (:713)
       GC_Gather(Stencil, startNode, BackgroundB_d, 3, bFinal);
     }
-    {
-      // Vector3D::Normalize, src/general/specfunc.h:969-981
-      double l, l0 = sqrt(bFinal[0] * bFinal[0] + bFinal[1] * bFinal[1] + bFinal[2] * bFinal[2]);
-      if (l0 > 0.0) {
-        l = 1.0 / l0;
-        for (int idim2 = 0; idim2 < 3; idim2++) bFinal[idim2] *= l;
-      }
-    }
+    Vector3D_Normalize(bFinal);
     misc = p / m0;
     for (idim = 0; idim < 3; idim++) v[idim] = misc * bFinal[idim];
     if (cfg.internal_sphere_radius > 0.0) {
@@ -2233,6 +2223,22 @@ struct oracle_ctx {
           }
     }
     return AMPS_GPU_OK;
+  }
+
+  // ::Relativistic::GetGyroFrequency with GetGamma and Vector3D::Length, src/general/specfunc.h:1290, :1214-1216, :763-765
+  // (pinned bit for bit against the reference's header by tests/test_reference_mesh.py through oracle/_ref/libref_mesh.so)
+  static double RelGyroFrequency(const double *v, double ParticleRestMass, double ElectricCharge, const double *B, double SpeedOfLight) {
+    const double PiTimes2 = 6.28318530717958647692;
+    return fabs(ElectricCharge) * sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) /
+           (PiTimes2 * ParticleRestMass * (1.0 / sqrt(1.0 - (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) / (SpeedOfLight * SpeedOfLight))));
+  }
+  // Vector3D::Normalize, src/general/specfunc.h:969-981
+  static void Vector3D_Normalize(double *x) {
+    double l, l0 = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    if (l0 > 0.0) {
+      l = 1.0 / l0;
+      for (int idim = 0; idim < 3; idim++) x[idim] *= l;
+    }
   }
 
   // ECSIM::isBoundaryCell != 0, src/pic/pic_field_solver_ecsim.cpp:6963-6999 with isFaceBoundary / isEdgeBoundary / isCornerBoundary
@@ -2880,6 +2886,9 @@ void oracle_set_background(oracle_ctx *o, const double *E_center, const double *
   if (B_center)
     for (int i = 0; i < o->n_centers; i++) memcpy(o->centerPool[i].data + BackgroundB_d, B_center + 3 * (size_t)i, 24);
 }
+// probes of the specfunc.h restatements (pinned against the reference's header in tests/test_reference_mesh.py)
+double oracle_probe_gyro_frequency(const double *v, double m, double q, const double *B, double c) { return oracle_ctx::RelGyroFrequency(v, m, q, B, c); }
+void oracle_probe_normalize(double *x) { oracle_ctx::Vector3D_Normalize(x); }
 int oracle_sample_cells(oracle_ctx *o, double *sample, int64_t *n_sampled) {
   int rc = o->SampleCells();
   if (sample) memcpy(sample, o->cellSample.data(), sizeof(double) * o->cellSample.size());

@@ -86,6 +86,9 @@ int oracle_deposit_JM(oracle_ctx *, int n_threads, double *J, double *M, double 
 int oracle_net_charge(oracle_ctx *, double charge_conv, double *rho);
 /* the _PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_ part of UpdateJMassMatrix: [n_corners][10*n_species] (spec may be NULL) */
 int oracle_species_moments(oracle_ctx *, double *spec);
+/* probes of the restated src/general/specfunc.h helpers */
+double oracle_probe_gyro_frequency(const double *v, double m, double q, const double *B, double c);
+void oracle_probe_normalize(double *x);
 /* PIC::Sampling::SamplingManager(): adds one sample to the collecting buffer [n_leaves*cells][n_species][13] and returns it */
 int oracle_sample_cells(oracle_ctx *, double *sample, int64_t *n_sampled);
 /* phi of the div-E correction on the unique centre nodes [n_centers] */

@@ -115,4 +115,11 @@ int ref_neib_levels(const double *x, int *minmax) {
   minmax[0] = n->minNeibRefinmentLevel, minmax[1] = n->maxNeibRefinmentLevel;
   return 0;
 }
+// helpers of src/general/specfunc.h that the restated movers use
+double ref_gyro_frequency(const double *v, double m, double q, const double *B) {
+  double vv[3] = {v[0], v[1], v[2]}, bb[3] = {B[0], B[1], B[2]};
+  return ::Relativistic::GetGyroFrequency(vv, m, q, bb);
+}
+void ref_normalize(double *x) { Vector3D::Normalize(x); }
+double ref_speed_of_light() { return SpeedOfLight; }
 }

@@ -132,3 +132,39 @@ def test_neighbours_and_level_limits_match_the_reference(pair):
                     finer += a[2] > lv
                     checked += 1
     assert checked > 2000 and coarser > 50 and finer > 50
+
+
+def test_specfunc_helpers_match_the_reference():
+    """::Relativistic::GetGyroFrequency (it sets the sub-cycle length of Relativistic::Boris, specfunc.h:1290) and Vector3D::Normalize
+    (:969-981) as restated in the oracle, against the reference's header compiled into libref_mesh.so: bit-identical"""
+    ref = C.CDLL(LIB)
+    ref.ref_gyro_frequency.restype = C.c_double
+    ref.ref_gyro_frequency.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+    ref.ref_speed_of_light.restype = C.c_double
+    ref.ref_normalize.argtypes = [C.c_void_p]
+    from oracle.oracle_py import load as _load
+
+    ora = _load("parity")
+    ora.oracle_probe_gyro_frequency.restype = C.c_double
+    ora.oracle_probe_gyro_frequency.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_double]
+    ora.oracle_probe_normalize.argtypes = [C.c_void_p]
+    c = ref.ref_speed_of_light()
+    assert c == 299792458.0
+    rng = np.random.default_rng(5)
+    qp, mp = 1.602176634e-19, 1.67262192369e-27
+    for i in range(2000):
+        d = rng.standard_normal(3)
+        v = np.ascontiguousarray(d / np.linalg.norm(d) * c * rng.uniform(1e-4, 0.9999))
+        B = np.ascontiguousarray(rng.standard_normal(3) * 10.0 ** rng.uniform(-9, -4))
+        q = qp * (1 if i % 3 else -1)
+        a = ref.ref_gyro_frequency(v.ctypes.data, mp, q, B.ctypes.data)
+        b = ora.oracle_probe_gyro_frequency(v.ctypes.data, mp, q, B.ctypes.data, c)
+        assert a == b and a > 0
+        x1 = np.ascontiguousarray(rng.standard_normal(3) * 10.0 ** rng.uniform(-12, 12))
+        x2 = x1.copy()
+        ref.ref_normalize(x1.ctypes.data)
+        ora.oracle_probe_normalize(x2.ctypes.data)
+        assert (x1 == x2).all() and abs(np.linalg.norm(x1) - 1.0) < 1e-15
+    z1, z2 = np.zeros(3), np.zeros(3)
+    ref.ref_normalize(z1.ctypes.data), ora.oracle_probe_normalize(z2.ctypes.data)
+    assert (z1 == 0).all() and (z2 == 0).all()
