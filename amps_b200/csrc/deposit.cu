@@ -369,15 +369,17 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
           const double2 a01 = reinterpret_cast<const double2 *>(row + OFF_A + 6 * h)[0];
           const double2 a23 = reinterpret_cast<const double2 *>(row + OFF_A + 6 * h)[1];
           const double2 a45 = reinterpret_cast<const double2 *>(row + OFF_A + 6 * h)[2];
-          const double u[9] = {xx * y01.x, xx * y01.y, xx * y23.x, xx * y23.y, xx * y45.x, xx * y45.y, xx * y67.x, xx * y67.y, xx * y8};
+          // u_cls a_col = (XX YZ_j) a_col = YZ_j (XX a_col): 6 products per particle and lane instead of 9
+          const double u[9] = {y01.x, y01.y, y23.x, y23.y, y45.x, y45.y, y67.x, y67.y, y8};
+          const double xa0 = xx * a01.x, xa1 = xx * a01.y, xa2 = xx * a23.x, xa3 = xx * a23.y, xa4 = xx * a45.x, xa5 = xx * a45.y;
 #pragma unroll
           for (int j = 0; j < 9; j++) {
-            acc[6 * j + 0] = fma(u[j], a01.x, acc[6 * j + 0]);
-            acc[6 * j + 1] = fma(u[j], a01.y, acc[6 * j + 1]);
-            acc[6 * j + 2] = fma(u[j], a23.x, acc[6 * j + 2]);
-            acc[6 * j + 3] = fma(u[j], a23.y, acc[6 * j + 3]);
-            acc[6 * j + 4] = fma(u[j], a45.x, acc[6 * j + 4]);
-            acc[6 * j + 5] = fma(u[j], a45.y, acc[6 * j + 5]);
+            acc[6 * j + 0] = fma(u[j], xa0, acc[6 * j + 0]);
+            acc[6 * j + 1] = fma(u[j], xa1, acc[6 * j + 1]);
+            acc[6 * j + 2] = fma(u[j], xa2, acc[6 * j + 2]);
+            acc[6 * j + 3] = fma(u[j], xa3, acc[6 * j + 3]);
+            acc[6 * j + 4] = fma(u[j], xa4, acc[6 * j + 4]);
+            acc[6 * j + 5] = fma(u[j], xa5, acc[6 * j + 5]);
           }
         }
       }
