@@ -1,11 +1,12 @@
 """Known-answer test of the reference for the test-particle path: the vertical Størmer cutoff of a centred dipole,
-Rc = R0 cos^4(lambda) / r^2, srcEarth/test/C1 (tests/golden/reference_C1_stormer.csv is that test's table, unchanged).
+Rc = R0 cos^4(lambda) / r^2, srcEarth/test/C1 (tests/golden/stormer_tables.json holds that test's table, written by
+tests/golden/make_stormer_tables.py from the reference tree).
 Protons are traced backward in time with PIC::Mover::Relativistic::Boris (a7) through the dipole tabulated on an AMR mesh, like
 the reference's Mode3D MESH variant: a vertical arrival 1.6 x above the cutoff connects to the outer boundary, one 0.6 x below
-does not (the reference accepts 5-35 % around Rc, run_C1.py:322-337).  srcEarth/test/C4/reference_C4_invariants.csv (also unchanged
-in tests/golden/) lists, for factors 0.5 and 2, whether the trajectory must reach the outer box, and bounds the rigidity change
+does not (the reference accepts 5-35 % around Rc, run_C1.py:322-337).  srcEarth/test/C4/reference_C4_invariants.csv (same fixture
+file) lists, for factors 0.5 and 2, whether the trajectory must reach the outer box, and bounds the rigidity change
 along it by 1e-6 (E = 0: the magnetic force does no work); both are asserted for every row."""
-import csv
+import json
 import math
 import os
 
@@ -19,9 +20,13 @@ from oracle.oracle_py import Oracle
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def _fixture():
+    with open(os.path.join(HERE, "golden", "stormer_tables.json")) as f:
+        return json.load(f)
+
+
 def _table():
-    with open(os.path.join(HERE, "golden", "reference_C1_stormer.csv")) as f:
-        return [(float(r["alt_km"]), float(r["lat_deg"]), float(r["Rc_stormer_GV"])) for r in csv.DictReader(f)]
+    return [(r["alt_km"], r["lat_deg"], r["Rc_stormer_GV"]) for r in _fixture()["C1"]]
 
 
 def test_table_is_the_stormer_formula():
@@ -33,9 +38,7 @@ def test_table_is_the_stormer_formula():
 
 
 def _table_c4():
-    with open(os.path.join(HERE, "golden", "reference_C4_invariants.csv")) as f:
-        return [(float(r["alt_km"]), float(r["lat_deg"]), float(r["factor"]), float(r["R_GV"]), float(r["Rc_stormer_GV"]), int(r["expected_allowed"]),
-                 float(r["rel_dR_limit"])) for r in csv.DictReader(f)]
+    return [(r["alt_km"], r["lat_deg"], r["factor"], r["R_GV"], r["Rc_stormer_GV"], r["expected_allowed"], r["rel_dR_limit"]) for r in _fixture()["C4"]]
 
 
 def test_c4_table_is_consistent_with_c1():
