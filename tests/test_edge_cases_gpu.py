@@ -219,3 +219,34 @@ def test_aos_round_trip_carries_the_reduced_state():
             assert cell_of[p] == c
             p = nxt[p]
     assert (seen[slots] == 1).all() and seen.sum() == n
+
+
+@pytest.mark.gpu
+def test_reduced_state_follows_the_fused_step():
+    """amps_gpu_step reorders the store inside the deposit (gather through the permutation): the optional magnetic moment and
+    v_parallel arrays must follow their particles there as they do in the stand-alone sort"""
+    m, cfg, parts, fields = pu.make_case(n_cells=(16, 16, 16), ppc=6, seed=97, vscale=6.0)
+    x, v, w, sp, cells = parts
+    n = x.shape[1]
+    cfg.carry_magnetic_moment, cfg.carry_v_parallel = 1, 1
+    mu0, vp0 = 1.0 + 1e-3 * np.arange(n), -2.0 - 1e-3 * np.arange(n)
+    g = api.Context(cfg, m)
+    g.fields_upload(*fields)
+    g.particles_upload(x, v, w, sp, cells)
+    g.magnetic_moment_upload(mu0)
+    g.v_parallel_upload(vp0)
+    for it in range(3):
+        g.step()
+    d = g.particles_download()
+    mu, vp = g.magnetic_moment_download(), g.v_parallel_download()
+    J = np.empty((m.n_corners, 3))
+    M = np.empty((m.n_corners, 243))
+    g.step_JM(J, M)  # the ranged deposit of the pipelined variant gathers too
+    d2 = g.particles_download()
+    mu2, vp2 = g.magnetic_moment_download(), g.v_parallel_download()
+    g.close()
+    assert len(d["ptrs"]) == n and (np.sort(d["ptrs"]) == np.arange(n)).all()
+    assert (mu == mu0[d["ptrs"]]).all() and (vp == vp0[d["ptrs"]]).all()
+    assert (mu2 == mu0[d2["ptrs"]]).all() and (vp2 == vp0[d2["ptrs"]]).all()
+    assert (np.diff(d2["cells"].astype(np.int64)) >= 0).all()
+    assert (d["ptrs"] != np.arange(n)).any()          # the steps really permuted the store
