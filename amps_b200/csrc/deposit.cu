@@ -30,6 +30,7 @@
 //
 // The energy / cfl diagnostics of UpdateJMassMatrix (:2228-2238, :2355-2359, :3860-3864) are folded into phase 1 for at most
 // two species (kDiag), a separate streaming kernel (diag_kernel) otherwise.
+#include <cstddef>
 #include "amps_dev.cuh"
 
 namespace amps {
@@ -42,6 +43,17 @@ constexpr int N_TILES = 6, N_SLICES = 5;   // 30 active lanes
 constexpr int N_T = 27 * 12;               // class sums per cell
 constexpr int SLAB = N_SLICES * N_T;       // doubles per warp: the particle rows of a chunk, later the 5 slice partials of T
 static_assert(SLAB >= CHUNK * ROW, "the particle rows must fit in the slab");
+
+// per-warp "cell header" in shared memory, double-buffered: the 27 x 3 centre (or 8 x 3 corner) values of B_cur the cell's
+// stencils can touch + the leaf geometry phase 1 needs.  The header of the warp's NEXT cell is fetched with 8-byte cp.async
+// (SASS LDGSTS: no registers are held while the copies are in flight) during the accumulation of the current one.
+static_assert(offsetof(LeafGeo, xmin) == 0 && offsetof(LeafGeo, xmax) == 24 && offsetof(LeafGeo, dxc) == 88 && offsetof(LeafGeo, invdxc) == 112,
+              "stage_header copies LeafGeo by double index");
+constexpr int HDR_GEO = 82, HDR = 96;  // doubles: B [0,81), xmin[3] xmax[3] dxc[3] invdxc[3] at [82,94)
+__device__ __forceinline__ void cp_async8(double *dstShared, const double *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dstShared)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ void atomicMaxPositiveDouble(unsigned long long *addr, double v) {
   // v >= 0 and not NaN: the bit patterns of non-negative doubles order like unsigned integers
@@ -78,7 +90,8 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
                                                                               const int *__restrict__ perm, ParticleSoA dst, int dep0, int dep1,
                                                                               int ghostPass) {
   extern __shared__ __align__(16) double sRows[];  // [DEP_WARPS][SLAB]
-  __shared__ double sBall[DEP_WARPS][27 * 3];  // B_cur on the 3x3x3 centres around the warp's cell
+  __shared__ double sHdr[DEP_WARPS][2][HDR];  // cell headers (B_cur around the cell + leaf geometry), current and next cell
+  __shared__ int sBoff[81];                   // centre-B mode: offset of stencil entry e = 3 n + d from the cell's own centre
   // flush tables: output o = (c*8+c')*9+col -> corner c (3 bits) | offset inside M[corner] (8 bits) | T index (9 bits)
   __shared__ unsigned int sFlush[576];
   __shared__ unsigned short sJcls[64];  // T index (without column) of pair (c,c')
@@ -92,6 +105,11 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     const int c = o / 72, r = o - 72 * c, d = r / 9, col = r - 9 * d;
     sFlush[o] = (unsigned)c | ((unsigned)(9 * index_matrix(c, d) + col) << 3) | ((unsigned)(pair_class(c, d) * 12 + col) << 11);
     if (o < 64) sJcls[o] = (unsigned short)(pair_class(o >> 3, o & 7) * 12);
+    if (o < 81) {
+      const int n = o / 3, d = o - 3 * n;
+      const int di = n % 3 - 1, dj = (n / 3) % 3 - 1, dk = n / 9 - 1;
+      sBoff[o] = 3 * (di + m.TN[0] * (dj + dk * m.TN[1])) + d;
+    }
   }
   __syncthreads();
 
@@ -103,7 +121,29 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
   // particles are requested while the current cell is still being accumulated.
   const int idx0 = dep0 * C, idx1 = dep1 * C;
   double *rows = sRows + (size_t)wib * SLAB;
-  double *sB = sBall[wib];
+  int hbuf = 0;         // header buffer of the current cell
+  bool staged = false;  // the header of the warp's next cell is already in flight
+  // fetch the header of cell c into h (asynchronously; complete after cp_async_wait_all + __syncwarp)
+  auto stage_header = [&](int c, double *h) {
+    const int lf = c / C, ci = c - lf * C;
+    const int k = ci / (m.N[0] * m.N[1]);
+    const int j = (ci - k * m.N[0] * m.N[1]) / m.N[0];
+    const int i = ci - k * m.N[0] * m.N[1] - j * m.N[0];
+    const double *bT = bCurTile + (size_t)lf * m.bTileStride;
+    if (kCornerB) {
+      // _PIC_FIELD_SOLVER_B_CORNER_BASED_: B_cur on the 8 corners of the cell, slot = 4*di + 2*dj + dk (:1932-1946)
+      if (lane < 24) {
+        const int n = lane / 3, d = lane - 3 * n;
+        cp_async8(h + lane, bT + 3 * cornerLocalNumber(m, i + ((n >> 2) & 1), j + ((n >> 1) & 1), k + (n & 1)) + d);
+      }
+    } else {
+      const double *b0 = bT + 3 * centerLocalNumber(m, i, j, k);
+#pragma unroll
+      for (int e = lane; e < 81; e += 32) cp_async8(h + e, b0 + sBoff[e]);
+    }
+    // xmin[3] xmax[3] are doubles 0..5 of LeafGeo, dxc[3] invdxc[3] doubles 11..16
+    if (lane < 12) cp_async8(h + HDR_GEO + lane, reinterpret_cast<const double *>(m.leaf + lf) + (lane < 6 ? lane : lane + 5));
+  };
 
   const bool active = lane < N_TILES * N_SLICES;
   const int tile = active ? lane % N_TILES : 0, slice = active ? lane / N_TILES : 0;
@@ -162,23 +202,15 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     __syncwarp();  // previous cell's totals fully flushed
     int uidLane = 0;
     if (lane < 8) uidLane = m.cornerUid[(size_t)leaf * m.nCornerLocal + cornerLocalNumber(m, ic + cox(lane), jc + coy(lane), kc + coz(lane))];
-    {
-      // stage the 27 centre values of B_cur the cell's stencils can touch
-      const double *bT = bCurTile + (size_t)leaf * m.bTileStride;
-      if (kCornerB) {
-        // _PIC_FIELD_SOLVER_B_CORNER_BASED_: B_cur on the 8 corners of the cell, slot = 4*di + 2*dj + dk (:1932-1946)
-        if (lane < 24) {
-          const int n = lane / 3, d = lane - 3 * n;
-          sB[lane] = __ldg(bT + 3 * cornerLocalNumber(m, ic + ((n >> 2) & 1), jc + ((n >> 1) & 1), kc + (n & 1)) + d);
-        }
-      } else {
-        for (int e = lane; e < 81; e += 32) {
-          const int n = e / 3, d = e - 3 * n;
-          const int di = n % 3 - 1, dj = (n / 3) % 3 - 1, dk = n / 9 - 1;
-          sB[e] = __ldg(bT + 3 * centerLocalNumber(m, ic + di, jc + dj, kc + dk) + d);
-        }
-      }
-    }
+    // the cell header: already in flight (requested during the previous cell) or fetched now; then request the next one
+    if (!staged) stage_header(cell, sHdr[wib][hbuf]);
+    cp_async_wait_all();
+    __syncwarp();
+    const double *sB = sHdr[wib][hbuf];
+    const double *sG = sB + HDR_GEO;
+    staged = nBegin < nEnd;
+    if (staged) stage_header(ncell, sHdr[wib][hbuf ^ 1]);
+    hbuf ^= 1;
     const double invV = lg.invV;
 
     double acc[54];
@@ -241,9 +273,9 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
 #pragma unroll
           for (int d = 0; d < 3; d++) {
             double xs = xx[d];
-            const double xmx = lg.xmax[d], dxc = lg.dxc[d];
+            const double xmx = sG[3 + d], dxc = sG[6 + d];
             if (fabs(xs - xmx) < 1e-10 * dxc) xs = xmx - 1e-10 * dxc;
-            double r = (xs - lg.xmin[d]) * lg.invdxc[d];
+            double r = (xs - sG[d]) * sG[9 + d];
             r -= (int)r;
             xl[d] = r;
           }
