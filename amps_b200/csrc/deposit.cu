@@ -47,9 +47,11 @@ static_assert(SLAB >= CHUNK * ROW, "the particle rows must fit in the slab");
 // per-warp "cell header" in shared memory, double-buffered: the 27 x 3 centre (or 8 x 3 corner) values of B_cur the cell's
 // stencils can touch + the leaf geometry phase 1 needs.  The header of the warp's NEXT cell is fetched with 8-byte cp.async
 // (SASS LDGSTS: no registers are held while the copies are in flight) during the accumulation of the current one.
-static_assert(offsetof(LeafGeo, xmin) == 0 && offsetof(LeafGeo, xmax) == 24 && offsetof(LeafGeo, dxc) == 88 && offsetof(LeafGeo, invdxc) == 112,
+static_assert(offsetof(LeafGeo, xmin) == 0 && offsetof(LeafGeo, xmax) == 24 && offsetof(LeafGeo, dxc) == 88 && offsetof(LeafGeo, invdxc) == 112 &&
+                  offsetof(LeafGeo, invV) == 136 && offsetof(LeafGeo, diag) == 144,
               "stage_header copies LeafGeo by double index");
-constexpr int HDR_GEO = 82, HDR = 96;  // doubles: B [0,81), xmin[3] xmax[3] dxc[3] invdxc[3] at [82,94)
+constexpr int DEC_MAX = 1024;
+constexpr int HDR_GEO = 82, HDR = 96;  // doubles: B [0,81), xmin[3] xmax[3] dxc[3] invdxc[3] invV diag at [82,96)
 __device__ __forceinline__ void cp_async8(double *dstShared, const double *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dstShared)), "l"(src) : "memory");
 }
@@ -91,6 +93,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
                                                                               int ghostPass) {
   extern __shared__ __align__(16) double sRows[];  // [DEP_WARPS][SLAB]
   __shared__ double sHdr[DEP_WARPS][2][HDR];  // cell headers (B_cur around the cell + leaf geometry), current and next cell
+  __shared__ unsigned sDec[DEC_MAX];          // cell number inside a block -> i | j << 10 | k << 20 (blocks of at most DEC_MAX cells)
   __shared__ int sBoff[81];                   // centre-B mode: offset of stencil entry e = 3 n + d from the cell's own centre
   // flush tables: output o = (c*8+c')*9+col -> corner c (3 bits) | offset inside M[corner] (8 bits) | T index (9 bits)
   __shared__ unsigned int sFlush[576];
@@ -101,6 +104,11 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     sQdt2m[threadIdx.x] = b;
     sInvBeta[threadIdx.x] = (b != 0.0) ? 1.0 / b : 0.0;  // neutral species deposit nothing
   }
+  if (m.cellsPerBlock <= DEC_MAX)
+    for (int o = threadIdx.x; o < m.cellsPerBlock; o += DEP_THREADS) {
+      const int k = o / (m.N[0] * m.N[1]), j = (o - k * m.N[0] * m.N[1]) / m.N[0], i = o - k * m.N[0] * m.N[1] - j * m.N[0];
+      sDec[o] = (unsigned)i | ((unsigned)j << 10) | ((unsigned)k << 20);
+    }
   for (int o = threadIdx.x; o < 576; o += DEP_THREADS) {
     const int c = o / 72, r = o - 72 * c, d = r / 9, col = r - 9 * d;
     sFlush[o] = (unsigned)c | ((unsigned)(9 * index_matrix(c, d) + col) << 3) | ((unsigned)(pair_class(c, d) * 12 + col) << 11);
@@ -123,12 +131,21 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
   double *rows = sRows + (size_t)wib * SLAB;
   int hbuf = 0;         // header buffer of the current cell
   bool staged = false;  // the header of the warp's next cell is already in flight
-  // fetch the header of cell c into h (asynchronously; complete after cp_async_wait_all + __syncwarp)
-  auto stage_header = [&](int c, double *h) {
-    const int lf = c / C, ci = c - lf * C;
-    const int k = ci / (m.N[0] * m.N[1]);
-    const int j = (ci - k * m.N[0] * m.N[1]) / m.N[0];
-    const int i = ci - k * m.N[0] * m.N[1] - j * m.N[0];
+  // cell number inside its block -> (i,j,k): a table lookup for the usual block sizes, no integer division per cell
+  auto decode = [&](int ci, int &i, int &j, int &k) {
+    if (C <= DEC_MAX) {
+      const unsigned t = sDec[ci];
+      i = t & 1023u, j = (t >> 10) & 1023u, k = t >> 20;
+    } else {
+      k = ci / (m.N[0] * m.N[1]);
+      j = (ci - k * m.N[0] * m.N[1]) / m.N[0];
+      i = ci - k * m.N[0] * m.N[1] - j * m.N[0];
+    }
+  };
+  // fetch the header of cell ci of leaf lf into h (asynchronously; complete after cp_async_wait_all + __syncwarp)
+  auto stage_header = [&](int lf, int ci, double *h) {
+    int i, j, k;
+    decode(ci, i, j, k);
     const double *bT = bCurTile + (size_t)lf * m.bTileStride;
     if (kCornerB) {
       // _PIC_FIELD_SOLVER_B_CORNER_BASED_: B_cur on the 8 corners of the cell, slot = 4*di + 2*dj + dk (:1932-1946)
@@ -141,15 +158,15 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
 #pragma unroll
       for (int e = lane; e < 81; e += 32) cp_async8(h + e, b0 + sBoff[e]);
     }
-    // xmin[3] xmax[3] are doubles 0..5 of LeafGeo, dxc[3] invdxc[3] doubles 11..16
-    if (lane < 12) cp_async8(h + HDR_GEO + lane, reinterpret_cast<const double *>(m.leaf + lf) + (lane < 6 ? lane : lane + 5));
+    // xmin[3] xmax[3] are doubles 0..5 of LeafGeo, dxc[3] invdxc[3] invV diag doubles 11..18
+    if (lane < 14) cp_async8(h + HDR_GEO + lane, reinterpret_cast<const double *>(m.leaf + lf) + (lane < 6 ? lane : lane + 5));
   };
 
   const bool active = lane < N_TILES * N_SLICES;
   const int tile = active ? lane % N_TILES : 0, slice = active ? lane / N_TILES : 0;
   const int px = tile % 3, h = tile / 3;  // classes px*9 .. px*9+8, columns 6h .. 6h+5
   const double invc = 1.0 / sp.LightSpeed;
-  double eAcc = 0.0, cflMax = 0.0;  // kDiag: per-lane energy; lane s keeps the cfl of species s
+  double eAcc = 0.0, cflMax = 0.0;  // kDiag: per-lane energy; lane 16 s keeps the cfl of species s
 
   // software prefetch: the particle of the NEXT chunk (of this cell, or the first chunk of the warp's next cell) is loaded
   // while phase 2 of the current one runs
@@ -159,31 +176,34 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
   int nptr = 0;             // kGather: its ParticleBuffer slot (travels to the sorted copy)
   bool pre = false;         // the first chunk of the next cell is already in flight
 
+  // the warp walks cells idx0 + warpGlobal + n nWarps of the deposit order; (rl, off) = (idx / C, idx % C) is advanced without
+  // a division
+  const int stepQ = nWarps / C, stepR = nWarps - stepQ * C;
   int idx = idx0 + warpGlobal;
-  int ncell = 0, nBegin = 0, nEnd = 0;  // the warp's NEXT cell and its cell table entry (requested one cell ahead)
+  int rl = idx / C, off = idx - rl * C;
+  int nleaf = 0, noff = 0, nBegin = 0, nEnd = 0;  // the warp's NEXT cell and its cell table entry (requested one cell ahead)
   if (idx < idx1) {
-    const int rl = idx / C;
-    ncell = m.depLeaf[rl] * C + (idx - rl * C);
-    nBegin = cellStart[ncell], nEnd = cellStart[ncell + 1];
+    nleaf = m.depLeaf[rl], noff = off;
+    const int nc = nleaf * C + noff;
+    nBegin = cellStart[nc], nEnd = cellStart[nc + 1];
   }
   while (idx < idx1) {
-    const int cell = ncell, begin = nBegin, end = nEnd;
+    const int leaf = nleaf, cin = noff, cell = leaf * C + cin, begin = nBegin, end = nEnd;
     idx += nWarps;
+    rl += stepQ, off += stepR;
+    if (off >= C) off -= C, rl++;
     if (idx < idx1) {
-      const int rl = idx / C;
-      ncell = m.depLeaf[rl] * C + (idx - rl * C);
-      nBegin = cellStart[ncell], nEnd = cellStart[ncell + 1];
+      nleaf = m.depLeaf[rl], noff = off;
+      const int nc = nleaf * C + noff;
+      nBegin = cellStart[nc], nEnd = cellStart[nc + 1];
     } else {
       nBegin = nEnd = 0;
     }
     if (begin == end) continue;  // ProcessCell returns false: nothing is flushed (never prefetched: pre is false)
-    const int leaf = cell / C;
     const LeafGeo &lg = m.leaf[leaf];
     const int face = lg.face;
-    const int cin = cell - leaf * C;
-    const int kc = cin / (m.N[0] * m.N[1]);
-    const int jc = (cin - kc * m.N[0] * m.N[1]) / m.N[0];
-    const int ic = cin - kc * m.N[0] * m.N[1] - jc * m.N[0];
+    int ic, jc, kc;
+    decode(cin, ic, jc, kc);
 
     if (!pre) {
       // first cell of the warp, or the previous one was empty: the first chunk's loads are issued before the B staging so
@@ -203,15 +223,15 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     int uidLane = 0;
     if (lane < 8) uidLane = m.cornerUid[(size_t)leaf * m.nCornerLocal + cornerLocalNumber(m, ic + cox(lane), jc + coy(lane), kc + coz(lane))];
     // the cell header: already in flight (requested during the previous cell) or fetched now; then request the next one
-    if (!staged) stage_header(cell, sHdr[wib][hbuf]);
+    if (!staged) stage_header(leaf, cin, sHdr[wib][hbuf]);
     cp_async_wait_all();
     __syncwarp();
     const double *sB = sHdr[wib][hbuf];
     const double *sG = sB + HDR_GEO;
     staged = nBegin < nEnd;
-    if (staged) stage_header(ncell, sHdr[wib][hbuf ^ 1]);
+    if (staged) stage_header(nleaf, noff, sHdr[wib][hbuf ^ 1]);
     hbuf ^= 1;
-    const double invV = lg.invV;
+    const double invV = sG[12];
 
     double acc[54];
 #pragma unroll
@@ -418,12 +438,17 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     }
 
     if (kDiag) {  // cfl of the cell per species (:2355-2359): sum|v|dt / (count |dx|)
+      // one butterfly for both species: after the first exchange the lower half-warp holds partial sums of species 0, the upper
+      // half those of species 1
+      const bool lo = lane < 16;
+      double a = lo ? vm0 : vm1;
+      a += __shfl_xor_sync(0xffffffffu, lo ? vm1 : vm0, 16);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) vm0 += __shfl_xor_sync(0xffffffffu, vm0, o), vm1 += __shfl_xor_sync(0xffffffffu, vm1, o);
+      for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
       const int c = __reduce_add_sync(0xffffffffu, cnt01);
-      const int cs = (lane == 0) ? (c & 0xffff) : (c >> 16);
-      if (lane < 2 && cs > 0) {  // 0/0 = NaN never wins the reference's '>' comparison
-        const double cfl = ((lane == 0) ? vm0 : vm1) / (cs * lg.diag);
+      const int cs = lo ? (c & 0xffff) : (c >> 16);
+      if ((lane & 15) == 0 && cs > 0) {  // lane 0: species 0, lane 16: species 1; 0/0 = NaN never wins the reference's '>' comparison
+        const double cfl = a / (cs * sG[13]);
         if (cfl > cflMax) cflMax = cfl;
       }
     }
@@ -447,7 +472,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     }
     __syncwarp();
     // ---- flush the mass matrix: 64 ordered corner pairs x 9 (both (c,c') and (c',c) get the same block, :2411-2420)
-#pragma unroll 6
+#pragma unroll
     for (int o = lane; o < 576; o += 32) {
       const unsigned e = sFlush[o];
       const int ui = __shfl_sync(0xffffffffu, uidLane, e & 7u);
@@ -484,7 +509,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) eAcc += __shfl_xor_sync(0xffffffffu, eAcc, o);
     if (lane == 0 && eAcc != 0.0) atomicAdd(energyOut, 8.0 * eAcc);
-    if (lane < 2 && lane < sp.n && cflMax > 0.0) atomicMaxPositiveDouble(&cflBits[lane], cflMax);
+    if ((lane & 15) == 0 && (lane >> 4) < sp.n && cflMax > 0.0) atomicMaxPositiveDouble(&cflBits[lane >> 4], cflMax);
   }
 }
 
