@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(256, FAST_CTAS) move_lapenta_fast_kernel(DevMe
   const int CS0 = kCube10 ? 11 : 1 + m.TN[0], CS1 = kCube10 ? 121 : (1 + m.TN[0]) * (1 + m.TN[1]);  // corner strides
   const int BS0 = kCube10 ? 10 : m.TN[0], BS1 = kCube10 ? 100 : m.TN[0] * m.TN[1];                  // centre strides
   const bool openFace = (!m.periodic) && lg.face != 0;
+  // a particle that stays in its block needs no node table: the flags of the start block are read once per CTA
+  const int startFlags = m.nodeFlags[lg.node];
 
   unsigned int nMoved = 0, nXCell = 0, nXBlock = 0, nWrap = 0, nRedo = 0;
 
@@ -201,17 +203,20 @@ __global__ void __launch_bounds__(256, FAST_CTAS) move_lapenta_fast_kernel(DevMe
       const bool in = ix[0] >= lg.imin[0] && ix[0] < lg.imin[0] + lg.isize && ix[1] >= lg.imin[1] && ix[1] < lg.imin[1] + lg.isize &&
                       ix[2] >= lg.imin[2] && ix[2] < lg.imin[2] + lg.isize;
       int node = in ? lg.node : find_node_ix(m, ix[0], ix[1], ix[2]);
-      if (node < 0 || !(m.nodeFlags[node] & AMPS_NODE_USED)) redo = true;
-      int newLeaf = redo ? -1 : (in ? leaf : m.nodeLeaf[node]);
+      // the three node-table entries of a block crosser are requested together (one exposed latency instead of three)
+      int nFlags = startFlags, nLeaf = leaf, nLevel = lg.level;
+      if (!in && node >= 0) nFlags = m.nodeFlags[node], nLeaf = m.nodeLeaf[node], nLevel = m.nodeLevel[node];
+      if (node < 0 || !(nFlags & AMPS_NODE_USED)) redo = true;
+      int newLeaf = redo ? -1 : nLeaf;
       if (newLeaf < 0) redo = true;
       if (!redo) {
         int ijk[3];
-        const bool sameLevel = in || m.nodeLevel[node] == lg.level;
+        const bool sameLevel = in || nLevel == lg.level;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
           const double lo = in ? lg.xmin[d] : m.nxmin[3 * node + d];
           const double hi = in ? lg.xmax[d] : m.nxmax[3 * node + d];
-          const double inv = sameLevel ? sC.invCell[d] : 1.0 / (m.dxRoot[d] / (1 << m.nodeLevel[node]) / double(m.N[d]));
+          const double inv = sameLevel ? sC.invCell[d] : 1.0 / (m.dxRoot[d] / (1 << nLevel) / double(m.N[d]));
           const double t = (xf[d] - lo) * inv;
           const double fl = floor(t);
           const double fr = t - fl;
