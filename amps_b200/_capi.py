@@ -199,7 +199,8 @@ PROTOTYPES = {
     "amps_gpu_synchronize": (C.c_int, [_vp]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libamps_gpu.so")
+# AMPS_GPU_LIB selects another build of the same library (A/B runs of kernel variants); there is still no fallback
+LIB_PATH = os.environ.get("AMPS_GPU_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libamps_gpu.so")
 _lib = None
 
 

@@ -400,12 +400,12 @@ def main():
     step_alg = (ALG_BYTES_FIXED + ALG_BYTES_PER_CELL / P)
     # DRAM bytes of one launch from the `ncu --set full` capture of this very workload (profiles/r1_final_ncu_summary.txt:
     # dram__bytes_read.sum + dram__bytes_write.sum); only quoted for the default size
-    ncu_traffic = {"move": 1.811570e9 + 1.602534e9, "deposit": 3.106720e9 + 2.751970e9, "sort": 0.139332e9 + 0.093713e9}
+    ncu_traffic = {"move": 1.811503e9 + 1.603445e9, "deposit": 3.131059e9 + 2.755923e9, "sort": 0.139377e9 + 0.091845e9}
     traffic = ncu_traffic[dom] if (args.cells == 64 and args.ppc == 64 and world == 1) else None
     roofline = {"bound": "hbm", "kernel": {"move": "move_lapenta_fast_kernel", "sort": "perm_kernel", "deposit": "deposit_kernel"}[dom],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "ms_per_launch": dom_ms, "alg_bytes_per_update": KERNEL_ALG_BYTES[dom_alg](P),
-                "note": "the kernel is bound by the fp64 pipe (ncu: 40 % of peak, 8 warps/SM at 239 registers), not by HBM; inside "
+                "note": "the kernel is bound by the fp64 pipe (ncu: 45 % of peak, 8 warps/SM at 242 registers), not by HBM; inside "
                         "amps_gpu_step it also writes the sorted particle copy (65 B/particle), which the algorithmic bytes do not count"}
     step_gbs = step_alg * (n_part * K / (ms * 1e-3)) / 1e9 if world == 1 else step_alg * (value / world) / 1e9
     line = {
