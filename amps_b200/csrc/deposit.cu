@@ -219,13 +219,12 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
       if (kGather && begin + CHUNK + lane < end) nsrc2 = perm[begin + CHUNK + lane];
     }
     pre = false;
-    __syncwarp();  // previous cell's totals fully flushed
     int uidLane = 0;
     if (lane < 8) uidLane = m.cornerUid[(size_t)leaf * m.nCornerLocal + cornerLocalNumber(m, ic + cox(lane), jc + coy(lane), kc + coz(lane))];
     // the cell header: already in flight (requested during the previous cell) or fetched now; then request the next one
     if (!staged) stage_header(leaf, cin, sHdr[wib][hbuf]);
     cp_async_wait_all();
-    __syncwarp();
+    __syncwarp();  // header visible to every lane; the previous cell's totals are fully flushed
     const double *sB = sHdr[wib][hbuf];
     const double *sG = sB + HDR_GEO;
     staged = nBegin < nEnd;
@@ -447,10 +446,10 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
       for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
       const int c = __reduce_add_sync(0xffffffffu, cnt01);
       const int cs = lo ? (c & 0xffff) : (c >> 16);
-      if ((lane & 15) == 0 && cs > 0) {  // lane 0: species 0, lane 16: species 1; 0/0 = NaN never wins the reference's '>' comparison
-        const double cfl = a / (cs * sG[13]);
-        if (cfl > cflMax) cflMax = cfl;
-      }
+      // lane 0: species 0, lane 16: species 1; 0/0 = NaN never wins the reference's '>' comparison.  cfl > cflMax is tested as
+      // a > cflMax (count |dx|) (all factors positive), so the division only runs when the maximum moves
+      const double den = cs * sG[13];
+      if ((lane & 15) == 0 && cs > 0 && a > cflMax * den) cflMax = a / den;
     }
     // ---- fold the 5 slices through shared memory: every lane stores its 54 partial sums at their T index in its
     //      slice's copy, then lane l sums entries l, l+32, ... over the slices (in place into copy 0) ----
