@@ -16,7 +16,7 @@
 //
 // The kernel is bound by the fp64 pipe and by shared-memory bandwidth, not by HBM (57 B/particle in,
 // ~4 KB/cell out).  Mapping: ONE WARP PER CELL, no block-level synchronisation at all; 8 warps per SM
-// (240 registers) are resident and drift apart, so the latency-bound phase of one warp overlaps the DFMA-bound
+// (242 registers) are resident and drift apart, so the latency-bound phase of one warp overlaps the DFMA-bound
 // phase of the others.  Per 32-particle chunk of its cell a warp runs
 //   phase 1  lane <-> particle: B gather (27 centres of the cell staged in shared memory), alpha, weights ->
 //            one 208-byte row per particle in the warp's shared-memory slab (row stride 26 doubles: the
@@ -26,7 +26,10 @@
 // and per cell
 //   reduce   the 5 slice partials are folded through the slab (every lane stores its 54 sums, then sums 11 entries over the slices)
 //   flush    one fp64 RED per value into J[nCorners][3], M[nCorners][243] (576 + 24 per cell).
-// The particles of the next chunk - of this cell or, in its last chunk, of the warp's next cell - are requested one chunk ahead.
+// The particles of the next chunk - of this cell or, in its last chunk, of the warp's next cell - are requested one chunk ahead,
+// and the "cell header" (the B_cur values around the cell + the leaf geometry, 96 doubles) of the warp's next cell one cell ahead
+// with cp.async into a double-buffered per-warp slot.  With two resident warps per scheduler every exposed latency of the per-cell
+// and per-chunk serial sections is paid in full, so the cell walk uses no integer division and no dependent global load.
 //
 // The energy / cfl diagnostics of UpdateJMassMatrix (:2228-2238, :2355-2359, :3860-3864) are folded into phase 1 for at most
 // two species (kDiag), a separate streaming kernel (diag_kernel) otherwise.
