@@ -57,3 +57,16 @@ def test_init_fails_loudly_without_a_device():
     h = ctypes.c_void_p()
     rc = lib.amps_gpu_init(ctypes.byref(cfg), ctypes.byref(h))
     assert rc == _capi.ERR_NO_DEVICE and not h  # no CPU fallback
+
+
+def test_a_missing_library_fails_loudly_also_through_the_variant_override(tmp_path):
+    # AMPS_GPU_LIB only points the loader at another build of the same library; a path that does not exist must raise
+    # (there is no CPU fallback behind it)
+    import subprocess
+    import sys
+
+    code = ("import os; os.environ['AMPS_GPU_LIB'] = r'%s'\n"
+            "from amps_b200 import _capi\n"
+            "try:\n    _capi.load_library()\nexcept RuntimeError as e:\n    print('RAISED', 'no CPU fallback' in str(e))\n" % (tmp_path / "nope.so"))
+    out = subprocess.check_output([sys.executable, "-c", code], cwd=ROOT, text=True)
+    assert "RAISED True" in out, out
