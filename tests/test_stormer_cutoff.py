@@ -5,7 +5,10 @@ Protons are traced backward in time with PIC::Mover::Relativistic::Boris (a7) th
 the reference's Mode3D MESH variant: a vertical arrival 1.6 x above the cutoff connects to the outer boundary, one 0.6 x below
 does not (the reference accepts 5-35 % around Rc, run_C1.py:322-337).  srcEarth/test/C4/reference_C4_invariants.csv (same fixture
 file) lists, for factors 0.5 and 2, whether the trajectory must reach the outer box, and bounds the rigidity change
-along it by 1e-6 (E = 0: the magnetic force does no work); both are asserted for every row."""
+along it by 1e-6 (E = 0: the magnetic force does no work); both are asserted for every row.
+srcEarth/test/C2/reference_C2_stormer_symmetry.csv (the cutoff of a centred dipole does not depend on the longitude: 12 longitudes per
+latitude) and the BORIS rows of srcEarth/test/C12/reference_C12_stormer_movers.csv (two shells, latitudes every 20 degrees) are
+bracketed the same way by the oracle."""
 import json
 import math
 import os
@@ -63,10 +66,12 @@ def _case(rows, factors):
     E = np.zeros_like(B)
     R0 = 0.299792458 * 0.25 * B0 * RE  # GV
     xs, vs, expect, rig = [], [], [], []
-    for alt, lat, _ in rows:
+    for row in rows:  # (alt_km, lat_deg, Rc) or (alt_km, lat_deg, Rc, lon_deg)
+        alt, lat = row[0], row[1]
+        phi = math.radians(row[3]) if len(row) > 3 else 0.0
         rr = RE + alt * 1e3
         lam = math.radians(lat)
-        pos = rr * np.array([math.cos(lam), 0.0, math.sin(lam)])
+        pos = rr * np.array([math.cos(lam) * math.cos(phi), math.cos(lam) * math.sin(phi), math.sin(lam)])
         rc = R0 * math.cos(lam) ** 4 / (rr / RE) ** 2
         for f in factors:
             p = f * rc * 1e9 * QP / CLIGHT
@@ -197,3 +202,47 @@ def test_gpu_c4_exits_and_rigidity_conservation():
     nrec, recs = g.exit_records()
     g.close()
     _check_c4(recs, expect, rig, lim)
+
+
+def _run_oracle_bracket(rows, n_steps):
+    m, cfg, parts, bg, expect, rig = _case(rows, (0.6, 1.6))
+    o = Oracle(cfg, m)
+    o.set_background(*bg)
+    o.add_particles(*parts)
+    for it in range(n_steps):
+        rc, st, ret, fc = o.move(_capi.MOVER_RELATIVISTIC_BORIS, 1)
+        assert rc == 0
+        if (fc < 0).all():
+            break
+    nrec, recs = o.exit_records()
+    o.close()
+    return _classify(len(expect), recs), expect
+
+
+def test_c2_and_c12_tables_are_the_stormer_formula():
+    fx = _fixture()
+    R0 = 0.299792458 * 0.25 * 3.12e-5 * (6371.2 * 1000.0)
+    assert len(fx["C2"]) == 60 and len(fx["C12"]) == 14
+    for r in fx["C2"] + fx["C12"]:
+        r_re = (6371.2 + r["alt_km"]) / 6371.2
+        assert abs(R0 * math.cos(math.radians(r["lat_deg"])) ** 4 / r_re ** 2 - r["Rc_stormer_GV"]) <= 1e-9 * r["Rc_stormer_GV"]
+    by_lat = {}
+    for r in fx["C2"]:  # run_C2.py: one cutoff per latitude whatever the longitude
+        by_lat.setdefault(r["lat_deg"], set()).add(r["Rc_stormer_GV"])
+    assert all(len(v) == 1 for v in by_lat.values()) and len(by_lat) == 5
+
+
+def test_oracle_cutoff_is_independent_of_longitude():
+    # C2: the twelve longitudes of the equatorial and the +-30 degree rows (the slow 60 degree rows stay with the GPU test above)
+    rows = [(r["alt_km"], r["lat_deg"], r["Rc_stormer_GV"], r["lon_deg"]) for r in _fixture()["C2"] if abs(r["lat_deg"]) <= 30.0]
+    assert len(rows) == 36
+    got, expect = _run_oracle_bracket(rows, N_STEPS)
+    assert (got == expect).all(), (got, expect)
+
+
+def test_oracle_brackets_the_c12_boris_rows():
+    # C12, BORIS: 9000 km and 25000 km shells, latitudes 0, +-20, +-40 (new latitudes and a second shell compared with C1)
+    rows = [(r["alt_km"], r["lat_deg"], r["Rc_stormer_GV"]) for r in _fixture()["C12"] if abs(r["lat_deg"]) <= 40.0]
+    assert len(rows) == 10
+    got, expect = _run_oracle_bracket(rows, 3 * N_STEPS)
+    assert (got == expect).all(), (got, expect)
