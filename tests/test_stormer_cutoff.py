@@ -246,3 +246,32 @@ def test_oracle_brackets_the_c12_boris_rows():
     assert len(rows) == 10
     got, expect = _run_oracle_bracket(rows, 3 * N_STEPS)
     assert (got == expect).all(), (got, expect)
+
+
+def _run_gpu_bracket(rows, n_steps):
+    m, cfg, parts, bg, expect, rig = _case(rows, (0.6, 1.6))
+    g = api.Context(cfg, m)
+    g.background_upload(*bg)
+    g.particles_upload(*parts)
+    for it in range(n_steps):
+        g.MoveParticles(_capi.MOVER_RELATIVISTIC_BORIS, stats=False)
+        g.sort()
+        if it % 100 == 99 and g.particle_count() == 0:
+            break
+    nrec, recs = g.exit_records()
+    g.close()
+    return _classify(len(expect), recs), expect
+
+
+@pytest.mark.gpu
+def test_gpu_cutoff_is_independent_of_longitude():
+    rows = [(r["alt_km"], r["lat_deg"], r["Rc_stormer_GV"], r["lon_deg"]) for r in _fixture()["C2"] if abs(r["lat_deg"]) <= 30.0]
+    got, expect = _run_gpu_bracket(rows, N_STEPS)
+    assert (got == expect).all(), (got, expect)
+
+
+@pytest.mark.gpu
+def test_gpu_brackets_the_c12_boris_rows():
+    rows = [(r["alt_km"], r["lat_deg"], r["Rc_stormer_GV"]) for r in _fixture()["C12"] if abs(r["lat_deg"]) <= 40.0]
+    got, expect = _run_gpu_bracket(rows, 3 * N_STEPS)
+    assert (got == expect).all(), (got, expect)
