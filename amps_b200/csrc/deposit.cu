@@ -53,7 +53,7 @@ static_assert(SLAB >= CHUNK * ROW, "the particle rows must fit in the slab");
 static_assert(offsetof(LeafGeo, xmin) == 0 && offsetof(LeafGeo, xmax) == 24 && offsetof(LeafGeo, dxc) == 88 && offsetof(LeafGeo, invdxc) == 112 &&
                   offsetof(LeafGeo, invV) == 136 && offsetof(LeafGeo, diag) == 144,
               "stage_header copies LeafGeo by double index");
-constexpr int DEC_MAX = 1024;
+constexpr int DEC_MAX = 1024;  // largest block (cells) whose (i,j,k) decode table is kept in shared memory; larger blocks divide
 constexpr int HDR_GEO = 82, HDR = 96;  // doubles: B [0,81), xmin[3] xmax[3] dxc[3] invdxc[3] invV diag at [82,96)
 __device__ __forceinline__ void cp_async8(double *dstShared, const double *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dstShared)), "l"(src) : "memory");
