@@ -14,17 +14,22 @@
 // the mass matrix is MM[c][c'] = T[cls(c,c')][0..8] and, because sum_c' W_c' = 1,
 // J[c] = sum_c' T[cls(c,c')][9..11].  That is 324 accumulators per cell and 324 DFMA per particle.
 //
-// The kernel is bound by the fp64 pipe and by shared-memory bandwidth, not by HBM (57 B/particle in,
-// ~4 KB/cell out).  Mapping: ONE WARP PER CELL, no block-level synchronisation at all; 8 warps per SM
-// (242 registers) are resident and drift apart, so the latency-bound phase of one warp overlaps the DFMA-bound
-// phase of the others.  Per 32-particle chunk of its cell a warp runs
-//   phase 1  lane <-> particle: B gather (27 centres of the cell staged in shared memory), alpha, weights ->
-//            one 208-byte row per particle in the warp's shared-memory slab (row stride 26 doubles: the
-//            16-byte vector accesses of consecutive rows are bank-conflict free)
-//   phase 2  30 lanes = 6 register tiles (9 classes of one px  x  6 of the 12 columns) x 5 particle slices;
-//            per particle a lane issues 8 LDS.128 + 2 LDS.64 for 9 DMUL + 54 DFMA
+// T = U^T A is a dense contraction over the particles of the cell (U[p][27], A[p][12]), so phase 2 runs on the fp64 MMA path
+// (mma.sync.m8n8k4.f64 -> SASS DMMA.884): measured on the B200 (tools/fp64_peak.cu) DMMA and DFMA share ONE pipe (33.6 / 37.2
+// TFLOP/s alone, 35 mixed), so the MMA form buys no arithmetic, but a DMMA carries 256 FMAs per issue slot, needs one 8-byte
+// shared-memory operand per lane per 256 FMAs and keeps a 8x8 tile of T in TWO registers per lane: the 108 accumulator registers
+// of the DFMA register-tile version (242 registers, 8 warps/SM, whose latency-bound phase 1 could not overlap) become 32.
+//
+// The kernel is bound by the fp64 pipe, not by HBM (57 B/particle in, ~4 KB/cell out).  Mapping: ONE WARP PER CELL, no
+// block-level synchronisation at all; the resident warps drift apart, so the latency-bound phase of one warp overlaps the
+// DMMA-bound phase of the others.  Per 32-particle chunk of its cell a warp runs
+//   phase 1  lane <-> particle: B gather (27 centres of the cell staged in shared memory), alpha, the 27 class weights and
+//            the 12 columns -> 39 doubles per particle in the warp's shared-memory slab, laid out [group of 4 particles][element]
+//            [particle in group] so that an MMA operand load of the warp is 32 consecutive doubles (conflict-free)
+//   phase 2  per group of 4 particles (the K of m8n8k4): 4 A operands (classes 8t+g), 2 B operands (columns 8n+g), 8 DMMA into
+//            the 4 x 2 tiles that cover T padded to 32 x 16 (rows >= 27 and columns >= 12 are never read)
 // and per cell
-//   reduce   the 5 slice partials are folded through the slab (every lane stores its 54 sums, then sums 11 entries over the slices)
+//   spill    the C fragments go to T[32][16] in the slab (the K sum is complete inside the MMA: nothing to fold)
 //   flush    one fp64 RED per value into J[nCorners][3], M[nCorners][243] (576 + 24 per cell).
 // The particles of the next chunk - of this cell or, in its last chunk, of the warp's next cell - are requested one chunk ahead,
 // and the "cell header" (the B_cur values around the cell + the leaf geometry, 96 doubles) of the warp's next cell one cell ahead
@@ -38,14 +43,24 @@
 
 namespace amps {
 
-constexpr int ROW = 26;  // doubles per particle row: XX[0..2] - YZ[4..12] - a[14..25] (k alpha[9], q~ alpha v/V [3])
-constexpr int OFF_YZ = 4, OFF_A = 14;
+constexpr int N_EL = 39;                   // doubles per particle: u[27] (class weights) - a[12] (k alpha[9], q~ alpha v/V [3])
+constexpr int EL_A = 27;
+constexpr int GRP = 4 * N_EL;              // doubles per group of 4 particles, [element][particle in group]; 2*GRP = 24 mod 32 words:
+                                           // the 39 phase-1 stores of a half-warp (4 groups x 4 particles) hit 32 distinct banks
 constexpr int CHUNK = 32;                  // particles per phase-1 pass (one per lane)
-constexpr int DEP_WARPS = 4, DEP_THREADS = 32 * DEP_WARPS, DEP_CTAS_PER_SM = 2;
-constexpr int N_TILES = 6, N_SLICES = 5;   // 30 active lanes
-constexpr int N_T = 27 * 12;               // class sums per cell
-constexpr int SLAB = N_SLICES * N_T;       // doubles per warp: the particle rows of a chunk, later the 5 slice partials of T
-static_assert(SLAB >= CHUNK * ROW, "the particle rows must fit in the slab");
+#ifndef AMPS_DEP_WARPS
+#define AMPS_DEP_WARPS 4
+#endif
+#ifndef AMPS_DEP_CTAS
+#define AMPS_DEP_CTAS 3
+#endif
+constexpr int DEP_WARPS = AMPS_DEP_WARPS, DEP_THREADS = 32 * DEP_WARPS, DEP_CTAS_PER_SM = AMPS_DEP_CTAS;
+constexpr int T_LD = 16;                   // leading dimension of T[32][16] after the spill
+constexpr int SLAB = (CHUNK / 4) * GRP;    // doubles per warp: the particle elements of a chunk, later T
+static_assert(SLAB >= 32 * T_LD, "T must fit in the slab");
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 // per-warp "cell header" in shared memory, double-buffered: the 27 x 3 centre (or 8 x 3 corner) values of B_cur the cell's
 // stencils can touch + the leaf geometry phase 1 needs.  The header of the warp's NEXT cell is fetched with 8-byte cp.async
@@ -114,14 +129,16 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     }
   for (int o = threadIdx.x; o < 576; o += DEP_THREADS) {
     const int c = o / 72, r = o - 72 * c, d = r / 9, col = r - 9 * d;
-    sFlush[o] = (unsigned)c | ((unsigned)(9 * index_matrix(c, d) + col) << 3) | ((unsigned)(pair_class(c, d) * 12 + col) << 11);
-    if (o < 64) sJcls[o] = (unsigned short)(pair_class(o >> 3, o & 7) * 12);
+    sFlush[o] = (unsigned)c | ((unsigned)(9 * index_matrix(c, d) + col) << 3) | ((unsigned)(pair_class(c, d) * T_LD + col) << 11);
+    if (o < 64) sJcls[o] = (unsigned short)(pair_class(o >> 3, o & 7) * T_LD);
     if (o < 81) {
       const int n = o / 3, d = o - 3 * n;
       const int di = n % 3 - 1, dj = (n / 3) % 3 - 1, dk = n / 9 - 1;
       sBoff[o] = 3 * (di + m.TN[0] * (dj + dk * m.TN[1])) + d;
     }
   }
+  // the slab starts finite: the elements of lanes beyond the end of a cell's last chunk are multiplied by zero weights
+  for (int o = threadIdx.x; o < DEP_WARPS * SLAB; o += DEP_THREADS) sRows[o] = 0.0;
   __syncthreads();
 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -165,9 +182,12 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     if (lane < 14) cp_async8(h + HDR_GEO + lane, reinterpret_cast<const double *>(m.leaf + lf) + (lane < 6 ? lane : lane + 5));
   };
 
-  const bool active = lane < N_TILES * N_SLICES;
-  const int tile = active ? lane % N_TILES : 0, slice = active ? lane / N_TILES : 0;
-  const int px = tile % 3, h = tile / 3;  // classes px*9 .. px*9+8, columns 6h .. 6h+5
+  // m8n8k4 fragments: A[row g][k kk] = u[particle 4 ks + kk][class 8 t + g], B[k kk][col g] = a[particle][column 8 n + g],
+  // C[row g][cols 2 kk, 2 kk + 1].  Rows >= 27 / columns >= 12 of the padded T read a clamped element: their sums are never used
+  const int g = lane >> 2, kk = lane & 3;
+  const int eA0 = 4 * g + kk, eA1 = 4 * (8 + g) + kk, eA2 = 4 * (16 + g) + kk, eA3 = 4 * min(24 + g, 26) + kk;
+  const int eB0 = 4 * (EL_A + g) + kk, eB1 = 4 * (EL_A + min(8 + g, 11)) + kk;
+  double *const el = rows + (lane >> 2) * GRP + (lane & 3);  // phase 1: element e of this lane's particle is el[4 e]
   const double invc = 1.0 / sp.LightSpeed;
   double eAcc = 0.0, cflMax = 0.0;  // kDiag: per-lane energy; lane 16 s keeps the cfl of species s
 
@@ -235,9 +255,9 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
     hbuf ^= 1;
     const double invV = sG[12];
 
-    double acc[54];
+    double acc[16];  // C fragments of the 4 x 2 tiles: acc[2 (2 t + n) + {0,1}]
 #pragma unroll
-    for (int i = 0; i < 54; i++) acc[i] = 0.0;
+    for (int i = 0; i < 16; i++) acc[i] = 0.0;
     double vm0 = 0.0, vm1 = 0.0;  // kDiag: sum |v| dt of species 0 / 1 seen by this lane
     int cnt01 = 0;                // counts: species 0 in the low half, species 1 in the high half
 
@@ -287,7 +307,6 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
       }
       if (lane < np) {
         const double LocalParticleWeight = sp.weight[spec] * pw;
-        double *row = rows + lane * ROW;
         // local coordinates: CornerBased::InitStencil (pic_interpolation_routines.cpp:1090-1098)
         double xl[3];
         {
@@ -303,16 +322,16 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
           }
         }
         {
-          // per-dimension pair products of the un-normalised corner weights WeightPG (:2200)
+          // the 27 class weights u = XX[px] YY[py] ZZ[pz]: per-dimension pair products of the un-normalised corner weights
+          // WeightPG (:2200)
           const double X0 = 1.0 - xl[0], X1 = xl[0], Y0 = 1.0 - xl[1], Y1 = xl[1], Z0 = 1.0 - xl[2], Z1 = xl[2];
-          const double yy0 = Y0 * Y0, yy1 = Y0 * Y1, yy2 = Y1 * Y1, zz0 = Z0 * Z0, zz1 = Z0 * Z1, zz2 = Z1 * Z1;
-          reinterpret_cast<double2 *>(row)[0] = make_double2(X0 * X0, X0 * X1);
-          row[2] = X1 * X1;
-          reinterpret_cast<double2 *>(row + OFF_YZ)[0] = make_double2(yy0 * zz0, yy0 * zz1);
-          reinterpret_cast<double2 *>(row + OFF_YZ)[1] = make_double2(yy0 * zz2, yy1 * zz0);
-          reinterpret_cast<double2 *>(row + OFF_YZ)[2] = make_double2(yy1 * zz1, yy1 * zz2);
-          reinterpret_cast<double2 *>(row + OFF_YZ)[3] = make_double2(yy2 * zz0, yy2 * zz1);
-          row[OFF_YZ + 8] = yy2 * zz2;
+          const double xx[3] = {X0 * X0, X0 * X1, X1 * X1};
+          const double yy[3] = {Y0 * Y0, Y0 * Y1, Y1 * Y1}, zz[3] = {Z0 * Z0, Z0 * Z1, Z1 * Z1};
+          double yz[9];
+#pragma unroll
+          for (int i = 0; i < 9; i++) yz[i] = yy[i / 3] * zz[i % 3];
+#pragma unroll
+          for (int i = 0; i < 27; i++) el[4 * i] = xx[i / 9] * yz[i % 9];
         }
         // B at the particle: cell-centred trilinear stencil on B_cur (:2100-2129); relative to this cell the
         // stencil cells are -1/0 (particle in the lower half) or 0/+1 (upper half) per dimension
@@ -400,41 +419,33 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
         const double a6 = S02 + A1, a7 = S12 - A0, a8 = fma(t2, cB2, kc);
         // Jg/CellVolume = q~/V alpha v = (k alpha v)/beta (:2367)
         const double ib = sInvBeta[spec];
-        double2 *a = reinterpret_cast<double2 *>(row + OFF_A);
-        a[0] = make_double2(a0, a1);
-        a[1] = make_double2(a2, a3);
-        a[2] = make_double2(a4, a5);
-        a[3] = make_double2(a6, a7);
-        a[4] = make_double2(a8, ib * (a0 * v0 + a1 * v1 + a2 * v2));
-        a[5] = make_double2(ib * (a3 * v0 + a4 * v1 + a5 * v2), ib * (a6 * v0 + a7 * v1 + a8 * v2));
+        double *a = el + 4 * EL_A;
+        a[0] = a0, a[4] = a1, a[8] = a2, a[12] = a3, a[16] = a4, a[20] = a5, a[24] = a6, a[28] = a7, a[32] = a8;
+        a[36] = ib * (a0 * v0 + a1 * v1 + a2 * v2);
+        a[40] = ib * (a3 * v0 + a4 * v1 + a5 * v2);
+        a[44] = ib * (a6 * v0 + a7 * v1 + a8 * v2);
+      } else if (lane < ((np + 3) & ~3)) {
+        // the last group of the cell is not full: zero class weights (the columns left there by earlier chunks are finite)
+#pragma unroll
+        for (int i = 0; i < 27; i++) el[4 * i] = 0.0;
       }
       __syncwarp();
-      // ---------------- phase 2: register-tile accumulation ----------------
-      if (active) {
+      // ---------------- phase 2: T += U^T A on the fp64 MMA path, 4 particles per step ----------------
+      {
+        const int nks = (np + 3) >> 2;
 #pragma unroll 2
-        for (int q = slice; q < np; q += N_SLICES) {
-          const double *row = rows + q * ROW;
-          const double xx = row[px];
-          const double2 y01 = reinterpret_cast<const double2 *>(row + OFF_YZ)[0];
-          const double2 y23 = reinterpret_cast<const double2 *>(row + OFF_YZ)[1];
-          const double2 y45 = reinterpret_cast<const double2 *>(row + OFF_YZ)[2];
-          const double2 y67 = reinterpret_cast<const double2 *>(row + OFF_YZ)[3];
-          const double y8 = row[OFF_YZ + 8];
-          const double2 a01 = reinterpret_cast<const double2 *>(row + OFF_A + 6 * h)[0];
-          const double2 a23 = reinterpret_cast<const double2 *>(row + OFF_A + 6 * h)[1];
-          const double2 a45 = reinterpret_cast<const double2 *>(row + OFF_A + 6 * h)[2];
-          // u_cls a_col = (XX YZ_j) a_col = YZ_j (XX a_col): 6 products per particle and lane instead of 9
-          const double u[9] = {y01.x, y01.y, y23.x, y23.y, y45.x, y45.y, y67.x, y67.y, y8};
-          const double xa0 = xx * a01.x, xa1 = xx * a01.y, xa2 = xx * a23.x, xa3 = xx * a23.y, xa4 = xx * a45.x, xa5 = xx * a45.y;
-#pragma unroll
-          for (int j = 0; j < 9; j++) {
-            acc[6 * j + 0] = fma(u[j], xa0, acc[6 * j + 0]);
-            acc[6 * j + 1] = fma(u[j], xa1, acc[6 * j + 1]);
-            acc[6 * j + 2] = fma(u[j], xa2, acc[6 * j + 2]);
-            acc[6 * j + 3] = fma(u[j], xa3, acc[6 * j + 3]);
-            acc[6 * j + 4] = fma(u[j], xa4, acc[6 * j + 4]);
-            acc[6 * j + 5] = fma(u[j], xa5, acc[6 * j + 5]);
-          }
+        for (int ks = 0; ks < nks; ks++) {
+          const double *q = rows + ks * GRP;
+          const double fa0 = q[eA0], fa1 = q[eA1], fa2 = q[eA2], fa3 = q[eA3];
+          const double fb0 = q[eB0], fb1 = q[eB1];
+          dmma884(acc[0], acc[1], fa0, fb0);
+          dmma884(acc[2], acc[3], fa0, fb1);
+          dmma884(acc[4], acc[5], fa1, fb0);
+          dmma884(acc[6], acc[7], fa1, fb1);
+          dmma884(acc[8], acc[9], fa2, fb0);
+          dmma884(acc[10], acc[11], fa2, fb1);
+          dmma884(acc[12], acc[13], fa3, fb0);
+          dmma884(acc[14], acc[15], fa3, fb1);
         }
       }
     }
@@ -454,24 +465,13 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
       const double den = cs * sG[13];
       if ((lane & 15) == 0 && cs > 0 && a > cflMax * den) cflMax = a / den;
     }
-    // ---- fold the 5 slices through shared memory: every lane stores its 54 partial sums at their T index in its
-    //      slice's copy, then lane l sums entries l, l+32, ... over the slices (in place into copy 0) ----
+    // ---- spill the C fragments: T[class 8 t + g][column 8 n + 2 kk + {0,1}] (the K sum is complete, nothing to fold) ----
     __syncwarp();  // phase 2 finished reading the slab
-    if (active) {
-      double *r = rows + slice * N_T + (px * 9) * 12 + 6 * h;
 #pragma unroll
-      for (int j = 0; j < 9; j++) {
-        reinterpret_cast<double2 *>(r + 12 * j)[0] = make_double2(acc[6 * j + 0], acc[6 * j + 1]);
-        reinterpret_cast<double2 *>(r + 12 * j)[1] = make_double2(acc[6 * j + 2], acc[6 * j + 3]);
-        reinterpret_cast<double2 *>(r + 12 * j)[2] = make_double2(acc[6 * j + 4], acc[6 * j + 5]);
-      }
-    }
-    __syncwarp();
+    for (int t = 0; t < 4; t++)
 #pragma unroll
-    for (int q = 0; q < (N_T + 31) / 32; q++) {
-      const int i = lane + 32 * q;
-      if (i < N_T) rows[i] = ((rows[i] + rows[N_T + i]) + (rows[2 * N_T + i] + rows[3 * N_T + i])) + rows[4 * N_T + i];
-    }
+      for (int n = 0; n < 2; n++)
+        *reinterpret_cast<double2 *>(rows + (8 * t + g) * T_LD + 8 * n + 2 * kk) = make_double2(acc[2 * (2 * t + n)], acc[2 * (2 * t + n) + 1]);
     __syncwarp();
     // ---- flush the mass matrix: 64 ordered corner pairs x 9 (both (c,c') and (c',c) get the same block, :2411-2420)
 #pragma unroll
