@@ -166,9 +166,12 @@ PROTOTYPES = {
     "amps_gpu_magnetic_moment_download": (C.c_int, [_vp, _vp, C.c_int64, _i64p]),
     "amps_gpu_particles_upload_aos": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.POINTER(AosLayout)]),
     "amps_gpu_particles_upload_soa": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64]),
+    "amps_gpu_particles_append_soa": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64]),
     "amps_gpu_particle_count": (C.c_int, [_vp, _i64p]),
     "amps_gpu_particles_download_soa": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, _i64p]),
     "amps_gpu_particles_download_aos": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.POINTER(AosLayout), _i64p]),
+    "amps_gpu_particles_slot_delta": (C.c_int, [_vp, _i64p, _vp, C.c_int64, _i64p]),
+    "amps_gpu_particles_assign_slots": (C.c_int, [_vp, _vp, C.c_int64]),
     "amps_gpu_cell_table_download": (C.c_int, [_vp, _vp, C.c_int64]),
     "amps_gpu_sort": (C.c_int, [_vp]),
     "amps_gpu_move": (C.c_int, [_vp, C.c_int, C.POINTER(MoveStats)]),

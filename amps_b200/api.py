@@ -176,6 +176,17 @@ class Context:
         ptrs = None if ptrs is None else np.ascontiguousarray(ptrs, dtype=np.int32)
         self._ck(self.lib.amps_gpu_particles_upload_soa(self._h, _ptr(x), _ptr(v), _ptr(w), _ptr(species), _ptr(cells), _ptr(ptrs), n))
 
+    def particles_append(self, x, v, w, species, cells, ptrs=None):
+        """the same behind the resident particles (injection; large populations in pieces)"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        n = x.shape[1]
+        w = None if w is None else np.ascontiguousarray(w, dtype=np.float64)
+        species = np.ascontiguousarray(species, dtype=np.uint8)
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        ptrs = None if ptrs is None else np.ascontiguousarray(ptrs, dtype=np.int32)
+        self._ck(self.lib.amps_gpu_particles_append_soa(self._h, _ptr(x), _ptr(v), _ptr(w), _ptr(species), _ptr(cells), _ptr(ptrs), n))
+
     def particle_count(self):
         n = C.c_int64()
         self._ck(self.lib.amps_gpu_particle_count(self._h, C.byref(n)))
@@ -192,6 +203,18 @@ class Context:
         self._ck(self.lib.amps_gpu_particles_download_soa(self._h, _ptr(x[0]), _ptr(x[1]), _ptr(w), _ptr(sp), _ptr(cells), _ptr(ptrs), n,
                                                           C.byref(nn)))
         return {"x": x[0], "v": x[1], "w": w, "species": sp, "cells": cells, "ptrs": ptrs}
+
+    def slot_delta(self):
+        """(n_new, released): records without a ParticleBuffer slot (arrivals) and the slots whose particle is gone."""
+        n_new, n_rel = C.c_int64(), C.c_int64()
+        self._ck(self.lib.amps_gpu_particles_slot_delta(self._h, C.byref(n_new), None, 0, C.byref(n_rel)))
+        rel = np.empty(max(1, int(n_rel.value)), dtype=np.int64)
+        self._ck(self.lib.amps_gpu_particles_slot_delta(self._h, C.byref(n_new), _ptr(rel), rel.size, C.byref(n_rel)))
+        return int(n_new.value), rel[: int(n_rel.value)].copy()
+
+    def assign_slots(self, slots):
+        slots = np.ascontiguousarray(slots, dtype=np.int64)
+        self._ck(self.lib.amps_gpu_particles_assign_slots(self._h, _ptr(slots), slots.size))
 
     def cell_table(self):
         t = np.empty(self.mesh.n_cells + 1, dtype=np.int64)

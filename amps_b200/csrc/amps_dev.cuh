@@ -149,6 +149,7 @@ void launch_net_charge(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, co
                        cudaStream_t s);
 size_t sort_scan_tmp_bytes(long long nCells);
 // migration record: 8 doubles (x,v,w,meta) + mu when the particles carry it
+constexpr int AMPS_MIGRATION_RECORD_MAX = 10;  // doubles: the send / receive regions are sized for it
 __host__ __device__ inline int migration_record_len(const ParticleSoA &p) { return 8 + (p.mu ? 1 : 0) + (p.vpar ? 1 : 0); }
 void launch_pack_leavers(const DevMesh &m, ParticleSoA p, const int *nSlots, long long nUpper, const int *leafOwner, const int *leafGlobal, int me,
                          double *sendBuf, long long capPerPeer, int *sendCount, int *cellCount, int *errFlag, cudaStream_t s);

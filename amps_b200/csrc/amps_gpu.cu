@@ -35,7 +35,11 @@ struct amps_gpu_ctx {
   ParticleSoA buf[2];
   int cur = 0;
   int *d_n = nullptr;  // [2]
-  long long nUpper = 0;
+  long long nUpper = 0;  // host-side bound of the used slots of buf[cur] (grid sizes); re-tightened after every sort (h_nSorted)
+  int *h_nSorted = nullptr;         // pinned: particle count written by the last sort (slots [0, count) are exactly the residents)
+  cudaEvent_t evSorted = nullptr;   // the copy into h_nSorted has completed
+  bool nSortedPending = false;
+  std::vector<int32_t> h_uploadedSlots;  // ParticleBuffer slots handed over by the last upload / slot assignment (download bookkeeping)
   bool sorted = false, countValid = false;
   int *d_cellCount = nullptr, *d_cellStart = nullptr, *d_cellFill = nullptr;
   void *d_scanTmp = nullptr;
@@ -324,6 +328,8 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   for (cudaEvent_t e : ctx->dlEvents) cudaEventDestroy(e);
   if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   if (ctx->evCounts) cudaEventDestroy(ctx->evCounts);
+  if (ctx->evSorted) cudaEventDestroy(ctx->evSorted);
+  if (ctx->h_nSorted) cudaFreeHost(ctx->h_nSorted);
   cudaFree(ctx->d_spec), cudaFree(ctx->d_phi), cudaFree(ctx->d_cplCount), cudaFree(ctx->d_sample), cudaFree(ctx->d_nSampled), cudaFree(ctx->d_pack);
   if (ctx->evBoundary) cudaEventDestroy(ctx->evBoundary);
   if (ctx->evRecv) cudaEventDestroy(ctx->evRecv);
@@ -639,8 +645,9 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
     if ((rc = upload_array(ctx, &t3, mesh->global_leaf_to_local, (size_t)mesh->n_global_leaves))) return rc;
     ctx->d_leafOwner = const_cast<int *>(t1), ctx->d_leafGlobal = const_cast<int *>(t2), ctx->d_g2l = const_cast<int *>(t3);
     ctx->capPerPeer = ctx->cfg.capacity / 32 > 65536 ? ctx->cfg.capacity / 32 : 65536;
-    if ((rc = dev_alloc(ctx, &ctx->d_sendBuf, (size_t)ctx->nRanks * ctx->capPerPeer * 9))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_recvBuf, (size_t)ctx->nRanks * ctx->capPerPeer * 9))) return rc;
+    // sized for the longest record (x, v, w, key|species + magnetic moment + v_parallel)
+    if ((rc = dev_alloc(ctx, &ctx->d_sendBuf, (size_t)ctx->nRanks * ctx->capPerPeer * AMPS_MIGRATION_RECORD_MAX))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_recvBuf, (size_t)ctx->nRanks * ctx->capPerPeer * AMPS_MIGRATION_RECORD_MAX))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_sendCount, (size_t)ctx->nRanks))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_allCounts, (size_t)ctx->nRanks * ctx->nRanks))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_errFlag, 1))) return rc;
@@ -834,6 +841,27 @@ int amps_gpu_exit_records(amps_gpu_ctx *ctx, amps_gpu_exit_record *buf, int64_t 
   return AMPS_GPU_OK;
 }
 
+// after a sort the residents are exactly slots [0, count): the count travels to pinned host memory behind the sort and
+// tighten_upper() adopts it once it has arrived, so the slot bound follows the resident population instead of growing with
+// every arrival (false ERR_CAPACITY after enough steps on several ranks)
+static int request_sorted_count(amps_gpu_ctx *ctx) {
+  if (!ctx->h_nSorted) {
+    CK(cudaMallocHost(&ctx->h_nSorted, sizeof(int)));
+    CK(cudaEventCreateWithFlags(&ctx->evSorted, cudaEventDisableTiming));
+  }
+  CK(cudaMemcpyAsync(ctx->h_nSorted, ctx->d_n + ctx->cur, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(ctx->evSorted, ctx->stream));
+  ctx->nSortedPending = true;
+  return AMPS_GPU_OK;
+}
+static void tighten_upper(amps_gpu_ctx *ctx, bool wait) {
+  if (!ctx->nSortedPending) return;
+  if (wait) cudaEventSynchronize(ctx->evSorted);
+  else if (cudaEventQuery(ctx->evSorted) != cudaSuccess) return;
+  ctx->nUpper = *ctx->h_nSorted;
+  ctx->nSortedPending = false;
+}
+
 static int do_sort(amps_gpu_ctx *ctx) {
   ProfScope prof(ctx, AMPS_GPU_PHASE_SORT);
   ParticleSoA &src = ctx->buf[ctx->cur], &dst = ctx->buf[1 - ctx->cur];
@@ -843,7 +871,7 @@ static int do_sort(amps_gpu_ctx *ctx) {
   ctx->cur = 1 - ctx->cur;
   ctx->sorted = true;
   ctx->countValid = false;
-  return AMPS_GPU_OK;
+  return request_sorted_count(ctx);
 }
 
 // amps_gpu_step: the counting sort only builds the permutation (8 B per particle); the deposit gathers through it and
@@ -923,7 +951,7 @@ static int do_sort_deposit_fused(amps_gpu_ctx *ctx) {
   ctx->cur = 1 - ctx->cur;
   ctx->sorted = true;
   ctx->countValid = false;
-  return AMPS_GPU_OK;
+  return request_sorted_count(ctx);
 }
 
 int amps_gpu_sort(amps_gpu_ctx *ctx) {
@@ -933,19 +961,39 @@ int amps_gpu_sort(amps_gpu_ctx *ctx) {
   return do_sort(ctx);
 }
 
+static int upload_soa(amps_gpu_ctx *ctx, const double *x, const double *v, const double *w, const uint8_t *species, const int32_t *cells,
+                      const int32_t *ptrs, int64_t n, bool append);
 int amps_gpu_particles_upload_soa(amps_gpu_ctx *ctx, const double *x, const double *v, const double *w, const uint8_t *species,
                                   const int32_t *cells, const int32_t *ptrs, int64_t n) {
+  return upload_soa(ctx, x, v, w, species, cells, ptrs, n, false);
+}
+// the same behind the resident particles (injection between epochs; large populations handed over in pieces)
+int amps_gpu_particles_append_soa(amps_gpu_ctx *ctx, const double *x, const double *v, const double *w, const uint8_t *species,
+                                  const int32_t *cells, const int32_t *ptrs, int64_t n) {
+  return upload_soa(ctx, x, v, w, species, cells, ptrs, n, true);
+}
+static int upload_soa(amps_gpu_ctx *ctx, const double *x, const double *v, const double *w, const uint8_t *species, const int32_t *cells,
+                      const int32_t *ptrs, int64_t n, bool append) {
   if (!ctx || !x || !v || !species || !cells || n < 0) return AMPS_GPU_ERR_ARG;
   if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "particles_upload before mesh_upload");
-  if (n > ctx->cfg.capacity) FAIL(AMPS_GPU_ERR_CAPACITY, "particle capacity exceeded");
   CK(cudaSetDevice(ctx->cfg.device));
-  for (int64_t i = 0; i < n; i++)
+  int64_t base = 0;
+  if (append) {
+    if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "particles_append needs the sorted layout (the residents are slots [0, count))");
+    int rc0 = amps_gpu_particle_count(ctx, &base);
+    if (rc0) return rc0;
+  }
+  if (base + n > ctx->cfg.capacity) FAIL(AMPS_GPU_ERR_CAPACITY, "particle capacity exceeded");
+  for (int64_t i = 0; i < n; i++) {
     if (cells[i] < 0 || cells[i] >= ctx->nCells) FAIL(AMPS_GPU_ERR_ARG, "particle cell out of range");
+    // the kernels index the species tables with bits 0-5 (SetI exits on an out-of-range species, pic.h ParticleBuffer::SetI)
+    if ((species[i] & 0x3f) >= ctx->sp.n) FAIL(AMPS_GPU_ERR_ARG, "particle species out of range");
+  }
   ParticleSoA &b = ctx->buf[ctx->cur];
   cudaStream_t s = ctx->stream;
   for (int d = 0; d < 3; d++) {
-    CK(cudaMemcpyAsync(b.x[d], x + (size_t)d * n, sizeof(double) * n, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(b.v[d], v + (size_t)d * n, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b.x[d] + base, x + (size_t)d * n, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b.v[d] + base, v + (size_t)d * n, sizeof(double) * n, cudaMemcpyHostToDevice, s));
   }
   std::vector<double> ones;
   std::vector<int32_t> iota;
@@ -955,18 +1003,25 @@ int amps_gpu_particles_upload_soa(amps_gpu_ctx *ctx, const double *x, const doub
   }
   if (!ptrs) {
     iota.resize((size_t)n);
-    for (int64_t i = 0; i < n; i++) iota[i] = (int32_t)i;
+    for (int64_t i = 0; i < n; i++) iota[i] = (int32_t)(base + i);
     ptrs = iota.data();
   }
-  CK(cudaMemcpyAsync(b.w, w, sizeof(double) * n, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(b.spec, species, n, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(b.key, cells, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(b.ptr, ptrs, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
-  const int n32 = (int)n;
+  CK(cudaMemcpyAsync(b.w + base, w, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(b.spec + base, species, n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(b.key + base, cells, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(b.ptr + base, ptrs, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+  if (append) {
+    if (b.mu) CK(cudaMemsetAsync(b.mu + base, 0, sizeof(double) * n, s));
+    if (b.vpar) CK(cudaMemsetAsync(b.vpar + base, 0, sizeof(double) * n, s));
+  }
+  const int n32 = (int)(base + n);
   CK(cudaMemcpyAsync(ctx->d_n + ctx->cur, &n32, sizeof(int), cudaMemcpyHostToDevice, s));
   CK(cudaStreamSynchronize(s));  // host temporaries
-  ctx->nUpper = n;
+  ctx->nUpper = base + n;
+  ctx->nSortedPending = false;
   ctx->countValid = false;
+  if (append) ctx->h_uploadedSlots.insert(ctx->h_uploadedSlots.end(), ptrs, ptrs + n);
+  else ctx->h_uploadedSlots.assign(ptrs, ptrs + n);
   return do_sort(ctx);
 }
 
@@ -1073,7 +1128,8 @@ int amps_gpu_particles_download_aos(amps_gpu_ctx *ctx, void *records, int64_t *f
     for (int64_t c = 0; c < ctx->nCells; c++) first_cell_particle[c] = -1;
   for (int64_t i = 0; i < n; i++) {
     const int64_t slot = pt[i];
-    if (slot < 0 || slot >= n_max) FAIL(AMPS_GPU_ERR_ARG, "particle slot outside the caller's buffer");
+    if (slot < 0) FAIL(AMPS_GPU_ERR_STATE, "a resident record has no ParticleBuffer slot (it arrived by migration): amps_gpu_particles_slot_delta + _assign_slots first");
+    if (slot >= n_max) FAIL(AMPS_GPU_ERR_ARG, "particle slot outside the caller's buffer");
     unsigned char *r = base + slot * lay->stride;
     double t[3] = {x[i], x[n + i], x[2 * n + i]};
     memcpy(r + lay->off_x, t, 24);
@@ -1096,6 +1152,61 @@ int amps_gpu_particles_download_aos(amps_gpu_ctx *ctx, void *records, int64_t *f
   return AMPS_GPU_OK;
 }
 
+// Slot bookkeeping of the caller's PIC::ParticleBuffer at an epoch end: arrivals of amps_gpu_migrate carry ptr = -1
+// (no record on this rank yet: GetNewParticle, pic_pbuffer.cpp:371-437), and the records of particles that a mover / boundary
+// deleted or that migrated away must go back to the free list (DeleteParticle, pic_pbuffer.cpp:594-666).
+int amps_gpu_particles_slot_delta(amps_gpu_ctx *ctx, int64_t *n_new, int64_t *released, int64_t max_released, int64_t *n_released) {
+  if (!ctx || !n_new || !n_released || max_released < 0 || (max_released > 0 && !released)) return AMPS_GPU_ERR_ARG;
+  int64_t n = 0;
+  int rc = amps_gpu_particle_count(ctx, &n);
+  if (rc) return rc;
+  std::vector<int32_t> pt((size_t)n + 1);
+  CK(cudaMemcpy(pt.data(), ctx->buf[ctx->cur].ptr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+  int32_t maxSlot = -1;
+  for (int32_t v : ctx->h_uploadedSlots) maxSlot = v > maxSlot ? v : maxSlot;
+  std::vector<char> present((size_t)maxSlot + 1, 0);
+  int64_t nNew = 0;
+  for (int64_t i = 0; i < n; i++) {
+    if (pt[i] < 0) nNew++;
+    else if (pt[i] <= maxSlot) present[pt[i]] = 1;
+  }
+  int64_t nRel = 0;
+  for (int32_t v : ctx->h_uploadedSlots)
+    if (v >= 0 && !present[v]) {
+      if (nRel < max_released) released[nRel] = v;
+      nRel++;
+    }
+  *n_new = nNew, *n_released = nRel;
+  if (nRel <= max_released) {  // delivered: the released slots leave the books
+    std::vector<int32_t> keep;
+    keep.reserve(ctx->h_uploadedSlots.size());
+    for (int32_t v : ctx->h_uploadedSlots)
+      if (v >= 0 && present[v]) keep.push_back(v);
+    ctx->h_uploadedSlots.swap(keep);
+  }
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_particles_assign_slots(amps_gpu_ctx *ctx, const int64_t *slots, int64_t n_slots) {
+  if (!ctx || n_slots < 0 || (n_slots > 0 && !slots)) return AMPS_GPU_ERR_ARG;
+  int64_t n = 0;
+  int rc = amps_gpu_particle_count(ctx, &n);
+  if (rc) return rc;
+  std::vector<int32_t> pt((size_t)n + 1);
+  CK(cudaMemcpy(pt.data(), ctx->buf[ctx->cur].ptr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+  int64_t k = 0;
+  for (int64_t i = 0; i < n; i++)
+    if (pt[i] < 0) {
+      if (k >= n_slots) FAIL(AMPS_GPU_ERR_ARG, "assign_slots: fewer slots than records without one (see amps_gpu_particles_slot_delta)");
+      if (slots[k] < 0 || slots[k] > 0x7fffffffLL) FAIL(AMPS_GPU_ERR_ARG, "assign_slots: slot out of range");
+      pt[i] = (int32_t)slots[k++];
+      ctx->h_uploadedSlots.push_back(pt[i]);
+    }
+  if (k != n_slots) FAIL(AMPS_GPU_ERR_ARG, "assign_slots: more slots than records without one");
+  CK(cudaMemcpy(ctx->buf[ctx->cur].ptr, pt.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+  return AMPS_GPU_OK;
+}
+
 int amps_gpu_cell_table_download(amps_gpu_ctx *ctx, int64_t *cell_start, int64_t n_cells_plus_1) {
   if (!ctx || !cell_start) return AMPS_GPU_ERR_ARG;
   if (!ctx->meshReady || n_cells_plus_1 != ctx->nCells + 1) FAIL(AMPS_GPU_ERR_ARG, "cell table size mismatch");
@@ -1110,6 +1221,7 @@ int amps_gpu_cell_table_download(amps_gpu_ctx *ctx, int64_t *cell_start, int64_t
 
 static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "move before mesh upload");
+  tighten_upper(ctx, false);
   if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "move needs the (block,cell)-sorted layout: call amps_gpu_sort");
   if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS && mover_id != AMPS_MOVER_BORIS &&
       mover_id != AMPS_MOVER_RELATIVISTIC_GCA && mover_id != AMPS_MOVER_GC_FIRST_ORDER && mover_id != AMPS_MOVER_GC_SECOND_ORDER &&
@@ -1556,14 +1668,21 @@ static int do_migrate(amps_gpu_ctx *ctx, int64_t *n_sent, int64_t *n_received, b
   } else {
     CK(cudaStreamSynchronize(s));
   }
-  if (err) FAIL(AMPS_GPU_ERR_CAPACITY, "migration send buffer overflow (more than capacity/32 leavers to one rank)");
+  // the stream is idle here: the count of the last sort has arrived, the slot bound drops back to the resident population
+  tighten_upper(ctx, true);
+  if (err) CK(cudaMemsetAsync(ctx->d_errFlag, 0, sizeof(int), s));  // reported once, not sticky
+  // Every rank holds the same R x R matrix, so every rank takes the same decision without another message: an overflowing
+  // pair (a rank packed more leavers for one peer than a send region holds) fails the exchange on ALL ranks after a matched
+  // transfer of the clamped counts -- no rank is left waiting in a receive nobody sends
+  bool overflow = false;
+  for (size_t i = 0; i < all.size(); i++)
+    if (all[i] > ctx->capPerPeer) all[i] = (int)ctx->capPerPeer, overflow = true;
   long long nRecv = 0, nSend = 0;
   std::vector<long long> roff(R, 0);
   for (int r = 0; r < R; r++) {
     roff[r] = nRecv;
     if (r != me) nRecv += all[(size_t)r * R + me], nSend += all[(size_t)me * R + r];
   }
-  if (nRecv > (long long)R * ctx->capPerPeer) FAIL(AMPS_GPU_ERR_CAPACITY, "migration receive buffer overflow");
   s1.end();
   Sub s2(ctx, 18);
   NCK(a.GroupStart());
@@ -1575,6 +1694,9 @@ static int do_migrate(amps_gpu_ctx *ctx, int64_t *n_sent, int64_t *n_received, b
   }
   NCK(a.GroupEnd());
   s2.end();
+  // (reported after the matched transfer, so that the peers of this rank are not left in a receive)
+  if (err & 2) FAIL(AMPS_GPU_ERR_STATE, "the previous exchange dropped arrivals (unknown leaf, foreign owner or no free slot): the mesh tables of the ranks disagree");
+  if (overflow) FAIL(AMPS_GPU_ERR_CAPACITY, "migration send buffer overflow (more than capacity/32 leavers from one rank to another); every rank reports it");
   if (ctx->nUpper + nRecv > ctx->cfg.capacity) FAIL(AMPS_GPU_ERR_CAPACITY, "particle capacity exceeded by arriving particles");
   Sub s3(ctx, 19);
   launch_unpack_arrivals(ctx->dm, ctx->d_recvBuf, (int)nRecv, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->d_g2l, ctx->d_leafOwner, me,
@@ -1789,6 +1911,7 @@ static int do_step_JM(amps_gpu_ctx *ctx, int mover_id, double *J_host, double *M
   ctx->cur = 1 - ctx->cur;
   ctx->sorted = true;
   ctx->countValid = false;
+  if ((rc = request_sorted_count(ctx))) return rc;
   CK(cudaStreamSynchronize(ctx->copyStream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (dbg) {

@@ -55,9 +55,12 @@ constexpr int CHUNK = 32;                  // particles per phase-1 pass (one pe
 #define AMPS_DEP_CTAS 3
 #endif
 constexpr int DEP_WARPS = AMPS_DEP_WARPS, DEP_THREADS = 32 * DEP_WARPS, DEP_CTAS_PER_SM = AMPS_DEP_CTAS;
-constexpr int T_LD = 16;                   // leading dimension of T[32][16] after the spill
-constexpr int SLAB = (CHUNK / 4) * GRP;    // doubles per warp: the particle elements of a chunk, later T
-static_assert(SLAB >= 32 * T_LD, "T must fit in the slab");
+constexpr int T_LD = 24;                   // leading dimension of T[32][16] after the spill: 2 T_LD = 16 mod 32 words, so the 16-byte
+                                           // fragment stores of a quarter-warp (rows g, g+1) fall on disjoint banks
+constexpr int T_J = 32 * T_LD;             // the three current columns once more, compact: Jt[27][3] (odd stride: the eight
+                                           // classes a lane of the J flush sums lie on different banks)
+constexpr int SLAB = (CHUNK / 4) * GRP;    // doubles per warp: the particle elements of a chunk, later T and Jt
+static_assert(SLAB >= T_J + 27 * 3, "T and Jt must fit in the slab");
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
   for (int o = threadIdx.x; o < 576; o += DEP_THREADS) {
     const int c = o / 72, r = o - 72 * c, d = r / 9, col = r - 9 * d;
     sFlush[o] = (unsigned)c | ((unsigned)(9 * index_matrix(c, d) + col) << 3) | ((unsigned)(pair_class(c, d) * T_LD + col) << 11);
-    if (o < 64) sJcls[o] = (unsigned short)(pair_class(o >> 3, o & 7) * T_LD);
+    if (o < 64) sJcls[o] = (unsigned short)(T_J + pair_class(o >> 3, o & 7) * 3);
     if (o < 81) {
       const int n = o / 3, d = o - 3 * n;
       const int di = n % 3 - 1, dj = (n / 3) % 3 - 1, dk = n / 9 - 1;
@@ -433,11 +436,16 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
       // ---------------- phase 2: T += U^T A on the fp64 MMA path, 4 particles per step ----------------
       {
         const int nks = (np + 3) >> 2;
+        // rows 27..31 and columns 12..15 of the padded T are never read: their lanes (all in the upper half-warp, so the
+        // 8-byte loads below touch one 128-byte wavefront instead of two) keep a constant operand
+        double fa3 = 0.0, fb1 = 0.0;
 #pragma unroll 2
         for (int ks = 0; ks < nks; ks++) {
           const double *q = rows + ks * GRP;
-          const double fa0 = q[eA0], fa1 = q[eA1], fa2 = q[eA2], fa3 = q[eA3];
-          const double fb0 = q[eB0], fb1 = q[eB1];
+          const double fa0 = q[eA0], fa1 = q[eA1], fa2 = q[eA2];
+          const double fb0 = q[eB0];
+          if (g < 3) fa3 = q[eA3];
+          if (g < 4) fb1 = q[eB1];
           dmma884(acc[0], acc[1], fa0, fb0);
           dmma884(acc[2], acc[3], fa0, fb1);
           dmma884(acc[4], acc[5], fa1, fb0);
@@ -472,6 +480,15 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
 #pragma unroll
       for (int n = 0; n < 2; n++)
         *reinterpret_cast<double2 *>(rows + (8 * t + g) * T_LD + 8 * n + 2 * kk) = make_double2(acc[2 * (2 * t + n)], acc[2 * (2 * t + n) + 1]);
+    // columns 9, 10, 11 (the current) live in the n = 1 fragments of the lanes kk = 0 (8, 9) and kk = 1 (10, 11)
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int cls = 8 * t + g;
+      if (cls < 27) {
+        if (kk == 0) rows[T_J + 3 * cls] = acc[2 * (2 * t + 1) + 1];
+        if (kk == 1) rows[T_J + 3 * cls + 1] = acc[2 * (2 * t + 1)], rows[T_J + 3 * cls + 2] = acc[2 * (2 * t + 1) + 1];
+      }
+    }
     __syncwarp();
     // ---- flush the mass matrix: 64 ordered corner pairs x 9 (both (c,c') and (c',c) get the same block, :2411-2420)
 #pragma unroll
@@ -487,7 +504,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
       if (lane < 24) {
         double val = 0.0;
 #pragma unroll
-        for (int d = 0; d < 8; d++) val += rows[sJcls[c * 8 + d] + 9 + dcol];
+        for (int d = 0; d < 8; d++) val += rows[sJcls[c * 8 + d] + dcol];
         atomicAdd(J + (size_t)ui * 3 + dcol, val);
       }
     }

@@ -23,7 +23,7 @@ __device__ __forceinline__ void pack_one_leaver(const ParticleSoA &p, int i, int
   if (dest == me) return;
   const int slot = atomicAdd(&sendCount[dest], 1);
   if (slot >= capPerPeer) {
-    atomicExch(errFlag, 1);
+    atomicOr(errFlag, 1);
     return;  // the particle stays (in a foreign block); the host reports AMPS_GPU_ERR_CAPACITY
   }
   const int L = migration_record_len(p);
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) unpack_arrivals_kernel(const double *__re
     const int leaf = g2l[gleaf];
     const long long i = (long long)base + j;
     if (leaf < 0 || leafOwner[leaf] != me || i >= capacity) {
-      atomicExch(errFlag, 2);
+      atomicOr(errFlag, 2);
       if (i < capacity) p.key[i] = -1;
       continue;
     }

@@ -117,7 +117,24 @@ class EcsimHost {
   // the collecting buffer sample[n_cells][n_species][13] and the particles sampled per species; clear starts a new period
   void SampledData(double *sample, int64_t *n_sampled, bool clear) { check(amps_gpu_sample_download(ctx_, sample, n_sampled, clear ? 1 : 0)); }
 
-  // epoch end: records and lists back into the caller's buffer
+  // epoch end on several ranks / with deleting boundaries: first settle the books of the caller's ParticleBuffer.
+  // getNewParticle() -> long int is PIC::ParticleBuffer::GetNewParticle (pic_pbuffer.cpp:371) for every arrival of the
+  // exchange, deleteParticle(long int) is PIC::ParticleBuffer::DeleteParticle (pic_pbuffer.cpp:594) for every record whose
+  // particle left this rank or was deleted by a mover / boundary; then the records and lists come back.
+  template <class GetNewParticle, class DeleteParticle>
+  int64_t DownloadParticles(ParticleBufferView &pb, long int *FirstCellParticleTable, GetNewParticle getNewParticle, DeleteParticle deleteParticle) {
+    int64_t nNew = 0, nRel = 0;
+    check(amps_gpu_particles_slot_delta(ctx_, &nNew, nullptr, 0, &nRel));
+    std::vector<int64_t> rel((size_t)nRel + 1);
+    check(amps_gpu_particles_slot_delta(ctx_, &nNew, rel.data(), nRel, &nRel));
+    for (int64_t i = 0; i < nRel; i++) deleteParticle((long int)rel[i]);  // first: arrivals may reuse these records
+    std::vector<int64_t> fresh((size_t)nNew);
+    for (int64_t i = 0; i < nNew; i++) fresh[i] = (int64_t)getNewParticle();
+    check(amps_gpu_particles_assign_slots(ctx_, fresh.data(), nNew));
+    return DownloadParticles(pb, FirstCellParticleTable);
+  }
+
+  // epoch end: records and lists back into the caller's buffer (single rank, nothing deleted: every record keeps its slot)
   int64_t DownloadParticles(ParticleBufferView &pb, long int *FirstCellParticleTable) {
     std::vector<int64_t> first((size_t)n_cells_);
     int64_t n = 0;

@@ -99,17 +99,110 @@ class ClockSampler:
 DECOMP = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 
 
-def build_box(n_cells, ppc, block_cells=(8, 8, 8), seed=100, capacity_slack=1.02, rank=0, world=1):
+def build_box(n_cells, ppc, block_cells=(8, 8, 8), seed=100, capacity_slack=1.02, rank=0, world=1, particles=True):
     from amps_b200 import api, mesh as meshmod, workload
 
     m = meshmod.uniform_periodic_box(n_cells, block_cells, (1, 1, 1), rank=rank, n_ranks=world, decomp=DECOMP[world])
     charge, mass, wgt = workload.species_tables(ppc, 1.0)
-    parts = workload.maxwellian_box(m, ppc, seed=seed)
-    n = parts[0].shape[1]
+    n = len(m.real_leaves()) * m.cells_per_block * 2 * ppc
+    parts = workload.maxwellian_box(m, ppc, seed=seed) if particles else None
     cfg = api.make_config(block_cells, (1, 1, 1), charge, mass, wgt, 1.0, periodic=True,
                           capacity=int(n * (capacity_slack if world == 1 else 1.10)) + 1024)
     E, B = workload.box_fields(m, E_amp=0.0)
     return m, cfg, parts, (E, B, B.copy())
+
+
+def upload_in_slabs(ctx, m, ppc, seed, leaves_per_slab=512):
+    """The plasma of a large box is generated and handed over in slabs of blocks (512 blocks of 8^3 cells = the particles of a
+    64^3-cell box, 2 GB of host memory) so that 2.7e8 particles per rank never sit in host memory at once."""
+    from amps_b200 import workload
+
+    leaves = m.real_leaves()
+    n = 0
+    for k, l0 in enumerate(range(0, len(leaves), leaves_per_slab)):
+        parts = workload.maxwellian_box(m, ppc, seed=seed + 1000 * k, leaves=leaves[l0:l0 + leaves_per_slab])
+        (ctx.particles_upload if k == 0 else ctx.particles_append)(*parts)
+        n += parts[0].shape[1]
+    return n
+
+
+def timed_steps(ctx, torch, dist, world, local, K, W):
+    """W warm-up steps, then exactly K steps between barriers; CUDA-event time on the library's stream, max over ranks"""
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(W):
+        ctx.step()
+    barrier()
+    ctx.profile(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(K):
+        ctx.step()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    phases = ctx.profile(False)
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    return ms, {p: phases[p][0] / max(1, K) for p in ("move", "sort", "deposit", "exchange")}
+
+
+def bench_large_box(torch, dist, rank, world, local, cells_per_gpu, ppc, K=10, W=3):
+    """BASELINE configs[2] series: cells_per_gpu^3 cells on every GPU (8 GPUs: the 256^3-cell, 64-ppc box the north-star's
+    efficiency target is quoted on; 2.7e8 particles per GPU).  At world > 1 rank 0 afterwards times the same per-GPU box alone
+    (no exchange) on its own GPU, so that the line carries the efficiency of the sharded run against world x one GPU."""
+    from amps_b200 import api
+
+    dec = DECOMP[world]
+    n_cells = tuple(cells_per_gpu * dec[d] for d in range(3))
+    t0 = time.time()
+    m, cfg, _, fields = build_box(n_cells, ppc, seed=300 + rank, rank=rank, world=world, particles=False)
+    cfg.device = local
+    ctx = api.Context(cfg, m)
+    if world > 1:
+        ctx.comm_init(dist)
+    ctx.fields_upload(*fields)
+    n_part = upload_in_slabs(ctx, m, ppc, seed=300 + 7919 * rank)
+    gen_s = time.time() - t0
+    ms, phases = timed_steps(ctx, torch, dist, world, local, K, W)
+    n_after = ctx.particle_count()
+    ctx.close()
+    if world > 1:
+        nn = torch.tensor([n_part, n_after], dtype=torch.float64, device="cuda")
+        dist.all_reduce(nn, op=dist.ReduceOp.SUM)
+        n_total, n_after = float(nn[0].item()), float(nn[1].item())
+    else:
+        n_total = float(n_part)
+    out = {"workload": f"ECSIM uniform periodic box {n_cells[0]}x{n_cells[1]}x{n_cells[2]} cells, {ppc} ppc/species, 8^3-cell blocks, "
+                       f"{cells_per_gpu}^3 cells per GPU (BASELINE configs[2] at 8 GPUs)",
+           "value": n_total * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "steps": K, "warmup": W, "particles_total": n_total,
+           "particles_after": n_after, "phases_ms_per_step": phases, "setup_s": round(gen_s, 1)}
+    if world > 1:
+        single = None
+        if rank == 0:
+            m1, cfg1, _, f1 = build_box((cells_per_gpu,) * 3, ppc, seed=300, particles=False)
+            cfg1.device = local
+            c1 = api.Context(cfg1, m1)
+            c1.fields_upload(*f1)
+            n1 = upload_in_slabs(c1, m1, ppc, seed=300)
+            ms1, ph1 = timed_steps(c1, torch, None, 1, local, K, W)
+            c1.close()
+            single = {"value": n1 * K / (ms1 * 1e-3), "ms_per_step": ms1 / K, "phases_ms_per_step": ph1}
+        dist.barrier()
+        if rank == 0:
+            out["single_gpu_same_box"] = single
+            out["parallel_efficiency"] = out["value"] / (world * single["value"])
+    return out
 
 
 def cpu_port_rate(n_cells, ppc, steps, threads, warmup=1, min_seconds=0.0, max_steps=400):
@@ -145,7 +238,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     threads = cores
-    cells = (32, 32, 32)
+    cells = (args.cells,) * 3  # the bench arm's own box (same_config): ~1.2 s per step at 64^3 cells on 16 cores
     W = max(1, args.warmup)
     n, per_step = cpu_port_rate(cells, args.ppc, max(1, args.steps), threads, warmup=W)
     dt = float(np.sum(per_step))
@@ -155,7 +248,7 @@ def run_reference(args):
         "ms_per_step": 1e3 * dt / len(per_step), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"ECSIM uniform periodic box {args.cells}^3 cells, {args.ppc} ppc/species e+p, 8^3-cell blocks, Maxwellian, dt=1",
-                   "sample": f"{cells[0]}^3-cell sub-box of the same plasma ({n} particles) per step"},
+                   "sample": f"the whole {cells[0]}^3-cell box ({n} particles) per step"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{cells[0]}^3 cells x {args.ppc} ppc x 2 species = {n} particles, {len(per_step)} steps, OpenMP by blocks/cells"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -218,6 +311,34 @@ def bench_test_particle_movers(torch, n_particles=2_000_000):
     return out
 
 
+def ncu_traffic_for(phase):
+    """(bytes, source) for the kernel of a phase from profiles/ncu_traffic.json, or (None, reason) when the kernel's source
+    changed since the capture"""
+    import hashlib
+
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tab = json.load(f)
+        e = tab[phase]
+        with open(os.path.join(ROOT, e["source_file"]), "rb") as f:
+            sha = hashlib.sha256(f.read()).hexdigest()
+        if sha != e["source_sha256"]:
+            return None, f"{e['source_file']} changed since {e['capture']}"
+        return float(e["dram_bytes_read"]) + float(e["dram_bytes_write"]), e["capture"]
+    except Exception as exc:  # noqa: BLE001
+        return None, repr(exc)[:120]
+
+
+def measure_fp64_peak():
+    """tools/fp64_peak (built by __graft_entry__.build): DFMA / DMMA peak of this GPU, ~1 s"""
+    exe = os.path.join(ROOT, "tools", "fp64_peak")
+    try:
+        r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=120)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception:  # noqa: BLE001
+        return None
+
+
 _REAL_STDOUT = None
 
 
@@ -249,6 +370,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tp", action="store_true", help="skip the test-particle mover side measurements")
+    ap.add_argument("--no-large", action="store_true", help="skip the 128^3-cells-per-GPU series (BASELINE configs[2])")
+    ap.add_argument("--large-cells", type=int, default=128, help="cells per GPU edge of the large-box series")
+    ap.add_argument("--no-mp-parity", action="store_true", help="world > 1: skip the sharded-step parity check before the timing")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -271,6 +395,21 @@ def main():
     if world > 1:
         dist.barrier()
     from amps_b200 import api
+
+    # world > 1: the sharded step is checked against the single-domain CPU oracle on a small box BEFORE anything is timed
+    # (tests/mp_parity.py; the oracle is the checker here, never the thing measured)
+    mp_parity = None
+    if world > 1 and not args.no_mp_parity:
+        from tests import mp_parity as mpp
+
+        try:
+            ok_mp, rep_mp = mpp.run(dist, rank, world, local)
+            if rank == 0:
+                keep = ("ok", "cells_equal", "x_bit_equal", "v_bit_equal", "max_rel_J", "max_rel_M", "stats_equal", "sent_total", "recv_total",
+                        "books_ok", "fused_step_equal", "fused_max_rel_M", "long_steps", "long_ok", "n_total", "n_expected")
+                mp_parity = {k: rep_mp.get(k) for k in keep}
+        except Exception as exc:  # the verdict must reach the line either way
+            mp_parity = {"ok": False, "error": repr(exc)[:300]}
 
     W = max(3, args.warmup)
     K = max(1, args.steps)
@@ -384,8 +523,18 @@ def main():
                       "note": "amps_gpu_step_JM_packed: M[c][d] == M[c+d][-d] (ProcessCell adds the same block to both corners), so 129 of the "
                               "246 doubles per corner cross PCIe and the host rebuilds the rest while scattering into the corner buffers"}
 
+    ctx.close()
+    del ctx
+
+    # ---- BASELINE configs[2] series: 128^3 cells per GPU (256^3 at 8 GPUs), its own short timed block ----
+    large = None
+    if not args.no_large:
+        try:
+            large = bench_large_box(torch, dist if world > 1 else None, rank, world, local, args.large_cells, args.ppc)
+        except Exception as exc:  # extra block: never lose the headline line
+            large = {"error": repr(exc)[:300]}
+
     if rank != 0:
-        ctx.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -398,15 +547,22 @@ def main():
     alg_bytes = KERNEL_ALG_BYTES[dom_alg](P) * n_part
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     step_alg = (ALG_BYTES_FIXED + ALG_BYTES_PER_CELL / P)
-    # DRAM bytes of one launch from the `ncu --set full` capture of this very workload (profiles/r1_final_ncu_summary.txt:
-    # dram__bytes_read.sum + dram__bytes_write.sum); only quoted for the default size
-    ncu_traffic = {"move": 1.811503e9 + 1.603445e9, "deposit": 3.131059e9 + 2.755923e9, "sort": 0.139377e9 + 0.091845e9}
-    traffic = ncu_traffic[dom] if (args.cells == 64 and args.ppc == 64 and world == 1) else None
+    # DRAM bytes of one launch from the `ncu --set full` capture of this very workload: profiles/ncu_traffic.json records, per
+    # kernel, dram__bytes_read.sum + dram__bytes_write.sum together with the sha256 of the kernel's source file at capture time;
+    # a kernel whose source changed since has no traffic figure (null) until it is profiled again
+    traffic, traffic_src = ncu_traffic_for(dom) if (args.cells == 64 and args.ppc == 64 and world == 1) else (None, None)
+    fp64 = measure_fp64_peak()
     roofline = {"bound": "hbm", "kernel": {"move": "move_lapenta_fast_kernel", "sort": "perm_kernel", "deposit": "deposit_kernel"}[dom],
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "ms_per_launch": dom_ms, "alg_bytes_per_update": KERNEL_ALG_BYTES[dom_alg](P),
-                "note": "the kernel is bound by the fp64 pipe (ncu: 45 % of peak, 8 warps/SM at 242 registers), not by HBM; inside "
-                        "amps_gpu_step it also writes the sorted particle copy (65 B/particle), which the algorithmic bytes do not count"}
+                "note": "the kernel is bound by the fp64 pipe (DMMA + DFMA share it: ncu sm__pipe_shared_cycles_active 63 %) and the shared-memory "
+                        "wavefronts of the MMA operand staging (l1tex 72 %), not by HBM; inside amps_gpu_step it also writes the sorted "
+                        "particle copy (65 B/particle), which the algorithmic bytes do not count"}
+    if fp64:
+        # the fp64 roofline of the same kernel: executed fp64 work of the deposit per update (DMMA tiles padded 27x12 -> 32x16:
+        # 512 FMA, + ~95 DFMA/DMUL of phase 1) against the measured DFMA peak of this GPU (tools/fp64_peak.cu)
+        roofline["fp64_peak_tflops"] = fp64.get("dfma_tflops")
+        roofline["fp64_dmma_peak_tflops"] = fp64.get("dmma_tflops")
     step_gbs = step_alg * (n_part * K / (ms * 1e-3)) / 1e9 if world == 1 else step_alg * (value / world) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
@@ -425,8 +581,13 @@ def main():
         "roofline": roofline,
         "phases_ms_per_step": {p: (phases[p][0] / max(1, K)) for p in ("move", "sort", "deposit", "exchange")},
         "roofline_step": {"alg_bytes_per_update": step_alg, "achieved_gbs_per_gpu": step_gbs, "frac_hbm": step_gbs / peak,
-                          "fp64_tflops_per_gpu": ALG_FLOP_PER_UPDATE * (value / world) / 1e12},
+                          "fp64_tflops_per_gpu": ALG_FLOP_PER_UPDATE * (value / world) / 1e12,
+                          "fp64_frac": (ALG_FLOP_PER_UPDATE * (value / world) / 1e12 / fp64["dfma_tflops"]) if fp64 else None},
     }
+    if mp_parity is not None:
+        line["mp_parity"] = mp_parity
+    if large is not None:
+        line["u256_series"] = large
     if world == 1 and not args.no_tp:
         try:
             line["test_particle_movers"] = bench_test_particle_movers(torch)
@@ -434,12 +595,12 @@ def main():
             line["test_particle_movers"] = {"error": repr(exc)}
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        n_cpu, per = cpu_port_rate((32, 32, 32), args.ppc, 2, cores, min_seconds=12.0)  # a bounded sample: ~12 s of CPU work
+        n_cpu, per = cpu_port_rate((args.cells,) * 3, args.ppc, 2, cores, min_seconds=12.0)  # a bounded sample: >= 12 s of CPU work
         v = n_cpu * len(per) / float(np.sum(per))
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"32^3 cells x {args.ppc} ppc x 2 species = {n_cpu} particles, {len(per)} steps, oracle -O3 OpenMP"}
+                                "sample": f"the bench box itself: {args.cells}^3 cells x {args.ppc} ppc x 2 species = {n_cpu} particles, {len(per)} steps, "
+                                          "oracle -O3 OpenMP"}
     _emit(line)
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -275,6 +275,11 @@ int amps_gpu_particles_upload_aos(amps_gpu_ctx *ctx, const void *records, const 
 int amps_gpu_particles_upload_soa(amps_gpu_ctx *ctx, const double *x, const double *v,
                                   const double *w, const uint8_t *species, const int32_t *cells,
                                   const int32_t *ptrs, int64_t n);
+/* the same, appended behind the resident particles (injection between epochs, PIC::ParticleBuffer::GetNewParticle +
+ * InitiateParticle pic_pbuffer.cpp:371-437, :939-1027; large populations handed over in pieces). ptrs NULL = count.. */
+int amps_gpu_particles_append_soa(amps_gpu_ctx *ctx, const double *x, const double *v,
+                                  const double *w, const uint8_t *species, const int32_t *cells,
+                                  const int32_t *ptrs, int64_t n);
 int amps_gpu_particle_count(amps_gpu_ctx *ctx, int64_t *n);
 /* current device order; any output pointer may be NULL */
 int amps_gpu_particles_download_soa(amps_gpu_ctx *ctx, double *x, double *v, double *w,
@@ -284,6 +289,15 @@ int amps_gpu_particles_download_soa(amps_gpu_ctx *ctx, double *x, double *v, dou
  * first_cell_particle[n_cells] like FirstCellParticleTable                        */
 int amps_gpu_particles_download_aos(amps_gpu_ctx *ctx, void *records, int64_t *first_cell_particle,
                                     int64_t n_max, const amps_gpu_aos_layout *lay, int64_t *n);
+/* Slot bookkeeping of the caller's ParticleBuffer before a download_aos when particles were deleted (boundary,
+ * movers) or exchanged between ranks.  n_new = resident records without a slot of the caller's buffer (arrivals of
+ * amps_gpu_migrate): the caller takes that many records with GetNewParticle (pic_pbuffer.cpp:371-437) and hands them
+ * over with amps_gpu_particles_assign_slots.  released[] = slots that were uploaded but whose particle is gone (deleted,
+ * migrated away): the caller returns each with DeleteParticle (pic_pbuffer.cpp:594-666).  When max_released is too small
+ * only n_released is reported and nothing changes.                                   */
+int amps_gpu_particles_slot_delta(amps_gpu_ctx *ctx, int64_t *n_new, int64_t *released, int64_t max_released,
+                                  int64_t *n_released);
+int amps_gpu_particles_assign_slots(amps_gpu_ctx *ctx, const int64_t *slots, int64_t n_slots);
 /* per-cell particle ranges after a sort: cell_start[n_cells+1] (CreateParticleTable,
  * pic_pbuffer.cpp:1160-1310)                                                      */
 int amps_gpu_cell_table_download(amps_gpu_ctx *ctx, int64_t *cell_start, int64_t n_cells_plus_1);

@@ -5,6 +5,13 @@ blocks, runs one ECSIM particle phase (move -> NCCL migration -> sort -> deposit
 C ABI, and rank 0 compares the union with the single-domain CPU oracle:
   * every particle ends in the same global (block,cell) with bit-identical x', v', on the rank that owns the block
   * J, M of every corner (summed across the ranks that share it) within 1e-10 of the array maximum
+Then, on the same inputs: the fused amps_gpu_step (what bench.py times) must leave the same particles and corner sums as the
+separate calls; the slot books of the caller's ParticleBuffer must balance (arrivals need a slot, leavers release theirs); and
+LONG_STEPS further steps with a tight particle capacity must neither fail nor lose a particle (the slot bound follows the
+resident population).
+
+bench.py imports run() and puts the verdict into its JSON line at world > 1, so the driver's own scaling job proves the
+multi-GPU path correct before it times it.
 """
 import json
 import os
@@ -16,16 +23,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    import torch
-    import torch.distributed as dist
+LONG_STEPS = 120
 
+
+def run(dist, rank, world, local, long_steps=LONG_STEPS):
+    """returns (ok, report) -- the report only on rank 0"""
     from amps_b200 import api, mesh as meshmod, workload
     from tests import parity_util as pu
 
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     decomp = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
     n_cells = (32, 32, 16)
     ppc, seed, vscale = 6, 31, 6.0
@@ -78,10 +83,52 @@ def main():
     en, cfl = g.UpdateJMassMatrix()   # local partial sums
     g.exchange_JM()
     J, M = g.JM_download()
-    import ctypes
-    e2 = ctypes.c_double()
     g.synchronize()
-    res = {"rank": rank, "stats": st, "sent": ns, "recv": nr, "n_after": int(after["x"].shape[1])}
+    # ---- the books of the caller's ParticleBuffer: arrivals have no slot yet, the slots of the leavers are released ----
+    n_new, released = g.slot_delta()
+    books_ok = n_new == nr == int((after["ptrs"] < 0).sum()) and released.size == ns and np.isin(released, idx).all()
+    g.assign_slots(n + 1 + np.arange(n_new, dtype=np.int64))
+    n_new2, released2 = g.slot_delta()
+    books_ok = bool(books_ok and n_new2 == 0 and released2.size == 0 and (g.particles_download()["ptrs"] >= 0).all())
+
+    # ---- the fused step on the same inputs: same particles, same corner sums ----
+    g2 = api.Context(cfg, m)
+    g2.comm_init(dist)
+    g2.fields_upload(El, Bl, Bcl)
+    g2.particles_upload(x[:, idx], v[:, idx], w[idx], sp[idx], lcells, ptrs=idx.astype(np.int32))
+    g2.magnetic_moment_upload(mu0)
+    g2.v_parallel_upload(vp0)
+    g2.step()
+    a2 = g2.particles_download()
+    J2, M2 = g2.JM_download()
+
+    def canon(a):
+        o = np.lexsort((a["x"][2].view(np.int64), a["x"][1].view(np.int64), a["x"][0].view(np.int64), a["cells"]))
+        return a["cells"][o], a["x"][:, o], a["v"][:, o]
+    c1, c2 = canon(after), canon(a2)
+    fused_ok = bool(c1[0].shape == c2[0].shape and (c1[0] == c2[0]).all() and (c1[1] == c2[1]).all() and (c1[2] == c2[2]).all())
+    fused_rel_M = float(np.abs(M2 - M).max() / max(np.abs(M).max(), 1e-300))
+    fused_rel_J = float(np.abs(J2 - J).max() / max(np.abs(J).max(), 1e-300))
+    g2.close()
+
+    # ---- many steps with a tight capacity: no false capacity error, no particle lost (periodic box) ----
+    long_ok, long_err, n_long = True, "", 0
+    if long_steps > 0:
+        cfg3 = api.make_config((8, 8, 8), (1, 1, 1), charge, mass, wgt, 1.0, periodic=True, capacity=int(idx.size * 1.04) + 256, device=local)
+        g3 = api.Context(cfg3, m)
+        g3.comm_init(dist)
+        g3.fields_upload(El, Bl, Bcl)
+        g3.particles_upload(x[:, idx], v[:, idx] / vscale, w[idx], sp[idx], lcells)
+        try:
+            for _ in range(long_steps):
+                g3.step()
+            n_long = g3.particle_count()
+        except Exception as exc:  # noqa: BLE001 - reported in the verdict
+            long_ok, long_err = False, repr(exc)[:200]
+        g3.close()
+
+    res = {"rank": rank, "stats": st, "sent": ns, "recv": nr, "n_after": int(after["x"].shape[1]), "books_ok": books_ok, "fused_ok": fused_ok,
+           "fused_rel_J": fused_rel_J, "fused_rel_M": fused_rel_M, "long_ok": long_ok, "long_err": long_err, "n_long": n_long}
     # global cell of every resident particle
     lg = m.leaf_global
     keys = after["cells"].astype(np.int64)
@@ -91,7 +138,7 @@ def main():
                "J": J, "M": M, "ckeys": m.corner_gkey, "targets": m.corner_target_gkeys}
     gathered = [None] * world
     dist.all_gather_object(gathered, payload)
-    ok = True
+    ok, out = True, None
     if rank == 0:
         cfg1 = api.make_config((8, 8, 8), (1, 1, 1), charge, mass, wgt, 1.0, periodic=True, capacity=n + 16)
         ora = pu.run_oracle(mg, cfg1, (x, v, w, sp, gcells), (E, B, Bcur))
@@ -126,12 +173,35 @@ def main():
         st_sum = {k: sum(p["res"]["stats"][k] for p in gathered) for k in ora["stats"]}
         out["stats_equal"] = st_sum == ora["stats"]
         out["stats_gpu"], out["stats_oracle"] = st_sum, ora["stats"]
+        out["books_ok"] = all(p["res"]["books_ok"] for p in gathered)
+        out["fused_step_equal"] = all(p["res"]["fused_ok"] for p in gathered)
+        out["fused_max_rel_J"] = max(p["res"]["fused_rel_J"] for p in gathered)
+        out["fused_max_rel_M"] = max(p["res"]["fused_rel_M"] for p in gathered)
+        out["long_steps"] = long_steps
+        out["long_ok"] = all(p["res"]["long_ok"] for p in gathered) and (long_steps == 0 or sum(p["res"]["n_long"] for p in gathered) == n)
+        out["long_err"] = [p["res"]["long_err"] for p in gathered if p["res"]["long_err"]][:1]
         ok = (out["cells_equal"] and out["x_bit_equal"] and out["v_bit_equal"] and out["owner_ok"] and out["reduced_state_travels"]
               and relJ <= 1e-10 and relM <= 1e-10
-              and out["stats_equal"] and out["sent_total"] == out["recv_total"] and out["sent_total"] > 0)
-        out["ok"] = ok
-        print("MP_PARITY " + json.dumps(out))
+              and out["stats_equal"] and out["sent_total"] == out["recv_total"] and out["sent_total"] > 0
+              and out["books_ok"] and out["fused_step_equal"] and out["fused_max_rel_J"] <= 1e-12 and out["fused_max_rel_M"] <= 1e-12
+              and out["long_ok"])
+        out["ok"] = bool(ok)
     g.close()
+    flag = [ok]
+    dist.broadcast_object_list(flag, src=0)
+    return bool(flag[0]), out
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok, out = run(dist, rank, world, local)
+    if rank == 0:
+        print("MP_PARITY " + json.dumps(out))
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
