@@ -436,16 +436,14 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM) deposit_kernel(D
       // ---------------- phase 2: T += U^T A on the fp64 MMA path, 4 particles per step ----------------
       {
         const int nks = (np + 3) >> 2;
-        // rows 27..31 and columns 12..15 of the padded T are never read: their lanes (all in the upper half-warp, so the
-        // 8-byte loads below touch one 128-byte wavefront instead of two) keep a constant operand
-        double fa3 = 0.0, fb1 = 0.0;
+        // rows 27..31 and columns 12..15 of the padded T are never read: their lanes load a clamped element.  (Predicating those
+        // loads off -- one 128-byte wavefront instead of two -- was measured SLOWER, 2.39 instead of 2.22 ms: the loop-carried
+        // operand registers break the software pipeline of the loop.)
 #pragma unroll 2
         for (int ks = 0; ks < nks; ks++) {
           const double *q = rows + ks * GRP;
-          const double fa0 = q[eA0], fa1 = q[eA1], fa2 = q[eA2];
-          const double fb0 = q[eB0];
-          if (g < 3) fa3 = q[eA3];
-          if (g < 4) fb1 = q[eB1];
+          const double fa0 = q[eA0], fa1 = q[eA1], fa2 = q[eA2], fa3 = q[eA3];
+          const double fb0 = q[eB0], fb1 = q[eB1];
           dmma884(acc[0], acc[1], fa0, fb0);
           dmma884(acc[2], acc[3], fa0, fb1);
           dmma884(acc[4], acc[5], fa1, fb0);
