@@ -4,5 +4,5 @@
 #include <cstdlib>
 template <class... A>
 inline void linear_solver_wrapper(A...) { abort(); }
-template <class... A>
-inline void linear_solver_matvec_c(A...) { abort(); }
+// the matrix-free operator the solver calls back (set by the reference before every Solve)
+extern void (*linear_solver_matvec_c)(double *VecIn, double *VecOut, int n);

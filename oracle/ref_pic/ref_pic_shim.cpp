@@ -1,0 +1,220 @@
+// ref_pic_shim.cpp -- OURS (test infrastructure).  Runs the reference's OWN PIC code as a one-rank checker of the oracle:
+// the translation units of src/pic, src/general, src/meshAMR, ... are compiled from the tree that the reference's
+// ampsConfig.pl generates for input/test/fast-wave.input (ECSIM, Lapenta2017, periodic box, 16x8x4-cell blocks), with our
+// stand-ins for mpi.h and the three un-vendored SWMF share headers (oracle/ref_pic/*.h, oracle/ref_mesh/mpi.h).  This file
+// includes the reference's fast-wave test program for its initial conditions (its main() renamed, never called) and exports a C
+// interface that drives  PIC::Mover::MoveParticles (-> Lapenta2017, CornerBased / CellCentered InitStencil, findTreeNode,
+// periodic wrap)  and  ECSIM::UpdateJMassMatrix (-> ProcessCell, ProcessJMassMatrix)  and reads the state back.
+#define main ref_fastwave_main_never_called
+#include "main.cpp"  // test/srcFastWave/main.cpp of the reference (found through -I, not copied)
+#undef main
+
+// ---- symbols of translation units that are not part of this build (the SWMF fluid coupler, Fortran readers, user models) ----
+void (*linear_solver_matvec_c)(double *VecIn, double *VecOut, int n) = nullptr;
+long int PIC::CPLR::FLUID::iCycle = 0;
+bool PIC::CPLR::FLUID::IsRestart = false;
+double PIC::CPLR::FLUID::EFieldTol = 1.0e-6;
+double PIC::CPLR::FLUID::EFieldIter = 200;
+void PIC::CPLR::FLUID::write_output(double, bool) {}
+void PIC::CPLR::FLUID::check_max_mem_usage(std::string) {}
+void PIC::CPLR::InitInterpolationStencil(double *, cTreeNodeAMR<PIC::Mesh::cDataBlockAMR> *) { abort(); }
+double Exosphere::GetSurfaceTemperature(double, double *) { abort(); }
+double Exosphere::SurfaceInteraction::StickingProbability(int, double &, double) { abort(); }
+int Exosphere::ColumnIntegral::GetVariableList(char *) { return 0; }
+void Exosphere::ColumnIntegral::ProcessColumnIntegrationVector(double *, int) {}
+void Exosphere::ColumnIntegral::CoulumnDensityIntegrant(double *, int, double *, cTreeNodeAMR<PIC::Mesh::cDataBlockAMR> *) {}
+double Exosphere::OrbitalMotion::GetTAA(SpiceDouble) { return 0.0; }
+extern "C" {
+void batsrus2amps_set_mpi_parameters_(...) { abort(); }
+void batsrus2amps_read_file_header_(...) { abort(); }
+void batsrus2amps_openfile_(...) { abort(); }
+void batsrus2amps_get_nvar_(...) { abort(); }
+void batsrus2amps_get_namevardata_(...) { abort(); }
+void batsrus2amps_get_nameunitdata_(...) { abort(); }
+void batsrus2amps_get_data_point_(...) { abort(); }
+void batsrus2amps_domain_limits_(...) { abort(); }
+void batsrus2amps_closefile_(...) { abort(); }
+}
+
+extern double TotalParticleEnergy;  // file-scope global of pic_field_solver_ecsim.cpp (:228)
+namespace {
+typedef cTreeNodeAMR<PIC::Mesh::cDataBlockAMR> Node;
+std::vector<Node *> g_blocks;  // every allocated block in BranchBottomNodeList order
+bool is_ghost(Node *node) {    // the reference's own test (PrepopulateDomain, UpdateJMassMatrix): a block at the domain boundary
+  for (int iface = 0; iface < 6; iface++)
+    if (node->GetNeibFace(iface, 0, 0, PIC::Mesh::mesh) == NULL) return true;
+  return false;
+}
+const int NX = _BLOCK_CELLS_X_, NY = _BLOCK_CELLS_Y_, NZ = _BLOCK_CELLS_Z_, GX = _GHOST_CELLS_X_, GY = _GHOST_CELLS_Y_, GZ = _GHOST_CELLS_Z_;
+}  // namespace
+
+extern "C" {
+// the set-up of the reference's main(), up to its time loop (file outputs left out)
+int ref_pic_init(void) {
+  PIC::InitMPI();
+  PIC::Init_BeforeParser();
+  rnd_seed(100);
+  PIC::Mesh::mesh->AllowBlockAllocation = false;
+  PIC::BC::ExternalBoundary::Periodic::Init(xmin, xmax, BulletLocalResolution);
+  PIC::Mesh::mesh->buildMesh();
+  PIC::Mesh::initCellSamplingDataBuffer();
+  PIC::Mesh::mesh->CreateNewParallelDistributionLists();
+  PIC::Mesh::mesh->AllowBlockAllocation = true;
+  PIC::Mesh::mesh->AllocateTreeBlocks();
+  PIC::Mesh::mesh->InitCellMeasure();
+  PIC::Init_AfterParser();
+  PIC::Mover::Init();
+  PIC::ParticleWeightTimeStep::LocalTimeStep = localTimeStep;
+  PIC::ParticleWeightTimeStep::initTimeStep();
+  PIC::BC::ExternalBoundary::Periodic::InitBlockPairTable();
+  PIC::ParticleWeightTimeStep::SetGlobalParticleWeight(0, 1e-2 * 0.0795774715459477);
+  PIC::ParticleWeightTimeStep::SetGlobalParticleWeight(1, 1e-2 * 0.0795774715459477);
+  PIC::DomainBlockDecomposition::UpdateBlockTable();
+  PIC::BC::ExternalBoundary::UpdateData();
+  PIC::FieldSolver::Electromagnetic::ECSIM::SetIC = ::SetIC;
+  PIC::FieldSolver::Electromagnetic::ECSIM::Init_IC();
+  PIC::BC::ExternalBoundary::UpdateData();
+  CleanParticles();
+  PrepopulateDomain();
+  PIC::BC::ExternalBoundary::UpdateData();
+  g_blocks.clear();
+  for (Node *node = PIC::Mesh::mesh->BranchBottomNodeList; node != NULL; node = node->nextBranchBottomNode)
+    if (node->block != NULL) g_blocks.push_back(node);
+  return (int)g_blocks.size();
+}
+
+// out[0..5] block cells and ghost cells, [6] blocks, [7] species, [8] particles, [9] ParticleDataLength
+void ref_pic_dims(long *out) {
+  out[0] = NX, out[1] = NY, out[2] = NZ, out[3] = GX, out[4] = GY, out[5] = GZ;
+  out[6] = (long)g_blocks.size(), out[7] = PIC::nTotalSpecies, out[8] = PIC::ParticleBuffer::GetAllPartNum(), out[9] = PIC::ParticleBuffer::ParticleDataLength;
+}
+// species tables and the constants ProcessCell / Lapenta2017 use: out = charge[nS] mass[nS] weight[nS] dt, LightSpeed, and the unit factors
+void ref_pic_constants(double *out) {
+  using namespace PIC::FieldSolver::Electromagnetic::ECSIM;
+  int n = 0;
+  for (int s = 0; s < PIC::nTotalSpecies; s++) out[n++] = PIC::MolecularData::GetElectricCharge(s);
+  for (int s = 0; s < PIC::nTotalSpecies; s++) out[n++] = PIC::MolecularData::GetMass(s);
+  for (int s = 0; s < PIC::nTotalSpecies; s++) out[n++] = PIC::ParticleWeightTimeStep::GlobalParticleWeight[s];
+  out[n++] = PIC::ParticleWeightTimeStep::GlobalTimeStep[0];
+  out[n++] = LightSpeed;
+  out[n++] = B_conv, out[n++] = E_conv, out[n++] = length_conv, out[n++] = charge_conv, out[n++] = mass_conv, out[n++] = cDt, out[n++] = theta;
+  out[n++] = _AMU_, out[n++] = ElectronCharge;
+}
+// charge and mass of the species as Lapenta2017 (pic_mover_boris.cpp:1181-1183) and ProcessCell (:2239-2241) form them
+void ref_pic_species(double *q_no, double *m_no) {
+  for (int s = 0; s < PIC::nTotalSpecies; s++) {
+    q_no[s] = picunits::si2no_q(PIC::MolecularData::GetElectricCharge(s), PIC::Units::Factors);
+    m_no[s] = picunits::si2no_m(PIC::MolecularData::GetMass(s), PIC::Units::Factors);
+  }
+}
+void ref_pic_blocks(double *bxmin, double *bxmax, int *ghost) {
+  for (size_t b = 0; b < g_blocks.size(); b++) {
+    for (int d = 0; d < 3; d++) bxmin[3 * b + d] = g_blocks[b]->xmin[d], bxmax[3 * b + d] = g_blocks[b]->xmax[d];
+    ghost[b] = is_ghost(g_blocks[b]) ? 1 : 0;
+  }
+}
+// corner data of every block, all nodes incl. the ghost layers, [block][k][j][i][len]; what: 0 E (current), 1 E at the half step,
+// 2 J (3 values), 3 the mass matrix (243 values).  Missing nodes read as NaN.
+static int corner_slice(int what, int *off) {
+  using namespace PIC::FieldSolver::Electromagnetic::ECSIM;
+  switch (what) {
+    case 0: *off = CurrentEOffset / (int)sizeof(double); return 3;
+    case 1: *off = OffsetE_HalfTimeStep / (int)sizeof(double); return 3;
+    case 2: *off = JxOffsetIndex; return 3;
+    case 3: *off = MassMatrixOffsetIndex; return 243;
+  }
+  return 0;
+}
+long ref_pic_corner_rw(int what, double *buf, int write) {
+  int off = 0;
+  const int len = corner_slice(what, &off);
+  long n = 0;
+  for (Node *node : g_blocks)
+    for (int k = -GZ; k <= NZ + GZ; k++)
+      for (int j = -GY; j <= NY + GY; j++)
+        for (int i = -GX; i <= NX + GX; i++) {
+          PIC::Mesh::cDataCornerNode *c = node->block->GetCornerNode(_getCornerNodeLocalNumber(i, j, k));
+          double *p = c ? (double *)(c->GetAssociatedDataBufferPointer() + PIC::CPLR::DATAFILE::Offset::ElectricField.RelativeOffset) + off : NULL;
+          for (int q = 0; q < len; q++, n++) {
+            if (write) { if (p && buf[n] == buf[n]) p[q] = buf[n]; }
+            else buf[n] = p ? p[q] : NAN;
+          }
+        }
+  return n;
+}
+// centre data [block][k][j][i][3] incl. ghost cells; what: 0 B (current), 1 B (previous)
+long ref_pic_center_rw(int what, double *buf, int write) {
+  using namespace PIC::FieldSolver::Electromagnetic::ECSIM;
+  const int off = (what == 0 ? CurrentBOffset : PrevBOffset) / (int)sizeof(double);
+  long n = 0;
+  for (Node *node : g_blocks)
+    for (int k = -GZ; k < NZ + GZ; k++)
+      for (int j = -GY; j < NY + GY; j++)
+        for (int i = -GX; i < NX + GX; i++) {
+          PIC::Mesh::cDataCenterNode *c = node->block->GetCenterNode(_getCenterNodeLocalNumber(i, j, k));
+          double *p = c ? (double *)(c->GetAssociatedDataBufferPointer() + PIC::CPLR::DATAFILE::Offset::MagneticField.RelativeOffset) + off : NULL;
+          for (int q = 0; q < 3; q++, n++) {
+            if (write) { if (p && buf[n] == buf[n]) p[q] = buf[n]; }
+            else buf[n] = p ? p[q] : NAN;
+          }
+        }
+  return n;
+}
+// every particle on a cell list: ParticleBuffer slot, x, v, individual weight correction, species, block (index of ref_pic_blocks)
+// and cell i + Nx (j + Ny k), in the reference's own iteration order (block, k, j, i, list order)
+long ref_pic_particles(long max_n, long *ptr, double *x, double *v, double *w, int *spec, int *block, int *cell) {
+  long n = 0;
+  for (size_t b = 0; b < g_blocks.size(); b++) {
+    long int *first = g_blocks[b]->block->FirstCellParticleTable;
+    if (!first) continue;
+    for (int k = 0; k < NZ; k++)
+      for (int j = 0; j < NY; j++)
+        for (int i = 0; i < NX; i++)
+          for (long int p = first[i + NX * (j + NY * k)]; p != -1; p = PIC::ParticleBuffer::GetNext(p)) {
+            if (n < max_n) {
+              ptr[n] = p;
+              memcpy(x + 3 * n, PIC::ParticleBuffer::GetX(p), 24);
+              memcpy(v + 3 * n, PIC::ParticleBuffer::GetV(p), 24);
+              w[n] = PIC::ParticleBuffer::GetIndividualStatWeightCorrection(p);
+              spec[n] = PIC::ParticleBuffer::GetI(p);
+              block[n] = (int)b, cell[n] = i + NX * (j + NY * k);
+            }
+            n++;
+          }
+  }
+  return n;
+}
+// keep every keep_every-th particle of the walk above, delete the others (PIC::ParticleBuffer::DeleteParticle): a population
+// small enough to commit as a fixture together with everything the reference computes from it
+long ref_pic_thin(int keep_every) {
+  long n = 0, kept = 0;
+  for (Node *node : g_blocks) {
+    long int *first = node->block->FirstCellParticleTable;
+    if (!first) continue;
+    for (int c = 0; c < NX * NY * NZ; c++) {
+      long int p = first[c];
+      while (p != -1) {
+        const long int next = PIC::ParticleBuffer::GetNext(p);
+        if (n++ % keep_every) PIC::ParticleBuffer::DeleteParticle(p, first[c]);
+        else kept++;
+        p = next;
+      }
+    }
+  }
+  return kept;
+}
+void ref_pic_set_weight_correction(long n, const long *ptr, const double *w) {
+  for (long i = 0; i < n; i++) PIC::ParticleBuffer::SetIndividualStatWeightCorrection(w[i], ptr[i]);
+}
+// PIC::TimeStep's particle phase: MoveParticles (Lapenta2017 per particle), the rank exchange, the periodic ghost -> real hand-off
+void ref_pic_move(void) {
+  PIC::Mover::MoveParticles();
+  PIC::Parallel::ExchangeParticleData();
+  PIC::BC::ExternalBoundary::Periodic::ExchangeParticles();
+}
+// (the per-species cfl maxima are locals of UpdateJMassMatrix: it prints them, "max cfl number for spec s :value")
+void ref_pic_update_JM(double *energy) {
+  PIC::FieldSolver::Electromagnetic::ECSIM::UpdateJMassMatrix();
+  if (energy) *energy = TotalParticleEnergy;
+}
+}

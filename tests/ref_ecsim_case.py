@@ -1,0 +1,116 @@
+"""The fast-wave case of the reference's own PIC core (oracle/_ref/libref_pic.so, built by oracle/ref_pic/build_ref_pic.sh from the
+reference tree) next to the same case expressed for this repo: mesh, unique-node fields, particles, configuration.
+
+The reference is initialised ONCE per process (its state is global), driven through one ECSIM particle phase
+   UpdateJMassMatrix (initial positions)  ->  MoveParticles + exchanges  ->  UpdateJMassMatrix
+and everything it produced is kept for the comparisons in tests/test_reference_ecsim.py."""
+import functools
+
+import numpy as np
+
+from amps_b200 import api, mesh as meshmod
+from oracle.ref_pic import ref_pic
+
+
+def _wrap_index(pos, xmin, n_cells, corner):
+    """lattice index of node positions wrapped into the periodic box (dx = 1 in the fast-wave case)"""
+    t = pos - xmin - (0.0 if corner else 0.5)
+    i = np.rint(t).astype(np.int64)
+    assert np.abs(t - i).max() < 1e-9
+    return np.mod(i, n_cells)
+
+
+@functools.lru_cache(maxsize=1)
+def case(keep_every=1):
+    r = ref_pic.RefPic()
+    if keep_every > 1:
+        r.thin(keep_every)
+    N, g = r.N, r.g
+    real = np.nonzero(r.ghost == 0)[0]
+    xmin = r.bxmin[real].min(axis=0)
+    xmax = r.bxmax[real].max(axis=0)
+    n_cells = np.rint(xmax - xmin).astype(np.int64)  # dx = 1
+    assert tuple(n_cells) == (32, 16, 8)
+    m = meshmod.uniform_periodic_box(tuple(int(c) for c in n_cells), N, g, dx=1.0, origin=tuple(xmin))
+
+    def uid_map(node_x, corner):
+        idx = _wrap_index(node_x, xmin, n_cells, corner)
+        key = idx[:, 0] + n_cells[0] * (idx[:, 1] + n_cells[1] * idx[:, 2])
+        table = np.full(int(np.prod(n_cells)), -1, dtype=np.int64)
+        table[key] = np.arange(len(key))
+        assert (table >= 0).all()  # every physical node of the periodic lattice has one unique id here
+        return table
+
+    ctab, ztab = uid_map(m.corner_x, True), uid_map(m.center_x, False)
+
+    def ref_to_uid(pos, tab, corner):
+        idx = _wrap_index(pos.reshape(-1, 3), xmin, n_cells, corner)
+        return tab[idx[:, 0] + n_cells[0] * (idx[:, 1] + n_cells[1] * idx[:, 2])].reshape(pos.shape[:-1])
+
+    cu = ref_to_uid(r.corner_positions(), ctab, True)   # [block][k][j][i] -> unique corner
+    zu = ref_to_uid(r.center_positions(), ztab, False)
+
+    # fields on the unique nodes (any smooth numbers: both sides get the same doubles), copied to every copy of a node the
+    # reference holds (ghost layers, periodic ghost blocks)
+    def smooth(x, amp, ph):
+        k = 2 * np.pi / (xmax - xmin)
+        return np.stack([amp * (1.0 + 0.5 * np.sin(k[0] * x[:, 0] + ph) * np.cos(k[1] * x[:, 1] - 0.3 * d) + 0.25 * np.sin(k[2] * x[:, 2] + d))
+                         for d in range(3)], axis=1)
+    E_u = smooth(m.corner_x, 0.01, 0.4) - 0.008
+    Bp_u = smooth(m.center_x, 0.04, 1.1)
+    Bc_u = smooth(m.center_x, 0.041, 0.7) + 0.001
+    r.set_corner(1, E_u[cu])      # E at the half step (what Lapenta2017 interpolates)
+    r.set_center(1, Bp_u[zu])     # B previous (the mover)
+    r.set_center(0, Bc_u[zu])     # B current (ProcessCell)
+
+    p0 = r.particles()
+    rng = np.random.default_rng(7)
+    w = rng.uniform(0.5, 1.5, size=p0["w"].shape)
+    r.set_weight_correction(p0["ptr"], w)
+    p0["w"] = w
+
+    # reference: deposit, move, deposit
+    e0 = r.update_JM()
+    J0, M0 = r.corner(2), r.corner(3)
+    r.move()
+    p1 = r.particles()
+    e1 = r.update_JM()
+    J1, M1 = r.corner(2), r.corner(3)
+
+    # particles in this repo's numbering: leaf by block position, same cell formula i + Nx (j + Ny k)
+    lx = m.leaf_xmin()
+    def leaf_of_block(b):
+        d = np.abs(lx - r.bxmin[b]).max(axis=1)
+        k = int(np.argmin(d))
+        assert d[k] == 0.0
+        return k
+    b2l = np.array([leaf_of_block(b) if r.ghost[b] == 0 else -1 for b in range(r.n_blocks)])
+    C = m.cells_per_block
+    assert (b2l[p0["block"]] >= 0).all() and (b2l[p1["block"]] >= 0).all()
+    cells0 = (b2l[p0["block"]] * C + p0["cell"]).astype(np.int32)
+    # after the move, by ParticleBuffer slot
+    order = np.argsort(p1["ptr"])
+    pos = np.searchsorted(p1["ptr"][order], p0["ptr"])
+    assert (p1["ptr"][order][pos] == p0["ptr"]).all()  # periodic box: nobody is deleted
+    sel = order[pos]
+    after = {"x": p1["x"][:, sel], "v": p1["v"][:, sel], "cells": (b2l[p1["block"][sel]] * C + p1["cell"][sel]).astype(np.int64)}
+
+    cfg = api.make_config(N, g, tuple(r.charge), tuple(r.mass), tuple(r.weight), r.dt, periodic=True, capacity=p0["x"].shape[1] + 16,
+                          B_conv=r.B_conv, length_conv=r.length_conv, light_speed=r.light_speed)
+
+    # the reference's J, M per unique corner: every copy of a corner a real block holds (its own corners, i in 0..N) must agree
+    def to_unique(arr):
+        out = np.full((m.n_corners, arr.shape[-1]), np.nan)
+        spread = 0.0
+        for b in real:
+            a = arr[b, g[2]:g[2] + N[2] + 1, g[1]:g[1] + N[1] + 1, g[0]:g[0] + N[0] + 1].reshape(-1, arr.shape[-1])
+            u = cu[b, g[2]:g[2] + N[2] + 1, g[1]:g[1] + N[1] + 1, g[0]:g[0] + N[0] + 1].reshape(-1)
+            have = ~np.isnan(out[u, 0])
+            if have.any():
+                spread = max(spread, float(np.abs(out[u[have]] - a[have]).max()))
+            out[u] = a
+        return out, spread
+    ref = {"J0": to_unique(J0), "M0": to_unique(M0), "J1": to_unique(J1), "M1": to_unique(M1), "energy0": e0, "energy1": e1, "after": after}
+    touched = ~np.isnan(ref["J0"][0][:, 0])
+    return {"ref": ref, "mesh": m, "cfg": cfg, "parts": (p0["x"], p0["v"], p0["w"], p0["species"].astype(np.uint8), cells0),
+            "fields": (E_u, Bp_u, Bc_u), "touched": touched, "refpic": r}
