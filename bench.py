@@ -339,6 +339,82 @@ def measure_fp64_peak():
         return None
 
 
+def bench_gca_large(torch, dist, rank, world, local, n_per_gpu, K=5, W=2, chunk=20_000_000):
+    """BASELINE configs[4] (input/gca_mover.input): the relativistic guiding-centre mover on n_per_gpu protons per GPU in the
+    MoverTest dipole + E = -v x B field tabulated on 512 blocks of 5^3 cells with 2 ghost layers.  Test particles do not interact:
+    every rank holds the whole (small) field table and its own share of the particles, so the path shards without any
+    data-path collective ("weak": n_per_gpu is fixed as the GPUs grow).  One step = MoveParticles + the list hand-off (sort)."""
+    from amps_b200 import _capi, api, workload as wl
+
+    kw = dict(n_blocks=8, block_cells=(5, 5, 5), ghost_cells=(2, 2, 2), rigidity_gv=(0.001, 0.05))
+    t0 = time.time()
+    m, parts = wl.dipole_test_particles(min(chunk, n_per_gpu), seed=11 + 1000 * rank, **kw)
+    cfg = api.make_config((5, 5, 5), (2, 2, 2), (wl.QP,), (wl.MP,), (1.0,), 0.05, periodic=False, capacity=n_per_gpu + 16, boundary_mode=_capi.BOUNDARY_DELETE)
+    cfg.time_step_mode = _capi.DT_SPECIES_GLOBAL
+    cfg.coupler_interpolation = _capi.CPLR_LINEAR
+    cfg.speed_of_light = wl.CLIGHT
+    cfg.internal_sphere_radius = wl.RE
+    cfg.exit_record_capacity = 1024
+    cfg.carry_magnetic_moment = 1
+    cfg.device = local
+    E, B = wl.background_analytic(m.center_x)
+    ctx = api.Context(cfg, m)
+    ctx.background_upload(E, B)
+    ctx.background_upload_gca(wl.gca_var15(m.center_x, 1.0e3))
+    ctx.particles_upload(*parts)
+    n = parts[0].shape[1]
+    k = 1
+    while n < n_per_gpu:
+        _, parts = wl.dipole_test_particles(min(chunk, n_per_gpu - n), seed=11 + 1000 * rank + k, **kw)
+        ctx.particles_append(*parts)
+        n += parts[0].shape[1]
+        k += 1
+    del parts
+    ctx.InitiateMagneticMoment(_capi.MOVER_RELATIVISTIC_GCA)
+    setup_s = time.time() - t0
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one():
+        ctx.MoveParticles(_capi.MOVER_RELATIVISTIC_GCA, stats=False)
+        ctx.sort()
+
+    for _ in range(W):
+        one()
+    barrier()
+    n_start = ctx.particle_count()
+    ctx.profile(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(K):
+        one()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    ph = ctx.profile(False)
+    n_end = ctx.particle_count()
+    ctx.close()
+    tot = float(n_start)
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+        nn = torch.tensor([tot], dtype=torch.float64, device="cuda")
+        dist.all_reduce(nn, op=dist.ReduceOp.SUM)
+        tot = float(nn.item())
+    return {"workload": f"input/gca_mover.input shape: relativistic GCA (first order), protons 1-50 MV in the MoverTest dipole + E = -v x B, 512 blocks of "
+                        f"5^3 cells, 2 ghost layers, dt = 0.05, {n_per_gpu} particles per GPU (field table replicated, particles sharded)",
+            "value": tot * K / (ms * 1e-3), "unit": "pushes/s", "ms_per_step": ms / K, "steps": K, "warmup": W, "particles_total": tot,
+            "particles_left_rank0": int(n_end), "move_ms": ph["move"][0] / K, "sort_ms": ph["sort"][0] / K, "alg_bytes_per_push": 113.0,
+            "achieved_gbs_per_gpu": 113.0 * (tot / world) * K / (ms * 1e-3) / 1e9, "setup_s": round(setup_s, 1)}
+
+
 _REAL_STDOUT = None
 
 
@@ -372,6 +448,7 @@ def main():
     ap.add_argument("--no-tp", action="store_true", help="skip the test-particle mover side measurements")
     ap.add_argument("--no-large", action="store_true", help="skip the 128^3-cells-per-GPU series (BASELINE configs[2])")
     ap.add_argument("--large-cells", type=int, default=128, help="cells per GPU edge of the large-box series")
+    ap.add_argument("--gca-particles", type=int, default=100_000_000, help="particles per GPU of the guiding-centre series (BASELINE configs[4]); 0 = skip")
     ap.add_argument("--no-mp-parity", action="store_true", help="world > 1: skip the sharded-step parity check before the timing")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -534,6 +611,14 @@ def main():
         except Exception as exc:  # extra block: never lose the headline line
             large = {"error": repr(exc)[:300]}
 
+    # ---- BASELINE configs[4] series: relativistic GCA, 1e8 particles per GPU ----
+    gca = None
+    if args.gca_particles > 0:
+        try:
+            gca = bench_gca_large(torch, dist if world > 1 else None, rank, world, local, args.gca_particles)
+        except Exception as exc:
+            gca = {"error": repr(exc)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -588,6 +673,8 @@ def main():
         line["mp_parity"] = mp_parity
     if large is not None:
         line["u256_series"] = large
+    if gca is not None:
+        line["gca_series"] = gca
     if world == 1 and not args.no_tp:
         try:
             line["test_particle_movers"] = bench_test_particle_movers(torch)
