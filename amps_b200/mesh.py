@@ -81,6 +81,34 @@ class FlatMesh:
                     nb[core[ok], s] = sh[ok]
         return nb
 
+    def field_solver_tables(self):
+        """Node adjacency of the ECSIM field solve on the unique nodes (single-level meshes), from the leaves' node tables:
+        corner_nb[n_corners, 27]      = corner_neighbours()
+        corner_cells[n_corners, 8]    centre node of the cell at corner index + (a, b, c), a, b, c in {-1, 0}; entry (a+1) + 2 (b+1) + 4 (c+1)
+        center_corners[n_centers, 8]  corner node at cell index + (ii, jj, kk) in {0, 1}^3; entry ii + 2 jj + 4 kk
+        (-1 where the mesh has no such node: outside an open domain)"""
+        N, g = np.array(self.block_cells), np.array(self.ghost_cells)
+        T = N + 2 * g
+        cu = self.arrays["leaf_corner_uid"].reshape(-1, T[2] + 1, T[1] + 1, T[0] + 1).astype(np.int64)
+        zu = self.arrays["leaf_center_uid"].reshape(-1, T[2], T[1], T[0]).astype(np.int64)
+        cc = np.full((self.n_corners, 8), -1, dtype=np.int64)
+        zc = np.full((self.n_centers, 8), -1, dtype=np.int64)
+        core = cu[:, g[2]:g[2] + N[2] + 1, g[1]:g[1] + N[1] + 1, g[0]:g[0] + N[0] + 1]
+        for c in (-1, 0):
+            for b in (-1, 0):
+                for a in (-1, 0):
+                    sh = zu[:, g[2] + c:g[2] + c + N[2] + 1, g[1] + b:g[1] + b + N[1] + 1, g[0] + a:g[0] + a + N[0] + 1]
+                    ok = (core >= 0) & (sh >= 0)
+                    cc[core[ok], (a + 1) + 2 * (b + 1) + 4 * (c + 1)] = sh[ok]
+        cells = zu[:, g[2]:g[2] + N[2], g[1]:g[1] + N[1], g[0]:g[0] + N[0]]
+        for kk in (0, 1):
+            for jj in (0, 1):
+                for ii in (0, 1):
+                    sh = cu[:, g[2] + kk:g[2] + kk + N[2], g[1] + jj:g[1] + jj + N[1], g[0] + ii:g[0] + ii + N[0]]
+                    ok = (cells >= 0) & (sh >= 0)
+                    zc[cells[ok], ii + 2 * jj + 4 * kk] = sh[ok]
+        return self.corner_neighbours().astype(np.int32), cc.astype(np.int32), zc.astype(np.int32)
+
     def leaf_level(self):
         return self.arrays["node_level"][self.arrays["leaf_node"]]
 

@@ -50,7 +50,8 @@ cd $B/\$(dirname \$f) && g++ $FLAGS $INC -c \$(basename \$f) -o \$o > \$o.log 2>
 EOS
 chmod +x cc.sh
 xargs -P "$JOBS" -n 1 ./cc.sh < tus.txt
-(cd "$B/pic" && g++ $FLAGS $INC -c "$HERE/ref_pic_shim.cpp" -o "$S/obj/ref_pic_shim.o")
+(cd "$B/pic" && g++ $FLAGS -fno-access-control $INC -c "$HERE/ref_pic_shim.cpp" -o "$S/obj/ref_pic_shim.o")
+g++ $FLAGS -I"$HERE" -c "$HERE/gmres_single.cpp" -o "$S/obj/gmres_single.o"
 g++ $FLAGS -I"$HERE" -I"$HERE/../ref_mesh" -c "$HERE/mpi_single.cpp" -o "$S/obj/mpi_single.o"
 g++ -shared -o "$OUT" obj/*.o -lpthread
 echo "built $OUT from $(wc -l < tus.txt) reference translation units"

@@ -10,7 +10,7 @@
 #undef main
 
 // ---- symbols of translation units that are not part of this build (the SWMF fluid coupler, Fortran readers, user models) ----
-void (*linear_solver_matvec_c)(double *VecIn, double *VecOut, int n) = nullptr;
+// (linear_solver_matvec_c and the GMRES behind linear_solver_wrapper: gmres_single.cpp)
 long int PIC::CPLR::FLUID::iCycle = 0;
 bool PIC::CPLR::FLUID::IsRestart = false;
 double PIC::CPLR::FLUID::EFieldTol = 1.0e-6;
@@ -212,6 +212,42 @@ void ref_pic_move(void) {
   PIC::Parallel::ExchangeParticleData();
   PIC::BC::ExternalBoundary::Periodic::ExchangeParticles();
 }
+// ---- the field half of ECSIM::TimeStep (pic_field_solver_ecsim.cpp:6449-6560): UpdateRhs, UpdateMatrixElement, the GMRES solve for
+// x = E_conv (E^{n+theta} - E^n), ProcessFinalSolution, UpdateB, UpdateE.  (Its first call also runs UpdateJMassMatrix + BuildMatrix.)
+int ref_pic_field_step(double tol, int max_iter, double *rel_residual) {
+  PIC::CPLR::FLUID::EFieldTol = tol;
+  PIC::CPLR::FLUID::EFieldIter = max_iter;
+  PIC::FieldSolver::Electromagnetic::ECSIM::TimeStep();
+  if (rel_residual) *rel_residual = ref_gmres_last_relative_residual;
+  return ref_gmres_last_iterations;
+}
+// the rows of the reference's linear system in its own order: block (index of ref_pic_blocks), corner i, j, k, component and the
+// right-hand side of the last UpdateRhs; returns the number of rows
+long ref_pic_solver_rows(long max_n, int *block, int *ijk, int *ivar, double *rhs) {
+  auto *S = PIC::FieldSolver::Electromagnetic::ECSIM::Solver;
+  long n = 0;
+  for (auto *row = S->MatrixRowListFirst; row != NULL; row = row->next, n++) {
+    if (n >= max_n) continue;
+    int b = -1;
+    for (size_t q = 0; q < g_blocks.size(); q++)
+      if (g_blocks[q] == row->node) b = (int)q;
+    block[n] = b, ijk[3 * n] = row->i, ijk[3 * n + 1] = row->j, ijk[3 * n + 2] = row->k, ivar[n] = row->iVar, rhs[n] = row->Rhs;
+  }
+  return n;
+}
+// y = A x with the reference's operator (vectors in the order of ref_pic_solver_rows: 3 components per corner)
+void ref_pic_matvec(double *x, double *y, int n) { PIC::FieldSolver::Electromagnetic::ECSIM::matvec(x, y, n); }
+// the reference's constant operator tables (InitDiscritizationStencil, pic_field_solver_ecsim.cpp:7451): kind 0 = LaplacianStencil[p],
+// kind 1 = GradDivStencil[p][q]; returns the number of taps (offsets di,dj,dk and the coefficient a)
+int ref_pic_stencil(int kind, int p, int q, int max_n, int *ijk, double *a) {
+  using namespace PIC::FieldSolver::Electromagnetic::ECSIM;
+  cStencil::cStencilData *st = (kind == 0) ? LaplacianStencil + p : &GradDivStencil[p][q];
+  for (int it = 0; it < st->Length && it < max_n; it++)
+    ijk[3 * it] = st->Data[it].i, ijk[3 * it + 1] = st->Data[it].j, ijk[3 * it + 2] = st->Data[it].k, a[it] = st->Data[it].a;
+  return st->Length;
+}
+double ref_pic_theta(void) { return PIC::FieldSolver::Electromagnetic::ECSIM::theta; }
+
 // (the per-species cfl maxima are locals of UpdateJMassMatrix: it prints them, "max cfl number for spec s :value")
 void ref_pic_update_JM(double *energy) {
   PIC::FieldSolver::Electromagnetic::ECSIM::UpdateJMassMatrix();

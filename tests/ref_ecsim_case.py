@@ -77,6 +77,53 @@ def case(keep_every=1):
     e1 = r.update_JM()
     J1, M1 = r.corner(2), r.corner(3)
 
+    # ---- the field half of the next step (ECSIM::TimeStep): E^n, B^n, J, M -> E^{n+theta}, E^{n+1}, B^{n+1} ----
+    import ctypes as C
+
+    def corner_u(arr):
+        out = np.full((m.n_corners, arr.shape[-1]), np.nan)
+        for b in real:
+            sl = (b, slice(g[2], g[2] + N[2] + 1), slice(g[1], g[1] + N[1] + 1), slice(g[0], g[0] + N[0] + 1))
+            out[cu[sl].reshape(-1)] = arr[sl].reshape(-1, arr.shape[-1])
+        return out
+
+    def center_u(arr):
+        out = np.full((m.n_centers, 3), np.nan)
+        for b in real:
+            sl = (b, slice(g[2], g[2] + N[2]), slice(g[1], g[1] + N[1]), slice(g[0], g[0] + N[0]))
+            out[zu[sl].reshape(-1)] = arr[sl].reshape(-1, 3)
+        return out
+    Efld = smooth(m.corner_x, 0.02, 2.1) - 0.015
+    r.set_corner(0, Efld[cu])  # E^n (the initial condition of fast-wave is E = 0: give the operator something to act on)
+    field = {"E": corner_u(r.corner(0)), "B": center_u(r.center(0)), "theta": 0.5}
+    rel_res = C.c_double()
+    with ref_pic.quiet():
+        field["iterations"] = r.lib.ref_pic_field_step(C.c_double(1e-12), 400, C.byref(rel_res))
+    field["rel_residual"] = float(rel_res.value)
+    r.lib.ref_pic_solver_rows.restype = C.c_long
+    nrow = r.lib.ref_pic_solver_rows(0, None, None, None, None)
+    blk, ijk, iv, rr = np.zeros(nrow, dtype=np.int32), np.zeros((nrow, 3), dtype=np.int32), np.zeros(nrow, dtype=np.int32), np.zeros(nrow)
+    r.lib.ref_pic_solver_rows(nrow, ref_pic._p(blk), ref_pic._p(ijk), ref_pic._p(iv), ref_pic._p(rr))
+    ru = cu[blk, ijk[:, 2] + g[2], ijk[:, 1] + g[1], ijk[:, 0] + g[0]]
+    field["rhs"] = np.zeros((m.n_corners, 3))
+    field["rhs"][ru, iv] = rr
+    xin = np.random.default_rng(5).standard_normal((m.n_corners, 3))
+    vin, vout = np.ascontiguousarray(xin[ru, iv]), np.zeros(nrow)
+    r.lib.ref_pic_matvec(ref_pic._p(vin), ref_pic._p(vout), int(nrow))
+    field["matvec_in"], field["matvec_out"] = xin, np.zeros((m.n_corners, 3))
+    field["matvec_out"][ru, iv] = vout
+    field["E_half"], field["E_new"], field["B_new"] = corner_u(r.corner(1)), corner_u(r.corner(0)), center_u(r.center(0))
+
+    def stencil(kind, p, q):
+        ijk3, aa = np.zeros((200, 3), dtype=np.int32), np.zeros(200)
+        n = r.lib.ref_pic_stencil(kind, p, q, 200, ref_pic._p(ijk3), ref_pic._p(aa))
+        T = np.zeros((3, 3, 3))
+        for t in range(n):
+            T[ijk3[t, 0] + 1, ijk3[t, 1] + 1, ijk3[t, 2] + 1] += aa[t]
+        return T
+    field["laplacian"] = [stencil(0, p, 0) for p in range(3)]
+    field["graddiv"] = [[stencil(1, p, q) for q in range(3)] for p in range(3)]
+
     # particles in this repo's numbering: leaf by block position, same cell formula i + Nx (j + Ny k)
     lx = m.leaf_xmin()
     def leaf_of_block(b):
@@ -112,5 +159,6 @@ def case(keep_every=1):
         return out, spread
     ref = {"J0": to_unique(J0), "M0": to_unique(M0), "J1": to_unique(J1), "M1": to_unique(M1), "energy0": e0, "energy1": e1, "after": after}
     touched = ~np.isnan(ref["J0"][0][:, 0])
+    ref["field"] = field
     return {"ref": ref, "mesh": m, "cfg": cfg, "parts": (p0["x"], p0["v"], p0["w"], p0["species"].astype(np.uint8), cells0),
             "fields": (E_u, Bp_u, Bc_u), "touched": touched, "refpic": r}
