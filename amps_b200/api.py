@@ -342,6 +342,34 @@ class Context:
     def step(self, mover=_capi.MOVER_LAPENTA2017):
         self._ck(self.lib.amps_gpu_step(self._h, mover))
 
+    # ---- ECSIM::TimeStep, the field half (row f1) -------------------------------------------------
+    def field_solver_init(self):
+        nb, cc, zc = self.mesh.field_solver_tables()
+        self._ck(self.lib.amps_gpu_field_solver_init(self._h, _ptr(np.ascontiguousarray(nb)), _ptr(np.ascontiguousarray(cc)), _ptr(np.ascontiguousarray(zc))))
+
+    def E_upload(self, E):
+        E = np.ascontiguousarray(E, dtype=np.float64)
+        assert E.shape == (self.mesh.n_corners, 3)
+        self._ck(self.lib.amps_gpu_E_upload(self._h, _ptr(E)))
+
+    def field_step(self, theta=0.5, tol=1e-6, max_iter=200, restart=30):
+        it, rel = C.c_int(), C.c_double()
+        self._ck(self.lib.amps_gpu_field_step(self._h, theta, tol, max_iter, restart, C.byref(it), C.byref(rel)))
+        return int(it.value), float(rel.value)
+
+    def fields_download(self, E=True, E_half=True, B=True, out=None):
+        """-> dict of the requested fields; out = preallocated (pinned) arrays to fill instead"""
+        res = out or {}
+        if E and "E" not in res:
+            res["E"] = np.empty((self.mesh.n_corners, 3))
+        if E_half and "E_half" not in res:
+            res["E_half"] = np.empty((self.mesh.n_corners, 3))
+        if B and "B" not in res:
+            res["B"] = np.empty((self.mesh.n_centers, 3))
+        self._ck(self.lib.amps_gpu_fields_download(self._h, _ptr(res.get("E")) if E else None, _ptr(res.get("E_half")) if E_half else None,
+                                                   _ptr(res.get("B")) if B else None))
+        return res
+
     # ---- multi-GPU (one rank per GPU) -------------------------------------------------------
     def comm_init(self, dist):
         """Join the library's NCCL communicator; `dist` = torch.distributed (initialised) used only to broadcast the id

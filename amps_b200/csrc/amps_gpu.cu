@@ -31,6 +31,16 @@ struct amps_gpu_ctx {
   double *d_Ehalf = nullptr, *d_Bprev = nullptr, *d_Bcur = nullptr;
   double *d_eTile = nullptr, *d_bPrevTile = nullptr, *d_bCurTile = nullptr;
 
+  // field solve (row f1): E^n on the unique corners, node adjacency, Krylov space
+  double *d_E = nullptr;
+  int *d_fNb = nullptr, *d_fCc = nullptr, *d_fZc = nullptr;
+  bool fieldSolverReady = false, eReady = false;
+  double dxc0[3] = {1.0, 1.0, 1.0};  // cell size of leaf 0 (single-level meshes: of every leaf)
+  double *d_krylov = nullptr;   // [(restart + 1) + 2][3 nCorners]: V_0.., w, x
+  int krylovVectors = 0;
+  double *d_hcol = nullptr, *h_hcol = nullptr;  // inner products of one iteration (device / pinned host), + the norm
+  double *d_ycoef = nullptr;
+
   // particles
   ParticleSoA buf[2];
   int cur = 0;
@@ -328,6 +338,8 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   for (cudaEvent_t e : ctx->dlEvents) cudaEventDestroy(e);
   if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   if (ctx->evCounts) cudaEventDestroy(ctx->evCounts);
+  cudaFree(ctx->d_E), cudaFree(ctx->d_fNb), cudaFree(ctx->d_fCc), cudaFree(ctx->d_fZc), cudaFree(ctx->d_krylov), cudaFree(ctx->d_hcol), cudaFree(ctx->d_ycoef);
+  if (ctx->h_hcol) cudaFreeHost(ctx->h_hcol);
   if (ctx->evSorted) cudaEventDestroy(ctx->evSorted);
   if (ctx->h_nSorted) cudaFreeHost(ctx->h_nSorted);
   cudaFree(ctx->d_spec), cudaFree(ctx->d_phi), cudaFree(ctx->d_cplCount), cudaFree(ctx->d_sample), cudaFree(ctx->d_nSampled), cudaFree(ctx->d_pack);
@@ -505,6 +517,7 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
       double vol = 1, d2 = 0;
       for (int d = 0; d < 3; d++) {
         g.dxc[d] = (g.xmax[d] - g.xmin[d]) / m.N[d];
+        if (l == 0) ctx->dxc0[d] = g.dxc[d];
         g.invdxc[d] = 1.0 / g.dxc[d];
         const double dxl = g.dxc[d] * ctx->cfg.ecsim_length_conv;
         vol *= dxl;
@@ -693,6 +706,220 @@ int amps_gpu_fields_upload(amps_gpu_ctx *ctx, const double *E_half, const double
   ctx->launches++;
   CK(cudaGetLastError());
   ctx->fieldsReady = true;
+  return AMPS_GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// f1: the field half of the ECSIM step (ECSIM::TimeStep, pic_field_solver_ecsim.cpp:6004-6157) on the unique nodes; field_solver.cu
+// ---------------------------------------------------------------------------------------------------------------------------
+int amps_gpu_field_solver_init(amps_gpu_ctx *ctx, const int32_t *corner_nb, const int32_t *corner_cells, const int32_t *center_corners) {
+  if (!ctx || !corner_nb || !corner_cells || !center_corners) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "field_solver_init before mesh_upload");
+  if (ctx->meshRefined) FAIL(AMPS_GPU_ERR_STATE, "the device field solve covers single-level meshes (the compact 27-node rows of GetStencil)");
+  if (ctx->cfg.b_mode != AMPS_B_CENTER_BASED) FAIL(AMPS_GPU_ERR_STATE, "the device field solve updates the centre-based B (UpdateB)");
+  if (ctx->nRanks > 1) FAIL(AMPS_GPU_ERR_STATE, "the device field solve is single-rank (no field halo exchange yet)");
+  if (ctx->cfg.ecsim_B_conv != 1.0) FAIL(AMPS_GPU_ERR_STATE, "the device field solve assumes normalised units (E_conv = B_conv = 1)");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const DevMesh &m = ctx->dm;
+  int rc;
+  cudaFree(ctx->d_fNb), cudaFree(ctx->d_fCc), cudaFree(ctx->d_fZc);
+  if ((rc = dev_alloc(ctx, &ctx->d_fNb, (size_t)27 * m.nCorners))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_fCc, (size_t)8 * m.nCorners))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_fZc, (size_t)8 * m.nCenters))) return rc;
+  CK(cudaMemcpy(ctx->d_fNb, corner_nb, sizeof(int) * 27 * (size_t)m.nCorners, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_fCc, corner_cells, sizeof(int) * 8 * (size_t)m.nCorners, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_fZc, center_corners, sizeof(int) * 8 * (size_t)m.nCenters, cudaMemcpyHostToDevice));
+  if (!ctx->d_E) {
+    if ((rc = dev_alloc(ctx, &ctx->d_E, (size_t)3 * m.nCorners))) return rc;
+    CK(cudaMemset(ctx->d_E, 0, sizeof(double) * 3 * (size_t)m.nCorners));
+  }
+  ctx->fieldSolverReady = true;
+  return AMPS_GPU_OK;
+}
+
+// E^n on the unique corners (E at the half step goes through amps_gpu_fields_upload)
+int amps_gpu_E_upload(amps_gpu_ctx *ctx, const double *E_cur) {
+  if (!ctx || !E_cur) return AMPS_GPU_ERR_ARG;
+  if (!ctx->fieldSolverReady) FAIL(AMPS_GPU_ERR_STATE, "E_upload before amps_gpu_field_solver_init");
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemcpyAsync(ctx->d_E, E_cur, sizeof(double) * 3 * (size_t)ctx->dm.nCorners, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->eReady = true;
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_fields_download(amps_gpu_ctx *ctx, double *E_cur, double *E_half, double *B_cur) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "fields_download before mesh_upload");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const DevMesh &m = ctx->dm;
+  const size_t nB = (ctx->cfg.b_mode == AMPS_B_CORNER_BASED) ? m.nCorners : m.nCenters;
+  if (E_cur) {
+    if (!ctx->d_E) FAIL(AMPS_GPU_ERR_STATE, "no E^n on the device (amps_gpu_field_solver_init)");
+    CK(cudaMemcpyAsync(E_cur, ctx->d_E, sizeof(double) * 3 * (size_t)m.nCorners, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (E_half) CK(cudaMemcpyAsync(E_half, ctx->d_Ehalf, sizeof(double) * 3 * (size_t)m.nCorners, cudaMemcpyDeviceToHost, ctx->stream));
+  if (B_cur) CK(cudaMemcpyAsync(B_cur, ctx->d_Bcur, sizeof(double) * 3 * nB, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AMPS_GPU_OK;
+}
+
+// One field step from the state on the device: E^n (amps_gpu_E_upload or the previous step), B^n (= B_cur of fields_upload or
+// the previous step), J and M of the last deposit.  UpdateRhs -> GMRES(restart) from x0 = 0 on the relative residual (what the
+// reference asks linear_solver_wrapper for, LinearSystemCornerNode.h:3282) -> E^{n+theta} = E^n + x (ProcessFinalSolution) ->
+// UpdateB (B_prev <- B^n, B_cur <- B^{n+1}) -> UpdateE (E^n <- E^{n+1}); the tiles of the movers and of the deposit are staged
+// again, so the particle step that follows sees E^{n+theta}, B^n and B^{n+1} exactly like PIC::TimeStep orders them.
+int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_iter, int restart, int *iterations, double *rel_residual) {
+  if (!ctx || theta <= 0.0 || tol <= 0.0 || max_iter < 1) return AMPS_GPU_ERR_ARG;
+  if (!ctx->fieldSolverReady) FAIL(AMPS_GPU_ERR_STATE, "field_step before amps_gpu_field_solver_init");
+  if (!ctx->fieldsReady) FAIL(AMPS_GPU_ERR_STATE, "field_step before amps_gpu_fields_upload (B^n)");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const DevMesh &m = ctx->dm;
+  cudaStream_t s = ctx->stream;
+  const int n = 3 * m.nCorners;
+  if (restart < 1) restart = 30;
+  if (restart > max_iter) restart = max_iter;
+  int rc;
+  if (ctx->krylovVectors < restart + 3) {
+    cudaFree(ctx->d_krylov);
+    ctx->d_krylov = nullptr;
+    if ((rc = dev_alloc(ctx, &ctx->d_krylov, (size_t)(restart + 3) * n))) return rc;
+    ctx->krylovVectors = restart + 3;
+    cudaFree(ctx->d_hcol), cudaFree(ctx->d_ycoef);
+    if (ctx->h_hcol) cudaFreeHost(ctx->h_hcol);
+    if ((rc = dev_alloc(ctx, &ctx->d_hcol, (size_t)restart + 4))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_ycoef, (size_t)restart + 4))) return rc;
+    CK(cudaMallocHost(&ctx->h_hcol, sizeof(double) * (restart + 4)));
+  }
+  // metric and time factors of GetStencil: coeff = theta c dt / dx, the operator constants K[9 slot + 3 p + q]
+  double dx[3], coeff[3], c4rhs[3], c4b[3];
+  const double cdt = ctx->cfg.ecsim_light_speed * ctx->cfg.ecsim_dt_total;
+  for (int d = 0; d < 3; d++) {
+    dx[d] = ctx->dxc0[d] * ctx->cfg.ecsim_length_conv;
+    coeff[d] = cdt / dx[d] * theta;
+    c4rhs[d] = 0.25 * coeff[d];
+    c4b[d] = 0.25 * (cdt / dx[d]);
+  }
+  {
+    static const double D2[3] = {1.0, -2.0, 1.0}, AV[3] = {0.25, 0.5, 0.25}, D1[3] = {-0.5, 0.0, 0.5};
+    auto gd = [&](int p, int q, const int o[3]) {  // GradDivStencil[p][q] (== LaplacianStencil[p] for p == q), InitDiscritizationStencil
+      double v = 1.0;
+      for (int d = 0; d < 3; d++) {
+        const double *t = (p == q) ? (d == p ? D2 : AV) : ((d == p || d == q) ? D1 : AV);
+        v *= t[o[d] + 1];
+      }
+      return v;
+    };
+    double K[243];
+    for (int a = -1; a <= 1; a++)
+      for (int b = -1; b <= 1; b++)
+        for (int c = -1; c <= 1; c++) {
+          const int o[3] = {a, b, c};
+          auto code = [](int d) { return (3 * d * d + d) >> 1; };
+          const int slot = code(a) + 3 * code(b) + 9 * code(c);
+          for (int p = 0; p < 3; p++)
+            for (int q = 0; q < 3; q++) {
+              double k = coeff[p] * coeff[q] * gd(p, q, o);
+              if (p == q) {
+                for (int e = 0; e < 3; e++) k -= coeff[e] * coeff[e] * gd(e, e, o);
+                if (slot == 0) k += 1.0;
+              }
+              K[9 * slot + 3 * p + q] = k;
+            }
+        }
+    field_set_constants(K);
+  }
+  const double f = 4.0 * 3.14159265358979323846 * ctx->cfg.ecsim_dt_total * theta;
+  double *V = ctx->d_krylov, *w = V + (size_t)(restart + 1) * n, *x = w + n;
+  const size_t ld = (size_t)n;
+  // right-hand side into w, then V_0 = r0 / |r0| (x0 = 0 -> r0 = rhs)
+  launch_ecsim_operator(true, m.nCorners, ctx->d_fNb, ctx->d_fCc, ctx->d_M, ctx->d_E, f, ctx->d_J, ctx->d_Bcur, c4rhs, w, s);
+  CK(cudaMemsetAsync(x, 0, sizeof(double) * n, s));
+  ctx->launches++;
+  std::vector<double> H((size_t)(restart + 1) * restart), cs(restart), sn(restart), g(restart + 1), y(restart);
+  double r0norm = -1.0, rel = 1.0;
+  int iters = 0;
+  bool first = true;
+  double *rhsKeep = nullptr;  // after a restart the residual needs the right-hand side again: kept in the last spare vector
+  while (iters < max_iter) {
+    if (first) {
+      // keep a copy of the right-hand side only if a restart can happen
+      if (max_iter > restart) {
+        if ((rc = dev_alloc(ctx, &rhsKeep, (size_t)n))) return rc;
+        CK(cudaMemcpyAsync(rhsKeep, w, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+      }
+    } else {
+      // r = rhs - A x
+      launch_ecsim_operator(false, m.nCorners, ctx->d_fNb, ctx->d_fCc, ctx->d_M, x, f, nullptr, nullptr, c4rhs, w, s);
+      launch_axpby(n, 1.0, rhsKeep, -1.0, w, nullptr, w, s);
+      ctx->launches += 2;
+    }
+    first = false;
+    launch_multi_dot(V, ld, 0, w, n, ctx->d_hcol, s);  // |w|^2
+    CK(cudaMemcpyAsync(ctx->h_hcol, ctx->d_hcol, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const double beta = sqrt(ctx->h_hcol[0]);
+    if (r0norm < 0.0) r0norm = beta;
+    rel = r0norm > 0.0 ? beta / r0norm : 0.0;
+    if (beta == 0.0 || rel <= tol) break;
+    launch_axpby(n, 1.0 / beta, w, 0.0, nullptr, nullptr, V, s);
+    ctx->launches += 2;
+    std::fill(g.begin(), g.end(), 0.0);
+    g[0] = beta;
+    int j = 0;
+    for (; j < restart && iters < max_iter; j++) {
+      double *vj = V + (size_t)j * ld, *vn = V + (size_t)(j + 1) * ld;
+      launch_ecsim_operator(false, m.nCorners, ctx->d_fNb, ctx->d_fCc, ctx->d_M, vj, f, nullptr, nullptr, c4rhs, vn, s);
+      iters++;
+      launch_multi_dot(V, ld, j + 1, vn, n, ctx->d_hcol, s);                             // h_i = V_i . w
+      launch_orthogonalize(V, ld, j + 1, ctx->d_hcol, vn, n, ctx->d_hcol + j + 2, s);    // w -= sum h_i V_i, |w|^2
+      launch_axpby(n, 1.0, vn, 0.0, nullptr, ctx->d_hcol + j + 2, vn, s);                // V_{j+1} = w / |w|
+      ctx->launches += 4;
+      CK(cudaMemcpyAsync(ctx->h_hcol, ctx->d_hcol, sizeof(double) * (j + 3), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      for (int i = 0; i <= j; i++) H[(size_t)i * restart + j] = ctx->h_hcol[i];
+      H[(size_t)(j + 1) * restart + j] = sqrt(ctx->h_hcol[j + 2]);
+      for (int i = 0; i < j; i++) {
+        const double t = cs[i] * H[(size_t)i * restart + j] + sn[i] * H[(size_t)(i + 1) * restart + j];
+        H[(size_t)(i + 1) * restart + j] = -sn[i] * H[(size_t)i * restart + j] + cs[i] * H[(size_t)(i + 1) * restart + j];
+        H[(size_t)i * restart + j] = t;
+      }
+      const double a = H[(size_t)j * restart + j], b = H[(size_t)(j + 1) * restart + j], d = sqrt(a * a + b * b);
+      cs[j] = a / d, sn[j] = b / d;
+      H[(size_t)j * restart + j] = d, H[(size_t)(j + 1) * restart + j] = 0.0;
+      g[j + 1] = -sn[j] * g[j];
+      g[j] = cs[j] * g[j];
+      rel = fabs(g[j + 1]) / r0norm;
+      if (rel <= tol) {
+        j++;
+        break;
+      }
+    }
+    for (int i = j - 1; i >= 0; i--) {
+      double t = g[i];
+      for (int q = i + 1; q < j; q++) t -= H[(size_t)i * restart + q] * y[q];
+      y[i] = t / H[(size_t)i * restart + i];
+    }
+    CK(cudaMemcpyAsync(ctx->d_ycoef, y.data(), sizeof(double) * j, cudaMemcpyHostToDevice, s));
+    launch_combine(V, ld, j, ctx->d_ycoef, x, n, s);
+    ctx->launches++;
+    CK(cudaStreamSynchronize(s));  // y is a host temporary
+    if (rel <= tol) break;
+  }
+  if (rhsKeep) cudaFree(rhsKeep);
+  // ProcessFinalSolution: E^{n+theta} = E^n + x
+  launch_axpby(n, 1.0, ctx->d_E, 1.0, x, nullptr, ctx->d_Ehalf, s);
+  // UpdateB: B^{n+1} into the buffer that held B_prev, then the two swap roles (CurrentBOffset <-> PrevBOffset)
+  launch_update_B(m.nCenters, ctx->d_fZc, ctx->d_Ehalf, ctx->d_Bcur, c4b, ctx->d_Bprev, s);
+  std::swap(ctx->d_Bcur, ctx->d_Bprev);
+  // UpdateE: E^{n+1} = (E^{n+theta} - (1 - theta) E^n) / theta
+  launch_axpby(n, 1.0 / theta, ctx->d_Ehalf, -(1.0 - theta) / theta, ctx->d_E, nullptr, ctx->d_E, s);
+  launch_stage_tiles(m, false, ctx->d_Ehalf, ctx->d_Bprev, ctx->d_Bcur, ctx->d_eTile, ctx->d_bPrevTile, ctx->d_bCurTile, s);
+  ctx->launches += 4;
+  CK(cudaGetLastError());
+  ctx->eReady = true;
+  if (iterations) *iterations = iters;
+  if (rel_residual) *rel_residual = rel;
   return AMPS_GPU_OK;
 }
 

@@ -1,0 +1,203 @@
+// field_solver.cu -- the field half of the ECSIM step on the device, sm_100a, fp64.
+//
+//   ECSIM::TimeStep                 src/pic/pic_field_solver_ecsim.cpp:6004-6157
+//   GetStencil (one matrix row)     src/pic/ecsim/get_stencil.cpp: identity + (theta c dt)^2 (grad div - laplace) + 4 pi theta dt M
+//   UpdateRhs / SampleRhsScalar     src/pic/ecsim/update_rhs.cpp
+//   UpdateMatrixElement             :6004-6020  value = parameter + 4 pi dt theta * (mass-matrix entry)
+//   cLinearSystemCornerNode::MultiplyVector / Solve   srcInterface/LinearSystemCornerNode.h:2749-3067, :3212 (GMRES of the SWMF library)
+//   UpdateB :5160, UpdateE :5909
+//
+// The reference stores an explicit sparse row per unknown (81 elements with pointers into the corner buffers) and walks it for every
+// product.  Here the operator is matrix-free on the unique corner nodes: the constant part is 243 numbers (3 x 3 components x 27
+// neighbour slots, the compact tables of InitDiscritizationStencil) in constant memory, the variable part IS the mass matrix the
+// deposit left in HBM (M[corner][9 slot + 3 p + q], the reference's MassMatrixOffsetTable), so a product reads M once, coalesced
+// (1944 B per corner), one warp per corner: 510 MB per product for the 64^3 box = HBM-bound, nothing is assembled.  The Krylov
+// vectors (6.3 MB each) live in L2.  GMRES(m) with classical Gram-Schmidt: all inner products of an iteration in ONE pass
+// (multi_dot_kernel), the update and the norm of the new direction in one more (orthogonalize_kernel), so an iteration is four
+// launches and one 8-byte-per-vector read-back for the Givens rotations on the host.
+#include "amps_dev.cuh"
+
+namespace amps {
+
+__constant__ double cFieldK[243];  // K[9 slot + 3 p + q]: parameter part of row component p, column component q, neighbour slot
+
+void field_set_constants(const double *K243) { cudaMemcpyToSymbol(cFieldK, K243, sizeof(double) * 243); }
+
+// kRhs = false: y = A x.  kRhs = true: y = -(A - I) E - f J + theta c dt curl B   (UpdateRhs; x = E^n)
+// nb[c][27] neighbour corner per slot (-1: none -> the row is the boundary row dE = 0), cc[c][8] the eight cells around the corner
+template <bool kRhs>
+__global__ void __launch_bounds__(256) ecsim_operator_kernel(int nCorners, const int *__restrict__ nb, const int *__restrict__ cc,
+                                                            const double *__restrict__ M, const double *__restrict__ x, double f,
+                                                            const double *__restrict__ J, const double *__restrict__ B, double c4x, double c4y,
+                                                            double c4z, double *__restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
+  for (int c = warp; c < nCorners; c += nWarps) {
+    const int *nbc = nb + (size_t)c * 27;
+    const int myNb = (lane < 27) ? nbc[lane] : 0;
+    const bool boundary = __any_sync(0xffffffffu, myNb < 0);
+    if (boundary) {  // dE = 0 on a domain boundary (GetStencil: unit row, zero right-hand side)
+      if (lane < 3) y[(size_t)3 * c + lane] = kRhs ? 0.0 : x[(size_t)3 * c + lane];
+      continue;
+    }
+    const double *Mc = M + (size_t)c * 243;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      const int e = lane + 32 * t;
+      const int s = min(e, 242) / 9;
+      const int n = __shfl_sync(0xffffffffu, myNb, s);  // (every lane takes part: the source lanes 24..26 are idle in the last trip)
+      if (e < 243) {
+        const int r = e - 9 * s, p = r / 3, q = r - 3 * p;
+        double k = cFieldK[e];
+        if (kRhs && e == 0) k -= 1.0;                       // p = q = 0, slot 0: the identity stays on the left-hand side
+        if (kRhs && (e == 4 || e == 8)) k -= 1.0;           // (p,q) = (1,1), (2,2) of slot 0
+        const double v = fma(f, Mc[e], k) * x[(size_t)3 * n + q];
+        a0 += (p == 0) ? v : 0.0, a1 += (p == 1) ? v : 0.0, a2 += (p == 2) ? v : 0.0;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (!kRhs) {
+      if (lane == 0) y[(size_t)3 * c] = a0, y[(size_t)3 * c + 1] = a1, y[(size_t)3 * c + 2] = a2;
+    } else if (lane < 3) {
+      // curl B^n from the 2 x 2 face averages of the centre values (get_stencil.cpp: coeff4 = 0.25 theta c dt / dx)
+      const int *cell = cc + (size_t)c * 8;
+      auto Bv = [&](int a, int b, int d, int comp) { return B[(size_t)3 * cell[(a + 1) + 2 * (b + 1) + 4 * (d + 1)] + comp]; };
+      double r = -((lane == 0) ? a0 : (lane == 1) ? a1 : a2) - f * J[(size_t)3 * c + lane];
+      for (int a = -1; a <= 0; a++)
+        for (int b = -1; b <= 0; b++) {
+          if (lane == 0) r += c4y * (Bv(a, 0, b, 2) - Bv(a, -1, b, 2)) - c4z * (Bv(a, b, 0, 1) - Bv(a, b, -1, 1));
+          if (lane == 1) r += c4z * (Bv(a, b, 0, 0) - Bv(a, b, -1, 0)) - c4x * (Bv(0, b, a, 2) - Bv(-1, b, a, 2));
+          if (lane == 2) r += c4x * (Bv(0, b, a, 1) - Bv(-1, b, a, 1)) - c4y * (Bv(b, 0, a, 0) - Bv(b, -1, a, 0));
+        }
+      y[(size_t)3 * c + lane] = r;
+    }
+  }
+}
+
+// out[j] += V_j . w for j < nVec (V_j = V + j ld), out[nVec] += w . w; every block covers one contiguous chunk of rows, so w is read
+// from HBM / L2 once and stays in L1 while the block walks the vectors
+__global__ void __launch_bounds__(256) multi_dot_kernel(const double *__restrict__ V, size_t ld, int nVec, const double *__restrict__ w, int n,
+                                                       double *__restrict__ out) {
+  __shared__ double sPart[8];
+  const int per = (n + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * per, r1 = min(n, r0 + per);
+  for (int j = 0; j <= nVec; j++) {
+    const double *v = (j < nVec) ? V + (size_t)j * ld : w;
+    double s = 0.0;
+    for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) s = fma(v[i], w[i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sPart[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int q = 0; q < (int)(blockDim.x >> 5); q++) t += sPart[q];
+      atomicAdd(out + j, t);
+    }
+    __syncthreads();
+  }
+}
+
+// w -= sum_j h[j] V_j  (classical Gram-Schmidt with the inner products of multi_dot_kernel); norm2 += |w|^2 of the result
+__global__ void __launch_bounds__(256) orthogonalize_kernel(const double *__restrict__ V, size_t ld, int nVec, const double *__restrict__ h,
+                                                           double *__restrict__ w, int n, double *__restrict__ norm2) {
+  __shared__ double sPart[8];
+  double s = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double a = w[i];
+    for (int j = 0; j < nVec; j++) a = fma(-h[j], V[(size_t)j * ld + i], a);
+    w[i] = a;
+    s = fma(a, a, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sPart[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); q++) t += sPart[q];
+    atomicAdd(norm2, t);
+  }
+}
+
+// out = alpha a + beta b (out may alias a or b); alpha, beta may come from device scalars: alpha *= 1/sqrt(*invSqrtOf) when given
+__global__ void __launch_bounds__(256) axpby_kernel(int n, double alpha, const double *a, double beta, const double *b, const double *invSqrtOf,
+                                                   double *out) {
+  if (invSqrtOf) alpha *= rsqrt(*invSqrtOf);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = alpha * a[i] + (b ? beta * b[i] : 0.0);
+}
+
+// x += sum_j y[j] V_j
+__global__ void __launch_bounds__(256) combine_kernel(const double *__restrict__ V, size_t ld, int nVec, const double *__restrict__ yv,
+                                                     double *__restrict__ x, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double a = x[i];
+    for (int j = 0; j < nVec; j++) a = fma(yv[j], V[(size_t)j * ld + i], a);
+    x[i] = a;
+  }
+}
+
+// UpdateB (:5160): B^{n+1} = B^n + sum over the four edge pairs of a face of -/+ 0.25 c dt / dx (E differences), E = E^{n+theta};
+// zc[z][8] the corner nodes of cell z (ii + 2 jj + 4 kk)
+__global__ void __launch_bounds__(256) update_B_kernel(int nCenters, const int *__restrict__ zc, const double *__restrict__ Eh,
+                                                      const double *__restrict__ Bn, double c4x, double c4y, double c4z, double *__restrict__ Bout) {
+  for (int z = blockIdx.x * blockDim.x + threadIdx.x; z < nCenters; z += gridDim.x * blockDim.x) {
+    const int *cn = zc + (size_t)z * 8;
+    if (cn[0] < 0 || cn[7] < 0) {  // not a cell of this rank's domain (ghost centre of an open boundary)
+      for (int d = 0; d < 3; d++) Bout[(size_t)3 * z + d] = Bn[(size_t)3 * z + d];
+      continue;
+    }
+    double E[2][2][2][3];
+    for (int kk = 0; kk < 2; kk++)
+      for (int jj = 0; jj < 2; jj++)
+        for (int ii = 0; ii < 2; ii++)
+          for (int d = 0; d < 3; d++) E[ii][jj][kk][d] = Eh[(size_t)3 * cn[ii + 2 * jj + 4 * kk] + d];
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    for (int a = 0; a < 2; a++)
+      for (int b = 0; b < 2; b++) {
+        t0 += -c4y * (E[a][1][b][2] - E[a][0][b][2]) + c4z * (E[a][b][1][1] - E[a][b][0][1]);
+        t1 += -c4z * (E[a][b][1][0] - E[a][b][0][0]) + c4x * (E[1][a][b][2] - E[0][a][b][2]);
+        t2 += -c4x * (E[1][a][b][1] - E[0][a][b][1]) + c4y * (E[a][1][b][0] - E[a][0][b][0]);
+      }
+    Bout[(size_t)3 * z] = Bn[(size_t)3 * z] + t0, Bout[(size_t)3 * z + 1] = Bn[(size_t)3 * z + 1] + t1, Bout[(size_t)3 * z + 2] = Bn[(size_t)3 * z + 2] + t2;
+  }
+}
+
+static inline int grid_rows(long long n, int perThread = 1) {
+  long long g = (n + 255LL * perThread) / (256LL * perThread);
+  if (g < 1) g = 1;
+  if (g > 148 * 8) g = 148 * 8;
+  return (int)g;
+}
+
+void launch_ecsim_operator(bool rhs, int nCorners, const int *nb, const int *cc, const double *M, const double *x, double f, const double *J,
+                           const double *B, const double c4[3], double *y, cudaStream_t s) {
+  const int grid = 148 * 8;  // 8 warps per CTA, one corner per warp and trip
+  if (rhs) ecsim_operator_kernel<true><<<grid, 256, 0, s>>>(nCorners, nb, cc, M, x, f, J, B, c4[0], c4[1], c4[2], y);
+  else ecsim_operator_kernel<false><<<grid, 256, 0, s>>>(nCorners, nb, cc, M, x, f, nullptr, nullptr, 0.0, 0.0, 0.0, y);
+}
+void launch_multi_dot(const double *V, size_t ld, int nVec, const double *w, int n, double *out, cudaStream_t s) {
+  cudaMemsetAsync(out, 0, sizeof(double) * (nVec + 1), s);
+  multi_dot_kernel<<<148 * 4, 256, 0, s>>>(V, ld, nVec, w, n, out);
+}
+void launch_orthogonalize(const double *V, size_t ld, int nVec, const double *h, double *w, int n, double *norm2, cudaStream_t s) {
+  cudaMemsetAsync(norm2, 0, sizeof(double), s);
+  orthogonalize_kernel<<<grid_rows(n), 256, 0, s>>>(V, ld, nVec, h, w, n, norm2);
+}
+void launch_axpby(int n, double alpha, const double *a, double beta, const double *b, const double *invSqrtOf, double *out, cudaStream_t s) {
+  axpby_kernel<<<grid_rows(n), 256, 0, s>>>(n, alpha, a, beta, b, invSqrtOf, out);
+}
+void launch_combine(const double *V, size_t ld, int nVec, const double *y, double *x, int n, cudaStream_t s) {
+  combine_kernel<<<grid_rows(n), 256, 0, s>>>(V, ld, nVec, y, x, n);
+}
+void launch_update_B(int nCenters, const int *zc, const double *Eh, const double *Bn, const double c4[3], double *Bout, cudaStream_t s) {
+  update_B_kernel<<<grid_rows(nCenters), 256, 0, s>>>(nCenters, zc, Eh, Bn, c4[0], c4[1], c4[2], Bout);
+}
+
+}  // namespace amps

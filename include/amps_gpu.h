@@ -238,6 +238,30 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh);
 int amps_gpu_fields_upload(amps_gpu_ctx *ctx, const double *E_half, const double *B_prev,
                            const double *B_cur);
 
+/* ---- the field half of the ECSIM step on the device (single rank, single-level mesh, centre-based B,
+ * normalised units).  Replaces PIC::FieldSolver::Electromagnetic::ECSIM::TimeStep (pic_field_solver_ecsim.cpp:6004-6157):
+ * UpdateRhs (ecsim/update_rhs.cpp), UpdateMatrixElement (:6004-6020), cLinearSystemCornerNode::Solve / MultiplyVector
+ * (srcInterface/LinearSystemCornerNode.h:3212, :2749; GMRES of the SWMF library), ProcessFinalSolution, UpdateB (:5160),
+ * UpdateE (:5909).  J and M stay on the device: the 2 KB per corner the host path downloads every step never cross PCIe.
+ *
+ * field_solver_init: node adjacency on the unique nodes (the host derives it from the leaves' node tables, like the row
+ * builder GetStencil walks GetCornerNode(i+di, j+dj, k+dk)):
+ *   corner_nb[n_corners][27]      neighbour corner per mass-matrix slot sx + 3 sy + 9 sz (0 -> 0, -1 -> 1, +1 -> 2); -1 = none:
+ *                                 such a corner gets the boundary row dE = 0
+ *   corner_cells[n_corners][8]    centre node of the cell at corner index + (a, b, c), a, b, c in {-1, 0}: (a+1) + 2 (b+1) + 4 (c+1)
+ *   center_corners[n_centers][8]  corner node at cell index + (ii, jj, kk) in {0, 1}^3: ii + 2 jj + 4 kk                      */
+int amps_gpu_field_solver_init(amps_gpu_ctx *ctx, const int32_t *corner_nb, const int32_t *corner_cells,
+                               const int32_t *center_corners);
+/* E^n on the unique corners [n_corners][3] (CurrentEOffset); B^n is B_cur of amps_gpu_fields_upload */
+int amps_gpu_E_upload(amps_gpu_ctx *ctx, const double *E_cur);
+/* one field step with J, M of the last deposit: GMRES(restart; <= 0 = 30) from x0 = 0 until |r| <= tol |r0| or max_iter
+ * products; afterwards E_half = E^{n+theta}, E = E^{n+1}, B_prev = B^n, B_cur = B^{n+1} on the device and in the tiles the
+ * movers / the deposit read, i.e. amps_gpu_step may follow directly (the order of PIC::TimeStep).                          */
+int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_iter, int restart, int *iterations,
+                        double *rel_residual);
+/* any pointer may be NULL; E_cur, E_half [n_corners][3], B_cur [n_centers][3] */
+int amps_gpu_fields_download(amps_gpu_ctx *ctx, double *E_cur, double *E_half, double *B_cur);
+
 /* background E, B of the coupler on the unique centre nodes, [n_centers][3] each (DATAFILE::Offset::ElectricField /
  * MagneticField of cDataCenterNode, pic.h:8338-8425); either may be NULL = keep / zero            */
 int amps_gpu_background_upload(amps_gpu_ctx *ctx, const double *E_center, const double *B_center);
