@@ -172,7 +172,7 @@ PROTOTYPES = {
     "amps_gpu_particles_download_aos": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.POINTER(AosLayout), _i64p]),
     "amps_gpu_field_solver_init": (C.c_int, [_vp, _vp, _vp, _vp]),
     "amps_gpu_E_upload": (C.c_int, [_vp, _vp]),
-    "amps_gpu_field_step": (C.c_int, [_vp, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "amps_gpu_field_step": (C.c_int, [_vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "amps_gpu_fields_download": (C.c_int, [_vp, _vp, _vp, _vp]),
     "amps_gpu_particles_slot_delta": (C.c_int, [_vp, _i64p, _vp, C.c_int64, _i64p]),
     "amps_gpu_particles_assign_slots": (C.c_int, [_vp, _vp, C.c_int64]),

@@ -352,9 +352,9 @@ class Context:
         assert E.shape == (self.mesh.n_corners, 3)
         self._ck(self.lib.amps_gpu_E_upload(self._h, _ptr(E)))
 
-    def field_step(self, theta=0.5, tol=1e-6, max_iter=200, restart=30):
+    def field_step(self, theta=0.5, tol=1e-6, max_iter=200, restart=30, warm_start=False):
         it, rel = C.c_int(), C.c_double()
-        self._ck(self.lib.amps_gpu_field_step(self._h, theta, tol, max_iter, restart, C.byref(it), C.byref(rel)))
+        self._ck(self.lib.amps_gpu_field_step(self._h, theta, tol, max_iter, restart, 1 if warm_start else 0, C.byref(it), C.byref(rel)))
         return int(it.value), float(rel.value)
 
     def fields_download(self, E=True, E_half=True, B=True, out=None):

@@ -121,9 +121,8 @@ enum : unsigned {
 
 // launch helpers (defined per TU that needs them)
 // field_solver.cu
-void field_set_constants(const double *K243);
-void launch_ecsim_operator(bool rhs, int nCorners, const int *nb, const int *cc, const double *M, const double *x, double f, const double *J,
-                           const double *B, const double c4[3], double *y, cudaStream_t s);
+void launch_ecsim_operator(bool rhs, int nCorners, const int *nb, const int *cc, const double *Kc, const double *M, const double *x, double f,
+                           const double *J, const double *B, const double c4[3], double *y, cudaStream_t s);
 void launch_multi_dot(const double *V, size_t ld, int nVec, const double *w, int n, double *out, cudaStream_t s);
 void launch_orthogonalize(const double *V, size_t ld, int nVec, const double *h, double *w, int n, double *norm2, cudaStream_t s);
 void launch_axpby(int n, double alpha, const double *a, double beta, const double *b, const double *invSqrtOf, double *out, cudaStream_t s);

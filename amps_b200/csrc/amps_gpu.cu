@@ -40,6 +40,10 @@ struct amps_gpu_ctx {
   int krylovVectors = 0;
   double *d_hcol = nullptr, *h_hcol = nullptr;  // inner products of one iteration (device / pinned host), + the norm
   double *d_ycoef = nullptr;
+  double *d_fieldK = nullptr;   // operator constants K[243] (+ the right-hand side kept for restarts behind the Krylov vectors)
+  double fieldKtheta = -1.0;    // theta the constants were built for
+  bool fieldWarmValid = false;  // the solution of the previous field step is still in the workspace
+  int fieldWarmN = 0;
 
   // particles
   ParticleSoA buf[2];
@@ -338,7 +342,7 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   for (cudaEvent_t e : ctx->dlEvents) cudaEventDestroy(e);
   if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   if (ctx->evCounts) cudaEventDestroy(ctx->evCounts);
-  cudaFree(ctx->d_E), cudaFree(ctx->d_fNb), cudaFree(ctx->d_fCc), cudaFree(ctx->d_fZc), cudaFree(ctx->d_krylov), cudaFree(ctx->d_hcol), cudaFree(ctx->d_ycoef);
+  cudaFree(ctx->d_E), cudaFree(ctx->d_fNb), cudaFree(ctx->d_fCc), cudaFree(ctx->d_fZc), cudaFree(ctx->d_krylov), cudaFree(ctx->d_hcol), cudaFree(ctx->d_ycoef), cudaFree(ctx->d_fieldK);
   if (ctx->h_hcol) cudaFreeHost(ctx->h_hcol);
   if (ctx->evSorted) cudaEventDestroy(ctx->evSorted);
   if (ctx->h_nSorted) cudaFreeHost(ctx->h_nSorted);
@@ -769,7 +773,8 @@ int amps_gpu_fields_download(amps_gpu_ctx *ctx, double *E_cur, double *E_half, d
 // reference asks linear_solver_wrapper for, LinearSystemCornerNode.h:3282) -> E^{n+theta} = E^n + x (ProcessFinalSolution) ->
 // UpdateB (B_prev <- B^n, B_cur <- B^{n+1}) -> UpdateE (E^n <- E^{n+1}); the tiles of the movers and of the deposit are staged
 // again, so the particle step that follows sees E^{n+theta}, B^n and B^{n+1} exactly like PIC::TimeStep orders them.
-int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_iter, int restart, int *iterations, double *rel_residual) {
+int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_iter, int restart, int warm_start, int *iterations,
+                        double *rel_residual) {
   if (!ctx || theta <= 0.0 || tol <= 0.0 || max_iter < 1) return AMPS_GPU_ERR_ARG;
   if (!ctx->fieldSolverReady) FAIL(AMPS_GPU_ERR_STATE, "field_step before amps_gpu_field_solver_init");
   if (!ctx->fieldsReady) FAIL(AMPS_GPU_ERR_STATE, "field_step before amps_gpu_fields_upload (B^n)");
@@ -780,11 +785,12 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
   if (restart < 1) restart = 30;
   if (restart > max_iter) restart = max_iter;
   int rc;
-  if (ctx->krylovVectors < restart + 3) {
+  if (ctx->krylovVectors < restart + 4) {
     cudaFree(ctx->d_krylov);
     ctx->d_krylov = nullptr;
-    if ((rc = dev_alloc(ctx, &ctx->d_krylov, (size_t)(restart + 3) * n))) return rc;
-    ctx->krylovVectors = restart + 3;
+    if ((rc = dev_alloc(ctx, &ctx->d_krylov, (size_t)(restart + 4) * n))) return rc;
+    ctx->krylovVectors = restart + 4;
+    ctx->fieldWarmValid = false;
     cudaFree(ctx->d_hcol), cudaFree(ctx->d_ycoef);
     if (ctx->h_hcol) cudaFreeHost(ctx->h_hcol);
     if ((rc = dev_alloc(ctx, &ctx->d_hcol, (size_t)restart + 4))) return rc;
@@ -800,7 +806,8 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
     c4rhs[d] = 0.25 * coeff[d];
     c4b[d] = 0.25 * (cdt / dx[d]);
   }
-  {
+  if (!ctx->d_fieldK && (rc = dev_alloc(ctx, &ctx->d_fieldK, (size_t)243))) return rc;
+  if (ctx->fieldKtheta != theta) {
     static const double D2[3] = {1.0, -2.0, 1.0}, AV[3] = {0.25, 0.5, 0.25}, D1[3] = {-0.5, 0.0, 0.5};
     auto gd = [&](int p, int q, const int o[3]) {  // GradDivStencil[p][q] (== LaplacianStencil[p] for p == q), InitDiscritizationStencil
       double v = 1.0;
@@ -827,30 +834,38 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
               K[9 * slot + 3 * p + q] = k;
             }
         }
-    field_set_constants(K);
+    CK(cudaMemcpyAsync(ctx->d_fieldK, K, sizeof(K), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));  // K is a local
+    ctx->fieldKtheta = theta;
   }
   const double f = 4.0 * 3.14159265358979323846 * ctx->cfg.ecsim_dt_total * theta;
-  double *V = ctx->d_krylov, *w = V + (size_t)(restart + 1) * n, *x = w + n;
+  double *V = ctx->d_krylov, *w = V + (size_t)(restart + 1) * n, *x = w + n, *rhsKeep = x + n;
+  const double *Kc = ctx->d_fieldK;
   const size_t ld = (size_t)n;
   // right-hand side into w, then V_0 = r0 / |r0| (x0 = 0 -> r0 = rhs)
-  launch_ecsim_operator(true, m.nCorners, ctx->d_fNb, ctx->d_fCc, ctx->d_M, ctx->d_E, f, ctx->d_J, ctx->d_Bcur, c4rhs, w, s);
-  CK(cudaMemsetAsync(x, 0, sizeof(double) * n, s));
+  launch_ecsim_operator(true, m.nCorners, ctx->d_fNb, ctx->d_fCc, Kc, ctx->d_M, ctx->d_E, f, ctx->d_J, ctx->d_Bcur, c4rhs, w, s);
+  // x0 = 0 like the reference's SetInitialGuess (:6566), or the increment of the previous step (warm_start): the fields change
+  // little from step to step, so most of the residual is gone before the first iteration.  Either way the iteration stops on
+  // |r| <= tol |rhs|, which for x0 = 0 is the reference's relative residual.
+  const bool warm = warm_start && ctx->fieldWarmValid && ctx->fieldWarmN == n;
+  if (!warm) CK(cudaMemsetAsync(x, 0, sizeof(double) * n, s));
   ctx->launches++;
   std::vector<double> H((size_t)(restart + 1) * restart), cs(restart), sn(restart), g(restart + 1), y(restart);
   double r0norm = -1.0, rel = 1.0;
   int iters = 0;
-  bool first = true;
-  double *rhsKeep = nullptr;  // after a restart the residual needs the right-hand side again: kept in the last spare vector
+  bool first = !warm;
+  if (warm || max_iter > restart) CK(cudaMemcpyAsync(rhsKeep, w, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+  if (warm) {  // |rhs| is the reference of the stopping test
+    launch_multi_dot(V, ld, 0, w, n, ctx->d_hcol, s);
+    CK(cudaMemcpyAsync(ctx->h_hcol, ctx->d_hcol, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    r0norm = sqrt(ctx->h_hcol[0]);
+  }
+  // (after a restart the residual needs the right-hand side again: kept in the last spare vector)
   while (iters < max_iter) {
-    if (first) {
-      // keep a copy of the right-hand side only if a restart can happen
-      if (max_iter > restart) {
-        if ((rc = dev_alloc(ctx, &rhsKeep, (size_t)n))) return rc;
-        CK(cudaMemcpyAsync(rhsKeep, w, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
-      }
-    } else {
+    if (!first) {
       // r = rhs - A x
-      launch_ecsim_operator(false, m.nCorners, ctx->d_fNb, ctx->d_fCc, ctx->d_M, x, f, nullptr, nullptr, c4rhs, w, s);
+      launch_ecsim_operator(false, m.nCorners, ctx->d_fNb, ctx->d_fCc, Kc, ctx->d_M, x, f, nullptr, nullptr, c4rhs, w, s);
       launch_axpby(n, 1.0, rhsKeep, -1.0, w, nullptr, w, s);
       ctx->launches += 2;
     }
@@ -869,7 +884,7 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
     int j = 0;
     for (; j < restart && iters < max_iter; j++) {
       double *vj = V + (size_t)j * ld, *vn = V + (size_t)(j + 1) * ld;
-      launch_ecsim_operator(false, m.nCorners, ctx->d_fNb, ctx->d_fCc, ctx->d_M, vj, f, nullptr, nullptr, c4rhs, vn, s);
+      launch_ecsim_operator(false, m.nCorners, ctx->d_fNb, ctx->d_fCc, Kc, ctx->d_M, vj, f, nullptr, nullptr, c4rhs, vn, s);
       iters++;
       launch_multi_dot(V, ld, j + 1, vn, n, ctx->d_hcol, s);                             // h_i = V_i . w
       launch_orthogonalize(V, ld, j + 1, ctx->d_hcol, vn, n, ctx->d_hcol + j + 2, s);    // w -= sum h_i V_i, |w|^2
@@ -906,7 +921,6 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
     CK(cudaStreamSynchronize(s));  // y is a host temporary
     if (rel <= tol) break;
   }
-  if (rhsKeep) cudaFree(rhsKeep);
   // ProcessFinalSolution: E^{n+theta} = E^n + x
   launch_axpby(n, 1.0, ctx->d_E, 1.0, x, nullptr, ctx->d_Ehalf, s);
   // UpdateB: B^{n+1} into the buffer that held B_prev, then the two swap roles (CurrentBOffset <-> PrevBOffset)
@@ -918,6 +932,7 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
   ctx->launches += 4;
   CK(cudaGetLastError());
   ctx->eReady = true;
+  ctx->fieldWarmValid = true, ctx->fieldWarmN = n;  // x stays in the Krylov workspace for a warm start of the next step
   if (iterations) *iterations = iters;
   if (rel_residual) *rel_residual = rel;
   return AMPS_GPU_OK;

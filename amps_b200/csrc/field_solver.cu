@@ -19,64 +19,70 @@
 
 namespace amps {
 
-__constant__ double cFieldK[243];  // K[9 slot + 3 p + q]: parameter part of row component p, column component q, neighbour slot
-
-void field_set_constants(const double *K243) { cudaMemcpyToSymbol(cFieldK, K243, sizeof(double) * 243); }
+// K[9 slot + 3 p + q], the parameter part of row component p, column component q, neighbour slot: 243 doubles, copied to shared
+// memory by every CTA (constant memory would serialise: the lanes of a warp read different entries)
 
 // kRhs = false: y = A x.  kRhs = true: y = -(A - I) E - f J + theta c dt curl B   (UpdateRhs; x = E^n)
 // nb[c][27] neighbour corner per slot (-1: none -> the row is the boundary row dE = 0), cc[c][8] the eight cells around the corner
+// Lane mapping: entry e = 9 slot + 3 p + q of a corner's row is handled by lane (e mod 27) in trip e / 27, so a lane keeps ONE (p, q)
+// for the whole row (e mod 9 = lane mod 9) and its neighbour slot is lane / 9 + 3 trip: one accumulator per lane, nine 216-byte
+// coalesced loads of M per corner, and the three row sums fall out of four shuffles.  (27 of 32 lanes work.)
 template <bool kRhs>
-__global__ void __launch_bounds__(256) ecsim_operator_kernel(int nCorners, const int *__restrict__ nb, const int *__restrict__ cc,
-                                                            const double *__restrict__ M, const double *__restrict__ x, double f,
-                                                            const double *__restrict__ J, const double *__restrict__ B, double c4x, double c4y,
-                                                            double c4z, double *__restrict__ y) {
+__global__ void __launch_bounds__(256, 4) ecsim_operator_kernel(int nCorners, const int *__restrict__ nb, const int *__restrict__ cc,
+                                                               const double *__restrict__ Kc, const double *__restrict__ M,
+                                                               const double *__restrict__ x, double f, const double *__restrict__ J,
+                                                               const double *__restrict__ B, double c4x, double c4y, double c4z,
+                                                               double *__restrict__ y) {
+  __shared__ double sK[243];
+  for (int e = threadIdx.x; e < 243; e += blockDim.x) sK[e] = Kc[e] - ((kRhs && (e == 0 || e == 4 || e == 8)) ? 1.0 : 0.0);  // slot 0, p == q
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
+  const bool work = lane < 27;
+  const int l27 = work ? lane : 0, q = l27 % 3, s0 = l27 / 9;
   for (int c = warp; c < nCorners; c += nWarps) {
-    const int *nbc = nb + (size_t)c * 27;
-    const int myNb = (lane < 27) ? nbc[lane] : 0;
+    const int myNb = work ? nb[(size_t)c * 27 + lane] : 0;
     const bool boundary = __any_sync(0xffffffffu, myNb < 0);
+    const double *Mc = M + (size_t)c * 243 + l27;
+    double m[9], xv[9];
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+      const int n = max(__shfl_sync(0xffffffffu, myNb, s0 + 3 * t), 0);
+      m[t] = Mc[27 * t];
+      xv[t] = x[(size_t)3 * n + q];
+    }
+    double a = 0.0;
+#pragma unroll
+    for (int t = 0; t < 9; t++) a = fma(fma(f, m[t], sK[l27 + 27 * t]), xv[t], a);
+    if (!work) a = 0.0;
+    // lanes l, l + 9, l + 18 hold the three slot groups of one (p, q); then the three q of a p
+    a += __shfl_down_sync(0xffffffffu, a, 9) + __shfl_down_sync(0xffffffffu, a, 18);
+    a += __shfl_down_sync(0xffffffffu, a, 1) + __shfl_down_sync(0xffffffffu, a, 2);
+    const double ap = __shfl_sync(0xffffffffu, a, 3 * (lane < 3 ? lane : 0));  // lane p (< 3) takes the sum of row component p
+    double curl = 0.0;
+    if (kRhs) {
+      // curl B^n from the 2 x 2 face averages of the centre values (get_stencil.cpp: coeff4 = 0.25 theta c dt / dx): 16 signed
+      // centre values per component; lane 8 comp + j takes the face-average point (a, b) = j >> 1 and the first / second difference
+      double t = 0.0;
+      if (lane < 24 && !boundary) {
+        const int *cell = cc + (size_t)c * 8;
+        auto Bv = [&](int aa, int b, int d, int comp) { return B[(size_t)3 * cell[(aa + 1) + 2 * (b + 1) + 4 * (d + 1)] + comp]; };
+        const int comp = lane >> 3, j = lane & 7, aa = -((j >> 2) & 1), b = -((j >> 1) & 1), second = j & 1;
+        if (comp == 0) t = second ? -c4z * (Bv(aa, b, 0, 1) - Bv(aa, b, -1, 1)) : c4y * (Bv(aa, 0, b, 2) - Bv(aa, -1, b, 2));
+        if (comp == 1) t = second ? -c4x * (Bv(0, b, aa, 2) - Bv(-1, b, aa, 2)) : c4z * (Bv(aa, b, 0, 0) - Bv(aa, b, -1, 0));
+        if (comp == 2) t = second ? -c4y * (Bv(b, 0, aa, 0) - Bv(b, -1, aa, 0)) : c4x * (Bv(0, b, aa, 1) - Bv(-1, b, aa, 1));
+      }
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      curl = __shfl_sync(0xffffffffu, t, 8 * (lane < 3 ? lane : 0));
+    }
+    if (lane >= 3) continue;
     if (boundary) {  // dE = 0 on a domain boundary (GetStencil: unit row, zero right-hand side)
-      if (lane < 3) y[(size_t)3 * c + lane] = kRhs ? 0.0 : x[(size_t)3 * c + lane];
+      y[(size_t)3 * c + lane] = kRhs ? 0.0 : x[(size_t)3 * c + lane];
       continue;
     }
-    const double *Mc = M + (size_t)c * 243;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-#pragma unroll
-    for (int t = 0; t < 8; t++) {
-      const int e = lane + 32 * t;
-      const int s = min(e, 242) / 9;
-      const int n = __shfl_sync(0xffffffffu, myNb, s);  // (every lane takes part: the source lanes 24..26 are idle in the last trip)
-      if (e < 243) {
-        const int r = e - 9 * s, p = r / 3, q = r - 3 * p;
-        double k = cFieldK[e];
-        if (kRhs && e == 0) k -= 1.0;                       // p = q = 0, slot 0: the identity stays on the left-hand side
-        if (kRhs && (e == 4 || e == 8)) k -= 1.0;           // (p,q) = (1,1), (2,2) of slot 0
-        const double v = fma(f, Mc[e], k) * x[(size_t)3 * n + q];
-        a0 += (p == 0) ? v : 0.0, a1 += (p == 1) ? v : 0.0, a2 += (p == 2) ? v : 0.0;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    }
-    if (!kRhs) {
-      if (lane == 0) y[(size_t)3 * c] = a0, y[(size_t)3 * c + 1] = a1, y[(size_t)3 * c + 2] = a2;
-    } else if (lane < 3) {
-      // curl B^n from the 2 x 2 face averages of the centre values (get_stencil.cpp: coeff4 = 0.25 theta c dt / dx)
-      const int *cell = cc + (size_t)c * 8;
-      auto Bv = [&](int a, int b, int d, int comp) { return B[(size_t)3 * cell[(a + 1) + 2 * (b + 1) + 4 * (d + 1)] + comp]; };
-      double r = -((lane == 0) ? a0 : (lane == 1) ? a1 : a2) - f * J[(size_t)3 * c + lane];
-      for (int a = -1; a <= 0; a++)
-        for (int b = -1; b <= 0; b++) {
-          if (lane == 0) r += c4y * (Bv(a, 0, b, 2) - Bv(a, -1, b, 2)) - c4z * (Bv(a, b, 0, 1) - Bv(a, b, -1, 1));
-          if (lane == 1) r += c4z * (Bv(a, b, 0, 0) - Bv(a, b, -1, 0)) - c4x * (Bv(0, b, a, 2) - Bv(-1, b, a, 2));
-          if (lane == 2) r += c4x * (Bv(0, b, a, 1) - Bv(-1, b, a, 1)) - c4y * (Bv(b, 0, a, 0) - Bv(b, -1, a, 0));
-        }
-      y[(size_t)3 * c + lane] = r;
-    }
+    y[(size_t)3 * c + lane] = kRhs ? (-ap - f * J[(size_t)3 * c + lane] + curl) : ap;
   }
 }
 
@@ -176,11 +182,11 @@ static inline int grid_rows(long long n, int perThread = 1) {
   return (int)g;
 }
 
-void launch_ecsim_operator(bool rhs, int nCorners, const int *nb, const int *cc, const double *M, const double *x, double f, const double *J,
-                           const double *B, const double c4[3], double *y, cudaStream_t s) {
+void launch_ecsim_operator(bool rhs, int nCorners, const int *nb, const int *cc, const double *Kc, const double *M, const double *x, double f,
+                           const double *J, const double *B, const double c4[3], double *y, cudaStream_t s) {
   const int grid = 148 * 8;  // 8 warps per CTA, one corner per warp and trip
-  if (rhs) ecsim_operator_kernel<true><<<grid, 256, 0, s>>>(nCorners, nb, cc, M, x, f, J, B, c4[0], c4[1], c4[2], y);
-  else ecsim_operator_kernel<false><<<grid, 256, 0, s>>>(nCorners, nb, cc, M, x, f, nullptr, nullptr, 0.0, 0.0, 0.0, y);
+  if (rhs) ecsim_operator_kernel<true><<<grid, 256, 0, s>>>(nCorners, nb, cc, Kc, M, x, f, J, B, c4[0], c4[1], c4[2], y);
+  else ecsim_operator_kernel<false><<<grid, 256, 0, s>>>(nCorners, nb, cc, Kc, M, x, f, nullptr, nullptr, 0.0, 0.0, 0.0, y);
 }
 void launch_multi_dot(const double *V, size_t ld, int nVec, const double *w, int n, double *out, cudaStream_t s) {
   cudaMemsetAsync(out, 0, sizeof(double) * (nVec + 1), s);

@@ -580,6 +580,53 @@ def main():
         e2e_ms = float(tt.item())
     e2e_value = n_total * KE / (e2e_ms * 1e-3)
 
+    # ---- end to end with the field solve on the device (row f1): the host keeps the master copy of E and B like AMPS's node buffers
+    # do; per step it sends E^n, B^n (H2D), the device runs ECSIM::TimeStep's field half (J, M never leave HBM) and the particle
+    # phase, and E^{n+1}, B^{n+1} come back (D2H).  GMRES tolerance 1e-8 = the reference's own ECSIM test (test/srcFastWave/main.cpp).
+    e2e_dev = None
+    if world == 1:
+        try:
+            ctx.field_solver_init()
+            Ecur = torch.zeros((m.n_corners, 3), dtype=torch.float64).pin_memory().numpy()
+            Bcur = torch.from_numpy(fields[2].copy()).pin_memory().numpy()
+            outp = {"E": Ecur, "B": Bcur}  # the host's node buffers: read back in place, sent again with the next step
+            ctx.fields_upload(Eh, Bp, Bc)
+            ctx.step()  # J, M of the resident plasma for the first solve
+            its_log = []
+
+            def cycle():
+                ctx.E_upload(Ecur)
+                ctx.fields_upload(None, None, Bcur)
+                its_log.append(ctx.field_step(theta=0.5, tol=1e-8, max_iter=200, restart=30))
+                ctx.step()
+                ctx.fields_download(E=True, E_half=False, B=True, out=outp)
+
+            for _ in range(2):
+                cycle()
+            barrier()
+            its_log.clear()
+            td0 = time.perf_counter()
+            e0.record(stream)
+            for _ in range(KE):
+                cycle()
+            e1.record(stream)
+            barrier()
+            td = time.perf_counter() - td0
+            d_ms = max(e0.elapsed_time(e1), td * 1e3)
+            ctx.profile(True)
+            ctx.field_step(theta=0.5, tol=1e-8, max_iter=200, restart=30)
+            torch.cuda.synchronize()
+            e2e_dev = {"value": n_total * KE / (d_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(Ecur.nbytes + Bcur.nbytes),
+                       "d2h_bytes_per_step": int(outp["E"].nbytes + outp["B"].nbytes), "steps": KE, "ms_per_step": d_ms / KE,
+                       "gmres_iterations": [i for i, _ in its_log], "gmres_rel_residual": max(r for _, r in its_log), "gmres_tol": 1e-8, "gmres_start": "x0 = 0 (the reference's SetInitialGuess)",
+                       "path": "amps_gpu_E_upload + amps_gpu_fields_upload(B^n) -> amps_gpu_field_step (UpdateRhs, GMRES, UpdateB, UpdateE on the "
+                               "device; J and M stay in HBM) -> amps_gpu_step -> amps_gpu_fields_download(E^{n+1}, B^{n+1})"}
+            ctx.profile(False)
+            # leave the frozen benchmark fields behind for what follows
+            ctx.fields_upload(Eh, Bp, Bc)
+        except Exception as exc:  # never lose the headline line
+            e2e_dev = {"error": repr(exc)[:300]}
+
     # ---- the same loop with the packed rows (J + the 14 independent neighbour blocks of the symmetric mass matrix) ----
     e2e_packed = None
     if world == 1:
@@ -648,6 +695,11 @@ def main():
         # 512 FMA, + ~95 DFMA/DMUL of phase 1) against the measured DFMA peak of this GPU (tools/fp64_peak.cu)
         roofline["fp64_peak_tflops"] = fp64.get("dfma_tflops")
         roofline["fp64_dmma_peak_tflops"] = fp64.get("dmma_tflops")
+    # the headline end-to-end number: the device-resident cycle where it exists (one rank), else the host-solver path
+    e2e_host = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": KE,
+                "ms_per_step": e2e_ms / KE,
+                "path": "amps_gpu_fields_upload -> amps_gpu_step_JM (J + the full mass matrix to the host's field solver every step)"}
+    e2e_main = e2e_dev if (e2e_dev is not None and "value" in e2e_dev) else e2e_host
     step_gbs = step_alg * (n_part * K / (ms * 1e-3)) / 1e9 if world == 1 else step_alg * (value / world) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
@@ -659,8 +711,8 @@ def main():
                    "step": "amps_gpu_step: move(Lapenta2017; contracted arithmetic + exact pass near cell faces) + permutation sort + "
                            "UpdateJMassMatrix (gathers through the permutation, writes the sorted copy)", "gen_s": round(t_gen, 1)},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": KE,
-                "ms_per_step": e2e_ms / KE},
+        "e2e": e2e_main,
+        "e2e_host_solver": e2e_host,
         "e2e_packed": e2e_packed,
         "gpu_launches": int(launches),
         "roofline": roofline,

@@ -256,9 +256,11 @@ int amps_gpu_field_solver_init(amps_gpu_ctx *ctx, const int32_t *corner_nb, cons
 int amps_gpu_E_upload(amps_gpu_ctx *ctx, const double *E_cur);
 /* one field step with J, M of the last deposit: GMRES(restart; <= 0 = 30) from x0 = 0 until |r| <= tol |r0| or max_iter
  * products; afterwards E_half = E^{n+theta}, E = E^{n+1}, B_prev = B^n, B_cur = B^{n+1} on the device and in the tiles the
- * movers / the deposit read, i.e. amps_gpu_step may follow directly (the order of PIC::TimeStep).                          */
-int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_iter, int restart, int *iterations,
-                        double *rel_residual);
+ * movers / the deposit read, i.e. amps_gpu_step may follow directly (the order of PIC::TimeStep).  warm_start != 0 starts
+ * from the increment of the previous step instead of the reference's zero guess (SetInitialGuess, :6566); the stopping test
+ * is |r| <= tol |rhs| in both cases.                                                                                       */
+int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_iter, int restart, int warm_start,
+                        int *iterations, double *rel_residual);
 /* any pointer may be NULL; E_cur, E_half [n_corners][3], B_cur [n_centers][3] */
 int amps_gpu_fields_download(amps_gpu_ctx *ctx, double *E_cur, double *E_half, double *B_cur);
 

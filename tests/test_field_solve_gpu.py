@@ -48,6 +48,14 @@ def test_field_step_matches_the_oracle_and_feeds_the_particle_step():
     got2 = g.fields_download()
     assert res2 <= 1e-12 and rel(got2["E_half"], Eh) <= 1e-9
 
+    # warm start: the same state solved again from the previous increment converges at once and lands on the same fields
+    g.fields_upload(E_half0, B_prev0, B_cur0)
+    g.E_upload(E_n)
+    its3, res3 = g.field_step(theta=0.5, tol=1e-12, max_iter=300, restart=7, warm_start=True)
+    got3 = g.fields_download()
+    assert its3 <= 2 and rel(got3["E_half"], Eh) <= 1e-9 and rel(got3["B"], Bn) <= 1e-9, (its3, res3)
+    got2 = got3
+
     # the particle step that follows reads the staged E^{n+theta}, B^n (mover) and B^{n+1} (deposit): compare with the oracle
     # given exactly those fields
     before = g.particles_download()
