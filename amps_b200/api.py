@@ -216,6 +216,21 @@ class Context:
         slots = np.ascontiguousarray(slots, dtype=np.int64)
         self._ck(self.lib.amps_gpu_particles_assign_slots(self._h, _ptr(slots), slots.size))
 
+    # ---- PIC::Restart (particle file of the reference's format) -------------------------------
+    def restart_save(self, fname, header, leaf_node_ids, lay):
+        ids = np.ascontiguousarray(leaf_node_ids, dtype=np.uint8)
+        assert ids.shape[0] == self.mesh.n_leaves
+        n = C.c_int64()
+        hb = bytes(header)
+        self._ck(self.lib.amps_gpu_restart_save(self._h, fname.encode(), C.c_char_p(hb), len(hb), _ptr(ids), ids.shape[1], C.byref(lay), C.byref(n)))
+        return int(n.value)
+
+    def restart_read(self, fname, header_bytes, leaf_node_ids, lay):
+        ids = np.ascontiguousarray(leaf_node_ids, dtype=np.uint8)
+        n = C.c_int64()
+        self._ck(self.lib.amps_gpu_restart_read(self._h, fname.encode(), int(header_bytes), _ptr(ids), ids.shape[1], C.byref(lay), C.byref(n)))
+        return int(n.value)
+
     def cell_table(self):
         t = np.empty(self.mesh.n_cells + 1, dtype=np.int64)
         self._ck(self.lib.amps_gpu_cell_table_download(self._h, _ptr(t), t.size))

@@ -53,6 +53,7 @@ struct amps_gpu_ctx {
   int *h_nSorted = nullptr;         // pinned: particle count written by the last sort (slots [0, count) are exactly the residents)
   cudaEvent_t evSorted = nullptr;   // the copy into h_nSorted has completed
   bool nSortedPending = false;
+  std::vector<int> h_leafOwnerHost;   // [nLeaves] owner rank (several ranks only)
   std::vector<int32_t> h_uploadedSlots;  // ParticleBuffer slots handed over by the last upload / slot assignment (download bookkeeping)
   bool sorted = false, countValid = false;
   int *d_cellCount = nullptr, *d_cellStart = nullptr, *d_cellFill = nullptr;
@@ -661,6 +662,7 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
     if ((rc = upload_array(ctx, &t2, mesh->leaf_global_id, (size_t)m.nLeaves))) return rc;
     if ((rc = upload_array(ctx, &t3, mesh->global_leaf_to_local, (size_t)mesh->n_global_leaves))) return rc;
     ctx->d_leafOwner = const_cast<int *>(t1), ctx->d_leafGlobal = const_cast<int *>(t2), ctx->d_g2l = const_cast<int *>(t3);
+    ctx->h_leafOwnerHost.assign(mesh->leaf_owner, mesh->leaf_owner + m.nLeaves);
     ctx->capPerPeer = ctx->cfg.capacity / 32 > 65536 ? ctx->cfg.capacity / 32 : 65536;
     // sized for the longest record (x, v, w, key|species + magnetic moment + v_parallel)
     if ((rc = dev_alloc(ctx, &ctx->d_sendBuf, (size_t)ctx->nRanks * ctx->capPerPeer * AMPS_MIGRATION_RECORD_MAX))) return rc;
@@ -1446,6 +1448,157 @@ int amps_gpu_particles_assign_slots(amps_gpu_ctx *ctx, const int64_t *slots, int
     }
   if (k != n_slots) FAIL(AMPS_GPU_ERR_ARG, "assign_slots: more slots than records without one");
   CK(cudaMemcpy(ctx->buf[ctx->cur].ptr, pt.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+  return AMPS_GPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// f3 (restart half): PIC::Restart::SaveParticleData / ReadParticleData (pic_restart.cpp:248-420, :430-600) straight from / into the
+// sorted device store, in the reference's own file format, so a restart file written here is read by AMPS and vice versa:
+//   [header written by the caller: user data, the 43-byte end marker, long ParticleDataLength, double GlobalParticleWeight[nS]]
+//   per block that holds particles:  cAMRnodeID (id_bytes) | int nTotal | int ParticleNumberTable[Nx][Ny][Nz] (k fastest) |
+//                                    nTotal records of ParticleDataLength bytes, cells in the loop order i, j, k (k innermost)
+// The caller supplies the node id of every leaf (node->AMRnodeID, opaque here).  Record fields the device does not hold stay zero.
+// ---------------------------------------------------------------------------------------------------------------------------
+int amps_gpu_restart_save(amps_gpu_ctx *ctx, const char *fname, const void *header, int64_t header_bytes, const void *leaf_node_ids,
+                          int32_t id_bytes, const amps_gpu_aos_layout *lay, int64_t *n_saved) {
+  if (!ctx || !fname || !leaf_node_ids || id_bytes < 1 || !lay || header_bytes < 0 || (header_bytes > 0 && !header)) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "restart_save before mesh_upload");
+  if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "restart_save needs the sorted layout: call amps_gpu_sort");
+  int64_t n = 0;
+  int rc = amps_gpu_particle_count(ctx, &n);
+  if (rc) return rc;
+  std::vector<double> x((size_t)3 * n + 1), v((size_t)3 * n + 1), w((size_t)n + 1), mu, vpar;
+  std::vector<uint8_t> sp((size_t)n + 1);
+  int64_t nn;
+  if ((rc = amps_gpu_particles_download_soa(ctx, x.data(), v.data(), w.data(), sp.data(), nullptr, nullptr, n, &nn))) return rc;
+  if (ctx->cfg.carry_magnetic_moment && lay->off_mu >= 0) {
+    mu.resize((size_t)n + 1);
+    if ((rc = amps_gpu_magnetic_moment_download(ctx, mu.data(), n, &nn))) return rc;
+  }
+  if (ctx->cfg.carry_v_parallel && lay->off_vpar >= 0) {
+    vpar.resize((size_t)n + 1);
+    if ((rc = amps_gpu_v_parallel_download(ctx, vpar.data(), n, &nn))) return rc;
+  }
+  std::vector<int> start((size_t)ctx->nCells + 1);
+  CK(cudaMemcpy(start.data(), ctx->d_cellStart, sizeof(int) * ((size_t)ctx->nCells + 1), cudaMemcpyDeviceToHost));
+  FILE *f = fopen(fname, "wb");
+  if (!f) FAIL(AMPS_GPU_ERR_ARG, "restart_save: cannot open the file");
+  if (header_bytes) fwrite(header, 1, (size_t)header_bytes, f);
+  const DevMesh &m = ctx->dm;
+  const int Nx = m.N[0], Ny = m.N[1], Nz = m.N[2], C = m.cellsPerBlock;
+  std::vector<int> table((size_t)C);
+  std::vector<unsigned char> rec((size_t)lay->stride);
+  int64_t saved = 0;
+  for (int l = 0; l < m.nLeaves; l++) {
+    const int total = start[(size_t)(l + 1) * C] - start[(size_t)l * C];
+    if (total == 0) continue;
+    fwrite((const unsigned char *)leaf_node_ids + (size_t)l * id_bytes, 1, (size_t)id_bytes, f);
+    fwrite(&total, sizeof(int), 1, f);
+    for (int i = 0; i < Nx; i++)
+      for (int j = 0; j < Ny; j++)
+        for (int k = 0; k < Nz; k++) {
+          const size_t c = (size_t)l * C + i + Nx * (j + Ny * k);
+          table[(size_t)k + Nz * (j + Ny * i)] = start[c + 1] - start[c];
+        }
+    fwrite(table.data(), sizeof(int), (size_t)C, f);
+    for (int i = 0; i < Nx; i++)
+      for (int j = 0; j < Ny; j++)
+        for (int k = 0; k < Nz; k++) {
+          const size_t c = (size_t)l * C + i + Nx * (j + Ny * k);
+          for (int q = start[c]; q < start[c + 1]; q++) {
+            std::fill(rec.begin(), rec.end(), 0);
+            const int64_t none = -1;
+            memcpy(rec.data() + lay->off_next, &none, 8), memcpy(rec.data() + lay->off_prev, &none, 8);
+            const double xx[3] = {x[q], x[n + q], x[2 * n + q]}, vv[3] = {v[q], v[n + q], v[2 * n + q]};
+            memcpy(rec.data() + lay->off_x, xx, 24), memcpy(rec.data() + lay->off_v, vv, 24);
+            if (lay->off_w >= 0) memcpy(rec.data() + lay->off_w, &w[q], 8);
+            if (!mu.empty()) memcpy(rec.data() + lay->off_mu, &mu[q], 8);
+            if (!vpar.empty()) memcpy(rec.data() + lay->off_vpar, &vpar[q], 8);
+            rec[lay->off_species] = (unsigned char)(0x80 | (sp[q] & 0x7f));  // allocated flag (bit 7) + InitFlag + species id
+            fwrite(rec.data(), 1, rec.size(), f);
+            saved++;
+          }
+        }
+  }
+  fclose(f);
+  if (n_saved) *n_saved = saved;
+  return AMPS_GPU_OK;
+}
+
+int amps_gpu_restart_read(amps_gpu_ctx *ctx, const char *fname, int64_t header_bytes, const void *leaf_node_ids, int32_t id_bytes,
+                          const amps_gpu_aos_layout *lay, int64_t *n_loaded) {
+  if (!ctx || !fname || !leaf_node_ids || id_bytes < 1 || !lay || header_bytes < 0) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "restart_read before mesh_upload");
+  FILE *f = fopen(fname, "rb");
+  if (!f) FAIL(AMPS_GPU_ERR_ARG, "restart_read: cannot open the file");
+  fseek(f, (long)header_bytes, SEEK_SET);
+  const DevMesh &m = ctx->dm;
+  const int Nx = m.N[0], Ny = m.N[1], Nz = m.N[2], C = m.cellsPerBlock;
+  std::map<std::string, int> leafOf;
+  for (int l = 0; l < m.nLeaves; l++) leafOf[std::string((const char *)leaf_node_ids + (size_t)l * id_bytes, (size_t)id_bytes)] = l;
+  std::vector<double> x[3], v[3], w, mu, vpar;
+  std::vector<uint8_t> sp;
+  std::vector<int32_t> cells;
+  std::vector<char> id((size_t)id_bytes);
+  std::vector<int> table((size_t)C);
+  std::vector<unsigned char> rec((size_t)lay->stride);
+  const bool wantMu = ctx->cfg.carry_magnetic_moment && lay->off_mu >= 0, wantVp = ctx->cfg.carry_v_parallel && lay->off_vpar >= 0;
+  while (fread(id.data(), 1, (size_t)id_bytes, f) == (size_t)id_bytes) {
+    int total = 0;
+    if (fread(&total, sizeof(int), 1, f) != 1) break;
+    if (total == 0) continue;
+    auto it = leafOf.find(std::string(id.data(), (size_t)id_bytes));
+    const bool mine = it != leafOf.end() && (ctx->nRanks <= 1 || ctx->h_leafOwnerHost.empty() || ctx->h_leafOwnerHost[it->second] == ctx->rank);
+    if (!mine) {  // a block of another rank (ReadParticleDataBlock skips it the same way, :457-465)
+      fseek(f, (long)(sizeof(int) * (size_t)C + (size_t)total * (size_t)lay->stride), SEEK_CUR);
+      continue;
+    }
+    if (fread(table.data(), sizeof(int), (size_t)C, f) != (size_t)C) {
+      fclose(f);
+      FAIL(AMPS_GPU_ERR_ARG, "restart_read: truncated file");
+    }
+    const int l = it->second;
+    for (int i = 0; i < Nx; i++)
+      for (int j = 0; j < Ny; j++)
+        for (int k = 0; k < Nz; k++)
+          for (int q = 0; q < table[(size_t)k + Nz * (j + Ny * i)]; q++) {
+            if (fread(rec.data(), 1, rec.size(), f) != rec.size()) {
+              fclose(f);
+              FAIL(AMPS_GPU_ERR_ARG, "restart_read: truncated file");
+            }
+            double t[3];
+            memcpy(t, rec.data() + lay->off_x, 24);
+            for (int d = 0; d < 3; d++) x[d].push_back(t[d]);
+            memcpy(t, rec.data() + lay->off_v, 24);
+            for (int d = 0; d < 3; d++) v[d].push_back(t[d]);
+            double ww = 1.0;
+            if (lay->off_w >= 0) memcpy(&ww, rec.data() + lay->off_w, 8);
+            w.push_back(ww);
+            sp.push_back(rec[lay->off_species] & 0x7f);
+            cells.push_back((int32_t)((size_t)l * C + i + Nx * (j + Ny * k)));
+            if (wantMu) {
+              double a;
+              memcpy(&a, rec.data() + lay->off_mu, 8);
+              mu.push_back(a);
+            }
+            if (wantVp) {
+              double a;
+              memcpy(&a, rec.data() + lay->off_vpar, 8);
+              vpar.push_back(a);
+            }
+          }
+  }
+  fclose(f);
+  const int64_t n = (int64_t)w.size();
+  std::vector<double> xs((size_t)3 * n + 1), vs((size_t)3 * n + 1);
+  for (int d = 0; d < 3; d++)
+    for (int64_t i = 0; i < n; i++) xs[(size_t)d * n + i] = x[d][i], vs[(size_t)d * n + i] = v[d][i];
+  int rc = amps_gpu_particles_upload_soa(ctx, xs.data(), vs.data(), w.data(), sp.data(), cells.data(), nullptr, n);
+  if (rc) return rc;
+  // upload_soa sorts; the optional state goes in by ParticleBuffer slot (= the order read)
+  if (wantMu && n && (rc = amps_gpu_magnetic_moment_upload(ctx, mu.data(), n))) return rc;
+  if (wantVp && n && (rc = amps_gpu_v_parallel_upload(ctx, vpar.data(), n))) return rc;
+  if (n_loaded) *n_loaded = n;
   return AMPS_GPU_OK;
 }
 

@@ -324,6 +324,16 @@ int amps_gpu_particles_download_aos(amps_gpu_ctx *ctx, void *records, int64_t *f
 int amps_gpu_particles_slot_delta(amps_gpu_ctx *ctx, int64_t *n_new, int64_t *released, int64_t max_released,
                                   int64_t *n_released);
 int amps_gpu_particles_assign_slots(amps_gpu_ctx *ctx, const int64_t *slots, int64_t n_slots);
+/* SURVEY 8f row f3, restart half: PIC::Restart::SaveParticleData / ReadParticleData (pic_restart.cpp:248-420, :430-600) from /
+ * into the sorted device store in the reference's own file format (AMPS reads what this writes and vice versa): after the caller's
+ * header (user data, end marker, ParticleDataLength, GlobalParticleWeight[]) one section per block with particles:
+ * cAMRnodeID | int nTotal | int ParticleNumberTable[Nx][Ny][Nz] | nTotal records of lay->stride bytes, cells in the loop order
+ * i, j, k.  leaf_node_ids[n_leaves][id_bytes] = node->AMRnodeID of every leaf (opaque bytes).  Record fields the device does not
+ * hold are written as zero.  restart_read replaces the resident particles by those of this rank's blocks.                       */
+int amps_gpu_restart_save(amps_gpu_ctx *ctx, const char *fname, const void *header, int64_t header_bytes,
+                          const void *leaf_node_ids, int32_t id_bytes, const amps_gpu_aos_layout *lay, int64_t *n_saved);
+int amps_gpu_restart_read(amps_gpu_ctx *ctx, const char *fname, int64_t header_bytes, const void *leaf_node_ids,
+                          int32_t id_bytes, const amps_gpu_aos_layout *lay, int64_t *n_loaded);
 /* per-cell particle ranges after a sort: cell_start[n_cells+1] (CreateParticleTable,
  * pic_pbuffer.cpp:1160-1310)                                                      */
 int amps_gpu_cell_table_download(amps_gpu_ctx *ctx, int64_t *cell_start, int64_t n_cells_plus_1);

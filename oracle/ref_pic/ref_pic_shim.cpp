@@ -203,6 +203,24 @@ long ref_pic_thin(int keep_every) {
   }
   return kept;
 }
+// ---- PIC::Restart with the reference's own writer / reader (pic_restart.cpp:248, :560) ----
+int ref_pic_node_id_bytes(void) { return (int)sizeof(cAMRnodeID); }
+void ref_pic_node_ids(unsigned char *out) {  // AMRnodeID of every block of ref_pic_blocks
+  for (size_t b = 0; b < g_blocks.size(); b++) memcpy(out + b * sizeof(cAMRnodeID), &g_blocks[b]->AMRnodeID, sizeof(cAMRnodeID));
+}
+void ref_pic_save_restart(const char *fname) { PIC::Restart::SaveParticleData(fname); }
+// delete every particle, then load the file
+long ref_pic_read_restart(const char *fname) {
+  CleanParticles();
+  PIC::Restart::ReadParticleData(fname);
+  return PIC::ParticleBuffer::GetAllPartNum();
+}
+// offsets of the particle record (picParticleDataMacro.h): stride, species, v, x, weight correction, next, prev
+void ref_pic_record_layout(long *out) {
+  out[0] = PIC::ParticleBuffer::ParticleDataLength, out[1] = _PIC_PARTICLE_DATA__SPECIES_ID_OFFSET_, out[2] = _PIC_PARTICLE_DATA__VELOCITY_OFFSET_;
+  out[3] = _PIC_PARTICLE_DATA__POSITION_OFFSET_, out[4] = _PIC_PARTICLE_DATA__WEIGHT_CORRECTION_OFFSET_;
+  out[5] = _PIC_PARTICLE_DATA__NEXT_OFFSET_, out[6] = _PIC_PARTICLE_DATA__PREV_OFFSET_;
+}
 void ref_pic_set_weight_correction(long n, const long *ptr, const double *w) {
   for (long i = 0; i < n; i++) PIC::ParticleBuffer::SetIndividualStatWeightCorrection(w[i], ptr[i]);
 }
