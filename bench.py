@@ -415,6 +415,81 @@ def bench_gca_large(torch, dist, rank, world, local, n_per_gpu, K=5, W=2, chunk=
             "achieved_gbs_per_gpu": 113.0 * (tot / world) * K / (ms * 1e-3) / 1e9, "setup_s": round(setup_s, 1)}
 
 
+def bench_amr_box(torch, local, base_blocks=16, ppc_by_level=(64, 16, 8), K=5, W=2, parity_sample=100_000):
+    """BASELINE configs[3]: 3-level AMR box, (8 base_blocks)^3 base cells (128^3), one more level inside each of two spheres (r < 24 and
+    r < 12 base cells) about the centre, 64 / 16 / 8 particles per cell and species on the levels ("mixed ppc", weights keep the
+    density uniform), drifting Maxwellian, open (DELETE) outer boundary, corner-based B (the ECSIM mode that is defined on a refined
+    mesh).  One GPU.  Before the timing, one step of a random sample of the particles is compared with the CPU oracle on the same
+    mesh (block hand-off across levels included): per-particle results do not depend on the other particles."""
+    from amps_b200 import _capi, api, workload as wl
+
+    t0 = time.time()
+    m = wl.amr_sphere_box((base_blocks,) * 3, (8, 8, 8), (1, 1, 1), radii=(24.0 * base_blocks / 16.0, 12.0 * base_blocks / 16.0))
+    lev = m.leaf_level()
+    n_est = sum(int((lev == l).sum()) * m.cells_per_block * 2 * p for l, p in enumerate(ppc_by_level))
+    charge, mass, wgt = wl.species_tables(ppc_by_level[0], 1.0)
+    cfg = api.make_config((8, 8, 8), (1, 1, 1), charge, mass, wgt, 1.0, periodic=False, capacity=int(n_est * 1.02) + 1024, boundary_mode=_capi.BOUNDARY_DELETE)
+    cfg.b_mode = _capi.B_CORNER_BASED
+    cfg.device = local
+    E, B = wl.box_fields(m, E_amp=0.0, b_on_corners=True)
+    ctx = api.Context(cfg, m)
+    ctx.fields_upload(E, B, B.copy())
+    n, first, sample = 0, True, None
+    rng = np.random.default_rng(17)
+    for l, ppc in enumerate(ppc_by_level):
+        leaves = np.nonzero(lev == l)[0]
+        for k, l0 in enumerate(range(0, len(leaves), 512)):
+            x, v, w, sp, cells = wl.maxwellian_box(m, ppc, seed=900 + 7919 * l + 131 * k, drift=(0.02, 0.0, 0.0), leaves=leaves[l0:l0 + 512])
+            w *= (ppc_by_level[0] / ppc) / 8.0 ** l
+            if sample is None or l > 0:  # keep a few particles of every level for the parity check
+                take = rng.choice(x.shape[1], size=min(x.shape[1], parity_sample // (2 * len(ppc_by_level))), replace=False)
+                part = (x[:, take].copy(), v[:, take].copy(), w[take].copy(), sp[take].copy(), cells[take].copy())
+                sample = part if sample is None else tuple(np.concatenate([a, b], axis=-1) for a, b in zip(sample, part))
+            (ctx.particles_upload if first else ctx.particles_append)(x, v, w, sp, cells)
+            first = False
+            n += x.shape[1]
+    setup_s = time.time() - t0
+    # ---- parity of the mover on the sample: a second, small context on the same mesh against the oracle ----
+    parity = None
+    try:
+        from oracle.oracle_py import Oracle
+
+        cfg2 = api.make_config((8, 8, 8), (1, 1, 1), charge, mass, wgt, 1.0, periodic=False, capacity=sample[0].shape[1] + 16, boundary_mode=_capi.BOUNDARY_DELETE)
+        cfg2.b_mode, cfg2.device = _capi.B_CORNER_BASED, local
+        g2 = api.Context(cfg2, m)
+        g2.fields_upload(E, B, B.copy())
+        g2.particles_upload(*sample)
+        st = g2.MoveParticles()
+        mv = g2.particles_download()
+        g2.close()
+        o = Oracle(cfg2, m, "parity")
+        o.set_fields(E, B, B.copy())
+        o.add_particles(*sample)
+        rc, st_o, ret, fc = o.move(0, os.cpu_count() or 1)
+        pp = o.particles()
+        o.close()
+        ns = sample[0].shape[1]
+        gx, gv, gc = np.empty((3, ns)), np.empty((3, ns)), np.empty(ns, dtype=np.int64)
+        gx[:, mv["ptrs"]], gv[:, mv["ptrs"]], gc[mv["ptrs"]] = mv["x"], mv["v"], mv["cells"]
+        alive = fc >= 0
+        nv = np.sqrt((pp["v"][:, alive] ** 2).sum(axis=0))
+        parity = {"sample": int(ns), "cells_equal": bool((gc == fc).all()), "stats_equal": all(st[k] == st_o[k] for k in st_o),
+                  "max_rel_x": float((np.abs(gx[:, alive] - pp["x"][:, alive]).max(axis=0) / np.sqrt((pp["x"][:, alive] ** 2).sum(axis=0))).max()),
+                  "max_rel_v": float((np.abs(gv[:, alive] - pp["v"][:, alive]).max(axis=0) / nv).max()),
+                  "n_cross_block": int(st["n_cross_block"]), "n_left_domain": int(st["n_left_domain"])}
+        parity["ok"] = bool(parity["cells_equal"] and parity["stats_equal"] and parity["max_rel_x"] <= 1e-10 and parity["max_rel_v"] <= 1e-10)
+    except Exception as exc:  # noqa: BLE001
+        parity = {"ok": False, "error": repr(exc)[:200]}
+    ms, phases = timed_steps(ctx, torch, None, 1, local, K, W)
+    n_after = ctx.particle_count()
+    ctx.close()
+    return {"workload": f"ECSIM 3-level AMR box: {8 * base_blocks}^3 base cells, +1 level inside r < {24.0 * base_blocks / 16.0:g} and r < {12.0 * base_blocks / 16.0:g} base cells, "
+                        f"ppc/species {ppc_by_level} by level, drift 0.02, open boundary, corner-based B; {m.n_leaves} blocks of 8^3 cells "
+                        f"({[int((lev == l).sum()) for l in range(len(ppc_by_level))]} per level)",
+            "value": n * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "steps": K, "warmup": W, "particles": n, "particles_after": n_after,
+            "phases_ms_per_step": phases, "mover_parity_on_sample": parity, "setup_s": round(setup_s, 1)}
+
+
 _REAL_STDOUT = None
 
 
@@ -449,6 +524,8 @@ def main():
     ap.add_argument("--no-large", action="store_true", help="skip the 128^3-cells-per-GPU series (BASELINE configs[2])")
     ap.add_argument("--large-cells", type=int, default=128, help="cells per GPU edge of the large-box series")
     ap.add_argument("--gca-particles", type=int, default=100_000_000, help="particles per GPU of the guiding-centre series (BASELINE configs[4]); 0 = skip")
+    ap.add_argument("--no-amr", action="store_true", help="skip the 3-level AMR box (BASELINE configs[3], one GPU)")
+    ap.add_argument("--amr-base-blocks", type=int, default=16, help="base blocks per edge of the AMR box (16 = 128^3 base cells)")
     ap.add_argument("--no-mp-parity", action="store_true", help="world > 1: skip the sharded-step parity check before the timing")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -727,6 +804,11 @@ def main():
         line["u256_series"] = large
     if gca is not None:
         line["gca_series"] = gca
+    if world == 1 and not args.no_amr:
+        try:
+            line["amr_box"] = bench_amr_box(torch, local, base_blocks=args.amr_base_blocks)
+        except Exception as exc:
+            line["amr_box"] = {"error": repr(exc)[:300]}
     if world == 1 and not args.no_tp:
         try:
             line["test_particle_movers"] = bench_test_particle_movers(torch)
