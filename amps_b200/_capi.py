@@ -174,6 +174,7 @@ PROTOTYPES = {
     "amps_gpu_E_upload": (C.c_int, [_vp, _vp]),
     "amps_gpu_field_step": (C.c_int, [_vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "amps_gpu_fields_download": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "amps_gpu_comm_uses_peer_memory": (C.c_int, [_vp]),
     "amps_gpu_restart_save": (C.c_int, [_vp, C.c_char_p, _vp, C.c_int64, _vp, C.c_int32, C.POINTER(AosLayout), _i64p]),
     "amps_gpu_restart_read": (C.c_int, [_vp, C.c_char_p, C.c_int64, _vp, C.c_int32, C.POINTER(AosLayout), _i64p]),
     "amps_gpu_particles_slot_delta": (C.c_int, [_vp, _i64p, _vp, C.c_int64, _i64p]),

@@ -358,6 +358,9 @@ class Context:
         self._ck(self.lib.amps_gpu_step(self._h, mover))
 
     # ---- ECSIM::TimeStep, the field half (row f1) -------------------------------------------------
+    def comm_uses_peer_memory(self):
+        return bool(self.lib.amps_gpu_comm_uses_peer_memory(self._h))
+
     def field_solver_init(self):
         nb, cc, zc = self.mesh.field_solver_tables()
         self._ck(self.lib.amps_gpu_field_solver_init(self._h, _ptr(np.ascontiguousarray(nb)), _ptr(np.ascontiguousarray(cc)), _ptr(np.ascontiguousarray(zc))))

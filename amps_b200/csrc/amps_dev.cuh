@@ -160,7 +160,10 @@ size_t sort_scan_tmp_bytes(long long nCells);
 constexpr int AMPS_MIGRATION_RECORD_MAX = 10;  // doubles: the send / receive regions are sized for it
 __host__ __device__ inline int migration_record_len(const ParticleSoA &p) { return 8 + (p.mu ? 1 : 0) + (p.vpar ? 1 : 0); }
 void launch_pack_leavers(const DevMesh &m, ParticleSoA p, const int *nSlots, long long nUpper, const int *leafOwner, const int *leafGlobal, int me,
-                         double *sendBuf, long long capPerPeer, int *sendCount, int *cellCount, int *errFlag, cudaStream_t s);
+                         double *sendBuf, long long capPerPeer, int *sendCount, int *cellCount, int *errFlag, double *const *peerRecv, cudaStream_t s);
+void launch_unpack_arrivals_peer(const DevMesh &m, const double *recvBuf, const int *allCounts, int R, long long capPerPeer, ParticleSoA p, int *nSlots,
+                                 const int *g2l, const int *leafOwner, int me, long long capacity, int *cellCount, int *errFlag, long long *sentRecv,
+                                 cudaStream_t s);
 void launch_unpack_arrivals(const DevMesh &m, const double *recvBuf, int nRecv, ParticleSoA p, int *nSlots, const int *g2l, const int *leafOwner, int me,
                             long long capacity, int *cellCount, int *errFlag, cudaStream_t s);
 void launch_pack_corners(const int *uids, int n, const double *J, const double *M, double *buf, cudaStream_t s);

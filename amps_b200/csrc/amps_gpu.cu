@@ -103,6 +103,13 @@ struct amps_gpu_ctx {
   double *d_sendBuf = nullptr, *d_recvBuf = nullptr;
   long long capPerPeer = 0;
   int *d_sendCount = nullptr, *d_allCounts = nullptr, *d_errFlag = nullptr;
+  // peer-memory migration: the receive buffers of the other ranks mapped through CUDA IPC; the leavers are written there directly
+  bool peerMigrate = false;
+  std::vector<void *> h_peerMapped;   // per rank: mapped base of its receive buffer (nullptr for this rank)
+  double **d_peerRecv = nullptr;      // the same table on the device
+  int *h_errLazy = nullptr;           // pinned: error flag of the last exchange, read back behind the next sort
+  int pendingErr = 0;
+  long long *d_sentRecv = nullptr;    // {sent, received} of the last peer exchange (device)
   std::vector<int *> d_sharedUid;      // per peer
   std::vector<long long> nShared;      // per peer
   double *d_cornerSend = nullptr, *d_cornerRecv = nullptr;
@@ -345,6 +352,10 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   if (ctx->evCounts) cudaEventDestroy(ctx->evCounts);
   cudaFree(ctx->d_E), cudaFree(ctx->d_fNb), cudaFree(ctx->d_fCc), cudaFree(ctx->d_fZc), cudaFree(ctx->d_krylov), cudaFree(ctx->d_hcol), cudaFree(ctx->d_ycoef), cudaFree(ctx->d_fieldK);
   if (ctx->h_hcol) cudaFreeHost(ctx->h_hcol);
+  for (void *q : ctx->h_peerMapped)
+    if (q) cudaIpcCloseMemHandle(q);
+  cudaFree(ctx->d_peerRecv), cudaFree(ctx->d_sentRecv);
+  if (ctx->h_errLazy) cudaFreeHost(ctx->h_errLazy);
   if (ctx->evSorted) cudaEventDestroy(ctx->evSorted);
   if (ctx->h_nSorted) cudaFreeHost(ctx->h_nSorted);
   cudaFree(ctx->d_spec), cudaFree(ctx->d_phi), cudaFree(ctx->d_cplCount), cudaFree(ctx->d_sample), cudaFree(ctx->d_nSampled), cudaFree(ctx->d_pack);
@@ -1094,6 +1105,10 @@ static int request_sorted_count(amps_gpu_ctx *ctx) {
     CK(cudaEventCreateWithFlags(&ctx->evSorted, cudaEventDisableTiming));
   }
   CK(cudaMemcpyAsync(ctx->h_nSorted, ctx->d_n + ctx->cur, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->peerMigrate) {  // the error flag of the exchange travels with it (nobody waited for it during the step)
+    CK(cudaMemcpyAsync(ctx->h_errLazy, ctx->d_errFlag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_errFlag, 0, sizeof(int), ctx->stream));
+  }
   CK(cudaEventRecord(ctx->evSorted, ctx->stream));
   ctx->nSortedPending = true;
   return AMPS_GPU_OK;
@@ -1104,6 +1119,7 @@ static void tighten_upper(amps_gpu_ctx *ctx, bool wait) {
   else if (cudaEventQuery(ctx->evSorted) != cudaSuccess) return;
   ctx->nUpper = *ctx->h_nSorted;
   ctx->nSortedPending = false;
+  if (ctx->peerMigrate && *ctx->h_errLazy) ctx->pendingErr |= *ctx->h_errLazy, *ctx->h_errLazy = 0;
 }
 
 static int do_sort(amps_gpu_ctx *ctx) {
@@ -1617,6 +1633,12 @@ int amps_gpu_cell_table_download(amps_gpu_ctx *ctx, int64_t *cell_start, int64_t
 static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "move before mesh upload");
   tighten_upper(ctx, false);
+  if (ctx->pendingErr) {
+    const int e = ctx->pendingErr;
+    ctx->pendingErr = 0;
+    if (e & 1) FAIL(AMPS_GPU_ERR_CAPACITY, "the previous particle exchange overflowed a receive region (more than capacity/32 leavers from one rank to another)");
+    FAIL(AMPS_GPU_ERR_STATE, "the previous particle exchange dropped arrivals (unknown leaf, foreign owner or no free slot)");
+  }
   if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "move needs the (block,cell)-sorted layout: call amps_gpu_sort");
   if (mover_id != AMPS_MOVER_LAPENTA2017 && mover_id != AMPS_MOVER_RELATIVISTIC_BORIS && mover_id != AMPS_MOVER_BORIS &&
       mover_id != AMPS_MOVER_RELATIVISTIC_GCA && mover_id != AMPS_MOVER_GC_FIRST_ORDER && mover_id != AMPS_MOVER_GC_SECOND_ORDER &&
@@ -1997,8 +2019,68 @@ int amps_gpu_comm_init(amps_gpu_ctx *ctx, const void *id128, int rank, int n_ran
   ncclUniqueId id;
   memcpy(&id, id128, 128);
   NCK(a.CommInitRank(&ctx->comm, n_ranks, id, rank));
+  // ---- peer memory for the particle migration (one box: every GPU reaches every other through NVLink / NVSwitch) ----
+  // Every rank publishes the IPC handle of its receive buffer; a rank that can map all the others writes its leavers straight
+  // into their buffers (pack_leavers_kernel), so the exchange needs no message sizes and the host never waits for counts.
+  // All ranks take the same decision (an all-reduce of "could map everything"); otherwise the NCCL send/recv path stays.
+  ctx->peerMigrate = false;
+  const char *env = getenv("AMPS_GPU_PEER_MIGRATE");
+  int want = (env && env[0] == '0') ? 0 : 1;
+  {
+    cudaIpcMemHandle_t mine;
+    unsigned char *d_h = nullptr;
+    int *d_ok = nullptr;
+    std::vector<cudaIpcMemHandle_t> all((size_t)n_ranks);
+    CK(cudaMalloc(&d_h, sizeof(cudaIpcMemHandle_t) * (size_t)(n_ranks + 1)));
+    CK(cudaMalloc(&d_ok, sizeof(int)));
+    if (cudaIpcGetMemHandle(&mine, ctx->d_recvBuf) != cudaSuccess) {
+      cudaGetLastError();
+      want = 0;
+      memset(&mine, 0, sizeof(mine));
+    }
+    CK(cudaMemcpy(d_h + sizeof(mine) * (size_t)n_ranks, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    NCK(a.AllGather(d_h + sizeof(mine) * (size_t)n_ranks, d_h, sizeof(mine), ncclChar, ctx->comm, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(all.data(), d_h, sizeof(mine) * (size_t)n_ranks, cudaMemcpyDeviceToHost));
+    ctx->h_peerMapped.assign((size_t)n_ranks, nullptr);
+    if (want)
+      for (int r = 0; r < n_ranks; r++) {
+        if (r == rank) continue;
+        void *ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          want = 0;
+          break;
+        }
+        ctx->h_peerMapped[r] = ptr;
+      }
+    CK(cudaMemcpy(d_ok, &want, sizeof(int), cudaMemcpyHostToDevice));
+    NCK(a.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, ctx->comm, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int okAll = 0;
+    CK(cudaMemcpy(&okAll, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_h), cudaFree(d_ok);
+    if (okAll) {
+      std::vector<double *> tab((size_t)n_ranks, nullptr);
+      for (int r = 0; r < n_ranks; r++) tab[r] = (r == rank) ? ctx->d_recvBuf : (double *)ctx->h_peerMapped[r];
+      cudaFree(ctx->d_peerRecv);
+      CK(cudaMalloc(&ctx->d_peerRecv, sizeof(double *) * (size_t)n_ranks));
+      CK(cudaMemcpy(ctx->d_peerRecv, tab.data(), sizeof(double *) * (size_t)n_ranks, cudaMemcpyHostToDevice));
+      if (!ctx->d_sentRecv) CK(cudaMalloc(&ctx->d_sentRecv, 2 * sizeof(long long)));
+      if (!ctx->h_errLazy) {
+        CK(cudaMallocHost(&ctx->h_errLazy, sizeof(int)));
+        *ctx->h_errLazy = 0;
+      }
+      ctx->peerMigrate = true;
+    } else {
+      for (void *&q : ctx->h_peerMapped)
+        if (q) cudaIpcCloseMemHandle(q), q = nullptr;
+    }
+  }
   return AMPS_GPU_OK;
 }
+
+int amps_gpu_comm_uses_peer_memory(amps_gpu_ctx *ctx) { return (ctx && ctx->peerMigrate) ? 1 : 0; }
 
 int amps_gpu_set_shared_corners(amps_gpu_ctx *ctx, int peer, const int32_t *uids, int64_t n) {
   if (!ctx || peer < 0 || n < 0 || (n > 0 && !uids)) return AMPS_GPU_ERR_ARG;
@@ -2027,7 +2109,7 @@ int amps_gpu_set_shared_corners(amps_gpu_ctx *ctx, int peer, const int32_t *uids
   return AMPS_GPU_OK;
 }
 
-static int do_migrate(amps_gpu_ctx *ctx, int64_t *n_sent, int64_t *n_received, bool zeroJM = false) {
+static int do_migrate(amps_gpu_ctx *ctx, int64_t *n_sent, int64_t *n_received, bool zeroJM = false, bool barrierFollows = false) {
   if (n_sent) *n_sent = 0;
   if (n_received) *n_received = 0;
   if (ctx->nRanks <= 1) return AMPS_GPU_OK;
@@ -2041,9 +2123,41 @@ static int do_migrate(amps_gpu_ctx *ctx, int64_t *n_sent, int64_t *n_received, b
   Sub s0(ctx, 16);
   CK(cudaMemsetAsync(ctx->d_sendCount, 0, sizeof(int) * R, s));
   launch_pack_leavers(ctx->dm, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper, ctx->d_leafOwner, ctx->d_leafGlobal, me, ctx->d_sendBuf,
-                      ctx->capPerPeer, ctx->d_sendCount, ctx->d_cellCount, ctx->d_errFlag, s);
+                      ctx->capPerPeer, ctx->d_sendCount, ctx->d_cellCount, ctx->d_errFlag, ctx->peerMigrate ? ctx->d_peerRecv : nullptr, s);
   ctx->launches++;
   s0.end();
+  if (ctx->peerMigrate) {
+    // the records already lie in the peers' receive buffers.  The all-gather of the counts is the only message: it announces
+    // them and, being ordered behind every rank's pack kernel, doubles as the barrier before anybody reads its buffer.
+    Sub sp1(ctx, 17);
+    NCK(a.AllGather(ctx->d_sendCount, ctx->d_allCounts, R, ncclInt, ctx->comm, s));
+    if (zeroJM) {
+      CK(cudaMemsetAsync(ctx->d_J, 0, sizeof(double) * 3 * (size_t)ctx->dm.nCorners, s));
+      CK(cudaMemsetAsync(ctx->d_M, 0, sizeof(double) * 243 * (size_t)ctx->dm.nCorners, s));
+      ctx->jmZeroed = true;
+    }
+    sp1.end();
+    Sub sp3(ctx, 19);
+    launch_unpack_arrivals_peer(ctx->dm, ctx->d_recvBuf, ctx->d_allCounts, R, ctx->capPerPeer, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->d_g2l,
+                                ctx->d_leafOwner, me, ctx->cfg.capacity, ctx->d_cellCount, ctx->d_errFlag, ctx->d_sentRecv, s);
+    // the next exchange may overwrite this rank's regions in the peers' buffers only after they have unpacked: the all-gather
+    // of the NEXT step is behind their unpack kernel in their streams, and this rank's next pack kernel is behind ITS previous
+    // all-gather only -- so a second, empty-payload barrier closes the exchange, unless one follows anyway (inside
+    // amps_gpu_step the all-reduces of the shared-corner exchange come after every rank's unpack kernel)
+    if (!barrierFollows) NCK(a.AllReduce(ctx->d_sendCount, ctx->d_sendCount, 1, ncclInt, ncclMax, ctx->comm, s));
+    sp3.end();
+    ctx->launches += 2;
+    ctx->nUpper = ctx->cfg.capacity;  // the arrivals are counted on the device only; the next sort reports the population
+    CK(cudaGetLastError());
+    if (n_sent || n_received) {  // (a caller that asks pays the round trip)
+      long long sr[2] = {0, 0};
+      CK(cudaMemcpyAsync(sr, ctx->d_sentRecv, sizeof(sr), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      if (n_sent) *n_sent = sr[0];
+      if (n_received) *n_received = sr[1];
+    }
+    return AMPS_GPU_OK;
+  }
   Sub s1(ctx, 17);
   // counts: every rank learns the whole R x R matrix (the reference's first message, pic_parallel.cpp:267-301)
   NCK(a.AllGather(ctx->d_sendCount, ctx->d_allCounts, R, ncclInt, ctx->comm, s));
@@ -2330,7 +2444,7 @@ int amps_gpu_step(amps_gpu_ctx *ctx, int mover_id) {
   int rc;
   ctx->jmZeroed = false;
   if ((rc = do_move(ctx, mover_id))) return rc;
-  if ((rc = do_migrate(ctx, nullptr, nullptr, ctx->meshReady && ctx->fieldsReady))) return rc;
+  if ((rc = do_migrate(ctx, nullptr, nullptr, ctx->meshReady && ctx->fieldsReady, true))) return rc;
   rc = do_sort_deposit_fused(ctx);
   ctx->jmZeroed = false;
   if (rc) return rc;

@@ -15,9 +15,11 @@
 namespace amps {
 
 // one candidate: append it to its owner's send buffer when the owner is another rank
+// peerRecv == nullptr: the record goes to region `dest` of the local send buffer (NCCL send/recv moves it);
+// peerRecv != nullptr: it is written straight into region `me` of rank dest's receive buffer over NVLink (peer memory)
 __device__ __forceinline__ void pack_one_leaver(const ParticleSoA &p, int i, int k, const int *__restrict__ leafOwner, const int *__restrict__ leafGlobal,
                                                 int C, int me, double *__restrict__ sendBuf, long long capPerPeer, int *__restrict__ sendCount,
-                                                int *__restrict__ cellCount, int *__restrict__ errFlag) {
+                                                int *__restrict__ cellCount, int *__restrict__ errFlag, double *const *__restrict__ peerRecv = nullptr) {
   const int leaf = k / C;
   const int dest = leafOwner[leaf];
   if (dest == me) return;
@@ -27,7 +29,7 @@ __device__ __forceinline__ void pack_one_leaver(const ParticleSoA &p, int i, int
     return;  // the particle stays (in a foreign block); the host reports AMPS_GPU_ERR_CAPACITY
   }
   const int L = migration_record_len(p);
-  double *r = sendBuf + ((size_t)dest * capPerPeer + slot) * L;
+  double *r = peerRecv ? peerRecv[dest] + ((size_t)me * capPerPeer + slot) * L : sendBuf + ((size_t)dest * capPerPeer + slot) * L;
   const long long gkey = (long long)leafGlobal[leaf] * C + (k - leaf * C);
   r[0] = p.x[0][i], r[1] = p.x[1][i], r[2] = p.x[2][i];
   r[3] = p.v[0][i], r[4] = p.v[1][i], r[5] = p.v[2][i];
@@ -42,7 +44,7 @@ __device__ __forceinline__ void pack_one_leaver(const ParticleSoA &p, int i, int
 __global__ void __launch_bounds__(256) pack_leavers_kernel(ParticleSoA p, const int *__restrict__ nSlots, const int *__restrict__ leafOwner,
                                                           const int *__restrict__ leafGlobal, int C, int me, double *__restrict__ sendBuf,
                                                           long long capPerPeer, int *__restrict__ sendCount, int *__restrict__ cellCount,
-                                                          int *__restrict__ errFlag) {
+                                                          int *__restrict__ errFlag, double *const *__restrict__ peerRecv) {
   const int n = *nSlots;
   // leavers are rare: the scan reads four keys per 16-byte load (the key array is a 256-byte aligned allocation)
   const int n4 = (n + 3) >> 2;
@@ -55,9 +57,67 @@ __global__ void __launch_bounds__(256) pack_leavers_kernel(ParticleSoA p, const 
     const int i = 4 * q + j;
     const int k = ks[j];
     if (i >= n || k < 0) continue;
-    pack_one_leaver(p, i, k, leafOwner, leafGlobal, C, me, sendBuf, capPerPeer, sendCount, cellCount, errFlag);
+    pack_one_leaver(p, i, k, leafOwner, leafGlobal, C, me, sendBuf, capPerPeer, sendCount, cellCount, errFlag, peerRecv);
     }
   }
+  if (peerRecv) __threadfence_system();  // the records must have reached the peers before the counts that announce them leave
+}
+
+// peer-memory variant: the arrivals of rank src lie in region src of this rank's receive buffer, their number in
+// allCounts[src * R + me] (all-gathered on the device): no count ever visits the host
+__global__ void __launch_bounds__(256) unpack_arrivals_peer_kernel(const double *__restrict__ recvBuf, const int *__restrict__ allCounts, int R,
+                                                                  long long capPerPeer, ParticleSoA p, const int *__restrict__ nSlots,
+                                                                  const int *__restrict__ g2l, const int *__restrict__ leafOwner, int C, int me,
+                                                                  long long capacity, int *__restrict__ cellCount, int *__restrict__ errFlag) {
+  const long long base = *nSlots;
+  const int L = migration_record_len(p);
+  long long off = 0;
+  for (int src = 0; src < R; src++) {
+    if (src == me) continue;
+    int cnt = allCounts[(size_t)src * R + me];
+    if (cnt > capPerPeer) {  // the sender overflowed its region (it flagged itself too)
+      if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(errFlag, 1);
+      cnt = (int)capPerPeer;
+    }
+    const double *reg = recvBuf + (size_t)src * capPerPeer * L;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
+      const double *r = reg + (size_t)j * L;
+      const long long meta = __double_as_longlong(r[7]);
+      const long long gkey = meta >> 8;
+      const int gleaf = (int)(gkey / C);
+      const int leaf = g2l[gleaf];
+      const long long i = base + off + j;
+      if (leaf < 0 || leafOwner[leaf] != me || i >= capacity) {
+        atomicOr(errFlag, 2);
+        if (i < capacity) p.key[i] = -1;
+        continue;
+      }
+      const int k = leaf * C + (int)(gkey - (long long)gleaf * C);
+      p.x[0][i] = r[0], p.x[1][i] = r[1], p.x[2][i] = r[2];
+      p.v[0][i] = r[3], p.v[1][i] = r[4], p.v[2][i] = r[5];
+      p.w[i] = r[6];
+      if (p.mu) p.mu[i] = r[8];
+      if (p.vpar) p.vpar[i] = r[L - 1];
+      p.spec[i] = (uint8_t)(meta & 0xff);
+      p.key[i] = k;
+      p.ptr[i] = -1;
+      atomicAdd(&cellCount[k], 1);
+    }
+    off += cnt;
+  }
+}
+__global__ void bump_count_peer_kernel(int *nSlots, const int *__restrict__ allCounts, int R, int me, long long capPerPeer, long long capacity,
+                                       long long *__restrict__ sentRecv) {
+  long long recv = 0, sent = 0;
+  for (int r = 0; r < R; r++) {
+    if (r == me) continue;
+    const long long a = allCounts[(size_t)r * R + me], b = allCounts[(size_t)me * R + r];
+    recv += a > capPerPeer ? capPerPeer : a;
+    sent += b > capPerPeer ? capPerPeer : b;
+  }
+  const long long v = (long long)*nSlots + recv;
+  *nSlots = (int)(v > capacity ? capacity : v);
+  if (sentRecv) sentRecv[0] = sent, sentRecv[1] = recv;
 }
 
 __global__ void __launch_bounds__(256) unpack_arrivals_kernel(const double *__restrict__ recvBuf, int nRecv, ParticleSoA p, int *__restrict__ nSlots,
@@ -157,9 +217,16 @@ static inline int grid_for(long long n) {
 }
 
 void launch_pack_leavers(const DevMesh &m, ParticleSoA p, const int *nSlots, long long nUpper, const int *leafOwner, const int *leafGlobal, int me,
-                         double *sendBuf, long long capPerPeer, int *sendCount, int *cellCount, int *errFlag, cudaStream_t s) {
+                         double *sendBuf, long long capPerPeer, int *sendCount, int *cellCount, int *errFlag, double *const *peerRecv, cudaStream_t s) {
   pack_leavers_kernel<<<grid_for((nUpper + 3) / 4), 256, 0, s>>>(p, nSlots, leafOwner, leafGlobal, m.cellsPerBlock, me, sendBuf, capPerPeer, sendCount, cellCount,
-                                                      errFlag);
+                                                      errFlag, peerRecv);
+}
+void launch_unpack_arrivals_peer(const DevMesh &m, const double *recvBuf, const int *allCounts, int R, long long capPerPeer, ParticleSoA p, int *nSlots,
+                                 const int *g2l, const int *leafOwner, int me, long long capacity, int *cellCount, int *errFlag, long long *sentRecv,
+                                 cudaStream_t s) {
+  unpack_arrivals_peer_kernel<<<148 * 4, 256, 0, s>>>(recvBuf, allCounts, R, capPerPeer, p, nSlots, g2l, leafOwner, m.cellsPerBlock, me, capacity,
+                                                      cellCount, errFlag);
+  bump_count_peer_kernel<<<1, 1, 0, s>>>(nSlots, allCounts, R, me, capPerPeer, capacity, sentRecv);
 }
 void launch_unpack_arrivals(const DevMesh &m, const double *recvBuf, int nRecv, ParticleSoA p, int *nSlots, const int *g2l, const int *leafOwner, int me,
                             long long capacity, int *cellCount, int *errFlag, cudaStream_t s) {

@@ -580,6 +580,8 @@ def main():
     ctx = api.Context(cfg, m)
     if world > 1:
         ctx.comm_init(dist)
+    exchange_kind = None if world == 1 else ("peer memory (CUDA IPC over NVLink): leavers written into the owner's buffer, counts stay on the device"
+                                             if ctx.comm_uses_peer_memory() else "NCCL send/recv with a count round trip through the host")
     ctx.fields_upload(*fields)
     ctx.particles_upload(*parts)
     del parts
@@ -784,7 +786,7 @@ def main():
         "config": {"workload": f"ECSIM uniform periodic box {n_cells[0]}x{n_cells[1]}x{n_cells[2]} cells ({args.cells}^3 per GPU, block decomposition "
                                f"{dec[0]}x{dec[1]}x{dec[2]}), {args.ppc} ppc/species e+p, 8^3-cell blocks, single AMR level, Maxwellian "
                                f"v_th,e=0.05, dt=1 (BASELINE configs[1]" + ("" if world == 1 else "; NCCL particle migration + corner J/M exchange each step") + ")",
-                   "particles_per_gpu": n_part, "particles_after": n_now, "l2": "inputs (2.2 GB particle SoA) larger than L2, no flush",
+                   "particles_per_gpu": n_part, "particles_after": n_now, "particle_exchange": exchange_kind, "l2": "inputs (2.2 GB particle SoA) larger than L2, no flush",
                    "step": "amps_gpu_step: move(Lapenta2017; contracted arithmetic + exact pass near cell faces) + permutation sort + "
                            "UpdateJMassMatrix (gathers through the permutation, writes the sorted copy)", "gen_s": round(t_gen, 1)},
         "clocks": clocks,

@@ -413,6 +413,10 @@ int amps_gpu_JM_device(amps_gpu_ctx *ctx, double **J_dev, double **M_dev);
  *    torch.distributed), every rank joins.                                                     */
 int amps_gpu_comm_unique_id(void *id128);
 int amps_gpu_comm_init(amps_gpu_ctx *ctx, const void *id128, int rank, int n_ranks);
+/* 1 when the ranks of the communicator could map each other's receive buffers (CUDA IPC over NVLink / NVSwitch): the particle
+ * migration then writes the leavers straight into the owner's buffer and never waits for counts on the host; 0 = NCCL
+ * send / recv with a count round trip (other boxes, or AMPS_GPU_PEER_MIGRATE=0)                                       */
+int amps_gpu_comm_uses_peer_memory(amps_gpu_ctx *ctx);
 /* corners that this rank and `peer` both deposit into: local unique-corner ids, both sides ordered by the
  * same global corner key (amps_b200/mesh.py: shared_corner_lists)                               */
 int amps_gpu_set_shared_corners(amps_gpu_ctx *ctx, int peer, const int32_t *uids, int64_t n);

@@ -127,7 +127,7 @@ def run(dist, rank, world, local, long_steps=LONG_STEPS):
             long_ok, long_err = False, repr(exc)[:200]
         g3.close()
 
-    res = {"rank": rank, "stats": st, "sent": ns, "recv": nr, "n_after": int(after["x"].shape[1]), "books_ok": books_ok, "fused_ok": fused_ok,
+    res = {"rank": rank, "peer_memory": g.comm_uses_peer_memory(), "stats": st, "sent": ns, "recv": nr, "n_after": int(after["x"].shape[1]), "books_ok": books_ok, "fused_ok": fused_ok,
            "fused_rel_J": fused_rel_J, "fused_rel_M": fused_rel_M, "long_ok": long_ok, "long_err": long_err, "n_long": n_long}
     # global cell of every resident particle
     lg = m.leaf_global
@@ -173,6 +173,7 @@ def run(dist, rank, world, local, long_steps=LONG_STEPS):
         st_sum = {k: sum(p["res"]["stats"][k] for p in gathered) for k in ora["stats"]}
         out["stats_equal"] = st_sum == ora["stats"]
         out["stats_gpu"], out["stats_oracle"] = st_sum, ora["stats"]
+        out["peer_memory"] = all(p["res"]["peer_memory"] for p in gathered)
         out["books_ok"] = all(p["res"]["books_ok"] for p in gathered)
         out["fused_step_equal"] = all(p["res"]["fused_ok"] for p in gathered)
         out["fused_max_rel_J"] = max(p["res"]["fused_rel_J"] for p in gathered)
