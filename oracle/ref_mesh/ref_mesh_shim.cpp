@@ -11,6 +11,8 @@
 
 #include <cstring>
 
+#include "../../amps_b200/host/amps_gpu_host_mesh.hpp"  // the PRODUCT's mesh flattener, run here on the reference's own mesh class
+
 // ---- globals / functions the headers expect from other translation units of AMPS ----
 MPI_Comm MPI_GLOBAL_COMMUNICATOR = 0;
 int ThisThread = 0, TotalThreadsNumber = 1;
@@ -114,6 +116,25 @@ int ref_neib_levels(const double *x, int *minmax) {
   n->SetNeibRefinmentLevelLimits(mesh);
   minmax[0] = n->minNeibRefinmentLevel, minmax[1] = n->maxNeibRefinmentLevel;
   return 0;
+}
+// amps_b200::FlattenMesh (amps_b200/host/amps_gpu_host_mesh.hpp) on the reference's mesh: sizes first (out == NULL), then the arrays
+static amps_b200::FlatMesh g_flat;
+int ref_flatten(int block_cells, int ghost_cells, int *sizes) {
+  amps_b200::FlattenOptions o;
+  for (int d = 0; d < 3; d++) o.block_cells[d] = block_cells, o.ghost_cells[d] = ghost_cells;
+  o.max_refinement_level = _MAX_REFINMENT_LEVEL_;
+  o.all_leaves = true;
+  g_flat = amps_b200::FlattenMesh<Mesh, Node>(mesh, o);
+  sizes[0] = g_flat.c.n_nodes, sizes[1] = g_flat.c.n_leaves, sizes[2] = g_flat.c.n_corners, sizes[3] = g_flat.c.n_centers;
+  sizes[4] = g_flat.n_corner_local, sizes[5] = g_flat.n_center_local;
+  return 0;
+}
+void ref_flatten_arrays(int *node_child, int *node_level, int *node_imin, int *node_isize, double *node_xmin, double *node_xmax, int *leaf_node,
+                        int *leaf_face, int *corner_uid, int *center_uid, double *corner_x, double *center_x) {
+  auto cp = [](auto *dst, const auto &v) { memcpy(dst, v.data(), v.size() * sizeof(v[0])); };
+  cp(node_child, g_flat.node_child), cp(node_level, g_flat.node_level), cp(node_imin, g_flat.node_imin), cp(node_isize, g_flat.node_isize);
+  cp(node_xmin, g_flat.node_xmin), cp(node_xmax, g_flat.node_xmax), cp(leaf_node, g_flat.leaf_node), cp(leaf_face, g_flat.leaf_face_boundary);
+  cp(corner_uid, g_flat.leaf_corner_uid), cp(center_uid, g_flat.leaf_center_uid), cp(corner_x, g_flat.corner_x), cp(center_x, g_flat.center_x);
 }
 // helpers of src/general/specfunc.h that the restated movers use
 double ref_gyro_frequency(const double *v, double m, double q, const double *B) {

@@ -168,3 +168,29 @@ def test_specfunc_helpers_match_the_reference():
     z1, z2 = np.zeros(3), np.zeros(3)
     ref.ref_normalize(z1.ctypes.data), ora.oracle_probe_normalize(z2.ctypes.data)
     assert (z1 == 0).all() and (z2 == 0).all()
+
+
+def test_cpp_flattener_matches_the_python_builder(pair):
+    """amps_b200/host/amps_gpu_host_mesh.hpp (the product's UploadMesh: a template over the reference's cMeshAMRgeneric / cTreeNodeAMR)
+    run on the reference's own mesh object gives the same flattened description as the Python builder that mirrors the tree:
+    nodes, lattice indices, geometry, leaves, boundary faces, unique corner / centre ids and their positions."""
+    ref, m, _ = pair
+    lib = ref.lib
+    N, G = lib.ref_mesh_block_cells(), lib.ref_mesh_ghost_cells()
+    sizes = np.zeros(6, dtype=np.int32)
+    assert lib.ref_flatten(N, G, _p(sizes)) == 0
+    n_nodes, n_leaves, n_corners, n_centers, ncl, nzl = (int(v) for v in sizes)
+    assert (n_nodes, n_leaves, n_corners, n_centers) == (m.c.n_nodes, m.c.n_leaves, m.c.n_corners, m.c.n_centers)
+    child, level, isize, leaf_node, face = (np.zeros(s, dtype=np.int32) for s in ((n_nodes, 8), n_nodes, n_nodes, n_leaves, n_leaves))
+    imin = np.zeros((n_nodes, 3), dtype=np.int32)
+    xmin, xmax = np.zeros((n_nodes, 3)), np.zeros((n_nodes, 3))
+    cu, zu = np.zeros((n_leaves, ncl), dtype=np.int32), np.zeros((n_leaves, nzl), dtype=np.int32)
+    cx, zx = np.zeros((n_corners, 3)), np.zeros((n_centers, 3))
+    lib.ref_flatten_arrays(_p(child), _p(level), _p(imin), _p(isize), _p(xmin), _p(xmax), _p(leaf_node), _p(face), _p(cu), _p(zu), _p(cx), _p(zx))
+    a = m.arrays
+    assert np.array_equal(child, a["node_child"].reshape(-1, 8)) and np.array_equal(level, a["node_level"])
+    assert np.array_equal(imin, a["node_imin"].reshape(-1, 3)) and np.array_equal(isize, a["node_isize"])
+    assert np.array_equal(xmin, a["node_xmin"].reshape(-1, 3)) and np.array_equal(xmax, a["node_xmax"].reshape(-1, 3))
+    assert np.array_equal(leaf_node, a["leaf_node"]) and np.array_equal(face, a["leaf_face_boundary"])
+    assert np.array_equal(cu, a["leaf_corner_uid"].reshape(n_leaves, -1)) and np.array_equal(zu, a["leaf_center_uid"].reshape(n_leaves, -1))
+    assert np.abs(cx - m.corner_x).max() <= 1e-12 * ref.L and np.abs(zx - m.center_x).max() <= 1e-12 * ref.L
