@@ -369,11 +369,13 @@ def build_mesh(xmin, xmax, n_blocks, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1
         den = (S * N) if corner else (2 * S * N)
         xx = x0[None, :] + kk / den[None, :] * dx_root[None, :]
         # deposit targets: in-block corners of own leaves (global keys, for the cross-rank corner exchange)
-        targets = np.unique(enc[:n_own][:, inside_block].ravel()) if corner else None
+        # (centres: the cells of own leaves -- every cell belongs to exactly one rank)
+        targets = np.unique(enc[:n_own][:, inside_block].ravel())
         return uid, len(pool), xx, pool, targets
 
     corner_uid, n_corners, corner_x, corner_gkey, corner_targets = uid_table(True)
-    center_uid, n_centers, center_x, center_gkey, _ = uid_table(False)
+    center_uid, n_centers, center_x, center_gkey, center_own = uid_table(False)
+    m.center_own_gkeys = center_own
     m.corner_x, m.center_x = corner_x, center_x
     m.corner_gkey, m.center_gkey = corner_gkey, center_gkey
     m.corner_target_gkeys = corner_targets
@@ -435,6 +437,46 @@ def shared_corner_lists(m, all_targets):
         if len(common):
             out[r] = np.searchsorted(m.corner_gkey, common).astype(np.int32)
     return out
+
+
+def field_halo_lists(m, gathered):
+    """Halo lists of the device field solve on several ranks.  gathered[r] = (corner_gkey, corner_target_gkeys, center_gkey,
+    center_own_gkeys) of rank r.  A corner is computed by every rank that deposits into it (its row needs only local data once the
+    shared J / M sums are exchanged); its PRIMARY rank -- the lowest of them -- counts it in the inner products and sends its value to
+    every other rank that holds the corner (as a target or in a ghost layer), after every operator product.  A centre (B) belongs to
+    the rank that owns its cell.  Returns (primary_mask[n_corners] uint8, {peer: (corner_send, corner_recv, center_send, center_recv)}),
+    all lists as local unique ids in the order of the global key, so that both sides of a pair agree."""
+    me = m.rank
+    R = len(gathered)
+    keys = np.concatenate([g[1] for g in gathered])
+    ranks = np.concatenate([np.full(len(g[1]), r, dtype=np.int32) for r, g in enumerate(gathered)])
+    order = np.lexsort((ranks, keys))
+    ks, rs = keys[order], ranks[order]
+    first = np.ones(len(ks), dtype=bool)
+    first[1:] = ks[1:] != ks[:-1]
+    prim_keys, prim_rank = ks[first], rs[first]          # primary rank of every target corner of the whole mesh
+
+    def primary_of(k):
+        pos = np.searchsorted(prim_keys, k)
+        pos = np.minimum(pos, len(prim_keys) - 1)
+        return np.where(prim_keys[pos] == k, prim_rank[pos], -1)
+
+    mask = np.zeros(m.n_corners, dtype=np.uint8)
+    mine_t = m.corner_target_gkeys
+    mask[np.searchsorted(m.corner_gkey, mine_t[primary_of(mine_t) == me])] = 1
+    lists = {}
+    for p in range(R):
+        if p == me:
+            continue
+        common = np.intersect1d(m.corner_gkey, gathered[p][0], assume_unique=True)
+        pr = primary_of(common)
+        c_send = np.searchsorted(m.corner_gkey, common[pr == me]).astype(np.int32)
+        c_recv = np.searchsorted(m.corner_gkey, common[pr == p]).astype(np.int32)
+        z_send = np.searchsorted(m.center_gkey, np.intersect1d(m.center_own_gkeys, gathered[p][2], assume_unique=True)).astype(np.int32)
+        z_recv = np.searchsorted(m.center_gkey, np.intersect1d(m.center_gkey, gathered[p][3], assume_unique=True)).astype(np.int32)
+        if len(c_send) or len(c_recv) or len(z_send) or len(z_recv):
+            lists[p] = (c_send, c_recv, z_send, z_recv)
+    return mask, lists
 
 
 def uniform_periodic_box(n_cells, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), dx=1.0, origin=(0.0, 0.0, 0.0),

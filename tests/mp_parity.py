@@ -32,7 +32,7 @@ def run(dist, rank, world, local, long_steps=LONG_STEPS):
     from tests import parity_util as pu
 
     decomp = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
-    n_cells = (32, 32, 16)
+    n_cells = tuple(int(v) for v in os.environ.get("MP_PARITY_CELLS", "32,32,16").split(","))
     ppc, seed, vscale = 6, 31, 6.0
 
     # the global problem (identical on every rank)
@@ -117,7 +117,9 @@ def run(dist, rank, world, local, long_steps=LONG_STEPS):
         cfg3 = api.make_config((8, 8, 8), (1, 1, 1), charge, mass, wgt, 1.0, periodic=True, capacity=int(idx.size * 1.04) + 256, device=local)
         g3 = api.Context(cfg3, m)
         g3.comm_init(dist)
-        g3.fields_upload(El, Bl, Bcl)
+        # E = 0: a static E would heat and bunch the plasma over 120 steps (frozen fields), and a rank's share could then
+        # legitimately outgrow a 4 % headroom; in B alone the density stays uniform and only the bookkeeping is tested
+        g3.fields_upload(np.zeros_like(El), Bl, Bcl)
         g3.particles_upload(x[:, idx], v[:, idx] / vscale, w[idx], sp[idx], lcells)
         try:
             for _ in range(long_steps):
