@@ -172,6 +172,8 @@ PROTOTYPES = {
     "amps_gpu_particles_download_aos": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.POINTER(AosLayout), _i64p]),
     "amps_gpu_field_solver_init": (C.c_int, [_vp, _vp, _vp, _vp]),
     "amps_gpu_E_upload": (C.c_int, [_vp, _vp]),
+    "amps_gpu_field_halo_set": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64]),
+    "amps_gpu_field_primary_set": (C.c_int, [_vp, _vp]),
     "amps_gpu_field_step": (C.c_int, [_vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "amps_gpu_fields_download": (C.c_int, [_vp, _vp, _vp, _vp]),
     "amps_gpu_comm_uses_peer_memory": (C.c_int, [_vp]),

@@ -361,9 +361,23 @@ class Context:
     def comm_uses_peer_memory(self):
         return bool(self.lib.amps_gpu_comm_uses_peer_memory(self._h))
 
-    def field_solver_init(self):
+    def field_solver_init(self, dist=None):
+        """dist (torch.distributed, several ranks): gathers the global node keys that define the field halo lists"""
         nb, cc, zc = self.mesh.field_solver_tables()
         self._ck(self.lib.amps_gpu_field_solver_init(self._h, _ptr(np.ascontiguousarray(nb)), _ptr(np.ascontiguousarray(cc)), _ptr(np.ascontiguousarray(zc))))
+        if self.mesh.n_ranks > 1:
+            from . import mesh as meshmod
+
+            m = self.mesh
+            gathered = [None] * m.n_ranks
+            dist.all_gather_object(gathered, (m.corner_gkey, m.corner_target_gkeys, m.center_gkey, m.center_own_gkeys))
+            mask, lists = meshmod.field_halo_lists(m, gathered)
+            self._ck(self.lib.amps_gpu_field_primary_set(self._h, _ptr(np.ascontiguousarray(mask, dtype=np.uint8))))
+            for peer, ls in lists.items():
+                a = [np.ascontiguousarray(v, dtype=np.int32) for v in ls]
+                self._ck(self.lib.amps_gpu_field_halo_set(self._h, peer, _ptr(a[0]), a[0].size, _ptr(a[1]), a[1].size, _ptr(a[2]), a[2].size,
+                                                          _ptr(a[3]), a[3].size))
+            self.field_primary = mask
 
     def E_upload(self, E):
         E = np.ascontiguousarray(E, dtype=np.float64)

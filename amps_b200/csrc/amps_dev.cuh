@@ -123,8 +123,11 @@ enum : unsigned {
 // field_solver.cu
 void launch_ecsim_operator(bool rhs, int nCorners, const int *nb, const int *cc, const double *Kc, const double *M, const double *x, double f,
                            const double *J, const double *B, const double c4[3], double *y, cudaStream_t s);
-void launch_multi_dot(const double *V, size_t ld, int nVec, const double *w, int n, double *out, cudaStream_t s);
-void launch_orthogonalize(const double *V, size_t ld, int nVec, const double *h, double *w, int n, double *norm2, cudaStream_t s);
+void launch_multi_dot(const double *V, size_t ld, int nVec, const double *w, int n, double *out, const unsigned char *mask, cudaStream_t s);
+void launch_orthogonalize(const double *V, size_t ld, int nVec, const double *h, double *w, int n, double *norm2, const unsigned char *mask,
+                          cudaStream_t s);
+void launch_halo_pack(const int *uid, int n, const double *vec, double *buf, cudaStream_t s);
+void launch_halo_unpack(const int *uid, int n, const double *buf, double *vec, cudaStream_t s);
 void launch_axpby(int n, double alpha, const double *a, double beta, const double *b, const double *invSqrtOf, double *out, cudaStream_t s);
 void launch_combine(const double *V, size_t ld, int nVec, const double *y, double *x, int n, cudaStream_t s);
 void launch_update_B(int nCenters, const int *zc, const double *Eh, const double *Bn, const double c4[3], double *Bout, cudaStream_t s);

@@ -40,6 +40,17 @@ struct amps_gpu_ctx {
   int krylovVectors = 0;
   double *d_hcol = nullptr, *h_hcol = nullptr;  // inner products of one iteration (device / pinned host), + the norm
   double *d_ycoef = nullptr;
+  // several ranks: halo lists of the field solve (per peer: corners to send / receive, centres to send / receive, concatenated in
+  // rank order) and the primary-owner mask of the inner products
+  struct FieldHalo {
+    std::vector<long long> cSendOff, cRecvOff, zSendOff, zRecvOff;  // [nRanks + 1] offsets into the concatenated lists
+    int *d_cSend = nullptr, *d_cRecv = nullptr, *d_zSend = nullptr, *d_zRecv = nullptr;
+    double *d_sendBuf = nullptr, *d_recvBuf = nullptr;
+    long long bufEntries = 0;
+    std::vector<std::vector<int>> h[4];  // per kind, per peer (host copies until the lists are concatenated)
+    bool dirty = true, set = false;
+  } fh;
+  unsigned char *d_primary = nullptr;  // [nCorners]
   double *d_fieldK = nullptr;   // operator constants K[243] (+ the right-hand side kept for restarts behind the Krylov vectors)
   double fieldKtheta = -1.0;    // theta the constants were built for
   bool fieldWarmValid = false;  // the solution of the previous field step is still in the workspace
@@ -734,7 +745,6 @@ int amps_gpu_field_solver_init(amps_gpu_ctx *ctx, const int32_t *corner_nb, cons
   if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "field_solver_init before mesh_upload");
   if (ctx->meshRefined) FAIL(AMPS_GPU_ERR_STATE, "the device field solve covers single-level meshes (the compact 27-node rows of GetStencil)");
   if (ctx->cfg.b_mode != AMPS_B_CENTER_BASED) FAIL(AMPS_GPU_ERR_STATE, "the device field solve updates the centre-based B (UpdateB)");
-  if (ctx->nRanks > 1) FAIL(AMPS_GPU_ERR_STATE, "the device field solve is single-rank (no field halo exchange yet)");
   if (ctx->cfg.ecsim_B_conv != 1.0) FAIL(AMPS_GPU_ERR_STATE, "the device field solve assumes normalised units (E_conv = B_conv = 1)");
   CK(cudaSetDevice(ctx->cfg.device));
   const DevMesh &m = ctx->dm;
@@ -751,6 +761,91 @@ int amps_gpu_field_solver_init(amps_gpu_ctx *ctx, const int32_t *corner_nb, cons
     CK(cudaMemset(ctx->d_E, 0, sizeof(double) * 3 * (size_t)m.nCorners));
   }
   ctx->fieldSolverReady = true;
+  return AMPS_GPU_OK;
+}
+
+// Several ranks: who sends which node values to whom (the host derives the lists from the global node keys, amps_b200/mesh.py
+// field_halo_lists; in AMPS: from the corner / centre nodes of DomainBoundaryLayerNodesList).  corner_send / corner_recv: local unique
+// corner ids whose E-type values this rank sends to / receives from `peer` after every operator product (the sender is the corner's
+// primary rank); center_send / center_recv: the same for B after UpdateB (the sender owns the cell).  Both sides list a pair's
+// nodes in the same order.  primary[n_corners]: 1 where this rank counts the corner in the inner products.
+int amps_gpu_field_halo_set(amps_gpu_ctx *ctx, int peer, const int32_t *corner_send, int64_t n_cs, const int32_t *corner_recv, int64_t n_cr,
+                            const int32_t *center_send, int64_t n_zs, const int32_t *center_recv, int64_t n_zr) {
+  if (!ctx || peer < 0 || peer >= ctx->nRanks || peer == ctx->rank) return AMPS_GPU_ERR_ARG;
+  const int32_t *src[4] = {corner_send, corner_recv, center_send, center_recv};
+  const int64_t cnt[4] = {n_cs, n_cr, n_zs, n_zr};
+  for (int k = 0; k < 4; k++) {
+    if (cnt[k] < 0 || (cnt[k] > 0 && !src[k])) return AMPS_GPU_ERR_ARG;
+    ctx->fh.h[k].resize((size_t)ctx->nRanks);
+    ctx->fh.h[k][peer].assign(src[k], src[k] + cnt[k]);
+    const int lim = (k < 2) ? ctx->dm.nCorners : ctx->dm.nCenters;
+    for (int v : ctx->fh.h[k][peer])
+      if (v < 0 || v >= lim) FAIL(AMPS_GPU_ERR_ARG, "field halo node id out of range");
+  }
+  ctx->fh.dirty = true, ctx->fh.set = true;
+  return AMPS_GPU_OK;
+}
+int amps_gpu_field_primary_set(amps_gpu_ctx *ctx, const uint8_t *primary) {
+  if (!ctx || !primary) return AMPS_GPU_ERR_ARG;
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "field_primary_set before mesh_upload");
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc;
+  if (!ctx->d_primary && (rc = dev_alloc(ctx, &ctx->d_primary, (size_t)ctx->dm.nCorners))) return rc;
+  CK(cudaMemcpy(ctx->d_primary, primary, (size_t)ctx->dm.nCorners, cudaMemcpyHostToDevice));
+  return AMPS_GPU_OK;
+}
+static int field_halo_build(amps_gpu_ctx *ctx) {
+  auto &fh = ctx->fh;
+  const int R = ctx->nRanks;
+  int **dst[4] = {&fh.d_cSend, &fh.d_cRecv, &fh.d_zSend, &fh.d_zRecv};
+  std::vector<long long> *off[4] = {&fh.cSendOff, &fh.cRecvOff, &fh.zSendOff, &fh.zRecvOff};
+  long long maxTot = 0;
+  for (int k = 0; k < 4; k++) {
+    std::vector<int> all;
+    off[k]->assign((size_t)R + 1, 0);
+    fh.h[k].resize((size_t)R);
+    for (int r = 0; r < R; r++) {
+      (*off[k])[r] = (long long)all.size();
+      all.insert(all.end(), fh.h[k][r].begin(), fh.h[k][r].end());
+    }
+    (*off[k])[R] = (long long)all.size();
+    cudaFree(*dst[k]);
+    *dst[k] = nullptr;
+    if (!all.empty()) {
+      CK(cudaMalloc(dst[k], all.size() * sizeof(int)));
+      CK(cudaMemcpy(*dst[k], all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    maxTot = std::max<long long>(maxTot, (long long)all.size());
+  }
+  if (3 * maxTot > fh.bufEntries) {
+    cudaFree(fh.d_sendBuf), cudaFree(fh.d_recvBuf);
+    fh.bufEntries = 3 * maxTot;
+    CK(cudaMalloc(&fh.d_sendBuf, sizeof(double) * (size_t)fh.bufEntries));
+    CK(cudaMalloc(&fh.d_recvBuf, sizeof(double) * (size_t)fh.bufEntries));
+  }
+  fh.dirty = false;
+  return AMPS_GPU_OK;
+}
+// refresh the copies other ranks hold of this rank's nodes: vec[n][3] on the corners (centers = false) or the centres
+static int field_halo_exchange(amps_gpu_ctx *ctx, double *vec, bool centers) {
+  if (ctx->nRanks <= 1) return AMPS_GPU_OK;
+  auto &fh = ctx->fh;
+  NcclApi &a = nccl_api();
+  cudaStream_t s = ctx->stream;
+  const std::vector<long long> &so = centers ? fh.zSendOff : fh.cSendOff, &ro = centers ? fh.zRecvOff : fh.cRecvOff;
+  const int *sIds = centers ? fh.d_zSend : fh.d_cSend, *rIds = centers ? fh.d_zRecv : fh.d_cRecv;
+  const int R = ctx->nRanks;
+  launch_halo_pack(sIds, (int)so[R], vec, fh.d_sendBuf, s);
+  NCK(a.GroupStart());
+  for (int r = 0; r < R; r++) {
+    if (r == ctx->rank) continue;
+    const long long ns = so[r + 1] - so[r], nr = ro[r + 1] - ro[r];
+    if (ns > 0) NCK(a.Send(fh.d_sendBuf + 3 * so[r], (size_t)(3 * ns), ncclDouble, r, ctx->comm, s));
+    if (nr > 0) NCK(a.Recv(fh.d_recvBuf + 3 * ro[r], (size_t)(3 * nr), ncclDouble, r, ctx->comm, s));
+  }
+  NCK(a.GroupEnd());
+  launch_halo_unpack(rIds, (int)ro[R], fh.d_recvBuf, vec, s);
+  ctx->launches += 2;
   return AMPS_GPU_OK;
 }
 
@@ -795,6 +890,20 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
   const DevMesh &m = ctx->dm;
   cudaStream_t s = ctx->stream;
   const int n = 3 * m.nCorners;
+  const bool multi = ctx->nRanks > 1;
+  if (multi) {
+    if (!ctx->comm) FAIL(AMPS_GPU_ERR_STATE, "field_step on several ranks before amps_gpu_comm_init");
+    if (!ctx->fh.set || !ctx->d_primary) FAIL(AMPS_GPU_ERR_STATE, "field_step on several ranks needs amps_gpu_field_halo_set and amps_gpu_field_primary_set");
+    int rch;
+    if (ctx->fh.dirty && (rch = field_halo_build(ctx))) return rch;
+  }
+  const unsigned char *mask = multi ? ctx->d_primary : nullptr;
+  NcclApi &nc = nccl_api();
+  // sums over all ranks of k doubles at p (device), in place
+  auto allsum = [&](double *p, int k) -> int {
+    if (multi) NCK(nc.AllReduce(p, p, (size_t)k, ncclDouble, ncclSum, ctx->comm, s));
+    return AMPS_GPU_OK;
+  };
   if (restart < 1) restart = 30;
   if (restart > max_iter) restart = max_iter;
   int rc;
@@ -857,6 +966,9 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
   const size_t ld = (size_t)n;
   // right-hand side into w, then V_0 = r0 / |r0| (x0 = 0 -> r0 = rhs)
   launch_ecsim_operator(true, m.nCorners, ctx->d_fNb, ctx->d_fCc, Kc, ctx->d_M, ctx->d_E, f, ctx->d_J, ctx->d_Bcur, c4rhs, w, s);
+  // several ranks: every vector of the iteration is kept consistent on the copies other ranks hold of a corner (ghost layers, shared
+  // corners): the primary rank's value goes out after every product; linear combinations with all-reduced coefficients keep it so
+  if ((rc = field_halo_exchange(ctx, w, false))) return rc;
   // x0 = 0 like the reference's SetInitialGuess (:6566), or the increment of the previous step (warm_start): the fields change
   // little from step to step, so most of the residual is gone before the first iteration.  Either way the iteration stops on
   // |r| <= tol |rhs|, which for x0 = 0 is the reference's relative residual.
@@ -869,7 +981,8 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
   bool first = !warm;
   if (warm || max_iter > restart) CK(cudaMemcpyAsync(rhsKeep, w, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
   if (warm) {  // |rhs| is the reference of the stopping test
-    launch_multi_dot(V, ld, 0, w, n, ctx->d_hcol, s);
+    launch_multi_dot(V, ld, 0, w, n, ctx->d_hcol, mask, s);
+    if ((rc = allsum(ctx->d_hcol, 1))) return rc;
     CK(cudaMemcpyAsync(ctx->h_hcol, ctx->d_hcol, sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     r0norm = sqrt(ctx->h_hcol[0]);
@@ -879,11 +992,13 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
     if (!first) {
       // r = rhs - A x
       launch_ecsim_operator(false, m.nCorners, ctx->d_fNb, ctx->d_fCc, Kc, ctx->d_M, x, f, nullptr, nullptr, c4rhs, w, s);
+      if ((rc = field_halo_exchange(ctx, w, false))) return rc;
       launch_axpby(n, 1.0, rhsKeep, -1.0, w, nullptr, w, s);
       ctx->launches += 2;
     }
     first = false;
-    launch_multi_dot(V, ld, 0, w, n, ctx->d_hcol, s);  // |w|^2
+    launch_multi_dot(V, ld, 0, w, n, ctx->d_hcol, mask, s);  // |w|^2
+    if ((rc = allsum(ctx->d_hcol, 1))) return rc;
     CK(cudaMemcpyAsync(ctx->h_hcol, ctx->d_hcol, sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     const double beta = sqrt(ctx->h_hcol[0]);
@@ -899,8 +1014,11 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
       double *vj = V + (size_t)j * ld, *vn = V + (size_t)(j + 1) * ld;
       launch_ecsim_operator(false, m.nCorners, ctx->d_fNb, ctx->d_fCc, Kc, ctx->d_M, vj, f, nullptr, nullptr, c4rhs, vn, s);
       iters++;
-      launch_multi_dot(V, ld, j + 1, vn, n, ctx->d_hcol, s);                             // h_i = V_i . w
-      launch_orthogonalize(V, ld, j + 1, ctx->d_hcol, vn, n, ctx->d_hcol + j + 2, s);    // w -= sum h_i V_i, |w|^2
+      if ((rc = field_halo_exchange(ctx, vn, false))) return rc;
+      launch_multi_dot(V, ld, j + 1, vn, n, ctx->d_hcol, mask, s);                             // h_i = V_i . w
+      if ((rc = allsum(ctx->d_hcol, j + 1))) return rc;
+      launch_orthogonalize(V, ld, j + 1, ctx->d_hcol, vn, n, ctx->d_hcol + j + 2, mask, s);    // w -= sum h_i V_i, |w|^2
+      if ((rc = allsum(ctx->d_hcol + j + 2, 1))) return rc;
       launch_axpby(n, 1.0, vn, 0.0, nullptr, ctx->d_hcol + j + 2, vn, s);                // V_{j+1} = w / |w|
       ctx->launches += 4;
       CK(cudaMemcpyAsync(ctx->h_hcol, ctx->d_hcol, sizeof(double) * (j + 3), cudaMemcpyDeviceToHost, s));
@@ -939,6 +1057,7 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
   // UpdateB: B^{n+1} into the buffer that held B_prev, then the two swap roles (CurrentBOffset <-> PrevBOffset)
   launch_update_B(m.nCenters, ctx->d_fZc, ctx->d_Ehalf, ctx->d_Bcur, c4b, ctx->d_Bprev, s);
   std::swap(ctx->d_Bcur, ctx->d_Bprev);
+  if ((rc = field_halo_exchange(ctx, ctx->d_Bcur, true))) return rc;  // the ghost cells of this rank are cells of its neighbours
   // UpdateE: E^{n+1} = (E^{n+theta} - (1 - theta) E^n) / theta
   launch_axpby(n, 1.0 / theta, ctx->d_Ehalf, -(1.0 - theta) / theta, ctx->d_E, nullptr, ctx->d_E, s);
   launch_stage_tiles(m, false, ctx->d_Ehalf, ctx->d_Bprev, ctx->d_Bcur, ctx->d_eTile, ctx->d_bPrevTile, ctx->d_bCurTile, s);

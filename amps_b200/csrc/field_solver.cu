@@ -88,15 +88,22 @@ __global__ void __launch_bounds__(256, 4) ecsim_operator_kernel(int nCorners, co
 
 // out[j] += V_j . w for j < nVec (V_j = V + j ld), out[nVec] += w . w; every block covers one contiguous chunk of rows, so w is read
 // from HBM / L2 once and stays in L1 while the block walks the vectors
+// mask (several ranks): 1 for the entries of the corners this rank is the primary owner of, 0 elsewhere, so that the all-reduced
+// sums count every physical corner once
 __global__ void __launch_bounds__(256) multi_dot_kernel(const double *__restrict__ V, size_t ld, int nVec, const double *__restrict__ w, int n,
-                                                       double *__restrict__ out) {
+                                                       double *__restrict__ out, const unsigned char *__restrict__ mask) {
   __shared__ double sPart[8];
   const int per = (n + gridDim.x - 1) / gridDim.x;
   const int r0 = blockIdx.x * per, r1 = min(n, r0 + per);
   for (int j = 0; j <= nVec; j++) {
     const double *v = (j < nVec) ? V + (size_t)j * ld : w;
     double s = 0.0;
-    for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) s = fma(v[i], w[i], s);
+    if (mask) {
+      for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+        if (mask[i / 3]) s = fma(v[i], w[i], s);
+    } else {
+      for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) s = fma(v[i], w[i], s);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) sPart[threadIdx.x >> 5] = s;
@@ -112,14 +119,15 @@ __global__ void __launch_bounds__(256) multi_dot_kernel(const double *__restrict
 
 // w -= sum_j h[j] V_j  (classical Gram-Schmidt with the inner products of multi_dot_kernel); norm2 += |w|^2 of the result
 __global__ void __launch_bounds__(256) orthogonalize_kernel(const double *__restrict__ V, size_t ld, int nVec, const double *__restrict__ h,
-                                                           double *__restrict__ w, int n, double *__restrict__ norm2) {
+                                                           double *__restrict__ w, int n, double *__restrict__ norm2,
+                                                           const unsigned char *__restrict__ mask) {
   __shared__ double sPart[8];
   double s = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     double a = w[i];
     for (int j = 0; j < nVec; j++) a = fma(-h[j], V[(size_t)j * ld + i], a);
     w[i] = a;
-    s = fma(a, a, s);
+    if (!mask || mask[i / 3]) s = fma(a, a, s);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -188,13 +196,28 @@ void launch_ecsim_operator(bool rhs, int nCorners, const int *nb, const int *cc,
   if (rhs) ecsim_operator_kernel<true><<<grid, 256, 0, s>>>(nCorners, nb, cc, Kc, M, x, f, J, B, c4[0], c4[1], c4[2], y);
   else ecsim_operator_kernel<false><<<grid, 256, 0, s>>>(nCorners, nb, cc, Kc, M, x, f, nullptr, nullptr, 0.0, 0.0, 0.0, y);
 }
-void launch_multi_dot(const double *V, size_t ld, int nVec, const double *w, int n, double *out, cudaStream_t s) {
+void launch_multi_dot(const double *V, size_t ld, int nVec, const double *w, int n, double *out, const unsigned char *mask, cudaStream_t s) {
   cudaMemsetAsync(out, 0, sizeof(double) * (nVec + 1), s);
-  multi_dot_kernel<<<148 * 4, 256, 0, s>>>(V, ld, nVec, w, n, out);
+  multi_dot_kernel<<<148 * 4, 256, 0, s>>>(V, ld, nVec, w, n, out, mask);
 }
-void launch_orthogonalize(const double *V, size_t ld, int nVec, const double *h, double *w, int n, double *norm2, cudaStream_t s) {
+void launch_orthogonalize(const double *V, size_t ld, int nVec, const double *h, double *w, int n, double *norm2, const unsigned char *mask,
+                          cudaStream_t s) {
   cudaMemsetAsync(norm2, 0, sizeof(double), s);
-  orthogonalize_kernel<<<grid_rows(n), 256, 0, s>>>(V, ld, nVec, h, w, n, norm2);
+  orthogonalize_kernel<<<grid_rows(n), 256, 0, s>>>(V, ld, nVec, h, w, n, norm2, mask);
+}
+
+// field halo (several ranks): buf[3 i + d] <- vec[3 uid[i] + d] and back
+__global__ void __launch_bounds__(256) halo_pack_kernel(const int *__restrict__ uid, int n, const double *__restrict__ vec, double *__restrict__ buf) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 3 * n; e += gridDim.x * blockDim.x) buf[e] = vec[(size_t)3 * uid[e / 3] + e % 3];
+}
+__global__ void __launch_bounds__(256) halo_unpack_kernel(const int *__restrict__ uid, int n, const double *__restrict__ buf, double *__restrict__ vec) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 3 * n; e += gridDim.x * blockDim.x) vec[(size_t)3 * uid[e / 3] + e % 3] = buf[e];
+}
+void launch_halo_pack(const int *uid, int n, const double *vec, double *buf, cudaStream_t s) {
+  if (n > 0) halo_pack_kernel<<<grid_rows(3LL * n), 256, 0, s>>>(uid, n, vec, buf);
+}
+void launch_halo_unpack(const int *uid, int n, const double *buf, double *vec, cudaStream_t s) {
+  if (n > 0) halo_unpack_kernel<<<grid_rows(3LL * n), 256, 0, s>>>(uid, n, buf, vec);
 }
 void launch_axpby(int n, double alpha, const double *a, double beta, const double *b, const double *invSqrtOf, double *out, cudaStream_t s) {
   axpby_kernel<<<grid_rows(n), 256, 0, s>>>(n, alpha, a, beta, b, invSqrtOf, out);

@@ -560,7 +560,7 @@ def main():
             ok_mp, rep_mp = mpp.run(dist, rank, world, local)
             if rank == 0:
                 keep = ("ok", "cells_equal", "x_bit_equal", "v_bit_equal", "max_rel_J", "max_rel_M", "stats_equal", "sent_total", "recv_total",
-                        "books_ok", "fused_step_equal", "fused_max_rel_M", "long_steps", "long_ok", "long_err", "peer_memory", "n_total", "n_expected")
+                        "books_ok", "fused_step_equal", "fused_max_rel_M", "long_steps", "long_ok", "long_err", "peer_memory", "field_ok", "field_rel_E", "field_rel_B", "field_iterations", "n_total", "n_expected")
                 mp_parity = {k: rep_mp.get(k) for k in keep}
         except Exception as exc:  # the verdict must reach the line either way
             mp_parity = {"ok": False, "error": repr(exc)[:300]}

@@ -238,11 +238,13 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh);
 int amps_gpu_fields_upload(amps_gpu_ctx *ctx, const double *E_half, const double *B_prev,
                            const double *B_cur);
 
-/* ---- the field half of the ECSIM step on the device (single rank, single-level mesh, centre-based B,
+/* ---- the field half of the ECSIM step on the device (single-level mesh, centre-based B,
  * normalised units).  Replaces PIC::FieldSolver::Electromagnetic::ECSIM::TimeStep (pic_field_solver_ecsim.cpp:6004-6157):
  * UpdateRhs (ecsim/update_rhs.cpp), UpdateMatrixElement (:6004-6020), cLinearSystemCornerNode::Solve / MultiplyVector
  * (srcInterface/LinearSystemCornerNode.h:3212, :2749; GMRES of the SWMF library), ProcessFinalSolution, UpdateB (:5160),
  * UpdateE (:5909).  J and M stay on the device: the 2 KB per corner the host path downloads every step never cross PCIe.
+ * One rank, or several with amps_gpu_field_halo_set (every Krylov vector is refreshed on the neighbours' copies after each
+ * product; the inner products are all-reduced).
  *
  * field_solver_init: node adjacency on the unique nodes (the host derives it from the leaves' node tables, like the row
  * builder GetStencil walks GetCornerNode(i+di, j+dj, k+dk)):
@@ -252,6 +254,16 @@ int amps_gpu_fields_upload(amps_gpu_ctx *ctx, const double *E_half, const double
  *   center_corners[n_centers][8]  corner node at cell index + (ii, jj, kk) in {0, 1}^3: ii + 2 jj + 4 kk                      */
 int amps_gpu_field_solver_init(amps_gpu_ctx *ctx, const int32_t *corner_nb, const int32_t *corner_cells,
                                const int32_t *center_corners);
+/* Several ranks (after amps_gpu_comm_init): the node values that cross rank boundaries in the field solve -- the reference's
+ * PIC::Parallel::UpdateGhostBlockData (pic_bc_periodic.cpp:298-303) / ParallelBlockDataExchange for E and B.  corner_send / corner_recv:
+ * local unique corner ids whose value this rank sends to / receives from `peer` after every operator product (the sender is the
+ * corner's PRIMARY rank: the lowest rank that deposits into it); center_send / center_recv: the same for B after UpdateB (the
+ * sender owns the cell).  Both sides list the nodes of a pair in the same order (ascending global key).  primary[n_corners] = 1
+ * where this rank counts the corner in the all-reduced inner products of the GMRES.                                          */
+int amps_gpu_field_halo_set(amps_gpu_ctx *ctx, int peer, const int32_t *corner_send, int64_t n_corner_send,
+                            const int32_t *corner_recv, int64_t n_corner_recv, const int32_t *center_send,
+                            int64_t n_center_send, const int32_t *center_recv, int64_t n_center_recv);
+int amps_gpu_field_primary_set(amps_gpu_ctx *ctx, const uint8_t *primary);
 /* E^n on the unique corners [n_corners][3] (CurrentEOffset); B^n is B_cur of amps_gpu_fields_upload */
 int amps_gpu_E_upload(amps_gpu_ctx *ctx, const double *E_cur);
 /* one field step with J, M of the last deposit: GMRES(restart; <= 0 = 30) from x0 = 0 until |r| <= tol |r0| or max_iter

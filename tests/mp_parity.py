@@ -91,6 +91,14 @@ def run(dist, rank, world, local, long_steps=LONG_STEPS):
     n_new2, released2 = g.slot_delta()
     books_ok = bool(books_ok and n_new2 == 0 and released2.size == 0 and (g.particles_download()["ptrs"] >= 0).all())
 
+    # ---- the field half of the step on the sharded mesh (halo exchange per product, all-reduced inner products) ----
+    En = 0.01 * np.random.default_rng(seed + 9).standard_normal((mg.n_corners, 3))
+    g.field_solver_init(dist)
+    g.E_upload(pick(En, mg.corner_gkey, m.corner_gkey))
+    f_its, f_res = g.field_step(theta=0.5, tol=1e-12, max_iter=300, restart=50)
+    fld = g.fields_download()
+    own_z = np.searchsorted(m.center_gkey, m.center_own_gkeys)
+
     # ---- the fused step on the same inputs: same particles, same corner sums ----
     g2 = api.Context(cfg, m)
     g2.comm_init(dist)
@@ -137,7 +145,8 @@ def run(dist, rank, world, local, long_steps=LONG_STEPS):
     gk = lg[keys // C].astype(np.int64) * C + keys % C
     owner_ok = bool((m.arrays["leaf_owner"][keys // C] == rank).all())
     payload = {"res": res, "x": after["x"], "v": after["v"], "gk": gk, "owner_ok": owner_ok, "mu": mu_after, "vpar": vp_after,
-               "J": J, "M": M, "ckeys": m.corner_gkey, "targets": m.corner_target_gkeys}
+               "J": J, "M": M, "ckeys": m.corner_gkey, "targets": m.corner_target_gkeys,
+               "Eh": fld["E_half"], "Enew": fld["E"], "Bnew": fld["B"][own_z], "zkeys": m.center_own_gkeys, "f_its": f_its, "f_res": f_res}
     gathered = [None] * world
     dist.all_gather_object(gathered, payload)
     ok, out = True, None
@@ -176,6 +185,21 @@ def run(dist, rank, world, local, long_steps=LONG_STEPS):
         out["stats_equal"] = st_sum == ora["stats"]
         out["stats_gpu"], out["stats_oracle"] = st_sum, ora["stats"]
         out["peer_memory"] = all(p["res"]["peer_memory"] for p in gathered)
+        # field step: every rank's E^{n+theta}, E^{n+1} at its deposit targets and B^{n+1} in its own cells against the single-domain oracle
+        from oracle import ecsim_field
+
+        fs = ecsim_field.EcsimField(mg, (1.0, 1.0, 1.0), cfg1.ecsim_light_speed, cfg1.ecsim_dt_total, theta=0.5)
+        Eh_o, En_o, Bn_o, its_o = fs.step(En, Bcur, ora["J"], ora["M"], tol=1e-12, max_iter=300)
+        relE = relB = 0.0
+        for p in gathered:
+            lpos = np.searchsorted(p["ckeys"], p["targets"])
+            gpos = np.searchsorted(mg.corner_gkey, p["targets"])
+            relE = max(relE, float(np.abs(p["Eh"][lpos] - Eh_o[gpos]).max() / np.abs(Eh_o).max()), float(np.abs(p["Enew"][lpos] - En_o[gpos]).max() / np.abs(En_o).max()))
+            zpos = np.searchsorted(mg.center_gkey, p["zkeys"])
+            relB = max(relB, float(np.abs(p["Bnew"] - Bn_o[zpos]).max() / np.abs(Bn_o).max()))
+        out["field_rel_E"], out["field_rel_B"] = relE, relB
+        out["field_iterations"], out["field_iterations_oracle"] = [p["f_its"] for p in gathered], its_o
+        out["field_ok"] = bool(relE <= 1e-9 and relB <= 1e-9 and max(p["f_res"] for p in gathered) <= 1e-12 and len(set(p["f_its"] for p in gathered)) == 1)
         out["books_ok"] = all(p["res"]["books_ok"] for p in gathered)
         out["fused_step_equal"] = all(p["res"]["fused_ok"] for p in gathered)
         out["fused_max_rel_J"] = max(p["res"]["fused_rel_J"] for p in gathered)
@@ -187,7 +211,7 @@ def run(dist, rank, world, local, long_steps=LONG_STEPS):
               and relJ <= 1e-10 and relM <= 1e-10
               and out["stats_equal"] and out["sent_total"] == out["recv_total"] and out["sent_total"] > 0
               and out["books_ok"] and out["fused_step_equal"] and out["fused_max_rel_J"] <= 1e-12 and out["fused_max_rel_M"] <= 1e-12
-              and out["long_ok"])
+              and out["long_ok"] and out["field_ok"])
         out["ok"] = bool(ok)
     g.close()
     flag = [ok]
