@@ -50,6 +50,39 @@ def _worker(rank, world, port, q):
     ghost = (fl & 2) != 0
     ok &= bool((real[ghost] >= 0).all()) and bool((real[~ghost] == -1).all())
     ok &= m.n_own_leaves == int(np.prod(np.array(n_cells) // 8)) // world
+    # ---- the halo lists of the sharded field solve (Context.field_solver_init): every physical corner has exactly one primary rank,
+    # what a rank sends to a peer is what the peer expects from it (same keys, same order), and one halo round of a vector that every
+    # rank fills only on its primary corners reproduces the global vector on every copy a rank holds
+    fg = [None] * world
+    dist.all_gather_object(fg, (m.corner_gkey, m.corner_target_gkeys, m.center_gkey, m.center_own_gkeys))
+    mask, hl = meshmod.field_halo_lists(m, fg)
+    prim = [None] * world
+    dist.all_gather_object(prim, m.corner_gkey[mask == 1])
+    allp = np.concatenate(prim)
+    ok &= len(allp) == len(np.unique(allp)) == mg.n_corners
+    send = {r: (m.corner_gkey[l[0]], m.center_gkey[l[2]]) for r, l in hl.items()}
+    recv = {r: (m.corner_gkey[l[1]], m.center_gkey[l[3]]) for r, l in hl.items()}
+    ex = [None] * world
+    dist.all_gather_object(ex, (send, recv))
+    for r, (snd, rcv) in enumerate(ex):
+        if r == rank:
+            continue
+        if rank in snd:  # what r sends to me == what I expect from r
+            ok &= bool(np.array_equal(snd[rank][0], recv[r][0]) and np.array_equal(snd[rank][1], recv[r][1]))
+        else:
+            ok &= r not in recv or (len(recv[r][0]) == 0 and len(recv[r][1]) == 0)
+    gvec = np.random.default_rng(5).standard_normal(mg.n_corners)
+    pos = np.searchsorted(mg.corner_gkey, m.corner_gkey)
+    loc = np.where(mask == 1, gvec[pos], np.nan)  # only the primary corners are filled
+    out_msgs = {r: loc[l[0]] for r, l in hl.items()}
+    msgs = [None] * world
+    dist.all_gather_object(msgs, out_msgs)
+    for r, l in hl.items():
+        loc[l[1]] = msgs[r][rank]
+    targets = np.searchsorted(m.corner_gkey, m.corner_target_gkeys)
+    tiles = np.unique(m.arrays["leaf_corner_uid"].reshape(m.n_leaves, -1)[: m.n_own_leaves])
+    tiles = tiles[tiles >= 0]
+    ok &= bool(np.array_equal(loc[targets], gvec[pos][targets])) and not np.isnan(loc[tiles]).any()
     q.put((rank, bool(ok), sizes))
     dist.destroy_process_group()
 
