@@ -898,10 +898,10 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
     if (ctx->fh.dirty && (rch = field_halo_build(ctx))) return rch;
   }
   const unsigned char *mask = multi ? ctx->d_primary : nullptr;
-  NcclApi &nc = nccl_api();
-  // sums over all ranks of k doubles at p (device), in place
+  // sums over all ranks of k doubles at p (device), in place.  (NCCL is only touched on several ranks: loading libnccl.so.2 into a
+  // one-rank process would shadow the copy a host such as torch brings along when it is imported later.)
   auto allsum = [&](double *p, int k) -> int {
-    if (multi) NCK(nc.AllReduce(p, p, (size_t)k, ncclDouble, ncclSum, ctx->comm, s));
+    if (multi) NCK(nccl_api().AllReduce(p, p, (size_t)k, ncclDouble, ncclSum, ctx->comm, s));
     return AMPS_GPU_OK;
   };
   if (restart < 1) restart = 30;
