@@ -128,7 +128,7 @@ def _local_numbers(N, g, corner):
 
 
 def build_mesh(xmin, xmax, n_blocks, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), periodic=True,
-               max_refinement_level=12, refine=None, max_level=0, rank=0, n_ranks=1, decomp=None):
+               max_refinement_level=12, refine=None, max_level=0, rank=0, n_ranks=1, decomp=None, leaf_weight=None):
     """Flatten a box mesh.
 
     xmin/xmax     user ("original") domain
@@ -136,8 +136,12 @@ def build_mesh(xmin, xmax, n_blocks, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1
     refine        callable(level, xmin[3], xmax[3]) -> bool : split this block? (AMR)
     max_level     deepest level ``refine`` may produce
     rank,n_ranks  this process and the number of processes (one per GPU)
-    decomp        (px,py,pz) Cartesian split of the user domain, px*py*pz == n_ranks.  Like the reference's
-                  space-filling-curve chunks (meshAMRgeneric.h:11787) every rank owns a contiguous set of blocks;
+    decomp        (px,py,pz) Cartesian split of the user domain, px*py*pz == n_ranks, or "sfc": the reference's own decomposition
+                  (CreateNewParallelDistributionLists / RedistributeParallelLoad, meshAMRgeneric.h:11787-11940): the leaves in the order
+                  of the Morton space-filling curve (tree traversal, children 0..7), their load measures normalised so that every rank's
+                  share is 1, and the curve cut where the cumulative load passes 1, 2, ... (the leaf that crosses the mark opens the
+                  next rank's chunk).  leaf_weight(level, xmin, xmax) -> load measure of a leaf (default 1 = blocks; the reference
+                  uses the particle number or the execution time).  Either way every rank owns a contiguous set of blocks;
                   the rank keeps the whole tree but allocates only its own blocks, the blocks around them
                   (DomainBoundaryLayerNodesList, meshAMRgeneric.h:1812) and the real images of adjacent
                   periodic ghost blocks.
@@ -246,17 +250,31 @@ def build_mesh(xmin, xmax, n_blocks, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1
             c = (c - S) % period + S
             gleaf_real[l] = find_gleaf_ix([int(v) for v in c])
 
-    # ---- ownership: Cartesian split of the user domain ----------------------
-    if decomp is None:
-        decomp = (n_ranks, 1, 1)
-    decomp = np.asarray(decomp, dtype=np.int64)
-    assert int(np.prod(decomp)) == n_ranks
-    ctr = gli + (gls // 2)[:, None] - shell * S  # block centre on the lattice of the user domain
-    ext = nb * S
+    # ---- ownership: Cartesian split of the user domain, or the reference's space-filling-curve chunks ----------------------
     gowner = np.zeros(n_gleaves, dtype=np.int32)
     real_mask = ~g_is_ghost
-    rc = np.clip((ctr * decomp[None, :]) // ext[None, :], 0, decomp[None, :] - 1)
-    gowner[:] = (rc[:, 0] + decomp[0] * (rc[:, 1] + decomp[1] * rc[:, 2])).astype(np.int32)
+    if isinstance(decomp, str):
+        assert decomp == "sfc"
+        curve = np.nonzero(real_mask)[0]  # the global leaf list is the tree traversal = the Morton curve
+        wts = np.ones(len(curve)) if leaf_weight is None else np.array(
+            [float(leaf_weight(int(level[gleaf_node[l]]), nxmin[gleaf_node[l]], nxmax[gleaf_node[l]])) for l in curve])
+        norm = wts.sum() / n_ranks  # LoadMeasureNormal: every rank's share is 1
+        cum, cur, load_cur = 0.0, 0, 0.0
+        for l, wl in zip(curve, wts / norm):
+            cum += wl
+            if cum > 1.0 + 1e-8 + cur and cur != n_ranks - 1 and load_cur > 0.0:  # RedistributeParallelLoad, :11925-11930
+                cur, load_cur = cur + 1, 0.0
+            load_cur += wl
+            gowner[l] = cur
+    else:
+        if decomp is None:
+            decomp = (n_ranks, 1, 1)
+        decomp = np.asarray(decomp, dtype=np.int64)
+        assert int(np.prod(decomp)) == n_ranks
+        ctr = gli + (gls // 2)[:, None] - shell * S  # block centre on the lattice of the user domain
+        ext = nb * S
+        rc = np.clip((ctr * decomp[None, :]) // ext[None, :], 0, decomp[None, :] - 1)
+        gowner[:] = (rc[:, 0] + decomp[0] * (rc[:, 1] + decomp[1] * rc[:, 2])).astype(np.int32)
     if periodic:
         gh = np.nonzero(g_is_ghost)[0]
         gowner[gh] = gowner[gleaf_real[gh]]
@@ -480,7 +498,7 @@ def field_halo_lists(m, gathered):
 
 
 def uniform_periodic_box(n_cells, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), dx=1.0, origin=(0.0, 0.0, 0.0),
-                         max_refinement_level=12, rank=0, n_ranks=1, decomp=None):
+                         max_refinement_level=12, rank=0, n_ranks=1, decomp=None, leaf_weight=None):
     """BASELINE config 2/3 geometry: [origin, origin+n_cells*dx) periodic, single AMR level."""
     n_cells = np.asarray(n_cells, dtype=np.int64)
     N = np.asarray(block_cells, dtype=np.int64)
@@ -488,4 +506,4 @@ def uniform_periodic_box(n_cells, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), 
     xmin = np.asarray(origin, dtype=np.float64)
     xmax = xmin + n_cells * dx
     return build_mesh(xmin, xmax, n_cells // N, block_cells, ghost_cells, True, max_refinement_level, rank=rank, n_ranks=n_ranks,
-                      decomp=decomp)
+                      decomp=decomp, leaf_weight=leaf_weight)

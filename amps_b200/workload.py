@@ -43,7 +43,7 @@ def box_fields(mesh, E_amp=0.0, b_on_corners=False):
     return E, B
 
 
-def amr_sphere_box(n_blocks, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), radii=(12.0, 6.0), rank=0, n_ranks=1, decomp=None):
+def amr_sphere_box(n_blocks, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), radii=(12.0, 6.0), rank=0, n_ranks=1, decomp=None, leaf_weight=None):
     """BASELINE config 4 geometry (scaled by the caller): open box [0,n)^3 of unit base cells, one more refinement level
     inside every sphere radii[l] (in base cells) about the centre; outer boundary = DELETE."""
     n_blocks = np.asarray(n_blocks, dtype=np.int64)
@@ -59,7 +59,7 @@ def amr_sphere_box(n_blocks, block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), radii
 
     from . import mesh as meshmod
     return meshmod.build_mesh((0.0, 0.0, 0.0), tuple(hi), tuple(int(v) for v in n_blocks), block_cells, ghost_cells, periodic=False,
-                              refine=refine, max_level=len(radii), rank=rank, n_ranks=n_ranks, decomp=decomp)
+                              refine=refine, max_level=len(radii), rank=rank, n_ranks=n_ranks, decomp=decomp, leaf_weight=leaf_weight)
 
 
 def maxwellian_amr(mesh, ppc_by_level, seed=100, drift=(0.02, 0.0, 0.0)):

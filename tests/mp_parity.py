@@ -32,6 +32,8 @@ def run(dist, rank, world, local, long_steps=LONG_STEPS):
     from tests import parity_util as pu
 
     decomp = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
+    if os.environ.get("MP_PARITY_DECOMP", "cart") == "sfc":  # the reference's space-filling-curve chunks (mesh.build_mesh)
+        decomp = "sfc"
     n_cells = tuple(int(v) for v in os.environ.get("MP_PARITY_CELLS", "32,32,16").split(","))
     ppc, seed, vscale = 6, 31, 6.0
 

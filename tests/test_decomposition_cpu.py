@@ -9,7 +9,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, kind="cart"):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
 
@@ -17,7 +17,7 @@ def _worker(rank, world, port, q):
 
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    decomp = {2: (2, 1, 1), 4: (2, 2, 1)}[world]
+    decomp = "sfc" if kind == "sfc" else {2: (2, 1, 1), 4: (2, 2, 1)}[world]
     n_cells = (32, 32, 16)
     m = meshmod.uniform_periodic_box(n_cells, rank=rank, n_ranks=world, decomp=decomp)
     gathered = [None] * world
@@ -87,14 +87,14 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_rank_views_are_consistent(world):
+@pytest.mark.parametrize("world,kind", [(2, "cart"), (4, "cart"), (2, "sfc"), (4, "sfc")])
+def test_rank_views_are_consistent(world, kind):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + world
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    port = 29700 + world + (10 if kind == "sfc" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, kind)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
@@ -102,5 +102,36 @@ def test_rank_views_are_consistent(world):
         p.join(timeout=60)
     assert all(r[1] for r in res), res
     # 2 ranks split along x share two faces (x = 16 and the periodic seam): 2 * 32*16... corners
-    if world == 2:
+    if world == 2 and kind == "cart":
         assert all(sum(r[2].values()) == 2 * 32 * 16 for r in res), res
+
+
+def test_space_filling_curve_chunks_follow_the_reference_rule():
+    """decomp="sfc" (RedistributeParallelLoad, meshAMRgeneric.h:11905-11940): the chunks are contiguous on the Morton curve, in rank
+    order, none empty; with the particle number as the load measure every rank's load is within one leaf of the mean; and the
+    leaf that crosses a whole-number mark of the normalised cumulative load is the first of the next chunk."""
+    sys.path.insert(0, ROOT)
+    from amps_b200 import workload
+
+    ppc = (64, 16, 8)
+    world = 4
+    views = [workload.amr_sphere_box((4, 4, 4), radii=(12.0, 6.0), rank=r, n_ranks=world, decomp="sfc",
+                                     leaf_weight=lambda lev, lo, hi: ppc[lev]) for r in range(world)]
+    g = workload.amr_sphere_box((4, 4, 4), radii=(12.0, 6.0))
+    real = g.real_leaves()
+    order = np.argsort(g.leaf_global[real])  # the global leaf numbering is the tree traversal = the Morton curve
+    gid = g.leaf_global[real][order]
+    wts = np.array([ppc[l] for l in g.leaf_level()[real][order]], dtype=np.float64)
+    norm = wts.sum() / world
+    owner = np.full(len(wts), -1)
+    for r, m in enumerate(views):
+        at = np.searchsorted(gid, m.leaf_global[: m.n_own_leaves])
+        assert (gid[at] == m.leaf_global[: m.n_own_leaves]).all() and (owner[at] == -1).all()
+        owner[at] = r
+    assert (owner >= 0).all() and (np.diff(owner) >= 0).all() and len(np.unique(owner)) == world
+    loads = np.array([wts[owner == r].sum() for r in range(world)])
+    assert np.abs(loads - norm).max() <= wts.max(), loads
+    cum = np.cumsum(wts / norm)
+    for r in range(1, world):
+        first = int(np.argmax(owner == r))
+        assert cum[first] > r + 1e-8 and cum[first - 1] <= r + 1e-8
