@@ -155,16 +155,40 @@ __global__ void __launch_bounds__(256, 5) scatter_kernel(ParticleSoA src, Partic
 
 // permutation only: perm[position in the (block,cell)-sorted order] = current slot.  8 B per particle instead of the 130 B of
 // the full scatter; the deposit that follows gathers through perm and writes the sorted copy as a by-product.
-__global__ void __launch_bounds__(256, 5) perm_kernel(const int *__restrict__ key, const int *__restrict__ nSrc, const int *__restrict__ cellStart,
+// A thread takes four consecutive slots (one 16-byte load); the four rounds of warp-aggregated atomics are issued before any of
+// their results is used, so that one trip of a warp has one DRAM and one L2 round trip for 128 keys (the kernel was latency bound
+// at one key per trip and thread: 99 us for 3.4e7 keys).  Empty slots (key < 0) form their own match group, which has no atomic.
+constexpr int PERM_VEC = 4;
+__global__ void __launch_bounds__(256, 4) perm_kernel(const int *__restrict__ key, const int *__restrict__ nSrc, const int *__restrict__ cellStart,
                                                      int *__restrict__ cellFill, int *__restrict__ perm) {
   const int n = *nSrc;
-  const int stride = gridDim.x * blockDim.x;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
-    const int j = i + stride;
-    const int ka = key[i];
-    const int kb = (j < n) ? key[j] : -1;
-    if (ka >= 0) perm[cellStart[ka] + warp_aggregated_slot(cellFill, ka)] = i;
-    if (kb >= 0) perm[cellStart[kb] + warp_aggregated_slot(cellFill, kb)] = j;
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * blockDim.x * PERM_VEC;
+  // the trip count is uniform over the warp (every lane takes part in the match / shuffle rounds)
+  for (long long w0 = ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * PERM_VEC; w0 < n; w0 += stride) {
+    const long long i0 = w0 + lane * PERM_VEC;
+    int k[PERM_VEC];
+    if (i0 + PERM_VEC <= n) {
+      const int4 q = *reinterpret_cast<const int4 *>(key + i0);
+      k[0] = q.x, k[1] = q.y, k[2] = q.z, k[3] = q.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < PERM_VEC; q++) k[q] = (i0 + q < n) ? key[i0 + q] : -1;
+    }
+    unsigned mask[PERM_VEC];
+    int base[PERM_VEC], start[PERM_VEC];
+#pragma unroll
+    for (int q = 0; q < PERM_VEC; q++) {
+      mask[q] = __match_any_sync(0xffffffffu, k[q]);
+      start[q] = k[q] >= 0 ? __ldg(cellStart + k[q]) : 0;
+      base[q] = 0;
+      if (k[q] >= 0 && lane == __ffs(mask[q]) - 1) base[q] = atomicAdd(&cellFill[k[q]], __popc(mask[q]));
+    }
+#pragma unroll
+    for (int q = 0; q < PERM_VEC; q++) {
+      base[q] = __shfl_sync(0xffffffffu, base[q], __ffs(mask[q]) - 1);
+      if (k[q] >= 0) perm[start[q] + base[q] + __popc(mask[q] & ((1u << lane) - 1u))] = (int)(i0 + q);
+    }
   }
 }
 
@@ -189,7 +213,10 @@ void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *
   scan_tile_offsets_kernel<<<1, SCAN_THREADS, 0, s>>>(tileSum, nTiles, nDst);
   scan_write_kernel<<<nTiles, SCAN_THREADS, 0, s>>>(cellCount, nCells, tileSum, nDst, cellStart);
   cudaMemsetAsync(cellFill, 0, sizeof(int) * nCells, s);
-  if (perm) perm_kernel<<<pgrid, 256, 0, s>>>(src.key, nSrc, cellStart, cellFill, perm);
+  if (perm) {
+    const long long want = (nUpper + 256 * PERM_VEC - 1) / (256 * PERM_VEC);
+    perm_kernel<<<(int)(want > 148 * 8 ? 148 * 8 : want < 1 ? 1 : want), 256, 0, s>>>(src.key, nSrc, cellStart, cellFill, perm);
+  }
   else scatter_kernel<<<pgrid, 256, 0, s>>>(src, dst, nSrc, cellStart, cellFill);
   (*launches) += 4;
 }

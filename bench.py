@@ -231,6 +231,42 @@ def cpu_port_rate(n_cells, ppc, steps, threads, warmup=1, min_seconds=0.0, max_s
     return n, per_step
 
 
+def reference_code_rate(steps=6):
+    """The reference's OWN mover + deposit (PIC::Mover::MoveParticles -> Lapenta2017, ECSIM::UpdateJMassMatrix -> ProcessCell), compiled
+    from /root/reference at -O3 into oracle/_ref/libref_pic_O3.so (oracle/ref_pic/build_ref_pic.sh), timed on one host core on the box
+    it is built for: the reference's fast-wave test (16x8x4-cell blocks, 783 360 particles, one rank).  A cross-check of the CPU arm
+    (the port runs the bench's own box on all cores), not the arm itself: the box differs.  Runs in a child process (the reference's
+    state is global and it prints to stdout).  None when the library is not there."""
+    lib = os.path.join(ROOT, "oracle", "_ref", "libref_pic_O3.so")
+    if not os.path.exists(lib):
+        return None
+    code = (
+        "import sys, os, time, json, ctypes as C, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import oracle.ref_pic.ref_pic as rp\n"
+        f"rp.LIB = {lib!r}\n"
+        "r = rp.RefPic(); e = np.zeros(1); per = []\n"
+        f"for it in range({steps} + 1):\n"
+        "    t = time.perf_counter()\n"
+        "    with rp.quiet():\n"
+        "        r.lib.ref_pic_move(); r.lib.ref_pic_update_JM(e.ctypes.data_as(C.c_void_p))\n"
+        "    per.append(time.perf_counter() - t)\n"
+        "sys.stderr.write('REFCODE ' + json.dumps({'n': int(r.n_particles), 'per': per[1:]}) + '\\n')\n"
+    )
+    try:
+        out = subprocess.run([sys.executable, "-c", code], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=300)
+        rec = json.loads([l for l in out.stderr.splitlines() if l.startswith("REFCODE ")][-1][8:])
+    except Exception as exc:
+        return {"error": repr(exc)[:200]}
+    v = rec["n"] * len(rec["per"]) / sum(rec["per"])
+    cores = os.cpu_count() or 1
+    return {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
+            "all_cores_upper_bound": v * cores,
+            "sample": f"the reference's own code (oracle/_ref/libref_pic_O3.so, g++ -O3, one rank) on its fast-wave test box: {rec['n']} particles, "
+                      f"{len(rec['per'])} steps of MoveParticles + UpdateJMassMatrix; all_cores_upper_bound = value x {cores} host cores "
+                      "(MPI ranks without any exchange cost)"}
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path on the box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -254,6 +290,9 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    rc = reference_code_rate()
+    if rc is not None:
+        line["cpu_baseline"]["reference_code"] = rc
     _emit(line)
 
 
@@ -823,6 +862,9 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"the bench box itself: {args.cells}^3 cells x {args.ppc} ppc x 2 species = {n_cpu} particles, {len(per)} steps, "
                                           "oracle -O3 OpenMP"}
+        rc = reference_code_rate()
+        if rc is not None:
+            line["cpu_baseline"]["reference_code"] = rc
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

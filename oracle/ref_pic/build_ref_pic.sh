@@ -41,7 +41,8 @@ for d in ['pic', 'general', 'meshAMR', 'interface', 'species', 'models/exosphere
 PY
 B="$S/build"
 INC="-include $HERE/ref_pic_stubs.h -I$HERE -I$S/test/srcFastWave -I$B/pic -I$B/general -I$B/meshAMR -I$B/interface -I$B/models/exosphere -I$B/models/dust -I$B/species -I$B/models/surface -I$B/models/sputtering -I$B/models/charge_exchange -I$B/models/electron_impact -I$B/models/photolytic_reactions -I$S/srcInterface -I$HERE/../ref_mesh"
-FLAGS="-std=c++17 -w -O1 -ffp-contract=off -fPIC"
+# REF_PIC_OPT: the checker is built -O1 -ffp-contract=off (bit-stable arithmetic); the timing copy libref_pic_O3.so with -O3
+FLAGS="-std=c++17 -w ${REF_PIC_OPT:--O1 -ffp-contract=off} -fPIC"
 mkdir -p obj
 cat > cc.sh <<EOS
 #!/bin/bash
