@@ -59,7 +59,11 @@ struct DevMesh {
   // periodic "ghost" leaves that do not
   const int *depLeaf;  // [nLeaves]
   int nDepReal;
-
+  // structure cache of the coupler's AMR stencil (cplr_stencil.cuh; built by launch_build_cplr_cache at the first test-particle
+  // move on a refined mesh, nullptr before / when switched off)
+  const int *neib26;           // [nLeaves][27] node across (sx,sy,sz) in {-1,0,+1}^3 of the leaf's block (cs_neib), slot sx+1+3(sy+1)+9(sz+1)
+  const int *mbSlot;           // [nLeaves] table of the leaf's block as the coarse block of a multi-block stencil, -1 = none
+  const unsigned char *mbTab;  // [tables][(N0+2)(N1+2)(N2+2)][MB_ENTRY]
 };
 
 struct DevSpecies {
@@ -118,6 +122,10 @@ enum : unsigned {
   DEP_SPARE_SMS = 16,  // leave a few SMs to concurrently running exchange kernels
   DEP_ALL = DEP_ZERO_JM | DEP_ZERO_DIAG | DEP_GHOST_PASS | DEP_FINAL
 };
+
+// mover_tp.cu: fills neib26 [nLeaves][27] and the tables of the nTab leaves tabLeaf[] (MB_ENTRY bytes per dual cell)
+size_t cplr_cache_table_bytes(const DevMesh &m);
+void launch_build_cplr_cache(const DevMesh &m, int *neib26, const int *tabLeaf, int nTab, unsigned char *tab, cudaStream_t s);
 
 // launch helpers (defined per TU that needs them)
 // field_solver.cu

@@ -81,6 +81,11 @@ struct amps_gpu_ctx {
   double *d_gcaVar = nullptr, *d_gcaTile = nullptr;  // relativistic GCA: 15 drift variables per centre node
   bool gcaReady = false;
   bool meshRefined = false;  // some leaf is below level 0
+  std::vector<int> h_leafNeib;   // [nLeaves] LeafGeo::neib (which blocks get a table of the coupler's stencil cache)
+  std::vector<int> h_leafLevel;
+  bool cplrCacheTried = false;   // build_cplr_cache ran for this mesh (it may have declined: table too large / switched off)
+  int *d_neib26 = nullptr, *d_mbSlot = nullptr, *d_mbLeaf = nullptr;
+  unsigned char *d_mbTab = nullptr;
   unsigned char *d_redoMask = nullptr;  // particles the fast mover left to the exact kernel
   int *d_perm = nullptr;      // sorted position -> slot (fused sort + deposit inside amps_gpu_step)
   double *d_rho = nullptr;    // ComputeNetCharge: rho_new on the unique centre nodes
@@ -423,6 +428,8 @@ static int release_mesh(amps_gpu_ctx *ctx) {
   drop(ctx->d_gcaVar), drop(ctx->d_gcaTile), drop(ctx->d_gradBVar), drop(ctx->d_gradBTile);
   drop(ctx->d_leafRedo), drop(ctx->d_rho), drop(ctx->d_spec), drop(ctx->d_phi), drop(ctx->d_sample), drop(ctx->d_nSampled), drop(ctx->d_pack);
   drop(ctx->d_bgE), drop(ctx->d_bgB), drop(ctx->d_bgTile);
+  drop(ctx->d_neib26), drop(ctx->d_mbSlot), drop(ctx->d_mbLeaf), drop(ctx->d_mbTab);
+  ctx->cplrCacheTried = false;
   drop(ctx->d_sendBuf), drop(ctx->d_recvBuf), drop(ctx->d_sendCount), drop(ctx->d_allCounts), drop(ctx->d_errFlag);
   for (int *&p : ctx->d_sharedUid) drop(p);
   ctx->d_sharedUid.clear(), ctx->nShared.clear(), ctx->h_sharedUid.clear();
@@ -478,6 +485,8 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
 
   // per-leaf geometry
   std::vector<LeafGeo> lg(m.nLeaves);
+  ctx->h_leafNeib.assign((size_t)m.nLeaves, 0), ctx->h_leafLevel.assign((size_t)m.nLeaves, 0);
+  ctx->cplrCacheTried = false;
   for (int l = 0; l < m.nLeaves; l++) {
     const int n = mesh->leaf_node[l];
     if (n < 0 || n >= m.nNodes) FAIL(AMPS_GPU_ERR_ARG, "leaf_node out of range");
@@ -539,6 +548,7 @@ int amps_gpu_mesh_upload(amps_gpu_ctx *ctx, const amps_gpu_mesh *mesh) {
             }
       }
       g.neib = (mn & 0xffff) | ((mx & 0xffff) << 16);
+      ctx->h_leafNeib[l] = g.neib, ctx->h_leafLevel[l] = g.level;
     }
     {
       double vol = 1, d2 = 0;
@@ -1749,6 +1759,36 @@ int amps_gpu_cell_table_download(amps_gpu_ctx *ctx, int64_t *cell_start, int64_t
   return AMPS_GPU_OK;
 }
 
+// Structure cache of the coupler's AMR stencil (cplr_stencil.cuh): neighbour nodes of every block and, for every block that has a
+// finer neighbour (the coarse block of a multi-block stencil), the cells behind the 8 logical centres of each dual cell.  Built at
+// the first test-particle move on a refined mesh; AMPS_GPU_CPLR_CACHE=0 keeps the uncached path (the equivalence test).
+static int build_cplr_cache(amps_gpu_ctx *ctx) {
+  ctx->cplrCacheTried = true;
+  const char *sw = getenv("AMPS_GPU_CPLR_CACHE");
+  if (sw && atoi(sw) == 0) return AMPS_GPU_OK;
+  DevMesh &m = ctx->dm;
+  std::vector<int> slot((size_t)m.nLeaves, -1), tabLeaf;
+  for (int l = 0; l < m.nLeaves; l++) {
+    const int mx = (int)(short)((ctx->h_leafNeib[l] >> 16) & 0xffff);
+    if (mx > ctx->h_leafLevel[l]) slot[l] = (int)tabLeaf.size(), tabLeaf.push_back(l);
+  }
+  const size_t bytes = cplr_cache_table_bytes(m) * tabLeaf.size();
+  if (bytes > ((size_t)8 << 30)) return AMPS_GPU_OK;  // declined: the stencils are built per particle
+  int rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_neib26, (size_t)m.nLeaves * 27))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_mbSlot, (size_t)m.nLeaves))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_mbLeaf, tabLeaf.size() + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_mbTab, bytes + 8))) return rc;
+  CK(cudaMemcpyAsync(ctx->d_mbSlot, slot.data(), sizeof(int) * slot.size(), cudaMemcpyHostToDevice, ctx->stream));
+  if (!tabLeaf.empty()) CK(cudaMemcpyAsync(ctx->d_mbLeaf, tabLeaf.data(), sizeof(int) * tabLeaf.size(), cudaMemcpyHostToDevice, ctx->stream));
+  launch_build_cplr_cache(m, ctx->d_neib26, ctx->d_mbLeaf, (int)tabLeaf.size(), ctx->d_mbTab, ctx->stream);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));  // slot / tabLeaf are locals
+  m.neib26 = ctx->d_neib26, m.mbSlot = ctx->d_mbSlot, m.mbTab = ctx->d_mbTab;
+  return AMPS_GPU_OK;
+}
+
 static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "move before mesh upload");
   tighten_upper(ctx, false);
@@ -1784,6 +1824,11 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
          "ECSIM on a refined mesh needs _PIC_FIELD_SOLVER_B_CORNER_BASED_: with centre-based B the reference indexes the start block's "
          "buffer with stencil ids of other blocks (pic_mover_boris.cpp:975-990)");
   if (mover_id != AMPS_MOVER_LAPENTA2017 && !ctx->backgroundReady) FAIL(AMPS_GPU_ERR_STATE, "the test-particle movers need amps_gpu_background_upload");
+  if (mover_id != AMPS_MOVER_LAPENTA2017 && ctx->meshRefined && !ctx->cplrCacheTried &&
+      ctx->cfg.coupler_interpolation == AMPS_CPLR_CELL_CENTERED_LINEAR) {
+    int rc;
+    if ((rc = build_cplr_cache(ctx))) return rc;
+  }
   const DevMesh &m = ctx->dm;
   ProfScope prof(ctx, AMPS_GPU_PHASE_MOVE);
   CK(cudaMemsetAsync(ctx->d_cellCount, 0, sizeof(int) * (size_t)ctx->nCells, ctx->stream));

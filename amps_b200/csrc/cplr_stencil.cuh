@@ -14,6 +14,12 @@
 // (LeafGeo::neib); include after find_tree_node_plain / find_cell_index.
 #pragma once
 
+// CPLR_INLINE: the kernels that include this header grew to 17 000 instructions with everything inlined (instruction-cache bound,
+// profiles/r2_tp_movers_ncu_summary.txt); the three stencil builders are calls now
+#ifndef CPLR_INLINE
+#define CPLR_INLINE __noinline__
+#endif
+
 namespace amps {
 
 constexpr int CPLR_MAX_STENCIL = 64;  // nMaxStencilLength, pic.h:7185
@@ -71,7 +77,7 @@ __device__ __forceinline__ void cs_add_physical(const DevMesh &m, BgStencil &S, 
 __device__ __forceinline__ void cs_flush(BgStencil &S) { S.n = 0, S.uid = 1, S.overflow = 0; }
 
 // Constant::InitStencil; false where the reference exit()s
-__device__ __forceinline__ bool cs_constant(const DevMesh &m, const double x[3], int node, BgStencil &S) {
+__device__ CPLR_INLINE bool cs_constant(const DevMesh &m, const double x[3], int node, BgStencil &S) {
   cs_flush(S);
   if (node < 0 || m.nodeLeaf[node] < 0) return false;
   int ijk[3];
@@ -83,7 +89,7 @@ __device__ __forceinline__ bool cs_constant(const DevMesh &m, const double x[3],
 }
 
 // GetTriliniarInterpolationStencil; tableLen points at the Length the reference tests at :903 (StencilTable->Length)
-__device__ __forceinline__ bool cs_trilinear(const DevMesh &m, const double loc[3], const double x[3], int node, BgStencil &S, const int *tableLen) {
+__device__ CPLR_INLINE bool cs_trilinear(const DevMesh &m, const double loc[3], const double x[3], int node, BgStencil &S, const int *tableLen) {
   if (m.nodeLeaf[node] < 0) return false;
   cs_flush(S);
   int o[3];
@@ -114,7 +120,12 @@ __device__ __forceinline__ bool cs_trilinear(const DevMesh &m, const double loc[
 }
 
 // GetTriliniarInterpolationMutiBlockStencil
-__device__ __forceinline__ bool cs_multiblock(const DevMesh &m, const double x[3], int node, BgStencil &S) {
+__device__ __forceinline__ bool cs_multiblock_cached(const DevMesh &m, const double x[3], int node, BgStencil &S, bool &ok);
+__device__ CPLR_INLINE bool cs_multiblock(const DevMesh &m, const double x[3], int node, BgStencil &S) {
+  {
+    bool ok;
+    if (cs_multiblock_cached(m, x, node, S, ok)) return ok;
+  }
   cs_flush(S);
   double dxCell[3], xLoc[3], nlo[3];
   int ijkMin[3];
@@ -171,9 +182,135 @@ __device__ __forceinline__ bool cs_multiblock(const DevMesh &m, const double x[3
   return true;
 }
 
+// ---- structure cache of cs_multiblock -------------------------------------------------------------------------------------------
+// Which cells the 8 logical coarse centres of a multi-block stencil resolve to (one coarse cell, the 8 fine cells that cover it, or
+// nothing) depends on the coarse block and on the dual cell ijkMin in [-1, N]^3 only, not on the point: 8 tree searches, up to 64
+// centre look-ups and the duplicate search of AddPhysicalStencilCell per particle and sub-step (16 000 instructions of a divergent
+// warp, profiles/r2_tp_movers_*) become a table entry that is replayed with the point's trilinear weights in the same order, so
+// the weights are bit-identical to the uncached path (tests/test_cplr_cache_gpu.py).
+constexpr int MB_ENTRY = 392;  // int hdr (adds | uniques << 8 | flags << 16), int pad, int uid[64], u8 slot[64], u8 code[64]
+constexpr int MB_UID = 8, MB_SLOT = 8 + 256, MB_CODE = 8 + 256 + 64;
+constexpr int MB_FALLBACK = 1, MB_OVERFLOW = 2;  // hdr flags: a logical centre had no geometry / physical cell; Length hit nMaxStencilLength
+constexpr int MB_FINE = 8, MB_FIRST = 16;        // code bits next to the corner number 4 di + 2 dj + dk
+
+__device__ __forceinline__ int mb_entries(const DevMesh &m) { return (m.N[0] + 2) * (m.N[1] + 2) * (m.N[2] + 2); }
+
+// the structure of cs_multiblock(m, *, node, *) for the dual cell ijkMin, written to ent[MB_ENTRY]
+__device__ inline void cs_multiblock_structure(const DevMesh &m, int node, const int ijkMin[3], unsigned char *ent) {
+  int *uid = reinterpret_cast<int *>(ent + MB_UID);
+  int nAdds = 0, nU = 0, flags = 0;
+  double dxCell[3], nlo[3];
+  const int nodeLevel = m.nodeLevel[node];
+  for (int d = 0; d < 3; d++) {
+    nlo[d] = m.nxmin[3 * node + d];
+    dxCell[d] = (m.nxmax[3 * node + d] - nlo[d]) / m.N[d];
+  }
+  auto add = [&](int id, int code, int owner, const int ijk[3]) {  // cs_add_physical
+    for (int e = 0; e < nU; e++)
+      if (uid[e] == id) {
+        ent[MB_SLOT + nAdds] = (unsigned char)e, ent[MB_CODE + nAdds] = (unsigned char)code;
+        nAdds++;
+        return;
+      }
+    if (nU == CPLR_MAX_STENCIL) {
+      flags |= MB_OVERFLOW;
+      return;
+    }
+    if (cs_center_outside(m, owner, ijk)) return;
+    uid[nU] = id;
+    ent[MB_SLOT + nAdds] = (unsigned char)nU, ent[MB_CODE + nAdds] = (unsigned char)(code | MB_FIRST);
+    nAdds++, nU++;
+  };
+  for (int di = 0; di < 2; di++)
+    for (int dj = 0; dj < 2; dj++)
+      for (int dk = 0; dk < 2; dk++) {
+        const int corner = 4 * di + 2 * dj + dk;
+        const int ijk[3] = {ijkMin[0] + di, ijkMin[1] + dj, ijkMin[2] + dk};
+        double xLogical[3];
+        for (int d = 0; d < 3; d++) xLogical[d] = nlo[d] + (ijk[d] + 0.5) * dxCell[d];
+        const int sn = find_tree_node_plain(m, xLogical, node);
+        if (sn < 0 || !(m.nodeFlags[sn] & AMPS_NODE_USED)) {
+          flags |= MB_FALLBACK;
+          continue;
+        }
+        if (m.nodeLevel[sn] == nodeLevel) {
+          const int id = cs_center_uid(m, node, ijk);
+          if (id >= 0) add(id, corner, node, ijk);
+          else flags |= MB_FALLBACK;
+        } else {
+          int iNeib[3];
+          for (int d = 0; d < 3; d++) iNeib[d] = 2 * ((int)((xLogical[d] - m.nxmin[3 * sn + d]) / dxCell[d]));
+          for (int ii = 0; ii < 2; ii++)
+            for (int jj = 0; jj < 2; jj++)
+              for (int kk = 0; kk < 2; kk++) {
+                const int f[3] = {iNeib[0] + ii, iNeib[1] + jj, iNeib[2] + kk};
+                const int id = cs_center_uid(m, sn, f);
+                if (id >= 0) add(id, corner | MB_FINE, sn, f);
+                else flags |= MB_FALLBACK;
+              }
+        }
+      }
+  *reinterpret_cast<int *>(ent) = nAdds | (nU << 8) | (flags << 16);
+}
+
+// cs_multiblock through the table of the coarse block; false = no table for this block / dual cell (the caller builds the stencil)
+__device__ __forceinline__ bool cs_multiblock_cached(const DevMesh &m, const double x[3], int node, BgStencil &S, bool &ok) {
+  if (m.mbSlot == nullptr) return false;
+  const int leaf = m.nodeLeaf[node];
+  if (leaf < 0) return false;
+  const int tab = m.mbSlot[leaf];
+  if (tab < 0) return false;
+  double xLoc[3];
+  int ijkMin[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const double nlo = m.nxmin[3 * node + d];
+    const double dxCell = (m.nxmax[3 * node + d] - nlo) / m.N[d];
+    ijkMin[d] = (x[d] - nlo < 0.5 * dxCell) ? -1 : (int)((x[d] - nlo - 0.5 * dxCell) / dxCell);
+    if (ijkMin[d] > m.N[d]) return false;
+    const double xLower = nlo + (ijkMin[d] + 0.5) * dxCell;
+    xLoc[d] = (x[d] - xLower) / dxCell;
+    if (xLoc[d] < 0.0) xLoc[d] = 0.0;
+    if (xLoc[d] > 1.0) xLoc[d] = 1.0;
+  }
+  const int e = (ijkMin[0] + 1) + (m.N[0] + 2) * ((ijkMin[1] + 1) + (m.N[1] + 2) * (ijkMin[2] + 1));
+  const unsigned char *ent = m.mbTab + ((size_t)tab * mb_entries(m) + e) * MB_ENTRY;
+  const int hdr = *reinterpret_cast<const int *>(ent);
+  const int nAdds = hdr & 255, nU = (hdr >> 8) & 255, flags = hdr >> 16;
+  cs_flush(S);
+  ok = true;
+  if (flags & MB_FALLBACK) {
+    const int in = find_tree_node_plain(m, x, node);
+    if (in >= 0 && m.nodeLeaf[in] >= 0) ok = cs_constant(m, x, in, S);
+    return true;
+  }
+  double W[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const double wi = (c & 4) ? xLoc[0] : 1.0 - xLoc[0], wj = (c & 2) ? xLoc[1] : 1.0 - xLoc[1], wk = (c & 1) ? xLoc[2] : 1.0 - xLoc[2];
+    W[c] = wi * wj * wk;
+  }
+  const int *uid = reinterpret_cast<const int *>(ent + MB_UID);
+  for (int q = 0; q < nU; q++) S.nd[q] = uid[q];
+  for (int k = 0; k < nAdds; k++) {
+    const int code = ent[MB_CODE + k], slot = ent[MB_SLOT + k];
+    double w = W[code & 7];
+    if (code & MB_FINE) w = (1.0 / 8.0) * w;
+    if (code & MB_FIRST) S.w[slot] = w;
+    else S.w[slot] += w;
+  }
+  S.n = nU;
+  S.overflow = (flags & MB_OVERFLOW) ? 1 : 0;
+  return true;
+}
+
 // neighbours through face / edge / corner, first segment (GetNeibFace(f,0,0), GetNeibEdge(e,0), GetNeibCorner(c))
-__device__ __forceinline__ int cs_neib(const DevMesh &m, int node, const int side[3]) {
+__device__ CPLR_INLINE int cs_neib(const DevMesh &m, int node, const int side[3]) {
   // side[d]: -1 beyond the low face, +1 beyond the high face, 0 = at the block's low index
+  if (m.neib26 != nullptr) {
+    const int leaf = m.nodeLeaf[node];
+    if (leaf >= 0) return m.neib26[(size_t)leaf * 27 + (side[0] + 1) + 3 * (side[1] + 1) + 9 * (side[2] + 1)];
+  }
   int ix[3];
 #pragma unroll
   for (int d = 0; d < 3; d++) {

@@ -384,6 +384,33 @@ __global__ void __launch_bounds__(128) move_relativistic_boris_kernel(DevMesh m,
   flush_move_counters(stats, nMoved, nXCell, nXBlock, nLeft, nNotUsed, nWrap, nErr);
 }
 
+// ---- structure cache of the AMR stencil (cplr_stencil.cuh): one thread per neighbour slot / per dual cell of a tabulated block ----
+__global__ void __launch_bounds__(128) build_cplr_cache_kernel(DevMesh m, int *__restrict__ neib26, const int *__restrict__ tabLeaf, int nTab,
+                                                              unsigned char *__restrict__ tab) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nNeib = (long long)m.nLeaves * 27;
+  if (t < nNeib) {
+    const int leaf = (int)(t / 27), q = (int)(t - 27LL * leaf);
+    const int side[3] = {q % 3 - 1, (q / 3) % 3 - 1, q / 9 - 1};
+    neib26[t] = cs_neib(m, m.leaf[leaf].node, side);  // m.neib26 is still null here: the lattice probe itself
+    return;
+  }
+  const long long u = t - nNeib;
+  const int nEnt = mb_entries(m);
+  if (u >= (long long)nTab * nEnt) return;
+  const int it = (int)(u / nEnt), e = (int)(u - (long long)it * nEnt);
+  const int n0 = m.N[0] + 2, n1 = m.N[1] + 2;
+  const int ijkMin[3] = {e % n0 - 1, (e / n0) % n1 - 1, e / (n0 * n1) - 1};
+  cs_multiblock_structure(m, m.leaf[tabLeaf[it]].node, ijkMin, tab + (size_t)u * MB_ENTRY);
+}
+size_t cplr_cache_table_bytes(const DevMesh &m) { return (size_t)(m.N[0] + 2) * (m.N[1] + 2) * (m.N[2] + 2) * MB_ENTRY; }
+void launch_build_cplr_cache(const DevMesh &m, int *neib26, const int *tabLeaf, int nTab, unsigned char *tab, cudaStream_t s) {
+  DevMesh bare = m;
+  bare.neib26 = nullptr, bare.mbSlot = nullptr, bare.mbTab = nullptr;
+  const long long n = (long long)m.nLeaves * 27 + (long long)nTab * (m.N[0] + 2) * (m.N[1] + 2) * (m.N[2] + 2);
+  build_cplr_cache_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(bare, neib26, tabLeaf, nTab, tab);
+}
+
 void launch_move_relativistic_boris(const DevMesh &m, const DevSpecies &sp, int interp, int backward, double c, double rSphere, long long exitCap,
                                     ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *uE, const double *uB,
                                     int *cellCount, DevMoveStats *stats, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount,
@@ -789,7 +816,10 @@ void launch_magnetic_moment_set(ParticleSoA p, double *target, const int *nSlots
   magnetic_moment_set_kernel<<<(int)g, 256, 0, s>>>(p, target, nSlots, muByPtr, nMu);
 }
 
-__global__ void __launch_bounds__(128) move_relativistic_gca_kernel(DevMesh m, DevSpecies sp, TpParams tp, ParticleSoA p, const int *__restrict__ nSlots,
+#ifndef GCA_MIN_CTAS
+#define GCA_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(128, GCA_MIN_CTAS) move_relativistic_gca_kernel(DevMesh m, DevSpecies sp, TpParams tp, ParticleSoA p, const int *__restrict__ nSlots,
                                                                    const double *__restrict__ bgTile, const double *__restrict__ gcaTile,
                                                                    const double *__restrict__ uVar, int *__restrict__ cellCount, DevMoveStats *__restrict__ stats,
                                                                    amps_gpu_exit_record *__restrict__ exitBuf, unsigned long long *__restrict__ exitCount) {

@@ -296,7 +296,7 @@ def run_reference(args):
     _emit(line)
 
 
-def bench_test_particle_movers(torch, n_particles=2_000_000):
+def bench_test_particle_movers(torch, n_particles=2_000_000, presort=True, only=None):
     """BASELINE configs[0] / [4] (scaled): pushes/s of the test-particle movers on one GPU, extra information next to the
     headline line.  Relativistic Boris: protons traced backward in a dipole on a 3-level AMR mesh with 4^3-cell blocks, sub-cycled
     by the local gyro period (pushes counted as mover calls, sub-cycles not counted).  Relativistic GCA: the MoverTest field
@@ -312,6 +312,8 @@ def bench_test_particle_movers(torch, n_particles=2_000_000):
                                         boundary=_capi.BOUNDARY_DELETE),
     }
     for name, c in cases.items():
+        if only is not None and name != only:
+            continue
         m, parts = wl.dipole_test_particles(n_particles, **c["kw"])
         bc = c["kw"].get("block_cells", (4, 4, 4))
         gc = c["kw"].get("ghost_cells", (1, 1, 1))
@@ -332,6 +334,8 @@ def bench_test_particle_movers(torch, n_particles=2_000_000):
         best = None
         for rep in range(3):
             ctx.particles_upload(*parts)
+            if presort:  # the mover's input comes from the reference's per-cell lists: cell order, not the generator's random order
+                ctx.sort()
             if gca:
                 ctx.InitiateMagneticMoment(_capi.MOVER_RELATIVISTIC_GCA)
             ctx.profile(True)
@@ -343,6 +347,7 @@ def bench_test_particle_movers(torch, n_particles=2_000_000):
         out[name] = {"pushes_per_s": n_particles / (best * 1e-3), "ms_per_move": best, "particles": n_particles,
                      "alg_bytes_per_push": 113.0 if gca else 105.0,
                      "achieved_gbs": (113.0 if gca else 105.0) * n_particles / (best * 1e-3) / 1e9,
+                     "input_order": "by cell (sorted after the upload)" if presort else "random",
                      "left_domain": st["n_left_domain"], "errors": st["n_error"], "sub_steps": st["n_sub_steps"],
                      "sub_steps_per_s": (st["n_sub_steps"] / (best * 1e-3)) if st["n_sub_steps"] else None,
                      "mesh": f"{m.c.n_leaves} blocks of {bc[0]}^3 cells, levels {sorted(set(int(v) for v in m.leaf_level()))}"}
