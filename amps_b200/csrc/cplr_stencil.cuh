@@ -39,6 +39,12 @@ __device__ __forceinline__ bool leaf_single_level(const LeafGeo &lg) { return le
 // cStencilGeneric::AddCell: a centre outside the global box is not added (non-periodic), pic.h:7235-7245
 __device__ __forceinline__ bool cs_center_outside(const DevMesh &m, int node, const int ijk[3]) {
   if (m.periodic) return false;
+  {
+    // a block with a neighbour across every face lies inside the box in all three directions with a margin of half its width (the
+    // neighbour is at most one level finer), and so do the centres of its ghost layers while g - 1/2 < N/2
+    const int leaf = m.nodeLeaf[node];
+    if (leaf >= 0 && m.leaf[leaf].face == 0 && 2 * m.g[0] - 1 < m.N[0] && 2 * m.g[1] - 1 < m.N[1] && 2 * m.g[2] - 1 < m.N[2]) return false;
+  }
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     const double lo = m.nxmin[3 * node + d], hi = m.nxmax[3 * node + d];

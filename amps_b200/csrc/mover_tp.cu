@@ -169,7 +169,10 @@ struct TpParams {
   CplrUnique U;
 };
 
-__global__ void __launch_bounds__(128) move_relativistic_boris_kernel(DevMesh m, DevSpecies sp, TpParams tp, ParticleSoA p, const int *__restrict__ nSlots,
+#ifndef TP_MIN_CTAS
+#define TP_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(128, TP_MIN_CTAS) move_relativistic_boris_kernel(DevMesh m, DevSpecies sp, TpParams tp, ParticleSoA p, const int *__restrict__ nSlots,
                                                                      const double *__restrict__ bgTile, int *__restrict__ cellCount,
                                                                      DevMoveStats *__restrict__ stats, amps_gpu_exit_record *__restrict__ exitBuf,
                                                                      unsigned long long *__restrict__ exitCount) {
