@@ -67,6 +67,8 @@ class Config(C.Structure):
         ("exact_arithmetic", C.c_int32),
         ("carry_v_parallel", C.c_int32),
         ("ideal_mhd", C.c_int32),
+        ("gc_species_mask", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 
@@ -187,6 +189,7 @@ PROTOTYPES = {
     "amps_gpu_deposit_JM": (C.c_int, [_vp, _vp, _vp]),
     "amps_gpu_diagnostics": (C.c_int, [_vp, _vp, _vp]),
     "amps_gpu_v_parallel_upload": (C.c_int, [_vp, _vp, C.c_int64]),
+    "amps_gpu_v_normal_upload": (C.c_int, [_vp, _vp, C.c_int64]),
     "amps_gpu_v_parallel_download": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "amps_gpu_net_charge": (C.c_int, [_vp, C.c_double, _vp]),
     "amps_gpu_JM_packed_slots": (C.POINTER(C.c_int32), []),

@@ -53,6 +53,7 @@ def make_config(block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), charge=(-1.0, 1.0)
     cfg.carry_magnetic_moment = 0
     cfg.carry_v_parallel = 0
     cfg.ideal_mhd = 1
+    cfg.gc_species_mask = 0
     cfg.exact_arithmetic = 0
     return cfg
 
@@ -144,6 +145,11 @@ class Context:
         k = C.c_int64()
         self._ck(self.lib.amps_gpu_magnetic_moment_download(self._h, _ptr(mu), mu.shape[0], C.byref(k)))
         return mu[: int(k.value)]
+
+    def v_normal_upload(self, vnormal_by_ptr):
+        """PB::GetVNormal of the guiding-centre species by ParticleBuffer slot (read by the deposit's diagnostics)"""
+        a = np.ascontiguousarray(vnormal_by_ptr, dtype=np.float64)
+        self._ck(self.lib.amps_gpu_v_normal_upload(self._h, _ptr(a), a.shape[0]))
 
     def v_parallel_upload(self, vpar_by_ptr):
         a = np.ascontiguousarray(vpar_by_ptr, dtype=np.float64)

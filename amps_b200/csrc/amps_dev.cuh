@@ -120,12 +120,17 @@ enum : unsigned {
   DEP_GHOST_PASS = 4,  // (gather) also copy the particles of the periodic ghost leaves into the sorted store
   DEP_FINAL = 8,       // last range of a deposit: run the >2-species diagnostics pass
   DEP_SPARE_SMS = 16,  // leave a few SMs to concurrently running exchange kernels
+  DEP_NO_DIAG = 32,    // neither the fused nor the separate energy / cfl pass (guiding-centre species: launch_gc_deposit does them)
   DEP_ALL = DEP_ZERO_JM | DEP_ZERO_DIAG | DEP_GHOST_PASS | DEP_FINAL
 };
 
 // mover_tp.cu: fills neib26 [nLeaves][27] and the tables of the nTab leaves tabLeaf[] (MB_ENTRY bytes per dual cell)
 size_t cplr_cache_table_bytes(const DevMesh &m);
 void launch_build_cplr_cache(const DevMesh &m, int *neib26, const int *tabLeaf, int nTab, unsigned char *tab, cudaStream_t s);
+
+// deposit_gc.cu: the guiding-centre species of cfg.gc_species_mask + the energy / cfl diagnostics of all species, on the sorted store
+void launch_gc_deposit(const DevMesh &m, const DevSpecies &sp, unsigned gcMask, ParticleSoA p, const int *cellStart, const double *bCurTile,
+                       const double *vnByPtr, long long nVn, double *J, double *energy, unsigned long long *cflBits, int nSM, cudaStream_t s);
 
 // launch helpers (defined per TU that needs them)
 // field_solver.cu

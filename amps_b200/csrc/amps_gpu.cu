@@ -83,6 +83,8 @@ struct amps_gpu_ctx {
   bool meshRefined = false;  // some leaf is below level 0
   std::vector<int> h_leafNeib;   // [nLeaves] LeafGeo::neib (which blocks get a table of the coupler's stencil cache)
   std::vector<int> h_leafLevel;
+  double *d_vnByPtr = nullptr;   // PB::GetVNormal by ParticleBuffer slot (guiding-centre species of the deposit)
+  long long nVn = 0;
   bool cplrCacheTried = false;   // build_cplr_cache ran for this mesh (it may have declined: table too large / switched off)
   int *d_neib26 = nullptr, *d_mbSlot = nullptr, *d_mbLeaf = nullptr;
   unsigned char *d_mbTab = nullptr;
@@ -371,6 +373,7 @@ int amps_gpu_finalize(amps_gpu_ctx *ctx) {
   for (void *q : ctx->h_peerMapped)
     if (q) cudaIpcCloseMemHandle(q);
   cudaFree(ctx->d_peerRecv), cudaFree(ctx->d_sentRecv);
+  cudaFree(ctx->d_vnByPtr), cudaFree(ctx->d_neib26), cudaFree(ctx->d_mbSlot), cudaFree(ctx->d_mbLeaf), cudaFree(ctx->d_mbTab);
   if (ctx->h_errLazy) cudaFreeHost(ctx->h_errLazy);
   if (ctx->evSorted) cudaEventDestroy(ctx->evSorted);
   if (ctx->h_nSorted) cudaFreeHost(ctx->h_nSorted);
@@ -1181,6 +1184,19 @@ int amps_gpu_magnetic_moment_upload(amps_gpu_ctx *ctx, const double *mu_by_ptr, 
   if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "magnetic_moment_upload needs cfg.carry_magnetic_moment");
   return upload_by_ptr(ctx, false, mu_by_ptr, n);
 }
+int amps_gpu_v_normal_upload(amps_gpu_ctx *ctx, const double *vnormal_by_ptr, int64_t n) {
+  if (!ctx || !vnormal_by_ptr || n < 0) return AMPS_GPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_vnByPtr) cudaFree(ctx->d_vnByPtr);
+  ctx->d_vnByPtr = nullptr, ctx->nVn = 0;
+  int rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_vnByPtr, (size_t)n))) return rc;
+  CK(cudaMemcpyAsync(ctx->d_vnByPtr, vnormal_by_ptr, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->nVn = n;
+  return AMPS_GPU_OK;
+}
 int amps_gpu_v_parallel_upload(amps_gpu_ctx *ctx, const double *vpar_by_ptr, int64_t n) {
   if (!ctx || !vpar_by_ptr || n < 0) return AMPS_GPU_ERR_ARG;
   if (!ctx->cfg.carry_v_parallel) FAIL(AMPS_GPU_ERR_STATE, "v_parallel_upload needs cfg.carry_v_parallel");
@@ -1299,12 +1315,38 @@ static int rebuild_deposit_order(amps_gpu_ctx *ctx) {
   return AMPS_GPU_OK;
 }
 
+// Guiding-centre species of the deposit (cfg.gc_species_mask): deposit_kernel sees them with zero charge (nothing to J, M) and runs
+// without its diagnostics; launch_gc_deposit then adds their explicit current, the magnetisation closure and the diagnostics of all
+// species from the sorted store.
+static int gc_check(amps_gpu_ctx *ctx) {
+  if (!ctx->cfg.gc_species_mask) return AMPS_GPU_OK;
+  if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "cfg.gc_species_mask needs cfg.carry_magnetic_moment (the closure deposits mu b)");
+  if (ctx->nRanks > 1) FAIL(AMPS_GPU_ERR_STATE, "the guiding-centre species of the ECSIM deposit are built for one rank");
+  return AMPS_GPU_OK;
+}
+static DevSpecies deposit_species(const amps_gpu_ctx *ctx) {
+  DevSpecies sp = ctx->sp;
+  for (int s = 0; s < sp.n; s++)
+    if ((ctx->cfg.gc_species_mask >> s) & 1) sp.charge[s] = 0.0;
+  return sp;
+}
+static unsigned gc_dep_flags(const amps_gpu_ctx *ctx) { return ctx->cfg.gc_species_mask ? (unsigned)DEP_NO_DIAG : 0u; }
+static int gc_pass(amps_gpu_ctx *ctx, const ParticleSoA &sorted) {
+  if (!ctx->cfg.gc_species_mask) return AMPS_GPU_OK;
+  launch_gc_deposit(ctx->dm, ctx->sp, (unsigned)ctx->cfg.gc_species_mask, sorted, ctx->d_cellStart, ctx->d_bCurTile, ctx->d_vnByPtr, ctx->nVn, ctx->d_J,
+                    ctx->d_energy, ctx->d_cfl, ctx->nSM, ctx->stream);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return AMPS_GPU_OK;
+}
+
 static int do_sort_deposit_fused(amps_gpu_ctx *ctx) {
   if (!ctx->meshReady || !ctx->fieldsReady) FAIL(AMPS_GPU_ERR_STATE, "deposit before mesh/fields upload");
   if (ctx->meshRefined && ctx->cfg.b_mode == AMPS_B_CENTER_BASED)
     FAIL(AMPS_GPU_ERR_STATE, "ECSIM on a refined mesh needs _PIC_FIELD_SOLVER_B_CORNER_BASED_ (see amps_gpu_move)");
   int rc;
   if (!ctx->d_perm && (rc = dev_alloc(ctx, &ctx->d_perm, (size_t)ctx->cfg.capacity))) return rc;
+  if ((rc = gc_check(ctx))) return rc;
   if (ctx->depDirty && ctx->nRanks > 1) {
     CK(cudaStreamSynchronize(ctx->stream));
     if ((rc = rebuild_deposit_order(ctx))) return rc;
@@ -1332,10 +1374,11 @@ static int do_sort_deposit_fused(amps_gpu_ctx *ctx) {
       launch_deposit(ctx->dm, ctx->sp, src, ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl, ctx->nSM, ctx->d_perm,
                      dst, nB, -1, DEP_FINAL | DEP_SPARE_SMS, ctx->stream, &ctx->launches);
     } else {
-      launch_deposit(ctx->dm, ctx->sp, src, ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl, ctx->nSM, ctx->d_perm,
-                     dst, 0, -1, zero | DEP_ZERO_DIAG | DEP_GHOST_PASS | DEP_FINAL, ctx->stream, &ctx->launches);
+      launch_deposit(ctx->dm, deposit_species(ctx), src, ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl, ctx->nSM,
+                     ctx->d_perm, dst, 0, -1, zero | DEP_ZERO_DIAG | DEP_GHOST_PASS | DEP_FINAL | gc_dep_flags(ctx), ctx->stream, &ctx->launches);
     }
     CK(cudaGetLastError());
+    if ((rc = gc_pass(ctx, dst))) return rc;
   }
   ctx->cur = 1 - ctx->cur;
   ctx->sorted = true;
@@ -1940,9 +1983,17 @@ static int do_deposit(amps_gpu_ctx *ctx) {
   if (!ctx->sorted) FAIL(AMPS_GPU_ERR_STATE, "deposit needs the (block,cell)-sorted layout: call amps_gpu_sort");
   if (ctx->meshRefined && ctx->cfg.b_mode == AMPS_B_CENTER_BASED)
     FAIL(AMPS_GPU_ERR_STATE, "ECSIM on a refined mesh needs _PIC_FIELD_SOLVER_B_CORNER_BASED_ (see amps_gpu_move)");
+  {
+    int rcGc;
+    if ((rcGc = gc_check(ctx))) return rcGc;
+  }
   ProfScope prof(ctx, AMPS_GPU_PHASE_DEPOSIT);
-  launch_deposit(ctx->dm, ctx->sp, ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl,
-                 ctx->nSM, nullptr, ctx->buf[ctx->cur], 0, -1, DEP_ALL, ctx->stream, &ctx->launches);
+  launch_deposit(ctx->dm, deposit_species(ctx), ctx->buf[ctx->cur], ctx->d_cellStart, ctx->d_bCurTile, ctx->d_J, ctx->d_M, ctx->d_energy, ctx->d_cfl,
+                 ctx->nSM, nullptr, ctx->buf[ctx->cur], 0, -1, DEP_ALL | gc_dep_flags(ctx), ctx->stream, &ctx->launches);
+  {
+    int rcGc;
+    if ((rcGc = gc_pass(ctx, ctx->buf[ctx->cur]))) return rcGc;
+  }
   CK(cudaGetLastError());
   return AMPS_GPU_OK;
 }
@@ -2515,7 +2566,7 @@ static int do_step_JM(amps_gpu_ctx *ctx, int mover_id, double *J_host, double *M
   int rc;
   const bool packed = JM_packed_host != nullptr;
   if (packed && ctx->meshRefined) FAIL(AMPS_GPU_ERR_STATE, "the packed J/M rows pair the neighbour slots of equal cells: single-level meshes only");
-  if (ctx->nRanks > 1) {  // shared corners change in the exchange: no early download
+  if (ctx->nRanks > 1 || ctx->cfg.gc_species_mask) {  // shared corners change in the exchange / the guiding-centre pass adds to J: no early download
     if ((rc = amps_gpu_step(ctx, mover_id))) return rc;
     if (packed) return amps_gpu_JM_download_packed(ctx, JM_packed_host);
     return amps_gpu_JM_download(ctx, J_host, M_host);

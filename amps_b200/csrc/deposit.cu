@@ -682,7 +682,7 @@ void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const
   // DEP_SPARE_SMS: a few SMs stay free for the exchange kernels that run next to this launch
   const int grid = ((flags & DEP_SPARE_SMS) && nSM > 32 ? nSM - 8 : nSM) * DEP_CTAS_PER_SM;
   const size_t smem = sizeof(double) * DEP_WARPS * SLAB;
-  const bool corner = sp.bMode == AMPS_B_CORNER_BASED, diag = sp.n <= 2, gather = perm != nullptr;
+  const bool corner = sp.bMode == AMPS_B_CORNER_BASED, diag = sp.n <= 2 && !(flags & DEP_NO_DIAG), gather = perm != nullptr;
   const int ghostPass = (flags & DEP_GHOST_PASS) ? 1 : 0;
 #define AMPS_DEP_LAUNCH(CB, DG, GA)                                                                                          \
   do {                                                                                                                       \
@@ -699,7 +699,7 @@ void launch_deposit(const DevMesh &m, const DevSpecies &sp, ParticleSoA p, const
   }
 #undef AMPS_DEP_LAUNCH
   (*launches) += 1;
-  if (!diag && (flags & DEP_FINAL)) {
+  if (!diag && (flags & DEP_FINAL) && !(flags & DEP_NO_DIAG)) {
     // more than two species: the diagnostics run as their own pass over the SORTED store (after the last range)
     diag_kernel<<<nSM * 4, 256, 0, s>>>(m, sp, gather ? dst : p, cellStart, energy, cflBits);
     (*launches) += 1;

@@ -118,6 +118,11 @@ typedef struct amps_gpu_config {
   int32_t carry_v_parallel;          /* particles carry v_parallel (_PIC_PARTICLE_DATA__V_PARALLEL_OFFSET_, picParticleDataMacro.h): the reduced state
                                         of the gyrokinetic movers (needs carry_magnetic_moment as well)                     */
   int32_t ideal_mhd;                 /* _PIC__IDEAL_MHD_MODE_ (picGlobal.dfn:339, default ON): E.b = 0 in the guiding-centre parallel force */
+  int32_t gc_species_mask;           /* bit s: species s is a guiding-centre species of PIC::GYROKINETIC (IsGuidingCenterSpecies, pic.h:5052) in
+                                        ECSIM::ProcessCell (pic_field_solver_ecsim.cpp:2084): explicit current q v_eff, no mass matrix, the
+                                        magnetisation current curl(M) of :1828 and |v_normal|^2 in the energy / cfl diagnostics.  Needs
+                                        carry_magnetic_moment; one rank.  0 = _PIC_GYROKINETIC_MODEL_MODE_ off                       */
+  int32_t reserved0;
 } amps_gpu_config;
 
 /* _PIC_COUPLER__INTERPOLATION_MODE_ */
@@ -298,6 +303,9 @@ int amps_gpu_magnetic_moment_upload(amps_gpu_ctx *ctx, const double *mu_by_ptr, 
 int amps_gpu_magnetic_moment_download(amps_gpu_ctx *ctx, double *mu, int64_t n_max, int64_t *n);
 /* v_parallel of the gyrokinetic reduced state (PB::SetVParallel / GetVParallel), same conventions as the magnetic moment */
 int amps_gpu_v_parallel_upload(amps_gpu_ctx *ctx, const double *vpar_by_ptr, int64_t n);
+/* PB::GetVNormal of the guiding-centre species (cfg.gc_species_mask), by ParticleBuffer slot: read by the deposit's energy / cfl
+ * diagnostics (pic_field_solver_ecsim.cpp:2232-2235); the device never changes it.  Slots beyond n read 0. */
+int amps_gpu_v_normal_upload(amps_gpu_ctx *ctx, const double *vnormal_by_ptr, int64_t n);
 int amps_gpu_v_parallel_download(amps_gpu_ctx *ctx, double *vpar, int64_t n_max, int64_t *n);
 /* exit records accumulated by the movers since the last call (clears them) */
 int amps_gpu_exit_records(amps_gpu_ctx *ctx, amps_gpu_exit_record *buf, int64_t max_records, int64_t *n);

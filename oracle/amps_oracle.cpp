@@ -187,7 +187,10 @@ struct oracle_ctx {
   // ---- PIC::ParticleBuffer accessors, packed layout picParticleDataMacro.h:55-81 ----
   // + _PIC_PARTICLE_DATA__MAGNETIC_MOMENT_OFFSET_ (picParticleDataMacro.h:178-187) right after the basic data
   // + _PIC_PARTICLE_DATA__V_PARALLEL_OFFSET_ of the gyrokinetic reduced state behind it
-  enum { OFF_NEXT = 0, OFF_PREV = 8, OFF_SPEC = 16, OFF_V = 17, OFF_X = 41, OFF_W = 65, OFF_MU = 73, OFF_VPAR = 81, BASIC_LEN = 89 };
+  // + _PIC_PARTICLE_DATA__V_NORMAL_OFFSET_ (read by ProcessCell for guiding-centre species, pic_field_solver_ecsim.cpp:2233)
+  enum { OFF_NEXT = 0, OFF_PREV = 8, OFF_SPEC = 16, OFF_V = 17, OFF_X = 41, OFF_W = 65, OFF_MU = 73, OFF_VPAR = 81, OFF_VNORMAL = 89, BASIC_LEN = 97 };
+  static double GetVNormal(const byte *p) { double m; memcpy(&m, p + OFF_VNORMAL, 8); return m; }
+  static void SetVNormal(double m, byte *p) { memcpy(p + OFF_VNORMAL, &m, 8); }
   static double GetVParallel(const byte *p) { double m; memcpy(&m, p + OFF_VPAR, 8); return m; }
   static void SetVParallel(double m, byte *p) { memcpy(p + OFF_VPAR, &m, 8); }
   static double GetMagneticMoment(const byte *p) { double m; memcpy(&m, p + OFF_MU, 8); return m; }
@@ -2536,8 +2539,37 @@ struct oracle_ctx {
   }
 
   // ------------------------------------------------------------------------------------------
+  // ECSIM_AddGuidingCenterMagnetizationCurrentToCorners, src/pic/pic_field_solver_ecsim.cpp:1828-1875: J_c += sum_a grad N_a(x_c^-) x M_a
+  // with M_a = MCornerSum[a] / CellVolume and the one-sided gradients of the trilinear basis at the corner
+  static void AddGuidingCenterMagnetizationCurrentToCorners(cCellData *CellData, const double MCornerSum[8][3], double CellVolume, const double dx[3]) {
+    const int CornerBits[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+    double Mnode[8][3];
+    for (int iCorner = 0; iCorner < 8; iCorner++)
+      for (int d = 0; d < 3; d++) Mnode[iCorner][d] = MCornerSum[iCorner][d] / CellVolume;
+    for (int iTargetCorner = 0; iTargetCorner < 8; iTargetCorner++) {
+      const int uc = CornerBits[iTargetCorner][0], vc = CornerBits[iTargetCorner][1], wc = CornerBits[iTargetCorner][2];
+      double Jcorner[3] = {0.0, 0.0, 0.0};
+      for (int iSourceCorner = 0; iSourceCorner < 8; iSourceCorner++) {
+        const int ua = CornerBits[iSourceCorner][0], va = CornerBits[iSourceCorner][1], wa = CornerBits[iSourceCorner][2];
+        double dNdx = 0.0, dNdy = 0.0, dNdz = 0.0;
+        if ((va == vc) && (wa == wc)) dNdx = ((ua == 1) ? 1.0 : -1.0) / dx[0];
+        if ((ua == uc) && (wa == wc)) dNdy = ((va == 1) ? 1.0 : -1.0) / dx[1];
+        if ((ua == uc) && (va == vc)) dNdz = ((wa == 1) ? 1.0 : -1.0) / dx[2];
+        const double *M = Mnode[iSourceCorner];
+        Jcorner[0] += dNdy * M[2] - dNdz * M[1];
+        Jcorner[1] += dNdz * M[0] - dNdx * M[2];
+        Jcorner[2] += dNdx * M[1] - dNdy * M[0];
+      }
+      double *CornerJ = CellData->CornerData[iTargetCorner].CornerJ;
+      CornerJ[0] += Jcorner[0];
+      CornerJ[1] += Jcorner[1];
+      CornerJ[2] += Jcorner[2];
+    }
+  }
+
   // ECSIM::ProcessCell, src/pic/pic_field_solver_ecsim.cpp:1881-2438 (scalar branch, B centre or
-  // corner based, no guiding-centre species, no per-species corner sampling)
+  // corner based, guiding-centre species of PIC::GYROKINETIC per cfg.gc_species_mask (:2084, :2205-2256, :2310, :2376), no
+  // per-species corner sampling)
   // ------------------------------------------------------------------------------------------
   bool ProcessCell(int iCellIn, int jCellIn, int kCellIn, cTreeNode *node, cCellData *CellData, double *MassTable, double *ChargeTable) {
     std::vector<double *> &B_Center = tlsBCenter();
@@ -2578,6 +2610,11 @@ struct oracle_ctx {
       for (int ii = 0; ii < 8; ii++)
         for (int jj = 0; jj < 3; jj++) Jg[ii][jj] = 0.0;
 
+      double MCornerSum[8][3];  // guiding-centre magnetisation closure (:1988-1996)
+      bool cell_has_gc = false;
+      for (int ii = 0; ii < 8; ii++)
+        for (int jj = 0; jj < 3; jj++) MCornerSum[ii][jj] = 0.0;
+
       double MassMatrix_GGD[8][8][9];
       for (int iCorner = 0; iCorner < 8; iCorner++)
         for (int jCorner = 0; jCorner < 8; jCorner++)
@@ -2610,6 +2647,7 @@ struct oracle_ctx {
         GetX(xInit, ParticleData);
         LocalParticleWeight = cfg.species_weight[spec];
         LocalParticleWeight *= GetIndividualStatWeightCorrection(ParticleData);
+        const bool use_gc_species = ((cfg.gc_species_mask >> spec) & 1) != 0;  // _PIC_GYROKINETIC_MODEL_MODE_ on && IsGuidingCenterSpecies (:2084)
 
         ptrNext = GetNext(ParticleData);
         if (ptrNext != -1) ParticleDataNext = GetParticleDataPointer(ptrNext);
@@ -2640,6 +2678,7 @@ struct oracle_ctx {
             B[idim] *= B_conv;
             vInit[idim] *= length_conv;
           }
+          const double Braw[3] = {B[0], B[1], B[2]};  // before the /LightSpeed scaling (:2141)
 
           double QdT_over_m, QdT_over_2m, alpha[9], chargeQ;
           double WeightPG[8];
@@ -2679,13 +2718,34 @@ struct oracle_ctx {
 
           CornerBased_InitStencil(xInit, node, CornerBasedStencil, WeightPG);
 
+          if (use_gc_species) {  // mu b to the corners (:2205-2225)
+            const double mu = GetMagneticMoment(ParticleData);
+            const double mu_tot = mu * LocalParticleWeight;
+            const double absB = sqrt(Braw[0] * Braw[0] + Braw[1] * Braw[1] + Braw[2] * Braw[2]);
+            if (absB > 0.0) {
+              const double b0 = Braw[0] / absB, b1 = Braw[1] / absB, b2 = Braw[2] / absB;
+              for (int iCorner = 0; iCorner < 8; iCorner++) {
+                const double w = mu_tot * WeightPG[iCorner];
+                MCornerSum[iCorner][0] += w * b0;
+                MCornerSum[iCorner][1] += w * b1;
+                MCornerSum[iCorner][2] += w * b2;
+              }
+              cell_has_gc = true;
+            }
+          }
+
           double vsqr = vInit[0] * vInit[0] + vInit[1] * vInit[1] + vInit[2] * vInit[2];
+          if (use_gc_species) {  // the unresolved gyration carried by v_normal (:2232-2235)
+            const double vperp = GetVNormal(ParticleData);
+            vsqr += vperp * vperp;
+          }
           vmean_cell[spec] += sqrt(vsqr) * GlobalTimeStep;
           ParticleEnergyCell += 0.5 * mass * vsqr;
 
           double vRot[3] = {0.0, 0.0, 0.0};
           for (int iDim = 0; iDim < 3; iDim++)
             for (int jj = 0; jj < 3; jj++) vRot[iDim] += alpha[3 * iDim + jj] * vInit[jj];
+          if (use_gc_species) vRot[0] = vInit[0], vRot[1] = vInit[1], vRot[2] = vInit[2];  // v_eff is deposited as it is (:2253-2257)
 
           for (int iCorner = 0; iCorner < 8; iCorner++) {
             double t = chargeQ * WeightPG[iCorner];
@@ -2694,6 +2754,7 @@ struct oracle_ctx {
           }
 
           double matrixConst = chargeQ * QdT_over_2m / CellVolume;
+          if (!use_gc_species)  // the implicit response is for full-orbit species only (:2310)
           for (int iCorner = 0; iCorner < 8; iCorner++) {
             double tempWeightConst = matrixConst * WeightPG[iCorner];
             for (int jCorner = 0; jCorner <= iCorner; jCorner++) {
@@ -2723,6 +2784,7 @@ struct oracle_ctx {
             double *CornerJ = CellData->CornerData[iCorner].CornerJ;
             for (int ii = 0; ii < 3; ii++) CornerJ[ii] += (Jg[iCorner][ii]) / CellVolume;
           }
+          if (cell_has_gc) AddGuidingCenterMagnetizationCurrentToCorners(CellData, MCornerSum, CellVolume, dx);  // :2376
           for (int iCorner = 0; iCorner < 8; iCorner++) {
             for (int jCorner = 0; jCorner <= iCorner; jCorner++) {
               if (iCorner == jCorner) {
@@ -2935,6 +2997,9 @@ void oracle_set_reduced_state(oracle_ctx *o, const double *mu, const double *vpa
     if (mu) oracle_ctx::SetMagneticMoment(mu[ptr], pd);
     if (vpar) oracle_ctx::SetVParallel(vpar[ptr], pd);
   }
+}
+void oracle_set_v_normal(oracle_ctx *o, const double *vnormal, int64_t n) {
+  for (int64_t ptr = 0; ptr < n; ptr++) oracle_ctx::SetVNormal(vnormal[ptr], o->GetParticleDataPointer(ptr));
 }
 void oracle_get_v_parallel(const oracle_ctx *o, double *vpar, int64_t n) {
   for (int64_t ptr = 0; ptr < n; ptr++) vpar[ptr] = oracle_ctx::GetVParallel(o->GetParticleDataPointer(ptr));

@@ -59,6 +59,8 @@ int oracle_magnetic_moment_init(oracle_ctx *, int mover_id, double *mu_out, int6
 void oracle_get_magnetic_moment(const oracle_ctx *, double *mu, uint8_t *init_flag, int64_t n);
 /* gyrokinetic reduced state by ptr: mu and v_parallel (either may be NULL) */
 void oracle_set_reduced_state(oracle_ctx *, const double *mu, const double *vpar, int64_t n);
+/* v_normal by ptr (PB::SetVNormal): read by ProcessCell for the guiding-centre species of cfg.gc_species_mask */
+void oracle_set_v_normal(oracle_ctx *o, const double *vnormal, int64_t n);
 void oracle_get_v_parallel(const oracle_ctx *, double *vpar, int64_t n);
 /* exit records (domain faces / internal sphere) accumulated since the last call; returns their number */
 int64_t oracle_exit_records(oracle_ctx *, amps_gpu_exit_record *buf, int64_t max_records);

@@ -37,6 +37,7 @@ def load(kind="parity"):
     lib.oracle_set_background_gradB.argtypes = [vp, vp]
     lib.oracle_get_magnetic_moment.argtypes = [vp, vp, vp, C.c_int64]
     lib.oracle_set_reduced_state.argtypes = [vp, vp, vp, C.c_int64]
+    lib.oracle_set_v_normal.argtypes = [vp, vp, C.c_int64]
     lib.oracle_get_v_parallel.argtypes = [vp, vp, C.c_int64]
     lib.oracle_add_particles.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64]
     lib.oracle_particle_count.restype = C.c_int64
@@ -108,6 +109,11 @@ class Oracle:
         flag = np.zeros(self.n_added, dtype=np.uint8)
         self.lib.oracle_get_magnetic_moment(self.h, _p(mu), _p(flag), self.n_added)
         return mu, flag
+
+    def set_v_normal(self, vnormal):
+        a = np.ascontiguousarray(vnormal, dtype=np.float64)
+        assert a.shape == (self.n_added,)
+        self.lib.oracle_set_v_normal(self.h, _p(a), self.n_added)
 
     def set_reduced_state(self, mu, vpar):
         mu = np.ascontiguousarray(mu, dtype=np.float64)
