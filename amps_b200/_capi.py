@@ -68,7 +68,7 @@ class Config(C.Structure):
         ("carry_v_parallel", C.c_int32),
         ("ideal_mhd", C.c_int32),
         ("gc_species_mask", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("gc_fields_ecsim", C.c_int32),
     ]
 
 

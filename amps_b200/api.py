@@ -54,6 +54,7 @@ def make_config(block_cells=(8, 8, 8), ghost_cells=(1, 1, 1), charge=(-1.0, 1.0)
     cfg.carry_v_parallel = 0
     cfg.ideal_mhd = 1
     cfg.gc_species_mask = 0
+    cfg.gc_fields_ecsim = 0
     cfg.exact_arithmetic = 0
     return cfg
 

@@ -195,11 +195,11 @@ void launch_move_boris(const DevMesh &m, const DevSpecies &sp, bool markidis, in
                        DevMoveStats *stats, amps_gpu_exit_record *exitBuf, unsigned long long *exitCount, cudaStream_t s);
 void launch_stage_center_table(const DevMesh &m, int nVar, const double *var, double *tile, cudaStream_t s);
 void launch_gc_magnetic_moment_init(const DevMesh &m, const DevSpecies &sp, int interp, ParticleSoA p, const int *nSlots, long long nUpper,
-                                    const double *bgTile, const double *uE, const double *uB, DevMoveStats *stats, cudaStream_t s);
+                                    const double *bgTile, const double *uE, const double *uB, DevMoveStats *stats, cudaStream_t s, const double *ecsimE = nullptr, const double *ecsimB = nullptr);
 void launch_move_guiding_center(const DevMesh &m, const DevSpecies &sp, int order, int interp, int idealMhd, double rSphere, long long exitCap,
                                 ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *gradBTile, const double *uE,
                                 const double *uB, const double *uGradB, int *cellCount, DevMoveStats *stats, amps_gpu_exit_record *exitBuf,
-                                unsigned long long *exitCount, cudaStream_t s);
+                                unsigned long long *exitCount, cudaStream_t s, const double *ecsimE = nullptr, const double *ecsimB = nullptr);
 void launch_magnetic_moment_init(const DevMesh &m, const DevSpecies &sp, int interp, double c, ParticleSoA p, const int *nSlots, long long nUpper,
                                  const double *bgTile, const double *uE, const double *uB, DevMoveStats *stats, cudaStream_t s);
 void launch_magnetic_moment_set(ParticleSoA p, double *target, const int *nSlots, long long nUpper, const double *muByPtr, long long nMu,

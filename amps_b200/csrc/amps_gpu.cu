@@ -433,6 +433,9 @@ static int release_mesh(amps_gpu_ctx *ctx) {
   drop(ctx->d_bgE), drop(ctx->d_bgB), drop(ctx->d_bgTile);
   drop(ctx->d_neib26), drop(ctx->d_mbSlot), drop(ctx->d_mbLeaf), drop(ctx->d_mbTab);
   ctx->cplrCacheTried = false;
+  // the field solve is sized by the mesh as well: a new epoch needs amps_gpu_field_solver_init (and the halo / primary lists) again
+  drop(ctx->d_E), drop(ctx->d_fNb), drop(ctx->d_fCc), drop(ctx->d_fZc), drop(ctx->d_krylov), drop(ctx->d_primary);
+  ctx->fieldSolverReady = ctx->eReady = false, ctx->fieldWarmValid = false, ctx->krylovVectors = 0;
   drop(ctx->d_sendBuf), drop(ctx->d_recvBuf), drop(ctx->d_sendCount), drop(ctx->d_allCounts), drop(ctx->d_errFlag);
   for (int *&p : ctx->d_sharedUid) drop(p);
   ctx->d_sharedUid.clear(), ctx->nShared.clear(), ctx->h_sharedUid.clear();
@@ -865,8 +868,12 @@ static int field_halo_exchange(amps_gpu_ctx *ctx, double *vec, bool centers) {
 // E^n on the unique corners (E at the half step goes through amps_gpu_fields_upload)
 int amps_gpu_E_upload(amps_gpu_ctx *ctx, const double *E_cur) {
   if (!ctx || !E_cur) return AMPS_GPU_ERR_ARG;
-  if (!ctx->fieldSolverReady) FAIL(AMPS_GPU_ERR_STATE, "E_upload before amps_gpu_field_solver_init");
+  if (!ctx->meshReady) FAIL(AMPS_GPU_ERR_STATE, "E_upload before amps_gpu_mesh_upload");
   CK(cudaSetDevice(ctx->cfg.device));
+  if (!ctx->d_E) {  // without the device field solve: the guiding-centre movers of cfg.gc_fields_ecsim read it
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_E, (size_t)3 * ctx->dm.nCorners))) return rc;
+  }
   CK(cudaMemcpyAsync(ctx->d_E, E_cur, sizeof(double) * 3 * (size_t)ctx->dm.nCorners, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->eReady = true;
@@ -1147,7 +1154,10 @@ int amps_gpu_magnetic_moment_init(amps_gpu_ctx *ctx, int mover_id) {
   if (mover_id != AMPS_MOVER_RELATIVISTIC_GCA && mover_id != AMPS_MOVER_GC_FIRST_ORDER && mover_id != AMPS_MOVER_GC_SECOND_ORDER)
     FAIL(AMPS_GPU_ERR_ARG, "magnetic_moment_init: not a guiding-centre mover");
   if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "magnetic_moment_init needs cfg.carry_magnetic_moment");
-  if (!ctx->meshReady || !ctx->backgroundReady) FAIL(AMPS_GPU_ERR_STATE, "magnetic_moment_init needs the mesh and amps_gpu_background_upload");
+  const bool gcEcsim = ctx->cfg.gc_fields_ecsim && mover_id != AMPS_MOVER_RELATIVISTIC_GCA;
+  if (gcEcsim && (!ctx->meshReady || !ctx->fieldsReady || ctx->meshRefined || ctx->cfg.b_mode != AMPS_B_CENTER_BASED))
+    FAIL(AMPS_GPU_ERR_STATE, "magnetic_moment_init with cfg.gc_fields_ecsim needs amps_gpu_fields_upload on a single-level mesh with centre-based B");
+  if (!gcEcsim && (!ctx->meshReady || !ctx->backgroundReady)) FAIL(AMPS_GPU_ERR_STATE, "magnetic_moment_init needs the mesh and amps_gpu_background_upload");
   CK(cudaSetDevice(ctx->cfg.device));
   CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevMoveStats), ctx->stream));
   if (mover_id == AMPS_MOVER_RELATIVISTIC_GCA)
@@ -1155,7 +1165,8 @@ int amps_gpu_magnetic_moment_init(amps_gpu_ctx *ctx, int mover_id) {
                                 ctx->nUpper, ctx->d_bgTile, ctx->d_bgE, ctx->d_bgB, ctx->d_stats, ctx->stream);
   else
     launch_gc_magnetic_moment_init(ctx->dm, ctx->sp, ctx->cfg.coupler_interpolation, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper,
-                                   ctx->d_bgTile, ctx->d_bgE, ctx->d_bgB, ctx->d_stats, ctx->stream);
+                                   ctx->d_bgTile, ctx->d_bgE, ctx->d_bgB, ctx->d_stats, ctx->stream, gcEcsim ? ctx->d_Bcur : nullptr,
+                                   gcEcsim ? ctx->d_Bcur : nullptr);
   ctx->launches++;
   CK(cudaGetLastError());
   DevMoveStats h;
@@ -1851,9 +1862,14 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
       FAIL(AMPS_GPU_ERR_STATE, "the gyrokinetic movers need cfg.carry_magnetic_moment and cfg.carry_v_parallel");
     if (!ctx->gradBReady) FAIL(AMPS_GPU_ERR_STATE, "PIC::GYROKINETIC needs amps_gpu_background_upload_gradB");
   }
+  const bool gcEcsim = ctx->cfg.gc_fields_ecsim && (mover_id == AMPS_MOVER_GC_FIRST_ORDER || mover_id == AMPS_MOVER_GC_SECOND_ORDER);
   if (mover_id == AMPS_MOVER_GC_FIRST_ORDER || mover_id == AMPS_MOVER_GC_SECOND_ORDER) {
     if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "the guiding-centre movers need cfg.carry_magnetic_moment");
-    if (!ctx->gradBReady) FAIL(AMPS_GPU_ERR_STATE, "GuidingCenter needs amps_gpu_background_upload_gradB");
+    if (gcEcsim) {
+      if (!ctx->fieldsReady || !ctx->eReady) FAIL(AMPS_GPU_ERR_STATE, "cfg.gc_fields_ecsim needs amps_gpu_fields_upload (B_cur) and the current E (amps_gpu_E_upload / field_step)");
+      if (ctx->meshRefined || ctx->cfg.b_mode != AMPS_B_CENTER_BASED)
+        FAIL(AMPS_GPU_ERR_STATE, "cfg.gc_fields_ecsim: single-level meshes with centre-based B (ECSIM::GetMagneticField reads the centre nodes)");
+    } else if (!ctx->gradBReady) FAIL(AMPS_GPU_ERR_STATE, "GuidingCenter needs amps_gpu_background_upload_gradB");
   }
   if (mover_id == AMPS_MOVER_RELATIVISTIC_GCA) {
     if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "the guiding-centre movers need cfg.carry_magnetic_moment");
@@ -1866,7 +1882,7 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
     FAIL(AMPS_GPU_ERR_STATE,
          "ECSIM on a refined mesh needs _PIC_FIELD_SOLVER_B_CORNER_BASED_: with centre-based B the reference indexes the start block's "
          "buffer with stencil ids of other blocks (pic_mover_boris.cpp:975-990)");
-  if (mover_id != AMPS_MOVER_LAPENTA2017 && !ctx->backgroundReady) FAIL(AMPS_GPU_ERR_STATE, "the test-particle movers need amps_gpu_background_upload");
+  if (mover_id != AMPS_MOVER_LAPENTA2017 && !gcEcsim && !ctx->backgroundReady) FAIL(AMPS_GPU_ERR_STATE, "the test-particle movers need amps_gpu_background_upload");
   if (mover_id != AMPS_MOVER_LAPENTA2017 && ctx->meshRefined && !ctx->cplrCacheTried &&
       ctx->cfg.coupler_interpolation == AMPS_CPLR_CELL_CENTERED_LINEAR) {
     int rc;
@@ -1890,7 +1906,8 @@ static int do_move(amps_gpu_ctx *ctx, int mover_id) {
   if (mover_id == AMPS_MOVER_GC_FIRST_ORDER || mover_id == AMPS_MOVER_GC_SECOND_ORDER) {
     launch_move_guiding_center(m, ctx->sp, mover_id == AMPS_MOVER_GC_SECOND_ORDER ? 2 : 1, ctx->cfg.coupler_interpolation, ctx->cfg.ideal_mhd,
                                ctx->cfg.internal_sphere_radius, ctx->cfg.exit_record_capacity, ctx->buf[ctx->cur], ctx->d_n + ctx->cur, ctx->nUpper,
-                               ctx->d_bgTile, ctx->d_gradBTile, ctx->d_bgE, ctx->d_bgB, ctx->d_gradBVar, ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount, ctx->stream);
+                               ctx->d_bgTile, ctx->d_gradBTile, ctx->d_bgE, ctx->d_bgB, ctx->d_gradBVar, ctx->d_cellCount, ctx->d_stats, ctx->d_exitBuf, ctx->d_exitCount, ctx->stream,
+                               gcEcsim ? ctx->d_E : nullptr, gcEcsim ? ctx->d_Bcur : nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
     ctx->sorted = false;

@@ -1025,16 +1025,129 @@ struct GcTables {
   const double *bg;     // [leaf][nCenterLocal][6]  E, B
   const double *gradB;  // [leaf][nCenterLocal][9]
   const double *uE, *uB, *uGradB;  // unique-node tables (AMR stencils)
+  // cfg.gc_fields_ecsim: the ECSIM arrays instead (unique corners / centres), read through the corner and centre stencils
+  const double *ecsimE = nullptr;  // [nCorners][3] current E
+  const double *ecsimB = nullptr;  // [nCenters][3] B_cur
 };
+
+// ---- the ECSIM field getters of the guiding-centre movers (reference built with the ECSIM field solver) ----
+// ECSIM::GetMagneticField, pic_field_solver_ecsim.cpp:7456-7469: CellCentered::Linear stencil (same-level branch: the trilinear stencil of
+// the block's own centres incl. the ghost layer, centres outside the global box dropped, Normalize()) on B_cur
+__device__ __forceinline__ bool ecsim_get_B(const DevMesh &m, const GcTables &T, const double x[3], int leaf, double B[3]) {
+  const LeafGeo &lg = m.leaf[leaf];
+  const double iLoc = (x[0] - lg.xmin[0]) / (lg.xmax[0] - lg.xmin[0]) * m.N[0];
+  const double jLoc = (x[1] - lg.xmin[1]) / (lg.xmax[1] - lg.xmin[1]) * m.N[1];
+  const double kLoc = (x[2] - lg.xmin[2]) / (lg.xmax[2] - lg.xmin[2]) * m.N[2];
+  const int i0 = (iLoc < 0.5) ? -1 : (int)(iLoc - 0.50);
+  const int j0 = (jLoc < 0.5) ? -1 : (int)(jLoc - 0.50);
+  const int k0 = (kLoc < 0.5) ? -1 : (int)(kLoc - 0.50);
+  B[0] = B[1] = B[2] = 0.0;
+  if (i0 < -m.g[0] || i0 + 1 > m.N[0] + m.g[0] - 1 || j0 < -m.g[1] || j0 + 1 > m.N[1] + m.g[1] - 1 || k0 < -m.g[2] || k0 + 1 > m.N[2] + m.g[2] - 1)
+    return false;  // outside the block's tile (out-of-bounds read in the reference)
+  const double w0 = iLoc - (i0 + 0.5), w1 = jLoc - (j0 + 0.5), w2 = kLoc - (k0 + 0.5);
+  double w[8];
+  w[0] = (1.0 - w0) * (1.0 - w1) * (1.0 - w2);
+  w[1] = (1.0 - w0) * (1.0 - w1) * w2;
+  w[2] = (1.0 - w0) * w1 * (1.0 - w2);
+  w[3] = (1.0 - w0) * w1 * w2;
+  w[4] = w0 * (1.0 - w1) * (1.0 - w2);
+  w[5] = w0 * (1.0 - w1) * w2;
+  w[6] = w0 * w1 * (1.0 - w2);
+  w[7] = w0 * w1 * w2;
+  unsigned valid = 0xffu;
+  if (!m.periodic && lg.face) {
+    if ((lg.face & 1) && i0 < 0) valid &= 0xf0u;
+    if ((lg.face & 2) && i0 + 1 >= m.N[0]) valid &= 0x0fu;
+    if ((lg.face & 4) && j0 < 0) valid &= 0xccu;
+    if ((lg.face & 8) && j0 + 1 >= m.N[1]) valid &= 0x33u;
+    if ((lg.face & 16) && k0 < 0) valid &= 0xaau;
+    if ((lg.face & 32) && k0 + 1 >= m.N[2]) valid &= 0x55u;
+  }
+  double norm = 0.0;
+#pragma unroll
+  for (int s = 0; s < 8; s++)
+    if (valid & (1u << s)) norm += w[s];
+  const int *cu = m.centerUid + (size_t)leaf * m.nCenterLocal;
+#pragma unroll
+  for (int s = 0; s < 8; s++)
+    if (valid & (1u << s)) {
+      const double ws = w[s] / norm;
+      const double *t = T.ecsimB + 3 * (size_t)cu[centerLocalNumber(m, i0 + ((s >> 2) & 1), j0 + ((s >> 1) & 1), k0 + (s & 1))];
+      B[0] += ws * t[0], B[1] += ws * t[1], B[2] += ws * t[2];
+    }
+  return true;
+}
+// ECSIM::GetElectricField, :7440-7453: CornerBased::InitStencil (pic_interpolation_routines.cpp:1074-1194, Normalize()) on the current E
+__device__ __forceinline__ bool ecsim_get_E(const DevMesh &m, const GcTables &T, const double x[3], int leaf, double E[3]) {
+  const LeafGeo &lg = m.leaf[leaf];
+  double xl[3];
+  int iX[3];
+  E[0] = E[1] = E[2] = 0.0;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const double dx = (lg.xmax[d] - lg.xmin[d]) / m.N[d];
+    double xs = x[d];
+    if ((xs < lg.xmin[d]) || (xs > lg.xmax[d])) return false;
+    if (fabs(xs - lg.xmax[d]) < 1e-10 * dx) xs = lg.xmax[d] - 1e-10 * dx;
+    xl[d] = (xs - lg.xmin[d]) / dx;
+    iX[d] = (int)(xl[d]);
+    xl[d] -= iX[d];
+  }
+  double w[8], norm = 0.0;
+  // stencil order of the reference: i, j, k loops, k fastest
+#pragma unroll
+  for (int s = 0; s < 8; s++) {
+    const int i = (s >> 2) & 1, j = (s >> 1) & 1, k = s & 1;
+    w[s] = (i ? xl[0] : 1.0 - xl[0]) * (j ? xl[1] : 1.0 - xl[1]) * (k ? xl[2] : 1.0 - xl[2]);
+    norm += w[s];
+  }
+  const int *cu = m.cornerUid + (size_t)leaf * m.nCornerLocal;
+#pragma unroll
+  for (int s = 0; s < 8; s++) {
+    const double ws = w[s] / norm;
+    const double *t = T.ecsimE + 3 * (size_t)cu[cornerLocalNumber(m, iX[0] + ((s >> 2) & 1), iX[1] + ((s >> 1) & 1), iX[2] + (s & 1))];
+    E[0] += ws * t[0], E[1] += ws * t[1], E[2] += ws * t[2];
+  }
+  return true;
+}
+// ECSIM::GetMagneticFieldGradient, :7473-7547: central differences over half a cell of the start block, one-sided where a probe leaves the domain
+__device__ __forceinline__ bool ecsim_get_gradB(const DevMesh &m, const GcTables &T, const double x[3], int leaf, double gradB[9]) {
+  const LeafGeo &lg = m.leaf[leaf];
+  double B0[3];
+  if (!ecsim_get_B(m, T, x, leaf, B0)) return false;
+#pragma unroll 1
+  for (int idim = 0; idim < 3; idim++) {
+    double xp[3] = {x[0], x[1], x[2]}, xm[3] = {x[0], x[1], x[2]};
+    const double dx = 0.5 * (lg.xmax[idim] - lg.xmin[idim]) / m.N[idim];
+    xp[idim] += dx, xm[idim] -= dx;
+    const int np = find_tree_node_plain(m, xp, lg.node), nm = find_tree_node_plain(m, xm, lg.node);
+    const bool hasP = np >= 0, hasM = nm >= 0;
+    double Bp[3], Bm[3];
+    if (hasP && (m.nodeLeaf[np] < 0 || !ecsim_get_B(m, T, xp, m.nodeLeaf[np], Bp))) return false;
+    if (hasM && (m.nodeLeaf[nm] < 0 || !ecsim_get_B(m, T, xm, m.nodeLeaf[nm], Bm))) return false;
+    for (int c = 0; c < 3; c++) {
+      double g = 0.0;
+      if (hasP && hasM) g = (Bp[c] - Bm[c]) / (2.0 * dx);
+      else if (hasP) g = (Bp[c] - B0[c]) / dx;
+      else if (hasM) g = (B0[c] - Bm[c]) / dx;
+      gradB[3 * c + idim] = g;
+    }
+  }
+  return true;
+}
 
 __device__ __forceinline__ bool gc_initiate_magnetic_moment(const DevMesh &m, const DevSpecies &sp, int interp, const GcTables &T, int spec,
                                                             const double x[3], double v[3], int leaf, double &muOut) {
-  BgStencil st;
-  BgStencil8 s8;
-  const int kind = background_stencil(m, interp, x, leaf, s8, st);
-  if (!kind) return false;
   double B[3];
-  background_gather<3>(kind, s8, st, T.bg + (size_t)leaf * m.nCenterLocal * 6, 6, 3, T.uB, B);
+  if (T.ecsimB != nullptr) {  // pic_mover_guiding_center.cpp:103-104
+    if (!ecsim_get_B(m, T, x, leaf, B)) return false;
+  } else {
+    BgStencil st;
+    BgStencil8 s8;
+    const int kind = background_stencil(m, interp, x, leaf, s8, st);
+    if (!kind) return false;
+    background_gather<3>(kind, s8, st, T.bg + (size_t)leaf * m.nCenterLocal * 6, 6, 3, T.uB, B);
+  }
   const double AbsB = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) + 1E-15;
   double v_par = 0.0, mu = 0.0;
   const double b[3] = {B[0] / AbsB, B[1] / AbsB, B[2] / AbsB};
@@ -1055,15 +1168,19 @@ __device__ __forceinline__ bool gc_initiate_magnetic_moment(const DevMesh &m, co
 __device__ __forceinline__ bool gc_motion(const DevMesh &m, const DevSpecies &sp, int interp, int idealMhd, const GcTables &T, double Vguide_perp[3],
                                           double &ForceParal, double &AbsBOut, double bOut[3], const double *PParal, int spec, double mu,
                                           const double x[3], const double v[3], int leaf) {
-  BgStencil st;
-  BgStencil8 s8;
-  const int kind = background_stencil(m, interp, x, leaf, s8, st);
-  if (!kind) return false;
   double E[3], B[3], gradB[9];
-  const double *tb = T.bg + (size_t)leaf * m.nCenterLocal * 6;
-  background_gather<3>(kind, s8, st, tb, 6, 0, T.uE, E);
-  background_gather<3>(kind, s8, st, tb, 6, 3, T.uB, B);
-  background_gather<9>(kind, s8, st, T.gradB + (size_t)leaf * m.nCenterLocal * 9, 9, 0, T.uGradB, gradB);
+  if (T.ecsimB != nullptr) {  // pic_mover_guiding_center.cpp:179-184
+    if (!ecsim_get_B(m, T, x, leaf, B) || !ecsim_get_E(m, T, x, leaf, E) || !ecsim_get_gradB(m, T, x, leaf, gradB)) return false;
+  } else {
+    BgStencil st;
+    BgStencil8 s8;
+    const int kind = background_stencil(m, interp, x, leaf, s8, st);
+    if (!kind) return false;
+    const double *tb = T.bg + (size_t)leaf * m.nCenterLocal * 6;
+    background_gather<3>(kind, s8, st, tb, 6, 0, T.uE, E);
+    background_gather<3>(kind, s8, st, tb, 6, 3, T.uB, B);
+    background_gather<9>(kind, s8, st, T.gradB + (size_t)leaf * m.nCenterLocal * 9, 9, 0, T.uGradB, gradB);
+  }
   const double AbsB = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) + 1E-15;
   double b[3], gradAbsB[3];
   b[0] = B[0] / AbsB;
@@ -1118,12 +1235,14 @@ __global__ void __launch_bounds__(128) gc_magnetic_moment_init_kernel(DevMesh m,
   flush_move_counters(stats, 0, 0, 0, 0, 0, 0, nErr);
 }
 void launch_gc_magnetic_moment_init(const DevMesh &m, const DevSpecies &sp, int interp, ParticleSoA p, const int *nSlots, long long nUpper,
-                                    const double *bgTile, const double *uE, const double *uB, DevMoveStats *stats, cudaStream_t s) {
+                                    const double *bgTile, const double *uE, const double *uB, DevMoveStats *stats, cudaStream_t s,
+                                    const double *ecsimE, const double *ecsimB) {
   long long g = (nUpper + 127) / 128;
   if (g < 1) g = 1;
   if (g > 148 * 32) g = 148 * 32;
   GcTables T;
   T.bg = bgTile, T.gradB = nullptr, T.uE = uE, T.uB = uB, T.uGradB = nullptr;
+  T.ecsimE = ecsimE, T.ecsimB = ecsimB;
   gc_magnetic_moment_init_kernel<<<(int)g, 128, 0, s>>>(m, sp, interp, T, p, nSlots, stats);
 }
 
@@ -1171,13 +1290,19 @@ __global__ void __launch_bounds__(128) move_guiding_center_kernel(DevMesh m, Dev
         if (node < 0) outcome = 1;
       }
       if (outcome == 0) {
-        BgStencil st;
-        BgStencil8 s8;
-        const int kind = background_stencil(m, tp.interp, x, startLeaf, s8, st);
-        if (!kind) outcome = 3;  // the START block, as written (:713)
+        double bFinal[3];
+        bool got;
+        if (T.ecsimB != nullptr) {  // the NEW block in the ECSIM branch (:727-729)
+          got = m.nodeLeaf[node] >= 0 && ecsim_get_B(m, T, x, m.nodeLeaf[node], bFinal);
+        } else {
+          BgStencil st;
+          BgStencil8 s8;
+          const int kind = background_stencil(m, tp.interp, x, startLeaf, s8, st);  // the START block, as written (:713)
+          got = kind != 0;
+          if (got) background_gather<3>(kind, s8, st, T.bg + (size_t)startLeaf * m.nCenterLocal * 6, 6, 3, T.uB, bFinal);
+        }
+        if (!got) outcome = 3;
         else {
-          double bFinal[3];
-          background_gather<3>(kind, s8, st, T.bg + (size_t)startLeaf * m.nCenterLocal * 6, 6, 3, T.uB, bFinal);
           const double l0 = sqrt(bFinal[0] * bFinal[0] + bFinal[1] * bFinal[1] + bFinal[2] * bFinal[2]);
           if (l0 > 0.0) {
             const double l = 1.0 / l0;
@@ -1281,11 +1406,12 @@ __global__ void __launch_bounds__(128) move_guiding_center_kernel(DevMesh m, Dev
 void launch_move_guiding_center(const DevMesh &m, const DevSpecies &sp, int order, int interp, int idealMhd, double rSphere, long long exitCap,
                                 ParticleSoA p, const int *nSlots, long long nUpper, const double *bgTile, const double *gradBTile, const double *uE,
                                 const double *uB, const double *uGradB, int *cellCount, DevMoveStats *stats, amps_gpu_exit_record *exitBuf,
-                                unsigned long long *exitCount, cudaStream_t s) {
+                                unsigned long long *exitCount, cudaStream_t s, const double *ecsimE, const double *ecsimB) {
   TpParams tp;
   tp.interp = interp, tp.backward = 0, tp.boundaryMode = sp.boundaryMode, tp.c = 0.0, tp.rSphere = rSphere, tp.exitCap = exitCap;
   GcTables T;
   T.bg = bgTile, T.gradB = gradBTile, T.uE = uE, T.uB = uB, T.uGradB = uGradB;
+  T.ecsimE = ecsimE, T.ecsimB = ecsimB;
   long long g = (nUpper + 127) / 128;
   if (g < 1) g = 1;
   if (g > 148 * 32) g = 148 * 32;

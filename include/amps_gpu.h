@@ -122,7 +122,12 @@ typedef struct amps_gpu_config {
                                         ECSIM::ProcessCell (pic_field_solver_ecsim.cpp:2084): explicit current q v_eff, no mass matrix, the
                                         magnetisation current curl(M) of :1828 and |v_normal|^2 in the energy / cfl diagnostics.  Needs
                                         carry_magnetic_moment; one rank.  0 = _PIC_GYROKINETIC_MODEL_MODE_ off                       */
-  int32_t reserved0;
+  int32_t gc_fields_ecsim;           /* 1: the guiding-centre movers (GC_FIRST_ORDER / GC_SECOND_ORDER) read the ECSIM arrays like the reference
+                                        built with _PIC_FIELD_SOLVER_MODE__ELECTROMAGNETIC__ECSIM_ (pic_mover_guiding_center.cpp:103, :179-184,
+                                        :727): E = the current E on the corners (amps_gpu_E_upload / amps_gpu_field_step) through the corner
+                                        stencil, B = B_cur on the centres through the centre stencil, grad B = ECSIM::GetMagneticFieldGradient
+                                        (pic_field_solver_ecsim.cpp:7473, differences over half a cell).  Single-level meshes, centre-based B.
+                                        0: the coupler's background tables                                                        */
 } amps_gpu_config;
 
 /* _PIC_COUPLER__INTERPOLATION_MODE_ */

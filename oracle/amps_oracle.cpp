@@ -1728,6 +1728,75 @@ struct oracle_ctx {
   // PIC::CPLR::InitInterpolationStencil(x,node) for a point that may lie OUTSIDE `node` (Mover_FirstOrder :713 builds the
   // stencil of the new position in the start block).  Indices beyond the block's ghost layer are out-of-bounds reads in
   // the reference -> reported as an error here (returns false), like every place where the reference exit()s.
+  // ---- the ECSIM field getters the guiding-centre movers use when _PIC_FIELD_SOLVER_MODE_ is ECSIM (cfg.gc_fields_ecsim) ----
+  // ECSIM::GetElectricField, pic_field_solver_ecsim.cpp:7440-7453: corner stencil on E (slot 0 of the corner data = the current E).
+  // (The reference hands the mover's own x to CornerBased::InitStencil, which snaps a point closer than 1e-10 dx to the block's upper
+  // face; here the snap stays local to the stencil.)
+  bool ECSIM_GetElectricField(double *E, const double *x, cTreeNode *node) const {
+    cStencil Stencil;
+    double xx[3] = {x[0], x[1], x[2]}, Wdummy[8];
+    for (int idim = 0; idim < 3; idim++) E[idim] = 0.0;
+    if (node == NULL || node->block == NULL) return false;
+    if (!CornerBased_InitStencil(xx, node, Stencil, Wdummy)) return false;
+    for (int iCornerNode = 0; iCornerNode < Stencil.Length; iCornerNode++) {
+      const double *t = node->block->cornerNodes[Stencil.LocalCellID[iCornerNode]]->data + ExOffsetIndex;
+      const double w = Stencil.Weight[iCornerNode];
+      for (int idim = 0; idim < 3; idim++) E[idim] += w * t[idim];
+    }
+    return true;
+  }
+  // ECSIM::GetMagneticField, :7456-7469: centre stencil on slot 0 of the centre data (the reference's CurrentBOffset / PrevBOffset swap
+  // every step, :5697-5700, while this getter always reads slot 0; here slot 0 is B_cur)
+  bool ECSIM_GetMagneticField(double *B, const double *x, cTreeNode *node) const {
+    cStencil Stencil;
+    for (int idim = 0; idim < 3; idim++) B[idim] = 0.0;
+    if (node == NULL || node->block == NULL) return false;
+    CellCentered_Linear_InitStencil(x, node, Stencil, true);
+    for (int iCenterNode = 0; iCenterNode < Stencil.Length; iCenterNode++) {
+      const double *t = node->block->centerNodes[Stencil.LocalCellID[iCenterNode]]->data + CurrentBOffset_d;
+      const double w = Stencil.Weight[iCenterNode];
+      for (int idim = 0; idim < 3; idim++) B[idim] += w * t[idim];
+    }
+    return true;
+  }
+  // ECSIM::GetMagneticFieldGradient, :7473-7547: central differences over half a cell, one-sided next to the domain boundary
+  bool ECSIM_GetMagneticFieldGradient(double *gradB, const double *x, cTreeNode *node) const {
+    double x_plus[3], x_minus[3], dx;
+    double B_plus[3], B_minus[3], B0[3];
+    if (!ECSIM_GetMagneticField(B0, x, node)) return false;
+    for (int idim = 0; idim < 3; idim++) {
+      memcpy(x_plus, x, 3 * sizeof(double));
+      memcpy(x_minus, x, 3 * sizeof(double));
+      if (idim == 0) dx = 0.5 * (node->xmax[0] - node->xmin[0]) / _BLOCK_CELLS_X_;
+      else if (idim == 1) dx = 0.5 * (node->xmax[1] - node->xmin[1]) / _BLOCK_CELLS_Y_;
+      else dx = 0.5 * (node->xmax[2] - node->xmin[2]) / _BLOCK_CELLS_Z_;
+      x_plus[idim] += dx;
+      x_minus[idim] -= dx;
+      cTreeNode *node_plus = findTreeNode(x_plus, node), *node_minus = findTreeNode(x_minus, node);
+      const bool has_plus = (node_plus != NULL), has_minus = (node_minus != NULL);
+      if (has_plus && !ECSIM_GetMagneticField(B_plus, x_plus, node_plus)) return false;
+      if (has_minus && !ECSIM_GetMagneticField(B_minus, x_minus, node_minus)) return false;
+      if (has_plus && has_minus) {
+        gradB[0 + idim] = (B_plus[0] - B_minus[0]) / (2.0 * dx);
+        gradB[3 + idim] = (B_plus[1] - B_minus[1]) / (2.0 * dx);
+        gradB[6 + idim] = (B_plus[2] - B_minus[2]) / (2.0 * dx);
+      } else if (has_plus) {
+        gradB[0 + idim] = (B_plus[0] - B0[0]) / dx;
+        gradB[3 + idim] = (B_plus[1] - B0[1]) / dx;
+        gradB[6 + idim] = (B_plus[2] - B0[2]) / dx;
+      } else if (has_minus) {
+        gradB[0 + idim] = (B0[0] - B_minus[0]) / dx;
+        gradB[3 + idim] = (B0[1] - B_minus[1]) / dx;
+        gradB[6 + idim] = (B0[2] - B_minus[2]) / dx;
+      } else {
+        gradB[0 + idim] = 0.0;
+        gradB[3 + idim] = 0.0;
+        gradB[6 + idim] = 0.0;
+      }
+    }
+    return true;
+  }
+
   bool GC_InitStencil(const double *x, cTreeNode *node, cStencil &Stencil) const { return CplrInitStencil(x, node, Stencil); }
   void GC_Gather(const cStencil &Stencil, cTreeNode *node, int offset, int nVars, double *out) const {
     (void)node;
@@ -1737,9 +1806,13 @@ struct oracle_ctx {
   // InitiateMagneticMoment, :85-144: mu from the perpendicular speed, then v is ALIGNED with B
   bool GC_InitiateMagneticMoment(int spec, const double *x, double *v, byte *ParticleData, cTreeNode *node) {
     double B[3] = {0.0, 0.0, 0.0}, AbsB = 0.0;
-    cStencil Stencil;
-    if (!GC_InitStencil(x, node, Stencil)) return false;
-    GC_Gather(Stencil, node, BackgroundB_d, 3, B);
+    if (cfg.gc_fields_ecsim) {  // :103-104
+      if (!ECSIM_GetMagneticField(B, x, node)) return false;
+    } else {
+      cStencil Stencil;
+      if (!GC_InitStencil(x, node, Stencil)) return false;
+      GC_Gather(Stencil, node, BackgroundB_d, 3, B);
+    }
     AbsB = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]) + 1E-15;
     double v_par = 0.0, v2, gamma2, m0, mu = 0.0;
     double b[3] = {B[0] / AbsB, B[1] / AbsB, B[2] / AbsB};
@@ -1763,11 +1836,17 @@ struct oracle_ctx {
     double Vguide_perp_LOC[3] = {0.0, 0.0, 0.0}, ForceParal_LOC = 0.0;
     double E[3], gradB[9], gradAbsB[3], AbsB = 0.0;
     double b[3], B[3];
-    cStencil Stencil;
-    if (!GC_InitStencil(x, startNode, Stencil)) return false;
-    GC_Gather(Stencil, startNode, BackgroundE_d, 3, E);
-    GC_Gather(Stencil, startNode, BackgroundB_d, 3, B);
-    GC_Gather(Stencil, startNode, BackgroundGradB_d, 9, gradB);
+    if (cfg.gc_fields_ecsim) {  // :179-184
+      if (!ECSIM_GetMagneticField(B, x, startNode)) return false;
+      if (!ECSIM_GetElectricField(E, x, startNode)) return false;
+      if (!ECSIM_GetMagneticFieldGradient(gradB, x, startNode)) return false;
+    } else {
+      cStencil Stencil;
+      if (!GC_InitStencil(x, startNode, Stencil)) return false;
+      GC_Gather(Stencil, startNode, BackgroundE_d, 3, E);
+      GC_Gather(Stencil, startNode, BackgroundB_d, 3, B);
+      GC_Gather(Stencil, startNode, BackgroundGradB_d, 9, gradB);
+    }
     AbsB = pow(B[0] * B[0] + B[1] * B[1] + B[2] * B[2], 0.5) + 1E-15;
     b[0] = B[0] / AbsB;
     b[1] = B[1] / AbsB;
@@ -1837,7 +1916,9 @@ struct oracle_ctx {
       return _PARTICLE_LEFT_THE_DOMAIN_;
     }
     double bFinal[3];
-    {
+    if (cfg.gc_fields_ecsim) {  // the NEW node in this branch (:727-729)
+      if (!ECSIM_GetMagneticField(bFinal, x, newNode)) return _ORACLE_ERROR_;
+    } else {
       cStencil Stencil;
       if (!GC_InitStencil(x, startNode, Stencil)) return _ORACLE_ERROR_;  // the START node, as written (:713)
       GC_Gather(Stencil, startNode, BackgroundB_d, 3, bFinal);
@@ -2997,6 +3078,10 @@ void oracle_set_reduced_state(oracle_ctx *o, const double *mu, const double *vpa
     if (mu) oracle_ctx::SetMagneticMoment(mu[ptr], pd);
     if (vpar) oracle_ctx::SetVParallel(vpar[ptr], pd);
   }
+}
+// the current E on the unique corners (slot 0 of the corner data: what ECSIM::GetElectricField reads)
+void oracle_set_E_current(oracle_ctx *o, const double *E) {
+  for (int i = 0; i < o->n_corners; i++) memcpy(o->cornerPool[i].data + ExOffsetIndex, E + 3 * (size_t)i, 24);
 }
 void oracle_set_v_normal(oracle_ctx *o, const double *vnormal, int64_t n) {
   for (int64_t ptr = 0; ptr < n; ptr++) oracle_ctx::SetVNormal(vnormal[ptr], o->GetParticleDataPointer(ptr));

@@ -61,6 +61,8 @@ void oracle_get_magnetic_moment(const oracle_ctx *, double *mu, uint8_t *init_fl
 void oracle_set_reduced_state(oracle_ctx *, const double *mu, const double *vpar, int64_t n);
 /* v_normal by ptr (PB::SetVNormal): read by ProcessCell for the guiding-centre species of cfg.gc_species_mask */
 void oracle_set_v_normal(oracle_ctx *o, const double *vnormal, int64_t n);
+/* the current E on the unique corners: read by the guiding-centre movers when cfg.gc_fields_ecsim */
+void oracle_set_E_current(oracle_ctx *o, const double *E);
 void oracle_get_v_parallel(const oracle_ctx *, double *vpar, int64_t n);
 /* exit records (domain faces / internal sphere) accumulated since the last call; returns their number */
 int64_t oracle_exit_records(oracle_ctx *, amps_gpu_exit_record *buf, int64_t max_records);

@@ -38,6 +38,7 @@ def load(kind="parity"):
     lib.oracle_get_magnetic_moment.argtypes = [vp, vp, vp, C.c_int64]
     lib.oracle_set_reduced_state.argtypes = [vp, vp, vp, C.c_int64]
     lib.oracle_set_v_normal.argtypes = [vp, vp, C.c_int64]
+    lib.oracle_set_E_current.argtypes = [vp, vp]
     lib.oracle_get_v_parallel.argtypes = [vp, vp, C.c_int64]
     lib.oracle_add_particles.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64]
     lib.oracle_particle_count.restype = C.c_int64
@@ -109,6 +110,11 @@ class Oracle:
         flag = np.zeros(self.n_added, dtype=np.uint8)
         self.lib.oracle_get_magnetic_moment(self.h, _p(mu), _p(flag), self.n_added)
         return mu, flag
+
+    def set_E_current(self, E):
+        a = np.ascontiguousarray(E, dtype=np.float64)
+        assert a.shape == (self.mesh.n_corners, 3)
+        self.lib.oracle_set_E_current(self.h, _p(a))
 
     def set_v_normal(self, vnormal):
         a = np.ascontiguousarray(vnormal, dtype=np.float64)
