@@ -159,22 +159,34 @@ __global__ void __launch_bounds__(256, 5) scatter_kernel(ParticleSoA src, Partic
 // their results is used, so that one trip of a warp has one DRAM and one L2 round trip for 128 keys (the kernel was latency bound
 // at one key per trip and thread: 99 us for 3.4e7 keys).  Empty slots (key < 0) form their own match group, which has no atomic.
 constexpr int PERM_VEC = 4;
-__global__ void __launch_bounds__(256, 4) perm_kernel(const int *__restrict__ key, const int *__restrict__ nSrc, const int *__restrict__ cellStart,
-                                                     int *__restrict__ cellFill, int *__restrict__ perm) {
+constexpr int PERM_CTAS = 6;  // CTAs per SM: 48 warps, each with the keys of its next trip already in flight
+                              // (finishing a trip one trip later, behind the next atomics, measured no faster: 64 registers, 4 CTAs)
+__device__ __forceinline__ void perm_load_keys(const int *__restrict__ key, long long i0, int n, int (&k)[PERM_VEC]) {
+  if (i0 + PERM_VEC <= n) {
+    const int4 q = *reinterpret_cast<const int4 *>(key + i0);
+    k[0] = q.x, k[1] = q.y, k[2] = q.z, k[3] = q.w;
+  } else {
+#pragma unroll
+    for (int q = 0; q < PERM_VEC; q++) k[q] = (i0 + q < n) ? key[i0 + q] : -1;
+  }
+}
+__global__ void __launch_bounds__(256, PERM_CTAS) perm_kernel(const int *__restrict__ key, const int *__restrict__ nSrc, const int *__restrict__ cellStart,
+                                                             int *__restrict__ cellFill, int *__restrict__ perm) {
   const int n = *nSrc;
   const int lane = threadIdx.x & 31;
   const long long stride = (long long)gridDim.x * blockDim.x * PERM_VEC;
-  // the trip count is uniform over the warp (every lane takes part in the match / shuffle rounds)
-  for (long long w0 = ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * PERM_VEC; w0 < n; w0 += stride) {
+  // the trip count is uniform over the warp (every lane takes part in the match / shuffle rounds).  The profile of the version
+  // without it showed the two exposed latencies of a trip, the key load (35 % of the stall samples at the first MATCH) and the
+  // atomics (28 % at the first SHFL): the keys of the NEXT trip are requested before the current one is processed.
+  long long w0 = ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * PERM_VEC;
+  int kn[PERM_VEC];
+  if (w0 < n) perm_load_keys(key, w0 + lane * PERM_VEC, n, kn);
+  for (; w0 < n; w0 += stride) {
     const long long i0 = w0 + lane * PERM_VEC;
     int k[PERM_VEC];
-    if (i0 + PERM_VEC <= n) {
-      const int4 q = *reinterpret_cast<const int4 *>(key + i0);
-      k[0] = q.x, k[1] = q.y, k[2] = q.z, k[3] = q.w;
-    } else {
 #pragma unroll
-      for (int q = 0; q < PERM_VEC; q++) k[q] = (i0 + q < n) ? key[i0 + q] : -1;
-    }
+    for (int q = 0; q < PERM_VEC; q++) k[q] = kn[q];
+    if (w0 + stride < n) perm_load_keys(key, i0 + stride, n, kn);
     unsigned mask[PERM_VEC];
     int base[PERM_VEC], start[PERM_VEC];
 #pragma unroll
@@ -215,7 +227,7 @@ void launch_sort(const DevMesh &m, ParticleSoA src, ParticleSoA dst, const int *
   cudaMemsetAsync(cellFill, 0, sizeof(int) * nCells, s);
   if (perm) {
     const long long want = (nUpper + 256 * PERM_VEC - 1) / (256 * PERM_VEC);
-    perm_kernel<<<(int)(want > 148 * 8 ? 148 * 8 : want < 1 ? 1 : want), 256, 0, s>>>(src.key, nSrc, cellStart, cellFill, perm);
+    perm_kernel<<<(int)(want > 148 * PERM_CTAS ? 148 * PERM_CTAS : want < 1 ? 1 : want), 256, 0, s>>>(src.key, nSrc, cellStart, cellFill, perm);
   }
   else scatter_kernel<<<pgrid, 256, 0, s>>>(src, dst, nSrc, cellStart, cellFill);
   (*launches) += 4;
