@@ -231,40 +231,65 @@ def cpu_port_rate(n_cells, ppc, steps, threads, warmup=1, min_seconds=0.0, max_s
     return n, per_step
 
 
-def reference_code_rate(steps=6):
+def reference_code_rate(steps=6, procs=None):
     """The reference's OWN mover + deposit (PIC::Mover::MoveParticles -> Lapenta2017, ECSIM::UpdateJMassMatrix -> ProcessCell), compiled
-    from /root/reference at -O3 into oracle/_ref/libref_pic_O3.so (oracle/ref_pic/build_ref_pic.sh), timed on one host core on the box
-    it is built for: the reference's fast-wave test (16x8x4-cell blocks, 783 360 particles, one rank).  A cross-check of the CPU arm
-    (the port runs the bench's own box on all cores), not the arm itself: the box differs.  Runs in a child process (the reference's
-    state is global and it prints to stdout).  None when the library is not there."""
+    from /root/reference at -O3 into oracle/_ref/libref_pic_O3.so (oracle/ref_pic/build_ref_pic.sh), timed on the box it is built for:
+    the reference's fast-wave test (16x8x4-cell blocks, 783 360 particles, one rank).  The reference parallelises with MPI ranks, the
+    library is one rank: `procs` (default: every host core) independent instances run the same steps at the same time (they start on a
+    common clock after their set-up), which is what a domain-decomposed run costs without its exchanges.  Each runs in a child process
+    (the reference's state is global and it prints to stdout).  None when the library is not there."""
     lib = os.path.join(ROOT, "oracle", "_ref", "libref_pic_O3.so")
     if not os.path.exists(lib):
         return None
+    procs = procs or (os.cpu_count() or 1)
+    t_start = time.time() + 12.0  # set-up of one instance takes 1-3 s
     code = (
         "import sys, os, time, json, ctypes as C, numpy as np\n"
         f"sys.path.insert(0, {ROOT!r})\n"
         "import oracle.ref_pic.ref_pic as rp\n"
         f"rp.LIB = {lib!r}\n"
-        "r = rp.RefPic(); e = np.zeros(1); per = []\n"
-        f"for it in range({steps} + 1):\n"
-        "    t = time.perf_counter()\n"
+        "r = rp.RefPic(); e = np.zeros(1)\n"
+        "with rp.quiet():\n"
+        "    r.lib.ref_pic_move(); r.lib.ref_pic_update_JM(e.ctypes.data_as(C.c_void_p))\n"
+        f"late = time.time() > {t_start!r}\n"
+        f"while time.time() < {t_start!r}: time.sleep(0.005)\n"
+        "t0 = time.time()\n"
+        f"for it in range({steps}):\n"
         "    with rp.quiet():\n"
         "        r.lib.ref_pic_move(); r.lib.ref_pic_update_JM(e.ctypes.data_as(C.c_void_p))\n"
-        "    per.append(time.perf_counter() - t)\n"
-        "sys.stderr.write('REFCODE ' + json.dumps({'n': int(r.n_particles), 'per': per[1:]}) + '\\n')\n"
+        "t1 = time.time()\n"
+        "sys.stderr.write('REFCODE ' + json.dumps({'n': int(r.n_particles), 't0': t0, 't1': t1, 'late': late}) + '\\n')\n"
     )
     try:
-        out = subprocess.run([sys.executable, "-c", code], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=300)
-        rec = json.loads([l for l in out.stderr.splitlines() if l.startswith("REFCODE ")][-1][8:])
-    except Exception as exc:
+        env = dict(os.environ, OMP_NUM_THREADS="1")
+        ps = [subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=env) for _ in range(procs)]
+        recs = []
+        for q in ps:
+            _, err = q.communicate(timeout=600)
+            recs.append(json.loads([l for l in err.splitlines() if l.startswith("REFCODE ")][-1][8:]))
+    except Exception as exc:  # noqa: BLE001
         return {"error": repr(exc)[:200]}
-    v = rec["n"] * len(rec["per"]) / sum(rec["per"])
-    cores = os.cpu_count() or 1
-    return {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
-            "all_cores_upper_bound": v * cores,
-            "sample": f"the reference's own code (oracle/_ref/libref_pic_O3.so, g++ -O3, one rank) on its fast-wave test box: {rec['n']} particles, "
-                      f"{len(rec['per'])} steps of MoveParticles + UpdateJMassMatrix; all_cores_upper_bound = value x {cores} host cores "
-                      "(MPI ranks without any exchange cost)"}
+    span = max(r["t1"] for r in recs) - min(r["t0"] for r in recs)
+    v = sum(r["n"] for r in recs) * steps / span
+    one = recs[0]["n"] * steps / min(r["t1"] - r["t0"] for r in recs)
+    return {"value": v, "unit": UNIT, "cores": procs, "kind": "reference", "fastest_instance": one, "late_starts": sum(1 for r in recs if r["late"]),
+            "sample": f"the reference's own code (oracle/_ref/libref_pic_O3.so, g++ -O3): {procs} one-rank instances at the same time, each on the "
+                      f"reference's fast-wave test box ({recs[0]['n']} particles, 16x8x4-cell blocks), {steps} steps of MoveParticles + UpdateJMassMatrix; "
+                      "value = all particle updates / the span from the first start to the last end"}
+
+
+def best_cpu_baseline(port):
+    """cpu_baseline of a bench line: the port on the bench's own box (same config) and, when it is built, the reference's own code on all
+    cores; the larger of the two is the baseline (the GPU is compared with the best CPU number this box gives), the other is kept beside it."""
+    ref = reference_code_rate()
+    if ref is None or "error" in ref or ref["value"] <= port["value"]:
+        out = dict(port)
+        if ref is not None:
+            out["reference_code"] = ref
+        return out
+    out = dict(ref)
+    out["port_same_config"] = port
+    return out
 
 
 def run_reference(args):
@@ -290,9 +315,15 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    rc = reference_code_rate()
-    if rc is not None:
-        line["cpu_baseline"]["reference_code"] = rc
+    best = best_cpu_baseline(line["cpu_baseline"])
+    if best["kind"] == "reference":  # the reference's own code on all cores beats the port on this box: it is the arm's number
+        line["cpu_baseline"] = best
+        line["value"] = best["value"]
+        line["e2e"]["value"] = best["value"]
+        line["ms_per_step"] = 1e3 * n / best["value"]  # what one step of the configured box costs at this rate
+        line["config"]["sample"] = best["sample"]
+    else:
+        line["cpu_baseline"] = best
     _emit(line)
 
 
@@ -867,9 +898,7 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"the bench box itself: {args.cells}^3 cells x {args.ppc} ppc x 2 species = {n_cpu} particles, {len(per)} steps, "
                                           "oracle -O3 OpenMP"}
-        rc = reference_code_rate()
-        if rc is not None:
-            line["cpu_baseline"]["reference_code"] = rc
+        line["cpu_baseline"] = best_cpu_baseline(line["cpu_baseline"])
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
