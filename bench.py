@@ -233,12 +233,12 @@ def cpu_port_rate(n_cells, ppc, steps, threads, warmup=1, min_seconds=0.0, max_s
 
 def reference_code_rate(steps=6, procs=None):
     """The reference's OWN mover + deposit (PIC::Mover::MoveParticles -> Lapenta2017, ECSIM::UpdateJMassMatrix -> ProcessCell), compiled
-    from /root/reference at -O3 into oracle/_ref/libref_pic_O3.so (oracle/ref_pic/build_ref_pic.sh), timed on the box it is built for:
+    from /root/reference at -O3 into oracle/_ref/libref_pic.so (the library that also pins the oracle) (oracle/ref_pic/build_ref_pic.sh), timed on the box it is built for:
     the reference's fast-wave test (16x8x4-cell blocks, 783 360 particles, one rank).  The reference parallelises with MPI ranks, the
     library is one rank: `procs` (default: every host core) independent instances run the same steps at the same time (they start on a
     common clock after their set-up), which is what a domain-decomposed run costs without its exchanges.  Each runs in a child process
     (the reference's state is global and it prints to stdout).  None when the library is not there."""
-    lib = os.path.join(ROOT, "oracle", "_ref", "libref_pic_O3.so")
+    lib = os.path.join(ROOT, "oracle", "_ref", "libref_pic.so")
     if not os.path.exists(lib):
         return None
     procs = procs or (os.cpu_count() or 1)
@@ -273,7 +273,7 @@ def reference_code_rate(steps=6, procs=None):
     v = sum(r["n"] for r in recs) * steps / span
     one = recs[0]["n"] * steps / min(r["t1"] - r["t0"] for r in recs)
     return {"value": v, "unit": UNIT, "cores": procs, "kind": "reference", "fastest_instance": one, "late_starts": sum(1 for r in recs if r["late"]),
-            "sample": f"the reference's own code (oracle/_ref/libref_pic_O3.so, g++ -O3): {procs} one-rank instances at the same time, each on the "
+            "sample": f"the reference's own code (oracle/_ref/libref_pic.so, g++ -O3): {procs} one-rank instances at the same time, each on the "
                       f"reference's fast-wave test box ({recs[0]['n']} particles, 16x8x4-cell blocks), {steps} steps of MoveParticles + UpdateJMassMatrix; "
                       "value = all particle updates / the span from the first start to the last end"}
 

@@ -7,7 +7,7 @@
 #  2. the reference's own Perl configuration for its ECSIM test `input/test/fast-wave.input` (ampsConfig.pl -no-compile): it
 #     generates build/ with _BLOCK_CELLS_ 16,8,4, Lapenta2017 as the mover, ECSIM as the field solver, the periodic mode,
 #  3. every translation unit the reference's makefiles list for that configuration (src/pic, general, meshAMR, interface,
-#     species, models/*; the SWMF fluid coupler pic_fluid.cpp / pic_swmf.cpp excepted) compiled with g++ -O1 -ffp-contract=off
+#     species, models/*; the SWMF fluid coupler pic_fluid.cpp / pic_swmf.cpp excepted) compiled with g++ -O3 -ffp-contract=off
 #     against our stand-ins for mpi.h (one rank) and the three un-vendored SWMF `share` headers (oracle/ref_pic/, oracle/ref_mesh/mpi.h),
 #  4. linked with oracle/ref_pic/ref_pic_shim.cpp (includes the reference's test/srcFastWave/main.cpp for the initial
 #     conditions) and oracle/ref_pic/mpi_single.cpp into the shared library.
@@ -41,8 +41,9 @@ for d in ['pic', 'general', 'meshAMR', 'interface', 'species', 'models/exosphere
 PY
 B="$S/build"
 INC="-include $HERE/ref_pic_stubs.h -I$HERE -I$S/test/srcFastWave -I$B/pic -I$B/general -I$B/meshAMR -I$B/interface -I$B/models/exosphere -I$B/models/dust -I$B/species -I$B/models/surface -I$B/models/sputtering -I$B/models/charge_exchange -I$B/models/electron_impact -I$B/models/photolytic_reactions -I$S/srcInterface -I$HERE/../ref_mesh"
-# REF_PIC_OPT: the checker is built -O1 -ffp-contract=off (bit-stable arithmetic); the timing copy libref_pic_O3.so with -O3
-FLAGS="-std=c++17 -w ${REF_PIC_OPT:--O1 -ffp-contract=off} -fPIC"
+# -O3 without FMA contraction: the same library is the checker of the oracle (bit-identical results, tests/test_reference_ecsim.py) and
+# the reference-code CPU arm of bench.py
+FLAGS="-std=c++17 -w ${REF_PIC_OPT:--O3 -ffp-contract=off} -fPIC"
 mkdir -p obj
 cat > cc.sh <<EOS
 #!/bin/bash

@@ -7,7 +7,7 @@ import tempfile
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB = os.path.join(os.path.dirname(HERE), "_ref", "libref_pic.so")
+LIB = os.environ.get("AMPS_REF_PIC_LIB") or os.path.join(os.path.dirname(HERE), "_ref", "libref_pic.so")
 
 
 def available():
