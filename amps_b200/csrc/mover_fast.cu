@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256, FAST_CTAS) move_lapenta_fast_kernel(DevMe
     }
 
     double xf[3], vf[3];
-    int newKey = -1;
+    int newKey = -1, keyLeaf = leaf;  // keyLeaf = newKey / C without the division
     bool wrapped = false;
     if (!redo) {
       // ---- velocity / position update (:1036-1081) ----
@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(256, FAST_CTAS) move_lapenta_fast_kernel(DevMe
             wrapped = true;
           }
           newKey = newLeaf * C + ijk[0] + m.N[0] * (ijk[1] + m.N[1] * ijk[2]);
+          keyLeaf = newLeaf;
         }
       }
     }
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(256, FAST_CTAS) move_lapenta_fast_kernel(DevMe
     }
     nMoved++;
     if (wrapped) nWrap++;
-    if (newKey / C != leaf) nXBlock++;
+    if (keyLeaf != leaf) nXBlock++;
     else if (newKey != oldKey) nXCell++;
     p.x[0][ip] = xf[0], p.x[1][ip] = xf[1], p.x[2][ip] = xf[2];
     p.v[0][ip] = vf[0], p.v[1][ip] = vf[1], p.v[2][ip] = vf[2];
