@@ -38,6 +38,7 @@ struct amps_gpu_ctx {
   double dxc0[3] = {1.0, 1.0, 1.0};  // cell size of leaf 0 (single-level meshes: of every leaf)
   double *d_krylov = nullptr;   // [(restart + 1) + 2][3 nCorners]: V_0.., w, x
   int krylovVectors = 0;
+  int lastFieldIters = 0;       // iterations of the previous field step: that many Arnoldi steps (less one) run before the host looks
   double *d_hcol = nullptr, *h_hcol = nullptr;  // inner products of one iteration (device / pinned host), + the norm
   double *d_ycoef = nullptr;
   // several ranks: halo lists of the field solve (per peer: corners to send / receive, centres to send / receive, concatenated in
@@ -435,7 +436,7 @@ static int release_mesh(amps_gpu_ctx *ctx) {
   ctx->cplrCacheTried = false;
   // the field solve is sized by the mesh as well: a new epoch needs amps_gpu_field_solver_init (and the halo / primary lists) again
   drop(ctx->d_E), drop(ctx->d_fNb), drop(ctx->d_fCc), drop(ctx->d_fZc), drop(ctx->d_krylov), drop(ctx->d_primary);
-  ctx->fieldSolverReady = ctx->eReady = false, ctx->fieldWarmValid = false, ctx->krylovVectors = 0;
+  ctx->fieldSolverReady = ctx->eReady = false, ctx->fieldWarmValid = false, ctx->krylovVectors = 0, ctx->lastFieldIters = 0;
   drop(ctx->d_sendBuf), drop(ctx->d_recvBuf), drop(ctx->d_sendCount), drop(ctx->d_allCounts), drop(ctx->d_errFlag);
   for (int *&p : ctx->d_sharedUid) drop(p);
   ctx->d_sharedUid.clear(), ctx->nShared.clear(), ctx->h_sharedUid.clear();
@@ -935,9 +936,9 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
     ctx->fieldWarmValid = false;
     cudaFree(ctx->d_hcol), cudaFree(ctx->d_ycoef);
     if (ctx->h_hcol) cudaFreeHost(ctx->h_hcol);
-    if ((rc = dev_alloc(ctx, &ctx->d_hcol, (size_t)restart + 4))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_hcol, (size_t)(restart + 1) * (restart + 4)))) return rc;  // one column per Arnoldi step
     if ((rc = dev_alloc(ctx, &ctx->d_ycoef, (size_t)restart + 4))) return rc;
-    CK(cudaMallocHost(&ctx->h_hcol, sizeof(double) * (restart + 4)));
+    CK(cudaMallocHost(&ctx->h_hcol, sizeof(double) * (restart + 1) * (restart + 4)));
   }
   // metric and time factors of GetStencil: coeff = theta c dt / dx, the operator constants K[9 slot + 3 p + q]
   double dx[3], coeff[3], c4rhs[3], c4b[3];
@@ -1029,36 +1030,52 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
     ctx->launches += 2;
     std::fill(g.begin(), g.end(), 0.0);
     g[0] = beta;
-    int j = 0;
-    for (; j < restart && iters < max_iter; j++) {
+    // The host only needs the Hessenberg columns to decide when to stop.  The previous field step took lastFieldIters iterations:
+    // that many Arnoldi steps less one are queued without a host round trip (every step has its own column on the device), the
+    // columns come back together and the Givens rotations catch up; from there on the host looks after every step.  A step that
+    // converges earlier than its predecessor has run a few products in vain; the solution uses the columns up to convergence only.
+    const int hs = restart + 4;  // stride of a column in d_hcol / h_hcol
+    const int blind = ctx->lastFieldIters - 1 - iters;
+    int j = 0, done = 0;  // done: columns the host has rotated
+    bool converged = false;
+    for (; j < restart && iters < max_iter && !converged;) {
       double *vj = V + (size_t)j * ld, *vn = V + (size_t)(j + 1) * ld;
+      double *hc = ctx->d_hcol + (size_t)j * hs;
       launch_ecsim_operator(false, m.nCorners, ctx->d_fNb, ctx->d_fCc, Kc, ctx->d_M, vj, f, nullptr, nullptr, c4rhs, vn, s);
       iters++;
       if ((rc = field_halo_exchange(ctx, vn, false))) return rc;
-      launch_multi_dot(V, ld, j + 1, vn, n, ctx->d_hcol, mask, s);                             // h_i = V_i . w
-      if ((rc = allsum(ctx->d_hcol, j + 1))) return rc;
-      launch_orthogonalize(V, ld, j + 1, ctx->d_hcol, vn, n, ctx->d_hcol + j + 2, mask, s);    // w -= sum h_i V_i, |w|^2
-      if ((rc = allsum(ctx->d_hcol + j + 2, 1))) return rc;
-      launch_axpby(n, 1.0, vn, 0.0, nullptr, ctx->d_hcol + j + 2, vn, s);                // V_{j+1} = w / |w|
+      launch_multi_dot(V, ld, j + 1, vn, n, hc, mask, s);                             // h_i = V_i . w
+      if ((rc = allsum(hc, j + 1))) return rc;
+      launch_orthogonalize(V, ld, j + 1, hc, vn, n, hc + j + 2, mask, s);    // w -= sum h_i V_i, |w|^2
+      if ((rc = allsum(hc + j + 2, 1))) return rc;
+      launch_axpby(n, 1.0, vn, 0.0, nullptr, hc + j + 2, vn, s);                // V_{j+1} = w / |w|
       ctx->launches += 4;
-      CK(cudaMemcpyAsync(ctx->h_hcol, ctx->d_hcol, sizeof(double) * (j + 3), cudaMemcpyDeviceToHost, s));
+      j++;
+      if (j < blind && j < restart && iters < max_iter) continue;
+      CK(cudaMemcpyAsync(ctx->h_hcol + (size_t)done * hs, ctx->d_hcol + (size_t)done * hs, sizeof(double) * (size_t)(j - done) * hs, cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
-      for (int i = 0; i <= j; i++) H[(size_t)i * restart + j] = ctx->h_hcol[i];
-      H[(size_t)(j + 1) * restart + j] = sqrt(ctx->h_hcol[j + 2]);
-      for (int i = 0; i < j; i++) {
-        const double t = cs[i] * H[(size_t)i * restart + j] + sn[i] * H[(size_t)(i + 1) * restart + j];
-        H[(size_t)(i + 1) * restart + j] = -sn[i] * H[(size_t)i * restart + j] + cs[i] * H[(size_t)(i + 1) * restart + j];
-        H[(size_t)i * restart + j] = t;
-      }
-      const double a = H[(size_t)j * restart + j], b = H[(size_t)(j + 1) * restart + j], d = sqrt(a * a + b * b);
-      cs[j] = a / d, sn[j] = b / d;
-      H[(size_t)j * restart + j] = d, H[(size_t)(j + 1) * restart + j] = 0.0;
-      g[j + 1] = -sn[j] * g[j];
-      g[j] = cs[j] * g[j];
-      rel = fabs(g[j + 1]) / r0norm;
-      if (rel <= tol) {
-        j++;
-        break;
+      for (; done < j; done++) {
+        const int c = done;
+        const double *hh = ctx->h_hcol + (size_t)c * hs;
+        for (int i = 0; i <= c; i++) H[(size_t)i * restart + c] = hh[i];
+        H[(size_t)(c + 1) * restart + c] = sqrt(hh[c + 2]);
+        for (int i = 0; i < c; i++) {
+          const double t = cs[i] * H[(size_t)i * restart + c] + sn[i] * H[(size_t)(i + 1) * restart + c];
+          H[(size_t)(i + 1) * restart + c] = -sn[i] * H[(size_t)i * restart + c] + cs[i] * H[(size_t)(i + 1) * restart + c];
+          H[(size_t)i * restart + c] = t;
+        }
+        const double a = H[(size_t)c * restart + c], b = H[(size_t)(c + 1) * restart + c], d = sqrt(a * a + b * b);
+        cs[c] = a / d, sn[c] = b / d;
+        H[(size_t)c * restart + c] = d, H[(size_t)(c + 1) * restart + c] = 0.0;
+        g[c + 1] = -sn[c] * g[c];
+        g[c] = cs[c] * g[c];
+        rel = fabs(g[c + 1]) / r0norm;
+        if (rel <= tol) {
+          iters -= j - (c + 1);  // the products past convergence are not iterations of the solve
+          j = c + 1;
+          converged = true;
+          break;
+        }
       }
     }
     for (int i = j - 1; i >= 0; i--) {
@@ -1085,6 +1102,7 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
   CK(cudaGetLastError());
   ctx->eReady = true;
   ctx->fieldWarmValid = true, ctx->fieldWarmN = n;  // x stays in the Krylov workspace for a warm start of the next step
+  ctx->lastFieldIters = iters;
   if (iterations) *iterations = iters;
   if (rel_residual) *rel_residual = rel;
   return AMPS_GPU_OK;
