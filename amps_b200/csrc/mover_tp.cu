@@ -819,10 +819,9 @@ void launch_magnetic_moment_set(ParticleSoA p, double *target, const int *nSlots
   magnetic_moment_set_kernel<<<(int)g, 256, 0, s>>>(p, target, nSlots, muByPtr, nMu);
 }
 
-#ifndef GCA_MIN_CTAS
-#define GCA_MIN_CTAS 3
-#endif
-__global__ void __launch_bounds__(128, GCA_MIN_CTAS) move_relativistic_gca_kernel(DevMesh m, DevSpecies sp, TpParams tp, ParticleSoA p, const int *__restrict__ nSlots,
+// (no minimum of resident CTAs: with 3, 4 or 5 per SM in the launch bounds the kernel measured 6 % slower / no faster: its 3 200
+// instructions per particle of IEEE divisions and gathers do not gain from occupancy, profiles/r2_gca_ncu_summary.txt)
+__global__ void __launch_bounds__(128) move_relativistic_gca_kernel(DevMesh m, DevSpecies sp, TpParams tp, ParticleSoA p, const int *__restrict__ nSlots,
                                                                    const double *__restrict__ bgTile, const double *__restrict__ gcaTile,
                                                                    const double *__restrict__ uVar, int *__restrict__ cellCount, DevMoveStats *__restrict__ stats,
                                                                    amps_gpu_exit_record *__restrict__ exitBuf, unsigned long long *__restrict__ exitCount) {
