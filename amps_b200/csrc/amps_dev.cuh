@@ -136,9 +136,11 @@ void launch_gc_deposit(const DevMesh &m, const DevSpecies &sp, unsigned gcMask, 
 // field_solver.cu
 void launch_ecsim_operator(bool rhs, int nCorners, const int *nb, const int *cc, const double *Kc, const double *M, const double *x, double f,
                            const double *J, const double *B, const double c4[3], double *y, cudaStream_t s);
-void launch_multi_dot(const double *V, size_t ld, int nVec, const double *w, int n, double *out, const unsigned char *mask, cudaStream_t s);
+// zero = false: the caller cleared the accumulators (the Arnoldi loop clears all its columns with one memset)
+void launch_multi_dot(const double *V, size_t ld, int nVec, const double *w, int n, double *out, const unsigned char *mask, cudaStream_t s,
+                      bool zero = true);
 void launch_orthogonalize(const double *V, size_t ld, int nVec, const double *h, double *w, int n, double *norm2, const unsigned char *mask,
-                          cudaStream_t s);
+                          cudaStream_t s, bool zero = true);
 void launch_halo_pack(const int *uid, int n, const double *vec, double *buf, cudaStream_t s);
 void launch_halo_unpack(const int *uid, int n, const double *buf, double *vec, cudaStream_t s);
 void launch_axpby(int n, double alpha, const double *a, double beta, const double *b, const double *invSqrtOf, double *out, cudaStream_t s);

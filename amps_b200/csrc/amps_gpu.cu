@@ -938,7 +938,7 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
     if (ctx->h_hcol) cudaFreeHost(ctx->h_hcol);
     if ((rc = dev_alloc(ctx, &ctx->d_hcol, (size_t)(restart + 1) * (restart + 4)))) return rc;  // one column per Arnoldi step
     if ((rc = dev_alloc(ctx, &ctx->d_ycoef, (size_t)restart + 4))) return rc;
-    CK(cudaMallocHost(&ctx->h_hcol, sizeof(double) * (restart + 1) * (restart + 4)));
+    CK(cudaMallocHost(&ctx->h_hcol, sizeof(double) * (restart + 2) * (restart + 4)));  // + one column for the coefficients y
   }
   // metric and time factors of GetStencil: coeff = theta c dt / dx, the operator constants K[9 slot + 3 p + q]
   double dx[3], coeff[3], c4rhs[3], c4b[3];
@@ -1038,15 +1038,16 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
     const int blind = ctx->lastFieldIters - 1 - iters;
     int j = 0, done = 0;  // done: columns the host has rotated
     bool converged = false;
+    CK(cudaMemsetAsync(ctx->d_hcol, 0, sizeof(double) * (size_t)(restart + 1) * hs, s));  // the accumulators of every column at once
     for (; j < restart && iters < max_iter && !converged;) {
       double *vj = V + (size_t)j * ld, *vn = V + (size_t)(j + 1) * ld;
       double *hc = ctx->d_hcol + (size_t)j * hs;
       launch_ecsim_operator(false, m.nCorners, ctx->d_fNb, ctx->d_fCc, Kc, ctx->d_M, vj, f, nullptr, nullptr, c4rhs, vn, s);
       iters++;
       if ((rc = field_halo_exchange(ctx, vn, false))) return rc;
-      launch_multi_dot(V, ld, j + 1, vn, n, hc, mask, s);                             // h_i = V_i . w
+      launch_multi_dot(V, ld, j + 1, vn, n, hc, mask, s, false);                      // h_i = V_i . w
       if ((rc = allsum(hc, j + 1))) return rc;
-      launch_orthogonalize(V, ld, j + 1, hc, vn, n, hc + j + 2, mask, s);    // w -= sum h_i V_i, |w|^2
+      launch_orthogonalize(V, ld, j + 1, hc, vn, n, hc + j + 2, mask, s, false);  // w -= sum h_i V_i, |w|^2
       if ((rc = allsum(hc + j + 2, 1))) return rc;
       launch_axpby(n, 1.0, vn, 0.0, nullptr, hc + j + 2, vn, s);                // V_{j+1} = w / |w|
       ctx->launches += 4;
@@ -1083,10 +1084,11 @@ int amps_gpu_field_step(amps_gpu_ctx *ctx, double theta, double tol, int max_ite
       for (int q = i + 1; q < j; q++) t -= H[(size_t)i * restart + q] * y[q];
       y[i] = t / H[(size_t)i * restart + i];
     }
-    CK(cudaMemcpyAsync(ctx->d_ycoef, y.data(), sizeof(double) * j, cudaMemcpyHostToDevice, s));
+    double *yPinned = ctx->h_hcol + (size_t)(restart + 1) * (restart + 4);  // pinned and owned by the context: no wait for the copy
+    for (int i = 0; i < j; i++) yPinned[i] = y[i];
+    CK(cudaMemcpyAsync(ctx->d_ycoef, yPinned, sizeof(double) * j, cudaMemcpyHostToDevice, s));
     launch_combine(V, ld, j, ctx->d_ycoef, x, n, s);
     ctx->launches++;
-    CK(cudaStreamSynchronize(s));  // y is a host temporary
     if (rel <= tol) break;
   }
   // ProcessFinalSolution: E^{n+theta} = E^n + x

@@ -196,13 +196,14 @@ void launch_ecsim_operator(bool rhs, int nCorners, const int *nb, const int *cc,
   if (rhs) ecsim_operator_kernel<true><<<grid, 256, 0, s>>>(nCorners, nb, cc, Kc, M, x, f, J, B, c4[0], c4[1], c4[2], y);
   else ecsim_operator_kernel<false><<<grid, 256, 0, s>>>(nCorners, nb, cc, Kc, M, x, f, nullptr, nullptr, 0.0, 0.0, 0.0, y);
 }
-void launch_multi_dot(const double *V, size_t ld, int nVec, const double *w, int n, double *out, const unsigned char *mask, cudaStream_t s) {
-  cudaMemsetAsync(out, 0, sizeof(double) * (nVec + 1), s);
+void launch_multi_dot(const double *V, size_t ld, int nVec, const double *w, int n, double *out, const unsigned char *mask, cudaStream_t s,
+                      bool zero) {
+  if (zero) cudaMemsetAsync(out, 0, sizeof(double) * (nVec + 1), s);
   multi_dot_kernel<<<148 * 4, 256, 0, s>>>(V, ld, nVec, w, n, out, mask);
 }
 void launch_orthogonalize(const double *V, size_t ld, int nVec, const double *h, double *w, int n, double *norm2, const unsigned char *mask,
-                          cudaStream_t s) {
-  cudaMemsetAsync(norm2, 0, sizeof(double), s);
+                          cudaStream_t s, bool zero) {
+  if (zero) cudaMemsetAsync(norm2, 0, sizeof(double), s);
   orthogonalize_kernel<<<grid_rows(n), 256, 0, s>>>(V, ld, nVec, h, w, n, norm2, mask);
 }
 
