@@ -3496,6 +3496,19 @@ int oracle_coupler_stencil(const oracle_ctx *o, const double *x, int leaf, int *
   for (int i = 0; i < s.Length; i++) uids[i] = (int)(s.cell[i] - o->centerPool.data()), w[i] = s.Weight[i];
   return s.Length;
 }
+// ECSIM::GetElectricField / GetMagneticField / GetMagneticFieldGradient (pic_field_solver_ecsim.cpp:7440-7547) at n points, each in
+// its `leaf`: E[n][3], B[n][3], gradB[n][9]; returns the number of points where the reference would have exit()ed
+int oracle_ecsim_fields(const oracle_ctx *o, int64_t n, const double *x, const int32_t *leaf, double *E, double *B, double *gradB) {
+  int bad = 0;
+  for (int64_t i = 0; i < n; i++) {
+    cTreeNode *node = o->BlockTable[leaf[i]];
+    bool ok = o->ECSIM_GetElectricField(E + 3 * i, x + 3 * i, node);
+    ok = o->ECSIM_GetMagneticField(B + 3 * i, x + 3 * i, node) && ok;
+    ok = o->ECSIM_GetMagneticFieldGradient(gradB + 9 * i, x + 3 * i, node) && ok;
+    if (!ok) bad++;
+  }
+  return bad;
+}
 // neighbour of a leaf: kind 0 = GetNeibFace(idx,0,0), 1 = GetNeibEdge(idx,0), 2 = GetNeibCorner(idx); returns the node id or -1,
 // geometry in lo/hi/level
 int oracle_neib(const oracle_ctx *o, int leaf, int kind, int idx, double *lo, double *hi, int *level) {

@@ -63,6 +63,8 @@ void oracle_set_reduced_state(oracle_ctx *, const double *mu, const double *vpar
 void oracle_set_v_normal(oracle_ctx *o, const double *vnormal, int64_t n);
 /* the current E on the unique corners: read by the guiding-centre movers when cfg.gc_fields_ecsim */
 void oracle_set_E_current(oracle_ctx *o, const double *E);
+/* ECSIM::GetElectricField / GetMagneticField / GetMagneticFieldGradient at n points (x[n][3], each in its leaf) */
+int oracle_ecsim_fields(const oracle_ctx *o, int64_t n, const double *x, const int32_t *leaf, double *E, double *B, double *gradB);
 void oracle_get_v_parallel(const oracle_ctx *, double *vpar, int64_t n);
 /* exit records (domain faces / internal sphere) accumulated since the last call; returns their number */
 int64_t oracle_exit_records(oracle_ctx *, amps_gpu_exit_record *buf, int64_t max_records);

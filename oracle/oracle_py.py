@@ -39,6 +39,7 @@ def load(kind="parity"):
     lib.oracle_set_reduced_state.argtypes = [vp, vp, vp, C.c_int64]
     lib.oracle_set_v_normal.argtypes = [vp, vp, C.c_int64]
     lib.oracle_set_E_current.argtypes = [vp, vp]
+    lib.oracle_ecsim_fields.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp]
     lib.oracle_get_v_parallel.argtypes = [vp, vp, C.c_int64]
     lib.oracle_add_particles.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64]
     lib.oracle_particle_count.restype = C.c_int64
@@ -115,6 +116,15 @@ class Oracle:
         a = np.ascontiguousarray(E, dtype=np.float64)
         assert a.shape == (self.mesh.n_corners, 3)
         self.lib.oracle_set_E_current(self.h, _p(a))
+
+    def ecsim_fields(self, x, leaf):
+        """ECSIM::GetElectricField / GetMagneticField / GetMagneticFieldGradient at the points x[n][3] (each inside block leaf[n])"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        leaf = np.ascontiguousarray(leaf, dtype=np.int32)
+        n = x.shape[0]
+        E, B, G = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 9))
+        bad = self.lib.oracle_ecsim_fields(self.h, n, _p(x), _p(leaf), _p(E), _p(B), _p(G))
+        return E, B, G, bad
 
     def set_v_normal(self, vnormal):
         a = np.ascontiguousarray(vnormal, dtype=np.float64)

@@ -265,6 +265,19 @@ int ref_pic_stencil(int kind, int p, int q, int max_n, int *ijk, double *a) {
   return st->Length;
 }
 double ref_pic_theta(void) { return PIC::FieldSolver::Electromagnetic::ECSIM::theta; }
+// the field getters the guiding-centre movers call when the field solver is ECSIM (pic_mover_guiding_center.cpp:103, :179-184, :727):
+// E[n][3], B[n][3], gradB[n][9] at the points x[n][3], each inside block[n] (BranchBottomNodeList order)
+void ref_pic_ecsim_fields(long n, const double *x, const int *block, double *E, double *B, double *gradB) {
+  using namespace PIC::FieldSolver::Electromagnetic::ECSIM;
+  for (long i = 0; i < n; i++) {
+    Node *node = g_blocks[block[i]];
+    double xx[3] = {x[3 * i], x[3 * i + 1], x[3 * i + 2]};
+    GetElectricField(E + 3 * i, xx, node);
+    xx[0] = x[3 * i], xx[1] = x[3 * i + 1], xx[2] = x[3 * i + 2];
+    GetMagneticField(B + 3 * i, xx, node);
+    GetMagneticFieldGradient(gradB + 9 * i, xx, node);
+  }
+}
 
 // (the per-species cfl maxima are locals of UpdateJMassMatrix: it prints them, "max cfl number for spec s :value")
 void ref_pic_update_JM(double *energy) {

@@ -96,6 +96,21 @@ def case(keep_every=1):
     Efld = smooth(m.corner_x, 0.02, 2.1) - 0.015
     r.set_corner(0, Efld[cu])  # E^n (the initial condition of fast-wave is E = 0: give the operator something to act on)
     field = {"E": corner_u(r.corner(0)), "B": center_u(r.center(0)), "theta": 0.5}
+    # the field getters of the guiding-centre movers in ECSIM mode (ECSIM::GetElectricField / GetMagneticField / GetMagneticFieldGradient),
+    # sampled before the field step touches E and swaps the B slots: uniform points in the real blocks, a few of them on block faces
+    if hasattr(r.lib, "ref_pic_ecsim_fields"):
+        rg = np.random.default_rng(11)
+        nP = 6000
+        gblk = rg.choice(real, nP).astype(np.int32)
+        u = rg.uniform(0.0, 1.0, (nP, 3))
+        u[:200, 0] = 0.0                       # on the lower x face of the block
+        u[200:400, 1] = 1.0                    # on the upper y face (the corner stencil snaps these)
+        u[400:600] = np.round(u[400:600] * 8) / 8  # on cell faces / corners (16 x 8 x 4 cells: multiples of 1/8 hit faces in every direction)
+        gx = r.bxmin[gblk] + u * (r.bxmax[gblk] - r.bxmin[gblk])
+        gE, gB, gG = np.zeros((nP, 3)), np.zeros((nP, 3)), np.zeros((nP, 9))
+        with ref_pic.quiet():
+            r.lib.ref_pic_ecsim_fields(C.c_long(nP), ref_pic._p(gx), ref_pic._p(gblk), ref_pic._p(gE), ref_pic._p(gB), ref_pic._p(gG))
+        field["getters"] = {"x": gx, "block": gblk, "E": gE, "B": gB, "gradB": gG, "E_u": Efld, "B_u": Bc_u}
     rel_res = C.c_double()
     with ref_pic.quiet():
         field["iterations"] = r.lib.ref_pic_field_step(C.c_double(1e-12), 400, C.byref(rel_res))
@@ -132,6 +147,8 @@ def case(keep_every=1):
         assert d[k] == 0.0
         return k
     b2l = np.array([leaf_of_block(b) if r.ghost[b] == 0 else -1 for b in range(r.n_blocks)])
+    if "getters" in field:
+        field["getters"]["leaf"] = b2l[field["getters"]["block"]].astype(np.int32)
     C = m.cells_per_block
     assert (b2l[p0["block"]] >= 0).all() and (b2l[p1["block"]] >= 0).all()
     cells0 = (b2l[p0["block"]] * C + p0["cell"]).astype(np.int32)

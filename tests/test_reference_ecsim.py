@@ -95,6 +95,26 @@ def test_oracle_reproduces_the_reference_compiled_here(live):
 
 
 @needs_ref
+def test_oracle_ecsim_field_getters_reproduce_the_reference(live):
+    """ECSIM::GetElectricField / GetMagneticField / GetMagneticFieldGradient (pic_field_solver_ecsim.cpp:7440-7547), what the
+    guiding-centre movers read when the field solver is ECSIM (cfg.gc_fields_ecsim): the oracle's restatement against the reference's own
+    functions at 6000 points of the fast-wave box, some of them on block and cell faces"""
+    from oracle.oracle_py import Oracle
+
+    gt = live["ref"]["field"].get("getters")
+    if gt is None:
+        pytest.skip("oracle/_ref/libref_pic.so predates ref_pic_ecsim_fields (rebuild: make -C oracle)")
+    E_u, Bp_u, Bc_u = live["fields"]
+    o = Oracle(live["cfg"], live["mesh"])
+    o.set_fields(E_u, Bp_u, gt["B_u"])
+    o.set_E_current(gt["E_u"])
+    E, B, G, bad = o.ecsim_fields(gt["x"], gt["leaf"])
+    o.close()
+    assert bad == 0
+    assert (E == gt["E"]).all() and (B == gt["B"]).all() and (G == gt["gradB"]).all()  # bit for bit
+
+
+@needs_ref
 @pytest.mark.gpu
 @pytest.mark.parametrize("exact", [True, False])
 def test_gpu_reproduces_the_reference_compiled_here(live, exact):
