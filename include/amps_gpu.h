@@ -127,7 +127,11 @@ typedef struct amps_gpu_config {
                                         :727): E = the current E on the corners (amps_gpu_E_upload / amps_gpu_field_step) through the corner
                                         stencil, B = B_cur on the centres through the centre stencil, grad B = ECSIM::GetMagneticFieldGradient
                                         (pic_field_solver_ecsim.cpp:7473, differences over half a cell).  Single-level meshes, centre-based B.
-                                        0: the coupler's background tables                                                        */
+                                        0: the coupler's background tables.
+                                        NOTE: the guiding-centre movers take charge[] / mass[] as PIC::MolecularData::GetElectricCharge /
+                                        GetMass, the RAW species tables (pic_mover_guiding_center.cpp:137, :216-217, :643), while Lapenta2017
+                                        and ProcessCell use the picunits::si2no values: in a NORM-unit ECSIM run the context that moves the
+                                        guiding-centre species is configured with the raw tables (tests/test_reference_gyrokinetic.py)  */
 } amps_gpu_config;
 
 /* _PIC_COUPLER__INTERPOLATION_MODE_ */

@@ -140,6 +140,27 @@ class RefPic:
         w = np.ascontiguousarray(w, dtype=np.float64)
         self.lib.ref_pic_set_weight_correction(C.c_long(ptr.size), _p(ptr), _p(w))
 
+    # ---- the gyrokinetic variant (oracle/_ref/libref_pic_gk.so: REF_PIC_VARIANT=gk of build_ref_pic.sh) ----
+    def gyrokinetic(self):
+        return hasattr(self.lib, "ref_pic_gyrokinetic") and self.lib.ref_pic_gyrokinetic() == 1
+
+    def set_gc_species(self, spec, on=True):
+        self.lib.ref_pic_set_gc_species(int(spec), 1 if on else 0)
+
+    def set_reduced(self, ptr, mu=None, vnormal=None, init_flag=None):
+        ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+        mu = None if mu is None else np.ascontiguousarray(mu, dtype=np.float64)
+        vn = None if vnormal is None else np.ascontiguousarray(vnormal, dtype=np.float64)
+        fl = None if init_flag is None else np.ascontiguousarray(init_flag, dtype=np.int32)
+        self.lib.ref_pic_set_reduced(C.c_long(ptr.size), _p(ptr), None if mu is None else _p(mu), None if vn is None else _p(vn),
+                                     None if fl is None else _p(fl))
+
+    def get_reduced(self, ptr):
+        ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+        mu, vn, fl = np.zeros(ptr.size), np.zeros(ptr.size), np.zeros(ptr.size, dtype=np.int32)
+        self.lib.ref_pic_get_reduced(C.c_long(ptr.size), _p(ptr), _p(mu), _p(vn), _p(fl))
+        return mu, vn, fl
+
     def move(self):
         with quiet():
             self.lib.ref_pic_move()

@@ -221,6 +221,31 @@ void ref_pic_record_layout(long *out) {
   out[3] = _PIC_PARTICLE_DATA__POSITION_OFFSET_, out[4] = _PIC_PARTICLE_DATA__WEIGHT_CORRECTION_OFFSET_;
   out[5] = _PIC_PARTICLE_DATA__NEXT_OFFSET_, out[6] = _PIC_PARTICLE_DATA__PREV_OFFSET_;
 }
+// ---- the gyrokinetic variant of the library (REF_PIC_VARIANT=gk: _PIC_GYROKINETIC_MODEL_MODE_ and _USE_MAGNETIC_MOMENT_ on) ----
+// 1 when this build carries the reduced state in the particle record and ProcessCell / MoveParticles take their guiding-centre branches
+int ref_pic_gyrokinetic(void) { return (_PIC_GYROKINETIC_MODEL_MODE_ == _PIC_MODE_ON_ && _USE_MAGNETIC_MOMENT_ == _PIC_MODE_ON_) ? 1 : 0; }
+#if _PIC_GYROKINETIC_MODEL_MODE_ == _PIC_MODE_ON_ && _USE_MAGNETIC_MOMENT_ == _PIC_MODE_ON_
+// offsets of the reduced state in the particle record: magnetic moment, v_parallel, v_normal
+void ref_pic_reduced_layout(long *out) {
+  out[0] = _PIC_PARTICLE_DATA__MAGNETIC_MOMENT_OFFSET_, out[1] = _PIC_PARTICLE_DATA__V_PARALLEL_OFFSET_, out[2] = _PIC_PARTICLE_DATA__V_NORMAL_OFFSET_;
+}
+void ref_pic_set_gc_species(int spec, int on) { PIC::GYROKINETIC::SetGuidingCenterSpecies(spec, on != 0); }
+// PB::SetMagneticMoment / SetVNormal / the InitFlag of GuidingCenter::Mover_FirstOrder (:640-644), by ParticleBuffer slot; NULL = leave
+void ref_pic_set_reduced(long n, const long *ptr, const double *mu, const double *vnormal, const int *init_flag) {
+  for (long i = 0; i < n; i++) {
+    if (mu) PIC::ParticleBuffer::SetMagneticMoment(mu[i], ptr[i]);
+    if (vnormal) PIC::ParticleBuffer::SetVNormal(vnormal[i], ptr[i]);
+    if (init_flag) PIC::ParticleBuffer::SetInitFlag(init_flag[i] != 0, PIC::ParticleBuffer::GetParticleDataPointer(ptr[i]));
+  }
+}
+void ref_pic_get_reduced(long n, const long *ptr, double *mu, double *vnormal, int *init_flag) {
+  for (long i = 0; i < n; i++) {
+    if (mu) mu[i] = PIC::ParticleBuffer::GetMagneticMoment(ptr[i]);
+    if (vnormal) vnormal[i] = PIC::ParticleBuffer::GetVNormal(PIC::ParticleBuffer::GetParticleDataPointer(ptr[i]));
+    if (init_flag) init_flag[i] = PIC::ParticleBuffer::TestInitFlag(PIC::ParticleBuffer::GetParticleDataPointer(ptr[i])) ? 1 : 0;
+  }
+}
+#endif
 void ref_pic_set_weight_correction(long n, const long *ptr, const double *w) {
   for (long i = 0; i < n; i++) PIC::ParticleBuffer::SetIndividualStatWeightCorrection(w[i], ptr[i]);
 }

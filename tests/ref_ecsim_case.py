@@ -21,7 +21,9 @@ def _wrap_index(pos, xmin, n_cells, corner):
 
 
 @functools.lru_cache(maxsize=1)
-def case(keep_every=1):
+def case(keep_every=1, prepare=None):
+    """prepare(r, p0, info): called once the fields and weights are set, before the first UpdateJMassMatrix (the gyrokinetic variant
+    marks its guiding-centre species and sets mu / v_normal there); info["E_cur"] is the current E it must put on the corners itself"""
     r = ref_pic.RefPic()
     if keep_every > 1:
         r.thin(keep_every)
@@ -68,6 +70,8 @@ def case(keep_every=1):
     w = rng.uniform(0.5, 1.5, size=p0["w"].shape)
     r.set_weight_correction(p0["ptr"], w)
     p0["w"] = w
+
+    extra = prepare(r, p0, {"cu": cu, "zu": zu, "mesh": m, "smooth": smooth}) if prepare is not None else None
 
     # reference: deposit, move, deposit
     e0 = r.update_JM()
@@ -178,4 +182,4 @@ def case(keep_every=1):
     touched = ~np.isnan(ref["J0"][0][:, 0])
     ref["field"] = field
     return {"ref": ref, "mesh": m, "cfg": cfg, "parts": (p0["x"], p0["v"], p0["w"], p0["species"].astype(np.uint8), cells0),
-            "fields": (E_u, Bp_u, Bc_u), "touched": touched, "refpic": r}
+            "fields": (E_u, Bp_u, Bc_u), "touched": touched, "refpic": r, "extra": extra, "ptr0": p0["ptr"], "ptr1_in_order0": p1["ptr"][sel]}
