@@ -62,6 +62,7 @@ class RefPic:
         self.charge_si, self.mass_si, self.weight = c[0:ns].copy(), c[ns:2 * ns].copy(), c[2 * ns:3 * ns].copy()
         k = 3 * ns
         self.dt, self.light_speed, self.B_conv, self.E_conv, self.length_conv = c[k], c[k + 1], c[k + 2], c[k + 3], c[k + 4]
+        self.charge_conv, self.mass_conv = c[k + 5], c[k + 6]
         q, mm = np.zeros(ns), np.zeros(ns)
         self.lib.ref_pic_species(_p(q), _p(mm))
         self.charge, self.mass = q, mm
@@ -160,6 +161,39 @@ class RefPic:
         mu, vn, fl = np.zeros(ptr.size), np.zeros(ptr.size), np.zeros(ptr.size, dtype=np.int32)
         self.lib.ref_pic_get_reduced(C.c_long(ptr.size), _p(ptr), _p(mu), _p(vn), _p(fl))
         return mu, vn, fl
+
+    # ---- the particle passes of ECSIM::divECorrection ----
+    def center_scalar_shape(self):
+        return self.center_shape()[:-1]
+
+    def center_scalar(self, index):
+        """one double of the ECSIM centre data, [block][k][j][i] incl. ghost cells: 6 netChargeOld, 7 netChargeNew, 8 divE, 9 phi"""
+        a = np.empty(self.center_scalar_shape())
+        self.lib.ref_pic_center_scalar_rw(int(index), _p(a), 0)
+        return a
+
+    def set_center_scalar(self, index, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.shape == self.center_scalar_shape()
+        self.lib.ref_pic_center_scalar_rw(int(index), _p(a), 1)
+
+    def compute_net_charge(self, update_old=False):
+        with quiet():
+            self.lib.ref_pic_compute_net_charge(1 if update_old else 0)
+        return self.center_scalar(7)
+
+    def samples_species_on_corners(self):
+        return hasattr(self.lib, "ref_pic_samples_species_on_corners") and self.lib.ref_pic_samples_species_on_corners() == 1
+
+    def species_moments(self):
+        """[block][k][j][i][species][10] on every corner node incl. ghost layers (after update_JM)"""
+        a = np.empty(self.corner_shape(10 * self.n_species))
+        self.lib.ref_pic_species_moments(_p(a))
+        return a.reshape(a.shape[:-1] + (self.n_species, 10))
+
+    def correct_particle_location(self):
+        with quiet():
+            self.lib.ref_pic_correct_particle_location()
 
     def move(self):
         with quiet():

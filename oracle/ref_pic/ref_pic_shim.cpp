@@ -160,6 +160,47 @@ long ref_pic_center_rw(int what, double *buf, int write) {
         }
   return n;
 }
+// one double of the ECSIM centre data of every centre node incl. ghost cells, [block][k][j][i]; index in doubles from
+// MagneticField.RelativeOffset: netChargeOldIndex 6, netChargeNewIndex 7, divEIndex 8, phiIndex 9 (pic_field_solver_ecsim.cpp:499-502)
+long ref_pic_center_scalar_rw(int index, double *buf, int write) {
+  long n = 0;
+  for (Node *node : g_blocks)
+    for (int k = -GZ; k < NZ + GZ; k++)
+      for (int j = -GY; j < NY + GY; j++)
+        for (int i = -GX; i < NX + GX; i++, n++) {
+          PIC::Mesh::cDataCenterNode *c = node->block->GetCenterNode(_getCenterNodeLocalNumber(i, j, k));
+          double *p = c ? (double *)(c->GetAssociatedDataBufferPointer() + PIC::CPLR::DATAFILE::Offset::MagneticField.RelativeOffset) + index : NULL;
+          if (write) { if (p && buf[n] == buf[n]) *p = buf[n]; }
+          else buf[n] = p ? *p : NAN;
+        }
+  return n;
+}
+// ECSIM::ComputeNetCharge (pic_field_solver_ecsim.cpp:4690): the charge density on the centre nodes (read it with index 7 above)
+void ref_pic_compute_net_charge(int update_old) { PIC::FieldSolver::Electromagnetic::ECSIM::ComputeNetCharge(update_old != 0); }
+// 1 when ProcessCell samples the species moments on the corners (_PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_, on in the gk variant)
+int ref_pic_samples_species_on_corners(void) { return _PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_ == _PIC_MODE_ON_ ? 1 : 0; }
+#if _PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_ == _PIC_MODE_ON_
+// the 10 moments per species UpdateJMassMatrix leaves on the corners (SpeciesDataIndex, :531), [block][k][j][i][10 nSpecies]
+long ref_pic_species_moments(double *buf) {
+  using namespace PIC::FieldSolver::Electromagnetic::ECSIM;
+  const int len = 10 * PIC::nTotalSpecies;
+  long n = 0;
+  for (Node *node : g_blocks)
+    for (int k = -GZ; k <= NZ + GZ; k++)
+      for (int j = -GY; j <= NY + GY; j++)
+        for (int i = -GX; i <= NX + GX; i++) {
+          PIC::Mesh::cDataCornerNode *c = node->block->GetCornerNode(_getCornerNodeLocalNumber(i, j, k));
+          double *p = c ? (double *)(c->GetAssociatedDataBufferPointer() + PIC::CPLR::DATAFILE::Offset::ElectricField.RelativeOffset) + SpeciesDataIndex[0] : NULL;
+          for (int q = 0; q < len; q++, n++) buf[n] = p ? p[q] : NAN;
+        }
+  return n;
+}
+// the particle half of ECSIM::divECorrection (:4354-4355): CorrectParticleLocation, then the rank exchange
+void ref_pic_correct_particle_location(void) {
+  PIC::FieldSolver::Electromagnetic::ECSIM::CorrectParticleLocation();
+  PIC::Parallel::ExchangeParticleData();
+}
+#endif
 // every particle on a cell list: ParticleBuffer slot, x, v, individual weight correction, species, block (index of ref_pic_blocks)
 // and cell i + Nx (j + Ny k), in the reference's own iteration order (block, k, j, i, list order)
 long ref_pic_particles(long max_n, long *ptr, double *x, double *v, double *w, int *spec, int *block, int *cell) {

@@ -43,6 +43,39 @@ ref, m, cfg, r = c["ref"], c["mesh"], c["cfg"], c["refpic"]
 x, v, w, sp, cells = c["parts"]
 E, Bp, Bc = c["fields"]
 mu1, vn1, flag1 = r.get_reduced(c["ptr0"])  # periodic box: every particle keeps its ParticleBuffer slot
+# ---- the particle passes of ECSIM::divECorrection on the moved plasma (the library samples the species moments on the corners) ----
+assert r.samples_species_on_corners()
+mp = c["maps"]
+N, g = r.N, r.g
+zu, real, b2l = mp["zu"], mp["real"], mp["b2l"]
+
+
+def center_scalar_unique(arr):
+    out = np.full(m.n_centers, np.nan)
+    for b in real:
+        sl = (b, slice(g[2], g[2] + N[2]), slice(g[1], g[1] + N[1]), slice(g[0], g[0] + N[0]))
+        out[zu[sl].reshape(-1)] = arr[sl].reshape(-1)
+    assert not np.isnan(out).any()
+    return out
+
+
+rho_u = center_scalar_unique(r.compute_net_charge(False))       # ComputeNetCharge(false)
+mom = r.species_moments()                                        # left on the corners by the last UpdateJMassMatrix
+mom_u, mom_spread = mp["to_unique"](mom.reshape(mom.shape[:-2] + (-1,)))
+xc = m.center_x
+L = np.array([32.0, 16.0, 8.0])
+kk = 2 * np.pi / L
+phi_u = 2.0e-4 * (np.sin(kk[0] * xc[:, 0]) * np.cos(kk[1] * xc[:, 1]) + 0.5 * np.sin(2 * kk[2] * xc[:, 2] + 0.3))
+r.set_center_scalar(9, phi_u[zu])                                # phi of the Poisson solve, every copy of a centre node
+r.correct_particle_location()                                    # CorrectParticleLocation + ExchangeParticleData
+p2 = r.particles()
+order = np.argsort(p2["ptr"])
+pos = np.searchsorted(p2["ptr"][order], c["ptr0"])
+assert (p2["ptr"][order][pos] == c["ptr0"]).all()
+sel2 = order[pos]
+x_corr = p2["x"][:, sel2]
+leaf2 = b2l[p2["block"][sel2]]
+cells_corr = np.where(leaf2 >= 0, leaf2 * m.cells_per_block + p2["cell"][sel2], -1).astype(np.int64)  # -1: in a periodic ghost block
 sub = np.arange(0, m.n_corners, 16)
 out = {
     "block_cells": np.array(cfg.block_cells[:3]), "ghost_cells": np.array(cfg.ghost_cells[:3]), "n_cells": np.array([32, 16, 8]),
@@ -58,6 +91,8 @@ out = {
     "init_flag_after": flag1,
     "J0": ref["J0"][0], "J1": ref["J1"][0], "M_corners": sub, "M0_sub": ref["M0"][0][sub], "M1_sub": ref["M1"][0][sub],
     "M0_rowsum": ref["M0"][0].sum(axis=1), "M1_rowsum": ref["M1"][0].sum(axis=1), "energy": np.array([ref["energy0"], ref["energy1"]]),
+    "conv": np.array([r.charge_conv, r.mass_conv]), "net_charge": rho_u, "species_moments": mom_u.reshape(m.n_corners, r.n_species, 10),
+    "species_moments_spread": np.array(mom_spread), "phi": phi_u, "x_corrected": x_corr, "cells_corrected": cells_corr,
 }
 path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "tests", "golden", "ref_gyrokinetic.npz")
 np.savez_compressed(path, **out)

@@ -182,4 +182,5 @@ def case(keep_every=1, prepare=None):
     touched = ~np.isnan(ref["J0"][0][:, 0])
     ref["field"] = field
     return {"ref": ref, "mesh": m, "cfg": cfg, "parts": (p0["x"], p0["v"], p0["w"], p0["species"].astype(np.uint8), cells0),
-            "fields": (E_u, Bp_u, Bc_u), "touched": touched, "refpic": r, "extra": extra, "ptr0": p0["ptr"], "ptr1_in_order0": p1["ptr"][sel]}
+            "fields": (E_u, Bp_u, Bc_u), "touched": touched, "refpic": r, "extra": extra, "ptr0": p0["ptr"], "ptr1_in_order0": p1["ptr"][sel],
+            "maps": {"cu": cu, "zu": zu, "b2l": b2l, "real": real, "to_unique": to_unique}}

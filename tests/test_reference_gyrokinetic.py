@@ -106,6 +106,51 @@ def test_oracle_gyrokinetic_mover_matches_the_reference():
             print("guiding-centre species: x words equal", int((x == z["x_after"][:, sel]).sum()), "of", x.size)
 
 
+def dive_conv(z):
+    """ComputeNetCharge and CorrectParticleLocation multiply the RAW species tables by charge_conv / mass_conv (:4704, :4449-4452), the
+    sampled moments use ProcessCell's si2no masses: with the si2no tables in the configuration the two factors carry the ratio"""
+    return float(z["conv"][0] * z["charge_table"][0] / z["charge"][0]), float(z["conv"][1] * z["mass_table"][0] / z["mass"][0])
+
+
+def inner_cells(z, m):
+    """the centres that are not in the outermost layer of the periodic box: there the reference's ComputeNetCharge leaves the contributions
+    of the periodic images in its ghost blocks and SetBoundaryChargeDivE (:4960-5009) zeroes the cell afterwards, while the library's one
+    unique centre per periodic image holds the folded sum"""
+    lo = np.asarray(z["origin"], dtype=np.float64)
+    hi = lo + np.asarray(z["n_cells"], dtype=np.float64)
+    xc = np.asarray(m.center_x)
+    return ((xc > lo + 1.0) & (xc < hi - 1.0)).all(axis=1)
+
+
+def test_oracle_dive_correction_passes_match_the_reference():
+    """ECSIM::ComputeNetCharge (:4690), the corner species moments of ProcessCell (_PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_, :2270-2300)
+    and CorrectParticleLocation (:4440-4688) of the same reference build, on the plasma after the move"""
+    z, m, cfg = gold_case()
+    cc, mc = dive_conv(z)
+    o = Oracle(cfg, m)
+    o.set_fields(z["E_half"], z["B_prev"], z["B_cur"])
+    o.add_particles(z["x_after"], z["v_after"], z["w"], z["species"], z["cells_after"].astype(np.int32))
+    rho = o.net_charge(cc)
+    inner = inner_cells(z, m)
+    assert inner.mean() > 0.6 and rel(rho[inner], z["net_charge"][inner]) <= 1e-13
+    mom = o.species_moments()
+    assert float(z["species_moments_spread"]) == 0.0
+    for s in range(2):
+        for k in range(10):
+            assert rel(mom[:, s, k], z["species_moments"][:, s, k]) <= 1e-13, (s, k)
+    o.set_phi(z["phi"])
+    rc, n_disp, n_del, fc = o.correct_particle_location(cc, mc)
+    after = o.particles()
+    o.close()
+    assert rc == 0 and n_del == 0 and n_disp == int((z["species"] == 0).sum())
+    moved = np.abs(z["x_corrected"] - z["x_after"]).max(axis=0) > 0
+    assert moved.sum() == n_disp
+    # the shift is a ratio of interpolated sums: it inherits their summation order
+    assert np.abs(after["x"] - z["x_corrected"]).max() <= 1e-12
+    inside = z["cells_corrected"] >= 0
+    assert (fc[inside] == z["cells_corrected"][inside]).all()
+
+
 @pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libref_pic_gk.so not built (REF_PIC_VARIANT=gk, needs /root/reference)")
 def test_committed_vectors_are_what_the_reference_library_produces(tmp_path):
     out = str(tmp_path / "gk.npz")
@@ -162,3 +207,25 @@ def test_gpu_gc_species_deposit_and_gyrokinetic_mover_match_the_reference():
             assert np.abs(gx - z["x_after"][:, sel]).max() <= 1e-12 * nx
             assert np.abs(gv - z["v_after"][:, sel]).max() <= 1e-10 * nv
             assert np.abs(gmu - z["mu_after"][sel]).max() <= 1e-12 * np.abs(z["mu_after"][sel]).max()
+    # the particle passes of the div-E correction on the moved plasma
+    z, m, cfg = gold_case()
+    cc, mc = dive_conv(z)
+    g = api.Context(cfg, m)
+    g.fields_upload(z["E_half"], z["B_prev"], z["B_cur"])
+    g.particles_upload(z["x_after"], z["v_after"], z["w"], sp, z["cells_after"].astype(np.int32))
+    g.sort()
+    rho = g.ComputeNetCharge(cc)
+    inner = inner_cells(z, m)
+    assert rel(rho[inner], z["net_charge"][inner]) <= 1e-10
+    mom = g.ComputeSpeciesMoments()
+    for s in range(2):
+        for k in range(10):
+            assert rel(mom[:, s, k], z["species_moments"][:, s, k]) <= 1e-10, (s, k)
+    g.SetPhi(z["phi"])
+    nd, nx = g.CorrectParticleLocation(cc, mc)
+    got = g.particles_download()
+    g.close()
+    assert nx == 0 and nd == int((sp == 0).sum())
+    gx = np.empty((3, n))
+    gx[:, got["ptrs"]] = got["x"]
+    assert np.abs(gx - z["x_corrected"]).max() <= 1e-10
