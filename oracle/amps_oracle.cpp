@@ -170,6 +170,7 @@ struct oracle_ctx {
   long int MaxNPart, ParticleDataLength, FirstPBufferParticle, NAllPart;
   long long nSubSteps = 0;  // Relativistic::Boris sub-steps of the current move (statistic)
   byte *ParticleDataBuffer;
+  int globalStencilLength = 0;  // Length of the stencil last built through the reference's global StencilTable (see GetTriliniarInterpolationStencil)
   // per-thread E/B staging, src/pic/pic_mover.cpp:660-711
   std::vector<std::vector<double>> E_Corner, B_Center;
 
@@ -401,8 +402,11 @@ struct oracle_ctx {
   }
 
   // CellCentered::Linear::GetTriliniarInterpolationStencil, src/pic/pic_interpolation_routines.cpp:820-907
-  // always_normalize: the reference tests the GLOBAL StencilTable->Length (:903), which in ECSIM
-  // runs is never filled (the movers pass their own stencil object) => Normalize() always runs.
+  // always_normalize: the reference tests the GLOBAL StencilTable->Length (:903) although the movers and ProcessCell pass their own
+  // stencil object: Normalize() runs unless the global table holds an 8-cell stencil.  Only ComputeNetCharge fills the global table
+  // (the StencilTable overload, :4783), so without the div-E correction Normalize() always runs; after a ComputeNetCharge whose last
+  // particle had a full stencil it never does (globalStencilLength below; found by comparing two consecutive moves with the
+  // reference-compiled code, tests/test_reference_gyrokinetic.py).
   void GetTriliniarInterpolationStencil(double iLoc, double jLoc, double kLoc, const double *x, cTreeNode *node, cStencil &Stencil, bool always_normalize) const {
     cCenterNode *cell;
     cBlock *block = node->block;
@@ -939,7 +943,7 @@ struct oracle_ctx {
     }
 
     if (cfg.b_mode == AMPS_B_CENTER_BASED) {
-      CellCentered_Linear_InitStencil(xInit, startNode, MagneticFieldStencil, true);
+      CellCentered_Linear_InitStencil(xInit, startNode, MagneticFieldStencil, globalStencilLength != 8);
       Length = MagneticFieldStencil.Length;
       LocalCellID = MagneticFieldStencil.LocalCellID;
       Weight = MagneticFieldStencil.Weight;
@@ -1751,7 +1755,7 @@ struct oracle_ctx {
     cStencil Stencil;
     for (int idim = 0; idim < 3; idim++) B[idim] = 0.0;
     if (node == NULL || node->block == NULL) return false;
-    CellCentered_Linear_InitStencil(x, node, Stencil, true);
+    CellCentered_Linear_InitStencil(x, node, Stencil, globalStencilLength != 8);
     for (int iCenterNode = 0; iCenterNode < Stencil.Length; iCenterNode++) {
       const double *t = node->block->centerNodes[Stencil.LocalCellID[iCenterNode]]->data + CurrentBOffset_d;
       const double w = Stencil.Weight[iCenterNode];
@@ -2526,6 +2530,7 @@ struct oracle_ctx {
               double chargeQ = q_I[spec] * LocalParticleWeight;
               cStencil NetChargeStencil;
               CellCentered_Linear_InitStencil(xInit, node, NetChargeStencil, false);  // the StencilTable overload: Normalize() only if Length != 8
+              globalStencilLength = NetChargeStencil.Length;  // PIC::InterpolationRoutines::CellCentered::StencilTable[thread] keeps it
               for (int iStencil = 0; iStencil < NetChargeStencil.Length; iStencil++)
                 q_Center[NetChargeStencil.LocalCellID[iStencil]] += NetChargeStencil.Weight[iStencil] * chargeQ;
               ptr = GetNext(ParticleData);
@@ -2737,7 +2742,7 @@ struct oracle_ctx {
           double B[3] = {0.0, 0.0, 0.0};
           double Wdummy[8];
           if (cfg.b_mode == AMPS_B_CENTER_BASED)
-            CellCentered_Linear_InitStencil(xInit, node, MagneticFieldStencil, true);
+            CellCentered_Linear_InitStencil(xInit, node, MagneticFieldStencil, globalStencilLength != 8);
           else
             CornerBased_InitStencil(xInit, node, MagneticFieldStencil, Wdummy);
 
@@ -3083,6 +3088,8 @@ void oracle_set_reduced_state(oracle_ctx *o, const double *mu, const double *vpa
 void oracle_set_E_current(oracle_ctx *o, const double *E) {
   for (int i = 0; i < o->n_corners; i++) memcpy(o->cornerPool[i].data + ExOffsetIndex, E + 3 * (size_t)i, 24);
 }
+// the state of the reference's global StencilTable (its Length): 8 after a ComputeNetCharge of a periodic box, 0 = never filled
+void oracle_set_global_stencil_length(oracle_ctx *o, int length) { o->globalStencilLength = length; }
 void oracle_set_v_normal(oracle_ctx *o, const double *vnormal, int64_t n) {
   for (int64_t ptr = 0; ptr < n; ptr++) oracle_ctx::SetVNormal(vnormal[ptr], o->GetParticleDataPointer(ptr));
 }

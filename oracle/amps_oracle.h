@@ -63,6 +63,9 @@ void oracle_set_reduced_state(oracle_ctx *, const double *mu, const double *vpar
 void oracle_set_v_normal(oracle_ctx *o, const double *vnormal, int64_t n);
 /* the current E on the unique corners: read by the guiding-centre movers when cfg.gc_fields_ecsim */
 void oracle_set_E_current(oracle_ctx *o, const double *E);
+/* Length of the stencil in the reference's global StencilTable (8 once ComputeNetCharge has run on a periodic box): the movers and
+ * ProcessCell skip Normalize() of their B stencil then (pic_interpolation_routines.cpp:903) */
+void oracle_set_global_stencil_length(oracle_ctx *o, int length);
 /* ECSIM::GetElectricField / GetMagneticField / GetMagneticFieldGradient at n points (x[n][3], each in its leaf) */
 int oracle_ecsim_fields(const oracle_ctx *o, int64_t n, const double *x, const int32_t *leaf, double *E, double *B, double *gradB);
 void oracle_get_v_parallel(const oracle_ctx *, double *vpar, int64_t n);

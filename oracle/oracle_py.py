@@ -39,6 +39,7 @@ def load(kind="parity"):
     lib.oracle_set_reduced_state.argtypes = [vp, vp, vp, C.c_int64]
     lib.oracle_set_v_normal.argtypes = [vp, vp, C.c_int64]
     lib.oracle_set_E_current.argtypes = [vp, vp]
+    lib.oracle_set_global_stencil_length.argtypes = [vp, C.c_int]
     lib.oracle_ecsim_fields.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp]
     lib.oracle_get_v_parallel.argtypes = [vp, vp, C.c_int64]
     lib.oracle_add_particles.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64]
@@ -125,6 +126,9 @@ class Oracle:
         E, B, G = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 9))
         bad = self.lib.oracle_ecsim_fields(self.h, n, _p(x), _p(leaf), _p(E), _p(B), _p(G))
         return E, B, G, bad
+
+    def set_global_stencil_length(self, length):
+        self.lib.oracle_set_global_stencil_length(self.h, int(length))
 
     def set_v_normal(self, vnormal):
         a = np.ascontiguousarray(vnormal, dtype=np.float64)

@@ -28,10 +28,11 @@ perl ampsConfig.pl -input fast-wave.input -no-compile > config.log 2>&1 || { tai
 # REF_PIC_VARIANT=gk: the same configuration with the gyrokinetic model switched on in the GENERATED picGlobal.dfn of the scratch tree
 # (what `ampsConfigLib::RedefineMacro` does for an input file that asks for it): particles carry the magnetic moment, v_parallel and
 # v_normal, ProcessCell takes its guiding-centre branch for the species of UseGuidingCenterSpeciesTable, MoveParticles calls
-# PIC::GYROKINETIC::Mover (guiding-centre mover for those species, Lapenta2017 for the rest); ProcessCell also samples the species
+# the shim's ref_pic_user_mover, which is PIC::GYROKINETIC::Mover (guiding-centre mover for those species, Lapenta2017 for the rest) or,
+# on request, GuidingCenter::Mover_SecondOrder for the guiding-centre species; ProcessCell also samples the species
 # moments on the corners (_PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_), which CorrectParticleLocation of the div-E correction reads
 if [ "${REF_PIC_VARIANT:-}" = "gk" ]; then
-  sed -i -E 's/^#define _USE_MAGNETIC_MOMENT_ .*/#define _USE_MAGNETIC_MOMENT_ _PIC_MODE_ON_/; s/^#define _PIC_GYROKINETIC_MODEL_MODE_ .*/#define _PIC_GYROKINETIC_MODEL_MODE_ _PIC_MODE_ON_/; s/^#define _PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_ .*/#define _PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_ _PIC_MODE_ON_/; s/^#define _PIC_PARTICLE_MOVER__MOVE_PARTICLE_TIME_STEP_\(ptr,LocalTimeStep,node\).*/#define _PIC_PARTICLE_MOVER__MOVE_PARTICLE_TIME_STEP_(ptr,LocalTimeStep,node) PIC::GYROKINETIC::Mover(ptr,LocalTimeStep,node);/' build/pic/picGlobal.dfn
+  sed -i -E 's/^#define _USE_MAGNETIC_MOMENT_ .*/#define _USE_MAGNETIC_MOMENT_ _PIC_MODE_ON_/; s/^#define _PIC_GYROKINETIC_MODEL_MODE_ .*/#define _PIC_GYROKINETIC_MODEL_MODE_ _PIC_MODE_ON_/; s/^#define _PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_ .*/#define _PIC_FIELD_SOLVER_SAMPLE_SPECIES_ON_CORNER_ _PIC_MODE_ON_/; s/^#define _PIC_PARTICLE_MOVER__MOVE_PARTICLE_TIME_STEP_\(ptr,LocalTimeStep,node\).*/#define _PIC_PARTICLE_MOVER__MOVE_PARTICLE_TIME_STEP_(ptr,LocalTimeStep,node) ref_pic_user_mover(ptr,LocalTimeStep,(void*)(node));/' build/pic/picGlobal.dfn
   grep -n "_USE_MAGNETIC_MOMENT_ \|_PIC_GYROKINETIC_MODEL_MODE_ \|MOVE_PARTICLE_TIME_STEP_(" build/pic/picGlobal.dfn
 fi
 # the object lists of the reference's own makefiles

@@ -148,6 +148,10 @@ class RefPic:
     def set_gc_species(self, spec, on=True):
         self.lib.ref_pic_set_gc_species(int(spec), 1 if on else 0)
 
+    def set_mover_mode(self, mode):
+        """0: PIC::GYROKINETIC::Mover (first-order guiding centre / Lapenta2017), 1: second-order guiding centre / Lapenta2017"""
+        self.lib.ref_pic_set_mover_mode(int(mode))
+
     def set_reduced(self, ptr, mu=None, vnormal=None, init_flag=None):
         ptr = np.ascontiguousarray(ptr, dtype=np.int64)
         mu = None if mu is None else np.ascontiguousarray(mu, dtype=np.float64)

@@ -271,6 +271,19 @@ void ref_pic_reduced_layout(long *out) {
   out[0] = _PIC_PARTICLE_DATA__MAGNETIC_MOMENT_OFFSET_, out[1] = _PIC_PARTICLE_DATA__V_PARALLEL_OFFSET_, out[2] = _PIC_PARTICLE_DATA__V_NORMAL_OFFSET_;
 }
 void ref_pic_set_gc_species(int spec, int on) { PIC::GYROKINETIC::SetGuidingCenterSpecies(spec, on != 0); }
+// what MoveParticles calls per particle in this variant: 0 = PIC::GYROKINETIC::Mover (pic_gyrokinetic.cpp:49: GuidingCenter::Mover_FirstOrder for
+// the guiding-centre species, Lapenta2017 for the rest), 1 = the same routing with GuidingCenter::Mover_SecondOrder
+static int g_mover_mode = 0;
+void ref_pic_set_mover_mode(int mode) { g_mover_mode = mode; }
+int ref_pic_user_mover(long int ptr, double dt, void *node) {
+  Node *n = (Node *)node;
+  if (g_mover_mode == 1) {
+    const int spec = PIC::ParticleBuffer::GetI(ptr);
+    if (PIC::GYROKINETIC::IsGuidingCenterSpecies(spec)) return PIC::Mover::GuidingCenter::Mover_SecondOrder(ptr, dt, n);
+    return PIC::Mover::Lapenta2017(ptr, dt, n);
+  }
+  return PIC::GYROKINETIC::Mover(ptr, dt, n);
+}
 // PB::SetMagneticMoment / SetVNormal / the InitFlag of GuidingCenter::Mover_FirstOrder (:640-644), by ParticleBuffer slot; NULL = leave
 void ref_pic_set_reduced(long n, const long *ptr, const double *mu, const double *vnormal, const int *init_flag) {
   for (long i = 0; i < n; i++) {

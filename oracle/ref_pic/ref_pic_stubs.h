@@ -28,3 +28,9 @@ int MPI_Comm_split_type(MPI_Comm, int, int, MPI_Info, MPI_Comm *);
 #ifdef __cplusplus
 }
 #endif
+
+/* the gyrokinetic variant (REF_PIC_VARIANT=gk) routes MoveParticles through the shim so that a test can choose the guiding-centre
+   mover of the reference at run time (ref_pic_shim.cpp); node is a cTreeNodeAMR<PIC::Mesh::cDataBlockAMR>* */
+#ifdef __cplusplus
+extern "C" int ref_pic_user_mover(long int ptr, double dt, void *node);
+#endif

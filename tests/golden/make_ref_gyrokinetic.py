@@ -7,7 +7,9 @@ of the fast-wave initial condition with species 0 (the electrons) as the guiding
     the energy) for given mu and v_normal,
   * PIC::Mover::MoveParticles -> PIC::GYROKINETIC::Mover: GuidingCenter::Mover_FirstOrder on ECSIM's own E, B, grad B for species 0
     (InitiateMagneticMoment included: the InitFlag of the particles is off), Lapenta2017 for species 1, then the periodic exchange,
-  * UpdateJMassMatrix again with the magnetic moments the mover left.
+  * UpdateJMassMatrix again with the magnetic moments the mover left,
+  * ComputeNetCharge, the corner species moments and CorrectParticleLocation of the div-E correction on the moved plasma,
+  * one more MoveParticles with GuidingCenter::Mover_SecondOrder for species 0.
 
 Run it in its own process (the library's state is global and must not share a process with libref_pic.so):
     AMPS_REF_PIC_LIB=oracle/_ref/libref_pic_gk.so python tests/golden/make_ref_gyrokinetic.py [out.npz]
@@ -38,7 +40,7 @@ def prepare(r, p0, info):
     return {"E_cur": E_cur, "mu0": mu, "vnormal": vn}
 
 
-c = rc.case(keep_every=31, prepare=prepare)  # an odd stride: the particle list alternates the two species
+c = rc.case(keep_every=31, prepare=prepare, do_field=False)  # an odd stride: the particle list alternates the two species
 ref, m, cfg, r = c["ref"], c["mesh"], c["cfg"], c["refpic"]
 x, v, w, sp, cells = c["parts"]
 E, Bp, Bc = c["fields"]
@@ -76,6 +78,19 @@ sel2 = order[pos]
 x_corr = p2["x"][:, sel2]
 leaf2 = b2l[p2["block"][sel2]]
 cells_corr = np.where(leaf2 >= 0, leaf2 * m.cells_per_block + p2["cell"][sel2], -1).astype(np.int64)  # -1: in a periodic ghost block
+# ---- one more MoveParticles with GuidingCenter::Mover_SecondOrder for the guiding-centre species (Lapenta2017 for the ions) ----
+r.set_mover_mode(1)
+r.move()
+p3 = r.particles()
+order3 = np.argsort(p3["ptr"])
+pos3 = np.searchsorted(p3["ptr"][order3], c["ptr0"])
+assert (p3["ptr"][order3][pos3] == c["ptr0"]).all()
+sel3 = order3[pos3]
+leaf3 = b2l[p3["block"][sel3]]
+assert (leaf3 >= 0).all()
+mu3, _, _ = r.get_reduced(c["ptr0"])
+second = {"x_second": p3["x"][:, sel3], "v_second": p3["v"][:, sel3], "cells_second": (leaf3 * m.cells_per_block + p3["cell"][sel3]).astype(np.int64),
+          "mu_second": mu3}
 sub = np.arange(0, m.n_corners, 16)
 out = {
     "block_cells": np.array(cfg.block_cells[:3]), "ghost_cells": np.array(cfg.ghost_cells[:3]), "n_cells": np.array([32, 16, 8]),
@@ -94,6 +109,7 @@ out = {
     "conv": np.array([r.charge_conv, r.mass_conv]), "net_charge": rho_u, "species_moments": mom_u.reshape(m.n_corners, r.n_species, 10),
     "species_moments_spread": np.array(mom_spread), "phi": phi_u, "x_corrected": x_corr, "cells_corrected": cells_corr,
 }
+out.update(second)
 path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "tests", "golden", "ref_gyrokinetic.npz")
 np.savez_compressed(path, **out)
 print(path, os.path.getsize(path), "bytes,", x.shape[1], "particles", "species-0:", int((sp == 0).sum()))

@@ -21,9 +21,10 @@ def _wrap_index(pos, xmin, n_cells, corner):
 
 
 @functools.lru_cache(maxsize=1)
-def case(keep_every=1, prepare=None):
+def case(keep_every=1, prepare=None, do_field=True):
     """prepare(r, p0, info): called once the fields and weights are set, before the first UpdateJMassMatrix (the gyrokinetic variant
-    marks its guiding-centre species and sets mu / v_normal there); info["E_cur"] is the current E it must put on the corners itself"""
+    marks its guiding-centre species and sets mu / v_normal there); info["E_cur"] is the current E it must put on the corners itself.
+    do_field=False leaves the field half out (it overwrites E and swaps the two B slots)"""
     r = ref_pic.RefPic()
     if keep_every > 1:
         r.thin(keep_every)
@@ -97,51 +98,53 @@ def case(keep_every=1, prepare=None):
             sl = (b, slice(g[2], g[2] + N[2]), slice(g[1], g[1] + N[1]), slice(g[0], g[0] + N[0]))
             out[zu[sl].reshape(-1)] = arr[sl].reshape(-1, 3)
         return out
-    Efld = smooth(m.corner_x, 0.02, 2.1) - 0.015
-    r.set_corner(0, Efld[cu])  # E^n (the initial condition of fast-wave is E = 0: give the operator something to act on)
-    field = {"E": corner_u(r.corner(0)), "B": center_u(r.center(0)), "theta": 0.5}
-    # the field getters of the guiding-centre movers in ECSIM mode (ECSIM::GetElectricField / GetMagneticField / GetMagneticFieldGradient),
-    # sampled before the field step touches E and swaps the B slots: uniform points in the real blocks, a few of them on block faces
-    if hasattr(r.lib, "ref_pic_ecsim_fields"):
-        rg = np.random.default_rng(11)
-        nP = 6000
-        gblk = rg.choice(real, nP).astype(np.int32)
-        u = rg.uniform(0.0, 1.0, (nP, 3))
-        u[:200, 0] = 0.0                       # on the lower x face of the block
-        u[200:400, 1] = 1.0                    # on the upper y face (the corner stencil snaps these)
-        u[400:600] = np.round(u[400:600] * 8) / 8  # on cell faces / corners (16 x 8 x 4 cells: multiples of 1/8 hit faces in every direction)
-        gx = r.bxmin[gblk] + u * (r.bxmax[gblk] - r.bxmin[gblk])
-        gE, gB, gG = np.zeros((nP, 3)), np.zeros((nP, 3)), np.zeros((nP, 9))
+    field = {}
+    if do_field:
+        Efld = smooth(m.corner_x, 0.02, 2.1) - 0.015
+        r.set_corner(0, Efld[cu])  # E^n (the initial condition of fast-wave is E = 0: give the operator something to act on)
+        field = {"E": corner_u(r.corner(0)), "B": center_u(r.center(0)), "theta": 0.5}
+        # the field getters of the guiding-centre movers in ECSIM mode (ECSIM::GetElectricField / GetMagneticField / GetMagneticFieldGradient),
+        # sampled before the field step touches E and swaps the B slots: uniform points in the real blocks, a few of them on block faces
+        if hasattr(r.lib, "ref_pic_ecsim_fields"):
+            rg = np.random.default_rng(11)
+            nP = 6000
+            gblk = rg.choice(real, nP).astype(np.int32)
+            u = rg.uniform(0.0, 1.0, (nP, 3))
+            u[:200, 0] = 0.0                       # on the lower x face of the block
+            u[200:400, 1] = 1.0                    # on the upper y face (the corner stencil snaps these)
+            u[400:600] = np.round(u[400:600] * 8) / 8  # on cell faces / corners (16 x 8 x 4 cells: multiples of 1/8 hit faces in every direction)
+            gx = r.bxmin[gblk] + u * (r.bxmax[gblk] - r.bxmin[gblk])
+            gE, gB, gG = np.zeros((nP, 3)), np.zeros((nP, 3)), np.zeros((nP, 9))
+            with ref_pic.quiet():
+                r.lib.ref_pic_ecsim_fields(C.c_long(nP), ref_pic._p(gx), ref_pic._p(gblk), ref_pic._p(gE), ref_pic._p(gB), ref_pic._p(gG))
+            field["getters"] = {"x": gx, "block": gblk, "E": gE, "B": gB, "gradB": gG, "E_u": Efld, "B_u": Bc_u}
+        rel_res = C.c_double()
         with ref_pic.quiet():
-            r.lib.ref_pic_ecsim_fields(C.c_long(nP), ref_pic._p(gx), ref_pic._p(gblk), ref_pic._p(gE), ref_pic._p(gB), ref_pic._p(gG))
-        field["getters"] = {"x": gx, "block": gblk, "E": gE, "B": gB, "gradB": gG, "E_u": Efld, "B_u": Bc_u}
-    rel_res = C.c_double()
-    with ref_pic.quiet():
-        field["iterations"] = r.lib.ref_pic_field_step(C.c_double(1e-12), 400, C.byref(rel_res))
-    field["rel_residual"] = float(rel_res.value)
-    r.lib.ref_pic_solver_rows.restype = C.c_long
-    nrow = r.lib.ref_pic_solver_rows(0, None, None, None, None)
-    blk, ijk, iv, rr = np.zeros(nrow, dtype=np.int32), np.zeros((nrow, 3), dtype=np.int32), np.zeros(nrow, dtype=np.int32), np.zeros(nrow)
-    r.lib.ref_pic_solver_rows(nrow, ref_pic._p(blk), ref_pic._p(ijk), ref_pic._p(iv), ref_pic._p(rr))
-    ru = cu[blk, ijk[:, 2] + g[2], ijk[:, 1] + g[1], ijk[:, 0] + g[0]]
-    field["rhs"] = np.zeros((m.n_corners, 3))
-    field["rhs"][ru, iv] = rr
-    xin = np.random.default_rng(5).standard_normal((m.n_corners, 3))
-    vin, vout = np.ascontiguousarray(xin[ru, iv]), np.zeros(nrow)
-    r.lib.ref_pic_matvec(ref_pic._p(vin), ref_pic._p(vout), int(nrow))
-    field["matvec_in"], field["matvec_out"] = xin, np.zeros((m.n_corners, 3))
-    field["matvec_out"][ru, iv] = vout
-    field["E_half"], field["E_new"], field["B_new"] = corner_u(r.corner(1)), corner_u(r.corner(0)), center_u(r.center(0))
+            field["iterations"] = r.lib.ref_pic_field_step(C.c_double(1e-12), 400, C.byref(rel_res))
+        field["rel_residual"] = float(rel_res.value)
+        r.lib.ref_pic_solver_rows.restype = C.c_long
+        nrow = r.lib.ref_pic_solver_rows(0, None, None, None, None)
+        blk, ijk, iv, rr = np.zeros(nrow, dtype=np.int32), np.zeros((nrow, 3), dtype=np.int32), np.zeros(nrow, dtype=np.int32), np.zeros(nrow)
+        r.lib.ref_pic_solver_rows(nrow, ref_pic._p(blk), ref_pic._p(ijk), ref_pic._p(iv), ref_pic._p(rr))
+        ru = cu[blk, ijk[:, 2] + g[2], ijk[:, 1] + g[1], ijk[:, 0] + g[0]]
+        field["rhs"] = np.zeros((m.n_corners, 3))
+        field["rhs"][ru, iv] = rr
+        xin = np.random.default_rng(5).standard_normal((m.n_corners, 3))
+        vin, vout = np.ascontiguousarray(xin[ru, iv]), np.zeros(nrow)
+        r.lib.ref_pic_matvec(ref_pic._p(vin), ref_pic._p(vout), int(nrow))
+        field["matvec_in"], field["matvec_out"] = xin, np.zeros((m.n_corners, 3))
+        field["matvec_out"][ru, iv] = vout
+        field["E_half"], field["E_new"], field["B_new"] = corner_u(r.corner(1)), corner_u(r.corner(0)), center_u(r.center(0))
 
-    def stencil(kind, p, q):
-        ijk3, aa = np.zeros((200, 3), dtype=np.int32), np.zeros(200)
-        n = r.lib.ref_pic_stencil(kind, p, q, 200, ref_pic._p(ijk3), ref_pic._p(aa))
-        T = np.zeros((3, 3, 3))
-        for t in range(n):
-            T[ijk3[t, 0] + 1, ijk3[t, 1] + 1, ijk3[t, 2] + 1] += aa[t]
-        return T
-    field["laplacian"] = [stencil(0, p, 0) for p in range(3)]
-    field["graddiv"] = [[stencil(1, p, q) for q in range(3)] for p in range(3)]
+        def stencil(kind, p, q):
+            ijk3, aa = np.zeros((200, 3), dtype=np.int32), np.zeros(200)
+            n = r.lib.ref_pic_stencil(kind, p, q, 200, ref_pic._p(ijk3), ref_pic._p(aa))
+            T = np.zeros((3, 3, 3))
+            for t in range(n):
+                T[ijk3[t, 0] + 1, ijk3[t, 1] + 1, ijk3[t, 2] + 1] += aa[t]
+            return T
+        field["laplacian"] = [stencil(0, p, 0) for p in range(3)]
+        field["graddiv"] = [[stencil(1, p, q) for q in range(3)] for p in range(3)]
 
     # particles in this repo's numbering: leaf by block position, same cell formula i + Nx (j + Ny k)
     lx = m.leaf_xmin()

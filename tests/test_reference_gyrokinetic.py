@@ -73,12 +73,13 @@ def mover_config(z, cfg, s):
     return cfg
 
 
-def oracle_move(z, m, cfg, sel, mover):
+def oracle_move(z, m, cfg, sel, mover, start=("x", "v", "cells", "mu0"), global_stencil=0):
     o = Oracle(cfg, m)
+    o.set_global_stencil_length(global_stencil)
     o.set_fields(z["E_half"], z["B_prev"], z["B_cur"])
     o.set_E_current(z["E_cur"])
-    o.add_particles(z["x"][:, sel], z["v"][:, sel], z["w"][sel], z["species"][sel], z["cells"][sel])
-    o.set_reduced_state(z["mu0"][sel], np.zeros(int(sel.sum())))
+    o.add_particles(z[start[0]][:, sel], z[start[1]][:, sel], z["w"][sel], z["species"][sel], z[start[2]][sel].astype(np.int32))
+    o.set_reduced_state(z[start[3]][sel], np.zeros(int(sel.sum())))
     rc, st, ret, fc = o.move(mover, 1)
     pp = o.particles()
     mu, flag = o.magnetic_moment()
@@ -110,6 +111,27 @@ def dive_conv(z):
     """ComputeNetCharge and CorrectParticleLocation multiply the RAW species tables by charge_conv / mass_conv (:4704, :4449-4452), the
     sampled moments use ProcessCell's si2no masses: with the si2no tables in the configuration the two factors carry the ratio"""
     return float(z["conv"][0] * z["charge_table"][0] / z["charge"][0]), float(z["conv"][1] * z["mass_table"][0] / z["mass"][0])
+
+
+def test_oracle_second_order_guiding_centre_mover_matches_the_reference():
+    """GuidingCenter::Mover_SecondOrder (pic_mover_guiding_center.cpp:292-619) on ECSIM's fields, from the state the div-E correction left"""
+    sp = np.load(GOLD)["species"]
+    for s, mover in ((0, _capi.MOVER_GC_SECOND_ORDER), (1, _capi.MOVER_LAPENTA2017)):
+        sel = sp == s
+        z, m, cfg = gold_case()
+        # ComputeNetCharge ran before this move: the reference's global StencilTable holds an 8-cell stencil, so the B stencils of
+        # Lapenta2017 and of ECSIM::GetMagneticField are no longer normalised (pic_interpolation_routines.cpp:903)
+        x, v, cells, mu, flag = oracle_move(z, m, mover_config(z, cfg, s), sel, mover, start=("x_corrected", "v_after", "cells_corrected", "mu_after"),
+                                            global_stencil=8)
+        assert (cells == z["cells_second"][sel]).all()
+        if s == 1:
+            assert (x == z["x_second"][:, sel]).all() and (v == z["v_second"][:, sel]).all()
+        else:
+            nx, nv = np.abs(z["x_second"][:, sel]).max(), np.abs(z["v_second"][:, sel]).max()
+            assert np.abs(x - z["x_second"][:, sel]).max() <= 1e-13 * nx
+            assert np.abs(v - z["v_second"][:, sel]).max() <= 1e-12 * nv
+            assert np.abs(mu - z["mu_second"][sel]).max() <= 1e-13 * np.abs(z["mu_second"][sel]).max()
+            print("second order: x words equal", int((x == z["x_second"][:, sel]).sum()), "of", x.size)
 
 
 def inner_cells(z, m):
@@ -207,6 +229,29 @@ def test_gpu_gc_species_deposit_and_gyrokinetic_mover_match_the_reference():
             assert np.abs(gx - z["x_after"][:, sel]).max() <= 1e-12 * nx
             assert np.abs(gv - z["v_after"][:, sel]).max() <= 1e-10 * nv
             assert np.abs(gmu - z["mu_after"][sel]).max() <= 1e-12 * np.abs(z["mu_after"][sel]).max()
+    # the second move (after ComputeNetCharge): second-order guiding centre for the electrons, Lapenta2017 for the ions.  The library
+    # always normalises the B stencil; the reference stopped doing so once ComputeNetCharge had filled its global StencilTable
+    # (pic_interpolation_routines.cpp:903, see the oracle), which moves x', v' by at most a few ulp
+    for s, mover in ((0, _capi.MOVER_GC_SECOND_ORDER), (1, _capi.MOVER_LAPENTA2017)):
+        sel = sp == s
+        ns = int(sel.sum())
+        z, m, cfg = gold_case()
+        cfg = mover_config(z, cfg, s)
+        cfg.exact_arithmetic = 1
+        g = api.Context(cfg, m)
+        g.fields_upload(z["E_half"], z["B_prev"], z["B_cur"])
+        g.E_upload(z["E_cur"])
+        g.particles_upload(z["x_corrected"][:, sel], z["v_after"][:, sel], z["w"][sel], sp[sel], z["cells_corrected"][sel].astype(np.int32))
+        g.magnetic_moment_upload(z["mu_after"][sel])
+        g.MoveParticles(mover)
+        mv = g.particles_download()
+        g.close()
+        gx, gv, gc = np.empty((3, ns)), np.empty((3, ns)), np.empty(ns, dtype=np.int64)
+        gx[:, mv["ptrs"]], gv[:, mv["ptrs"]], gc[mv["ptrs"]] = mv["x"], mv["v"], mv["cells"]
+        assert (gc == z["cells_second"][sel]).all()
+        nx, nv = np.abs(z["x_second"][:, sel]).max(), np.abs(z["v_second"][:, sel]).max()
+        tol = 1e-12 if s == 0 else 1e-15
+        assert np.abs(gx - z["x_second"][:, sel]).max() <= tol * nx and np.abs(gv - z["v_second"][:, sel]).max() <= 100 * tol * nv
     # the particle passes of the div-E correction on the moved plasma
     z, m, cfg = gold_case()
     cc, mc = dive_conv(z)
