@@ -190,6 +190,7 @@ PROTOTYPES = {
     "amps_gpu_diagnostics": (C.c_int, [_vp, _vp, _vp]),
     "amps_gpu_v_parallel_upload": (C.c_int, [_vp, _vp, C.c_int64]),
     "amps_gpu_v_normal_upload": (C.c_int, [_vp, _vp, C.c_int64]),
+    "amps_gpu_global_stencil_set": (C.c_int, [_vp, C.c_int32]),
     "amps_gpu_v_parallel_download": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "amps_gpu_net_charge": (C.c_int, [_vp, C.c_double, _vp]),
     "amps_gpu_JM_packed_slots": (C.POINTER(C.c_int32), []),

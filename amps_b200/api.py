@@ -147,6 +147,10 @@ class Context:
         self._ck(self.lib.amps_gpu_magnetic_moment_download(self._h, _ptr(mu), mu.shape[0], C.byref(k)))
         return mu[: int(k.value)]
 
+    def global_stencil_set(self, full):
+        """the reference's global StencilTable holds an 8-cell stencil (ComputeNetCharge ran): full B stencils stay un-normalised"""
+        self._ck(self.lib.amps_gpu_global_stencil_set(self._h, 1 if full else 0))
+
     def v_normal_upload(self, vnormal_by_ptr):
         """PB::GetVNormal of the guiding-centre species by ParticleBuffer slot (read by the deposit's diagnostics)"""
         a = np.ascontiguousarray(vnormal_by_ptr, dtype=np.float64)

@@ -71,6 +71,9 @@ struct DevSpecies {
   int timeStepMode;
   int bMode;
   int boundaryMode;
+  int globalStencilFull;  // the reference's global StencilTable holds an 8-cell stencil (ComputeNetCharge ran): full B stencils are not
+                          // normalised any more (pic_interpolation_routines.cpp:903); amps_gpu_global_stencil_set
+  int pad0;
   double charge[AMPS_GPU_MAX_SPECIES], mass[AMPS_GPU_MAX_SPECIES], weight[AMPS_GPU_MAX_SPECIES], dt[AMPS_GPU_MAX_SPECIES];
   double dtTotal, B_conv, length_conv, LightSpeed;
 };

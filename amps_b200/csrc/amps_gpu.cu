@@ -1215,6 +1215,11 @@ int amps_gpu_magnetic_moment_upload(amps_gpu_ctx *ctx, const double *mu_by_ptr, 
   if (!ctx->cfg.carry_magnetic_moment) FAIL(AMPS_GPU_ERR_STATE, "magnetic_moment_upload needs cfg.carry_magnetic_moment");
   return upload_by_ptr(ctx, false, mu_by_ptr, n);
 }
+int amps_gpu_global_stencil_set(amps_gpu_ctx *ctx, int32_t full) {
+  if (!ctx) return AMPS_GPU_ERR_ARG;
+  ctx->sp.globalStencilFull = full ? 1 : 0;
+  return AMPS_GPU_OK;
+}
 int amps_gpu_v_normal_upload(amps_gpu_ctx *ctx, const double *vnormal_by_ptr, int64_t n) {
   if (!ctx || !vnormal_by_ptr || n < 0) return AMPS_GPU_ERR_ARG;
   CK(cudaSetDevice(ctx->cfg.device));

@@ -284,8 +284,9 @@ __global__ void __launch_bounds__(256, 2) move_lapenta_kernel(DevMesh m, DevSpec
 #pragma unroll
       for (int s = 0; s < 8; s++)
         if (valid & (1u << s)) norm += w[s];
-      // Normalize(): the reference tests the global StencilTable->Length (:903) => always runs in ECSIM
-      normalize8(w, norm);
+      // Normalize(): the reference tests the GLOBAL StencilTable->Length (:903): it runs unless ComputeNetCharge has left an 8-cell
+      // stencil there (sp.globalStencilFull); a stencil that lost cells at the domain boundary is always normalised
+      if (!(sp.globalStencilFull && valid == 0xffu)) normalize8(w, norm);
       const int nd0 = centerLocalNumber(m, i0, j0, k0);
 #pragma unroll
       for (int s = 0; s < 8; s++) {

@@ -1027,6 +1027,7 @@ struct GcTables {
   // cfg.gc_fields_ecsim: the ECSIM arrays instead (unique corners / centres), read through the corner and centre stencils
   const double *ecsimE = nullptr;  // [nCorners][3] current E
   const double *ecsimB = nullptr;  // [nCenters][3] B_cur
+  int globalStencilFull = 0;
 };
 
 // ---- the ECSIM field getters of the guiding-centre movers (reference built with the ECSIM field solver) ----
@@ -1067,10 +1068,11 @@ __device__ __forceinline__ bool ecsim_get_B(const DevMesh &m, const GcTables &T,
   for (int s = 0; s < 8; s++)
     if (valid & (1u << s)) norm += w[s];
   const int *cu = m.centerUid + (size_t)leaf * m.nCenterLocal;
+  const bool skipNorm = T.globalStencilFull && valid == 0xffu;  // see DevSpecies::globalStencilFull
 #pragma unroll
   for (int s = 0; s < 8; s++)
     if (valid & (1u << s)) {
-      const double ws = w[s] / norm;
+      const double ws = skipNorm ? w[s] : w[s] / norm;
       const double *t = T.ecsimB + 3 * (size_t)cu[centerLocalNumber(m, i0 + ((s >> 2) & 1), j0 + ((s >> 1) & 1), k0 + (s & 1))];
       B[0] += ws * t[0], B[1] += ws * t[1], B[2] += ws * t[2];
     }
@@ -1241,7 +1243,7 @@ void launch_gc_magnetic_moment_init(const DevMesh &m, const DevSpecies &sp, int 
   if (g > 148 * 32) g = 148 * 32;
   GcTables T;
   T.bg = bgTile, T.gradB = nullptr, T.uE = uE, T.uB = uB, T.uGradB = nullptr;
-  T.ecsimE = ecsimE, T.ecsimB = ecsimB;
+  T.ecsimE = ecsimE, T.ecsimB = ecsimB, T.globalStencilFull = sp.globalStencilFull;
   gc_magnetic_moment_init_kernel<<<(int)g, 128, 0, s>>>(m, sp, interp, T, p, nSlots, stats);
 }
 
@@ -1410,7 +1412,7 @@ void launch_move_guiding_center(const DevMesh &m, const DevSpecies &sp, int orde
   tp.interp = interp, tp.backward = 0, tp.boundaryMode = sp.boundaryMode, tp.c = 0.0, tp.rSphere = rSphere, tp.exitCap = exitCap;
   GcTables T;
   T.bg = bgTile, T.gradB = gradBTile, T.uE = uE, T.uB = uB, T.uGradB = uGradB;
-  T.ecsimE = ecsimE, T.ecsimB = ecsimB;
+  T.ecsimE = ecsimE, T.ecsimB = ecsimB, T.globalStencilFull = sp.globalStencilFull;
   long long g = (nUpper + 127) / 128;
   if (g < 1) g = 1;
   if (g > 148 * 32) g = 148 * 32;

@@ -315,6 +315,12 @@ int amps_gpu_v_parallel_upload(amps_gpu_ctx *ctx, const double *vpar_by_ptr, int
 /* PB::GetVNormal of the guiding-centre species (cfg.gc_species_mask), by ParticleBuffer slot: read by the deposit's energy / cfl
  * diagnostics (pic_field_solver_ecsim.cpp:2232-2235); the device never changes it.  Slots beyond n read 0. */
 int amps_gpu_v_normal_upload(amps_gpu_ctx *ctx, const double *vnormal_by_ptr, int64_t n);
+/* State of the reference's global StencilTable (PIC::InterpolationRoutines::CellCentered::StencilTable): GetTriliniarInterpolationStencil
+ * normalises a caller's stencil unless the GLOBAL table holds an 8-cell stencil (pic_interpolation_routines.cpp:903), and only
+ * ComputeNetCharge fills it (:4783).  full = 1 after the first ComputeNetCharge of a run with the div-E correction: the exact
+ * Lapenta2017 kernel and the ECSIM-field guiding-centre movers then leave a full B stencil un-normalised like the reference (x', v'
+ * change by <= 2 ulp; the contracted production mover and the deposit are not affected).  Default 0. */
+int amps_gpu_global_stencil_set(amps_gpu_ctx *ctx, int32_t full);
 int amps_gpu_v_parallel_download(amps_gpu_ctx *ctx, double *vpar, int64_t n_max, int64_t *n);
 /* exit records accumulated by the movers since the last call (clears them) */
 int amps_gpu_exit_records(amps_gpu_ctx *ctx, amps_gpu_exit_record *buf, int64_t max_records, int64_t *n);
