@@ -166,6 +166,14 @@ class RefPic:
         self.lib.ref_pic_get_reduced(C.c_long(ptr.size), _p(ptr), _p(mu), _p(vn), _p(fl))
         return mu, vn, fl
 
+    def sample_cells(self):
+        """PIC::Sampling::SamplingManager once more -> (collecting buffer [block][cell][species][10], particles sampled per species)"""
+        out = np.zeros((self.n_blocks, self.N[0] * self.N[1] * self.N[2], self.n_species, 10))
+        cnt = np.zeros(self.n_species, dtype=np.int64)
+        with quiet():
+            self.lib.ref_pic_sample_cells(_p(out), _p(cnt))
+        return out, cnt
+
     # ---- the particle passes of ECSIM::divECorrection ----
     def center_scalar_shape(self):
         return self.center_shape()[:-1]

@@ -201,6 +201,34 @@ void ref_pic_correct_particle_location(void) {
   PIC::Parallel::ExchangeParticleData();
 }
 #endif
+// PIC::Sampling::SamplingManager (pic.cpp:1049 -> ProcessCell :705): one more sample of every cell into the collecting buffer.
+// out[block][cell i + Nx (j + Ny k)][species][10] = weight, number, number density, velocity[3], velocity2[3], speed as the collecting buffer
+// holds them afterwards (NAN for a datum this configuration does not sample); counts[species] = particles sampled by this call
+void ref_pic_sample_cells(double *out, long *counts) {
+  const int nS = PIC::nTotalSpecies;
+  std::vector<int> tab(nS, 0);
+  int *row = tab.data();
+  PIC::Sampling::SamplingManager(&row);
+  for (int s = 0; s < nS; s++) counts[s] = tab[s];
+  PIC::Datum::cDatumSampled *datum[6] = {&PIC::Mesh::DatumParticleWeight, &PIC::Mesh::DatumParticleNumber, &PIC::Mesh::DatumNumberDensity,
+                                         &PIC::Mesh::DatumParticleVelocity, &PIC::Mesh::DatumParticleVelocity2, &PIC::Mesh::DatumParticleSpeed};
+  const int at[6] = {0, 1, 2, 3, 6, 9};
+  long n = 0;
+  for (Node *node : g_blocks)
+    for (int k = 0; k < NZ; k++)
+      for (int j = 0; j < NY; j++)
+        for (int i = 0; i < NX; i++) {
+          PIC::Mesh::cDataCenterNode *c = node->block->GetCenterNode(_getCenterNodeLocalNumber(i, j, k));
+          for (int s = 0; s < nS; s++, n += 10) {
+            for (int q = 0; q < 10; q++) out[n + q] = NAN;
+            if (!c) continue;
+            char *base = c->GetAssociatedDataBufferPointer() + PIC::Mesh::collectingCellSampleDataPointerOffset;
+            for (int d = 0; d < 6; d++)
+              if (datum[d]->offset >= 0)
+                for (int q = 0; q < datum[d]->length; q++) out[n + at[d] + q] = *(q + datum[d]->length * s + (double *)(base + datum[d]->offset));
+          }
+        }
+}
 // every particle on a cell list: ParticleBuffer slot, x, v, individual weight correction, species, block (index of ref_pic_blocks)
 // and cell i + Nx (j + Ny k), in the reference's own iteration order (block, k, j, i, list order)
 long ref_pic_particles(long max_n, long *ptr, double *x, double *v, double *w, int *spec, int *block, int *cell) {

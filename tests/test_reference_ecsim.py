@@ -95,6 +95,40 @@ def test_oracle_reproduces_the_reference_compiled_here(live):
 
 
 @needs_ref
+def test_oracle_cell_sampling_reproduces_the_reference(live):
+    """PIC::Sampling::SamplingManager -> ProcessCell (pic.cpp:1049, :705) of the reference build on the moved fast-wave plasma: weight,
+    particle number, number density, velocity, velocity^2 and speed sums of every real cell and species in the collecting buffer
+    (the velocity tensor is off in this configuration)"""
+    from oracle.oracle_py import Oracle
+
+    r = live["refpic"]
+    if not hasattr(r.lib, "ref_pic_sample_cells"):
+        pytest.skip("oracle/_ref/libref_pic.so predates ref_pic_sample_cells (rebuild: make -C oracle)")
+    before, _ = None, None
+    ref, cnt = r.sample_cells()       # the collecting buffer after one more sample ...
+    ref2, cnt2 = r.sample_cells()     # ... and after a second one: the difference is exactly one sample
+    one = ref2 - ref
+    m, cfg = live["mesh"], live["cfg"]
+    x, v, w, sp, cells0 = live["parts"]
+    a = live["ref"]["after"]
+    o = Oracle(cfg, m)
+    o.add_particles(a["x"], a["v"], w, sp, a["cells"].astype(np.int32))
+    got, n_sampled = o.sample_cells()
+    o.close()
+    b2l, real = live["maps"]["b2l"], live["maps"]["real"]
+    C = m.cells_per_block
+    got = got.reshape(m.n_leaves, C, cfg.n_species, 13)
+    assert int(cnt2.sum()) == x.shape[1] and list(n_sampled[: cfg.n_species]) == list(cnt2)
+    worst = 0.0
+    for b in real:
+        for q in range(10):
+            d = np.abs(got[b2l[b], :, :, q] - one[b, :, :, q]).max()
+            worst = max(worst, d / max(np.abs(one[:, :, :, q]).max(), 1e-300))
+    assert worst <= 1e-14, worst
+    assert np.abs(one[real][..., 1].sum() - x.shape[1]) == 0  # particle numbers are exact
+
+
+@needs_ref
 def test_oracle_ecsim_field_getters_reproduce_the_reference(live):
     """ECSIM::GetElectricField / GetMagneticField / GetMagneticFieldGradient (pic_field_solver_ecsim.cpp:7440-7547), what the
     guiding-centre movers read when the field solver is ECSIM (cfg.gc_fields_ecsim): the oracle's restatement against the reference's own
