@@ -104,7 +104,6 @@ def test_oracle_cell_sampling_reproduces_the_reference(live):
     r = live["refpic"]
     if not hasattr(r.lib, "ref_pic_sample_cells"):
         pytest.skip("oracle/_ref/libref_pic.so predates ref_pic_sample_cells (rebuild: make -C oracle)")
-    before, _ = None, None
     ref, cnt = r.sample_cells()       # the collecting buffer after one more sample ...
     ref2, cnt2 = r.sample_cells()     # ... and after a second one: the difference is exactly one sample
     one = ref2 - ref
