@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,decomp", [(2, "cart"), (4, "cart"), (8, "cart"), (2, "sfc"), (4, "sfc")])
+@pytest.mark.parametrize("world,decomp", [(2, "cart"), (4, "cart"), (8, "cart"), (2, "sfc")])
 def test_sharded_step_matches_single_domain_oracle(world, decomp):
     import torch
 
