@@ -94,8 +94,20 @@ class EcsimHost {
   // half the PCIe volume; the caller mirrors the other 13 blocks while scattering into the corner buffers
   void MoveAndDepositPacked(double *JM129, int mover = AMPS_MOVER_LAPENTA2017) { check(amps_gpu_step_JM_packed(ctx_, mover, JM129)); }
 
-  // ECSIM::ComputeNetCharge(): rho_new on the unique centre nodes
-  void ComputeNetCharge(double charge_conv, double *rho_center) { check(amps_gpu_net_charge(ctx_, charge_conv, rho_center)); }
+  // ECSIM::ComputeNetCharge(): rho_new on the unique centre nodes.  The reference fills its global StencilTable here, after which its
+  // movers leave full B stencils un-normalised (pic_interpolation_routines.cpp:903): the library is put into the same state
+  void ComputeNetCharge(double charge_conv, double *rho_center) {
+    check(amps_gpu_net_charge(ctx_, charge_conv, rho_center));
+    check(amps_gpu_global_stencil_set(ctx_, 1));
+  }
+
+  // the guiding-centre species of PIC::GYROKINETIC (cfg.gc_species_mask): PB::GetMagneticMoment / PB::GetVNormal by ParticleBuffer slot
+  void SetGuidingCentreState(const double *mu_by_ptr, const double *vnormal_by_ptr, int64_t n) {
+    if (mu_by_ptr) check(amps_gpu_magnetic_moment_upload(ctx_, mu_by_ptr, n));
+    if (vnormal_by_ptr) check(amps_gpu_v_normal_upload(ctx_, vnormal_by_ptr, n));
+  }
+  // the current E on the unique corners: what the guiding-centre movers read with cfg.gc_fields_ecsim (ECSIM::GetElectricField)
+  void SetCurrentE(const double *E_cur) { check(amps_gpu_E_upload(ctx_, E_cur)); }
 
   // ECSIM::CorrectParticleLocation() with phi of the Poisson solve on the unique centre nodes; returns {shifted, deleted}.
   // The species corner moments it reads are sampled here (UpdateJMassMatrix does that in the reference); the lists are rebuilt.
